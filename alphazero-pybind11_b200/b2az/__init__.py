@@ -1,0 +1,217 @@
+"""b2az — ctypes binding of the C ABI in include/b2az.h (libb2az.so, CUDA sm_100a).
+
+This is the thin Python face used by tests/, bench.py and __graft_entry__.py. It mirrors the
+reference's pybind11 surface for the self-play hot path (src/py_wrapper.cc:352-504:
+PlayManager / PlayParams / build_batch / update_inferences / build_history_batch) on top of the
+C ABI; see INTEGRATION.md for the pybind11 stub a maintainer of the reference would add instead.
+
+There is no CPU fallback: `load()` raises if the CUDA library is missing and every call raises
+B2azError when no CUDA device is usable. (`load(path)` with an explicit path exists so the CPU
+test-suite can point the same binding at the host-emulation build of the engine logic.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(os.path.dirname(_HERE), "libb2az.so")
+
+EVAL_NN, EVAL_RANDOM = 0, 1
+RNG_PER_GAME, RNG_GLOBAL = 0, 1
+CANON_SHAPE = (4, 6, 7)
+NUM_MOVES = 7
+NUM_PLAYERS = 2
+
+
+class B2azError(RuntimeError):
+    """Mirrors the reference's std::runtime_error -> RuntimeError convention."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"b2az error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("game", C.c_uint32), ("games_to_play", C.c_uint32), ("concurrent_games", C.c_uint32),
+        ("max_batch_size", C.c_uint32), ("max_cache_size", C.c_uint32), ("mcts_visits", C.c_uint32 * 2),
+        ("cpuct", C.c_float), ("start_temp", C.c_float), ("final_temp", C.c_float),
+        ("temp_decay_half_life", C.c_float), ("history_enabled", C.c_uint8), ("self_play", C.c_uint8),
+        ("tree_reuse", C.c_uint8), ("playout_cap_randomization", C.c_uint8), ("epsilon", C.c_float),
+        ("mcts_root_temp", C.c_float), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
+        ("fpu_reduction", C.c_float), ("root_fpu_zero", C.c_uint8), ("shaped_dirichlet", C.c_uint8),
+        ("policy_target_pruning", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("resign_percent", C.c_float),
+        ("resign_playthrough_percent", C.c_float), ("eval_type", C.c_uint8), ("rng_mode", C.c_uint8),
+        ("pad0_", C.c_uint8), ("pad1_", C.c_uint8), ("seed", C.c_uint64), ("pool_nodes", C.c_uint64),
+        ("history_capacity", C.c_uint32), ("lanes_per_game", C.c_uint32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("simulations", C.c_uint64), ("moves", C.c_uint64), ("games_completed", C.c_uint32),
+        ("games_started", C.c_uint32), ("active_games", C.c_uint32), ("leaf_count", C.c_uint32),
+        ("hist_count", C.c_uint32), ("scores", C.c_float * 3), ("resign_scores", C.c_float * 3),
+        ("avg_game_length", C.c_float), ("avg_leaf_depth", C.c_float), ("avg_search_entropy", C.c_float),
+        ("fast_avg_leaf_depth", C.c_float), ("fast_avg_search_entropy", C.c_float),
+        ("avg_moves_per_turn", C.c_float), ("avg_valid_moves", C.c_float),
+        ("cache_hits", C.c_uint64), ("cache_misses", C.c_uint64), ("cache_evictions", C.c_uint64),
+        ("cache_reinserts", C.c_uint64), ("cache_size", C.c_uint64), ("cache_max_size", C.c_uint64),
+        ("pool_pages_total", C.c_uint64), ("pool_pages_free", C.c_uint64), ("device_error", C.c_uint32),
+    ]
+
+
+_libs = {}
+
+
+def load(path=None):
+    """dlopen the engine. Without `path` this is the product library; it must exist."""
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise B2azError(-2, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                            " (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u32, u64p = C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)
+    L.b2az_last_error.restype = C.c_char_p
+    L.b2az_params_default.argtypes = [C.POINTER(Params)]
+    L.b2az_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(vp)]
+    L.b2az_destroy.argtypes = [vp]
+    L.b2az_step.argtypes = [vp, u32, vp]
+    L.b2az_leaf_batch.argtypes = [vp, vp, C.POINTER(u32), C.POINTER(vp), C.POINTER(vp)]
+    L.b2az_leaf_batch_host.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32)]
+    L.b2az_submit_eval.argtypes = [vp, vp, vp, u32]
+    L.b2az_submit_eval_host.argtypes = [vp, vp, vp, vp, vp, u32]
+    L.b2az_drain_history.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
+    L.b2az_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
+    L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
+    L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
+    _libs[path] = L
+    return L
+
+
+def default_params(lib=None, **kw):
+    L = lib or load()
+    p = Params()
+    L.b2az_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k == "mcts_visits":
+            p.mcts_visits[0], p.mcts_visits[1] = v
+        else:
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One device-resident self-play pool (the reference's PlayManager for one model group)."""
+
+    def __init__(self, params, device=0, lib=None):
+        self.L = lib or load()
+        self.params = params
+        self.h = C.c_void_p()
+        self._check(self.L.b2az_create(C.byref(params), device, C.byref(self.h)))
+        self.G = params.concurrent_games
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2azError(rc, self.L.b2az_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.b2az_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- PlayManager::play() loop body over every slot
+    def step(self, n_steps=1, stream=None):
+        self._check(self.L.b2az_step(self.h, n_steps, stream))
+
+    # -- build_batch (device pointers): returns (count, canon_ptr, ids_ptr)
+    def leaf_batch(self, stream=None):
+        n, cp, ip = C.c_uint32(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.b2az_leaf_batch(self.h, stream, C.byref(n), C.byref(cp), C.byref(ip)))
+        return n.value, cp.value, ip.value
+
+    # -- build_batch (host buffers): returns (ids uint32[n], canonical float32[n,4,6,7])
+    def leaf_batch_host(self, max_rows=None, stream=None):
+        m = max_rows or self.G
+        canon = np.empty((m,) + CANON_SHAPE, np.float32)
+        ids = np.empty(m, np.uint32)
+        n = C.c_uint32()
+        self._check(self.L.b2az_leaf_batch_host(self.h, stream, m, _ptr(canon), _ptr(ids), C.byref(n)))
+        return ids[: n.value], canon[: n.value]
+
+    def submit_eval(self, v_dev_ptr, pi_dev_ptr, count):
+        self._check(self.L.b2az_submit_eval(self.h, v_dev_ptr, pi_dev_ptr, count))
+
+    # -- update_inferences(group, indices, v, pi)
+    def submit_eval_host(self, ids, v, pi, stream=None):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        v = np.ascontiguousarray(v, np.float32)
+        pi = np.ascontiguousarray(pi, np.float32)
+        assert v.shape == (len(ids), NUM_PLAYERS + 1) and pi.shape == (len(ids), NUM_MOVES)
+        self._check(self.L.b2az_submit_eval_host(self.h, stream, _ptr(ids), _ptr(v), _ptr(pi), len(ids)))
+
+    # -- build_history_batch
+    def drain_history(self, max_rows, stream=None):
+        canon = np.empty((max_rows,) + CANON_SHAPE, np.float32)
+        v = np.empty((max_rows, NUM_PLAYERS + 1), np.float32)
+        pi = np.empty((max_rows, NUM_MOVES), np.float32)
+        n = C.c_uint32()
+        self._check(self.L.b2az_drain_history(self.h, stream, max_rows, _ptr(canon), _ptr(v), _ptr(pi), 0, C.byref(n)))
+        return canon[: n.value], v[: n.value], pi[: n.value]
+
+    def drain_history_device(self, max_rows, canon_ptr, v_ptr, pi_ptr, stream=None):
+        n = C.c_uint32()
+        self._check(self.L.b2az_drain_history(self.h, stream, max_rows, canon_ptr, v_ptr, pi_ptr, 1, C.byref(n)))
+        return n.value
+
+    def stats(self, stream=None):
+        s = Stats()
+        self._check(self.L.b2az_get_stats(self.h, stream, C.byref(s)))
+        return s
+
+    def peek(self, game, seat, stream=None):
+        state = np.zeros(89, np.uint8)
+        counts = np.zeros(7, np.uint32)
+        q = np.zeros(7, np.float32)
+        pol = np.zeros(7, np.float32)
+        rv = np.zeros(3, np.float32)
+        depth, root_n = C.c_uint32(), C.c_uint32()
+        self._check(self.L.b2az_peek(self.h, stream, game, seat, _ptr(state), _ptr(counts), _ptr(q), _ptr(rv),
+                                     C.byref(depth), C.byref(root_n), _ptr(pol)))
+        return dict(state=state, counts=counts, q=q, policy=pol, root_value=rv, depth=depth.value,
+                    root_n=root_n.value)
+
+
+def c4_batch(boards, players, turns, moves=None, device=0, lib=None):
+    """Batched Connect4 game kernels (valid_moves / play_move / scores / canonicalized)."""
+    L = lib or load()
+    boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 84)
+    n = boards.shape[0]
+    players = np.ascontiguousarray(players, np.uint8)
+    turns = np.ascontiguousarray(turns, np.uint32)
+    mv = None if moves is None else np.ascontiguousarray(moves, np.uint32)
+    out = dict(boards=np.zeros((n, 2, 6, 7), np.int8), players=np.zeros(n, np.uint8),
+               valid=np.zeros((n, 7), np.uint8), scores=np.zeros((n, 3), np.float32),
+               terminal=np.zeros(n, np.uint8), canonical=np.zeros((n, 4, 6, 7), np.float32),
+               status=np.zeros(n, np.int32))
+    rc = L.b2az_c4_batch(device, n, _ptr(boards), _ptr(players), _ptr(turns), _ptr(mv), _ptr(out["boards"]),
+                         _ptr(out["players"]), _ptr(out["valid"]), _ptr(out["scores"]), _ptr(out["terminal"]),
+                         _ptr(out["canonical"]), _ptr(out["status"]))
+    if rc != 0:
+        raise B2azError(rc, L.b2az_last_error().decode())
+    return out

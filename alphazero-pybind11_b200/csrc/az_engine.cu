@@ -1,0 +1,861 @@
+// az_engine.cu — kernels + host side of the C ABI declared in include/b2az.h.
+//
+// Kernels (sm_100a):
+//   k_step<W>        one group of W lanes per game slot; per step runs game_step<W>() =
+//                    process_result -> [move] -> find_leaf (az_engine_logic.h). With RANDOM eval the
+//                    evaluator is inline and n_steps are fused into one launch (persistent per slot).
+//   k_step_serial<W> B2AZ_RNG_GLOBAL: one group walks the slots in ascending order so the single
+//                    pcg32 stream is consumed in the reference's order (bit-exact parity mode).
+//   k_canonicalize   compact leaf positions -> dense float32[B][4][6][7] for the torch net.
+//   k_hist_expand    compact finished samples -> canonical / v / pi arrays.
+//   k_peek, k_stats, k_c4_batch: inspection + the batched bitboard game kernels.
+//
+// The file also compiles as plain C++ with -DB2AZ_HOST_EMU (kernels become loops over W = 1
+// groups, device memory becomes calloc). That build exists ONLY for the CPU test-suite
+// (tests/cpp/, build/libb2az_hostemu.so); the product library never defines the macro and every
+// entry point fails with B2AZ_ECUDA when no CUDA device is usable.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2az.h"
+#include "az_engine_logic.h"
+
+#ifndef B2AZ_HOST_EMU
+#include <cuda_runtime.h>
+#endif
+
+using namespace b2az;
+
+namespace {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#ifndef B2AZ_HOST_EMU
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t err__ = (expr);                                                              \
+    if (err__ != cudaSuccess)                                                                \
+      return fail(B2AZ_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));       \
+  } while (0)
+typedef cudaStream_t stream_t;
+#else
+#define CUDA_TRY(expr) \
+  do {                 \
+    (void)(expr);      \
+  } while (0)
+typedef void* stream_t;
+#endif
+
+// ------------------------------------------------------------------------------------ memory shims
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  CUDA_TRY(cudaMemset(*p, 0, count * sizeof(T)));
+#else
+  *p = static_cast<T*>(calloc(count ? count : 1, sizeof(T)));
+  if (!*p) return fail(B2AZ_ENOMEM, "calloc failed");
+#endif
+  return 0;
+}
+template <typename T>
+void dev_free(T* p) {
+  if (!p) return;
+#ifndef B2AZ_HOST_EMU
+  cudaFree(const_cast<typename std::remove_const<T>::type*>(p));
+#else
+  free(const_cast<typename std::remove_const<T>::type*>(p));
+#endif
+}
+int copy_h2d(void* dst, const void* src, size_t bytes, stream_t s) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+#else
+  (void)s;
+  memcpy(dst, src, bytes);
+#endif
+  return 0;
+}
+int copy_d2h(void* dst, const void* src, size_t bytes, stream_t s) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+#else
+  (void)s;
+  memcpy(dst, src, bytes);
+#endif
+  return 0;
+}
+int copy_d2d(void* dst, const void* src, size_t bytes, stream_t s) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+#else
+  (void)s;
+  memcpy(dst, src, bytes);
+#endif
+  return 0;
+}
+int dev_zero(void* dst, size_t bytes, stream_t s) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaMemsetAsync(dst, 0, bytes, s));
+#else
+  (void)s;
+  memset(dst, 0, bytes);
+#endif
+  return 0;
+}
+int stream_sync(stream_t s) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaStreamSynchronize(s));
+#else
+  (void)s;
+#endif
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ kernels
+#ifndef B2AZ_HOST_EMU
+#define KERNEL __global__
+#define GLOBAL_TID (blockIdx.x * blockDim.x + threadIdx.x)
+#define GLOBAL_NT (gridDim.x * blockDim.x)
+#else
+#define KERNEL
+#endif
+
+struct InitArgs {
+  u64 seed;
+  u32 rng_mode;
+};
+
+#ifndef B2AZ_HOST_EMU
+__global__ void k_init_pool(EngineView E) {
+  // pages are dealt round-robin onto the stack shards: page p -> shard p % kNumStacks, chained
+  // p -> p + kNumStacks; the heads are written by k_init_heads.
+  for (u32 p = GLOBAL_TID; p < E.num_pages; p += GLOBAL_NT) {
+    const u32 nx = p + (u32)kNumStacks;
+    E.page_next[p] = nx < E.num_pages ? nx : kNil;
+    E.page_fill[p] = 0;
+  }
+}
+__global__ void k_init_games(EngineView E, InitArgs a) {
+  for (u32 g = GLOBAL_TID; g < E.G; g += GLOBAL_NT) {
+    GameSlot gs;
+    memset(&gs, 0, sizeof(gs));
+    gs.active = 1;
+    pcg32_seed_stream(gs.rng, a.seed, (u64)g);
+    E.games[g] = gs;
+    TreeHdr T;
+    tree_reset(T);
+    E.trees[(size_t)g * kP + 0] = T;
+    E.trees[(size_t)g * kP + 1] = T;
+  }
+  if (GLOBAL_TID == 0) {
+    Globals* G = E.glob;
+    memset(G, 0, sizeof(Globals));
+    G->games_started = E.G;
+    G->active_games = E.G;
+    pcg32_seed(G->global_rng, a.seed);
+    for (u32 s = 0; s < (u32)kNumStacks; ++s) E.stack_head[s] = (unsigned long long)(s < E.num_pages ? s : kNil);
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_step(EngineView E, u32 n_steps) {
+  const u32 group = GLOBAL_TID / W;
+  const u32 ngroups = GLOBAL_NT / W;
+  for (u32 g = group; g < E.G; g += ngroups)
+    for (u32 s = 0; s < n_steps; ++s) game_step<W>(E, g);
+}
+template <int W>
+__global__ void k_step_serial(EngineView E, u32 n_steps) {
+  for (u32 s = 0; s < n_steps; ++s)
+    for (u32 g = 0; g < E.G; ++g) game_step<W>(E, g);
+}
+
+__global__ void k_canonicalize(EngineView E, const u32* __restrict__ count_ptr, float* __restrict__ out) {
+  const u32 count = *count_ptr;
+  const size_t total = (size_t)count * C4_CANON;
+  for (size_t i = GLOBAL_TID; i < total; i += GLOBAL_NT) {
+    const u32 row = (u32)(i / C4_CANON), e = (u32)(i % C4_CANON);
+    out[i] = c4_canon_elem(E.leaf_p0[row], E.leaf_p1[row], E.leaf_player[row], e);
+  }
+}
+__global__ void k_hist_expand(EngineView E, unsigned long long first, u32 count, float* __restrict__ canon,
+                              float* __restrict__ v, float* __restrict__ pi) {
+  const size_t total = (size_t)count * C4_CANON;
+  for (size_t i = GLOBAL_TID; i < total; i += GLOBAL_NT) {
+    const u32 row = (u32)(i / C4_CANON), e = (u32)(i % C4_CANON);
+    const HistEntry& h = E.hist_out[(first + row) % (unsigned long long)E.hist_capacity];
+    canon[i] = c4_canon_elem(h.p0, h.p1, h.player, e);
+    if (e < 3u) v[(size_t)row * 3 + e] = (h.result == e + 1u) ? 1.0f : 0.0f;
+    if (e < (u32)kA) pi[(size_t)row * kA + e] = h.pi[e];
+  }
+}
+#endif  // !B2AZ_HOST_EMU
+
+struct PeekOut {
+  u8 state[89];
+  u32 counts[kA];
+  float q[kA];
+  float policy[kA];
+  float root_value[3];
+  u32 depth, root_n;
+};
+AZ_HD void peek_impl(const EngineView& E, u32 g, u32 seat, PeekOut* o) {
+  const GameSlot& gs = E.games[g];
+  C4State s;
+  s.p[0] = gs.p0; s.p[1] = gs.p1; s.turn = gs.turn; s.player = gs.player;
+  c4_to_board(s, reinterpret_cast<signed char*>(o->state));
+  o->state[84] = gs.player;
+  const u32 turn = gs.turn;
+  o->state[85] = (u8)(turn & 0xFF); o->state[86] = (u8)((turn >> 8) & 0xFF);
+  o->state[87] = (u8)((turn >> 16) & 0xFF); o->state[88] = (u8)((turn >> 24) & 0xFF);
+  const TreeHdr& T = E.trees[(size_t)g * kP + seat];
+  RootView R;
+  root_view<1>(E, T, R);
+  for (int m = 0; m < kA; ++m) { o->counts[m] = 0; o->q[m] = 0.0f; o->policy[m] = 0.0f; }
+  for (u32 j = 0; j < R.k; ++j) {
+    o->counts[R.mv[j]] = R.K.n[j];
+    o->q[R.mv[j]] = R.K.n[j] ? R.K.q[j] : 0.0f;
+    o->policy[R.mv[j]] = R.K.pol[j];
+  }
+  mcts_root_value(E, T, R, o->root_value);
+  o->depth = T.depth;
+  o->root_n = T.n;
+}
+struct StatsOut {
+  unsigned long long sims, moves;
+};
+#ifndef B2AZ_HOST_EMU
+__global__ void k_peek(EngineView E, u32 g, u32 seat, PeekOut* o) { peek_impl(E, g, seat, o); }
+__global__ void k_stats(EngineView E, StatsOut* o) {
+  unsigned long long s = 0, m = 0;
+  for (u32 g = GLOBAL_TID; g < E.G; g += GLOBAL_NT) { s += E.games[g].sims; m += E.games[g].nmoves; }
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_down_sync(0xFFFFFFFFu, s, off);
+    m += __shfl_down_sync(0xFFFFFFFFu, m, off);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&o->sims, s); atomicAdd(&o->moves, m); }
+}
+__global__ void k_count_free_pages(EngineView E, unsigned long long* out) {
+  // walks the stacks; only meaningful while no step kernel is running
+  if (GLOBAL_TID < (u32)kNumStacks) {
+    unsigned long long c = 0;
+    u32 p = (u32)E.stack_head[GLOBAL_TID];
+    while (p != kNil) { ++c; p = E.page_next[p]; }
+    atomicAdd(out, c);
+  }
+}
+#endif
+
+struct C4BatchArgs {
+  u32 n;
+  const signed char* boards;
+  const u8* players;
+  const u32* turns;
+  const u32* moves;
+  signed char* boards_out;
+  u8* players_out;
+  u8* valid;
+  float* scores;
+  u8* terminal;
+  float* canonical;
+  i32* status;
+};
+AZ_HD void c4_batch_one(const C4BatchArgs& a, u32 i) {
+  C4State s;
+  c4_from_board(s, a.boards + (size_t)i * 84, a.players[i], (int)a.turns[i]);
+  i32 st = 0;
+  if (a.moves && a.moves[i] != 0xFFFFFFFFu) {
+    if (a.moves[i] >= (u32)kA || !c4_play(s, a.moves[i])) st = B2AZ_EMOVE;
+  }
+  if (a.status) a.status[i] = st;
+  if (a.boards_out) c4_to_board(s, a.boards_out + (size_t)i * 84);
+  if (a.players_out) a.players_out[i] = s.player;
+  if (a.valid) {
+    const u32 vm = c4_valid_mask(s);
+    for (int w = 0; w < kA; ++w) a.valid[(size_t)i * kA + w] = (u8)((vm >> w) & 1u);
+  }
+  const u32 term = c4_terminal(s);
+  if (a.terminal) a.terminal[i] = term ? 1 : 0;
+  if (a.scores)
+    for (u32 e = 0; e < 3u; ++e) a.scores[(size_t)i * 3 + e] = (term == e + 1u) ? 1.0f : 0.0f;
+  if (a.canonical)
+    for (u32 e = 0; e < (u32)C4_CANON; ++e)
+      a.canonical[(size_t)i * C4_CANON + e] = c4_canon_elem(s.p[0], s.p[1], s.player, e);
+}
+#ifndef B2AZ_HOST_EMU
+__global__ void k_c4_batch(C4BatchArgs a) {
+  for (u32 i = GLOBAL_TID; i < a.n; i += GLOBAL_NT) c4_batch_one(a, i);
+}
+#endif
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ engine object
+struct b2az_engine {
+  b2az_params params;
+  int device = 0;
+  int num_sms = 148;
+  u32 lanes = 8;
+  EngineView view;
+  // owned device buffers
+  float* canon_buf = nullptr;   // [G][168]
+  float* ev_v_buf = nullptr;    // [G][3]   (legacy host path staging target)
+  float* ev_pi_buf = nullptr;   // [G][7]
+  PeekOut* peek_buf = nullptr;
+  StatsOut* stats_buf = nullptr;
+  unsigned long long* freepages_buf = nullptr;
+  float* hist_canon = nullptr;  // drain staging when the destination is host memory
+  float* hist_v = nullptr;
+  float* hist_pi = nullptr;
+  u32 hist_stage_cap = 0;
+  // host-side bookkeeping of the current leaf batch
+  bool leaves_pending = false;      // a step produced leaves that have not all been answered
+  u32 leaf_count = 0;               // valid once leaf_count_known
+  bool leaf_count_known = false;
+  bool canon_ready = false;
+  u32 leaves_taken = 0;             // legacy build_batch cursor
+  u32 evals_submitted = 0;
+  std::vector<u32> leaf_ids_host;   // slot id of every leaf row (for submit_eval_host)
+  std::vector<u32> row_of_game;     // slot id -> row
+  std::vector<float> stage_v, stage_pi;
+  bool started = false;
+};
+
+namespace {
+
+int sync_leaf_count(b2az_engine* e, stream_t s) {
+  if (e->leaf_count_known) return 0;
+  u32 c = 0;
+  if (int rc = copy_d2h(&c, &e->view.glob->leaf_count, sizeof(u32), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  e->leaf_count = c;
+  e->leaf_count_known = true;
+  return 0;
+}
+
+int ensure_canon(b2az_engine* e, stream_t s) {
+  if (e->canon_ready) return 0;
+#ifndef B2AZ_HOST_EMU
+  const int blocks = e->num_sms * 8;
+  k_canonicalize<<<blocks, 256, 0, s>>>(e->view, &e->view.glob->leaf_count, e->canon_buf);
+  CUDA_TRY(cudaGetLastError());
+#else
+  const u32 count = e->view.glob->leaf_count;
+  for (size_t i = 0; i < (size_t)count * C4_CANON; ++i) {
+    const u32 row = (u32)(i / C4_CANON), el = (u32)(i % C4_CANON);
+    e->canon_buf[i] = c4_canon_elem(e->view.leaf_p0[row], e->view.leaf_p1[row], e->view.leaf_player[row], el);
+  }
+#endif
+  e->canon_ready = true;
+  return 0;
+}
+
+int check_device_error(b2az_engine* e, stream_t s) {
+  u32 err = 0;
+  if (int rc = copy_d2h(&err, &e->view.glob->error, sizeof(u32), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  if (err & B2AZ_DEVERR_POOL) return fail(B2AZ_ENOMEM, "device tree-node pool exhausted: raise b2az_params.pool_nodes");
+  if (err & B2AZ_DEVERR_MOVE) return fail(B2AZ_EMOVE, "device: update_root could not find the move / illegal move");
+  if (err & B2AZ_DEVERR_DEPTH) return fail(B2AZ_ESTATE, "device: selection path exceeded the path buffer");
+  if (err & B2AZ_DEVERR_HIST) return fail(B2AZ_ENOMEM, "device history ring overflowed: drain more often or raise history_capacity");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2az_last_error(void) { return g_last_error.c_str(); }
+
+int b2az_params_default(b2az_params* p) {
+  if (!p) return fail(B2AZ_EINVAL, "null params");
+  memset(p, 0, sizeof(*p));
+  p->game = B2AZ_GAME_CONNECT4;
+  p->games_to_play = 1;
+  p->concurrent_games = 1;
+  p->max_batch_size = 0;
+  p->mcts_visits[0] = p->mcts_visits[1] = 100;
+  p->cpuct = 2.0f;          // PlayParams defaults (play_manager.h:83-102)
+  p->start_temp = 1.0f;
+  p->final_temp = 1.0f;
+  p->temp_decay_half_life = 0.0f;
+  p->tree_reuse = 1;
+  p->epsilon = 0.0f;
+  p->mcts_root_temp = 1.0f;
+  p->playout_cap_depth = 25;
+  p->playout_cap_percent = 0.75f;
+  p->eval_type = B2AZ_EVAL_NN;
+  p->rng_mode = B2AZ_RNG_PER_GAME;
+  p->seed = 0;
+  return 0;
+}
+
+int b2az_destroy(b2az_engine* e) {
+  if (!e) return 0;
+#ifndef B2AZ_HOST_EMU
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+#endif
+  EngineView& V = e->view;
+  dev_free(V.q); dev_free(V.pol); dev_free(V.n); dev_free(V.mv); dev_free(V.rec);
+  dev_free(V.page_next); dev_free(V.page_fill); dev_free(V.stack_head);
+  dev_free(V.trees); dev_free(V.games); dev_free(V.path);
+  dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game);
+  dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
+  dev_free(e->canon_buf); dev_free(e->ev_v_buf); dev_free(e->ev_pi_buf);
+  dev_free(e->peek_buf); dev_free(e->stats_buf); dev_free(e->freepages_buf);
+  dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
+  delete e;
+  return 0;
+}
+
+int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
+  if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
+  *out = nullptr;
+  if (p->game != B2AZ_GAME_CONNECT4) return fail(B2AZ_EINVAL, "only B2AZ_GAME_CONNECT4 is implemented");
+  if (p->concurrent_games == 0) return fail(B2AZ_EINVAL, "concurrent_games must be > 0");
+  if (p->games_to_play < p->concurrent_games)
+    return fail(B2AZ_EINVAL, "games_to_play must be >= concurrent_games (every slot starts a game)");
+  if (p->mcts_visits[0] == 0 || p->mcts_visits[1] == 0)
+    return fail(B2AZ_EINVAL, "You must specify MCTS visits for each player");  // play_manager.cc:21
+  if (p->gumbel_enabled) return fail(B2AZ_EINVAL, "gumbel_enabled is not implemented yet");
+  if (p->resign_percent != 0.0f) return fail(B2AZ_EINVAL, "resign_percent is not implemented yet");
+  if (p->playout_cap_randomization) return fail(B2AZ_EINVAL, "playout_cap_randomization is not implemented yet");
+  if (p->eval_type != B2AZ_EVAL_NN && p->eval_type != B2AZ_EVAL_RANDOM) return fail(B2AZ_EINVAL, "bad eval_type");
+  if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
+  if (p->max_cache_size != 0) return fail(B2AZ_EINVAL, "the device position cache is not implemented yet");
+  u32 lanes = p->lanes_per_game ? p->lanes_per_game : 8u;
+  if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 32)
+    return fail(B2AZ_EINVAL, "lanes_per_game must be 1, 4, 8 or 32");
+#ifdef B2AZ_HOST_EMU
+  lanes = 1;
+  (void)device;
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(B2AZ_EINVAL, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+#endif
+  b2az_engine* e = new b2az_engine();
+  e->params = *p;
+  e->device = device;
+  e->lanes = lanes;
+#ifndef B2AZ_HOST_EMU
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  e->num_sms = prop.multiProcessorCount;
+#endif
+  const u32 G = p->concurrent_games;
+  EngineView& V = e->view;
+  memset(&V, 0, sizeof(V));
+  V.G = G;
+  V.games_to_play = p->games_to_play;
+  V.visits[0] = p->mcts_visits[0]; V.visits[1] = p->mcts_visits[1];
+  V.cap_visits[0] = V.cap_visits[1] = p->playout_cap_depth;
+  V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.epsilon = p->epsilon; V.root_temp = p->mcts_root_temp;
+  V.start_temp = p->start_temp; V.final_temp = p->final_temp; V.half_life = p->temp_decay_half_life;
+  V.playout_cap_percent = p->playout_cap_percent;
+  V.history_enabled = p->history_enabled; V.tree_reuse = p->tree_reuse; V.root_fpu_zero = p->root_fpu_zero;
+  V.shaped_dirichlet = p->shaped_dirichlet; V.policy_target_pruning = p->policy_target_pruning;
+  V.playout_cap = 0; V.eval_type = p->eval_type; V.rng_mode = p->rng_mode;
+
+  // ---- pool sizing: pages of 256 nodes, 30 B per node
+  u64 pool_nodes = p->pool_nodes;
+  if (pool_nodes == 0) {
+    // default: room for every tree to hold a full search's worth of children twice over
+    const u64 per_tree = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]) * 8ull * 3ull + 2ull * kPageNodes;
+    pool_nodes = per_tree * (u64)G * kP;
+#ifndef B2AZ_HOST_EMU
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const u64 cap = (u64)(free_b * 0.6) / 30ull;
+    if (pool_nodes > cap) pool_nodes = cap;
+#endif
+  }
+  u64 pages = (pool_nodes + kPageNodes - 1) / kPageNodes;
+  if (pages < (u64)kNumStacks) pages = kNumStacks;
+  if (pages > 0x00FFFFFFull) pages = 0x00FFFFFFull;  // node index must fit 32 bits
+  V.num_pages = (u32)pages;
+  const size_t nodes = (size_t)pages * kPageNodes;
+  V.hist_capacity = p->history_capacity ? p->history_capacity : std::max<u32>(1u << 16, G * (u32)kMaxHist);
+
+  int rc = 0;
+  auto A = [&](int r) { if (r && !rc) rc = r; };
+  A(dev_alloc(&V.q, nodes)); A(dev_alloc(&V.pol, nodes)); A(dev_alloc(&V.n, nodes));
+  A(dev_alloc(&V.mv, nodes)); A(dev_alloc(&V.rec, nodes));
+  A(dev_alloc(&V.page_next, pages)); A(dev_alloc(&V.page_fill, pages));
+  A(dev_alloc(&V.stack_head, (size_t)kNumStacks));
+  A(dev_alloc(&V.trees, (size_t)G * kP)); A(dev_alloc(&V.games, (size_t)G));
+  A(dev_alloc(&V.path, (size_t)G * kMaxPath));
+  A(dev_alloc(&V.leaf_p0, (size_t)G)); A(dev_alloc(&V.leaf_p1, (size_t)G));
+  A(dev_alloc(&V.leaf_player, (size_t)G)); A(dev_alloc(&V.leaf_game, (size_t)G));
+  A(dev_alloc(&V.hist_partial, p->history_enabled ? (size_t)G * kMaxHist : 1));
+  A(dev_alloc(&V.hist_out, p->history_enabled ? (size_t)V.hist_capacity : 1));
+  A(dev_alloc(&V.glob, 1));
+  A(dev_alloc(&e->canon_buf, (size_t)G * C4_CANON));
+  A(dev_alloc(&e->ev_v_buf, (size_t)G * (kP + 1))); A(dev_alloc(&e->ev_pi_buf, (size_t)G * kA));
+  A(dev_alloc(&e->peek_buf, 1)); A(dev_alloc(&e->stats_buf, 1)); A(dev_alloc(&e->freepages_buf, 1));
+  if (rc) { b2az_destroy(e); return rc; }
+  V.ev_v = e->ev_v_buf;
+  V.ev_pi = e->ev_pi_buf;
+
+  // ---- init
+#ifndef B2AZ_HOST_EMU
+  InitArgs ia{p->seed, p->rng_mode};
+  k_init_pool<<<e->num_sms * 4, 256>>>(V);
+  k_init_games<<<e->num_sms * 4, 256>>>(V, ia);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+#else
+  for (u32 pg = 0; pg < V.num_pages; ++pg) {
+    const u32 nx = pg + (u32)kNumStacks;
+    V.page_next[pg] = nx < V.num_pages ? nx : kNil;
+  }
+  for (u32 g = 0; g < G; ++g) {
+    GameSlot gs;
+    memset(&gs, 0, sizeof(gs));
+    gs.active = 1;
+    pcg32_seed_stream(gs.rng, p->seed, (u64)g);
+    V.games[g] = gs;
+    TreeHdr T;
+    tree_reset(T);
+    V.trees[(size_t)g * kP + 0] = T;
+    V.trees[(size_t)g * kP + 1] = T;
+  }
+  memset(V.glob, 0, sizeof(Globals));
+  V.glob->games_started = G;
+  V.glob->active_games = G;
+  pcg32_seed(V.glob->global_rng, p->seed);
+  for (u32 s = 0; s < (u32)kNumStacks; ++s) V.stack_head[s] = (unsigned long long)(s < V.num_pages ? s : kNil);
+#endif
+  e->row_of_game.assign(G, 0);
+  *out = e;
+  return 0;
+}
+
+int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
+  if (!e) return fail(B2AZ_EINVAL, "null engine");
+  if (n_steps == 0) return 0;
+  stream_t s = static_cast<stream_t>(stream);
+  EngineView& V = e->view;
+  if (V.eval_type == B2AZ_EVAL_NN) {
+    if (n_steps != 1) return fail(B2AZ_EINVAL, "n_steps must be 1 with B2AZ_EVAL_NN");
+    if (e->leaves_pending) {
+      if (int rc = sync_leaf_count(e, s)) return rc;
+      if (e->evals_submitted < e->leaf_count)
+        return fail(B2AZ_ESTATE, "b2az_step: leaves of the previous step are still waiting for b2az_submit_eval");
+    }
+    if (int rc = dev_zero(&V.glob->leaf_count, sizeof(u32), s)) return rc;
+  }
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (V.rng_mode == B2AZ_RNG_GLOBAL) {
+    switch (e->lanes) {
+      case 1: k_step_serial<1><<<1, 32, 0, s>>>(V, n_steps); break;
+      case 4: k_step_serial<4><<<1, 32, 0, s>>>(V, n_steps); break;
+      case 8: k_step_serial<8><<<1, 32, 0, s>>>(V, n_steps); break;
+      default: k_step_serial<32><<<1, 32, 0, s>>>(V, n_steps); break;
+    }
+  } else {
+    const u32 threads = 256;
+    const u64 want = ((u64)V.G * e->lanes + threads - 1) / threads;
+    const u32 blocks = (u32)std::max<u64>(1, want);
+    switch (e->lanes) {
+      case 1: k_step<1><<<blocks, threads, 0, s>>>(V, n_steps); break;
+      case 4: k_step<4><<<blocks, threads, 0, s>>>(V, n_steps); break;
+      case 8: k_step<8><<<blocks, threads, 0, s>>>(V, n_steps); break;
+      default: k_step<32><<<blocks, threads, 0, s>>>(V, n_steps); break;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+#else
+  // B2AZ_RNG_GLOBAL needs slot-major order inside a step (matches k_step_serial); per-game RNG is
+  // order independent, so the same loop serves both.
+  for (u32 st = 0; st < n_steps; ++st)
+    for (u32 g = 0; g < V.G; ++g) game_step<1>(V, g);
+#endif
+  e->started = true;
+  if (V.eval_type == B2AZ_EVAL_NN) {
+    e->leaves_pending = true;
+    e->leaf_count_known = false;
+    e->canon_ready = false;
+    e->leaves_taken = 0;
+    e->evals_submitted = 0;
+    V.ev_v = e->ev_v_buf;
+    V.ev_pi = e->ev_pi_buf;
+  }
+  return 0;
+}
+
+int b2az_leaf_batch(b2az_engine* e, void* stream, uint32_t* count, const float** canon_dev, const uint32_t** ids_dev) {
+  if (!e || !count) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
+  if (!e->leaves_pending) { *count = 0; return 0; }
+  if (int rc = ensure_canon(e, s)) return rc;
+  if (int rc = sync_leaf_count(e, s)) return rc;
+  if (int rc = check_device_error(e, s)) return rc;
+  *count = e->leaf_count;
+  if (canon_dev) *canon_dev = e->canon_buf;
+  if (ids_dev) *ids_dev = e->view.leaf_game;
+  return 0;
+}
+
+int b2az_leaf_batch_host(b2az_engine* e, void* stream, uint32_t max, float* canon_host, uint32_t* ids_host,
+                         uint32_t* count) {
+  if (!e || !count || !canon_host || !ids_host) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
+  *count = 0;
+  if (!e->leaves_pending) return 0;
+  if (int rc = ensure_canon(e, s)) return rc;
+  if (int rc = sync_leaf_count(e, s)) return rc;
+  if (int rc = check_device_error(e, s)) return rc;
+  if (e->leaf_ids_host.size() != e->leaf_count || e->leaves_taken == 0) {
+    e->leaf_ids_host.resize(e->leaf_count);
+    if (e->leaf_count) {
+      if (int rc = copy_d2h(e->leaf_ids_host.data(), e->view.leaf_game, (size_t)e->leaf_count * 4, s)) return rc;
+      if (int rc = stream_sync(s)) return rc;
+    }
+    for (u32 r = 0; r < e->leaf_count; ++r) e->row_of_game[e->leaf_ids_host[r]] = r;
+  }
+  const u32 n = std::min(max, e->leaf_count - e->leaves_taken);
+  if (n == 0) return 0;
+  if (int rc = copy_d2h(canon_host, e->canon_buf + (size_t)e->leaves_taken * C4_CANON, (size_t)n * C4_CANON * 4, s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  memcpy(ids_host, e->leaf_ids_host.data() + e->leaves_taken, (size_t)n * 4);
+  e->leaves_taken += n;
+  *count = n;
+  return 0;
+}
+
+int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, uint32_t count) {
+  if (!e || (count && (!v_dev || !pi_dev))) return fail(B2AZ_EINVAL, "null argument");
+  if (!e->leaves_pending) return fail(B2AZ_ESTATE, "no leaf batch is waiting for evaluations");
+  if (!e->leaf_count_known) return fail(B2AZ_ESTATE, "call b2az_leaf_batch before b2az_submit_eval");
+  if (count != e->leaf_count) return fail(B2AZ_EINVAL, "b2az_submit_eval: count must equal the leaf count");
+  e->view.ev_v = v_dev;
+  e->view.ev_pi = pi_dev;
+  e->evals_submitted = count;
+  return 0;
+}
+
+int b2az_submit_eval_host(b2az_engine* e, void* stream, const uint32_t* ids_host, const float* v_host,
+                          const float* pi_host, uint32_t count) {
+  if (!e || (count && (!ids_host || !v_host || !pi_host))) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (!e->leaves_pending || !e->leaf_count_known) return fail(B2AZ_ESTATE, "no leaf batch is waiting for evaluations");
+  if (e->evals_submitted + count > e->leaf_count) return fail(B2AZ_EINVAL, "more evaluations than leaves");
+  // contiguous run of rows? (the common case: ids come straight from b2az_leaf_batch_host)
+  bool contiguous = true;
+  for (u32 i = 0; i < count; ++i) {
+    if (ids_host[i] >= e->view.G) return fail(B2AZ_EINVAL, "bad slot id");
+    if (e->row_of_game[ids_host[i]] != e->row_of_game[ids_host[0]] + i) contiguous = false;
+  }
+  if (count == 0) return 0;
+  if (contiguous) {
+    const u32 r0 = e->row_of_game[ids_host[0]];
+    if (int rc = copy_h2d(e->ev_v_buf + (size_t)r0 * (kP + 1), v_host, (size_t)count * (kP + 1) * 4, s)) return rc;
+    if (int rc = copy_h2d(e->ev_pi_buf + (size_t)r0 * kA, pi_host, (size_t)count * kA * 4, s)) return rc;
+  } else {
+    for (u32 i = 0; i < count; ++i) {
+      const u32 r = e->row_of_game[ids_host[i]];
+      if (int rc = copy_h2d(e->ev_v_buf + (size_t)r * (kP + 1), v_host + (size_t)i * (kP + 1), (kP + 1) * 4, s)) return rc;
+      if (int rc = copy_h2d(e->ev_pi_buf + (size_t)r * kA, pi_host + (size_t)i * kA, kA * 4, s)) return rc;
+    }
+  }
+  if (int rc = stream_sync(s)) return rc;  // the host buffers may be reused by the caller
+  e->view.ev_v = e->ev_v_buf;
+  e->view.ev_pi = e->ev_pi_buf;
+  e->evals_submitted += count;
+  return 0;
+}
+
+int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
+                       int dst_is_device, uint32_t* count) {
+  if (!e || !count) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  *count = 0;
+  if (!e->params.history_enabled || max == 0) return 0;
+  unsigned long long wr[2];
+  if (int rc = copy_d2h(wr, &e->view.glob->hist_written, sizeof(wr), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  const unsigned long long avail = wr[0] - wr[1];
+  const u32 n = (u32)std::min<unsigned long long>(avail, max);
+  if (n == 0) return 0;
+  float *dc = canon, *dv = v, *dp = pi;
+#ifndef B2AZ_HOST_EMU
+  if (!dst_is_device) {
+    if (e->hist_stage_cap < n) {
+      dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
+      e->hist_canon = e->hist_v = e->hist_pi = nullptr;
+      const u32 cap = std::max<u32>(n, 4096);
+      if (int rc = dev_alloc(&e->hist_canon, (size_t)cap * C4_CANON)) return rc;
+      if (int rc = dev_alloc(&e->hist_v, (size_t)cap * 3)) return rc;
+      if (int rc = dev_alloc(&e->hist_pi, (size_t)cap * kA)) return rc;
+      e->hist_stage_cap = cap;
+    }
+    dc = e->hist_canon; dv = e->hist_v; dp = e->hist_pi;
+  }
+  k_hist_expand<<<e->num_sms * 4, 256, 0, s>>>(e->view, wr[1], n, dc, dv, dp);
+  CUDA_TRY(cudaGetLastError());
+  if (!dst_is_device) {
+    if (int rc = copy_d2h(canon, dc, (size_t)n * C4_CANON * 4, s)) return rc;
+    if (int rc = copy_d2h(v, dv, (size_t)n * 3 * 4, s)) return rc;
+    if (int rc = copy_d2h(pi, dp, (size_t)n * kA * 4, s)) return rc;
+  }
+#else
+  (void)dst_is_device;
+  for (u32 row = 0; row < n; ++row) {
+    const HistEntry& h = e->view.hist_out[(wr[1] + row) % (unsigned long long)e->view.hist_capacity];
+    for (u32 el = 0; el < (u32)C4_CANON; ++el) dc[(size_t)row * C4_CANON + el] = c4_canon_elem(h.p0, h.p1, h.player, el);
+    for (u32 el = 0; el < 3u; ++el) dv[(size_t)row * 3 + el] = (h.result == el + 1u) ? 1.0f : 0.0f;
+    for (u32 el = 0; el < (u32)kA; ++el) dp[(size_t)row * kA + el] = h.pi[el];
+  }
+#endif
+  const unsigned long long new_read = wr[1] + n;
+  if (int rc = copy_h2d(&e->view.glob->hist_read, &new_read, sizeof(new_read), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  *count = n;
+  return 0;
+}
+
+int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
+  if (!e || !out) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  memset(out, 0, sizeof(*out));
+  Globals G;
+  StatsOut so{0, 0};
+  unsigned long long free_pages = 0;
+#ifndef B2AZ_HOST_EMU
+  if (int rc = dev_zero(e->stats_buf, sizeof(StatsOut), s)) return rc;
+  if (int rc = dev_zero(e->freepages_buf, sizeof(unsigned long long), s)) return rc;
+  k_stats<<<e->num_sms * 2, 256, 0, s>>>(e->view, e->stats_buf);
+  k_count_free_pages<<<1, kNumStacks, 0, s>>>(e->view, e->freepages_buf);
+  CUDA_TRY(cudaGetLastError());
+  if (int rc = copy_d2h(&so, e->stats_buf, sizeof(so), s)) return rc;
+  if (int rc = copy_d2h(&free_pages, e->freepages_buf, sizeof(free_pages), s)) return rc;
+#else
+  for (u32 g = 0; g < e->view.G; ++g) { so.sims += e->view.games[g].sims; so.moves += e->view.games[g].nmoves; }
+  for (u32 st = 0; st < (u32)kNumStacks; ++st) {
+    u32 p = (u32)e->view.stack_head[st];
+    while (p != kNil) { ++free_pages; p = e->view.page_next[p]; }
+  }
+#endif
+  if (int rc = copy_d2h(&G, e->view.glob, sizeof(G), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  out->simulations = so.sims;
+  out->moves = so.moves;
+  out->games_completed = G.games_completed;
+  out->games_started = std::min(G.games_started, e->view.games_to_play);
+  out->active_games = G.active_games;
+  out->leaf_count = e->leaves_pending ? G.leaf_count : 0;
+  out->hist_count = (u32)(G.hist_written - G.hist_read);
+  for (int i = 0; i < 3; ++i) { out->scores[i] = (float)G.wins[i]; out->resign_scores[i] = (float)G.resign_wins[i]; }
+  // getters of play_manager.h:288-315 (same float/double conversions)
+  out->avg_game_length = (float)G.game_length / (float)G.games_completed;
+  out->avg_leaf_depth = G.full_move_count ? (float)(G.total_avg_leaf_depth / (double)G.full_move_count) : 0.0f;
+  out->avg_search_entropy = G.full_move_count ? (float)(G.total_search_entropy / (double)G.full_move_count) : 0.0f;
+  out->fast_avg_leaf_depth = G.fast_move_count ? (float)(G.fast_total_avg_leaf_depth / (double)G.fast_move_count) : 0.0f;
+  out->fast_avg_search_entropy = G.fast_move_count ? (float)(G.fast_total_search_entropy / (double)G.fast_move_count) : 0.0f;
+  out->avg_moves_per_turn = G.game_length ? (float)G.total_move_count / (float)G.game_length : 0.0f;
+  out->avg_valid_moves = G.total_move_count ? (float)(G.total_valid_moves / (double)G.total_move_count) : 0.0f;
+  out->pool_pages_total = e->view.num_pages;
+  out->pool_pages_free = free_pages;
+  out->device_error = G.error;
+  return 0;
+}
+
+int b2az_peek(b2az_engine* e, void* stream, uint32_t game, uint32_t seat, uint8_t* state89, uint32_t* counts7,
+              float* root_q7, float* root_value3, uint32_t* depth, uint32_t* root_n, float* root_policy7) {
+  if (!e) return fail(B2AZ_EINVAL, "null engine");
+  if (game >= e->view.G || seat >= (u32)kP) return fail(B2AZ_EINVAL, "bad game/seat");
+  stream_t s = static_cast<stream_t>(stream);
+  PeekOut po;
+#ifndef B2AZ_HOST_EMU
+  k_peek<<<1, 1, 0, s>>>(e->view, game, seat, e->peek_buf);
+  CUDA_TRY(cudaGetLastError());
+  if (int rc = copy_d2h(&po, e->peek_buf, sizeof(po), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+#else
+  (void)s;
+  peek_impl(e->view, game, seat, &po);
+#endif
+  if (state89) memcpy(state89, po.state, 89);
+  if (counts7) memcpy(counts7, po.counts, sizeof(po.counts));
+  if (root_q7) memcpy(root_q7, po.q, sizeof(po.q));
+  if (root_policy7) memcpy(root_policy7, po.policy, sizeof(po.policy));
+  if (root_value3) memcpy(root_value3, po.root_value, sizeof(po.root_value));
+  if (depth) *depth = po.depth;
+  if (root_n) *root_n = po.root_n;
+  return 0;
+}
+
+int b2az_c4_batch(int device, uint32_t n, const int8_t* boards_host, const uint8_t* players, const uint32_t* turns,
+                  const uint32_t* moves, int8_t* boards_out, uint8_t* players_out, uint8_t* valid, float* scores,
+                  uint8_t* terminal, float* canonical, int32_t* status) {
+  if (n == 0) return 0;
+  if (!boards_host || !players || !turns) return fail(B2AZ_EINVAL, "null argument");
+#ifdef B2AZ_HOST_EMU
+  (void)device;
+  C4BatchArgs a{n, reinterpret_cast<const signed char*>(boards_host), players, turns, moves,
+                reinterpret_cast<signed char*>(boards_out), players_out, valid, scores, terminal, canonical, status};
+  for (u32 i = 0; i < n; ++i) c4_batch_one(a, i);
+  return 0;
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  C4BatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n;
+  std::vector<void*> owned;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    owned.push_back(d);
+    if (src) cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    return d;
+  };
+  a.boards = static_cast<const signed char*>(up(boards_host, (size_t)n * 84));
+  a.players = static_cast<const u8*>(up(players, n));
+  a.turns = static_cast<const u32*>(up(turns, (size_t)n * 4));
+  a.moves = moves ? static_cast<const u32*>(up(moves, (size_t)n * 4)) : nullptr;
+  a.boards_out = boards_out ? static_cast<signed char*>(up(nullptr, (size_t)n * 84)) : nullptr;
+  a.players_out = players_out ? static_cast<u8*>(up(nullptr, n)) : nullptr;
+  a.valid = valid ? static_cast<u8*>(up(nullptr, (size_t)n * kA)) : nullptr;
+  a.scores = scores ? static_cast<float*>(up(nullptr, (size_t)n * 12)) : nullptr;
+  a.terminal = terminal ? static_cast<u8*>(up(nullptr, n)) : nullptr;
+  a.canonical = canonical ? static_cast<float*>(up(nullptr, (size_t)n * C4_CANON * 4)) : nullptr;
+  a.status = status ? static_cast<i32*>(up(nullptr, (size_t)n * 4)) : nullptr;
+  int rc = 0;
+  k_c4_batch<<<std::max(1u, std::min((n + 255u) / 256u, 148u * 8u)), 256>>>(a);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) rc = fail(B2AZ_ECUDA, std::string("k_c4_batch: ") + cudaGetErrorString(err));
+  auto down = [&](void* dst, const void* src, size_t bytes) {
+    if (dst && src && !rc) cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+  };
+  down(boards_out, a.boards_out, (size_t)n * 84);
+  down(players_out, a.players_out, n);
+  down(valid, a.valid, (size_t)n * kA);
+  down(scores, a.scores, (size_t)n * 12);
+  down(terminal, a.terminal, n);
+  down(canonical, a.canonical, (size_t)n * C4_CANON * 4);
+  down(status, a.status, (size_t)n * 4);
+  for (void* d : owned) cudaFree(d);
+  return rc;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+/* b2az.h — C ABI of the B200-native batched self-play engine (libb2az.so).
+ *
+ * The reference (bhansconnect/alphazero-pybind11) has no C ABI: its boundary is the pybind11
+ * module `alphazero` (src/py_wrapper.cc:108-788). This header is the layer the new build adds
+ * UNDERNEATH that module: plain pointers and sizes, no torch / pybind / C++ types. Each entry
+ * point names the reference interface it replaces; INTEGRATION.md shows the binding a maintainer
+ * adds on the reference side (pybind11 and ctypes stubs).
+ *
+ * Conventions: every function returns 0 on success, a negative B2AZ_E* code otherwise, and the
+ * text of the last error on the calling thread is available from b2az_last_error(). C++
+ * exceptions never cross this boundary. Pointers named *_dev are CUDA device pointers, *_host are
+ * host pointers (pinned or pageable). `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream). All device work is issued on that stream; calls taking host buffers
+ * synchronise it before returning.
+ */
+#ifndef B2AZ_H_
+#define B2AZ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2AZ_OK 0
+#define B2AZ_EINVAL (-1)   /* bad argument / unsupported parameter combination */
+#define B2AZ_ECUDA (-2)    /* CUDA runtime error */
+#define B2AZ_ENOMEM (-3)   /* node pool / history ring exhausted on the device */
+#define B2AZ_ESTATE (-4)   /* call not valid in the current state (e.g. step with evals pending) */
+#define B2AZ_EMOVE (-5)    /* illegal move (reference: std::runtime_error, connect4_gs.cc:57, mcts.cc:161) */
+
+#define B2AZ_GAME_CONNECT4 0
+
+#define B2AZ_EVAL_NN 0      /* EvalType::NN      (play_manager.h:20) */
+#define B2AZ_EVAL_RANDOM 1  /* EvalType::RANDOM: dumb_eval on the device (game_state.h:160-173) */
+
+#define B2AZ_RNG_PER_GAME 0 /* one pcg32 stream per game slot: pcg32(seed, game_index) */
+#define B2AZ_RNG_GLOBAL 1   /* ONE pcg32(seed) consumed in ascending game order, exactly like a single
+                               reference worker thread after MCTS::seed_thread_rng(seed) (mcts.cc:19-21).
+                               Serial by construction; this is the bit-exact parity mode. */
+
+/* Mirrors PlayParams (play_manager.h:60-154) for the Connect4 PUCT path, plus engine sizing.
+ * Fields keep the reference's names and meaning. Not (yet) carried: per-seat 2-D overrides,
+ * Gumbel, resign, model groups / seat permutations, playout eval. b2az_create rejects a
+ * non-default value for anything it does not implement instead of ignoring it. */
+typedef struct b2az_params {
+  uint32_t game;                 /* B2AZ_GAME_* */
+  uint32_t games_to_play;
+  uint32_t concurrent_games;
+  uint32_t max_batch_size;       /* legacy build_batch cap; 0 = concurrent_games */
+  uint32_t max_cache_size;       /* entries; 0 = no cache */
+  uint32_t mcts_visits[2];       /* per seat (mcts_visits, play_manager.h:82) */
+  float cpuct;
+  float start_temp, final_temp, temp_decay_half_life;
+  uint8_t history_enabled;
+  uint8_t self_play;
+  uint8_t tree_reuse;
+  uint8_t playout_cap_randomization;
+  float epsilon;
+  float mcts_root_temp;
+  uint32_t playout_cap_depth;
+  float playout_cap_percent;
+  float fpu_reduction;
+  uint8_t root_fpu_zero;
+  uint8_t shaped_dirichlet;
+  uint8_t policy_target_pruning;
+  uint8_t gumbel_enabled;        /* must be 0 for now */
+  float resign_percent;          /* must be 0 for now */
+  float resign_playthrough_percent;
+  uint8_t eval_type;             /* B2AZ_EVAL_*; applies to every seat */
+  uint8_t rng_mode;              /* B2AZ_RNG_* */
+  uint8_t pad0_, pad1_;
+  uint64_t seed;
+  /* engine sizing (no reference counterpart) */
+  uint64_t pool_nodes;           /* tree-node pool size in nodes; 0 = sized from free HBM */
+  uint32_t history_capacity;     /* finished-sample ring, in samples; 0 = default */
+  uint32_t lanes_per_game;       /* cooperative lanes per game slot: 1, 4, 8 or 32; 0 = default (8) */
+} b2az_params;
+
+/* Counters and metrics of PlayManager (play_manager.h:173-366). */
+typedef struct b2az_stats {
+  uint64_t simulations;          /* find_leaf+process_result pairs completed (mcts.cc:553 ++depth_) */
+  uint64_t moves;                /* game moves played */
+  uint32_t games_completed;      /* games_completed() */
+  uint32_t games_started;
+  uint32_t active_games;         /* slots still cycling */
+  uint32_t leaf_count;           /* leaves waiting for an evaluation (awaiting_inference_count) */
+  uint32_t hist_count;           /* hist_count() */
+  float scores[3];               /* scores(): wins seat0, wins seat1, draws */
+  float resign_scores[3];
+  float avg_game_length, avg_leaf_depth, avg_search_entropy;
+  float fast_avg_leaf_depth, fast_avg_search_entropy;
+  float avg_moves_per_turn, avg_valid_moves;
+  uint64_t cache_hits, cache_misses, cache_evictions, cache_reinserts, cache_size, cache_max_size;
+  uint64_t pool_pages_total, pool_pages_free; /* tree-node pool occupancy */
+  uint32_t device_error;         /* sticky device-side error bits (B2AZ_DEVERR_*) */
+} b2az_stats;
+
+#define B2AZ_DEVERR_POOL 1u      /* node pool exhausted */
+#define B2AZ_DEVERR_HIST 2u      /* history ring overflow (samples dropped) */
+#define B2AZ_DEVERR_MOVE 4u      /* update_root could not find the move (mcts.cc:159-162) */
+#define B2AZ_DEVERR_DEPTH 8u     /* selection path longer than the path buffer */
+
+typedef struct b2az_engine b2az_engine;
+
+const char* b2az_last_error(void);
+int b2az_params_default(b2az_params* p);
+
+/* PlayManager::PlayManager(gs, params) (play_manager.cc:12-256): allocates the device pool on
+ * `device`, initialises concurrent_games slots (fresh game, one tree per seat). */
+int b2az_create(const b2az_params* p, int device, b2az_engine** out);
+int b2az_destroy(b2az_engine* e);
+
+/* One pass of PlayManager::play()'s loop body (play_manager.cc:272-599) over EVERY active slot:
+ * process_result for the evaluation submitted since the last step, play a move when the search
+ * budget is reached (move choice, history capture, re-root, game end / restart), then find_leaf.
+ * With B2AZ_EVAL_NN `n_steps` must be 1 and every leaf of the previous step must have been
+ * answered (b2az_submit_eval*); leaves go to the leaf batch. With B2AZ_EVAL_RANDOM the evaluator
+ * runs inline and `n_steps` passes are fused into one kernel launch. Returns when the work is
+ * enqueued on `stream`. */
+int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream);
+
+/* build_batch (py_wrapper.cc:449-504), zero-copy flavour: device pointers to the dense
+ * canonical batch float32[count][4][6][7] and the slot ids uint32[count] of the leaves produced
+ * by the last step. Synchronises `stream` to read `count`. Pointers stay valid until the next
+ * b2az_step. */
+int b2az_leaf_batch(b2az_engine* e, void* stream, uint32_t* count, const float** canon_dev,
+                    const uint32_t** ids_dev);
+/* build_batch, legacy host-buffer flavour: copies up to `max` not-yet-taken leaves into host
+ * buffers (canonical rows + slot ids), FIFO. */
+int b2az_leaf_batch_host(b2az_engine* e, void* stream, uint32_t max, float* canon_host, uint32_t* ids_host,
+                         uint32_t* count);
+
+/* update_inferences (play_manager.cc:619-642), zero-copy flavour: v_dev float32[count][3],
+ * pi_dev float32[count][7] in leaf-batch row order, count == the leaf count. The buffers are
+ * read by the next b2az_step (keep them alive until it has run). */
+int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, uint32_t count);
+/* update_inferences, legacy flavour: row i answers slot ids_host[i]; may be called several times
+ * with disjoint subsets. */
+int b2az_submit_eval_host(b2az_engine* e, void* stream, const uint32_t* ids_host, const float* v_host,
+                          const float* pi_host, uint32_t count);
+
+/* build_history_batch (py_wrapper.cc:393-424): pops up to `max` finished training samples in the
+ * order the reference's history_ queue would hold them; canonical float32[n][4][6][7],
+ * v float32[n][3], pi float32[n][7]. dst_is_device selects device or host destination. */
+int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
+                       int dst_is_device, uint32_t* count);
+
+int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out);
+
+/* GameData / MCTS peeks for parity tests (py_wrapper.cc:265-288 game_data(i); mcts.h:101-115
+ * counts/root_q_values/root_value/depth/root_n). state89 = Connect4GS::to_bytes layout
+ * (connect4_gs.cc:172-178). Any pointer may be NULL. */
+int b2az_peek(b2az_engine* e, void* stream, uint32_t game, uint32_t seat, uint8_t* state89, uint32_t* counts7,
+              float* root_q7, float* root_value3, uint32_t* depth, uint32_t* root_n, float* root_policy7);
+
+/* Bitboard game kernels on a batch of positions (GameState::play_move / valid_moves / scores /
+ * canonicalized, connect4_gs.cc:39-149). boards_host: int8[n][2][6][7]; players/turns per
+ * position; moves: one move per position or 0xFFFFFFFF for "no move". Outputs (host, any may be
+ * NULL): boards_out int8[n][84], players_out, valid uint8[n][7], scores float[n][3] with
+ * terminal[n] = 0/1, canonical float[n][168], status[n] = 0 or B2AZ_EMOVE. */
+int b2az_c4_batch(int device, uint32_t n, const int8_t* boards_host, const uint8_t* players, const uint32_t* turns,
+                  const uint32_t* moves, int8_t* boards_out, uint8_t* players_out, uint8_t* valid, float* scores,
+                  uint8_t* terminal, float* canonical, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2AZ_H_ */

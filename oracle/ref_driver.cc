@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "connect4_gs.h"
+#include "pcg/pcg_random.hpp"
 #include "mcts.h"
 #include "play_manager.h"
 #include "s3fifo_cache.h"
@@ -426,6 +427,32 @@ uint32_t azref_pm_game_depth(void* h, uint32_t i, uint32_t seat) {
 }
 uint32_t azref_pm_game_root_n(void* h, uint32_t i, uint32_t seat) {
   return static_cast<RefPM*>(h)->pm->game_data(i).mcts[seat].root_n();
+}
+
+// ----------------------------------------------------------------------------- RNG ground truth
+// A free-standing pcg32 driving the real libstdc++ algorithms, exactly as mcts.cc uses them
+// (mcts.cc:19 `thread_local pcg32 re`, :100 shuffle, :205 extreme_value, :430-436 gamma, :718 uniform_real).
+void* azref_rng_new(uint64_t seed, int use_stream, uint64_t stream) {
+  return use_stream ? new pcg32(seed, stream) : new pcg32(seed);
+}
+void azref_rng_free(void* r) { delete static_cast<pcg32*>(r); }
+uint32_t azref_rng_u32(void* r) { return (*static_cast<pcg32*>(r))(); }
+void azref_rng_shuffle(void* r, uint32_t n, uint32_t* inout) {
+  std::vector<uint32_t> v(inout, inout + n);
+  std::shuffle(v.begin(), v.end(), *static_cast<pcg32*>(r));
+  std::memcpy(inout, v.data(), n * 4);
+}
+float azref_rng_uniform01(void* r) {
+  std::uniform_real_distribution<float> d{0.0F, 1.0F};
+  return d(*static_cast<pcg32*>(r));
+}
+void azref_rng_gamma(void* r, float alpha, uint32_t n, float* out) {
+  auto dist = std::gamma_distribution<float>{alpha, 1.0};
+  for (uint32_t i = 0; i < n; ++i) out[i] = dist(*static_cast<pcg32*>(r));
+}
+float azref_rng_gumbel(void* r) {
+  std::extreme_value_distribution<float> d{0.0f, 1.0f};
+  return d(*static_cast<pcg32*>(r));
 }
 
 // ----------------------------------------------------------------------------- S3FIFOCache
