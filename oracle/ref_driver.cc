@@ -244,6 +244,8 @@ static PlayParams to_params(const AzRefPlayCfg& c) {
   p.temp_decay_half_life = c.temp_decay_half_life;
   p.history_enabled = c.history_enabled;
   p.self_play = c.self_play;
+  // self_play(): every seat is the same network => one model group (game_runner.py:773-787, 2053-2055)
+  if (c.self_play) p.model_groups = {0, 0};
   p.tree_reuse = c.tree_reuse;
   p.epsilon = c.epsilon;
   p.mcts_root_temp = c.mcts_root_temp;

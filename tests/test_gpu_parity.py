@@ -1,0 +1,155 @@
+"""GPU parity tests proper: the CUDA library (libb2az.so, sm_100a) through the C ABI vs the oracle.
+
+  * serial kernel (B2AZ_RNG_GLOBAL) vs golden traces generated from the unmodified reference — bit-exact
+    move lists, leaf batches, visit counts, Q, history targets;
+  * serial kernel vs the reference itself when oracle/_ref/libazref.so travelled with the snapshot;
+  * parallel kernels (B2AZ_RNG_PER_GAME, every lane width) vs the oracle port with per-game streams;
+  * bitboard game kernels vs the port on random walks and the reference's known answers;
+  * size-independent properties at the full BASELINE size (65,536 games).
+Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import b2az
+import parity_harness as ph
+from conftest import has_cuda, needs_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+
+@pytest.mark.parametrize("name", sorted(ph.GOLDEN_CASES))
+def test_serial_kernel_reproduces_golden(name):
+    G, games, visits, level, seed, et = ph.GOLDEN_CASES[name]
+    pm = ph.EnginePM(None, G=G, games_to_play=games, visits=visits, eval_type=et, rng_mode=b2az.RNG_GLOBAL, seed=seed,
+                     **ph.level_params(level))
+    got = ph.trace_run(pm, et)
+    pm.close()
+    ph.compare_trace(got, dict(np.load(ph.golden_path(name))), f"CUDA serial kernel vs golden {name}")
+
+
+@needs_ref
+@pytest.mark.parametrize("level", [0, 1])
+def test_serial_kernel_vs_reference_live(level):
+    r = ph.run_lockstep_parity(None, G=6, games_to_play=9, visits=64, level=level, seed=777, oracle="ref")
+    assert r["games"] == 9
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 8, 32])
+@pytest.mark.parametrize("level", [0, 1])
+def test_parallel_kernel_lockstep_vs_port(lanes, level):
+    r = ph.run_lockstep_parity(None, G=48, games_to_play=80, visits=40, level=level, seed=2024, oracle="port",
+                               rng_mode=b2az.RNG_PER_GAME, lanes=lanes, peek_every=13)
+    assert r["games"] == 80 and r["moves_compared"] > 500
+
+
+@pytest.mark.parametrize("lanes", [1, 8, 32])
+def test_parallel_kernel_random_eval_vs_port(lanes):
+    r = ph.run_random_parity(None, G=512, games_to_play=1200, visits=100, seed=31337, oracle="port",
+                             rng_mode=b2az.RNG_PER_GAME, level=1, lanes=lanes, chunk=128)
+    assert r["games"] == 1200
+
+
+def test_parallel_kernel_400_sims_vs_port():
+    # the headline search size (400 sims/move) on a batch the port finishes in seconds
+    r = ph.run_random_parity(None, G=256, games_to_play=256, visits=400, seed=5, oracle="port",
+                             rng_mode=b2az.RNG_PER_GAME, level=0, chunk=400)
+    assert r["games"] == 256
+
+
+def test_no_tree_reuse_gpu():
+    ph.run_random_parity(None, G=64, games_to_play=100, visits=50, seed=3, oracle="port", level=2, tree_reuse=False)
+
+
+def test_c4_kernels_random_walks_vs_port():
+    Pt = ph.port_lib()
+    rng = np.random.default_rng(11)
+    boards, players, turns = [], [], []
+    for game in range(2000):
+        board = np.zeros(84, np.int8)
+        player, turn = C.c_uint8(0), C.c_uint32(0)
+        for ply in range(rng.integers(0, 43)):
+            v = np.zeros(7, np.uint8)
+            Pt.azo_c4_valid(ph._P(board), ph._P(v))
+            s = np.zeros(3, np.float32)
+            if Pt.azo_c4_scores(ph._P(board), ph._P(s)) or v.sum() == 0:
+                break
+            Pt.azo_c4_play(ph._P(board), C.byref(player), C.byref(turn), int(rng.choice(np.flatnonzero(v))))
+        boards.append(board.copy()); players.append(player.value); turns.append(turn.value)
+    boards = np.stack(boards)
+    moves = rng.integers(0, 7, len(boards)).astype(np.uint32)
+    out = b2az.c4_batch(boards, np.array(players, np.uint8), np.array(turns, np.uint32), moves)
+    for i in range(len(boards)):
+        b = boards[i].copy()
+        pl, tu = C.c_uint8(players[i]), C.c_uint32(turns[i])
+        rc = Pt.azo_c4_play(ph._P(b), C.byref(pl), C.byref(tu), int(moves[i]))
+        assert (out["status"][i] == 0) == (rc == 0)
+        assert np.array_equal(out["boards"][i].reshape(-1), b) and out["players"][i] == pl.value
+        v = np.zeros(7, np.uint8); Pt.azo_c4_valid(ph._P(b), ph._P(v))
+        assert np.array_equal(out["valid"][i], v)
+        s = np.zeros(3, np.float32); t = Pt.azo_c4_scores(ph._P(b), ph._P(s))
+        assert out["terminal"][i] == t and np.array_equal(out["scores"][i], s)
+        c = np.zeros(168, np.float32); Pt.azo_c4_canonical(ph._P(b), pl, ph._P(c))
+        assert np.array_equal(out["canonical"][i].reshape(-1), c)
+
+
+def test_device_zero_copy_path_matches_host_path():
+    """b2az_leaf_batch / b2az_submit_eval (device pointers, the DLPack-style feed) must drive the engine to the
+    same result as the legacy host-buffer calls."""
+    import torch
+
+    kw = ph.level_params(1)
+    mk = lambda: ph.make_engine(None, 64, 96, 32, b2az.EVAL_NN, b2az.RNG_PER_GAME, 17, **kw)
+    a, b = mk(), mk()
+    mix = torch.from_numpy(ph._MIX).cuda()
+    for _ in range(100000):
+        a.step(1)
+        b.step(1)
+        ids, canon = a.leaf_batch_host()
+        n, cptr, iptr = b.leaf_batch()
+        assert n == len(ids)
+        if n == 0:
+            break
+        v, pi = ph.fake_net(canon)
+        a.submit_eval_host(ids, v, pi)
+        # evaluate b's batch on the device, rows in b's own order
+        cb = torch.empty((n, 168), dtype=torch.float32, device="cuda")
+        C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(cb.data_ptr()), C.c_void_p(cptr), C.c_size_t(n * 168 * 4), 3)
+        h = cb.to(torch.int64) @ mix
+        wp = (1 + (h[:, :7] % 13) ** 2).to(torch.float32)
+        wv = (1 + (h[:, 7:] % 17)).to(torch.float32)
+        pi_d = (wp / wp.sum(1, keepdim=True)).contiguous()
+        v_d = (wv / wv.sum(1, keepdim=True)).contiguous()
+        # float32 sums of <= 7 small integers are exact, so the device evaluator equals fake_net bit for bit
+        torch.cuda.synchronize()
+        b.submit_eval(v_d.data_ptr(), pi_d.data_ptr(), n)
+        b._keep = (v_d, pi_d)
+    sa, sb = a.stats(), b.stats()
+    assert sa.games_completed == sb.games_completed == 96 and list(sa.scores) == list(sb.scores)
+    ph.compare_history(a.drain_history(1 << 16), b.drain_history(1 << 16), ordered=False)
+    a.close()
+    b.close()
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (65,536 concurrent games, 400 sims/move): properties that do not need the
+    oracle — simulation/move accounting, legal finished samples, pool accounting, determinism across runs."""
+    G = 65536
+
+    def run(steps):
+        e = ph.make_engine(None, G, 2 * G, 400, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, 1, history=True,
+                           history_capacity=G * 4, **ph.level_params(0))
+        e.step(steps)
+        st = e.stats()
+        hist = e.drain_history(G * 4)
+        e.close()
+        return st, hist
+
+    st, (canon, v, pi) = run(1201)
+    assert st.device_error == 0
+    assert st.simulations == G * 1200, "every active slot finishes exactly one simulation per step"
+    assert st.moves == G * 3, "a move every 400 simulations"
+    assert st.games_completed == 0 and len(canon) == 0
+    st2, _ = run(1201)
+    assert (st2.simulations, st2.moves, st2.pool_pages_free) == (st.simulations, st.moves, st.pool_pages_free)
