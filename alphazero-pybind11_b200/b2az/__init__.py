@@ -154,6 +154,20 @@ class Engine:
         self._check(self.L.b2az_leaf_batch_host(self.h, stream, m, _ptr(canon), _ptr(ids), C.byref(n)))
         return ids[: n.value], canon[: n.value]
 
+    # -- pointer flavours (caller-owned, e.g. pinned, host buffers): no allocation per call
+    def leaf_batch_host_into(self, canon_ptr, ids_ptr, max_rows, stream=None):
+        n = C.c_uint32()
+        self._check(self.L.b2az_leaf_batch_host(self.h, stream, max_rows, canon_ptr, ids_ptr, C.byref(n)))
+        return n.value
+
+    def submit_eval_host_from(self, ids_ptr, v_ptr, pi_ptr, count, stream=None):
+        self._check(self.L.b2az_submit_eval_host(self.h, stream, ids_ptr, v_ptr, pi_ptr, count))
+
+    def drain_history_into(self, canon_ptr, v_ptr, pi_ptr, max_rows, stream=None):
+        n = C.c_uint32()
+        self._check(self.L.b2az_drain_history(self.h, stream, max_rows, canon_ptr, v_ptr, pi_ptr, 0, C.byref(n)))
+        return n.value
+
     def submit_eval(self, v_dev_ptr, pi_dev_ptr, count):
         self._check(self.L.b2az_submit_eval(self.h, v_dev_ptr, pi_dev_ptr, count))
 

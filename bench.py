@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py — MCTS simulations/s of the B200 self-play engine (BASELINE.json metric), one JSON line.
+
+Workload (config.workload, BASELINE.json configs[1]): Connect4, 65,536 concurrent games PER GPU, 400
+simulations per move, device-resident trees, EvalType::RANDOM evaluator on the device (uniform priors over
+the legal moves, value 1/3 — src/game_state.h:160-173), cache off: "Throughput A" of SURVEY.md §8(d), the
+same workload the reference's own benchmark uses (src/play_manager_bench.cc:39-48, RANDOM eval).
+
+A "step" is one launch of the step kernel = `--gens` (default 400) iterations of PlayManager::play()'s
+loop body (process_result -> [move] -> find_leaf) for every game slot, i.e. G*gens simulations.
+
+  value        whole-job simulations/s, tree pools resident in HBM, CUDA events on the launching stream,
+               barrier + synchronize on both sides, max over ranks
+  e2e          same metric through the public API with HOST result buffers: every step additionally drains
+               the finished training samples (canonical planes, value and policy targets: what self-play
+               produces) into pinned host memory and reads the statistics struct back. This workload has no
+               per-step host inputs (the evaluator is the reference's RANDOM backend), hence h2d bytes = 0.
+  e2e_nn_host  the legacy per-leaf host round trip of the reference API (build_batch -> update_inferences
+               with host buffers, py_wrapper.cc:449-504 / play_manager.cc:619-642) for comparison
+  roofline     algorithmic HBM bytes of the step kernel / its measured duration vs MEASURED_PEAKS.json
+  cpu_baseline the unmodified reference PlayManager (oracle/_ref) on this box's host cores, same workload
+
+`--impl reference` times the reference's own CPU implementation instead (all host threads).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "alphazero-pybind11_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SIMS = 400
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=65536, help="concurrent games per GPU")
+    ap.add_argument("--gens", type=int, default=400, help="loop iterations per game slot per step (one launch)")
+    ap.add_argument("--preroll", type=int, default=24, help="untimed moves per game before warm-up (steady state)")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ CPU side
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference_cpu(seconds_warm, seconds_timed, threads, windows=1):
+    """The reference PlayManager (unmodified, oracle/_ref/libazref.so) on `threads` worker threads, RANDOM eval,
+    400 visits, concurrent_games = 64*threads (the StreamPool shape of src/play_manager_bench.cc:170-181),
+    queue_shards = threads (src/config.py:428-433). Returns (kind, sims/s per window list)."""
+    import refdriver
+
+    if refdriver.available():
+        L = refdriver.lib()
+        G = 64 * threads
+        cfg = refdriver.play_cfg(games_to_play=2 ** 31 - 1, concurrent_games=G, max_batch_size=G,
+                                 queue_shards=min(threads, 255), cache_shards=1, mcts_visits=(SIMS, SIMS), cpuct=1.25,
+                                 fpu_reduction=0.25, self_play=1, tree_reuse=1, eval_type=1, history_enabled=0)
+        pm = refdriver.RefPlayManager(cfg)
+        pm.start_workers(threads, 12345, True)
+        time.sleep(seconds_warm)
+        rates = []
+        for _ in range(windows):
+            c0, t0 = L.azref_pm_progress_sims(pm.h, SIMS), time.perf_counter()
+            time.sleep(seconds_timed)
+            c1, t1 = L.azref_pm_progress_sims(pm.h, SIMS), time.perf_counter()
+            rates.append((c1 - c0) / (t1 - t0))
+        L.azref_pm_stop(pm.h)
+        pm.join()
+        pm.close()
+        return "reference", rates
+    # fallback: the oracle port, one independent PlayManager per thread (no shared queue => an upper bound)
+    import parity_harness as ph
+
+    done = []
+
+    def worker(k):
+        kw = dict(G=64, visits=SIMS, eval_type=1, rng_mode=1, history=False, **ph.level_params(0))
+        cal = ph.PortPM(games_to_play=128, seed=100 + k, **kw)  # calibrate, then size a bounded run
+        t0 = time.perf_counter()
+        cal.advance()
+        dt = time.perf_counter() - t0
+        cal.close()
+        run = ph.PortPM(games_to_play=max(128, int(128 * seconds_timed * windows / dt)), seed=200 + k, **kw)
+        t0 = time.perf_counter()
+        run.advance()
+        done.append(run.simulations() / (time.perf_counter() - t0))
+        run.close()
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return "port", [sum(done)] * windows
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = f"/tmp/b2az_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        return out
+
+
+# ------------------------------------------------------------------------------------ main arms
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    workers = max(1, threads - 1)  # reference default: mcts_workers = cpu_count - 1 (src/config.py:229, 440-441)
+    per = max(1.0, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
+    kind, rates = run_reference_cpu(per * args.warmup, per, workers, windows=args.steps)
+    v = sum(rates) / len(rates)
+    sample = (f"{kind} PlayManager, Connect4, EvalType::RANDOM, {SIMS} sims/move, {workers} worker threads, "
+              f"concurrent_games={64 * workers}, {args.steps} windows of {per:.1f} s after {per * args.warmup:.1f} s warm-up")
+    line = {"impl": "reference", "metric": "mcts_simulations_per_second", "value": v, "unit": "sims/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "sims/s", "cores": workers, "kind": kind, "sample": sample,
+                             "cpu_model": cpu_model(), "host_threads": threads},
+            "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": f"connect4 self-play, {args.games} concurrent games/GPU, {SIMS} sims/move, EvalType::RANDOM "
+                        f"evaluator, tree reuse on, cache off (BASELINE.json configs[1], SURVEY.md 8d Throughput A)",
+            "concurrent_games_per_gpu": args.games, "sims_per_move": SIMS, "gens_per_step": args.gens,
+            "parallelism": f"games sharded over {n} GPU(s), no data-path collective",
+            "l2_policy": "working set (tree pools, tens of GB) far larger than the 126 MB L2; no flush needed"}
+
+
+def roofline_bytes_per_sim(avg_leaf_depth, avg_children):
+    """DESIGN.md 'Algorithmic bytes per simulation' (RANDOM-eval variant: no canonical write,
+    no evaluation read)."""
+    D, k = avg_leaf_depth, avg_children
+    select = D * (12.0 * k + 8.0)
+    backprop = D * 28.0
+    expand = 16.0 * k + 16.0
+    state = 24.0
+    return select + backprop + expand + state
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import b2az
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream().cuda_stream
+    G, gens, K, W = args.games, args.gens, args.steps, args.warmup
+
+    def make(history):
+        p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=G, mcts_visits=(SIMS, SIMS), cpuct=1.25,
+                                fpu_reduction=0.25, eval_type=b2az.EVAL_RANDOM, rng_mode=b2az.RNG_PER_GAME,
+                                seed=1000 + rank, tree_reuse=1, history_enabled=int(history), self_play=1,
+                                lanes_per_game=args.lanes, history_capacity=(8 * G if history else 0))
+        return b2az.Engine(p, device=local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- value: device-resident throughput
+    eng = make(history=False)
+    for _ in range(args.preroll):
+        eng.step(SIMS, stream)
+    for _ in range(W):
+        eng.step(gens, stream)
+    barrier()
+    s0 = eng.stats(stream)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(K):
+        eng.step(gens, stream)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    total_ms = evs[0].elapsed_time(evs[K])
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    s1 = eng.stats(stream)
+    if s1.device_error:
+        raise SystemExit(f"bench.py: device error bits {s1.device_error}")
+    sims_rank = s1.simulations - s0.simulations
+    assert sims_rank == G * gens * K, (sims_rank, G * gens * K)
+    moves_rank = s1.moves - s0.moves
+    kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    total_ms = max_over_ranks(total_ms)
+    value = world * sims_rank / (total_ms * 1e-3)
+    moves_per_s = world * moves_rank / (total_ms * 1e-3)
+    depth = float(s1.avg_leaf_depth) if s1.avg_leaf_depth > 0 else 5.0
+    kids = float(s1.avg_valid_moves) if s1.avg_valid_moves > 0 else 6.5
+    pool = (int(s1.pool_pages_total), int(s1.pool_pages_free))
+    eng.close()
+
+    # ---------------------------------------------------------------- e2e: public API, host result buffers
+    e2e = None
+    e2e_nn = None
+    if not args.no_e2e:
+        eng = make(history=True)
+        cap = 4 * G
+        h_canon = torch.empty((cap, 4, 6, 7), dtype=torch.float32).pin_memory()
+        h_v = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
+        h_pi = torch.empty((cap, 7), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            eng.step(gens, stream)
+            n = eng.drain_history_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, stream)
+            st = eng.stats(stream)
+            return n, st
+
+        for _ in range(args.preroll):
+            eng.step(SIMS, stream)
+            eng.drain_history_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, stream)
+        for _ in range(W):
+            e2e_step()
+        barrier()
+        st0 = eng.stats(stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        a.record()
+        samples = 0
+        for _ in range(K):
+            n, st = e2e_step()
+            samples += n
+        b.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ev_ms = a.elapsed_time(b)
+        barrier()
+        e_ms = max_over_ranks(max(wall_ms, ev_ms))
+        e_sims = st.simulations - st0.simulations
+        e2e = {"value": world * e_sims / (e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": int(samples / K * (168 + 3 + 7) * 4 + C.sizeof(b2az.Stats) + 16),
+               "samples_per_step": samples / K, "ms_per_step": e_ms / K,
+               "note": "step kernel + drain of finished training samples to pinned host buffers + stats read, every "
+                       "step; the RANDOM-eval workload has no per-step host inputs"}
+        eng.close()
+
+        # legacy per-leaf host round trip (EVAL_NN + host buffers), a few generations
+        p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=G, mcts_visits=(SIMS, SIMS), cpuct=1.25,
+                                fpu_reduction=0.25, eval_type=b2az.EVAL_NN, rng_mode=b2az.RNG_PER_GAME,
+                                seed=2000 + rank, tree_reuse=1, history_enabled=0, self_play=1, lanes_per_game=args.lanes)
+        eng = b2az.Engine(p, device=local)
+        hb = torch.empty((G, 4, 6, 7), dtype=torch.float32).pin_memory()
+        hid = torch.empty((G,), dtype=torch.int32).pin_memory()
+        hv = torch.full((G, 3), 1.0 / 3.0, dtype=torch.float32).pin_memory()
+        hp = torch.full((G, 7), 1.0 / 7.0, dtype=torch.float32).pin_memory()
+
+        def nn_gen():
+            eng.step(1, stream)
+            n = eng.leaf_batch_host_into(hb.data_ptr(), hid.data_ptr(), G, stream)
+            eng.submit_eval_host_from(hid.data_ptr(), hv.data_ptr(), hp.data_ptr(), n, stream)
+            return n
+
+        ngen = 40
+        for _ in range(10):
+            nn_gen()
+        barrier()
+        t0 = time.perf_counter()
+        leaves = 0
+        for _ in range(ngen):
+            leaves += nn_gen()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_nn = {"value": world * leaves / dt, "unit": "sims/s", "h2d_bytes_per_step": G * (3 + 7) * 4,
+                  "d2h_bytes_per_step": G * (168 * 4 + 4), "generations": ngen,
+                  "note": "reference-API compatibility path: one generation = b2az_step(1) + b2az_leaf_batch_host "
+                          "(fp32 canonical planes D2H) + b2az_submit_eval_host (v, pi H2D); pinned buffers"}
+        eng.close()
+
+    # ---------------------------------------------------------------- roofline + cpu baseline (rank 0)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bps = roofline_bytes_per_sim(depth, kids)
+    launch_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = (bps * G * gens) / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
+        traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_step", "bytes_per_sim": bps, "avg_leaf_depth": depth,
+                "avg_children": kids, "launch_ms": launch_ms,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        workers = max(1, threads - 1)
+        kind, rates = run_reference_cpu(min(4.0, args.cpu_seconds / 3), args.cpu_seconds * 2 / 3, workers)
+        _, r1 = run_reference_cpu(1.5, 4.0, 1)
+        cpu = {"value": rates[0], "unit": "sims/s", "cores": workers, "kind": kind, "value_1_thread": r1[0],
+               "cpu_model": cpu_model(), "host_threads": threads,
+               "sample": f"{kind} PlayManager, Connect4, EvalType::RANDOM, {SIMS} sims/move, {workers} worker threads, "
+                         f"concurrent_games={64 * workers}, {args.cpu_seconds * 2 / 3:.0f} s window after warm-up"}
+    line = {"metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "moves_per_second": moves_per_s, "clocks": clocks, "e2e": e2e, "e2e_nn_host": e2e_nn,
+            "gpu_launches": K * world, "roofline": roofline, "cpu_baseline": cpu,
+            "pool_pages": {"total": pool[0], "free": pool[1]}}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

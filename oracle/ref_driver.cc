@@ -406,6 +406,22 @@ void azref_pm_cache_stats(void* h, uint64_t* out6) {
   out6[4] = pm.cache_size();
   out6[5] = pm.cache_max_size();
 }
+// bench.py only: simulations finished so far = visits * (moves of completed games + moves of the games in
+// progress) + simulations of the searches in progress. Read while the workers run: only plain integers that
+// live in place (GameData::move_count, MCTS::depth_) are touched, no pointers are followed, so the race is
+// benign and the error is bounded by a few simulations per slot.
+double azref_pm_progress_sims(void* h, uint32_t visits) {
+  auto* r = static_cast<RefPM*>(h);
+  const double done_moves = static_cast<double>(r->pm->avg_game_length()) * r->pm->games_completed();
+  double moves = r->pm->games_completed() ? done_moves : 0.0;
+  double partial = 0.0;
+  for (uint32_t i = 0; i < r->cfg.concurrent_games; ++i) {
+    const auto& g = r->pm->game_data(i);
+    moves += *static_cast<const volatile uint32_t*>(&g.move_count);
+    for (const auto& m : g.mcts) partial += m.depth();
+  }
+  return moves * visits + partial;
+}
 // Peeks into GameData (py_wrapper.cc:265-288 exposes gs/v/pi/canonical; the trees are C++-only).
 // Only call while the worker is quiescent.
 void azref_pm_game_state_bytes(void* h, uint32_t i, uint8_t* out89) {

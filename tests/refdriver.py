@@ -105,6 +105,8 @@ def lib():
             getattr(L, name).restype = u32
         for name in ("azref_pm_scores", "azref_pm_resign_scores", "azref_pm_metrics", "azref_pm_cache_stats"):
             getattr(L, name).argtypes = [vp, vp]
+        L.azref_pm_progress_sims.argtypes = [vp, u32]
+        L.azref_pm_progress_sims.restype = C.c_double
         L.azref_pm_game_state_bytes.argtypes = [vp, u32, vp]
         L.azref_pm_game_counts.argtypes = [vp, u32, u32, vp]
         L.azref_pm_game_root_q.argtypes = [vp, u32, u32, vp]
