@@ -560,10 +560,11 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
 #ifndef B2AZ_HOST_EMU
   CUDA_TRY(cudaSetDevice(e->device));
   if (V.rng_mode == B2AZ_RNG_GLOBAL) {
+    // exactly ONE group walks the slots: the block has W threads
     switch (e->lanes) {
-      case 1: k_step_serial<1><<<1, 32, 0, s>>>(V, n_steps); break;
-      case 4: k_step_serial<4><<<1, 32, 0, s>>>(V, n_steps); break;
-      case 8: k_step_serial<8><<<1, 32, 0, s>>>(V, n_steps); break;
+      case 1: k_step_serial<1><<<1, 1, 0, s>>>(V, n_steps); break;
+      case 4: k_step_serial<4><<<1, 4, 0, s>>>(V, n_steps); break;
+      case 8: k_step_serial<8><<<1, 8, 0, s>>>(V, n_steps); break;
       default: k_step_serial<32><<<1, 32, 0, s>>>(V, n_steps); break;
     }
   } else {

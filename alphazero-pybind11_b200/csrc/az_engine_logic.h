@@ -184,6 +184,7 @@ AZ_HD u32 tree_alloc_block(const EngineView& E, TreeHdr& T, u32 home, u32 kk) {
         at_or(&E.glob->error, B2AZ_DEVERR_POOL);
       }
     }
+    Grp<W>::sync();  // page_next / page_fill written by lane 0 are read by every lane (Cheney scan)
     p = Grp<W>::bcast(p, 0);
     if (p == kNil) return kNil;
     if (T.cur_page == kNil) T.first_page = p;
@@ -736,6 +737,7 @@ AZ_HD void update_root(const EngineView& E, u32 home, TreeHdr& T, u32 move, u32 
             E.mv[dst + j] = E.mv[r.fc + j];
             E.rec[dst + j] = E.rec[r.fc + j];
           }
+          Grp<W>::sync();  // every lane has read rec[base + i] and finished its share of the copy
           if (lane == 0) {
             NodeRec r2 = r;
             r2.fc = dst;
