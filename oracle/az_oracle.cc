@@ -586,6 +586,15 @@ uint32_t azo_pm_run(void* h) {
   }
   return static_cast<uint32_t>(pm->awaiting_inference.size());
 }
+uint32_t azo_pm_run_iterations(void* h, uint64_t n) {
+  auto* pm = static_cast<PM*>(h);
+  while (n-- > 0 && pm->games_completed < pm->cfg.games_to_play && !pm->awaiting_mcts.empty()) {
+    const uint32_t i = pm->awaiting_mcts.front();
+    pm->awaiting_mcts.pop_front();
+    play_iteration(*pm, i);
+  }
+  return static_cast<uint32_t>(pm->awaiting_inference.size());
+}
 uint32_t azo_pm_build_batch(void* h, uint32_t max, uint32_t* ids, float* canon) {
   auto* pm = static_cast<PM*>(h);
   uint32_t n = 0;

@@ -47,6 +47,9 @@ void azo_pm_free(void* h);
  * this plays every game to the end; with NN eval it returns once every active game waits for an
  * evaluation. Returns the number of leaves waiting. */
 uint32_t azo_pm_run(void* h);
+/* Same, but at most `n` loop iterations (RANDOM eval never drains: n = G * generations while every slot
+ * is active). */
+uint32_t azo_pm_run_iterations(void* h, uint64_t n);
 uint32_t azo_pm_build_batch(void* h, uint32_t max, uint32_t* ids, float* canon /* [max][168] */);
 void azo_pm_update_inferences(void* h, const uint32_t* ids, uint32_t n, const float* v /* [n][3] */,
                               const float* pi /* [n][7] */);

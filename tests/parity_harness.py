@@ -90,6 +90,8 @@ def port_lib():
         L.azo_pm_free.argtypes = [vp]
         L.azo_pm_run.argtypes = [vp]
         L.azo_pm_run.restype = u32
+        L.azo_pm_run_iterations.argtypes = [vp, C.c_uint64]
+        L.azo_pm_run_iterations.restype = u32
         L.azo_pm_build_batch.argtypes = [vp, u32, vp, vp]
         L.azo_pm_build_batch.restype = u32
         L.azo_pm_update_inferences.argtypes = [vp, vp, u32, vp, vp]
@@ -150,6 +152,9 @@ class PortPM:
         """Drain awaiting_mcts_. Returns False when the run is over."""
         self.L.azo_pm_run(self.h)
         return self.L.azo_pm_remaining_games(self.h) > 0
+
+    def run_iterations(self, n):
+        self.L.azo_pm_run_iterations(self.h, n)
 
     def build_batch(self):
         ids = np.empty(self.G, np.uint32)
@@ -345,8 +350,13 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
             gens += 1
         st = eng.stats()
         assert st.device_error == 0, f"device error bits {st.device_error}"
-        assert st.games_completed == ora.games_completed() == games_to_play
+        assert st.games_completed == ora.games_completed()
+        if gens < max_generations:
+            assert st.games_completed == games_to_play
         assert np.array_equal(np.array(st.scores[:], np.float32), ora.scores()), "scores differ"
+        if st.games_completed == 0:
+            return dict(generations=gens, leaves=leaves, games=0, moves_compared=0, scores=[0, 0, 0],
+                        simulations=int(st.simulations))
         m = ora.metrics()
         for name in ("avg_game_length", "avg_moves_per_turn", "avg_valid_moves"):
             assert np.float32(getattr(st, name)) == np.float32(m[name]), name
@@ -366,7 +376,7 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
 
 
 def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port", rng_mode=None, level=0,
-                      tree_reuse=True, lanes=0, chunk=64):
+                      tree_reuse=True, lanes=0, chunk=64, steps=None):
     """RANDOM-eval run (EvalType::RANDOM, the reference's own fake backend: play_manager_test.cc): the engine
     fuses `chunk` loop iterations per launch; the oracle plays to the end; final scores, metrics and the
     training samples must agree."""
@@ -379,14 +389,25 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
     ora = make_oracle(oracle, G=G, games_to_play=games_to_play, visits=visits, eval_type=b2az.EVAL_RANDOM,
                       rng_mode=rng_mode, seed=seed, tree_reuse=tree_reuse, **kw)
     try:
-        ora.advance()
-        for _ in range(10 ** 6):
-            eng.step(chunk)
+        if steps is None:  # play every game to the end
+            ora.advance()
+            for _ in range(10 ** 6):
+                eng.step(chunk)
+                st = eng.stats()
+                if st.active_games == 0:
+                    break
+            assert st.games_completed == games_to_play
+        else:  # a fixed number of generations while no slot can retire (order-independent: see DESIGN.md)
+            ora.run_iterations(G * steps)
+            done = 0
+            while done < steps:
+                n = min(chunk, steps - done)
+                eng.step(n)
+                done += n
             st = eng.stats()
-            if st.active_games == 0:
-                break
+            assert st.active_games == G, "pick games_to_play large enough that no slot retires"
         assert st.device_error == 0, f"device error bits {st.device_error}"
-        assert st.games_completed == ora.games_completed() == games_to_play
+        assert st.games_completed == ora.games_completed()
         assert np.array_equal(np.array(st.scores[:], np.float32), ora.scores()), \
             f"scores differ {st.scores[:]} vs {ora.scores()}"
         m = ora.metrics()
