@@ -44,7 +44,8 @@ class Params(C.Structure):
         ("policy_target_pruning", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("resign_percent", C.c_float),
         ("resign_playthrough_percent", C.c_float), ("eval_type", C.c_uint8), ("rng_mode", C.c_uint8),
         ("pad0_", C.c_uint8), ("pad1_", C.c_uint8), ("seed", C.c_uint64), ("pool_nodes", C.c_uint64),
-        ("history_capacity", C.c_uint32), ("lanes_per_game", C.c_uint32),
+        ("history_capacity", C.c_uint32), ("lanes_per_game", C.c_uint32), ("compact_pages", C.c_uint32),
+        ("pad2_", C.c_uint32),
     ]
 
 
@@ -59,6 +60,7 @@ class Stats(C.Structure):
         ("cache_hits", C.c_uint64), ("cache_misses", C.c_uint64), ("cache_evictions", C.c_uint64),
         ("cache_reinserts", C.c_uint64), ("cache_size", C.c_uint64), ("cache_max_size", C.c_uint64),
         ("pool_pages_total", C.c_uint64), ("pool_pages_free", C.c_uint64), ("device_error", C.c_uint32),
+        ("pad_", C.c_uint32), ("compactions", C.c_uint64),
     ]
 
 

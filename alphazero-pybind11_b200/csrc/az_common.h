@@ -7,9 +7,12 @@
 #if defined(__CUDACC__)
 #define AZ_HD __host__ __device__ __forceinline__
 #define AZ_D __device__ __forceinline__
+// cold paths (move making, root noise, compaction): kept out of line so the per-simulation loop stays small
+#define AZ_COLD __host__ __device__ __noinline__
 #else
 #define AZ_HD inline
 #define AZ_D inline
+#define AZ_COLD inline
 #endif
 
 namespace b2az {

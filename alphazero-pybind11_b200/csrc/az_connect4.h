@@ -47,7 +47,10 @@ AZ_HD bool c4_play(C4State& s, u32 w) {
   const u64 occ = s.p[0] | s.p[1];
   const u64 free_cells = ~occ & (0x3FULL << (7 * w));
   if (!free_cells) return false;
-  s.p[s.player] |= free_cells & (0 - free_cells);  // lowest empty cell
+  const u64 stone = free_cells & (0 - free_cells);  // lowest empty cell
+  // selects, not s.p[s.player]: a dynamically indexed member would live in local memory on the device
+  s.p[0] |= s.player == 0 ? stone : 0ULL;
+  s.p[1] |= s.player == 0 ? 0ULL : stone;
   s.player ^= 1;
   ++s.turn;
   return true;

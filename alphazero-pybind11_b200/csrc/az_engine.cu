@@ -1,10 +1,11 @@
 // az_engine.cu — kernels + host side of the C ABI declared in include/b2az.h.
 //
 // Kernels (sm_100a):
-//   k_step<W>        one group of W lanes per game slot; per step runs game_step<W>() =
+//   k_step           one THREAD per game slot; per step runs game_step() =
 //                    process_result -> [move] -> find_leaf (az_engine_logic.h). With RANDOM eval the
-//                    evaluator is inline and n_steps are fused into one launch (persistent per slot).
-//   k_step_serial<W> B2AZ_RNG_GLOBAL: one group walks the slots in ascending order so the single
+//                    evaluator is inline and n_steps are fused into one launch: the game slot, the
+//                    mover's tree header and the RNG stay in registers across the steps.
+//   k_step_serial    B2AZ_RNG_GLOBAL: one thread walks the slots in ascending order so the single
 //                    pcg32 stream is consumed in the reference's order (bit-exact parity mode).
 //   k_canonicalize   compact leaf positions -> dense float32[B][4][6][7] for the torch net.
 //   k_hist_expand    compact finished samples -> canonical / v / pi arrays.
@@ -63,6 +64,16 @@ int dev_alloc(T** p, size_t count) {
 #else
   *p = static_cast<T*>(calloc(count ? count : 1, sizeof(T)));
   if (!*p) return fail(B2AZ_ENOMEM, "calloc failed");
+#endif
+  return 0;
+}
+template <typename T>
+int dev_alloc_raw(T** p, size_t count) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+#else
+  *p = static_cast<T*>(malloc((count ? count : 1) * sizeof(T)));
+  if (!*p) return fail(B2AZ_ENOMEM, "malloc failed");
 #endif
   return 0;
 }
@@ -136,12 +147,10 @@ struct InitArgs {
 
 #ifndef B2AZ_HOST_EMU
 __global__ void k_init_pool(EngineView E) {
-  // pages are dealt round-robin onto the stack shards: page p -> shard p % kNumStacks, chained
-  // p -> p + kNumStacks; the heads are written by k_init_heads.
+  // every page starts as a one-page chain in its own ring slot
   for (u32 p = GLOBAL_TID; p < E.num_pages; p += GLOBAL_NT) {
-    const u32 nx = p + (u32)kNumStacks;
-    E.page_next[p] = nx < E.num_pages ? nx : kNil;
-    E.page_fill[p] = 0;
+    E.page_next[p] = kNil;
+    E.ring[p] = p;
   }
 }
 __global__ void k_init_games(EngineView E, InitArgs a) {
@@ -151,6 +160,9 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
     gs.active = 1;
     pcg32_seed_stream(gs.rng, a.seed, (u64)g);
     E.games[g] = gs;
+    GameCold gc;
+    memset(&gc, 0, sizeof(gc));
+    E.cold[g] = gc;
     TreeHdr T;
     tree_reset(T);
     E.trees[(size_t)g * kP + 0] = T;
@@ -161,22 +173,32 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
     memset(G, 0, sizeof(Globals));
     G->games_started = E.G;
     G->active_games = E.G;
+    G->ring_push = E.num_pages;
+    G->ring_pop = 0;
     pcg32_seed(G->global_rng, a.seed);
-    for (u32 s = 0; s < (u32)kNumStacks; ++s) E.stack_head[s] = (unsigned long long)(s < E.num_pages ? s : kNil);
   }
 }
 
-template <int W>
-__global__ void __launch_bounds__(256) k_step(EngineView E, u32 n_steps) {
-  const u32 group = GLOBAL_TID / W;
-  const u32 ngroups = GLOBAL_NT / W;
-  for (u32 g = group; g < E.G; g += ngroups)
-    for (u32 s = 0; s < n_steps; ++s) game_step<W>(E, g);
+// One thread per game slot. <= 144 registers so that seven 64-thread CTAs (14 warps) fit an SM: at the
+// BASELINE size (65,536 games over 148 SMs = 443 threads per SM) every game is resident at once.
+__global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
+  const u32 g = GLOBAL_TID;
+  if (g >= E.G) return;
+  Ctx c;
+  ctx_load(E, g, c);
+  if (!c.gs.active) return;
+  for (u32 s = 0; s < n_steps; ++s) game_step(E, g, c);
+  ctx_store(E, g, c);
 }
-template <int W>
 __global__ void k_step_serial(EngineView E, u32 n_steps) {
   for (u32 s = 0; s < n_steps; ++s)
-    for (u32 g = 0; g < E.G; ++g) game_step<W>(E, g);
+    for (u32 g = 0; g < E.G; ++g) {
+      Ctx c;
+      ctx_load(E, g, c);
+      if (!c.gs.active) continue;
+      game_step(E, g, c);
+      ctx_store(E, g, c);
+    }
 }
 
 __global__ void k_canonicalize(EngineView E, const u32* __restrict__ count_ptr, float* __restrict__ out) {
@@ -219,14 +241,14 @@ AZ_HD void peek_impl(const EngineView& E, u32 g, u32 seat, PeekOut* o) {
   o->state[87] = (u8)((turn >> 16) & 0xFF); o->state[88] = (u8)((turn >> 24) & 0xFF);
   const TreeHdr& T = E.trees[(size_t)g * kP + seat];
   RootView R;
-  root_view<1>(E, T, R);
+  root_view(E, T, R);
   for (int m = 0; m < kA; ++m) { o->counts[m] = 0; o->q[m] = 0.0f; o->policy[m] = 0.0f; }
   for (u32 j = 0; j < R.k; ++j) {
-    o->counts[R.mv[j]] = R.K.n[j];
-    o->q[R.mv[j]] = R.K.n[j] ? R.K.q[j] : 0.0f;
-    o->policy[R.mv[j]] = R.K.pol[j];
+    o->counts[R.mv[j]] = R.n[j];
+    o->q[R.mv[j]] = R.n[j] ? R.q[j] : 0.0f;
+    o->policy[R.mv[j]] = R.pol[j];
   }
-  mcts_root_value(E, T, R, o->root_value);
+  mcts_root_value(T, R, o->root_value);
   o->depth = T.depth;
   o->root_n = T.n;
 }
@@ -237,7 +259,7 @@ struct StatsOut {
 __global__ void k_peek(EngineView E, u32 g, u32 seat, PeekOut* o) { peek_impl(E, g, seat, o); }
 __global__ void k_stats(EngineView E, StatsOut* o) {
   unsigned long long s = 0, m = 0;
-  for (u32 g = GLOBAL_TID; g < E.G; g += GLOBAL_NT) { s += E.games[g].sims; m += E.games[g].nmoves; }
+  for (u32 g = GLOBAL_TID; g < E.G; g += GLOBAL_NT) { s += E.cold[g].sims; m += E.cold[g].nmoves; }
   for (int off = 16; off > 0; off >>= 1) {
     s += __shfl_down_sync(0xFFFFFFFFu, s, off);
     m += __shfl_down_sync(0xFFFFFFFFu, m, off);
@@ -245,13 +267,14 @@ __global__ void k_stats(EngineView E, StatsOut* o) {
   if ((threadIdx.x & 31) == 0) { atomicAdd(&o->sims, s); atomicAdd(&o->moves, m); }
 }
 __global__ void k_count_free_pages(EngineView E, unsigned long long* out) {
-  // walks the stacks; only meaningful while no step kernel is running
-  if (GLOBAL_TID < (u32)kNumStacks) {
-    unsigned long long c = 0;
-    u32 p = (u32)E.stack_head[GLOBAL_TID];
+  // walks every chain in the ring; only meaningful while no step kernel is running
+  unsigned long long c = 0;
+  for (u32 i = GLOBAL_TID; i < E.num_pages; i += GLOBAL_NT) {
+    u32 p = E.ring[i];
     while (p != kNil) { ++c; p = E.page_next[p]; }
-    atomicAdd(out, c);
   }
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 #endif
 
@@ -304,7 +327,6 @@ struct b2az_engine {
   b2az_params params;
   int device = 0;
   int num_sms = 148;
-  u32 lanes = 8;
   EngineView view;
   // owned device buffers
   float* canon_buf = nullptr;   // [G][168]
@@ -406,9 +428,8 @@ int b2az_destroy(b2az_engine* e) {
   cudaDeviceSynchronize();
 #endif
   EngineView& V = e->view;
-  dev_free(V.q); dev_free(V.pol); dev_free(V.n); dev_free(V.mv); dev_free(V.rec);
-  dev_free(V.page_next); dev_free(V.page_fill); dev_free(V.stack_head);
-  dev_free(V.trees); dev_free(V.games); dev_free(V.path);
+  dev_free(V.blocks); dev_free(V.page_next); dev_free(V.ring);
+  dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot);
   dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game);
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
   dev_free(e->canon_buf); dev_free(e->ev_v_buf); dev_free(e->ev_pi_buf);
@@ -433,11 +454,9 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->eval_type != B2AZ_EVAL_NN && p->eval_type != B2AZ_EVAL_RANDOM) return fail(B2AZ_EINVAL, "bad eval_type");
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
   if (p->max_cache_size != 0) return fail(B2AZ_EINVAL, "the device position cache is not implemented yet");
-  u32 lanes = p->lanes_per_game ? p->lanes_per_game : 8u;
-  if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 32)
-    return fail(B2AZ_EINVAL, "lanes_per_game must be 1, 4, 8 or 32");
+  if (p->lanes_per_game > 1)
+    return fail(B2AZ_EINVAL, "lanes_per_game must be 0 or 1: Connect4 runs one thread per game slot (DESIGN.md 3)");
 #ifdef B2AZ_HOST_EMU
-  lanes = 1;
   (void)device;
 #else
   int ndev = 0;
@@ -449,7 +468,6 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   b2az_engine* e = new b2az_engine();
   e->params = *p;
   e->device = device;
-  e->lanes = lanes;
 #ifndef B2AZ_HOST_EMU
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -469,34 +487,36 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.shaped_dirichlet = p->shaped_dirichlet; V.policy_target_pruning = p->policy_target_pruning;
   V.playout_cap = 0; V.eval_type = p->eval_type; V.rng_mode = p->rng_mode;
 
-  // ---- pool sizing: pages of 256 nodes, 30 B per node
-  u64 pool_nodes = p->pool_nodes;
-  if (pool_nodes == 0) {
-    // default: room for every tree to hold a full search's worth of children twice over
-    const u64 per_tree = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]) * 8ull * 3ull + 2ull * kPageNodes;
-    pool_nodes = per_tree * (u64)G * kP;
+  // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
+  const u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
+  // a search adds <= one block per simulation; budget = 4 searches' worth + slack per tree
+  const u64 tree_blocks = 4ull * max_visits + 2ull * kPageBlocks;
+  u64 pool_blocks = p->pool_nodes ? (p->pool_nodes + kKMax - 1) / kKMax : tree_blocks * (u64)G * kP;
 #ifndef B2AZ_HOST_EMU
+  if (p->pool_nodes == 0) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const u64 cap = (u64)(free_b * 0.6) / 30ull;
-    if (pool_nodes > cap) pool_nodes = cap;
-#endif
+    const u64 cap = (u64)(free_b * 0.6) / sizeof(Block);
+    if (pool_blocks > cap) pool_blocks = cap;
   }
-  u64 pages = (pool_nodes + kPageNodes - 1) / kPageNodes;
-  if (pages < (u64)kNumStacks) pages = kNumStacks;
-  if (pages > 0x00FFFFFFull) pages = 0x00FFFFFFull;  // node index must fit 32 bits
+#endif
+  u64 pages = (pool_blocks + kPageBlocks - 1) / kPageBlocks;
+  const u64 min_pages = (u64)G * kP + 16ull;  // every tree can at least hold one page
+  if (pages < min_pages) pages = min_pages;
+  if (pages > (0xFFFFFFF0ull >> kPageLog2)) pages = 0xFFFFFFF0ull >> kPageLog2;  // block index must fit 32 bits
   V.num_pages = (u32)pages;
-  const size_t nodes = (size_t)pages * kPageNodes;
+  // compact a tree at a move once it holds more than half of its share of the pool
+  V.compact_pages = p->compact_pages ? std::min<u32>(p->compact_pages, 60000u)
+                                     : (u32)std::max<u64>(4, std::min<u64>(pages / ((u64)G * kP) / 2, 60000));
+  const size_t nblocks = (size_t)pages * kPageBlocks;
   V.hist_capacity = p->history_capacity ? p->history_capacity : std::max<u32>(1u << 16, G * (u32)kMaxHist);
 
   int rc = 0;
   auto A = [&](int r) { if (r && !rc) rc = r; };
-  A(dev_alloc(&V.q, nodes)); A(dev_alloc(&V.pol, nodes)); A(dev_alloc(&V.n, nodes));
-  A(dev_alloc(&V.mv, nodes)); A(dev_alloc(&V.rec, nodes));
-  A(dev_alloc(&V.page_next, pages)); A(dev_alloc(&V.page_fill, pages));
-  A(dev_alloc(&V.stack_head, (size_t)kNumStacks));
-  A(dev_alloc(&V.trees, (size_t)G * kP)); A(dev_alloc(&V.games, (size_t)G));
-  A(dev_alloc(&V.path, (size_t)G * kMaxPath));
+  A(dev_alloc_raw(&V.blocks, nblocks));  // every block is fully written before it is read: no memset
+  A(dev_alloc(&V.page_next, pages)); A(dev_alloc(&V.ring, pages));
+  A(dev_alloc(&V.trees, (size_t)G * kP)); A(dev_alloc(&V.games, (size_t)G)); A(dev_alloc(&V.cold, (size_t)G));
+  A(dev_alloc(&V.path, (size_t)G * kMaxPath)); A(dev_alloc(&V.pslot, (size_t)G * kMaxPath));
   A(dev_alloc(&V.leaf_p0, (size_t)G)); A(dev_alloc(&V.leaf_p1, (size_t)G));
   A(dev_alloc(&V.leaf_player, (size_t)G)); A(dev_alloc(&V.leaf_game, (size_t)G));
   A(dev_alloc(&V.hist_partial, p->history_enabled ? (size_t)G * kMaxHist : 1));
@@ -518,8 +538,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   CUDA_TRY(cudaDeviceSynchronize());
 #else
   for (u32 pg = 0; pg < V.num_pages; ++pg) {
-    const u32 nx = pg + (u32)kNumStacks;
-    V.page_next[pg] = nx < V.num_pages ? nx : kNil;
+    V.page_next[pg] = kNil;
+    V.ring[pg] = pg;
   }
   for (u32 g = 0; g < G; ++g) {
     GameSlot gs;
@@ -527,6 +547,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
     gs.active = 1;
     pcg32_seed_stream(gs.rng, p->seed, (u64)g);
     V.games[g] = gs;
+    memset(&V.cold[g], 0, sizeof(GameCold));
     TreeHdr T;
     tree_reset(T);
     V.trees[(size_t)g * kP + 0] = T;
@@ -535,8 +556,9 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   memset(V.glob, 0, sizeof(Globals));
   V.glob->games_started = G;
   V.glob->active_games = G;
+  V.glob->ring_push = V.num_pages;
+  V.glob->ring_pop = 0;
   pcg32_seed(V.glob->global_rng, p->seed);
-  for (u32 s = 0; s < (u32)kNumStacks; ++s) V.stack_head[s] = (unsigned long long)(s < V.num_pages ? s : kNil);
 #endif
   e->row_of_game.assign(G, 0);
   *out = e;
@@ -560,30 +582,25 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
 #ifndef B2AZ_HOST_EMU
   CUDA_TRY(cudaSetDevice(e->device));
   if (V.rng_mode == B2AZ_RNG_GLOBAL) {
-    // exactly ONE group walks the slots: the block has W threads
-    switch (e->lanes) {
-      case 1: k_step_serial<1><<<1, 1, 0, s>>>(V, n_steps); break;
-      case 4: k_step_serial<4><<<1, 4, 0, s>>>(V, n_steps); break;
-      case 8: k_step_serial<8><<<1, 8, 0, s>>>(V, n_steps); break;
-      default: k_step_serial<32><<<1, 32, 0, s>>>(V, n_steps); break;
-    }
+    k_step_serial<<<1, 1, 0, s>>>(V, n_steps);  // exactly ONE thread walks the slots
   } else {
-    const u32 threads = 256;
-    const u64 want = ((u64)V.G * e->lanes + threads - 1) / threads;
-    const u32 blocks = (u32)std::max<u64>(1, want);
-    switch (e->lanes) {
-      case 1: k_step<1><<<blocks, threads, 0, s>>>(V, n_steps); break;
-      case 4: k_step<4><<<blocks, threads, 0, s>>>(V, n_steps); break;
-      case 8: k_step<8><<<blocks, threads, 0, s>>>(V, n_steps); break;
-      default: k_step<32><<<blocks, threads, 0, s>>>(V, n_steps); break;
-    }
+    // small CTAs spread the (one thread per game) population evenly over the SMs
+    const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;
+    const u32 blocks = (V.G + threads - 1) / threads;
+    k_step<<<blocks, threads, 0, s>>>(V, n_steps);
   }
   CUDA_TRY(cudaGetLastError());
 #else
   // B2AZ_RNG_GLOBAL needs slot-major order inside a step (matches k_step_serial); per-game RNG is
   // order independent, so the same loop serves both.
   for (u32 st = 0; st < n_steps; ++st)
-    for (u32 g = 0; g < V.G; ++g) game_step<1>(V, g);
+    for (u32 g = 0; g < V.G; ++g) {
+      Ctx c;
+      ctx_load(V, g, c);
+      if (!c.gs.active) continue;
+      game_step(V, g, c);
+      ctx_store(V, g, c);
+    }
 #endif
   e->started = true;
   if (V.eval_type == B2AZ_EVAL_NN) {
@@ -742,14 +759,14 @@ int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   if (int rc = dev_zero(e->stats_buf, sizeof(StatsOut), s)) return rc;
   if (int rc = dev_zero(e->freepages_buf, sizeof(unsigned long long), s)) return rc;
   k_stats<<<e->num_sms * 2, 256, 0, s>>>(e->view, e->stats_buf);
-  k_count_free_pages<<<1, kNumStacks, 0, s>>>(e->view, e->freepages_buf);
+  k_count_free_pages<<<e->num_sms * 4, 256, 0, s>>>(e->view, e->freepages_buf);
   CUDA_TRY(cudaGetLastError());
   if (int rc = copy_d2h(&so, e->stats_buf, sizeof(so), s)) return rc;
   if (int rc = copy_d2h(&free_pages, e->freepages_buf, sizeof(free_pages), s)) return rc;
 #else
-  for (u32 g = 0; g < e->view.G; ++g) { so.sims += e->view.games[g].sims; so.moves += e->view.games[g].nmoves; }
-  for (u32 st = 0; st < (u32)kNumStacks; ++st) {
-    u32 p = (u32)e->view.stack_head[st];
+  for (u32 g = 0; g < e->view.G; ++g) { so.sims += e->view.cold[g].sims; so.moves += e->view.cold[g].nmoves; }
+  for (u32 i = 0; i < e->view.num_pages; ++i) {
+    u32 p = e->view.ring[i];
     while (p != kNil) { ++free_pages; p = e->view.page_next[p]; }
   }
 #endif
@@ -774,6 +791,7 @@ int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   out->pool_pages_total = e->view.num_pages;
   out->pool_pages_free = free_pages;
   out->device_error = G.error;
+  out->compactions = G.compactions;
   return 0;
 }
 

@@ -1,19 +1,27 @@
-// az_engine_logic.h — the self-play hot path as cooperative device functions.
+// az_engine_logic.h — the self-play hot path as device functions, ONE THREAD PER GAME SLOT.
 //
-// One GROUP of W lanes (W = 1..32, a power of two; W lanes of one warp) owns one game slot and runs,
-// per step, exactly one iteration of PlayManager::play()'s loop body (play_manager.cc:272-599):
+// Per step a thread runs exactly one iteration of PlayManager::play()'s loop body
+// (play_manager.cc:272-599) for its game:
 //     process_result -> [play a move] -> find_leaf
-// All control flow is group-uniform: every lane keeps the same copy of the small state (tree header,
-// game slot, RNG), loads of child statistics are spread over the lanes (one 32 B sector per field
-// for a Connect4 block) and all-gathered with warp shuffles, and every lane then evaluates the same
-// scalar code. That keeps the float operation ORDER identical to the reference's sequential loops
-// (SURVEY.md Appendix A "Float order"), which is what makes visit counts bit-exact.
+// Why a thread and not a warp per tree: Connect4 has <= 7 children per node, and the per-simulation
+// work is a short scalar chain whose float operation ORDER must equal the reference's sequential
+// loops (SURVEY.md Appendix A "Float order") for visit counts to be bit-exact. Measured on the B200
+// (profiles/r1_*): 8 or 32 cooperating lanes replicate that scalar chain in every lane (697 warp
+// instructions per simulation, 29 % issue utilisation at 25 % occupancy) and lose to one thread per game
+// by 2x. So the parallelism is ACROSS games (65,536 independent threads), memory-level parallelism
+// comes from loading a node's whole child block (five 32 B sectors) in one burst, and the hot loop
+// keeps every small array in registers (no indexed local arrays).
 //
-// Everything here is __host__ __device__: the host instantiation (W = 1, plain memory instead of
-// atomics/shuffles) exists only for tests/cpp/engine_host_capi.cc, which lets the CPU test-suite
-// compare this logic with the oracle without a GPU. The product (az_engine.cu) only instantiates
-// the device side and fails loudly without CUDA.
+// Hot (inlined): find_leaf, process_result for interior leaves. Cold (AZ_COLD, out of line): playing a
+// move, root priors (temperature, Dirichlet), re-rooting, Cheney compaction, the page ring.
+//
+// Everything here is __host__ __device__: the host instantiation exists only for the
+// -DB2AZ_HOST_EMU test build (tests/cpp/libb2az_hostemu.so), which lets the CPU test-suite compare this
+// logic with the oracle without a GPU. The product (az_engine.cu) only runs the device side and
+// fails loudly without CUDA.
 #pragma once
+
+#include <string.h>
 
 #include "az_engine_types.h"
 
@@ -46,6 +54,20 @@ AZ_HD void at_or(u32* p, u32 v) {
   *p |= v;
 #endif
 }
+AZ_HD u32 at_exch(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+  return atomicExch(p, v);
+#else
+  u32 o = *p; *p = v; return o;
+#endif
+}
+AZ_HD u32 at_cas(u32* p, u32 cmp, u32 v) {
+#if defined(__CUDA_ARCH__)
+  return atomicCAS(p, cmp, v);
+#else
+  u32 o = *p; if (o == cmp) *p = v; return o;
+#endif
+}
 AZ_HD unsigned long long at_add64(unsigned long long* p, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
   return atomicAdd(p, v);
@@ -60,13 +82,6 @@ AZ_HD void at_addd(double* p, double v) {
   *p += v;
 #endif
 }
-AZ_HD unsigned long long at_cas64(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
-#if defined(__CUDA_ARCH__)
-  return atomicCAS(p, cmp, val);
-#else
-  unsigned long long o = *p; if (o == cmp) *p = val; return o;
-#endif
-}
 AZ_HD void mem_fence() {
 #if defined(__CUDA_ARCH__)
   __threadfence();
@@ -74,41 +89,8 @@ AZ_HD void mem_fence() {
 }
 template <typename T>
 AZ_HD T ld_volatile(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
-
-// ------------------------------------------------------------------------------------ lane groups
-template <int W>
-struct Grp {
-  AZ_HD static int lane() {
-#if defined(__CUDA_ARCH__)
-    return (int)(threadIdx.x & (W - 1));
-#else
-    return 0;
-#endif
-  }
-  AZ_HD static unsigned mask() {
-#if defined(__CUDA_ARCH__)
-    if (W == 32) return 0xFFFFFFFFu;
-    return ((1u << (W & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(W - 1));
-#else
-    return 1u;
-#endif
-  }
-  template <typename T>
-  AZ_HD static T bcast(T v, int src) {
-#if defined(__CUDA_ARCH__)
-    if (W == 1) return v;
-    return __shfl_sync(mask(), v, src, W);
-#else
-    (void)src;
-    return v;
-#endif
-  }
-  AZ_HD static void sync() {
-#if defined(__CUDA_ARCH__)
-    if (W > 1) __syncwarp(mask());
-#endif
-  }
-};
+template <typename T>
+AZ_HD void st_volatile(T* p, T v) { *reinterpret_cast<volatile T*>(p) = v; }
 
 // std::min / std::max argument-order semantics (they differ from fminf/fmaxf on NaN)
 AZ_HD float std_min(float a, float b) { return (b < a) ? b : a; }
@@ -122,256 +104,297 @@ AZ_HD int popc32(u32 x) {
 #endif
 }
 
-// ------------------------------------------------------------------------------------ page pool
-// Sharded lock-free stacks of free pages; head = (tag << 32) | top, next links in page_next[].
-AZ_HD u32 pool_pop_page(const EngineView& E, u32 home) {
-  for (u32 s = 0; s < (u32)kNumStacks; ++s) {
-    unsigned long long* head = &E.stack_head[(home + s) % (u32)kNumStacks];
-    unsigned long long old = ld_volatile(head);
-    while ((u32)old != kNil) {
-      const u32 top = (u32)old;
-      const u32 nxt = ld_volatile(&E.page_next[top]);
-      const unsigned long long nw = (((old >> 32) + 1ULL) << 32) | (unsigned long long)nxt;
-      const unsigned long long got = at_cas64(head, old, nw);
-      if (got == old) return top;
-      old = got;
-    }
-  }
-  return kNil;
+// ------------------------------------------------------------------------------------ sectors
+// One 32 B sector of a block as eight registers (two 16 B vector accesses on the device).
+struct Sec {
+  u32 w[8];
+};
+AZ_HD Sec ld_sec(const void* p) {
+  Sec s;
+#if defined(__CUDA_ARCH__)
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0];
+  const uint4 b = reinterpret_cast<const uint4*>(p)[1];
+  s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
+  s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
+#else
+  memcpy(s.w, p, 32);
+#endif
+  return s;
 }
-AZ_HD void pool_push_chain(const EngineView& E, u32 home, u32 first, u32 last) {
-  unsigned long long* head = &E.stack_head[home % (u32)kNumStacks];
-  unsigned long long old = ld_volatile(head);
-  for (;;) {
-    E.page_next[last] = (u32)old;
-    mem_fence();
-    const unsigned long long nw = (((old >> 32) + 1ULL) << 32) | (unsigned long long)first;
-    const unsigned long long got = at_cas64(head, old, nw);
-    if (got == old) return;
-    old = got;
-  }
+AZ_HD void st_sec(void* p, const Sec& s) {
+#if defined(__CUDA_ARCH__)
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+#else
+  memcpy(p, s.w, 32);
+#endif
 }
-// Free every page of a tree's chain (lane 0 of the group).
-template <int W>
-AZ_HD void tree_free_pages(const EngineView& E, u32 home, u32 first_page) {
-  if (first_page == kNil) return;
-  if (Grp<W>::lane() == 0) {
-    u32 last = first_page;
-    for (;;) {
-      const u32 nx = E.page_next[last];
-      if (nx == kNil) break;
-      last = nx;
-    }
-    pool_push_chain(E, home, first_page, last);
-  }
+// the mixed sector (Block::mv .. Block::player) decoded from registers
+AZ_HD u32 mix_mv(const Sec& m, int j) { return (m.w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu; }
+AZ_HD u32 mix_term(const Sec& m, int j) { return (m.w[4 + (j >> 2)] >> (8 * (j & 3))) & 0xFFu; }
+AZ_HD float mix_v(const Sec& m) { return u2f(m.w[6]); }
+AZ_HD u32 mix_k(const Sec& m) { return m.w[7] & 0xFFu; }
+AZ_HD u32 mix_player(const Sec& m) { return (m.w[7] >> 8) & 0xFFu; }
+// scalar accessors (cold paths)
+AZ_HD u32 blk_mv(const Block* B, u32 j) { return (B->mix[j >> 1] >> (16u * (j & 1u))) & 0xFFFFu; }
+AZ_HD u32 blk_term(const Block* B, u32 j) { return (B->mix[4u + (j >> 2)] >> (8u * (j & 3u))) & 0xFFu; }
+AZ_HD float blk_v(const Block* B) { return u2f(B->mix[6]); }
+AZ_HD u32 blk_k(const Block* B) { return B->mix[7] & 0xFFu; }
+AZ_HD u32 blk_player(const Block* B) { return (B->mix[7] >> 8) & 0xFFu; }
+
+// ------------------------------------------------------------------------------------ page ring
+// Free pages travel as CHAINS (linked through page_next[]) in one ring of chain heads. pop and push
+// each take a ticket with one atomicAdd and then own ring[ticket % num_pages]; the slot itself is
+// handed over with atomicExch / atomicCAS, so there is no retry storm under contention (the first
+// version's tagged-CAS stacks cost 12-28 ms in a generation where every game re-rooted).
+// Freeing a whole tree is ONE push; a pop takes the head page of a chain and pushes the rest back.
+AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
+  mem_fence();  // the chain's page_next links must be visible before the head is
+  const unsigned long long t = at_add64(&E.glob->ring_push, 1ULL);
+  u32* slot = &E.ring[t % (unsigned long long)E.num_pages];
+#if defined(__CUDA_ARCH__)
+  for (u32 spin = 0; spin < (1u << 22); ++spin)
+    if (at_cas(slot, kNil, head) == kNil) return;
+  at_or(&E.glob->error, B2AZ_DEVERR_POOL);  // cannot happen: there are never more chains than pages
+#else
+  *slot = head;
+#endif
 }
-// Bump-allocate a child block of kk nodes (padded to 8) in the tree's arena. Group-uniform.
-template <int W>
-AZ_HD u32 tree_alloc_block(const EngineView& E, TreeHdr& T, u32 home, u32 kk) {
-  const u32 need = (kk + 7u) & ~7u;
-  if (T.cur_page == kNil || T.bump + need > kPageNodes) {
-    u32 p = kNil;
-    if (Grp<W>::lane() == 0) {
-      p = pool_pop_page(E, home);
-      if (p != kNil) {
-        E.page_next[p] = kNil;
-        E.page_fill[p] = 0;
-        if (T.cur_page != kNil) {
-          E.page_fill[T.cur_page] = T.bump;
-          E.page_next[T.cur_page] = p;
-        }
-      } else {
-        at_or(&E.glob->error, B2AZ_DEVERR_POOL);
-      }
+AZ_COLD u32 pool_pop_page(const EngineView E) {
+  Globals* G = E.glob;
+  if (ld_volatile(&G->error) & B2AZ_DEVERR_POOL) return kNil;  // already fatal: do not spin again
+  const unsigned long long t = at_add64(&G->ring_pop, 1ULL);
+  u32* slot = &E.ring[t % (unsigned long long)E.num_pages];
+  u32 head = kNil;
+#if defined(__CUDA_ARCH__)
+  for (u32 spin = 0; spin < (1u << 16); ++spin) {
+    head = at_exch(slot, kNil);
+    if (head != kNil) break;
+  }
+#else
+  head = at_exch(slot, kNil);
+#endif
+  if (head == kNil) return kNil;  // ring empty: pool exhausted (fatal, reported by the caller)
+  mem_fence();
+  const u32 rest = ld_volatile(&E.page_next[head]);
+  if (rest != kNil) pool_push_chain(E, rest);
+  return head;
+}
+// Bump-allocate one block in the tree's arena.
+AZ_HD u32 tree_alloc_block(const EngineView& E, TreeHdr& T) {
+  if (T.cur_page == kNil || T.bump >= kPageBlocks) {
+    const u32 p = pool_pop_page(E);
+    if (p == kNil) {
+      at_or(&E.glob->error, B2AZ_DEVERR_POOL);
+      return kNil;
     }
-    Grp<W>::sync();  // page_next / page_fill written by lane 0 are read by every lane (Cheney scan)
-    p = Grp<W>::bcast(p, 0);
-    if (p == kNil) return kNil;
-    if (T.cur_page == kNil) T.first_page = p;
+    st_volatile(&E.page_next[p], kNil);
+    if (T.cur_page != kNil) st_volatile(&E.page_next[T.cur_page], p);
+    else T.first_page = p;
     T.cur_page = p;
     T.bump = 0;
+    ++T.pages_used;
   }
-  const u32 base = (T.cur_page << kPageLog2) + T.bump;
-  T.bump += need;
-  return base;
+  return (T.cur_page << kPageLog2) + T.bump++;
+}
+AZ_HD void arena_clear(TreeHdr& T) {
+  T.first_page = T.cur_page = kNil;
+  T.bump = 0;
+  T.pages_used = 0;
+}
+AZ_HD void tree_free_pages(const EngineView& E, TreeHdr& T) {
+  if (T.first_page != kNil) pool_push_chain(E, T.first_page);
+  arena_clear(T);
 }
 AZ_HD void tree_reset(TreeHdr& T) {  // a freshly constructed MCTS (mcts.h:52-73): root_ = Node{}
   T.q = T.d = T.v = T.policy = 0.0f;
   T.n = 0;
   T.fc = kNil;
+  T.move = 0;
   T.k = 0;
   T.player = 0;
   T.term = 0;
-  T.move = 0;
+  T.leaf_term = T.leaf_k = T.leaf_player = 0;
+  T.leaf_blk = kNil;
   T.path_len = 0;
   T.depth = 0;
   T.total_leaf_depth = 0;
-  T.first_page = T.cur_page = kNil;
-  T.bump = 0;
-  T.leaf = kRootRef;
-  T.pad_[0] = T.pad_[1] = 0;
+  arena_clear(T);
+  T.pad_ = 0;
 }
 
-// ------------------------------------------------------------------------------------ child blocks
-struct Kids {  // statistics of one (<= 8 wide) child block, replicated in every lane
-  u32 n[kKMax];
-  float pol[kKMax];
-  float q[kKMax];
+// ------------------------------------------------------------------------------------ path cache
+// The first kPathRegs edges of the selection path also stay in registers between find_leaf and the
+// process_result of the next fused step (the HBM copy in E.path / E.pslot is what a later launch reads).
+constexpr int kPathRegs = 8;
+struct PathRegs {
+  u32 blk[kPathRegs];
+  u32 slots_lo, slots_hi;  // 8 bits per level: child slot | parent's player << 4
+  u32 valid;               // the registers describe the pending leaf's path
 };
-// Coalesced load of n/pol/q (one 32 B sector each) + all-gather inside the group.
-template <int W, bool WITH_Q>
-AZ_HD void kids_load(const EngineView& E, u32 fc, Kids& K) {
-  constexpr int R = (kKMax + W - 1) / W;
-  u32 mn[R];
-  float mp[R], mq[R];
-  const int lane = Grp<W>::lane();
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int j = r * W + lane;
-    mn[r] = 0; mp[r] = 0.0f; mq[r] = 0.0f;
-    if (j < kKMax) {
-      mn[r] = E.n[fc + j];
-      mp[r] = E.pol[fc + j];
-      if (WITH_Q) mq[r] = E.q[fc + j];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kKMax; ++i) {
-    K.n[i] = Grp<W>::bcast(mn[i / W], i % W);
-    K.pol[i] = Grp<W>::bcast(mp[i / W], i % W);
-    K.q[i] = WITH_Q ? Grp<W>::bcast(mq[i / W], i % W) : 0.0f;
-  }
-}
-template <int W>
-AZ_HD void moves_load(const EngineView& E, u32 fc, u32* mv8) {
-  constexpr int R = (kKMax + W - 1) / W;
-  u32 mm[R];
-  const int lane = Grp<W>::lane();
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int j = r * W + lane;
-    mm[r] = (j < kKMax) ? (u32)E.mv[fc + j] : 0u;
-  }
-#pragma unroll
-  for (int i = 0; i < kKMax; ++i) mv8[i] = Grp<W>::bcast(mm[i / W], i % W);
-}
-// Store one float per child from a replicated array (lane j%W writes child j).
-template <int W>
-AZ_HD void kids_store_pol(const EngineView& E, u32 fc, u32 k, const float* p8) {
-  const int lane = Grp<W>::lane();
-#pragma unroll
-  for (int j = 0; j < kKMax; ++j)
-    if ((j % W) == lane && (u32)j < k) E.pol[fc + j] = p8[j];
+AZ_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
 }
 
-// Node::best_child (mcts.cc:130-149) + Node::uct (mcts.cc:123-128); n_in_flight is always 0 on
-// this path (the WU-UCT variant is not used by PlayManager).
-AZ_HD int best_child(const Kids& K, u32 k, u32 parent_n, float parent_v, float cpuct, float fpu_reduction) {
-  float seen = 0.0f;
-  for (u32 j = 0; j < k; ++j)
-    if (K.n[j] > 0) seen = fadd(seen, K.pol[j]);
-  const float fpu_value = fsub(parent_v, fmul(fpu_reduction, fsqrt(seen)));
-  const float sqrt_n = fsqrt((float)parent_n);
-  int best_i = 0;
-  float best_u = 0.0f;
-  for (u32 j = 0; j < k; ++j) {
-    const float base = (K.n[j] == 0) ? fpu_value : K.q[j];
-    const float u = fadd(base, fdiv(fmul(fmul(cpuct, K.pol[j]), sqrt_n), (float)(K.n[j] + 1u)));
-    if (j == 0 || u > best_u) {
-      best_u = u;
-      best_i = (int)j;
-    }
-  }
-  return best_i;
-}
-
-struct Leaf {  // what find_leaf hands to the evaluator
-  C4State s;
-  u32 k;     // legal moves at the leaf
-  u32 term;  // terminal code of the leaf node
-};
-
-// MCTS::find_leaf (mcts.cc:462-498), PUCT branch.
-template <int W>
-AZ_HD void find_leaf(const EngineView& E, u32 g, u32 tree, TreeHdr& T, const GameSlot& gs, Pcg32& rng, Leaf& out) {
+// ------------------------------------------------------------------------------------ find_leaf
+// MCTS::find_leaf (mcts.cc:462-498), PUCT branch; Node::best_child (mcts.cc:130-149) and Node::uct
+// (mcts.cc:123-128) inlined. n_in_flight is always 0 on this path (the WU-UCT variant is not used by
+// PlayManager).
+AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32& rng, PathRegs& pr) {
   C4State s;
   s.p[0] = gs.p0; s.p[1] = gs.p1; s.turn = gs.turn; s.player = gs.player;
   u32* path = E.path + (size_t)g * kMaxPath;
-  u32 cur = kRootRef;
-  u32 cur_n = T.n, cur_term = T.term, cur_fc = T.fc, cur_k = T.k;
+  u8* pslot = E.pslot + (size_t)g * kMaxPath;
+  u32 blk = T.fc;
+  u32 cur_n = T.n, cur_term = T.term, cur_player = T.player;
   float cur_v = T.v;
+  u32 cur_k = T.k;
+  bool at_root = true;
+  u32 par_blk = kNil, par_slot = 0;
   u32 plen = 0;
-  const int lane = Grp<W>::lane();
+  pr.slots_lo = pr.slots_hi = 0;
+  pr.valid = 1;
   while (cur_n > 0 && cur_term == 0) {
-    if (cur_k == 0 || plen >= (u32)kMaxPath) {  // cannot happen for a non-terminal Connect4 node
+    if (blk == kNil || plen >= (u32)kMaxPath) {  // cannot happen for a non-terminal Connect4 node
       at_or(&E.glob->error, B2AZ_DEVERR_DEPTH);
       break;
     }
-    Kids K;
-    kids_load<W, true>(E, cur_fc, K);
-    const float fpu = (cur == kRootRef && E.root_fpu_zero) ? 0.0f : E.fpu_reduction;
-    const int j = best_child(K, cur_k, cur_n, cur_v, E.cpuct, fpu);
-    const u32 c = cur_fc + (u32)j;
-    if (lane == 0) path[plen] = c;
-    ++plen;
-    const u32 move = E.mv[c];
-    c4_play(s, move);
-    cur = c;
-    cur_n = K.n[j];
-    if (cur_n > 0) {
-      const NodeRec r = E.rec[c];
-      cur_term = r.term; cur_fc = r.fc; cur_k = r.k; cur_v = r.v;
+    const Block* B = E.blocks + blk;
+    // one burst: everything this level needs (5 sectors, independent loads)
+    const Sec sn = ld_sec(B->n), sq = ld_sec(B->q), sp = ld_sec(B->pol), sf = ld_sec(B->fc), sm = ld_sec(B->mix);
+    if (!at_root) {
+      cur_v = mix_v(sm);
+      cur_k = mix_k(sm);
+      cur_player = mix_player(sm);
     }
+    const float fpu = (at_root && E.root_fpu_zero) ? 0.0f : E.fpu_reduction;
+    float seen = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kKMax; ++j)
+      if ((u32)j < cur_k && sn.w[j] > 0) seen = fadd(seen, u2f(sp.w[j]));
+    const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
+    const float sqrt_n = fsqrt((float)cur_n);
+    u32 best = 0, best_n = 0, best_fc = kNil;
+    float best_u = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kKMax; ++j) {
+      if (j > 0 && (u32)j >= cur_k) continue;  // pad slots: 0 / 1 would take the division's slow path
+      const u32 nj = sn.w[j];
+      const float base = (nj == 0) ? fpu_value : u2f(sq.w[j]);
+      const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(sp.w[j])), sqrt_n), (float)(nj + 1u)));
+      if (j == 0 || u > best_u) {
+        best_u = u;
+        best = (u32)j;
+        best_n = nj;
+        best_fc = sf.w[j];
+      }
+    }
+    prefetch_l2(&B->d[best]);  // the backprop of this simulation reads d[best]: have it on its way
+    // move and terminal code of the chosen child out of the mixed sector (select chain, no indexing)
+    u32 mvw = sm.w[0], tw = sm.w[4];
+    if (best >= 2) mvw = sm.w[1];
+    if (best >= 4) { mvw = sm.w[2]; tw = sm.w[5]; }
+    if (best >= 6) mvw = sm.w[3];
+    const u32 move = (mvw >> (16u * (best & 1u))) & 0xFFFFu;
+    const u32 cterm = (tw >> (8u * (best & 3u))) & 0xFFu;
+    const u32 slot_byte = best | (cur_player << 4);
+    path[plen] = blk;
+    pslot[plen] = (u8)slot_byte;
+#pragma unroll
+    for (int i = 0; i < kPathRegs; ++i)
+      if (plen == (u32)i) pr.blk[i] = blk;
+    if (plen < 4u) pr.slots_lo |= slot_byte << (8u * plen);
+    else if (plen < 8u) pr.slots_hi |= slot_byte << (8u * (plen - 4u));
+    ++plen;
+    c4_play(s, move);
+    par_blk = blk;
+    par_slot = best;
+    cur_n = best_n;
+    cur_term = cterm;
+    blk = best_fc;
+    at_root = false;
   }
   T.total_leaf_depth += plen;
-  out.term = cur_term;
-  out.k = cur_k;
+  T.path_len = (u16)plen;
   if (cur_n == 0) {
     // expand: current_->player, scores, add_children(valid_moves) incl. the shuffle (mcts.cc:490-496, 93-101)
     const u32 term = c4_terminal(s);
     const u32 vm = c4_valid_mask(s);
-    u32 moves[kKMax];
-    u32 k = 0;
+    u32 moves = 0, k = 0;  // ascending legal moves as nibbles
 #pragma unroll
     for (u32 w = 0; w < (u32)kA; ++w)
-      if ((vm >> w) & 1u) moves[k++] = w;
-    rng_shuffle(rng, moves, k);
+      if ((vm >> w) & 1u) moves |= w << (4u * k++);
+    rng_shuffle_nib(rng, moves, k);
     // Children of a terminal node are never visited (selection stops at scores != nullptr,
     // mcts.cc:473) — their RNG draws are consumed above, their storage is skipped.
     const u32 kk = term ? 0u : k;
-    u32 fc = kNil;
+    u32 nb = kNil;
     if (kk > 0) {
-      fc = tree_alloc_block<W>(E, T, g, kk);
-      if (fc != kNil) {
+      nb = tree_alloc_block(E, T);
+      if (nb != kNil) {
+        Block* N = E.blocks + nb;
+        Sec z, f, m;
 #pragma unroll
-        for (int j = 0; j < kKMax; ++j)
-          if ((j % W) == lane) {
-            E.n[fc + j] = 0u;  // full-sector write; pads stay n = 0 forever
-            E.mv[fc + j] = (u16)((u32)j < kk ? moves[j] : 0u);
-          }
+        for (int j = 0; j < 8; ++j) { z.w[j] = 0u; f.w[j] = kNil; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const u32 lo = (u32)(2 * j) < kk ? ((moves >> (8u * j)) & 15u) : 0u;
+          const u32 hi = (u32)(2 * j + 1) < kk ? ((moves >> (8u * j + 4u)) & 15u) : 0u;
+          m.w[j] = lo | (hi << 16);
+        }
+        m.w[4] = m.w[5] = 0u;       // term[8]
+        m.w[6] = 0u;                // v: written by the first backprop through this node
+        m.w[7] = kk | ((u32)s.player << 8);
+        st_sec(N->n, z); st_sec(N->q, z); st_sec(N->pol, z); st_sec(N->fc, f); st_sec(N->d, z); st_sec(N->mix, m);
       }
     }
-    const u32 k_eff = (fc == kNil) ? 0u : kk;
-    if (cur == kRootRef) {
-      T.player = s.player; T.term = (u8)term; T.fc = fc; T.k = (u16)k_eff;
-    } else if (lane == 0) {
-      // only the structural half of the record; v/d are written by the first backprop
-      NodeRec r = E.rec[cur];
-      r.fc = fc; r.k = (u16)k_eff; r.player = s.player; r.term = (u8)term;
-      E.rec[cur] = r;
+    const u32 k_eff = (nb == kNil) ? 0u : kk;
+    if (at_root) {
+      T.player = s.player; T.term = (u8)term; T.fc = nb; T.k = (u8)k_eff;
+    } else {
+      Block* Pb = E.blocks + par_blk;
+      Pb->fc[par_slot] = nb;
+      if (term) Pb->mix[4u + (par_slot >> 2)] |= term << (8u * (par_slot & 3u));  // was 0 (unknown)
     }
-    out.term = term;
-    out.k = k;  // dumb_eval counts every legal move, terminal or not
-  } else {
-    out.k = (u32)popc32(c4_valid_mask(s));
+    T.leaf_term = (u8)term;
+    T.leaf_k = (u8)k_eff;
+    T.leaf_player = s.player;
+    T.leaf_blk = nb;
+  } else {  // a terminal node visited again
+    T.leaf_term = (u8)cur_term;
+    T.leaf_k = 0;
+    T.leaf_player = s.player;
+    T.leaf_blk = kNil;
   }
-  T.leaf = cur;
-  T.path_len = (u16)plen;
-  out.s = s;
+  if (E.eval_type == 0) {  // the net's input: the leaf position (compact; expanded by k_canonicalize)
+    u32 row;
+#if defined(__CUDA_ARCH__)
+    // leaf-batch compaction: one atomicAdd per warp, rows handed out by ballot rank
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(active) - 1;
+    u32 base = 0;
+    if ((int)lane == leader) base = atomicAdd(&E.glob->leaf_count, (u32)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    row = base + (u32)__popc(active & ((1u << lane) - 1u));
+#else
+    row = at_add(&E.glob->leaf_count, 1u);
+#endif
+    E.leaf_p0[row] = s.p[0];
+    E.leaf_p1[row] = s.p[1];
+    E.leaf_player[row] = s.player;
+    E.leaf_game[row] = g;
+    gs.eval_row = row;
+  }
 }
 
-// MCTS::add_root_noise (mcts.cc:403-446). `pol` = root child priors in child order (replicated).
-AZ_HD void add_root_noise(const EngineView& E, Pcg32& rng, float* pol, u32 k) {
+// ------------------------------------------------------------------------------------ root priors (cold)
+// MCTS::add_root_noise (mcts.cc:403-446). `pol` = root child priors in child order.
+AZ_COLD void add_root_noise(const EngineView& E, Pcg32& rng, float* pol, u32 k) {
   float noise[kKMax];
   double sum = 0.0;
   if (E.shaped_dirichlet && k > 1) {
@@ -408,90 +431,158 @@ AZ_HD void add_root_noise(const EngineView& E, Pcg32& rng, float* pol, u32 k) {
   for (u32 j = 0; j < k; ++j) pol[j] = fadd(fmul(pol[j], keep), fdiv(fmul(E.epsilon, noise[j]), fsum));
 }
 
-// MCTS::process_result (mcts.cc:500-555).
-template <int W>
-AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot& gs, Pcg32& rng, bool noise_enabled) {
-  float value[kP + 1];
-  const u32 leaf = T.leaf;
-  u32 lterm, lfc, lk, lplayer;
-  if (leaf == kRootRef) {
-    lterm = T.term; lfc = T.fc; lk = T.k; lplayer = T.player;
-  } else {
-    const NodeRec r = E.rec[leaf];
-    lterm = r.term; lfc = r.fc; lk = r.k; lplayer = r.player;
+// set_policy_normalized at the root (mcts.cc:109-121 with the temperature branch) + add_root_noise
+// (mcts.cc:511-519): the priors of a root that has just been evaluated.
+AZ_COLD void root_leaf_priors(const EngineView E, Pcg32& rng, float* p8, u32 lk, bool noise_enabled) {
+  const bool apply_temp = (E.root_temp != 1.0f);
+  const float inv_temp = fdiv(1.0f, E.root_temp);
+  float sum = 0.0f;
+  for (u32 j = 0; j < lk; ++j) {
+    if (apply_temp) p8[j] = az_powf(p8[j], inv_temp);
+    sum = fadd(sum, p8[j]);
   }
+  for (u32 j = 0; j < lk; ++j) p8[j] = fdiv(p8[j], sum);
+  if (noise_enabled && lk > 0) add_root_noise(E, rng, p8, lk);
+}
+
+// ------------------------------------------------------------------------------------ process_result
+// MCTS::process_result (mcts.cc:500-555).
+AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot& gs, Pcg32& rng, bool noise_enabled,
+                          PathRegs& pr) {
+  float val0, val1, vald;  // value[0], value[1], value[P] (draw share)
+  const u32 lterm = T.leaf_term, lk = T.leaf_k, lplayer = T.leaf_player, lblk = T.leaf_blk;
+  const u32 plen = T.path_len;
   if (lterm != 0) {
-    value[0] = (lterm == 1) ? 1.0f : 0.0f;
-    value[1] = (lterm == 2) ? 1.0f : 0.0f;
-    value[2] = (lterm == 3) ? 1.0f : 0.0f;
+    val0 = (lterm == 1) ? 1.0f : 0.0f;
+    val1 = (lterm == 2) ? 1.0f : 0.0f;
+    vald = (lterm == 3) ? 1.0f : 0.0f;
   } else {
-    float p8[kKMax];
-    if (E.eval_type == 1) {  // dumb_eval (game_state.h:160-173)
+    Sec ps;  // the leaf's child priors, child order
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ps.w[j] = 0u;
+    if (E.eval_type == 1) {  // dumb_eval (game_state.h:160-173): uniform over the legal moves, value 1/3
       const float third = (float)(1.0 / 3.0);
-      value[0] = value[1] = value[2] = third;
-      const float sum = (float)(gs.leaf_k & 0xFFu);  // Vector<uint8_t>::sum() is uint8-typed
-      for (u32 j = 0; j < lk; ++j) p8[j] = fdiv(1.0f, sum);
+      val0 = val1 = vald = third;
+      // every legal move is a child here, so Vector<uint8_t>::sum() == lk
+      const float p = fdiv(1.0f, (float)lk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((u32)j < lk) ps.w[j] = f2u(p);
     } else {
       const float* vrow = E.ev_v + (size_t)gs.eval_row * (kP + 1);
       const float* prow = E.ev_pi + (size_t)gs.eval_row * kA;
-      value[0] = vrow[0]; value[1] = vrow[1]; value[2] = vrow[2];
-      u32 mv8[kKMax];
-      if (lk > 0) moves_load<W>(E, lfc, mv8);
-      for (u32 j = 0; j < lk; ++j) p8[j] = prow[mv8[j]];
+      val0 = vrow[0]; val1 = vrow[1]; vald = vrow[2];
+      if (lk > 0) {
+        const Sec sm = ld_sec((E.blocks + lblk)->mix);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((u32)j < lk) ps.w[j] = f2u(prow[mix_mv(sm, j)]);
+      }
     }
-    // set_policy_normalized (mcts.cc:109-121)
-    const bool apply_temp = (leaf == kRootRef) && (E.root_temp != 1.0f);
-    const float inv_temp = fdiv(1.0f, E.root_temp);
-    float sum = 0.0f;
-    for (u32 j = 0; j < lk; ++j) {
-      if (apply_temp) p8[j] = az_powf(p8[j], inv_temp);
-      sum = fadd(sum, p8[j]);
+    if (plen == 0) {  // the leaf is the root: temperature + Dirichlet noise (cold)
+      // copies keep the addresses handed to the out-of-line code away from the register-resident state
+      float p8[kKMax];
+      Pcg32 r = rng;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p8[j] = u2f(ps.w[j]);
+      root_leaf_priors(E, r, p8, lk, noise_enabled);
+      rng = r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ps.w[j] = ((u32)j < lk) ? f2u(p8[j]) : 0u;
+    } else {  // set_policy_normalized (mcts.cc:109-121), interior node: no temperature
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((u32)j < lk) sum = fadd(sum, u2f(ps.w[j]));
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((u32)j < lk) ps.w[j] = f2u(fdiv(u2f(ps.w[j]), sum));
     }
-    for (u32 j = 0; j < lk; ++j) p8[j] = fdiv(p8[j], sum);
-    if (leaf == kRootRef && noise_enabled && lk > 0) add_root_noise(E, rng, p8, lk);
-    if (lk > 0) kids_store_pol<W>(E, lfc, lk, p8);
+    if (lk > 0) st_sec((E.blocks + lblk)->pol, ps);
   }
-  // backprop (mcts.cc:527-545): level i updates node path[i]; its parent is path[i-1] or the root
+  // backprop (mcts.cc:527-545): level i updates the child slot selected at level i. The levels touch
+  // different blocks, so their loads are issued together (4 levels at a time) instead of one dependent
+  // round trip per level.
   const u32* path = E.path + (size_t)g * kMaxPath;
-  const float dshare = fdiv(value[kP], (float)kP);
-  const u32 plen = T.path_len;
-  const int lane = Grp<W>::lane();
-  for (u32 i = (u32)lane; i < plen; i += W) {
-    const u32 c = path[i];
-    const u32 pp = (i == 0) ? (u32)T.player : (u32)E.rec[path[i - 1]].player;
-    const float v = fadd(value[pp], dshare);
-    const u32 nc = E.n[c];
-    NodeRec r = E.rec[c];
-    const float qc = nc ? E.q[c] : 0.0f;
-    const float dc = nc ? r.d : 0.0f;
-    E.q[c] = fdiv(fadd(fmul(qc, (float)nc), v), (float)(nc + 1u));
-    r.d = fdiv(fadd(fmul(dc, (float)nc), value[kP]), (float)(nc + 1u));
-    if (nc == 0) r.v = fadd(value[r.player], dshare);
-    E.rec[c] = r;
-    E.n[c] = nc + 1u;
+  const u8* pslot = E.pslot + (size_t)g * kMaxPath;
+  const float dshare = fdiv(vald, (float)kP);
+  const bool cached = pr.valid != 0;
+  pr.valid = 0;
+  for (u32 base = 0; base < plen; base += 4u) {
+    u32 bi[4], sb[4], nc[4], qb[4], db[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const u32 i = base + (u32)t;
+      bi[t] = kNil;
+      sb[t] = 0;
+      if (i < plen) {
+        if (cached && i < (u32)kPathRegs) {
+          u32 b = pr.blk[0];
+#pragma unroll
+          for (int r = 1; r < kPathRegs; ++r)
+            if (i == (u32)r) b = pr.blk[r];
+          bi[t] = b;
+          sb[t] = ((i < 4u ? pr.slots_lo : pr.slots_hi) >> (8u * (i & 3u))) & 0xFFu;
+        } else {
+          bi[t] = path[i];
+          sb[t] = pslot[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      nc[t] = qb[t] = db[t] = 0;
+      if (bi[t] != kNil) {
+        const Block* B = E.blocks + bi[t];
+        const u32 sl = sb[t] & 15u;
+        nc[t] = B->n[sl];
+        qb[t] = B->q[sl];
+        db[t] = B->d[sl];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (bi[t] == kNil) continue;
+      Block* B = E.blocks + bi[t];
+      const u32 sl = sb[t] & 15u, pp = sb[t] >> 4;
+      const float v = fadd(pp == 0 ? val0 : val1, dshare);
+      const u32 n0 = nc[t];
+      const float qc = n0 ? u2f(qb[t]) : 0.0f;
+      const float dc = n0 ? u2f(db[t]) : 0.0f;
+      B->q[sl] = f2u(fdiv(fadd(fmul(qc, (float)n0), v), (float)(n0 + 1u)));
+      B->d[sl] = f2u(fdiv(fadd(fmul(dc, (float)n0), vald), (float)(n0 + 1u)));
+      B->n[sl] = n0 + 1u;
+      // first visit of the node (only the leaf can be new): node.v from its own seat (mcts.cc:538-542)
+      if (n0 == 0 && lblk != kNil) (E.blocks + lblk)->mix[6] = f2u(fadd(lplayer == 0 ? val0 : val1, dshare));
+    }
   }
   if (T.n == 0) {
-    T.v = fadd(value[lplayer], dshare);  // root_.player == the leaf's player when the root is the leaf
-    T.d = value[kP];
+    T.v = fadd(lplayer == 0 ? val0 : val1, dshare);  // root_.player == the leaf's player when the root is the leaf
+    T.d = vald;
   }
   ++T.depth;
   ++T.n;
   T.path_len = 0;
-  (void)lplayer;
 }
 
+// ------------------------------------------------------------------------------------ per-move (cold)
 // counts()/probs() family works on dense arrays in MOVE order (mcts.cc:557-618).
 struct RootView {
   u32 k;
   u32 mv[kKMax];
-  Kids K;
+  u32 n[kKMax];
+  float pol[kKMax];
+  float q[kKMax];
+  float d[kKMax];
 };
-template <int W>
 AZ_HD void root_view(const EngineView& E, const TreeHdr& T, RootView& R) {
   R.k = T.k;
-  if (T.k > 0) {
-    kids_load<W, true>(E, T.fc, R.K);
-    moves_load<W>(E, T.fc, R.mv);
+  for (int j = 0; j < kKMax; ++j) { R.mv[j] = 0; R.n[j] = 0; R.pol[j] = R.q[j] = R.d[j] = 0.0f; }
+  if (T.k > 0 && T.fc != kNil) {
+    const Block* B = E.blocks + T.fc;
+    for (u32 j = 0; j < (u32)kKMax; ++j) {
+      R.mv[j] = blk_mv(B, j); R.n[j] = B->n[j]; R.pol[j] = u2f(B->pol[j]); R.q[j] = u2f(B->q[j]); R.d[j] = u2f(B->d[j]);
+    }
   }
 }
 AZ_HD float sum7(const float* a) {  // Vector::sum(): sequential, starting from 0
@@ -500,15 +591,15 @@ AZ_HD float sum7(const float* a) {  // Vector::sum(): sequential, starting from 
   return s;
 }
 // MCTS::probs(temp) (mcts.cc:575-618)
-AZ_HD void mcts_probs(const RootView& R, float temp, float* probs) {
+AZ_COLD void mcts_probs(const RootView& R, float temp, float* probs) {
   u32 counts[kA];
   for (int m = 0; m < kA; ++m) counts[m] = 0;
-  for (u32 j = 0; j < R.k; ++j) counts[R.mv[j]] = R.K.n[j];
+  for (u32 j = 0; j < R.k; ++j) counts[R.mv[j]] = R.n[j];
   float count_sum = 0.0f;
   for (int m = 0; m < kA; ++m) count_sum = fadd(count_sum, (float)counts[m]);
   if (count_sum == 0.0f) {
     for (int m = 0; m < kA; ++m) probs[m] = 0.0f;
-    for (u32 j = 0; j < R.k; ++j) probs[R.mv[j]] = R.K.pol[j];
+    for (u32 j = 0; j < R.k; ++j) probs[R.mv[j]] = R.pol[j];
     if (temp != 0.0f) {
       const float e = fdiv(1.0f, temp);
       for (int m = 0; m < kA; ++m) probs[m] = az_powf(probs[m], e);
@@ -536,24 +627,24 @@ AZ_HD void mcts_probs(const RootView& R, float temp, float* probs) {
   for (int m = 0; m < kA; ++m) probs[m] = fdiv(probs[m], s);
 }
 // MCTS::probs_pruned(temp) (mcts.cc:620-674)
-AZ_HD void mcts_probs_pruned(const EngineView& E, const TreeHdr& T, const RootView& R, float temp, float* out) {
+AZ_COLD void mcts_probs_pruned(const EngineView& E, const TreeHdr& T, const RootView& R, float temp, float* out) {
   if (T.n <= 1) { mcts_probs(R, temp, out); return; }
   const float es = fmul(E.cpuct, fsqrt((float)T.n));
   float best_sel = -1e30f;
   for (u32 j = 0; j < R.k; ++j) {
-    if (R.K.n[j] == 0) continue;
-    const float sel = fadd(R.K.q[j], fdiv(fmul(es, R.K.pol[j]), (float)(R.K.n[j] + 1u)));
+    if (R.n[j] == 0) continue;
+    const float sel = fadd(R.q[j], fdiv(fmul(es, R.pol[j]), (float)(R.n[j] + 1u)));
     if (sel > best_sel) best_sel = sel;
   }
   float pruned[kA];
   for (int m = 0; m < kA; ++m) pruned[m] = 0.0f;
   for (u32 j = 0; j < R.k; ++j) {
-    if (R.K.n[j] == 0) continue;
-    const float gap = fsub(best_sel, R.K.q[j]);
+    if (R.n[j] == 0) continue;
+    const float gap = fsub(best_sel, R.q[j]);
     float desired;
-    if (gap <= 0.0f) desired = (float)R.K.n[j];
-    else desired = fsub(fdiv(fmul(es, R.K.pol[j]), gap), 1.0f);
-    pruned[R.mv[j]] = std_min((float)R.K.n[j], std_max(0.0f, desired));
+    if (gap <= 0.0f) desired = (float)R.n[j];
+    else desired = fsub(fdiv(fmul(es, R.pol[j]), gap), 1.0f);
+    pruned[R.mv[j]] = std_min((float)R.n[j], std_max(0.0f, desired));
   }
   const float total = sum7(pruned);
   if (total == 0.0f) { mcts_probs(R, temp, out); return; }
@@ -586,28 +677,28 @@ AZ_HD u32 mcts_pick_move(Pcg32& rng, const float* p) {
   return (u32)kA;
 }
 // MCTS::normalized_root_entropy (mcts.cc:737-750)
-AZ_HD float mcts_root_entropy(const TreeHdr& T, const RootView& R) {
+AZ_COLD float mcts_root_entropy(const TreeHdr& T, const RootView& R) {
   const float k = (float)R.k;
   if (R.k <= 1 || T.n <= 1) return 0.0f;
   const float log_k = az_logf(k);
   float entropy = 0.0f;
   const float total_n = (float)T.n;
   for (u32 j = 0; j < R.k; ++j) {
-    if (R.K.n[j] > 0) {
-      const float p = fdiv((float)R.K.n[j], total_n);
+    if (R.n[j] > 0) {
+      const float p = fdiv((float)R.n[j], total_n);
       entropy = fsub(entropy, fmul(p, az_logf(p)));
     }
   }
   return fdiv(entropy, log_k);
 }
 // MCTS::root_value (mcts.h:78-100) -> (w, l, d)
-AZ_HD void mcts_root_value(const EngineView& E, const TreeHdr& T, const RootView& R, float* wld) {
+AZ_HD void mcts_root_value(const TreeHdr& T, const RootView& R, float* wld) {
   float q = 0.0f, d = 0.0f;
   bool found = false;
   for (u32 j = 0; j < R.k; ++j) {
-    if (R.K.n[j] > 0 && R.K.q[j] > q) {
-      q = R.K.q[j];
-      d = E.rec[T.fc + j].d;
+    if (R.n[j] > 0 && R.q[j] > q) {
+      q = R.q[j];
+      d = R.d[j];
       found = true;
     }
   }
@@ -618,321 +709,317 @@ AZ_HD void mcts_root_value(const EngineView& E, const TreeHdr& T, const RootView
   wld[2] = d;
 }
 
-// MCTS::apply_root_policy_temp (mcts.cc:448-460) on the (reused) root's children
-template <int W>
-AZ_HD void apply_root_policy_temp(const EngineView& E, const TreeHdr& T, float* pol8_out, bool* changed) {
-  *changed = false;
-  if (E.root_temp == 1.0f || T.k == 0) return;
-  Kids K;
-  kids_load<W, false>(E, T.fc, K);
-  const float e = fdiv(1.0f, E.root_temp);
-  float sum = 0.0f;
-  for (u32 j = 0; j < T.k; ++j) {
-    pol8_out[j] = az_powf(K.pol[j], e);
-    sum = fadd(sum, pol8_out[j]);
+// Cheney copy of the live tree into fresh pages, breadth first (the device equivalent of the
+// reference's `root_ = std::move(child)` + recursive ~Node of the discarded siblings, mcts.cc:163-172,
+// done lazily: only when the arena has outgrown E.compact_pages).
+AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
+  if (T.fc == kNil) return;
+  TreeHdr A;
+  arena_clear(A);
+  const u32 root_new = tree_alloc_block(E, A);
+  if (root_new == kNil) return;
+  {
+    const Block* S = E.blocks + T.fc;
+    Block* D = E.blocks + root_new;
+    st_sec(D->n, ld_sec(S->n)); st_sec(D->q, ld_sec(S->q)); st_sec(D->pol, ld_sec(S->pol));
+    st_sec(D->fc, ld_sec(S->fc)); st_sec(D->d, ld_sec(S->d)); st_sec(D->mix, ld_sec(S->mix));
   }
-  if (sum > 0.0f)
-    for (u32 j = 0; j < T.k; ++j) pol8_out[j] = fdiv(pol8_out[j], sum);
-  *changed = true;
+  u32 scan_page = A.first_page, scan_off = 0;
+  bool failed = false;
+  for (;;) {
+    if (scan_page == A.cur_page && scan_off >= A.bump) break;
+    if (scan_off >= kPageBlocks) {
+      scan_page = ld_volatile(&E.page_next[scan_page]);
+      scan_off = 0;
+      continue;
+    }
+    Block* B = E.blocks + ((scan_page << kPageLog2) + scan_off);
+    Sec f = ld_sec(B->fc);
+    bool changed = false;
+#pragma unroll 1
+    for (int j = 0; j < kKMax; ++j) {
+      const u32 src = f.w[j];
+      if (src == kNil) continue;
+      const u32 dst = tree_alloc_block(E, A);
+      if (dst == kNil) { failed = true; break; }
+      const Block* S = E.blocks + src;
+      Block* D = E.blocks + dst;
+      st_sec(D->n, ld_sec(S->n)); st_sec(D->q, ld_sec(S->q)); st_sec(D->pol, ld_sec(S->pol));
+      st_sec(D->fc, ld_sec(S->fc)); st_sec(D->d, ld_sec(S->d)); st_sec(D->mix, ld_sec(S->mix));
+      B->fc[j] = dst;
+      changed = true;
+    }
+    (void)changed;
+    if (failed) break;
+    ++scan_off;
+  }
+  if (failed) {  // pool exhausted mid-copy (already flagged): keep the old, intact tree
+    tree_free_pages(E, A);
+    return;
+  }
+  if (T.first_page != kNil) pool_push_chain(E, T.first_page);
+  T.first_page = A.first_page;
+  T.cur_page = A.cur_page;
+  T.bump = A.bump;
+  T.pages_used = A.pages_used;
+  T.fc = root_new;
+  at_add64(&E.glob->compactions, 1ULL);
 }
 
 // MCTS::update_root (mcts.cc:151-173). `vm_before` = valid-move mask of the game state BEFORE the
-// move (update_root receives the pre-move state, play_manager.cc:436-439).
-template <int W>
-AZ_HD void update_root(const EngineView& E, u32 home, TreeHdr& T, u32 move, u32 vm_before, Pcg32& rng) {
+// move (update_root receives the pre-move state, play_manager.cc:436-439). Re-rooting re-points the
+// header at the chosen child's block; nothing is copied unless the arena is over budget.
+AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_before, Pcg32& rng) {
   T.depth = 0;
   T.total_leaf_depth = 0;
   T.path_len = 0;
-  T.leaf = kRootRef;
-  const int lane = Grp<W>::lane();
-  if (T.k == 0) {
+  T.leaf_term = T.leaf_k = T.leaf_player = 0;
+  T.leaf_blk = kNil;
+  if (T.k == 0 || T.fc == kNil) {
     // root_.children.empty(): add_children(valid_moves()) shuffles children that are discarded by
     // the re-root onto the (unvisited) chosen child two lines later — only the RNG draws survive.
     rng_shuffle_discard(rng, (u32)popc32(vm_before));
     if (((vm_before >> move) & 1u) == 0u) at_or(&E.glob->error, B2AZ_DEVERR_MOVE);
-    const u32 old_first = T.first_page;
+    tree_free_pages(E, T);
     tree_reset(T);
     T.move = (u16)move;
-    tree_free_pages<W>(E, home, old_first);
     return;
   }
-  u32 mv8[kKMax];
-  moves_load<W>(E, T.fc, mv8);
+  const Block* B = E.blocks + T.fc;
   int ci = -1;
   for (u32 j = 0; j < T.k; ++j)
-    if (mv8[j] == move) { ci = (int)j; break; }
-  const u32 old_first = T.first_page;
+    if (blk_mv(B, j) == move) { ci = (int)j; break; }
   if (ci < 0) {
     at_or(&E.glob->error, B2AZ_DEVERR_MOVE);
+    tree_free_pages(E, T);
     tree_reset(T);
-    tree_free_pages<W>(E, home, old_first);
     return;
   }
-  const u32 c = T.fc + (u32)ci;
   // the chosen child becomes the root (Node tmp = std::move(*x); root_ = std::move(tmp))
-  const u32 cn = E.n[c];
-  TreeHdr N;
-  tree_reset(N);
-  N.policy = E.pol[c];
-  N.move = (u16)move;
-  N.n = cn;
-  u32 src_fc = kNil, src_k = 0;
-  if (cn > 0) {
-    const NodeRec r = E.rec[c];
-    N.q = E.q[c]; N.d = r.d; N.v = r.v; N.player = r.player; N.term = r.term;
-    src_fc = r.fc; src_k = r.k;
+  const u32 cn = B->n[ci];
+  const float cpol = u2f(B->pol[ci]);
+  if (cn == 0) {  // never visited: a fresh root that only keeps its prior and move; nothing stays live
+    tree_free_pages(E, T);
+    tree_reset(T);
+    T.policy = cpol;
+    T.move = (u16)move;
+    return;
   }
-  // Cheney copy of the kept subtree into fresh pages, BFS order.
-  if (src_k > 0 && src_fc != kNil) {
-    const u32 nb = tree_alloc_block<W>(E, N, home, src_k);
-    if (nb != kNil) {
-      const u32 need = (src_k + 7u) & ~7u;
-      for (u32 j = (u32)lane; j < need; j += W) {
-        E.q[nb + j] = E.q[src_fc + j];
-        E.pol[nb + j] = E.pol[src_fc + j];
-        E.n[nb + j] = E.n[src_fc + j];
-        E.mv[nb + j] = E.mv[src_fc + j];
-        E.rec[nb + j] = E.rec[src_fc + j];
-      }
-      N.fc = nb;
-      N.k = (u16)src_k;
-      Grp<W>::sync();
-      // scan the to-space; every expanded node found gets its child block copied behind
-      u32 scan_page = N.first_page, scan_off = 0;
-      for (;;) {
-        const u32 limit = (scan_page == N.cur_page) ? N.bump : E.page_fill[scan_page];
-        if (scan_off >= limit) {
-          if (scan_page == N.cur_page) break;
-          scan_page = E.page_next[scan_page];
-          scan_off = 0;
-          continue;
-        }
-        // 8 nodes at a time (blocks are 8-aligned): every lane inspects all 8 (replicated, uniform)
-        const u32 base = (scan_page << kPageLog2) + scan_off;
-        u32 n8[kKMax];
-        {
-          constexpr int R = (kKMax + W - 1) / W;
-          u32 mn[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int j = r * W + lane;
-            mn[r] = (j < kKMax) ? E.n[base + j] : 0u;
-          }
-#pragma unroll
-          for (int i = 0; i < kKMax; ++i) n8[i] = Grp<W>::bcast(mn[i / W], i % W);
-        }
-        bool failed = false;
-#pragma unroll 1
-        for (int i = 0; i < kKMax; ++i) {
-          if (n8[i] == 0) continue;
-          const NodeRec r = E.rec[base + i];
-          if (r.k == 0 || r.fc == kNil) continue;
-          const u32 dst = tree_alloc_block<W>(E, N, home, r.k);
-          if (dst == kNil) { failed = true; break; }
-          const u32 need2 = ((u32)r.k + 7u) & ~7u;
-          for (u32 j = (u32)lane; j < need2; j += W) {
-            E.q[dst + j] = E.q[r.fc + j];
-            E.pol[dst + j] = E.pol[r.fc + j];
-            E.n[dst + j] = E.n[r.fc + j];
-            E.mv[dst + j] = E.mv[r.fc + j];
-            E.rec[dst + j] = E.rec[r.fc + j];
-          }
-          Grp<W>::sync();  // every lane has read rec[base + i] and finished its share of the copy
-          if (lane == 0) {
-            NodeRec r2 = r;
-            r2.fc = dst;
-            E.rec[base + i] = r2;
-          }
-          Grp<W>::sync();
-        }
-        if (failed) break;
-        scan_off += kKMax;
-      }
-    }
+  const u32 cfc = B->fc[ci];
+  T.q = u2f(B->q[ci]);
+  T.d = u2f(B->d[ci]);
+  T.policy = cpol;
+  T.n = cn;
+  T.move = (u16)move;
+  T.term = (u8)blk_term(B, (u32)ci);
+  if (cfc != kNil) {
+    const Block* CB = E.blocks + cfc;
+    T.v = blk_v(CB);
+    T.k = (u8)blk_k(CB);
+    T.player = (u8)blk_player(CB);
+    T.fc = cfc;
+    if ((u32)T.pages_used > E.compact_pages) tree_compact(E, T);
+  } else {  // a terminal child: the game is over and both trees are reset right after (play_manager.cc:440-513)
+    T.v = 0.0f;
+    T.k = 0;
+    T.player ^= 1;
+    T.fc = kNil;
+    tree_free_pages(E, T);
   }
-  T = N;
-  Grp<W>::sync();
-  tree_free_pages<W>(E, home, old_first);
 }
 
-// The canonical 4x6x7 planes are rebuilt from the compact position wherever they are needed
-// (leaf batch, history drain): Connect4GS::canonicalized (connect4_gs.cc:131-149).
+struct Ctx {       // what a thread keeps in registers across the fused steps of one launch
+  GameSlot gs;
+  TreeHdr T;       // the tree of the side to move (gs.player); the other seat's stays in HBM
+  Pcg32 rng;
+  PathRegs pr;
+  u32 sims;        // simulations finished since ctx_load
+};
+AZ_HD void ctx_load(const EngineView& E, u32 g, Ctx& c) {
+  c.gs = E.games[g];
+  c.T = E.trees[(size_t)g * kP + c.gs.player];
+  c.rng = (E.rng_mode == 1) ? E.glob->global_rng : c.gs.rng;
+  c.sims = 0;
+  c.pr.valid = 0;  // the pending leaf's path (if any) is in HBM
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < kPathRegs; ++i) c.pr.blk[i] = kNil;
+  c.pr.slots_lo = c.pr.slots_hi = 0;
+}
+AZ_HD void ctx_store(const EngineView& E, u32 g, Ctx& c) {
+  if (E.rng_mode == 1) E.glob->global_rng = c.rng; else c.gs.rng = c.rng;
+  E.trees[(size_t)g * kP + c.gs.player] = c.T;
+  E.games[g] = c.gs;
+  if (c.sims) E.cold[g].sims += c.sims;
+}
 
-// One iteration of PlayManager::play()'s loop body for slot g (play_manager.cc:272-599).
-template <int W>
-AZ_HD void game_step(const EngineView& E, u32 g) {
+// The move part of PlayManager::play()'s loop body (play_manager.cc:286-555). Works on the slot's state
+// in HBM (the caller stores its register copy before and reloads it after), so nothing of the hot
+// loop's state has its address taken. Returns true when the slot retired.
+AZ_COLD bool play_move(const EngineView E, u32 g) {
   GameSlot gs = E.games[g];
-  if (!gs.active) return;
-  const int lane = Grp<W>::lane();
   Pcg32 rng = (E.rng_mode == 1) ? E.glob->global_rng : gs.rng;
+  const u32 cp = gs.player;
   TreeHdr T[kP];
   T[0] = E.trees[(size_t)g * kP + 0];
   T[1] = E.trees[(size_t)g * kP + 1];
+  GameCold cold = E.cold[g];
   bool retired = false;
 
-  if (gs.initialized) {
-    const u32 cp = gs.player;
-    const bool noise = (E.epsilon > 0.0f) && !gs.capped;
-    process_result<W>(E, g, T[cp], gs, rng, noise);
-    Grp<W>::sync();
-    ++gs.sims;
-    const u32 goal = gs.capped ? E.cap_visits[cp] : E.visits[cp];
-    if (T[cp].depth >= goal) {
-      // ---------------------------------------------------------------- play a move (:286-555)
-      float temp = E.start_temp;
-      if (E.half_life != 0.0f) {
-        const float lambda = fdiv(0.693f, E.half_life);
-        temp = fsub(temp, E.final_temp);
-        temp = fmul(temp, az_expf(fmul(-lambda, (float)gs.turn)));
-        temp = fadd(temp, E.final_temp);
+  float temp = E.start_temp;
+  if (E.half_life != 0.0f) {
+    const float lambda = fdiv(0.693f, E.half_life);
+    temp = fsub(temp, E.final_temp);
+    temp = fmul(temp, az_expf(fmul(-lambda, (float)gs.turn)));
+    temp = fadd(temp, E.final_temp);
+  }
+  RootView R;
+  root_view(E, T[cp], R);
+  float pi[kA];
+  mcts_probs(R, temp, pi);
+  u32 chosen = mcts_pick_move(rng, pi);
+  if (chosen >= (u32)kA) { at_or(&E.glob->error, B2AZ_DEVERR_MOVE); chosen = R.k ? R.mv[0] : 0u; }
+  if (E.history_enabled && !gs.capped) {
+    float target[kA];
+    if (E.policy_target_pruning && E.epsilon > 0.0f) mcts_probs_pruned(E, T[cp], R, 1.0f, target);
+    else mcts_probs(R, 1.0f, target);
+    if (gs.hist_n < (u32)kMaxHist) {
+      HistEntry h;
+      h.p0 = gs.p0; h.p1 = gs.p1; h.player = gs.player; h.result = 0; h.pad_[0] = h.pad_[1] = 0;
+      for (int m = 0; m < kA; ++m) h.pi[m] = target[m];
+      E.hist_partial[(size_t)g * kMaxHist + gs.hist_n] = h;
+    }
+    ++gs.hist_n;
+  }
+  const float ald = (T[cp].depth == 0) ? 0.0f : fdiv((float)T[cp].total_leaf_depth, (float)T[cp].depth);
+  const float ent = mcts_root_entropy(T[cp], R);
+  if (!gs.capped) {
+    cold.total_avg_leaf_depth += (double)ald;
+    cold.total_search_entropy += (double)ent;
+    ++gs.full_move_count;
+  } else {
+    cold.fast_total_avg_leaf_depth += (double)ald;
+    cold.fast_total_search_entropy += (double)ent;
+    ++gs.fast_move_count;
+  }
+  cold.total_valid_moves += (double)T[cp].k;
+  ++gs.move_count;
+  C4State s;
+  s.p[0] = gs.p0; s.p[1] = gs.p1; s.turn = gs.turn; s.player = gs.player;
+  const u32 vm_before = c4_valid_mask(s);
+  for (int seat = 0; seat < kP; ++seat) update_root(E, T[seat], chosen, vm_before, rng);
+  if (!c4_play(s, chosen)) at_or(&E.glob->error, B2AZ_DEVERR_MOVE);
+  gs.p0 = s.p[0]; gs.p1 = s.p[1]; gs.turn = s.turn; gs.player = s.player;
+  ++cold.nmoves;
+  const u32 term = c4_terminal(s);
+  if (term != 0) {
+    // ---- game over: flush history newest-first (:448-460), accumulate (:463-505), restart
+    if (E.history_enabled && gs.hist_n > 0) {
+      const u32 cnt = gs.hist_n < (u32)kMaxHist ? gs.hist_n : (u32)kMaxHist;
+      const unsigned long long at = at_add64(&E.glob->hist_written, (unsigned long long)cnt);
+      const unsigned long long rd = ld_volatile(&E.glob->hist_read);
+      if (at + cnt - rd > (unsigned long long)E.hist_capacity) at_or(&E.glob->error, B2AZ_DEVERR_HIST);
+      for (u32 i = 0; i < cnt; ++i) {
+        HistEntry h = E.hist_partial[(size_t)g * kMaxHist + (cnt - 1u - i)];
+        h.result = (u8)term;
+        E.hist_out[(at + i) % (unsigned long long)E.hist_capacity] = h;
       }
-      RootView R;
-      root_view<W>(E, T[cp], R);
-      float pi[kA];
-      mcts_probs(R, temp, pi);
-      u32 chosen = mcts_pick_move(rng, pi);
-      if (chosen >= (u32)kA) { at_or(&E.glob->error, B2AZ_DEVERR_MOVE); chosen = R.k ? R.mv[0] : 0u; }
-      if (E.history_enabled && !gs.capped) {
-        float target[kA];
-        if (E.policy_target_pruning && E.epsilon > 0.0f) mcts_probs_pruned(E, T[cp], R, 1.0f, target);
-        else mcts_probs(R, 1.0f, target);
-        if (lane == 0 && gs.hist_n < (u32)kMaxHist) {
-          HistEntry h;
-          h.p0 = gs.p0; h.p1 = gs.p1; h.player = gs.player; h.result = 0; h.pad_[0] = h.pad_[1] = 0;
-          for (int m = 0; m < kA; ++m) h.pi[m] = target[m];
-          E.hist_partial[(size_t)g * kMaxHist + gs.hist_n] = h;
-        }
-        ++gs.hist_n;
+    }
+    gs.hist_n = 0;
+    Globals* G = E.glob;
+    at_add64(&G->wins[term - 1u], 1ULL);
+    at_add(&G->games_completed, 1u);
+    at_add64(&G->game_length, (unsigned long long)gs.turn);
+    at_addd(&G->total_avg_leaf_depth, cold.total_avg_leaf_depth);
+    at_addd(&G->total_search_entropy, cold.total_search_entropy);
+    at_addd(&G->fast_total_avg_leaf_depth, cold.fast_total_avg_leaf_depth);
+    at_addd(&G->fast_total_search_entropy, cold.fast_total_search_entropy);
+    at_addd(&G->total_valid_moves, cold.total_valid_moves);
+    at_add64(&G->total_move_count, (unsigned long long)gs.move_count);
+    at_add64(&G->full_move_count, (unsigned long long)gs.full_move_count);
+    at_add64(&G->fast_move_count, (unsigned long long)gs.fast_move_count);
+    const u32 started = at_add(&G->games_started, 1u);
+    cold.total_avg_leaf_depth = cold.total_search_entropy = 0.0;
+    cold.fast_total_avg_leaf_depth = cold.fast_total_search_entropy = 0.0;
+    cold.total_valid_moves = 0.0;
+    gs.move_count = gs.full_move_count = gs.fast_move_count = 0;
+    for (int seat = 0; seat < kP; ++seat) {
+      tree_free_pages(E, T[seat]);
+      tree_reset(T[seat]);
+    }
+    if (started >= E.games_to_play) {
+      retired = true;  // play_manager.cc:506-509
+      gs.active = 0;
+      at_sub(&E.glob->active_games, 1u);
+    } else {
+      gs.p0 = gs.p1 = 0; gs.turn = 0; gs.player = 0;  // base_gs_->copy(); randomize_start() is a no-op
+    }
+  }
+  if (!retired) {
+    gs.capped = 0;  // playout-cap randomisation draws from an unseedable engine; not carried yet
+    if (!E.tree_reuse) {
+      for (int seat = 0; seat < kP; ++seat) {
+        tree_free_pages(E, T[seat]);
+        tree_reset(T[seat]);
       }
-      const float ald = (T[cp].depth == 0) ? 0.0f : fdiv((float)T[cp].total_leaf_depth, (float)T[cp].depth);
-      const float ent = mcts_root_entropy(T[cp], R);
-      if (!gs.capped) {
-        gs.total_avg_leaf_depth += (double)ald;
-        gs.total_search_entropy += (double)ent;
-        ++gs.full_move_count;
-      } else {
-        gs.fast_total_avg_leaf_depth += (double)ald;
-        gs.fast_total_search_entropy += (double)ent;
-        ++gs.fast_move_count;
-      }
-      gs.total_valid_moves += (double)T[cp].k;
-      ++gs.move_count;
-      C4State s;
-      s.p[0] = gs.p0; s.p[1] = gs.p1; s.turn = gs.turn; s.player = gs.player;
-      const u32 vm_before = c4_valid_mask(s);
-      for (int seat = 0; seat < kP; ++seat) update_root<W>(E, g, T[seat], chosen, vm_before, rng);
-      if (!c4_play(s, chosen)) at_or(&E.glob->error, B2AZ_DEVERR_MOVE);
-      gs.p0 = s.p[0]; gs.p1 = s.p[1]; gs.turn = s.turn; gs.player = s.player;
-      ++gs.nmoves;
-      const u32 term = c4_terminal(s);
-      if (term != 0) {
-        // ---- game over: flush history newest-first (:448-460), accumulate (:463-505), restart
-        if (E.history_enabled && lane == 0 && gs.hist_n > 0) {
-          const u32 cnt = gs.hist_n < (u32)kMaxHist ? gs.hist_n : (u32)kMaxHist;
-          const unsigned long long at = at_add64(&E.glob->hist_written, (unsigned long long)cnt);
-          const unsigned long long rd = ld_volatile(&E.glob->hist_read);
-          if (at + cnt - rd > (unsigned long long)E.hist_capacity) at_or(&E.glob->error, B2AZ_DEVERR_HIST);
-          for (u32 i = 0; i < cnt; ++i) {
-            HistEntry h = E.hist_partial[(size_t)g * kMaxHist + (cnt - 1u - i)];
-            h.result = (u8)term;
-            E.hist_out[(at + i) % (unsigned long long)E.hist_capacity] = h;
+    } else {
+      // the reused root gets the root temperature again and fresh noise (play_manager.cc:546-553,
+      // mcts.cc:448-460)
+      TreeHdr& NT = T[gs.player];
+      if (NT.n > 0 && NT.k > 0 && NT.fc != kNil) {
+        Block* B = E.blocks + NT.fc;
+        float p8[kKMax];
+        for (int j = 0; j < kKMax; ++j) p8[j] = u2f(B->pol[j]);
+        bool changed = false;
+        if (E.root_temp != 1.0f) {
+          const float e = fdiv(1.0f, E.root_temp);
+          float sum = 0.0f;
+          for (u32 j = 0; j < NT.k; ++j) {
+            p8[j] = az_powf(p8[j], e);
+            sum = fadd(sum, p8[j]);
           }
+          if (sum > 0.0f)
+            for (u32 j = 0; j < NT.k; ++j) p8[j] = fdiv(p8[j], sum);
+          changed = true;
         }
-        gs.hist_n = 0;
-        u32 started = 0;
-        if (lane == 0) {
-          Globals* G = E.glob;
-          at_add64(&G->wins[term - 1u], 1ULL);
-          at_add(&G->games_completed, 1u);
-          at_add64(&G->game_length, (unsigned long long)gs.turn);
-          at_addd(&G->total_avg_leaf_depth, gs.total_avg_leaf_depth);
-          at_addd(&G->total_search_entropy, gs.total_search_entropy);
-          at_addd(&G->fast_total_avg_leaf_depth, gs.fast_total_avg_leaf_depth);
-          at_addd(&G->fast_total_search_entropy, gs.fast_total_search_entropy);
-          at_addd(&G->total_valid_moves, gs.total_valid_moves);
-          at_add64(&G->total_move_count, (unsigned long long)gs.move_count);
-          at_add64(&G->full_move_count, (unsigned long long)gs.full_move_count);
-          at_add64(&G->fast_move_count, (unsigned long long)gs.fast_move_count);
-          started = at_add(&G->games_started, 1u);
+        if (E.epsilon > 0.0f && !gs.capped) {
+          add_root_noise(E, rng, p8, NT.k);
+          changed = true;
         }
-        started = Grp<W>::bcast(started, 0);
-        gs.total_avg_leaf_depth = gs.total_search_entropy = 0.0;
-        gs.fast_total_avg_leaf_depth = gs.fast_total_search_entropy = 0.0;
-        gs.total_valid_moves = 0.0;
-        gs.move_count = gs.full_move_count = gs.fast_move_count = 0;
-        for (int seat = 0; seat < kP; ++seat) {
-          const u32 old_first = T[seat].first_page;
-          tree_reset(T[seat]);
-          tree_free_pages<W>(E, g, old_first);
-        }
-        if (started >= E.games_to_play) {
-          retired = true;  // play_manager.cc:506-509
-          gs.active = 0;
-          if (lane == 0) at_sub(&E.glob->active_games, 1u);
-        } else {
-          gs.p0 = gs.p1 = 0; gs.turn = 0; gs.player = 0;  // base_gs_->copy(); randomize_start() is a no-op
-        }
+        if (changed)
+          for (u32 j = 0; j < NT.k; ++j) B->pol[j] = f2u(p8[j]);
       }
-      if (!retired) {
-        gs.capped = 0;  // playout-cap randomisation draws from an unseedable engine; not carried yet
-        if (!E.tree_reuse) {
-          for (int seat = 0; seat < kP; ++seat) {
-            const u32 old_first = T[seat].first_page;
-            tree_reset(T[seat]);
-            tree_free_pages<W>(E, g, old_first);
-          }
-        } else {
-          TreeHdr& NT = T[gs.player];
-          if (NT.n > 0) {
-            float p8[kKMax];
-            bool changed = false;
-            apply_root_policy_temp<W>(E, NT, p8, &changed);
-            if (!changed && E.epsilon > 0.0f && NT.k > 0) {
-              Kids K;
-              kids_load<W, false>(E, NT.fc, K);
-              for (u32 j = 0; j < NT.k; ++j) p8[j] = K.pol[j];
-            }
-            if (E.epsilon > 0.0f && !gs.capped && NT.k > 0) {
-              add_root_noise(E, rng, p8, NT.k);
-              changed = true;
-            }
-            if (changed) kids_store_pol<W>(E, NT.fc, NT.k, p8);
-            Grp<W>::sync();
-          }
-        }
-      }
+    }
+  }
+  E.trees[(size_t)g * kP + 0] = T[0];
+  E.trees[(size_t)g * kP + 1] = T[1];
+  E.cold[g] = cold;
+  if (E.rng_mode == 1) E.glob->global_rng = rng; else gs.rng = rng;
+  E.games[g] = gs;
+  return retired;
+}
+
+// One iteration of PlayManager::play()'s loop body for slot g (play_manager.cc:272-599).
+AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
+  if (!c.gs.active) return;
+  bool retired = false;
+  if (c.gs.initialized) {
+    const u32 cp = c.gs.player;
+    const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
+    process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
+    ++c.sims;
+    const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
+    if (c.T.depth >= goal) {
+      ctx_store(E, g, c);
+      retired = play_move(E, g);
+      ctx_load(E, g, c);
     }
   } else {
-    gs.initialized = 1;
-    gs.capped = 0;
+    c.gs.initialized = 1;
+    c.gs.capped = 0;
   }
-
-  if (!retired) {
-    const u32 cp = gs.player;
-    Leaf leaf;
-    find_leaf<W>(E, g, (u32)(g * kP + cp), T[cp], gs, rng, leaf);
-    gs.leaf_k = leaf.k;
-    if (E.eval_type == 0) {
-      u32 row = 0;
-      if (lane == 0) {
-        row = at_add(&E.glob->leaf_count, 1u);
-        E.leaf_p0[row] = leaf.s.p[0];
-        E.leaf_p1[row] = leaf.s.p[1];
-        E.leaf_player[row] = leaf.s.player;
-        E.leaf_game[row] = g;
-      }
-      gs.eval_row = Grp<W>::bcast(row, 0);
-    }
-    Grp<W>::sync();
-  }
-
-  if (lane == 0) {
-    E.trees[(size_t)g * kP + 0] = T[0];
-    E.trees[(size_t)g * kP + 1] = T[1];
-    if (E.rng_mode == 1) E.glob->global_rng = rng; else gs.rng = rng;
-    E.games[g] = gs;
-  }
-  Grp<W>::sync();
+  if (!retired) find_leaf(E, g, c.T, c.gs, c.rng, c.pr);
 }
 
 }  // namespace b2az

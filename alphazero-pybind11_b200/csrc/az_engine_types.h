@@ -1,19 +1,22 @@
 // az_engine_types.h — device-resident data layout of the self-play pool.
 //
 // Layout in HBM (DESIGN.md "Data layout"):
-//   node pool     structure-of-arrays over a global node index: q[], pol[], n[] (the three fields a
-//                 PUCT scan reads), mv[] (u16 move of the edge into the node) and rec[] (16 B:
-//                 first-child index, child count, side to move, terminal code, v, d). The children
-//                 of a node form ONE contiguous block, 8-node aligned and padded to a multiple of
-//                 8, so q/pol/n of a Connect4 block are exactly one 32 B sector each.
-//   pages         the pool is cut into pages of 2^kPageLog2 nodes; a tree owns a chain of pages
-//                 and bump-allocates blocks inside its current page. Free pages sit on sharded
-//                 lock-free stacks. Re-rooting (MCTS::update_root, mcts.cc:151-173) Cheney-copies
-//                 the kept subtree into fresh pages in BFS order and frees the old chain, which
-//                 is the device equivalent of the reference's move + recursive ~Node.
-//   trees         one TreeHdr per (game slot, seat): the root node's scalars live here, not in
-//                 the pool (reference: MCTS::root_ member, mcts.h:161).
-//   games         one GameSlot per concurrent game (reference: GameData, play_manager.h:33-58).
+//   block pool    the unit of tree storage is the CHILD BLOCK of one expanded node: 192 B = six 32 B
+//                 sectors holding, for its (<= 8) children, n[8] | q[8] | pol[8] | fc[8] | d[8] and one
+//                 mixed sector (move u16[8], terminal code u8[8], and the OWNING node's v / k / player).
+//                 A PUCT step is therefore ONE independent burst of 5 sector loads (everything the
+//                 selection, the move replay and the next hop need), instead of the pointer chase
+//                 node -> children vector -> child -> its vector of the reference (mcts.h:14-48).
+//   pages         the pool is cut into pages of 64 blocks (12 KB); a tree owns a chain of pages and
+//                 bump-allocates blocks in its last page. Free pages travel as CHAINS through one
+//                 ticket ring (two atomicAdd tickets, no CAS loop): freeing a whole tree is O(1).
+//   trees         one 64 B TreeHdr per (game slot, seat): the root node's scalars live here
+//                 (reference: MCTS::root_, mcts.h:161) plus the pending leaf and the arena cursor.
+//                 Re-rooting (MCTS::update_root, mcts.cc:151-173) just re-points the header at the
+//                 chosen child's block; the garbage left behind is squeezed out by a Cheney copy
+//                 only when the arena has outgrown its budget (amortised over several moves).
+//   games         GameSlot (64 B, hot) + GameCold (64 B, metric accumulators) per concurrent game
+//                 (reference: GameData, play_manager.h:33-58).
 #pragma once
 
 #include "az_common.h"
@@ -23,43 +26,47 @@
 namespace b2az {
 
 constexpr u32 kNil = 0xFFFFFFFFu;
-constexpr u32 kRootRef = 0xFFFFFFFEu;  // "the leaf / current node is the tree's root"
-constexpr int kPageLog2 = 8;           // 256 nodes per page
-constexpr u32 kPageNodes = 1u << kPageLog2;
+constexpr int kPageLog2 = 6;           // 64 blocks per page
+constexpr u32 kPageBlocks = 1u << kPageLog2;
 constexpr int kMaxPath = 44;           // Connect4: at most 42 plies below any root
 constexpr int kMaxHist = 42;           // recorded moves per game
-constexpr int kNumStacks = 64;         // free-page stack shards
 constexpr int kA = 7;                  // Connect4 action count
 constexpr int kP = 2;                  // players
-constexpr int kKMax = 8;               // padded child-block size for Connect4
+constexpr int kKMax = 8;               // children per block
 
-struct __attribute__((aligned(16))) NodeRec {
-  u32 fc;     // first child (global node index) — valid once the node is expanded
-  u16 k;      // number of children (0: terminal or no legal move)
-  u8 player;  // side to move AT this node (mcts.cc:491)
-  u8 term;    // 0 = not terminal, else 1 + index of the one-hot score (mcts.cc:492-494)
-  float v;    // node value from its own player's perspective, set on first visit (mcts.cc:538-542)
-  float d;    // running mean of the draw share (mcts.cc:535-537)
+// Every field is a 32-bit word (floats are stored as their bit patterns) so that scalar accesses and
+// the 16 B vector accesses of whole sectors are the same type for the compiler's alias analysis.
+struct __attribute__((aligned(32))) Block {
+  u32 n[kKMax];    // +0    visit counts                               (Node::n)
+  u32 q[kKMax];    // +32   f32 mean value from the parent's seat      (Node::q)
+  u32 pol[kKMax];  // +64   f32 priors                                 (Node::policy)
+  u32 fc[kKMax];   // +96   the child's OWN block, kNil while unexpanded / terminal
+  u32 d[kKMax];    // +128  f32 running mean of the draw share         (Node::d)
+  u32 mix[kKMax];  // +160  w0-3: move u16 x8 (Node::move); w4-5: terminal code u8 x8 (0 = not terminal /
+                   //       unknown, else 1 + one-hot score index, Node::scores); w6: f32 v of the node that
+                   //       OWNS this block (Node::v, set on its first visit); w7: k | player << 8 of that node
 };
+static_assert(sizeof(Block) == 192, "Block must stay six 32 B sectors");
 
 struct __attribute__((aligned(16))) TreeHdr {
   // root node scalars (Node fields, mcts.h:18-26)
   float q, d, v, policy;
   u32 n;
-  u32 fc;
-  u16 k;
-  u8 player;
-  u8 term;
+  u32 fc;           // the root's child block
   u16 move;
-  u16 path_len;     // length of the stored selection path (MCTS::path_)
+  u8 k, player, term;
+  // the pending leaf (MCTS::current_ / path_): what process_result needs, recorded by find_leaf
+  u8 leaf_term, leaf_k, leaf_player;
+  u32 leaf_blk;     // the leaf's own (fresh) block, kNil for a terminal / childless leaf
+  u16 path_len;
+  u16 pages_used;
   // MCTS members (mcts.h:159-160)
   u32 depth;            // depth_: simulations finished in this search
   u32 total_leaf_depth; // total_leaf_depth_
   // arena
   u32 first_page, cur_page;
-  u32 bump;             // next free node offset inside cur_page
-  u32 leaf;             // current_: node index of the pending leaf, or kRootRef
-  u32 pad_[2];
+  u32 bump;             // next free block offset inside cur_page
+  u32 pad_;
 };
 static_assert(sizeof(TreeHdr) == 64, "TreeHdr must stay one 64 B record");
 
@@ -72,7 +79,7 @@ struct __attribute__((aligned(16))) HistEntry {  // one training sample, compact
 };
 static_assert(sizeof(HistEntry) == 48, "HistEntry layout");
 
-struct __attribute__((aligned(16))) GameSlot {
+struct __attribute__((aligned(16))) GameSlot {  // hot: touched every simulation
   u64 p0, p1;
   u32 turn;
   u8 player;
@@ -82,16 +89,20 @@ struct __attribute__((aligned(16))) GameSlot {
   u32 eval_row;    // row of this game's leaf in the evaluation batch
   u32 hist_n;      // entries in partial_history
   u32 move_count, full_move_count, fast_move_count;
-  u32 leaf_k;      // legal-move count at the pending leaf (RANDOM eval: dumb_eval needs only this)
+  u32 pad_;
+  Pcg32 rng;       // per-game stream (B2AZ_RNG_PER_GAME)
+};
+static_assert(sizeof(GameSlot) == 64, "GameSlot must stay one 64 B record");
+
+struct __attribute__((aligned(16))) GameCold {  // touched once per move / per launch
   double total_avg_leaf_depth, total_search_entropy;
   double fast_total_avg_leaf_depth, fast_total_search_entropy;
   double total_valid_moves;
-  Pcg32 rng;       // per-game stream (B2AZ_RNG_PER_GAME)
   unsigned long long sims;    // simulations finished in this slot (summed on demand; no global atomic per sim)
   unsigned long long nmoves;  // moves played in this slot
   u32 pad_[2];
 };
-static_assert(sizeof(GameSlot) == 128, "GameSlot must stay one 128 B line");
+static_assert(sizeof(GameCold) == 64, "GameCold layout");
 
 struct Globals {
   unsigned long long simulations, moves, game_length;
@@ -99,11 +110,14 @@ struct Globals {
   unsigned long long total_move_count, full_move_count, fast_move_count;
   unsigned long long hist_written, hist_read;
   unsigned long long cache_hits, cache_misses, cache_evictions, cache_reinserts, cache_size;
+  unsigned long long compactions, pages_popped;
   double total_avg_leaf_depth, total_search_entropy, fast_total_avg_leaf_depth, fast_total_search_entropy;
   double total_valid_moves;
   u32 games_completed, games_started, active_games, error;
   u32 leaf_count;
   u32 pad_;
+  // free-page ring tickets (chains of pages; see pool_pop_page / pool_push_chain)
+  unsigned long long ring_pop, ring_push;
   Pcg32 global_rng;  // B2AZ_RNG_GLOBAL
 };
 
@@ -116,19 +130,17 @@ struct EngineView {
   u8 history_enabled, tree_reuse, root_fpu_zero, shaped_dirichlet;
   u8 policy_target_pruning, playout_cap, eval_type, rng_mode;
   u32 num_pages, hist_capacity;
-  // ---- node pool
-  float* q;
-  float* pol;
-  u32* n;
-  u16* mv;
-  NodeRec* rec;
-  u32* page_next;
-  u32* page_fill;
-  unsigned long long* stack_head;  // [kNumStacks] (tag << 32 | top page)
+  u32 compact_pages;   // a tree is compacted at a move once its arena holds more pages than this
+  // ---- block pool
+  Block* blocks;       // [num_pages * kPageBlocks]
+  u32* page_next;      // [num_pages] chain links
+  u32* ring;           // [num_pages] free-chain heads (kNil = empty slot)
   // ---- per tree / per game
-  TreeHdr* trees;    // [G * kP]
-  GameSlot* games;   // [G]
-  u32* path;         // [G][kMaxPath]
+  TreeHdr* trees;      // [G * kP]
+  GameSlot* games;     // [G]
+  GameCold* cold;      // [G]
+  u32* path;           // [G][kMaxPath]  block index of every selected edge
+  u8* pslot;           // [G][kMaxPath]  child slot (bits 0-3) | parent's player (bits 4-7)
   // ---- evaluation in (batch-row order) and leaf batch out
   const float* ev_v;   // [rows][kP + 1]
   const float* ev_pi;  // [rows][kA]

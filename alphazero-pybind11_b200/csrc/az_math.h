@@ -21,7 +21,7 @@
 
 namespace b2az {
 
-AZ_HD float az_logf(float x) {
+AZ_COLD float az_logf(float x) {
   const double T[32] = AZ_LOGF_TAB_INIT;
   u32 ix = f2u(x);
   if (ix == 0x3f800000u) return 0.0f;
@@ -47,7 +47,7 @@ AZ_HD float az_logf(float x) {
   return (float)y;
 }
 
-AZ_HD float az_expf(float x) {
+AZ_COLD float az_expf(float x) {
   const unsigned long long T[32] = AZ_EXP2_TAB_INIT;
   const double xd = (double)x;
   const u32 ux = f2u(x);
@@ -83,7 +83,7 @@ AZ_HD int az_checkint(u32 iy) {
   return 2;
 }
 
-AZ_HD float az_powf(float x, float y) {
+AZ_COLD float az_powf(float x, float y) {
   const double TL[32] = AZ_POWLOG2_TAB_INIT;
   const unsigned long long TE[32] = AZ_EXP2_TAB_INIT;
   u64 sign_bias = 0;

@@ -82,6 +82,31 @@ AZ_HD void rng_shuffle(Pcg32& r, T* a, u32 n) {
     ++i;
   }
 }
+// std::shuffle over a list of <= 8 small values packed as 4-bit nibbles in one register (element i =
+// bits 4i..4i+3): the same draw sequence and the same swaps as rng_shuffle, without an addressable
+// array (an indexed local array would live in local memory on the device).
+AZ_HD void nib_swap(u32& a, u32 i, u32 j) {
+  const u32 x = ((a >> (4u * i)) ^ (a >> (4u * j))) & 15u;
+  a ^= (x << (4u * i)) | (x << (4u * j));
+}
+AZ_HD void rng_shuffle_nib(Pcg32& r, u32& a, u32 n) {
+  if (n == 0) return;
+  u32 i = 1;
+  if ((n % 2u) == 0u) {
+    const u32 j = rng_below(r, 2u);
+    nib_swap(a, i, j);
+    ++i;
+  }
+  while (i < n) {
+    const u32 swap_range = i + 1u;
+    const u32 x = rng_below(r, swap_range * (swap_range + 1u));
+    const u32 p0 = x / (swap_range + 1u), p1 = x % (swap_range + 1u);
+    nib_swap(a, i, p0);
+    ++i;
+    nib_swap(a, i, p1);
+    ++i;
+  }
+}
 // Same draw sequence as rng_shuffle, result discarded (update_root on a never-expanded root:
 // mcts.cc:154-156 shuffles children that are thrown away on the next line).
 AZ_HD void rng_shuffle_discard(Pcg32& r, u32 n) {

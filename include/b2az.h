@@ -72,9 +72,12 @@ typedef struct b2az_params {
   uint8_t pad0_, pad1_;
   uint64_t seed;
   /* engine sizing (no reference counterpart) */
-  uint64_t pool_nodes;           /* tree-node pool size in nodes; 0 = sized from free HBM */
+  uint64_t pool_nodes;           /* tree-node pool size in nodes (8 per 192 B block); 0 = sized from visits and free HBM */
   uint32_t history_capacity;     /* finished-sample ring, in samples; 0 = default */
-  uint32_t lanes_per_game;       /* cooperative lanes per game slot: 1, 4, 8 or 32; 0 = default (8) */
+  uint32_t lanes_per_game;       /* threads per game slot: 0 or 1 (Connect4 runs one thread per game) */
+  uint32_t compact_pages;        /* a tree's arena (12 KB pages) is compacted at a move once it holds more
+                                    pages than this; 0 = half of the tree's share of the pool */
+  uint32_t pad2_;
 } b2az_params;
 
 /* Counters and metrics of PlayManager (play_manager.h:173-366). */
@@ -94,6 +97,8 @@ typedef struct b2az_stats {
   uint64_t cache_hits, cache_misses, cache_evictions, cache_reinserts, cache_size, cache_max_size;
   uint64_t pool_pages_total, pool_pages_free; /* tree-node pool occupancy */
   uint32_t device_error;         /* sticky device-side error bits (B2AZ_DEVERR_*) */
+  uint32_t pad_;
+  uint64_t compactions;          /* tree arenas compacted (Cheney copies) so far */
 } b2az_stats;
 
 #define B2AZ_DEVERR_POOL 1u      /* node pool exhausted */

@@ -306,7 +306,7 @@ def compare_peek(pe, po, where):
 
 
 def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracle="port", rng_mode=None,
-                        tree_reuse=True, lanes=0, peek_every=7, max_generations=10 ** 7):
+                        tree_reuse=True, lanes=0, peek_every=7, max_generations=10 ** 7, compact_pages=0):
     """NN-eval lock-step run (SURVEY.md Appendix A 'Scheduling order'): every generation both sides expose
     their leaf batch (ids + canonical planes, compared bit for bit), get the same fake_net answers and
     advance. Visit counts / Q / root values are peeked every `peek_every` generations and the finished
@@ -316,7 +316,7 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
     ordered = rng_mode == b2az.RNG_GLOBAL or engine_lib is not None
     kw = level_params(level)
     eng = make_engine(engine_lib, G, games_to_play, visits, b2az.EVAL_NN, rng_mode, seed, tree_reuse=tree_reuse,
-                      lanes=lanes, **kw)
+                      lanes=lanes, compact_pages=compact_pages, **kw)
     ora = make_oracle(oracle, G=G, games_to_play=games_to_play, visits=visits, eval_type=b2az.EVAL_NN,
                       rng_mode=rng_mode, seed=seed, tree_reuse=tree_reuse, **kw)
     gens = 0
@@ -356,7 +356,7 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
         assert np.array_equal(np.array(st.scores[:], np.float32), ora.scores()), "scores differ"
         if st.games_completed == 0:
             return dict(generations=gens, leaves=leaves, games=0, moves_compared=0, scores=[0, 0, 0],
-                        simulations=int(st.simulations))
+                        simulations=int(st.simulations), compactions=int(st.compactions))
         m = ora.metrics()
         for name in ("avg_game_length", "avg_moves_per_turn", "avg_valid_moves"):
             assert np.float32(getattr(st, name)) == np.float32(m[name]), name
@@ -369,14 +369,15 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
         ho = ora.drain_history(1 << 20)
         compare_history(he, ho, ordered)
         return dict(generations=gens, leaves=leaves, games=int(st.games_completed), moves_compared=len(ho[0]),
-                    scores=[float(x) for x in st.scores[:]], simulations=int(st.simulations))
+                    scores=[float(x) for x in st.scores[:]], simulations=int(st.simulations),
+                    compactions=int(st.compactions))
     finally:
         eng.close()
         ora.close()
 
 
 def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port", rng_mode=None, level=0,
-                      tree_reuse=True, lanes=0, chunk=64, steps=None):
+                      tree_reuse=True, lanes=0, chunk=64, steps=None, compact_pages=0, pool_nodes=0):
     """RANDOM-eval run (EvalType::RANDOM, the reference's own fake backend: play_manager_test.cc): the engine
     fuses `chunk` loop iterations per launch; the oracle plays to the end; final scores, metrics and the
     training samples must agree."""
@@ -385,7 +386,8 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
     ordered = rng_mode == b2az.RNG_GLOBAL or engine_lib is not None
     kw = level_params(level)
     eng = make_engine(engine_lib, G, games_to_play, visits, b2az.EVAL_RANDOM, rng_mode, seed, tree_reuse=tree_reuse,
-                      lanes=lanes, history_capacity=max(1 << 16, games_to_play * 42), **kw)
+                      lanes=lanes, history_capacity=max(1 << 16, games_to_play * 42), compact_pages=compact_pages,
+                      pool_nodes=pool_nodes, **kw)
     ora = make_oracle(oracle, G=G, games_to_play=games_to_play, visits=visits, eval_type=b2az.EVAL_RANDOM,
                       rng_mode=rng_mode, seed=seed, tree_reuse=tree_reuse, **kw)
     try:
@@ -422,7 +424,8 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
         compare_history(he, ho, ordered)
         return dict(games=int(st.games_completed), scores=[float(x) for x in st.scores[:]],
                     simulations=int(st.simulations), moves=int(st.moves), samples=len(ho[0]),
-                    avg_game_length=float(st.avg_game_length), avg_leaf_depth=float(st.avg_leaf_depth))
+                    avg_game_length=float(st.avg_game_length), avg_leaf_depth=float(st.avg_leaf_depth),
+                    compactions=int(st.compactions))
     finally:
         eng.close()
         ora.close()

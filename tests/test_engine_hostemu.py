@@ -73,6 +73,19 @@ def test_pool_pages_are_recycled():
     e.close()
 
 
+@pytest.mark.parametrize("compact_pages", [1, 2, 50000])
+def test_compaction_threshold_does_not_change_results(compact_pages):
+    """Re-rooting re-points the tree header; the Cheney copy only runs when the arena is over budget. Whatever
+    the budget (compact at every move ... never), the run must equal the oracle bit for bit."""
+    r = ph.run_lockstep_parity(EMU, G=5, games_to_play=9, visits=48, level=1, seed=4242, oracle="port",
+                               rng_mode=b2az.RNG_GLOBAL, compact_pages=compact_pages)
+    assert r["games"] == 9
+    if compact_pages == 1:
+        assert r["compactions"] > 50
+    if compact_pages == 50000:
+        assert r["compactions"] == 0
+
+
 def test_pool_exhaustion_is_reported():
     lib = b2az.load(EMU)
     p = b2az.default_params(lib, games_to_play=8, concurrent_games=8, mcts_visits=(400, 400), eval_type=b2az.EVAL_NN,

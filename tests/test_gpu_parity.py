@@ -36,21 +36,26 @@ def test_serial_kernel_vs_reference_live(level):
     assert r["games"] == 9
 
 
-@pytest.mark.parametrize("lanes", [1, 4, 8, 32])
+@pytest.mark.parametrize("compact_pages", [0, 1, 50000])
 @pytest.mark.parametrize("level", [0, 1])
-def test_parallel_kernel_lockstep_vs_port(lanes, level):
+def test_parallel_kernel_lockstep_vs_port(compact_pages, level):
     # games_to_play is out of reach, so no slot retires: which slot takes the LAST games of a run depends on
     # completion order (atomics here, thread timing in the reference) and is not a parity target
     r = ph.run_lockstep_parity(None, G=48, games_to_play=10 ** 6, visits=40, level=level, seed=2024, oracle="port",
-                               rng_mode=b2az.RNG_PER_GAME, lanes=lanes, peek_every=13, max_generations=1600)
+                               rng_mode=b2az.RNG_PER_GAME, compact_pages=compact_pages, peek_every=13,
+                               max_generations=1600)
     assert r["games"] > 48 and r["moves_compared"] > 500
+    assert (r["compactions"] > 0) == (compact_pages != 50000)
 
 
-@pytest.mark.parametrize("lanes", [1, 8, 32])
-def test_parallel_kernel_random_eval_vs_port(lanes):
+@pytest.mark.parametrize("chunk,compact_pages", [(128, 0), (1, 2), (400, 50000)])
+def test_parallel_kernel_random_eval_vs_port(chunk, compact_pages):
+    # fused launches (the game slot, tree header and RNG stay in registers across `chunk` generations)
     r = ph.run_random_parity(None, G=512, games_to_play=10 ** 6, visits=100, seed=31337, oracle="port",
-                             rng_mode=b2az.RNG_PER_GAME, level=1, lanes=lanes, chunk=128, steps=4000)
-    assert r["games"] > 512
+                             rng_mode=b2az.RNG_PER_GAME, level=1, chunk=chunk, steps=4000 if chunk > 1 else 1500,
+                             compact_pages=compact_pages,
+                             pool_nodes=40_000_000 if compact_pages == 50000 else 0)  # never compacting needs room
+    assert r["games"] > (512 if chunk > 1 else 100)
 
 
 def test_parallel_kernel_400_sims_vs_port():

@@ -25,7 +25,7 @@ ap.add_argument("--reuse", type=int, default=1)
 a = ap.parse_args()
 p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=a.games, mcts_visits=(a.sims, a.sims), cpuct=1.25,
                         fpu_reduction=0.25, eval_type=b2az.EVAL_RANDOM, rng_mode=b2az.RNG_PER_GAME, seed=1000,
-                        tree_reuse=a.reuse, history_enabled=0, self_play=1, lanes_per_game=a.lanes)
+                        tree_reuse=a.reuse, history_enabled=0, self_play=1, lanes_per_game=0)
 e = b2az.Engine(p)
 stream = torch.cuda.current_stream().cuda_stream
 for _ in range(a.preroll):

@@ -37,6 +37,10 @@ def sass_lines(so, kernel_pat):
         if m:
             pend.append((os.path.basename(m.group(1)), int(m.group(2))))
             continue
+        m = re.match(r"^(\$[\w$]+):\s*$", line)
+        if m:  # an internal helper (division slow path, 64-bit remainder ...): no line info of its own
+            cur, pend = [(m.group(1), 0)], []
+            continue
         m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(.*);", line)
         if m:
             if pend:
