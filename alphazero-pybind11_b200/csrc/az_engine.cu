@@ -269,10 +269,7 @@ __global__ void k_stats(EngineView E, StatsOut* o) {
 __global__ void k_count_free_pages(EngineView E, unsigned long long* out) {
   // walks every chain in the ring; only meaningful while no step kernel is running
   unsigned long long c = 0;
-  for (u32 i = GLOBAL_TID; i < E.num_pages; i += GLOBAL_NT) {
-    u32 p = E.ring[i];
-    while (p != kNil) { ++c; p = E.page_next[p]; }
-  }
+  for (u32 i = GLOBAL_TID; i < E.num_pages; i += GLOBAL_NT) c += (E.ring[i] != kNil);
   for (int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, off);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
@@ -765,10 +762,7 @@ int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   if (int rc = copy_d2h(&free_pages, e->freepages_buf, sizeof(free_pages), s)) return rc;
 #else
   for (u32 g = 0; g < e->view.G; ++g) { so.sims += e->view.cold[g].sims; so.moves += e->view.cold[g].nmoves; }
-  for (u32 i = 0; i < e->view.num_pages; ++i) {
-    u32 p = e->view.ring[i];
-    while (p != kNil) { ++free_pages; p = e->view.page_next[p]; }
-  }
+  for (u32 i = 0; i < e->view.num_pages; ++i) free_pages += (e->view.ring[i] != kNil);
 #endif
   if (int rc = copy_d2h(&G, e->view.glob, sizeof(G), s)) return rc;
   if (int rc = stream_sync(s)) return rc;

@@ -112,6 +112,7 @@ struct Sec {
 AZ_HD Sec ld_sec(const void* p) {
   Sec s;
 #if defined(__CUDA_ARCH__)
+  // (ld.global.v8.b32 was tried: ptxas for sm_100a splits it into the same two LDG.E.128)
   const uint4 a = reinterpret_cast<const uint4*>(p)[0];
   const uint4 b = reinterpret_cast<const uint4*>(p)[1];
   s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
@@ -143,21 +144,21 @@ AZ_HD u32 blk_k(const Block* B) { return B->mix[7] & 0xFFu; }
 AZ_HD u32 blk_player(const Block* B) { return (B->mix[7] >> 8) & 0xFFu; }
 
 // ------------------------------------------------------------------------------------ page ring
-// Free pages travel as CHAINS (linked through page_next[]) in one ring of chain heads. pop and push
-// each take a ticket with one atomicAdd and then own ring[ticket % num_pages]; the slot itself is
-// handed over with atomicExch / atomicCAS, so there is no retry storm under contention (the first
-// version's tagged-CAS stacks cost 12-28 ms in a generation where every game re-rooted).
-// Freeing a whole tree is ONE push; a pop takes the head page of a chain and pushes the rest back.
-AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
-  mem_fence();  // the chain's page_next links must be visible before the head is
+// Free pages sit in one ring of page ids. pop and push each take a ticket with one atomicAdd and then
+// own ring[ticket % num_pages]; the slot itself is handed over with atomicExch / atomicCAS, so there
+// is no retry storm under contention (the first version's tagged-CAS stacks cost 12-28 ms in a
+// generation where every game re-rooted). A slot carries everything (the page id), so no memory fence
+// is needed: a gpu-scope __threadfence compiles to MEMBAR + CCTL.IVALL, which throws away the whole
+// SM's L1 on every page pop (profiles/r3: L1 hit rate 43 %).
+AZ_COLD void pool_push_page(const EngineView E, u32 page) {
   const unsigned long long t = at_add64(&E.glob->ring_push, 1ULL);
   u32* slot = &E.ring[t % (unsigned long long)E.num_pages];
 #if defined(__CUDA_ARCH__)
   for (u32 spin = 0; spin < (1u << 22); ++spin)
-    if (at_cas(slot, kNil, head) == kNil) return;
-  at_or(&E.glob->error, B2AZ_DEVERR_POOL);  // cannot happen: there are never more chains than pages
+    if (at_cas(slot, kNil, page) == kNil) return;
+  at_or(&E.glob->error, B2AZ_DEVERR_POOL);  // cannot happen: there are never more free pages than pages
 #else
-  *slot = head;
+  *slot = page;
 #endif
 }
 AZ_COLD u32 pool_pop_page(const EngineView E) {
@@ -165,20 +166,25 @@ AZ_COLD u32 pool_pop_page(const EngineView E) {
   if (ld_volatile(&G->error) & B2AZ_DEVERR_POOL) return kNil;  // already fatal: do not spin again
   const unsigned long long t = at_add64(&G->ring_pop, 1ULL);
   u32* slot = &E.ring[t % (unsigned long long)E.num_pages];
-  u32 head = kNil;
+  u32 page = kNil;
 #if defined(__CUDA_ARCH__)
   for (u32 spin = 0; spin < (1u << 16); ++spin) {
-    head = at_exch(slot, kNil);
-    if (head != kNil) break;
+    page = at_exch(slot, kNil);
+    if (page != kNil) break;
   }
 #else
-  head = at_exch(slot, kNil);
+  page = at_exch(slot, kNil);
 #endif
-  if (head == kNil) return kNil;  // ring empty: pool exhausted (fatal, reported by the caller)
-  mem_fence();
-  const u32 rest = ld_volatile(&E.page_next[head]);
-  if (rest != kNil) pool_push_chain(E, rest);
-  return head;
+  return page;  // kNil: ring empty = pool exhausted (fatal, reported by the caller)
+}
+// Give every page of a tree's chain back (the chain links are this thread's own writes).
+AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
+  u32 p = head;
+  for (u32 guard = 0; p != kNil && guard < 0x10000u; ++guard) {
+    const u32 nx = E.page_next[p];
+    pool_push_page(E, p);
+    p = nx;
+  }
 }
 // Bump-allocate one block in the tree's arena.
 AZ_HD u32 tree_alloc_block(const EngineView& E, TreeHdr& T) {
@@ -188,8 +194,8 @@ AZ_HD u32 tree_alloc_block(const EngineView& E, TreeHdr& T) {
       at_or(&E.glob->error, B2AZ_DEVERR_POOL);
       return kNil;
     }
-    st_volatile(&E.page_next[p], kNil);
-    if (T.cur_page != kNil) st_volatile(&E.page_next[T.cur_page], p);
+    E.page_next[p] = kNil;
+    if (T.cur_page != kNil) E.page_next[T.cur_page] = p;
     else T.first_page = p;
     T.cur_page = p;
     T.bump = 0;
@@ -232,14 +238,6 @@ struct PathRegs {
   u32 slots_lo, slots_hi;  // 8 bits per level: child slot | parent's player << 4
   u32 valid;               // the registers describe the pending leaf's path
 };
-AZ_HD void prefetch_l2(const void* p) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-
 // ------------------------------------------------------------------------------------ find_leaf
 // MCTS::find_leaf (mcts.cc:462-498), PUCT branch; Node::best_child (mcts.cc:130-149) and Node::uct
 // (mcts.cc:123-128) inlined. n_in_flight is always 0 on this path (the WU-UCT variant is not used by
@@ -293,7 +291,7 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
         best_fc = sf.w[j];
       }
     }
-    prefetch_l2(&B->d[best]);  // the backprop of this simulation reads d[best]: have it on its way
+    // (an L2 prefetch of d[best] for the coming backprop was measured: -6 %, the LSU queue is the scarcer resource)
     // move and terminal code of the chosen child out of the mixed sector (select chain, no indexing)
     u32 mvw = sm.w[0], tw = sm.w[4];
     if (best >= 2) mvw = sm.w[1];
@@ -506,7 +504,11 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
   const u32* path = E.path + (size_t)g * kMaxPath;
   const u8* pslot = E.pslot + (size_t)g * kMaxPath;
   const float dshare = fdiv(vald, (float)kP);
+#if defined(B2AZ_NO_PATHREGS)
+  const bool cached = false;
+#else
   const bool cached = pr.valid != 0;
+#endif
   pr.valid = 0;
   for (u32 base = 0; base < plen; base += 4u) {
     u32 bi[4], sb[4], nc[4], qb[4], db[4];
@@ -729,13 +731,12 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
   for (;;) {
     if (scan_page == A.cur_page && scan_off >= A.bump) break;
     if (scan_off >= kPageBlocks) {
-      scan_page = ld_volatile(&E.page_next[scan_page]);
+      scan_page = E.page_next[scan_page];
       scan_off = 0;
       continue;
     }
     Block* B = E.blocks + ((scan_page << kPageLog2) + scan_off);
     Sec f = ld_sec(B->fc);
-    bool changed = false;
 #pragma unroll 1
     for (int j = 0; j < kKMax; ++j) {
       const u32 src = f.w[j];
@@ -747,9 +748,7 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
       st_sec(D->n, ld_sec(S->n)); st_sec(D->q, ld_sec(S->q)); st_sec(D->pol, ld_sec(S->pol));
       st_sec(D->fc, ld_sec(S->fc)); st_sec(D->d, ld_sec(S->d)); st_sec(D->mix, ld_sec(S->mix));
       B->fc[j] = dst;
-      changed = true;
     }
-    (void)changed;
     if (failed) break;
     ++scan_off;
   }

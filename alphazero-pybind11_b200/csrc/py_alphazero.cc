@@ -1,0 +1,745 @@
+// py_alphazero.cc — the pybind11 module `alphazero`, backed by the B200 engine through the C ABI.
+//
+// Drop-in for the reference's src/py_wrapper.cc (module name, class names, method names, argument
+// meaning and error behaviour) for the self-play hot path: PlayParams (py_wrapper.cc:295-349),
+// PlayManager (352-504), GameData (265-288), GameState / Connect4GS (157-189, 560-586), PlayHistory
+// (111-155), EvalType (290-293) and the Tracy no-op hooks (772-787). Everything that touches a game
+// tree goes through include/b2az.h (libb2az.so, CUDA) — this file holds no search code.
+//
+// How the reference's thread pipeline maps onto a device engine (game_runner.py:648-745):
+//   play()               the first caller becomes the DRIVER: it runs one generation at a time —
+//                        b2az_step (process_result -> move -> find_leaf for every slot), then publishes the
+//                        generation's leaf batch and waits until every leaf has been answered. Further callers
+//                        (the reference starts `mcts_workers` threads) just wait for the run to end.
+//   build_batch()        hands out rows of the published leaf batch, FIFO, with the reference's 500 us
+//                        sub-timeouts / eager hand-off (py_wrapper.cc:449-504).
+//   update_inferences()  stores v/pi by row; the call that answers the last leaf submits the whole
+//                        generation to the device (b2az_submit_eval_host) and wakes the driver.
+//   build_history_batch  b2az_drain_history into the caller's arrays.
+// Not carried (rejected with RuntimeError instead of being ignored): Gumbel, resign, playout-cap
+// randomisation, model groups / seat permutations / per-seat overrides, PLAYOUT eval, external caches.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b2az.h"
+#include "az_connect4.h"
+
+namespace py = pybind11;
+using b2az::C4State;
+
+namespace {
+
+constexpr int kA = 7, kP = 2, kCanon = 168;
+
+[[noreturn]] void throw_last(const char* what) {
+  throw std::runtime_error(std::string(what) + ": " + b2az_last_error());
+}
+
+// ------------------------------------------------------------------------------------ PlayHistory
+struct PlayHistory {  // game_state.h:14-18
+  std::vector<float> canonical;  // [C][H][W]
+  std::array<ssize_t, 3> dims{0, 0, 0};
+  std::vector<float> v, pi;
+};
+
+// ------------------------------------------------------------------------------------ GameState
+// Host-side view of ONE position (what Python tools hold); rules come from the same bitboard header the
+// kernels use. Batched rule evaluation on the device is b2az_c4_batch.
+class GameState {
+ public:
+  virtual ~GameState() = default;
+  virtual std::unique_ptr<GameState> copy() const = 0;
+  virtual bool equals(const GameState& o) const = 0;
+  virtual std::string dump() const = 0;
+  virtual uint32_t current_turn() const = 0;
+  virtual uint8_t current_player() const = 0;
+  virtual uint8_t num_players() const = 0;
+  virtual uint32_t num_moves() const = 0;
+  virtual uint8_t num_symmetries() const = 0;
+  virtual bool relative_values() const { return false; }
+  virtual std::vector<PlayHistory> symmetries(const PlayHistory& base) const = 0;
+  virtual py::array_t<uint8_t> valid_moves() const = 0;
+  virtual void play_move(uint32_t m) = 0;
+  virtual py::object scores() const = 0;
+  virtual void randomize_start() {}
+  virtual int num_variants() const { return 0; }
+  virtual int get_variant_id() const { return -1; }
+  virtual py::array_t<float> canonicalized() const = 0;
+  virtual std::string to_bytes() const { throw std::runtime_error("to_bytes() not implemented for this game type"); }
+  virtual uint64_t hash() const = 0;
+};
+
+class Connect4GS : public GameState {  // connect4_gs.h:24-92
+ public:
+  C4State s;
+  Connect4GS() { b2az::c4_init(s); }
+  Connect4GS(const signed char* board84, int player, int turn) { b2az::c4_from_board(s, board84, player, turn); }
+  std::unique_ptr<GameState> copy() const override { return std::make_unique<Connect4GS>(*this); }
+  bool equals(const GameState& o) const override {  // connect4_gs.cc:23-31: board and player, not the turn
+    auto* c = dynamic_cast<const Connect4GS*>(&o);
+    return c && c->s.p[0] == s.p[0] && c->s.p[1] == s.p[1] && c->s.player == s.player;
+  }
+  std::string dump() const override {  // connect4_gs.cc:194-212
+    std::string out = "Current Player: " + std::to_string((int)s.player) + '\n';
+    for (int h = 0; h < 6; ++h) {
+      for (int w = 0; w < 7; ++w) {
+        if ((s.p[0] >> b2az::c4_bit(h, w)) & 1ULL) out += 'X';
+        else if ((s.p[1] >> b2az::c4_bit(h, w)) & 1ULL) out += 'O';
+        else out += '.';
+      }
+      out += '\n';
+    }
+    return out;
+  }
+  uint32_t current_turn() const override { return s.turn; }
+  uint8_t current_player() const override { return s.player; }
+  uint8_t num_players() const override { return kP; }
+  uint32_t num_moves() const override { return kA; }
+  uint8_t num_symmetries() const override { return 2; }
+  std::vector<PlayHistory> symmetries(const PlayHistory& base) const override {  // connect4_gs.cc:151-170
+    std::vector<PlayHistory> out{base};
+    PlayHistory m;
+    m.v = base.v;
+    m.dims = base.dims;
+    m.canonical.resize(base.canonical.size());
+    const ssize_t C = base.dims[0], H = base.dims[1], W = base.dims[2];
+    for (ssize_t f = 0; f < C; ++f)
+      for (ssize_t h = 0; h < H; ++h)
+        for (ssize_t w = 0; w < W; ++w) m.canonical[(f * H + h) * W + w] = base.canonical[(f * H + h) * W + (W - 1 - w)];
+    m.pi.resize(base.pi.size());
+    for (size_t w = 0; w < base.pi.size(); ++w) m.pi[w] = base.pi[base.pi.size() - 1 - w];
+    out.push_back(std::move(m));
+    return out;
+  }
+  py::array_t<uint8_t> valid_moves() const override {
+    py::array_t<uint8_t> a(kA);
+    const uint32_t vm = b2az::c4_valid_mask(s);
+    for (int w = 0; w < kA; ++w) a.mutable_at(w) = (vm >> w) & 1u;
+    return a;
+  }
+  void play_move(uint32_t m) override {  // connect4_gs.cc:48-58
+    if (m >= (uint32_t)kA || !b2az::c4_play(s, m)) throw std::runtime_error("Invalid move: You have a bug in your code.");
+  }
+  py::object scores() const override {
+    const uint32_t t = b2az::c4_terminal(s);
+    if (!t) return py::none();
+    py::array_t<float> a(kP + 1);
+    for (int i = 0; i < kP + 1; ++i) a.mutable_at(i) = (t == (uint32_t)i + 1u) ? 1.0f : 0.0f;
+    return std::move(a);
+  }
+  py::array_t<float> canonicalized() const override {
+    py::array_t<float> a({4, 6, 7});
+    float* d = a.mutable_data();
+    for (uint32_t e = 0; e < (uint32_t)kCanon; ++e) d[e] = b2az::c4_canon_elem(s.p[0], s.p[1], s.player, e);
+    return a;
+  }
+  std::string to_bytes() const override {  // connect4_gs.cc:172-178
+    std::string out(89, '\0');
+    b2az::c4_to_board(s, reinterpret_cast<signed char*>(&out[0]));
+    out[84] = (char)s.player;
+    const int32_t turn = (int32_t)s.turn;
+    std::memcpy(&out[85], &turn, 4);
+    return out;
+  }
+  static Connect4GS from_bytes(const std::string& data) {
+    if (data.size() != 89) throw std::runtime_error("Connect4GS::from_bytes: wrong byte length");
+    int32_t turn = 0;
+    std::memcpy(&turn, &data[85], 4);
+    return Connect4GS(reinterpret_cast<const signed char*>(&data[0]), (signed char)data[84], turn);
+  }
+  uint64_t hash() const override { return b2az::c4_hash(s); }  // equality class of connect4_gs.cc:33-37
+};
+
+// ------------------------------------------------------------------------------------ PlayParams
+enum class EvalType : uint8_t { NN = 0, RANDOM = 1, PLAYOUT = 2 };
+
+struct PlayParams {  // play_manager.h:60-154, same defaults
+  uint32_t games_to_play = 0;
+  uint32_t concurrent_games = 0;
+  uint32_t max_batch_size = 1;
+  uint32_t max_cache_size = 0;
+  uint8_t cache_shards = 1;
+  uint8_t queue_shards = 1;
+  uint8_t eval_pipelines = 1;
+  std::vector<uint32_t> mcts_visits{};
+  float cpuct = 2.0f;
+  float start_temp = 1.0f;
+  float final_temp = 1.0f;
+  float temp_decay_half_life = 0.0f;
+  std::vector<float> temp_decay_half_life_by_variant{};
+  bool history_enabled = false;
+  bool self_play = false;
+  bool tree_reuse = true;
+  float epsilon = 0.0f;
+  float mcts_root_temp = 1.0f;
+  bool playout_cap_randomization = false;
+  uint32_t playout_cap_depth = 25;
+  float playout_cap_percent = 0.75f;
+  float fpu_reduction = 0.0f;
+  bool root_fpu_zero = false;
+  bool shaped_dirichlet = false;
+  bool policy_target_pruning = false;
+  bool gumbel_enabled = false;
+  uint32_t gumbel_m = 16;
+  float gumbel_c_visit = 50.0f;
+  float gumbel_c_scale = 1.0f;
+  bool gumbel_full = false;
+  bool fast_search_uses_gumbel = false;
+  float resign_percent = 0.0f;
+  float resign_playthrough_percent = 0.0f;
+  std::vector<EvalType> eval_type{};
+  std::vector<uint8_t> model_groups{};
+  std::vector<std::vector<uint8_t>> seat_perms{};
+  std::vector<std::vector<uint32_t>> seat_visits{};
+  std::vector<std::vector<uint32_t>> seat_cap_visits{};
+  std::vector<std::vector<float>> seat_epsilon{};
+  std::vector<std::vector<float>> seat_mcts_root_temp{};
+  std::vector<std::vector<uint8_t>> seat_root_fpu_zero{};
+  std::vector<std::vector<uint8_t>> seat_gumbel_enabled{};
+  std::vector<std::vector<uint32_t>> seat_gumbel_m{};
+  std::vector<std::vector<float>> seat_gumbel_c_visit{};
+  std::vector<std::vector<float>> seat_gumbel_c_scale{};
+  std::vector<std::vector<uint8_t>> seat_gumbel_full{};
+  std::vector<std::vector<uint8_t>> seat_gumbel_use_improved_policy{};
+  std::vector<std::vector<float>> seat_resign_threshold{};
+  std::vector<std::vector<uint32_t>> seat_resign_consecutive{};
+  // additive (no reference counterpart): engine placement / determinism
+  int device = 0;
+  uint64_t seed = 0;
+  bool deterministic = false;  // one pcg32 stream in slot order (the reference's single-thread order)
+  uint64_t pool_nodes = 0;
+};
+
+// ------------------------------------------------------------------------------------ PlayManager
+class PlayManager;
+struct GameData {  // play_manager.h:33-58, the part Python sees (py_wrapper.cc:265-288)
+  PlayManager* pm;
+  uint32_t index;
+};
+
+class PlayManager {
+ public:
+  PlayManager(const GameState* gs, PlayParams p) : params_(std::move(p)) {
+    auto* c4 = dynamic_cast<const Connect4GS*>(gs);
+    if (!c4) throw std::runtime_error("the B200 engine implements Connect4GS only");
+    if (c4->s.p[0] || c4->s.p[1] || c4->s.player || c4->s.turn)
+      throw std::runtime_error("the B200 engine starts every game from the initial Connect4 position");
+    const auto& P = params_;
+    // play_manager.cc:19-22
+    if (P.mcts_visits.size() != (size_t)kP) throw std::runtime_error("You must specify MCTS visits for each player");
+    auto reject = [](bool bad, const char* what) {
+      if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
+    };
+    reject(P.gumbel_enabled || !P.seat_gumbel_enabled.empty(), "gumbel_enabled");
+    reject(P.resign_percent != 0.0f || !P.seat_resign_threshold.empty(), "resign");
+    reject(P.playout_cap_randomization, "playout_cap_randomization");
+    reject(P.max_cache_size != 0, "max_cache_size (the position cache)");
+    reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
+    reject(!P.seat_visits.empty() || !P.seat_cap_visits.empty() || !P.seat_epsilon.empty() ||
+               !P.seat_mcts_root_temp.empty() || !P.seat_root_fpu_zero.empty(),
+           "per-seat overrides");
+    reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
+    EvalType et = EvalType::NN;
+    if (!P.eval_type.empty()) {
+      et = P.eval_type[0];
+      for (auto e : P.eval_type) reject(e != et, "mixed eval_type");
+      reject(et == EvalType::PLAYOUT, "EvalType.PLAYOUT");
+    }
+    random_eval_ = (et == EvalType::RANDOM);
+    b2az_params bp;
+    b2az_params_default(&bp);
+    bp.games_to_play = P.games_to_play;
+    bp.concurrent_games = P.concurrent_games;
+    bp.max_batch_size = P.max_batch_size;
+    bp.mcts_visits[0] = P.mcts_visits[0];
+    bp.mcts_visits[1] = P.mcts_visits[1];
+    bp.cpuct = P.cpuct;
+    bp.start_temp = P.start_temp;
+    bp.final_temp = P.final_temp;
+    bp.temp_decay_half_life = P.temp_decay_half_life;
+    bp.history_enabled = P.history_enabled;
+    bp.self_play = P.self_play;
+    bp.tree_reuse = P.tree_reuse;
+    bp.epsilon = P.epsilon;
+    bp.mcts_root_temp = P.mcts_root_temp;
+    bp.playout_cap_depth = P.playout_cap_depth;
+    bp.playout_cap_percent = P.playout_cap_percent;
+    bp.fpu_reduction = P.fpu_reduction;
+    bp.root_fpu_zero = P.root_fpu_zero;
+    bp.shaped_dirichlet = P.shaped_dirichlet;
+    bp.policy_target_pruning = P.policy_target_pruning;
+    bp.eval_type = random_eval_ ? B2AZ_EVAL_RANDOM : B2AZ_EVAL_NN;
+    bp.rng_mode = P.deterministic ? B2AZ_RNG_GLOBAL : B2AZ_RNG_PER_GAME;
+    bp.seed = P.seed;
+    bp.pool_nodes = P.pool_nodes;
+    if (b2az_create(&bp, P.device, &eng_) != 0) throw_last("PlayManager");
+    G_ = P.concurrent_games;
+    canon_.resize((size_t)G_ * kCanon);
+    ids_.resize(G_);
+    v_.assign((size_t)G_ * (kP + 1), 0.0f);
+    pi_.assign((size_t)G_ * kA, 0.0f);
+    row_of_game_.assign(G_, 0xFFFFFFFFu);
+    refresh_stats_locked();
+  }
+  ~PlayManager() {
+    stop();
+    if (eng_) b2az_destroy(eng_);
+  }
+  PlayManager(const PlayManager&) = delete;
+
+  const PlayParams& params() const { return params_; }
+  void stop() {
+    stopped_.store(true);
+    cv_.notify_all();
+  }
+  bool stopped() const { return stopped_.load(); }
+  uint32_t games_completed() const { return games_completed_.load(); }
+  uint32_t remaining_games() const {  // play_manager.h:177-180
+    if (stopped_.load()) return 0;
+    const uint32_t done = games_completed_.load();
+    return done >= params_.games_to_play ? 0 : params_.games_to_play - done;
+  }
+
+  // PlayManager::play (play_manager.cc:258-600)
+  void play() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      if (driver_active_ || finished_) {  // the reference's extra worker threads: nothing left for them to do
+        cv_.wait(lk, [&] { return finished_ || stopped_.load(); });
+        return;
+      }
+      driver_active_ = true;
+    }
+    try {
+      drive();
+    } catch (...) {
+      std::lock_guard<std::mutex> lk(mu_);
+      driver_active_ = false;
+      finished_ = true;
+      stopped_.store(true);
+      cv_.notify_all();
+      throw;
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    driver_active_ = false;
+    finished_ = true;
+    cv_.notify_all();
+  }
+
+  // build_batch (py_wrapper.cc:449-504)
+  std::vector<uint32_t> build_batch(uint32_t group, float* batch, ssize_t ndim, const ssize_t* shape, uint32_t /*shard*/) {
+    if (group != 0) throw std::runtime_error("model group out of range");
+    std::vector<uint32_t> out;
+    const uint32_t mbs = params_.max_batch_size;
+    out.reserve(mbs);
+    auto max_bs = [&]() -> uint32_t {
+      const uint32_t rem = remaining_games();
+      return std::min(mbs, rem > 0 ? rem : 1u);
+    };
+    uint32_t empty = 0;
+    bool checked = false;
+    std::unique_lock<std::mutex> lk(mu_);
+    while (out.size() < max_bs()) {
+      if (eager_.load() && !out.empty()) break;
+      if (remaining_games() == 0) break;
+      const uint32_t avail = leaf_count_ - next_row_;
+      if (avail == 0) {
+        if (++empty >= 20u) break;  // MAX_EMPTY x SUB_TIMEOUT = ~10 ms
+        cv_.wait_for(lk, std::chrono::microseconds(500));
+        continue;
+      }
+      empty = 0;
+      if (!checked) {
+        if (ndim != 4 || shape[1] != 4 || shape[2] != 6 || shape[3] != 7) throw std::runtime_error("Improper batch size");
+        checked = true;
+      }
+      const uint32_t cap = (uint32_t)std::min<ssize_t>(shape[0], (ssize_t)max_bs());
+      if (out.size() >= cap) break;
+      const uint32_t n = std::min<uint32_t>(avail, cap - (uint32_t)out.size());
+      std::memcpy(batch + out.size() * kCanon, canon_.data() + (size_t)next_row_ * kCanon, (size_t)n * kCanon * sizeof(float));
+      out.insert(out.end(), ids_.begin() + next_row_, ids_.begin() + next_row_ + n);
+      next_row_ += n;
+    }
+    return out;
+  }
+
+  // PlayManager::update_inferences (play_manager.cc:619-642)
+  void update_inferences(uint32_t group, const std::vector<uint32_t>& idx, const float* v, ssize_t vrows, ssize_t vcols,
+                         const float* pi, ssize_t prows, ssize_t pcols) {
+    if (group != 0) throw std::runtime_error("model group out of range");
+    if (vcols != kP + 1 || pcols != kA || vrows < (ssize_t)idx.size() || prows < (ssize_t)idx.size())
+      throw std::runtime_error("Eigen is angry!!!");  // shapes.h:4-6: the reference asserts on bad shapes
+    std::unique_lock<std::mutex> lk(mu_);
+    for (size_t i = 0; i < idx.size(); ++i) {
+      if (idx[i] >= G_ || row_of_game_[idx[i]] == 0xFFFFFFFFu) throw std::runtime_error("update_inferences: game has no pending leaf");
+      const uint32_t r = row_of_game_[idx[i]];
+      std::memcpy(&v_[(size_t)r * (kP + 1)], v + i * (kP + 1), (kP + 1) * sizeof(float));
+      std::memcpy(&pi_[(size_t)r * kA], pi + i * kA, kA * sizeof(float));
+      row_of_game_[idx[i]] = 0xFFFFFFFFu;
+    }
+    answered_ += (uint32_t)idx.size();
+    if (answered_ == leaf_count_ && leaf_count_ > 0) cv_.notify_all();
+  }
+
+  // pop_game / pop_games_upto / push_inference: the per-game flavour of the same hand-off
+  py::object pop_game(uint32_t group) {
+    auto v = pop_games_upto(group, 1);
+    if (v.empty()) return py::none();
+    return py::int_(v[0]);
+  }
+  std::vector<uint32_t> pop_games_upto(uint32_t group, size_t n) {
+    if (group != 0) throw std::runtime_error("model group out of range");
+    std::unique_lock<std::mutex> lk(mu_);
+    if (leaf_count_ == next_row_) cv_.wait_for(lk, std::chrono::milliseconds(10));  // MAX_WAIT (play_manager.h:26)
+    const uint32_t take = (uint32_t)std::min<size_t>(n, leaf_count_ - next_row_);
+    std::vector<uint32_t> out(ids_.begin() + next_row_, ids_.begin() + next_row_ + take);
+    next_row_ += take;
+    return out;
+  }
+  void push_inference(uint32_t i) {  // the caller has written game_data(i).v() / .pi() in place
+    std::unique_lock<std::mutex> lk(mu_);
+    if (i >= G_ || row_of_game_[i] == 0xFFFFFFFFu) throw std::runtime_error("push_inference: game has no pending leaf");
+    row_of_game_[i] = 0xFFFFFFFFu;
+    if (++answered_ == leaf_count_) cv_.notify_all();
+  }
+
+  // build_history_batch (py_wrapper.cc:393-424)
+  uint32_t build_history_batch(float* canon, ssize_t n, float* v, float* pi) {
+    uint32_t cur = 0;
+    while (cur < (uint32_t)n && (remaining_games() > 0 || hist_count() > 0)) {
+      uint32_t got = 0;
+      {
+        std::lock_guard<std::mutex> lk(api_);
+        if (b2az_drain_history(eng_, nullptr, (uint32_t)n - cur, canon + (size_t)cur * kCanon, v + (size_t)cur * (kP + 1),
+                               pi + (size_t)cur * kA, 0, &got) != 0)
+          throw_last("build_history_batch");
+      }
+      cur += got;
+      if (got == 0) {
+        if (finished_.load()) {
+          refresh_stats();
+          if (hist_count() == 0) break;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      }
+    }
+    refresh_stats();
+    return cur;
+  }
+
+  b2az_stats stats() {
+    refresh_stats();
+    std::lock_guard<std::mutex> lk(mu_);
+    return stats_;
+  }
+  uint32_t hist_count() const { return hist_count_.load(); }
+  size_t awaiting_inference_count() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return leaf_count_ - next_row_;
+  }
+  size_t awaiting_mcts_count() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return leaf_count_ ? answered_ : 0;
+  }
+  void set_eager(bool e) { eager_.store(e); }
+  uint32_t concurrent() const { return G_; }
+
+  // GameData accessors
+  Connect4GS game_state(uint32_t i) {
+    uint8_t st[89];
+    std::lock_guard<std::mutex> lk(api_);
+    if (b2az_peek(eng_, nullptr, i, 0, st, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != 0) throw_last("game_data");
+    return Connect4GS::from_bytes(std::string(reinterpret_cast<char*>(st), 89));
+  }
+  // the slot's pending leaf row (canonical planes + the v / pi the evaluator writes), or -1
+  ssize_t row(uint32_t i) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (i >= G_) throw std::runtime_error("game index out of range");
+    for (uint32_t r = 0; r < leaf_count_; ++r)
+      if (ids_[r] == i) return r;
+    return -1;
+  }
+  float* canon_row(size_t r) { return canon_.data() + r * kCanon; }
+  float* v_row(size_t r) { return v_.data() + r * (kP + 1); }
+  float* pi_row(size_t r) { return pi_.data() + r * kA; }
+
+ private:
+  void refresh_stats() {
+    std::lock_guard<std::mutex> lk(mu_);
+    refresh_stats_locked();
+  }
+  void refresh_stats_locked() {
+    std::lock_guard<std::mutex> lk(api_);
+    if (b2az_get_stats(eng_, nullptr, &stats_) != 0) throw_last("stats");
+    games_completed_.store(stats_.games_completed);
+    hist_count_.store(stats_.hist_count);
+  }
+  void drive() {
+    if (random_eval_) {
+      // EvalType::RANDOM: the evaluator runs inside the step kernel; fuse a search's worth of generations
+      const uint32_t chunk = std::max<uint32_t>(1, std::min<uint32_t>(params_.mcts_visits[0], 512));
+      for (;;) {
+        if (stopped_.load()) return;
+        {
+          std::lock_guard<std::mutex> lk(api_);
+          if (b2az_step(eng_, chunk, nullptr) != 0) throw_last("play");
+        }
+        refresh_stats();
+        std::lock_guard<std::mutex> lk(mu_);
+        if (stats_.device_error) throw std::runtime_error("play: device error (pool / history ring exhausted)");
+        if (stats_.active_games == 0) return;
+      }
+    }
+    for (;;) {
+      if (stopped_.load()) return;
+      uint32_t n = 0;
+      {
+        std::lock_guard<std::mutex> lk(api_);
+        if (b2az_step(eng_, 1, nullptr) != 0) throw_last("play");
+        if (b2az_leaf_batch_host(eng_, nullptr, G_, canon_.data(), ids_.data(), &n) != 0) throw_last("play");
+      }
+      std::unique_lock<std::mutex> lk(mu_);
+      refresh_stats_locked();
+      if (n == 0) return;  // every slot retired
+      for (uint32_t r = 0; r < n; ++r) row_of_game_[ids_[r]] = r;
+      answered_ = 0;
+      next_row_ = 0;
+      leaf_count_ = n;
+      cv_.notify_all();
+      cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
+      if (stopped_.load()) return;
+      leaf_count_ = 0;
+      next_row_ = 0;
+      {
+        std::lock_guard<std::mutex> lk2(api_);
+        if (b2az_submit_eval_host(eng_, nullptr, ids_.data(), v_.data(), pi_.data(), n) != 0) throw_last("update_inferences");
+      }
+    }
+  }
+
+  PlayParams params_;
+  b2az_engine* eng_ = nullptr;
+  uint32_t G_ = 0;
+  bool random_eval_ = false;
+  std::mutex mu_;   // generation state below
+  std::mutex api_;  // serialises calls into the C ABI (one engine, one stream)
+  std::condition_variable cv_;
+  bool driver_active_ = false;
+  std::atomic<bool> finished_{false};
+  std::atomic<bool> stopped_{false};
+  std::atomic<bool> eager_{false};
+  std::atomic<uint32_t> games_completed_{0}, hist_count_{0};
+  std::vector<float> canon_, v_, pi_;
+  std::vector<uint32_t> ids_, row_of_game_;
+  uint32_t leaf_count_ = 0, next_row_ = 0, answered_ = 0;
+  b2az_stats stats_{};
+};
+
+py::array_t<float> vec3(const float* p) {
+  py::array_t<float> a(3);
+  for (int i = 0; i < 3; ++i) a.mutable_at(i) = p[i];
+  return a;
+}
+
+}  // namespace
+
+// NOLINTNEXTLINE
+PYBIND11_MODULE(alphazero, m) {
+  m.doc() = "the c++ parts of an alphazero implementation (B200 engine behind the reference's API)";
+
+  py::class_<PlayHistory>(m, "PlayHistory")
+      .def(py::init([](py::array_t<float, py::array::c_style | py::array::forcecast> canonical,
+                       py::array_t<float, py::array::c_style | py::array::forcecast> v,
+                       py::array_t<float, py::array::c_style | py::array::forcecast> pi) {
+             if (canonical.ndim() != 3 || v.ndim() != 1 || pi.ndim() != 1) throw std::runtime_error("PlayHistory: bad shapes");
+             PlayHistory ph;
+             ph.dims = {canonical.shape(0), canonical.shape(1), canonical.shape(2)};
+             ph.canonical.assign(canonical.data(), canonical.data() + canonical.size());
+             ph.v.assign(v.data(), v.data() + v.size());
+             ph.pi.assign(pi.data(), pi.data() + pi.size());
+             return ph;
+           }),
+           py::arg().none(false), py::arg().none(false), py::arg().none(false))
+      .def("v", [](PlayHistory& ph) { return py::array_t<float>({(ssize_t)ph.v.size()}, ph.v.data(), py::cast(&ph)); })
+      .def("pi", [](PlayHistory& ph) { return py::array_t<float>({(ssize_t)ph.pi.size()}, ph.pi.data(), py::cast(&ph)); })
+      .def("canonical", [](PlayHistory& ph) {
+        const ssize_t sz = sizeof(float);
+        return py::memoryview::from_buffer(ph.canonical.data(), {ph.dims[0], ph.dims[1], ph.dims[2]},
+                                           {sz * ph.dims[1] * ph.dims[2], sz * ph.dims[2], sz});
+      }, py::keep_alive<0, 1>());
+
+  py::class_<GameState>(m, "GameState")
+      .def("copy", &GameState::copy)
+      .def("__eq__", [](const GameState& a, const GameState& b) { return a.equals(b); })
+      .def("__str__", &GameState::dump)
+      .def("current_turn", &GameState::current_turn)
+      .def("current_player", &GameState::current_player)
+      .def("num_players", &GameState::num_players)
+      .def("num_moves", &GameState::num_moves)
+      .def("num_symmetries", &GameState::num_symmetries)
+      .def("relative_values", &GameState::relative_values)
+      .def("symmetries", &GameState::symmetries)
+      .def("valid_moves", &GameState::valid_moves)
+      .def("play_move", &GameState::play_move)
+      .def("scores", &GameState::scores)
+      .def("randomize_start", &GameState::randomize_start)
+      .def("num_variants", &GameState::num_variants)
+      .def("get_variant_id", &GameState::get_variant_id)
+      .def("canonicalized", &GameState::canonicalized);
+
+  m.def("hash_game_state", [](const GameState& gs) { return gs.hash(); }, py::arg("gs"));
+
+  py::class_<Connect4GS, GameState>(m, "Connect4GS")
+      .def(py::init<>())
+      .def(py::init([](const py::array_t<int8_t, py::array::c_style | py::array::forcecast>& board, int8_t player, int32_t turn) {
+        if (board.ndim() != 3 || board.shape(0) != 2 || board.shape(1) != 6 || board.shape(2) != 7)
+          throw std::runtime_error{"Improper connect 4 board shape"};
+        return Connect4GS(reinterpret_cast<const signed char*>(board.data()), player, turn);
+      }))
+      .def_static("NUM_PLAYERS", [] { return 2; })
+      .def_static("NUM_MOVES", [] { return 7; })
+      .def_static("NUM_SYMMETRIES", [] { return 2; })
+      .def_static("CANONICAL_SHAPE", [] { return std::array<int64_t, 3>{4, 6, 7}; })
+      .def(py::pickle([](const Connect4GS& gs) { return py::bytes(gs.to_bytes()); },
+                      [](py::bytes b) { return Connect4GS::from_bytes(std::string(b)); }));
+
+  py::enum_<EvalType>(m, "EvalType").value("NN", EvalType::NN).value("RANDOM", EvalType::RANDOM).value("PLAYOUT", EvalType::PLAYOUT);
+
+  py::class_<PlayParams>(m, "PlayParams")
+      .def(py::init<>())
+#define RW(f) .def_readwrite(#f, &PlayParams::f)
+      RW(games_to_play) RW(concurrent_games) RW(max_batch_size) RW(max_cache_size) RW(cache_shards) RW(queue_shards)
+      RW(eval_pipelines) RW(mcts_visits) RW(cpuct) RW(playout_cap_randomization) RW(playout_cap_depth)
+      RW(playout_cap_percent) RW(start_temp) RW(final_temp) RW(temp_decay_half_life) RW(temp_decay_half_life_by_variant)
+      RW(history_enabled) RW(tree_reuse) RW(self_play) RW(epsilon) RW(fpu_reduction) RW(root_fpu_zero) RW(shaped_dirichlet)
+      RW(policy_target_pruning) RW(gumbel_enabled) RW(gumbel_m) RW(gumbel_c_visit) RW(gumbel_c_scale) RW(gumbel_full)
+      RW(fast_search_uses_gumbel) RW(mcts_root_temp) RW(resign_percent) RW(resign_playthrough_percent) RW(eval_type)
+      RW(model_groups) RW(seat_perms) RW(seat_visits) RW(seat_cap_visits) RW(seat_epsilon) RW(seat_mcts_root_temp)
+      RW(seat_root_fpu_zero) RW(seat_gumbel_enabled) RW(seat_gumbel_m) RW(seat_gumbel_c_visit) RW(seat_gumbel_c_scale)
+      RW(seat_gumbel_full) RW(seat_gumbel_use_improved_policy) RW(seat_resign_threshold) RW(seat_resign_consecutive)
+      RW(device) RW(seed) RW(deterministic) RW(pool_nodes)
+#undef RW
+      ;
+
+  py::class_<GameData>(m, "GameData")
+      .def("gs", [](const GameData& gd) { return gd.pm->game_state(gd.index); })
+      .def("valid_moves", [](const GameData& gd) { return gd.pm->game_state(gd.index).valid_moves(); })
+      .def("v", [](const GameData& gd) {
+        const ssize_t r = gd.pm->row(gd.index);
+        if (r < 0) throw std::runtime_error("GameData.v(): the game has no pending leaf");
+        return py::array_t<float>({(ssize_t)3}, gd.pm->v_row((size_t)r), py::cast(gd.pm));
+      })
+      .def("pi", [](const GameData& gd) {
+        const ssize_t r = gd.pm->row(gd.index);
+        if (r < 0) throw std::runtime_error("GameData.pi(): the game has no pending leaf");
+        return py::array_t<float>({(ssize_t)7}, gd.pm->pi_row((size_t)r), py::cast(gd.pm));
+      })
+      .def("canonical", [](const GameData& gd) {
+        const ssize_t r = gd.pm->row(gd.index);
+        if (r < 0) throw std::runtime_error("GameData.canonical(): the game has no pending leaf");
+        const ssize_t sz = sizeof(float);
+        return py::memoryview::from_buffer(gd.pm->canon_row((size_t)r), {(ssize_t)4, (ssize_t)6, (ssize_t)7}, {sz * 42, sz * 7, sz});
+      });
+
+  py::class_<PlayManager>(m, "PlayManager")
+      .def(py::init([](const GameState* gs, PlayParams params) { return std::make_unique<PlayManager>(gs, std::move(params)); }),
+           py::arg().none(false), py::arg())
+      .def(py::init([](const GameState* gs, PlayParams params, std::vector<py::object> caches) {
+             for (auto& c : caches)
+               if (!c.is_none()) throw std::runtime_error("external caches are not implemented by the B200 engine yet");
+             return std::make_unique<PlayManager>(gs, std::move(params));
+           }),
+           py::arg().none(false), py::arg(), py::arg("caches"))
+      .def("game_data", [](PlayManager& pm, uint32_t i) {
+        if (i >= pm.concurrent()) throw std::runtime_error("game index out of range");
+        return GameData{&pm, i};
+      }, py::keep_alive<0, 1>())
+      .def("params", &PlayManager::params, py::return_value_policy::reference_internal)
+      .def("scores", [](PlayManager& pm) { auto s = pm.stats(); return vec3(s.scores); })
+      .def("resign_scores", [](PlayManager& pm) { auto s = pm.stats(); return vec3(s.resign_scores); })
+      .def("games_completed", &PlayManager::games_completed)
+      .def("remaining_games", &PlayManager::remaining_games)
+      .def("stop", &PlayManager::stop)
+      .def("stopped", &PlayManager::stopped)
+      .def("awaiting_inference_count", &PlayManager::awaiting_inference_count)
+      .def("awaiting_mcts_count", &PlayManager::awaiting_mcts_count)
+      .def("hist_count", [](PlayManager& pm) { return pm.stats().hist_count; })
+      .def("cache_hits", [](PlayManager& pm) { return pm.stats().cache_hits; })
+      .def("cache_misses", [](PlayManager& pm) { return pm.stats().cache_misses; })
+      .def("cache_evictions", [](PlayManager& pm) { return pm.stats().cache_evictions; })
+      .def("cache_reinserts", [](PlayManager& pm) { return pm.stats().cache_reinserts; })
+      .def("cache_max_size", [](PlayManager& pm) { return pm.stats().cache_max_size; })
+      .def("cache_size", [](PlayManager& pm) { return pm.stats().cache_size; })
+      .def("avg_game_length", [](PlayManager& pm) { return pm.stats().avg_game_length; })
+      .def("avg_leaf_depth", [](PlayManager& pm) { return pm.stats().avg_leaf_depth; })
+      .def("avg_search_entropy", [](PlayManager& pm) { return pm.stats().avg_search_entropy; })
+      .def("fast_avg_leaf_depth", [](PlayManager& pm) { return pm.stats().fast_avg_leaf_depth; })
+      .def("fast_avg_search_entropy", [](PlayManager& pm) { return pm.stats().fast_avg_search_entropy; })
+      .def("avg_moves_per_turn", [](PlayManager& pm) { return pm.stats().avg_moves_per_turn; })
+      .def("avg_valid_moves", [](PlayManager& pm) { return pm.stats().avg_valid_moves; })
+      .def("simulations", [](PlayManager& pm) { return pm.stats().simulations; })  // additive
+      .def("play", &PlayManager::play, py::call_guard<py::gil_scoped_release>())
+      .def("pop_game", [](PlayManager& pm, uint32_t g) {
+        std::vector<uint32_t> v;
+        { py::gil_scoped_release rel; v = pm.pop_games_upto(g, 1); }
+        return v.empty() ? py::object(py::none()) : py::object(py::int_(v[0]));
+      })
+      .def("pop_games_upto", &PlayManager::pop_games_upto, py::call_guard<py::gil_scoped_release>())
+      .def("push_inference", &PlayManager::push_inference, py::call_guard<py::gil_scoped_release>())
+      .def("update_inferences",
+           [](PlayManager& pm, uint8_t group, const std::vector<uint32_t>& idx,
+              py::array_t<float, py::array::c_style | py::array::forcecast> v,
+              py::array_t<float, py::array::c_style | py::array::forcecast> pi) {
+             if (v.ndim() != 2 || pi.ndim() != 2) throw std::runtime_error("Eigen is angry!!!");
+             const float *vp = v.data(), *pp = pi.data();
+             const ssize_t vr = v.shape(0), vc = v.shape(1), pr = pi.shape(0), pc = pi.shape(1);
+             py::gil_scoped_release rel;
+             pm.update_inferences(group, idx, vp, vr, vc, pp, pr, pc);
+           })
+      .def("build_history_batch",
+           [](PlayManager& pm, py::array_t<float, py::array::c_style>& canonical, py::array_t<float, py::array::c_style>& v,
+              py::array_t<float, py::array::c_style>& pi) {
+             if (canonical.ndim() != 4 || v.ndim() != 2 || pi.ndim() != 2 || canonical.shape(1) != 4 || canonical.shape(2) != 6 ||
+                 canonical.shape(3) != 7 || v.shape(1) != 3 || pi.shape(1) != 7)
+               throw std::runtime_error("Improper history batch shape");
+             const ssize_t n = std::min(canonical.shape(0), std::min(v.shape(0), pi.shape(0)));
+             float *c = canonical.mutable_data(), *vv = v.mutable_data(), *pp = pi.mutable_data();
+             py::gil_scoped_release rel;
+             return pm.build_history_batch(c, n, vv, pp);
+           })
+      .def("num_model_groups", [](PlayManager&) { return 1; })
+      .def("num_seat_perms", [](PlayManager&) { return 1; })
+      .def("perm_scores", [](PlayManager& pm, size_t) { auto s = pm.stats(); return vec3(s.scores); })
+      .def("perm_games_completed", [](PlayManager& pm, size_t) { return pm.games_completed(); })
+      .def("num_tracked_variants", [](PlayManager&) { return 0; })
+      .def("set_eager", &PlayManager::set_eager)
+      .def("build_batch",
+           [](PlayManager& pm, uint32_t group, py::array_t<float, py::array::c_style>& batch, uint32_t shard) {
+             float* data = batch.mutable_data();
+             const ssize_t nd = batch.ndim();
+             ssize_t shape[4] = {0, 0, 0, 0};
+             for (ssize_t i = 0; i < std::min<ssize_t>(nd, 4); ++i) shape[i] = batch.shape(i);
+             py::gil_scoped_release rel;
+             return pm.build_batch(group, data, nd, shape, shard);
+           },
+           py::arg("group"), py::arg("batch"), py::arg("shard") = 0);
+
+  // Tracy hooks (py_wrapper.cc:772-787): profiling is off in this build
+  m.def("_tracy_zone_begin", [](const std::string&, const std::string&, uint32_t) {});
+  m.def("_tracy_zone_end", [] {});
+  m.def("tracy_frame_mark", [] {});
+  m.def("_tracy_set_thread_name", [](const std::string&) {});
+  m.def("tracy_is_enabled", [] { return false; });
+}

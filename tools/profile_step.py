@@ -21,7 +21,7 @@ a = ap.parse_args()
 p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=a.games, mcts_visits=(400, 400), cpuct=1.25,
                         fpu_reduction=0.25, eval_type=b2az.EVAL_RANDOM, rng_mode=b2az.RNG_PER_GAME, seed=1000,
                         tree_reuse=1, history_enabled=0, self_play=1, lanes_per_game=0)
-e = b2az.Engine(p)
+e = b2az.Engine(p, lib=b2az.load(os.environ["B2AZ_LIB_PATH"]) if os.environ.get("B2AZ_LIB_PATH") else None)
 for _ in range(a.preroll):
     e.step(400)
 for _ in range(a.launches):
