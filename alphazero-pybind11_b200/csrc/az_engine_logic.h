@@ -104,44 +104,53 @@ AZ_HD int popc32(u32 x) {
 #endif
 }
 
-// ------------------------------------------------------------------------------------ sectors
-// One 32 B sector of a block as eight registers (two 16 B vector accesses on the device).
-struct Sec {
-  u32 w[8];
+// ------------------------------------------------------------------------------------ 16 B vectors
+struct V4 {
+  u32 x, y, z, w;
 };
-AZ_HD Sec ld_sec(const void* p) {
-  Sec s;
+AZ_HD V4 ld_v4(const void* p) {
+  V4 r;
 #if defined(__CUDA_ARCH__)
-  // (ld.global.v8.b32 was tried: ptxas for sm_100a splits it into the same two LDG.E.128)
-  const uint4 a = reinterpret_cast<const uint4*>(p)[0];
-  const uint4 b = reinterpret_cast<const uint4*>(p)[1];
-  s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
-  s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  r.x = a.x; r.y = a.y; r.z = a.z; r.w = a.w;
 #else
-  memcpy(s.w, p, 32);
+  memcpy(&r, p, 16);
 #endif
-  return s;
+  return r;
 }
-AZ_HD void st_sec(void* p, const Sec& s) {
+AZ_HD void st_v4(void* p, const V4& v) {
 #if defined(__CUDA_ARCH__)
-  reinterpret_cast<uint4*>(p)[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
-  reinterpret_cast<uint4*>(p)[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+  *reinterpret_cast<uint4*>(p) = make_uint4(v.x, v.y, v.z, v.w);
 #else
-  memcpy(p, s.w, 32);
+  memcpy(p, &v, 16);
 #endif
 }
-// the mixed sector (Block::mv .. Block::player) decoded from registers
-AZ_HD u32 mix_mv(const Sec& m, int j) { return (m.w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu; }
-AZ_HD u32 mix_term(const Sec& m, int j) { return (m.w[4 + (j >> 2)] >> (8 * (j & 3))) & 0xFFu; }
-AZ_HD float mix_v(const Sec& m) { return u2f(m.w[6]); }
-AZ_HD u32 mix_k(const Sec& m) { return m.w[7] & 0xFFu; }
-AZ_HD u32 mix_player(const Sec& m) { return (m.w[7] >> 8) & 0xFFu; }
+AZ_HD V4 mk_v4(u32 x, u32 y, u32 z, u32 w) {
+  V4 r;
+  r.x = x; r.y = y; r.z = z; r.w = w;
+  return r;
+}
 // scalar accessors (cold paths)
-AZ_HD u32 blk_mv(const Block* B, u32 j) { return (B->mix[j >> 1] >> (16u * (j & 1u))) & 0xFFFFu; }
-AZ_HD u32 blk_term(const Block* B, u32 j) { return (B->mix[4u + (j >> 2)] >> (8u * (j & 3u))) & 0xFFu; }
-AZ_HD float blk_v(const Block* B) { return u2f(B->mix[6]); }
-AZ_HD u32 blk_k(const Block* B) { return B->mix[7] & 0xFFu; }
-AZ_HD u32 blk_player(const Block* B) { return (B->mix[7] >> 8) & 0xFFu; }
+AZ_HD u32 blk_n(const Block* B, u32 j) { return B->rec[j][0]; }
+AZ_HD float blk_q(const Block* B, u32 j) { return u2f(B->rec[j][1]); }
+AZ_HD float blk_pol(const Block* B, u32 j) { return u2f(B->rec[j][2]); }
+AZ_HD float blk_d(const Block* B, u32 j) { return u2f(B->rec[j][3]); }
+AZ_HD u32 blk_mv(const Block* B, u32 j) { return (B->mv >> (4u * j)) & 15u; }
+AZ_HD u32 blk_term(const Block* B, u32 j) { return (B->term >> (2u * j)) & 3u; }
+AZ_HD float blk_v(const Block* B) { return u2f(B->v); }
+AZ_HD u32 blk_k(const Block* B) { return B->kp & 0xFFu; }
+AZ_HD u32 blk_player(const Block* B) { return (B->kp >> 8) & 0xFFu; }
+AZ_HD void blk_copy(Block* D, const Block* S) {
+  V4 t[10];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 10; ++i) t[i] = ld_v4(reinterpret_cast<const u32*>(S) + 4 * i);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 10; ++i) st_v4(reinterpret_cast<u32*>(D) + 4 * i, t[i]);
+}
 
 // ------------------------------------------------------------------------------------ page ring
 // Free pages sit in one ring of page ids. pop and push each take a ticket with one atomicAdd and then
@@ -262,18 +271,21 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
       break;
     }
     const Block* B = E.blocks + blk;
-    // one burst: everything this level needs (5 sectors, independent loads)
-    const Sec sn = ld_sec(B->n), sq = ld_sec(B->q), sp = ld_sec(B->pol), sf = ld_sec(B->fc), sm = ld_sec(B->mix);
+    // one burst: everything this level (and its backprop) needs — ten independent 16 B loads
+    V4 r[kKMax];
+#pragma unroll
+    for (int j = 0; j < kKMax; ++j) r[j] = ld_v4(B->rec[j]);
+    const V4 f0 = ld_v4(&B->fc[0]), f1 = ld_v4(&B->fc[4]), hd = ld_v4(&B->mv);
     if (!at_root) {
-      cur_v = mix_v(sm);
-      cur_k = mix_k(sm);
-      cur_player = mix_player(sm);
+      cur_v = u2f(hd.z);
+      cur_k = hd.w & 0xFFu;
+      cur_player = (hd.w >> 8) & 0xFFu;
     }
     const float fpu = (at_root && E.root_fpu_zero) ? 0.0f : E.fpu_reduction;
     float seen = 0.0f;
 #pragma unroll
     for (int j = 0; j < kKMax; ++j)
-      if ((u32)j < cur_k && sn.w[j] > 0) seen = fadd(seen, u2f(sp.w[j]));
+      if ((u32)j < cur_k && r[j].x > 0) seen = fadd(seen, u2f(r[j].z));
     const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
     const float sqrt_n = fsqrt((float)cur_n);
     u32 best = 0, best_n = 0, best_fc = kNil;
@@ -281,27 +293,23 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
 #pragma unroll
     for (int j = 0; j < kKMax; ++j) {
       if (j > 0 && (u32)j >= cur_k) continue;  // pad slots: 0 / 1 would take the division's slow path
-      const u32 nj = sn.w[j];
-      const float base = (nj == 0) ? fpu_value : u2f(sq.w[j]);
-      const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(sp.w[j])), sqrt_n), (float)(nj + 1u)));
+      const u32 nj = r[j].x;
+      const float base = (nj == 0) ? fpu_value : u2f(r[j].y);
+      const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
       if (j == 0 || u > best_u) {
         best_u = u;
         best = (u32)j;
         best_n = nj;
-        best_fc = sf.w[j];
+        best_fc = j == 0 ? f0.x : j == 1 ? f0.y : j == 2 ? f0.z : j == 3 ? f0.w : j == 4 ? f1.x : j == 5 ? f1.y : f1.z;
       }
     }
-    // (an L2 prefetch of d[best] for the coming backprop was measured: -6 %, the LSU queue is the scarcer resource)
-    // move and terminal code of the chosen child out of the mixed sector (select chain, no indexing)
-    u32 mvw = sm.w[0], tw = sm.w[4];
-    if (best >= 2) mvw = sm.w[1];
-    if (best >= 4) { mvw = sm.w[2]; tw = sm.w[5]; }
-    if (best >= 6) mvw = sm.w[3];
-    const u32 move = (mvw >> (16u * (best & 1u))) & 0xFFFFu;
-    const u32 cterm = (tw >> (8u * (best & 3u))) & 0xFFu;
+    const u32 move = (hd.x >> (4u * best)) & 15u;
+    const u32 cterm = (hd.y >> (2u * best)) & 3u;
     const u32 slot_byte = best | (cur_player << 4);
-    path[plen] = blk;
-    pslot[plen] = (u8)slot_byte;
+    if (plen >= (u32)kPathRegs) {  // the first kPathRegs levels reach HBM in ctx_store only
+      path[plen] = blk;
+      pslot[plen] = (u8)slot_byte;
+    }
 #pragma unroll
     for (int i = 0; i < kPathRegs; ++i)
       if (plen == (u32)i) pr.blk[i] = blk;
@@ -335,19 +343,13 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
       nb = tree_alloc_block(E, T);
       if (nb != kNil) {
         Block* N = E.blocks + nb;
-        Sec z, f, m;
+        const V4 z = mk_v4(0u, 0u, 0u, 0u), f = mk_v4(kNil, kNil, kNil, kNil);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { z.w[j] = 0u; f.w[j] = kNil; }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const u32 lo = (u32)(2 * j) < kk ? ((moves >> (8u * j)) & 15u) : 0u;
-          const u32 hi = (u32)(2 * j + 1) < kk ? ((moves >> (8u * j + 4u)) & 15u) : 0u;
-          m.w[j] = lo | (hi << 16);
-        }
-        m.w[4] = m.w[5] = 0u;       // term[8]
-        m.w[6] = 0u;                // v: written by the first backprop through this node
-        m.w[7] = kk | ((u32)s.player << 8);
-        st_sec(N->n, z); st_sec(N->q, z); st_sec(N->pol, z); st_sec(N->fc, f); st_sec(N->d, z); st_sec(N->mix, m);
+        for (int j = 0; j < kKMax; ++j) st_v4(N->rec[j], z);
+        st_v4(&N->fc[0], f);
+        st_v4(&N->fc[4], f);
+        // moves (already nibble-packed in child order), no terminal codes yet, v by the first backprop
+        st_v4(&N->mv, mk_v4(kk >= 7u ? moves : (moves & ((1u << (4u * kk)) - 1u)), 0u, 0u, kk | ((u32)s.player << 8)));
       }
     }
     const u32 k_eff = (nb == kNil) ? 0u : kk;
@@ -356,7 +358,7 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
     } else {
       Block* Pb = E.blocks + par_blk;
       Pb->fc[par_slot] = nb;
-      if (term) Pb->mix[4u + (par_slot >> 2)] |= term << (8u * (par_slot & 3u));  // was 0 (unknown)
+      if (term) Pb->term |= term << (2u * par_slot);  // was 0 (unknown)
     }
     T.leaf_term = (u8)term;
     T.leaf_k = (u8)k_eff;
@@ -455,26 +457,26 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
     val1 = (lterm == 2) ? 1.0f : 0.0f;
     vald = (lterm == 3) ? 1.0f : 0.0f;
   } else {
-    Sec ps;  // the leaf's child priors, child order
+    u32 ps[kKMax];  // the leaf's child priors (f32 bits), child order
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ps.w[j] = 0u;
+    for (int j = 0; j < kKMax; ++j) ps[j] = 0u;
     if (E.eval_type == 1) {  // dumb_eval (game_state.h:160-173): uniform over the legal moves, value 1/3
       const float third = (float)(1.0 / 3.0);
       val0 = val1 = vald = third;
       // every legal move is a child here, so Vector<uint8_t>::sum() == lk
       const float p = fdiv(1.0f, (float)lk);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if ((u32)j < lk) ps.w[j] = f2u(p);
+      for (int j = 0; j < kKMax; ++j)
+        if ((u32)j < lk) ps[j] = f2u(p);
     } else {
       const float* vrow = E.ev_v + (size_t)gs.eval_row * (kP + 1);
       const float* prow = E.ev_pi + (size_t)gs.eval_row * kA;
       val0 = vrow[0]; val1 = vrow[1]; vald = vrow[2];
       if (lk > 0) {
-        const Sec sm = ld_sec((E.blocks + lblk)->mix);
+        const u32 mvs = (E.blocks + lblk)->mv;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if ((u32)j < lk) ps.w[j] = f2u(prow[mix_mv(sm, j)]);
+        for (int j = 0; j < kKMax; ++j)
+          if ((u32)j < lk) ps[j] = f2u(prow[(mvs >> (4 * j)) & 15u]);
       }
     }
     if (plen == 0) {  // the leaf is the root: temperature + Dirichlet noise (cold)
@@ -482,21 +484,26 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
       float p8[kKMax];
       Pcg32 r = rng;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) p8[j] = u2f(ps.w[j]);
+      for (int j = 0; j < kKMax; ++j) p8[j] = u2f(ps[j]);
       root_leaf_priors(E, r, p8, lk, noise_enabled);
       rng = r;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ps.w[j] = ((u32)j < lk) ? f2u(p8[j]) : 0u;
+      for (int j = 0; j < kKMax; ++j) ps[j] = ((u32)j < lk) ? f2u(p8[j]) : 0u;
     } else {  // set_policy_normalized (mcts.cc:109-121), interior node: no temperature
       float sum = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if ((u32)j < lk) sum = fadd(sum, u2f(ps.w[j]));
+      for (int j = 0; j < kKMax; ++j)
+        if ((u32)j < lk) sum = fadd(sum, u2f(ps[j]));
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if ((u32)j < lk) ps.w[j] = f2u(fdiv(u2f(ps.w[j]), sum));
+      for (int j = 0; j < kKMax; ++j)
+        if ((u32)j < lk) ps[j] = f2u(fdiv(u2f(ps[j]), sum));
     }
-    if (lk > 0) st_sec((E.blocks + lblk)->pol, ps);
+    if (lk > 0) {  // the leaf was never visited: its records are {n 0, q 0, pol, d 0}
+      Block* L = E.blocks + lblk;
+#pragma unroll
+      for (int j = 0; j < kKMax; ++j)
+        if ((u32)j < lk) st_v4(L->rec[j], mk_v4(0u, 0u, ps[j], 0u));
+    }
   }
   // backprop (mcts.cc:527-545): level i updates the child slot selected at level i. The levels touch
   // different blocks, so their loads are issued together (4 levels at a time) instead of one dependent
@@ -511,7 +518,8 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
 #endif
   pr.valid = 0;
   for (u32 base = 0; base < plen; base += 4u) {
-    u32 bi[4], sb[4], nc[4], qb[4], db[4];
+    u32 bi[4], sb[4];
+    V4 rc[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const u32 i = base + (u32)t;
@@ -533,14 +541,8 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      nc[t] = qb[t] = db[t] = 0;
-      if (bi[t] != kNil) {
-        const Block* B = E.blocks + bi[t];
-        const u32 sl = sb[t] & 15u;
-        nc[t] = B->n[sl];
-        qb[t] = B->q[sl];
-        db[t] = B->d[sl];
-      }
+      rc[t] = mk_v4(0u, 0u, 0u, 0u);
+      if (bi[t] != kNil) rc[t] = ld_v4((E.blocks + bi[t])->rec[sb[t] & 15u]);
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -548,14 +550,14 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
       Block* B = E.blocks + bi[t];
       const u32 sl = sb[t] & 15u, pp = sb[t] >> 4;
       const float v = fadd(pp == 0 ? val0 : val1, dshare);
-      const u32 n0 = nc[t];
-      const float qc = n0 ? u2f(qb[t]) : 0.0f;
-      const float dc = n0 ? u2f(db[t]) : 0.0f;
-      B->q[sl] = f2u(fdiv(fadd(fmul(qc, (float)n0), v), (float)(n0 + 1u)));
-      B->d[sl] = f2u(fdiv(fadd(fmul(dc, (float)n0), vald), (float)(n0 + 1u)));
-      B->n[sl] = n0 + 1u;
+      const u32 n0 = rc[t].x;
+      const float qc = n0 ? u2f(rc[t].y) : 0.0f;
+      const float dc = n0 ? u2f(rc[t].w) : 0.0f;
+      const float qn = fdiv(fadd(fmul(qc, (float)n0), v), (float)(n0 + 1u));
+      const float dn = fdiv(fadd(fmul(dc, (float)n0), vald), (float)(n0 + 1u));
+      st_v4(B->rec[sl], mk_v4(n0 + 1u, f2u(qn), rc[t].z, f2u(dn)));
       // first visit of the node (only the leaf can be new): node.v from its own seat (mcts.cc:538-542)
-      if (n0 == 0 && lblk != kNil) (E.blocks + lblk)->mix[6] = f2u(fadd(lplayer == 0 ? val0 : val1, dshare));
+      if (n0 == 0 && lblk != kNil) (E.blocks + lblk)->v = f2u(fadd(lplayer == 0 ? val0 : val1, dshare));
     }
   }
   if (T.n == 0) {
@@ -583,7 +585,7 @@ AZ_HD void root_view(const EngineView& E, const TreeHdr& T, RootView& R) {
   if (T.k > 0 && T.fc != kNil) {
     const Block* B = E.blocks + T.fc;
     for (u32 j = 0; j < (u32)kKMax; ++j) {
-      R.mv[j] = blk_mv(B, j); R.n[j] = B->n[j]; R.pol[j] = u2f(B->pol[j]); R.q[j] = u2f(B->q[j]); R.d[j] = u2f(B->d[j]);
+      R.mv[j] = blk_mv(B, j); R.n[j] = blk_n(B, j); R.pol[j] = blk_pol(B, j); R.q[j] = blk_q(B, j); R.d[j] = blk_d(B, j);
     }
   }
 }
@@ -720,12 +722,7 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
   arena_clear(A);
   const u32 root_new = tree_alloc_block(E, A);
   if (root_new == kNil) return;
-  {
-    const Block* S = E.blocks + T.fc;
-    Block* D = E.blocks + root_new;
-    st_sec(D->n, ld_sec(S->n)); st_sec(D->q, ld_sec(S->q)); st_sec(D->pol, ld_sec(S->pol));
-    st_sec(D->fc, ld_sec(S->fc)); st_sec(D->d, ld_sec(S->d)); st_sec(D->mix, ld_sec(S->mix));
-  }
+  blk_copy(E.blocks + root_new, E.blocks + T.fc);
   u32 scan_page = A.first_page, scan_off = 0;
   bool failed = false;
   for (;;) {
@@ -736,17 +733,13 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
       continue;
     }
     Block* B = E.blocks + ((scan_page << kPageLog2) + scan_off);
-    Sec f = ld_sec(B->fc);
 #pragma unroll 1
     for (int j = 0; j < kKMax; ++j) {
-      const u32 src = f.w[j];
+      const u32 src = B->fc[j];
       if (src == kNil) continue;
       const u32 dst = tree_alloc_block(E, A);
       if (dst == kNil) { failed = true; break; }
-      const Block* S = E.blocks + src;
-      Block* D = E.blocks + dst;
-      st_sec(D->n, ld_sec(S->n)); st_sec(D->q, ld_sec(S->q)); st_sec(D->pol, ld_sec(S->pol));
-      st_sec(D->fc, ld_sec(S->fc)); st_sec(D->d, ld_sec(S->d)); st_sec(D->mix, ld_sec(S->mix));
+      blk_copy(E.blocks + dst, E.blocks + src);
       B->fc[j] = dst;
     }
     if (failed) break;
@@ -795,8 +788,8 @@ AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_befor
     return;
   }
   // the chosen child becomes the root (Node tmp = std::move(*x); root_ = std::move(tmp))
-  const u32 cn = B->n[ci];
-  const float cpol = u2f(B->pol[ci]);
+  const u32 cn = blk_n(B, (u32)ci);
+  const float cpol = blk_pol(B, (u32)ci);
   if (cn == 0) {  // never visited: a fresh root that only keeps its prior and move; nothing stays live
     tree_free_pages(E, T);
     tree_reset(T);
@@ -805,8 +798,8 @@ AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_befor
     return;
   }
   const u32 cfc = B->fc[ci];
-  T.q = u2f(B->q[ci]);
-  T.d = u2f(B->d[ci]);
+  T.q = blk_q(B, (u32)ci);
+  T.d = blk_d(B, (u32)ci);
   T.policy = cpol;
   T.n = cn;
   T.move = (u16)move;
@@ -847,6 +840,18 @@ AZ_HD void ctx_load(const EngineView& E, u32 g, Ctx& c) {
   c.pr.slots_lo = c.pr.slots_hi = 0;
 }
 AZ_HD void ctx_store(const EngineView& E, u32 g, Ctx& c) {
+  if (c.pr.valid) {  // the pending leaf's path: a later launch (or the move code) reads it from HBM
+    u32* path = E.path + (size_t)g * kMaxPath;
+    u8* pslot = E.pslot + (size_t)g * kMaxPath;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < kPathRegs; ++i)
+      if ((u32)i < (u32)c.T.path_len) {
+        path[i] = c.pr.blk[i];
+        pslot[i] = (u8)(((i < 4 ? c.pr.slots_lo : c.pr.slots_hi) >> (8 * (i & 3))) & 0xFFu);
+      }
+  }
   if (E.rng_mode == 1) E.glob->global_rng = c.rng; else c.gs.rng = c.rng;
   E.trees[(size_t)g * kP + c.gs.player] = c.T;
   E.games[g] = c.gs;
@@ -969,7 +974,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
       if (NT.n > 0 && NT.k > 0 && NT.fc != kNil) {
         Block* B = E.blocks + NT.fc;
         float p8[kKMax];
-        for (int j = 0; j < kKMax; ++j) p8[j] = u2f(B->pol[j]);
+        for (int j = 0; j < kKMax; ++j) p8[j] = blk_pol(B, (u32)j);
         bool changed = false;
         if (E.root_temp != 1.0f) {
           const float e = fdiv(1.0f, E.root_temp);
@@ -987,7 +992,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
           changed = true;
         }
         if (changed)
-          for (u32 j = 0; j < NT.k; ++j) B->pol[j] = f2u(p8[j]);
+          for (u32 j = 0; j < NT.k; ++j) B->rec[j][2] = f2u(p8[j]);
       }
     }
   }

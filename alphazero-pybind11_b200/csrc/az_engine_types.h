@@ -1,15 +1,16 @@
 // az_engine_types.h — device-resident data layout of the self-play pool.
 //
 // Layout in HBM (DESIGN.md "Data layout"):
-//   block pool    the unit of tree storage is the CHILD BLOCK of one expanded node: 192 B = six 32 B
-//                 sectors holding, for its (<= 8) children, n[8] | q[8] | pol[8] | fc[8] | d[8] and one
-//                 mixed sector (move u16[8], terminal code u8[8], and the OWNING node's v / k / player).
-//                 A PUCT step is therefore ONE independent burst of 5 sector loads (everything the
-//                 selection, the move replay and the next hop need), instead of the pointer chase
-//                 node -> children vector -> child -> its vector of the reference (mcts.h:14-48).
-//   pages         the pool is cut into pages of 64 blocks (12 KB); a tree owns a chain of pages and
-//                 bump-allocates blocks in its last page. Free pages travel as CHAINS through one
-//                 ticket ring (two atomicAdd tickets, no CAS loop): freeing a whole tree is O(1).
+//   block pool    the unit of tree storage is the CHILD BLOCK of one expanded node: 160 B = five 32 B
+//                 sectors holding, for its (<= 7) children, one 16 B record {n, q, pol, d} each, the
+//                 children's own block indices fc[7], and a 16 B header (moves as nibbles, terminal codes,
+//                 and the OWNING node's v / k / player). A PUCT step is therefore ONE independent burst of
+//                 ten 16 B loads (everything the selection, the move replay, the next hop AND the later
+//                 backprop need), instead of the pointer chase node -> children vector -> child -> its
+//                 vector of the reference (mcts.h:14-48); backprop dirties one sector per level.
+//   pages         the pool is cut into pages of 64 blocks (10 KB); a tree owns a chain of pages and
+//                 bump-allocates blocks in its last page. Free pages sit in one ticket ring (two
+//                 atomicAdd tickets, no CAS loop, no fence).
 //   trees         one 64 B TreeHdr per (game slot, seat): the root node's scalars live here
 //                 (reference: MCTS::root_, mcts.h:161) plus the pending leaf and the arena cursor.
 //                 Re-rooting (MCTS::update_root, mcts.cc:151-173) just re-points the header at the
@@ -32,21 +33,22 @@ constexpr int kMaxPath = 44;           // Connect4: at most 42 plies below any r
 constexpr int kMaxHist = 42;           // recorded moves per game
 constexpr int kA = 7;                  // Connect4 action count
 constexpr int kP = 2;                  // players
-constexpr int kKMax = 8;               // children per block
+constexpr int kKMax = 7;               // children per block (= Connect4 actions)
 
 // Every field is a 32-bit word (floats are stored as their bit patterns) so that scalar accesses and
-// the 16 B vector accesses of whole sectors are the same type for the compiler's alias analysis.
-struct __attribute__((aligned(32))) Block {
-  u32 n[kKMax];    // +0    visit counts                               (Node::n)
-  u32 q[kKMax];    // +32   f32 mean value from the parent's seat      (Node::q)
-  u32 pol[kKMax];  // +64   f32 priors                                 (Node::policy)
-  u32 fc[kKMax];   // +96   the child's OWN block, kNil while unexpanded / terminal
-  u32 d[kKMax];    // +128  f32 running mean of the draw share         (Node::d)
-  u32 mix[kKMax];  // +160  w0-3: move u16 x8 (Node::move); w4-5: terminal code u8 x8 (0 = not terminal /
-                   //       unknown, else 1 + one-hot score index, Node::scores); w6: f32 v of the node that
-                   //       OWNS this block (Node::v, set on its first visit); w7: k | player << 8 of that node
+// the 16 B vector accesses are the same type for the compiler's alias analysis.
+struct __attribute__((aligned(32))) Block {   // 160 B = five 32 B sectors, ten 16 B vectors
+  u32 rec[kKMax][4];  // +0    per child: n | q | pol | d  (Node::n, ::q, ::policy, ::d; f32 bit patterns).
+                      //       One 16 B vector per child: selection reads it, backprop rewrites it whole.
+  u32 fc[kKMax];      // +112  the child's OWN block, kNil while unexpanded / terminal
+  u32 pad_;           // +140
+  u32 mv;             // +144  move of child j in nibble j                       (Node::move)
+  u32 term;           // +148  terminal code of child j in bits 2j..2j+1: 0 = not terminal / unknown, else
+                      //       1 + one-hot score index                                (Node::scores)
+  u32 v;              // +152  f32 v of the node that OWNS this block (Node::v, set on its first visit)
+  u32 kp;             // +156  k | player << 8 of that node
 };
-static_assert(sizeof(Block) == 192, "Block must stay six 32 B sectors");
+static_assert(sizeof(Block) == 160, "Block must stay five 32 B sectors");
 
 struct __attribute__((aligned(16))) TreeHdr {
   // root node scalars (Node fields, mcts.h:18-26)
