@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
   Ctx c;
   ctx_load(E, g, c);
   if (!c.gs.active) return;
-  for (u32 s = 0; s < n_steps; ++s) game_step(E, g, c);
+  run_flat(E, g, c, n_steps);
   ctx_store(E, g, c);
 }
 __global__ void k_step_serial(EngineView E, u32 n_steps) {
@@ -590,14 +590,28 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
 #else
   // B2AZ_RNG_GLOBAL needs slot-major order inside a step (matches k_step_serial); per-game RNG is
   // order independent, so the same loop serves both.
-  for (u32 st = 0; st < n_steps; ++st)
+  // Test build only. Default: slot-major inside every step (the order of k_step_serial, and the one in
+  // which a single reference worker thread visits the slots). B2AZ_EMU_FLAT=1 runs the fused kernel's
+  // flattened loop game by game instead (what one GPU thread does), to exercise run_flat() on the CPU.
+  const char* flat = getenv("B2AZ_EMU_FLAT");
+  if (!(flat && flat[0] == '1' && V.rng_mode == B2AZ_RNG_PER_GAME && V.eval_type == B2AZ_EVAL_RANDOM)) {
+    for (u32 st = 0; st < n_steps; ++st)
+      for (u32 g = 0; g < V.G; ++g) {
+        Ctx c;
+        ctx_load(V, g, c);
+        if (!c.gs.active) continue;
+        game_step(V, g, c);
+        ctx_store(V, g, c);
+      }
+  } else {
     for (u32 g = 0; g < V.G; ++g) {
       Ctx c;
       ctx_load(V, g, c);
       if (!c.gs.active) continue;
-      game_step(V, g, c);
+      run_flat(V, g, c, n_steps);
       ctx_store(V, g, c);
     }
+  }
 #endif
   e->started = true;
   if (V.eval_type == B2AZ_EVAL_NN) {

@@ -27,6 +27,15 @@
 
 namespace b2az {
 
+// experiment knobs (profiles/): how many top levels of a tree are loaded with an L2 evict_last policy, and
+// whether deeper levels / fresh blocks use evict_first
+#ifndef B2AZ_L2_KEEP_LEVELS
+#define B2AZ_L2_KEEP_LEVELS 0
+#endif
+#ifndef B2AZ_L2_STREAM_DEEP
+#define B2AZ_L2_STREAM_DEEP 0
+#endif
+
 #define B2AZ_DEVERR_POOL 1u
 #define B2AZ_DEVERR_HIST 2u
 #define B2AZ_DEVERR_MOVE 4u
@@ -123,6 +132,50 @@ AZ_HD void st_v4(void* p, const V4& v) {
   *reinterpret_cast<uint4*>(p) = make_uint4(v.x, v.y, v.z, v.w);
 #else
   memcpy(p, &v, 16);
+#endif
+}
+// L2 residency hints (sm_80+: createpolicy + ld/st .L2::cache_hint). The top of every tree (root block and
+// its children's blocks: 8 x 160 B x 65,536 games = 84 MB) is touched by every simulation and fits the
+// 126 MB L2; deeper blocks are touched rarely and only pollute it.
+AZ_HD u64 l2_policy_keep() {
+#if defined(__CUDA_ARCH__)
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#else
+  return 0;
+#endif
+}
+AZ_HD u64 l2_policy_stream() {
+#if defined(__CUDA_ARCH__)
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#else
+  return 0;
+#endif
+}
+AZ_HD V4 ld_v4_hint(const void* p, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  V4 r;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return r;
+#else
+  (void)pol;
+  return ld_v4(p);
+#endif
+}
+AZ_HD void st_v4_hint(void* p, const V4& v, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(pol)
+               : "memory");
+#else
+  (void)pol;
+  st_v4(p, v);
 #endif
 }
 AZ_HD V4 mk_v4(u32 x, u32 y, u32 z, u32 w) {
@@ -250,83 +303,108 @@ struct PathRegs {
 // ------------------------------------------------------------------------------------ find_leaf
 // MCTS::find_leaf (mcts.cc:462-498), PUCT branch; Node::best_child (mcts.cc:130-149) and Node::uct
 // (mcts.cc:123-128) inlined. n_in_flight is always 0 on this path (the WU-UCT variant is not used by
-// PlayManager).
-AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32& rng, PathRegs& pr) {
-  C4State s;
-  s.p[0] = gs.p0; s.p[1] = gs.p1; s.turn = gs.turn; s.player = gs.player;
-  u32* path = E.path + (size_t)g * kMaxPath;
-  u8* pslot = E.pslot + (size_t)g * kMaxPath;
-  u32 blk = T.fc;
-  u32 cur_n = T.n, cur_term = T.term, cur_player = T.player;
-  float cur_v = T.v;
-  u32 cur_k = T.k;
-  bool at_root = true;
-  u32 par_blk = kNil, par_slot = 0;
-  u32 plen = 0;
+// PlayManager). Split in three pieces so that the fused kernel can run the descent ONE
+// LEVEL PER LOOP ITERATION for every game of a warp (run_flat below): begin / level / finish.
+struct Descent {
+  C4State s;          // the position replayed along the path
+  u32 blk;            // child block of the current node
+  u32 cur_n, cur_term, cur_player, cur_k;
+  float cur_v;
+  u32 par_blk, par_slot;
+  u32 plen;
+  bool at_root;
+};
+AZ_HD void descent_begin(const TreeHdr& T, const GameSlot& gs, Descent& D, PathRegs& pr) {
+  D.s.p[0] = gs.p0; D.s.p[1] = gs.p1; D.s.turn = gs.turn; D.s.player = gs.player;
+  D.blk = T.fc;
+  D.cur_n = T.n; D.cur_term = T.term; D.cur_player = T.player; D.cur_k = T.k;
+  D.cur_v = T.v;
+  D.at_root = true;
+  D.par_blk = kNil; D.par_slot = 0;
+  D.plen = 0;
   pr.slots_lo = pr.slots_hi = 0;
   pr.valid = 1;
-  while (cur_n > 0 && cur_term == 0) {
-    if (blk == kNil || plen >= (u32)kMaxPath) {  // cannot happen for a non-terminal Connect4 node
-      at_or(&E.glob->error, B2AZ_DEVERR_DEPTH);
-      break;
-    }
-    const Block* B = E.blocks + blk;
-    // one burst: everything this level (and its backprop) needs — ten independent 16 B loads
-    V4 r[kKMax];
+}
+AZ_HD bool descent_more(const Descent& D) { return D.cur_n > 0 && D.cur_term == 0; }
+// One level: load the node's child block, pick best_child, replay the move. Returns false on the
+// (impossible for Connect4) structural error, which ends the descent.
+AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
+  if (D.blk == kNil || D.plen >= (u32)kMaxPath) {  // cannot happen for a non-terminal Connect4 node
+    at_or(&E.glob->error, B2AZ_DEVERR_DEPTH);
+    return false;
+  }
+  const Block* B = E.blocks + D.blk;
+  // one burst: everything this level (and its backprop) needs — ten independent 16 B loads
+  V4 r[kKMax], f0, f1, hd;
+#if B2AZ_L2_KEEP_LEVELS > 0
+  if (D.plen < (u32)B2AZ_L2_KEEP_LEVELS) {
+    const u64 keep = l2_policy_keep();
+#pragma unroll
+    for (int j = 0; j < kKMax; ++j) r[j] = ld_v4_hint(B->rec[j], keep);
+    f0 = ld_v4_hint(&B->fc[0], keep); f1 = ld_v4_hint(&B->fc[4], keep); hd = ld_v4_hint(&B->mv, keep);
+  } else
+#endif
+  {
 #pragma unroll
     for (int j = 0; j < kKMax; ++j) r[j] = ld_v4(B->rec[j]);
-    const V4 f0 = ld_v4(&B->fc[0]), f1 = ld_v4(&B->fc[4]), hd = ld_v4(&B->mv);
-    if (!at_root) {
-      cur_v = u2f(hd.z);
-      cur_k = hd.w & 0xFFu;
-      cur_player = (hd.w >> 8) & 0xFFu;
-    }
-    const float fpu = (at_root && E.root_fpu_zero) ? 0.0f : E.fpu_reduction;
-    float seen = 0.0f;
-#pragma unroll
-    for (int j = 0; j < kKMax; ++j)
-      if ((u32)j < cur_k && r[j].x > 0) seen = fadd(seen, u2f(r[j].z));
-    const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
-    const float sqrt_n = fsqrt((float)cur_n);
-    u32 best = 0, best_n = 0, best_fc = kNil;
-    float best_u = 0.0f;
-#pragma unroll
-    for (int j = 0; j < kKMax; ++j) {
-      if (j > 0 && (u32)j >= cur_k) continue;  // pad slots: 0 / 1 would take the division's slow path
-      const u32 nj = r[j].x;
-      const float base = (nj == 0) ? fpu_value : u2f(r[j].y);
-      const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
-      if (j == 0 || u > best_u) {
-        best_u = u;
-        best = (u32)j;
-        best_n = nj;
-        best_fc = j == 0 ? f0.x : j == 1 ? f0.y : j == 2 ? f0.z : j == 3 ? f0.w : j == 4 ? f1.x : j == 5 ? f1.y : f1.z;
-      }
-    }
-    const u32 move = (hd.x >> (4u * best)) & 15u;
-    const u32 cterm = (hd.y >> (2u * best)) & 3u;
-    const u32 slot_byte = best | (cur_player << 4);
-    if (plen >= (u32)kPathRegs) {  // the first kPathRegs levels reach HBM in ctx_store only
-      path[plen] = blk;
-      pslot[plen] = (u8)slot_byte;
-    }
-#pragma unroll
-    for (int i = 0; i < kPathRegs; ++i)
-      if (plen == (u32)i) pr.blk[i] = blk;
-    if (plen < 4u) pr.slots_lo |= slot_byte << (8u * plen);
-    else if (plen < 8u) pr.slots_hi |= slot_byte << (8u * (plen - 4u));
-    ++plen;
-    c4_play(s, move);
-    par_blk = blk;
-    par_slot = best;
-    cur_n = best_n;
-    cur_term = cterm;
-    blk = best_fc;
-    at_root = false;
+    f0 = ld_v4(&B->fc[0]); f1 = ld_v4(&B->fc[4]); hd = ld_v4(&B->mv);
   }
-  T.total_leaf_depth += plen;
-  T.path_len = (u16)plen;
-  if (cur_n == 0) {
+  if (!D.at_root) {
+    D.cur_v = u2f(hd.z);
+    D.cur_k = hd.w & 0xFFu;
+    D.cur_player = (hd.w >> 8) & 0xFFu;
+  }
+  const float fpu = (D.at_root && E.root_fpu_zero) ? 0.0f : E.fpu_reduction;
+  float seen = 0.0f;
+#pragma unroll
+  for (int j = 0; j < kKMax; ++j)
+    if ((u32)j < D.cur_k && r[j].x > 0) seen = fadd(seen, u2f(r[j].z));
+  const float fpu_value = fsub(D.cur_v, fmul(fpu, fsqrt(seen)));
+  const float sqrt_n = fsqrt((float)D.cur_n);
+  u32 best = 0, best_n = 0, best_fc = kNil;
+  float best_u = 0.0f;
+#pragma unroll
+  for (int j = 0; j < kKMax; ++j) {
+    if (j > 0 && (u32)j >= D.cur_k) continue;  // pad slots: 0 / 1 would take the division's slow path
+    const u32 nj = r[j].x;
+    const float base = (nj == 0) ? fpu_value : u2f(r[j].y);
+    const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
+    if (j == 0 || u > best_u) {
+      best_u = u;
+      best = (u32)j;
+      best_n = nj;
+      best_fc = j == 0 ? f0.x : j == 1 ? f0.y : j == 2 ? f0.z : j == 3 ? f0.w : j == 4 ? f1.x : j == 5 ? f1.y : f1.z;
+    }
+  }
+  const u32 move = (hd.x >> (4u * best)) & 15u;
+  const u32 cterm = (hd.y >> (2u * best)) & 3u;
+  const u32 slot_byte = best | (D.cur_player << 4);
+  const u32 plen = D.plen;
+  if (plen >= (u32)kPathRegs) {  // the first kPathRegs levels reach HBM in ctx_store only
+    E.path[(size_t)g * kMaxPath + plen] = D.blk;
+    E.pslot[(size_t)g * kMaxPath + plen] = (u8)slot_byte;
+  }
+#pragma unroll
+  for (int i = 0; i < kPathRegs; ++i)
+    if (plen == (u32)i) pr.blk[i] = D.blk;
+  if (plen < 4u) pr.slots_lo |= slot_byte << (8u * plen);
+  else if (plen < 8u) pr.slots_hi |= slot_byte << (8u * (plen - 4u));
+  D.plen = plen + 1u;
+  c4_play(D.s, move);
+  D.par_blk = D.blk;
+  D.par_slot = best;
+  D.cur_n = best_n;
+  D.cur_term = cterm;
+  D.blk = best_fc;
+  D.at_root = false;
+  return true;
+}
+// The leaf: expansion of a new node (or a terminal node visited again), and the net's input row.
+AZ_HD void descent_finish(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32& rng, const Descent& D) {
+  const C4State& s = D.s;
+  T.total_leaf_depth += D.plen;
+  T.path_len = (u16)D.plen;
+  if (D.cur_n == 0) {
     // expand: current_->player, scores, add_children(valid_moves) incl. the shuffle (mcts.cc:490-496, 93-101)
     const u32 term = c4_terminal(s);
     const u32 vm = c4_valid_mask(s);
@@ -349,23 +427,23 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
         st_v4(&N->fc[0], f);
         st_v4(&N->fc[4], f);
         // moves (already nibble-packed in child order), no terminal codes yet, v by the first backprop
-        st_v4(&N->mv, mk_v4(kk >= 7u ? moves : (moves & ((1u << (4u * kk)) - 1u)), 0u, 0u, kk | ((u32)s.player << 8)));
+        st_v4(&N->mv, mk_v4(moves, 0u, 0u, kk | ((u32)s.player << 8)));
       }
     }
     const u32 k_eff = (nb == kNil) ? 0u : kk;
-    if (at_root) {
+    if (D.at_root) {
       T.player = s.player; T.term = (u8)term; T.fc = nb; T.k = (u8)k_eff;
     } else {
-      Block* Pb = E.blocks + par_blk;
-      Pb->fc[par_slot] = nb;
-      if (term) Pb->term |= term << (2u * par_slot);  // was 0 (unknown)
+      Block* Pb = E.blocks + D.par_blk;
+      Pb->fc[D.par_slot] = nb;
+      if (term) Pb->term |= term << (2u * D.par_slot);  // was 0 (unknown)
     }
     T.leaf_term = (u8)term;
     T.leaf_k = (u8)k_eff;
     T.leaf_player = s.player;
     T.leaf_blk = nb;
   } else {  // a terminal node visited again
-    T.leaf_term = (u8)cur_term;
+    T.leaf_term = (u8)D.cur_term;
     T.leaf_k = 0;
     T.leaf_player = s.player;
     T.leaf_blk = kNil;
@@ -390,6 +468,13 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
     E.leaf_game[row] = g;
     gs.eval_row = row;
   }
+}
+AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32& rng, PathRegs& pr) {
+  Descent D;
+  descent_begin(T, gs, D, pr);
+  while (descent_more(D))
+    if (!descent_level(E, g, D, pr)) break;
+  descent_finish(E, g, T, gs, rng, D);
 }
 
 // ------------------------------------------------------------------------------------ root priors (cold)
@@ -1024,6 +1109,45 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
     c.gs.capped = 0;
   }
   if (!retired) find_leaf(E, g, c.T, c.gs, c.rng, c.pr);
+}
+
+// n_steps iterations of game_step() for ONE slot with the two nested loops (steps x tree levels)
+// flattened into a single loop that advances the game by one tree level per iteration. In a warp of 32
+// independent games every iteration then holds exactly one block-load wait for EVERY game, instead of
+// the warp idling until its deepest descent is done (measured: mean path 3, deepest of 32 about 7).
+// The per-game order of operations — hence every result — is the one of game_step().
+AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
+  Descent D;
+  bool in_descent = false;
+  u32 left = n_steps;
+  while (left > 0) {
+    if (!in_descent) {  // step boundary: finish the previous simulation, maybe play a move, start a descent
+      if (!c.gs.active) break;
+      bool retired = false;
+      if (c.gs.initialized) {
+        const u32 cp = c.gs.player;
+        const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
+        process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
+        ++c.sims;
+        const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
+        if (c.T.depth >= goal) {
+          ctx_store(E, g, c);
+          retired = play_move(E, g);
+          ctx_load(E, g, c);
+        }
+      } else {
+        c.gs.initialized = 1;
+        c.gs.capped = 0;
+      }
+      if (retired) break;
+      descent_begin(c.T, c.gs, D, c.pr);
+      in_descent = true;
+    }
+    if (descent_more(D) && descent_level(E, g, D, c.pr)) continue;
+    descent_finish(E, g, c.T, c.gs, c.rng, D);
+    in_descent = false;
+    --left;
+  }
 }
 
 }  // namespace b2az

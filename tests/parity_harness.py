@@ -377,13 +377,14 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
 
 
 def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port", rng_mode=None, level=0,
-                      tree_reuse=True, lanes=0, chunk=64, steps=None, compact_pages=0, pool_nodes=0):
+                      tree_reuse=True, lanes=0, chunk=64, steps=None, compact_pages=0, pool_nodes=0, ordered=None):
     """RANDOM-eval run (EvalType::RANDOM, the reference's own fake backend: play_manager_test.cc): the engine
     fuses `chunk` loop iterations per launch; the oracle plays to the end; final scores, metrics and the
     training samples must agree."""
     if rng_mode is None:
         rng_mode = b2az.RNG_GLOBAL if oracle == "ref" else b2az.RNG_PER_GAME
-    ordered = rng_mode == b2az.RNG_GLOBAL or engine_lib is not None
+    if ordered is None:
+        ordered = rng_mode == b2az.RNG_GLOBAL or engine_lib is not None
     kw = level_params(level)
     eng = make_engine(engine_lib, G, games_to_play, visits, b2az.EVAL_RANDOM, rng_mode, seed, tree_reuse=tree_reuse,
                       lanes=lanes, history_capacity=max(1 << 16, games_to_play * 42), compact_pages=compact_pages,

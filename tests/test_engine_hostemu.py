@@ -86,6 +86,17 @@ def test_compaction_threshold_does_not_change_results(compact_pages):
         assert r["compactions"] == 0
 
 
+@pytest.mark.parametrize("chunk", [1, 7, 400])
+def test_flattened_loop_matches_port(chunk, monkeypatch):
+    """run_flat() — the fused kernel's one-tree-level-per-iteration loop — run game by game on the CPU
+    (B2AZ_EMU_FLAT=1) must produce what the step-by-step loop produces. No slot retires, so the comparison is
+    order independent."""
+    monkeypatch.setenv("B2AZ_EMU_FLAT", "1")
+    r = ph.run_random_parity(EMU, G=24, games_to_play=10 ** 6, visits=60, seed=77, oracle="port",
+                             rng_mode=b2az.RNG_PER_GAME, level=1, chunk=chunk, steps=1200, ordered=False)
+    assert r["games"] > 5 and r["samples"] > 100
+
+
 def test_pool_exhaustion_is_reported():
     lib = b2az.load(EMU)
     p = b2az.default_params(lib, games_to_play=8, concurrent_games=8, mcts_visits=(400, 400), eval_type=b2az.EVAL_NN,
