@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--games", type=int, default=65536, help="concurrent games per GPU")
     ap.add_argument("--gens", type=int, default=400, help="loop iterations per game slot per step (one launch)")
     ap.add_argument("--preroll", type=int, default=24, help="untimed moves per game before warm-up (steady state)")
-    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0, help="threads per game slot (0/1: one thread per game)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -388,12 +388,14 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
-        traffic = prof.get("dram_bytes_per_launch")
+        traffic = prof["dram_bytes_per_simulation"] * G * gens  # per launch, like `achieved`
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_step", "bytes_per_sim": bps, "avg_leaf_depth": depth,
-                "avg_children": kids, "launch_ms": launch_ms,
+                "avg_children": kids, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": bps * G * gens,
+                "note": "latency bound, not bandwidth bound: one dependent block load per tree level per simulation "
+                        "(DESIGN.md 3); tensor cores unused by design",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

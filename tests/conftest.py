@@ -30,6 +30,7 @@ def native_build():
     ge.build_oracle()
     if not os.path.exists(ge.LIB):
         ge.build_cuda()
+    ge.build_pybind()
     return ge
 
 
