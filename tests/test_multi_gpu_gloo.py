@@ -1,0 +1,90 @@
+"""The N>1 path on CPU: two processes (gloo), each with its own pool of games on the host-emulation build of the
+engine, sharded / reduced / gathered with b2az.dist exactly the way bench.py and a multi-GPU self-play run do it
+with NCCL. Checks: the shards cover the budget, the reduced statistics equal a single-process run of the same
+games, and rank 0 receives every training sample."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import b2az
+import parity_harness as ph
+from b2az import dist as bd
+
+WORKER = r"""
+import os, sys, json
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["B2AZ_PKG"]); sys.path.insert(0, os.environ["B2AZ_TESTS"])
+import b2az, parity_harness as ph
+from b2az import dist as bd
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lib = b2az.load(ph.HOSTEMU_LIB)
+base = b2az.default_params(lib, games_to_play=22, concurrent_games=10, mcts_visits=(24, 24), eval_type=b2az.EVAL_RANDOM,
+                           rng_mode=b2az.RNG_GLOBAL, seed=100, history_enabled=1, self_play=1, **ph.level_params(1))
+p = bd.shard_params(base, rank, world)
+p.seed = 100 + rank  # the single-process check below replays exactly these two pools
+e = b2az.Engine(p, lib=lib)
+while e.stats().active_games:
+    e.step(32)
+st = e.stats()
+red = bd.allreduce_stats(st)
+hist = e.drain_history(1 << 16)
+got = bd.gather_history(*hist)
+tmax = bd.max_over_ranks(rank + 1.5)
+if rank == 0:
+    c, v, pi = [x.numpy() for x in got]
+    np.savez(os.environ["B2AZ_OUT"], canon=c, v=v, pi=pi)
+    print(json.dumps({"red": red, "tmax": tmax, "local_games": [p.games_to_play, p.concurrent_games]}))
+dist.destroy_process_group()
+"""
+
+
+def test_shard_games_covers_the_budget():
+    for total, world in [(22, 2), (65536, 8), (7, 8), (100, 3)]:
+        spans = [bd.shard_games(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_run_matches_single_process(tmp_path):
+    out = tmp_path / "hist.npz"
+    env = dict(os.environ, B2AZ_PKG=os.path.join(ph.ROOT, "alphazero-pybind11_b200"), B2AZ_TESTS=os.path.join(ph.ROOT, "tests"),
+               B2AZ_OUT=str(out), MASTER_ADDR="127.0.0.1")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29731", str(script)], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["tmax"] == 2.5 and res["local_games"] == [11, 5]
+    # the same two pools in this process
+    lib = b2az.load(ph.HOSTEMU_LIB)
+    tot = dict(sims=0, moves=0, games=0, scores=np.zeros(3), hist=[])
+    for rank in range(2):
+        p = b2az.default_params(lib, games_to_play=11, concurrent_games=5, mcts_visits=(24, 24), eval_type=b2az.EVAL_RANDOM,
+                                rng_mode=b2az.RNG_GLOBAL, seed=100 + rank, history_enabled=1, self_play=1, **ph.level_params(1))
+        e = b2az.Engine(p, lib=lib)
+        while e.stats().active_games:
+            e.step(32)
+        st = e.stats()
+        tot["sims"] += st.simulations; tot["moves"] += st.moves; tot["games"] += st.games_completed
+        tot["scores"] += np.array(st.scores[:])
+        tot["hist"].append(e.drain_history(1 << 16))
+        e.close()
+    red = res["red"]
+    assert (red["simulations"], red["moves"], red["games_completed"]) == (tot["sims"], tot["moves"], tot["games"]) and tot["games"] == 22
+    assert red["scores"] == tot["scores"].tolist() and red["active_games"] == 0
+    got = np.load(out)
+    want = [np.concatenate([h[i] for h in tot["hist"]]) for i in range(3)]
+    assert np.array_equal(got["canon"], want[0]) and np.array_equal(got["v"], want[1])
+    assert np.array_equal(got["pi"].view(np.uint32), want[2].view(np.uint32))
