@@ -190,6 +190,13 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
   run_flat(E, g, c, n_steps);
   ctx_store(E, g, c);
 }
+// update_inferences' cache half (play_manager.cc:619-642: insert_many of every evaluated leaf), as its own
+// launch BEFORE the step kernel: during k_step the table is then read-only (plus frequency bumps), so lookups
+// need neither fences nor locks.
+__global__ void k_cache_insert(EngineView E, u32 count) {
+  for (u32 r = GLOBAL_TID; r < count; r += GLOBAL_NT)
+    cache_insert(E, E.leaf_key[r], E.ev_v + (size_t)r * (kP + 1), E.ev_pi + (size_t)r * kA);
+}
 __global__ void k_step_serial(EngineView E, u32 n_steps) {
   for (u32 s = 0; s < n_steps; ++s)
     for (u32 g = 0; g < E.G; ++g) {
@@ -429,6 +436,8 @@ int b2az_destroy(b2az_engine* e) {
   dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot);
   dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game);
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
+  dev_free(V.cache_keys); dev_free(V.cache_meta); dev_free(V.cache_lock); dev_free(V.cache_vals);
+  dev_free(V.cache_ghost); dev_free(V.leaf_key); dev_free(V.hit_val);
   dev_free(e->canon_buf); dev_free(e->ev_v_buf); dev_free(e->ev_pi_buf);
   dev_free(e->peek_buf); dev_free(e->stats_buf); dev_free(e->freepages_buf);
   dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
@@ -450,7 +459,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->playout_cap_randomization) return fail(B2AZ_EINVAL, "playout_cap_randomization is not implemented yet");
   if (p->eval_type != B2AZ_EVAL_NN && p->eval_type != B2AZ_EVAL_RANDOM) return fail(B2AZ_EINVAL, "bad eval_type");
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
-  if (p->max_cache_size != 0) return fail(B2AZ_EINVAL, "the device position cache is not implemented yet");
+  if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
+    return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
   if (p->lanes_per_game > 1)
     return fail(B2AZ_EINVAL, "lanes_per_game must be 0 or 1: Connect4 runs one thread per game slot (DESIGN.md 3)");
 #ifdef B2AZ_HOST_EMU
@@ -519,6 +529,18 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   A(dev_alloc(&V.hist_partial, p->history_enabled ? (size_t)G * kMaxHist : 1));
   A(dev_alloc(&V.hist_out, p->history_enabled ? (size_t)V.hist_capacity : 1));
   A(dev_alloc(&V.glob, 1));
+  if (p->max_cache_size != 0 && p->eval_type == B2AZ_EVAL_NN) {
+    // per-model-group cache of max_cache_size entries, ghost set of 9/10 of that (play_manager.cc:195-203)
+    V.cache_buckets = std::max<u32>(1u, (p->max_cache_size + kCacheWays - 1) / kCacheWays);
+    V.cache_ghost_slots = std::max<u32>(1u, (u32)((u64)p->max_cache_size * 9ull / 10ull));
+    A(dev_alloc(&V.cache_keys, (size_t)V.cache_buckets * kCacheWays));
+    A(dev_alloc(&V.cache_meta, (size_t)V.cache_buckets));
+    A(dev_alloc(&V.cache_lock, (size_t)V.cache_buckets));
+    A(dev_alloc(&V.cache_vals, (size_t)V.cache_buckets * kCacheWays));
+    A(dev_alloc(&V.cache_ghost, (size_t)V.cache_ghost_slots));
+    A(dev_alloc(&V.leaf_key, (size_t)G));
+    A(dev_alloc(&V.hit_val, (size_t)G));
+  }
   A(dev_alloc(&e->canon_buf, (size_t)G * C4_CANON));
   A(dev_alloc(&e->ev_v_buf, (size_t)G * (kP + 1))); A(dev_alloc(&e->ev_pi_buf, (size_t)G * kA));
   A(dev_alloc(&e->peek_buf, 1)); A(dev_alloc(&e->stats_buf, 1)); A(dev_alloc(&e->freepages_buf, 1));
@@ -527,6 +549,13 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.ev_pi = e->ev_pi_buf;
 
   // ---- init
+  if (V.hit_val) {
+#ifndef B2AZ_HOST_EMU
+    CUDA_TRY(cudaMemset(V.hit_val, 0xFF, (size_t)G * sizeof(u32)));
+#else
+    memset(V.hit_val, 0xFF, (size_t)G * sizeof(u32));
+#endif
+  }
 #ifndef B2AZ_HOST_EMU
   InitArgs ia{p->seed, p->rng_mode};
   k_init_pool<<<e->num_sms * 4, 256>>>(V);
@@ -574,6 +603,16 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
       if (e->evals_submitted < e->leaf_count)
         return fail(B2AZ_ESTATE, "b2az_step: leaves of the previous step are still waiting for b2az_submit_eval");
     }
+    if (V.cache_buckets && e->leaves_pending && e->leaf_count > 0) {
+      // the evaluations of the previous generation enter the cache before anybody looks anything up
+#ifndef B2AZ_HOST_EMU
+      k_cache_insert<<<std::max(1u, std::min((e->leaf_count + 127u) / 128u, (u32)e->num_sms * 8u)), 128, 0, s>>>(V, e->leaf_count);
+      CUDA_TRY(cudaGetLastError());
+#else
+      for (u32 r = 0; r < e->leaf_count; ++r)
+        cache_insert(V, V.leaf_key[r], V.ev_v + (size_t)r * (kP + 1), V.ev_pi + (size_t)r * kA);
+#endif
+    }
     if (int rc = dev_zero(&V.glob->leaf_count, sizeof(u32), s)) return rc;
   }
 #ifndef B2AZ_HOST_EMU
@@ -594,7 +633,7 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
   // which a single reference worker thread visits the slots). B2AZ_EMU_FLAT=1 runs the fused kernel's
   // flattened loop game by game instead (what one GPU thread does), to exercise run_flat() on the CPU.
   const char* flat = getenv("B2AZ_EMU_FLAT");
-  if (!(flat && flat[0] == '1' && V.rng_mode == B2AZ_RNG_PER_GAME && V.eval_type == B2AZ_EVAL_RANDOM)) {
+  if (!(flat && flat[0] == '1' && V.rng_mode == B2AZ_RNG_PER_GAME)) {
     for (u32 st = 0; st < n_steps; ++st)
       for (u32 g = 0; g < V.G; ++g) {
         Ctx c;
@@ -800,6 +839,9 @@ int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   out->pool_pages_free = free_pages;
   out->device_error = G.error;
   out->compactions = G.compactions;
+  out->cache_hits = G.cache_hits; out->cache_misses = G.cache_misses; out->cache_evictions = G.cache_evictions;
+  out->cache_reinserts = G.cache_reinserts; out->cache_size = G.cache_size;
+  out->cache_max_size = (unsigned long long)e->view.cache_buckets * kCacheWays;
   return 0;
 }
 

@@ -448,26 +448,150 @@ AZ_HD void descent_finish(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, 
     T.leaf_player = s.player;
     T.leaf_blk = kNil;
   }
-  if (E.eval_type == 0) {  // the net's input: the leaf position (compact; expanded by k_canonicalize)
-    u32 row;
-#if defined(__CUDA_ARCH__)
-    // leaf-batch compaction: one atomicAdd per warp, rows handed out by ballot rank
-    const unsigned active = __activemask();
-    const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(active) - 1;
-    u32 base = 0;
-    if ((int)lane == leader) base = atomicAdd(&E.glob->leaf_count, (u32)__popc(active));
-    base = __shfl_sync(active, base, leader);
-    row = base + (u32)__popc(active & ((1u << lane) - 1u));
-#else
-    row = at_add(&E.glob->leaf_count, 1u);
-#endif
-    E.leaf_p0[row] = s.p[0];
-    E.leaf_p1[row] = s.p[1];
-    E.leaf_player[row] = s.player;
-    E.leaf_game[row] = g;
-    gs.eval_row = row;
+}
+
+// ------------------------------------------------------------------------------------ position cache
+// Exact key of a (gravity-valid) Connect4 position: stones of player 0 + all stones is injective per column
+// (the classic position + mask encoding), the side to move goes in bit 63, and 0 stays "empty slot".
+AZ_HD u64 c4_cache_key(const C4State& s) { return ((s.p[0] + (s.p[0] | s.p[1]) + 1ULL) & 0x7FFFFFFFFFFFFFFFULL) | ((u64)s.player << 63); }
+AZ_HD u64 mix64(u64 x) {
+  x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL;
+  x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL;
+  x ^= x >> 33;
+  return x;
+}
+// S3FIFOCache::find (s3fifo_cache.h:41-60): returns the value index or kNil; counts hits / misses /
+// reinserts (a miss whose key sits in the ghost set); a hit bumps the 2-bit frequency.
+AZ_HD u32 cache_find(const EngineView& E, u64 key) {
+  const u64 h = mix64(key);
+  const u32 b = (u32)(h % (u64)E.cache_buckets);
+  const u64* K = E.cache_keys + (size_t)b * kCacheWays;
+  const V4 k01 = ld_v4(K), k23 = ld_v4(K + 2);
+  const u64 k0 = (u64)k01.x | ((u64)k01.y << 32), k1 = (u64)k01.z | ((u64)k01.w << 32);
+  const u64 k2 = (u64)k23.x | ((u64)k23.y << 32), k3 = (u64)k23.z | ((u64)k23.w << 32);
+  int way = -1;
+  if (k0 == key) way = 0;
+  else if (k1 == key) way = 1;
+  else if (k2 == key) way = 2;
+  else if (k3 == key) way = 3;
+  if (way < 0) {
+    at_add64(&E.glob->cache_misses, 1ULL);
+    if (E.cache_ghost_slots) {
+      const u32 fp = (u32)(h >> 32) | 1u;
+      if (E.cache_ghost[(u32)((h >> 20) % (u64)E.cache_ghost_slots)] == fp) at_add64(&E.glob->cache_reinserts, 1ULL);
+    }
+    return kNil;
   }
+  at_add64(&E.glob->cache_hits, 1ULL);
+  const u32 m = E.cache_meta[b];
+  if (((m >> (8 * way)) & 3u) < 3u) at_add(&E.cache_meta[b], 1u << (8 * way));  // freq saturates at 3 (:53)
+  return b * (u32)kCacheWays + (u32)way;
+}
+// S3FIFOCache::insert (s3fifo_cache.h:62-110) for one key, under the bucket's lock. Existing key: no-op.
+// New keys enter the "small" generation (main flag 0) unless the ghost set remembers them; the victim of a
+// full bucket is chosen S3-FIFO style: small entries that were never hit again go first, hit small entries
+// are promoted to main, main entries get second chances while their frequency lasts.
+AZ_HD void cache_insert(const EngineView& E, u64 key, const float* v, const float* pi) {
+  const u64 h = mix64(key);
+  const u32 b = (u32)(h % (u64)E.cache_buckets);
+  u64* K = E.cache_keys + (size_t)b * kCacheWays;
+#if defined(__CUDA_ARCH__)
+  bool locked = false;
+  for (u32 spin = 0; spin < 4096u; ++spin)
+    if (at_cas(&E.cache_lock[b], 0u, 1u) == 0u) { locked = true; break; }
+  if (!locked) return;  // best effort: a cache may always forget
+  mem_fence();
+#endif
+  u64 k[kCacheWays];
+  for (int w = 0; w < kCacheWays; ++w) k[w] = ld_volatile(&K[w]);
+  int way = -1;
+  bool present = false;
+  for (int w = 0; w < kCacheWays; ++w) {
+    if (k[w] == key) present = true;
+    if (k[w] == 0 && way < 0) way = w;
+  }
+  if (!present) {
+    u32 m = ld_volatile(&E.cache_meta[b]);
+    const u32 fp = (u32)(h >> 32) | 1u;
+    u32* ghost = E.cache_ghost_slots ? &E.cache_ghost[(u32)((h >> 20) % (u64)E.cache_ghost_slots)] : nullptr;
+    bool to_main = false;
+    if (ghost && ld_volatile(ghost) == fp) {  // ghost hit: admitted to Main (:86-104)
+      to_main = true;
+      st_volatile(ghost, 0u);
+    }
+    if (way < 0) {  // evict_one (:118-149)
+      for (int round = 0; round < 6 && way < 0; ++round) {
+        for (int w = 0; w < kCacheWays && way < 0; ++w) {  // the small generation first
+          const u32 mw = (m >> (8 * w)) & 0xFFu;
+          if (mw & 4u) continue;
+          if (mw & 3u) m = (m & ~(0xFFu << (8 * w))) | (4u << (8 * w));  // hit while small: promote, freq 0
+          else way = w;
+        }
+        for (int w = 0; w < kCacheWays && way < 0; ++w) {  // then Main with second chances
+          const u32 mw = (m >> (8 * w)) & 0xFFu;
+          if (!(mw & 4u)) continue;
+          if (mw & 3u) m -= 1u << (8 * w);
+          else way = w;
+        }
+      }
+      if (way < 0) way = (int)(h >> 60) & 3;
+      if (!(((m >> (8 * way)) & 4u)) && ghost) {  // evicted from Small: remember it in the ghost set
+        const u64 hv = mix64(k[way]);
+        E.cache_ghost[(u32)((hv >> 20) % (u64)E.cache_ghost_slots)] = (u32)(hv >> 32) | 1u;
+      }
+      at_add64(&E.glob->cache_evictions, 1ULL);
+    } else {
+      at_add64(&E.glob->cache_size, 1ULL);
+    }
+    CacheVal* V = E.cache_vals + (size_t)b * kCacheWays + way;
+    for (int i = 0; i < kA; ++i) V->pi[i] = pi[i];
+    for (int i = 0; i < kP + 1; ++i) V->v[i] = v[i];
+    m = (m & ~(0xFFu << (8 * way))) | ((to_main ? 4u : 0u) << (8 * way));
+    st_volatile(&E.cache_meta[b], m);
+    st_volatile(&K[way], key);
+  }
+#if defined(__CUDA_ARCH__)
+  mem_fence();
+  at_exch(&E.cache_lock[b], 0u);
+#endif
+}
+
+// What happens to a fresh leaf with the NN evaluator (play_manager.cc:586-598): look the position up in the
+// cache — every leaf, terminal ones included, like the reference — and on a miss put it into the leaf batch.
+// Returns true on a cache hit (the caller goes on with the next simulation right away).
+AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s, bool allow_hit) {
+  u64 key = 0;
+  if (E.cache_buckets) {
+    key = c4_cache_key(s);
+    const u32 hit = cache_find(E, key);
+    if (hit != kNil && allow_hit) {
+      E.hit_val[g] = hit;
+      return true;
+    }
+  }
+  u32 row;
+#if defined(__CUDA_ARCH__)
+  // leaf-batch compaction: one atomicAdd per warp, rows handed out by ballot rank
+  const unsigned active = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(active) - 1;
+  u32 base = 0;
+  if ((int)lane == leader) base = atomicAdd(&E.glob->leaf_count, (u32)__popc(active));
+  base = __shfl_sync(active, base, leader);
+  row = base + (u32)__popc(active & ((1u << lane) - 1u));
+#else
+  row = at_add(&E.glob->leaf_count, 1u);
+#endif
+  E.leaf_p0[row] = s.p[0];
+  E.leaf_p1[row] = s.p[1];
+  E.leaf_player[row] = s.player;
+  E.leaf_game[row] = g;
+  if (E.cache_buckets) {
+    E.leaf_key[row] = key;
+    E.hit_val[g] = kNil;
+  }
+  gs.eval_row = row;
+  return false;
 }
 AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32& rng, PathRegs& pr) {
   Descent D;
@@ -475,6 +599,7 @@ AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32
   while (descent_more(D))
     if (!descent_level(E, g, D, pr)) break;
   descent_finish(E, g, T, gs, rng, D);
+  if (E.eval_type == 0) leaf_emit(E, g, gs, D.s, /*allow_hit=*/false);
 }
 
 // ------------------------------------------------------------------------------------ root priors (cold)
@@ -556,6 +681,13 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
     } else {
       const float* vrow = E.ev_v + (size_t)gs.eval_row * (kP + 1);
       const float* prow = E.ev_pi + (size_t)gs.eval_row * kA;
+      if (E.cache_buckets) {  // a cache hit answers the leaf instead of the evaluation batch
+        const u32 hit = E.hit_val[g];
+        if (hit != kNil) {
+          vrow = E.cache_vals[hit].v;
+          prow = E.cache_vals[hit].pi;
+        }
+      }
       val0 = vrow[0]; val1 = vrow[1]; vald = vrow[2];
       if (lk > 0) {
         const u32 mvs = (E.blocks + lblk)->mv;
@@ -1119,7 +1251,7 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
 AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
   Descent D;
   bool in_descent = false;
-  u32 left = n_steps;
+  u32 left = n_steps, hits = 0;
   while (left > 0) {
     if (!in_descent) {  // step boundary: finish the previous simulation, maybe play a move, start a descent
       if (!c.gs.active) break;
@@ -1146,6 +1278,14 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
     if (descent_more(D) && descent_level(E, g, D, c.pr)) continue;
     descent_finish(E, g, c.T, c.gs, c.rng, D);
     in_descent = false;
+    if (E.eval_type == 0) {
+      // a cache hit is an answered leaf: go on with the next simulation in the same launch (the reference
+      // re-queues the game for MCTS at once, play_manager.cc:589-594); bounded so a launch stays short
+      if (leaf_emit(E, g, c.gs, D.s, hits < 64u)) {
+        ++hits;
+        continue;
+      }
+    }
     --left;
   }
 }

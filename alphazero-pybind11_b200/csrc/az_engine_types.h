@@ -106,6 +106,15 @@ struct __attribute__((aligned(16))) GameCold {  // touched once per move / per l
 };
 static_assert(sizeof(GameCold) == 64, "GameCold layout");
 
+// Position cache (replaces S3FIFOCache / ShardedS3FIFOCache, s3fifo_cache.h): 4-way set-associative, keyed by
+// an exact 64-bit encoding of the position (equality class of Connect4GS::hash, connect4_gs.cc:33-37).
+constexpr int kCacheWays = 4;
+struct __attribute__((aligned(8))) CacheVal {  // what a hit returns: pi[A] and v[P+1] (s3fifo_cache.h:41-60)
+  float pi[kA];
+  float v[kP + 1];
+};
+static_assert(sizeof(CacheVal) == 40, "CacheVal layout");
+
 struct Globals {
   unsigned long long simulations, moves, game_length;
   unsigned long long wins[3], resign_wins[3];
@@ -150,6 +159,15 @@ struct EngineView {
   u64* leaf_p1;
   u8* leaf_player;
   u32* leaf_game;
+  // ---- position cache (NULL / 0 when max_cache_size == 0)
+  u64* cache_keys;        // [buckets][kCacheWays]  0 = empty  (one 32 B sector per bucket)
+  u32* cache_meta;        // [buckets]  per way one byte: freq (bits 0-1) | main-queue flag (bit 2)
+  u32* cache_lock;        // [buckets]  insert-side spin lock
+  CacheVal* cache_vals;   // [buckets * kCacheWays]
+  u32* cache_ghost;       // [ghost_slots] fingerprints of keys evicted from the small queue
+  u32 cache_buckets, cache_ghost_slots;
+  u64* leaf_key;          // [G] cache key of every leaf row (insert after the evaluation)
+  u32* hit_val;           // [G] per game: index into cache_vals of a pending cache hit, kNil if none
   // ---- history
   HistEntry* hist_partial;  // [G][kMaxHist]
   HistEntry* hist_out;      // ring of hist_capacity

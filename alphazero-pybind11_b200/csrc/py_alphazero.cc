@@ -16,6 +16,7 @@
 //   update_inferences()  stores v/pi by row; the call that answers the last leaf submits the whole
 //                        generation to the device (b2az_submit_eval_host) and wakes the driver.
 //   build_history_batch  b2az_drain_history into the caller's arrays.
+// max_cache_size > 0 turns on the device position cache (the engine's replacement for ShardedS3FIFOCache).
 // Not carried (rejected with RuntimeError instead of being ignored): Gumbel, resign, playout-cap
 // randomisation, model groups / seat permutations / per-seat overrides, PLAYOUT eval, external caches.
 #include <pybind11/numpy.h>
@@ -245,7 +246,6 @@ class PlayManager {
     reject(P.gumbel_enabled || !P.seat_gumbel_enabled.empty(), "gumbel_enabled");
     reject(P.resign_percent != 0.0f || !P.seat_resign_threshold.empty(), "resign");
     reject(P.playout_cap_randomization, "playout_cap_randomization");
-    reject(P.max_cache_size != 0, "max_cache_size (the position cache)");
     reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
     reject(!P.seat_visits.empty() || !P.seat_cap_visits.empty() || !P.seat_epsilon.empty() ||
                !P.seat_mcts_root_temp.empty() || !P.seat_root_fpu_zero.empty(),
@@ -263,6 +263,7 @@ class PlayManager {
     bp.games_to_play = P.games_to_play;
     bp.concurrent_games = P.concurrent_games;
     bp.max_batch_size = P.max_batch_size;
+    bp.max_cache_size = P.max_cache_size;  // one model group: the whole budget (play_manager.cc:195-203)
     bp.mcts_visits[0] = P.mcts_visits[0];
     bp.mcts_visits[1] = P.mcts_visits[1];
     bp.cpuct = P.cpuct;

@@ -266,6 +266,20 @@ def test_small_batches_and_game_data_views(kind):
 
 
 @pytest.mark.parametrize("kind", kinds())
+def test_cache_counters_through_the_module(kind, monkeypatch):
+    """max_cache_size > 0: the reference's throughput counter (cache_hits + cache_misses, network_pareto.py:415-423)
+    equals the simulations, and hits answer leaves without the evaluator."""
+    monkeypatch.setenv("B2AZ_EMU_FLAT", "1")
+    az = module(kind)
+    p = _params(az, G=16, games=16, visits=32, level=1, seed=3, max_batch=16, deterministic=False)
+    p.max_cache_size = 50000
+    pm, gens = _run_pipeline(az, p, workers=1)
+    assert pm.games_completed() == 16
+    assert pm.cache_hits() > 0 and pm.cache_hits() + pm.cache_misses() == pm.simulations()
+    assert 0 < pm.cache_size() <= pm.cache_max_size() == 50000
+
+
+@pytest.mark.parametrize("kind", kinds())
 def test_random_eval_play_returns_when_done(kind):
     """EvalType.RANDOM: play() alone finishes the run (play_manager_test.cc); stop() ends it early."""
     az = module(kind)
