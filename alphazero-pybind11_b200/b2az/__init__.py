@@ -86,6 +86,8 @@ def load(path=None):
     L.b2az_leaf_batch_host.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32)]
     L.b2az_submit_eval.argtypes = [vp, vp, vp, u32]
     L.b2az_submit_eval_host.argtypes = [vp, vp, vp, vp, vp, u32]
+    L.b2az_leaf_batch_device.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.b2az_submit_eval_all.argtypes = [vp, vp, vp]
     L.b2az_drain_history.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
     L.b2az_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
@@ -169,6 +171,15 @@ class Engine:
         n = C.c_uint32()
         self._check(self.L.b2az_drain_history(self.h, stream, max_rows, canon_ptr, v_ptr, pi_ptr, 0, C.byref(n)))
         return n.value
+
+    # -- the same without any host synchronisation: (canon_ptr, ids_ptr, count_ptr), all DEVICE pointers
+    def leaf_batch_device(self, stream=None):
+        cp, ip, np_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.b2az_leaf_batch_device(self.h, stream, C.byref(cp), C.byref(ip), C.byref(np_)))
+        return cp.value, ip.value, np_.value
+
+    def submit_eval_all(self, v_dev_ptr, pi_dev_ptr):
+        self._check(self.L.b2az_submit_eval_all(self.h, v_dev_ptr, pi_dev_ptr))
 
     def submit_eval(self, v_dev_ptr, pi_dev_ptr, count):
         self._check(self.L.b2az_submit_eval(self.h, v_dev_ptr, pi_dev_ptr, count))

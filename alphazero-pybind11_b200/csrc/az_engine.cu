@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
 // update_inferences' cache half (play_manager.cc:619-642: insert_many of every evaluated leaf), as its own
 // launch BEFORE the step kernel: during k_step the table is then read-only (plus frequency bumps), so lookups
 // need neither fences nor locks.
-__global__ void k_cache_insert(EngineView E, u32 count) {
+__global__ void k_cache_insert(EngineView E) {
+  const u32 count = E.glob->leaf_count;  // still the previous generation's: the step zeroes it after this launch
   for (u32 r = GLOBAL_TID; r < count; r += GLOBAL_NT)
     cache_insert(E, E.leaf_key[r], E.ev_v + (size_t)r * (kP + 1), E.ev_pi + (size_t)r * kA);
 }
@@ -350,6 +351,7 @@ struct b2az_engine {
   bool canon_ready = false;
   u32 leaves_taken = 0;             // legacy build_batch cursor
   u32 evals_submitted = 0;
+  bool evals_all = false;           // b2az_submit_eval_all: the whole batch was answered on the device
   std::vector<u32> leaf_ids_host;   // slot id of every leaf row (for submit_eval_host)
   std::vector<u32> row_of_game;     // slot id -> row
   std::vector<float> stage_v, stage_pi;
@@ -455,8 +457,10 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->mcts_visits[0] == 0 || p->mcts_visits[1] == 0)
     return fail(B2AZ_EINVAL, "You must specify MCTS visits for each player");  // play_manager.cc:21
   if (p->gumbel_enabled) return fail(B2AZ_EINVAL, "gumbel_enabled is not implemented yet");
-  if (p->resign_percent != 0.0f) return fail(B2AZ_EINVAL, "resign_percent is not implemented yet");
-  if (p->playout_cap_randomization) return fail(B2AZ_EINVAL, "playout_cap_randomization is not implemented yet");
+  if ((p->resign_percent != 0.0f || p->playout_cap_randomization) && p->rng_mode == B2AZ_RNG_GLOBAL)
+    return fail(B2AZ_EINVAL, "resign_percent / playout_cap_randomization flip coins from an unseedable engine in the "
+                             "reference: not available in B2AZ_RNG_GLOBAL (parity) mode");
+  if (p->playout_cap_randomization && p->playout_cap_depth == 0) return fail(B2AZ_EINVAL, "playout_cap_depth must be > 0");
   if (p->eval_type != B2AZ_EVAL_NN && p->eval_type != B2AZ_EVAL_RANDOM) return fail(B2AZ_EINVAL, "bad eval_type");
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
   if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
@@ -492,7 +496,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.playout_cap_percent = p->playout_cap_percent;
   V.history_enabled = p->history_enabled; V.tree_reuse = p->tree_reuse; V.root_fpu_zero = p->root_fpu_zero;
   V.shaped_dirichlet = p->shaped_dirichlet; V.policy_target_pruning = p->policy_target_pruning;
-  V.playout_cap = 0; V.eval_type = p->eval_type; V.rng_mode = p->rng_mode;
+  V.playout_cap = p->playout_cap_randomization ? 1 : 0; V.eval_type = p->eval_type; V.rng_mode = p->rng_mode;
+  V.resign_percent = p->resign_percent; V.resign_playthrough_percent = p->resign_playthrough_percent;
 
   // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
   const u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
@@ -598,18 +603,18 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
   EngineView& V = e->view;
   if (V.eval_type == B2AZ_EVAL_NN) {
     if (n_steps != 1) return fail(B2AZ_EINVAL, "n_steps must be 1 with B2AZ_EVAL_NN");
-    if (e->leaves_pending) {
+    if (e->leaves_pending && !e->evals_all) {
       if (int rc = sync_leaf_count(e, s)) return rc;
       if (e->evals_submitted < e->leaf_count)
         return fail(B2AZ_ESTATE, "b2az_step: leaves of the previous step are still waiting for b2az_submit_eval");
     }
-    if (V.cache_buckets && e->leaves_pending && e->leaf_count > 0) {
+    if (V.cache_buckets && e->leaves_pending) {
       // the evaluations of the previous generation enter the cache before anybody looks anything up
 #ifndef B2AZ_HOST_EMU
-      k_cache_insert<<<std::max(1u, std::min((e->leaf_count + 127u) / 128u, (u32)e->num_sms * 8u)), 128, 0, s>>>(V, e->leaf_count);
+      k_cache_insert<<<std::max(1u, std::min((V.G + 127u) / 128u, (u32)e->num_sms * 8u)), 128, 0, s>>>(V);
       CUDA_TRY(cudaGetLastError());
 #else
-      for (u32 r = 0; r < e->leaf_count; ++r)
+      for (u32 r = 0; r < V.glob->leaf_count; ++r)
         cache_insert(V, V.leaf_key[r], V.ev_v + (size_t)r * (kP + 1), V.ev_pi + (size_t)r * kA);
 #endif
     }
@@ -659,6 +664,7 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
     e->canon_ready = false;
     e->leaves_taken = 0;
     e->evals_submitted = 0;
+    e->evals_all = false;
     V.ev_v = e->ev_v_buf;
     V.ev_pi = e->ev_pi_buf;
   }
@@ -715,6 +721,28 @@ int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, ui
   e->view.ev_v = v_dev;
   e->view.ev_pi = pi_dev;
   e->evals_submitted = count;
+  return 0;
+}
+
+int b2az_leaf_batch_device(b2az_engine* e, void* stream, const float** canon_dev, const uint32_t** ids_dev,
+                           const uint32_t** count_dev) {
+  if (!e) return fail(B2AZ_EINVAL, "null engine");
+  stream_t s = static_cast<stream_t>(stream);
+  if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
+  if (!e->leaves_pending) return fail(B2AZ_ESTATE, "call b2az_step first");
+  if (int rc = ensure_canon(e, s)) return rc;
+  if (canon_dev) *canon_dev = e->canon_buf;
+  if (ids_dev) *ids_dev = e->view.leaf_game;
+  if (count_dev) *count_dev = &e->view.glob->leaf_count;
+  return 0;
+}
+
+int b2az_submit_eval_all(b2az_engine* e, const float* v_dev, const float* pi_dev) {
+  if (!e || !v_dev || !pi_dev) return fail(B2AZ_EINVAL, "null argument");
+  if (!e->leaves_pending) return fail(B2AZ_ESTATE, "no leaf batch is waiting for evaluations");
+  e->view.ev_v = v_dev;
+  e->view.ev_pi = pi_dev;
+  e->evals_all = true;
   return 0;
 }
 

@@ -1097,6 +1097,22 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
   }
   RootView R;
   root_view(E, T[cp], R);
+  // resign_percent (play_manager.cc:305-337). The playthrough coin comes from the game's own stream (the
+  // reference uses an unseedable thread_local engine for it).
+  u32 resign_term = 0;
+  if (E.resign_percent > 0.0f && !gs.playthrough) {
+    float wld[3];
+    mcts_root_value(T[cp], R, wld);
+    const double resign_val = dsub(1.0, (double)E.resign_percent);
+    u32 t = 0;
+    if ((double)wld[0] > resign_val) t = cp + 1u;
+    else if ((double)wld[1] > resign_val) t = ((cp + 1u) % 2u) + 1u;
+    else if ((double)wld[2] > resign_val) t = (u32)kP + 1u;
+    if (t != 0) {
+      if (rng_uniform01(rng) < E.resign_playthrough_percent) gs.playthrough = 1;
+      else resign_term = t;
+    }
+  }
   float pi[kA];
   mcts_probs(R, temp, pi);
   u32 chosen = mcts_pick_move(rng, pi);
@@ -1133,7 +1149,9 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
   if (!c4_play(s, chosen)) at_or(&E.glob->error, B2AZ_DEVERR_MOVE);
   gs.p0 = s.p[0]; gs.p1 = s.p[1]; gs.turn = s.turn; gs.player = s.player;
   ++cold.nmoves;
-  const u32 term = c4_terminal(s);
+  u32 term = c4_terminal(s);
+  if (term == 0 && resign_term != 0) term = resign_term;  // play_manager.cc:440-444
+  else resign_term = 0;
   if (term != 0) {
     // ---- game over: flush history newest-first (:448-460), accumulate (:463-505), restart
     if (E.history_enabled && gs.hist_n > 0) {
@@ -1150,6 +1168,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     gs.hist_n = 0;
     Globals* G = E.glob;
     at_add64(&G->wins[term - 1u], 1ULL);
+    if (resign_term != 0) at_add64(&G->resign_wins[resign_term - 1u], 1ULL);
     at_add(&G->games_completed, 1u);
     at_add64(&G->game_length, (unsigned long long)gs.turn);
     at_addd(&G->total_avg_leaf_depth, cold.total_avg_leaf_depth);
@@ -1178,7 +1197,8 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     }
   }
   if (!retired) {
-    gs.capped = 0;  // playout-cap randomisation draws from an unseedable engine; not carried yet
+    // a move has been played: update the playout cap (play_manager.cc:523-524; `&&` short-circuits the draw)
+    gs.capped = (E.playout_cap && rng_uniform01(rng) < E.playout_cap_percent) ? 1 : 0;
     if (!E.tree_reuse) {
       for (int seat = 0; seat < kP; ++seat) {
         tree_free_pages(E, T[seat]);
@@ -1238,7 +1258,7 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
     }
   } else {
     c.gs.initialized = 1;
-    c.gs.capped = 0;
+    c.gs.capped = (E.playout_cap && rng_uniform01(c.rng) < E.playout_cap_percent) ? 1 : 0;  // play_manager.cc:559-560
   }
   if (!retired) find_leaf(E, g, c.T, c.gs, c.rng, c.pr);
 }
@@ -1269,7 +1289,7 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
         }
       } else {
         c.gs.initialized = 1;
-        c.gs.capped = 0;
+        c.gs.capped = (E.playout_cap && rng_uniform01(c.rng) < E.playout_cap_percent) ? 1 : 0;
       }
       if (retired) break;
       descent_begin(c.T, c.gs, D, c.pr);

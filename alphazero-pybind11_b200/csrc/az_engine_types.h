@@ -91,7 +91,8 @@ struct __attribute__((aligned(16))) GameSlot {  // hot: touched every simulation
   u32 eval_row;    // row of this game's leaf in the evaluation batch
   u32 hist_n;      // entries in partial_history
   u32 move_count, full_move_count, fast_move_count;
-  u32 pad_;
+  u8 playthrough;  // GameData::playthrough: set once, never cleared — like the reference (play_manager.cc:328-329)
+  u8 pad_[3];
   Pcg32 rng;       // per-game stream (B2AZ_RNG_PER_GAME)
 };
 static_assert(sizeof(GameSlot) == 64, "GameSlot must stay one 64 B record");
@@ -138,6 +139,7 @@ struct EngineView {
   u32 visits[2], cap_visits[2];
   float cpuct, fpu_reduction, epsilon, root_temp;
   float start_temp, final_temp, half_life, playout_cap_percent;
+  float resign_percent, resign_playthrough_percent;
   u8 history_enabled, tree_reuse, root_fpu_zero, shaped_dirichlet;
   u8 policy_target_pruning, playout_cap, eval_type, rng_mode;
   u32 num_pages, hist_capacity;

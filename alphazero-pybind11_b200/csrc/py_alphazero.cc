@@ -244,8 +244,7 @@ class PlayManager {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
     };
     reject(P.gumbel_enabled || !P.seat_gumbel_enabled.empty(), "gumbel_enabled");
-    reject(P.resign_percent != 0.0f || !P.seat_resign_threshold.empty(), "resign");
-    reject(P.playout_cap_randomization, "playout_cap_randomization");
+    reject(!P.seat_resign_threshold.empty(), "seat_resign_threshold");
     reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
     reject(!P.seat_visits.empty() || !P.seat_cap_visits.empty() || !P.seat_epsilon.empty() ||
                !P.seat_mcts_root_temp.empty() || !P.seat_root_fpu_zero.empty(),
@@ -275,6 +274,9 @@ class PlayManager {
     bp.tree_reuse = P.tree_reuse;
     bp.epsilon = P.epsilon;
     bp.mcts_root_temp = P.mcts_root_temp;
+    bp.playout_cap_randomization = P.playout_cap_randomization;
+    bp.resign_percent = P.resign_percent;
+    bp.resign_playthrough_percent = P.resign_playthrough_percent;
     bp.playout_cap_depth = P.playout_cap_depth;
     bp.playout_cap_percent = P.playout_cap_percent;
     bp.fpu_reduction = P.fpu_reduction;

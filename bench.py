@@ -215,6 +215,87 @@ def roofline_bytes_per_sim(avg_leaf_depth, avg_children):
     return select + backprop + expand + state
 
 
+def nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, world, rank):
+    """SURVEY.md 8d "Throughput B": the PyTorch net stays the evaluator, fed zero-copy from the engine's device
+    leaf batch (b2az_leaf_batch_device) and answered in place (b2az_submit_eval_all): no host synchronisation and
+    no host copy per generation. Random-init dense conv net of the connect4 default shape (depth 4, 12 channels,
+    5x5 kernels: src/config.py:44-47), bf16 autocast, self-play settings of connect4.yaml, position cache of
+    200,000 entries (src/config.py:197), history on."""
+    import ctypes as C
+
+    nn = torch.nn
+    G = args.games
+
+    class C4Net(nn.Module):
+        def __init__(self, depth=4, ch=12, k=5):
+            super().__init__()
+            self.convs = nn.ModuleList()
+            c_in = 4
+            for _ in range(depth):  # dense connectivity: every layer sees all earlier feature maps
+                self.convs.append(nn.Conv2d(c_in, ch, k, padding=k // 2))
+                c_in += ch
+            self.v_head = nn.Sequential(nn.Conv2d(c_in, 4, 1), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 42, 3))
+            self.pi_head = nn.Sequential(nn.Conv2d(c_in, 4, 1), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 42, 7))
+
+        def forward(self, x):
+            for conv in self.convs:
+                x = torch.cat([x, torch.relu(conv(x))], 1)
+            return torch.softmax(self.v_head(x).float(), 1), torch.softmax(self.pi_head(x).float(), 1)
+
+    torch.manual_seed(0)
+    net = C4Net().cuda().eval().to(memory_format=torch.channels_last)
+    p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=G, mcts_visits=(SIMS, SIMS), cpuct=1.25,
+                            fpu_reduction=0.25, epsilon=0.25, mcts_root_temp=1.25, start_temp=1.0, final_temp=0.2,
+                            temp_decay_half_life=10.0, root_fpu_zero=1, shaped_dirichlet=1, policy_target_pruning=1,
+                            eval_type=b2az.EVAL_NN, rng_mode=b2az.RNG_PER_GAME, seed=3000 + rank, tree_reuse=1,
+                            history_enabled=1, self_play=1, max_cache_size=200000, history_capacity=8 * G)
+    eng = b2az.Engine(p, device=local)
+
+    class _View:  # zero-copy: torch wraps the engine's device batch through __cuda_array_interface__
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    v_d = torch.empty((G, 3), dtype=torch.float32, device="cuda")
+    pi_d = torch.empty((G, 7), dtype=torch.float32, device="cuda")
+    x = None
+
+    def generation():
+        nonlocal x
+        eng.step(1, stream)
+        cptr, iptr, nptr = eng.leaf_batch_device(stream)
+        if x is None:
+            x = torch.as_tensor(_View(cptr, (G, 4, 6, 7)), device="cuda")
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            v, pi = net(x)
+        v_d.copy_(v)
+        pi_d.copy_(pi)
+        eng.submit_eval_all(v_d.data_ptr(), pi_d.data_ptr())
+
+    warm, timed = 60, 200
+    for _ in range(warm):
+        generation()
+    barrier()
+    s0 = eng.stats(stream)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(timed):
+        generation()
+    b.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b))
+    s1 = eng.stats(stream)
+    sims = s1.simulations - s0.simulations
+    hits, misses = s1.cache_hits - s0.cache_hits, s1.cache_misses - s0.cache_misses
+    out = {"value": world * sims / (ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+           "generations": timed, "ms_per_generation": ms / timed, "net_rows_per_generation": G,
+           "cache_hit_rate": hits / max(1, hits + misses), "device_error": int(s1.device_error),
+           "note": "one generation = b2az_step(1) + k_canonicalize + torch net (bf16 autocast, all concurrent_games rows) + "
+                   "b2az_submit_eval_all; leaf batch and evaluations never leave the device, no host sync per generation; "
+                   "cache hits are answered inside the step kernel"}
+    eng.close()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -371,6 +452,11 @@ def main():
                           "(fp32 canonical planes D2H) + b2az_submit_eval_host (v, pi H2D); pinned buffers"}
         eng.close()
 
+    # ---------------------------------------------------------------- NN evaluator on the device, zero host sync
+    e2e_nn_dev = None
+    if not args.no_e2e:
+        e2e_nn_dev = nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, world, rank)
+
     # ---------------------------------------------------------------- roofline + cpu baseline (rank 0)
     if rank != 0:
         if dist is not None:
@@ -411,6 +497,7 @@ def main():
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "moves_per_second": moves_per_s, "clocks": clocks, "e2e": e2e, "e2e_nn_host": e2e_nn,
+            "e2e_nn_device": e2e_nn_dev,
             "gpu_launches": K * world, "roofline": roofline, "cpu_baseline": cpu,
             "pool_pages": {"total": pool[0], "free": pool[1]}}
     print(json.dumps(line), flush=True)

@@ -65,7 +65,7 @@ typedef struct b2az_params {
   uint8_t shaped_dirichlet;
   uint8_t policy_target_pruning;
   uint8_t gumbel_enabled;        /* must be 0 for now */
-  float resign_percent;          /* must be 0 for now */
+  float resign_percent;          /* with playout_cap_randomization: B2AZ_RNG_PER_GAME only (coins from the game's stream) */
   float resign_playthrough_percent;
   uint8_t eval_type;             /* B2AZ_EVAL_*; applies to every seat */
   uint8_t rng_mode;              /* B2AZ_RNG_* */
@@ -140,6 +140,15 @@ int b2az_leaf_batch_host(b2az_engine* e, void* stream, uint32_t max, float* cano
  * pi_dev float32[count][7] in leaf-batch row order, count == the leaf count. The buffers are
  * read by the next b2az_step (keep them alive until it has run). */
 int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, uint32_t count);
+/* The same pair with NO host synchronisation at all (the whole generation stays stream-ordered and can be
+ * captured in a CUDA graph): b2az_leaf_batch_device returns device pointers to the canonical batch
+ * float32[concurrent_games][4][6][7] (rows >= *count_dev are unspecified), the slot ids and the row COUNT
+ * itself (uint32 in device memory); b2az_submit_eval_all declares that rows [0, count) of v_dev
+ * float32[>= concurrent_games][3] / pi_dev float32[>= concurrent_games][7] answer the whole batch. The evaluator
+ * simply runs on all concurrent_games rows. */
+int b2az_leaf_batch_device(b2az_engine* e, void* stream, const float** canon_dev, const uint32_t** ids_dev,
+                           const uint32_t** count_dev);
+int b2az_submit_eval_all(b2az_engine* e, const float* v_dev, const float* pi_dev);
 /* update_inferences, legacy flavour: row i answers slot ids_host[i]; may be called several times
  * with disjoint subsets. */
 int b2az_submit_eval_host(b2az_engine* e, void* stream, const uint32_t* ids_host, const float* v_host,

@@ -432,9 +432,10 @@ struct Game {  // GameData, play_manager.h:33-58
   float pi[A] = {0};
   float canonical[168];
   std::vector<Sample> partial;
-  bool initialized = false, capped = false;
+  bool initialized = false, capped = false, playthrough = false;
   double total_avg_leaf_depth = 0, total_search_entropy = 0, total_valid_moves = 0;
-  uint32_t move_count = 0, full_move_count = 0;
+  double fast_total_avg_leaf_depth = 0, fast_total_search_entropy = 0;
+  uint32_t move_count = 0, full_move_count = 0, fast_move_count = 0;
   std::unique_ptr<Pcg> rng;
 };
 struct PM {
@@ -444,9 +445,11 @@ struct PM {
   std::deque<Sample> history;
   std::unique_ptr<Pcg> global_rng;
   uint32_t games_started = 0, games_completed = 0;
-  uint64_t game_length = 0, total_move_count = 0, full_move_count = 0, simulations = 0, moves = 0;
+  uint64_t game_length = 0, total_move_count = 0, full_move_count = 0, fast_move_count = 0, simulations = 0, moves = 0;
   double total_avg_leaf_depth = 0, total_search_entropy = 0, total_valid_moves = 0;
+  double fast_total_avg_leaf_depth = 0, fast_total_search_entropy = 0;
   float scores[3] = {0, 0, 0};
+  float resign_scores[3] = {0, 0, 0};
   Pcg& re(uint32_t g) { return cfg.rng_mode == 1 ? *global_rng : *games[g].rng; }
 };
 
@@ -473,7 +476,7 @@ void play_iteration(PM& pm, uint32_t i) {
     Tree& mcts = game.mcts[cp];
     process_result(mcts, c, game.v, game.pi, c.epsilon > 0 && !game.capped, re);
     ++pm.simulations;
-    const uint32_t goal_depth = c.mcts_visits[cp];
+    const uint32_t goal_depth = game.capped ? c.playout_cap_depth : c.mcts_visits[cp];
     if (mcts.depth >= goal_depth) {
       float temp = c.start_temp;
       const float half_life = c.temp_decay_half_life;
@@ -484,6 +487,22 @@ void play_iteration(PM& pm, uint32_t i) {
         temp -= c.final_temp;
         temp *= std::exp(-lambda * t);
         temp += c.final_temp;
+      }
+      // resign_percent (play_manager.cc:305-337)
+      int resign_term = 0;
+      if (c.resign_percent > 0 && !game.playthrough) {
+        float wld[3];
+        root_value(mcts, wld);
+        const double resign_val = 1.0 - c.resign_percent;
+        int t = 0;
+        if (wld[0] > resign_val) t = cp + 1;
+        else if (wld[1] > resign_val) t = (cp + 1) % 2 + 1;
+        else if (wld[2] > resign_val) t = P + 1;
+        if (t != 0) {
+          std::uniform_real_distribution<float> dist{0.0F, 1.0F};
+          if (dist(re) < c.resign_playthrough_percent) game.playthrough = true;
+          else resign_term = t;
+        }
       }
       float pi[A];
       probs_of(mcts, temp, pi);
@@ -498,15 +517,23 @@ void play_iteration(PM& pm, uint32_t i) {
       }
       // avg_leaf_depth(): mcts.h:116-119
       const float ald = mcts.depth == 0 ? 0.0f : static_cast<float>(mcts.total_leaf_depth) / static_cast<float>(mcts.depth);
-      game.total_avg_leaf_depth += ald;
-      game.total_search_entropy += root_entropy(mcts);
-      ++game.full_move_count;
+      if (!game.capped) {
+        game.total_avg_leaf_depth += ald;
+        game.total_search_entropy += root_entropy(mcts);
+        ++game.full_move_count;
+      } else {
+        game.fast_total_avg_leaf_depth += ald;
+        game.fast_total_search_entropy += root_entropy(mcts);
+        ++game.fast_move_count;
+      }
       game.total_valid_moves += mcts.root.children.size();
       ++game.move_count;
       for (auto& m : game.mcts) update_root(m, game.gs, chosen, re);
       c4_play(game.gs, chosen);
       ++pm.moves;
-      const int term = c4_term(game.gs);
+      int term = c4_term(game.gs);
+      if (term == 0 && resign_term != 0) term = resign_term;  // :440-444
+      else resign_term = 0;
       if (term != 0) {
         if (c.history_enabled) {
           while (!game.partial.empty()) {
@@ -517,6 +544,7 @@ void play_iteration(PM& pm, uint32_t i) {
           }
         }
         pm.scores[term - 1] += 1.0f;
+        if (resign_term != 0) pm.resign_scores[resign_term - 1] += 1.0f;
         ++pm.games_completed;
         pm.game_length += game.gs.turn;
         pm.total_avg_leaf_depth += game.total_avg_leaf_depth;
@@ -524,14 +552,21 @@ void play_iteration(PM& pm, uint32_t i) {
         pm.total_valid_moves += game.total_valid_moves;
         pm.total_move_count += game.move_count;
         pm.full_move_count += game.full_move_count;
+        pm.fast_total_avg_leaf_depth += game.fast_total_avg_leaf_depth;
+        pm.fast_total_search_entropy += game.fast_total_search_entropy;
+        pm.fast_move_count += game.fast_move_count;
         game.total_avg_leaf_depth = game.total_search_entropy = game.total_valid_moves = 0;
-        game.move_count = game.full_move_count = 0;
+        game.fast_total_avg_leaf_depth = game.fast_total_search_entropy = 0;
+        game.move_count = game.full_move_count = game.fast_move_count = 0;
         if (pm.games_started >= c.games_to_play) return;  // `continue`: the slot retires (:506-509)
         ++pm.games_started;
         c4_clear(game.gs);
         for (auto& m : game.mcts) m = Tree{};
       }
-      game.capped = false;  // playout_cap_randomization is off in every parity configuration
+      {  // :523-524 (`&&` short-circuits: no draw when the flag is off)
+        std::uniform_real_distribution<float> dist{0.0F, 1.0F};
+        game.capped = c.playout_cap_randomization && (dist(re) < c.playout_cap_percent);
+      }
       if (!c.tree_reuse) {
         for (auto& m : game.mcts) m = Tree{};
       } else {
@@ -544,7 +579,8 @@ void play_iteration(PM& pm, uint32_t i) {
     }
   } else {
     game.initialized = true;
-    game.capped = false;
+    std::uniform_real_distribution<float> dist{0.0F, 1.0F};
+    game.capped = c.playout_cap_randomization && (dist(re) < c.playout_cap_percent);  // :559-560
   }
   const int cp = game.gs.player;
   Board leaf;
@@ -638,13 +674,14 @@ uint32_t azo_pm_remaining_games(void* h) {
 uint64_t azo_pm_simulations(void* h) { return static_cast<PM*>(h)->simulations; }
 uint64_t azo_pm_moves(void* h) { return static_cast<PM*>(h)->moves; }
 void azo_pm_scores(void* h, float* out3) { std::memcpy(out3, static_cast<PM*>(h)->scores, sizeof(float) * 3); }
+void azo_pm_resign_scores(void* h, float* out3) { std::memcpy(out3, static_cast<PM*>(h)->resign_scores, sizeof(float) * 3); }
 void azo_pm_metrics(void* h, float* out7) {  // play_manager.h:288-315
   auto* pm = static_cast<PM*>(h);
   out7[0] = static_cast<float>(pm->game_length) / static_cast<float>(pm->games_completed);
   out7[1] = pm->full_move_count ? static_cast<float>(pm->total_avg_leaf_depth / pm->full_move_count) : 0.0f;
   out7[2] = pm->full_move_count ? static_cast<float>(pm->total_search_entropy / pm->full_move_count) : 0.0f;
-  out7[3] = 0.0f;
-  out7[4] = 0.0f;
+  out7[3] = pm->fast_move_count ? static_cast<float>(pm->fast_total_avg_leaf_depth / pm->fast_move_count) : 0.0f;
+  out7[4] = pm->fast_move_count ? static_cast<float>(pm->fast_total_search_entropy / pm->fast_move_count) : 0.0f;
   out7[5] = pm->game_length ? static_cast<float>(pm->total_move_count) / static_cast<float>(pm->game_length) : 0.0f;
   out7[6] = pm->total_move_count ? static_cast<float>(pm->total_valid_moves / pm->total_move_count) : 0.0f;
 }

@@ -39,6 +39,13 @@ typedef struct azo_cfg {
   uint8_t policy_target_pruning, eval_type /* 0 NN, 1 RANDOM */, rng_mode /* 0 per game, 1 global */, pad_;
   float epsilon, mcts_root_temp, fpu_reduction;
   uint64_t seed;
+  /* playout-cap randomisation and resign (play_manager.cc:306-337, 523-524, 559-560). The reference flips these
+   * coins with a thread_local, unseedable std::default_random_engine; here they come from the same stream as every
+   * other draw (per game or global), which is what the engine does — a parity definition of this repo, not of the
+   * reference. */
+  uint8_t playout_cap_randomization, pad2_[3];
+  uint32_t playout_cap_depth;
+  float playout_cap_percent, resign_percent, resign_playthrough_percent;
 } azo_cfg;
 
 void* azo_pm_new(const azo_cfg* c);
@@ -60,6 +67,7 @@ uint32_t azo_pm_remaining_games(void* h);
 uint64_t azo_pm_simulations(void* h);
 uint64_t azo_pm_moves(void* h);
 void azo_pm_scores(void* h, float* out3);
+void azo_pm_resign_scores(void* h, float* out3);
 /* avg_game_length, avg_leaf_depth, avg_search_entropy, fast_avg_leaf_depth, fast_avg_search_entropy,
  * avg_moves_per_turn, avg_valid_moves (play_manager.h:288-315) */
 void azo_pm_metrics(void* h, float* out7);

@@ -74,6 +74,8 @@ class AzoCfg(C.Structure):
         ("shaped_dirichlet", C.c_uint8), ("policy_target_pruning", C.c_uint8), ("eval_type", C.c_uint8),
         ("rng_mode", C.c_uint8), ("pad_", C.c_uint8), ("epsilon", C.c_float), ("mcts_root_temp", C.c_float),
         ("fpu_reduction", C.c_float), ("seed", C.c_uint64),
+        ("playout_cap_randomization", C.c_uint8), ("pad2_", C.c_uint8 * 3), ("playout_cap_depth", C.c_uint32),
+        ("playout_cap_percent", C.c_float), ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
     ]
 
 
@@ -104,6 +106,7 @@ def port_lib():
             getattr(L, n).argtypes = [vp]
             getattr(L, n).restype = C.c_uint64
         L.azo_pm_scores.argtypes = [vp, vp]
+        L.azo_pm_resign_scores.argtypes = [vp, vp]
         L.azo_pm_metrics.argtypes = [vp, vp]
         L.azo_pm_peek.argtypes = [vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
         L.azo_c4_play.argtypes = [vp, vp, vp, u32]
@@ -179,6 +182,11 @@ class PortPM:
     def scores(self):
         s = np.zeros(3, np.float32)
         self.L.azo_pm_scores(self.h, _P(s))
+        return s
+
+    def resign_scores(self):
+        s = np.zeros(3, np.float32)
+        self.L.azo_pm_resign_scores(self.h, _P(s))
         return s
 
     def metrics(self):
@@ -306,7 +314,7 @@ def compare_peek(pe, po, where):
 
 
 def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracle="port", rng_mode=None,
-                        tree_reuse=True, lanes=0, peek_every=7, max_generations=10 ** 7, compact_pages=0):
+                        tree_reuse=True, lanes=0, peek_every=7, max_generations=10 ** 7, compact_pages=0, extra=None):
     """NN-eval lock-step run (SURVEY.md Appendix A 'Scheduling order'): every generation both sides expose
     their leaf batch (ids + canonical planes, compared bit for bit), get the same fake_net answers and
     advance. Visit counts / Q / root values are peeked every `peek_every` generations and the finished
@@ -314,7 +322,7 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
     if rng_mode is None:
         rng_mode = b2az.RNG_GLOBAL if oracle == "ref" else b2az.RNG_PER_GAME
     ordered = rng_mode == b2az.RNG_GLOBAL or engine_lib is not None
-    kw = level_params(level)
+    kw = dict(level_params(level), **(extra or {}))
     eng = make_engine(engine_lib, G, games_to_play, visits, b2az.EVAL_NN, rng_mode, seed, tree_reuse=tree_reuse,
                       lanes=lanes, compact_pages=compact_pages, **kw)
     ora = make_oracle(oracle, G=G, games_to_play=games_to_play, visits=visits, eval_type=b2az.EVAL_NN,
@@ -354,6 +362,8 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
         if gens < max_generations:
             assert st.games_completed == games_to_play
         assert np.array_equal(np.array(st.scores[:], np.float32), ora.scores()), "scores differ"
+        if hasattr(ora, "resign_scores"):
+            assert np.array_equal(np.array(st.resign_scores[:], np.float32), ora.resign_scores()), "resign scores differ"
         if st.games_completed == 0:
             return dict(generations=gens, leaves=leaves, games=0, moves_compared=0, scores=[0, 0, 0],
                         simulations=int(st.simulations), compactions=int(st.compactions))
@@ -377,7 +387,8 @@ def run_lockstep_parity(engine_lib, G, games_to_play, visits, level, seed, oracl
 
 
 def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port", rng_mode=None, level=0,
-                      tree_reuse=True, lanes=0, chunk=64, steps=None, compact_pages=0, pool_nodes=0, ordered=None):
+                      tree_reuse=True, lanes=0, chunk=64, steps=None, compact_pages=0, pool_nodes=0, ordered=None,
+                      extra=None):
     """RANDOM-eval run (EvalType::RANDOM, the reference's own fake backend: play_manager_test.cc): the engine
     fuses `chunk` loop iterations per launch; the oracle plays to the end; final scores, metrics and the
     training samples must agree."""
@@ -385,7 +396,7 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
         rng_mode = b2az.RNG_GLOBAL if oracle == "ref" else b2az.RNG_PER_GAME
     if ordered is None:
         ordered = rng_mode == b2az.RNG_GLOBAL or engine_lib is not None
-    kw = level_params(level)
+    kw = dict(level_params(level), **(extra or {}))
     eng = make_engine(engine_lib, G, games_to_play, visits, b2az.EVAL_RANDOM, rng_mode, seed, tree_reuse=tree_reuse,
                       lanes=lanes, history_capacity=max(1 << 16, games_to_play * 42), compact_pages=compact_pages,
                       pool_nodes=pool_nodes, **kw)
@@ -416,8 +427,10 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
         m = ora.metrics()
         for name in ("avg_game_length", "avg_moves_per_turn", "avg_valid_moves"):
             assert np.float32(getattr(st, name)) == np.float32(m[name]), name
-        for name in ("avg_leaf_depth", "avg_search_entropy"):
+        for name in ("avg_leaf_depth", "avg_search_entropy", "fast_avg_leaf_depth", "fast_avg_search_entropy"):
             assert abs(getattr(st, name) - m[name]) <= 1e-5 * max(1.0, abs(m[name])), name
+        if hasattr(ora, "resign_scores"):
+            assert np.array_equal(np.array(st.resign_scores[:], np.float32), ora.resign_scores()), "resign scores differ"
         if hasattr(ora, "simulations"):
             assert st.simulations == ora.simulations() and st.moves == ora.moves()
         he = eng.drain_history(1 << 20)
@@ -426,7 +439,8 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
         return dict(games=int(st.games_completed), scores=[float(x) for x in st.scores[:]],
                     simulations=int(st.simulations), moves=int(st.moves), samples=len(ho[0]),
                     avg_game_length=float(st.avg_game_length), avg_leaf_depth=float(st.avg_leaf_depth),
-                    compactions=int(st.compactions))
+                    compactions=int(st.compactions), resign_scores=[float(x) for x in st.resign_scores[:]],
+                    fast_avg_leaf_depth=float(st.fast_avg_leaf_depth))
     finally:
         eng.close()
         ora.close()

@@ -97,6 +97,31 @@ def test_flattened_loop_matches_port(chunk, monkeypatch):
     assert r["games"] > 5 and r["samples"] > 100
 
 
+CAP_RESIGN = dict(playout_cap_randomization=1, playout_cap_depth=6, playout_cap_percent=0.6, resign_percent=0.35,
+                  resign_playthrough_percent=0.3)
+
+
+@pytest.mark.parametrize("flat", ["0", "1"])
+def test_playout_cap_and_resign_vs_port(flat, monkeypatch):
+    """Playout-cap randomisation (capped searches: cap visits, no noise, not recorded, fast_* metrics) and
+    resign_percent / playthrough (play_manager.cc:305-337, 440-444, 486-488, 523-524, 559-560) against the port;
+    the coin flips come from each game's own stream on both sides."""
+    monkeypatch.setenv("B2AZ_EMU_FLAT", flat)
+    r = ph.run_random_parity(EMU, G=20, games_to_play=10 ** 6, visits=40, seed=8, oracle="port", rng_mode=b2az.RNG_PER_GAME,
+                             level=1, chunk=37, steps=1500, ordered=False, extra=CAP_RESIGN)
+    assert r["games"] > 20 and sum(r["resign_scores"]) > 0 and r["fast_avg_leaf_depth"] > 0
+    r = ph.run_lockstep_parity(EMU, G=6, games_to_play=10 ** 6, visits=24, level=1, seed=8, oracle="port",
+                               rng_mode=b2az.RNG_PER_GAME, max_generations=1500, extra=CAP_RESIGN)
+    assert r["games"] > 6
+
+
+def test_cap_and_resign_rejected_in_reference_parity_mode():
+    lib = b2az.load(EMU)
+    for kw in (dict(playout_cap_randomization=1), dict(resign_percent=0.1)):
+        with pytest.raises(b2az.B2azError, match="unseedable"):
+            b2az.Engine(b2az.default_params(lib, rng_mode=b2az.RNG_GLOBAL, **kw), lib=lib)
+
+
 def test_pool_exhaustion_is_reported():
     lib = b2az.load(EMU)
     p = b2az.default_params(lib, games_to_play=8, concurrent_games=8, mcts_visits=(400, 400), eval_type=b2az.EVAL_NN,

@@ -65,6 +65,19 @@ def test_parallel_kernel_400_sims_vs_port():
     assert r["games"] > 100
 
 
+def test_playout_cap_and_resign_gpu():
+    """Playout-cap randomisation + resign_percent / playthrough on the device vs the port (coins from each game's own
+    stream on both sides): fused RANDOM-eval launches and the lock-step NN loop."""
+    extra = dict(playout_cap_randomization=1, playout_cap_depth=25, playout_cap_percent=0.75, resign_percent=0.35,
+                 resign_playthrough_percent=0.3)
+    r = ph.run_random_parity(None, G=384, games_to_play=10 ** 6, visits=100, seed=12, oracle="port",
+                             rng_mode=b2az.RNG_PER_GAME, level=1, chunk=96, steps=3000, extra=extra)
+    assert r["games"] > 384 and sum(r["resign_scores"]) > 0 and r["fast_avg_leaf_depth"] > 0
+    r = ph.run_lockstep_parity(None, G=32, games_to_play=10 ** 6, visits=40, level=1, seed=12, oracle="port",
+                               rng_mode=b2az.RNG_PER_GAME, max_generations=1200, extra=extra)
+    assert r["games"] > 32
+
+
 def test_no_tree_reuse_gpu():
     ph.run_random_parity(None, G=64, games_to_play=10 ** 6, visits=50, seed=3, oracle="port", level=2, tree_reuse=False,
                          steps=3000)
@@ -139,6 +152,53 @@ def test_device_zero_copy_path_matches_host_path():
     sa, sb = a.stats(), b.stats()
     assert sa.games_completed == sb.games_completed > 64 and list(sa.scores) == list(sb.scores)
     ph.compare_history(a.drain_history(1 << 16), b.drain_history(1 << 16), ordered=False)
+    a.close()
+    b.close()
+
+
+def test_sync_free_generation_loop_matches_host_path():
+    """b2az_leaf_batch_device / b2az_submit_eval_all: no host synchronisation per generation (the evaluator runs
+    on all concurrent_games rows, the row count stays on the device). Same games as the host-buffer path; with
+    the position cache on in both."""
+    import torch
+
+    G = 96
+    kw = ph.level_params(1)
+    mk = lambda: ph.make_engine(None, G, G, 48, b2az.EVAL_NN, b2az.RNG_PER_GAME, 23, max_cache_size=100000,
+                                history_capacity=G * 42, **kw)
+    a, b = mk(), mk()
+    mix = torch.from_numpy(ph._MIX).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    # host path to the end
+    while True:
+        a.step(1)
+        ids, canon = a.leaf_batch_host()
+        if len(ids) == 0:
+            break
+        v, pi = ph.fake_net(canon)
+        a.submit_eval_host(ids, v, pi)
+    # device path: fixed number of generations, everything stream ordered
+    v_d = torch.empty((G, 3), dtype=torch.float32, device="cuda")
+    pi_d = torch.empty((G, 7), dtype=torch.float32, device="cuda")
+    cudart = C.CDLL("libcudart.so")
+    cb = torch.zeros((G, 168), dtype=torch.float32, device="cuda")
+    for gen in range(4000):
+        b.step(1, stream)
+        cptr, iptr, nptr = b.leaf_batch_device(stream)
+        cudart.cudaMemcpyAsync(C.c_void_p(cb.data_ptr()), C.c_void_p(cptr), C.c_size_t(G * 168 * 4), 3, C.c_void_p(stream))
+        h = (cb.double() @ mix.double()).to(torch.int64)
+        wp = (1 + (h[:, :7] % 13) ** 2).to(torch.float32)
+        wv = (1 + (h[:, 7:] % 17)).to(torch.float32)
+        pi_d.copy_(wp / wp.sum(1, keepdim=True))
+        v_d.copy_(wv / wv.sum(1, keepdim=True))
+        b.submit_eval_all(v_d.data_ptr(), pi_d.data_ptr())
+        if gen % 64 == 63 and b.stats(stream).active_games == 0:
+            break
+    sa, sb = a.stats(), b.stats(stream)
+    assert sb.active_games == 0 and sb.device_error == 0
+    assert sa.games_completed == sb.games_completed == G and list(sa.scores) == list(sb.scores)
+    assert sa.simulations == sb.simulations and sb.cache_hits > 0
+    ph.compare_history(a.drain_history(G * 42), b.drain_history(G * 42), ordered=False)
     a.close()
     b.close()
 
