@@ -562,6 +562,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
 #endif
   }
 #ifndef B2AZ_HOST_EMU
+  if (const char* cv = getenv("B2AZ_CARVEOUT"))  // experiment knob: shared-memory carveout of the step kernel, percent
+    CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
   InitArgs ia{p->seed, p->rng_mode};
   k_init_pool<<<e->num_sms * 4, 256>>>(V);
   k_init_games<<<e->num_sms * 4, 256>>>(V, ia);

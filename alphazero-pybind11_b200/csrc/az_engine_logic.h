@@ -120,7 +120,11 @@ struct V4 {
 AZ_HD V4 ld_v4(const void* p) {
   V4 r;
 #if defined(__CUDA_ARCH__)
+#if defined(B2AZ_LDCG)
+  const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p));  // experiment: bypass L1
+#else
   const uint4 a = *reinterpret_cast<const uint4*>(p);
+#endif
   r.x = a.x; r.y = a.y; r.z = a.z; r.w = a.w;
 #else
   memcpy(&r, p, 16);

@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r10_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r10_pytest.log
-tail -n 6 gpurun_out/r10_pytest.log
-( timeout 700 python bench.py --no-cpu-baseline --steps 5 ) > gpurun_out/r10_bench.json 2> gpurun_out/r10_bench.err; echo "bench rc=$?" >> gpurun_out/r10_bench.err
-python -c "
-import json; d=json.load(open('gpurun_out/r10_bench.json')); print(d['value'], d['e2e'], d['e2e_nn_host'], d['e2e_nn_device'])"; tail -n 5 gpurun_out/r10_bench.err
+for v in 100 50 25 0; do echo "carveout=$v" >> gpurun_out/r14_variants.json; ( B2AZ_CARVEOUT=$v timeout 300 python tools/gen_profile.py --span 410 ) >> gpurun_out/r14_variants.json 2>> gpurun_out/r14_variants.err; done
+echo "ldcg" >> gpurun_out/r14_variants.json; ( B2AZ_LIB_PATH=build/variants/libb2az_ldcg.so timeout 300 python tools/gen_profile.py --span 410 ) >> gpurun_out/r14_variants.json 2>> gpurun_out/r14_variants.err
+echo "ldcg carveout 100" >> gpurun_out/r14_variants.json; ( B2AZ_CARVEOUT=100 B2AZ_LIB_PATH=build/variants/libb2az_ldcg.so timeout 300 python tools/gen_profile.py --span 410 ) >> gpurun_out/r14_variants.json 2>> gpurun_out/r14_variants.err
+cut -c1-140 gpurun_out/r14_variants.json; tail -n 3 gpurun_out/r14_variants.err
