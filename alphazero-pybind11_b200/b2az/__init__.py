@@ -45,6 +45,8 @@ class Params(C.Structure):
         ("resign_playthrough_percent", C.c_float), ("eval_type", C.c_uint8), ("rng_mode", C.c_uint8),
         ("pad0_", C.c_uint8), ("pad1_", C.c_uint8), ("seed", C.c_uint64), ("pool_nodes", C.c_uint64),
         ("history_capacity", C.c_uint32), ("lanes_per_game", C.c_uint32), ("compact_pages", C.c_uint32),
+        ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float), ("gumbel_c_scale", C.c_float),
+        ("gumbel_full", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad3_", C.c_uint8 * 2),
         ("pad2_", C.c_uint32),
     ]
 

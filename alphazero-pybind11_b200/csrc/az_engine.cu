@@ -421,6 +421,9 @@ int b2az_params_default(b2az_params* p) {
   p->mcts_root_temp = 1.0f;
   p->playout_cap_depth = 25;
   p->playout_cap_percent = 0.75f;
+  p->gumbel_m = 16;
+  p->gumbel_c_visit = 50.0f;
+  p->gumbel_c_scale = 1.0f;
   p->eval_type = B2AZ_EVAL_NN;
   p->rng_mode = B2AZ_RNG_PER_GAME;
   p->seed = 0;
@@ -435,7 +438,7 @@ int b2az_destroy(b2az_engine* e) {
 #endif
   EngineView& V = e->view;
   dev_free(V.blocks); dev_free(V.page_next); dev_free(V.ring);
-  dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot);
+  dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot); dev_free(V.gum);
   dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game);
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
   dev_free(V.cache_keys); dev_free(V.cache_meta); dev_free(V.cache_lock); dev_free(V.cache_vals);
@@ -456,7 +459,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
     return fail(B2AZ_EINVAL, "games_to_play must be >= concurrent_games (every slot starts a game)");
   if (p->mcts_visits[0] == 0 || p->mcts_visits[1] == 0)
     return fail(B2AZ_EINVAL, "You must specify MCTS visits for each player");  // play_manager.cc:21
-  if (p->gumbel_enabled) return fail(B2AZ_EINVAL, "gumbel_enabled is not implemented yet");
+  if (p->gumbel_enabled && p->gumbel_m == 0) return fail(B2AZ_EINVAL, "gumbel_m must be > 0");
   if ((p->resign_percent != 0.0f || p->playout_cap_randomization) && p->rng_mode == B2AZ_RNG_GLOBAL)
     return fail(B2AZ_EINVAL, "resign_percent / playout_cap_randomization flip coins from an unseedable engine in the "
                              "reference: not available in B2AZ_RNG_GLOBAL (parity) mode");
@@ -498,6 +501,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.shaped_dirichlet = p->shaped_dirichlet; V.policy_target_pruning = p->policy_target_pruning;
   V.playout_cap = p->playout_cap_randomization ? 1 : 0; V.eval_type = p->eval_type; V.rng_mode = p->rng_mode;
   V.resign_percent = p->resign_percent; V.resign_playthrough_percent = p->resign_playthrough_percent;
+  V.gumbel_enabled = p->gumbel_enabled; V.gumbel_full = p->gumbel_full; V.fast_search_uses_gumbel = p->fast_search_uses_gumbel;
+  V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
 
   // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
   const u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
@@ -528,6 +533,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   A(dev_alloc_raw(&V.blocks, nblocks));  // every block is fully written before it is read: no memset
   A(dev_alloc(&V.page_next, pages)); A(dev_alloc(&V.ring, pages));
   A(dev_alloc(&V.trees, (size_t)G * kP)); A(dev_alloc(&V.games, (size_t)G)); A(dev_alloc(&V.cold, (size_t)G));
+  if (p->gumbel_enabled) A(dev_alloc(&V.gum, (size_t)G * kP));  // zero = reset state, no sims target
   A(dev_alloc(&V.path, (size_t)G * kMaxPath)); A(dev_alloc(&V.pslot, (size_t)G * kMaxPath));
   A(dev_alloc(&V.leaf_p0, (size_t)G)); A(dev_alloc(&V.leaf_p1, (size_t)G));
   A(dev_alloc(&V.leaf_player, (size_t)G)); A(dev_alloc(&V.leaf_game, (size_t)G));

@@ -304,6 +304,201 @@ struct PathRegs {
   u32 slots_lo, slots_hi;  // 8 bits per level: child slot | parent's player << 4
   u32 valid;               // the registers describe the pending leaf's path
 };
+// ------------------------------------------------------------------------------------ Gumbel root search
+// MCTS::set_gumbel_num_sims / reset / init / advance_phase / next_root_child / interior_select /
+// improved_policy / final_action (mcts.cc:28-89, 175-401). All cold: they run once per simulation at the
+// root (one 80 B state record per tree) or once per move.
+#define AZ_GUMBEL_LOG_FLOOR 1e-20f
+AZ_HD void gumbel_reset(GumbelState& S) {  // reset_gumbel_state (mcts.cc:180-188)
+  S.initialized = 0;
+  S.effective_m = 0;
+  S.n_surv = 0;
+  S.survivors = 0;
+  S.n_phases = 0;
+  S.phase_idx = 0;
+  S.sims_in_phase = 0;
+  for (int j = 0; j < kKMax; ++j) S.g[j] = 0.0f;
+}
+AZ_HD void gumbel_set_num_sims(GumbelState& S, u32 n) {  // mcts.cc:175-178
+  S.num_sims_target = n;
+  gumbel_reset(S);
+}
+// seq_halving_phase_plan (mcts.cc:28-66)
+AZ_HD void gumbel_phase_plan(GumbelState& S, u32 m, u32 n) {
+  S.n_phases = 0;
+  if (m <= 1) {
+    S.phase_numc[0] = 1; S.phase_vper[0] = n; S.n_phases = 1;
+    return;
+  }
+  u32 log2m = 0;
+  for (u32 v = m - 1; v > 0; v >>= 1) ++log2m;
+  if (log2m == 0) log2m = 1;
+  u32 base_v = n / (log2m * m);
+  if (base_v < 1u) base_v = 1u;
+  u32 sims_used = 0, num_c = m;
+  for (u32 phase_idx = 0; phase_idx < log2m && S.n_phases < (u8)kMaxPhases; ++phase_idx) {
+    if (sims_used >= n) break;
+    const u32 remaining = n - sims_used;
+    const bool is_final = (phase_idx == log2m - 1);
+    u32 v_per = is_final ? (remaining / num_c < 1u ? 1u : remaining / num_c) : base_v * (1u << phase_idx);
+    if (num_c * v_per > remaining) {
+      v_per = remaining / num_c;
+      if (v_per == 0) { num_c = remaining; v_per = 1; }
+    }
+    S.phase_numc[S.n_phases] = num_c;
+    S.phase_vper[S.n_phases] = v_per;
+    ++S.n_phases;
+    sims_used += num_c * v_per;
+    num_c = num_c / 2 < 1u ? 1u : num_c / 2;
+  }
+}
+// Top-`take` of k scores, descending. std::partial_sort in the reference; with continuous Gumbel noise in
+// every score ties have probability zero, so a plain selection gives the same ranking.
+AZ_HD u32 rank_top(const float* score, const u32* idx, u32 k, u32 take) {
+  u32 used = 0, out = 0;
+  for (u32 r = 0; r < take; ++r) {
+    int best = -1;
+    for (u32 i = 0; i < k; ++i) {
+      if ((used >> i) & 1u) continue;
+      if (best < 0 || score[i] > score[best]) best = (int)i;
+    }
+    used |= 1u << best;
+    out |= idx[best] << (4u * r);
+  }
+  return out;
+}
+// init_gumbel_state (mcts.cc:190-227)
+AZ_COLD void gumbel_init(const EngineView E, GumbelState& S, const TreeHdr& T, Pcg32& rng) {
+  const u32 num_legal = T.k;
+  if (num_legal == 0 || T.fc == kNil) return;
+  const u32 remaining = T.depth < S.num_sims_target ? S.num_sims_target - T.depth : 0u;
+  if (remaining == 0) return;
+  u32 m = E.gumbel_m < num_legal ? E.gumbel_m : num_legal;
+  if (remaining < m) m = remaining;
+  if (m < 1u) m = 1u;
+  S.effective_m = (u8)m;
+  const Block* B = E.blocks + T.fc;
+  float score[kKMax];
+  u32 idx[kKMax];
+  for (u32 i = 0; i < num_legal; ++i) S.g[i] = rng_gumbel(rng);
+  for (u32 i = 0; i < num_legal; ++i) {
+    score[i] = fadd(S.g[i], az_logf(fadd(blk_pol(B, i), AZ_GUMBEL_LOG_FLOOR)));
+    idx[i] = i;
+  }
+  S.survivors = rank_top(score, idx, num_legal, m);
+  S.n_surv = (u8)m;
+  gumbel_phase_plan(S, m, remaining);
+  S.phase_idx = 0;
+  S.sims_in_phase = 0;
+  S.initialized = 1;
+}
+AZ_HD float gumbel_sigma_scale(const EngineView& E, u32 max_visit) {
+  return fmul(fadd(E.gumbel_c_visit, (float)max_visit), E.gumbel_c_scale);
+}
+// gumbel_advance_phase (mcts.cc:229-264)
+AZ_HD void gumbel_advance_phase(const EngineView& E, GumbelState& S, const TreeHdr& T) {
+  if ((u32)S.phase_idx + 1u >= (u32)S.n_phases) return;
+  const u32 next_num_c = S.phase_numc[S.phase_idx + 1];
+  if (next_num_c >= (u32)S.n_surv) {
+    ++S.phase_idx;
+    S.sims_in_phase = 0;
+    return;
+  }
+  const Block* B = E.blocks + T.fc;
+  u32 max_visit = 0;
+  for (u32 r = 0; r < (u32)S.n_surv; ++r) {
+    const u32 c = (S.survivors >> (4u * r)) & 15u;
+    if (blk_n(B, c) > max_visit) max_visit = blk_n(B, c);
+  }
+  const float sigma_scale = gumbel_sigma_scale(E, max_visit);
+  float score[kKMax];
+  u32 idx[kKMax];
+  for (u32 r = 0; r < (u32)S.n_surv; ++r) {
+    const u32 c = (S.survivors >> (4u * r)) & 15u;
+    const float logit = az_logf(fadd(blk_pol(B, c), AZ_GUMBEL_LOG_FLOOR));
+    const float q_hat = blk_n(B, c) > 0 ? blk_q(B, c) : 0.0f;
+    score[r] = fadd(fadd(S.g[c], logit), fmul(sigma_scale, q_hat));
+    idx[r] = c;
+  }
+  S.survivors = rank_top(score, idx, S.n_surv, next_num_c);
+  S.n_surv = (u8)next_num_c;
+  ++S.phase_idx;
+  S.sims_in_phase = 0;
+}
+// gumbel_next_root_child (mcts.cc:266-283)
+AZ_COLD u32 gumbel_next_root_child(const EngineView E, GumbelState& S, const TreeHdr& T) {
+  if ((u32)S.phase_idx < (u32)S.n_phases) {
+    if (S.sims_in_phase >= S.phase_numc[S.phase_idx] * S.phase_vper[S.phase_idx]) gumbel_advance_phase(E, S, T);
+  }
+  if (S.n_surv == 0) return 0;
+  const u32 pick = S.sims_in_phase % (u32)S.n_surv;
+  ++S.sims_in_phase;
+  return (S.survivors >> (4u * pick)) & 15u;
+}
+// compute_v_mix_from_children (mcts.cc:71-89) + the softmax of logits + sigma * completedQ shared by
+// gumbel_interior_select and gumbel_improved_policy. z_out[i] = exp(z_i - z_max); returns z_sum.
+AZ_HD float gumbel_pi_prime(const EngineView& E, const Block* B, u32 k, float raw_v, float* z, u32* ns, u32* sum_visits_out) {
+  u32 max_visit = 0, sum_n = 0;
+  float sum_visits = 0.0f, sum_priors_visited = 0.0f, weighted_num = 0.0f;
+  for (u32 i = 0; i < k; ++i) {
+    ns[i] = blk_n(B, i);
+    if (ns[i] > max_visit) max_visit = ns[i];
+    sum_n += ns[i];
+    sum_visits = fadd(sum_visits, (float)ns[i]);
+    if (ns[i] > 0) {
+      sum_priors_visited = fadd(sum_priors_visited, blk_pol(B, i));
+      weighted_num = fadd(weighted_num, fmul(blk_pol(B, i), blk_q(B, i)));
+    }
+  }
+  float v_mix = raw_v;
+  if (sum_priors_visited > 0.0f) {
+    const float weighted_q = fdiv(weighted_num, sum_priors_visited);
+    v_mix = fdiv(fadd(raw_v, fmul(sum_visits, weighted_q)), fadd(sum_visits, 1.0f));
+  }
+  const float sigma_scale = gumbel_sigma_scale(E, max_visit);
+  float z_max = -INFINITY;
+  for (u32 i = 0; i < k; ++i) {
+    const float completed_q = ns[i] > 0 ? blk_q(B, i) : v_mix;
+    z[i] = fadd(az_logf(fadd(blk_pol(B, i), AZ_GUMBEL_LOG_FLOOR)), fmul(sigma_scale, completed_q));
+    if (z[i] > z_max) z_max = z[i];
+  }
+  float z_sum = 0.0f;
+  for (u32 i = 0; i < k; ++i) {
+    z[i] = az_expf(fsub(z[i], z_max));
+    z_sum = fadd(z_sum, z[i]);
+  }
+  *sum_visits_out = sum_n;
+  return z_sum;
+}
+// gumbel_interior_select (mcts.cc:285-334)
+AZ_COLD u32 gumbel_interior_select(const EngineView E, u32 blk, u32 k, float node_v) {
+  const Block* B = E.blocks + blk;
+  float z[kKMax];
+  u32 ns[kKMax], sum_visits = 0;
+  const float z_sum = gumbel_pi_prime(E, B, k, node_v, z, ns, &sum_visits);
+  const float inv = z_sum > 0.0f ? fdiv(1.0f, z_sum) : 0.0f;
+  const float denom = fadd(1.0f, (float)sum_visits);
+  u32 best = 0;
+  float best_score = -INFINITY;
+  for (u32 i = 0; i < k; ++i) {
+    const float score = fsub(fmul(z[i], inv), fdiv((float)ns[i], denom));
+    if (score > best_score) { best_score = score; best = i; }
+  }
+  return best;
+}
+// gumbel_improved_policy (mcts.cc:336-373): pi' over all moves (zeros for illegal ones)
+AZ_COLD void gumbel_improved_policy(const EngineView E, const TreeHdr& T, float* out) {
+  for (int m = 0; m < kA; ++m) out[m] = 0.0f;
+  const u32 k = T.k;
+  if (k == 0 || T.fc == kNil) return;
+  const Block* B = E.blocks + T.fc;
+  float z[kKMax];
+  u32 ns[kKMax], sum_visits = 0;
+  const float z_sum = gumbel_pi_prime(E, B, k, T.v, z, ns, &sum_visits);
+  if (z_sum <= 0.0f) return;
+  for (u32 i = 0; i < k; ++i) out[blk_mv(B, i)] = fdiv(z[i], z_sum);
+}
+
 // ------------------------------------------------------------------------------------ find_leaf
 // MCTS::find_leaf (mcts.cc:462-498), PUCT branch; Node::best_child (mcts.cc:130-149) and Node::uct
 // (mcts.cc:123-128) inlined. n_in_flight is always 0 on this path (the WU-UCT variant is not used by
@@ -317,8 +512,25 @@ struct Descent {
   u32 par_blk, par_slot;
   u32 plen;
   bool at_root;
+  bool gumbel;        // Gumbel selection is active for this descent (MCTS::gumbel_initialized_)
 };
-AZ_HD void descent_begin(const TreeHdr& T, const GameSlot& gs, Descent& D, PathRegs& pr) {
+// Lazy Gumbel init (mcts.cc:468-472): after the root has been expanded, when a sims target is set.
+AZ_COLD bool gumbel_begin(const EngineView E, u32 tree, const TreeHdr T, Pcg32& rng) {
+  GumbelState S = E.gum[tree];
+  if (!S.initialized && S.num_sims_target > 0 && T.n > 0 && T.k > 0) {
+    gumbel_init(E, S, T, rng);
+    E.gum[tree] = S;
+  }
+  return S.initialized != 0;
+}
+AZ_HD void descent_begin(const EngineView& E, u32 g, const TreeHdr& T, const GameSlot& gs, Descent& D, PathRegs& pr,
+                         Pcg32& rng) {
+  D.gumbel = false;
+  if (E.gumbel_enabled) {
+    Pcg32 r = rng;  // a copy keeps the address handed to the out-of-line code away from the hot state
+    D.gumbel = gumbel_begin(E, g * (u32)kP + gs.player, T, r);
+    rng = r;
+  }
   D.s.p[0] = gs.p0; D.s.p[1] = gs.p1; D.s.turn = gs.turn; D.s.player = gs.player;
   D.blk = T.fc;
   D.cur_n = T.n; D.cur_term = T.term; D.cur_player = T.player; D.cur_k = T.k;
@@ -358,6 +570,19 @@ AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
     D.cur_k = hd.w & 0xFFu;
     D.cur_player = (hd.w >> 8) & 0xFFu;
   }
+  u32 forced = kNil;  // Gumbel: the root child comes from the halving schedule, interior nodes (gumbel_full) from pi'
+  if (D.gumbel) {
+    if (D.at_root) {
+      const u32 tree = g * (u32)kP + D.cur_player;  // the searching seat's tree: the root's side to move
+      GumbelState S = E.gum[tree];
+      TreeHdr R;  // the fields gumbel_next_root_child reads
+      R.fc = D.blk; R.k = (u8)D.cur_k;
+      forced = gumbel_next_root_child(E, S, R);
+      E.gum[tree] = S;
+    } else if (E.gumbel_full) {
+      forced = gumbel_interior_select(E, D.blk, D.cur_k, D.cur_v);
+    }
+  }
   const float fpu = (D.at_root && E.root_fpu_zero) ? 0.0f : E.fpu_reduction;
   float seen = 0.0f;
 #pragma unroll
@@ -373,7 +598,7 @@ AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
     const u32 nj = r[j].x;
     const float base = (nj == 0) ? fpu_value : u2f(r[j].y);
     const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
-    if (j == 0 || u > best_u) {
+    if (forced == kNil ? (j == 0 || u > best_u) : ((u32)j == forced)) {
       best_u = u;
       best = (u32)j;
       best_n = nj;
@@ -599,7 +824,7 @@ AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s,
 }
 AZ_HD void find_leaf(const EngineView& E, u32 g, TreeHdr& T, GameSlot& gs, Pcg32& rng, PathRegs& pr) {
   Descent D;
-  descent_begin(T, gs, D, pr);
+  descent_begin(E, g, T, gs, D, pr, rng);
   while (descent_more(D))
     if (!descent_level(E, g, D, pr)) break;
   descent_finish(E, g, T, gs, rng, D);
@@ -706,7 +931,7 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
       Pcg32 r = rng;
 #pragma unroll
       for (int j = 0; j < kKMax; ++j) p8[j] = u2f(ps[j]);
-      root_leaf_priors(E, r, p8, lk, noise_enabled);
+      root_leaf_priors(E, r, p8, lk, noise_enabled && !E.gumbel_enabled);  // Gumbel replaces Dirichlet (mcts.cc:514-518)
       rng = r;
 #pragma unroll
       for (int j = 0; j < kKMax; ++j) ps[j] = ((u32)j < lk) ? f2u(p8[j]) : 0u;
@@ -1041,6 +1266,15 @@ AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_befor
   }
 }
 
+// set_gumbel_num_sims for the tree that searches next (play_manager.cc:531-539, 562-570): the full budget, or for a
+// capped search the cap when fast_search_uses_gumbel, else 0 = "PUCT for this search".
+AZ_COLD void gumbel_arm(const EngineView E, u32 g, u32 seat, bool capped) {
+  const u32 target = capped ? (E.fast_search_uses_gumbel ? E.cap_visits[seat] : 0u) : E.visits[seat];
+  GumbelState S = E.gum[(size_t)g * kP + seat];
+  gumbel_set_num_sims(S, target);
+  E.gum[(size_t)g * kP + seat] = S;
+}
+
 struct Ctx {       // what a thread keeps in registers across the fused steps of one launch
   GameSlot gs;
   TreeHdr T;       // the tree of the side to move (gs.player); the other seat's stays in HBM
@@ -1118,12 +1352,38 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     }
   }
   float pi[kA];
-  mcts_probs(R, temp, pi);
-  u32 chosen = mcts_pick_move(rng, pi);
+  u32 chosen;
+  GumbelState GS[kP];
+  if (E.gumbel_enabled) {
+    GS[0] = E.gum[(size_t)g * kP + 0];
+    GS[1] = E.gum[(size_t)g * kP + 1];
+  }
+  if (E.gumbel_enabled && !gs.capped && GS[cp].initialized && GS[cp].n_surv > 0) {
+    // gumbel_final_action (mcts.cc:375-401): argmax over the surviving candidates of g + logit + sigma(q_hat)
+    u32 max_visit = 0;
+    for (u32 j = 0; j < R.k; ++j)
+      if (R.n[j] > max_visit) max_visit = R.n[j];
+    const float sigma_scale = gumbel_sigma_scale(E, max_visit);
+    u32 best = GS[cp].survivors & 15u;
+    float best_score = -INFINITY;
+    for (u32 r = 0; r < (u32)GS[cp].n_surv; ++r) {
+      const u32 c = (GS[cp].survivors >> (4u * r)) & 15u;
+      const float logit = az_logf(fadd(R.pol[c], AZ_GUMBEL_LOG_FLOOR));
+      const float q_hat = R.n[c] > 0 ? R.q[c] : 0.0f;
+      const float score = fadd(fadd(GS[cp].g[c], logit), fmul(sigma_scale, q_hat));
+      if (score > best_score) { best_score = score; best = c; }
+    }
+    chosen = R.mv[best];
+  } else {
+    // PUCT acting — and Gumbel's fallback when the state never initialised: pick_move(probs(0)) (mcts.cc:379-381)
+    mcts_probs(R, (E.gumbel_enabled && !gs.capped) ? 0.0f : temp, pi);
+    chosen = mcts_pick_move(rng, pi);
+  }
   if (chosen >= (u32)kA) { at_or(&E.glob->error, B2AZ_DEVERR_MOVE); chosen = R.k ? R.mv[0] : 0u; }
   if (E.history_enabled && !gs.capped) {
     float target[kA];
-    if (E.policy_target_pruning && E.epsilon > 0.0f) mcts_probs_pruned(E, T[cp], R, 1.0f, target);
+    if (E.gumbel_enabled) gumbel_improved_policy(E, T[cp], target);  // play_manager.cc:411-417
+    else if (E.policy_target_pruning && E.epsilon > 0.0f) mcts_probs_pruned(E, T[cp], R, 1.0f, target);
     else mcts_probs(R, 1.0f, target);
     if (gs.hist_n < (u32)kMaxHist) {
       HistEntry h;
@@ -1149,7 +1409,10 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
   C4State s;
   s.p[0] = gs.p0; s.p[1] = gs.p1; s.turn = gs.turn; s.player = gs.player;
   const u32 vm_before = c4_valid_mask(s);
-  for (int seat = 0; seat < kP; ++seat) update_root(E, T[seat], chosen, vm_before, rng);
+  for (int seat = 0; seat < kP; ++seat) {
+    update_root(E, T[seat], chosen, vm_before, rng);
+    if (E.gumbel_enabled) gumbel_reset(GS[seat]);  // update_root ends with reset_gumbel_state() (mcts.cc:172)
+  }
   if (!c4_play(s, chosen)) at_or(&E.glob->error, B2AZ_DEVERR_MOVE);
   gs.p0 = s.p[0]; gs.p1 = s.p[1]; gs.turn = s.turn; gs.player = s.player;
   ++cold.nmoves;
@@ -1191,6 +1454,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     for (int seat = 0; seat < kP; ++seat) {
       tree_free_pages(E, T[seat]);
       tree_reset(T[seat]);
+      if (E.gumbel_enabled) gumbel_set_num_sims(GS[seat], 0u);  // make_mcts: a fresh MCTS has no sims target
     }
     if (started >= E.games_to_play) {
       retired = true;  // play_manager.cc:506-509
@@ -1203,10 +1467,17 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
   if (!retired) {
     // a move has been played: update the playout cap (play_manager.cc:523-524; `&&` short-circuits the draw)
     gs.capped = (E.playout_cap && rng_uniform01(rng) < E.playout_cap_percent) ? 1 : 0;
+    if (E.gumbel_enabled) {  // set_gumbel_num_sims for the seat that searches next (play_manager.cc:531-539)
+      const u32 ncp = gs.player;
+      gumbel_set_num_sims(GS[ncp], gs.capped ? (E.fast_search_uses_gumbel ? E.cap_visits[ncp] : 0u) : E.visits[ncp]);
+    }
     if (!E.tree_reuse) {
       for (int seat = 0; seat < kP; ++seat) {
         tree_free_pages(E, T[seat]);
         tree_reset(T[seat]);
+        // make_mcts AFTER set_gumbel_num_sims: the fresh MCTS has target 0, so without tree reuse the reference
+        // never starts a Gumbel search after the first move (play_manager.cc:540-545) — kept as is
+        if (E.gumbel_enabled) gumbel_set_num_sims(GS[seat], 0u);
       }
     } else {
       // the reused root gets the root temperature again and fresh noise (play_manager.cc:546-553,
@@ -1239,6 +1510,10 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
   }
   E.trees[(size_t)g * kP + 0] = T[0];
   E.trees[(size_t)g * kP + 1] = T[1];
+  if (E.gumbel_enabled) {
+    E.gum[(size_t)g * kP + 0] = GS[0];
+    E.gum[(size_t)g * kP + 1] = GS[1];
+  }
   E.cold[g] = cold;
   if (E.rng_mode == 1) E.glob->global_rng = rng; else gs.rng = rng;
   E.games[g] = gs;
@@ -1263,6 +1538,7 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
   } else {
     c.gs.initialized = 1;
     c.gs.capped = (E.playout_cap && rng_uniform01(c.rng) < E.playout_cap_percent) ? 1 : 0;  // play_manager.cc:559-560
+    if (E.gumbel_enabled) gumbel_arm(E, g, c.gs.player, c.gs.capped != 0);                       // :562-570
   }
   if (!retired) find_leaf(E, g, c.T, c.gs, c.rng, c.pr);
 }
@@ -1294,9 +1570,10 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
       } else {
         c.gs.initialized = 1;
         c.gs.capped = (E.playout_cap && rng_uniform01(c.rng) < E.playout_cap_percent) ? 1 : 0;
+        if (E.gumbel_enabled) gumbel_arm(E, g, c.gs.player, c.gs.capped != 0);
       }
       if (retired) break;
-      descent_begin(c.T, c.gs, D, c.pr);
+      descent_begin(E, g, c.T, c.gs, D, c.pr, c.rng);
       in_descent = true;
     }
     if (descent_more(D) && descent_level(E, g, D, c.pr)) continue;

@@ -116,6 +116,21 @@ struct __attribute__((aligned(8))) CacheVal {  // what a hit returns: pi[A] and 
 };
 static_assert(sizeof(CacheVal) == 40, "CacheVal layout");
 
+// Gumbel root-search state of one tree (MCTS::gumbel_* members, mcts.h:163-176). Connect4: <= 7 root
+// children, so at most ceil(log2 7) = 3 halving phases.
+constexpr int kMaxPhases = 4;
+struct __attribute__((aligned(16))) GumbelState {
+  float g[kKMax];             // gumbel_g_: one draw per root child, child order
+  u32 survivors;              // gumbel_survivors_: child indices as nibbles, in rank order
+  u32 phase_numc[kMaxPhases]; // gumbel_phases_[i].first
+  u32 phase_vper[kMaxPhases]; // gumbel_phases_[i].second
+  u32 num_sims_target;        // gumbel_num_sims_target_
+  u32 sims_in_phase;          // gumbel_sims_in_phase_
+  u8 n_surv, n_phases, phase_idx, initialized;
+  u8 effective_m, pad_[3];
+};
+static_assert(sizeof(GumbelState) == 80, "GumbelState layout");
+
 struct Globals {
   unsigned long long simulations, moves, game_length;
   unsigned long long wins[3], resign_wins[3];
@@ -140,6 +155,9 @@ struct EngineView {
   float cpuct, fpu_reduction, epsilon, root_temp;
   float start_temp, final_temp, half_life, playout_cap_percent;
   float resign_percent, resign_playthrough_percent;
+  float gumbel_c_visit, gumbel_c_scale;
+  u32 gumbel_m;
+  u8 gumbel_enabled, gumbel_full, fast_search_uses_gumbel, pad0_;
   u8 history_enabled, tree_reuse, root_fpu_zero, shaped_dirichlet;
   u8 policy_target_pruning, playout_cap, eval_type, rng_mode;
   u32 num_pages, hist_capacity;
@@ -150,6 +168,7 @@ struct EngineView {
   u32* ring;           // [num_pages] free-chain heads (kNil = empty slot)
   // ---- per tree / per game
   TreeHdr* trees;      // [G * kP]
+  GumbelState* gum;    // [G * kP], NULL unless gumbel_enabled
   GameSlot* games;     // [G]
   GameCold* cold;      // [G]
   u32* path;           // [G][kMaxPath]  block index of every selected edge

@@ -17,8 +17,9 @@
 //                        generation to the device (b2az_submit_eval_host) and wakes the driver.
 //   build_history_batch  b2az_drain_history into the caller's arrays.
 // max_cache_size > 0 turns on the device position cache (the engine's replacement for ShardedS3FIFOCache).
-// Not carried (rejected with RuntimeError instead of being ignored): Gumbel, resign, playout-cap
-// randomisation, model groups / seat permutations / per-seat overrides, PLAYOUT eval, external caches.
+// Gumbel root search, playout-cap randomisation and resign_percent are carried by the engine.
+// Not carried (rejected with RuntimeError instead of being ignored): model groups / seat permutations /
+// per-seat overrides (incl. per-seat resign thresholds), PLAYOUT eval, external caches.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -243,7 +244,9 @@ class PlayManager {
     auto reject = [](bool bad, const char* what) {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
     };
-    reject(P.gumbel_enabled || !P.seat_gumbel_enabled.empty(), "gumbel_enabled");
+    reject(!P.seat_gumbel_enabled.empty() || !P.seat_gumbel_m.empty() || !P.seat_gumbel_c_visit.empty() ||
+               !P.seat_gumbel_c_scale.empty() || !P.seat_gumbel_full.empty() || !P.seat_gumbel_use_improved_policy.empty(),
+           "per-seat Gumbel overrides");
     reject(!P.seat_resign_threshold.empty(), "seat_resign_threshold");
     reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
     reject(!P.seat_visits.empty() || !P.seat_cap_visits.empty() || !P.seat_epsilon.empty() ||
@@ -274,6 +277,12 @@ class PlayManager {
     bp.tree_reuse = P.tree_reuse;
     bp.epsilon = P.epsilon;
     bp.mcts_root_temp = P.mcts_root_temp;
+    bp.gumbel_enabled = P.gumbel_enabled;
+    bp.gumbel_m = P.gumbel_m;
+    bp.gumbel_c_visit = P.gumbel_c_visit;
+    bp.gumbel_c_scale = P.gumbel_c_scale;
+    bp.gumbel_full = P.gumbel_full;
+    bp.fast_search_uses_gumbel = P.fast_search_uses_gumbel;
     bp.playout_cap_randomization = P.playout_cap_randomization;
     bp.resign_percent = P.resign_percent;
     bp.resign_playthrough_percent = P.resign_playthrough_percent;

@@ -64,7 +64,7 @@ typedef struct b2az_params {
   uint8_t root_fpu_zero;
   uint8_t shaped_dirichlet;
   uint8_t policy_target_pruning;
-  uint8_t gumbel_enabled;        /* must be 0 for now */
+  uint8_t gumbel_enabled;        /* Gumbel root search (mcts.cc:175-401); parameters at the end of the struct */
   float resign_percent;          /* with playout_cap_randomization: B2AZ_RNG_PER_GAME only (coins from the game's stream) */
   float resign_playthrough_percent;
   uint8_t eval_type;             /* B2AZ_EVAL_*; applies to every seat */
@@ -77,6 +77,13 @@ typedef struct b2az_params {
   uint32_t lanes_per_game;       /* threads per game slot: 0 or 1 (Connect4 runs one thread per game) */
   uint32_t compact_pages;        /* a tree's arena (12 KB pages) is compacted at a move once it holds more
                                     pages than this; 0 = half of the tree's share of the pool */
+  /* Gumbel AlphaZero (play_manager.h:104-116) */
+  uint32_t gumbel_m;             /* 16 */
+  float gumbel_c_visit;          /* 50 */
+  float gumbel_c_scale;          /* 1 */
+  uint8_t gumbel_full;           /* pi'-matching at interior nodes too */
+  uint8_t fast_search_uses_gumbel;
+  uint8_t pad3_[2];
   uint32_t pad2_;
 } b2az_params;
 

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstring>
 #include <deque>
+#include <limits>
 #include <memory>
 #include <random>
 #include <vector>
@@ -128,11 +129,20 @@ struct Node {  // mcts.h:14-48
   std::vector<Node> children;
 };
 
-struct Tree {  // MCTS, mcts.h:50-201 (PUCT members only)
+struct Tree {  // MCTS, mcts.h:50-201
   Node root;
   Node* current = nullptr;
   std::vector<Node*> path;
   uint32_t depth = 0, total_leaf_depth = 0;
+  // Gumbel state (mcts.h:163-176)
+  uint32_t gumbel_num_sims_target = 0;
+  bool gumbel_initialized = false;
+  uint32_t gumbel_effective_m = 0;
+  std::vector<float> gumbel_g;
+  std::vector<size_t> gumbel_survivors;
+  std::vector<std::pair<uint32_t, uint32_t>> gumbel_phases;
+  size_t gumbel_phase_idx = 0;
+  uint32_t gumbel_sims_in_phase = 0;
 };
 
 struct Cfg : azo_cfg {};
@@ -226,13 +236,207 @@ void apply_root_policy_temp(Tree& t, const Cfg& c) {
     for (auto& ch : t.root.children) ch.policy /= sum;
 }
 // mcts.cc:462-498 (PUCT branch). Returns the leaf position in `leaf`.
+// ---------------------------------------------------------------------------- Gumbel (mcts.cc:24-89, 175-401)
+constexpr float GUMBEL_LOG_FLOOR = 1e-20f;
+// mcts.cc:28-66
+std::vector<std::pair<uint32_t, uint32_t>> seq_halving_phase_plan(uint32_t m, uint32_t n) {
+  std::vector<std::pair<uint32_t, uint32_t>> phases;
+  if (m <= 1) {
+    phases.emplace_back(1, n);
+    return phases;
+  }
+  uint32_t log2m = 0;
+  for (uint32_t v = m - 1; v > 0; v >>= 1) ++log2m;
+  if (log2m == 0) log2m = 1;
+  const uint32_t base_v = std::max<uint32_t>(1u, n / (log2m * m));
+  uint32_t sims_used = 0, num_c = m;
+  for (uint32_t phase_idx = 0; phase_idx < log2m; ++phase_idx) {
+    if (sims_used >= n) break;
+    const uint32_t remaining = n - sims_used;
+    const bool is_final = (phase_idx == log2m - 1);
+    uint32_t v_per = is_final ? std::max<uint32_t>(1u, remaining / num_c) : base_v * (1u << phase_idx);
+    if (num_c * v_per > remaining) {
+      v_per = remaining / num_c;
+      if (v_per == 0) {
+        num_c = remaining;
+        v_per = 1;
+      }
+    }
+    phases.emplace_back(num_c, v_per);
+    sims_used += num_c * v_per;
+    num_c = std::max<uint32_t>(1u, num_c / 2);
+  }
+  return phases;
+}
+// mcts.cc:71-89
+float compute_v_mix_from_children(float raw_v, const std::vector<float>& qs, const std::vector<uint32_t>& ns,
+                                  const std::vector<float>& priors) {
+  float sum_visits = 0.0f, sum_priors_visited = 0.0f, weighted_num = 0.0f;
+  for (size_t i = 0; i < qs.size(); ++i) {
+    sum_visits += static_cast<float>(ns[i]);
+    if (ns[i] > 0) {
+      sum_priors_visited += priors[i];
+      weighted_num += priors[i] * qs[i];
+    }
+  }
+  if (sum_priors_visited <= 0.0f) return raw_v;
+  const float weighted_q = weighted_num / sum_priors_visited;
+  return (raw_v + sum_visits * weighted_q) / (sum_visits + 1.0f);
+}
+// mcts.cc:180-188, 175-178
+void reset_gumbel_state(Tree& t) {
+  t.gumbel_initialized = false;
+  t.gumbel_effective_m = 0;
+  t.gumbel_g.clear();
+  t.gumbel_survivors.clear();
+  t.gumbel_phases.clear();
+  t.gumbel_phase_idx = 0;
+  t.gumbel_sims_in_phase = 0;
+}
+void set_gumbel_num_sims(Tree& t, uint32_t n) {
+  t.gumbel_num_sims_target = n;
+  reset_gumbel_state(t);
+}
+// mcts.cc:190-227
+void init_gumbel_state(Tree& t, const Cfg& c, Pcg& re) {
+  const auto num_legal = static_cast<uint32_t>(t.root.children.size());
+  if (num_legal == 0) return;
+  const uint32_t remaining = t.depth < t.gumbel_num_sims_target ? t.gumbel_num_sims_target - t.depth : 0;
+  if (remaining == 0) return;
+  t.gumbel_effective_m = std::max<uint32_t>(1u, std::min({c.gumbel_m, num_legal, remaining}));
+  std::extreme_value_distribution<float> gumbel_dist{0.0f, 1.0f};
+  t.gumbel_g.resize(num_legal);
+  for (uint32_t i = 0; i < num_legal; ++i) t.gumbel_g[i] = gumbel_dist(re);
+  std::vector<size_t> idx(num_legal);
+  for (uint32_t i = 0; i < num_legal; ++i) idx[i] = i;
+  std::partial_sort(idx.begin(), idx.begin() + t.gumbel_effective_m, idx.end(), [&t](size_t a, size_t b) {
+    const float la = std::log(t.root.children[a].policy + GUMBEL_LOG_FLOOR);
+    const float lb = std::log(t.root.children[b].policy + GUMBEL_LOG_FLOOR);
+    return t.gumbel_g[a] + la > t.gumbel_g[b] + lb;
+  });
+  t.gumbel_survivors.assign(idx.begin(), idx.begin() + t.gumbel_effective_m);
+  t.gumbel_phases = seq_halving_phase_plan(t.gumbel_effective_m, remaining);
+  t.gumbel_phase_idx = 0;
+  t.gumbel_sims_in_phase = 0;
+  t.gumbel_initialized = true;
+}
+// mcts.cc:229-264
+void gumbel_advance_phase(Tree& t, const Cfg& c) {
+  if (t.gumbel_phase_idx + 1 >= t.gumbel_phases.size()) return;
+  const auto next_num_c = t.gumbel_phases[t.gumbel_phase_idx + 1].first;
+  if (next_num_c >= t.gumbel_survivors.size()) {
+    ++t.gumbel_phase_idx;
+    t.gumbel_sims_in_phase = 0;
+    return;
+  }
+  uint32_t max_visit = 0;
+  for (const auto child_idx : t.gumbel_survivors) max_visit = std::max(max_visit, t.root.children[child_idx].n);
+  const float sigma_scale = (c.gumbel_c_visit + static_cast<float>(max_visit)) * c.gumbel_c_scale;
+  std::vector<std::pair<float, size_t>> scored;
+  for (const auto child_idx : t.gumbel_survivors) {
+    const auto& ch = t.root.children[child_idx];
+    const float logit = std::log(ch.policy + GUMBEL_LOG_FLOOR);
+    const float q_hat = ch.n > 0 ? ch.q : 0.0f;
+    const float score = t.gumbel_g[child_idx] + logit + sigma_scale * q_hat;
+    scored.emplace_back(score, child_idx);
+  }
+  std::partial_sort(scored.begin(), scored.begin() + next_num_c, scored.end(),
+                    [](const auto& a, const auto& b) { return a.first > b.first; });
+  t.gumbel_survivors.resize(next_num_c);
+  for (size_t i = 0; i < next_num_c; ++i) t.gumbel_survivors[i] = scored[i].second;
+  ++t.gumbel_phase_idx;
+  t.gumbel_sims_in_phase = 0;
+}
+// mcts.cc:266-283
+size_t gumbel_next_root_child(Tree& t, const Cfg& c) {
+  if (t.gumbel_phase_idx < t.gumbel_phases.size()) {
+    const auto& [num_c, v_per] = t.gumbel_phases[t.gumbel_phase_idx];
+    if (t.gumbel_sims_in_phase >= num_c * v_per) gumbel_advance_phase(t, c);
+  }
+  if (t.gumbel_survivors.empty()) return 0;
+  const size_t pick = t.gumbel_sims_in_phase % t.gumbel_survivors.size();
+  ++t.gumbel_sims_in_phase;
+  return t.gumbel_survivors[pick];
+}
+// softmax(log prior + sigma * completedQ) shared by mcts.cc:285-334 and :336-373
+float gumbel_z(const Node& node, const Cfg& c, std::vector<float>& z, std::vector<uint32_t>& ns, uint32_t& sum_visits) {
+  const auto k = node.children.size();
+  uint32_t max_visit = 0;
+  sum_visits = 0;
+  std::vector<float> qs(k), priors(k);
+  ns.assign(k, 0);
+  for (size_t i = 0; i < k; ++i) {
+    max_visit = std::max(max_visit, node.children[i].n);
+    sum_visits += node.children[i].n;
+    qs[i] = node.children[i].q;
+    ns[i] = node.children[i].n;
+    priors[i] = node.children[i].policy;
+  }
+  const float v_mix = compute_v_mix_from_children(node.v, qs, ns, priors);
+  const float sigma_scale = (c.gumbel_c_visit + static_cast<float>(max_visit)) * c.gumbel_c_scale;
+  z.assign(k, 0.0f);
+  float z_max = -std::numeric_limits<float>::infinity();
+  for (size_t i = 0; i < k; ++i) {
+    const float completed_q = ns[i] > 0 ? qs[i] : v_mix;
+    z[i] = std::log(priors[i] + GUMBEL_LOG_FLOOR) + sigma_scale * completed_q;
+    if (z[i] > z_max) z_max = z[i];
+  }
+  float z_sum = 0.0f;
+  for (size_t i = 0; i < k; ++i) {
+    z[i] = std::exp(z[i] - z_max);
+    z_sum += z[i];
+  }
+  return z_sum;
+}
+// mcts.cc:285-334
+size_t gumbel_interior_select(const Node& node, const Cfg& c) {
+  std::vector<float> z;
+  std::vector<uint32_t> ns;
+  uint32_t sum_visits = 0;
+  const float z_sum = gumbel_z(node, c, z, ns, sum_visits);
+  const float inv = z_sum > 0 ? (1.0f / z_sum) : 0.0f;
+  const float denom = 1.0f + static_cast<float>(sum_visits);
+  size_t best = 0;
+  float best_score = -std::numeric_limits<float>::infinity();
+  for (size_t i = 0; i < z.size(); ++i) {
+    const float pi_prime = z[i] * inv;
+    const float score = pi_prime - static_cast<float>(ns[i]) / denom;
+    if (score > best_score) {
+      best_score = score;
+      best = i;
+    }
+  }
+  return best;
+}
+// mcts.cc:336-373
+void gumbel_improved_policy(const Tree& t, const Cfg& c, float* out) {
+  for (int m = 0; m < A; ++m) out[m] = 0.0f;
+  if (t.root.children.empty()) return;
+  std::vector<float> z;
+  std::vector<uint32_t> ns;
+  uint32_t sum_visits = 0;
+  const float z_sum = gumbel_z(t.root, c, z, ns, sum_visits);
+  if (z_sum <= 0) return;
+  for (size_t i = 0; i < z.size(); ++i) out[t.root.children[i].move] = z[i] / z_sum;
+}
+
 void find_leaf(Tree& t, const Cfg& c, const Board& gs, Board& leaf, Pcg& re) {
   t.current = &t.root;
   leaf = gs;
+  if (c.gumbel_enabled && !t.gumbel_initialized && t.gumbel_num_sims_target > 0 && t.root.n > 0 &&
+      !t.root.children.empty()) {
+    init_gumbel_state(t, c, re);  // :468-472
+  }
   while (t.current->n > 0 && t.current->term == 0) {
     t.path.push_back(t.current);
-    const float fpu = (t.current == &t.root && c.root_fpu_zero) ? 0.0f : c.fpu_reduction;
-    t.current = best_child(*t.current, c.cpuct, fpu);
+    if (c.gumbel_enabled && t.gumbel_initialized && t.current == &t.root) {
+      t.current = &t.root.children[gumbel_next_root_child(t, c)];
+    } else if (c.gumbel_enabled && t.gumbel_initialized && c.gumbel_full) {
+      t.current = &t.current->children[gumbel_interior_select(*t.current, c)];
+    } else {
+      const float fpu = (t.current == &t.root && c.root_fpu_zero) ? 0.0f : c.fpu_reduction;
+      t.current = best_child(*t.current, c.cpuct, fpu);
+    }
     c4_play(leaf, t.current->move);
   }
   t.total_leaf_depth += static_cast<uint32_t>(t.path.size());
@@ -250,7 +454,7 @@ void process_result(Tree& t, const Cfg& c, float* value, const float* pi, bool r
     for (int i = 0; i < P + 1; ++i) value[i] = (t.current->term == i + 1) ? 1.0f : 0.0f;
   } else if (t.current == &t.root) {
     set_policy_normalized(*t.current, pi, c.mcts_root_temp != 1.0f, 1.0f / c.mcts_root_temp);
-    if (root_noise) add_root_noise(t, c, re);
+    if (root_noise && !c.gumbel_enabled) add_root_noise(t, c, re);  // :514-518
   } else {
     set_policy_normalized(*t.current, pi, false, 1.0f);
   }
@@ -287,6 +491,7 @@ bool update_root(Tree& t, const Board& gs, uint32_t move, Pcg& re) {
   if (x == t.root.children.end()) return false;
   Node tmp = std::move(*x);
   t.root = std::move(tmp);
+  reset_gumbel_state(t);  // mcts.cc:172
   return true;
 }
 void counts_of(const Tree& t, uint32_t* out) {  // mcts.cc:557-564
@@ -505,13 +710,40 @@ void play_iteration(PM& pm, uint32_t i) {
         }
       }
       float pi[A];
-      probs_of(mcts, temp, pi);
-      const uint32_t chosen = pick_move(pi, re);
+      uint32_t chosen;
+      if (c.gumbel_enabled && !game.capped) {
+        // gumbel_final_action (mcts.cc:375-401); the improved-policy-sampling opt-in (G3) is a per-seat override
+        if (!mcts.gumbel_initialized || mcts.gumbel_survivors.empty()) {
+          probs_of(mcts, 0.0f, pi);
+          chosen = pick_move(pi, re);
+        } else {
+          uint32_t max_visit = 0;
+          for (const auto& ch : mcts.root.children) max_visit = std::max(max_visit, ch.n);
+          const float sigma_scale = (c.gumbel_c_visit + static_cast<float>(max_visit)) * c.gumbel_c_scale;
+          size_t best = mcts.gumbel_survivors[0];
+          float best_score = -std::numeric_limits<float>::infinity();
+          for (const auto child_idx : mcts.gumbel_survivors) {
+            const auto& ch = mcts.root.children[child_idx];
+            const float logit = std::log(ch.policy + GUMBEL_LOG_FLOOR);
+            const float q_hat = ch.n > 0 ? ch.q : 0.0f;
+            const float score = mcts.gumbel_g[child_idx] + logit + sigma_scale * q_hat;
+            if (score > best_score) {
+              best_score = score;
+              best = child_idx;
+            }
+          }
+          chosen = mcts.root.children[best].move;
+        }
+      } else {
+        probs_of(mcts, temp, pi);
+        chosen = pick_move(pi, re);
+      }
       if (c.history_enabled && !game.capped) {
         Sample s;
         c4_canon(game.gs, s.canon);
         for (int k = 0; k < P + 1; ++k) s.v[k] = 0.0f;
-        if (c.policy_target_pruning && c.epsilon > 0) probs_pruned_of(mcts, c, 1.0f, s.pi);
+        if (c.gumbel_enabled) gumbel_improved_policy(mcts, c, s.pi);  // play_manager.cc:411-417
+        else if (c.policy_target_pruning && c.epsilon > 0) probs_pruned_of(mcts, c, 1.0f, s.pi);
         else probs_of(mcts, 1.0f, s.pi);
         game.partial.push_back(s);
       }
@@ -567,6 +799,11 @@ void play_iteration(PM& pm, uint32_t i) {
         std::uniform_real_distribution<float> dist{0.0F, 1.0F};
         game.capped = c.playout_cap_randomization && (dist(re) < c.playout_cap_percent);
       }
+      {  // :531-539
+        const int next_cp_g = game.gs.player;
+        const uint32_t sims_target = game.capped ? (c.fast_search_uses_gumbel ? c.playout_cap_depth : 0u) : c.mcts_visits[next_cp_g];
+        set_gumbel_num_sims(game.mcts[next_cp_g], sims_target);
+      }
       if (!c.tree_reuse) {
         for (auto& m : game.mcts) m = Tree{};
       } else {
@@ -581,6 +818,11 @@ void play_iteration(PM& pm, uint32_t i) {
     game.initialized = true;
     std::uniform_real_distribution<float> dist{0.0F, 1.0F};
     game.capped = c.playout_cap_randomization && (dist(re) < c.playout_cap_percent);  // :559-560
+    {  // :562-570
+      const int first_cp = game.gs.player;
+      const uint32_t sims_target = game.capped ? (c.fast_search_uses_gumbel ? c.playout_cap_depth : 0u) : c.mcts_visits[first_cp];
+      set_gumbel_num_sims(game.mcts[first_cp], sims_target);
+    }
   }
   const int cp = game.gs.player;
   Board leaf;

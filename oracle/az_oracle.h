@@ -46,6 +46,10 @@ typedef struct azo_cfg {
   uint8_t playout_cap_randomization, pad2_[3];
   uint32_t playout_cap_depth;
   float playout_cap_percent, resign_percent, resign_playthrough_percent;
+  /* Gumbel AlphaZero (play_manager.h:104-116, mcts.cc:175-401) */
+  uint8_t gumbel_enabled, gumbel_full, fast_search_uses_gumbel, pad3_;
+  uint32_t gumbel_m;
+  float gumbel_c_visit, gumbel_c_scale;
 } azo_cfg;
 
 void* azo_pm_new(const azo_cfg* c);

@@ -62,6 +62,14 @@ def level_params(level):
     if level == 2:  # plain (unshaped) Dirichlet, no root temperature, fast temperature decay
         return dict(cpuct=2.0, fpu_reduction=0.0, epsilon=0.4, mcts_root_temp=1.0, start_temp=1.5, final_temp=0.3,
                     temp_decay_half_life=3.0, root_fpu_zero=0, shaped_dirichlet=0, policy_target_pruning=1)
+    if level == 3:  # Gumbel AlphaZero root search (+ improved-policy targets), no Dirichlet
+        return dict(cpuct=1.25, fpu_reduction=0.25, epsilon=0.0, mcts_root_temp=1.0, start_temp=1.0, final_temp=1.0,
+                    temp_decay_half_life=0.0, root_fpu_zero=0, shaped_dirichlet=0, policy_target_pruning=0,
+                    gumbel_enabled=1, gumbel_m=16, gumbel_c_visit=50.0, gumbel_c_scale=1.0)
+    if level == 4:  # Gumbel everywhere: interior pi'-matching, m < legal moves, epsilon > 0 (noise only on reused roots)
+        return dict(cpuct=1.25, fpu_reduction=0.25, epsilon=0.25, mcts_root_temp=1.25, start_temp=1.0, final_temp=0.2,
+                    temp_decay_half_life=10.0, root_fpu_zero=1, shaped_dirichlet=1, policy_target_pruning=1,
+                    gumbel_enabled=1, gumbel_m=4, gumbel_c_visit=50.0, gumbel_c_scale=0.5, gumbel_full=1)
     raise ValueError(level)
 
 
@@ -76,6 +84,8 @@ class AzoCfg(C.Structure):
         ("fpu_reduction", C.c_float), ("seed", C.c_uint64),
         ("playout_cap_randomization", C.c_uint8), ("pad2_", C.c_uint8 * 3), ("playout_cap_depth", C.c_uint32),
         ("playout_cap_percent", C.c_float), ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
+        ("gumbel_enabled", C.c_uint8), ("gumbel_full", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8),
+        ("pad3_", C.c_uint8), ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float), ("gumbel_c_scale", C.c_float),
     ]
 
 
@@ -531,6 +541,9 @@ GOLDEN_CASES = {
     "nn_level2": (3, 5, 30, 2, 7, 0),
     "random_level0": (8, 20, 64, 0, 12345, 1),
     "random_level1": (8, 16, 40, 1, 99, 1),
+    "nn_level3_gumbel": (4, 6, 50, 3, 4242, 0),
+    "nn_level4_gumbel_full": (3, 5, 40, 4, 777, 0),
+    "random_level3_gumbel": (8, 16, 48, 3, 31, 1),
 }
 
 

@@ -115,6 +115,28 @@ def test_playout_cap_and_resign_vs_port(flat, monkeypatch):
     assert r["games"] > 6
 
 
+@needs_ref
+@pytest.mark.parametrize("level", [3, 4])
+def test_gumbel_vs_reference_live(level):
+    """Gumbel root search (init / halving phases / next root child / interior select / improved policy / final action,
+    mcts.cc:175-401) against the UNMODIFIED reference, lock-step, bit for bit."""
+    r = ph.run_lockstep_parity(EMU, G=5, games_to_play=9, visits=40, level=level, seed=99, oracle="ref")
+    assert r["games"] == 9
+
+
+@pytest.mark.parametrize("flat", ["0", "1"])
+def test_gumbel_with_playout_cap_vs_port(flat, monkeypatch):
+    monkeypatch.setenv("B2AZ_EMU_FLAT", flat)
+    extra = dict(fast_search_uses_gumbel=1, playout_cap_randomization=1, playout_cap_depth=12, playout_cap_percent=0.5)
+    for level in (3, 4):
+        r = ph.run_random_parity(EMU, G=16, games_to_play=10 ** 6, visits=40, seed=5, oracle="port", rng_mode=b2az.RNG_PER_GAME,
+                                 level=level, steps=1200, chunk=29, ordered=False, extra=extra)
+        assert r["games"] > 16
+    r = ph.run_lockstep_parity(EMU, G=6, games_to_play=10 ** 6, visits=40, level=4, seed=99, oracle="port",
+                               rng_mode=b2az.RNG_PER_GAME, max_generations=1200, extra=dict(extra, fast_search_uses_gumbel=0))
+    assert r["games"] > 6
+
+
 def test_cap_and_resign_rejected_in_reference_parity_mode():
     lib = b2az.load(EMU)
     for kw in (dict(playout_cap_randomization=1), dict(resign_percent=0.1)):
@@ -143,8 +165,8 @@ def test_error_conventions():
         b2az.Engine(b2az.default_params(lib, mcts_visits=(0, 10)), lib=lib)
     with pytest.raises(b2az.B2azError):
         b2az.Engine(b2az.default_params(lib, concurrent_games=0), lib=lib)
-    with pytest.raises(b2az.B2azError, match="not implemented"):
-        b2az.Engine(b2az.default_params(lib, gumbel_enabled=1), lib=lib)
+    with pytest.raises(b2az.B2azError, match="gumbel_m"):
+        b2az.Engine(b2az.default_params(lib, gumbel_enabled=1, gumbel_m=0), lib=lib)
     e = b2az.Engine(b2az.default_params(lib, concurrent_games=2, games_to_play=2, mcts_visits=(8, 8)), lib=lib)
     e.step(1)
     with pytest.raises(b2az.B2azError, match="still waiting"):  # stepping with unanswered leaves

@@ -78,6 +78,25 @@ def test_playout_cap_and_resign_gpu():
     assert r["games"] > 32
 
 
+@pytest.mark.parametrize("level", [3, 4])
+def test_gumbel_parallel_kernel_vs_port(level):
+    """Gumbel root search on the device (per-game streams) vs the port: fused RANDOM-eval launches incl. Gumbel
+    fast searches under playout-cap randomisation, and the lock-step NN loop."""
+    extra = dict(fast_search_uses_gumbel=1, playout_cap_randomization=1, playout_cap_depth=16, playout_cap_percent=0.5)
+    r = ph.run_random_parity(None, G=256, games_to_play=10 ** 6, visits=64, seed=77, oracle="port",
+                             rng_mode=b2az.RNG_PER_GAME, level=level, chunk=64, steps=2500, extra=extra)
+    assert r["games"] > 256
+    r = ph.run_lockstep_parity(None, G=32, games_to_play=10 ** 6, visits=48, level=level, seed=77, oracle="port",
+                               rng_mode=b2az.RNG_PER_GAME, max_generations=1500)
+    assert r["games"] > 32
+
+
+@needs_ref
+def test_gumbel_serial_kernel_vs_reference_live():
+    r = ph.run_lockstep_parity(None, G=5, games_to_play=8, visits=48, level=4, seed=31, oracle="ref")
+    assert r["games"] == 8
+
+
 def test_no_tree_reuse_gpu():
     ph.run_random_parity(None, G=64, games_to_play=10 ** 6, visits=50, seed=3, oracle="port", level=2, tree_reuse=False,
                          steps=3000)

@@ -52,7 +52,7 @@ def _lockstep_two_oracles(G, games, visits, level, seed):
     return gens
 
 
-@pytest.mark.parametrize("level", [0, 1, 2])
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
 def test_port_matches_reference_lockstep(level):
     gens = _lockstep_two_oracles(G=6, games=10, visits=40, level=level, seed=12345)
     assert gens > 100

@@ -146,10 +146,10 @@ def test_error_conventions():
     with pytest.raises(RuntimeError, match="You must specify MCTS visits for each player"):  # play_manager.cc:21
         az.PlayManager(az.Connect4GS(), p)
     p.mcts_visits = [8, 8]
-    p.gumbel_enabled = True
+    p.seat_perms = [[0, 1], [1, 0]]
     with pytest.raises(RuntimeError, match="not implemented"):
         az.PlayManager(az.Connect4GS(), p)
-    p.gumbel_enabled = False
+    p.seat_perms = []
     with pytest.raises(TypeError):
         az.PlayManager(None, p)
     pm = az.PlayManager(az.Connect4GS(), p)
@@ -199,7 +199,7 @@ def _run_pipeline(az, p, workers=2, record=None):
 
 
 @pytest.mark.parametrize("kind", kinds())
-@pytest.mark.parametrize("name", ["nn_level0", "nn_level1_100sims"])
+@pytest.mark.parametrize("name", ["nn_level0", "nn_level1_100sims", "nn_level4_gumbel_full"])
 def test_pipeline_reproduces_reference_golden(kind, name):
     """Deterministic mode through the Python surface == the unmodified reference, bit for bit: every leaf batch
     (ids + canonical planes), every training sample, scores and metrics (tests/golden, tools/make_golden.py)."""

@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-for v in 100 50 25 0; do echo "carveout=$v" >> gpurun_out/r14_variants.json; ( B2AZ_CARVEOUT=$v timeout 300 python tools/gen_profile.py --span 410 ) >> gpurun_out/r14_variants.json 2>> gpurun_out/r14_variants.err; done
-echo "ldcg" >> gpurun_out/r14_variants.json; ( B2AZ_LIB_PATH=build/variants/libb2az_ldcg.so timeout 300 python tools/gen_profile.py --span 410 ) >> gpurun_out/r14_variants.json 2>> gpurun_out/r14_variants.err
-echo "ldcg carveout 100" >> gpurun_out/r14_variants.json; ( B2AZ_CARVEOUT=100 B2AZ_LIB_PATH=build/variants/libb2az_ldcg.so timeout 300 python tools/gen_profile.py --span 410 ) >> gpurun_out/r14_variants.json 2>> gpurun_out/r14_variants.err
-cut -c1-140 gpurun_out/r14_variants.json; tail -n 3 gpurun_out/r14_variants.err
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline ) > gpurun_out/r15_bench_2gpu.json 2> gpurun_out/r15_bench_2gpu.err; echo "rc=$?" >> gpurun_out/r15_bench_2gpu.err
+python -c "
+import json
+for l in open('gpurun_out/r15_bench_2gpu.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['n_gpus'], d['value'], d['e2e']['value'], d['e2e_nn_device']['value'], d['clocks'])"; tail -n 4 gpurun_out/r15_bench_2gpu.err
