@@ -35,6 +35,10 @@ namespace b2az {
 #ifndef B2AZ_L2_STREAM_DEEP
 #define B2AZ_L2_STREAM_DEEP 0
 #endif
+// lanes of a warp that must be ready before the warp runs a step boundary (run_flat); 0 = no gating
+#ifndef B2AZ_GATE
+#define B2AZ_GATE 0
+#endif
 
 #define B2AZ_DEVERR_POOL 1u
 #define B2AZ_DEVERR_HIST 2u
@@ -1553,6 +1557,15 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
   bool in_descent = false;
   u32 left = n_steps, hits = 0;
   while (left > 0) {
+#if defined(__CUDA_ARCH__) && B2AZ_GATE > 0
+    // Step boundaries are the long, divergent part of the loop body (backprop, expansion bookkeeping, maybe a
+    // move). Gate them: the lanes of a warp that reached their leaf wait until at least B2AZ_GATE of them can
+    // cross the boundary together (or nobody is descending any more), so that code runs with fuller warps.
+    // Per-game order of operations is untouched, so results do not depend on the gate.
+    const unsigned act = __activemask();
+    const unsigned rdy = __ballot_sync(act, !in_descent);
+    if (!in_descent && __popc(rdy) < B2AZ_GATE && rdy != act) continue;
+#endif
     if (!in_descent) {  // step boundary: finish the previous simulation, maybe play a move, start a descent
       if (!c.gs.active) break;
       bool retired = false;
