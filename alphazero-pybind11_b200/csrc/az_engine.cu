@@ -181,13 +181,14 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
 
 // One thread per game slot. <= 144 registers so that seven 64-thread CTAs (14 warps) fit an SM: at the
 // BASELINE size (65,536 games over 148 SMs = 443 threads per SM) every game is resident at once.
+template <bool GB>
 __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
   const u32 g = GLOBAL_TID;
   if (g >= E.G) return;
   Ctx c;
   ctx_load(E, g, c);
   if (!c.gs.active) return;
-  run_flat(E, g, c, n_steps);
+  run_flat<GB>(E, g, c, n_steps);
   ctx_store(E, g, c);
 }
 // update_inferences' cache half (play_manager.cc:619-642: insert_many of every evaluated leaf), as its own
@@ -569,7 +570,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   }
 #ifndef B2AZ_HOST_EMU
   if (const char* cv = getenv("B2AZ_CARVEOUT"))  // experiment knob: shared-memory carveout of the step kernel, percent
-    CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
   InitArgs ia{p->seed, p->rng_mode};
   k_init_pool<<<e->num_sms * 4, 256>>>(V);
   k_init_games<<<e->num_sms * 4, 256>>>(V, ia);
@@ -636,7 +637,8 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
     // small CTAs spread the (one thread per game) population evenly over the SMs
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;
     const u32 blocks = (V.G + threads - 1) / threads;
-    k_step<<<blocks, threads, 0, s>>>(V, n_steps);
+    if (V.gumbel_enabled) k_step<true><<<blocks, threads, 0, s>>>(V, n_steps);
+    else k_step<false><<<blocks, threads, 0, s>>>(V, n_steps);
   }
   CUDA_TRY(cudaGetLastError());
 #else

@@ -527,10 +527,14 @@ AZ_COLD bool gumbel_begin(const EngineView E, u32 tree, const TreeHdr T, Pcg32& 
   }
   return S.initialized != 0;
 }
+// GB = false compiles the Gumbel hooks out of the descent (the step kernel picks the instantiation from
+// params.gumbel_enabled): no out-of-line call sites, hence no caller-saved registers, inside the hot loop
+// (spill stores 178 B -> 32 B; throughput unchanged).
+template <bool GB = true>
 AZ_HD void descent_begin(const EngineView& E, u32 g, const TreeHdr& T, const GameSlot& gs, Descent& D, PathRegs& pr,
                          Pcg32& rng) {
   D.gumbel = false;
-  if (E.gumbel_enabled) {
+  if (GB && E.gumbel_enabled) {
     Pcg32 r = rng;  // a copy keeps the address handed to the out-of-line code away from the hot state
     D.gumbel = gumbel_begin(E, g * (u32)kP + gs.player, T, r);
     rng = r;
@@ -548,6 +552,7 @@ AZ_HD void descent_begin(const EngineView& E, u32 g, const TreeHdr& T, const Gam
 AZ_HD bool descent_more(const Descent& D) { return D.cur_n > 0 && D.cur_term == 0; }
 // One level: load the node's child block, pick best_child, replay the move. Returns false on the
 // (impossible for Connect4) structural error, which ends the descent.
+template <bool GB = true>
 AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
   if (D.blk == kNil || D.plen >= (u32)kMaxPath) {  // cannot happen for a non-terminal Connect4 node
     at_or(&E.glob->error, B2AZ_DEVERR_DEPTH);
@@ -575,7 +580,7 @@ AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
     D.cur_player = (hd.w >> 8) & 0xFFu;
   }
   u32 forced = kNil;  // Gumbel: the root child comes from the halving schedule, interior nodes (gumbel_full) from pi'
-  if (D.gumbel) {
+  if (GB && D.gumbel) {
     if (D.at_root) {
       const u32 tree = g * (u32)kP + D.cur_player;  // the searching seat's tree: the root's side to move
       GumbelState S = E.gum[tree];
@@ -602,7 +607,7 @@ AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
     const u32 nj = r[j].x;
     const float base = (nj == 0) ? fpu_value : u2f(r[j].y);
     const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
-    if (forced == kNil ? (j == 0 || u > best_u) : ((u32)j == forced)) {
+    if ((!GB || forced == kNil) ? (j == 0 || u > best_u) : ((u32)j == forced)) {
       best_u = u;
       best = (u32)j;
       best_n = nj;
@@ -1552,6 +1557,7 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
 // independent games every iteration then holds exactly one block-load wait for EVERY game, instead of
 // the warp idling until its deepest descent is done (measured: mean path 3, deepest of 32 about 7).
 // The per-game order of operations — hence every result — is the one of game_step().
+template <bool GB = true>
 AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
   Descent D;
   bool in_descent = false;
@@ -1561,7 +1567,8 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
     // Step boundaries are the long, divergent part of the loop body (backprop, expansion bookkeeping, maybe a
     // move). Gate them: the lanes of a warp that reached their leaf wait until at least B2AZ_GATE of them can
     // cross the boundary together (or nobody is descending any more), so that code runs with fuller warps.
-    // Per-game order of operations is untouched, so results do not depend on the gate.
+    // Per-game order of operations is untouched, so results do not depend on the gate. Measured (r17): slower,
+    // 1.33 G -> 1.25 G sims/s at 12 lanes — the idle lanes cost more than the fuller warps save.
     const unsigned act = __activemask();
     const unsigned rdy = __ballot_sync(act, !in_descent);
     if (!in_descent && __popc(rdy) < B2AZ_GATE && rdy != act) continue;
@@ -1583,13 +1590,13 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
       } else {
         c.gs.initialized = 1;
         c.gs.capped = (E.playout_cap && rng_uniform01(c.rng) < E.playout_cap_percent) ? 1 : 0;
-        if (E.gumbel_enabled) gumbel_arm(E, g, c.gs.player, c.gs.capped != 0);
+        if (GB && E.gumbel_enabled) gumbel_arm(E, g, c.gs.player, c.gs.capped != 0);
       }
       if (retired) break;
-      descent_begin(E, g, c.T, c.gs, D, c.pr, c.rng);
+      descent_begin<GB>(E, g, c.T, c.gs, D, c.pr, c.rng);
       in_descent = true;
     }
-    if (descent_more(D) && descent_level(E, g, D, c.pr)) continue;
+    if (descent_more(D) && descent_level<GB>(E, g, D, c.pr)) continue;
     descent_finish(E, g, c.T, c.gs, c.rng, D);
     in_descent = false;
     if (E.eval_type == 0) {
