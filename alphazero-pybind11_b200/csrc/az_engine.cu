@@ -966,3 +966,5 @@ int b2az_c4_batch(int device, uint32_t n, const int8_t* boards_host, const uint8
 }
 
 }  // extern "C"
+
+#include "az_tafl_kernels.h"

@@ -1,0 +1,134 @@
+// oracle/ref_tafl_driver.cc — extern "C" driver around the UNMODIFIED reference tafl games
+// (/root/reference/src/{brandubh,opentafl,tawlbwrdd}_gs.cc, compiled in place against oracle/shim/).
+// TEST INFRASTRUCTURE ONLY — nothing in the product path links it.
+//
+// The three game files are pulled into THIS translation unit with #include: their headers define
+// non-inline functions (brandubh_gs.h:85-98 operator==, tafl_helper.h:7-14 policyLocation ...), so two
+// translation units that both include them cannot be linked together. Nothing is copied: the
+// preprocessor reads the sources where they lie (-I$(REF)).
+//
+// Built by oracle/Makefile into oracle/_ref/libazref_tafl.so (git-ignored, travels to the GPU box).
+//
+//   azref_tafl_dims         board side, action count, canonical planes of a game
+//   azref_tafl_random_game  a random legal game from the start position (moves chosen with a small
+//                           deterministic generator, so the same transcript can be regenerated)
+//   azref_tafl_replay       replays a transcript through GameState::play_move and records, after
+//                           every move: to_bytes() board, player, turn, repetition count, scores(),
+//                           valid_moves(), canonicalized()
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "brandubh_gs.cc"
+#include "opentafl_gs.cc"
+#include "tawlbwrdd_gs.cc"
+
+using namespace alphazero;
+
+namespace {
+thread_local std::string g_err;
+
+std::unique_ptr<GameState> make_game(int game, uint16_t max_turns) {
+  switch (game) {
+    case 0: return std::make_unique<brandubh_gs::BrandubhGS>(max_turns);
+    case 1: return std::make_unique<opentafl_gs::OpenTaflGS>(max_turns);
+    case 2: return std::make_unique<tawlbwrdd_gs::TawlbwrddGS>(max_turns);
+  }
+  return nullptr;
+}
+std::string state_bytes(int game, const GameState& gs) {
+  switch (game) {
+    case 0: return static_cast<const brandubh_gs::BrandubhGS&>(gs).to_bytes();
+    case 1: return static_cast<const opentafl_gs::OpenTaflGS&>(gs).to_bytes();
+    default: return static_cast<const tawlbwrdd_gs::TawlbwrddGS&>(gs).to_bytes();
+  }
+}
+uint64_t next_u64(uint64_t& s) {  // splitmix64
+  uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+}  // namespace
+
+extern "C" {
+
+const char* azref_tafl_last_error() { return g_err.c_str(); }
+
+int azref_tafl_dims(int game, uint32_t* side, uint32_t* actions, uint32_t* planes) {
+  auto gs = make_game(game, 10);
+  if (!gs) return -1;
+  auto c = gs->canonicalized();
+  *planes = (uint32_t)c.dimension(0);
+  *side = (uint32_t)c.dimension(1);
+  *actions = gs->num_moves();
+  return 0;
+}
+
+// Plays uniformly random legal moves until scores() reports the end or max_len moves; returns the length.
+uint32_t azref_tafl_random_game(int game, uint16_t max_turns, uint64_t seed, uint32_t max_len, uint32_t* moves_out) {
+  auto gs = make_game(game, max_turns);
+  if (!gs) return 0;
+  uint32_t len = 0;
+  std::vector<uint32_t> legal;
+  while (len < max_len && !gs->scores().has_value()) {
+    auto vm = gs->valid_moves();
+    legal.clear();
+    for (uint32_t m = 0; m < (uint32_t)vm.size(); ++m)
+      if (vm(m)) legal.push_back(m);
+    if (legal.empty()) break;
+    const uint32_t mv = legal[next_u64(seed) % legal.size()];
+    gs->play_move(mv);
+    moves_out[len++] = mv;
+  }
+  return len;
+}
+
+// Records the state after k = 0..len moves. Array shapes: boards [len+1][3*S*S], players/reps/terminal [len+1],
+// turns [len+1], scores [len+1][3], n_valid [len+1], valid [len+1][A] (may be NULL), canonical [len+1][C*S*S]
+// (may be NULL). terminal = 0 (scores() == nullopt) or 1 + argmax of the one-hot score vector.
+int azref_tafl_replay(int game, uint16_t max_turns, const uint32_t* moves, uint32_t len, int8_t* boards,
+                      uint8_t* players, uint32_t* turns, uint8_t* reps, uint8_t* terminal, float* scores,
+                      uint32_t* n_valid, uint8_t* valid, float* canonical) {
+  try {
+    auto gs = make_game(game, max_turns);
+    if (!gs) { g_err = "unknown game"; return -1; }
+    auto c0 = gs->canonicalized();
+    const size_t S = (size_t)c0.dimension(1), planes = (size_t)c0.dimension(0), A = gs->num_moves();
+    const size_t bb = 3 * S * S;
+    for (uint32_t k = 0; k <= len; ++k) {
+      if (k > 0) gs->play_move(moves[k - 1]);
+      const std::string bytes = state_bytes(game, *gs);
+      std::memcpy(boards + k * bb, bytes.data(), bb);
+      players[k] = gs->current_player();
+      turns[k] = gs->current_turn();
+      reps[k] = (uint8_t)bytes[bb + 5];  // board | turn u16 | max_turns u16 | player i8 | rep_count u8
+      auto sc = gs->scores();
+      terminal[k] = 0;
+      for (int j = 0; j < 3; ++j) scores[k * 3 + j] = 0.0f;
+      if (sc.has_value()) {
+        for (int j = 0; j < 3; ++j) {
+          scores[k * 3 + j] = (*sc)(j);
+          if ((*sc)(j) == 1.0f && terminal[k] == 0) terminal[k] = (uint8_t)(j + 1);
+        }
+      }
+      auto vm = gs->valid_moves();
+      uint32_t nv = 0;
+      for (size_t m = 0; m < A; ++m) nv += vm(m) ? 1u : 0u;
+      n_valid[k] = nv;
+      if (valid) std::memcpy(valid + k * A, vm.data(), A);
+      if (canonical) {
+        auto c = gs->canonicalized();
+        std::memcpy(canonical + k * planes * S * S, c.data(), planes * S * S * sizeof(float));
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"

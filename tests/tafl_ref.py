@@ -1,0 +1,59 @@
+"""ctypes face of oracle/_ref/libazref_tafl.so — the UNMODIFIED reference tafl games (brandubh / opentafl /
+tawlbwrdd) compiled against oracle/shim (oracle/ref_tafl_driver.cc). Test infrastructure only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libazref_tafl.so")
+BRANDUBH, OPENTAFL, TAWLBWRDD = 0, 1, 2
+_lib = None
+
+
+def available():
+    return os.path.exists(REF_LIB)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(REF_LIB)
+        vp, u32 = C.c_void_p, C.c_uint32
+        L.azref_tafl_last_error.restype = C.c_char_p
+        L.azref_tafl_dims.argtypes = [C.c_int, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.azref_tafl_random_game.argtypes = [C.c_int, C.c_uint16, C.c_uint64, u32, vp]
+        L.azref_tafl_random_game.restype = u32
+        L.azref_tafl_replay.argtypes = [C.c_int, C.c_uint16, vp, u32] + [vp] * 9
+        _lib = L
+    return _lib
+
+
+def dims(game):
+    s, a, p = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    assert lib().azref_tafl_dims(game, C.byref(s), C.byref(a), C.byref(p)) == 0
+    return s.value, a.value, p.value
+
+
+def random_game(game, seed, max_turns=150, max_len=512):
+    buf = np.zeros(max_len, np.uint32)
+    n = lib().azref_tafl_random_game(game, max_turns, seed, max_len, buf.ctypes.data_as(C.c_void_p))
+    return buf[:n].copy()
+
+
+def replay(game, moves, max_turns=150, want_valid=True, want_canonical=True):
+    """The reference's observable state after k = 0..len moves."""
+    S, A, P = dims(game)
+    moves = np.ascontiguousarray(moves, np.uint32)
+    n = len(moves) + 1
+    out = dict(boards=np.zeros((n, 3, S, S), np.int8), players=np.zeros(n, np.uint8), turns=np.zeros(n, np.uint32),
+               reps=np.zeros(n, np.uint8), terminal=np.zeros(n, np.uint8), scores=np.zeros((n, 3), np.float32),
+               n_valid=np.zeros(n, np.uint32), valid=np.zeros((n, A), np.uint8) if want_valid else None,
+               canonical=np.zeros((n, P, S, S), np.float32) if want_canonical else None)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = lib().azref_tafl_replay(game, max_turns, p(moves), len(moves), p(out["boards"]), p(out["players"]),
+                                 p(out["turns"]), p(out["reps"]), p(out["terminal"]), p(out["scores"]),
+                                 p(out["n_valid"]), p(out["valid"]), p(out["canonical"]))
+    if rc != 0:
+        raise RuntimeError(lib().azref_tafl_last_error().decode())
+    return out
