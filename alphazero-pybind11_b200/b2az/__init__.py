@@ -94,7 +94,7 @@ def load(path=None):
     L.b2az_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
-    L.b2az_brandubh_replay.argtypes = [C.c_int, u32, u32, u32] + [vp] * 11
+    L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
     _libs[path] = L
     return L
 
@@ -247,26 +247,28 @@ def c4_batch(boards, players, turns, moves=None, device=0, lib=None):
     return out
 
 
-BR_ACTIONS, BR_CANON = 686, 343
+TAFL_BRANDUBH, TAFL_OPENTAFL, TAFL_TAWLBWRDD = 0, 1, 2
+TAFL_DIMS = {0: (7, 7), 1: (11, 8), 2: (11, 7)}  # game -> (board side S, canonical planes)
 
 
-def brandubh_replay(moves, lens, max_turns=150, want_valid=True, want_canonical=True, device=0, lib=None):
-    """Brandubh game kernels on a batch of transcripts: the position after every move of every game.
+def tafl_replay(game, moves, lens, max_turns, want_valid=True, want_canonical=True, device=0, lib=None):
+    """Tafl game kernels on a batch of transcripts: the position after every move of every game.
     moves uint16[n][max_len], lens[n]. Returns arrays shaped [n][max_len + 1][...] (rows beyond a game's length
     stay zero)."""
     L = lib or load()
+    S, P = TAFL_DIMS[game]
     moves = np.ascontiguousarray(moves, np.uint16)
     n, max_len = moves.shape
     lens = np.ascontiguousarray(lens, np.uint32)
     R = (n, max_len + 1)
-    out = dict(boards=np.zeros(R + (3, 7, 7), np.int8), players=np.zeros(R, np.uint8), turns=np.zeros(R, np.uint32),
+    out = dict(boards=np.zeros(R + (3, S, S), np.int8), players=np.zeros(R, np.uint8), turns=np.zeros(R, np.uint32),
                reps=np.zeros(R, np.uint8), terminal=np.zeros(R, np.uint8), n_valid=np.zeros(R, np.uint32),
-               valid=np.zeros(R + (BR_ACTIONS,), np.uint8) if want_valid else None,
-               canonical=np.zeros(R + (7, 7, 7), np.float32) if want_canonical else None,
+               valid=np.zeros(R + (2 * S ** 3,), np.uint8) if want_valid else None,
+               canonical=np.zeros(R + (P, S, S), np.float32) if want_canonical else None,
                status=np.zeros(n, np.int32))
-    rc = L.b2az_brandubh_replay(device, n, max_len, max_turns, _ptr(moves), _ptr(lens), _ptr(out["boards"]),
-                                _ptr(out["players"]), _ptr(out["turns"]), _ptr(out["reps"]), _ptr(out["terminal"]),
-                                _ptr(out["n_valid"]), _ptr(out["valid"]), _ptr(out["canonical"]), _ptr(out["status"]))
+    rc = L.b2az_tafl_replay(device, game, n, max_len, max_turns, _ptr(moves), _ptr(lens), _ptr(out["boards"]),
+                            _ptr(out["players"]), _ptr(out["turns"]), _ptr(out["reps"]), _ptr(out["terminal"]),
+                            _ptr(out["n_valid"]), _ptr(out["valid"]), _ptr(out["canonical"]), _ptr(out["status"]))
     if rc != 0:
         raise B2azError(rc, L.b2az_last_error().decode())
     return out

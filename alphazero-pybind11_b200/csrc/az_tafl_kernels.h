@@ -1,82 +1,85 @@
-// az_tafl_kernels.h — batched Brandubh game kernels behind the C ABI (b2az_brandubh_replay). Included at the end
-// of az_engine.cu (same translation unit: it uses that file's error / launch helpers).
+// az_tafl_kernels.h — batched tafl game kernels behind the C ABI (b2az_tafl_replay). Included at the end of
+// az_engine.cu (same translation unit: it uses that file's error / launch helpers).
 //
 // One WARP per game transcript. Every lane replays the moves on its own register copy of the 3-bitboard state
 // (identical work, no divergence), so no state has to be broadcast; the lanes then split the OUTPUT of each
-// position between them: the 147 board bytes, the 686-byte legal-move mask (14 bytes per source square,
-// squares lane and lane + 32), the 343 canonical floats (coalesced 4 B stores), and a shuffle reduction for the
-// legal-move count. The repetition history (24 B keys since the last capture) lives in HBM, one row per game.
+// position between them: the board bytes, the legal-move mask (2S bytes per source square, squares lane,
+// lane + 32, ...), the canonical floats (coalesced 4 B stores), and a shuffle reduction for the legal-move
+// count. The repetition history (48 B keys since the last capture) lives in HBM, one row per game.
+// HBM bytes per position (what the kernel is bound by): 4*PLANES*S*S canonical + 2*S^3 mask + 3*S^2 board + 14
+// = 2,219 B (Brandubh), 6,911 B (OpenTafl), 6,427 B (Tawlbwrdd).
 #pragma once
 
-#include "az_brandubh.h"
+#include "az_tafl.h"
 
 namespace b2az {
 
-struct BrReplayArgs {
+struct TaflReplayArgs {
   u32 n, max_len, max_turns;
   const u16* moves;   // [n][max_len]
   const u32* lens;    // [n]
-  BrKey* hist;        // [n][max_len + 2]
+  TaflKey* hist;      // [n][max_len + 2]
   // outputs, [n][max_len + 1][...]; any may be null
-  signed char* boards;  // [..][147]
+  signed char* boards;  // [..][3*S*S]
   u8* players;
   u32* turns;
   u8* reps;
   u8* terminal;
   u32* n_valid;
-  u8* valid;          // [..][686]
-  float* canonical;   // [..][343]
+  u8* valid;          // [..][2*S^3]
+  float* canonical;   // [..][PLANES*S*S]
   i32* status;        // [n]: 0, or B2AZ_EMOVE at the first move the reference would have thrown on
 };
 
 // lane's share of the outputs of one position (lane in [0, nl))
-AZ_HD void br_emit(const BrReplayArgs& a, size_t row, const BrState& s, u32 lane, u32 nl) {
+template <int GAME>
+AZ_HD void tafl_emit(const TaflReplayArgs& a, size_t row, const TaflState& s, u32 lane, u32 nl) {
+  typedef Tafl<GAME> T;
   if (a.boards)
-    for (u32 e = lane; e < 147u; e += nl) {
-      const u64 plane = e < 49u ? s.king : e < 98u ? s.def : s.atk;
-      a.boards[row * 147 + e] = (signed char)((plane >> (e % 49u)) & 1ULL);
-    }
+    for (u32 e = lane; e < (u32)T::BOARD_BYTES; e += nl) a.boards[row * T::BOARD_BYTES + e] = T::board_byte(s, e);
   if (a.valid)
-    for (u32 sq = lane; sq < (u32)kBrCells; sq += nl) br_valid_bytes(s, (int)sq, a.valid + row * kBrA + sq * 14u);
+    for (u32 c = lane; c < (u32)T::CELLS; c += nl) T::valid_bytes(s, (int)c, a.valid + row * T::A + c * (2u * T::S));
   if (a.canonical)
-    for (u32 e = lane; e < (u32)kBrCanon; e += nl) a.canonical[row * kBrCanon + e] = br_canon_elem(s, e);
+    for (u32 e = lane; e < (u32)T::CANON; e += nl) a.canonical[row * T::CANON + e] = T::canon_elem(s, e);
   if (lane == 0) {
     if (a.players) a.players[row] = s.player;
     if (a.turns) a.turns[row] = s.turn;
     if (a.reps) a.reps[row] = s.rep;
-    if (a.terminal) a.terminal[row] = (u8)br_terminal(s);
+    if (a.terminal) a.terminal[row] = (u8)T::terminal(s);
   }
 }
 
 #ifndef B2AZ_HOST_EMU
-__global__ void __launch_bounds__(128) k_brandubh_replay(BrReplayArgs a) {
+template <int GAME>
+__global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
+  typedef Tafl<GAME> T;
   const u32 lane = threadIdx.x & 31u;
   const u32 warp = GLOBAL_TID >> 5, nwarps = GLOBAL_NT >> 5;
   for (u32 g = warp; g < a.n; g += nwarps) {
-    BrState s;
-    br_init(s, a.max_turns);
-    BrKey* hist = a.hist + (size_t)g * (a.max_len + 2u);
+    TaflState s;
+    T::init(s, a.max_turns);
+    TaflKey* hist = a.hist + (size_t)g * (a.max_len + 2u);
     u32 hist_len = 0;
     const u32 len = a.lens[g] < a.max_len ? a.lens[g] : a.max_len;
     i32 st = 0;
     for (u32 k = 0; k <= len; ++k) {
       if (k > 0) {
         // all lanes write the same key to the same history slot: benign, and every lane later reads its own write
-        if (!br_play_hist(s, a.moves[(size_t)g * a.max_len + (k - 1u)], hist, hist_len)) {
+        if (!T::play_hist(s, a.moves[(size_t)g * a.max_len + (k - 1u)], hist, hist_len)) {
           st = B2AZ_EMOVE;
           break;
         }
       }
       const size_t row = (size_t)g * (a.max_len + 1u) + k;
-      br_emit(a, row, s, lane, 32u);
+      tafl_emit<GAME>(a, row, s, lane, 32u);
       if (a.n_valid) {
         u32 cnt = 0;
-        const u64 own = br_own(s);
-        for (u32 sq = lane; sq < (u32)kBrCells; sq += 32u)
-          if ((own >> sq) & 1ULL) {
-            u32 r, c;
-            br_slides(s, (int)(sq / 7u), (int)(sq % 7u), r, c);
-            cnt += (u32)__popc(r) + (u32)__popc(c);
+        const B128 mine = T::own(s);
+        for (u32 c = lane; c < (u32)T::CELLS; c += 32u)
+          if (b128_test(mine, (int)c)) {
+            u32 r, cl;
+            T::slides(s, (int)(c / (u32)T::S), (int)(c % (u32)T::S), r, cl);
+            cnt += (u32)__popc(r) + (u32)__popc(cl);
           }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
@@ -88,49 +91,46 @@ __global__ void __launch_bounds__(128) k_brandubh_replay(BrReplayArgs a) {
 }
 #endif
 
-AZ_HD void br_replay_host_one(const BrReplayArgs& a, u32 g) {  // the same work by one thread (host-emulation build)
-  BrState s;
-  br_init(s, a.max_turns);
-  BrKey* hist = a.hist + (size_t)g * (a.max_len + 2u);
+template <int GAME>
+void tafl_replay_host_one(const TaflReplayArgs& a, u32 g) {  // the same work by one thread (host-emulation build)
+  typedef Tafl<GAME> T;
+  TaflState s;
+  T::init(s, a.max_turns);
+  TaflKey* hist = a.hist + (size_t)g * (a.max_len + 2u);
   u32 hist_len = 0;
   const u32 len = a.lens[g] < a.max_len ? a.lens[g] : a.max_len;
   i32 st = 0;
   for (u32 k = 0; k <= len; ++k) {
-    if (k > 0 && !br_play_hist(s, a.moves[(size_t)g * a.max_len + (k - 1u)], hist, hist_len)) {
+    if (k > 0 && !T::play_hist(s, a.moves[(size_t)g * a.max_len + (k - 1u)], hist, hist_len)) {
       st = B2AZ_EMOVE;
       break;
     }
     const size_t row = (size_t)g * (a.max_len + 1u) + k;
-    br_emit(a, row, s, 0u, 1u);
-    if (a.n_valid) a.n_valid[row] = br_moves(s, nullptr);
+    tafl_emit<GAME>(a, row, s, 0u, 1u);
+    if (a.n_valid) a.n_valid[row] = T::moves(s, nullptr);
   }
   if (a.status) a.status[g] = st;
 }
 
-}  // namespace b2az
-
-extern "C" int b2az_brandubh_replay(int device, uint32_t n, uint32_t max_len, uint32_t max_turns, const uint16_t* moves,
-                                    const uint32_t* lens, int8_t* boards, uint8_t* players, uint32_t* turns,
-                                    uint8_t* reps, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid,
-                                    float* canonical, int32_t* status) {
-  using namespace b2az;
-  if (n == 0) return 0;
-  if (!moves || !lens || max_len == 0) return fail(B2AZ_EINVAL, "null argument");
+template <int GAME>
+int tafl_replay_impl(int device, uint32_t n, uint32_t max_len, uint32_t max_turns, const uint16_t* moves,
+                     const uint32_t* lens, int8_t* boards, uint8_t* players, uint32_t* turns, uint8_t* reps,
+                     uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical, int32_t* status) {
+  typedef Tafl<GAME> T;
   const size_t rows = (size_t)n * (max_len + 1u);
 #ifdef B2AZ_HOST_EMU
-  (void)device;
-  std::vector<BrKey> hist((size_t)n * (max_len + 2u));
-  BrReplayArgs a{n, max_len, max_turns, moves, lens, hist.data(), reinterpret_cast<signed char*>(boards), players, turns,
-                 reps, terminal, n_valid, valid, canonical, status};
-  for (u32 g = 0; g < n; ++g) br_replay_host_one(a, g);
-  (void)rows;
+  (void)device; (void)rows;
+  std::vector<TaflKey> hist((size_t)n * (max_len + 2u));
+  TaflReplayArgs a{n, max_len, max_turns, moves, lens, hist.data(), reinterpret_cast<signed char*>(boards), players,
+                   turns, reps, terminal, n_valid, valid, canonical, status};
+  for (u32 g = 0; g < n; ++g) tafl_replay_host_one<GAME>(a, g);
   return 0;
 #else
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
   CUDA_TRY(cudaSetDevice(device));
-  BrReplayArgs a;
+  TaflReplayArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n; a.max_len = max_len; a.max_turns = max_turns;
   std::vector<void*> owned;
@@ -145,38 +145,62 @@ extern "C" int b2az_brandubh_replay(int device, uint32_t n, uint32_t max_len, ui
   };
   a.moves = static_cast<const u16*>(up(moves, (size_t)n * max_len * 2));
   a.lens = static_cast<const u32*>(up(lens, (size_t)n * 4));
-  a.hist = static_cast<BrKey*>(up(nullptr, (size_t)n * (max_len + 2u) * sizeof(BrKey)));
-  a.boards = boards ? static_cast<signed char*>(up(nullptr, rows * 147)) : nullptr;
+  a.hist = static_cast<TaflKey*>(up(nullptr, (size_t)n * (max_len + 2u) * sizeof(TaflKey)));
+  a.boards = boards ? static_cast<signed char*>(up(nullptr, rows * T::BOARD_BYTES)) : nullptr;
   a.players = players ? static_cast<u8*>(up(nullptr, rows)) : nullptr;
   a.turns = turns ? static_cast<u32*>(up(nullptr, rows * 4)) : nullptr;
   a.reps = reps ? static_cast<u8*>(up(nullptr, rows)) : nullptr;
   a.terminal = terminal ? static_cast<u8*>(up(nullptr, rows)) : nullptr;
   a.n_valid = n_valid ? static_cast<u32*>(up(nullptr, rows * 4)) : nullptr;
-  a.valid = valid ? static_cast<u8*>(up(nullptr, rows * kBrA)) : nullptr;
-  a.canonical = canonical ? static_cast<float*>(up(nullptr, rows * kBrCanon * 4)) : nullptr;
+  a.valid = valid ? static_cast<u8*>(up(nullptr, rows * T::A)) : nullptr;
+  a.canonical = canonical ? static_cast<float*>(up(nullptr, rows * T::CANON * 4)) : nullptr;
   a.status = status ? static_cast<i32*>(up(nullptr, (size_t)n * 4)) : nullptr;
   int rc = 0;
-  if (oom) rc = fail(B2AZ_ENOMEM, "b2az_brandubh_replay: cudaMalloc failed");
+  if (oom) rc = fail(B2AZ_ENOMEM, "b2az_tafl_replay: cudaMalloc failed");
   if (!rc) {
     const u32 warps_per_cta = 4;
     const u32 ctas = std::max(1u, std::min((n + warps_per_cta - 1u) / warps_per_cta, 148u * 8u));
-    k_brandubh_replay<<<ctas, warps_per_cta * 32u>>>(a);
+    k_tafl_replay<GAME><<<ctas, warps_per_cta * 32u>>>(a);
     cudaError_t err = cudaDeviceSynchronize();
-    if (err != cudaSuccess) rc = fail(B2AZ_ECUDA, std::string("k_brandubh_replay: ") + cudaGetErrorString(err));
+    if (err != cudaSuccess) rc = fail(B2AZ_ECUDA, std::string("k_tafl_replay: ") + cudaGetErrorString(err));
   }
   auto down = [&](void* dst, const void* src, size_t bytes) {
     if (dst && src && !rc) cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
   };
-  down(boards, a.boards, rows * 147);
+  down(boards, a.boards, rows * T::BOARD_BYTES);
   down(players, a.players, rows);
   down(turns, a.turns, rows * 4);
   down(reps, a.reps, rows);
   down(terminal, a.terminal, rows);
   down(n_valid, a.n_valid, rows * 4);
-  down(valid, a.valid, rows * kBrA);
-  down(canonical, a.canonical, rows * kBrCanon * 4);
+  down(valid, a.valid, rows * T::A);
+  down(canonical, a.canonical, rows * T::CANON * 4);
   down(status, a.status, (size_t)n * 4);
   for (void* d : owned) cudaFree(d);
   return rc;
 #endif
+}
+
+}  // namespace b2az
+
+extern "C" int b2az_tafl_replay(int device, uint32_t game, uint32_t n, uint32_t max_len, uint32_t max_turns,
+                                const uint16_t* moves, const uint32_t* lens, int8_t* boards, uint8_t* players,
+                                uint32_t* turns, uint8_t* reps, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid,
+                                float* canonical, int32_t* status) {
+  using namespace b2az;
+  if (n == 0) return 0;
+  if (!moves || !lens || max_len == 0) return fail(B2AZ_EINVAL, "null argument");
+  if (max_turns == 0 || max_turns > 65535u) return fail(B2AZ_EINVAL, "max_turns must fit uint16_t");
+  switch (game) {
+    case B2AZ_TAFL_BRANDUBH:
+      return tafl_replay_impl<B2AZ_TAFL_BRANDUBH>(device, n, max_len, max_turns, moves, lens, boards, players, turns, reps,
+                                                  terminal, n_valid, valid, canonical, status);
+    case B2AZ_TAFL_OPENTAFL:
+      return tafl_replay_impl<B2AZ_TAFL_OPENTAFL>(device, n, max_len, max_turns, moves, lens, boards, players, turns, reps,
+                                                  terminal, n_valid, valid, canonical, status);
+    case B2AZ_TAFL_TAWLBWRDD:
+      return tafl_replay_impl<B2AZ_TAFL_TAWLBWRDD>(device, n, max_len, max_turns, moves, lens, boards, players, turns,
+                                                   reps, terminal, n_valid, valid, canonical, status);
+  }
+  return fail(B2AZ_EINVAL, "unknown tafl game");
 }

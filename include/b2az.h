@@ -184,17 +184,24 @@ int b2az_c4_batch(int device, uint32_t n, const int8_t* boards_host, const uint8
                   const uint32_t* moves, int8_t* boards_out, uint8_t* players_out, uint8_t* valid, float* scores,
                   uint8_t* terminal, float* canonical, int32_t* status);
 
-/* Brandubh (7x7 tafl) game kernels on a batch of game transcripts: BrandubhGS::play_move / valid_moves /
- * scores / canonicalized / the repetition table (brandubh_gs.cc:225-289, 338-427, 441-537) replayed on the
- * device, one warp per game. moves uint16[n][max_len] (move id = (h*7+w)*14 + (row slide ? new_w : 7+new_h),
- * tafl_helper.h:7-14), lens[n]. Outputs (host, any may be NULL) hold the position after k = 0..lens[i] moves
- * at row i*(max_len+1)+k: boards int8[..][3][7][7] (king / defenders / attackers), players, turns, reps
- * (current_repetition_count_), terminal (0 = scores() is nullopt, else 1 + index of the winner, 3 = draw),
- * n_valid (number of legal moves), valid uint8[..][686], canonical float[..][7][7][7]; status[n] = 0 or
- * B2AZ_EMOVE at the first move the reference would have thrown on (rows from there on are unspecified). */
-int b2az_brandubh_replay(int device, uint32_t n, uint32_t max_len, uint32_t max_turns, const uint16_t* moves,
-                         const uint32_t* lens, int8_t* boards, uint8_t* players, uint32_t* turns, uint8_t* reps,
-                         uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical, int32_t* status);
+#define B2AZ_TAFL_BRANDUBH 0   /* 7x7,   686 actions, 7 canonical planes (brandubh_gs.h:27-62) */
+#define B2AZ_TAFL_OPENTAFL 1   /* 11x11, 2662 actions, 8 planes (opentafl_gs.h:18-50) */
+#define B2AZ_TAFL_TAWLBWRDD 2  /* 11x11, 2662 actions, 7 planes (tawlbwrdd_gs.h:20-51) */
+
+/* Tafl game kernels on a batch of game transcripts: {Brandubh,OpenTafl,Tawlbwrdd}GS::play_move / valid_moves /
+ * scores / canonicalized / the repetition table (brandubh_gs.cc:225-289, 338-427, 441-537; opentafl_gs.cc:
+ * 154-276, 295-428, 441-582; tawlbwrdd_gs.cc:141-213, 221-330, 340-440) replayed on the device from the start
+ * position, one warp per game. S = board side, A = 2*S^3 actions, P = canonical planes. moves uint16[n][max_len]
+ * (move id = (h*S+w)*2S + (row slide ? new_w : S+new_h), tafl_helper.h:7-14), lens[n]. Outputs (host, any may be
+ * NULL) hold the position after k = 0..lens[i] moves at row i*(max_len+1)+k: boards int8[..][3][S][S] (king /
+ * defenders / attackers), players, turns, reps (current_repetition_count_), terminal (0 = scores() is nullopt,
+ * else 1 + index of the winner, 3 = draw), n_valid (number of legal moves), valid uint8[..][A],
+ * canonical float[..][P][S][S]; status[n] = 0 or B2AZ_EMOVE at the first move the reference would have thrown
+ * on (rows from there on are unspecified). */
+int b2az_tafl_replay(int device, uint32_t game, uint32_t n, uint32_t max_len, uint32_t max_turns,
+                     const uint16_t* moves, const uint32_t* lens, int8_t* boards, uint8_t* players, uint32_t* turns,
+                     uint8_t* reps, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical,
+                     int32_t* status);
 
 #ifdef __cplusplus
 }

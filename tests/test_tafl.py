@@ -1,7 +1,7 @@
-"""Brandubh game kernels (b2az_brandubh_replay: BrandubhGS::play_move / valid_moves / scores / canonicalized /
-repetition table on the device) against the UNMODIFIED reference: committed golden transcripts
-(tests/golden/brandubh_transcripts.npz, tools/make_golden_tafl.py) and, where oracle/_ref/libazref_tafl.so
-exists, fresh random games replayed through the reference live. Everything is compared bit-exact.
+"""Tafl game kernels (b2az_tafl_replay: {Brandubh,OpenTafl,Tawlbwrdd}GS::play_move / valid_moves / scores /
+canonicalized / repetition table on the device) against the UNMODIFIED reference: committed golden transcripts
+(tests/golden/tafl_*_transcripts.npz, tools/make_golden_tafl.py) and, where oracle/_ref/libazref_tafl.so exists,
+fresh random games replayed through the reference live. Everything is compared bit-exact.
 CPU tests run the same rule header through the host-emulation build; `-m gpu` tests run the CUDA library."""
 import os
 import zlib
@@ -13,17 +13,22 @@ import b2az
 import parity_harness as ph
 import tafl_ref
 
-GOLDEN = os.path.join(ph.ROOT, "tests", "golden", "brandubh_transcripts.npz")
+NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
+MAX_TURNS = {0: 150, 1: 400, 2: 400}
 needs_tafl_ref = pytest.mark.skipif(not tafl_ref.available(), reason="oracle/_ref/libazref_tafl.so not built")
 
 
-def _replay_grouped(lib, moves, lens, max_turns):
-    """b2az_brandubh_replay takes one max_turns per call: run the batch in groups."""
-    n, L = moves.shape
+def golden(game):
+    return dict(np.load(os.path.join(ph.ROOT, "tests", "golden", f"tafl_{NAMES[game]}_transcripts.npz")))
+
+
+def _replay_grouped(lib, game, moves, lens, max_turns):
+    """b2az_tafl_replay takes one max_turns per call: run the batch in groups."""
+    n = len(lens)
     out = None
     for mt in sorted(set(int(x) for x in max_turns)):
         idx = np.nonzero(max_turns == mt)[0]
-        r = b2az.brandubh_replay(moves[idx], lens[idx], max_turns=mt, lib=lib)
+        r = b2az.tafl_replay(game, moves[idx], lens[idx], mt, lib=lib)
         assert (r["status"] == 0).all()
         if out is None:
             out = {k: np.zeros((n,) + v.shape[1:], v.dtype) for k, v in r.items()}
@@ -32,21 +37,20 @@ def _replay_grouped(lib, moves, lens, max_turns):
     return out
 
 
-def _check_against_golden(lib):
-    g = dict(np.load(GOLDEN))
+def _check_against_golden(lib, game):
+    g = golden(game)
     moves, lens = g["moves"], g["lens"]
-    r = _replay_grouped(lib, moves, lens, g["max_turns"])
+    r = _replay_grouped(lib, game, moves, lens, g["max_turns"])
     n = len(lens)
     for i in range(n):
         m = int(lens[i]) + 1
         for k in ("boards", "players", "turns", "reps", "terminal", "n_valid"):
-            assert np.array_equal(r[k][i, :m], g[k][i, :m]), f"game {i}: {k} differs from the reference"
+            assert np.array_equal(r[k][i, :m], g[k][i, :m]), f"{NAMES[game]} game {i}: {k} differs from the reference"
         for k in range(m):
             assert zlib.crc32(r["valid"][i, k].tobytes()) == g["valid_crc"][i, k], f"game {i} move {k}: legal-move mask"
             assert zlib.crc32(r["canonical"][i, k].tobytes()) == g["canon_crc"][i, k], f"game {i} move {k}: canonical"
         assert r["valid"][i, :m].sum(axis=1).tolist() == g["n_valid"][i, :m].tolist()
-    F = g["valid_full"].shape[0]
-    for i in range(F):
+    for i in range(g["valid_full"].shape[0]):
         m = int(lens[i]) + 1
         assert np.array_equal(r["valid"][i, :m], g["valid_full"][i, :m])
         assert np.array_equal(r["canonical"][i, :m].view(np.uint32), g["canon_full"][i, :m].view(np.uint32))
@@ -55,56 +59,64 @@ def _check_against_golden(lib):
         assert r["terminal"][i, lens[i]] != 0 and (r["terminal"][i, :lens[i]] == 0).all()
 
 
-def _check_against_live_reference(lib, n_games, seed0):
-    games = [tafl_ref.random_game(tafl_ref.BRANDUBH, seed0 + i, max_turns=150, max_len=200) for i in range(n_games)]
+def _check_against_live_reference(lib, game, n_games, seed0):
+    mt = MAX_TURNS[game]
+    games = [tafl_ref.random_game(game, seed0 + i, max_turns=mt, max_len=mt + 8) for i in range(n_games)]
     L = max(len(x) for x in games)
     moves = np.zeros((n_games, L), np.uint16)
     lens = np.array([len(x) for x in games], np.uint32)
     for i, x in enumerate(games):
         moves[i, :len(x)] = x
-    r = b2az.brandubh_replay(moves, lens, max_turns=150, lib=lib)
+    r = b2az.tafl_replay(game, moves, lens, mt, lib=lib)
     assert (r["status"] == 0).all()
     for i, x in enumerate(games):
-        ref = tafl_ref.replay(tafl_ref.BRANDUBH, x, max_turns=150)
+        ref = tafl_ref.replay(game, x, max_turns=mt)
         m = len(x) + 1
         for k in ("boards", "players", "turns", "reps", "terminal", "n_valid", "valid"):
-            assert np.array_equal(r[k][i, :m], ref[k]), f"game {i}: {k} differs from the live reference"
+            assert np.array_equal(r[k][i, :m], ref[k]), f"{NAMES[game]} game {i}: {k} differs from the live reference"
         assert np.array_equal(r["canonical"][i, :m].view(np.uint32), ref["canonical"].view(np.uint32))
 
 
-def test_rules_host_build_reproduces_golden():
-    _check_against_golden(b2az.load(ph.HOSTEMU_LIB))
+@pytest.mark.parametrize("game", [0, 1, 2])
+def test_rules_host_build_reproduces_golden(game):
+    _check_against_golden(b2az.load(ph.HOSTEMU_LIB), game)
 
 
 @needs_tafl_ref
-def test_rules_host_build_vs_live_reference():
-    _check_against_live_reference(b2az.load(ph.HOSTEMU_LIB), 64, 5000)
+@pytest.mark.parametrize("game,n", [(0, 64), (1, 12), (2, 16)])
+def test_rules_host_build_vs_live_reference(game, n):
+    _check_against_live_reference(b2az.load(ph.HOSTEMU_LIB), game, n, 5000)
 
 
 def test_illegal_move_is_reported():
     lib = b2az.load(ph.HOSTEMU_LIB)
     moves = np.array([[700], [0]], np.uint16)  # out of range; empty source square (0,0)
-    r = b2az.brandubh_replay(moves, np.array([1, 1], np.uint32), lib=lib)
+    r = b2az.tafl_replay(0, moves, np.array([1, 1], np.uint32), 150, lib=lib)
     assert r["status"].tolist() == [-5, -5]
 
 
 def test_start_position_and_move_ids():
     lib = b2az.load(ph.HOSTEMU_LIB)
-    r = b2az.brandubh_replay(np.zeros((1, 1), np.uint16), np.zeros(1, np.uint32), lib=lib)
+    r = b2az.tafl_replay(0, np.zeros((1, 1), np.uint16), np.zeros(1, np.uint32), 150, lib=lib)
     assert r["boards"][0, 0, 0, 3, 3] == 1 and r["boards"][0, 0, 1].sum() == 4 and r["boards"][0, 0, 2].sum() == 8
     assert r["players"][0, 0] == 0 and r["reps"][0, 0] == 1 and r["terminal"][0, 0] == 0
     # attackers to move: 8 pieces; e.g. (0,3) slides along row 0 to columns 1,2,4,5 (corners are king-only)
     v = r["valid"][0, 0].reshape(49, 14)
     assert v[3, :7].tolist() == [0, 1, 1, 0, 1, 1, 0] and v[3, 7:].sum() == 0
     assert r["n_valid"][0, 0] == v.sum()
+    for game, pieces in ((1, (1, 12, 24)), (2, (1, 12, 24))):
+        r = b2az.tafl_replay(game, np.zeros((1, 1), np.uint16), np.zeros(1, np.uint32), 400, lib=lib)
+        assert tuple(int(r["boards"][0, 0, p].sum()) for p in range(3)) == pieces
 
 
 @pytest.mark.gpu
-def test_cuda_rules_reproduce_golden():
-    _check_against_golden(None)
+@pytest.mark.parametrize("game", [0, 1, 2])
+def test_cuda_rules_reproduce_golden(game):
+    _check_against_golden(None, game)
 
 
 @pytest.mark.gpu
 @needs_tafl_ref
-def test_cuda_rules_vs_live_reference():
-    _check_against_live_reference(None, 256, 9000)
+@pytest.mark.parametrize("game,n", [(0, 256), (1, 32), (2, 48)])
+def test_cuda_rules_vs_live_reference(game, n):
+    _check_against_live_reference(None, game, n, 9000)
