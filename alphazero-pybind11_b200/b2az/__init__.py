@@ -95,6 +95,7 @@ def load(path=None):
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
+    L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
     _libs[path] = L
     return L
 
@@ -269,6 +270,28 @@ def tafl_replay(game, moves, lens, max_turns, want_valid=True, want_canonical=Tr
     rc = L.b2az_tafl_replay(device, game, n, max_len, max_turns, _ptr(moves), _ptr(lens), _ptr(out["boards"]),
                             _ptr(out["players"]), _ptr(out["turns"]), _ptr(out["reps"]), _ptr(out["terminal"]),
                             _ptr(out["n_valid"]), _ptr(out["valid"]), _ptr(out["canonical"]), _ptr(out["status"]))
+    if rc != 0:
+        raise B2azError(rc, L.b2az_last_error().decode())
+    return out
+
+
+def tafl_positions(game, boards, players, turns, reps, max_turns, moves=None, device=0, lib=None):
+    """Tafl game kernels on arbitrary positions: scores / valid_moves / canonicalized of each position and,
+    with `moves`, the board after play_move (no repetition bookkeeping) + whether anything was captured."""
+    L = lib or load()
+    S, P = TAFL_DIMS[game]
+    boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 3, S, S)
+    n = boards.shape[0]
+    players = np.ascontiguousarray(players, np.uint8)
+    turns = np.ascontiguousarray(turns, np.uint32)
+    reps = np.ascontiguousarray(reps, np.uint8)
+    mv = None if moves is None else np.ascontiguousarray(moves, np.uint32)
+    out = dict(terminal=np.zeros(n, np.uint8), n_valid=np.zeros(n, np.uint32), valid=np.zeros((n, 2 * S ** 3), np.uint8),
+               canonical=np.zeros((n, P, S, S), np.float32), boards_out=np.zeros((n, 3, S, S), np.int8),
+               captured_any=np.zeros(n, np.uint8), status=np.zeros(n, np.int32))
+    rc = L.b2az_tafl_positions(device, game, n, max_turns, _ptr(boards), _ptr(players), _ptr(turns), _ptr(reps), _ptr(mv),
+                               _ptr(out["terminal"]), _ptr(out["n_valid"]), _ptr(out["valid"]), _ptr(out["canonical"]),
+                               _ptr(out["boards_out"]), _ptr(out["captured_any"]), _ptr(out["status"]))
     if rc != 0:
         raise B2azError(rc, L.b2az_last_error().decode())
     return out

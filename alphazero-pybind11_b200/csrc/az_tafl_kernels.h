@@ -181,7 +181,142 @@ int tafl_replay_impl(int device, uint32_t n, uint32_t max_len, uint32_t max_turn
 #endif
 }
 
+// ---- arbitrary positions (b2az_tafl_positions): one warp per position
+struct TaflPosArgs {
+  u32 n, max_turns;
+  const signed char* boards;  // [n][3*S*S]
+  const u8* players;
+  const u32* turns;
+  const u8* reps;
+  const u32* moves;           // may be null; 0xFFFFFFFF = no move
+  TaflReplayArgs out;         // terminal / n_valid / valid / canonical of the INPUT position, row = position
+  signed char* boards_out;    // [n][3*S*S] after the move
+  u8* captured_any;           // [n]
+  i32* status;                // [n]
+};
+template <int GAME>
+AZ_HD void tafl_position_one(const TaflPosArgs& a, u32 i, u32 lane, u32 nl) {
+  typedef Tafl<GAME> T;
+  TaflState s;
+  s.king = s.def = s.atk = b128(0, 0);
+  const signed char* b = a.boards + (size_t)i * T::BOARD_BYTES;
+  for (int c = 0; c < T::CELLS; ++c) {
+    if (b[c]) s.king = s.king | b128_bit(c);
+    if (b[T::CELLS + c]) s.def = s.def | b128_bit(c);
+    if (b[2 * T::CELLS + c]) s.atk = s.atk | b128_bit(c);
+  }
+  s.player = a.players[i];
+  s.turn = a.turns[i];
+  s.max_turns = (u16)a.max_turns;
+  s.rep = a.reps[i];
+  tafl_emit<GAME>(a.out, i, s, lane, nl);
+  if (a.out.n_valid && lane == 0) a.out.n_valid[i] = T::moves(s, nullptr);
+  i32 st = 0;
+  if (a.moves && a.moves[i] != 0xFFFFFFFFu) {
+    bool cap = false;
+    if (!T::play(s, a.moves[i], &cap)) st = B2AZ_EMOVE;
+    if (st == 0 && a.boards_out)
+      for (u32 e = lane; e < (u32)T::BOARD_BYTES; e += nl) a.boards_out[(size_t)i * T::BOARD_BYTES + e] = T::board_byte(s, e);
+    if (lane == 0 && a.captured_any) a.captured_any[i] = cap ? 1 : 0;
+  }
+  if (lane == 0 && a.status) a.status[i] = st;
+}
+#ifndef B2AZ_HOST_EMU
+template <int GAME>
+__global__ void __launch_bounds__(128) k_tafl_positions(TaflPosArgs a) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 i = GLOBAL_TID >> 5; i < a.n; i += GLOBAL_NT >> 5) tafl_position_one<GAME>(a, i, lane, 32u);
+}
+#endif
+template <int GAME>
+int tafl_positions_impl(int device, uint32_t n, uint32_t max_turns, const int8_t* boards, const uint8_t* players,
+                        const uint32_t* turns, const uint8_t* reps, const uint32_t* moves, uint8_t* terminal,
+                        uint32_t* n_valid, uint8_t* valid, float* canonical, int8_t* boards_out, uint8_t* captured_any,
+                        int32_t* status) {
+  typedef Tafl<GAME> T;
+  TaflPosArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.max_turns = max_turns;
+#ifdef B2AZ_HOST_EMU
+  (void)device;
+  a.boards = reinterpret_cast<const signed char*>(boards); a.players = players; a.turns = turns; a.reps = reps;
+  a.moves = moves;
+  a.out.terminal = terminal; a.out.n_valid = n_valid; a.out.valid = valid; a.out.canonical = canonical;
+  a.boards_out = reinterpret_cast<signed char*>(boards_out); a.captured_any = captured_any; a.status = status;
+  for (u32 i = 0; i < n; ++i) tafl_position_one<GAME>(a, i, 0u, 1u);
+  return 0;
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  std::vector<void*> owned;
+  bool oom = false;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { oom = true; return nullptr; }
+    owned.push_back(d);
+    if (src) cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    else cudaMemset(d, 0, bytes);
+    return d;
+  };
+  a.boards = static_cast<const signed char*>(up(boards, (size_t)n * T::BOARD_BYTES));
+  a.players = static_cast<const u8*>(up(players, n));
+  a.turns = static_cast<const u32*>(up(turns, (size_t)n * 4));
+  a.reps = static_cast<const u8*>(up(reps, n));
+  a.moves = moves ? static_cast<const u32*>(up(moves, (size_t)n * 4)) : nullptr;
+  a.out.terminal = terminal ? static_cast<u8*>(up(nullptr, n)) : nullptr;
+  a.out.n_valid = n_valid ? static_cast<u32*>(up(nullptr, (size_t)n * 4)) : nullptr;
+  a.out.valid = valid ? static_cast<u8*>(up(nullptr, (size_t)n * T::A)) : nullptr;
+  a.out.canonical = canonical ? static_cast<float*>(up(nullptr, (size_t)n * T::CANON * 4)) : nullptr;
+  a.boards_out = boards_out ? static_cast<signed char*>(up(nullptr, (size_t)n * T::BOARD_BYTES)) : nullptr;
+  a.captured_any = captured_any ? static_cast<u8*>(up(nullptr, n)) : nullptr;
+  a.status = status ? static_cast<i32*>(up(nullptr, (size_t)n * 4)) : nullptr;
+  int rc = 0;
+  if (oom) rc = fail(B2AZ_ENOMEM, "b2az_tafl_positions: cudaMalloc failed");
+  if (!rc) {
+    k_tafl_positions<GAME><<<std::max(1u, std::min((n + 3u) / 4u, 148u * 8u)), 128>>>(a);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) rc = fail(B2AZ_ECUDA, std::string("k_tafl_positions: ") + cudaGetErrorString(err));
+  }
+  auto down = [&](void* dst, const void* src, size_t bytes) {
+    if (dst && src && !rc) cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+  };
+  down(terminal, a.out.terminal, n);
+  down(n_valid, a.out.n_valid, (size_t)n * 4);
+  down(valid, a.out.valid, (size_t)n * T::A);
+  down(canonical, a.out.canonical, (size_t)n * T::CANON * 4);
+  down(boards_out, a.boards_out, (size_t)n * T::BOARD_BYTES);
+  down(captured_any, a.captured_any, n);
+  down(status, a.status, (size_t)n * 4);
+  for (void* d : owned) cudaFree(d);
+  return rc;
+#endif
+}
+
 }  // namespace b2az
+
+extern "C" int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turns, const int8_t* boards,
+                                   const uint8_t* players, const uint32_t* turns, const uint8_t* reps,
+                                   const uint32_t* moves, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid,
+                                   float* canonical, int8_t* boards_out, uint8_t* captured_any, int32_t* status) {
+  using namespace b2az;
+  if (n == 0) return 0;
+  if (!boards || !players || !turns || !reps) return fail(B2AZ_EINVAL, "null argument");
+  if (max_turns == 0 || max_turns > 65535u) return fail(B2AZ_EINVAL, "max_turns must fit uint16_t");
+  switch (game) {
+    case B2AZ_TAFL_BRANDUBH:
+      return tafl_positions_impl<B2AZ_TAFL_BRANDUBH>(device, n, max_turns, boards, players, turns, reps, moves, terminal,
+                                                     n_valid, valid, canonical, boards_out, captured_any, status);
+    case B2AZ_TAFL_OPENTAFL:
+      return tafl_positions_impl<B2AZ_TAFL_OPENTAFL>(device, n, max_turns, boards, players, turns, reps, moves, terminal,
+                                                     n_valid, valid, canonical, boards_out, captured_any, status);
+    case B2AZ_TAFL_TAWLBWRDD:
+      return tafl_positions_impl<B2AZ_TAFL_TAWLBWRDD>(device, n, max_turns, boards, players, turns, reps, moves, terminal,
+                                                      n_valid, valid, canonical, boards_out, captured_any, status);
+  }
+  return fail(B2AZ_EINVAL, "unknown tafl game");
+}
 
 extern "C" int b2az_tafl_replay(int device, uint32_t game, uint32_t n, uint32_t max_len, uint32_t max_turns,
                                 const uint16_t* moves, const uint32_t* lens, int8_t* boards, uint8_t* players,

@@ -203,6 +203,17 @@ int b2az_tafl_replay(int device, uint32_t game, uint32_t n, uint32_t max_len, ui
                      uint8_t* reps, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical,
                      int32_t* status);
 
+/* The same game kernels on a batch of ARBITRARY positions (the 7-argument GameState constructors, e.g.
+ * brandubh_gs.h:124-151): boards int8[n][3][S][S], players, turns, reps (current_repetition_count_) per position.
+ * Outputs for the position itself: terminal, n_valid, valid uint8[n][A], canonical float[n][P][S][S]; and, when
+ * moves != NULL and moves[i] != 0xFFFFFFFF, play_move(moves[i]) WITHOUT the repetition bookkeeping: boards_out
+ * int8[n][3][S][S], captured_any[n] (a capture clears the reference's repetition table), status[n] = 0 or
+ * B2AZ_EMOVE. One warp per position. */
+int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turns, const int8_t* boards,
+                        const uint8_t* players, const uint32_t* turns, const uint8_t* reps, const uint32_t* moves,
+                        uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical, int8_t* boards_out,
+                        uint8_t* captured_any, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

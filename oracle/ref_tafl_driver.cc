@@ -131,4 +131,65 @@ int azref_tafl_replay(int game, uint16_t max_turns, const uint32_t* moves, uint3
   }
 }
 
+// One arbitrary position (the 7-argument constructors, e.g. brandubh_gs.h:124-151, with an empty repetition
+// table): scores / valid_moves / canonicalized of the position itself, then optionally play_move(move) and the
+// board afterwards. boards int8[3][S][S]. Returns 0, or -1 when the reference threw (message in last_error).
+int azref_tafl_position(int game, const int8_t* board, int8_t player, uint16_t turn, uint16_t max_turns, uint8_t rep,
+                        uint32_t move, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical,
+                        int8_t* board_out) {
+  try {
+    std::unique_ptr<GameState> gs;
+    if (game == 0) {
+      brandubh_gs::BoardTensor b{};
+      std::memcpy(b.data(), board, b.size());
+      gs = std::make_unique<brandubh_gs::BrandubhGS>(
+          b, player, turn, max_turns, rep,
+          absl::flat_hash_map<const std::shared_ptr<brandubh_gs::RepetitionKey>, uint8_t>{},
+          std::make_shared<absl::flat_hash_set<brandubh_gs::RepetitionKeyWrapper>>());
+    } else if (game == 1) {
+      opentafl_gs::BoardTensor b{};
+      std::memcpy(b.data(), board, b.size());
+      gs = std::make_unique<opentafl_gs::OpenTaflGS>(
+          b, player, turn, max_turns, rep,
+          absl::flat_hash_map<const std::shared_ptr<opentafl_gs::RepetitionKey>, uint8_t>{},
+          std::make_shared<absl::flat_hash_set<opentafl_gs::RepetitionKeyWrapper>>());
+    } else if (game == 2) {
+      tawlbwrdd_gs::BoardTensor b{};
+      std::memcpy(b.data(), board, b.size());
+      gs = std::make_unique<tawlbwrdd_gs::TawlbwrddGS>(
+          b, player, turn, max_turns, rep,
+          absl::flat_hash_map<const std::shared_ptr<tawlbwrdd_gs::RepetitionKey>, uint8_t>{},
+          std::make_shared<absl::flat_hash_set<tawlbwrdd_gs::RepetitionKeyWrapper>>());
+    } else {
+      g_err = "unknown game";
+      return -1;
+    }
+    auto sc = gs->scores();
+    *terminal = 0;
+    if (sc.has_value())
+      for (int j = 0; j < 3; ++j)
+        if ((*sc)(j) == 1.0f && *terminal == 0) *terminal = (uint8_t)(j + 1);
+    auto vm = gs->valid_moves();
+    uint32_t nv = 0;
+    for (long m = 0; m < (long)vm.size(); ++m) nv += vm(m) ? 1u : 0u;
+    *n_valid = nv;
+    if (valid) std::memcpy(valid, vm.data(), vm.size());
+    if (canonical) {
+      auto c = gs->canonicalized();
+      std::memcpy(canonical, c.data(), c.size() * sizeof(float));
+    }
+    if (move != 0xFFFFFFFFu && board_out) {
+      gs->play_move(move);
+      const std::string bytes = state_bytes(game, *gs);
+      auto c = gs->canonicalized();
+      const size_t S = (size_t)c.dimension(1);
+      std::memcpy(board_out, bytes.data(), 3 * S * S);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 }  // extern "C"

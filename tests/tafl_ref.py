@@ -25,6 +25,7 @@ def lib():
         L.azref_tafl_random_game.argtypes = [C.c_int, C.c_uint16, C.c_uint64, u32, vp]
         L.azref_tafl_random_game.restype = u32
         L.azref_tafl_replay.argtypes = [C.c_int, C.c_uint16, vp, u32] + [vp] * 9
+        L.azref_tafl_position.argtypes = [C.c_int, vp, C.c_int8, C.c_uint16, C.c_uint16, C.c_uint8, u32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -57,3 +58,20 @@ def replay(game, moves, max_turns=150, want_valid=True, want_canonical=True):
     if rc != 0:
         raise RuntimeError(lib().azref_tafl_last_error().decode())
     return out
+
+
+def position(game, board, player, turn, max_turns, rep, move=None):
+    """One arbitrary position through the reference: terminal code, legal-move mask, canonical planes, and the
+    board after play_move(move). Returns None for board_out when the reference threw."""
+    S, A, P = dims(game)
+    board = np.ascontiguousarray(board, np.int8)
+    term, nv = C.c_uint8(0), C.c_uint32(0)
+    valid = np.zeros(A, np.uint8)
+    canon = np.zeros((P, S, S), np.float32)
+    bout = np.zeros((3, S, S), np.int8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().azref_tafl_position(game, p(board), int(player), int(turn), int(max_turns), int(rep),
+                                   0xFFFFFFFF if move is None else int(move), C.cast(C.byref(term), C.c_void_p),
+                                   C.cast(C.byref(nv), C.c_void_p), p(valid), p(canon), p(bout))
+    return dict(terminal=term.value, n_valid=nv.value, valid=valid, canonical=canon, board_out=bout if rc == 0 else None,
+                threw=rc != 0)

@@ -120,3 +120,77 @@ def test_cuda_rules_reproduce_golden(game):
 @pytest.mark.parametrize("game,n", [(0, 256), (1, 32), (2, 48)])
 def test_cuda_rules_vs_live_reference(game, n):
     _check_against_live_reference(None, game, n, 9000)
+
+
+# ---------------------------------------------------------------------------------- arbitrary positions
+def _random_positions(game, n, seed):
+    """Random piece placements (non-king pieces keep off the restricted squares, like in any reachable position):
+    dense and sparse boards, kings next to attackers, so captures / encirclement / blocked sides all occur."""
+    S = b2az.TAFL_DIMS[game][0]
+    rng = np.random.default_rng(seed)
+    restricted = {0, S - 1, S * (S - 1), S * S - 1, (S // 2) * S + S // 2} if game != 2 else set()
+    boards = np.zeros((n, 3, S, S), np.int8)
+    for i in range(n):
+        cells = list(rng.permutation(S * S))
+        n_def = int(rng.integers(0, 5 if game == 0 else 13))
+        n_atk = int(rng.integers(0, 9 if game == 0 else 40))
+        if rng.random() < 0.95:
+            k = cells.pop()
+            boards[i, 0].flat[k] = 1
+            # crowd the king with attackers half of the time
+            if rng.random() < 0.5:
+                h, w = divmod(int(k), S)
+                for dh, dw in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+                    c = (h + dh) * S + (w + dw)
+                    if 0 <= h + dh < S and 0 <= w + dw < S and c in cells and c not in restricted and rng.random() < 0.8:
+                        cells.remove(c)
+                        boards[i, 2].flat[c] = 1
+        free = [c for c in cells if c not in restricted]
+        for c in free[:n_def]:
+            boards[i, 1].flat[c] = 1
+        for c in free[n_def:n_def + n_atk]:
+            boards[i, 2].flat[c] = 1
+    players = rng.integers(0, 2, n).astype(np.uint8)
+    turns = rng.integers(1, 60, n).astype(np.uint32)
+    reps = rng.choice([1, 1, 1, 2, 3], n).astype(np.uint8)
+    return boards, players, turns, reps, rng
+
+
+def _check_positions(lib, game, n, seed):
+    mt = MAX_TURNS[game]
+    boards, players, turns, reps, rng = _random_positions(game, n, seed)
+    refs = [tafl_ref.position(game, boards[i], players[i], turns[i], mt, reps[i]) for i in range(n)]
+    moves = np.full(n, 0xFFFFFFFF, np.uint32)
+    for i, r in enumerate(refs):
+        legal = np.nonzero(r["valid"])[0]
+        if len(legal):
+            moves[i] = legal[rng.integers(0, len(legal))]
+    got = b2az.tafl_positions(game, boards, players, turns, reps, mt, moves=moves, lib=lib)
+    seen_terminal = set()
+    captures = 0
+    for i, r in enumerate(refs):
+        assert got["terminal"][i] == r["terminal"], f"{NAMES[game]} position {i}: scores()"
+        assert got["n_valid"][i] == r["n_valid"] and np.array_equal(got["valid"][i], r["valid"]), f"position {i}: valid_moves()"
+        assert np.array_equal(got["canonical"][i].view(np.uint32), r["canonical"].view(np.uint32))
+        seen_terminal.add(int(r["terminal"]))
+        if moves[i] != 0xFFFFFFFF:
+            after = tafl_ref.position(game, boards[i], players[i], turns[i], mt, reps[i], move=moves[i])
+            assert not after["threw"] and got["status"][i] == 0
+            assert np.array_equal(got["boards_out"][i], after["board_out"]), f"{NAMES[game]} position {i}: play_move()"
+            removed = int(boards[i].sum() - after["board_out"].sum())
+            assert bool(got["captured_any"][i]) == (removed > 0)
+            captures += removed > 0
+    assert {0, 1, 2} <= seen_terminal and captures > n // 100  # the sample exercises wins of both sides and captures
+
+
+@needs_tafl_ref
+@pytest.mark.parametrize("game", [0, 1, 2])
+def test_positions_host_build_vs_live_reference(game):
+    _check_positions(b2az.load(ph.HOSTEMU_LIB), game, 600, 31 + game)
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game", [0, 1, 2])
+def test_cuda_positions_vs_live_reference(game):
+    _check_positions(None, game, 1500, 77 + game)
