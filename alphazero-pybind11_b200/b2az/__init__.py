@@ -95,6 +95,7 @@ def load(path=None):
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
+    L.b2az_tafl_replay_device.argtypes = [u32, u32, u32, u32] + [vp] * 10
     L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
     _libs[path] = L
     return L

@@ -50,10 +50,42 @@ AZ_HD void tafl_emit(const TaflReplayArgs& a, size_t row, const TaflState& s, u3
 }
 
 #ifndef B2AZ_HOST_EMU
+// The legal-move mask of one position, written by a whole warp: the per-square slide masks are computed once
+// (squares lane, lane + 32, ...) into shared memory, then the A mask bytes leave as coalesced 16-bit stores
+// (2S is even, so a byte pair never straddles two source squares and every row starts 2-byte aligned).
+template <int GAME>
+__device__ __forceinline__ u32 tafl_emit_valid_warp(const TaflState& s, u8* valid_row, u32* sm_row, u32* sm_col, u32 lane) {
+  typedef Tafl<GAME> T;
+  u32 cnt = 0;
+  const B128 mine = T::own(s);
+  for (u32 c = lane; c < (u32)T::CELLS; c += 32u) {
+    u32 r = 0, cl = 0;
+    if (b128_test(mine, (int)c)) T::slides(s, (int)(c / (u32)T::S), (int)(c % (u32)T::S), r, cl);
+    sm_row[c] = r;
+    sm_col[c] = cl;
+    cnt += (u32)__popc(r) + (u32)__popc(cl);
+  }
+  __syncwarp();
+  if (valid_row) {
+    unsigned short* out = reinterpret_cast<unsigned short*>(valid_row);
+    for (u32 p = lane; p < (u32)T::A / 2u; p += 32u) {
+      const u32 b = 2u * p, c = b / (u32)(2 * T::S), t = b % (u32)(2 * T::S);
+      // bytes t, t+1 of square c: columns 0..S-1 from the row mask, then rows 0..S-1 from the column mask
+      const u32 bits = sm_row[c] | (sm_col[c] << T::S);
+      out[p] = (unsigned short)(((bits >> t) & 1u) | (((bits >> (t + 1u)) & 1u) << 8));
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+  return cnt;
+}
+
 template <int GAME>
 __global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
   typedef Tafl<GAME> T;
-  const u32 lane = threadIdx.x & 31u;
+  __shared__ u32 sm_row[4][128], sm_col[4][128];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   const u32 warp = GLOBAL_TID >> 5, nwarps = GLOBAL_NT >> 5;
   for (u32 g = warp; g < a.n; g += nwarps) {
     TaflState s;
@@ -62,6 +94,8 @@ __global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
     u32 hist_len = 0;
     const u32 len = a.lens[g] < a.max_len ? a.lens[g] : a.max_len;
     i32 st = 0;
+    TaflReplayArgs b = a;  // everything but the mask goes through the shared emit code
+    b.valid = nullptr;
     for (u32 k = 0; k <= len; ++k) {
       if (k > 0) {
         // all lanes write the same key to the same history slot: benign, and every lane later reads its own write
@@ -71,19 +105,10 @@ __global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
         }
       }
       const size_t row = (size_t)g * (a.max_len + 1u) + k;
-      tafl_emit<GAME>(a, row, s, lane, 32u);
-      if (a.n_valid) {
-        u32 cnt = 0;
-        const B128 mine = T::own(s);
-        for (u32 c = lane; c < (u32)T::CELLS; c += 32u)
-          if (b128_test(mine, (int)c)) {
-            u32 r, cl;
-            T::slides(s, (int)(c / (u32)T::S), (int)(c % (u32)T::S), r, cl);
-            cnt += (u32)__popc(r) + (u32)__popc(cl);
-          }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-        if (lane == 0) a.n_valid[row] = cnt;
+      tafl_emit<GAME>(b, row, s, lane, 32u);
+      if (a.valid || a.n_valid) {
+        const u32 cnt = tafl_emit_valid_warp<GAME>(s, a.valid ? a.valid + row * T::A : nullptr, sm_row[wib], sm_col[wib], lane);
+        if (lane == 0 && a.n_valid) a.n_valid[row] = cnt;
       }
     }
     if (lane == 0 && a.status) a.status[g] = st;
@@ -294,7 +319,43 @@ int tafl_positions_impl(int device, uint32_t n, uint32_t max_turns, const int8_t
 #endif
 }
 
+template <int GAME>
+int tafl_replay_device_impl(const TaflReplayArgs& a, void* stream) {
+#ifdef B2AZ_HOST_EMU
+  (void)stream;
+  for (u32 g = 0; g < a.n; ++g) tafl_replay_host_one<GAME>(a, g);
+  return 0;
+#else
+  const u32 ctas = std::max(1u, std::min((a.n + 3u) / 4u, 148u * 8u));
+  k_tafl_replay<GAME><<<ctas, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+#endif
+}
+
 }  // namespace b2az
+
+extern "C" int b2az_tafl_replay_device(uint32_t game, uint32_t n, uint32_t max_len, uint32_t max_turns,
+                                       const uint16_t* moves_dev, const uint32_t* lens_dev, void* hist_dev,
+                                       int8_t* boards_dev, uint8_t* terminal_dev, uint32_t* n_valid_dev,
+                                       uint8_t* valid_dev, float* canonical_dev, int32_t* status_dev, void* stream) {
+  using namespace b2az;
+  if (n == 0) return 0;
+  if (!moves_dev || !lens_dev || !hist_dev || max_len == 0) return fail(B2AZ_EINVAL, "null argument");
+  if (max_turns == 0 || max_turns > 65535u) return fail(B2AZ_EINVAL, "max_turns must fit uint16_t");
+  TaflReplayArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.max_len = max_len; a.max_turns = max_turns;
+  a.moves = moves_dev; a.lens = lens_dev; a.hist = static_cast<TaflKey*>(hist_dev);
+  a.boards = reinterpret_cast<signed char*>(boards_dev); a.terminal = terminal_dev; a.n_valid = n_valid_dev;
+  a.valid = valid_dev; a.canonical = canonical_dev; a.status = status_dev;
+  switch (game) {
+    case B2AZ_TAFL_BRANDUBH: return tafl_replay_device_impl<B2AZ_TAFL_BRANDUBH>(a, stream);
+    case B2AZ_TAFL_OPENTAFL: return tafl_replay_device_impl<B2AZ_TAFL_OPENTAFL>(a, stream);
+    case B2AZ_TAFL_TAWLBWRDD: return tafl_replay_device_impl<B2AZ_TAFL_TAWLBWRDD>(a, stream);
+  }
+  return fail(B2AZ_EINVAL, "unknown tafl game");
+}
 
 extern "C" int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turns, const int8_t* boards,
                                    const uint8_t* players, const uint32_t* turns, const uint8_t* reps,

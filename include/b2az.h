@@ -203,6 +203,14 @@ int b2az_tafl_replay(int device, uint32_t game, uint32_t n, uint32_t max_len, ui
                      uint8_t* reps, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical,
                      int32_t* status);
 
+/* b2az_tafl_replay with every buffer already in device memory (zero-copy flavour: what a device-resident
+ * self-play loop and the throughput measurement use): hist_dev is scratch of n*(max_len+2)*48 bytes for the
+ * repetition histories; output pointers may be NULL; the launch is enqueued on `stream`. */
+int b2az_tafl_replay_device(uint32_t game, uint32_t n, uint32_t max_len, uint32_t max_turns, const uint16_t* moves_dev,
+                            const uint32_t* lens_dev, void* hist_dev, int8_t* boards_dev, uint8_t* terminal_dev,
+                            uint32_t* n_valid_dev, uint8_t* valid_dev, float* canonical_dev, int32_t* status_dev,
+                            void* stream);
+
 /* The same game kernels on a batch of ARBITRARY positions (the 7-argument GameState constructors, e.g.
  * brandubh_gs.h:124-151): boards int8[n][3][S][S], players, turns, reps (current_repetition_count_) per position.
  * Outputs for the position itself: terminal, n_valid, valid uint8[n][A], canonical float[n][P][S][S]; and, when
