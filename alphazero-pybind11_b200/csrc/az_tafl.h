@@ -269,42 +269,58 @@ struct Tafl {
     s.rep = (u8)(count > 255u ? 255u : count);
     return true;
   }
+  // board masks, evaluated at compile time: 0 all squares, 1 edge squares, 2 not in column 0, 3 not in the last
+  // column, 4 the four corners
+  static AZ_HD constexpr u64 mask_word(int kind, int word) {
+    u64 m = 0;
+    for (int h = 0; h < S; ++h)
+      for (int w = 0; w < S; ++w) {
+        const int c = S * h + w;
+        const bool edge = h == 0 || h == S - 1 || w == 0 || w == S - 1;
+        const bool in = kind == 0 ? true : kind == 1 ? edge : kind == 2 ? (w != 0) : kind == 3 ? (w != S - 1)
+                                                                       : ((h == 0 || h == S - 1) && (w == 0 || w == S - 1));
+        if (in && (c >> 6) == word) m |= 1ULL << (c & 63);
+      }
+    return m;
+  }
+  template <int KIND>
+  static AZ_HD B128 mask() {
+    constexpr u64 lo = mask_word(KIND, 0), hi = mask_word(KIND, 1);
+    return b128(lo, hi);
+  }
   // OpenTafl encirclement (opentafl_gs.cc:466-506): flood from every edge square through squares without an
   // attacker; the defenders can escape iff the flood touches a king/defender square.
   static AZ_HD bool can_escape(const TaflState& s) {
-    B128 all = b128(0, 0), edge = b128(0, 0), not_left = b128(0, 0), not_right = b128(0, 0);
-    for (int h = 0; h < S; ++h)
-      for (int w = 0; w < S; ++w) {
-        const B128 b = b128_bit(sq(h, w));
-        all = all | b;
-        if (h == 0 || h == S - 1 || w == 0 || w == S - 1) edge = edge | b;
-        if (w != 0) not_left = not_left | b;
-        if (w != S - 1) not_right = not_right | b;
-      }
+    const B128 all = mask<0>(), not_left = mask<2>(), not_right = mask<3>();
     const B128 open = ~s.atk & all;
-    B128 seen = edge;
+    const B128 goal = s.king | s.def;
+    B128 seen = mask<1>();
     for (;;) {
+      if (b128_any(seen & goal)) return true;
       const B128 src = seen & open;  // squares that spread to their neighbours
-      const B128 grown = seen | (b128_shl(src, S) & all) | b128_shr(src, S) | (b128_shl(src & not_right, 1)) |
+      const B128 grown = seen | (b128_shl(src, S) & all) | b128_shr(src, S) | b128_shl(src & not_right, 1) |
                          b128_shr(src & not_left, 1);
-      if (b128_eq(grown, seen)) break;
+      if (b128_eq(grown, seen)) return false;
       seen = grown;
     }
-    return b128_any(seen & (s.king | s.def));
   }
-  // scores(): 0 = not over, else 1 + index of the winner (2 = defenders, 3 = draw)
-  static AZ_HD u32 terminal(const TaflState& s) {
+  // scores() in two halves around the legal-move test (the callers that already know the move count pass it in):
+  // 0 = not over, else 1 + index of the winner (2 = defenders, 3 = draw)
+  static AZ_HD u32 terminal_pre(const TaflState& s) {
     if (s.rep >= 3) return 1u + s.player;
-    for (int c = 0; c < CELLS; ++c) {
-      if (!b128_test(s.king, c)) continue;
-      const int h = c / S, w = c % S;
-      if (R::EDGE_WIN ? (h == 0 || h == S - 1 || w == 0 || w == S - 1) : is_corner(h, w)) return 2;
-    }
+    if (b128_any(s.king & (R::EDGE_WIN ? mask<1>() : mask<4>()))) return 2;
     if (!b128_any(s.king)) return 1;
     if (R::ENCIRCLE && !can_escape(s)) return 1;
-    if (!has_moves(s)) return 1u + (s.player ^ 1u);
+    return 0;
+  }
+  static AZ_HD u32 terminal_post(const TaflState& s, bool any_move) {
+    if (!any_move) return 1u + (s.player ^ 1u);
     if (s.turn >= s.max_turns) return 3;
     return 0;
+  }
+  static AZ_HD u32 terminal(const TaflState& s) {
+    const u32 pre = terminal_pre(s);
+    return pre ? pre : terminal_post(s, has_moves(s));
   }
   // canonicalized() element e in [0, CANON): plane = e / CELLS, cell = e % CELLS
   static AZ_HD float canon_elem(const TaflState& s, u32 e) {

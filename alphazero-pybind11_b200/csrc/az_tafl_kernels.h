@@ -50,11 +50,21 @@ AZ_HD void tafl_emit(const TaflReplayArgs& a, size_t row, const TaflState& s, u3
 }
 
 #ifndef B2AZ_HOST_EMU
-// The legal-move mask of one position, written by a whole warp: the per-square slide masks are computed once
-// (squares lane, lane + 32, ...) into shared memory, then the A mask bytes leave as coalesced 16-bit stores
-// (2S is even, so a byte pair never straddles two source squares and every row starts 2-byte aligned).
+__device__ __forceinline__ u32 warp_sum(u32 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+// Everything one position writes, by a whole warp (`a`'s pointers; row = output row):
+//   legal moves  the per-square slide masks are computed once (squares lane, lane + 32, ...) into shared memory,
+//                then the A mask bytes leave as coalesced 16-bit stores (2S is even: a byte pair never straddles
+//                two source squares and every row starts 2-byte aligned); the shuffle-reduced count also answers
+//                scores()'s "side to move has no legal move"
+//   canonical    plane by plane, consecutive lanes = consecutive floats; planes 3.. are constants per position
+//   board bytes, terminal code, scalars
 template <int GAME>
-__device__ __forceinline__ u32 tafl_emit_valid_warp(const TaflState& s, u8* valid_row, u32* sm_row, u32* sm_col, u32 lane) {
+__device__ __forceinline__ void tafl_emit_warp(const TaflReplayArgs& a, size_t row, const TaflState& s, u32* sm_row,
+                                                u32* sm_col, u32 lane) {
   typedef Tafl<GAME> T;
   u32 cnt = 0;
   const B128 mine = T::own(s);
@@ -66,8 +76,8 @@ __device__ __forceinline__ u32 tafl_emit_valid_warp(const TaflState& s, u8* vali
     cnt += (u32)__popc(r) + (u32)__popc(cl);
   }
   __syncwarp();
-  if (valid_row) {
-    unsigned short* out = reinterpret_cast<unsigned short*>(valid_row);
+  if (a.valid) {
+    unsigned short* out = reinterpret_cast<unsigned short*>(a.valid + row * T::A);
     for (u32 p = lane; p < (u32)T::A / 2u; p += 32u) {
       const u32 b = 2u * p, c = b / (u32)(2 * T::S), t = b % (u32)(2 * T::S);
       // bytes t, t+1 of square c: columns 0..S-1 from the row mask, then rows 0..S-1 from the column mask
@@ -76,9 +86,36 @@ __device__ __forceinline__ u32 tafl_emit_valid_warp(const TaflState& s, u8* vali
     }
   }
   __syncwarp();
+  cnt = warp_sum(cnt);
+  if (a.canonical) {
+    float* out = a.canonical + row * T::CANON;
+    for (u32 c = lane; c < (u32)T::CELLS; c += 32u) {
+      out[c] = b128_test(s.king, (int)c) ? 1.0f : 0.0f;
+      out[T::CELLS + c] = b128_test(s.def, (int)c) ? 1.0f : 0.0f;
+      out[2 * T::CELLS + c] = b128_test(s.atk, (int)c) ? 1.0f : 0.0f;
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-  return cnt;
+    for (int pl = 3; pl < T::PLANES; ++pl) {
+      const float v = T::canon_elem(s, (u32)(pl * T::CELLS));  // constant over the plane
+      for (u32 c = lane; c < (u32)T::CELLS; c += 32u) out[pl * T::CELLS + c] = v;
+    }
+  }
+  if (a.boards) {
+    signed char* out = a.boards + row * T::BOARD_BYTES;
+    for (u32 c = lane; c < (u32)T::CELLS; c += 32u) {
+      out[c] = (signed char)(b128_test(s.king, (int)c) ? 1 : 0);
+      out[T::CELLS + c] = (signed char)(b128_test(s.def, (int)c) ? 1 : 0);
+      out[2 * T::CELLS + c] = (signed char)(b128_test(s.atk, (int)c) ? 1 : 0);
+    }
+  }
+  const u32 pre = T::terminal_pre(s);  // uniform over the warp
+  if (lane == 0) {
+    if (a.n_valid) a.n_valid[row] = cnt;
+    if (a.terminal) a.terminal[row] = (u8)(pre ? pre : T::terminal_post(s, cnt != 0));
+    if (a.players) a.players[row] = s.player;
+    if (a.turns) a.turns[row] = s.turn;
+    if (a.reps) a.reps[row] = s.rep;
+  }
 }
 
 template <int GAME>
@@ -88,28 +125,38 @@ __global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   const u32 warp = GLOBAL_TID >> 5, nwarps = GLOBAL_NT >> 5;
   for (u32 g = warp; g < a.n; g += nwarps) {
+    // every lane keeps its own register copy of the state and replays the move (uniform, no broadcast needed)
     TaflState s;
     T::init(s, a.max_turns);
     TaflKey* hist = a.hist + (size_t)g * (a.max_len + 2u);
     u32 hist_len = 0;
     const u32 len = a.lens[g] < a.max_len ? a.lens[g] : a.max_len;
     i32 st = 0;
-    TaflReplayArgs b = a;  // everything but the mask goes through the shared emit code
-    b.valid = nullptr;
     for (u32 k = 0; k <= len; ++k) {
       if (k > 0) {
-        // all lanes write the same key to the same history slot: benign, and every lane later reads its own write
-        if (!T::play_hist(s, a.moves[(size_t)g * a.max_len + (k - 1u)], hist, hist_len)) {
+        // play_move incl. the repetition table (Tafl::play_hist), the history scan split over the lanes
+        const u32 mv = a.moves[(size_t)g * a.max_len + (k - 1u)];
+        if (s.turn == 0) {
+          if (lane == 0) hist[0] = T::key(s);
+          hist_len = 1;
+          __syncwarp();
+        }
+        bool cap;
+        if (!T::play(s, mv, &cap)) {
           st = B2AZ_EMOVE;
           break;
         }
+        if (cap) hist_len = 0;
+        const TaflKey key = T::key(s);
+        u32 same = 0;
+        for (u32 i = lane; i < hist_len; i += 32u) same += T::key_eq(hist[i], key) ? 1u : 0u;
+        same = warp_sum(same) + 1u;
+        if (lane == 0) hist[hist_len] = key;
+        ++hist_len;
+        __syncwarp();
+        s.rep = (u8)(same > 255u ? 255u : same);
       }
-      const size_t row = (size_t)g * (a.max_len + 1u) + k;
-      tafl_emit<GAME>(b, row, s, lane, 32u);
-      if (a.valid || a.n_valid) {
-        const u32 cnt = tafl_emit_valid_warp<GAME>(s, a.valid ? a.valid + row * T::A : nullptr, sm_row[wib], sm_col[wib], lane);
-        if (lane == 0 && a.n_valid) a.n_valid[row] = cnt;
-      }
+      tafl_emit_warp<GAME>(a, (size_t)g * (a.max_len + 1u) + k, s, sm_row[wib], sm_col[wib], lane);
     }
     if (lane == 0 && a.status) a.status[g] = st;
   }
@@ -220,9 +267,8 @@ struct TaflPosArgs {
   i32* status;                // [n]
 };
 template <int GAME>
-AZ_HD void tafl_position_one(const TaflPosArgs& a, u32 i, u32 lane, u32 nl) {
+AZ_HD void tafl_load_position(const TaflPosArgs& a, u32 i, TaflState& s) {
   typedef Tafl<GAME> T;
-  TaflState s;
   s.king = s.def = s.atk = b128(0, 0);
   const signed char* b = a.boards + (size_t)i * T::BOARD_BYTES;
   for (int c = 0; c < T::CELLS; ++c) {
@@ -234,8 +280,10 @@ AZ_HD void tafl_position_one(const TaflPosArgs& a, u32 i, u32 lane, u32 nl) {
   s.turn = a.turns[i];
   s.max_turns = (u16)a.max_turns;
   s.rep = a.reps[i];
-  tafl_emit<GAME>(a.out, i, s, lane, nl);
-  if (a.out.n_valid && lane == 0) a.out.n_valid[i] = T::moves(s, nullptr);
+}
+template <int GAME>
+AZ_HD void tafl_position_move(const TaflPosArgs& a, u32 i, TaflState& s, u32 lane, u32 nl) {
+  typedef Tafl<GAME> T;
   i32 st = 0;
   if (a.moves && a.moves[i] != 0xFFFFFFFFu) {
     bool cap = false;
@@ -246,11 +294,27 @@ AZ_HD void tafl_position_one(const TaflPosArgs& a, u32 i, u32 lane, u32 nl) {
   }
   if (lane == 0 && a.status) a.status[i] = st;
 }
+template <int GAME>
+void tafl_position_one(const TaflPosArgs& a, u32 i) {  // host-emulation build
+  typedef Tafl<GAME> T;
+  TaflState s;
+  tafl_load_position<GAME>(a, i, s);
+  tafl_emit<GAME>(a.out, i, s, 0u, 1u);
+  if (a.out.n_valid) a.out.n_valid[i] = T::moves(s, nullptr);
+  tafl_position_move<GAME>(a, i, s, 0u, 1u);
+}
 #ifndef B2AZ_HOST_EMU
 template <int GAME>
 __global__ void __launch_bounds__(128) k_tafl_positions(TaflPosArgs a) {
-  const u32 lane = threadIdx.x & 31u;
-  for (u32 i = GLOBAL_TID >> 5; i < a.n; i += GLOBAL_NT >> 5) tafl_position_one<GAME>(a, i, lane, 32u);
+  typedef Tafl<GAME> T;
+  __shared__ u32 sm_row[4][128], sm_col[4][128];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 i = GLOBAL_TID >> 5; i < a.n; i += GLOBAL_NT >> 5) {
+    TaflState s;
+    tafl_load_position<GAME>(a, i, s);
+    tafl_emit_warp<GAME>(a.out, i, s, sm_row[wib], sm_col[wib], lane);
+    tafl_position_move<GAME>(a, i, s, lane, 32u);
+  }
 }
 #endif
 template <int GAME>
@@ -268,7 +332,7 @@ int tafl_positions_impl(int device, uint32_t n, uint32_t max_turns, const int8_t
   a.moves = moves;
   a.out.terminal = terminal; a.out.n_valid = n_valid; a.out.valid = valid; a.out.canonical = canonical;
   a.boards_out = reinterpret_cast<signed char*>(boards_out); a.captured_any = captured_any; a.status = status;
-  for (u32 i = 0; i < n; ++i) tafl_position_one<GAME>(a, i, 0u, 1u);
+  for (u32 i = 0; i < n; ++i) tafl_position_one<GAME>(a, i);
   return 0;
 #else
   int ndev = 0;
