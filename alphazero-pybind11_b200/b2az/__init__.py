@@ -91,6 +91,7 @@ def load(path=None):
     L.b2az_leaf_batch_device.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.b2az_submit_eval_all.argtypes = [vp, vp, vp]
     L.b2az_drain_history.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
+    L.b2az_drain_history_sym.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
     L.b2az_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
@@ -205,6 +206,15 @@ class Engine:
         n = C.c_uint32()
         self._check(self.L.b2az_drain_history(self.h, stream, max_rows, _ptr(canon), _ptr(v), _ptr(pi), 0, C.byref(n)))
         return canon[: n.value], v[: n.value], pi[: n.value]
+
+    def drain_history_sym(self, max_samples, stream=None):
+        """build_history_batch + exploit_symmetries: every sample followed by its mirror image (2 rows per sample)."""
+        canon = np.empty((2 * max_samples,) + CANON_SHAPE, np.float32)
+        v = np.empty((2 * max_samples, NUM_PLAYERS + 1), np.float32)
+        pi = np.empty((2 * max_samples, NUM_MOVES), np.float32)
+        n = C.c_uint32()
+        self._check(self.L.b2az_drain_history_sym(self.h, stream, max_samples, _ptr(canon), _ptr(v), _ptr(pi), 0, C.byref(n)))
+        return canon[: 2 * n.value], v[: 2 * n.value], pi[: 2 * n.value]
 
     def drain_history_device(self, max_rows, canon_ptr, v_ptr, pi_ptr, stream=None):
         n = C.c_uint32()

@@ -79,6 +79,9 @@ AZ_HD float c4_canon_elem(u64 p0, u64 p1, u32 player, u32 e) {
   if (c < 2u) return (float)(((c == 0u ? p0 : p1) >> (7u * w + (5u - h))) & 1ULL);
   return (c - 2u == player) ? 1.0f : 0.0f;
 }
+// index of the canonical element that the mirror image shows at position e (Connect4GS::symmetries,
+// connect4_gs.cc:156-162: mirror(f, h, w) = base(f, h, 6 - w))
+AZ_HD u32 c4_mirror_elem(u32 e) { return e - (e % 7u) + (6u - e % 7u); }
 // int8[2][6][7] (the reference's to_bytes/from-board layout, connect4_gs.cc:172-178) -> bitboards
 AZ_HD void c4_from_board(C4State& s, const signed char* board84, int player, int turn) {
   s.p[0] = s.p[1] = 0;

@@ -218,15 +218,19 @@ __global__ void k_canonicalize(EngineView E, const u32* __restrict__ count_ptr, 
     out[i] = c4_canon_elem(E.leaf_p0[row], E.leaf_p1[row], E.leaf_player[row], e);
   }
 }
-__global__ void k_hist_expand(EngineView E, unsigned long long first, u32 count, float* __restrict__ canon,
+// nsym = 1: one row per sample. nsym = 2: every sample followed by its mirror image (Connect4GS::symmetries,
+// connect4_gs.cc:151-170: canonical(f, h, w) <- canonical(f, h, 6 - w), pi(w) <- pi(6 - w), v unchanged), the
+// order game_runner.exploit_symmetries writes them in (game_runner.py:1083-1115).
+__global__ void k_hist_expand(EngineView E, unsigned long long first, u32 count, u32 nsym, float* __restrict__ canon,
                               float* __restrict__ v, float* __restrict__ pi) {
-  const size_t total = (size_t)count * C4_CANON;
+  const size_t total = (size_t)count * nsym * C4_CANON;
   for (size_t i = GLOBAL_TID; i < total; i += GLOBAL_NT) {
     const u32 row = (u32)(i / C4_CANON), e = (u32)(i % C4_CANON);
-    const HistEntry& h = E.hist_out[(first + row) % (unsigned long long)E.hist_capacity];
-    canon[i] = c4_canon_elem(h.p0, h.p1, h.player, e);
+    const u32 sample = row / nsym, mirror = row % nsym;
+    const HistEntry& h = E.hist_out[(first + sample) % (unsigned long long)E.hist_capacity];
+    canon[i] = c4_canon_elem(h.p0, h.p1, h.player, mirror ? c4_mirror_elem(e) : e);
     if (e < 3u) v[(size_t)row * 3 + e] = (h.result == e + 1u) ? 1.0f : 0.0f;
-    if (e < (u32)kA) pi[(size_t)row * kA + e] = h.pi[e];
+    if (e < (u32)kA) pi[(size_t)row * kA + e] = h.pi[mirror ? (u32)kA - 1u - e : e];
   }
 }
 #endif  // !B2AZ_HOST_EMU
@@ -787,8 +791,8 @@ int b2az_submit_eval_host(b2az_engine* e, void* stream, const uint32_t* ids_host
   return 0;
 }
 
-int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
-                       int dst_is_device, uint32_t* count) {
+static int drain_history_impl(b2az_engine* e, void* stream, uint32_t max, u32 nsym, float* canon, float* v, float* pi,
+                              int dst_is_device, uint32_t* count) {
   if (!e || !count) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
   *count = 0;
@@ -799,13 +803,14 @@ int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon,
   const unsigned long long avail = wr[0] - wr[1];
   const u32 n = (u32)std::min<unsigned long long>(avail, max);
   if (n == 0) return 0;
+  const size_t rows = (size_t)n * nsym;
   float *dc = canon, *dv = v, *dp = pi;
 #ifndef B2AZ_HOST_EMU
   if (!dst_is_device) {
-    if (e->hist_stage_cap < n) {
+    if (e->hist_stage_cap < rows) {
       dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
       e->hist_canon = e->hist_v = e->hist_pi = nullptr;
-      const u32 cap = std::max<u32>(n, 4096);
+      const u32 cap = (u32)std::max<size_t>(rows, 4096);
       if (int rc = dev_alloc(&e->hist_canon, (size_t)cap * C4_CANON)) return rc;
       if (int rc = dev_alloc(&e->hist_v, (size_t)cap * 3)) return rc;
       if (int rc = dev_alloc(&e->hist_pi, (size_t)cap * kA)) return rc;
@@ -813,20 +818,22 @@ int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon,
     }
     dc = e->hist_canon; dv = e->hist_v; dp = e->hist_pi;
   }
-  k_hist_expand<<<e->num_sms * 4, 256, 0, s>>>(e->view, wr[1], n, dc, dv, dp);
+  k_hist_expand<<<e->num_sms * 4, 256, 0, s>>>(e->view, wr[1], n, nsym, dc, dv, dp);
   CUDA_TRY(cudaGetLastError());
   if (!dst_is_device) {
-    if (int rc = copy_d2h(canon, dc, (size_t)n * C4_CANON * 4, s)) return rc;
-    if (int rc = copy_d2h(v, dv, (size_t)n * 3 * 4, s)) return rc;
-    if (int rc = copy_d2h(pi, dp, (size_t)n * kA * 4, s)) return rc;
+    if (int rc = copy_d2h(canon, dc, rows * C4_CANON * 4, s)) return rc;
+    if (int rc = copy_d2h(v, dv, rows * 3 * 4, s)) return rc;
+    if (int rc = copy_d2h(pi, dp, rows * kA * 4, s)) return rc;
   }
 #else
   (void)dst_is_device;
-  for (u32 row = 0; row < n; ++row) {
-    const HistEntry& h = e->view.hist_out[(wr[1] + row) % (unsigned long long)e->view.hist_capacity];
-    for (u32 el = 0; el < (u32)C4_CANON; ++el) dc[(size_t)row * C4_CANON + el] = c4_canon_elem(h.p0, h.p1, h.player, el);
-    for (u32 el = 0; el < 3u; ++el) dv[(size_t)row * 3 + el] = (h.result == el + 1u) ? 1.0f : 0.0f;
-    for (u32 el = 0; el < (u32)kA; ++el) dp[(size_t)row * kA + el] = h.pi[el];
+  for (size_t row = 0; row < rows; ++row) {
+    const u32 sample = (u32)(row / nsym), mirror = (u32)(row % nsym);
+    const HistEntry& h = e->view.hist_out[(wr[1] + sample) % (unsigned long long)e->view.hist_capacity];
+    for (u32 el = 0; el < (u32)C4_CANON; ++el)
+      dc[row * C4_CANON + el] = c4_canon_elem(h.p0, h.p1, h.player, mirror ? c4_mirror_elem(el) : el);
+    for (u32 el = 0; el < 3u; ++el) dv[row * 3 + el] = (h.result == el + 1u) ? 1.0f : 0.0f;
+    for (u32 el = 0; el < (u32)kA; ++el) dp[row * kA + el] = h.pi[mirror ? (u32)kA - 1u - el : el];
   }
 #endif
   const unsigned long long new_read = wr[1] + n;
@@ -834,6 +841,15 @@ int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon,
   if (int rc = stream_sync(s)) return rc;
   *count = n;
   return 0;
+}
+
+int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
+                       int dst_is_device, uint32_t* count) {
+  return drain_history_impl(e, stream, max, 1u, canon, v, pi, dst_is_device, count);
+}
+int b2az_drain_history_sym(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
+                           int dst_is_device, uint32_t* count) {
+  return drain_history_impl(e, stream, max, 2u, canon, v, pi, dst_is_device, count);
 }
 
 int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {

@@ -47,6 +47,15 @@ AZ_HD B128 b128_shr(const B128& a, int n) {
   return b128((a.lo >> n) | (a.hi << (64 - n)), a.hi >> n);
 }
 
+// `nbits` (<= 32) bits starting at bit `off` (0 <= off < 128)
+AZ_HD u32 b128_bits(const B128& a, int off, int nbits) {
+  const u64 v = off < 64 ? ((a.lo >> off) | (off ? (a.hi << (64 - off)) : 0ULL)) : (a.hi >> (off - 64));
+  return (u32)v & (nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u));
+}
+AZ_HD u32 b128_word(const B128& a, int j) {  // 32-bit chunk j = squares 32j .. 32j+31
+  return j == 0 ? (u32)a.lo : j == 1 ? (u32)(a.lo >> 32) : j == 2 ? (u32)a.hi : (u32)(a.hi >> 32);
+}
+
 #define B2AZ_TAFL_BRANDUBH 0
 #define B2AZ_TAFL_OPENTAFL 1
 #define B2AZ_TAFL_TAWLBWRDD 2
@@ -148,6 +157,38 @@ struct Tafl {
       }
     }
   }
+  // The same landing sets from the occupancy of the piece's row and column as S-bit lines (bit i = square i of the
+  // line): the free run next to the piece on either side, by count-trailing / count-leading zeros instead of a
+  // walk. `row_occ` bit w' = square (h, w'), `col_occ` bit h' = square (h', w).
+  static AZ_HD u32 line_reach(u32 occ, int pos) {
+    const u32 above = occ >> (pos + 1);
+#if defined(__CUDA_ARCH__)
+    const int run_up = above ? (__ffs((int)above) - 1) : (S - 1 - pos);
+#else
+    const int run_up = above ? __builtin_ctz(above) : (S - 1 - pos);
+#endif
+    const u32 up = ((1u << run_up) - 1u) << (pos + 1);
+    const u32 below_mask = (1u << pos) - 1u;
+    const u32 low = occ & below_mask;
+#if defined(__CUDA_ARCH__)
+    const u32 blocked = low ? ((2u << (31 - __clz((int)low))) - 1u) : 0u;
+#else
+    const u32 blocked = low ? ((2u << (31 - __builtin_clz(low))) - 1u) : 0u;
+#endif
+    return up | (below_mask & ~blocked);
+  }
+  static AZ_HD void slides_lines(bool is_king, int h, int w, u32 row_occ, u32 col_occ, u32& row, u32& col) {
+    row = line_reach(row_occ, w);
+    col = line_reach(col_occ, h);
+    if (R::RESTRICTED && !is_king) {
+      const u32 ends = 1u | (1u << (S - 1));
+      if (h == 0 || h == S - 1) row &= ~ends;   // corners admit only the king
+      if (w == 0 || w == S - 1) col &= ~ends;
+      if (h == MID) row &= ~(1u << MID);        // the empty throne may be passed, not landed on
+      if (w == MID) col &= ~(1u << MID);
+    }
+  }
+
   // valid_moves() as the ascending list of legal move ids (the order Node::add_children walks the mask in,
   // mcts.cc:93-101). Returns the count; `out` may be null (count only).
   static AZ_HD u32 moves(const TaflState& s, u16* out) {

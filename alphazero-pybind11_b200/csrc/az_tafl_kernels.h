@@ -62,50 +62,101 @@ __device__ __forceinline__ u32 warp_sum(u32 v) {
 //                scores()'s "side to move has no legal move"
 //   canonical    plane by plane, consecutive lanes = consecutive floats; planes 3.. are constants per position
 //   board bytes, terminal code, scalars
+// Per-warp shared memory of the emit code: the occupancy of every row and column as S-bit lines, and the
+// legal-move mask of the position as bytes, staged so that it leaves in aligned 4-byte words.
 template <int GAME>
-__device__ __forceinline__ void tafl_emit_warp(const TaflReplayArgs& a, size_t row, const TaflState& s, u32* sm_row,
-                                                u32* sm_col, u32 lane) {
+struct TaflWarpSmem {
+  u32 lines[2 * Tafl<GAME>::S + 2];
+  u32 bytes[(Tafl<GAME>::A + 8) / 4];
+};
+template <int GAME>
+__device__ __forceinline__ void tafl_emit_warp(const TaflReplayArgs& a, size_t row, const TaflState& s,
+                                                TaflWarpSmem<GAME>& sm, u32 lane) {
   typedef Tafl<GAME> T;
-  u32 cnt = 0;
-  const B128 mine = T::own(s);
-  for (u32 c = lane; c < (u32)T::CELLS; c += 32u) {
-    u32 r = 0, cl = 0;
-    if (b128_test(mine, (int)c)) T::slides(s, (int)(c / (u32)T::S), (int)(c % (u32)T::S), r, cl);
-    sm_row[c] = r;
-    sm_col[c] = cl;
-    cnt += (u32)__popc(r) + (u32)__popc(cl);
+  constexpr int S = T::S, CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
+  // (1) occupancy lines: lane r < S extracts row r, lane S + c gathers column c
+  const B128 occ = s.king | s.def | s.atk;
+  if (lane < (u32)S) {
+    sm.lines[lane] = b128_bits(occ, S * (int)lane, S);
+  } else if (lane < 2u * S) {
+    const int c = (int)lane - S;
+    u32 v = 0;
+#pragma unroll
+    for (int h = 0; h < S; ++h) v |= (b128_test(occ, S * h + c) ? 1u : 0u) << h;
+    sm.lines[lane] = v;
   }
   __syncwarp();
-  if (a.valid) {
-    unsigned short* out = reinterpret_cast<unsigned short*>(a.valid + row * T::A);
-    for (u32 p = lane; p < (u32)T::A / 2u; p += 32u) {
-      const u32 b = 2u * p, c = b / (u32)(2 * T::S), t = b % (u32)(2 * T::S);
-      // bytes t, t+1 of square c: columns 0..S-1 from the row mask, then rows 0..S-1 from the column mask
-      const u32 bits = sm_row[c] | (sm_col[c] << T::S);
-      out[p] = (unsigned short)(((bits >> t) & 1u) | (((bits >> (t + 1u)) & 1u) << 8));
+  // (2) legal moves: squares lane, lane + 32, ...: the 2S mask bytes of a square into the staging row, at the
+  // same 4-byte phase as their place in global memory (rows are 2-byte aligned: 2S^3 is even)
+  u8* vdst = a.valid ? a.valid + row * T::A : nullptr;
+  const u32 mis = a.valid ? (u32)(reinterpret_cast<size_t>(vdst) & 3u) : 0u;
+  unsigned short* stage = reinterpret_cast<unsigned short*>(sm.bytes) + (mis >> 1);
+  const B128 mine = T::own(s);
+  u32 cnt = 0;
+#pragma unroll
+  for (int j = 0; j < CHUNKS; ++j) {
+    const u32 c = 32u * j + lane;
+    if (c < (u32)CELLS) {
+      u32 r = 0, cl = 0;
+      if ((b128_word(mine, j) >> lane) & 1u) {
+        const int h = (int)(c / (u32)S), w = (int)(c % (u32)S);
+        T::slides_lines(((b128_word(s.king, j) >> lane) & 1u) != 0, h, w, sm.lines[h], sm.lines[S + w], r, cl);
+      }
+      cnt += (u32)__popc(r) + (u32)__popc(cl);
+      if (vdst) {
+        const u32 bits = r | (cl << S);
+#pragma unroll
+        for (int t = 0; t < S; ++t)
+          stage[c * S + t] = (unsigned short)(((bits >> (2 * t)) & 1u) | (((bits >> (2 * t + 1)) & 1u) << 8));
+      }
+    }
+  }
+  __syncwarp();
+  if (vdst) {
+    const u32 end = mis + (u32)T::A, first = (mis + 3u) >> 2, last = end >> 2;
+    u32* gw = reinterpret_cast<u32*>(vdst - mis);
+    for (u32 wi = first + lane; wi < last; wi += 32u) gw[wi] = sm.bytes[wi];
+    if (lane == 0) {
+      const unsigned short* s16 = reinterpret_cast<const unsigned short*>(sm.bytes);
+      unsigned short* g16 = reinterpret_cast<unsigned short*>(vdst - mis);
+      if (mis & 3u) g16[mis >> 1] = s16[mis >> 1];
+      if (end & 3u) g16[last * 2u] = s16[last * 2u];
     }
   }
   __syncwarp();
   cnt = warp_sum(cnt);
+  // (3) canonical planes and board bytes: consecutive lanes = consecutive squares; planes 3.. are constants
   if (a.canonical) {
     float* out = a.canonical + row * T::CANON;
-    for (u32 c = lane; c < (u32)T::CELLS; c += 32u) {
-      out[c] = b128_test(s.king, (int)c) ? 1.0f : 0.0f;
-      out[T::CELLS + c] = b128_test(s.def, (int)c) ? 1.0f : 0.0f;
-      out[2 * T::CELLS + c] = b128_test(s.atk, (int)c) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j) {
+      const u32 c = 32u * j + lane;
+      if (c < (u32)CELLS) {
+        out[c] = (float)((b128_word(s.king, j) >> lane) & 1u);
+        out[CELLS + c] = (float)((b128_word(s.def, j) >> lane) & 1u);
+        out[2 * CELLS + c] = (float)((b128_word(s.atk, j) >> lane) & 1u);
+      }
     }
 #pragma unroll
     for (int pl = 3; pl < T::PLANES; ++pl) {
-      const float v = T::canon_elem(s, (u32)(pl * T::CELLS));  // constant over the plane
-      for (u32 c = lane; c < (u32)T::CELLS; c += 32u) out[pl * T::CELLS + c] = v;
+      const float v = T::canon_elem(s, (u32)(pl * CELLS));  // constant over the plane
+#pragma unroll
+      for (int j = 0; j < CHUNKS; ++j) {
+        const u32 c = 32u * j + lane;
+        if (c < (u32)CELLS) out[pl * CELLS + c] = v;
+      }
     }
   }
   if (a.boards) {
     signed char* out = a.boards + row * T::BOARD_BYTES;
-    for (u32 c = lane; c < (u32)T::CELLS; c += 32u) {
-      out[c] = (signed char)(b128_test(s.king, (int)c) ? 1 : 0);
-      out[T::CELLS + c] = (signed char)(b128_test(s.def, (int)c) ? 1 : 0);
-      out[2 * T::CELLS + c] = (signed char)(b128_test(s.atk, (int)c) ? 1 : 0);
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j) {
+      const u32 c = 32u * j + lane;
+      if (c < (u32)CELLS) {
+        out[c] = (signed char)((b128_word(s.king, j) >> lane) & 1u);
+        out[CELLS + c] = (signed char)((b128_word(s.def, j) >> lane) & 1u);
+        out[2 * CELLS + c] = (signed char)((b128_word(s.atk, j) >> lane) & 1u);
+      }
     }
   }
   const u32 pre = T::terminal_pre(s);  // uniform over the warp
@@ -118,10 +169,13 @@ __device__ __forceinline__ void tafl_emit_warp(const TaflReplayArgs& a, size_t r
   }
 }
 
+#ifndef B2AZ_TAFL_MINB
+#define B2AZ_TAFL_MINB 1
+#endif
 template <int GAME>
-__global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
+__global__ void __launch_bounds__(128, B2AZ_TAFL_MINB) k_tafl_replay(TaflReplayArgs a) {
   typedef Tafl<GAME> T;
-  __shared__ u32 sm_row[4][128], sm_col[4][128];
+  __shared__ TaflWarpSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   const u32 warp = GLOBAL_TID >> 5, nwarps = GLOBAL_NT >> 5;
   for (u32 g = warp; g < a.n; g += nwarps) {
@@ -156,7 +210,7 @@ __global__ void __launch_bounds__(128) k_tafl_replay(TaflReplayArgs a) {
         __syncwarp();
         s.rep = (u8)(same > 255u ? 255u : same);
       }
-      tafl_emit_warp<GAME>(a, (size_t)g * (a.max_len + 1u) + k, s, sm_row[wib], sm_col[wib], lane);
+      tafl_emit_warp<GAME>(a, (size_t)g * (a.max_len + 1u) + k, s, sm[wib], lane);
     }
     if (lane == 0 && a.status) a.status[g] = st;
   }
@@ -180,6 +234,22 @@ void tafl_replay_host_one(const TaflReplayArgs& a, u32 g) {  // the same work by
     const size_t row = (size_t)g * (a.max_len + 1u) + k;
     tafl_emit<GAME>(a, row, s, 0u, 1u);
     if (a.n_valid) a.n_valid[row] = T::moves(s, nullptr);
+    // cross-check of the device kernel's line-based move generation against the square walk (CPU test-suite)
+    const B128 occ = s.king | s.def | s.atk;
+    u32 lines[2 * T::S];
+    for (int i = 0; i < T::S; ++i) {
+      lines[i] = b128_bits(occ, T::S * i, T::S);
+      u32 v = 0;
+      for (int h = 0; h < T::S; ++h) v |= (b128_test(occ, T::S * h + i) ? 1u : 0u) << h;
+      lines[T::S + i] = v;
+    }
+    for (int c = 0; c < T::CELLS; ++c)
+      if (b128_test(T::own(s), c)) {
+        u32 r0, c0, r1, c1;
+        T::slides(s, c / T::S, c % T::S, r0, c0);
+        T::slides_lines(b128_test(s.king, c), c / T::S, c % T::S, lines[c / T::S], lines[T::S + c % T::S], r1, c1);
+        if (r0 != r1 || c0 != c1) st = -99;
+      }
   }
   if (a.status) a.status[g] = st;
 }
@@ -307,12 +377,12 @@ void tafl_position_one(const TaflPosArgs& a, u32 i) {  // host-emulation build
 template <int GAME>
 __global__ void __launch_bounds__(128) k_tafl_positions(TaflPosArgs a) {
   typedef Tafl<GAME> T;
-  __shared__ u32 sm_row[4][128], sm_col[4][128];
+  __shared__ TaflWarpSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 i = GLOBAL_TID >> 5; i < a.n; i += GLOBAL_NT >> 5) {
     TaflState s;
     tafl_load_position<GAME>(a, i, s);
-    tafl_emit_warp<GAME>(a.out, i, s, sm_row[wib], sm_col[wib], lane);
+    tafl_emit_warp<GAME>(a.out, i, s, sm[wib], lane);
     tafl_position_move<GAME>(a, i, s, lane, 32u);
   }
 }

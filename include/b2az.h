@@ -167,6 +167,13 @@ int b2az_submit_eval_host(b2az_engine* e, void* stream, const uint32_t* ids_host
 int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
                        int dst_is_device, uint32_t* count);
 
+/* build_history_batch followed by game_runner.exploit_symmetries (game_runner.py:1050-1144), on the device: every
+ * popped sample is written together with its symmetric images in GameState::symmetries order (Connect4: the
+ * sample, then its mirror image — connect4_gs.cc:151-170), i.e. 2 * *count rows; `max` counts SAMPLES, the
+ * buffers must hold 2 * max rows. *count = samples popped. */
+int b2az_drain_history_sym(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
+                           int dst_is_device, uint32_t* count);
+
 int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out);
 
 /* GameData / MCTS peeks for parity tests (py_wrapper.cc:265-288 game_data(i); mcts.h:101-115
