@@ -66,6 +66,13 @@ class Stats(C.Structure):
     ]
 
 
+class ForestParams(C.Structure):  # b2az_forest_params (include/b2az.h)
+    _fields_ = [("game", C.c_uint32), ("n_trees", C.c_uint32), ("max_turns", C.c_uint32), ("words_per_tree", C.c_uint32),
+                ("cpuct", C.c_float), ("fpu_reduction", C.c_float), ("epsilon", C.c_float), ("root_policy_temp", C.c_float),
+                ("root_fpu_zero", C.c_uint8), ("relative_values", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("pad_", C.c_uint8),
+                ("pad2_", C.c_uint32), ("seed", C.c_uint64)]
+
+
 _libs = {}
 
 
@@ -97,6 +104,16 @@ def load(path=None):
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
     L.b2az_tafl_replay_device.argtypes = [u32, u32, u32, u32] + [vp] * 10
+    L.b2az_forest_create.argtypes = [C.POINTER(ForestParams), C.c_int, C.POINTER(vp)]
+    L.b2az_forest_destroy.argtypes = [vp]
+    L.b2az_forest_find_leaf.argtypes = [vp, vp, C.POINTER(vp)]
+    L.b2az_forest_leaf_canon_host.argtypes = [vp, vp, vp]
+    L.b2az_forest_process_result.argtypes = [vp, vp, vp, vp]
+    L.b2az_forest_process_result_host.argtypes = [vp, vp, vp, vp]
+    L.b2az_forest_simulate.argtypes = [vp, vp, u32]
+    L.b2az_forest_advance.argtypes = [vp, vp]
+    L.b2az_forest_update_root.argtypes = [vp, vp, vp]
+    L.b2az_forest_counts.argtypes = [vp, vp, vp, vp, vp]
     L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
     _libs[path] = L
     return L
@@ -306,3 +323,68 @@ def tafl_positions(game, boards, players, turns, reps, max_turns, moves=None, de
     if rc != 0:
         raise B2azError(rc, L.b2az_last_error().decode())
     return out
+
+
+class Forest:
+    """n_trees device-resident single-tree searches over a tafl game: the reference's `MCTS` class, batched
+    (find_leaf / process_result / update_root / counts)."""
+    INFO = ("depth", "root_n", "root_k", "root_term", "root_player", "turn", "rep", "error", "words_used", "root_v_bits",
+            "total_leaf_depth", "player")
+
+    def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
+                 words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, device=0, lib=None):
+        self.L = lib or load()
+        self.game, self.n = game, n_trees
+        S, P = TAFL_DIMS[game]
+        self.S, self.P, self.A = S, P, 2 * S ** 3
+        p = ForestParams(game=game, n_trees=n_trees, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
+                         fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
+                         root_fpu_zero=int(root_fpu_zero), seed=seed)
+        self.h = C.c_void_p()
+        self._check(self.L.b2az_forest_create(C.byref(p), device, C.byref(self.h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2azError(rc, self.L.b2az_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.b2az_forest_destroy(self.h)
+            self.h = None
+
+    def find_leaf(self, stream=None):
+        ptr = C.c_void_p()
+        self._check(self.L.b2az_forest_find_leaf(self.h, stream, C.byref(ptr)))
+        return ptr.value
+
+    def leaf_canon(self, stream=None):
+        out = np.zeros((self.n, self.P, self.S, self.S), np.float32)
+        self._check(self.L.b2az_forest_leaf_canon_host(self.h, stream, _ptr(out)))
+        return out
+
+    def process_result(self, v, pi, stream=None):
+        v = np.ascontiguousarray(v, np.float32)
+        pi = np.ascontiguousarray(pi, np.float32)
+        assert v.shape == (self.n, 3) and pi.shape == (self.n, self.A)
+        self._check(self.L.b2az_forest_process_result_host(self.h, stream, _ptr(v), _ptr(pi)))
+
+    def process_result_device(self, v_ptr, pi_ptr, stream=None):
+        self._check(self.L.b2az_forest_process_result(self.h, stream, v_ptr, pi_ptr))
+
+    def simulate(self, n_sims, stream=None):
+        self._check(self.L.b2az_forest_simulate(self.h, stream, n_sims))
+
+    def advance(self, stream=None):
+        self._check(self.L.b2az_forest_advance(self.h, stream))
+
+    def update_root(self, moves, stream=None):
+        moves = np.ascontiguousarray(moves, np.uint32)
+        assert moves.shape == (self.n,)
+        self._check(self.L.b2az_forest_update_root(self.h, stream, _ptr(moves)))
+
+    def counts(self, stream=None, want_q=True):
+        counts = np.zeros((self.n, self.A), np.uint32)
+        q = np.zeros((self.n, self.A), np.float32) if want_q else None
+        info = np.zeros((self.n, 12), np.uint32)
+        self._check(self.L.b2az_forest_counts(self.h, stream, _ptr(counts), _ptr(q), _ptr(info)))
+        return counts, q, {k: info[:, i] for i, k in enumerate(self.INFO)}

@@ -1,0 +1,720 @@
+// az_forest.h — batched wide-tree MCTS ("forest") over the tafl games: MCTS::find_leaf / process_result /
+// update_root / counts (mcts.cc:93-173, 462-573) for MANY trees at once, ONE WARP PER TREE. Included at the end
+// of az_engine.cu (same translation unit: it uses that file's error / launch helpers).
+//
+// This is the wide-game counterpart of the Connect4 step kernel (az_engine_logic.h, one thread per game): a tafl
+// node has 30-120 children, so the per-node work is spread over the 32 lanes of a warp —
+//   selection   Node::best_child (mcts.cc:130-149): the children's {n, q, policy} are read as coalesced arrays, 32
+//               children per pass; `seen_policy` is summed IN CHILD ORDER (float addition is not associative: the
+//               lanes hand their values round with shuffles and every lane accumulates the same sequence), the PUCT
+//               scores are computed one child per lane and reduced to the FIRST maximum (ties -> lowest index)
+//   expansion   Node::add_children (mcts.cc:93-101): legal moves in ascending id order from the row/column
+//               occupancy lines (az_tafl.h slides_lines), written with a warp prefix sum, then std::shuffle with the
+//               tree's own pcg32 stream (lane 0; the draws are sequential by definition)
+//   priors      Node::set_policy_normalized (mcts.cc:109-121): gather pi[move] per lane, sequential sum in child
+//               order as above, one division per lane
+//   backprop    lane 0 walks the (short) path
+// The game state is replayed along the path on every lane's register copy (Tafl<GAME>::play); repetition counts
+// come from the root's history (HBM) plus the keys of the current path, scanned lane-parallel.
+//
+// Node storage: a fixed slab of 32-bit words per tree; an expanded node owns one block [k | n[k] q[k] policy[k]
+// d[k] v[k] first_child[k] move|player|terminal[k]] (structure of arrays: Node::n/q/policy/d/v/children/move/
+// player/scores, mcts.h:14-48), bump-allocated. Re-rooting re-points the root at the chosen child's block
+// (MCTS::update_root, mcts.cc:151-173); the discarded siblings stay in the slab (no compaction yet).
+//
+// Scope of this first version: PUCT selection (no Gumbel), root_policy_temp == 1, no Dirichlet noise,
+// relative_values == false — the MCTS(cpuct, num_players, num_moves, 0, 1, fpu_reduction, false, root_fpu_zero)
+// constructor. b2az_forest_create rejects anything else.
+#pragma once
+
+#include "az_rng.h"
+#include "az_tafl.h"
+
+namespace b2az {
+
+constexpr int kFPath = 96;      // longest selection path kept (a tafl game is at most max_turns plies deep)
+constexpr int kFMaxK = 512;     // most legal moves of one position (11x11: 36 pieces x <= 20 targets in theory)
+
+struct ForestTree {             // one per tree, HBM
+  TaflState state;              // the root position (GameState of the caller in the reference)
+  u32 n;                        // root_.n
+  float v, d;                   // root_.v, root_.d
+  u32 blk, k;                   // root_'s children block (0 = none) and their number
+  u32 player, term;             // root_.player, root_.scores (0 none, else 1 + winner index / 3 = draw)
+  u32 depth, total_leaf_depth;  // MCTS::depth_, total_leaf_depth_
+  u32 bump;                     // next free word of the slab (word 0 is reserved: 0 = "no block")
+  u32 hist_len;                 // repetition history of the root position (keys since the last capture)
+  Pcg32 rng;
+  u32 path_len;                 // MCTS::path_ / current_: the pending leaf
+  u32 leaf_blk, leaf_k, leaf_term, leaf_player, leaf_new;
+  u32 error;                    // sticky: 1 slab full, 2 path too long, 4 too many legal moves, 8 unknown move
+  u32 path_blk[kFPath];         // block that holds the child selected at level i
+  u16 path_slot[kFPath];
+  u8 path_player[kFPath];       // player of the node the selection was made AT (the parent of that child)
+};
+
+struct ForestView {
+  u32 n_trees, words_per_tree, max_turns, game;
+  float cpuct, fpu_reduction;
+  u32 root_fpu_zero;
+  ForestTree* trees;
+  u32* pool;           // [n_trees][words_per_tree]
+  TaflKey* hist;       // [n_trees][max_turns + 2]
+  TaflKey* pkeys;      // [n_trees][kFPath + 2] keys of the positions along the current path
+  float* leaf_canon;   // [n_trees][CANON]
+};
+
+#ifndef B2AZ_HOST_EMU
+// block field offsets (words) for a block of k children at word b: [b] = k, then seven arrays of k words
+__device__ __forceinline__ u32 fb_n(u32 b, u32 k) { (void)k; return b + 1u; }
+__device__ __forceinline__ u32 fb_q(u32 b, u32 k) { return b + 1u + k; }
+__device__ __forceinline__ u32 fb_pol(u32 b, u32 k) { return b + 1u + 2u * k; }
+__device__ __forceinline__ u32 fb_d(u32 b, u32 k) { return b + 1u + 3u * k; }
+__device__ __forceinline__ u32 fb_v(u32 b, u32 k) { return b + 1u + 4u * k; }
+__device__ __forceinline__ u32 fb_fc(u32 b, u32 k) { return b + 1u + 5u * k; }
+__device__ __forceinline__ u32 fb_mv(u32 b, u32 k) { return b + 1u + 6u * k; }  // move | player << 16 | term << 20
+
+template <int GAME>
+struct ForestSmem {   // per warp
+  u32 lines[2 * Tafl<GAME>::S + 2];
+  u16 moves[kFMaxK];
+};
+
+// Σ x_j over j in [0, k) in index order, x_j = `val` of lane (j mod 32) in pass j / 32 — every lane returns the same sum
+__device__ __forceinline__ float seq_sum_chunk(float acc, float val, bool take, u32 count) {
+  for (u32 t = 0; t < count; ++t) {
+    const float x = __shfl_sync(0xFFFFFFFFu, val, (int)t);
+    const int tk = __shfl_sync(0xFFFFFFFFu, take ? 1 : 0, (int)t);
+    if (tk) acc = fadd(acc, x);
+  }
+  return acc;
+}
+
+// play_move along the selection path, repetition count from the root's history + the path's own keys
+// (BrandubhGS::play_move & co; az_tafl.h play_hist restated for a read-only root history)
+template <int GAME>
+__device__ __forceinline__ bool forest_play(TaflState& s, u32 mv, const TaflKey* hist, u32& base_len, TaflKey* pkeys,
+                                            u32& pk_len, u32 lane) {
+  typedef Tafl<GAME> T;
+  if (s.turn == 0) {  // the start position enters the (copy's) table with the first move
+    base_len = 0;
+    if (lane == 0) pkeys[0] = T::key(s);
+    pk_len = 1;
+    __syncwarp();
+  }
+  bool cap;
+  if (!T::play(s, mv, &cap)) return false;
+  if (cap) { base_len = 0; pk_len = 0; }
+  const TaflKey key = T::key(s);
+  u32 same = 0;
+  for (u32 i = lane; i < base_len; i += 32u) same += T::key_eq(hist[i], key) ? 1u : 0u;
+  for (u32 i = lane; i < pk_len; i += 32u) same += T::key_eq(pkeys[i], key) ? 1u : 0u;
+  same = warp_sum(same) + 1u;
+  if (lane == 0) pkeys[pk_len] = key;
+  ++pk_len;
+  __syncwarp();
+  s.rep = (u8)(same > 255u ? 255u : same);
+  return true;
+}
+
+// Node::add_children(valid_moves()) into sm.moves (ascending ids, then std::shuffle); returns k
+template <int GAME>
+__device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem<GAME>& sm, Pcg32& rng, u32 lane, u32* err) {
+  typedef Tafl<GAME> T;
+  constexpr int S = T::S, CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
+  const B128 occ = s.king | s.def | s.atk;
+  if (lane < (u32)S) {
+    sm.lines[lane] = b128_bits(occ, S * (int)lane, S);
+  } else if (lane < 2u * S) {
+    const int c = (int)lane - S;
+    u32 v = 0;
+#pragma unroll
+    for (int h = 0; h < S; ++h) v |= (b128_test(occ, S * h + c) ? 1u : 0u) << h;
+    sm.lines[lane] = v;
+  }
+  __syncwarp();
+  const B128 mine = T::own(s);
+  u32 base = 0;
+#pragma unroll
+  for (int j = 0; j < CHUNKS; ++j) {
+    const u32 c = 32u * j + lane;
+    u32 r = 0, cl = 0;
+    if (c < (u32)CELLS && ((b128_word(mine, j) >> lane) & 1u)) {
+      const int h = (int)(c / (u32)S), w = (int)(c % (u32)S);
+      T::slides_lines(((b128_word(s.king, j) >> lane) & 1u) != 0, h, w, sm.lines[h], sm.lines[S + w], r, cl);
+    }
+    const u32 mycnt = (u32)__popc(r) + (u32)__popc(cl);
+    u32 incl = mycnt;  // inclusive warp prefix sum
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((int)lane >= o) incl += up;
+    }
+    u32 off = base + incl - mycnt;
+    const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (base + total <= (u32)kFMaxK) {
+      for (u32 m = r; m; m &= m - 1u) sm.moves[off++] = (u16)(c * (u32)(2 * S) + (u32)(__ffs((int)m) - 1));
+      for (u32 m = cl; m; m &= m - 1u) sm.moves[off++] = (u16)(c * (u32)(2 * S) + (u32)S + (u32)(__ffs((int)m) - 1));
+    }
+    base += total;
+  }
+  __syncwarp();
+  u32 k = base;
+  if (k > (u32)kFMaxK) { *err |= 4u; k = 0; }
+  if (lane == 0) rng_shuffle<u16>(rng, sm.moves, k);
+  // every lane keeps the same generator state: lane 0's result is broadcast
+  rng.state = __shfl_sync(0xFFFFFFFFu, rng.state, 0);
+  __syncwarp();
+  return k;
+}
+
+// MCTS::find_leaf (mcts.cc:462-498) for tree t
+template <int GAME>
+__device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon) {
+  typedef Tafl<GAME> T;
+  ForestTree& R = F.trees[t];
+  u32* pool = F.pool + (size_t)t * F.words_per_tree;
+  const TaflKey* hist = F.hist + (size_t)t * (F.max_turns + 2u);
+  TaflKey* pkeys = F.pkeys + (size_t)t * (kFPath + 2);
+  TaflState s = R.state;
+  u32 base_len = R.hist_len, pk_len = 0;
+  u32 err = 0;
+  // current_ = &root_
+  u32 cur_n = R.n, cur_term = R.term, cur_blk = R.blk, cur_k = R.k, cur_player = R.player;
+  float cur_v = R.v;
+  u32 par_blk = 0, par_slot = 0, par_k = 0;  // where the current node's own fields live (0 = it is the root)
+  u32 plen = 0;
+  bool at_root = true;
+  while (cur_n > 0 && cur_term == 0) {
+    if (plen >= (u32)kFPath || cur_blk == 0) { err |= 2u; break; }
+    // Node::best_child (mcts.cc:130-149)
+    const u32 b = cur_blk, k = cur_k;
+    float seen = 0.0f;
+    for (u32 c0 = 0; c0 < k; c0 += 32u) {
+      const u32 j = c0 + lane;
+      const u32 nj = j < k ? pool[fb_n(b, k) + j] : 0u;
+      const float pj = j < k ? u2f(pool[fb_pol(b, k) + j]) : 0.0f;
+      seen = seq_sum_chunk(seen, pj, nj > 0, k - c0 < 32u ? k - c0 : 32u);
+    }
+    const float fpu = (at_root && F.root_fpu_zero) ? 0.0f : F.fpu_reduction;
+    const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
+    const float sqrt_n = fsqrt((float)cur_n);
+    float best_u = 0.0f;
+    u32 best_j = 0xFFFFFFFFu;
+    for (u32 c0 = 0; c0 < k; c0 += 32u) {
+      const u32 j = c0 + lane;
+      if (j < k) {
+        const u32 nj = pool[fb_n(b, k) + j];
+        const float qj = u2f(pool[fb_q(b, k) + j]), pj = u2f(pool[fb_pol(b, k) + j]);
+        const float u = fadd(nj == 0 ? fpu_value : qj, fdiv(fmul(fmul(F.cpuct, pj), sqrt_n), (float)(nj + 1u)));
+        if (best_j == 0xFFFFFFFFu || u > best_u) { best_u = u; best_j = j; }  // per lane: ascending j, strict >
+      }
+    }
+    // first maximum over the lanes: larger u wins, equal u -> lower index (child 0 is the reference's start value)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ou = __shfl_xor_sync(0xFFFFFFFFu, best_u, o);
+      const u32 oj = __shfl_xor_sync(0xFFFFFFFFu, best_j, o);
+      const bool take = oj != 0xFFFFFFFFu && (best_j == 0xFFFFFFFFu || ou > best_u || (ou == best_u && oj < best_j));
+      if (take) { best_u = ou; best_j = oj; }
+    }
+    if (best_j == 0xFFFFFFFFu) best_j = 0;  // (all scores NaN: the reference keeps child 0)
+    // NaN scores lose every comparison in the reference loop as well, except at index 0, which is only replaced by
+    // a strictly greater score; with finite scores both orders agree.
+    const u32 mvw = pool[fb_mv(b, k) + best_j];
+    if (lane == 0) {
+      R.path_blk[plen] = b;
+      R.path_slot[plen] = (u16)best_j;
+      R.path_player[plen] = (u8)cur_player;
+    }
+    ++plen;
+    if (!forest_play<GAME>(s, mvw & 0xFFFFu, hist, base_len, pkeys, pk_len, lane)) { err |= 8u; break; }
+    par_blk = b; par_slot = best_j; par_k = k;
+    cur_n = pool[fb_n(b, k) + best_j];
+    cur_v = u2f(pool[fb_v(b, k) + best_j]);
+    cur_blk = pool[fb_fc(b, k) + best_j];
+    cur_k = cur_blk ? pool[cur_blk] : 0u;
+    cur_player = (mvw >> 16) & 3u;
+    cur_term = (mvw >> 20) & 3u;
+    at_root = false;
+  }
+  u32 leaf_new = 0, leaf_blk = cur_blk, leaf_k = cur_k, leaf_term = cur_term, leaf_player = cur_player;
+  if (cur_n == 0 && !err) {
+    // current_->player, scores, add_children(valid_moves) incl. the shuffle (mcts.cc:490-496)
+    leaf_new = 1;
+    leaf_player = s.player;
+    Pcg32 rng = R.rng;
+    const u32 k = forest_legal_moves<GAME>(s, sm, rng, lane, &err);
+    const u32 pre = T::terminal_pre(s);
+    leaf_term = pre ? pre : T::terminal_post(s, k != 0);
+    // children of a terminal node are never visited: their draws are consumed above, their storage is skipped
+    leaf_k = leaf_term ? 0u : k;
+    leaf_blk = 0;
+    if (leaf_k) {
+      const u32 need = 1u + 7u * leaf_k;
+      const u32 b = R.bump;
+      if (b + need > F.words_per_tree) {
+        err |= 1u;
+        leaf_k = 0;
+      } else {
+        leaf_blk = b;
+        if (lane == 0) pool[b] = leaf_k;
+        for (u32 i = lane; i < 6u * leaf_k; i += 32u) pool[b + 1u + i] = 0u;      // n q policy d v first_child
+        for (u32 j = lane; j < leaf_k; j += 32u) pool[fb_mv(b, leaf_k) + j] = sm.moves[j];
+        if (lane == 0) R.bump = b + need;
+      }
+    }
+    if (lane == 0) {
+      R.rng = rng;
+      if (par_blk == 0 && plen == 0) {
+        R.player = leaf_player; R.term = leaf_term; R.blk = leaf_blk; R.k = leaf_k;
+      } else {
+        pool[fb_fc(par_blk, par_k) + par_slot] = leaf_blk;
+        pool[fb_mv(par_blk, par_k) + par_slot] |= (leaf_player << 16) | (leaf_term << 20);
+      }
+    }
+  }
+  if (emit_canon) {
+    float* out = F.leaf_canon + (size_t)t * T::CANON;
+    constexpr int CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j) {
+      const u32 c = 32u * j + lane;
+      if (c < (u32)CELLS) {
+        out[c] = (float)((b128_word(s.king, j) >> lane) & 1u);
+        out[CELLS + c] = (float)((b128_word(s.def, j) >> lane) & 1u);
+        out[2 * CELLS + c] = (float)((b128_word(s.atk, j) >> lane) & 1u);
+      }
+    }
+#pragma unroll
+    for (int pl = 3; pl < T::PLANES; ++pl) {
+      const float v = T::canon_elem(s, (u32)(pl * CELLS));
+#pragma unroll
+      for (int j = 0; j < CHUNKS; ++j) {
+        const u32 c = 32u * j + lane;
+        if (c < (u32)CELLS) out[pl * CELLS + c] = v;
+      }
+    }
+  }
+  if (lane == 0) {
+    R.total_leaf_depth += plen;
+    R.path_len = plen;
+    R.leaf_blk = leaf_blk; R.leaf_k = leaf_k; R.leaf_term = leaf_term; R.leaf_player = leaf_player; R.leaf_new = leaf_new;
+    if (err) R.error |= err;
+  }
+  __syncwarp();
+}
+
+// MCTS::process_result (mcts.cc:500-555) for tree t. RANDOM = dumb_eval (game_state.h:160-173) instead of (v, pi).
+template <int GAME, bool RANDOM>
+__device__ void forest_process_result(const ForestView& F, u32 t, const float* ev_v, const float* ev_pi, u32 lane) {
+  typedef Tafl<GAME> T;
+  ForestTree& R = F.trees[t];
+  u32* pool = F.pool + (size_t)t * F.words_per_tree;
+  float val0, val1, vald;
+  const u32 lterm = R.leaf_term, lk = R.leaf_k, lblk = R.leaf_blk, lplayer = R.leaf_player, plen = R.path_len;
+  if (lterm != 0) {
+    val0 = lterm == 1 ? 1.0f : 0.0f; val1 = lterm == 2 ? 1.0f : 0.0f; vald = lterm == 3 ? 1.0f : 0.0f;
+  } else {
+    if (RANDOM) {
+      val0 = val1 = vald = (float)(1.0 / 3.0);
+    } else {
+      val0 = ev_v[(size_t)t * 3 + 0]; val1 = ev_v[(size_t)t * 3 + 1]; vald = ev_v[(size_t)t * 3 + 2];
+    }
+    if (lk > 0 && lblk != 0) {
+      // set_policy_normalized (mcts.cc:109-121); the same code for the root and interior nodes here
+      // (root_policy_temp == 1, no noise)
+      float rp = 0.0f;
+      if (RANDOM) {  // valids.cast<float>() / float(Vector<uint8_t>::sum()) — the uint8 sum wraps mod 256
+        const u32 s8 = lk & 255u;
+        rp = s8 ? fdiv(1.0f, (float)s8) : 0.0f;
+      }
+      float sum = 0.0f;
+      for (u32 c0 = 0; c0 < lk; c0 += 32u) {
+        const u32 j = c0 + lane;
+        float p = 0.0f;
+        if (j < lk) {
+          p = RANDOM ? rp : ev_pi[(size_t)t * T::A + (pool[fb_mv(lblk, lk) + j] & 0xFFFFu)];
+          pool[fb_pol(lblk, lk) + j] = f2u(p);
+        }
+        sum = seq_sum_chunk(sum, p, true, lk - c0 < 32u ? lk - c0 : 32u);
+      }
+      __syncwarp();
+      for (u32 j = lane; j < lk; j += 32u) pool[fb_pol(lblk, lk) + j] = f2u(fdiv(u2f(pool[fb_pol(lblk, lk) + j]), sum));
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const float dshare = fdiv(vald, 2.0f);
+    for (u32 i = plen; i-- > 0;) {
+      const u32 b = R.path_blk[i], sl = R.path_slot[i], pp = R.path_player[i], k = pool[b];
+      const float v = fadd(pp == 0 ? val0 : val1, dshare);
+      const u32 n0 = pool[fb_n(b, k) + sl];
+      const float q0 = u2f(pool[fb_q(b, k) + sl]), d0 = u2f(pool[fb_d(b, k) + sl]);
+      pool[fb_q(b, k) + sl] = f2u(fdiv(fadd(fmul(q0, (float)n0), v), (float)(n0 + 1u)));
+      pool[fb_d(b, k) + sl] = f2u(fdiv(fadd(fmul(d0, (float)n0), vald), (float)(n0 + 1u)));
+      if (n0 == 0) pool[fb_v(b, k) + sl] = f2u(fadd(lplayer == 0 ? val0 : val1, dshare));  // only the leaf can be new
+      pool[fb_n(b, k) + sl] = n0 + 1u;
+    }
+    if (R.n == 0) {
+      R.v = fadd(R.player == 0 ? val0 : val1, dshare);
+      R.d = vald;
+    }
+    ++R.depth;
+    ++R.n;
+    R.path_len = 0;
+  }
+  __syncwarp();
+}
+
+// MCTS::update_root(gs, move) (mcts.cc:151-173) followed by gs.play_move(move) on the tree's root position
+template <int GAME>
+__device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestSmem<GAME>& sm, u32 lane) {
+  typedef Tafl<GAME> T;
+  ForestTree& R = F.trees[t];
+  u32* pool = F.pool + (size_t)t * F.words_per_tree;
+  TaflKey* hist = F.hist + (size_t)t * (F.max_turns + 2u);
+  u32 err = 0;
+  TaflState s = R.state;
+  u32 blk = R.blk, k = R.k;
+  const u32 root_term = R.term;
+  if (blk == 0) {
+    // root_.children.empty(): add_children(gs.valid_moves()) — the shuffle draws happen; the block is only stored
+    // when it can be descended into later (a terminal root keeps no children here, see find_leaf)
+    Pcg32 rng = R.rng;
+    k = forest_legal_moves<GAME>(s, sm, rng, lane, &err);
+    if (lane == 0) R.rng = rng;
+    // the chosen child is a fresh node whatever its slot: only membership matters
+    bool found = false;
+    for (u32 j = lane; j < k; j += 32u) found |= sm.moves[j] == move;
+    found = __any_sync(0xFFFFFFFFu, found);
+    if (!found) err |= 8u;
+    if (lane == 0) { R.n = 0; R.v = 0.0f; R.d = 0.0f; R.blk = 0; R.k = 0; R.player = 0; R.term = 0; }
+  } else {
+    u32 slot = 0xFFFFFFFFu;
+    for (u32 j = lane; j < k; j += 32u)
+      if ((pool[fb_mv(blk, k) + j] & 0xFFFFu) == move) slot = j;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const u32 os = __shfl_xor_sync(0xFFFFFFFFu, slot, o);
+      slot = os < slot ? os : slot;
+    }
+    if (slot == 0xFFFFFFFFu) {
+      err |= 8u;
+    } else if (lane == 0) {
+      const u32 mvw = pool[fb_mv(blk, k) + slot];
+      const u32 nb = pool[fb_fc(blk, k) + slot];
+      R.n = pool[fb_n(blk, k) + slot];
+      R.v = u2f(pool[fb_v(blk, k) + slot]);
+      R.d = u2f(pool[fb_d(blk, k) + slot]);
+      R.blk = nb;
+      R.k = nb ? pool[nb] : 0u;
+      R.player = (mvw >> 16) & 3u;
+      R.term = (mvw >> 20) & 3u;
+    }
+  }
+  (void)root_term;
+  // gs.play_move(move) with the persistent repetition history
+  u32 hist_len = R.hist_len;
+  if (!err) {
+    if (s.turn == 0) {
+      if (lane == 0) hist[0] = T::key(s);
+      hist_len = 1;
+      __syncwarp();
+    }
+    bool cap;
+    if (!T::play(s, move, &cap)) {
+      err |= 8u;
+    } else {
+      if (cap) hist_len = 0;
+      const TaflKey key = T::key(s);
+      u32 same = 0;
+      for (u32 i = lane; i < hist_len; i += 32u) same += T::key_eq(hist[i], key) ? 1u : 0u;
+      same = warp_sum(same) + 1u;
+      if (hist_len + 1u > F.max_turns + 2u) {
+        err |= 2u;
+      } else {
+        if (lane == 0) hist[hist_len] = key;
+        ++hist_len;
+      }
+      s.rep = (u8)(same > 255u ? 255u : same);
+    }
+  }
+  if (lane == 0) {
+    if (!err) { R.state = s; R.hist_len = hist_len; }
+    R.depth = 0;
+    R.total_leaf_depth = 0;
+    R.path_len = 0;
+    if (err) R.error |= err;
+  }
+  __syncwarp();
+}
+
+// ---- kernels: one warp per tree, 4 warps per CTA
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_find_leaf(ForestView F) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) forest_find_leaf<GAME>(F, t, sm[wib], lane, true);
+}
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, const float* ev_v, const float* ev_pi) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
+    forest_process_result<GAME, false>(F, t, ev_v, ev_pi, lane);
+}
+// n_sims x (find_leaf + dumb_eval + process_result) fused: the RANDOM-evaluator search (EvalType::RANDOM)
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_simulate(ForestView F, u32 n_sims) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
+    for (u32 i = 0; i < n_sims; ++i) {
+      forest_find_leaf<GAME>(F, t, sm[wib], lane, false);
+      forest_process_result<GAME, true>(F, t, nullptr, nullptr, lane);
+    }
+}
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_update_root(ForestView F, const u32* moves) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
+    if (moves[t] != 0xFFFFFFFFu) forest_update_root<GAME>(F, t, moves[t], sm[wib], lane);
+}
+// Greedy self-play step entirely on the device: every tree that is not over plays its most visited root move
+// (lowest move id on ties — argmax of MCTS::counts()) through update_root + play_move. Used by the throughput tool.
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_advance(ForestView F) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    const ForestTree& R = F.trees[t];
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    const u32 b = R.blk, k = R.k;
+    if (b == 0 || R.term != 0) continue;
+    u32 best_n = 0, best_mv = 0xFFFFFFFFu;
+    for (u32 j = lane; j < k; j += 32u) {
+      const u32 nj = pool[fb_n(b, k) + j], mv = pool[fb_mv(b, k) + j] & 0xFFFFu;
+      if (best_mv == 0xFFFFFFFFu || nj > best_n || (nj == best_n && mv < best_mv)) { best_n = nj; best_mv = mv; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const u32 on = __shfl_xor_sync(0xFFFFFFFFu, best_n, o), om = __shfl_xor_sync(0xFFFFFFFFu, best_mv, o);
+      if (om != 0xFFFFFFFFu && (best_mv == 0xFFFFFFFFu || on > best_n || (on == best_n && om < best_mv))) { best_n = on; best_mv = om; }
+    }
+    if (best_mv != 0xFFFFFFFFu) forest_update_root<GAME>(F, t, best_mv, sm[wib], lane);
+  }
+}
+// MCTS::counts / root_q_values (mcts.cc:557-573) + a few scalars per tree
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_counts(ForestView F, u32* counts, float* q, u32* info) {
+  typedef Tafl<GAME> T;
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    const ForestTree& R = F.trees[t];
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    for (u32 m = lane; m < (u32)T::A; m += 32u) {
+      if (counts) counts[(size_t)t * T::A + m] = 0u;
+      if (q) q[(size_t)t * T::A + m] = 0.0f;
+    }
+    __syncwarp();
+    const u32 b = R.blk, k = R.k;
+    if (b)
+      for (u32 j = lane; j < k; j += 32u) {
+        const u32 mv = pool[fb_mv(b, k) + j] & 0xFFFFu;
+        if (counts) counts[(size_t)t * T::A + mv] = pool[fb_n(b, k) + j];
+        if (q) q[(size_t)t * T::A + mv] = u2f(pool[fb_q(b, k) + j]);
+      }
+    if (info && lane == 0) {
+      u32* o = info + (size_t)t * 12;
+      o[0] = R.depth; o[1] = R.n; o[2] = R.k; o[3] = R.term; o[4] = R.player; o[5] = R.state.turn; o[6] = R.state.rep;
+      o[7] = R.error; o[8] = R.bump; o[9] = f2u(R.v); o[10] = R.total_leaf_depth; o[11] = R.state.player;
+    }
+  }
+}
+template <int GAME>
+__global__ void k_forest_init(ForestView F, unsigned long long seed) {
+  typedef Tafl<GAME> T;
+  for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
+    ForestTree& R = F.trees[t];
+    memset(&R, 0, sizeof(ForestTree));
+    T::init(R.state, F.max_turns);
+    R.bump = 1;
+    pcg32_seed(R.rng, seed + t);  // tree t == a reference MCTS driven after MCTS::seed_thread_rng(seed + t)
+  }
+}
+#endif  // !B2AZ_HOST_EMU
+
+}  // namespace b2az
+
+struct b2az_forest {
+  b2az::ForestView view;
+  int device = 0;
+  uint32_t actions = 0, canon = 0;
+  uint32_t* moves_dev = nullptr;
+  float *ev_v = nullptr, *ev_pi = nullptr;
+};
+
+#ifndef B2AZ_HOST_EMU
+#define FOREST_DISPATCH(F, CALL)                                                          \
+  switch ((F)->view.game) {                                                               \
+    case B2AZ_TAFL_BRANDUBH: { constexpr int G_ = B2AZ_TAFL_BRANDUBH; CALL; } break;      \
+    case B2AZ_TAFL_OPENTAFL: { constexpr int G_ = B2AZ_TAFL_OPENTAFL; CALL; } break;      \
+    default: { constexpr int G_ = B2AZ_TAFL_TAWLBWRDD; CALL; } break;                     \
+  }
+static inline unsigned forest_ctas(const b2az_forest* f) { return std::max(1u, std::min((f->view.n_trees + 3u) / 4u, 148u * 8u)); }
+#endif
+
+extern "C" {
+
+int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out) {
+  using namespace b2az;
+  if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
+  if (p->game > B2AZ_TAFL_TAWLBWRDD) return fail(B2AZ_EINVAL, "b2az_forest: unknown tafl game");
+  if (p->n_trees == 0 || p->max_turns == 0 || p->max_turns > 65535u) return fail(B2AZ_EINVAL, "b2az_forest: bad n_trees / max_turns");
+  if (p->epsilon != 0.0f) return fail(B2AZ_EINVAL, "b2az_forest: root Dirichlet noise (epsilon) is not implemented yet");
+  if (p->root_policy_temp != 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp != 1 is not implemented yet");
+  if (p->gumbel_enabled) return fail(B2AZ_EINVAL, "b2az_forest: Gumbel root search is not implemented yet");
+  if (p->relative_values) return fail(B2AZ_EINVAL, "b2az_forest: relative_values is not implemented (tafl values are absolute)");
+#ifdef B2AZ_HOST_EMU
+  (void)device;
+  return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  b2az_forest* f = new b2az_forest();
+  f->device = device;
+  ForestView& V = f->view;
+  memset(&V, 0, sizeof(V));
+  V.n_trees = p->n_trees; V.max_turns = p->max_turns; V.game = p->game;
+  V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.root_fpu_zero = p->root_fpu_zero ? 1u : 0u;
+  const uint32_t S = p->game == B2AZ_TAFL_BRANDUBH ? 7u : 11u, planes = p->game == B2AZ_TAFL_OPENTAFL ? 8u : 7u;
+  f->actions = 2u * S * S * S;
+  f->canon = planes * S * S;
+  V.words_per_tree = p->words_per_tree ? p->words_per_tree : (1u << 20);
+  auto bail = [&](int rc) { b2az_forest_destroy(f); return rc; };
+  if (int rc = dev_alloc(&V.trees, (size_t)V.n_trees)) return bail(rc);
+  if (int rc = dev_alloc_raw(&V.pool, (size_t)V.n_trees * V.words_per_tree)) return bail(rc);
+  if (int rc = dev_alloc(&V.hist, (size_t)V.n_trees * (V.max_turns + 2u))) return bail(rc);
+  if (int rc = dev_alloc(&V.pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
+  if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon)) return bail(rc);
+  if (int rc = dev_alloc(&f->moves_dev, (size_t)V.n_trees)) return bail(rc);
+  FOREST_DISPATCH(f, (k_forest_init<G_><<<148, 128>>>(V, p->seed)));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = f;
+  return 0;
+#endif
+}
+
+int b2az_forest_destroy(b2az_forest* f) {
+  using namespace b2az;
+  if (!f) return 0;
+  dev_free(f->view.trees); dev_free(f->view.pool); dev_free(f->view.hist); dev_free(f->view.pkeys);
+  dev_free(f->view.leaf_canon); dev_free(f->moves_dev); dev_free(f->ev_v); dev_free(f->ev_pi);
+  delete f;
+  return 0;
+}
+
+#ifdef B2AZ_HOST_EMU
+#define FOREST_NO_CUDA(...) { return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback"); }
+int b2az_forest_find_leaf(b2az_forest*, void*, const float**) FOREST_NO_CUDA()
+int b2az_forest_leaf_canon_host(b2az_forest*, void*, float*) FOREST_NO_CUDA()
+int b2az_forest_process_result(b2az_forest*, void*, const float*, const float*) FOREST_NO_CUDA()
+int b2az_forest_process_result_host(b2az_forest*, void*, const float*, const float*) FOREST_NO_CUDA()
+int b2az_forest_simulate(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
+int b2az_forest_advance(b2az_forest*, void*) FOREST_NO_CUDA()
+int b2az_forest_update_root(b2az_forest*, void*, const uint32_t*) FOREST_NO_CUDA()
+int b2az_forest_counts(b2az_forest*, void*, uint32_t*, float*, uint32_t*) FOREST_NO_CUDA()
+#else
+int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_find_leaf<G_><<<forest_ctas(f), 128, 0, s>>>(f->view)));
+  CUDA_TRY(cudaGetLastError());
+  if (canon_dev) *canon_dev = f->view.leaf_canon;
+  return 0;
+}
+int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host) {
+  using namespace b2az;
+  if (!f || !canon_host) return fail(B2AZ_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = copy_d2h(canon_host, f->view.leaf_canon, (size_t)f->view.n_trees * f->canon * 4, s)) return rc;
+  return stream_sync(s);
+}
+int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev) {
+  using namespace b2az;
+  if (!f || !v_dev || !pi_dev) return fail(B2AZ_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_process_result<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, v_dev, pi_dev)));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host) {
+  using namespace b2az;
+  if (!f || !v_host || !pi_host) return fail(B2AZ_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees;
+  if (!f->ev_v) {
+    if (int rc = dev_alloc(&f->ev_v, n * 3)) return rc;
+    if (int rc = dev_alloc(&f->ev_pi, n * f->actions)) return rc;
+  }
+  if (int rc = copy_h2d(f->ev_v, v_host, n * 3 * 4, s)) return rc;
+  if (int rc = copy_h2d(f->ev_pi, pi_host, n * f->actions * 4, s)) return rc;
+  if (int rc = b2az_forest_process_result(f, stream, f->ev_v, f->ev_pi)) return rc;
+  return stream_sync(s);
+}
+int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (n_sims == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_simulate<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, n_sims)));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_advance(b2az_forest* f, void* stream) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_advance<G_><<<forest_ctas(f), 128, 0, s>>>(f->view)));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_host) {
+  using namespace b2az;
+  if (!f || !moves_host) return fail(B2AZ_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = copy_h2d(f->moves_dev, moves_host, (size_t)f->view.n_trees * 4, s)) return rc;
+  FOREST_DISPATCH(f, (k_forest_update_root<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, f->moves_dev)));
+  CUDA_TRY(cudaGetLastError());
+  return stream_sync(s);
+}
+int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees, A = f->actions;
+  u32 *dc = nullptr, *di = nullptr;
+  float* dq = nullptr;
+  int rc = 0;
+  if (counts_host) rc = rc ? rc : dev_alloc(&dc, n * A);
+  if (q_host) rc = rc ? rc : dev_alloc(&dq, n * A);
+  if (info_host) rc = rc ? rc : dev_alloc(&di, n * 12);
+  if (!rc) {
+    FOREST_DISPATCH(f, (k_forest_counts<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, dc, dq, di)));
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_counts launch failed");
+  }
+  if (!rc && counts_host) rc = copy_d2h(counts_host, dc, n * A * 4, s);
+  if (!rc && q_host) rc = copy_d2h(q_host, dq, n * A * 4, s);
+  if (!rc && info_host) rc = copy_d2h(info_host, di, n * 12 * 4, s);
+  if (!rc) rc = stream_sync(s);
+  dev_free(dc); dev_free(dq); dev_free(di);
+  return rc;
+}
+#endif
+
+}  // extern "C"

@@ -229,6 +229,47 @@ int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turn
                         uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical, int8_t* boards_out,
                         uint8_t* captured_any, int32_t* status);
 
+/* ---- Batched single-tree MCTS over the tafl games ("forest"): the reference's `MCTS` class (mcts.h:50-150, bound at
+ * py_wrapper.cc:192-220) for n_trees trees at once, one warp per tree on the device. Tree i starts at the game's
+ * start position and draws from pcg32(seed + i) — a reference MCTS driven after MCTS::seed_thread_rng(seed + i).
+ * Mirrors MCTS(cpuct, num_players = 2, num_moves, epsilon, root_policy_temp, fpu_reduction, relative_values,
+ * root_fpu_zero, ..., gumbel_enabled): this version implements PUCT with epsilon == 0, root_policy_temp == 1,
+ * relative_values == 0, gumbel_enabled == 0 and rejects anything else. */
+typedef struct b2az_forest_params {
+  uint32_t game;                 /* B2AZ_TAFL_* */
+  uint32_t n_trees;
+  uint32_t max_turns;            /* the game's max_turns (BrandubhGS(max_turns) ...) */
+  uint32_t words_per_tree;       /* node slab per tree in 32-bit words (1 + 7k words per expanded node); 0 = 2^20 */
+  float cpuct, fpu_reduction, epsilon, root_policy_temp;
+  uint8_t root_fpu_zero, relative_values, gumbel_enabled, pad_;
+  uint32_t pad2_;
+  uint64_t seed;
+} b2az_forest_params;
+typedef struct b2az_forest b2az_forest;
+int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out);
+int b2az_forest_destroy(b2az_forest* f);
+/* MCTS::find_leaf(gs) (mcts.cc:462-498) for every tree: PUCT descent from the tree's root position, expansion of
+ * the new node (terminal test, legal moves, std::shuffle). *canon_dev = DEVICE pointer to the leaves' canonical
+ * planes float32[n_trees][P][S][S] (the evaluator's input); b2az_forest_leaf_canon_host copies them out. */
+int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev);
+int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host);
+/* MCTS::process_result(gs, value, pi, root_noise_enabled = false) (mcts.cc:500-555): v float32[n_trees][3],
+ * pi float32[n_trees][A], device or host pointers. */
+int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev);
+int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host);
+/* n_sims x (find_leaf -> dumb_eval (game_state.h:160-173) -> process_result) fused in one launch. */
+int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims);
+/* Greedy self-play step on the device: every tree whose root is expanded and not terminal plays its most visited
+ * move (argmax of MCTS::counts(), lowest move id on ties) through update_root + play_move. No host round trip. */
+int b2az_forest_advance(b2az_forest* f, void* stream);
+/* MCTS::update_root(gs, move) (mcts.cc:151-173) followed by gs.play_move(move) on the tree's root position;
+ * moves_host[n_trees], 0xFFFFFFFF = leave that tree alone. */
+int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_host);
+/* MCTS::counts / root_q_values (mcts.cc:557-573): uint32[n_trees][A], float32[n_trees][A]; info uint32[n_trees][12] =
+ * depth, root n, root children, root terminal code, root player, turn, repetition count, error bits, slab words
+ * used, root v (bits), total_leaf_depth, side to move. Any pointer may be NULL. */
+int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host);
+
 #ifdef __cplusplus
 }
 #endif

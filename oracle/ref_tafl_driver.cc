@@ -12,6 +12,8 @@
 //   azref_tafl_dims         board side, action count, canonical planes of a game
 //   azref_tafl_random_game  a random legal game from the start position (moves chosen with a small
 //                           deterministic generator, so the same transcript can be regenerated)
+//   azref_tafl_search       a whole single-tree MCTS run (MCTS::find_leaf / process_result / update_root,
+//                           mcts.cc) over one game with a caller-supplied or dumb_eval evaluator
 //   azref_tafl_replay       replays a transcript through GameState::play_move and records, after
 //                           every move: to_bytes() board, player, turn, repetition count, scores(),
 //                           valid_moves(), canonicalized()
@@ -22,6 +24,7 @@
 #include <vector>
 
 #include "brandubh_gs.cc"
+#include "mcts.h"
 #include "opentafl_gs.cc"
 #include "tawlbwrdd_gs.cc"
 
@@ -186,6 +189,57 @@ int azref_tafl_position(int game, const int8_t* board, int8_t player, uint16_t t
       std::memcpy(board_out, bytes.data(), 3 * S * S);
     }
     return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// One single-tree search run through the reference's MCTS class (mcts.h:50-150), exactly the way Python drives it
+// (py_wrapper.cc:192-220; play.py): seed the thread's generator, then for every move `sims` x (find_leaf ->
+// evaluate -> process_result(root_noise_enabled = false)), record counts() / root_q_values(), play the most
+// visited move (lowest id on ties) with update_root + play_move. eval_kind 0: `cb(canonical, v3, piA, user)`
+// supplies the evaluation; 1: dumb_eval (game_state.h:160-173). Stops when the game is over; returns the number
+// of moves searched, or -1 when the reference threw.
+typedef void (*azref_eval_fn)(const float* canonical, float* v3, float* pi, void* user);
+int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, float fpu_reduction, int root_fpu_zero,
+                      uint32_t n_moves, uint32_t sims, int eval_kind, azref_eval_fn cb, void* user, uint32_t* counts_out,
+                      float* q_out, uint32_t* moves_out, uint32_t* depth_sum_out) {
+  try {
+    auto gs = make_game(game, max_turns);
+    if (!gs) { g_err = "unknown game"; return -1; }
+    const uint32_t A = gs->num_moves();
+    MCTS::seed_thread_rng(seed);
+    MCTS mcts{cpuct, 2, A, 0.0f, 1.0f, fpu_reduction, false, root_fpu_zero != 0, false, false, 16, 50.0f, 1.0f, false};
+    uint32_t played = 0;
+    for (uint32_t m = 0; m < n_moves; ++m) {
+      if (gs->scores().has_value()) break;
+      for (uint32_t i = 0; i < sims; ++i) {
+        auto leaf = mcts.find_leaf(*gs);
+        Vector<float> v{3}, pi{A};
+        if (eval_kind == 1) {
+          auto [vv, pp] = dumb_eval(*leaf);
+          v = vv; pi = pp;
+        } else {
+          auto c = leaf->canonicalized();
+          cb(c.data(), v.data(), pi.data(), user);
+        }
+        mcts.process_result(*gs, v, pi, false);
+      }
+      auto counts = mcts.counts();
+      auto q = mcts.root_q_values();
+      std::memcpy(counts_out + (size_t)m * A, counts.data(), A * 4);
+      std::memcpy(q_out + (size_t)m * A, q.data(), A * 4);
+      if (depth_sum_out) depth_sum_out[m] = (uint32_t)(mcts.avg_leaf_depth() * (float)mcts.depth() + 0.5f);
+      uint32_t best = 0;
+      for (uint32_t a = 1; a < A; ++a)
+        if (counts(a) > counts(best)) best = a;
+      moves_out[m] = best;
+      mcts.update_root(*gs, best);
+      gs->play_move(best);
+      ++played;
+    }
+    return (int)played;
   } catch (const std::exception& e) {
     g_err = e.what();
     return -1;

@@ -25,6 +25,7 @@ def lib():
         L.azref_tafl_random_game.argtypes = [C.c_int, C.c_uint16, C.c_uint64, u32, vp]
         L.azref_tafl_random_game.restype = u32
         L.azref_tafl_replay.argtypes = [C.c_int, C.c_uint16, vp, u32] + [vp] * 9
+        L.azref_tafl_search.argtypes = [C.c_int, C.c_uint16, C.c_uint64, C.c_float, C.c_float, C.c_int, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp]
         L.azref_tafl_position.argtypes = [C.c_int, vp, C.c_int8, C.c_uint16, C.c_uint16, C.c_uint8, u32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -75,3 +76,31 @@ def position(game, board, player, turn, max_turns, rep, move=None):
                                    C.cast(C.byref(nv), C.c_void_p), p(valid), p(canon), p(bout))
     return dict(terminal=term.value, n_valid=nv.value, valid=valid, canonical=canon, board_out=bout if rc == 0 else None,
                 threw=rc != 0)
+
+
+EVAL_FN = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+
+
+def search(game, seed, n_moves, sims, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, evaluator=None):
+    """One single-tree MCTS run through the reference's MCTS class. evaluator(canonical[P,S,S]) -> (v[3], pi[A]), or
+    None for dumb_eval. Returns counts[m][A], q[m][A], moves[m], total leaf depth per move for the moves searched."""
+    S, A, P = dims(game)
+    counts = np.zeros((n_moves, A), np.uint32)
+    q = np.zeros((n_moves, A), np.float32)
+    moves = np.zeros(n_moves, np.uint32)
+    depth = np.zeros(n_moves, np.uint32)
+
+    def cb(canon_p, v_p, pi_p, _user):
+        canon = np.ctypeslib.as_array(canon_p, shape=(P, S, S))
+        v, pi = evaluator(canon)
+        np.ctypeslib.as_array(v_p, shape=(3,))[:] = v
+        np.ctypeslib.as_array(pi_p, shape=(A,))[:] = pi
+
+    fn = EVAL_FN(cb) if evaluator is not None else None
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = lib().azref_tafl_search(game, max_turns, seed, cpuct, fpu_reduction, int(root_fpu_zero), n_moves, sims,
+                                0 if evaluator is not None else 1, C.cast(fn, C.c_void_p) if fn else None, None,
+                                p(counts), p(q), p(moves), p(depth))
+    if n < 0:
+        raise RuntimeError(lib().azref_tafl_last_error().decode())
+    return counts[:n], q[:n], moves[:n], depth[:n]

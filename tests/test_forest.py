@@ -1,0 +1,122 @@
+"""The batched single-tree MCTS over the tafl games (b2az_forest_*: MCTS::find_leaf / process_result / update_root /
+counts for many trees, one warp per tree) against the UNMODIFIED reference's MCTS class driven over the unmodified
+tafl games (oracle/_ref/libazref_tafl.so: azref_tafl_search). Tree i of the forest == a reference MCTS run after
+MCTS::seed_thread_rng(seed + i). Visit counts and Q values after every move's search are compared bit-exact, with
+the reference's dumb_eval evaluator (fused device launches) and with a deterministic pseudo-network supplied by
+the host on both sides (leaf canonical planes out, v / pi in). Golden fixtures (tools/make_golden_forest.py) make
+the dumb_eval cases runnable without the reference."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import b2az
+import parity_harness as ph
+import tafl_ref
+
+NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
+MAX_TURNS = {0: 150, 1: 400, 2: 400}
+needs_tafl_ref = pytest.mark.skipif(not tafl_ref.available(), reason="oracle/_ref/libazref_tafl.so not built")
+GOLDEN = os.path.join(ph.ROOT, "tests", "golden", "forest_random_eval.npz")
+# (game, trees, moves, sims per move, seed, cpuct, fpu_reduction, root_fpu_zero)
+GOLDEN_CASES = {"brandubh": (0, 6, 12, 60, 100, 1.25, 0.25, False), "opentafl": (1, 3, 6, 50, 200, 2.0, 0.2, True),
+                "tawlbwrdd": (2, 3, 6, 50, 300, 1.25, 0.0, False)}
+
+
+def pseudo_net(canon):
+    """Deterministic evaluator: a function of the canonical planes' bytes only (so both sides see identical v, pi)."""
+    A = 2 * canon.shape[1] ** 3
+    rng = np.random.default_rng(zlib.crc32(np.ascontiguousarray(canon, np.float32).tobytes()))
+    v = rng.random(3).astype(np.float32) + np.float32(0.05)
+    v /= v.sum()
+    pi = rng.random(A).astype(np.float32) ** 4 + np.float32(1e-3)
+    pi /= pi.sum()
+    return v.astype(np.float32), pi.astype(np.float32)
+
+
+def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None):
+    """Drives the forest like the reference run; plays `moves_ref[i][m]` when given (else the most visited move)."""
+    # no compaction yet: the slab must hold every node expanded during the run (1 + 7k words per node)
+    words = 1 + (n_moves + 1) * sims * (1 + 7 * (64 if game == 0 else 200))
+    f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=cpuct, fpu_reduction=fpu, root_fpu_zero=rfz, seed=seed,
+                    words_per_tree=words)
+    out = []
+    alive = np.ones(trees, bool)
+    for m in range(n_moves):
+        if evaluator is None:
+            f.simulate(sims)
+        else:
+            for _ in range(sims):
+                f.find_leaf()
+                canon = f.leaf_canon()
+                ev = [evaluator(canon[i]) for i in range(trees)]
+                f.process_result(np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]))
+        counts, q, info = f.counts()
+        assert (info["error"] == 0).all(), info["error"]
+        out.append((counts, q, info))
+        mv = np.full(trees, 0xFFFFFFFF, np.uint32)
+        for i in range(trees):
+            if moves_ref is not None:
+                if m < len(moves_ref[i]):
+                    mv[i] = moves_ref[i][m]
+                else:
+                    alive[i] = False
+            else:
+                mv[i] = int(np.argmax(counts[i]))
+        f.update_root(mv)
+    f.close()
+    return out
+
+
+def _compare(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator):
+    refs = [tafl_ref.search(game, seed + i, n_moves, sims, MAX_TURNS[game], cpuct, fpu, rfz, evaluator) for i in range(trees)]
+    got = run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=[r[2] for r in refs])
+    compared = 0
+    for i, (rc, rq, rm, rd) in enumerate(refs):
+        for m in range(len(rm)):
+            counts, q, info = got[m]
+            assert np.array_equal(counts[i], rc[m]), f"{NAMES[game]} tree {i} move {m}: visit counts differ"
+            assert np.array_equal(q[i].view(np.uint32), rq[m].view(np.uint32)), f"tree {i} move {m}: Q values differ"
+            assert info["total_leaf_depth"][i] == rd[m]
+            compared += 1
+    assert compared >= trees
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,trees,n_moves,sims", [(0, 8, 20, 80), (1, 4, 8, 60), (2, 4, 8, 60)])
+def test_forest_random_eval_vs_reference(game, trees, n_moves, sims):
+    _compare(game, trees, n_moves, sims, 4242, 1.25, 0.25, False, None)
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,trees,n_moves,sims,rfz", [(0, 4, 8, 40, True), (2, 2, 4, 30, False)])
+def test_forest_host_evaluator_vs_reference(game, trees, n_moves, sims, rfz):
+    _compare(game, trees, n_moves, sims, 77, 1.5, 0.3, rfz, pseudo_net)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_forest_reproduces_golden(name):
+    game, trees, n_moves, sims, seed, cpuct, fpu, rfz = GOLDEN_CASES[name]
+    g = np.load(GOLDEN)
+    moves, lens = g[f"{name}_moves"], g[f"{name}_lens"]
+    got = run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, None,
+                     moves_ref=[moves[i, :lens[i]] for i in range(trees)])
+    for i in range(trees):
+        for m in range(int(lens[i])):
+            counts, q, _ = got[m]
+            assert zlib.crc32(counts[i].tobytes()) == g[f"{name}_counts_crc"][i, m], f"{name} tree {i} move {m}: counts"
+            assert zlib.crc32(q[i].tobytes()) == g[f"{name}_q_crc"][i, m], f"{name} tree {i} move {m}: Q"
+
+
+def test_forest_refuses_without_cuda_or_unsupported_params():
+    lib = b2az.load(ph.HOSTEMU_LIB)
+    with pytest.raises(b2az.B2azError) as ei:
+        b2az.Forest(0, 4, 150, epsilon=0.25, lib=lib)
+    assert "not implemented" in str(ei.value)
+    with pytest.raises(b2az.B2azError) as ei:
+        b2az.Forest(0, 4, 150, lib=lib)
+    assert ei.value.code == -2

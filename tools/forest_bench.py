@@ -1,0 +1,59 @@
+"""Throughput of the batched wide-tree MCTS (b2az_forest_*) in greedy self-play with the reference's dumb_eval
+evaluator: `--trees` trees each run `--sims` simulations per move (one fused launch), then play their most visited
+move on the device; simulations/s over `--moves` moves, next to the unmodified reference's MCTS class doing the same
+on one host core.   python tools/forest_bench.py [--game 0|1|2] [--trees N] [--sims 120] [--moves 12]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "alphazero-pybind11_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import b2az  # noqa: E402
+import tafl_ref  # noqa: E402
+
+NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
+MAX_TURNS = {0: 150, 1: 400, 2: 400}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--game", type=int, default=0)
+    ap.add_argument("--trees", type=int, default=16384)
+    ap.add_argument("--sims", type=int, default=120)  # configs/brandubh.yaml mcts_visits
+    ap.add_argument("--moves", type=int, default=12)
+    a = ap.parse_args()
+    words = 1 + (a.moves + 1) * a.sims * (1 + 7 * (48 if a.game == 0 else 140))
+    f = b2az.Forest(a.game, a.trees, MAX_TURNS[a.game], cpuct=1.25, fpu_reduction=0.25, seed=1, words_per_tree=words)
+    stream = torch.cuda.current_stream().cuda_stream
+    f.simulate(a.sims, stream)  # warm-up move
+    f.advance(stream)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.moves + 1)]
+    ev[0].record()
+    for m in range(a.moves):
+        f.simulate(a.sims, stream)
+        f.advance(stream)
+        ev[m + 1].record()
+    torch.cuda.synchronize()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.moves)]
+    _, _, info = f.counts(want_q=False)
+    f.close()
+    assert (info["error"] == 0).all(), set(info["error"].tolist())
+    sims_total = a.trees * a.sims * a.moves
+    t0 = time.perf_counter()
+    n_ref, ref_sims = 0, 0
+    while time.perf_counter() - t0 < 10:
+        c, _, mv, _ = tafl_ref.search(a.game, 900 + n_ref, a.moves + 1, a.sims, MAX_TURNS[a.game], 1.25, 0.25, False, None)
+        ref_sims += len(mv) * a.sims
+        n_ref += 1
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"kernel": "k_forest_simulate", "game": NAMES[a.game], "trees": a.trees, "sims_per_move": a.sims,
+                      "moves": a.moves, "ms_per_move": [round(x, 2) for x in ms],
+                      "simulations_per_second": sims_total / (sum(ms) * 1e-3), "moves_per_second": a.trees * a.moves / (sum(ms) * 1e-3),
+                      "mean_slab_words_used": float(info["words_used"].mean()), "games_over": int((info["root_term"] != 0).sum()),
+                      "cpu_baseline": {"value": ref_sims / cpu_s, "unit": "sims/s", "cores": 1, "kind": "reference",
+                                       "sample": f"{n_ref} single-tree runs of the unmodified reference MCTS class, dumb_eval, same settings"}}))
