@@ -19,8 +19,9 @@
 //
 // Node storage: a fixed slab of 32-bit words per tree; an expanded node owns one block [k | n[k] q[k] policy[k]
 // d[k] v[k] first_child[k] move|player|terminal[k]] (structure of arrays: Node::n/q/policy/d/v/children/move/
-// player/scores, mcts.h:14-48), bump-allocated. Re-rooting re-points the root at the chosen child's block
-// (MCTS::update_root, mcts.cc:151-173); the discarded siblings stay in the slab (no compaction yet).
+// player/scores, mcts.h:14-48), bump-allocated in one half of the slab. Re-rooting (MCTS::update_root,
+// mcts.cc:151-173) copies the chosen child's subtree breadth first into the other half (a Cheney copy by the
+// whole warp), which is what frees the discarded siblings.
 //
 // Scope of this first version: PUCT selection (no Gumbel), root_policy_temp == 1, no Dirichlet noise,
 // relative_values == false — the MCTS(cpuct, num_players, num_moves, 0, 1, fpu_reduction, false, root_fpu_zero)
@@ -43,6 +44,7 @@ struct ForestTree {             // one per tree, HBM
   u32 player, term;             // root_.player, root_.scores (0 none, else 1 + winner index / 3 = draw)
   u32 depth, total_leaf_depth;  // MCTS::depth_, total_leaf_depth_
   u32 bump;                     // next free word of the slab (word 0 is reserved: 0 = "no block")
+  u32 half;                     // which half of the slab is in use (the other one receives the next compaction)
   u32 hist_len;                 // repetition history of the root position (keys since the last capture)
   Pcg32 rng;
   u32 path_len;                 // MCTS::path_ / current_: the pending leaf
@@ -253,7 +255,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     if (leaf_k) {
       const u32 need = 1u + 7u * leaf_k;
       const u32 b = R.bump;
-      if (b + need > F.words_per_tree) {
+      if (b + need > (R.half ? F.words_per_tree : F.words_per_tree / 2u)) {
         err |= 1u;
         leaf_k = 0;
       } else {
@@ -414,6 +416,50 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     }
   }
   (void)root_term;
+  __syncwarp();
+  // The siblings of the chosen child are garbage now (the reference frees them: `root_ = std::move(tmp)` + ~Node).
+  // Cheney copy of the kept subtree, breadth first, into the idle half of the slab; block indices are opaque to the
+  // search and the children keep their order inside a block, so results do not depend on it.
+  if (!err) {
+    const u32 half_words = F.words_per_tree / 2u;
+    const u32 to_base = R.half ? 1u : half_words, to_end = R.half ? half_words : F.words_per_tree;
+    u32 to = to_base;
+    const u32 old_root = R.blk;
+    u32 new_root = 0;
+    if (old_root) {
+      const u32 rk = pool[old_root], rw = 1u + 7u * rk;
+      if (to + rw > to_end) {
+        err |= 1u;
+      } else {
+        for (u32 i = lane; i < rw; i += 32u) pool[to + i] = pool[old_root + i];
+        new_root = to;
+        to += rw;
+        __syncwarp();
+        for (u32 scan = new_root; scan < to && !err;) {
+          const u32 sk = pool[scan];
+          for (u32 c0 = 0; c0 < sk && !err; c0 += 32u) {
+            const u32 j = c0 + lane;
+            const u32 fcj = j < sk ? pool[fb_fc(scan, sk) + j] : 0u;
+            u32 live = __ballot_sync(0xFFFFFFFFu, fcj != 0u);
+            while (live) {
+              const int src_lane = __ffs((int)live) - 1;
+              live &= live - 1u;
+              const u32 src = __shfl_sync(0xFFFFFFFFu, fcj, src_lane);
+              const u32 ck = pool[src], cw = 1u + 7u * ck;
+              if (to + cw > to_end) { err |= 1u; break; }
+              for (u32 i = lane; i < cw; i += 32u) pool[to + i] = pool[src + i];
+              if (lane == 0) pool[fb_fc(scan, sk) + c0 + (u32)src_lane] = to;
+              to += cw;
+            }
+          }
+          __syncwarp();
+          scan += 1u + 7u * sk;
+        }
+      }
+    }
+    if (lane == 0 && !err) { R.blk = new_root; R.bump = to; R.half ^= 1u; }
+    __syncwarp();
+  }
   // gs.play_move(move) with the persistent repetition history
   u32 hist_len = R.hist_len;
   if (!err) {

@@ -35,10 +35,11 @@ def pseudo_net(canon):
     return v.astype(np.float32), pi.astype(np.float32)
 
 
-def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None):
+def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None, slab_moves=None):
     """Drives the forest like the reference run; plays `moves_ref[i][m]` when given (else the most visited move)."""
-    # no compaction yet: the slab must hold every node expanded during the run (1 + 7k words per node)
-    words = 1 + (n_moves + 1) * sims * (1 + 7 * (64 if game == 0 else 200))
+    # each half of the slab must hold the kept subtree + one move's search (1 + 7k words per expanded node);
+    # slab_moves = how many moves' worth of nodes one half can hold (re-rooting compacts into the other half)
+    words = 2 * (1 + (slab_moves or n_moves + 1) * sims * (1 + 7 * (64 if game == 0 else 200)))
     f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=cpuct, fpu_reduction=fpu, root_fpu_zero=rfz, seed=seed,
                     words_per_tree=words)
     out = []
@@ -69,9 +70,10 @@ def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, mov
     return out
 
 
-def _compare(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator):
+def _compare(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, slab_moves=None):
     refs = [tafl_ref.search(game, seed + i, n_moves, sims, MAX_TURNS[game], cpuct, fpu, rfz, evaluator) for i in range(trees)]
-    got = run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=[r[2] for r in refs])
+    got = run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=[r[2] for r in refs],
+                     slab_moves=slab_moves)
     compared = 0
     for i, (rc, rq, rm, rd) in enumerate(refs):
         for m in range(len(rm)):
@@ -88,6 +90,13 @@ def _compare(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator):
 @pytest.mark.parametrize("game,trees,n_moves,sims", [(0, 8, 20, 80), (1, 4, 8, 60), (2, 4, 8, 60)])
 def test_forest_random_eval_vs_reference(game, trees, n_moves, sims):
     _compare(game, trees, n_moves, sims, 4242, 1.25, 0.25, False, None)
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+def test_forest_long_game_in_a_small_slab():
+    """60 moves in a slab that holds two moves' worth of nodes per half: only works because re-rooting compacts."""
+    _compare(0, 6, 60, 60, 999, 1.25, 0.25, False, None, slab_moves=2)
 
 
 @pytest.mark.gpu

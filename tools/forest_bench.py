@@ -26,7 +26,8 @@ if __name__ == "__main__":
     ap.add_argument("--sims", type=int, default=120)  # configs/brandubh.yaml mcts_visits
     ap.add_argument("--moves", type=int, default=12)
     a = ap.parse_args()
-    words = 1 + (a.moves + 1) * a.sims * (1 + 7 * (48 if a.game == 0 else 140))
+    # each half of a tree's slab: the kept subtree + one move's new nodes (1 + 7k words each), with head room
+    words = 2 * (1 + 3 * a.sims * (1 + 7 * (48 if a.game == 0 else 140)))
     f = b2az.Forest(a.game, a.trees, MAX_TURNS[a.game], cpuct=1.25, fpu_reduction=0.25, seed=1, words_per_tree=words)
     stream = torch.cuda.current_stream().cuda_stream
     f.simulate(a.sims, stream)  # warm-up move
