@@ -69,8 +69,9 @@ class Stats(C.Structure):
 class ForestParams(C.Structure):  # b2az_forest_params (include/b2az.h)
     _fields_ = [("game", C.c_uint32), ("n_trees", C.c_uint32), ("max_turns", C.c_uint32), ("words_per_tree", C.c_uint32),
                 ("cpuct", C.c_float), ("fpu_reduction", C.c_float), ("epsilon", C.c_float), ("root_policy_temp", C.c_float),
-                ("root_fpu_zero", C.c_uint8), ("relative_values", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("pad_", C.c_uint8),
-                ("pad2_", C.c_uint32), ("seed", C.c_uint64)]
+                ("root_fpu_zero", C.c_uint8), ("relative_values", C.c_uint8), ("gumbel_enabled", C.c_uint8),
+                ("gumbel_full", C.c_uint8), ("gumbel_m", C.c_uint32), ("seed", C.c_uint64), ("gumbel_c_visit", C.c_float),
+                ("gumbel_c_scale", C.c_float)]
 
 
 _libs = {}
@@ -112,6 +113,8 @@ def load(path=None):
     L.b2az_forest_process_result_host.argtypes = [vp, vp, vp, vp]
     L.b2az_forest_simulate.argtypes = [vp, vp, u32]
     L.b2az_forest_advance.argtypes = [vp, vp]
+    L.b2az_forest_set_gumbel_num_sims.argtypes = [vp, vp, u32]
+    L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
     L.b2az_forest_update_root.argtypes = [vp, vp, vp]
     L.b2az_forest_counts.argtypes = [vp, vp, vp, vp, vp]
     L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
@@ -332,14 +335,16 @@ class Forest:
             "total_leaf_depth", "player")
 
     def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
-                 words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, device=0, lib=None):
+                 words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0,
+                 gumbel_full=False, device=0, lib=None):
         self.L = lib or load()
         self.game, self.n = game, n_trees
         S, P = TAFL_DIMS[game]
         self.S, self.P, self.A = S, P, 2 * S ** 3
         p = ForestParams(game=game, n_trees=n_trees, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
                          fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
-                         root_fpu_zero=int(root_fpu_zero), seed=seed)
+                         root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
+                         gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, gumbel_full=int(gumbel_full))
         self.h = C.c_void_p()
         self._check(self.L.b2az_forest_create(C.byref(p), device, C.byref(self.h)))
 
@@ -373,6 +378,16 @@ class Forest:
 
     def simulate(self, n_sims, stream=None):
         self._check(self.L.b2az_forest_simulate(self.h, stream, n_sims))
+
+    def set_gumbel_num_sims(self, n, stream=None):
+        self._check(self.L.b2az_forest_set_gumbel_num_sims(self.h, stream, n))
+
+    def gumbel_result(self, stream=None):
+        """(gumbel_final_action per tree, gumbel_improved_policy [n_trees][A])"""
+        action = np.zeros(self.n, np.uint32)
+        policy = np.zeros((self.n, self.A), np.float32)
+        self._check(self.L.b2az_forest_gumbel_result(self.h, stream, _ptr(action), _ptr(policy)))
+        return action, policy
 
     def advance(self, stream=None):
         self._check(self.L.b2az_forest_advance(self.h, stream))

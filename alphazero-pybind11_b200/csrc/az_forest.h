@@ -23,9 +23,9 @@
 // mcts.cc:151-173) copies the chosen child's subtree breadth first into the other half (a Cheney copy by the
 // whole warp), which is what frees the discarded siblings.
 //
-// Scope of this first version: PUCT selection (no Gumbel), root_policy_temp == 1, no Dirichlet noise,
-// relative_values == false — the MCTS(cpuct, num_players, num_moves, 0, 1, fpu_reduction, false, root_fpu_zero)
-// constructor. b2az_forest_create rejects anything else.
+// Scope of this version: PUCT selection, or Gumbel root search (sequential halving over the top-m root children,
+// improved-policy targets, final action; mcts.cc:175-283, 336-401) with PUCT below the root; root_policy_temp == 1,
+// no Dirichlet noise, relative_values == false, gumbel_full == false. b2az_forest_create rejects anything else.
 #pragma once
 
 #include "az_rng.h"
@@ -55,10 +55,23 @@ struct ForestTree {             // one per tree, HBM
   u8 path_player[kFPath];       // player of the node the selection was made AT (the parent of that child)
 };
 
+constexpr int kFMaxM = 64;       // most Gumbel candidates kept at the root (PlayParams::gumbel_m, default 16)
+constexpr int kFMaxPhases = 8;   // ceil(log2 kFMaxM) sequential-halving phases + slack
+struct ForestGumbel {            // MCTS::gumbel_* members (mcts.h:163-176), one per tree
+  u32 num_sims_target, sims_in_phase;
+  u32 n_surv, n_phases, phase_idx, initialized, effective_m, pad_;
+  u32 phase_numc[kFMaxPhases], phase_vper[kFMaxPhases];
+  u16 survivors[kFMaxM];         // child indices in rank order
+};
+
 struct ForestView {
   u32 n_trees, words_per_tree, max_turns, game;
   float cpuct, fpu_reduction;
   u32 root_fpu_zero;
+  u32 gumbel_enabled, gumbel_m;
+  float gumbel_c_visit, gumbel_c_scale;
+  ForestGumbel* gum;   // [n_trees], null unless gumbel_enabled
+  float* gum_g;        // [n_trees][2 * kFMaxK]: gumbel_g_ per root child, then scratch scores
   ForestTree* trees;
   u32* pool;           // [n_trees][words_per_tree]
   TaflKey* hist;       // [n_trees][max_turns + 2]
@@ -170,6 +183,182 @@ __device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem
   return k;
 }
 
+// ---- Gumbel root search over a wide root (mcts.cc:28-66, 175-283, 336-401). Root-only and a few hundred scalar
+// steps per move, so it runs on lane 0; the formulas and their float order are those of the Connect4 engine's
+// (az_engine_logic.h gumbel_*), with arrays in HBM instead of nibble-packed registers.
+#define FG_LOG_FLOOR 1e-20f
+__device__ __forceinline__ void fg_reset(ForestGumbel& G) {  // reset_gumbel_state (mcts.cc:180-188)
+  G.initialized = 0; G.effective_m = 0; G.n_surv = 0; G.n_phases = 0; G.phase_idx = 0; G.sims_in_phase = 0;
+}
+__device__ inline void fg_phase_plan(ForestGumbel& G, u32 m, u32 n) {  // seq_halving_phase_plan (mcts.cc:28-66)
+  G.n_phases = 0;
+  if (m <= 1) { G.phase_numc[0] = 1; G.phase_vper[0] = n; G.n_phases = 1; return; }
+  u32 log2m = 0;
+  for (u32 v = m - 1; v > 0; v >>= 1) ++log2m;
+  if (log2m == 0) log2m = 1;
+  u32 base_v = n / (log2m * m);
+  if (base_v < 1u) base_v = 1u;
+  u32 sims_used = 0, num_c = m;
+  for (u32 ph = 0; ph < log2m && G.n_phases < (u32)kFMaxPhases; ++ph) {
+    if (sims_used >= n) break;
+    const u32 remaining = n - sims_used;
+    const bool is_final = (ph == log2m - 1);
+    u32 v_per = is_final ? (remaining / num_c < 1u ? 1u : remaining / num_c) : base_v * (1u << ph);
+    if (num_c * v_per > remaining) {
+      v_per = remaining / num_c;
+      if (v_per == 0) { num_c = remaining; v_per = 1; }
+    }
+    G.phase_numc[G.n_phases] = num_c;
+    G.phase_vper[G.n_phases] = v_per;
+    ++G.n_phases;
+    sims_used += num_c * v_per;
+    num_c = num_c / 2 < 1u ? 1u : num_c / 2;
+  }
+}
+// Top-`take` of `cnt` scores, descending (std::partial_sort in the reference: with continuous Gumbel noise in every
+// score ties have probability zero, so a plain selection gives the same ranking). `ids[i]` names score i.
+__device__ inline void fg_rank_top(const float* score, const u16* ids, u32 cnt, u32 take, u16* out) {
+  u32 used[kFMaxK / 32];
+  for (int i = 0; i < kFMaxK / 32; ++i) used[i] = 0;
+  for (u32 r = 0; r < take; ++r) {
+    int best = -1;
+    float bs = 0.0f;
+    for (u32 i = 0; i < cnt; ++i) {
+      if ((used[i >> 5] >> (i & 31u)) & 1u) continue;
+      const float sc = score[i];
+      if (best < 0 || sc > bs) { best = (int)i; bs = sc; }
+    }
+    used[best >> 5] |= 1u << (best & 31);
+    out[r] = ids ? ids[best] : (u16)best;
+  }
+}
+__device__ __forceinline__ float fg_sigma_scale(const ForestView& F, u32 max_visit) {
+  return fmul(fadd(F.gumbel_c_visit, (float)max_visit), F.gumbel_c_scale);
+}
+// init_gumbel_state (mcts.cc:190-227); lane 0 only
+__device__ inline void fg_init(const ForestView& F, u32 t, ForestTree& R, ForestGumbel& G, const u32* pool) {
+  const u32 num_legal = R.k, b = R.blk;
+  if (num_legal == 0 || b == 0) return;
+  const u32 remaining = R.depth < G.num_sims_target ? G.num_sims_target - R.depth : 0u;
+  if (remaining == 0) return;
+  u32 m = F.gumbel_m < num_legal ? F.gumbel_m : num_legal;
+  if (remaining < m) m = remaining;
+  if (m < 1u) m = 1u;
+  G.effective_m = m;
+  float* g = F.gum_g + (size_t)t * (2 * kFMaxK);
+  float* score = g + kFMaxK;
+  Pcg32 rng = R.rng;
+  for (u32 i = 0; i < num_legal; ++i) g[i] = rng_gumbel(rng);
+  R.rng = rng;
+  for (u32 i = 0; i < num_legal; ++i) score[i] = fadd(g[i], az_logf(fadd(u2f(pool[fb_pol(b, num_legal) + i]), FG_LOG_FLOOR)));
+  fg_rank_top(score, nullptr, num_legal, m, G.survivors);
+  G.n_surv = m;
+  fg_phase_plan(G, m, remaining);
+  G.phase_idx = 0;
+  G.sims_in_phase = 0;
+  G.initialized = 1;
+}
+// gumbel_advance_phase (mcts.cc:229-264)
+__device__ inline void fg_advance_phase(const ForestView& F, u32 t, const ForestTree& R, ForestGumbel& G, const u32* pool) {
+  if (G.phase_idx + 1u >= G.n_phases) return;
+  const u32 next_num_c = G.phase_numc[G.phase_idx + 1];
+  if (next_num_c >= G.n_surv) { ++G.phase_idx; G.sims_in_phase = 0; return; }
+  const u32 b = R.blk, k = R.k;
+  const float* g = F.gum_g + (size_t)t * (2 * kFMaxK);
+  u32 max_visit = 0;
+  for (u32 r = 0; r < G.n_surv; ++r) {
+    const u32 n = pool[fb_n(b, k) + G.survivors[r]];
+    if (n > max_visit) max_visit = n;
+  }
+  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  float score[kFMaxM];
+  u16 ids[kFMaxM];
+  for (u32 r = 0; r < G.n_surv; ++r) {
+    const u32 c = G.survivors[r];
+    const float logit = az_logf(fadd(u2f(pool[fb_pol(b, k) + c]), FG_LOG_FLOOR));
+    const float q_hat = pool[fb_n(b, k) + c] > 0 ? u2f(pool[fb_q(b, k) + c]) : 0.0f;
+    score[r] = fadd(fadd(g[c], logit), fmul(sigma_scale, q_hat));
+    ids[r] = (u16)c;
+  }
+  u16 next[kFMaxM];
+  fg_rank_top(score, ids, G.n_surv, next_num_c, next);
+  for (u32 r = 0; r < next_num_c; ++r) G.survivors[r] = next[r];
+  G.n_surv = next_num_c;
+  ++G.phase_idx;
+  G.sims_in_phase = 0;
+}
+// gumbel_next_root_child (mcts.cc:266-283)
+__device__ inline u32 fg_next_root_child(const ForestView& F, u32 t, const ForestTree& R, ForestGumbel& G, const u32* pool) {
+  if (G.phase_idx < G.n_phases) {
+    if (G.sims_in_phase >= G.phase_numc[G.phase_idx] * G.phase_vper[G.phase_idx]) fg_advance_phase(F, t, R, G, pool);
+  }
+  if (G.n_surv == 0) return 0;
+  const u32 pick = G.sims_in_phase % G.n_surv;
+  ++G.sims_in_phase;
+  return G.survivors[pick];
+}
+// gumbel_final_action (mcts.cc:375-401) when the search initialised; 0xFFFFFFFF otherwise (the reference then falls
+// back to pick_move(probs(0)), which the caller does from the counts)
+__device__ inline u32 fg_final_action(const ForestView& F, u32 t, const ForestTree& R, const ForestGumbel& G, const u32* pool) {
+  if (!G.initialized || G.n_surv == 0 || R.blk == 0) return 0xFFFFFFFFu;
+  const u32 b = R.blk, k = R.k;
+  const float* g = F.gum_g + (size_t)t * (2 * kFMaxK);
+  u32 max_visit = 0;
+  for (u32 i = 0; i < k; ++i) {
+    const u32 n = pool[fb_n(b, k) + i];
+    if (n > max_visit) max_visit = n;
+  }
+  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  u32 best = G.survivors[0];
+  float best_score = -INFINITY;
+  for (u32 r = 0; r < G.n_surv; ++r) {
+    const u32 c = G.survivors[r];
+    const float logit = az_logf(fadd(u2f(pool[fb_pol(b, k) + c]), FG_LOG_FLOOR));
+    const float q_hat = pool[fb_n(b, k) + c] > 0 ? u2f(pool[fb_q(b, k) + c]) : 0.0f;
+    const float score = fadd(fadd(g[c], logit), fmul(sigma_scale, q_hat));
+    if (score > best_score) { best_score = score; best = c; }
+  }
+  return pool[fb_mv(b, k) + best] & 0xFFFFu;
+}
+// gumbel_improved_policy (mcts.cc:336-373) incl. compute_v_mix_from_children (mcts.cc:71-89): pi'[move] for the
+// root's children into out[A] (already zeroed); z lives in the tree's scratch row. lane 0 only.
+__device__ inline void fg_improved_policy(const ForestView& F, u32 t, const ForestTree& R, const u32* pool, float* out) {
+  const u32 b = R.blk, k = R.k;
+  if (k == 0 || b == 0) return;
+  float* z = F.gum_g + (size_t)t * (2 * kFMaxK) + kFMaxK;
+  u32 max_visit = 0;
+  float sum_visits = 0.0f, sum_priors_visited = 0.0f, weighted_num = 0.0f;
+  for (u32 i = 0; i < k; ++i) {
+    const u32 n = pool[fb_n(b, k) + i];
+    if (n > max_visit) max_visit = n;
+    sum_visits = fadd(sum_visits, (float)n);
+    if (n > 0) {
+      const float p = u2f(pool[fb_pol(b, k) + i]);
+      sum_priors_visited = fadd(sum_priors_visited, p);
+      weighted_num = fadd(weighted_num, fmul(p, u2f(pool[fb_q(b, k) + i])));
+    }
+  }
+  float v_mix = R.v;
+  if (sum_priors_visited > 0.0f) {
+    const float weighted_q = fdiv(weighted_num, sum_priors_visited);
+    v_mix = fdiv(fadd(R.v, fmul(sum_visits, weighted_q)), fadd(sum_visits, 1.0f));
+  }
+  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  float z_max = -INFINITY;
+  for (u32 i = 0; i < k; ++i) {
+    const float completed_q = pool[fb_n(b, k) + i] > 0 ? u2f(pool[fb_q(b, k) + i]) : v_mix;
+    z[i] = fadd(az_logf(fadd(u2f(pool[fb_pol(b, k) + i]), FG_LOG_FLOOR)), fmul(sigma_scale, completed_q));
+    if (z[i] > z_max) z_max = z[i];
+  }
+  float z_sum = 0.0f;
+  for (u32 i = 0; i < k; ++i) {
+    z[i] = az_expf(fsub(z[i], z_max));
+    z_sum = fadd(z_sum, z[i]);
+  }
+  if (z_sum <= 0.0f) return;
+  for (u32 i = 0; i < k; ++i) out[pool[fb_mv(b, k) + i] & 0xFFFFu] = fdiv(z[i], z_sum);
+}
+
 // MCTS::find_leaf (mcts.cc:462-498) for tree t
 template <int GAME>
 __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon) {
@@ -187,6 +376,14 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   u32 par_blk = 0, par_slot = 0, par_k = 0;  // where the current node's own fields live (0 = it is the root)
   u32 plen = 0;
   bool at_root = true;
+  // lazy Gumbel init (mcts.cc:468-472): once the root is expanded and a sims target is set
+  bool gumbel_on = false;
+  if (F.gumbel_enabled) {
+    ForestGumbel& G = F.gum[t];
+    if (lane == 0 && !G.initialized && G.num_sims_target > 0 && R.n > 0 && R.k > 0 && R.blk != 0) fg_init(F, t, R, G, pool);
+    __syncwarp();
+    gumbel_on = G.initialized != 0;
+  }
   while (cur_n > 0 && cur_term == 0) {
     if (plen >= (u32)kFPath || cur_blk == 0) { err |= 2u; break; }
     // Node::best_child (mcts.cc:130-149)
@@ -221,6 +418,11 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       if (take) { best_u = ou; best_j = oj; }
     }
     if (best_j == 0xFFFFFFFFu) best_j = 0;  // (all scores NaN: the reference keeps child 0)
+    if (gumbel_on && at_root) {  // the root child comes from the sequential-halving schedule (mcts.cc:476-478)
+      u32 forced = 0;
+      if (lane == 0) forced = fg_next_root_child(F, t, R, F.gum[t], pool);
+      best_j = __shfl_sync(0xFFFFFFFFu, forced, 0);
+    }
     // NaN scores lose every comparison in the reference loop as well, except at index 0, which is only replaced by
     // a strictly greater score; with finite scores both orders agree.
     const u32 mvw = pool[fb_mv(b, k) + best_j];
@@ -487,6 +689,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     }
   }
   if (lane == 0) {
+    if (F.gumbel_enabled) fg_reset(F.gum[t]);  // update_root ends with reset_gumbel_state() (mcts.cc:172)
     if (!err) { R.state = s; R.hist_len = hist_len; }
     R.depth = 0;
     R.total_leaf_depth = 0;
@@ -578,6 +781,30 @@ __global__ void __launch_bounds__(128) k_forest_counts(ForestView F, u32* counts
     }
   }
 }
+// MCTS::set_gumbel_num_sims(n) (mcts.cc:175-178) for every tree
+__global__ void k_forest_gumbel_arm(ForestView F, u32 n) {
+  for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
+    F.gum[t].num_sims_target = n;
+    fg_reset(F.gum[t]);
+  }
+}
+// gumbel_final_action + gumbel_improved_policy per tree
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_gumbel_result(ForestView F, u32* action, float* policy) {
+  typedef Tafl<GAME> T;
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    const ForestTree& R = F.trees[t];
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    if (policy) {
+      for (u32 m = lane; m < (u32)T::A; m += 32u) policy[(size_t)t * T::A + m] = 0.0f;
+      __syncwarp();
+      if (lane == 0) fg_improved_policy(F, t, R, pool, policy + (size_t)t * T::A);
+    }
+    if (action && lane == 0) action[t] = fg_final_action(F, t, R, F.gum[t], pool);
+    __syncwarp();
+  }
+}
 template <int GAME>
 __global__ void k_forest_init(ForestView F, unsigned long long seed) {
   typedef Tafl<GAME> T;
@@ -620,7 +847,9 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (p->n_trees == 0 || p->max_turns == 0 || p->max_turns > 65535u) return fail(B2AZ_EINVAL, "b2az_forest: bad n_trees / max_turns");
   if (p->epsilon != 0.0f) return fail(B2AZ_EINVAL, "b2az_forest: root Dirichlet noise (epsilon) is not implemented yet");
   if (p->root_policy_temp != 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp != 1 is not implemented yet");
-  if (p->gumbel_enabled) return fail(B2AZ_EINVAL, "b2az_forest: Gumbel root search is not implemented yet");
+  if (p->gumbel_enabled && (p->gumbel_m == 0 || p->gumbel_m > (uint32_t)kFMaxM))
+    return fail(B2AZ_EINVAL, "b2az_forest: gumbel_m must be in [1, 64]");
+  if (p->gumbel_full) return fail(B2AZ_EINVAL, "b2az_forest: gumbel_full (pi'-matching at interior nodes) is not implemented yet");
   if (p->relative_values) return fail(B2AZ_EINVAL, "b2az_forest: relative_values is not implemented (tafl values are absolute)");
 #ifdef B2AZ_HOST_EMU
   (void)device;
@@ -647,6 +876,12 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (int rc = dev_alloc(&V.pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
   if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon)) return bail(rc);
   if (int rc = dev_alloc(&f->moves_dev, (size_t)V.n_trees)) return bail(rc);
+  V.gumbel_enabled = p->gumbel_enabled ? 1u : 0u;
+  V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
+  if (V.gumbel_enabled) {
+    if (int rc = dev_alloc(&V.gum, (size_t)V.n_trees)) return bail(rc);
+    if (int rc = dev_alloc(&V.gum_g, (size_t)V.n_trees * 2 * kFMaxK)) return bail(rc);
+  }
   FOREST_DISPATCH(f, (k_forest_init<G_><<<148, 128>>>(V, p->seed)));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
@@ -660,6 +895,7 @@ int b2az_forest_destroy(b2az_forest* f) {
   if (!f) return 0;
   dev_free(f->view.trees); dev_free(f->view.pool); dev_free(f->view.hist); dev_free(f->view.pkeys);
   dev_free(f->view.leaf_canon); dev_free(f->moves_dev); dev_free(f->ev_v); dev_free(f->ev_pi);
+  dev_free(f->view.gum); dev_free(f->view.gum_g);
   delete f;
   return 0;
 }
@@ -672,6 +908,8 @@ int b2az_forest_process_result(b2az_forest*, void*, const float*, const float*) 
 int b2az_forest_process_result_host(b2az_forest*, void*, const float*, const float*) FOREST_NO_CUDA()
 int b2az_forest_simulate(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
 int b2az_forest_advance(b2az_forest*, void*) FOREST_NO_CUDA()
+int b2az_forest_set_gumbel_num_sims(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
+int b2az_forest_gumbel_result(b2az_forest*, void*, uint32_t*, float*) FOREST_NO_CUDA()
 int b2az_forest_update_root(b2az_forest*, void*, const uint32_t*) FOREST_NO_CUDA()
 int b2az_forest_counts(b2az_forest*, void*, uint32_t*, float*, uint32_t*) FOREST_NO_CUDA()
 #else
@@ -721,6 +959,35 @@ int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims) {
   FOREST_DISPATCH(f, (k_forest_simulate<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, n_sims)));
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (!f->view.gumbel_enabled) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
+  k_forest_gumbel_arm<<<148, 128, 0, static_cast<cudaStream_t>(stream)>>>(f->view, n);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_host, float* policy_host) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (!f->view.gumbel_enabled) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees, A = f->actions;
+  u32* da = nullptr;
+  float* dp = nullptr;
+  int rc = 0;
+  if (action_host) rc = rc ? rc : dev_alloc(&da, n);
+  if (policy_host) rc = rc ? rc : dev_alloc(&dp, n * A);
+  if (!rc) {
+    FOREST_DISPATCH(f, (k_forest_gumbel_result<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, da, dp)));
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_gumbel_result launch failed");
+  }
+  if (!rc && action_host) rc = copy_d2h(action_host, da, n * 4, s);
+  if (!rc && policy_host) rc = copy_d2h(policy_host, dp, n * A * 4, s);
+  if (!rc) rc = stream_sync(s);
+  dev_free(da); dev_free(dp);
+  return rc;
 }
 int b2az_forest_advance(b2az_forest* f, void* stream) {
   using namespace b2az;

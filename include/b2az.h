@@ -233,17 +233,19 @@ int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turn
  * py_wrapper.cc:192-220) for n_trees trees at once, one warp per tree on the device. Tree i starts at the game's
  * start position and draws from pcg32(seed + i) — a reference MCTS driven after MCTS::seed_thread_rng(seed + i).
  * Mirrors MCTS(cpuct, num_players = 2, num_moves, epsilon, root_policy_temp, fpu_reduction, relative_values,
- * root_fpu_zero, ..., gumbel_enabled): this version implements PUCT with epsilon == 0, root_policy_temp == 1,
- * relative_values == 0, gumbel_enabled == 0 and rejects anything else. */
+ * root_fpu_zero, shaped_dirichlet, gumbel_enabled, gumbel_m, gumbel_c_visit, gumbel_c_scale, gumbel_full): this
+ * version implements PUCT and Gumbel root search with epsilon == 0, root_policy_temp == 1, relative_values == 0,
+ * gumbel_full == 0 and rejects anything else. */
 typedef struct b2az_forest_params {
   uint32_t game;                 /* B2AZ_TAFL_* */
   uint32_t n_trees;
   uint32_t max_turns;            /* the game's max_turns (BrandubhGS(max_turns) ...) */
   uint32_t words_per_tree;       /* node slab per tree in 32-bit words (1 + 7k words per expanded node); 0 = 2^20 */
   float cpuct, fpu_reduction, epsilon, root_policy_temp;
-  uint8_t root_fpu_zero, relative_values, gumbel_enabled, pad_;
-  uint32_t pad2_;
+  uint8_t root_fpu_zero, relative_values, gumbel_enabled, gumbel_full;
+  uint32_t gumbel_m;             /* PlayParams::gumbel_m (16) */
   uint64_t seed;
+  float gumbel_c_visit, gumbel_c_scale;  /* 50, 1 */
 } b2az_forest_params;
 typedef struct b2az_forest b2az_forest;
 int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out);
@@ -259,6 +261,13 @@ int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev,
 int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host);
 /* n_sims x (find_leaf -> dumb_eval (game_state.h:160-173) -> process_result) fused in one launch. */
 int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims);
+/* MCTS::set_gumbel_num_sims(n) (mcts.cc:175-178) on every tree — call before each move's search, like
+ * PlayManager does (play_manager.cc:531-539); n == 0 = PUCT for that search. */
+int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n);
+/* MCTS::gumbel_final_action() (uint32[n_trees]; 0xFFFFFFFF where the search never initialised: the reference then
+ * falls back to pick_move(probs(0))) and MCTS::gumbel_improved_policy() (float32[n_trees][A]) (mcts.cc:336-401).
+ * Host pointers, either may be NULL. */
+int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_host, float* policy_host);
 /* Greedy self-play step on the device: every tree whose root is expanded and not terminal plays its most visited
  * move (argmax of MCTS::counts(), lowest move id on ties) through update_root + play_move. No host round trip. */
 int b2az_forest_advance(b2az_forest* f, void* stream);

@@ -202,18 +202,24 @@ int azref_tafl_position(int game, const int8_t* board, int8_t player, uint16_t t
 // supplies the evaluation; 1: dumb_eval (game_state.h:160-173). Stops when the game is over; returns the number
 // of moves searched, or -1 when the reference threw.
 typedef void (*azref_eval_fn)(const float* canonical, float* v3, float* pi, void* user);
+// gumbel_m > 0: Gumbel root search (MCTS built with gumbel_enabled; set_gumbel_num_sims(sims) before every move's
+// search like PlayManager, play_manager.cc:531-539); the move played is gumbel_final_action() and
+// gumbel_improved_policy() is recorded in policy_out [n_moves][A] (may be NULL).
 int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, float fpu_reduction, int root_fpu_zero,
                       uint32_t n_moves, uint32_t sims, int eval_kind, azref_eval_fn cb, void* user, uint32_t* counts_out,
-                      float* q_out, uint32_t* moves_out, uint32_t* depth_sum_out) {
+                      float* q_out, uint32_t* moves_out, uint32_t* depth_sum_out, uint32_t gumbel_m, float gumbel_c_visit,
+                      float gumbel_c_scale, float* policy_out) {
   try {
     auto gs = make_game(game, max_turns);
     if (!gs) { g_err = "unknown game"; return -1; }
     const uint32_t A = gs->num_moves();
     MCTS::seed_thread_rng(seed);
-    MCTS mcts{cpuct, 2, A, 0.0f, 1.0f, fpu_reduction, false, root_fpu_zero != 0, false, false, 16, 50.0f, 1.0f, false};
+    MCTS mcts{cpuct, 2, A, 0.0f, 1.0f, fpu_reduction, false, root_fpu_zero != 0, false, gumbel_m > 0,
+              gumbel_m > 0 ? gumbel_m : 16u, gumbel_c_visit, gumbel_c_scale, false};
     uint32_t played = 0;
     for (uint32_t m = 0; m < n_moves; ++m) {
       if (gs->scores().has_value()) break;
+      if (gumbel_m > 0) mcts.set_gumbel_num_sims(sims);
       for (uint32_t i = 0; i < sims; ++i) {
         auto leaf = mcts.find_leaf(*gs);
         Vector<float> v{3}, pi{A};
@@ -232,8 +238,16 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
       std::memcpy(q_out + (size_t)m * A, q.data(), A * 4);
       if (depth_sum_out) depth_sum_out[m] = (uint32_t)(mcts.avg_leaf_depth() * (float)mcts.depth() + 0.5f);
       uint32_t best = 0;
-      for (uint32_t a = 1; a < A; ++a)
-        if (counts(a) > counts(best)) best = a;
+      if (gumbel_m > 0) {
+        if (policy_out) {
+          auto ip = mcts.gumbel_improved_policy();
+          std::memcpy(policy_out + (size_t)m * A, ip.data(), A * 4);
+        }
+        best = mcts.gumbel_final_action();
+      } else {
+        for (uint32_t a = 1; a < A; ++a)
+          if (counts(a) > counts(best)) best = a;
+      }
       moves_out[m] = best;
       mcts.update_root(*gs, best);
       gs->play_move(best);

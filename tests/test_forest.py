@@ -35,16 +35,19 @@ def pseudo_net(canon):
     return v.astype(np.float32), pi.astype(np.float32)
 
 
-def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None, slab_moves=None):
+def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None, slab_moves=None, gumbel=None):
     """Drives the forest like the reference run; plays `moves_ref[i][m]` when given (else the most visited move)."""
     # each half of the slab must hold the kept subtree + one move's search (1 + 7k words per expanded node);
     # slab_moves = how many moves' worth of nodes one half can hold (re-rooting compacts into the other half)
     words = 2 * (1 + (slab_moves or n_moves + 1) * sims * (1 + 7 * (64 if game == 0 else 200)))
+    gkw = dict(gumbel_m=gumbel[0], gumbel_c_visit=gumbel[1], gumbel_c_scale=gumbel[2]) if gumbel else {}
     f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=cpuct, fpu_reduction=fpu, root_fpu_zero=rfz, seed=seed,
-                    words_per_tree=words)
+                    words_per_tree=words, **gkw)
     out = []
     alive = np.ones(trees, bool)
     for m in range(n_moves):
+        if gumbel:
+            f.set_gumbel_num_sims(sims)
         if evaluator is None:
             f.simulate(sims)
         else:
@@ -55,7 +58,7 @@ def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, mov
                 f.process_result(np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]))
         counts, q, info = f.counts()
         assert (info["error"] == 0).all(), info["error"]
-        out.append((counts, q, info))
+        out.append((counts, q, info) + (f.gumbel_result() if gumbel else ()))
         mv = np.full(trees, 0xFFFFFFFF, np.uint32)
         for i in range(trees):
             if moves_ref is not None:
@@ -77,7 +80,7 @@ def _compare(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, slab_
     compared = 0
     for i, (rc, rq, rm, rd) in enumerate(refs):
         for m in range(len(rm)):
-            counts, q, info = got[m]
+            counts, q, info = got[m][:3]
             assert np.array_equal(counts[i], rc[m]), f"{NAMES[game]} tree {i} move {m}: visit counts differ"
             assert np.array_equal(q[i].view(np.uint32), rq[m].view(np.uint32)), f"tree {i} move {m}: Q values differ"
             assert info["total_leaf_depth"][i] == rd[m]
@@ -116,9 +119,30 @@ def test_forest_reproduces_golden(name):
                      moves_ref=[moves[i, :lens[i]] for i in range(trees)])
     for i in range(trees):
         for m in range(int(lens[i])):
-            counts, q, _ = got[m]
+            counts, q, _ = got[m][:3]
             assert zlib.crc32(counts[i].tobytes()) == g[f"{name}_counts_crc"][i, m], f"{name} tree {i} move {m}: counts"
             assert zlib.crc32(q[i].tobytes()) == g[f"{name}_q_crc"][i, m], f"{name} tree {i} move {m}: Q"
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,trees,n_moves,sims,m", [(0, 8, 16, 120, 16), (0, 4, 10, 30, 4), (1, 3, 5, 120, 16), (2, 3, 5, 64, 8)])
+def test_forest_gumbel_root_search_vs_reference(game, trees, n_moves, sims, m):
+    """configs/brandubh.yaml-style search: Gumbel top-m + sequential halving at the root, PUCT below; the move
+    played is gumbel_final_action, the training target gumbel_improved_policy."""
+    gum = (m, 50.0, 1.0)
+    refs = [tafl_ref.search(game, 31 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, None, *gum) for i in range(trees)]
+    got = run_forest(game, trees, n_moves, sims, 31, 1.25, 0.25, False, None, moves_ref=[r[2] for r in refs], gumbel=gum)
+    compared = 0
+    for i, (rc, rq, rm, rd, rp) in enumerate(refs):
+        for mv in range(len(rm)):
+            counts, q, info, action, policy = got[mv]
+            assert np.array_equal(counts[i], rc[mv]), f"{NAMES[game]} tree {i} move {mv}: visit counts differ"
+            assert np.array_equal(q[i].view(np.uint32), rq[mv].view(np.uint32)), f"tree {i} move {mv}: Q values differ"
+            assert action[i] == rm[mv], f"tree {i} move {mv}: gumbel_final_action {action[i]} != {rm[mv]}"
+            assert np.array_equal(policy[i].view(np.uint32), rp[mv].view(np.uint32)), f"tree {i} move {mv}: improved policy"
+            compared += 1
+    assert compared >= trees * 3
 
 
 def test_forest_refuses_without_cuda_or_unsupported_params():
