@@ -71,7 +71,7 @@ class ForestParams(C.Structure):  # b2az_forest_params (include/b2az.h)
                 ("cpuct", C.c_float), ("fpu_reduction", C.c_float), ("epsilon", C.c_float), ("root_policy_temp", C.c_float),
                 ("root_fpu_zero", C.c_uint8), ("relative_values", C.c_uint8), ("gumbel_enabled", C.c_uint8),
                 ("gumbel_full", C.c_uint8), ("gumbel_m", C.c_uint32), ("seed", C.c_uint64), ("gumbel_c_visit", C.c_float),
-                ("gumbel_c_scale", C.c_float)]
+                ("gumbel_c_scale", C.c_float), ("shaped_dirichlet", C.c_uint8), ("pad2_", C.c_uint8 * 7)]
 
 
 _libs = {}
@@ -109,9 +109,10 @@ def load(path=None):
     L.b2az_forest_destroy.argtypes = [vp]
     L.b2az_forest_find_leaf.argtypes = [vp, vp, C.POINTER(vp)]
     L.b2az_forest_leaf_canon_host.argtypes = [vp, vp, vp]
-    L.b2az_forest_process_result.argtypes = [vp, vp, vp, vp]
-    L.b2az_forest_process_result_host.argtypes = [vp, vp, vp, vp]
-    L.b2az_forest_simulate.argtypes = [vp, vp, u32]
+    L.b2az_forest_process_result.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.b2az_forest_process_result_host.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.b2az_forest_simulate.argtypes = [vp, vp, u32, C.c_int]
+    L.b2az_forest_root_noise.argtypes = [vp, vp, C.c_int]
     L.b2az_forest_advance.argtypes = [vp, vp]
     L.b2az_forest_set_gumbel_num_sims.argtypes = [vp, vp, u32]
     L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
@@ -336,7 +337,7 @@ class Forest:
 
     def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
                  words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0,
-                 gumbel_full=False, device=0, lib=None):
+                 gumbel_full=False, shaped_dirichlet=False, device=0, lib=None):
         self.L = lib or load()
         self.game, self.n = game, n_trees
         S, P = TAFL_DIMS[game]
@@ -344,7 +345,8 @@ class Forest:
         p = ForestParams(game=game, n_trees=n_trees, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
                          fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
                          root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
-                         gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, gumbel_full=int(gumbel_full))
+                         gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, gumbel_full=int(gumbel_full),
+                         shaped_dirichlet=int(shaped_dirichlet))
         self.h = C.c_void_p()
         self._check(self.L.b2az_forest_create(C.byref(p), device, C.byref(self.h)))
 
@@ -367,17 +369,21 @@ class Forest:
         self._check(self.L.b2az_forest_leaf_canon_host(self.h, stream, _ptr(out)))
         return out
 
-    def process_result(self, v, pi, stream=None):
+    def process_result(self, v, pi, root_noise=False, stream=None):
         v = np.ascontiguousarray(v, np.float32)
         pi = np.ascontiguousarray(pi, np.float32)
         assert v.shape == (self.n, 3) and pi.shape == (self.n, self.A)
-        self._check(self.L.b2az_forest_process_result_host(self.h, stream, _ptr(v), _ptr(pi)))
+        self._check(self.L.b2az_forest_process_result_host(self.h, stream, _ptr(v), _ptr(pi), int(root_noise)))
 
-    def process_result_device(self, v_ptr, pi_ptr, stream=None):
-        self._check(self.L.b2az_forest_process_result(self.h, stream, v_ptr, pi_ptr))
+    def process_result_device(self, v_ptr, pi_ptr, root_noise=False, stream=None):
+        self._check(self.L.b2az_forest_process_result(self.h, stream, v_ptr, pi_ptr, int(root_noise)))
 
-    def simulate(self, n_sims, stream=None):
-        self._check(self.L.b2az_forest_simulate(self.h, stream, n_sims))
+    def simulate(self, n_sims, stream=None, root_noise=False):
+        self._check(self.L.b2az_forest_simulate(self.h, stream, n_sims, int(root_noise)))
+
+    def root_noise(self, add_noise=True, stream=None):
+        """apply_root_policy_temp + add_root_noise on the reused roots (PlayManager after a move)."""
+        self._check(self.L.b2az_forest_root_noise(self.h, stream, int(add_noise)))
 
     def set_gumbel_num_sims(self, n, stream=None):
         self._check(self.L.b2az_forest_set_gumbel_num_sims(self.h, stream, n))

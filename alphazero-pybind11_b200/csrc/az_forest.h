@@ -24,8 +24,9 @@
 // whole warp), which is what frees the discarded siblings.
 //
 // Scope of this version: PUCT selection, or Gumbel root search (sequential halving over the top-m root children,
-// improved-policy targets, final action; mcts.cc:175-283, 336-401) with PUCT below the root; root_policy_temp == 1,
-// no Dirichlet noise, relative_values == false, gumbel_full == false. b2az_forest_create rejects anything else.
+// improved-policy targets, final action; mcts.cc:175-283, 336-401) with PUCT below the root; root policy
+// temperature and (shaped) Dirichlet noise (mcts.cc:403-460); relative_values == false, gumbel_full == false.
+// b2az_forest_create rejects anything else.
 #pragma once
 
 #include "az_rng.h"
@@ -70,8 +71,11 @@ struct ForestView {
   u32 root_fpu_zero;
   u32 gumbel_enabled, gumbel_m;
   float gumbel_c_visit, gumbel_c_scale;
+  float epsilon, root_policy_temp;
+  u32 shaped_dirichlet;
   ForestGumbel* gum;   // [n_trees], null unless gumbel_enabled
   float* gum_g;        // [n_trees][2 * kFMaxK]: gumbel_g_ per root child, then scratch scores
+  float* noise;        // [n_trees][kFMaxK] Dirichlet draws, null unless epsilon > 0
   ForestTree* trees;
   u32* pool;           // [n_trees][words_per_tree]
   TaflKey* hist;       // [n_trees][max_turns + 2]
@@ -95,13 +99,20 @@ struct ForestSmem {   // per warp
   u16 moves[kFMaxK];
 };
 
-// Σ x_j over j in [0, k) in index order, x_j = `val` of lane (j mod 32) in pass j / 32 — every lane returns the same sum
-__device__ __forceinline__ float seq_sum_chunk(float acc, float val, bool take, u32 count) {
-  for (u32 t = 0; t < count; ++t) {
-    const float x = __shfl_sync(0xFFFFFFFFu, val, (int)t);
-    const int tk = __shfl_sync(0xFFFFFFFFu, take ? 1 : 0, (int)t);
-    if (tk) acc = fadd(acc, x);
+// In-order float sums over a chunk of 32 children held one per lane (float addition is not associative and the
+// children are in shuffled order, so the order of the reference's loop must be kept): the lanes hand their value
+// round with shuffles and every lane accumulates the same sequence.
+__device__ __forceinline__ float seq_sum_masked(float acc, float val, bool take) {  // only lanes with `take`, ascending
+  u32 m = __ballot_sync(0xFFFFFFFFu, take);
+  while (m) {
+    const int t = __ffs((int)m) - 1;
+    m &= m - 1u;
+    acc = fadd(acc, __shfl_sync(0xFFFFFFFFu, val, t));
   }
+  return acc;
+}
+__device__ __forceinline__ float seq_sum_all(float acc, float val, u32 count) {  // lanes 0 .. count-1
+  for (u32 t = 0; t < count; ++t) acc = fadd(acc, __shfl_sync(0xFFFFFFFFu, val, (int)t));
   return acc;
 }
 
@@ -359,6 +370,60 @@ __device__ inline void fg_improved_policy(const ForestView& F, u32 t, const Fore
   for (u32 i = 0; i < k; ++i) out[pool[fb_mv(b, k) + i] & 0xFFFFu] = fdiv(z[i], z_sum);
 }
 
+// ---- root policy temperature and Dirichlet noise over a wide root (mcts.cc:403-460); lane 0, policy array in HBM.
+// Same formulas / float order as the Connect4 engine's add_root_noise (az_engine_logic.h); the noise values live
+// in the tree's Gumbel scratch row (never needed at the same time: Gumbel replaces the noise, mcts.cc:514-518).
+__device__ inline void fr_apply_root_policy_temp(const ForestView& F, u32* pool, u32 b, u32 k) {  // mcts.cc:448-460
+  if (F.root_policy_temp == 1.0f || b == 0) return;
+  const float e = fdiv(1.0f, F.root_policy_temp);
+  float sum = 0.0f;
+  for (u32 j = 0; j < k; ++j) {
+    const float p = az_powf(u2f(pool[fb_pol(b, k) + j]), e);
+    pool[fb_pol(b, k) + j] = f2u(p);
+    sum = fadd(sum, p);
+  }
+  if (sum > 0.0f)
+    for (u32 j = 0; j < k; ++j) pool[fb_pol(b, k) + j] = f2u(fdiv(u2f(pool[fb_pol(b, k) + j]), sum));
+}
+__device__ inline void fr_add_root_noise(const ForestView& F, u32 t, Pcg32& rng, u32* pool, u32 b, u32 k) {  // mcts.cc:403-446
+  if (b == 0 || k == 0) return;
+  float* noise = F.noise + (size_t)t * kFMaxK;
+  double sum = 0.0;
+  if (F.shaped_dirichlet && k > 1) {
+    const float N = (float)k;
+    float log_sum = 0.0f;
+    for (u32 j = 0; j < k; ++j) log_sum = fadd(log_sum, az_logf(fadd(std_min(u2f(pool[fb_pol(b, k) + j]), 0.01f), 1e-20f)));
+    const float log_mean = fdiv(log_sum, N);
+    float shaped_sum = 0.0f;
+    for (u32 j = 0; j < k; ++j) {
+      const float lp = az_logf(fadd(std_min(u2f(pool[fb_pol(b, k) + j]), 0.01f), 1e-20f));
+      shaped_sum = fadd(shaped_sum, std_max(0.0f, fsub(lp, log_mean)));
+    }
+    const float uniform = fdiv(1.0f, N);
+    for (u32 j = 0; j < k; ++j) {
+      const float lp = az_logf(fadd(std_min(u2f(pool[fb_pol(b, k) + j]), 0.01f), 1e-20f));
+      const float shaped = std_max(0.0f, fsub(lp, log_mean));
+      float alpha_prop = (shaped_sum > 0.0f) ? fmul(0.5f, fadd(fdiv(shaped, shaped_sum), uniform)) : uniform;
+      alpha_prop = std_max(alpha_prop, 1e-6f);
+      GammaDist gd;
+      gamma_init(gd, fmul(10.83f, alpha_prop));
+      noise[j] = gamma_draw(rng, gd);
+      sum = dadd(sum, (double)noise[j]);
+    }
+  } else {
+    GammaDist gd;
+    gamma_init(gd, fdiv(10.83f, (float)k));
+    for (u32 j = 0; j < k; ++j) {
+      noise[j] = gamma_draw(rng, gd);
+      sum = dadd(sum, (double)noise[j]);
+    }
+  }
+  const float fsum = (float)sum;
+  const float keep = fsub(1.0f, F.epsilon);
+  for (u32 j = 0; j < k; ++j)
+    pool[fb_pol(b, k) + j] = f2u(fadd(fmul(u2f(pool[fb_pol(b, k) + j]), keep), fdiv(fmul(F.epsilon, noise[j]), fsum)));
+}
+
 // MCTS::find_leaf (mcts.cc:462-498) for tree t
 template <int GAME>
 __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon) {
@@ -393,7 +458,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       const u32 j = c0 + lane;
       const u32 nj = j < k ? pool[fb_n(b, k) + j] : 0u;
       const float pj = j < k ? u2f(pool[fb_pol(b, k) + j]) : 0.0f;
-      seen = seq_sum_chunk(seen, pj, nj > 0, k - c0 < 32u ? k - c0 : 32u);
+      seen = seq_sum_masked(seen, pj, j < k && nj > 0);  // usually a handful of visited children
     }
     const float fpu = (at_root && F.root_fpu_zero) ? 0.0f : F.fpu_reduction;
     const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
@@ -511,7 +576,8 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
 
 // MCTS::process_result (mcts.cc:500-555) for tree t. RANDOM = dumb_eval (game_state.h:160-173) instead of (v, pi).
 template <int GAME, bool RANDOM>
-__device__ void forest_process_result(const ForestView& F, u32 t, const float* ev_v, const float* ev_pi, u32 lane) {
+__device__ void forest_process_result(const ForestView& F, u32 t, const float* ev_v, const float* ev_pi, u32 lane,
+                                      bool root_noise_enabled) {
   typedef Tafl<GAME> T;
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
@@ -541,10 +607,38 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
           p = RANDOM ? rp : ev_pi[(size_t)t * T::A + (pool[fb_mv(lblk, lk) + j] & 0xFFFFu)];
           pool[fb_pol(lblk, lk) + j] = f2u(p);
         }
-        sum = seq_sum_chunk(sum, p, true, lk - c0 < 32u ? lk - c0 : 32u);
+        const u32 cnt = lk - c0 < 32u ? lk - c0 : 32u;
+        if (RANDOM) {  // all priors equal: the same in-order sum without the shuffles
+          for (u32 q = 0; q < cnt; ++q) sum = fadd(sum, rp);
+        } else {
+          sum = seq_sum_all(sum, p, cnt);
+        }
       }
       __syncwarp();
-      for (u32 j = lane; j < lk; j += 32u) pool[fb_pol(lblk, lk) + j] = f2u(fdiv(u2f(pool[fb_pol(lblk, lk) + j]), sum));
+      const bool is_root = plen == 0;
+      if (is_root && F.root_policy_temp != 1.0f) {
+        // set_policy_normalized(pi, apply_temp = true, 1 / T): every prior is raised to 1/T BEFORE the in-order sum
+        // (mcts.cc:111-120); az_powf is out of line and scalar: lane 0 redoes the root's priors serially
+        if (lane == 0) {
+          const float e = fdiv(1.0f, F.root_policy_temp);
+          float tsum = 0.0f;
+          for (u32 j = 0; j < lk; ++j) {
+            const float p = az_powf(u2f(pool[fb_pol(lblk, lk) + j]), e);
+            pool[fb_pol(lblk, lk) + j] = f2u(p);
+            tsum = fadd(tsum, p);
+          }
+          for (u32 j = 0; j < lk; ++j) pool[fb_pol(lblk, lk) + j] = f2u(fdiv(u2f(pool[fb_pol(lblk, lk) + j]), tsum));
+        }
+      } else {
+        for (u32 j = lane; j < lk; j += 32u) pool[fb_pol(lblk, lk) + j] = f2u(fdiv(u2f(pool[fb_pol(lblk, lk) + j]), sum));
+      }
+      __syncwarp();
+      // Gumbel replaces Dirichlet noise (mcts.cc:514-518)
+      if (is_root && root_noise_enabled && F.epsilon > 0.0f && !F.gumbel_enabled && lane == 0) {
+        Pcg32 rng = R.rng;
+        fr_add_root_noise(F, t, rng, pool, lblk, lk);
+        R.rng = rng;
+      }
     }
   }
   __syncwarp();
@@ -707,20 +801,39 @@ __global__ void __launch_bounds__(128) k_forest_find_leaf(ForestView F) {
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) forest_find_leaf<GAME>(F, t, sm[wib], lane, true);
 }
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, const float* ev_v, const float* ev_pi) {
+__global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, const float* ev_v, const float* ev_pi,
+                                                               u32 root_noise_enabled) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
-    forest_process_result<GAME, false>(F, t, ev_v, ev_pi, lane);
+    forest_process_result<GAME, false>(F, t, ev_v, ev_pi, lane, root_noise_enabled != 0);
+}
+// PlayManager's step after a move under tree reuse (play_manager.cc:546-553): the reused root gets the root
+// temperature again and fresh noise — MCTS::apply_root_policy_temp() then add_root_noise() for trees with root_n > 0
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_root_noise(ForestView F, u32 add_noise) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    ForestTree& R = F.trees[t];
+    if (lane == 0 && R.n > 0 && R.blk != 0) {
+      u32* pool = F.pool + (size_t)t * F.words_per_tree;
+      fr_apply_root_policy_temp(F, pool, R.blk, R.k);
+      if (add_noise && F.epsilon > 0.0f) {
+        Pcg32 rng = R.rng;
+        fr_add_root_noise(F, t, rng, pool, R.blk, R.k);
+        R.rng = rng;
+      }
+    }
+  }
 }
 // n_sims x (find_leaf + dumb_eval + process_result) fused: the RANDOM-evaluator search (EvalType::RANDOM)
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_simulate(ForestView F, u32 n_sims) {
+__global__ void __launch_bounds__(128) k_forest_simulate(ForestView F, u32 n_sims, u32 root_noise_enabled) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
     for (u32 i = 0; i < n_sims; ++i) {
       forest_find_leaf<GAME>(F, t, sm[wib], lane, false);
-      forest_process_result<GAME, true>(F, t, nullptr, nullptr, lane);
+      forest_process_result<GAME, true>(F, t, nullptr, nullptr, lane, root_noise_enabled != 0);
     }
 }
 template <int GAME>
@@ -845,8 +958,8 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
   if (p->game > B2AZ_TAFL_TAWLBWRDD) return fail(B2AZ_EINVAL, "b2az_forest: unknown tafl game");
   if (p->n_trees == 0 || p->max_turns == 0 || p->max_turns > 65535u) return fail(B2AZ_EINVAL, "b2az_forest: bad n_trees / max_turns");
-  if (p->epsilon != 0.0f) return fail(B2AZ_EINVAL, "b2az_forest: root Dirichlet noise (epsilon) is not implemented yet");
-  if (p->root_policy_temp != 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp != 1 is not implemented yet");
+  if (!(p->root_policy_temp > 0.0f)) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp must be positive (1 = off)");
+  if (p->epsilon < 0.0f || p->epsilon > 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: epsilon must be in [0, 1]");
   if (p->gumbel_enabled && (p->gumbel_m == 0 || p->gumbel_m > (uint32_t)kFMaxM))
     return fail(B2AZ_EINVAL, "b2az_forest: gumbel_m must be in [1, 64]");
   if (p->gumbel_full) return fail(B2AZ_EINVAL, "b2az_forest: gumbel_full (pi'-matching at interior nodes) is not implemented yet");
@@ -876,6 +989,9 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (int rc = dev_alloc(&V.pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
   if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon)) return bail(rc);
   if (int rc = dev_alloc(&f->moves_dev, (size_t)V.n_trees)) return bail(rc);
+  V.epsilon = p->epsilon; V.root_policy_temp = p->root_policy_temp; V.shaped_dirichlet = p->shaped_dirichlet ? 1u : 0u;
+  if (V.epsilon > 0.0f)
+    if (int rc = dev_alloc(&V.noise, (size_t)V.n_trees * kFMaxK)) return bail(rc);
   V.gumbel_enabled = p->gumbel_enabled ? 1u : 0u;
   V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
   if (V.gumbel_enabled) {
@@ -895,7 +1011,7 @@ int b2az_forest_destroy(b2az_forest* f) {
   if (!f) return 0;
   dev_free(f->view.trees); dev_free(f->view.pool); dev_free(f->view.hist); dev_free(f->view.pkeys);
   dev_free(f->view.leaf_canon); dev_free(f->moves_dev); dev_free(f->ev_v); dev_free(f->ev_pi);
-  dev_free(f->view.gum); dev_free(f->view.gum_g);
+  dev_free(f->view.gum); dev_free(f->view.gum_g); dev_free(f->view.noise);
   delete f;
   return 0;
 }
@@ -904,9 +1020,10 @@ int b2az_forest_destroy(b2az_forest* f) {
 #define FOREST_NO_CUDA(...) { return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback"); }
 int b2az_forest_find_leaf(b2az_forest*, void*, const float**) FOREST_NO_CUDA()
 int b2az_forest_leaf_canon_host(b2az_forest*, void*, float*) FOREST_NO_CUDA()
-int b2az_forest_process_result(b2az_forest*, void*, const float*, const float*) FOREST_NO_CUDA()
-int b2az_forest_process_result_host(b2az_forest*, void*, const float*, const float*) FOREST_NO_CUDA()
-int b2az_forest_simulate(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
+int b2az_forest_process_result(b2az_forest*, void*, const float*, const float*, int) FOREST_NO_CUDA()
+int b2az_forest_process_result_host(b2az_forest*, void*, const float*, const float*, int) FOREST_NO_CUDA()
+int b2az_forest_simulate(b2az_forest*, void*, uint32_t, int) FOREST_NO_CUDA()
+int b2az_forest_root_noise(b2az_forest*, void*, int) FOREST_NO_CUDA()
 int b2az_forest_advance(b2az_forest*, void*) FOREST_NO_CUDA()
 int b2az_forest_set_gumbel_num_sims(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
 int b2az_forest_gumbel_result(b2az_forest*, void*, uint32_t*, float*) FOREST_NO_CUDA()
@@ -929,15 +1046,17 @@ int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host)
   if (int rc = copy_d2h(canon_host, f->view.leaf_canon, (size_t)f->view.n_trees * f->canon * 4, s)) return rc;
   return stream_sync(s);
 }
-int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev) {
+int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev,
+                               int root_noise_enabled) {
   using namespace b2az;
   if (!f || !v_dev || !pi_dev) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  FOREST_DISPATCH(f, (k_forest_process_result<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, v_dev, pi_dev)));
+  FOREST_DISPATCH(f, (k_forest_process_result<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, v_dev, pi_dev, root_noise_enabled ? 1u : 0u)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host) {
+int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host,
+                                    int root_noise_enabled) {
   using namespace b2az;
   if (!f || !v_host || !pi_host) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -948,15 +1067,23 @@ int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v
   }
   if (int rc = copy_h2d(f->ev_v, v_host, n * 3 * 4, s)) return rc;
   if (int rc = copy_h2d(f->ev_pi, pi_host, n * f->actions * 4, s)) return rc;
-  if (int rc = b2az_forest_process_result(f, stream, f->ev_v, f->ev_pi)) return rc;
+  if (int rc = b2az_forest_process_result(f, stream, f->ev_v, f->ev_pi, root_noise_enabled)) return rc;
   return stream_sync(s);
 }
-int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims) {
+int b2az_forest_root_noise(b2az_forest* f, void* stream, int add_noise) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_root_noise<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, add_noise ? 1u : 0u)));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims, int root_noise_enabled) {
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (n_sims == 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  FOREST_DISPATCH(f, (k_forest_simulate<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, n_sims)));
+  FOREST_DISPATCH(f, (k_forest_simulate<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, n_sims, root_noise_enabled ? 1u : 0u)));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

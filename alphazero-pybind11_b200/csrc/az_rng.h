@@ -63,6 +63,20 @@ AZ_HD u32 rng_below(Pcg32& r, u32 range) {
 }
 
 // std::shuffle(first, last, pcg32) for n <= 65535 (pairwise path, stl_algo.h:3766-3799).
+// x / d and x % d for x < 2^22, d < 2^11 (the pairwise shuffle's x < (i+1)(i+2)): float quotient estimate + one
+// correction step instead of the 32-bit integer division sequence; exact (float(x) and float(d) are exact, the
+// estimate is off by at most one).
+AZ_HD void small_divmod(u32 x, u32 d, u32& q, u32& rem) {
+#if defined(__CUDA_ARCH__)
+  u32 qq = (u32)__fdividef((float)x, (float)d);
+  int rr = (int)(x - qq * d);
+  if (rr < 0) { --qq; rr += (int)d; }
+  else if (rr >= (int)d) { ++qq; rr -= (int)d; }
+  q = qq; rem = (u32)rr;
+#else
+  q = x / d; rem = x % d;
+#endif
+}
 template <typename T>
 AZ_HD void rng_shuffle(Pcg32& r, T* a, u32 n) {
   if (n == 0) return;
@@ -75,7 +89,9 @@ AZ_HD void rng_shuffle(Pcg32& r, T* a, u32 n) {
   while (i < n) {
     const u32 swap_range = i + 1u;
     const u32 x = rng_below(r, swap_range * (swap_range + 1u));
-    const u32 p0 = x / (swap_range + 1u), p1 = x % (swap_range + 1u);
+    u32 p0, p1;
+    if (n <= 1024u) small_divmod(x, swap_range + 1u, p0, p1);
+    else { p0 = x / (swap_range + 1u); p1 = x % (swap_range + 1u); }
     T t = a[i]; a[i] = a[p0]; a[p0] = t;
     ++i;
     t = a[i]; a[i] = a[p1]; a[p1] = t;

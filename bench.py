@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the tafl legs (BASELINE.json configs[2..3], secondary)")
     return ap.parse_args()
 
 
@@ -493,13 +494,28 @@ def main():
                "cpu_model": cpu_model(), "host_threads": threads,
                "sample": f"{kind} PlayManager, Connect4, EvalType::RANDOM, {SIMS} sims/move, {workers} worker threads, "
                          f"concurrent_games={64 * workers}, {args.cpu_seconds * 2 / 3:.0f} s window after warm-up"}
+    # ---------------------------------------------------------------- secondary: the tafl configs (parity-test
+    # cases of BASELINE.json, not the headline): wide-tree search and game kernels, each in its own process
+    extra = None
+    if world == 1 and not args.no_extra:
+        extra = {}
+        for key, cmd in (("brandubh_gumbel_search", ["tools/forest_bench.py", "--game", "0", "--trees", "8192", "--moves", "6",
+                                                     "--gumbel-m", "16"]),
+                         ("opentafl_game_kernels", ["tools/tafl_bench.py", "--game", "1", "--games", "8192", "--reps", "3"])):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], stdout=subprocess.PIPE,
+                                   stderr=subprocess.PIPE, text=True, timeout=300)
+                rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+                extra[key] = json.loads(rows[-1]) if rows else {"failed": r.stderr[-300:]}
+            except Exception as ex:  # never let a secondary leg break the headline line
+                extra[key] = {"failed": repr(ex)[:300]}
     line = {"metric": "mcts_simulations_per_second", "value": value, "unit": "sims/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "moves_per_second": moves_per_s, "clocks": clocks, "e2e": e2e, "e2e_nn_host": e2e_nn,
             "e2e_nn_device": e2e_nn_dev,
             "gpu_launches": K * world, "roofline": roofline, "cpu_baseline": cpu,
-            "pool_pages": {"total": pool[0], "free": pool[1]}}
+            "pool_pages": {"total": pool[0], "free": pool[1]}, "other_configs": extra}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

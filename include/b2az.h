@@ -234,8 +234,8 @@ int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turn
  * start position and draws from pcg32(seed + i) — a reference MCTS driven after MCTS::seed_thread_rng(seed + i).
  * Mirrors MCTS(cpuct, num_players = 2, num_moves, epsilon, root_policy_temp, fpu_reduction, relative_values,
  * root_fpu_zero, shaped_dirichlet, gumbel_enabled, gumbel_m, gumbel_c_visit, gumbel_c_scale, gumbel_full): this
- * version implements PUCT and Gumbel root search with epsilon == 0, root_policy_temp == 1, relative_values == 0,
- * gumbel_full == 0 and rejects anything else. */
+ * version implements PUCT and Gumbel root search, root policy temperature and (shaped) Dirichlet noise, with
+ * relative_values == 0 and gumbel_full == 0, and rejects anything else. */
 typedef struct b2az_forest_params {
   uint32_t game;                 /* B2AZ_TAFL_* */
   uint32_t n_trees;
@@ -246,6 +246,7 @@ typedef struct b2az_forest_params {
   uint32_t gumbel_m;             /* PlayParams::gumbel_m (16) */
   uint64_t seed;
   float gumbel_c_visit, gumbel_c_scale;  /* 50, 1 */
+  uint8_t shaped_dirichlet, pad_[7];
 } b2az_forest_params;
 typedef struct b2az_forest b2az_forest;
 int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out);
@@ -255,12 +256,17 @@ int b2az_forest_destroy(b2az_forest* f);
  * planes float32[n_trees][P][S][S] (the evaluator's input); b2az_forest_leaf_canon_host copies them out. */
 int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev);
 int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host);
-/* MCTS::process_result(gs, value, pi, root_noise_enabled = false) (mcts.cc:500-555): v float32[n_trees][3],
+/* MCTS::process_result(gs, value, pi, root_noise_enabled) (mcts.cc:500-555): v float32[n_trees][3],
  * pi float32[n_trees][A], device or host pointers. */
-int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev);
-int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host);
+int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev,
+                               int root_noise_enabled);
+int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host,
+                                    int root_noise_enabled);
 /* n_sims x (find_leaf -> dumb_eval (game_state.h:160-173) -> process_result) fused in one launch. */
-int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims);
+int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims, int root_noise_enabled);
+/* MCTS::apply_root_policy_temp() then (add_noise != 0 and epsilon > 0) MCTS::add_root_noise() on every tree whose
+ * root has been visited: what PlayManager does to the reused root after a move (play_manager.cc:546-553). */
+int b2az_forest_root_noise(b2az_forest* f, void* stream, int add_noise);
 /* MCTS::set_gumbel_num_sims(n) (mcts.cc:175-178) on every tree — call before each move's search, like
  * PlayManager does (play_manager.cc:531-539); n == 0 = PUCT for that search. */
 int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n);

@@ -208,13 +208,15 @@ typedef void (*azref_eval_fn)(const float* canonical, float* v3, float* pi, void
 int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, float fpu_reduction, int root_fpu_zero,
                       uint32_t n_moves, uint32_t sims, int eval_kind, azref_eval_fn cb, void* user, uint32_t* counts_out,
                       float* q_out, uint32_t* moves_out, uint32_t* depth_sum_out, uint32_t gumbel_m, float gumbel_c_visit,
-                      float gumbel_c_scale, float* policy_out) {
+                      float gumbel_c_scale, float* policy_out, float epsilon, float root_policy_temp, int shaped_dirichlet) {
   try {
     auto gs = make_game(game, max_turns);
     if (!gs) { g_err = "unknown game"; return -1; }
     const uint32_t A = gs->num_moves();
     MCTS::seed_thread_rng(seed);
-    MCTS mcts{cpuct, 2, A, 0.0f, 1.0f, fpu_reduction, false, root_fpu_zero != 0, false, gumbel_m > 0,
+    // epsilon > 0: process_result(root_noise_enabled = true), and after every move the reused root gets the root
+    // temperature again and fresh noise, as PlayManager does (play_manager.cc:546-553)
+    MCTS mcts{cpuct, 2, A, epsilon, root_policy_temp, fpu_reduction, false, root_fpu_zero != 0, shaped_dirichlet != 0, gumbel_m > 0,
               gumbel_m > 0 ? gumbel_m : 16u, gumbel_c_visit, gumbel_c_scale, false};
     uint32_t played = 0;
     for (uint32_t m = 0; m < n_moves; ++m) {
@@ -230,7 +232,7 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
           auto c = leaf->canonicalized();
           cb(c.data(), v.data(), pi.data(), user);
         }
-        mcts.process_result(*gs, v, pi, false);
+        mcts.process_result(*gs, v, pi, epsilon > 0.0f);
       }
       auto counts = mcts.counts();
       auto q = mcts.root_q_values();
@@ -251,6 +253,10 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
       moves_out[m] = best;
       mcts.update_root(*gs, best);
       gs->play_move(best);
+      if (mcts.root_n() > 0) {
+        mcts.apply_root_policy_temp();
+        if (epsilon > 0.0f) mcts.add_root_noise();
+      }
       ++played;
     }
     return (int)played;

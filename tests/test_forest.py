@@ -35,12 +35,16 @@ def pseudo_net(canon):
     return v.astype(np.float32), pi.astype(np.float32)
 
 
-def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None, slab_moves=None, gumbel=None):
+def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None, slab_moves=None, gumbel=None,
+               noise=None):
     """Drives the forest like the reference run; plays `moves_ref[i][m]` when given (else the most visited move)."""
     # each half of the slab must hold the kept subtree + one move's search (1 + 7k words per expanded node);
     # slab_moves = how many moves' worth of nodes one half can hold (re-rooting compacts into the other half)
     words = 2 * (1 + (slab_moves or n_moves + 1) * sims * (1 + 7 * (64 if game == 0 else 200)))
     gkw = dict(gumbel_m=gumbel[0], gumbel_c_visit=gumbel[1], gumbel_c_scale=gumbel[2]) if gumbel else {}
+    if noise:  # (epsilon, root_policy_temp, shaped_dirichlet)
+        gkw.update(epsilon=noise[0], root_policy_temp=noise[1], shaped_dirichlet=noise[2])
+    rn = bool(noise and noise[0] > 0)
     f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=cpuct, fpu_reduction=fpu, root_fpu_zero=rfz, seed=seed,
                     words_per_tree=words, **gkw)
     out = []
@@ -49,13 +53,13 @@ def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, mov
         if gumbel:
             f.set_gumbel_num_sims(sims)
         if evaluator is None:
-            f.simulate(sims)
+            f.simulate(sims, root_noise=rn)
         else:
             for _ in range(sims):
                 f.find_leaf()
                 canon = f.leaf_canon()
                 ev = [evaluator(canon[i]) for i in range(trees)]
-                f.process_result(np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]))
+                f.process_result(np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]), root_noise=rn)
         counts, q, info = f.counts()
         assert (info["error"] == 0).all(), info["error"]
         out.append((counts, q, info) + (f.gumbel_result() if gumbel else ()))
@@ -69,6 +73,8 @@ def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, mov
             else:
                 mv[i] = int(np.argmax(counts[i]))
         f.update_root(mv)
+        if noise:
+            f.root_noise(add_noise=rn)  # the reused root: temperature again + fresh noise (play_manager.cc:546-553)
     f.close()
     return out
 
@@ -145,10 +151,28 @@ def test_forest_gumbel_root_search_vs_reference(game, trees, n_moves, sims, m):
     assert compared >= trees * 3
 
 
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,trees,n_moves,sims,noise,evaluator", [
+    (0, 6, 12, 60, (0.25, 1.25, False), None), (0, 4, 8, 50, (0.25, 1.25, True), pseudo_net),
+    (0, 4, 8, 40, (0.0, 1.4, False), pseudo_net), (1, 2, 4, 40, (0.25, 1.25, True), None), (2, 2, 4, 40, (0.3, 1.0, False), None)])
+def test_forest_root_noise_and_temperature_vs_reference(game, trees, n_moves, sims, noise, evaluator):
+    """Self-play settings of the non-Gumbel configs: root policy temperature, (shaped) Dirichlet noise at the first
+    root evaluation and again on every reused root (gamma / normal / pow / log restated bit-exactly on the device)."""
+    refs = [tafl_ref.search(game, 555 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, True, evaluator, epsilon=noise[0],
+                            root_policy_temp=noise[1], shaped_dirichlet=noise[2]) for i in range(trees)]
+    got = run_forest(game, trees, n_moves, sims, 555, 1.25, 0.25, True, evaluator, moves_ref=[r[2] for r in refs], noise=noise)
+    for i, (rc, rq, rm, rd) in enumerate(refs):
+        for m in range(len(rm)):
+            counts, q, info = got[m][:3]
+            assert np.array_equal(counts[i], rc[m]), f"{NAMES[game]} tree {i} move {m}: visit counts differ"
+            assert np.array_equal(q[i].view(np.uint32), rq[m].view(np.uint32)), f"tree {i} move {m}: Q values differ"
+
+
 def test_forest_refuses_without_cuda_or_unsupported_params():
     lib = b2az.load(ph.HOSTEMU_LIB)
     with pytest.raises(b2az.B2azError) as ei:
-        b2az.Forest(0, 4, 150, epsilon=0.25, lib=lib)
+        b2az.Forest(0, 4, 150, gumbel_m=16, gumbel_full=True, lib=lib)
     assert "not implemented" in str(ei.value)
     with pytest.raises(b2az.B2azError) as ei:
         b2az.Forest(0, 4, 150, lib=lib)

@@ -25,19 +25,25 @@ if __name__ == "__main__":
     ap.add_argument("--trees", type=int, default=16384)
     ap.add_argument("--sims", type=int, default=120)  # configs/brandubh.yaml mcts_visits
     ap.add_argument("--moves", type=int, default=12)
+    ap.add_argument("--gumbel-m", type=int, default=0, help="Gumbel root search with m candidates (configs/brandubh.yaml: 16)")
     a = ap.parse_args()
     # each half of a tree's slab: the kept subtree + one move's new nodes (1 + 7k words each), with head room
     words = 2 * (1 + 3 * a.sims * (1 + 7 * (48 if a.game == 0 else 140)))
-    f = b2az.Forest(a.game, a.trees, MAX_TURNS[a.game], cpuct=1.25, fpu_reduction=0.25, seed=1, words_per_tree=words)
+    f = b2az.Forest(a.game, a.trees, MAX_TURNS[a.game], cpuct=1.25, fpu_reduction=0.25, seed=1, words_per_tree=words,
+                    gumbel_m=a.gumbel_m)
     stream = torch.cuda.current_stream().cuda_stream
+    if a.gumbel_m:
+        f.set_gumbel_num_sims(a.sims, stream)
     f.simulate(a.sims, stream)  # warm-up move
     f.advance(stream)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.moves + 1)]
     ev[0].record()
     for m in range(a.moves):
+        if a.gumbel_m:
+            f.set_gumbel_num_sims(a.sims, stream)
         f.simulate(a.sims, stream)
-        f.advance(stream)
+        f.advance(stream)  # (greedy by visit count in both modes: the throughput does not depend on the move rule)
         ev[m + 1].record()
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.moves)]
@@ -48,11 +54,11 @@ if __name__ == "__main__":
     t0 = time.perf_counter()
     n_ref, ref_sims = 0, 0
     while time.perf_counter() - t0 < 10:
-        c, _, mv, _ = tafl_ref.search(a.game, 900 + n_ref, a.moves + 1, a.sims, MAX_TURNS[a.game], 1.25, 0.25, False, None)
-        ref_sims += len(mv) * a.sims
+        r = tafl_ref.search(a.game, 900 + n_ref, a.moves + 1, a.sims, MAX_TURNS[a.game], 1.25, 0.25, False, None, a.gumbel_m)
+        ref_sims += len(r[2]) * a.sims
         n_ref += 1
     cpu_s = time.perf_counter() - t0
-    print(json.dumps({"kernel": "k_forest_simulate", "game": NAMES[a.game], "trees": a.trees, "sims_per_move": a.sims,
+    print(json.dumps({"kernel": "k_forest_simulate", "game": NAMES[a.game], "trees": a.trees, "gumbel_m": a.gumbel_m, "sims_per_move": a.sims,
                       "moves": a.moves, "ms_per_move": [round(x, 2) for x in ms],
                       "simulations_per_second": sims_total / (sum(ms) * 1e-3), "moves_per_second": a.trees * a.moves / (sum(ms) * 1e-3),
                       "mean_slab_words_used": float(info["words_used"].mean()), "games_over": int((info["root_term"] != 0).sum()),
