@@ -71,7 +71,8 @@ class ForestParams(C.Structure):  # b2az_forest_params (include/b2az.h)
                 ("cpuct", C.c_float), ("fpu_reduction", C.c_float), ("epsilon", C.c_float), ("root_policy_temp", C.c_float),
                 ("root_fpu_zero", C.c_uint8), ("relative_values", C.c_uint8), ("gumbel_enabled", C.c_uint8),
                 ("gumbel_full", C.c_uint8), ("gumbel_m", C.c_uint32), ("seed", C.c_uint64), ("gumbel_c_visit", C.c_float),
-                ("gumbel_c_scale", C.c_float), ("shaped_dirichlet", C.c_uint8), ("pad2_", C.c_uint8 * 7)]
+                ("gumbel_c_scale", C.c_float), ("shaped_dirichlet", C.c_uint8), ("debug_serial_shuffle", C.c_uint8),
+                ("pad2_", C.c_uint8 * 6)]
 
 
 _libs = {}
@@ -337,7 +338,7 @@ class Forest:
 
     def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
                  words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0,
-                 gumbel_full=False, shaped_dirichlet=False, device=0, lib=None):
+                 gumbel_full=False, shaped_dirichlet=False, serial_shuffle=False, device=0, lib=None):
         self.L = lib or load()
         self.game, self.n = game, n_trees
         S, P = TAFL_DIMS[game]
@@ -346,7 +347,7 @@ class Forest:
                          fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
                          root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
                          gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, gumbel_full=int(gumbel_full),
-                         shaped_dirichlet=int(shaped_dirichlet))
+                         shaped_dirichlet=int(shaped_dirichlet), debug_serial_shuffle=int(serial_shuffle))
         self.h = C.c_void_p()
         self._check(self.L.b2az_forest_create(C.byref(p), device, C.byref(self.h)))
 

@@ -73,6 +73,7 @@ struct ForestView {
   float gumbel_c_visit, gumbel_c_scale;
   float epsilon, root_policy_temp;
   u32 shaped_dirichlet;
+  u32 serial_shuffle;  // diagnostics: always take the sequential std::shuffle path
   ForestGumbel* gum;   // [n_trees], null unless gumbel_enabled
   float* gum_g;        // [n_trees][2 * kFMaxK]: gumbel_g_ per root child, then scratch scores
   float* noise;        // [n_trees][kFMaxK] Dirichlet draws, null unless epsilon > 0
@@ -97,7 +98,78 @@ template <int GAME>
 struct ForestSmem {   // per warp
   u32 lines[2 * Tafl<GAME>::S + 2];
   u16 moves[kFMaxK];
+  u32 draws[kFMaxK / 2 + 2];   // the shuffle's uniform draws, generated lane-parallel (pcg32 jump-ahead)
 };
+
+// pcg32 is an LCG underneath: state_d = A_d * state_0 + C_d * inc with A_d = M^d, C_d = 1 + M + ... + M^(d-1)
+// (mod 2^64). With the table every lane can produce "the d-th output from now" on its own, so the k/2 draws of a
+// std::shuffle are generated 32 at a time instead of one after the other on lane 0.
+struct PcgJump {
+  u64 a[kFMaxK / 2 + 2], c[kFMaxK / 2 + 2];
+};
+constexpr PcgJump make_pcg_jump() {
+  PcgJump t{};
+  u64 a = 1, c = 0;
+  for (int i = 0; i < kFMaxK / 2 + 2; ++i) {
+    t.a[i] = a;
+    t.c[i] = c;
+    a = a * AZ_PCG_MULT;
+    c = c * AZ_PCG_MULT + 1ULL;
+  }
+  return t;
+}
+__device__ constexpr PcgJump kPcgJump = make_pcg_jump();
+__device__ __forceinline__ u32 pcg32_output(u64 old) {  // XSH-RR of a state (pcg32_next without the advance)
+  const u32 xorshifted = (u32)(((old >> 18) ^ old) >> 27);
+  const u32 rot = (u32)(old >> 59);
+  return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
+}
+// std::shuffle(moves, moves + k, rng) (pairwise path, stl_algo.h:3766-3799) with the draws generated by all lanes.
+// Lemire's method rejects (and redraws) with probability range / 2^32 per draw: any draw that MIGHT reject sends
+// the whole shuffle down the sequential path (rng_shuffle on lane 0), so the result is always the reference's.
+__device__ __forceinline__ void forest_shuffle(Pcg32& rng, u16* a, u32* draws, u32 k, u32 lane, bool force_serial) {
+  if (k < 2u) return;
+  const u32 even = (k & 1u) ? 0u : 1u, i0 = even ? 2u : 1u;
+  const u32 pairs = k > i0 ? (k - i0 + 1u) / 2u : 0u, D = even + pairs;
+  // measured: below ~64 children the table loads and 64-bit multiplies cost more than lane 0's serial draws
+  // (Brandubh, k ~ 33: 136 -> 129 M sims/s with the parallel path; OpenTafl, k ~ 113: 47.6 -> 48.6 M)
+  bool risky = force_serial || k < 64u;
+  if (!risky)
+  for (u32 d = lane; d < D; d += 32u) {
+    const u64 st = kPcgJump.a[d] * rng.state + kPcgJump.c[d] * rng.inc;
+    u32 range = 2u;
+    if (!(even && d == 0u)) {
+      const u32 i = i0 + 2u * (d - even);
+      range = (i + 1u) * (i + 2u);
+    }
+    const u64 product = (u64)pcg32_output(st) * (u64)range;
+    risky |= (u32)product < range;
+    draws[d] = (u32)(product >> 32);
+  }
+  if (__any_sync(0xFFFFFFFFu, risky)) {
+    if (lane == 0) rng_shuffle<u16>(rng, a, k);
+    rng.state = __shfl_sync(0xFFFFFFFFu, rng.state, 0);
+    __syncwarp();
+    return;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    u32 d = 0, i = 1;
+    if (even) {
+      const u32 j = draws[d++];
+      const u16 t = a[1]; a[1] = a[j]; a[j] = t;
+      i = 2;
+    }
+    for (; i < k; i += 2u) {
+      u32 p0, p1;
+      small_divmod(draws[d++], i + 2u, p0, p1);
+      u16 t = a[i]; a[i] = a[p0]; a[p0] = t;
+      t = a[i + 1u]; a[i + 1u] = a[p1]; a[p1] = t;
+    }
+  }
+  rng.state = kPcgJump.a[D] * rng.state + kPcgJump.c[D] * rng.inc;
+  __syncwarp();
+}
 
 // In-order float sums over a chunk of 32 children held one per lane (float addition is not associative and the
 // children are in shuffled order, so the order of the reference's loop must be kept): the lanes hand their value
@@ -145,7 +217,8 @@ __device__ __forceinline__ bool forest_play(TaflState& s, u32 mv, const TaflKey*
 
 // Node::add_children(valid_moves()) into sm.moves (ascending ids, then std::shuffle); returns k
 template <int GAME>
-__device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem<GAME>& sm, Pcg32& rng, u32 lane, u32* err) {
+__device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem<GAME>& sm, Pcg32& rng, u32 lane, u32* err,
+                                                  bool serial_shuffle = false) {
   typedef Tafl<GAME> T;
   constexpr int S = T::S, CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
   const B128 occ = s.king | s.def | s.atk;
@@ -187,10 +260,7 @@ __device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem
   __syncwarp();
   u32 k = base;
   if (k > (u32)kFMaxK) { *err |= 4u; k = 0; }
-  if (lane == 0) rng_shuffle<u16>(rng, sm.moves, k);
-  // every lane keeps the same generator state: lane 0's result is broadcast
-  rng.state = __shfl_sync(0xFFFFFFFFu, rng.state, 0);
-  __syncwarp();
+  forest_shuffle(rng, sm.moves, sm.draws, k, lane, serial_shuffle);  // every lane ends with the same generator state
   return k;
 }
 
@@ -201,7 +271,7 @@ __device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem
 __device__ __forceinline__ void fg_reset(ForestGumbel& G) {  // reset_gumbel_state (mcts.cc:180-188)
   G.initialized = 0; G.effective_m = 0; G.n_surv = 0; G.n_phases = 0; G.phase_idx = 0; G.sims_in_phase = 0;
 }
-__device__ inline void fg_phase_plan(ForestGumbel& G, u32 m, u32 n) {  // seq_halving_phase_plan (mcts.cc:28-66)
+__device__ __noinline__ void fg_phase_plan(ForestGumbel& G, u32 m, u32 n) {  // seq_halving_phase_plan (mcts.cc:28-66)
   G.n_phases = 0;
   if (m <= 1) { G.phase_numc[0] = 1; G.phase_vper[0] = n; G.n_phases = 1; return; }
   u32 log2m = 0;
@@ -228,7 +298,7 @@ __device__ inline void fg_phase_plan(ForestGumbel& G, u32 m, u32 n) {  // seq_ha
 }
 // Top-`take` of `cnt` scores, descending (std::partial_sort in the reference: with continuous Gumbel noise in every
 // score ties have probability zero, so a plain selection gives the same ranking). `ids[i]` names score i.
-__device__ inline void fg_rank_top(const float* score, const u16* ids, u32 cnt, u32 take, u16* out) {
+__device__ __noinline__ void fg_rank_top(const float* score, const u16* ids, u32 cnt, u32 take, u16* out) {
   u32 used[kFMaxK / 32];
   for (int i = 0; i < kFMaxK / 32; ++i) used[i] = 0;
   for (u32 r = 0; r < take; ++r) {
@@ -247,7 +317,7 @@ __device__ __forceinline__ float fg_sigma_scale(const ForestView& F, u32 max_vis
   return fmul(fadd(F.gumbel_c_visit, (float)max_visit), F.gumbel_c_scale);
 }
 // init_gumbel_state (mcts.cc:190-227); lane 0 only
-__device__ inline void fg_init(const ForestView& F, u32 t, ForestTree& R, ForestGumbel& G, const u32* pool) {
+__device__ __noinline__ void fg_init(const ForestView& F, u32 t, ForestTree& R, ForestGumbel& G, const u32* pool) {
   const u32 num_legal = R.k, b = R.blk;
   if (num_legal == 0 || b == 0) return;
   const u32 remaining = R.depth < G.num_sims_target ? G.num_sims_target - R.depth : 0u;
@@ -270,7 +340,7 @@ __device__ inline void fg_init(const ForestView& F, u32 t, ForestTree& R, Forest
   G.initialized = 1;
 }
 // gumbel_advance_phase (mcts.cc:229-264)
-__device__ inline void fg_advance_phase(const ForestView& F, u32 t, const ForestTree& R, ForestGumbel& G, const u32* pool) {
+__device__ __noinline__ void fg_advance_phase(const ForestView& F, u32 t, const ForestTree& R, ForestGumbel& G, const u32* pool) {
   if (G.phase_idx + 1u >= G.n_phases) return;
   const u32 next_num_c = G.phase_numc[G.phase_idx + 1];
   if (next_num_c >= G.n_surv) { ++G.phase_idx; G.sims_in_phase = 0; return; }
@@ -299,7 +369,7 @@ __device__ inline void fg_advance_phase(const ForestView& F, u32 t, const Forest
   G.sims_in_phase = 0;
 }
 // gumbel_next_root_child (mcts.cc:266-283)
-__device__ inline u32 fg_next_root_child(const ForestView& F, u32 t, const ForestTree& R, ForestGumbel& G, const u32* pool) {
+__device__ __noinline__ u32 fg_next_root_child(const ForestView& F, u32 t, const ForestTree& R, ForestGumbel& G, const u32* pool) {
   if (G.phase_idx < G.n_phases) {
     if (G.sims_in_phase >= G.phase_numc[G.phase_idx] * G.phase_vper[G.phase_idx]) fg_advance_phase(F, t, R, G, pool);
   }
@@ -310,7 +380,7 @@ __device__ inline u32 fg_next_root_child(const ForestView& F, u32 t, const Fores
 }
 // gumbel_final_action (mcts.cc:375-401) when the search initialised; 0xFFFFFFFF otherwise (the reference then falls
 // back to pick_move(probs(0)), which the caller does from the counts)
-__device__ inline u32 fg_final_action(const ForestView& F, u32 t, const ForestTree& R, const ForestGumbel& G, const u32* pool) {
+__device__ __noinline__ u32 fg_final_action(const ForestView& F, u32 t, const ForestTree& R, const ForestGumbel& G, const u32* pool) {
   if (!G.initialized || G.n_surv == 0 || R.blk == 0) return 0xFFFFFFFFu;
   const u32 b = R.blk, k = R.k;
   const float* g = F.gum_g + (size_t)t * (2 * kFMaxK);
@@ -333,7 +403,7 @@ __device__ inline u32 fg_final_action(const ForestView& F, u32 t, const ForestTr
 }
 // gumbel_improved_policy (mcts.cc:336-373) incl. compute_v_mix_from_children (mcts.cc:71-89): pi'[move] for the
 // root's children into out[A] (already zeroed); z lives in the tree's scratch row. lane 0 only.
-__device__ inline void fg_improved_policy(const ForestView& F, u32 t, const ForestTree& R, const u32* pool, float* out) {
+__device__ __noinline__ void fg_improved_policy(const ForestView& F, u32 t, const ForestTree& R, const u32* pool, float* out) {
   const u32 b = R.blk, k = R.k;
   if (k == 0 || b == 0) return;
   float* z = F.gum_g + (size_t)t * (2 * kFMaxK) + kFMaxK;
@@ -373,7 +443,7 @@ __device__ inline void fg_improved_policy(const ForestView& F, u32 t, const Fore
 // ---- root policy temperature and Dirichlet noise over a wide root (mcts.cc:403-460); lane 0, policy array in HBM.
 // Same formulas / float order as the Connect4 engine's add_root_noise (az_engine_logic.h); the noise values live
 // in the tree's Gumbel scratch row (never needed at the same time: Gumbel replaces the noise, mcts.cc:514-518).
-__device__ inline void fr_apply_root_policy_temp(const ForestView& F, u32* pool, u32 b, u32 k) {  // mcts.cc:448-460
+__device__ __noinline__ void fr_apply_root_policy_temp(const ForestView& F, u32* pool, u32 b, u32 k) {  // mcts.cc:448-460
   if (F.root_policy_temp == 1.0f || b == 0) return;
   const float e = fdiv(1.0f, F.root_policy_temp);
   float sum = 0.0f;
@@ -385,7 +455,7 @@ __device__ inline void fr_apply_root_policy_temp(const ForestView& F, u32* pool,
   if (sum > 0.0f)
     for (u32 j = 0; j < k; ++j) pool[fb_pol(b, k) + j] = f2u(fdiv(u2f(pool[fb_pol(b, k) + j]), sum));
 }
-__device__ inline void fr_add_root_noise(const ForestView& F, u32 t, Pcg32& rng, u32* pool, u32 b, u32 k) {  // mcts.cc:403-446
+__device__ __noinline__ void fr_add_root_noise(const ForestView& F, u32 t, Pcg32& rng, u32* pool, u32 b, u32 k) {  // mcts.cc:403-446
   if (b == 0 || k == 0) return;
   float* noise = F.noise + (size_t)t * kFMaxK;
   double sum = 0.0;
@@ -451,8 +521,14 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   }
   while (cur_n > 0 && cur_term == 0) {
     if (plen >= (u32)kFPath || cur_blk == 0) { err |= 2u; break; }
-    // Node::best_child (mcts.cc:130-149)
     const u32 b = cur_blk, k = cur_k;
+    u32 best_j = 0xFFFFFFFFu;
+    if (gumbel_on && at_root) {  // the root child comes from the sequential-halving schedule (mcts.cc:476-478)
+      u32 forced = 0;
+      if (lane == 0) forced = fg_next_root_child(F, t, R, F.gum[t], pool);
+      best_j = __shfl_sync(0xFFFFFFFFu, forced, 0);
+    } else {
+    // Node::best_child (mcts.cc:130-149)
     float seen = 0.0f;
     for (u32 c0 = 0; c0 < k; c0 += 32u) {
       const u32 j = c0 + lane;
@@ -464,7 +540,6 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
     const float sqrt_n = fsqrt((float)cur_n);
     float best_u = 0.0f;
-    u32 best_j = 0xFFFFFFFFu;
     for (u32 c0 = 0; c0 < k; c0 += 32u) {
       const u32 j = c0 + lane;
       if (j < k) {
@@ -483,10 +558,6 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       if (take) { best_u = ou; best_j = oj; }
     }
     if (best_j == 0xFFFFFFFFu) best_j = 0;  // (all scores NaN: the reference keeps child 0)
-    if (gumbel_on && at_root) {  // the root child comes from the sequential-halving schedule (mcts.cc:476-478)
-      u32 forced = 0;
-      if (lane == 0) forced = fg_next_root_child(F, t, R, F.gum[t], pool);
-      best_j = __shfl_sync(0xFFFFFFFFu, forced, 0);
     }
     // NaN scores lose every comparison in the reference loop as well, except at index 0, which is only replaced by
     // a strictly greater score; with finite scores both orders agree.
@@ -513,7 +584,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     leaf_new = 1;
     leaf_player = s.player;
     Pcg32 rng = R.rng;
-    const u32 k = forest_legal_moves<GAME>(s, sm, rng, lane, &err);
+    const u32 k = forest_legal_moves<GAME>(s, sm, rng, lane, &err, F.serial_shuffle != 0);
     const u32 pre = T::terminal_pre(s);
     leaf_term = pre ? pre : T::terminal_post(s, k != 0);
     // children of a terminal node are never visited: their draws are consumed above, their storage is skipped
@@ -680,7 +751,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     // root_.children.empty(): add_children(gs.valid_moves()) — the shuffle draws happen; the block is only stored
     // when it can be descended into later (a terminal root keeps no children here, see find_leaf)
     Pcg32 rng = R.rng;
-    k = forest_legal_moves<GAME>(s, sm, rng, lane, &err);
+    k = forest_legal_moves<GAME>(s, sm, rng, lane, &err, F.serial_shuffle != 0);
     if (lane == 0) R.rng = rng;
     // the chosen child is a fresh node whatever its slot: only membership matters
     bool found = false;
@@ -826,8 +897,11 @@ __global__ void __launch_bounds__(128) k_forest_root_noise(ForestView F, u32 add
   }
 }
 // n_sims x (find_leaf + dumb_eval + process_result) fused: the RANDOM-evaluator search (EvalType::RANDOM)
+#ifndef B2AZ_FOREST_MINB
+#define B2AZ_FOREST_MINB 8  /* 64 registers, 32 warps per SM: 100 -> 140 M sims/s (Brandubh, Gumbel) */
+#endif
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_simulate(ForestView F, u32 n_sims, u32 root_noise_enabled) {
+__global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_forest_simulate(ForestView F, u32 n_sims, u32 root_noise_enabled) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
@@ -990,6 +1064,7 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon)) return bail(rc);
   if (int rc = dev_alloc(&f->moves_dev, (size_t)V.n_trees)) return bail(rc);
   V.epsilon = p->epsilon; V.root_policy_temp = p->root_policy_temp; V.shaped_dirichlet = p->shaped_dirichlet ? 1u : 0u;
+  V.serial_shuffle = p->debug_serial_shuffle ? 1u : 0u;
   if (V.epsilon > 0.0f)
     if (int rc = dev_alloc(&V.noise, (size_t)V.n_trees * kFMaxK)) return bail(rc);
   V.gumbel_enabled = p->gumbel_enabled ? 1u : 0u;

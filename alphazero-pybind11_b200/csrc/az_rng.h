@@ -116,7 +116,8 @@ AZ_HD void rng_shuffle_nib(Pcg32& r, u32& a, u32 n) {
   while (i < n) {
     const u32 swap_range = i + 1u;
     const u32 x = rng_below(r, swap_range * (swap_range + 1u));
-    const u32 p0 = x / (swap_range + 1u), p1 = x % (swap_range + 1u);
+    u32 p0, p1;
+    small_divmod(x, swap_range + 1u, p0, p1);
     nib_swap(a, i, p0);
     ++i;
     nib_swap(a, i, p1);

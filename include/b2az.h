@@ -246,7 +246,9 @@ typedef struct b2az_forest_params {
   uint32_t gumbel_m;             /* PlayParams::gumbel_m (16) */
   uint64_t seed;
   float gumbel_c_visit, gumbel_c_scale;  /* 50, 1 */
-  uint8_t shaped_dirichlet, pad_[7];
+  uint8_t shaped_dirichlet;
+  uint8_t debug_serial_shuffle;  /* diagnostics: std::shuffle draws one after the other on one lane (same results) */
+  uint8_t pad_[6];
 } b2az_forest_params;
 typedef struct b2az_forest b2az_forest;
 int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out);

@@ -169,6 +169,24 @@ def test_forest_root_noise_and_temperature_vs_reference(game, trees, n_moves, si
             assert np.array_equal(q[i].view(np.uint32), rq[m].view(np.uint32)), f"tree {i} move {m}: Q values differ"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("game", [0, 1])
+def test_parallel_shuffle_draws_equal_sequential(game):
+    """std::shuffle's draws come from a pcg32 jump-ahead table on all lanes (and fall back to the sequential path when
+    Lemire's rejection could fire): forcing the sequential path everywhere must give the same trees."""
+    outs = []
+    for serial in (False, True):
+        f = b2az.Forest(game, 64, MAX_TURNS[game], seed=9, words_per_tree=2 * (1 + 4 * 100 * (1 + 7 * 200)), serial_shuffle=serial)
+        for _ in range(3):
+            f.simulate(100)
+            f.advance()
+        f.simulate(100)
+        outs.append(f.counts())
+        f.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    assert (outs[0][2]["error"] == 0).all() and outs[0][0].sum() > 0
+
+
 def test_forest_refuses_without_cuda_or_unsupported_params():
     lib = b2az.load(ph.HOSTEMU_LIB)
     with pytest.raises(b2az.B2azError) as ei:

@@ -30,7 +30,7 @@ if __name__ == "__main__":
     # each half of a tree's slab: the kept subtree + one move's new nodes (1 + 7k words each), with head room
     words = 2 * (1 + 3 * a.sims * (1 + 7 * (48 if a.game == 0 else 140)))
     f = b2az.Forest(a.game, a.trees, MAX_TURNS[a.game], cpuct=1.25, fpu_reduction=0.25, seed=1, words_per_tree=words,
-                    gumbel_m=a.gumbel_m)
+                    gumbel_m=a.gumbel_m, lib=b2az.load(os.environ.get("B2AZ_LIB_PATH")))  # experiment builds via env
     stream = torch.cuda.current_stream().cuda_stream
     if a.gumbel_m:
         f.set_gumbel_num_sims(a.sims, stream)
