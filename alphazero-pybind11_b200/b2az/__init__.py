@@ -290,6 +290,8 @@ def tafl_replay(game, moves, lens, max_turns, want_valid=True, want_canonical=Tr
     moves uint16[n][max_len], lens[n]. Returns arrays shaped [n][max_len + 1][...] (rows beyond a game's length
     stay zero)."""
     L = lib or load()
+    if game not in TAFL_DIMS:
+        raise B2azError(-1, f"unknown tafl game {game}")
     S, P = TAFL_DIMS[game]
     moves = np.ascontiguousarray(moves, np.uint16)
     n, max_len = moves.shape

@@ -194,3 +194,41 @@ def test_positions_host_build_vs_live_reference(game):
 @pytest.mark.parametrize("game", [0, 1, 2])
 def test_cuda_positions_vs_live_reference(game):
     _check_positions(None, game, 1500, 77 + game)
+
+
+# ---------------------------------------------------------------------------------- edge cases of the batch API
+def test_empty_ragged_and_full_length_batches():
+    lib = b2az.load(ph.HOSTEMU_LIB)
+    # n == 0 is a no-op
+    r = b2az.tafl_replay(0, np.zeros((0, 4), np.uint16), np.zeros(0, np.uint32), 150, lib=lib)
+    assert r["boards"].shape == (0, 5, 3, 7, 7)
+    # ragged: lengths 0, 1 and a whole golden game in one batch; rows beyond a game's length stay untouched (zero)
+    g = golden(0)
+    i = int(np.argmax(g["lens"][:-2]))  # the longest 150-turn game
+    L = int(g["lens"][i])
+    moves = np.zeros((3, L), np.uint16)
+    moves[1, 0] = g["moves"][i, 0]
+    moves[2] = g["moves"][i, :L]
+    lens = np.array([0, 1, L], np.uint32)
+    r = b2az.tafl_replay(0, moves, lens, 150, lib=lib)
+    assert (r["status"] == 0).all()
+    assert np.array_equal(r["boards"][2, :L + 1], g["boards"][i, :L + 1]) and np.array_equal(r["terminal"][2, :L + 1], g["terminal"][i, :L + 1])
+    assert np.array_equal(r["boards"][1, 1], g["boards"][i, 1]) and np.array_equal(r["boards"][0, 0], g["boards"][i, 0])
+    assert not r["boards"][0, 1:].any() and not r["valid"][1, 2:].any() and not r["canonical"][0, 1:].any()
+    # lens larger than max_len are clamped
+    r2 = b2az.tafl_replay(0, moves[2:3, :5], np.array([999], np.uint32), 150, lib=lib)
+    assert np.array_equal(r2["boards"][0], g["boards"][i, :6])
+
+
+def test_bad_arguments_are_rejected():
+    lib = b2az.load(ph.HOSTEMU_LIB)
+    with pytest.raises(b2az.B2azError):
+        b2az.tafl_replay(7, np.zeros((1, 1), np.uint16), np.zeros(1, np.uint32), 150, lib=lib)  # unknown game
+    with pytest.raises(b2az.B2azError):
+        b2az.tafl_replay(0, np.zeros((1, 1), np.uint16), np.zeros(1, np.uint32), 70000, lib=lib)  # max_turns > uint16
+    # a move that lands on an occupied square is not validated by the reference either (play_move copies the source
+    # layers over the destination): status stays 0; an empty SOURCE square is where the reference throws
+    S = 7
+    mv_occupied = (0 * S + 3) * 14 + 7 + 1  # (0,3) down to (1,3), occupied by an attacker
+    r = b2az.tafl_replay(0, np.array([[mv_occupied]], np.uint16), np.array([1], np.uint32), 150, lib=lib)
+    assert r["status"][0] == 0 and r["boards"][0, 1, 2].sum() == 7  # one attacker overwritten
