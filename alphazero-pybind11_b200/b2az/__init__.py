@@ -72,7 +72,7 @@ class ForestParams(C.Structure):  # b2az_forest_params (include/b2az.h)
                 ("root_fpu_zero", C.c_uint8), ("relative_values", C.c_uint8), ("gumbel_enabled", C.c_uint8),
                 ("gumbel_full", C.c_uint8), ("gumbel_m", C.c_uint32), ("seed", C.c_uint64), ("gumbel_c_visit", C.c_float),
                 ("gumbel_c_scale", C.c_float), ("shaped_dirichlet", C.c_uint8), ("debug_serial_shuffle", C.c_uint8),
-                ("pad2_", C.c_uint8 * 6)]
+                ("pad2_", C.c_uint8 * 2), ("max_in_flight", C.c_uint32)]
 
 
 _libs = {}
@@ -114,6 +114,11 @@ def load(path=None):
     L.b2az_forest_process_result_host.argtypes = [vp, vp, vp, vp, C.c_int]
     L.b2az_forest_simulate.argtypes = [vp, vp, u32, C.c_int]
     L.b2az_forest_root_noise.argtypes = [vp, vp, C.c_int]
+    L.b2az_forest_find_leaf_batched.argtypes = [vp, vp, C.POINTER(vp)]
+    L.b2az_forest_process_result_batched.argtypes = [vp, vp, u32, vp, vp, C.c_int, C.c_int]
+    L.b2az_forest_simulate_batched.argtypes = [vp, vp, u32, u32]
+    L.b2az_forest_reset_batch.argtypes = [vp, vp]
+    L.b2az_forest_probs.argtypes = [vp, vp, C.c_float, C.c_int, vp, vp]
     L.b2az_forest_advance.argtypes = [vp, vp]
     L.b2az_forest_set_gumbel_num_sims.argtypes = [vp, vp, u32]
     L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
@@ -340,7 +345,7 @@ class Forest:
 
     def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
                  words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0,
-                 gumbel_full=False, shaped_dirichlet=False, serial_shuffle=False, device=0, lib=None):
+                 gumbel_full=False, shaped_dirichlet=False, serial_shuffle=False, max_in_flight=0, device=0, lib=None):
         self.L = lib or load()
         self.game, self.n = game, n_trees
         S, P = TAFL_DIMS[game]
@@ -349,7 +354,9 @@ class Forest:
                          fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
                          root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
                          gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, gumbel_full=int(gumbel_full),
-                         shaped_dirichlet=int(shaped_dirichlet), debug_serial_shuffle=int(serial_shuffle))
+                         shaped_dirichlet=int(shaped_dirichlet), debug_serial_shuffle=int(serial_shuffle),
+                         max_in_flight=max_in_flight)
+        self.slots = max(1, max_in_flight)
         self.h = C.c_void_p()
         self._check(self.L.b2az_forest_create(C.byref(p), device, C.byref(self.h)))
 
@@ -368,9 +375,28 @@ class Forest:
         return ptr.value
 
     def leaf_canon(self, stream=None):
-        out = np.zeros((self.n, self.P, self.S, self.S), np.float32)
+        """Leaf canonical planes: [n_trees][P][S][S], or [max_in_flight][n_trees][P][S][S] for a WU-UCT forest."""
+        out = np.zeros((self.slots, self.n, self.P, self.S, self.S), np.float32)
         self._check(self.L.b2az_forest_leaf_canon_host(self.h, stream, _ptr(out)))
-        return out
+        return out if self.slots > 1 else out[0]
+
+    # -- WU-UCT (find_leaf_batched / process_result_batched / reset_batch)
+    def find_leaf_batched(self, stream=None):
+        ptr = C.c_void_p()
+        self._check(self.L.b2az_forest_find_leaf_batched(self.h, stream, C.byref(ptr)))
+        return ptr.value
+
+    def process_result_batched(self, leaf_index, v, pi, root_noise=False, stream=None):
+        v = np.ascontiguousarray(v, np.float32)
+        pi = np.ascontiguousarray(pi, np.float32)
+        assert v.shape == (self.n, 3) and pi.shape == (self.n, self.A)
+        self._check(self.L.b2az_forest_process_result_batched(self.h, stream, leaf_index, _ptr(v), _ptr(pi), int(root_noise), 1))
+
+    def simulate_batched(self, n_rounds, width, stream=None):
+        self._check(self.L.b2az_forest_simulate_batched(self.h, stream, n_rounds, width))
+
+    def reset_batch(self, stream=None):
+        self._check(self.L.b2az_forest_reset_batch(self.h, stream))
 
     def process_result(self, v, pi, root_noise=False, stream=None):
         v = np.ascontiguousarray(v, np.float32)
@@ -397,6 +423,13 @@ class Forest:
         policy = np.zeros((self.n, self.A), np.float32)
         self._check(self.L.b2az_forest_gumbel_result(self.h, stream, _ptr(action), _ptr(policy)))
         return action, policy
+
+    def probs(self, temp, pick=False, stream=None):
+        """MCTS::probs(temp) per tree; with pick=True also pick_move(probs) (one RNG draw per tree)."""
+        probs = np.zeros((self.n, self.A), np.float32)
+        moves = np.zeros(self.n, np.uint32)
+        self._check(self.L.b2az_forest_probs(self.h, stream, temp, int(pick), _ptr(probs), _ptr(moves)))
+        return (probs, moves) if pick else probs
 
     def advance(self, stream=None):
         self._check(self.L.b2az_forest_advance(self.h, stream))

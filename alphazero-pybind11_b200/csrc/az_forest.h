@@ -37,6 +37,13 @@ namespace b2az {
 constexpr int kFPath = 96;      // longest selection path kept (a tafl game is at most max_turns plies deep)
 constexpr int kFMaxK = 512;     // most legal moves of one position (11x11: 36 pieces x <= 20 targets in theory)
 
+struct ForestLeaf {             // a pending leaf and the path to it (MCTS::path_/current_, or one InFlightLeaf, mcts.h:129-136)
+  u32 path_len;
+  u32 leaf_blk, leaf_k, leaf_term, leaf_player, leaf_new;
+  u32 path_blk[kFPath];         // block that holds the child selected at level i
+  u16 path_slot[kFPath];
+  u8 path_player[kFPath];       // player of the node the selection was made AT (the parent of that child)
+};
 struct ForestTree {             // one per tree, HBM
   TaflState state;              // the root position (GameState of the caller in the reference)
   u32 n;                        // root_.n
@@ -48,12 +55,12 @@ struct ForestTree {             // one per tree, HBM
   u32 half;                     // which half of the slab is in use (the other one receives the next compaction)
   u32 hist_len;                 // repetition history of the root position (keys since the last capture)
   Pcg32 rng;
-  u32 path_len;                 // MCTS::path_ / current_: the pending leaf
-  u32 leaf_blk, leaf_k, leaf_term, leaf_player, leaf_new;
-  u32 error;                    // sticky: 1 slab full, 2 path too long, 4 too many legal moves, 8 unknown move
-  u32 path_blk[kFPath];         // block that holds the child selected at level i
-  u16 path_slot[kFPath];
-  u8 path_player[kFPath];       // player of the node the selection was made AT (the parent of that child)
+  u32 error;                    // sticky: 1 slab full, 2 path too long, 4 too many legal moves, 8 unknown move,
+                                //         16 too many in-flight leaves
+  u32 nif;                      // root_.n_in_flight (WU-UCT)
+  u32 expanded;                 // root_ has had add_children() called (its children may be unstored: terminal root)
+  u32 in_flight;                // MCTS::in_flight_.size()
+  ForestLeaf leaf;              // MCTS::path_ / current_: the pending leaf of find_leaf
 };
 
 constexpr int kFMaxM = 64;       // most Gumbel candidates kept at the root (PlayParams::gumbel_m, default 16)
@@ -81,18 +88,22 @@ struct ForestView {
   u32* pool;           // [n_trees][words_per_tree]
   TaflKey* hist;       // [n_trees][max_turns + 2]
   TaflKey* pkeys;      // [n_trees][kFPath + 2] keys of the positions along the current path
-  float* leaf_canon;   // [n_trees][CANON]
+  float* leaf_canon;   // [max(1, max_in_flight)][n_trees][CANON]
+  ForestLeaf* inflight; // [n_trees][max_in_flight] (WU-UCT), null when max_in_flight == 0
+  u32 max_in_flight;
 };
 
 #ifndef B2AZ_HOST_EMU
-// block field offsets (words) for a block of k children at word b: [b] = k, then seven arrays of k words
+// block field offsets (words) for a block of k children at word b: [b] = k, then eight arrays of k words
 __device__ __forceinline__ u32 fb_n(u32 b, u32 k) { (void)k; return b + 1u; }
 __device__ __forceinline__ u32 fb_q(u32 b, u32 k) { return b + 1u + k; }
 __device__ __forceinline__ u32 fb_pol(u32 b, u32 k) { return b + 1u + 2u * k; }
 __device__ __forceinline__ u32 fb_d(u32 b, u32 k) { return b + 1u + 3u * k; }
 __device__ __forceinline__ u32 fb_v(u32 b, u32 k) { return b + 1u + 4u * k; }
 __device__ __forceinline__ u32 fb_fc(u32 b, u32 k) { return b + 1u + 5u * k; }
-__device__ __forceinline__ u32 fb_mv(u32 b, u32 k) { return b + 1u + 6u * k; }  // move | player << 16 | term << 20
+__device__ __forceinline__ u32 fb_mv(u32 b, u32 k) { return b + 1u + 6u * k; }  // move | player << 16 | term << 20 | expanded << 22
+__device__ __forceinline__ u32 fb_nif(u32 b, u32 k) { return b + 1u + 7u * k; } // Node::n_in_flight (WU-UCT)
+__device__ __forceinline__ u32 fb_words(u32 k) { return 1u + 8u * k; }
 
 template <int GAME>
 struct ForestSmem {   // per warp
@@ -495,8 +506,12 @@ __device__ __noinline__ void fr_add_root_noise(const ForestView& F, u32 t, Pcg32
 }
 
 // MCTS::find_leaf (mcts.cc:462-498) for tree t
-template <int GAME>
-__device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon) {
+// BATCHED = MCTS::find_leaf_batched (mcts.cc:752-789, WU-UCT): the descent may pass nodes that a previous in-flight
+// call expanded but that have no visit yet, every node on the path (and the leaf) gets ++n_in_flight AFTER the
+// selection made at it, and the leaf goes to the tree's in-flight list instead of current_/path_.
+template <int GAME, bool BATCHED>
+__device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon,
+                                 ForestLeaf& Lf, float* canon_out) {
   typedef Tafl<GAME> T;
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
@@ -507,6 +522,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   u32 err = 0;
   // current_ = &root_
   u32 cur_n = R.n, cur_term = R.term, cur_blk = R.blk, cur_k = R.k, cur_player = R.player;
+  u32 cur_nif = R.nif, cur_expanded = R.expanded;
   float cur_v = R.v;
   u32 par_blk = 0, par_slot = 0, par_k = 0;  // where the current node's own fields live (0 = it is the root)
   u32 plen = 0;
@@ -519,7 +535,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     __syncwarp();
     gumbel_on = G.initialized != 0;
   }
-  while (cur_n > 0 && cur_term == 0) {
+  while ((BATCHED ? ((cur_n > 0 || cur_nif > 0) && cur_blk != 0) : (cur_n > 0)) && cur_term == 0) {
     if (plen >= (u32)kFPath || cur_blk == 0) { err |= 2u; break; }
     const u32 b = cur_blk, k = cur_k;
     u32 best_j = 0xFFFFFFFFu;
@@ -538,14 +554,15 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     }
     const float fpu = (at_root && F.root_fpu_zero) ? 0.0f : F.fpu_reduction;
     const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
-    const float sqrt_n = fsqrt((float)cur_n);
+    const float sqrt_n = fsqrt((float)(cur_n + (BATCHED ? cur_nif : 0u)));  // sqrt(n + n_in_flight) (mcts.cc:138)
     float best_u = 0.0f;
     for (u32 c0 = 0; c0 < k; c0 += 32u) {
       const u32 j = c0 + lane;
       if (j < k) {
         const u32 nj = pool[fb_n(b, k) + j];
+        const u32 fj = BATCHED ? pool[fb_nif(b, k) + j] : 0u;  // Node::uct: n + n_in_flight + 1 (mcts.cc:125-127)
         const float qj = u2f(pool[fb_q(b, k) + j]), pj = u2f(pool[fb_pol(b, k) + j]);
-        const float u = fadd(nj == 0 ? fpu_value : qj, fdiv(fmul(fmul(F.cpuct, pj), sqrt_n), (float)(nj + 1u)));
+        const float u = fadd(nj == 0 ? fpu_value : qj, fdiv(fmul(fmul(F.cpuct, pj), sqrt_n), (float)(nj + fj + 1u)));
         if (best_j == 0xFFFFFFFFu || u > best_u) { best_u = u; best_j = j; }  // per lane: ascending j, strict >
       }
     }
@@ -563,9 +580,13 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     // a strictly greater score; with finite scores both orders agree.
     const u32 mvw = pool[fb_mv(b, k) + best_j];
     if (lane == 0) {
-      R.path_blk[plen] = b;
-      R.path_slot[plen] = (u16)best_j;
-      R.path_player[plen] = (u8)cur_player;
+      Lf.path_blk[plen] = b;
+      Lf.path_slot[plen] = (u16)best_j;
+      Lf.path_player[plen] = (u8)cur_player;
+      if (BATCHED) {  // ++cur->n_in_flight, after the selection made at cur
+        if (at_root) R.nif = cur_nif + 1u;
+        else pool[fb_nif(par_blk, par_k) + par_slot] = cur_nif + 1u;
+      }
     }
     ++plen;
     if (!forest_play<GAME>(s, mvw & 0xFFFFu, hist, base_len, pkeys, pk_len, lane)) { err |= 8u; break; }
@@ -576,10 +597,17 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     cur_k = cur_blk ? pool[cur_blk] : 0u;
     cur_player = (mvw >> 16) & 3u;
     cur_term = (mvw >> 20) & 3u;
+    cur_expanded = (mvw >> 22) & 1u;
+    cur_nif = BATCHED ? pool[fb_nif(b, k) + best_j] : 0u;
     at_root = false;
   }
+  if (BATCHED && lane == 0 && !err) {  // ++cur->n_in_flight on the leaf itself
+    if (plen == 0) R.nif = cur_nif + 1u;
+    else pool[fb_nif(par_blk, par_k) + par_slot] = cur_nif + 1u;
+  }
   u32 leaf_new = 0, leaf_blk = cur_blk, leaf_k = cur_k, leaf_term = cur_term, leaf_player = cur_player;
-  if (cur_n == 0 && !err) {
+  // (batched: only if a prior in-flight call has not expanded it already, mcts.cc:776-783)
+  if (cur_n == 0 && !err && !(BATCHED && cur_expanded)) {
     // current_->player, scores, add_children(valid_moves) incl. the shuffle (mcts.cc:490-496)
     leaf_new = 1;
     leaf_player = s.player;
@@ -591,7 +619,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     leaf_k = leaf_term ? 0u : k;
     leaf_blk = 0;
     if (leaf_k) {
-      const u32 need = 1u + 7u * leaf_k;
+      const u32 need = fb_words(leaf_k);
       const u32 b = R.bump;
       if (b + need > (R.half ? F.words_per_tree : F.words_per_tree / 2u)) {
         err |= 1u;
@@ -600,6 +628,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
         leaf_blk = b;
         if (lane == 0) pool[b] = leaf_k;
         for (u32 i = lane; i < 6u * leaf_k; i += 32u) pool[b + 1u + i] = 0u;      // n q policy d v first_child
+        for (u32 j = lane; j < leaf_k; j += 32u) pool[fb_nif(b, leaf_k) + j] = 0u;
         for (u32 j = lane; j < leaf_k; j += 32u) pool[fb_mv(b, leaf_k) + j] = sm.moves[j];
         if (lane == 0) R.bump = b + need;
       }
@@ -607,15 +636,15 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     if (lane == 0) {
       R.rng = rng;
       if (par_blk == 0 && plen == 0) {
-        R.player = leaf_player; R.term = leaf_term; R.blk = leaf_blk; R.k = leaf_k;
+        R.player = leaf_player; R.term = leaf_term; R.blk = leaf_blk; R.k = leaf_k; R.expanded = 1;
       } else {
         pool[fb_fc(par_blk, par_k) + par_slot] = leaf_blk;
-        pool[fb_mv(par_blk, par_k) + par_slot] |= (leaf_player << 16) | (leaf_term << 20);
+        pool[fb_mv(par_blk, par_k) + par_slot] |= (leaf_player << 16) | (leaf_term << 20) | (1u << 22);
       }
     }
   }
   if (emit_canon) {
-    float* out = F.leaf_canon + (size_t)t * T::CANON;
+    float* out = canon_out;
     constexpr int CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
 #pragma unroll
     for (int j = 0; j < CHUNKS; ++j) {
@@ -638,22 +667,23 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   }
   if (lane == 0) {
     R.total_leaf_depth += plen;
-    R.path_len = plen;
-    R.leaf_blk = leaf_blk; R.leaf_k = leaf_k; R.leaf_term = leaf_term; R.leaf_player = leaf_player; R.leaf_new = leaf_new;
+    Lf.path_len = plen;
+    Lf.leaf_blk = leaf_blk; Lf.leaf_k = leaf_k; Lf.leaf_term = leaf_term; Lf.leaf_player = leaf_player; Lf.leaf_new = leaf_new;
     if (err) R.error |= err;
   }
   __syncwarp();
 }
 
 // MCTS::process_result (mcts.cc:500-555) for tree t. RANDOM = dumb_eval (game_state.h:160-173) instead of (v, pi).
-template <int GAME, bool RANDOM>
+// BATCHED = MCTS::process_result_batched (mcts.cc:791-845): the same with --n_in_flight along the path.
+template <int GAME, bool RANDOM, bool BATCHED>
 __device__ void forest_process_result(const ForestView& F, u32 t, const float* ev_v, const float* ev_pi, u32 lane,
-                                      bool root_noise_enabled) {
+                                      bool root_noise_enabled, ForestLeaf& Lf) {
   typedef Tafl<GAME> T;
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
   float val0, val1, vald;
-  const u32 lterm = R.leaf_term, lk = R.leaf_k, lblk = R.leaf_blk, lplayer = R.leaf_player, plen = R.path_len;
+  const u32 lterm = Lf.leaf_term, lk = Lf.leaf_k, lblk = Lf.leaf_blk, lplayer = Lf.leaf_player, plen = Lf.path_len;
   if (lterm != 0) {
     val0 = lterm == 1 ? 1.0f : 0.0f; val1 = lterm == 2 ? 1.0f : 0.0f; vald = lterm == 3 ? 1.0f : 0.0f;
   } else {
@@ -715,8 +745,16 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
   __syncwarp();
   if (lane == 0) {
     const float dshare = fdiv(vald, 2.0f);
+    if (BATCHED) {  // --current_->n_in_flight on the leaf, --parent->n_in_flight on every node of the path
+      if (plen == 0) --R.nif;
+      else { const u32 b = Lf.path_blk[plen - 1u], k = pool[b]; --pool[fb_nif(b, k) + Lf.path_slot[plen - 1u]]; }
+      for (u32 i = 0; i < plen; ++i) {
+        if (i == 0) --R.nif;
+        else { const u32 b = Lf.path_blk[i - 1u], k = pool[b]; --pool[fb_nif(b, k) + Lf.path_slot[i - 1u]]; }
+      }
+    }
     for (u32 i = plen; i-- > 0;) {
-      const u32 b = R.path_blk[i], sl = R.path_slot[i], pp = R.path_player[i], k = pool[b];
+      const u32 b = Lf.path_blk[i], sl = Lf.path_slot[i], pp = Lf.path_player[i], k = pool[b];
       const float v = fadd(pp == 0 ? val0 : val1, dshare);
       const u32 n0 = pool[fb_n(b, k) + sl];
       const float q0 = u2f(pool[fb_q(b, k) + sl]), d0 = u2f(pool[fb_d(b, k) + sl]);
@@ -731,7 +769,7 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
     }
     ++R.depth;
     ++R.n;
-    R.path_len = 0;
+    Lf.path_len = 0;
   }
   __syncwarp();
 }
@@ -758,7 +796,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     for (u32 j = lane; j < k; j += 32u) found |= sm.moves[j] == move;
     found = __any_sync(0xFFFFFFFFu, found);
     if (!found) err |= 8u;
-    if (lane == 0) { R.n = 0; R.v = 0.0f; R.d = 0.0f; R.blk = 0; R.k = 0; R.player = 0; R.term = 0; }
+    if (lane == 0) { R.n = 0; R.v = 0.0f; R.d = 0.0f; R.blk = 0; R.k = 0; R.player = 0; R.term = 0; R.nif = 0; R.expanded = 0; }
   } else {
     u32 slot = 0xFFFFFFFFu;
     for (u32 j = lane; j < k; j += 32u)
@@ -780,6 +818,8 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
       R.k = nb ? pool[nb] : 0u;
       R.player = (mvw >> 16) & 3u;
       R.term = (mvw >> 20) & 3u;
+      R.expanded = (mvw >> 22) & 1u;
+      R.nif = pool[fb_nif(blk, k) + slot];
     }
   }
   (void)root_term;
@@ -794,7 +834,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     const u32 old_root = R.blk;
     u32 new_root = 0;
     if (old_root) {
-      const u32 rk = pool[old_root], rw = 1u + 7u * rk;
+      const u32 rk = pool[old_root], rw = fb_words(rk);
       if (to + rw > to_end) {
         err |= 1u;
       } else {
@@ -812,7 +852,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
               const int src_lane = __ffs((int)live) - 1;
               live &= live - 1u;
               const u32 src = __shfl_sync(0xFFFFFFFFu, fcj, src_lane);
-              const u32 ck = pool[src], cw = 1u + 7u * ck;
+              const u32 ck = pool[src], cw = fb_words(ck);
               if (to + cw > to_end) { err |= 1u; break; }
               for (u32 i = lane; i < cw; i += 32u) pool[to + i] = pool[src + i];
               if (lane == 0) pool[fb_fc(scan, sk) + c0 + (u32)src_lane] = to;
@@ -820,7 +860,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
             }
           }
           __syncwarp();
-          scan += 1u + 7u * sk;
+          scan += fb_words(sk);
         }
       }
     }
@@ -858,7 +898,8 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     if (!err) { R.state = s; R.hist_len = hist_len; }
     R.depth = 0;
     R.total_leaf_depth = 0;
-    R.path_len = 0;
+    R.leaf.path_len = 0;
+    R.in_flight = 0;
     if (err) R.error |= err;
   }
   __syncwarp();
@@ -869,14 +910,15 @@ template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_find_leaf(ForestView F) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) forest_find_leaf<GAME>(F, t, sm[wib], lane, true);
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
+    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, F.leaf_canon + (size_t)t * Tafl<GAME>::CANON);
 }
 template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, const float* ev_v, const float* ev_pi,
                                                                u32 root_noise_enabled) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
-    forest_process_result<GAME, false>(F, t, ev_v, ev_pi, lane, root_noise_enabled != 0);
+    forest_process_result<GAME, false, false>(F, t, ev_v, ev_pi, lane, root_noise_enabled != 0, F.trees[t].leaf);
 }
 // PlayManager's step after a move under tree reuse (play_manager.cc:546-553): the reused root gets the root
 // temperature again and fresh noise — MCTS::apply_root_policy_temp() then add_root_noise() for trees with root_n > 0
@@ -906,9 +948,54 @@ __global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_forest_simulate(Fores
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
     for (u32 i = 0; i < n_sims; ++i) {
-      forest_find_leaf<GAME>(F, t, sm[wib], lane, false);
-      forest_process_result<GAME, true>(F, t, nullptr, nullptr, lane, root_noise_enabled != 0);
+      forest_find_leaf<GAME, false>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr);
+      forest_process_result<GAME, true, false>(F, t, nullptr, nullptr, lane, root_noise_enabled != 0, F.trees[t].leaf);
     }
+}
+// ---- WU-UCT: MCTS::find_leaf_batched / process_result_batched / reset_batch (mcts.cc:752-851)
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_find_leaf_batched(ForestView F) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    ForestTree& R = F.trees[t];
+    const u32 li = R.in_flight;
+    if (li >= F.max_in_flight) {
+      if (lane == 0) R.error |= 16u;
+      continue;
+    }
+    forest_find_leaf<GAME, true>(F, t, sm[wib], lane, true, F.inflight[(size_t)t * F.max_in_flight + li],
+                                 F.leaf_canon + ((size_t)li * F.n_trees + t) * Tafl<GAME>::CANON);
+    if (lane == 0) R.in_flight = li + 1u;
+    __syncwarp();
+  }
+}
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_process_result_batched(ForestView F, u32 leaf_index, const float* ev_v,
+                                                                       const float* ev_pi, u32 root_noise_enabled) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    if (leaf_index >= F.trees[t].in_flight) continue;  // in_flight_.at(leaf_index) throws in the reference
+    forest_process_result<GAME, false, true>(F, t, ev_v, ev_pi, lane, root_noise_enabled != 0,
+                                             F.inflight[(size_t)t * F.max_in_flight + leaf_index]);
+  }
+}
+// n_rounds x (width x find_leaf_batched, then width x process_result_batched with dumb_eval, then reset_batch) fused
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_simulate_batched(ForestView F, u32 n_rounds, u32 width) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    ForestLeaf* fl = F.inflight + (size_t)t * F.max_in_flight;
+    for (u32 r = 0; r < n_rounds; ++r) {
+      for (u32 i = 0; i < width; ++i) forest_find_leaf<GAME, true>(F, t, sm[wib], lane, false, fl[i], nullptr);
+      for (u32 i = 0; i < width; ++i) forest_process_result<GAME, true, true>(F, t, nullptr, nullptr, lane, false, fl[i]);
+    }
+    if (lane == 0) F.trees[t].in_flight = 0;
+  }
+}
+__global__ void k_forest_reset_batch(ForestView F) {
+  for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) F.trees[t].in_flight = 0;
 }
 template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_update_root(ForestView F, const u32* moves) {
@@ -939,6 +1026,77 @@ __global__ void __launch_bounds__(128) k_forest_advance(ForestView F) {
       if (om != 0xFFFFFFFFu && (best_mv == 0xFFFFFFFFu || on > best_n || (on == best_n && om < best_mv))) { best_n = on; best_mv = om; }
     }
     if (best_mv != 0xFFFFFFFFu) forest_update_root<GAME>(F, t, best_mv, sm[wib], lane);
+  }
+}
+// MCTS::probs(temp) (mcts.cc:575-618) into out[A] and, with `pick`, MCTS::pick_move(probs) (mcts.cc:717-735: one
+// uniform draw, first move whose running sum exceeds it). The reference works on dense num_moves-long vectors and
+// sums them in MOVE order: the counts (or priors) are scattered into the dense row by all lanes, the sums, pow() and
+// the cumulative pick run on lane 0 over the A entries (once per move: not a hot path).
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick) {
+  typedef Tafl<GAME> T;
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+    ForestTree& R = F.trees[t];
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    float* out = probs + (size_t)t * T::A;
+    const u32 b = R.blk, k = b ? R.k : 0u;
+    for (u32 m = lane; m < (u32)T::A; m += 32u) out[m] = 0.0f;
+    __syncwarp();
+    u32 total = 0;
+    for (u32 j = lane; j < k; j += 32u) total += pool[fb_n(b, k) + j];
+    total = warp_sum(total);  // counts.cast<float>().sum() == 0 <=> no child has a visit
+    for (u32 j = lane; j < k; j += 32u) {
+      const u32 mv = pool[fb_mv(b, k) + j] & 0xFFFFu;
+      out[mv] = total == 0 ? u2f(pool[fb_pol(b, k) + j]) : (float)pool[fb_n(b, k) + j];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (total == 0) {  // the prior policy (raw-policy mode), tempered
+        if (temp != 0.0f) {
+          const float e = fdiv(1.0f, temp);
+          for (u32 m = 0; m < (u32)T::A; ++m) out[m] = az_powf(out[m], e);
+        }
+        float sum = 0.0f;
+        for (u32 m = 0; m < (u32)T::A; ++m) sum = fadd(sum, out[m]);
+        for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum);
+      } else if (temp == 0.0f) {  // uniform over the most visited moves
+        float best = out[0];
+        u32 ties = 1;
+        for (u32 m = 1; m < (u32)T::A; ++m) {
+          if (out[m] > best) { best = out[m]; ties = 1; }
+          else if (out[m] == best) ++ties;
+        }
+        const float share = (float)(1.0 / (double)ties);
+        for (u32 m = 0; m < (u32)T::A; ++m) out[m] = out[m] == best ? share : 0.0f;
+      } else {
+        float sum = 0.0f;
+        for (u32 m = 0; m < (u32)T::A; ++m) sum = fadd(sum, out[m]);
+        const float e = fdiv(1.0f, temp);  // `1 / temp`: int / float
+        float sum2 = 0.0f;
+        for (u32 m = 0; m < (u32)T::A; ++m) {
+          out[m] = az_powf(fdiv(out[m], sum), e);
+          sum2 = fadd(sum2, out[m]);
+        }
+        for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum2);
+      }
+      if (pick) {
+        Pcg32 rng = R.rng;
+        const float choice = rng_uniform01(rng);
+        R.rng = rng;
+        u32 mvp = 0xFFFFFFFFu;
+        float sum = 0.0f;
+        for (u32 m = 0; m < (u32)T::A; ++m) {
+          sum = fadd(sum, out[m]);
+          if (sum > choice) { mvp = m; break; }
+        }
+        if (mvp == 0xFFFFFFFFu)
+          for (int m = T::A - 1; m >= 0; --m)
+            if (out[m] > 0.0f) { mvp = (u32)m; break; }
+        picked[t] = mvp;
+      }
+    }
+    __syncwarp();
   }
 }
 // MCTS::counts / root_q_values (mcts.cc:557-573) + a few scalars per tree
@@ -1061,7 +1219,11 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (int rc = dev_alloc_raw(&V.pool, (size_t)V.n_trees * V.words_per_tree)) return bail(rc);
   if (int rc = dev_alloc(&V.hist, (size_t)V.n_trees * (V.max_turns + 2u))) return bail(rc);
   if (int rc = dev_alloc(&V.pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
-  if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon)) return bail(rc);
+  V.max_in_flight = p->max_in_flight;
+  if (V.max_in_flight > 64u) return bail(fail(B2AZ_EINVAL, "b2az_forest: max_in_flight must be <= 64"));
+  if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon * std::max(1u, V.max_in_flight))) return bail(rc);
+  if (V.max_in_flight)
+    if (int rc = dev_alloc(&V.inflight, (size_t)V.n_trees * V.max_in_flight)) return bail(rc);
   if (int rc = dev_alloc(&f->moves_dev, (size_t)V.n_trees)) return bail(rc);
   V.epsilon = p->epsilon; V.root_policy_temp = p->root_policy_temp; V.shaped_dirichlet = p->shaped_dirichlet ? 1u : 0u;
   V.serial_shuffle = p->debug_serial_shuffle ? 1u : 0u;
@@ -1086,7 +1248,7 @@ int b2az_forest_destroy(b2az_forest* f) {
   if (!f) return 0;
   dev_free(f->view.trees); dev_free(f->view.pool); dev_free(f->view.hist); dev_free(f->view.pkeys);
   dev_free(f->view.leaf_canon); dev_free(f->moves_dev); dev_free(f->ev_v); dev_free(f->ev_pi);
-  dev_free(f->view.gum); dev_free(f->view.gum_g); dev_free(f->view.noise);
+  dev_free(f->view.gum); dev_free(f->view.gum_g); dev_free(f->view.noise); dev_free(f->view.inflight);
   delete f;
   return 0;
 }
@@ -1099,6 +1261,11 @@ int b2az_forest_process_result(b2az_forest*, void*, const float*, const float*, 
 int b2az_forest_process_result_host(b2az_forest*, void*, const float*, const float*, int) FOREST_NO_CUDA()
 int b2az_forest_simulate(b2az_forest*, void*, uint32_t, int) FOREST_NO_CUDA()
 int b2az_forest_root_noise(b2az_forest*, void*, int) FOREST_NO_CUDA()
+int b2az_forest_find_leaf_batched(b2az_forest*, void*, const float**) FOREST_NO_CUDA()
+int b2az_forest_process_result_batched(b2az_forest*, void*, uint32_t, const float*, const float*, int, int) FOREST_NO_CUDA()
+int b2az_forest_simulate_batched(b2az_forest*, void*, uint32_t, uint32_t) FOREST_NO_CUDA()
+int b2az_forest_reset_batch(b2az_forest*, void*) FOREST_NO_CUDA()
+int b2az_forest_probs(b2az_forest*, void*, float, int, float*, uint32_t*) FOREST_NO_CUDA()
 int b2az_forest_advance(b2az_forest*, void*) FOREST_NO_CUDA()
 int b2az_forest_set_gumbel_num_sims(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
 int b2az_forest_gumbel_result(b2az_forest*, void*, uint32_t*, float*) FOREST_NO_CUDA()
@@ -1118,7 +1285,9 @@ int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host)
   using namespace b2az;
   if (!f || !canon_host) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = copy_d2h(canon_host, f->view.leaf_canon, (size_t)f->view.n_trees * f->canon * 4, s)) return rc;
+  // every in-flight slot's rows (one slot for the plain find_leaf)
+  const size_t slots = std::max(1u, f->view.max_in_flight);
+  if (int rc = copy_d2h(canon_host, f->view.leaf_canon, slots * f->view.n_trees * f->canon * 4, s)) return rc;
   return stream_sync(s);
 }
 int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev,
@@ -1144,6 +1313,73 @@ int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v
   if (int rc = copy_h2d(f->ev_pi, pi_host, n * f->actions * 4, s)) return rc;
   if (int rc = b2az_forest_process_result(f, stream, f->ev_v, f->ev_pi, root_noise_enabled)) return rc;
   return stream_sync(s);
+}
+int b2az_forest_find_leaf_batched(b2az_forest* f, void* stream, const float** canon_dev) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (!f->view.max_in_flight) return fail(B2AZ_ESTATE, "b2az_forest: created with max_in_flight == 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_find_leaf_batched<G_><<<forest_ctas(f), 128, 0, s>>>(f->view)));
+  CUDA_TRY(cudaGetLastError());
+  if (canon_dev) *canon_dev = f->view.leaf_canon;
+  return 0;
+}
+int b2az_forest_process_result_batched(b2az_forest* f, void* stream, uint32_t leaf_index, const float* v, const float* pi,
+                                       int root_noise_enabled, int host_pointers) {
+  using namespace b2az;
+  if (!f || !v || !pi) return fail(B2AZ_EINVAL, "null argument");
+  if (leaf_index >= f->view.max_in_flight) return fail(B2AZ_EINVAL, "b2az_forest: leaf_index out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees;
+  if (host_pointers) {
+    if (!f->ev_v) {
+      if (int rc = dev_alloc(&f->ev_v, n * 3)) return rc;
+      if (int rc = dev_alloc(&f->ev_pi, n * f->actions)) return rc;
+    }
+    if (int rc = copy_h2d(f->ev_v, v, n * 3 * 4, s)) return rc;
+    if (int rc = copy_h2d(f->ev_pi, pi, n * f->actions * 4, s)) return rc;
+    v = f->ev_v; pi = f->ev_pi;
+  }
+  FOREST_DISPATCH(f, (k_forest_process_result_batched<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, leaf_index, v, pi,
+                                                                                        root_noise_enabled ? 1u : 0u)));
+  CUDA_TRY(cudaGetLastError());
+  return host_pointers ? stream_sync(s) : 0;
+}
+int b2az_forest_simulate_batched(b2az_forest* f, void* stream, uint32_t n_rounds, uint32_t width) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (width == 0 || width > f->view.max_in_flight) return fail(B2AZ_EINVAL, "b2az_forest: width must be in [1, max_in_flight]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOREST_DISPATCH(f, (k_forest_simulate_batched<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, n_rounds, width)));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_reset_batch(b2az_forest* f, void* stream) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  k_forest_reset_batch<<<148, 128, 0, static_cast<cudaStream_t>(stream)>>>(f->view);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pick_move, float* probs_host, uint32_t* moves_host) {
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (pick_move && !moves_host) return fail(B2AZ_EINVAL, "b2az_forest_probs: pick_move needs moves_host");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees, A = f->actions;
+  float* dp = nullptr;
+  u32* dm = nullptr;
+  int rc = dev_alloc(&dp, n * A);
+  if (!rc) rc = dev_alloc(&dm, n);
+  if (!rc) {
+    FOREST_DISPATCH(f, (k_forest_probs<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, temp, dp, dm, pick_move ? 1u : 0u)));
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_probs launch failed");
+  }
+  if (!rc && probs_host) rc = copy_d2h(probs_host, dp, n * A * 4, s);
+  if (!rc && pick_move) rc = copy_d2h(moves_host, dm, n * 4, s);
+  if (!rc) rc = stream_sync(s);
+  dev_free(dp); dev_free(dm);
+  return rc;
 }
 int b2az_forest_root_noise(b2az_forest* f, void* stream, int add_noise) {
   using namespace b2az;

@@ -248,14 +248,16 @@ typedef struct b2az_forest_params {
   float gumbel_c_visit, gumbel_c_scale;  /* 50, 1 */
   uint8_t shaped_dirichlet;
   uint8_t debug_serial_shuffle;  /* diagnostics: std::shuffle draws one after the other on one lane (same results) */
-  uint8_t pad_[6];
+  uint8_t pad_[2];
+  uint32_t max_in_flight;        /* WU-UCT: most pending leaves per tree (find_leaf_batched); 0 = batched calls off */
 } b2az_forest_params;
 typedef struct b2az_forest b2az_forest;
 int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out);
 int b2az_forest_destroy(b2az_forest* f);
 /* MCTS::find_leaf(gs) (mcts.cc:462-498) for every tree: PUCT descent from the tree's root position, expansion of
  * the new node (terminal test, legal moves, std::shuffle). *canon_dev = DEVICE pointer to the leaves' canonical
- * planes float32[n_trees][P][S][S] (the evaluator's input); b2az_forest_leaf_canon_host copies them out. */
+ * planes float32[n_trees][P][S][S] (the evaluator's input); b2az_forest_leaf_canon_host copies them out (all
+ * max(1, max_in_flight) slots: float32[slots][n_trees][P][S][S]). */
 int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev);
 int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host);
 /* MCTS::process_result(gs, value, pi, root_noise_enabled) (mcts.cc:500-555): v float32[n_trees][3],
@@ -269,6 +271,17 @@ int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims, int root
 /* MCTS::apply_root_policy_temp() then (add_noise != 0 and epsilon > 0) MCTS::add_root_noise() on every tree whose
  * root has been visited: what PlayManager does to the reused root after a move (play_manager.cc:546-553). */
 int b2az_forest_root_noise(b2az_forest* f, void* stream, int add_noise);
+/* WU-UCT (mcts.cc:752-851): find_leaf_batched appends one pending leaf per tree (virtual loss: ++n_in_flight along
+ * the path; at most max_in_flight of them); *canon_dev = DEVICE pointer to float32[max_in_flight][n_trees][P][S][S],
+ * slot i = the i-th call since the last reset. process_result_batched(leaf_index, ...) answers slot leaf_index of
+ * every tree (v float32[n_trees][3], pi float32[n_trees][A]; host_pointers selects host or device buffers);
+ * reset_batch forgets the list (in_flight_.clear()). simulate_batched fuses n_rounds x (width find_leaf_batched,
+ * width process_result_batched with dumb_eval, reset_batch) into one launch. */
+int b2az_forest_find_leaf_batched(b2az_forest* f, void* stream, const float** canon_dev);
+int b2az_forest_process_result_batched(b2az_forest* f, void* stream, uint32_t leaf_index, const float* v, const float* pi,
+                                       int root_noise_enabled, int host_pointers);
+int b2az_forest_simulate_batched(b2az_forest* f, void* stream, uint32_t n_rounds, uint32_t width);
+int b2az_forest_reset_batch(b2az_forest* f, void* stream);
 /* MCTS::set_gumbel_num_sims(n) (mcts.cc:175-178) on every tree — call before each move's search, like
  * PlayManager does (play_manager.cc:531-539); n == 0 = PUCT for that search. */
 int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n);
@@ -276,6 +289,11 @@ int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n);
  * falls back to pick_move(probs(0))) and MCTS::gumbel_improved_policy() (float32[n_trees][A]) (mcts.cc:336-401).
  * Host pointers, either may be NULL. */
 int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_host, float* policy_host);
+/* MCTS::probs(temp) (mcts.cc:575-618: visit-count policy with temperature; temp == 0 = uniform over the most
+ * visited moves; the tempered priors when nothing has a visit) into probs_host float32[n_trees][A] (may be NULL),
+ * and with pick_move != 0 MCTS::pick_move(probs) (mcts.cc:717-735, exactly one draw from the tree's generator) into
+ * moves_host uint32[n_trees] — PlayManager's acting rule (play_manager.cc:372-381). */
+int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pick_move, float* probs_host, uint32_t* moves_host);
 /* Greedy self-play step on the device: every tree whose root is expanded and not terminal plays its most visited
  * move (argmax of MCTS::counts(), lowest move id on ties) through update_root + play_move. No host round trip. */
 int b2az_forest_advance(b2az_forest* f, void* stream);

@@ -208,7 +208,8 @@ typedef void (*azref_eval_fn)(const float* canonical, float* v3, float* pi, void
 int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, float fpu_reduction, int root_fpu_zero,
                       uint32_t n_moves, uint32_t sims, int eval_kind, azref_eval_fn cb, void* user, uint32_t* counts_out,
                       float* q_out, uint32_t* moves_out, uint32_t* depth_sum_out, uint32_t gumbel_m, float gumbel_c_visit,
-                      float gumbel_c_scale, float* policy_out, float epsilon, float root_policy_temp, int shaped_dirichlet) {
+                      float gumbel_c_scale, float* policy_out, float epsilon, float root_policy_temp, int shaped_dirichlet,
+                      uint32_t batch_width, float act_temp, float* probs_out) {
   try {
     auto gs = make_game(game, max_turns);
     if (!gs) { g_err = "unknown game"; return -1; }
@@ -222,7 +223,27 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
     for (uint32_t m = 0; m < n_moves; ++m) {
       if (gs->scores().has_value()) break;
       if (gumbel_m > 0) mcts.set_gumbel_num_sims(sims);
-      for (uint32_t i = 0; i < sims; ++i) {
+      // batch_width > 0: WU-UCT — rounds of `batch_width` find_leaf_batched calls, then their process_result_batched
+      // in the same order, then reset_batch (how play.py / mcts_analysis.py drive a tree with a batched net)
+      for (uint32_t r = 0; batch_width > 0 && r < sims / batch_width; ++r) {
+        std::vector<Vector<float>> vs, pis;
+        for (uint32_t i = 0; i < batch_width; ++i) {
+          auto leaf = mcts.find_leaf_batched(*gs);
+          Vector<float> v{3}, pi{A};
+          if (eval_kind == 1) {
+            auto [vv, pp] = dumb_eval(*leaf);
+            v = vv; pi = pp;
+          } else {
+            auto c = leaf->canonicalized();
+            cb(c.data(), v.data(), pi.data(), user);
+          }
+          vs.push_back(v);
+          pis.push_back(pi);
+        }
+        for (uint32_t i = 0; i < batch_width; ++i) mcts.process_result_batched(*gs, i, vs[i], pis[i], epsilon > 0.0f);
+        mcts.reset_batch();
+      }
+      for (uint32_t i = 0; batch_width == 0 && i < sims; ++i) {
         auto leaf = mcts.find_leaf(*gs);
         Vector<float> v{3}, pi{A};
         if (eval_kind == 1) {
@@ -246,6 +267,10 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
           std::memcpy(policy_out + (size_t)m * A, ip.data(), A * 4);
         }
         best = mcts.gumbel_final_action();
+      } else if (act_temp >= 0.0f) {  // PlayManager's PUCT acting rule: pick_move(probs(temp)) (play_manager.cc:372-381)
+        auto pr = mcts.probs(act_temp);
+        if (probs_out) std::memcpy(probs_out + (size_t)m * A, pr.data(), A * 4);
+        best = MCTS::pick_move(pr);
       } else {
         for (uint32_t a = 1; a < A; ++a)
           if (counts(a) > counts(best)) best = a;

@@ -36,23 +36,34 @@ def pseudo_net(canon):
 
 
 def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, moves_ref=None, slab_moves=None, gumbel=None,
-               noise=None):
+               noise=None, width=0):
     """Drives the forest like the reference run; plays `moves_ref[i][m]` when given (else the most visited move)."""
-    # each half of the slab must hold the kept subtree + one move's search (1 + 7k words per expanded node);
+    # each half of the slab must hold the kept subtree + one move's search (1 + 8k words per expanded node);
     # slab_moves = how many moves' worth of nodes one half can hold (re-rooting compacts into the other half)
-    words = 2 * (1 + (slab_moves or n_moves + 1) * sims * (1 + 7 * (64 if game == 0 else 200)))
+    words = 2 * (1 + (slab_moves or n_moves + 1) * sims * (1 + 8 * (64 if game == 0 else 200)))
     gkw = dict(gumbel_m=gumbel[0], gumbel_c_visit=gumbel[1], gumbel_c_scale=gumbel[2]) if gumbel else {}
     if noise:  # (epsilon, root_policy_temp, shaped_dirichlet)
         gkw.update(epsilon=noise[0], root_policy_temp=noise[1], shaped_dirichlet=noise[2])
     rn = bool(noise and noise[0] > 0)
     f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=cpuct, fpu_reduction=fpu, root_fpu_zero=rfz, seed=seed,
-                    words_per_tree=words, **gkw)
+                    words_per_tree=words, max_in_flight=width, **gkw)
     out = []
     alive = np.ones(trees, bool)
     for m in range(n_moves):
         if gumbel:
             f.set_gumbel_num_sims(sims)
-        if evaluator is None:
+        if width and evaluator is None:
+            f.simulate_batched(sims // width, width)
+        elif width:  # WU-UCT with the host evaluator: `width` pending leaves per tree and round
+            for _ in range(sims // width):
+                for _i in range(width):
+                    f.find_leaf_batched()
+                canon = f.leaf_canon()
+                for li in range(width):
+                    ev = [evaluator(canon[li, i]) for i in range(trees)]
+                    f.process_result_batched(li, np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]))
+                f.reset_batch()
+        elif evaluator is None:
             f.simulate(sims, root_noise=rn)
         else:
             for _ in range(sims):
@@ -185,6 +196,52 @@ def test_parallel_shuffle_draws_equal_sequential(game):
         f.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
     assert (outs[0][2]["error"] == 0).all() and outs[0][0].sum() > 0
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,trees,n_moves,sims,width,evaluator", [
+    (0, 6, 10, 64, 8, None), (0, 4, 6, 48, 4, pseudo_net), (1, 2, 4, 64, 16, None), (2, 2, 4, 60, 6, None)])
+def test_forest_wu_uct_batched_vs_reference(game, trees, n_moves, sims, width, evaluator):
+    """find_leaf_batched / process_result_batched / reset_batch (virtual loss through n_in_flight, mcts.cc:752-851):
+    rounds of `width` pending leaves per tree, answered in order."""
+    refs = [tafl_ref.search(game, 808 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, evaluator, batch_width=width)
+            for i in range(trees)]
+    got = run_forest(game, trees, n_moves, sims, 808, 1.25, 0.25, False, evaluator, moves_ref=[r[2] for r in refs], width=width)
+    for i, (rc, rq, rm, rd) in enumerate(refs):
+        for m in range(len(rm)):
+            counts, q, info = got[m][:3]
+            assert np.array_equal(counts[i], rc[m]), f"{NAMES[game]} tree {i} move {m}: visit counts differ"
+            assert np.array_equal(q[i].view(np.uint32), rq[m].view(np.uint32)), f"tree {i} move {m}: Q values differ"
+            assert info["total_leaf_depth"][i] == rd[m]
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,temp,sims", [(0, 1.0, 60), (0, 0.5, 60), (0, 0.0, 40), (2, 0.8, 40), (0, 1.0, 1)])
+def test_forest_probs_and_pick_move_vs_reference(game, temp, sims):
+    """PlayManager's PUCT acting rule: probs(temp) over the dense move vector (sums in move order, pow through the
+    restated powf) and pick_move (one uniform draw). sims = 1 exercises the raw-policy branch (no child visited)."""
+    trees, n_moves = 5, 8
+    refs = [tafl_ref.search(game, 1300 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, pseudo_net, act_temp=temp)
+            for i in range(trees)]
+    f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=1.25, fpu_reduction=0.25, seed=1300,
+                    words_per_tree=2 * (1 + (n_moves + 1) * sims * (1 + 8 * (64 if game == 0 else 200))))
+    for m in range(n_moves):
+        for _ in range(sims):
+            f.find_leaf()
+            canon = f.leaf_canon()
+            ev = [pseudo_net(canon[i]) for i in range(trees)]
+            f.process_result(np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]))
+        probs, picked = f.probs(temp, pick=True)
+        mv = np.full(trees, 0xFFFFFFFF, np.uint32)
+        for i, r in enumerate(refs):
+            if m < len(r[2]):
+                assert np.array_equal(probs[i].view(np.uint32), r[4][m].view(np.uint32)), f"tree {i} move {m}: probs({temp})"
+                assert picked[i] == r[2][m], f"tree {i} move {m}: pick_move {picked[i]} != {r[2][m]}"
+                mv[i] = r[2][m]
+        f.update_root(mv)
+    f.close()
 
 
 def test_forest_refuses_without_cuda_or_unsupported_params():

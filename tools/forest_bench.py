@@ -28,7 +28,7 @@ if __name__ == "__main__":
     ap.add_argument("--gumbel-m", type=int, default=0, help="Gumbel root search with m candidates (configs/brandubh.yaml: 16)")
     a = ap.parse_args()
     # each half of a tree's slab: the kept subtree + one move's new nodes (1 + 7k words each), with head room
-    words = 2 * (1 + 3 * a.sims * (1 + 7 * (48 if a.game == 0 else 140)))
+    words = 2 * (1 + 3 * a.sims * (1 + 8 * (48 if a.game == 0 else 140)))
     f = b2az.Forest(a.game, a.trees, MAX_TURNS[a.game], cpuct=1.25, fpu_reduction=0.25, seed=1, words_per_tree=words,
                     gumbel_m=a.gumbel_m, lib=b2az.load(os.environ.get("B2AZ_LIB_PATH")))  # experiment builds via env
     stream = torch.cuda.current_stream().cuda_stream
