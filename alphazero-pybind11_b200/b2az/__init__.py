@@ -118,7 +118,7 @@ def load(path=None):
     L.b2az_forest_process_result_batched.argtypes = [vp, vp, u32, vp, vp, C.c_int, C.c_int]
     L.b2az_forest_simulate_batched.argtypes = [vp, vp, u32, u32]
     L.b2az_forest_reset_batch.argtypes = [vp, vp]
-    L.b2az_forest_probs.argtypes = [vp, vp, C.c_float, C.c_int, vp, vp]
+    L.b2az_forest_probs.argtypes = [vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]
     L.b2az_forest_advance.argtypes = [vp, vp]
     L.b2az_forest_set_gumbel_num_sims.argtypes = [vp, vp, u32]
     L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
@@ -424,11 +424,11 @@ class Forest:
         self._check(self.L.b2az_forest_gumbel_result(self.h, stream, _ptr(action), _ptr(policy)))
         return action, policy
 
-    def probs(self, temp, pick=False, stream=None):
-        """MCTS::probs(temp) per tree; with pick=True also pick_move(probs) (one RNG draw per tree)."""
+    def probs(self, temp, pick=False, pruned=False, stream=None):
+        """MCTS::probs(temp) (or probs_pruned) per tree; with pick=True also pick_move(probs) (one RNG draw per tree)."""
         probs = np.zeros((self.n, self.A), np.float32)
         moves = np.zeros(self.n, np.uint32)
-        self._check(self.L.b2az_forest_probs(self.h, stream, temp, int(pick), _ptr(probs), _ptr(moves)))
+        self._check(self.L.b2az_forest_probs(self.h, stream, temp, int(pruned), int(pick), _ptr(probs), _ptr(moves)))
         return (probs, moves) if pick else probs
 
     def advance(self, stream=None):

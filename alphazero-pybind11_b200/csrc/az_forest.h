@@ -1033,7 +1033,7 @@ __global__ void __launch_bounds__(128) k_forest_advance(ForestView F) {
 // sums them in MOVE order: the counts (or priors) are scattered into the dense row by all lanes, the sums, pow() and
 // the cumulative pick run on lane 0 over the A entries (once per move: not a hot path).
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick) {
+__global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick, u32 pruned) {
   typedef Tafl<GAME> T;
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1046,13 +1046,73 @@ __global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, 
     u32 total = 0;
     for (u32 j = lane; j < k; j += 32u) total += pool[fb_n(b, k) + j];
     total = warp_sum(total);  // counts.cast<float>().sum() == 0 <=> no child has a visit
-    for (u32 j = lane; j < k; j += 32u) {
-      const u32 mv = pool[fb_mv(b, k) + j] & 0xFFFFu;
-      out[mv] = total == 0 ? u2f(pool[fb_pol(b, k) + j]) : (float)pool[fb_n(b, k) + j];
+    // MCTS::probs_pruned (mcts.cc:620-674, KataGo's policy-target pruning by PUCT inversion) when asked for and the
+    // root has more than one visit: reduced visit counts instead of the raw ones; falls back to probs() when
+    // nothing survives
+    bool use_pruned = false;
+    if (pruned && R.n > 1 && k > 0) {
+      const float es = fmul(F.cpuct, fsqrt((float)R.n));
+      float best_sel = -1e30f;
+      for (u32 j = lane; j < k; j += 32u) {
+        const u32 nj = pool[fb_n(b, k) + j];
+        if (nj == 0) continue;
+        const float sel = fadd(u2f(pool[fb_q(b, k) + j]), fdiv(fmul(es, u2f(pool[fb_pol(b, k) + j])), (float)(nj + 1u)));
+        if (sel > best_sel) best_sel = sel;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {  // a maximum: order independent
+        const float ob = __shfl_xor_sync(0xFFFFFFFFu, best_sel, o);
+        if (ob > best_sel) best_sel = ob;
+      }
+      for (u32 j = lane; j < k; j += 32u) {
+        const u32 nj = pool[fb_n(b, k) + j];
+        if (nj == 0) continue;
+        const float qj = u2f(pool[fb_q(b, k) + j]);
+        const float gap = fsub(best_sel, qj);
+        const float desired = gap <= 0.0f ? (float)nj : fsub(fdiv(fmul(es, u2f(pool[fb_pol(b, k) + j])), gap), 1.0f);
+        out[pool[fb_mv(b, k) + j] & 0xFFFFu] = std_min((float)nj, std_max(0.0f, desired));
+      }
+      __syncwarp();
+      float ptotal = 0.0f;  // pruned.sum() over the dense vector, move order (lane 0 decides, then broadcast)
+      if (lane == 0)
+        for (u32 m = 0; m < (u32)T::A; ++m) ptotal = fadd(ptotal, out[m]);
+      ptotal = __shfl_sync(0xFFFFFFFFu, ptotal, 0);
+      use_pruned = ptotal != 0.0f;
+      if (!use_pruned) {
+        for (u32 m = lane; m < (u32)T::A; m += 32u) out[m] = 0.0f;
+        __syncwarp();
+      }
     }
+    if (!use_pruned)
+      for (u32 j = lane; j < k; j += 32u) {
+        const u32 mv = pool[fb_mv(b, k) + j] & 0xFFFFu;
+        out[mv] = total == 0 ? u2f(pool[fb_pol(b, k) + j]) : (float)pool[fb_n(b, k) + j];
+      }
     __syncwarp();
     if (lane == 0) {
-      if (total == 0) {  // the prior policy (raw-policy mode), tempered
+      if (use_pruned) {
+        float tot = 0.0f;
+        for (u32 m = 0; m < (u32)T::A; ++m) tot = fadd(tot, out[m]);
+        if (temp == 0.0f) {
+          float best = out[0];
+          for (u32 m = 1; m < (u32)T::A; ++m) best = out[m] > best ? out[m] : best;  // maxCoeff
+          u32 cnt = 0;
+          for (u32 m = 0; m < (u32)T::A; ++m) cnt += out[m] == best ? 1u : 0u;
+          const float share = fdiv(1.0f, (float)cnt);
+          for (u32 m = 0; m < (u32)T::A; ++m) out[m] = out[m] == best ? share : 0.0f;
+        } else {
+          for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], tot);
+          if (temp != 1.0f) {
+            const float e = fdiv(1.0f, temp);
+            float sum2 = 0.0f;
+            for (u32 m = 0; m < (u32)T::A; ++m) {
+              out[m] = az_powf(out[m], e);
+              sum2 = fadd(sum2, out[m]);
+            }
+            for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum2);
+          }
+        }
+      } else if (total == 0) {  // the prior policy (raw-policy mode), tempered
         if (temp != 0.0f) {
           const float e = fdiv(1.0f, temp);
           for (u32 m = 0; m < (u32)T::A; ++m) out[m] = az_powf(out[m], e);
@@ -1265,7 +1325,7 @@ int b2az_forest_find_leaf_batched(b2az_forest*, void*, const float**) FOREST_NO_
 int b2az_forest_process_result_batched(b2az_forest*, void*, uint32_t, const float*, const float*, int, int) FOREST_NO_CUDA()
 int b2az_forest_simulate_batched(b2az_forest*, void*, uint32_t, uint32_t) FOREST_NO_CUDA()
 int b2az_forest_reset_batch(b2az_forest*, void*) FOREST_NO_CUDA()
-int b2az_forest_probs(b2az_forest*, void*, float, int, float*, uint32_t*) FOREST_NO_CUDA()
+int b2az_forest_probs(b2az_forest*, void*, float, int, int, float*, uint32_t*) FOREST_NO_CUDA()
 int b2az_forest_advance(b2az_forest*, void*) FOREST_NO_CUDA()
 int b2az_forest_set_gumbel_num_sims(b2az_forest*, void*, uint32_t) FOREST_NO_CUDA()
 int b2az_forest_gumbel_result(b2az_forest*, void*, uint32_t*, float*) FOREST_NO_CUDA()
@@ -1361,7 +1421,8 @@ int b2az_forest_reset_batch(b2az_forest* f, void* stream) {
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pick_move, float* probs_host, uint32_t* moves_host) {
+int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pruned, int pick_move, float* probs_host,
+                      uint32_t* moves_host) {
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (pick_move && !moves_host) return fail(B2AZ_EINVAL, "b2az_forest_probs: pick_move needs moves_host");
@@ -1372,7 +1433,7 @@ int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pick_move, f
   int rc = dev_alloc(&dp, n * A);
   if (!rc) rc = dev_alloc(&dm, n);
   if (!rc) {
-    FOREST_DISPATCH(f, (k_forest_probs<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, temp, dp, dm, pick_move ? 1u : 0u)));
+    FOREST_DISPATCH(f, (k_forest_probs<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, temp, dp, dm, pick_move ? 1u : 0u, pruned ? 1u : 0u)));
     if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_probs launch failed");
   }
   if (!rc && probs_host) rc = copy_d2h(probs_host, dp, n * A * 4, s);

@@ -292,8 +292,10 @@ int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_hos
 /* MCTS::probs(temp) (mcts.cc:575-618: visit-count policy with temperature; temp == 0 = uniform over the most
  * visited moves; the tempered priors when nothing has a visit) into probs_host float32[n_trees][A] (may be NULL),
  * and with pick_move != 0 MCTS::pick_move(probs) (mcts.cc:717-735, exactly one draw from the tree's generator) into
- * moves_host uint32[n_trees] — PlayManager's acting rule (play_manager.cc:372-381). */
-int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pick_move, float* probs_host, uint32_t* moves_host);
+ * moves_host uint32[n_trees] — PlayManager's acting rule (play_manager.cc:372-381). pruned != 0: MCTS::probs_pruned
+ * (mcts.cc:620-674, the policy target under policy_target_pruning, play_manager.cc:418-421). */
+int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pruned, int pick_move, float* probs_host,
+                      uint32_t* moves_host);
 /* Greedy self-play step on the device: every tree whose root is expanded and not terminal plays its most visited
  * move (argmax of MCTS::counts(), lowest move id on ties) through update_root + play_move. No host round trip. */
 int b2az_forest_advance(b2az_forest* f, void* stream);

@@ -209,7 +209,7 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
                       uint32_t n_moves, uint32_t sims, int eval_kind, azref_eval_fn cb, void* user, uint32_t* counts_out,
                       float* q_out, uint32_t* moves_out, uint32_t* depth_sum_out, uint32_t gumbel_m, float gumbel_c_visit,
                       float gumbel_c_scale, float* policy_out, float epsilon, float root_policy_temp, int shaped_dirichlet,
-                      uint32_t batch_width, float act_temp, float* probs_out) {
+                      uint32_t batch_width, float act_temp, float* probs_out, float pruned_temp) {
   try {
     auto gs = make_game(game, max_turns);
     if (!gs) { g_err = "unknown game"; return -1; }
@@ -270,6 +270,10 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
       } else if (act_temp >= 0.0f) {  // PlayManager's PUCT acting rule: pick_move(probs(temp)) (play_manager.cc:372-381)
         auto pr = mcts.probs(act_temp);
         if (probs_out) std::memcpy(probs_out + (size_t)m * A, pr.data(), A * 4);
+        if (policy_out) {  // the training target under policy_target_pruning (play_manager.cc:418-421)
+          auto pp = mcts.probs_pruned(pruned_temp);
+          std::memcpy(policy_out + (size_t)m * A, pp.data(), A * 4);
+        }
         best = MCTS::pick_move(pr);
       } else {
         for (uint32_t a = 1; a < A; ++a)

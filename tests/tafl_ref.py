@@ -25,7 +25,7 @@ def lib():
         L.azref_tafl_random_game.argtypes = [C.c_int, C.c_uint16, C.c_uint64, u32, vp]
         L.azref_tafl_random_game.restype = u32
         L.azref_tafl_replay.argtypes = [C.c_int, C.c_uint16, vp, u32] + [vp] * 9
-        L.azref_tafl_search.argtypes = [C.c_int, C.c_uint16, C.c_uint64, C.c_float, C.c_float, C.c_int, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp, u32, C.c_float, C.c_float, vp, C.c_float, C.c_float, C.c_int, u32, C.c_float, vp]
+        L.azref_tafl_search.argtypes = [C.c_int, C.c_uint16, C.c_uint64, C.c_float, C.c_float, C.c_int, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp, u32, C.c_float, C.c_float, vp, C.c_float, C.c_float, C.c_int, u32, C.c_float, vp, C.c_float]
         L.azref_tafl_position.argtypes = [C.c_int, vp, C.c_int8, C.c_uint16, C.c_uint16, C.c_uint8, u32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -83,7 +83,7 @@ EVAL_FN = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTE
 
 def search(game, seed, n_moves, sims, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, evaluator=None,
            gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0, epsilon=0.0, root_policy_temp=1.0, shaped_dirichlet=False,
-           batch_width=0, act_temp=None):
+           batch_width=0, act_temp=None, pruned_temp=1.0):
     """One single-tree MCTS run through the reference's MCTS class. evaluator(canonical[P,S,S]) -> (v[3], pi[A]), or
     None for dumb_eval. Returns counts[m][A], q[m][A], moves[m], total leaf depth per move for the moves searched."""
     S, A, P = dims(game)
@@ -106,11 +106,11 @@ def search(game, seed, n_moves, sims, max_turns, cpuct=1.25, fpu_reduction=0.25,
                                 0 if evaluator is not None else 1, C.cast(fn, C.c_void_p) if fn else None, None,
                                 p(counts), p(q), p(moves), p(depth), gumbel_m, gumbel_c_visit, gumbel_c_scale, p(policy),
                                 epsilon, root_policy_temp, int(shaped_dirichlet), batch_width,
-                                -1.0 if act_temp is None else act_temp, p(probs))
+                                -1.0 if act_temp is None else act_temp, p(probs), pruned_temp)
     if n < 0:
         raise RuntimeError(lib().azref_tafl_last_error().decode())
     if act_temp is not None:
-        return counts[:n], q[:n], moves[:n], depth[:n], probs[:n]
+        return counts[:n], q[:n], moves[:n], depth[:n], probs[:n], policy[:n]
     if gumbel_m:
         return counts[:n], q[:n], moves[:n], depth[:n], policy[:n]
     return counts[:n], q[:n], moves[:n], depth[:n]

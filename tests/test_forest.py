@@ -223,8 +223,9 @@ def test_forest_probs_and_pick_move_vs_reference(game, temp, sims):
     """PlayManager's PUCT acting rule: probs(temp) over the dense move vector (sums in move order, pow through the
     restated powf) and pick_move (one uniform draw). sims = 1 exercises the raw-policy branch (no child visited)."""
     trees, n_moves = 5, 8
-    refs = [tafl_ref.search(game, 1300 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, pseudo_net, act_temp=temp)
-            for i in range(trees)]
+    ptemp = {1.0: 1.0, 0.5: 0.7, 0.0: 0.0, 0.8: 1.0}[temp]
+    refs = [tafl_ref.search(game, 1300 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, pseudo_net, act_temp=temp,
+                            pruned_temp=ptemp) for i in range(trees)]
     f = b2az.Forest(game, trees, MAX_TURNS[game], cpuct=1.25, fpu_reduction=0.25, seed=1300,
                     words_per_tree=2 * (1 + (n_moves + 1) * sims * (1 + 8 * (64 if game == 0 else 200))))
     for m in range(n_moves):
@@ -233,10 +234,12 @@ def test_forest_probs_and_pick_move_vs_reference(game, temp, sims):
             canon = f.leaf_canon()
             ev = [pseudo_net(canon[i]) for i in range(trees)]
             f.process_result(np.stack([e[0] for e in ev]), np.stack([e[1] for e in ev]))
+        pruned = f.probs(ptemp, pruned=True)  # the policy target (no draw), then the acting rule (one draw)
         probs, picked = f.probs(temp, pick=True)
         mv = np.full(trees, 0xFFFFFFFF, np.uint32)
         for i, r in enumerate(refs):
             if m < len(r[2]):
+                assert np.array_equal(pruned[i].view(np.uint32), r[5][m].view(np.uint32)), f"tree {i} move {m}: probs_pruned({ptemp})"
                 assert np.array_equal(probs[i].view(np.uint32), r[4][m].view(np.uint32)), f"tree {i} move {m}: probs({temp})"
                 assert picked[i] == r[2][m], f"tree {i} move {m}: pick_move {picked[i]} != {r[2][m]}"
                 mv[i] = r[2][m]
