@@ -124,6 +124,7 @@ def load(path=None):
     L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
     L.b2az_forest_update_root.argtypes = [vp, vp, vp]
     L.b2az_forest_counts.argtypes = [vp, vp, vp, vp, vp]
+    L.b2az_tafl_symmetries.argtypes = [C.c_int, u32, u32] + [vp] * 6
     L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
     _libs[path] = L
     return L
@@ -445,3 +446,19 @@ class Forest:
         info = np.zeros((self.n, 12), np.uint32)
         self._check(self.L.b2az_forest_counts(self.h, stream, _ptr(counts), _ptr(q), _ptr(info)))
         return counts, q, {k: info[:, i] for i, k in enumerate(self.INFO)}
+
+
+def tafl_symmetries(game, canon, v, pi, device=0, lib=None):
+    """The eight symmetric images of each sample (tafl_helper::eightSym order): ([n,8,P,S,S], [n,8,3], [n,8,A])."""
+    L = lib or load()
+    S, P = TAFL_DIMS[game]
+    A = 2 * S ** 3
+    canon = np.ascontiguousarray(canon, np.float32).reshape(-1, P, S, S)
+    n = canon.shape[0]
+    v = np.ascontiguousarray(v, np.float32).reshape(n, 3)
+    pi = np.ascontiguousarray(pi, np.float32).reshape(n, A)
+    co, vo, po = np.zeros((n, 8, P, S, S), np.float32), np.zeros((n, 8, 3), np.float32), np.zeros((n, 8, A), np.float32)
+    rc = L.b2az_tafl_symmetries(device, game, n, _ptr(canon), _ptr(v), _ptr(pi), _ptr(co), _ptr(vo), _ptr(po))
+    if rc != 0:
+        raise B2azError(rc, L.b2az_last_error().decode())
+    return co, vo, po

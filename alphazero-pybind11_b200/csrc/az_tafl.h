@@ -243,22 +243,34 @@ struct Tafl {
     return opponent_piece(s, player, sq(h, w));
   }
   // captured(): 1 if the piece next to `from` in direction (dh, dw) is captured, 0 if not, 2 where the reference
-  // throws (empty `from` square)
+  // throws (empty `from` square). Mask form: the target and the square beyond it as single-bit sets, the squares
+  // hostile to the target's side as one set (the mover's pieces, plus corners / throne where the game has them),
+  // evaluated on the CURRENT board (a capture made by an earlier direction of the same move is visible, as in the
+  // reference's sequential board updates).
   static AZ_HD u32 captured(const TaflState& s, int fh, int fw, int dh, int dw) {
     const int th = fh + dh, tw = fw + dw;
     if (tw < 0 || tw >= S || th < 0 || th >= S) return 0;
-    if (R::KING_FOUR_SIDES && b128_test(s.king, sq(th, tw))) {
+    const B128 tgt = b128_bit(sq(th, tw));
+    if (R::KING_FOUR_SIDES && b128_any(s.king & tgt)) {
       if (th == 0 || th == S - 1 || tw == 0 || tw == S - 1) return 0;
       return (hostile_to(s, 1, th - 1, tw) && hostile_to(s, 1, th + 1, tw) && hostile_to(s, 1, th, tw - 1) &&
               hostile_to(s, 1, th, tw + 1)) ? 1u : 0u;
     }
-    const u32 from_player = piece_player(s, sq(fh, fw));
+    const B128 from = b128_bit(sq(fh, fw));
+    const B128 defs = s.king | s.def;
+    const u32 from_player = b128_any(s.atk & from) ? 0u : b128_any(defs & from) ? 1u : 2u;
     if (from_player == 2) return 2;
-    if (!opponent_piece(s, from_player, sq(th, tw))) return 0;
-    const u32 target_player = from_player ^ 1u;
+    if (!b128_any((from_player == 0 ? defs : s.atk) & tgt)) return 0;  // only opponent pieces can be captured
     const int lh = th + dh, lw = tw + dw;
     if (lw < 0 || lw >= S || lh < 0 || lh >= S) return 0;
-    return hostile_to(s, target_player, lh, lw) ? 1u : 0u;
+    // squares hostile to the target (the opponent of the mover): the mover's own pieces ...
+    B128 hostile = from_player == 0 ? s.atk : defs;
+    if (R::RESTRICTED) {  // ... the corners, and the throne — to defenders only while the king is not on it
+      hostile = hostile | mask<4>();
+      const B128 throne = b128_bit(THRONE);
+      if (from_player == 1 /* target: attackers */ || !b128_any(s.king & throne)) hostile = hostile | throne;
+    }
+    return b128_any(hostile & b128_bit(sq(lh, lw))) ? 1u : 0u;
   }
   // play_move() without the repetition bookkeeping. Returns false where the reference throws.
   static AZ_HD bool play(TaflState& s, u32 move, bool* captured_any) {

@@ -469,6 +469,119 @@ int tafl_replay_device_impl(const TaflReplayArgs& a, void* stream) {
 
 }  // namespace b2az
 
+// ---- tafl_helper::eightSym (tafl_helper.h:16-149): the eight symmetric images of a training sample, in the
+// reference's order [base, rot90, rot180, rot270, mirror(base), mirror(rot90), mirror(rot180), mirror(rot270)]
+// (rot = rot90Clockwise, mirror = mirrorWidth). Pure data movement: every output element gathers its source.
+//   rot90Clockwise  canonical out(c, h, w) = in(c, S-1-w, h)
+//                   pi  out[(h,w) row-slide to w'] = in[(S-1-w, h) column-slide to S-1-w']
+//                       out[(h,w) column-slide to h'] = in[(S-1-w, h) row-slide to h']
+//   mirrorWidth     canonical out(c, h, w) = in(c, h, S-1-w)
+//                   pi  out[(h,w) row-slide to w'] = in[(h, S-1-w) row-slide to S-1-w'];  column slides keep h'
+// Symmetry i = i%4 rotations then (i >= 4) a mirror, so an output index is pulled back through the mirror first and
+// then through the rotations.
+namespace b2az {
+template <int S>
+AZ_HD u32 tafl_sym_src_cell(u32 sym, u32 h, u32 w) {  // source (h, w) of output cell (h, w), as h * S + w
+  if (sym >= 4u) w = (u32)S - 1u - w;
+  for (u32 r = 0; r < (sym & 3u); ++r) {
+    const u32 nh = (u32)S - 1u - w, nw = h;
+    h = nh; w = nw;
+  }
+  return h * (u32)S + w;
+}
+template <int S>
+AZ_HD u32 tafl_sym_src_move(u32 sym, u32 mv) {  // source move id of output move id
+  u32 loc = mv % (u32)(2 * S), cell = mv / (u32)(2 * S);
+  u32 h = cell / (u32)S, w = cell % (u32)S;
+  bool col = loc >= (u32)S;
+  u32 t = col ? loc - (u32)S : loc;
+  if (sym >= 4u) {
+    w = (u32)S - 1u - w;
+    if (!col) t = (u32)S - 1u - t;
+  }
+  for (u32 r = 0; r < (sym & 3u); ++r) {
+    const u32 nh = (u32)S - 1u - w, nw = h;
+    h = nh; w = nw;
+    if (!col) { col = true; t = (u32)S - 1u - t; }  // a row slide was a column slide before the rotation
+    else col = false;
+  }
+  return (h * (u32)S + w) * (u32)(2 * S) + (col ? (u32)S + t : t);
+}
+#ifndef B2AZ_HOST_EMU
+template <int S>
+__global__ void k_tafl_symmetries(u32 n, u32 planes, const float* __restrict__ canon, const float* __restrict__ v,
+                                  const float* __restrict__ pi, float* __restrict__ canon_out, float* __restrict__ v_out,
+                                  float* __restrict__ pi_out) {
+  const size_t C = (size_t)planes * S * S, A = (size_t)2 * S * S * S, per = C + A + 3;
+  const size_t total = (size_t)n * 8u * per;
+  for (size_t i = GLOBAL_TID; i < total; i += GLOBAL_NT) {
+    const size_t row = i / per, e = i % per;  // row = sample * 8 + sym
+    const u32 sample = (u32)(row / 8u), sym = (u32)(row % 8u);
+    if (e < C) {
+      const u32 c = (u32)(e / (S * S)), cell = (u32)(e % (S * S));
+      canon_out[row * C + e] = canon[(size_t)sample * C + (size_t)c * S * S + tafl_sym_src_cell<S>(sym, cell / S, cell % S)];
+    } else if (e < C + A) {
+      const u32 mv = (u32)(e - C);
+      pi_out[row * A + mv] = pi[(size_t)sample * A + tafl_sym_src_move<S>(sym, mv)];
+    } else {
+      const u32 j = (u32)(e - C - A);
+      v_out[row * 3 + j] = v[(size_t)sample * 3 + j];
+    }
+  }
+}
+#endif
+}  // namespace b2az
+
+extern "C" int b2az_tafl_symmetries(int device, uint32_t game, uint32_t n, const float* canon_host, const float* v_host,
+                                    const float* pi_host, float* canon_out, float* v_out, float* pi_out) {
+  using namespace b2az;
+  if (n == 0) return 0;
+  if (!canon_host || !v_host || !pi_host || !canon_out || !v_out || !pi_out) return fail(B2AZ_EINVAL, "null argument");
+  if (game > B2AZ_TAFL_TAWLBWRDD) return fail(B2AZ_EINVAL, "unknown tafl game");
+  const u32 S = game == B2AZ_TAFL_BRANDUBH ? 7u : 11u, planes = game == B2AZ_TAFL_OPENTAFL ? 8u : 7u;
+  const size_t C = (size_t)planes * S * S, A = (size_t)2 * S * S * S;
+#ifdef B2AZ_HOST_EMU
+  (void)device;
+  for (size_t row = 0; row < (size_t)n * 8u; ++row) {
+    const u32 sample = (u32)(row / 8u), sym = (u32)(row % 8u);
+    for (size_t e = 0; e < C; ++e) {
+      const u32 c = (u32)(e / (S * S)), cell = (u32)(e % (S * S));
+      const u32 src = S == 7u ? tafl_sym_src_cell<7>(sym, cell / S, cell % S) : tafl_sym_src_cell<11>(sym, cell / S, cell % S);
+      canon_out[row * C + e] = canon_host[(size_t)sample * C + (size_t)c * S * S + src];
+    }
+    for (size_t mv = 0; mv < A; ++mv)
+      pi_out[row * A + mv] = pi_host[(size_t)sample * A + (S == 7u ? tafl_sym_src_move<7>(sym, (u32)mv) : tafl_sym_src_move<11>(sym, (u32)mv))];
+    for (int j = 0; j < 3; ++j) v_out[row * 3 + j] = v_host[(size_t)sample * 3 + j];
+  }
+  return 0;
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  float *dc = nullptr, *dv = nullptr, *dp = nullptr, *oc = nullptr, *ov = nullptr, *op = nullptr;
+  int rc = 0;
+  auto al = [&](float** p, size_t count) { if (!rc && cudaMalloc(p, count * 4) != cudaSuccess) rc = fail(B2AZ_ENOMEM, "b2az_tafl_symmetries: cudaMalloc failed"); };
+  al(&dc, n * C); al(&dv, (size_t)n * 3); al(&dp, n * A); al(&oc, (size_t)n * 8 * C); al(&ov, (size_t)n * 24); al(&op, (size_t)n * 8 * A);
+  if (!rc) {
+    cudaMemcpy(dc, canon_host, n * C * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dv, v_host, (size_t)n * 12, cudaMemcpyHostToDevice);
+    cudaMemcpy(dp, pi_host, n * A * 4, cudaMemcpyHostToDevice);
+    if (S == 7u) k_tafl_symmetries<7><<<148 * 8, 256>>>(n, planes, dc, dv, dp, oc, ov, op);
+    else k_tafl_symmetries<11><<<148 * 8, 256>>>(n, planes, dc, dv, dp, oc, ov, op);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) rc = fail(B2AZ_ECUDA, std::string("k_tafl_symmetries: ") + cudaGetErrorString(err));
+  }
+  if (!rc) {
+    cudaMemcpy(canon_out, oc, (size_t)n * 8 * C * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(v_out, ov, (size_t)n * 24 * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(pi_out, op, (size_t)n * 8 * A * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dc); cudaFree(dv); cudaFree(dp); cudaFree(oc); cudaFree(ov); cudaFree(op);
+  return rc;
+#endif
+}
+
 extern "C" int b2az_tafl_replay_device(uint32_t game, uint32_t n, uint32_t max_len, uint32_t max_turns,
                                        const uint16_t* moves_dev, const uint32_t* lens_dev, void* hist_dev,
                                        int8_t* boards_dev, uint8_t* terminal_dev, uint32_t* n_valid_dev,

@@ -229,6 +229,14 @@ int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turn
                         uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical, int8_t* boards_out,
                         uint8_t* captured_any, int32_t* status);
 
+/* GameState::symmetries for the tafl games (tafl_helper::eightSym, tafl_helper.h:16-149): for each of n samples
+ * (canonical float32[n][P][S][S], v float32[n][3], pi float32[n][A]; host pointers) the eight symmetric images in the
+ * reference's order [base, rot90, rot180, rot270, mirror(base), mirror(rot90), mirror(rot180), mirror(rot270)] —
+ * canon_out float32[n][8][P][S][S], v_out float32[n][8][3], pi_out float32[n][8][A]: the augmentation
+ * game_runner.exploit_symmetries (game_runner.py:1050-1144) does sample by sample on the host. */
+int b2az_tafl_symmetries(int device, uint32_t game, uint32_t n, const float* canon_host, const float* v_host,
+                         const float* pi_host, float* canon_out, float* v_out, float* pi_out);
+
 /* ---- Batched single-tree MCTS over the tafl games ("forest"): the reference's `MCTS` class (mcts.h:50-150, bound at
  * py_wrapper.cc:192-220) for n_trees trees at once, one warp per tree on the device. Tree i starts at the game's
  * start position and draws from pcg32(seed + i) — a reference MCTS driven after MCTS::seed_thread_rng(seed + i).

@@ -295,4 +295,29 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
   }
 }
 
+// GameState::symmetries(PlayHistory) (tafl_helper::eightSym through {Brandubh,OpenTafl,Tawlbwrdd}GS::symmetries):
+// canon [P][S][S], v [3], pi [A] -> canon_out [8][P][S][S], v_out [8][3], pi_out [8][A]; returns the count (8).
+int azref_tafl_symmetries(int game, const float* canon, const float* v, const float* pi, float* canon_out, float* v_out,
+                          float* pi_out) {
+  auto gs = make_game(game, 10);
+  if (!gs) return -1;
+  auto c0 = gs->canonicalized();
+  const long P = c0.dimension(0), S = c0.dimension(1);
+  const size_t C = (size_t)(P * S * S), A = gs->num_moves();
+  PlayHistory base;
+  base.canonical = Tensor<float, 3>(P, S, S);
+  std::memcpy(base.canonical.data(), canon, C * 4);
+  base.v = Vector<float>{3};
+  std::memcpy(base.v.data(), v, 12);
+  base.pi = Vector<float>{(long)A};
+  std::memcpy(base.pi.data(), pi, A * 4);
+  auto syms = gs->symmetries(base);
+  for (size_t i = 0; i < syms.size(); ++i) {
+    std::memcpy(canon_out + i * C, syms[i].canonical.data(), C * 4);
+    std::memcpy(v_out + i * 3, syms[i].v.data(), 12);
+    std::memcpy(pi_out + i * A, syms[i].pi.data(), A * 4);
+  }
+  return (int)syms.size();
+}
+
 }  // extern "C"

@@ -26,6 +26,7 @@ def lib():
         L.azref_tafl_random_game.restype = u32
         L.azref_tafl_replay.argtypes = [C.c_int, C.c_uint16, vp, u32] + [vp] * 9
         L.azref_tafl_search.argtypes = [C.c_int, C.c_uint16, C.c_uint64, C.c_float, C.c_float, C.c_int, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp, u32, C.c_float, C.c_float, vp, C.c_float, C.c_float, C.c_int, u32, C.c_float, vp, C.c_float]
+        L.azref_tafl_symmetries.argtypes = [C.c_int] + [vp] * 6
         L.azref_tafl_position.argtypes = [C.c_int, vp, C.c_int8, C.c_uint16, C.c_uint16, C.c_uint8, u32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -114,3 +115,16 @@ def search(game, seed, n_moves, sims, max_turns, cpuct=1.25, fpu_reduction=0.25,
     if gumbel_m:
         return counts[:n], q[:n], moves[:n], depth[:n], policy[:n]
     return counts[:n], q[:n], moves[:n], depth[:n]
+
+
+def symmetries(game, canon, v, pi):
+    """GameState::symmetries of one sample through the reference: ([8,P,S,S], [8,3], [8,A])."""
+    S, A, P = dims(game)
+    canon = np.ascontiguousarray(canon, np.float32)
+    v = np.ascontiguousarray(v, np.float32)
+    pi = np.ascontiguousarray(pi, np.float32)
+    co, vo, po = np.zeros((8, P, S, S), np.float32), np.zeros((8, 3), np.float32), np.zeros((8, A), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = lib().azref_tafl_symmetries(game, p(canon), p(v), p(pi), p(co), p(vo), p(po))
+    assert n == 8
+    return co, vo, po

@@ -232,3 +232,33 @@ def test_bad_arguments_are_rejected():
     mv_occupied = (0 * S + 3) * 14 + 7 + 1  # (0,3) down to (1,3), occupied by an attacker
     r = b2az.tafl_replay(0, np.array([[mv_occupied]], np.uint16), np.array([1], np.uint32), 150, lib=lib)
     assert r["status"][0] == 0 and r["boards"][0, 1, 2].sum() == 7  # one attacker overwritten
+
+
+# ---------------------------------------------------------------------------------- symmetries (eightSym)
+def _check_symmetries(lib, game, n, seed):
+    S, P = b2az.TAFL_DIMS[game]
+    rng = np.random.default_rng(seed)
+    canon = rng.random((n, P, S, S)).astype(np.float32)
+    v = rng.random((n, 3)).astype(np.float32)
+    pi = rng.random((n, 2 * S ** 3)).astype(np.float32)
+    co, vo, po = b2az.tafl_symmetries(game, canon, v, pi, lib=lib)
+    for i in range(n):
+        rc, rv, rp = tafl_ref.symmetries(game, canon[i], v[i], pi[i])
+        assert np.array_equal(co[i].view(np.uint32), rc.view(np.uint32)), f"{NAMES[game]} sample {i}: canonical images"
+        assert np.array_equal(vo[i], rv) and np.array_equal(po[i].view(np.uint32), rp.view(np.uint32)), f"sample {i}: pi images"
+    # image 0 is the sample itself; every image is a permutation of it
+    assert np.array_equal(co[:, 0], canon) and np.array_equal(po[:, 0], pi)
+    assert np.array_equal(np.sort(po.reshape(n, 8, -1), axis=2), np.sort(np.repeat(pi[:, None], 8, 1), axis=2))
+
+
+@needs_tafl_ref
+@pytest.mark.parametrize("game", [0, 1, 2])
+def test_symmetries_host_build_vs_reference(game):
+    _check_symmetries(b2az.load(ph.HOSTEMU_LIB), game, 3, 11 + game)
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game", [0, 1, 2])
+def test_cuda_symmetries_vs_reference(game):
+    _check_symmetries(None, game, 24, 21 + game)
