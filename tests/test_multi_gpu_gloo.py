@@ -88,3 +88,55 @@ def test_two_rank_run_matches_single_process(tmp_path):
     want = [np.concatenate([h[i] for h in tot["hist"]]) for i in range(3)]
     assert np.array_equal(got["canon"], want[0]) and np.array_equal(got["v"], want[1])
     assert np.array_equal(got["pi"].view(np.uint32), want[2].view(np.uint32))
+
+
+TAFL_WORKER = r"""
+import os, sys, json, zlib
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["B2AZ_PKG"]); sys.path.insert(0, os.environ["B2AZ_TESTS"])
+import b2az, parity_harness as ph
+from b2az import dist as bd
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lib = b2az.load(ph.HOSTEMU_LIB)
+g = np.load(os.path.join(ph.ROOT, "tests", "golden", "tafl_brandubh_transcripts.npz"))
+idx = np.nonzero(g["max_turns"] == 150)[0]
+lo, hi = bd.shard_games(len(idx), rank, world)          # independent transcripts: rank r replays its own slice
+mine = idx[lo:hi]
+r = b2az.tafl_replay(0, g["moves"][mine], g["lens"][mine], 150, lib=lib)
+positions = int((g["lens"][mine] + 1).sum())
+ends = np.array([r["terminal"][j, g["lens"][i]] for j, i in enumerate(mine)], np.int64)
+t = torch.tensor([positions, (ends == 1).sum(), (ends == 2).sum(), (ends == 3).sum()], dtype=torch.float64)
+dist.all_reduce(t)                                       # the only collective: additive statistics
+crc = np.array([zlib.crc32(r["canonical"][j, : g["lens"][i] + 1].tobytes()) for j, i in enumerate(mine)], np.int64)
+got = bd.gather_history(crc.reshape(-1, 1), ends.reshape(-1, 1), mine.reshape(-1, 1).astype(np.int64))
+if rank == 0:
+    print(json.dumps({"tot": t.tolist(), "crc": got[0].flatten().tolist(), "ends": got[1].flatten().tolist(),
+                      "idx": got[2].flatten().tolist()}))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_tafl_replay_shards_match_single_process(tmp_path):
+    """The tafl game kernels shard like the self-play pool: independent transcripts per rank, no data-path collective."""
+    import json
+    import zlib
+
+    env = dict(os.environ, B2AZ_PKG=os.path.join(ph.ROOT, "alphazero-pybind11_b200"), B2AZ_TESTS=os.path.join(ph.ROOT, "tests"),
+               MASTER_ADDR="127.0.0.1")
+    script = tmp_path / "tafl_worker.py"
+    script.write_text(TAFL_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29741", str(script)], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    g = np.load(os.path.join(ph.ROOT, "tests", "golden", "tafl_brandubh_transcripts.npz"))
+    idx = np.nonzero(g["max_turns"] == 150)[0]
+    one = b2az.tafl_replay(0, g["moves"][idx], g["lens"][idx], 150, lib=b2az.load(ph.HOSTEMU_LIB))
+    ends = [int(one["terminal"][j, g["lens"][i]]) for j, i in enumerate(idx)]
+    crc = [zlib.crc32(one["canonical"][j, : g["lens"][i] + 1].tobytes()) for j, i in enumerate(idx)]
+    assert res["idx"] == idx.tolist() and res["ends"] == ends and res["crc"] == crc
+    assert res["tot"] == [float((g["lens"][idx] + 1).sum()), float(ends.count(1)), float(ends.count(2)), float(ends.count(3))]

@@ -83,7 +83,14 @@ if __name__ == "__main__":
         ev[m + 1].record()
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.moves)]
+    if a.gumbel_m:
+        f.set_gumbel_num_sims(a.sims, stream)
+    search()  # one more (untimed) search, kept un-advanced so that the depth statistics can be read
+    torch.cuda.synchronize()
     _, _, info = f.counts(want_q=False)
+    live = info["depth"] > 0
+    leaf_depth = float(info["total_leaf_depth"][live].sum() / max(1, info["depth"][live].sum()))
+    root_k = float(info["root_k"][live].mean()) if live.any() else 0.0
     f.close()
     assert (info["error"] == 0).all(), set(info["error"].tolist())
     sims_total = a.trees * a.sims * a.moves
@@ -99,6 +106,6 @@ if __name__ == "__main__":
                       "game": NAMES[a.game], "trees": a.trees, "gumbel_m": a.gumbel_m, "sims_per_move": a.sims,
                       "moves": a.moves, "ms_per_move": [round(x, 2) for x in ms],
                       "simulations_per_second": sims_total / (sum(ms) * 1e-3), "moves_per_second": a.trees * a.moves / (sum(ms) * 1e-3),
-                      "mean_slab_words_used": float(info["words_used"].mean()), "games_over": int((info["root_term"] != 0).sum()),
+                      "mean_slab_words_used": float(info["words_used"].mean()), "mean_leaf_depth": leaf_depth, "mean_root_children": root_k, "games_over": int((info["root_term"] != 0).sum()),
                       "cpu_baseline": {"value": ref_sims / cpu_s, "unit": "sims/s", "cores": 1, "kind": "reference",
                                        "sample": f"{n_ref} single-tree runs of the unmodified reference MCTS class, dumb_eval, same settings"}}))
