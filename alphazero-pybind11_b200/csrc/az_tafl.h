@@ -95,9 +95,15 @@ struct Tafl {
   static constexpr int S = R::S, CELLS = S * S, A = CELLS * 2 * S, PLANES = R::PLANES, CANON = PLANES * CELLS;
   static constexpr int BOARD_BYTES = 3 * CELLS, MID = S / 2, THRONE = MID * S + MID;
 
+  // Boards of up to 64 squares (Brandubh) never touch the high word: single-word forms of the variable-index helpers
+  static constexpr bool NARROW = CELLS <= 64;
+  static AZ_HD bool test(const B128& a, int i) { return NARROW ? (((a.lo >> i) & 1ULL) != 0) : b128_test(a, i); }
+  static AZ_HD B128 bit(int i) { return NARROW ? b128(1ULL << i, 0) : b128_bit(i); }
+  static AZ_HD bool any(const B128& a) { return NARROW ? (a.lo != 0) : b128_any(a); }
+  static AZ_HD bool same(const B128& a, const B128& b) { return NARROW ? (a.lo == b.lo) : b128_eq(a, b); }
   static AZ_HD int sq(int h, int w) { return S * h + w; }
   static AZ_HD bool is_corner(int h, int w) { return (h == 0 || h == S - 1) && (w == 0 || w == S - 1); }
-  static AZ_HD void put(B128& b, int h, int w) { b = b | b128_bit(sq(h, w)); }
+  static AZ_HD void put(B128& b, int h, int w) { b = b | bit(sq(h, w)); }
 
   // the constructors of BrandubhGS / OpenTaflGS / TawlbwrddGS (brandubh_gs.h:102-123, opentafl_gs.h:90-134,
   // tawlbwrdd_gs.h:91-134)
@@ -129,11 +135,12 @@ struct Tafl {
   static AZ_HD TaflKey key(const TaflState& s) {
     TaflKey k;
     k.king = s.king; k.def = s.def; k.atkp = s.atk;
-    k.atkp.hi |= (u64)s.player << 63;
+    if (NARROW) k.atkp.lo |= (u64)s.player << 63;  // 49 squares: bit 63 of the low word is free
+    else k.atkp.hi |= (u64)s.player << 63;
     return k;
   }
   static AZ_HD bool key_eq(const TaflKey& a, const TaflKey& b) {
-    return b128_eq(a.king, b.king) && b128_eq(a.def, b.def) && b128_eq(a.atkp, b.atkp);
+    return same(a.king, b.king) && same(a.def, b.def) && same(a.atkp, b.atkp);
   }
   static AZ_HD B128 own(const TaflState& s) { return s.player == 0 ? s.atk : (s.king | s.def); }
 
@@ -141,7 +148,7 @@ struct Tafl {
   // exception of the four slide loops).
   static AZ_HD void slides(const TaflState& s, int h, int w, u32& row, u32& col) {
     const B128 occ = s.king | s.def | s.atk;
-    const bool is_king = b128_test(s.king, sq(h, w));
+    const bool is_king = test(s.king, sq(h, w));
     row = col = 0;
     for (int dir = 0; dir < 4; ++dir) {
       const int dh = dir == 2 ? 1 : dir == 3 ? -1 : 0, dw = dir == 0 ? 1 : dir == 1 ? -1 : 0;
@@ -149,7 +156,7 @@ struct Tafl {
       while (th >= 0 && th < S && tw >= 0 && tw < S) {
         // is_valid_square: a corner is decided by the piece alone (king only), any other square must be empty
         if (R::RESTRICTED && is_corner(th, tw)) { if (!is_king) break; }
-        else if (b128_test(occ, sq(th, tw))) break;
+        else if (test(occ, sq(th, tw))) break;
         if (!(R::RESTRICTED && !is_king && th == MID && tw == MID)) {  // may pass the empty throne, not land on it
           if (dh == 0) row |= 1u << tw; else col |= 1u << th;
         }
@@ -195,7 +202,7 @@ struct Tafl {
     const B128 mine = own(s);
     u32 n = 0;
     for (int c = 0; c < CELLS; ++c) {
-      if (!b128_test(mine, c)) continue;
+      if (!test(mine, c)) continue;
       u32 row, col;
       slides(s, c / S, c % S, row, col);
       for (int t = 0; t < S; ++t)
@@ -208,7 +215,7 @@ struct Tafl {
   static AZ_HD bool has_moves(const TaflState& s) {
     const B128 mine = own(s);
     for (int c = 0; c < CELLS; ++c) {
-      if (!b128_test(mine, c)) continue;
+      if (!test(mine, c)) continue;
       u32 row, col;
       slides(s, c / S, c % S, row, col);
       if (row | col) return true;
@@ -218,7 +225,7 @@ struct Tafl {
   // the 2S mask bytes of one source square (valid_moves()[c*2S .. c*2S + 2S - 1])
   static AZ_HD void valid_bytes(const TaflState& s, int c, u8* out) {
     u32 row = 0, col = 0;
-    if (b128_test(own(s), c)) slides(s, c / S, c % S, row, col);
+    if (test(own(s), c)) slides(s, c / S, c % S, row, col);
     for (int t = 0; t < S; ++t) {
       out[t] = (u8)((row >> t) & 1u);
       out[S + t] = (u8)((col >> t) & 1u);
@@ -227,18 +234,18 @@ struct Tafl {
 
   // piece_to_player: 0 attackers, 1 defenders, 2 = empty square (the reference throws)
   static AZ_HD u32 piece_player(const TaflState& s, int c) {
-    if (b128_test(s.atk, c)) return 0;
-    if (b128_test(s.king | s.def, c)) return 1;
+    if (test(s.atk, c)) return 0;
+    if (test(s.king | s.def, c)) return 1;
     return 2;
   }
   static AZ_HD bool opponent_piece(const TaflState& s, u32 player, int c) {
-    return b128_test(player == 0 ? (s.king | s.def) : s.atk, c);
+    return test(player == 0 ? (s.king | s.def) : s.atk, c);
   }
   // is_hostile_to (brandubh_gs.cc:291-318, opentafl_gs.cc:278-293, tawlbwrdd_gs.cc:215-219)
   static AZ_HD bool hostile_to(const TaflState& s, u32 player, int h, int w) {
     if (R::RESTRICTED) {
       if (is_corner(h, w)) return true;
-      if (h == MID && w == MID) return player == 1 ? !b128_test(s.king, THRONE) : true;
+      if (h == MID && w == MID) return player == 1 ? !test(s.king, THRONE) : true;
     }
     return opponent_piece(s, player, sq(h, w));
   }
@@ -250,27 +257,27 @@ struct Tafl {
   static AZ_HD u32 captured(const TaflState& s, int fh, int fw, int dh, int dw) {
     const int th = fh + dh, tw = fw + dw;
     if (tw < 0 || tw >= S || th < 0 || th >= S) return 0;
-    const B128 tgt = b128_bit(sq(th, tw));
-    if (R::KING_FOUR_SIDES && b128_any(s.king & tgt)) {
+    const B128 tgt = bit(sq(th, tw));
+    if (R::KING_FOUR_SIDES && any(s.king & tgt)) {
       if (th == 0 || th == S - 1 || tw == 0 || tw == S - 1) return 0;
       return (hostile_to(s, 1, th - 1, tw) && hostile_to(s, 1, th + 1, tw) && hostile_to(s, 1, th, tw - 1) &&
               hostile_to(s, 1, th, tw + 1)) ? 1u : 0u;
     }
-    const B128 from = b128_bit(sq(fh, fw));
+    const B128 from = bit(sq(fh, fw));
     const B128 defs = s.king | s.def;
-    const u32 from_player = b128_any(s.atk & from) ? 0u : b128_any(defs & from) ? 1u : 2u;
+    const u32 from_player = any(s.atk & from) ? 0u : any(defs & from) ? 1u : 2u;
     if (from_player == 2) return 2;
-    if (!b128_any((from_player == 0 ? defs : s.atk) & tgt)) return 0;  // only opponent pieces can be captured
+    if (!any((from_player == 0 ? defs : s.atk) & tgt)) return 0;  // only opponent pieces can be captured
     const int lh = th + dh, lw = tw + dw;
     if (lw < 0 || lw >= S || lh < 0 || lh >= S) return 0;
     // squares hostile to the target (the opponent of the mover): the mover's own pieces ...
     B128 hostile = from_player == 0 ? s.atk : defs;
     if (R::RESTRICTED) {  // ... the corners, and the throne — to defenders only while the king is not on it
       hostile = hostile | mask<4>();
-      const B128 throne = b128_bit(THRONE);
-      if (from_player == 1 /* target: attackers */ || !b128_any(s.king & throne)) hostile = hostile | throne;
+      const B128 throne = bit(THRONE);
+      if (from_player == 1 /* target: attackers */ || !any(s.king & throne)) hostile = hostile | throne;
     }
-    return b128_any(hostile & b128_bit(sq(lh, lw))) ? 1u : 0u;
+    return any(hostile & bit(sq(lh, lw))) ? 1u : 0u;
   }
   // play_move() without the repetition bookkeeping. Returns false where the reference throws.
   static AZ_HD bool play(TaflState& s, u32 move, bool* captured_any) {
@@ -283,9 +290,9 @@ struct Tafl {
     const int pw = (int)(piece_loc % (u32)S), ph = (int)(piece_loc / (u32)S);
     const int nh = height_move ? (int)new_loc : ph, nw = height_move ? pw : (int)new_loc;
     const int from = sq(ph, pw), to = sq(nh, nw);
-    const B128 fb = b128_bit(from), tb = b128_bit(to);
+    const B128 fb = bit(from), tb = bit(to);
     // the three layers of the source square are copied onto the destination, then the source is cleared
-    const bool k = b128_test(s.king, from), d = b128_test(s.def, from), a = b128_test(s.atk, from);
+    const bool k = test(s.king, from), d = test(s.def, from), a = test(s.atk, from);
     s.king = (s.king & ~tb) | (k ? tb : b128(0, 0));
     s.def = (s.def & ~tb) | (d ? tb : b128(0, 0));
     s.atk = (s.atk & ~tb) | (a ? tb : b128(0, 0));
@@ -295,7 +302,7 @@ struct Tafl {
       const u32 c = captured(s, nh, nw, dh, dw);
       if (c == 2) return false;
       if (c == 1) {
-        const B128 rm = ~b128_bit(sq(nh + dh, nw + dw));
+        const B128 rm = ~bit(sq(nh + dh, nw + dw));
         s.king = s.king & rm; s.def = s.def & rm; s.atk = s.atk & rm;
         *captured_any = true;
       }
@@ -349,11 +356,11 @@ struct Tafl {
     const B128 goal = s.king | s.def;
     B128 seen = mask<1>();
     for (;;) {
-      if (b128_any(seen & goal)) return true;
+      if (any(seen & goal)) return true;
       const B128 src = seen & open;  // squares that spread to their neighbours
       const B128 grown = seen | (b128_shl(src, S) & all) | b128_shr(src, S) | b128_shl(src & not_right, 1) |
                          b128_shr(src & not_left, 1);
-      if (b128_eq(grown, seen)) return false;
+      if (same(grown, seen)) return false;
       seen = grown;
     }
   }
@@ -361,8 +368,8 @@ struct Tafl {
   // 0 = not over, else 1 + index of the winner (2 = defenders, 3 = draw)
   static AZ_HD u32 terminal_pre(const TaflState& s) {
     if (s.rep >= 3) return 1u + s.player;
-    if (b128_any(s.king & (R::EDGE_WIN ? mask<1>() : mask<4>()))) return 2;
-    if (!b128_any(s.king)) return 1;
+    if (any(s.king & (R::EDGE_WIN ? mask<1>() : mask<4>()))) return 2;
+    if (!any(s.king)) return 1;
     if (R::ENCIRCLE && !can_escape(s)) return 1;
     return 0;
   }
@@ -379,9 +386,9 @@ struct Tafl {
   static AZ_HD float canon_elem(const TaflState& s, u32 e) {
     const u32 c = e / (u32)CELLS;
     const int cell = (int)(e % (u32)CELLS);
-    if (c == 0) return b128_test(s.king, cell) ? 1.0f : 0.0f;
-    if (c == 1) return b128_test(s.def, cell) ? 1.0f : 0.0f;
-    if (c == 2) return b128_test(s.atk, cell) ? 1.0f : 0.0f;
+    if (c == 0) return test(s.king, cell) ? 1.0f : 0.0f;
+    if (c == 1) return test(s.def, cell) ? 1.0f : 0.0f;
+    if (c == 2) return test(s.atk, cell) ? 1.0f : 0.0f;
     if (c < 5) return (c - 3u == s.player) ? 1.0f : 0.0f;
     if (c == 5) return (s.rep == 1 || s.rep > 2) ? 1.0f : 0.0f;
     if (c == 6) return (s.rep >= 2) ? 1.0f : 0.0f;
@@ -389,7 +396,7 @@ struct Tafl {
   }
   static AZ_HD signed char board_byte(const TaflState& s, u32 e) {  // int8[3][S][S] element e (to_bytes layout)
     const B128& plane = e < (u32)CELLS ? s.king : e < (u32)(2 * CELLS) ? s.def : s.atk;
-    return (signed char)(b128_test(plane, (int)(e % (u32)CELLS)) ? 1 : 0);
+    return (signed char)(test(plane, (int)(e % (u32)CELLS)) ? 1 : 0);
   }
 };
 
