@@ -75,6 +75,21 @@ class ForestParams(C.Structure):  # b2az_forest_params (include/b2az.h)
                 ("pad2_", C.c_uint8 * 2), ("max_in_flight", C.c_uint32)]
 
 
+class TaflSelfplayParams(C.Structure):  # b2az_tafl_selfplay_params (include/b2az.h)
+    _fields_ = [("forest", ForestParams), ("n_games", C.c_uint32), ("games_per_slot", C.c_uint32), ("visits", C.c_uint32),
+                ("start_temp", C.c_float), ("final_temp", C.c_float), ("temp_decay_half_life", C.c_float),
+                ("history_enabled", C.c_uint8), ("policy_target_pruning", C.c_uint8), ("tree_reuse", C.c_uint8),
+                ("pad_", C.c_uint8), ("hist_capacity", C.c_uint32)]
+
+
+SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_completed", "u4"), ("pending", "u4"),
+                       ("move_count", "u4"), ("full_move_count", "u4"), ("total_move_count", "u4"),
+                       ("total_full_move_count", "u4"), ("game_length", "u4"), ("picked", "u4"), ("error", "u4"),
+                       ("pad_", "u4"), ("g_leaf_depth", "f8"), ("g_entropy", "f8"), ("g_valid_moves", "f8"),
+                       ("leaf_depth", "f8"), ("entropy", "f8"), ("valid_moves", "f8"), ("simulations", "u8"),
+                       ("scores", "f4", 3), ("pad2_", "u4")])  # b2az_tafl_selfplay_slot
+assert SLOT_DTYPE.itemsize == 120
+
 _libs = {}
 
 
@@ -126,6 +141,13 @@ def load(path=None):
     L.b2az_forest_counts.argtypes = [vp, vp, vp, vp, vp]
     L.b2az_tafl_symmetries.argtypes = [C.c_int, u32, u32] + [vp] * 6
     L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
+    L.b2az_tafl_selfplay_create.argtypes = [C.POINTER(TaflSelfplayParams), C.c_int, C.POINTER(vp)]
+    L.b2az_tafl_selfplay_destroy.argtypes = [vp]
+    L.b2az_tafl_selfplay_play.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.b2az_tafl_selfplay_find_leaf.argtypes = [vp, vp, C.POINTER(vp)]
+    L.b2az_tafl_selfplay_process_result.argtypes = [vp, vp, vp, vp, C.c_int, C.POINTER(u32)]
+    L.b2az_tafl_selfplay_drain_history.argtypes = [vp, vp, u32, vp, vp, vp, vp, C.POINTER(u32)]
+    L.b2az_tafl_selfplay_slots.argtypes = [vp, vp, vp, vp]
     _libs[path] = L
     return L
 
@@ -462,3 +484,75 @@ def tafl_symmetries(game, canon, v, pi, device=0, lib=None):
     if rc != 0:
         raise B2azError(rc, L.b2az_last_error().decode())
     return co, vo, po
+
+
+class TaflSelfplay:
+    """PlayManager::play over a tafl game on the device (b2az_tafl_selfplay_*): n_games slots, each playing
+    games_per_slot games with the two seats' trees and one generator — slot g == the reference PlayManager with
+    concurrent_games = 1 run after MCTS::seed_thread_rng(seed + g)."""
+
+    def __init__(self, game, n_games, max_turns, visits, games_per_slot=1, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False,
+                 seed=0, words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, shaped_dirichlet=False, gumbel_m=0,
+                 gumbel_c_visit=50.0, gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0,
+                 history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None):
+        self.L = lib or load()
+        self.game, self.n = game, n_games
+        S, P = TAFL_DIMS[game]
+        self.S, self.P, self.A = S, P, 2 * S ** 3
+        fp = ForestParams(game=game, n_trees=2 * n_games, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
+                          fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
+                          root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
+                          gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, shaped_dirichlet=int(shaped_dirichlet))
+        p = TaflSelfplayParams(forest=fp, n_games=n_games, games_per_slot=games_per_slot, visits=visits, start_temp=start_temp,
+                               final_temp=final_temp, temp_decay_half_life=temp_decay_half_life,
+                               history_enabled=int(history_enabled), policy_target_pruning=int(policy_target_pruning),
+                               tree_reuse=int(tree_reuse), hist_capacity=hist_capacity)
+        self.hist_capacity = hist_capacity or n_games * max_turns
+        self.h = C.c_void_p()
+        self._check(self.L.b2az_tafl_selfplay_create(C.byref(p), device, C.byref(self.h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2azError(rc, self.L.b2az_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.b2az_tafl_selfplay_destroy(self.h)
+            self.h = None
+
+    def play(self, n_moves, stream=None, want_active=True):
+        """n_moves x (search + move) for every active slot; returns the number of slots still cycling."""
+        act = C.c_uint32(0)
+        self._check(self.L.b2az_tafl_selfplay_play(self.h, stream, n_moves, C.byref(act) if want_active else None))
+        return act.value if want_active else None
+
+    def find_leaf(self, stream=None):
+        ptr = C.c_void_p()
+        self._check(self.L.b2az_tafl_selfplay_find_leaf(self.h, stream, C.byref(ptr)))
+        return ptr.value
+
+    def process_result(self, v, pi, host=True, stream=None, want_active=False):
+        act = C.c_uint32(0)
+        if host:
+            v, pi = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(pi, np.float32)
+            assert v.shape == (self.n, 3) and pi.shape == (self.n, self.A)
+            v, pi = _ptr(v), _ptr(pi)
+        self._check(self.L.b2az_tafl_selfplay_process_result(self.h, stream, v, pi, int(host),
+                                                             C.byref(act) if want_active else None))
+        return act.value if want_active else None
+
+    def drain_history(self, stream=None):
+        cap = self.hist_capacity
+        canon = np.zeros((cap, self.P, self.S, self.S), np.float32)
+        v, pi = np.zeros((cap, 3), np.float32), np.zeros((cap, self.A), np.float32)
+        slot = np.zeros(cap, np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.L.b2az_tafl_selfplay_drain_history(self.h, stream, cap, _ptr(canon), _ptr(v), _ptr(pi), _ptr(slot),
+                                                            C.byref(n)))
+        return canon[:n.value], v[:n.value], pi[:n.value], slot[:n.value]
+
+    def slots(self, stream=None):
+        out = np.zeros(self.n, SLOT_DTYPE)
+        err = np.zeros(2 * self.n, np.uint32)
+        self._check(self.L.b2az_tafl_selfplay_slots(self.h, stream, _ptr(out), _ptr(err)))
+        return out, err

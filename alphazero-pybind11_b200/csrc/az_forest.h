@@ -91,7 +91,11 @@ struct ForestView {
   float* leaf_canon;   // [max(1, max_in_flight)][n_trees][CANON]
   ForestLeaf* inflight; // [n_trees][max_in_flight] (WU-UCT), null when max_in_flight == 0
   u32 max_in_flight;
+  u32 rng_pair;         // self-play: trees 2g and 2g+1 (the two seats' MCTS objects of game g, play_manager.h game.mcts[])
+                        // draw from ONE generator (the reference's thread-local one), kept in tree 2g
 };
+// the generator tree t draws from
+#define FOREST_RNG(F, t) ((F).trees[(F).rng_pair ? ((t) & ~1u) : (t)].rng)
 
 #ifndef B2AZ_HOST_EMU
 // block field offsets (words) for a block of k children at word b: [b] = k, then eight arrays of k words
@@ -339,9 +343,9 @@ __device__ __noinline__ void fg_init(const ForestView& F, u32 t, ForestTree& R, 
   G.effective_m = m;
   float* g = F.gum_g + (size_t)t * (2 * kFMaxK);
   float* score = g + kFMaxK;
-  Pcg32 rng = R.rng;
+  Pcg32 rng = FOREST_RNG(F, t);
   for (u32 i = 0; i < num_legal; ++i) g[i] = rng_gumbel(rng);
-  R.rng = rng;
+  FOREST_RNG(F, t) = rng;
   for (u32 i = 0; i < num_legal; ++i) score[i] = fadd(g[i], az_logf(fadd(u2f(pool[fb_pol(b, num_legal) + i]), FG_LOG_FLOOR)));
   fg_rank_top(score, nullptr, num_legal, m, G.survivors);
   G.n_surv = m;
@@ -611,7 +615,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     // current_->player, scores, add_children(valid_moves) incl. the shuffle (mcts.cc:490-496)
     leaf_new = 1;
     leaf_player = s.player;
-    Pcg32 rng = R.rng;
+    Pcg32 rng = FOREST_RNG(F, t);
     const u32 k = forest_legal_moves<GAME>(s, sm, rng, lane, &err, F.serial_shuffle != 0);
     const u32 pre = T::terminal_pre(s);
     leaf_term = pre ? pre : T::terminal_post(s, k != 0);
@@ -634,7 +638,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       }
     }
     if (lane == 0) {
-      R.rng = rng;
+      FOREST_RNG(F, t) = rng;
       if (par_blk == 0 && plen == 0) {
         R.player = leaf_player; R.term = leaf_term; R.blk = leaf_blk; R.k = leaf_k; R.expanded = 1;
       } else {
@@ -736,9 +740,9 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
       __syncwarp();
       // Gumbel replaces Dirichlet noise (mcts.cc:514-518)
       if (is_root && root_noise_enabled && F.epsilon > 0.0f && !F.gumbel_enabled && lane == 0) {
-        Pcg32 rng = R.rng;
+        Pcg32 rng = FOREST_RNG(F, t);
         fr_add_root_noise(F, t, rng, pool, lblk, lk);
-        R.rng = rng;
+        FOREST_RNG(F, t) = rng;
       }
     }
   }
@@ -788,9 +792,9 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
   if (blk == 0) {
     // root_.children.empty(): add_children(gs.valid_moves()) — the shuffle draws happen; the block is only stored
     // when it can be descended into later (a terminal root keeps no children here, see find_leaf)
-    Pcg32 rng = R.rng;
+    Pcg32 rng = FOREST_RNG(F, t);
     k = forest_legal_moves<GAME>(s, sm, rng, lane, &err, F.serial_shuffle != 0);
-    if (lane == 0) R.rng = rng;
+    if (lane == 0) FOREST_RNG(F, t) = rng;
     // the chosen child is a fresh node whatever its slot: only membership matters
     bool found = false;
     for (u32 j = lane; j < k; j += 32u) found |= sm.moves[j] == move;
@@ -931,9 +935,9 @@ __global__ void __launch_bounds__(128) k_forest_root_noise(ForestView F, u32 add
       u32* pool = F.pool + (size_t)t * F.words_per_tree;
       fr_apply_root_policy_temp(F, pool, R.blk, R.k);
       if (add_noise && F.epsilon > 0.0f) {
-        Pcg32 rng = R.rng;
+        Pcg32 rng = FOREST_RNG(F, t);
         fr_add_root_noise(F, t, rng, pool, R.blk, R.k);
-        R.rng = rng;
+        FOREST_RNG(F, t) = rng;
       }
     }
   }
@@ -1033,13 +1037,11 @@ __global__ void __launch_bounds__(128) k_forest_advance(ForestView F) {
 // sums them in MOVE order: the counts (or priors) are scattered into the dense row by all lanes, the sums, pow() and
 // the cumulative pick run on lane 0 over the A entries (once per move: not a hot path).
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick, u32 pruned) {
+__device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out, u32* picked_out, u32 pick, u32 pruned, u32 lane) {
   typedef Tafl<GAME> T;
-  const u32 lane = threadIdx.x & 31u;
-  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
+  {
     ForestTree& R = F.trees[t];
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
-    float* out = probs + (size_t)t * T::A;
     const u32 b = R.blk, k = b ? R.k : 0u;
     for (u32 m = lane; m < (u32)T::A; m += 32u) out[m] = 0.0f;
     __syncwarp();
@@ -1141,9 +1143,9 @@ __global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, 
         for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum2);
       }
       if (pick) {
-        Pcg32 rng = R.rng;
+        Pcg32 rng = FOREST_RNG(F, t);
         const float choice = rng_uniform01(rng);
-        R.rng = rng;
+        FOREST_RNG(F, t) = rng;
         u32 mvp = 0xFFFFFFFFu;
         float sum = 0.0f;
         for (u32 m = 0; m < (u32)T::A; ++m) {
@@ -1153,11 +1155,17 @@ __global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, 
         if (mvp == 0xFFFFFFFFu)
           for (int m = T::A - 1; m >= 0; --m)
             if (out[m] > 0.0f) { mvp = (u32)m; break; }
-        picked[t] = mvp;
+        *picked_out = mvp;
       }
     }
     __syncwarp();
   }
+}
+template <int GAME>
+__global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick, u32 pruned) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
+    forest_probs<GAME>(F, t, temp, probs + (size_t)t * Tafl<GAME>::A, picked + t, pick, pruned, lane);
 }
 // MCTS::counts / root_q_values (mcts.cc:557-573) + a few scalars per tree
 template <int GAME>

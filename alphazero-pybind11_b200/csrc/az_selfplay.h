@@ -1,0 +1,476 @@
+// az_selfplay.h — PlayManager::play (play_manager.cc:258-600) over the tafl games, on the device: the scheduler loop
+// of the reference (search `mcts_visits` simulations with the tree of the seat to move, temperature schedule, acting
+// rule, training-sample capture, both seats' trees re-rooted, game end / restart, Gumbel arming and root noise on the
+// reused root) with one warp per GAME SLOT, built on the wide-tree search of az_forest.h.
+//
+// Layout. Slot g owns trees 2g and 2g+1 of a forest (GameData::mcts[0..1], play_manager.h:36) and ONE pcg32 stream
+// (kept in tree 2g, ForestView::rng_pair): in the reference every draw of a worker thread — the child shuffles of
+// BOTH seats' trees (update_root expands an unexpanded root, mcts.cc:154-156), Dirichlet / Gumbel noise, pick_move —
+// comes from the thread-local generator, so slot g == the unmodified PlayManager with concurrent_games = 1 and
+// games_to_play = games_per_slot run after MCTS::seed_thread_rng(seed + g). Every slot needs exactly `visits`
+// simulations per move (no playout cap here), so all slots advance in lock step: k_sp_search (the hot kernel:
+// visits x (find_leaf, evaluator, process_result)) then k_sp_move (cold, once per move).
+// Training samples are staged per slot ([max_turns] rows of canonical + policy target) and appended to the output
+// ring when the game ends, last move first like PlayManager's partial_history.pop_back() loop (play_manager.cc:446-460).
+#pragma once
+
+namespace b2az {
+
+struct SpSlot {                       // b2az_tafl_selfplay_slot in include/b2az.h (same layout)
+  u32 active;                         // the slot is still cycling (play_manager.cc:506-508)
+  u32 games_started, games_completed;
+  u32 pending;                        // samples staged for the current game (GameData::partial_history.size())
+  u32 move_count, full_move_count;    // GameData counters of the current game
+  u32 total_move_count, total_full_move_count, game_length;  // PlayManager::total_move_count_ / full_move_count_ / game_length_
+  u32 picked;                         // scratch: the move pick_move returned
+  u32 error;                          // 1 = output ring full (samples dropped)
+  u32 pad_;
+  double g_leaf_depth, g_entropy, g_valid_moves;  // GameData::total_avg_leaf_depth / total_search_entropy / total_valid_moves
+  double leaf_depth, entropy, valid_moves;        // PlayManager::total_avg_leaf_depth_ / total_search_entropy_ / total_valid_moves_
+  unsigned long long simulations;
+  float scores[3];
+  u32 pad2_;
+};
+static_assert(sizeof(SpSlot) == 120, "b2az_tafl_selfplay_slot layout");
+
+struct SpView {
+  SpSlot* slots;
+  u32 n_games, games_per_slot, visits;
+  float start_temp, final_temp, half_life;
+  u32 history_enabled, policy_target_pruning, tree_reuse;
+  float* st_canon;    // [n_games][max_turns][CANON]
+  float* st_pi;       // [n_games][max_turns][A]
+  u8* st_player;      // [n_games][max_turns]
+  float* scratch_pi;  // [n_games][A]: the acting distribution
+  float *out_canon, *out_v, *out_pi;  // output ring [out_cap] rows
+  u32* out_slot;
+  u32 out_cap;
+  u32* out_count;     // rows appended since the last drain
+};
+
+#ifndef B2AZ_HOST_EMU
+// a fresh MCTS object (make_mcts, play_manager.cc): empty root, counters zero, Gumbel state reset with no target
+__device__ __forceinline__ void sp_reset_search(const ForestView& F, u32 t) {
+  ForestTree& R = F.trees[t];
+  R.n = 0; R.v = 0.0f; R.d = 0.0f; R.blk = 0; R.k = 0; R.player = 0; R.term = 0;
+  R.depth = 0; R.total_leaf_depth = 0; R.bump = 1; R.half = 0; R.nif = 0; R.expanded = 0; R.in_flight = 0;
+  if (F.gum) { F.gum[t].num_sims_target = 0; fg_reset(F.gum[t]); }
+}
+template <int GAME>
+__device__ __forceinline__ void sp_emit_canon(const TaflState& s, float* out, u32 lane) {  // GameState::canonicalized()
+  typedef Tafl<GAME> T;
+  constexpr int CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
+#pragma unroll
+  for (int j = 0; j < CHUNKS; ++j) {
+    const u32 c = 32u * j + lane;
+    if (c < (u32)CELLS) {
+      out[c] = (float)((b128_word(s.king, j) >> lane) & 1u);
+      out[CELLS + c] = (float)((b128_word(s.def, j) >> lane) & 1u);
+      out[2 * CELLS + c] = (float)((b128_word(s.atk, j) >> lane) & 1u);
+    }
+  }
+  for (int pl = 3; pl < T::PLANES; ++pl) {
+    const float v = T::canon_elem(s, (u32)(pl * CELLS));
+    for (u32 c = lane; c < (u32)CELLS; c += 32u) out[pl * CELLS + c] = v;
+  }
+}
+// MCTS::set_gumbel_num_sims(visits) on the tree of the seat to move, then under tree reuse the root temperature and
+// fresh noise on a root that has been visited (play_manager.cc:523-553; also the first call of a run, 556-568)
+__device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, u32 tn, u32 lane, bool reused_root) {
+  if (lane == 0) {
+    if (F.gum) { F.gum[tn].num_sims_target = S.visits; fg_reset(F.gum[tn]); }
+    if (reused_root) {
+      ForestTree& R = F.trees[tn];
+      if (R.n > 0 && R.blk != 0) {
+        u32* pool = F.pool + (size_t)tn * F.words_per_tree;
+        fr_apply_root_policy_temp(F, pool, R.blk, R.k);
+        if (F.epsilon > 0.0f) {
+          Pcg32 rng = FOREST_RNG(F, tn);
+          fr_add_root_noise(F, tn, rng, pool, R.blk, R.k);
+          FOREST_RNG(F, tn) = rng;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
+  for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) {
+    pcg32_seed(F.trees[2u * g].rng, seed + g);  // slot g == a reference run after MCTS::seed_thread_rng(seed + g)
+    SpSlot& G = S.slots[g];
+    G.active = 1;
+    G.games_started = 1;
+    // game.initialized = true; set_gumbel_num_sims on the first seat's tree (play_manager.cc:556-568)
+    const u32 t0 = 2u * g + F.trees[2u * g].state.player;
+    if (F.gum) { F.gum[t0].num_sims_target = S.visits; fg_reset(F.gum[t0]); }
+  }
+}
+
+// the hot kernel: `n_sims` x (MCTS::find_leaf, dumb_eval, MCTS::process_result) on the tree of the seat to move
+template <int GAME>
+__global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_sp_search(ForestView F, SpView S, u32 n_sims) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
+    if (!S.slots[g].active) continue;
+    const u32 t = 2u * g + F.trees[2u * g].state.player;
+    const bool noise = F.epsilon > 0.0f;  // seat_epsilon > 0 && !capped
+    for (u32 i = 0; i < n_sims; ++i) {
+      forest_find_leaf<GAME, false>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr);
+      forest_process_result<GAME, true, false>(F, t, nullptr, nullptr, lane, noise, F.trees[t].leaf);
+    }
+    if (lane == 0) S.slots[g].simulations += n_sims;
+  }
+}
+// the evaluator-in-the-middle form of the same step (EvalType::NN): leaves' canonical planes out, (v, pi) rows in;
+// row g of both belongs to slot g
+template <int GAME>
+__global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, float* canon) {
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
+    if (!S.slots[g].active) continue;
+    const u32 t = 2u * g + F.trees[2u * g].state.player;
+    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, canon + (size_t)g * Tafl<GAME>::CANON);
+  }
+}
+template <int GAME>
+__global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView S, const float* ev_v, const float* ev_pi) {
+  const u32 lane = threadIdx.x & 31u;
+  for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
+    if (!S.slots[g].active) continue;
+    const u32 t = 2u * g + F.trees[2u * g].state.player;
+    // forest_process_result reads row t of its inputs: hand it pointers moved so that row t is row g
+    forest_process_result<GAME, false, false>(F, t, ev_v + (size_t)g * 3 - (size_t)t * 3,
+                                              ev_pi + (size_t)g * Tafl<GAME>::A - (size_t)t * Tafl<GAME>::A, lane,
+                                              F.epsilon > 0.0f, F.trees[t].leaf);
+    if (lane == 0) S.slots[g].simulations += 1;
+  }
+}
+
+// "Actually play a move" (play_manager.cc:283-553) for every slot whose search has reached its visit count
+template <int GAME>
+__global__ void __launch_bounds__(128) k_sp_move(ForestView F, SpView S) {
+  typedef Tafl<GAME> T;
+  __shared__ ForestSmem<GAME> sm[4];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
+    SpSlot& G = S.slots[g];
+    if (!G.active) continue;
+    const u32 cp = F.trees[2u * g].state.player, t = 2u * g + cp;
+    ForestTree& R = F.trees[t];
+    if (R.depth < S.visits) continue;  // mcts.depth() >= goal_depth
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    // temperature schedule (play_manager.cc:285-302)
+    float temp = S.start_temp;
+    if (S.half_life != 0.0f) {
+      const float lambda = fdiv(0.693f, S.half_life);
+      temp = fsub(temp, S.final_temp);
+      temp = fmul(temp, az_expf(fmul(-lambda, (float)R.state.turn)));
+      temp = fadd(temp, S.final_temp);
+    }
+    // acting rule (play_manager.cc:372-416)
+    float* act = S.scratch_pi + (size_t)g * T::A;
+    u32 chosen = 0xFFFFFFFFu;
+    if (F.gumbel_enabled) {
+      if (lane == 0) chosen = fg_final_action(F, t, R, F.gum[t], pool);
+      chosen = __shfl_sync(0xFFFFFFFFu, chosen, 0);
+      if (chosen == 0xFFFFFFFFu) {  // the search never initialised: pick_move(probs(0)) (mcts.cc:379-381)
+        forest_probs<GAME>(F, t, 0.0f, act, &G.picked, 1u, 0u, lane);
+        chosen = G.picked;
+      }
+    } else {
+      forest_probs<GAME>(F, t, temp, act, &G.picked, 1u, 0u, lane);
+      chosen = G.picked;
+    }
+    // training sample (play_manager.cc:417-435)
+    if (S.history_enabled) {
+      const size_t row = (size_t)g * F.max_turns + G.pending;
+      sp_emit_canon<GAME>(R.state, S.st_canon + row * T::CANON, lane);
+      float* pi = S.st_pi + row * T::A;
+      if (F.gumbel_enabled) {
+        for (u32 m = lane; m < (u32)T::A; m += 32u) pi[m] = 0.0f;
+        __syncwarp();
+        if (lane == 0) fg_improved_policy(F, t, R, pool, pi);
+        __syncwarp();
+      } else {
+        forest_probs<GAME>(F, t, 1.0f, pi, nullptr, 0u, (S.policy_target_pruning && F.epsilon > 0.0f) ? 1u : 0u, lane);
+      }
+      if (lane == 0) S.st_player[row] = (u8)cp;
+    }
+    if (lane == 0) {
+      if (S.history_enabled) G.pending += 1;
+      // metrics (play_manager.cc:436-446; MCTS::avg_leaf_depth mcts.h:112, normalized_root_entropy mcts.cc:737-750)
+      const float ald = R.depth == 0 ? 0.0f : fdiv((float)R.total_leaf_depth, (float)R.depth);
+      G.g_leaf_depth += (double)ald;
+      float ent = 0.0f;
+      const u32 b = R.blk, k = b ? R.k : 0u;
+      if (k > 1 && R.n > 1) {
+        const float log_k = az_logf((float)k), total_n = (float)R.n;
+        float e = 0.0f;
+        for (u32 j = 0; j < k; ++j) {
+          const u32 nj = pool[fb_n(b, k) + j];
+          if (nj > 0) {
+            const float p = fdiv((float)nj, total_n);
+            e = fsub(e, fmul(p, az_logf(p)));
+          }
+        }
+        ent = fdiv(e, log_k);
+      }
+      G.g_entropy += (double)ent;
+      G.full_move_count += 1;
+      G.g_valid_moves += (double)k;
+      G.move_count += 1;
+    }
+    __syncwarp();
+    // for (auto& m : game.mcts) m.update_root(*game.gs, chosen_m); game.gs->play_move(chosen_m)  — seat 0's tree first:
+    // an unexpanded root draws its child shuffle from the shared stream
+    forest_update_root<GAME>(F, 2u * g, chosen, sm[wib], lane);
+    __syncwarp();
+    forest_update_root<GAME>(F, 2u * g + 1u, chosen, sm[wib], lane);
+    __syncwarp();
+    const TaflState ns = F.trees[2u * g].state;
+    const u32 term = T::terminal(ns);
+    if (term != 0) {
+      const float s0 = term == 1 ? 1.0f : 0.0f, s1 = term == 2 ? 1.0f : 0.0f, sd = term == 3 ? 1.0f : 0.0f;
+      if (S.history_enabled) {
+        const u32 cnt = G.pending;
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(S.out_count, cnt);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (u32 i = 0; i < cnt; ++i) {  // partial_history.back() first
+          const u32 dst = base + i;
+          if (dst >= S.out_cap) { if (lane == 0) G.error |= 1u; break; }
+          const size_t src = (size_t)g * F.max_turns + (cnt - 1u - i);
+          for (u32 e = lane; e < (u32)T::CANON; e += 32u) S.out_canon[(size_t)dst * T::CANON + e] = S.st_canon[src * T::CANON + e];
+          for (u32 e = lane; e < (u32)T::A; e += 32u) S.out_pi[(size_t)dst * T::A + e] = S.st_pi[src * T::A + e];
+          if (lane == 0) {
+            S.out_v[(size_t)dst * 3 + 0] = s0; S.out_v[(size_t)dst * 3 + 1] = s1; S.out_v[(size_t)dst * 3 + 2] = sd;
+            S.out_slot[dst] = g;
+          }
+        }
+      }
+      bool retire = false;
+      if (lane == 0) {
+        G.pending = 0;
+        G.scores[0] = fadd(G.scores[0], s0); G.scores[1] = fadd(G.scores[1], s1); G.scores[2] = fadd(G.scores[2], sd);
+        G.games_completed += 1;
+        G.game_length += ns.turn;
+        G.leaf_depth += G.g_leaf_depth; G.entropy += G.g_entropy; G.valid_moves += G.g_valid_moves;
+        G.total_move_count += G.move_count; G.total_full_move_count += G.full_move_count;
+        G.g_leaf_depth = 0; G.g_entropy = 0; G.g_valid_moves = 0; G.move_count = 0; G.full_move_count = 0;
+        if (G.games_started >= S.games_per_slot) {
+          G.active = 0;  // `continue`: the slot is not pushed back
+          retire = true;
+        } else {
+          G.games_started += 1;
+          for (u32 j = 0; j < 2u; ++j) {  // game.gs = base_gs_->copy(); fresh MCTS per seat
+            ForestTree& N = F.trees[2u * g + j];
+            T::init(N.state, F.max_turns);
+            N.hist_len = 0;
+            sp_reset_search(F, 2u * g + j);
+          }
+        }
+      }
+      retire = __shfl_sync(0xFFFFFFFFu, retire ? 1u : 0u, 0) != 0;
+      __syncwarp();
+      if (retire) continue;
+    }
+    const u32 tn = 2u * g + F.trees[2u * g].state.player;
+    if (!S.tree_reuse) {
+      // set_gumbel_num_sims happens BEFORE the trees are replaced by fresh MCTS objects (play_manager.cc:531-545), so
+      // without tree reuse the new objects have no simulation target (the reference's behaviour, reproduced)
+      if (lane == 0) { sp_reset_search(F, 2u * g); sp_reset_search(F, 2u * g + 1u); }
+      __syncwarp();
+    } else {
+      sp_arm(F, S, tn, lane, true);
+    }
+  }
+}
+__global__ void k_sp_count_active(SpView S, u32* out) {
+  u32 c = 0;
+  for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) c += S.slots[g].active ? 1u : 0u;
+  if (c) atomicAdd(out, c);
+}
+#endif  // !B2AZ_HOST_EMU
+
+}  // namespace b2az
+
+struct b2az_tafl_selfplay {
+  b2az_forest* forest = nullptr;
+  b2az::SpView view;
+  uint32_t* active_dev = nullptr;
+  float *ev_v = nullptr, *ev_pi = nullptr, *leaf_canon = nullptr;
+};
+
+extern "C" {
+
+int b2az_tafl_selfplay_destroy(b2az_tafl_selfplay* sp) {
+  using namespace b2az;
+  if (!sp) return 0;
+  dev_free(sp->view.slots); dev_free(sp->view.st_canon); dev_free(sp->view.st_pi); dev_free(sp->view.st_player);
+  dev_free(sp->view.scratch_pi); dev_free(sp->view.out_canon); dev_free(sp->view.out_v); dev_free(sp->view.out_pi);
+  dev_free(sp->view.out_slot); dev_free(sp->view.out_count); dev_free(sp->active_dev);
+  dev_free(sp->ev_v); dev_free(sp->ev_pi); dev_free(sp->leaf_canon);
+  b2az_forest_destroy(sp->forest);
+  delete sp;
+  return 0;
+}
+
+int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2az_tafl_selfplay** out) {
+  using namespace b2az;
+  if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
+  if (p->n_games == 0 || p->n_games > 0x7FFFFFFFu / 2u) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: bad n_games");
+  if (p->games_per_slot == 0 || p->visits == 0) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: games_per_slot and visits must be positive");
+  if (p->forest.max_in_flight != 0) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: PlayManager runs one leaf per game (max_in_flight must be 0)");
+  b2az_forest_params fp = p->forest;
+  fp.n_trees = 2u * p->n_games;
+  b2az_forest* f = nullptr;
+  if (int rc = b2az_forest_create(&fp, device, &f)) return rc;
+#ifdef B2AZ_HOST_EMU
+  return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+#else
+  b2az_tafl_selfplay* sp = new b2az_tafl_selfplay();
+  sp->forest = f;
+  f->view.rng_pair = 1;
+  SpView& S = sp->view;
+  memset(&S, 0, sizeof(S));
+  S.n_games = p->n_games; S.games_per_slot = p->games_per_slot; S.visits = p->visits;
+  S.start_temp = p->start_temp; S.final_temp = p->final_temp; S.half_life = p->temp_decay_half_life;
+  S.history_enabled = p->history_enabled ? 1u : 0u;
+  S.policy_target_pruning = p->policy_target_pruning ? 1u : 0u;
+  S.tree_reuse = p->tree_reuse ? 1u : 0u;
+  S.out_cap = S.history_enabled ? (p->hist_capacity ? p->hist_capacity : p->n_games * fp.max_turns) : 1u;
+  const size_t G = p->n_games, MT = fp.max_turns, A = f->actions, C = f->canon;
+  auto bail = [&](int rc) { b2az_tafl_selfplay_destroy(sp); return rc; };
+  if (int rc = dev_alloc(&S.slots, G)) return bail(rc);
+  if (int rc = dev_alloc_raw(&S.scratch_pi, G * A)) return bail(rc);
+  if (S.history_enabled) {
+    if (int rc = dev_alloc_raw(&S.st_canon, G * MT * C)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.st_pi, G * MT * A)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.st_player, G * MT)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.out_canon, (size_t)S.out_cap * C)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.out_v, (size_t)S.out_cap * 3)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.out_pi, (size_t)S.out_cap * A)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.out_slot, (size_t)S.out_cap)) return bail(rc);
+  }
+  if (int rc = dev_alloc(&S.out_count, 1)) return bail(rc);
+  if (int rc = dev_alloc(&sp->active_dev, 1)) return bail(rc);
+  k_sp_init<<<148, 128>>>(f->view, S, p->forest.seed);
+  if (cudaGetLastError() != cudaSuccess) return bail(fail(B2AZ_ECUDA, "k_sp_init launch failed"));
+  if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B2AZ_ECUDA, "k_sp_init failed"));
+  *out = sp;
+  return 0;
+#endif
+}
+
+#ifdef B2AZ_HOST_EMU
+int b2az_tafl_selfplay_play(b2az_tafl_selfplay*, void*, uint32_t, uint32_t*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_find_leaf(b2az_tafl_selfplay*, void*, const float**) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay*, void*, const float*, const float*, int, uint32_t*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay*, void*, uint32_t, float*, float*, float*, uint32_t*, uint32_t*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_slots(b2az_tafl_selfplay*, void*, b2az_tafl_selfplay_slot*, uint32_t*) FOREST_NO_CUDA()
+#else
+#define SP_CTAS(sp) std::max(1u, std::min(((sp)->view.n_games + 3u) / 4u, 148u * 8u))
+static int sp_active(b2az_tafl_selfplay* sp, cudaStream_t s, uint32_t* active_out) {
+  using namespace b2az;
+  if (!active_out) return 0;
+  CUDA_TRY(cudaMemsetAsync(sp->active_dev, 0, 4, s));
+  k_sp_count_active<<<148, 128, 0, s>>>(sp->view, sp->active_dev);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(active_out, sp->active_dev, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+int b2az_tafl_selfplay_play(b2az_tafl_selfplay* sp, void* stream, uint32_t n_moves, uint32_t* active_out) {
+  using namespace b2az;
+  if (!sp) return fail(B2AZ_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  b2az_forest* f = sp->forest;
+  for (uint32_t m = 0; m < n_moves; ++m) {
+    FOREST_DISPATCH(f, (k_sp_search<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, sp->view.visits)));
+    FOREST_DISPATCH(f, (k_sp_move<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view)));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return sp_active(sp, s, active_out);
+}
+int b2az_tafl_selfplay_find_leaf(b2az_tafl_selfplay* sp, void* stream, const float** canon_dev) {
+  using namespace b2az;
+  if (!sp || !canon_dev) return fail(B2AZ_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  b2az_forest* f = sp->forest;
+  if (!sp->leaf_canon)
+    if (int rc = dev_alloc(&sp->leaf_canon, (size_t)sp->view.n_games * f->canon)) return rc;
+  FOREST_DISPATCH(f, (k_sp_find_leaf<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, sp->leaf_canon)));
+  CUDA_TRY(cudaGetLastError());
+  *canon_dev = sp->leaf_canon;
+  return 0;
+}
+int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay* sp, void* stream, const float* v, const float* pi, int host_pointers,
+                                      uint32_t* active_out) {
+  using namespace b2az;
+  if (!sp || !v || !pi) return fail(B2AZ_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  b2az_forest* f = sp->forest;
+  const size_t G = sp->view.n_games;
+  if (host_pointers) {
+    if (!sp->ev_v) {
+      if (int rc = dev_alloc(&sp->ev_v, G * 3)) return rc;
+      if (int rc = dev_alloc(&sp->ev_pi, G * f->actions)) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(sp->ev_v, v, G * 3 * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(sp->ev_pi, pi, G * f->actions * 4, cudaMemcpyHostToDevice, s));
+    v = sp->ev_v; pi = sp->ev_pi;
+  }
+  FOREST_DISPATCH(f, (k_sp_process_result<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, v, pi)));
+  FOREST_DISPATCH(f, (k_sp_move<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view)));
+  CUDA_TRY(cudaGetLastError());
+  return sp_active(sp, s, active_out);
+}
+int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay* sp, void* stream, uint32_t max_rows, float* canon_host, float* v_host,
+                                     float* pi_host, uint32_t* slot_host, uint32_t* n_out) {
+  using namespace b2az;
+  if (!sp || !n_out) return fail(B2AZ_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  uint32_t n = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n, sp->view.out_count, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  n = std::min(n, sp->view.out_cap);
+  if (!sp->view.history_enabled) n = 0;
+  if (n > max_rows) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_drain_history: " + std::to_string(n) + " rows are waiting, max_rows is smaller");
+  const size_t A = sp->forest->actions, C = sp->forest->canon;
+  if (n) {
+    if (canon_host) CUDA_TRY(cudaMemcpyAsync(canon_host, sp->view.out_canon, (size_t)n * C * 4, cudaMemcpyDeviceToHost, s));
+    if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, sp->view.out_v, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    if (pi_host) CUDA_TRY(cudaMemcpyAsync(pi_host, sp->view.out_pi, (size_t)n * A * 4, cudaMemcpyDeviceToHost, s));
+    if (slot_host) CUDA_TRY(cudaMemcpyAsync(slot_host, sp->view.out_slot, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaMemsetAsync(sp->view.out_count, 0, 4, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *n_out = n;
+  return 0;
+}
+int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host) {
+  using namespace b2az;
+  if (!sp) return fail(B2AZ_EINVAL, "null argument");
+  static_assert(sizeof(b2az_tafl_selfplay_slot) == sizeof(SpSlot), "slot layout");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (slots_host)
+    CUDA_TRY(cudaMemcpyAsync(slots_host, sp->view.slots, (size_t)sp->view.n_games * sizeof(SpSlot), cudaMemcpyDeviceToHost, s));
+  if (tree_errors_host) {
+    // sticky error bits of the 2 * n_games trees (slab full, path too long, ...)
+    CUDA_TRY(cudaMemcpy2DAsync(tree_errors_host, 4, &sp->forest->view.trees[0].error, sizeof(ForestTree), 4,
+                               (size_t)sp->forest->view.n_trees, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+#endif
+
+}  // extern "C"

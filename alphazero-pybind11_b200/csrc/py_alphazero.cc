@@ -313,7 +313,10 @@ class PlayManager {
 
   const PlayParams& params() const { return params_; }
   void stop() {
-    stopped_.store(true);
+    {
+      std::lock_guard<std::mutex> lk(mu_);  // under the waiters' mutex: a wait that has just tested its predicate cannot miss this
+      stopped_.store(true);
+    }
     cv_.notify_all();
   }
   bool stopped() const { return stopped_.load(); }

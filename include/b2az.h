@@ -315,6 +315,53 @@ int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_
  * used, root v (bits), total_leaf_depth, side to move. Any pointer may be NULL. */
 int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host);
 
+/* ---- PlayManager::play (play_manager.cc:258-600) over the tafl games on the device: n_games game slots, each with the
+ * two seats' search trees (GameData::mcts[0..1]) and ONE pcg32 stream, playing games_per_slot games one after the
+ * other. Slot g reproduces the unmodified reference PlayManager with concurrent_games = 1, games_to_play =
+ * games_per_slot, mcts_visits = {visits, visits}, self_play, no playout cap, no resignation, run on one thread after
+ * MCTS::seed_thread_rng(forest.seed + g): moves, training samples (canonical, outcome, policy target: the Gumbel
+ * improved policy / probs_pruned(1) / probs(1), play_manager.cc:417-435), scores and metrics, bit for bit.
+ * forest.n_trees is ignored (2 * n_games trees are made); forest.max_in_flight must be 0. */
+typedef struct b2az_tafl_selfplay_params {
+  b2az_forest_params forest;     /* game, max_turns, search parameters (cpuct, epsilon, Gumbel ...), seed, slab size */
+  uint32_t n_games;              /* PlayParams::concurrent_games */
+  uint32_t games_per_slot;       /* games every slot plays before it retires (games_to_play = n_games * games_per_slot) */
+  uint32_t visits;               /* PlayParams::mcts_visits (both seats) */
+  float start_temp, final_temp, temp_decay_half_life;  /* play_manager.cc:285-302 */
+  uint8_t history_enabled, policy_target_pruning, tree_reuse, pad_;
+  uint32_t hist_capacity;        /* rows of the training-sample ring between drains; 0 = n_games * max_turns */
+} b2az_tafl_selfplay_params;
+typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
+  uint32_t active, games_started, games_completed, pending;
+  uint32_t move_count, full_move_count;                          /* current game */
+  uint32_t total_move_count, total_full_move_count, game_length; /* finished games */
+  uint32_t picked, error, pad_;                                  /* error: 1 = sample ring full (samples dropped) */
+  double g_leaf_depth, g_entropy, g_valid_moves;                 /* current game */
+  double leaf_depth, entropy, valid_moves;                       /* total_avg_leaf_depth_, total_search_entropy_, total_valid_moves_ */
+  unsigned long long simulations;
+  float scores[3];                                               /* scores_: seat 0 wins, seat 1 wins, draws */
+  uint32_t pad2_;
+} b2az_tafl_selfplay_slot;
+typedef struct b2az_tafl_selfplay b2az_tafl_selfplay;
+int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2az_tafl_selfplay** out);
+int b2az_tafl_selfplay_destroy(b2az_tafl_selfplay* sp);
+/* EvalType::RANDOM: n_moves x (visits simulations with dumb_eval fused, then the move step) for every active slot,
+ * two launches per move, no host synchronisation unless active_out (host, number of slots still cycling) is given. */
+int b2az_tafl_selfplay_play(b2az_tafl_selfplay* sp, void* stream, uint32_t n_moves, uint32_t* active_out);
+/* EvalType::NN, one simulation per call pair: find_leaf writes the active slots' leaf positions (row g = slot g of
+ * DEVICE float32[n_games][P][S][S], the evaluator's input, zero copy); process_result takes (v float32[n_games][3],
+ * pi float32[n_games][A]) in the same row order (device pointers, or host ones with host_pointers != 0) and plays the
+ * move of every slot whose search has reached `visits` simulations. */
+int b2az_tafl_selfplay_find_leaf(b2az_tafl_selfplay* sp, void* stream, const float** canon_dev);
+int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay* sp, void* stream, const float* v, const float* pi, int host_pointers,
+                                      uint32_t* active_out);
+/* PlayManager::build_history_batch (py_wrapper.cc:393-424): the samples of the games finished since the last drain
+ * (each game's moves last first, like history_), with the slot they came from; fails if more than max_rows wait. */
+int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay* sp, void* stream, uint32_t max_rows, float* canon_host, float* v_host,
+                                     float* pi_host, uint32_t* slot_host, uint32_t* n_out);
+/* slots_host[n_games]; tree_errors_host[2 * n_games] = the trees' sticky error bits (see b2az_forest_counts). */
+int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host);
+
 #ifdef __cplusplus
 }
 #endif

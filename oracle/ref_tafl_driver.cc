@@ -14,6 +14,9 @@
 //                           deterministic generator, so the same transcript can be regenerated)
 //   azref_tafl_search       a whole single-tree MCTS run (MCTS::find_leaf / process_result / update_root,
 //                           mcts.cc) over one game with a caller-supplied or dumb_eval evaluator
+//   azref_tafl_selfplay     the UNMODIFIED PlayManager (play_manager.cc) playing `games_to_play` tafl games one after the
+//                           other in ONE slot on the calling thread (EvalType::RANDOM), after
+//                           MCTS::seed_thread_rng(seed): history samples, scores and metrics
 //   azref_tafl_replay       replays a transcript through GameState::play_move and records, after
 //                           every move: to_bytes() board, player, turn, repetition count, scores(),
 //                           valid_moves(), canonicalized()
@@ -25,6 +28,7 @@
 
 #include "brandubh_gs.cc"
 #include "mcts.h"
+#include "play_manager.h"
 #include "opentafl_gs.cc"
 #include "tawlbwrdd_gs.cc"
 
@@ -318,6 +322,80 @@ int azref_tafl_symmetries(int game, const float* canon, const float* v, const fl
     std::memcpy(pi_out + i * A, syms[i].pi.data(), A * 4);
   }
   return (int)syms.size();
+}
+
+// One slot of PlayManager::play (play_manager.cc:258-600) over a tafl game: concurrent_games = 1, games_to_play = K,
+// EvalType::RANDOM for both seats, on the calling thread after MCTS::seed_thread_rng(seed) — every draw of the run
+// (child shuffles of BOTH seats' trees, Dirichlet / Gumbel noise, pick_move) then comes from that one stream.
+// History rows come out in history_ order (a game's samples last move first, game after game).
+struct AzRefTaflSpCfg {
+  uint32_t games_to_play, visits;
+  float cpuct, fpu_reduction, epsilon, mcts_root_temp;
+  float start_temp, final_temp, temp_decay_half_life;
+  uint32_t gumbel_m;
+  float gumbel_c_visit, gumbel_c_scale;
+  uint8_t root_fpu_zero, shaped_dirichlet, policy_target_pruning, gumbel_enabled, tree_reuse, history_enabled, pad_[2];
+};
+int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRefTaflSpCfg* c, uint32_t hist_cap,
+                        float* canon_out, float* v_out, float* pi_out, uint32_t* n_hist, float* scores3,
+                        uint32_t* games_completed, float* metrics4) {
+  try {
+    auto gs = make_game(game, max_turns);
+    if (!gs) { g_err = "unknown game"; return -1; }
+    PlayParams p{};
+    p.games_to_play = c->games_to_play;
+    p.concurrent_games = 1;
+    p.max_batch_size = 1;
+    p.max_cache_size = 0;
+    p.mcts_visits = {c->visits, c->visits};
+    p.cpuct = c->cpuct;
+    p.fpu_reduction = c->fpu_reduction;
+    p.root_fpu_zero = c->root_fpu_zero != 0;
+    p.epsilon = c->epsilon;
+    p.mcts_root_temp = c->mcts_root_temp;
+    p.shaped_dirichlet = c->shaped_dirichlet != 0;
+    p.policy_target_pruning = c->policy_target_pruning != 0;
+    p.start_temp = c->start_temp;
+    p.final_temp = c->final_temp;
+    p.temp_decay_half_life = c->temp_decay_half_life;
+    p.gumbel_enabled = c->gumbel_enabled != 0;
+    p.gumbel_m = c->gumbel_m;
+    p.gumbel_c_visit = c->gumbel_c_visit;
+    p.gumbel_c_scale = c->gumbel_c_scale;
+    p.tree_reuse = c->tree_reuse != 0;
+    p.history_enabled = c->history_enabled != 0;
+    p.self_play = true;
+    p.model_groups = {0, 0};
+    p.playout_cap_randomization = false;
+    p.resign_percent = 0.0f;
+    p.eval_type = {EvalType::RANDOM, EvalType::RANDOM};
+    PlayManager pm{std::move(gs), p};
+    MCTS::seed_thread_rng(seed);
+    pm.play();
+    const size_t A = pm.params().mcts_visits.size() ? (size_t)make_game(game, max_turns)->num_moves() : 0;
+    uint32_t n = 0;
+    while (auto h = pm.pop_hist()) {
+      if (n < hist_cap) {
+        const size_t C = (size_t)h->canonical.size();
+        if (canon_out) std::memcpy(canon_out + (size_t)n * C, h->canonical.data(), C * 4);
+        if (v_out) std::memcpy(v_out + (size_t)n * 3, h->v.data(), 12);
+        if (pi_out) std::memcpy(pi_out + (size_t)n * A, h->pi.data(), A * 4);
+      }
+      ++n;
+    }
+    *n_hist = n;
+    auto sc = pm.scores();
+    for (int i = 0; i < 3; ++i) scores3[i] = sc(i);
+    *games_completed = pm.games_completed();
+    metrics4[0] = pm.avg_game_length();
+    metrics4[1] = pm.avg_leaf_depth();
+    metrics4[2] = pm.avg_valid_moves();
+    metrics4[3] = pm.avg_search_entropy();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
 }
 
 }  // extern "C"

@@ -27,9 +27,48 @@ def lib():
         L.azref_tafl_replay.argtypes = [C.c_int, C.c_uint16, vp, u32] + [vp] * 9
         L.azref_tafl_search.argtypes = [C.c_int, C.c_uint16, C.c_uint64, C.c_float, C.c_float, C.c_int, u32, u32, C.c_int, vp, vp, vp, vp, vp, vp, u32, C.c_float, C.c_float, vp, C.c_float, C.c_float, C.c_int, u32, C.c_float, vp, C.c_float]
         L.azref_tafl_symmetries.argtypes = [C.c_int] + [vp] * 6
+        L.azref_tafl_selfplay.argtypes = [C.c_int, C.c_uint16, C.c_uint64, C.POINTER(SelfplayCfg), u32] + [vp] * 7
         L.azref_tafl_position.argtypes = [C.c_int, vp, C.c_int8, C.c_uint16, C.c_uint16, C.c_uint8, u32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
+
+
+class SelfplayCfg(C.Structure):  # AzRefTaflSpCfg (oracle/ref_tafl_driver.cc)
+    _fields_ = [("games_to_play", C.c_uint32), ("visits", C.c_uint32), ("cpuct", C.c_float), ("fpu_reduction", C.c_float),
+                ("epsilon", C.c_float), ("mcts_root_temp", C.c_float), ("start_temp", C.c_float), ("final_temp", C.c_float),
+                ("temp_decay_half_life", C.c_float), ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float),
+                ("gumbel_c_scale", C.c_float), ("root_fpu_zero", C.c_uint8), ("shaped_dirichlet", C.c_uint8),
+                ("policy_target_pruning", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("tree_reuse", C.c_uint8),
+                ("history_enabled", C.c_uint8), ("pad_", C.c_uint8 * 2)]
+
+
+def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, epsilon=0.0,
+             root_policy_temp=1.0, shaped_dirichlet=False, policy_target_pruning=False, gumbel_m=0, gumbel_c_visit=50.0,
+             gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0, tree_reuse=True):
+    """The unmodified PlayManager, one slot, games_to_play games one after the other (EvalType::RANDOM) after
+    MCTS::seed_thread_rng(seed). Returns dict(canonical, v, pi in history_ order, scores, games_completed,
+    avg_game_length, avg_leaf_depth, avg_valid_moves, avg_search_entropy)."""
+    S, A, P = dims(game)
+    cap = games_to_play * max_turns
+    cfg = SelfplayCfg(games_to_play=games_to_play, visits=visits, cpuct=cpuct, fpu_reduction=fpu_reduction, epsilon=epsilon,
+                      mcts_root_temp=root_policy_temp, start_temp=start_temp, final_temp=final_temp,
+                      temp_decay_half_life=temp_decay_half_life, gumbel_m=gumbel_m or 16, gumbel_c_visit=gumbel_c_visit,
+                      gumbel_c_scale=gumbel_c_scale, root_fpu_zero=int(root_fpu_zero), shaped_dirichlet=int(shaped_dirichlet),
+                      policy_target_pruning=int(policy_target_pruning), gumbel_enabled=int(gumbel_m > 0),
+                      tree_reuse=int(tree_reuse), history_enabled=1)
+    canon = np.zeros((cap, P, S, S), np.float32)
+    v, pi = np.zeros((cap, 3), np.float32), np.zeros((cap, A), np.float32)
+    n, done = C.c_uint32(0), C.c_uint32(0)
+    scores, metrics = np.zeros(3, np.float32), np.zeros(4, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().azref_tafl_selfplay(game, max_turns, seed, C.byref(cfg), cap, p(canon), p(v), p(pi),
+                                   C.cast(C.byref(n), C.c_void_p), p(scores), C.cast(C.byref(done), C.c_void_p), p(metrics))
+    if rc != 0:
+        raise RuntimeError(lib().azref_tafl_last_error().decode())
+    k = n.value
+    return dict(canonical=canon[:k], v=v[:k], pi=pi[:k], scores=scores, games_completed=done.value,
+                avg_game_length=metrics[0], avg_leaf_depth=metrics[1], avg_valid_moves=metrics[2],
+                avg_search_entropy=metrics[3])
 
 
 def dims(game):

@@ -1,0 +1,150 @@
+"""PlayManager::play over the tafl games on the device (b2az_tafl_selfplay_*) against the UNMODIFIED reference
+PlayManager (oracle/_ref/libazref_tafl.so: azref_tafl_selfplay — play_manager.cc + mcts.cc + the tafl games compiled in
+place). Slot g of the device run == a reference PlayManager with concurrent_games = 1, games_to_play = games_per_slot,
+EvalType::RANDOM, run on one thread after MCTS::seed_thread_rng(seed + g). Compared bit for bit (floats by bit
+pattern): the training samples in history_ order (canonical planes, outcome, policy target — Gumbel improved policy /
+probs_pruned(1) / probs(1)), scores, games completed, game length, and the metric sums (leaf depth, root entropy,
+legal moves). Golden CRCs (tools/make_golden_tafl_selfplay.py) cover the same cases without the reference."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import b2az
+import parity_harness as ph
+import tafl_ref
+
+NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
+needs_tafl_ref = pytest.mark.skipif(not tafl_ref.available(), reason="oracle/_ref/libazref_tafl.so not built")
+GOLDEN = os.path.join(ph.ROOT, "tests", "golden", "tafl_selfplay.npz")
+
+# self-play settings of configs/brandubh.yaml-style runs, small: name -> (game, slots, games per slot, max_turns, visits, kwargs)
+CASES = {
+    "brandubh_puct_plain": (0, 6, 2, 40, 40, dict()),
+    "brandubh_puct_selfplay": (0, 6, 2, 40, 40, dict(epsilon=0.25, root_policy_temp=1.25, shaped_dirichlet=True,
+                                                     policy_target_pruning=True, root_fpu_zero=True, start_temp=1.0,
+                                                     final_temp=0.2, temp_decay_half_life=10.0)),
+    "brandubh_gumbel": (0, 6, 2, 40, 48, dict(gumbel_m=16, root_policy_temp=1.25)),
+    "brandubh_no_tree_reuse": (0, 4, 2, 30, 32, dict(tree_reuse=False, epsilon=0.25, gumbel_m=8)),
+    "opentafl_gumbel": (1, 3, 1, 24, 40, dict(gumbel_m=16, cpuct=2.0)),
+    "tawlbwrdd_puct_selfplay": (2, 3, 1, 24, 40, dict(epsilon=0.25, root_policy_temp=1.1, policy_target_pruning=True,
+                                                      start_temp=1.0, final_temp=0.5, temp_decay_half_life=6.0)),
+}
+
+
+def run_device(game, slots, per_slot, max_turns, visits, kw, seed):
+    words = 2 * (1 + (max_turns + 2) * visits * (1 + 8 * (64 if game == 0 else 200)))
+    sp = b2az.TaflSelfplay(game, slots, max_turns, visits, games_per_slot=per_slot, seed=seed, words_per_tree=words, **kw)
+    active, rounds = slots, 0
+    while active:
+        active = sp.play(8)
+        rounds += 1
+        assert rounds < 10000
+    canon, v, pi, slot = sp.drain_history()
+    st, err = sp.slots()
+    sp.close()
+    assert (err == 0).all() and (st["error"] == 0).all()
+    return canon, v, pi, slot, st
+
+
+def crc(*arrays):
+    c = 0
+    for a in arrays:
+        c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+    return c
+
+
+def f32(x):
+    return np.float32(x)
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_selfplay_equals_the_reference_playmanager(name):
+    game, slots, per_slot, max_turns, visits, kw = CASES[name]
+    seed = 1000 + 17 * sorted(CASES).index(name)
+    canon, v, pi, slot, st = run_device(game, slots, per_slot, max_turns, visits, kw, seed)
+    for g in range(slots):
+        ref = tafl_ref.selfplay(game, seed + g, max_turns, per_slot, visits, **kw)
+        rows = slot == g
+        assert rows.sum() == len(ref["v"]), f"{name} slot {g}: {rows.sum()} samples vs {len(ref['v'])}"
+        assert np.array_equal(canon[rows].view(np.uint32), ref["canonical"].view(np.uint32)), f"{name} slot {g}: canonical"
+        assert np.array_equal(v[rows].view(np.uint32), ref["v"].view(np.uint32)), f"{name} slot {g}: outcomes"
+        assert np.array_equal(pi[rows].view(np.uint32), ref["pi"].view(np.uint32)), f"{name} slot {g}: policy targets"
+        s = st[g]
+        assert s["games_completed"] == ref["games_completed"] == per_slot and s["active"] == 0
+        assert np.array_equal(s["scores"], ref["scores"])
+        # the getters of play_manager.h:288-316 on the slot's sums
+        assert f32(f32(s["game_length"]) / f32(s["games_completed"])) == ref["avg_game_length"]
+        assert f32(s["leaf_depth"] / float(s["total_full_move_count"])) == ref["avg_leaf_depth"]
+        assert f32(s["entropy"] / float(s["total_full_move_count"])) == ref["avg_search_entropy"]
+        assert f32(s["valid_moves"] / float(s["total_move_count"])) == ref["avg_valid_moves"]
+        assert s["simulations"] == visits * s["total_move_count"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_selfplay_equals_the_golden_fixture(name):
+    game, slots, per_slot, max_turns, visits, kw = CASES[name]
+    seed = 1000 + 17 * sorted(CASES).index(name)
+    gold = np.load(GOLDEN)
+    canon, v, pi, slot, st = run_device(game, slots, per_slot, max_turns, visits, kw, seed)
+    for g in range(slots):
+        rows = slot == g
+        want = gold[name][g]
+        got = (rows.sum(), crc(canon[rows]), crc(v[rows]), crc(pi[rows]), int(st[g]["game_length"]), crc(st[g]["scores"]))
+        assert tuple(int(x) for x in want) == tuple(int(x) for x in got), f"{name} slot {g}"
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+def test_selfplay_with_a_host_evaluator_in_the_middle():
+    """EvalType::NN form: find_leaf -> evaluator -> process_result per simulation. With the evaluator answering
+    dumb_eval's numbers (uniform over the legal moves of the leaf, 1/3 each) the run equals the fused RANDOM one."""
+    game, slots, max_turns, visits = 0, 4, 30, 24
+    words = 2 * (1 + (max_turns + 2) * visits * (1 + 8 * 64))
+    kw = dict(epsilon=0.25, root_policy_temp=1.25, policy_target_pruning=True)
+    fused = run_device(game, slots, 1, max_turns, visits, kw, 77)
+    import ctypes as C
+    cudart = C.CDLL("libcudart.so.12")
+    sp = b2az.TaflSelfplay(game, slots, max_turns, visits, games_per_slot=1, seed=77, words_per_tree=words, **kw)
+    S, P, A = sp.S, sp.P, sp.A
+    active, steps = slots, 0
+    canon = np.zeros((slots, P, S, S), np.float32)
+    while active:
+        ptr = sp.find_leaf()
+        assert cudart.cudaMemcpy(canon.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), canon.nbytes, 2) == 0  # D2H, syncs
+        vs, pis = np.zeros((slots, 3), np.float32), np.zeros((slots, A), np.float32)
+        for g in range(slots):
+            board = np.zeros((3, S, S), np.int8)
+            board[:] = canon[g, :3] > 0
+            player = 0 if canon[g, 3, 0, 0] > 0 else 1
+            pos = tafl_ref.position(game, board, player, 0, max_turns, 0)
+            valid = pos["valid"].astype(np.float32)
+            # dumb_eval (game_state.h:160-173): Vector<uint8_t>::sum() wraps mod 256
+            total = np.float32(int(valid.sum()) % 256)
+            pis[g] = valid / total if total > 0 else valid
+            vs[g] = np.float32(1.0 / 3.0)
+        active = sp.process_result(vs, pis, want_active=True)
+        steps += 1
+        assert steps < 200000
+    canon, v, pi, slot = sp.drain_history()
+    sp.close()
+    # outcomes and sample counts: the same games were played (policy targets too, when no leaf had > 255 legal moves)
+    assert np.array_equal(slot, fused[3]) and np.array_equal(v, fused[1])
+    assert np.array_equal(canon.view(np.uint32), fused[0].view(np.uint32))
+    assert np.array_equal(pi.view(np.uint32), fused[2].view(np.uint32))
+
+
+def test_selfplay_fails_loudly_without_a_gpu_and_on_bad_arguments():
+    from conftest import has_cuda
+    with pytest.raises(b2az.B2azError):
+        b2az.TaflSelfplay(0, 0, 30, 8)  # no slots
+    with pytest.raises(b2az.B2azError):
+        b2az.TaflSelfplay(0, 2, 30, 0)  # no visits
+    if not has_cuda():
+        with pytest.raises(b2az.B2azError) as ei:
+            b2az.TaflSelfplay(0, 2, 30, 8)
+        assert "no CPU fallback" in str(ei.value)

@@ -1,0 +1,85 @@
+"""Throughput of PlayManager::play over a tafl game on the device (b2az_tafl_selfplay_*): `--games` concurrent game
+slots (two search trees each), `--sims` simulations per move with the reference's dumb_eval evaluator fused in, the
+self-play settings of configs/brandubh.yaml / open_tafl.yaml / tawlbwrdd.yaml (Gumbel root search m = 16, or --puct:
+Dirichlet noise + temperature schedule + pruned policy targets), training samples captured and drained to the host
+every `--drain` moves. Simulations/s and moves/s over `--moves` lock-step moves after `--warm` warm-up moves, next to
+the UNMODIFIED reference PlayManager doing the same on the host (one thread per slot-sized run, `--cpu-seconds`).
+    python tools/tafl_selfplay_bench.py [--game 0|1|2] [--games N] [--sims 120] [--moves 24]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "alphazero-pybind11_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import b2az  # noqa: E402
+import tafl_ref  # noqa: E402
+
+NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
+MAX_TURNS = {0: 150, 1: 400, 2: 400}  # configs/*.yaml max_turns
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--game", type=int, default=0)
+    ap.add_argument("--games", type=int, default=8192)
+    ap.add_argument("--sims", type=int, default=120)
+    ap.add_argument("--moves", type=int, default=24)
+    ap.add_argument("--warm", type=int, default=4)
+    ap.add_argument("--drain", type=int, default=8)
+    ap.add_argument("--max-turns", type=int, default=0)
+    ap.add_argument("--puct", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    a = ap.parse_args()
+    mt = a.max_turns or MAX_TURNS[a.game]
+    kw = (dict(epsilon=0.25, root_policy_temp=1.25, shaped_dirichlet=True, policy_target_pruning=True, start_temp=1.0,
+               final_temp=0.2, temp_decay_half_life=10.0) if a.puct else dict(gumbel_m=16, root_policy_temp=1.25))
+    words = 2 * (1 + 3 * a.sims * (1 + 8 * (48 if a.game == 0 else 140)))
+    sp = b2az.TaflSelfplay(a.game, a.games, mt, a.sims, games_per_slot=1 << 20, seed=1, words_per_tree=words,
+                           hist_capacity=a.games * (a.drain + 2) * 4, **kw)
+    stream = torch.cuda.current_stream().cuda_stream
+    sp.play(a.warm, stream, want_active=False)
+    torch.cuda.synchronize()
+    st0, _ = sp.slots()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples, t0 = 0, time.perf_counter()
+    e0.record()
+    done = 0
+    while done < a.moves:
+        n = min(a.drain, a.moves - done)
+        sp.play(n, stream, want_active=False)
+        done += n
+        samples += len(sp.drain_history(stream)[1])  # finished games' samples to the host (synchronises)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    st1, err = sp.slots()
+    sp.close()
+    assert (err == 0).all() and (st1["error"] == 0).all(), (set(err.tolist()), set(st1["error"].tolist()))
+    sims = int(st1["simulations"].sum() - st0["simulations"].sum())
+    moves = sims // a.sims
+    games = int(st1["games_completed"].sum() - st0["games_completed"].sum())
+    full = max(1, int(st1["total_full_move_count"].sum()))
+    # the unmodified reference PlayManager on one host thread, same settings
+    t0 = time.perf_counter()
+    ref_moves, n_ref = 0, 0
+    while time.perf_counter() - t0 < a.cpu_seconds:
+        r = tafl_ref.selfplay(a.game, 900 + n_ref, mt, 1, a.sims, **kw)
+        ref_moves += len(r["v"])
+        n_ref += 1
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({
+        "kernel": "k_sp_search + k_sp_move", "workload": f"{NAMES[a.game]} self-play (PlayManager::play on the device), "
+        f"{a.games} concurrent games, {a.sims} sims/move, " + ("PUCT + Dirichlet + pruned targets" if a.puct else "Gumbel m=16") +
+        ", dumb_eval, tree reuse, history on", "ms": round(ms, 2), "moves_timed": a.moves,
+        "simulations_per_second": sims / (ms * 1e-3), "moves_per_second": moves / (ms * 1e-3),
+        "games_finished_in_window": games, "samples_drained": samples, "wall_s": round(wall, 3),
+        "mean_leaf_depth_finished_games": float(st1["leaf_depth"].sum() / full),
+        "mean_legal_moves_finished_games": float(st1["valid_moves"].sum() / max(1, int(st1["total_move_count"].sum()))),
+        "cpu_baseline": {"value": ref_moves * a.sims / cpu_s, "unit": "sims/s", "moves_per_second": ref_moves / cpu_s, "cores": 1,
+                         "kind": "reference", "sample": f"{n_ref} games of the unmodified reference PlayManager (concurrent_games=1, "
+                                                       f"EvalType::RANDOM), same settings, one host thread"}}))
