@@ -33,6 +33,14 @@ def shard_params(params, rank, world, total_games=None, total_concurrent=None):
     return p
 
 
+def shard_slots(n_games, seed, rank, world):
+    """Tafl self-play (b2az.TaflSelfplay): slot g draws from pcg32(seed + g), so rank r takes the contiguous slot range
+    [lo, hi) and passes seed + lo — the union over the ranks is the single-process run, slot for slot
+    (tests/test_tafl_selfplay.py::test_sharded_slots_equal_the_unsharded_run). Returns (n_games_local, seed_local, lo)."""
+    lo, hi = shard_games(n_games, rank, world)
+    return hi - lo, int(seed) + lo, lo
+
+
 def _device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 

@@ -501,6 +501,8 @@ def main():
         extra = {}
         for key, cmd in (("brandubh_gumbel_search", ["tools/forest_bench.py", "--game", "0", "--trees", "8192", "--moves", "6",
                                                      "--gumbel-m", "16"]),
+                         ("brandubh_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "0", "--games", "8192", "--moves", "16",
+                                                "--cpu-seconds", "5"]),
                          ("opentafl_game_kernels", ["tools/tafl_bench.py", "--game", "1", "--games", "8192", "--reps", "3"])):
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], stdout=subprocess.PIPE,

@@ -52,6 +52,16 @@ def test_shard_games_covers_the_budget():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_slots_keeps_every_slot_on_its_own_stream():
+    for n, world in [(8192, 8), (10, 3), (5, 8)]:
+        seen = []
+        for r in range(world):
+            k, seed, lo = bd.shard_slots(n, 1000, r, world)
+            seen += [seed + g for g in range(k)]
+            assert seed == 1000 + lo
+        assert seen == list(range(1000, 1000 + n))
+
+
 def test_two_rank_run_matches_single_process(tmp_path):
     out = tmp_path / "hist.npz"
     env = dict(os.environ, B2AZ_PKG=os.path.join(ph.ROOT, "alphazero-pybind11_b200"), B2AZ_TESTS=os.path.join(ph.ROOT, "tests"),

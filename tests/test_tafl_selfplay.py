@@ -138,6 +138,23 @@ def test_selfplay_with_a_host_evaluator_in_the_middle():
     assert np.array_equal(pi.view(np.uint32), fused[2].view(np.uint32))
 
 
+@pytest.mark.gpu
+def test_sharded_slots_equal_the_unsharded_run():
+    """Multi-GPU sharding: slots are independent, rank r takes slots [r*n, (r+1)*n) with seed + r*n — the
+    union of two half-size runs is the full run, sample for sample."""
+    game, slots, max_turns, visits = 0, 8, 30, 32
+    kw = dict(gumbel_m=16)
+    full = run_device(game, slots, 1, max_turns, visits, kw, 500)
+    for r in range(2):
+        part = run_device(game, slots // 2, 1, max_turns, visits, kw, 500 + r * (slots // 2))
+        for g in range(slots // 2):
+            a, b = full[3] == g + r * (slots // 2), part[3] == g
+            assert a.sum() == b.sum() > 0
+            for k in range(3):
+                assert np.array_equal(full[k][a].view(np.uint32), part[k][b].view(np.uint32))
+            assert full[4][g + r * (slots // 2)]["game_length"] == part[4][g]["game_length"]
+
+
 def test_selfplay_fails_loudly_without_a_gpu_and_on_bad_arguments():
     from conftest import has_cuda
     with pytest.raises(b2az.B2azError):

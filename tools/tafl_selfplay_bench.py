@@ -33,6 +33,8 @@ if __name__ == "__main__":
     ap.add_argument("--max-turns", type=int, default=0)
     ap.add_argument("--puct", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--net", action="store_true", help="EvalType::NN: a random-init torch conv net between find_leaf and "
+                                                       "process_result, zero copy (device canonical batch in, v / pi out)")
     a = ap.parse_args()
     mt = a.max_turns or MAX_TURNS[a.game]
     kw = (dict(epsilon=0.25, root_policy_temp=1.25, shaped_dirichlet=True, policy_target_pruning=True, start_temp=1.0,
@@ -41,7 +43,38 @@ if __name__ == "__main__":
     sp = b2az.TaflSelfplay(a.game, a.games, mt, a.sims, games_per_slot=1 << 20, seed=1, words_per_tree=words,
                            hist_capacity=a.games * (a.drain + 2) * 4, **kw)
     stream = torch.cuda.current_stream().cuda_stream
-    sp.play(a.warm, stream, want_active=False)
+    play = lambda n: sp.play(n, stream, want_active=False)
+    if a.net:
+        import ctypes as C
+        S, P, A = sp.S, sp.P, sp.A
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Conv2d(P, 64, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 3, padding=1),
+                                  torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(64 * S * S, A + 3)).cuda().eval()
+        canon_ptr = sp.find_leaf(stream)
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (a.games, P, S, S), "typestr": "<f4", "data": (canon_ptr, False), "version": 3}
+        x = torch.as_tensor(_Dev(), device="cuda")
+        v_buf = torch.empty((a.games, 3), dtype=torch.float32, device="cuda")
+        pi_buf = torch.empty((a.games, A), dtype=torch.float32, device="cuda")
+
+        def evaluate():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(x)
+            torch.softmax(out[:, :A].float(), dim=1, out=pi_buf)
+            torch.softmax(out[:, A:].float(), dim=1, out=v_buf)
+            sp.process_result(C.c_void_p(v_buf.data_ptr()), C.c_void_p(pi_buf.data_ptr()), host=False, stream=stream)
+
+        def play(n):
+            for _ in range(n * a.sims):
+                sp.find_leaf(stream)
+                evaluate()
+        evaluate()  # answers the leaf found above: the first simulation of the warm-up
+        for _ in range(a.sims - 1):
+            sp.find_leaf(stream)
+            evaluate()
+        a.warm -= 1
+    play(a.warm)
     torch.cuda.synchronize()
     st0, _ = sp.slots()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -50,7 +83,7 @@ if __name__ == "__main__":
     done = 0
     while done < a.moves:
         n = min(a.drain, a.moves - done)
-        sp.play(n, stream, want_active=False)
+        play(n)
         done += n
         samples += len(sp.drain_history(stream)[1])  # finished games' samples to the host (synchronises)
     e1.record()
@@ -73,7 +106,8 @@ if __name__ == "__main__":
         n_ref += 1
     cpu_s = time.perf_counter() - t0
     print(json.dumps({
-        "kernel": "k_sp_search + k_sp_move", "workload": f"{NAMES[a.game]} self-play (PlayManager::play on the device), "
+        "kernel": "k_sp_find_leaf + torch net + k_sp_process_result + k_sp_move" if a.net else "k_sp_search + k_sp_move",
+        "evaluator": "torch conv net (2x64 conv + linear heads, bf16 autocast), zero-copy" if a.net else "dumb_eval", "workload": f"{NAMES[a.game]} self-play (PlayManager::play on the device), "
         f"{a.games} concurrent games, {a.sims} sims/move, " + ("PUCT + Dirichlet + pruned targets" if a.puct else "Gumbel m=16") +
         ", dumb_eval, tree reuse, history on", "ms": round(ms, 2), "moves_timed": a.moves,
         "simulations_per_second": sims / (ms * 1e-3), "moves_per_second": moves / (ms * 1e-3),
