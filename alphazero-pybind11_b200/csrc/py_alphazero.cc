@@ -37,6 +37,7 @@
 
 #include "../../include/b2az.h"
 #include "az_connect4.h"
+#include "az_tafl.h"
 
 namespace py = pybind11;
 using b2az::C4State;
@@ -163,6 +164,8 @@ class Connect4GS : public GameState {  // connect4_gs.h:24-92
   }
   uint64_t hash() const override { return b2az::c4_hash(s); }  // equality class of connect4_gs.cc:33-37
 };
+
+#include "py_tafl_gs.h"  // BrandubhGS / OpenTaflGS / TawlbwrddGS
 
 // ------------------------------------------------------------------------------------ PlayParams
 enum class EvalType : uint8_t { NN = 0, RANDOM = 1, PLAYOUT = 2 };
@@ -629,6 +632,10 @@ PYBIND11_MODULE(alphazero, m) {
       .def_static("CANONICAL_SHAPE", [] { return std::array<int64_t, 3>{4, 6, 7}; })
       .def(py::pickle([](const Connect4GS& gs) { return py::bytes(gs.to_bytes()); },
                       [](py::bytes b) { return Connect4GS::from_bytes(std::string(b)); }));
+
+  bind_tafl_gs<BrandubhGS>(m, "BrandubhGS");    // py_wrapper.cc:527-536
+  bind_tafl_gs<OpenTaflGS>(m, "OpenTaflGS");    // py_wrapper.cc:538-547
+  bind_tafl_gs<TawlbwrddGS>(m, "TawlbwrddGS");  // py_wrapper.cc:549-558
 
   py::enum_<EvalType>(m, "EvalType").value("NN", EvalType::NN).value("RANDOM", EvalType::RANDOM).value("PLAYOUT", EvalType::PLAYOUT);
 
