@@ -50,7 +50,8 @@ def kinds():
 # ------------------------------------------------------------------------------------ surface
 def test_reference_surface_is_present():
     az = module("emu")
-    for name in ["PlayManager", "PlayParams", "GameData", "GameState", "Connect4GS", "PlayHistory", "EvalType",
+    for name in ["PlayManager", "PlayParams", "GameData", "GameState", "Connect4GS", "BrandubhGS", "OpenTaflGS", "TawlbwrddGS",
+                 "PlayHistory", "EvalType",
                  "hash_game_state", "tracy_is_enabled", "tracy_frame_mark", "_tracy_zone_begin", "_tracy_zone_end",
                  "_tracy_set_thread_name"]:
         assert hasattr(az, name), name

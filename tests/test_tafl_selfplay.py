@@ -26,6 +26,9 @@ CASES = {
                                                      policy_target_pruning=True, root_fpu_zero=True, start_temp=1.0,
                                                      final_temp=0.2, temp_decay_half_life=10.0)),
     "brandubh_gumbel": (0, 6, 2, 40, 48, dict(gumbel_m=16, root_policy_temp=1.25)),
+    # epsilon > 0 with Gumbel: no noise at the first root evaluation (mcts.cc:514-518) but PlayManager still re-noises the
+    # reused root after every move (play_manager.cc:546-553)
+    "brandubh_gumbel_with_noise": (0, 4, 1, 40, 48, dict(gumbel_m=16, epsilon=0.25, root_policy_temp=1.25, shaped_dirichlet=True)),
     "brandubh_no_tree_reuse": (0, 4, 2, 30, 32, dict(tree_reuse=False, epsilon=0.25, gumbel_m=8)),
     "opentafl_gumbel": (1, 3, 1, 24, 40, dict(gumbel_m=16, cpuct=2.0)),
     "tawlbwrdd_puct_selfplay": (2, 3, 1, 24, 40, dict(epsilon=0.25, root_policy_temp=1.1, policy_target_pruning=True,
