@@ -148,6 +148,9 @@ def load(path=None):
     L.b2az_tafl_selfplay_process_result.argtypes = [vp, vp, vp, vp, C.c_int, C.POINTER(u32)]
     L.b2az_tafl_selfplay_drain_history.argtypes = [vp, vp, u32, vp, vp, vp, vp, C.POINTER(u32)]
     L.b2az_tafl_selfplay_slots.argtypes = [vp, vp, vp, vp]
+    L.b2az_tafl_selfplay_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
+    L.b2az_tafl_selfplay_leaf_batch_host.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32)]
+    L.b2az_tafl_selfplay_submit_eval_host.argtypes = [vp, vp, vp, vp, vp, u32]
     _libs[path] = L
     return L
 
@@ -550,6 +553,11 @@ class TaflSelfplay:
         self._check(self.L.b2az_tafl_selfplay_drain_history(self.h, stream, cap, _ptr(canon), _ptr(v), _ptr(pi), _ptr(slot),
                                                             C.byref(n)))
         return canon[:n.value], v[:n.value], pi[:n.value], slot[:n.value]
+
+    def stats(self, stream=None):
+        st = Stats()
+        self._check(self.L.b2az_tafl_selfplay_get_stats(self.h, stream, C.byref(st)))
+        return st
 
     def slots(self, stream=None):
         out = np.zeros(self.n, SLOT_DTYPE)

@@ -302,6 +302,10 @@ struct b2az_tafl_selfplay {
   b2az::SpView view;
   uint32_t* active_dev = nullptr;
   float *ev_v = nullptr, *ev_pi = nullptr, *leaf_canon = nullptr;
+  uint32_t hist_head = 0;  // rows of the sample ring already handed out (the ring restarts once it has been emptied)
+  std::vector<float> h_canon, h_v, h_pi;  // host staging of the reference-API flavour (leaf_batch_host / submit_eval_host)
+  std::vector<b2az::SpSlot> h_slots;
+  std::vector<uint32_t> h_tree_err;
 };
 
 extern "C" {
@@ -371,6 +375,9 @@ int b2az_tafl_selfplay_find_leaf(b2az_tafl_selfplay*, void*, const float**) FORE
 int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay*, void*, const float*, const float*, int, uint32_t*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay*, void*, uint32_t, float*, float*, float*, uint32_t*, uint32_t*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_slots(b2az_tafl_selfplay*, void*, b2az_tafl_selfplay_slot*, uint32_t*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay*, void*, b2az_stats*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay*, void*, uint32_t, float*, uint32_t*, uint32_t*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay*, void*, const uint32_t*, const float*, const float*, uint32_t) FOREST_NO_CUDA()
 #else
 #define SP_CTAS(sp) std::max(1u, std::min(((sp)->view.n_games + 3u) / 4u, 148u * 8u))
 static int sp_active(b2az_tafl_selfplay* sp, cudaStream_t s, uint32_t* active_out) {
@@ -437,23 +444,116 @@ int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay* sp, void* stream, uint3
   if (!sp || !n_out) return fail(B2AZ_EINVAL, "null argument");
   CUDA_TRY(cudaSetDevice(sp->forest->device));
   cudaStream_t s = (cudaStream_t)stream;
-  uint32_t n = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n, sp->view.out_count, 4, cudaMemcpyDeviceToHost, s));
+  uint32_t count = 0;
+  CUDA_TRY(cudaMemcpyAsync(&count, sp->view.out_count, 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  n = std::min(n, sp->view.out_cap);
-  if (!sp->view.history_enabled) n = 0;
-  if (n > max_rows) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_drain_history: " + std::to_string(n) + " rows are waiting, max_rows is smaller");
+  count = std::min(count, sp->view.out_cap);
+  if (!sp->view.history_enabled) count = 0;
+  const uint32_t head = std::min(sp->hist_head, count);
+  const uint32_t n = std::min(count - head, max_rows);  // oldest rows first (history_ is a FIFO)
   const size_t A = sp->forest->actions, C = sp->forest->canon;
   if (n) {
-    if (canon_host) CUDA_TRY(cudaMemcpyAsync(canon_host, sp->view.out_canon, (size_t)n * C * 4, cudaMemcpyDeviceToHost, s));
-    if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, sp->view.out_v, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
-    if (pi_host) CUDA_TRY(cudaMemcpyAsync(pi_host, sp->view.out_pi, (size_t)n * A * 4, cudaMemcpyDeviceToHost, s));
-    if (slot_host) CUDA_TRY(cudaMemcpyAsync(slot_host, sp->view.out_slot, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (canon_host) CUDA_TRY(cudaMemcpyAsync(canon_host, sp->view.out_canon + (size_t)head * C, (size_t)n * C * 4, cudaMemcpyDeviceToHost, s));
+    if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, sp->view.out_v + (size_t)head * 3, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    if (pi_host) CUDA_TRY(cudaMemcpyAsync(pi_host, sp->view.out_pi + (size_t)head * A, (size_t)n * A * 4, cudaMemcpyDeviceToHost, s));
+    if (slot_host) CUDA_TRY(cudaMemcpyAsync(slot_host, sp->view.out_slot + head, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   }
-  CUDA_TRY(cudaMemsetAsync(sp->view.out_count, 0, 4, s));
+  sp->hist_head = head + n;
+  if (sp->hist_head == count) {  // emptied: the ring restarts at row 0 (no launch is in flight: the stream was synchronised)
+    CUDA_TRY(cudaMemsetAsync(sp->view.out_count, 0, 4, s));
+    sp->hist_head = 0;
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   *n_out = n;
   return 0;
+}
+// b2az_get_stats for this engine: PlayManager's getters (play_manager.h:173-180, 288-316) over all slots
+int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stats* out) {
+  using namespace b2az;
+  if (!sp || !out) return fail(B2AZ_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t G = sp->view.n_games;
+  sp->h_slots.resize(G);
+  uint32_t count = 0;
+  CUDA_TRY(cudaMemcpyAsync(sp->h_slots.data(), sp->view.slots, (size_t)G * sizeof(SpSlot), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&count, sp->view.out_count, 4, cudaMemcpyDeviceToHost, s));
+  sp->h_tree_err.resize(sp->forest->view.n_trees);
+  CUDA_TRY(cudaMemcpy2DAsync(sp->h_tree_err.data(), 4, &sp->forest->view.trees[0].error, sizeof(ForestTree), 4,
+                             (size_t)sp->forest->view.n_trees, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  memset(out, 0, sizeof(*out));
+  for (uint32_t e : sp->h_tree_err) {  // the trees' sticky bits (az_forest.h ForestTree::error)
+    if (e & (1u | 4u | 16u)) out->device_error |= B2AZ_DEVERR_POOL;
+    if (e & 2u) out->device_error |= B2AZ_DEVERR_DEPTH;
+    if (e & 8u) out->device_error |= B2AZ_DEVERR_MOVE;
+  }
+  double leaf_depth = 0, entropy = 0, valid = 0;
+  uint64_t moves = 0, full = 0, length = 0;
+  for (const SpSlot& g : sp->h_slots) {
+    out->simulations += g.simulations;
+    out->games_completed += g.games_completed;
+    out->games_started += g.games_started;
+    out->active_games += g.active ? 1u : 0u;
+    for (int i = 0; i < 3; ++i) out->scores[i] += g.scores[i];
+    leaf_depth += g.leaf_depth; entropy += g.entropy; valid += g.valid_moves;
+    moves += g.total_move_count; full += g.total_full_move_count; length += g.game_length;
+    if (g.error & 1u) out->device_error |= B2AZ_DEVERR_HIST;
+  }
+  out->moves = moves;
+  out->hist_count = sp->view.history_enabled ? std::min(count, sp->view.out_cap) - std::min(sp->hist_head, count) : 0u;
+  out->avg_game_length = (float)length / (float)out->games_completed;
+  if (full) {
+    out->avg_leaf_depth = (float)(leaf_depth / (double)full);
+    out->avg_search_entropy = (float)(entropy / (double)full);
+  }
+  if (length) out->avg_moves_per_turn = (float)moves / (float)length;
+  if (moves) out->avg_valid_moves = (float)(valid / (double)moves);
+  return 0;
+}
+// The reference-API flavour of one simulation (build_batch / update_inferences with HOST buffers, py_wrapper.cc:449-504,
+// play_manager.cc:619-642): find_leaf for every active slot, then the leaves' canonical planes compacted into
+// canon_host float32[n][P][S][S] with the slot ids in ids_host[n] (ascending) ...
+int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay* sp, void* stream, uint32_t max_rows, float* canon_host,
+                                       uint32_t* ids_host, uint32_t* n_out) {
+  using namespace b2az;
+  if (!sp || !canon_host || !ids_host || !n_out) return fail(B2AZ_EINVAL, "null argument");
+  const float* dev = nullptr;
+  if (int rc = b2az_tafl_selfplay_find_leaf(sp, stream, &dev)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t G = sp->view.n_games;
+  const size_t C = sp->forest->canon;
+  sp->h_canon.resize((size_t)G * C);
+  sp->h_slots.resize(G);
+  CUDA_TRY(cudaMemcpyAsync(sp->h_canon.data(), dev, (size_t)G * C * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(sp->h_slots.data(), sp->view.slots, (size_t)G * sizeof(SpSlot), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  uint32_t n = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    if (!sp->h_slots[g].active) continue;
+    if (n >= max_rows) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_leaf_batch_host: more active slots than max_rows");
+    memcpy(canon_host + (size_t)n * C, sp->h_canon.data() + (size_t)g * C, C * 4);
+    ids_host[n++] = g;
+  }
+  *n_out = n;
+  return 0;
+}
+// ... and the answers (v float32[n][3], pi float32[n][A], row i for slot ids[i]; every active slot must be answered):
+// process_result + the move of every slot whose search is complete.
+int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay* sp, void* stream, const uint32_t* ids, const float* v, const float* pi,
+                                        uint32_t n) {
+  using namespace b2az;
+  if (!sp || (n && (!ids || !v || !pi))) return fail(B2AZ_EINVAL, "null argument");
+  const uint32_t G = sp->view.n_games;
+  const size_t A = sp->forest->actions;
+  sp->h_v.assign((size_t)G * 3, 0.0f);
+  sp->h_pi.resize((size_t)G * A);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (ids[i] >= G) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_submit_eval_host: slot id out of range");
+    memcpy(&sp->h_v[(size_t)ids[i] * 3], v + (size_t)i * 3, 12);
+    memcpy(&sp->h_pi[(size_t)ids[i] * A], pi + (size_t)i * A, A * 4);
+  }
+  return b2az_tafl_selfplay_process_result(sp, stream, sp->h_v.data(), sp->h_pi.data(), 1, nullptr);
 }
 int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host) {
   using namespace b2az;

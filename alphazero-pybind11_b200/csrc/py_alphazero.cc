@@ -236,9 +236,75 @@ struct GameData {  // play_manager.h:33-58, the part Python sees (py_wrapper.cc:
 
 class PlayManager {
  public:
+  // PlayManager(BrandubhGS | OpenTaflGS | TawlbwrddGS, params): the tafl self-play engine (b2az_tafl_selfplay_*)
+  template <int GAME>
+  bool try_tafl(const GameState* gs) {
+    auto* t = dynamic_cast<const TaflGS<GAME>*>(gs);
+    if (!t) return false;
+    if (t->s.turn != 0 || t->hist_len != 0) throw std::runtime_error("the B200 engine starts every game from the initial position");
+    const auto& P = params_;
+    if (P.mcts_visits.size() != (size_t)kP) throw std::runtime_error("You must specify MCTS visits for each player");
+    auto reject = [](bool bad, const char* what) {
+      if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 tafl engine yet");
+    };
+    reject(!P.seat_gumbel_enabled.empty() || !P.seat_gumbel_m.empty() || !P.seat_gumbel_c_visit.empty() ||
+               !P.seat_gumbel_c_scale.empty() || !P.seat_gumbel_full.empty() || !P.seat_gumbel_use_improved_policy.empty() ||
+               !P.seat_resign_threshold.empty() || !P.seat_visits.empty() || !P.seat_cap_visits.empty() ||
+               !P.seat_epsilon.empty() || !P.seat_mcts_root_temp.empty() || !P.seat_root_fpu_zero.empty(),
+           "per-seat overrides");
+    reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
+    reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
+    reject(P.mcts_visits[0] != P.mcts_visits[1], "different mcts_visits per seat");
+    reject(P.playout_cap_randomization, "playout_cap_randomization");
+    reject(P.resign_percent > 0.0f, "resign_percent");
+    reject(P.max_cache_size != 0, "max_cache_size (position cache)");
+    reject(P.gumbel_full, "gumbel_full");
+    reject(P.concurrent_games == 0 || P.games_to_play % P.concurrent_games != 0, "games_to_play not a multiple of concurrent_games");
+    EvalType et = EvalType::NN;
+    if (!P.eval_type.empty()) {
+      et = P.eval_type[0];
+      for (auto e : P.eval_type) reject(e != et, "mixed eval_type");
+      reject(et == EvalType::PLAYOUT, "EvalType.PLAYOUT");
+    }
+    random_eval_ = (et == EvalType::RANDOM);
+    b2az_tafl_selfplay_params sp{};
+    sp.forest.game = GAME;
+    sp.forest.max_turns = t->s.max_turns;
+    // slab per tree: each half holds the kept subtree + one move's new nodes (1 + 8k words per expanded node)
+    sp.forest.words_per_tree = P.pool_nodes ? (uint32_t)P.pool_nodes
+                                            : 2u * (1u + 4u * P.mcts_visits[0] * (1u + 8u * (GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u)));
+    sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
+    sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
+    sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
+    sp.forest.gumbel_c_visit = P.gumbel_c_visit; sp.forest.gumbel_c_scale = P.gumbel_c_scale;
+    sp.forest.shaped_dirichlet = P.shaped_dirichlet;
+    sp.n_games = P.concurrent_games;
+    sp.games_per_slot = P.games_to_play / P.concurrent_games;
+    sp.visits = P.mcts_visits[0];
+    sp.start_temp = P.start_temp; sp.final_temp = P.final_temp; sp.temp_decay_half_life = P.temp_decay_half_life;
+    sp.history_enabled = P.history_enabled; sp.policy_target_pruning = P.policy_target_pruning; sp.tree_reuse = P.tree_reuse;
+    if (b2az_tafl_selfplay_create(&sp, P.device, &tsp_) != 0) throw_last("PlayManager");
+    canon_sz_ = TaflGS<GAME>::P * TaflGS<GAME>::S * TaflGS<GAME>::S;
+    A_ = TaflGS<GAME>::A;
+    cdims_[0] = TaflGS<GAME>::P; cdims_[1] = cdims_[2] = TaflGS<GAME>::S;
+    return true;
+  }
+  void size_buffers() {
+    G_ = params_.concurrent_games;
+    canon_.resize((size_t)G_ * canon_sz_);
+    ids_.resize(G_);
+    v_.assign((size_t)G_ * (kP + 1), 0.0f);
+    pi_.assign((size_t)G_ * A_, 0.0f);
+    row_of_game_.assign(G_, 0xFFFFFFFFu);
+    refresh_stats_locked();
+  }
   PlayManager(const GameState* gs, PlayParams p) : params_(std::move(p)) {
+    if (try_tafl<B2AZ_TAFL_BRANDUBH>(gs) || try_tafl<B2AZ_TAFL_OPENTAFL>(gs) || try_tafl<B2AZ_TAFL_TAWLBWRDD>(gs)) {
+      size_buffers();
+      return;
+    }
     auto* c4 = dynamic_cast<const Connect4GS*>(gs);
-    if (!c4) throw std::runtime_error("the B200 engine implements Connect4GS only");
+    if (!c4) throw std::runtime_error("the B200 engine implements Connect4GS and the tafl games only");
     if (c4->s.p[0] || c4->s.p[1] || c4->s.player || c4->s.turn)
       throw std::runtime_error("the B200 engine starts every game from the initial Connect4 position");
     const auto& P = params_;
@@ -300,17 +366,12 @@ class PlayManager {
     bp.seed = P.seed;
     bp.pool_nodes = P.pool_nodes;
     if (b2az_create(&bp, P.device, &eng_) != 0) throw_last("PlayManager");
-    G_ = P.concurrent_games;
-    canon_.resize((size_t)G_ * kCanon);
-    ids_.resize(G_);
-    v_.assign((size_t)G_ * (kP + 1), 0.0f);
-    pi_.assign((size_t)G_ * kA, 0.0f);
-    row_of_game_.assign(G_, 0xFFFFFFFFu);
-    refresh_stats_locked();
+    size_buffers();
   }
   ~PlayManager() {
     stop();
     if (eng_) b2az_destroy(eng_);
+    if (tsp_) b2az_tafl_selfplay_destroy(tsp_);
   }
   PlayManager(const PlayManager&) = delete;
 
@@ -380,13 +441,13 @@ class PlayManager {
       }
       empty = 0;
       if (!checked) {
-        if (ndim != 4 || shape[1] != 4 || shape[2] != 6 || shape[3] != 7) throw std::runtime_error("Improper batch size");
+        if (ndim != 4 || shape[1] != cdims_[0] || shape[2] != cdims_[1] || shape[3] != cdims_[2]) throw std::runtime_error("Improper batch size");
         checked = true;
       }
       const uint32_t cap = (uint32_t)std::min<ssize_t>(shape[0], (ssize_t)max_bs());
       if (out.size() >= cap) break;
       const uint32_t n = std::min<uint32_t>(avail, cap - (uint32_t)out.size());
-      std::memcpy(batch + out.size() * kCanon, canon_.data() + (size_t)next_row_ * kCanon, (size_t)n * kCanon * sizeof(float));
+      std::memcpy(batch + out.size() * canon_sz_, canon_.data() + (size_t)next_row_ * canon_sz_, (size_t)n * canon_sz_ * sizeof(float));
       out.insert(out.end(), ids_.begin() + next_row_, ids_.begin() + next_row_ + n);
       next_row_ += n;
     }
@@ -397,14 +458,14 @@ class PlayManager {
   void update_inferences(uint32_t group, const std::vector<uint32_t>& idx, const float* v, ssize_t vrows, ssize_t vcols,
                          const float* pi, ssize_t prows, ssize_t pcols) {
     if (group != 0) throw std::runtime_error("model group out of range");
-    if (vcols != kP + 1 || pcols != kA || vrows < (ssize_t)idx.size() || prows < (ssize_t)idx.size())
+    if (vcols != kP + 1 || pcols != (ssize_t)A_ || vrows < (ssize_t)idx.size() || prows < (ssize_t)idx.size())
       throw std::runtime_error("Eigen is angry!!!");  // shapes.h:4-6: the reference asserts on bad shapes
     std::unique_lock<std::mutex> lk(mu_);
     for (size_t i = 0; i < idx.size(); ++i) {
       if (idx[i] >= G_ || row_of_game_[idx[i]] == 0xFFFFFFFFu) throw std::runtime_error("update_inferences: game has no pending leaf");
       const uint32_t r = row_of_game_[idx[i]];
       std::memcpy(&v_[(size_t)r * (kP + 1)], v + i * (kP + 1), (kP + 1) * sizeof(float));
-      std::memcpy(&pi_[(size_t)r * kA], pi + i * kA, kA * sizeof(float));
+      std::memcpy(&pi_[(size_t)r * A_], pi + i * A_, A_ * sizeof(float));
       row_of_game_[idx[i]] = 0xFFFFFFFFu;
     }
     answered_ += (uint32_t)idx.size();
@@ -440,9 +501,11 @@ class PlayManager {
       uint32_t got = 0;
       {
         std::lock_guard<std::mutex> lk(api_);
-        if (b2az_drain_history(eng_, nullptr, (uint32_t)n - cur, canon + (size_t)cur * kCanon, v + (size_t)cur * (kP + 1),
-                               pi + (size_t)cur * kA, 0, &got) != 0)
-          throw_last("build_history_batch");
+        const int rc = tsp_ ? b2az_tafl_selfplay_drain_history(tsp_, nullptr, (uint32_t)n - cur, canon + (size_t)cur * canon_sz_,
+                                                               v + (size_t)cur * (kP + 1), pi + (size_t)cur * A_, nullptr, &got)
+                            : b2az_drain_history(eng_, nullptr, (uint32_t)n - cur, canon + (size_t)cur * canon_sz_,
+                                                 v + (size_t)cur * (kP + 1), pi + (size_t)cur * A_, 0, &got);
+        if (rc != 0) throw_last("build_history_batch");
       }
       cur += got;
       if (got == 0) {
@@ -476,6 +539,7 @@ class PlayManager {
 
   // GameData accessors
   Connect4GS game_state(uint32_t i) {
+    if (tsp_) throw std::runtime_error("game_data(i).gs() is not implemented by the B200 tafl engine yet");
     uint8_t st[89];
     std::lock_guard<std::mutex> lk(api_);
     if (b2az_peek(eng_, nullptr, i, 0, st, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != 0) throw_last("game_data");
@@ -489,9 +553,11 @@ class PlayManager {
       if (ids_[r] == i) return r;
     return -1;
   }
-  float* canon_row(size_t r) { return canon_.data() + r * kCanon; }
+  float* canon_row(size_t r) { return canon_.data() + r * canon_sz_; }
   float* v_row(size_t r) { return v_.data() + r * (kP + 1); }
-  float* pi_row(size_t r) { return pi_.data() + r * kA; }
+  float* pi_row(size_t r) { return pi_.data() + r * A_; }
+  ssize_t num_actions() const { return (ssize_t)A_; }
+  const ssize_t* canon_dims() const { return cdims_; }
 
  private:
   void refresh_stats() {
@@ -500,11 +566,50 @@ class PlayManager {
   }
   void refresh_stats_locked() {
     std::lock_guard<std::mutex> lk(api_);
-    if (b2az_get_stats(eng_, nullptr, &stats_) != 0) throw_last("stats");
+    if ((tsp_ ? b2az_tafl_selfplay_get_stats(tsp_, nullptr, &stats_) : b2az_get_stats(eng_, nullptr, &stats_)) != 0) throw_last("stats");
     games_completed_.store(stats_.games_completed);
     hist_count_.store(stats_.hist_count);
   }
+  void drive_tafl() {
+    for (;;) {
+      if (stopped_.load()) return;
+      uint32_t n = 0;
+      if (random_eval_) {  // EvalType::RANDOM: searches and moves stay on the device, eight moves per call
+        {
+          std::lock_guard<std::mutex> lk(api_);
+          if (b2az_tafl_selfplay_play(tsp_, nullptr, 8, &n) != 0) throw_last("play");
+        }
+        refresh_stats();
+        std::lock_guard<std::mutex> lk(mu_);
+        if (stats_.device_error) throw std::runtime_error("play: device error (training-sample ring exhausted)");
+        if (n == 0) return;
+        continue;
+      }
+      {
+        std::lock_guard<std::mutex> lk(api_);
+        if (b2az_tafl_selfplay_leaf_batch_host(tsp_, nullptr, G_, canon_.data(), ids_.data(), &n) != 0) throw_last("play");
+      }
+      std::unique_lock<std::mutex> lk(mu_);
+      refresh_stats_locked();
+      if (stats_.device_error) throw std::runtime_error("play: device error (tree slab / training-sample ring exhausted)");
+      if (n == 0) return;  // every slot retired
+      for (uint32_t r = 0; r < n; ++r) row_of_game_[ids_[r]] = r;
+      answered_ = 0;
+      next_row_ = 0;
+      leaf_count_ = n;
+      cv_.notify_all();
+      cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
+      if (stopped_.load()) return;
+      leaf_count_ = 0;
+      next_row_ = 0;
+      {
+        std::lock_guard<std::mutex> lk2(api_);
+        if (b2az_tafl_selfplay_submit_eval_host(tsp_, nullptr, ids_.data(), v_.data(), pi_.data(), n) != 0) throw_last("update_inferences");
+      }
+    }
+  }
   void drive() {
+    if (tsp_) return drive_tafl();
     if (random_eval_) {
       // EvalType::RANDOM: the evaluator runs inside the step kernel; fuse a search's worth of generations
       const uint32_t chunk = std::max<uint32_t>(1, std::min<uint32_t>(params_.mcts_visits[0], 512));
@@ -549,6 +654,9 @@ class PlayManager {
 
   PlayParams params_;
   b2az_engine* eng_ = nullptr;
+  b2az_tafl_selfplay* tsp_ = nullptr;  // set instead of eng_ for a tafl GameState
+  uint32_t canon_sz_ = kCanon, A_ = kA;
+  ssize_t cdims_[3] = {4, 6, 7};
   uint32_t G_ = 0;
   bool random_eval_ = false;
   std::mutex mu_;   // generation state below
@@ -666,13 +774,14 @@ PYBIND11_MODULE(alphazero, m) {
       .def("pi", [](const GameData& gd) {
         const ssize_t r = gd.pm->row(gd.index);
         if (r < 0) throw std::runtime_error("GameData.pi(): the game has no pending leaf");
-        return py::array_t<float>({(ssize_t)7}, gd.pm->pi_row((size_t)r), py::cast(gd.pm));
+        return py::array_t<float>({gd.pm->num_actions()}, gd.pm->pi_row((size_t)r), py::cast(gd.pm));
       })
       .def("canonical", [](const GameData& gd) {
         const ssize_t r = gd.pm->row(gd.index);
         if (r < 0) throw std::runtime_error("GameData.canonical(): the game has no pending leaf");
         const ssize_t sz = sizeof(float);
-        return py::memoryview::from_buffer(gd.pm->canon_row((size_t)r), {(ssize_t)4, (ssize_t)6, (ssize_t)7}, {sz * 42, sz * 7, sz});
+        const ssize_t* d = gd.pm->canon_dims();
+        return py::memoryview::from_buffer(gd.pm->canon_row((size_t)r), {d[0], d[1], d[2]}, {sz * d[1] * d[2], sz * d[2], sz});
       });
 
   py::class_<PlayManager>(m, "PlayManager")
@@ -733,8 +842,9 @@ PYBIND11_MODULE(alphazero, m) {
       .def("build_history_batch",
            [](PlayManager& pm, py::array_t<float, py::array::c_style>& canonical, py::array_t<float, py::array::c_style>& v,
               py::array_t<float, py::array::c_style>& pi) {
-             if (canonical.ndim() != 4 || v.ndim() != 2 || pi.ndim() != 2 || canonical.shape(1) != 4 || canonical.shape(2) != 6 ||
-                 canonical.shape(3) != 7 || v.shape(1) != 3 || pi.shape(1) != 7)
+             const ssize_t* d = pm.canon_dims();
+             if (canonical.ndim() != 4 || v.ndim() != 2 || pi.ndim() != 2 || canonical.shape(1) != d[0] || canonical.shape(2) != d[1] ||
+                 canonical.shape(3) != d[2] || v.shape(1) != 3 || pi.shape(1) != pm.num_actions())
                throw std::runtime_error("Improper history batch shape");
              const ssize_t n = std::min(canonical.shape(0), std::min(v.shape(0), pi.shape(0)));
              float *c = canonical.mutable_data(), *vv = v.mutable_data(), *pp = pi.mutable_data();

@@ -355,10 +355,20 @@ int b2az_tafl_selfplay_play(b2az_tafl_selfplay* sp, void* stream, uint32_t n_mov
 int b2az_tafl_selfplay_find_leaf(b2az_tafl_selfplay* sp, void* stream, const float** canon_dev);
 int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay* sp, void* stream, const float* v, const float* pi, int host_pointers,
                                       uint32_t* active_out);
-/* PlayManager::build_history_batch (py_wrapper.cc:393-424): the samples of the games finished since the last drain
- * (each game's moves last first, like history_), with the slot they came from; fails if more than max_rows wait. */
+/* PlayManager::build_history_batch (py_wrapper.cc:393-424): up to max_rows of the waiting samples, oldest first (each
+ * game's moves last first, like history_), with the slot they came from; the rest stay for the next call. */
 int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay* sp, void* stream, uint32_t max_rows, float* canon_host, float* v_host,
                                      float* pi_host, uint32_t* slot_host, uint32_t* n_out);
+/* b2az_get_stats for this engine: PlayManager's counters and getters (play_manager.h:173-180, 288-316) over all slots. */
+int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stats* out);
+/* The reference-API flavour of one simulation with HOST buffers (build_batch / update_inferences, py_wrapper.cc:449-504,
+ * play_manager.cc:619-642): find_leaf for every active slot, their canonical planes compacted into canon_host
+ * float32[n][P][S][S] with the slot ids in ids_host[n]; then the answers v float32[n][3], pi float32[n][A] (row i for
+ * slot ids[i]; every active slot must be answered): process_result + the move of every slot whose search is complete. */
+int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay* sp, void* stream, uint32_t max_rows, float* canon_host,
+                                       uint32_t* ids_host, uint32_t* n_out);
+int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay* sp, void* stream, const uint32_t* ids, const float* v, const float* pi,
+                                        uint32_t n);
 /* slots_host[n_games]; tree_errors_host[2 * n_games] = the trees' sticky error bits (see b2az_forest_counts). */
 int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host);
 

@@ -1,0 +1,133 @@
+"""`PlayManager(BrandubhGS | OpenTaflGS | TawlbwrddGS, params)` of the drop-in `alphazero` module: the tafl self-play
+engine (b2az_tafl_selfplay_*) behind the reference's PlayManager surface — play() with EvalType.RANDOM, the
+build_batch / update_inferences hand-off with EvalType.NN, build_history_batch, scores and the metric getters — against
+the UNMODIFIED reference PlayManager (oracle/_ref/libazref_tafl.so) slot by slot. (Named zz: it runs after the engine's
+own parity tests.)"""
+import threading
+
+import numpy as np
+import pytest
+
+import parity_harness as ph
+import tafl_ref
+from conftest import has_cuda
+from test_pybind_module import module
+
+needs_tafl_ref = pytest.mark.skipif(not tafl_ref.available(), reason="oracle/_ref/libazref_tafl.so not built")
+gpu = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+CLS = {0: "BrandubhGS", 1: "OpenTaflGS", 2: "TawlbwrddGS"}
+
+
+def _params(az, G, per_slot, visits, seed, random_eval, **kw):
+    p = az.PlayParams()
+    p.games_to_play, p.concurrent_games, p.max_batch_size = G * per_slot, G, G
+    p.mcts_visits = [visits, visits]
+    p.history_enabled = p.self_play = p.tree_reuse = True
+    p.cpuct, p.fpu_reduction = 1.25, 0.25
+    for k, v in kw.items():
+        setattr(p, k, v)
+    p.seed = seed
+    if random_eval:
+        p.eval_type = [az.EvalType.RANDOM, az.EvalType.RANDOM]
+    return p
+
+
+def _history(az, pm, game, cap):
+    S, A, P = tafl_ref.dims(game) if tafl_ref.available() else {0: (7, 686, 7), 1: (11, 2662, 8), 2: (11, 2662, 7)}[game]
+    canon, v, pi = np.zeros((cap, P, S, S), np.float32), np.zeros((cap, 3), np.float32), np.zeros((cap, A), np.float32)
+    n = pm.build_history_batch(canon, v, pi)
+    return canon[:n], v[:n], pi[:n]
+
+
+def _rows(canon, v, pi):
+    """Order-free view of a sample set: one byte string per sample, sorted."""
+    return sorted(canon[i].tobytes() + v[i].tobytes() + pi[i].tobytes() for i in range(len(v)))
+
+
+REF_KW = {"mcts_root_temp": "root_policy_temp"}
+
+
+@pytest.mark.parametrize("game,G,per_slot,max_turns,visits,kw", [
+    pytest.param(0, 5, 2, 40, 40, dict(epsilon=0.25, mcts_root_temp=1.25, shaped_dirichlet=True, policy_target_pruning=True,
+                                       start_temp=1.0, final_temp=0.2, temp_decay_half_life=10.0), marks=gpu, id="brandubh-puct"),
+    pytest.param(0, 5, 1, 40, 48, dict(gumbel_enabled=True, gumbel_m=16), marks=gpu, id="brandubh-gumbel"),
+    pytest.param(1, 3, 1, 20, 40, dict(gumbel_enabled=True, gumbel_m=16), marks=gpu, id="opentafl-gumbel"),
+])
+@needs_tafl_ref
+def test_random_eval_play_equals_the_reference(game, G, per_slot, max_turns, visits, kw):
+    az = module("cuda")
+    seed = 4000 + game
+    pm = az.PlayManager(getattr(az, CLS[game])(max_turns), _params(az, G, per_slot, visits, seed, True, **kw))
+    pm.play()
+    assert pm.games_completed() == G * per_slot and pm.remaining_games() == 0
+    canon, v, pi = _history(az, pm, game, G * per_slot * max_turns)
+    rkw = {REF_KW.get(k, k): x for k, x in kw.items() if k != "gumbel_enabled"}
+    refs = [tafl_ref.selfplay(game, seed + g, max_turns, per_slot, visits, **rkw) for g in range(G)]
+    want = _rows(np.concatenate([r["canonical"] for r in refs]), np.concatenate([r["v"] for r in refs]),
+                 np.concatenate([r["pi"] for r in refs]))
+    assert _rows(canon, v, pi) == want
+    assert np.array_equal(pm.scores(), np.sum([r["scores"] for r in refs], axis=0))
+    lengths = sum(int(round(float(r["avg_game_length"]) * r["games_completed"])) for r in refs)
+    assert pm.avg_game_length() == np.float32(np.float32(lengths) / np.float32(G * per_slot))
+    assert pm.hist_count() == 0 and pm.simulations() == visits * len(v)
+
+
+@pytest.mark.parametrize("kind", [pytest.param("cuda", marks=gpu)])
+@needs_tafl_ref
+def test_nn_hand_off_equals_the_random_eval_run(kind):
+    """EvalType.NN through build_batch / update_inferences (the reference's batcher and result worker): with the
+    evaluator answering dumb_eval's numbers the games equal the EvalType.RANDOM run, sample for sample."""
+    az = module(kind)
+    game, G, max_turns, visits, seed = 0, 4, 30, 24, 4100
+    kw = dict(epsilon=0.25, mcts_root_temp=1.25, policy_target_pruning=True)
+    pm0 = az.PlayManager(az.BrandubhGS(max_turns), _params(az, G, 1, visits, seed, True, **kw))
+    pm0.play()
+    want = _rows(*_history(az, pm0, game, G * max_turns))
+    pm = az.PlayManager(az.BrandubhGS(max_turns), _params(az, G, 1, visits, seed, False, **kw))
+    t = threading.Thread(target=pm.play)
+    t.start()
+    S, A, P = tafl_ref.dims(game)
+    batch = np.zeros((G, P, S, S), np.float32)
+    while pm.remaining_games() > 0:
+        ids = pm.build_batch(0, batch)
+        if not ids:
+            continue
+        v, pi = np.zeros((len(ids), 3), np.float32), np.zeros((len(ids), A), np.float32)
+        for r in range(len(ids)):
+            board = (batch[r, :3] > 0).astype(np.int8)
+            pos = tafl_ref.position(game, board, 0 if batch[r, 3, 0, 0] > 0 else 1, 0, max_turns, 0)
+            valid = pos["valid"].astype(np.float32)
+            total = np.float32(int(valid.sum()) % 256)  # dumb_eval: Vector<uint8_t>::sum() wraps (game_state.h:160-173)
+            pi[r] = valid / total if total > 0 else valid
+            v[r] = np.float32(1.0 / 3.0)
+        pm.update_inferences(0, ids, v, pi)
+    t.join(timeout=60)
+    assert not t.is_alive() and pm.games_completed() == G
+    assert _rows(*_history(az, pm, game, G * max_turns)) == want
+    assert np.array_equal(pm.scores(), pm0.scores()) and pm.avg_game_length() == pm0.avg_game_length()
+
+
+def test_tafl_playmanager_validation_and_no_cpu_fallback():
+    az = module("emu")
+    gs = az.BrandubhGS(30)
+    with pytest.raises(RuntimeError, match="You must specify MCTS visits for each player"):
+        p = _params(az, 2, 1, 8, 1, True)
+        p.mcts_visits = [8]
+        az.PlayManager(gs, p)
+    with pytest.raises(RuntimeError, match="not implemented"):
+        p = _params(az, 2, 1, 8, 1, True)
+        p.mcts_visits = [8, 16]
+        az.PlayManager(gs, p)
+    with pytest.raises(RuntimeError, match="not implemented"):
+        az.PlayManager(gs, _params(az, 2, 1, 8, 1, True, playout_cap_randomization=True))
+    with pytest.raises(RuntimeError, match="multiple of concurrent_games"):
+        p = _params(az, 2, 1, 8, 1, True)
+        p.games_to_play = 3
+        az.PlayManager(gs, p)
+    moved = az.BrandubhGS(30)
+    moved.play_move(int(np.flatnonzero(np.asarray(moved.valid_moves()))[0]))
+    with pytest.raises(RuntimeError, match="initial position"):
+        az.PlayManager(moved, _params(az, 2, 1, 8, 1, True))
+    if not has_cuda():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            az.PlayManager(gs, _params(az, 2, 1, 8, 1, True))
