@@ -283,6 +283,12 @@ class PlayManager {
     sp.visits = P.mcts_visits[0];
     sp.start_temp = P.start_temp; sp.final_temp = P.final_temp; sp.temp_decay_half_life = P.temp_decay_half_life;
     sp.history_enabled = P.history_enabled; sp.policy_target_pruning = P.policy_target_pruning; sp.tree_reuse = P.tree_reuse;
+    // history_ is unbounded in the reference; here the sample ring holds what a run can produce between drains: every
+    // sample of the run when that fits an 8 GB budget (play() first, build_history_batch afterwards works), else the
+    // budget — a full ring drops samples and play() then fails loudly (B2AZ_DEVERR_HIST)
+    const uint64_t row_bytes = 4ull * (TaflGS<GAME>::P * TaflGS<GAME>::S * TaflGS<GAME>::S + TaflGS<GAME>::A + 4);
+    const uint64_t want = (uint64_t)P.games_to_play * t->s.max_turns, floor_rows = (uint64_t)P.concurrent_games * t->s.max_turns;
+    sp.hist_capacity = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(floor_rows, std::min<uint64_t>(want, (8ull << 30) / row_bytes)));
     if (b2az_tafl_selfplay_create(&sp, P.device, &tsp_) != 0) throw_last("PlayManager");
     canon_sz_ = TaflGS<GAME>::P * TaflGS<GAME>::S * TaflGS<GAME>::S;
     A_ = TaflGS<GAME>::A;

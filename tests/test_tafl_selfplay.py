@@ -38,7 +38,8 @@ CASES = {
 
 def run_device(game, slots, per_slot, max_turns, visits, kw, seed):
     words = 2 * (1 + (max_turns + 2) * visits * (1 + 8 * (64 if game == 0 else 200)))
-    sp = b2az.TaflSelfplay(game, slots, max_turns, visits, games_per_slot=per_slot, seed=seed, words_per_tree=words, **kw)
+    sp = b2az.TaflSelfplay(game, slots, max_turns, visits, games_per_slot=per_slot, seed=seed, words_per_tree=words,
+                           hist_capacity=slots * per_slot * max_turns, **kw)  # drained once, at the end
     active, rounds = slots, 0
     while active:
         active = sp.play(8)
