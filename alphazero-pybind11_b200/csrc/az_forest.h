@@ -1075,10 +1075,11 @@ __device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out,
         out[pool[fb_mv(b, k) + j] & 0xFFFFu] = std_min((float)nj, std_max(0.0f, desired));
       }
       __syncwarp();
-      float ptotal = 0.0f;  // pruned.sum() over the dense vector, move order (lane 0 decides, then broadcast)
-      if (lane == 0)
-        for (u32 m = 0; m < (u32)T::A; ++m) ptotal = fadd(ptotal, out[m]);
-      ptotal = __shfl_sync(0xFFFFFFFFu, ptotal, 0);
+      float ptotal = 0.0f;  // pruned.sum() over the dense vector in move order (zero entries do not change a sum)
+      for (u32 c0 = 0; c0 < (u32)T::A; c0 += 32u) {
+        const float val = c0 + lane < (u32)T::A ? out[c0 + lane] : 0.0f;
+        ptotal = seq_sum_masked(ptotal, val, val != 0.0f);
+      }
       use_pruned = ptotal != 0.0f;
       if (!use_pruned) {
         for (u32 m = lane; m < (u32)T::A; m += 32u) out[m] = 0.0f;
@@ -1091,72 +1092,95 @@ __device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out,
         out[mv] = total == 0 ? u2f(pool[fb_pol(b, k) + j]) : (float)pool[fb_n(b, k) + j];
       }
     __syncwarp();
-    if (lane == 0) {
-      if (use_pruned) {
-        float tot = 0.0f;
-        for (u32 m = 0; m < (u32)T::A; ++m) tot = fadd(tot, out[m]);
-        if (temp == 0.0f) {
-          float best = out[0];
-          for (u32 m = 1; m < (u32)T::A; ++m) best = out[m] > best ? out[m] : best;  // maxCoeff
-          u32 cnt = 0;
-          for (u32 m = 0; m < (u32)T::A; ++m) cnt += out[m] == best ? 1u : 0u;
-          const float share = fdiv(1.0f, (float)cnt);
-          for (u32 m = 0; m < (u32)T::A; ++m) out[m] = out[m] == best ? share : 0.0f;
-        } else {
-          for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], tot);
-          if (temp != 1.0f) {
-            const float e = fdiv(1.0f, temp);
-            float sum2 = 0.0f;
-            for (u32 m = 0; m < (u32)T::A; ++m) {
-              out[m] = az_powf(out[m], e);
-              sum2 = fadd(sum2, out[m]);
-            }
-            for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum2);
-          }
-        }
-      } else if (total == 0) {  // the prior policy (raw-policy mode), tempered
-        if (temp != 0.0f) {
-          const float e = fdiv(1.0f, temp);
-          for (u32 m = 0; m < (u32)T::A; ++m) out[m] = az_powf(out[m], e);
-        }
-        float sum = 0.0f;
-        for (u32 m = 0; m < (u32)T::A; ++m) sum = fadd(sum, out[m]);
-        for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum);
-      } else if (temp == 0.0f) {  // uniform over the most visited moves
-        float best = out[0];
-        u32 ties = 1;
-        for (u32 m = 1; m < (u32)T::A; ++m) {
-          if (out[m] > best) { best = out[m]; ties = 1; }
-          else if (out[m] == best) ++ties;
-        }
-        const float share = (float)(1.0 / (double)ties);
-        for (u32 m = 0; m < (u32)T::A; ++m) out[m] = out[m] == best ? share : 0.0f;
+    // The reference works on the dense num_moves-long vector in MOVE order. Adding a zero entry never changes a float
+    // sum and pow(0, e > 0) == 0, so only the non-zero entries (at most k of the A) carry the arithmetic: every chunk of
+    // 32 moves is loaded one per lane and its non-zero values are folded in ascending move order with ballots + shuffles
+    // (every lane accumulates the same sequence); the element-wise steps run one move per lane.
+    constexpr u32 A = (u32)T::A;
+    auto dense_sum = [&]() {
+      float acc = 0.0f;
+      for (u32 c0 = 0; c0 < A; c0 += 32u) {
+        const float val = c0 + lane < A ? out[c0 + lane] : 0.0f;
+        acc = seq_sum_masked(acc, val, val != 0.0f);
+      }
+      return acc;
+    };
+    auto dense_pow = [&](float e, float divide_by, bool divide_first) {  // out = pow(divide_first ? out / d : out, e), then Σ
+      for (u32 m = lane; m < A; m += 32u) {
+        float val = out[m];
+        if (divide_first) val = fdiv(val, divide_by);
+        if (val != 0.0f || !(e > 0.0f)) val = az_powf(val, e);
+        out[m] = val;
+      }
+      __syncwarp();
+      return dense_sum();
+    };
+    auto dense_div = [&](float d) {
+      for (u32 m = lane; m < A; m += 32u) out[m] = fdiv(out[m], d);
+      __syncwarp();
+    };
+    auto dense_argmax_share = [&](bool double_share) {  // uniform over the largest entries (order independent)
+      float best = -INFINITY;
+      for (u32 m = lane; m < A; m += 32u) best = out[m] > best ? out[m] : best;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        best = ob > best ? ob : best;
+      }
+      u32 ties = 0;
+      for (u32 m = lane; m < A; m += 32u) ties += out[m] == best ? 1u : 0u;
+      ties = warp_sum(ties);
+      const float share = double_share ? (float)(1.0 / (double)ties) : fdiv(1.0f, (float)ties);
+      for (u32 m = lane; m < A; m += 32u) out[m] = out[m] == best ? share : 0.0f;
+      __syncwarp();
+    };
+    if (use_pruned) {
+      const float tot = dense_sum();
+      if (temp == 0.0f) {
+        dense_argmax_share(false);
       } else {
-        float sum = 0.0f;
-        for (u32 m = 0; m < (u32)T::A; ++m) sum = fadd(sum, out[m]);
-        const float e = fdiv(1.0f, temp);  // `1 / temp`: int / float
-        float sum2 = 0.0f;
-        for (u32 m = 0; m < (u32)T::A; ++m) {
-          out[m] = az_powf(fdiv(out[m], sum), e);
-          sum2 = fadd(sum2, out[m]);
+        dense_div(tot);
+        if (temp != 1.0f) {
+          const float sum2 = dense_pow(fdiv(1.0f, temp), 1.0f, false);
+          dense_div(sum2);
         }
-        for (u32 m = 0; m < (u32)T::A; ++m) out[m] = fdiv(out[m], sum2);
       }
-      if (pick) {
+    } else if (total == 0) {  // the prior policy (raw-policy mode), tempered
+      float sum;
+      if (temp != 0.0f) sum = dense_pow(fdiv(1.0f, temp), 1.0f, false);
+      else sum = dense_sum();
+      dense_div(sum);
+    } else if (temp == 0.0f) {  // uniform over the most visited moves
+      dense_argmax_share(true);
+    } else {
+      const float sum = dense_sum();
+      const float sum2 = dense_pow(fdiv(1.0f, temp), sum, true);  // `1 / temp`: int / float
+      dense_div(sum2);
+    }
+    if (pick) {  // MCTS::pick_move: one uniform draw, first move whose running sum exceeds it, else the last positive one
+      float choice = 0.0f;
+      if (lane == 0) {
         Pcg32 rng = FOREST_RNG(F, t);
-        const float choice = rng_uniform01(rng);
+        choice = rng_uniform01(rng);
         FOREST_RNG(F, t) = rng;
-        u32 mvp = 0xFFFFFFFFu;
-        float sum = 0.0f;
-        for (u32 m = 0; m < (u32)T::A; ++m) {
-          sum = fadd(sum, out[m]);
-          if (sum > choice) { mvp = m; break; }
-        }
-        if (mvp == 0xFFFFFFFFu)
-          for (int m = T::A - 1; m >= 0; --m)
-            if (out[m] > 0.0f) { mvp = (u32)m; break; }
-        *picked_out = mvp;
       }
+      choice = __shfl_sync(0xFFFFFFFFu, choice, 0);
+      u32 mvp = 0xFFFFFFFFu, last_pos = 0xFFFFFFFFu;
+      float sum = 0.0f;
+      for (u32 c0 = 0; c0 < A && mvp == 0xFFFFFFFFu; c0 += 32u) {
+        const float val = c0 + lane < A ? out[c0 + lane] : 0.0f;
+        u32 nz = __ballot_sync(0xFFFFFFFFu, val != 0.0f);
+        const u32 pos = __ballot_sync(0xFFFFFFFFu, val > 0.0f);
+        if (pos) last_pos = c0 + 31u - (u32)__clz((int)pos);
+        while (nz) {
+          const int src = __ffs((int)nz) - 1;
+          nz &= nz - 1u;
+          sum = fadd(sum, __shfl_sync(0xFFFFFFFFu, val, src));
+          if (sum > choice) { mvp = c0 + (u32)src; break; }
+        }
+      }
+      if (mvp == 0xFFFFFFFFu) mvp = last_pos;  // (the scan ran to the end: last_pos covers the whole row)
+      if (lane == 0) *picked_out = mvp;
     }
     __syncwarp();
   }
