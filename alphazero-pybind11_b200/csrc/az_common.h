@@ -52,8 +52,14 @@ AZ_HD float fsub(float a, float b) {
   return r;
 #endif
 }
+#if defined(__CUDACC__) && defined(B2AZ_FDIV_NOINLINE)
+// experiment knob: one out-of-line copy of the IEEE division sequence instead of one per call site (code size)
+static __device__ __noinline__ float fdiv_out_of_line(float a, float b) { return __fdiv_rn(a, b); }
+#endif
 AZ_HD float fdiv(float a, float b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(B2AZ_FDIV_NOINLINE)
+  return fdiv_out_of_line(a, b);
+#elif defined(__CUDA_ARCH__)
   return __fdiv_rn(a, b);
 #else
   volatile float r = a / b;

@@ -41,7 +41,8 @@ if __name__ == "__main__":
                final_temp=0.2, temp_decay_half_life=10.0) if a.puct else dict(gumbel_m=16, root_policy_temp=1.25))
     words = 2 * (1 + 3 * a.sims * (1 + 8 * (48 if a.game == 0 else 140)))
     sp = b2az.TaflSelfplay(a.game, a.games, mt, a.sims, games_per_slot=1 << 20, seed=1, words_per_tree=words,
-                           hist_capacity=a.games * (a.drain + 2) * 4, **kw)
+                           hist_capacity=a.games * (a.drain + 2) * 4,
+                           lib=b2az.load(os.environ.get("B2AZ_LIB_PATH")), **kw)  # experiment builds via env
     stream = torch.cuda.current_stream().cuda_stream
     play = lambda n: sp.play(n, stream, want_active=False)
     if a.net:
