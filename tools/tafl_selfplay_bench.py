@@ -81,16 +81,20 @@ if __name__ == "__main__":
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     samples, t0 = 0, time.perf_counter()
     e0.record()
-    done = 0
+    done, seg = 0, []
     while done < a.moves:
         n = min(a.drain, a.moves - done)
+        seg.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+        seg[-1][0].record()
         play(n)
+        seg[-1][1].record()
         done += n
         samples += len(sp.drain_history(stream)[1])  # finished games' samples to the host (synchronises)
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     ms = e0.elapsed_time(e1)
+    dev_ms = sum(x.elapsed_time(y) for x, y in seg)  # the search + move launches alone (samples stay in HBM)
     st1, err = sp.slots()
     sp.close()
     assert (err == 0).all() and (st1["error"] == 0).all(), (set(err.tolist()), set(st1["error"].tolist()))
@@ -106,12 +110,26 @@ if __name__ == "__main__":
         ref_moves += len(r["v"])
         n_ref += 1
     cpu_s = time.perf_counter() - t0
+    # algorithmic bytes per simulation (RANDOM-eval form: no canonical write, no evaluation read), with the
+    # depth D and children k measured by the engine in this run; peak = MEASURED_PEAKS.json hbm_gbs (else 6650)
+    D = float(st1["leaf_depth"].sum() / full)
+    k = float(st1["valid_moves"].sum() / max(1, int(st1["total_move_count"].sum())))
+    bps = D * (12 * k + 8) + D * 28 + (16 * k + 16) + 3 * 16 + 8
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    ach = bps * sims / (dev_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "kernel": "k_sp_search", "bytes_per_sim": bps, "note": "instruction / latency bound (profiles/*k_sp_search*): "
+            "the fraction of the HBM roofline is reported for completeness"}
     print(json.dumps({
         "kernel": "k_sp_find_leaf + torch net + k_sp_process_result + k_sp_move" if a.net else "k_sp_search + k_sp_move",
         "evaluator": "torch conv net (2x64 conv + linear heads, bf16 autocast), zero-copy" if a.net else "dumb_eval", "workload": f"{NAMES[a.game]} self-play (PlayManager::play on the device), "
         f"{a.games} concurrent games, {a.sims} sims/move, " + ("PUCT + Dirichlet + pruned targets" if a.puct else "Gumbel m=16") +
         ", dumb_eval, tree reuse, history on", "ms": round(ms, 2), "moves_timed": a.moves,
         "simulations_per_second": sims / (ms * 1e-3), "moves_per_second": moves / (ms * 1e-3),
+        "device_ms": round(dev_ms, 2), "simulations_per_second_device": sims / (dev_ms * 1e-3), "roofline": roof,
         "games_finished_in_window": games, "samples_drained": samples, "wall_s": round(wall, 3),
         "mean_leaf_depth_finished_games": float(st1["leaf_depth"].sum() / full),
         "mean_legal_moves_finished_games": float(st1["valid_moves"].sum() / max(1, int(st1["total_move_count"].sum()))),
