@@ -544,13 +544,16 @@ class TaflSelfplay:
                                                              C.byref(act) if want_active else None))
         return act.value if want_active else None
 
-    def drain_history(self, stream=None):
-        cap = self.hist_capacity
-        canon = np.zeros((cap, self.P, self.S, self.S), np.float32)
-        v, pi = np.zeros((cap, 3), np.float32), np.zeros((cap, self.A), np.float32)
-        slot = np.zeros(cap, np.uint32)
+    def drain_history(self, stream=None, out=None):
+        """Waiting samples, oldest first: (canonical, v, pi, slot). `out` = preallocated (canonical[cap,P,S,S], v[cap,3],
+        pi[cap,A], slot[cap]) arrays to fill (e.g. views of pinned memory); else arrays sized for what is waiting."""
+        if out is None:
+            cap = max(1, int(self.stats(stream).hist_count))
+            out = (np.empty((cap, self.P, self.S, self.S), np.float32), np.empty((cap, 3), np.float32),
+                   np.empty((cap, self.A), np.float32), np.empty(cap, np.uint32))
+        canon, v, pi, slot = out
         n = C.c_uint32(0)
-        self._check(self.L.b2az_tafl_selfplay_drain_history(self.h, stream, cap, _ptr(canon), _ptr(v), _ptr(pi), _ptr(slot),
+        self._check(self.L.b2az_tafl_selfplay_drain_history(self.h, stream, len(slot), _ptr(canon), _ptr(v), _ptr(pi), _ptr(slot),
                                                             C.byref(n)))
         return canon[:n.value], v[:n.value], pi[:n.value], slot[:n.value]
 

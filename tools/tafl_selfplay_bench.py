@@ -44,6 +44,11 @@ if __name__ == "__main__":
                            hist_capacity=a.games * (a.drain + 2) * 4,
                            lib=b2az.load(os.environ.get("B2AZ_LIB_PATH")), **kw)  # experiment builds via env
     stream = torch.cuda.current_stream().cuda_stream
+    # the consumer's buffers: pinned host memory, allocated once (what a history saver would hold)
+    cap = a.games * (a.drain + 2) * 4
+    pinned = (torch.empty((cap, sp.P, sp.S, sp.S), dtype=torch.float32).pin_memory(), torch.empty((cap, 3), dtype=torch.float32).pin_memory(),
+              torch.empty((cap, sp.A), dtype=torch.float32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory())
+    host_out = (pinned[0].numpy(), pinned[1].numpy(), pinned[2].numpy(), pinned[3].numpy().view("uint32"))
     play = lambda n: sp.play(n, stream, want_active=False)
     if a.net:
         import ctypes as C
@@ -89,7 +94,7 @@ if __name__ == "__main__":
         play(n)
         seg[-1][1].record()
         done += n
-        samples += len(sp.drain_history(stream)[1])  # finished games' samples to the host (synchronises)
+        samples += len(sp.drain_history(stream, out=host_out)[1])  # finished games' samples to pinned host memory (synchronises)
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
