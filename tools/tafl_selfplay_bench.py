@@ -36,11 +36,22 @@ if __name__ == "__main__":
     ap.add_argument("--net", action="store_true", help="EvalType::NN: a random-init torch conv net between find_leaf and "
                                                        "process_result, zero copy (device canonical batch in, v / pi out)")
     a = ap.parse_args()
+    # one process per GPU under torchrun (weak scaling: --games slots PER GPU, slot streams sharded with
+    # b2az.dist.shard_slots, no data-path collective; NCCL only for the barrier and the max-over-ranks time)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        from b2az import dist as bd
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        _, seed, _ = bd.shard_slots(a.games * world, 1, rank, world)
+    else:
+        seed = 1
     mt = a.max_turns or MAX_TURNS[a.game]
     kw = (dict(epsilon=0.25, root_policy_temp=1.25, shaped_dirichlet=True, policy_target_pruning=True, start_temp=1.0,
                final_temp=0.2, temp_decay_half_life=10.0) if a.puct else dict(gumbel_m=16, root_policy_temp=1.25))
     words = 2 * (1 + 3 * a.sims * (1 + 8 * (48 if a.game == 0 else 140)))
-    sp = b2az.TaflSelfplay(a.game, a.games, mt, a.sims, games_per_slot=1 << 20, seed=1, words_per_tree=words,
+    sp = b2az.TaflSelfplay(a.game, a.games, mt, a.sims, games_per_slot=1 << 20, seed=seed, words_per_tree=words, device=local,
                            hist_capacity=a.games * (a.drain + 2) * 4,
                            lib=b2az.load(os.environ.get("B2AZ_LIB_PATH")), **kw)  # experiment builds via env
     stream = torch.cuda.current_stream().cuda_stream
@@ -82,6 +93,9 @@ if __name__ == "__main__":
         a.warm -= 1
     play(a.warm)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     st0, _ = sp.slots()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     samples, t0 = 0, time.perf_counter()
@@ -104,6 +118,16 @@ if __name__ == "__main__":
     sp.close()
     assert (err == 0).all() and (st1["error"] == 0).all(), (set(err.tolist()), set(st1["error"].tolist()))
     sims = int(st1["simulations"].sum() - st0["simulations"].sum())
+    if world > 1:  # whole-job figures: units of all ranks over the slowest rank's time
+        t = torch.tensor([ms, dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, dev_ms = float(t[0]), float(t[1])
+        c = torch.tensor([sims, samples], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c)
+        sims, samples = int(c[0]), int(c[1])
+        dist.destroy_process_group()
+        if rank != 0:
+            sys.exit(0)
     moves = sims // a.sims
     games = int(st1["games_completed"].sum() - st0["games_completed"].sum())
     full = max(1, int(st1["total_full_move_count"].sum()))
@@ -132,7 +156,7 @@ if __name__ == "__main__":
         "kernel": "k_sp_find_leaf + torch net + k_sp_process_result + k_sp_move" if a.net else "k_sp_search + k_sp_move",
         "evaluator": "torch conv net (2x64 conv + linear heads, bf16 autocast), zero-copy" if a.net else "dumb_eval", "workload": f"{NAMES[a.game]} self-play (PlayManager::play on the device), "
         f"{a.games} concurrent games, {a.sims} sims/move, " + ("PUCT + Dirichlet + pruned targets" if a.puct else "Gumbel m=16") +
-        ", dumb_eval, tree reuse, history on", "ms": round(ms, 2), "moves_timed": a.moves,
+        ", dumb_eval, tree reuse, history on", "n_gpus": world, "scaling": "weak", "ms": round(ms, 2), "moves_timed": a.moves,
         "simulations_per_second": sims / (ms * 1e-3), "moves_per_second": moves / (ms * 1e-3),
         "device_ms": round(dev_ms, 2), "simulations_per_second_device": sims / (dev_ms * 1e-3), "roofline": roof,
         "games_finished_in_window": games, "samples_drained": samples, "wall_s": round(wall, 3),
