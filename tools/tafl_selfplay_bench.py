@@ -148,7 +148,7 @@ if __name__ == "__main__":
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         peak = 6650.0
-    ach = bps * sims / (dev_ms * 1e-3) / 1e9
+    ach = bps * sims / world / (dev_ms * 1e-3) / 1e9  # per GPU
     roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "kernel": "k_sp_search", "bytes_per_sim": bps, "note": "instruction / latency bound (profiles/*k_sp_search*): "
             "the fraction of the HBM roofline is reported for completeness"}
