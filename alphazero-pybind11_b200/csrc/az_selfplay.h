@@ -150,8 +150,11 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
 }
 
 // "Actually play a move" (play_manager.cc:283-553) for every slot whose search has reached its visit count
+#ifndef B2AZ_SP_MOVE_MINB
+#define B2AZ_SP_MOVE_MINB 8  /* 64 registers, 32 warps per SM: the lane-0 stretches of the move step are latency bound (measured: 1 / 4 / 6 / 8 -> Brandubh 112.6 / 112.7 / 115.7 / 118.2 M sims/s, OpenTafl 46.8 / 46.9 / 46.5 / 49.1) */
+#endif
 template <int GAME>
-__global__ void __launch_bounds__(128) k_sp_move(ForestView F, SpView S) {
+__global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F, SpView S) {
   typedef Tafl<GAME> T;
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
