@@ -19,6 +19,7 @@ DEFAULT_LIB = os.path.join(os.path.dirname(_HERE), "libb2az.so")
 
 EVAL_NN, EVAL_RANDOM = 0, 1
 RNG_PER_GAME, RNG_GLOBAL = 0, 1
+STEP_QUEUE, STEP_FLAT = 0, 1
 CANON_SHAPE = (4, 6, 7)
 NUM_MOVES = 7
 NUM_PLAYERS = 2
@@ -43,11 +44,11 @@ class Params(C.Structure):
         ("fpu_reduction", C.c_float), ("root_fpu_zero", C.c_uint8), ("shaped_dirichlet", C.c_uint8),
         ("policy_target_pruning", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("resign_percent", C.c_float),
         ("resign_playthrough_percent", C.c_float), ("eval_type", C.c_uint8), ("rng_mode", C.c_uint8),
-        ("pad0_", C.c_uint8), ("pad1_", C.c_uint8), ("seed", C.c_uint64), ("pool_nodes", C.c_uint64),
+        ("per_slot_quota", C.c_uint8), ("pad1_", C.c_uint8), ("seed", C.c_uint64), ("pool_nodes", C.c_uint64),
         ("history_capacity", C.c_uint32), ("lanes_per_game", C.c_uint32), ("compact_pages", C.c_uint32),
         ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float), ("gumbel_c_scale", C.c_float),
         ("gumbel_full", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad3_", C.c_uint8 * 2),
-        ("pad2_", C.c_uint32),
+        ("step_kernel", C.c_uint32),
     ]
 
 

@@ -24,6 +24,7 @@
 
 #include "../../include/b2az.h"
 #include "az_engine_logic.h"
+#include "az_engine_queue.h"
 
 #ifndef B2AZ_HOST_EMU
 #include <cuda_runtime.h>
@@ -158,7 +159,7 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
     GameSlot gs;
     memset(&gs, 0, sizeof(gs));
     gs.active = 1;
-    pcg32_seed_stream(gs.rng, a.seed, (u64)g);
+    pcg32_seed(gs.rng, a.seed + (u64)g);
     E.games[g] = gs;
     GameCold gc;
     memset(&gc, 0, sizeof(gc));
@@ -361,9 +362,21 @@ struct b2az_engine {
   std::vector<u32> row_of_game;     // slot id -> row
   std::vector<float> stage_v, stage_pi;
   bool started = false;
+  u32 step_kernel = 0;              // B2AZ_STEP_*
 };
 
 namespace {
+
+// The CUDA current device is per host thread (a fresh Python thread starts on device 0): every entry point that
+// launches or copies binds the engine's device first.
+int bind_device(b2az_engine* e) {
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaSetDevice(e->device));
+#else
+  (void)e;
+#endif
+  return 0;
+}
 
 int sync_leaf_count(b2az_engine* e, stream_t s) {
   if (e->leaf_count_known) return 0;
@@ -399,6 +412,7 @@ int check_device_error(b2az_engine* e, stream_t s) {
   if (err & B2AZ_DEVERR_POOL) return fail(B2AZ_ENOMEM, "device tree-node pool exhausted: raise b2az_params.pool_nodes");
   if (err & B2AZ_DEVERR_MOVE) return fail(B2AZ_EMOVE, "device: update_root could not find the move / illegal move");
   if (err & B2AZ_DEVERR_DEPTH) return fail(B2AZ_ESTATE, "device: selection path exceeded the path buffer");
+  if (err & B2AZ_DEVERR_QUEUE) return fail(B2AZ_ESTATE, "device: the step kernel's work queues stalled (watchdog)");
   if (err & B2AZ_DEVERR_HIST) return fail(B2AZ_ENOMEM, "device history ring overflowed: drain more often or raise history_capacity");
   return 0;
 }
@@ -473,6 +487,9 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
   if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
     return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
+  if (p->step_kernel > B2AZ_STEP_FLAT) return fail(B2AZ_EINVAL, "bad step_kernel");
+  if (p->per_slot_quota && p->games_to_play % p->concurrent_games != 0)
+    return fail(B2AZ_EINVAL, "per_slot_quota: games_to_play must be a multiple of concurrent_games");
   if (p->lanes_per_game > 1)
     return fail(B2AZ_EINVAL, "lanes_per_game must be 0 or 1: Connect4 runs one thread per game slot (DESIGN.md 3)");
 #ifdef B2AZ_HOST_EMU
@@ -487,6 +504,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   b2az_engine* e = new b2az_engine();
   e->params = *p;
   e->device = device;
+  e->step_kernel = p->step_kernel;
+  if (const char* sk = getenv("B2AZ_STEP_KERNEL")) e->step_kernel = (sk[0] == 'f' || sk[0] == '1') ? B2AZ_STEP_FLAT : B2AZ_STEP_QUEUE;
 #ifndef B2AZ_HOST_EMU
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -508,6 +527,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.resign_percent = p->resign_percent; V.resign_playthrough_percent = p->resign_playthrough_percent;
   V.gumbel_enabled = p->gumbel_enabled; V.gumbel_full = p->gumbel_full; V.fast_search_uses_gumbel = p->fast_search_uses_gumbel;
   V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
+  V.slot_quota = p->per_slot_quota ? p->games_to_play / p->concurrent_games : 0u;
 
   // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
   const u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
@@ -575,6 +595,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
 #ifndef B2AZ_HOST_EMU
   if (const char* cv = getenv("B2AZ_CARVEOUT"))  // experiment knob: shared-memory carveout of the step kernel, percent
     CUDA_TRY(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+  CUDA_TRY(cudaFuncSetAttribute(k_step_q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared)));
+  CUDA_TRY(cudaFuncSetAttribute(k_step_q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared)));
   InitArgs ia{p->seed, p->rng_mode};
   k_init_pool<<<e->num_sms * 4, 256>>>(V);
   k_init_games<<<e->num_sms * 4, 256>>>(V, ia);
@@ -589,7 +611,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
     GameSlot gs;
     memset(&gs, 0, sizeof(gs));
     gs.active = 1;
-    pcg32_seed_stream(gs.rng, p->seed, (u64)g);
+    pcg32_seed(gs.rng, p->seed + (u64)g);
     V.games[g] = gs;
     memset(&V.cold[g], 0, sizeof(GameCold));
     TreeHdr T;
@@ -614,6 +636,7 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
   if (n_steps == 0) return 0;
   stream_t s = static_cast<stream_t>(stream);
   EngineView& V = e->view;
+  if (int rc = bind_device(e)) return rc;
   if (V.eval_type == B2AZ_EVAL_NN) {
     if (n_steps != 1) return fail(B2AZ_EINVAL, "n_steps must be 1 with B2AZ_EVAL_NN");
     if (e->leaves_pending && !e->evals_all) {
@@ -634,9 +657,18 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
     if (int rc = dev_zero(&V.glob->leaf_count, sizeof(u32), s)) return rc;
   }
 #ifndef B2AZ_HOST_EMU
-  CUDA_TRY(cudaSetDevice(e->device));
   if (V.rng_mode == B2AZ_RNG_GLOBAL) {
     k_step_serial<<<1, 1, 0, s>>>(V, n_steps);  // exactly ONE thread walks the slots
+  } else if (e->step_kernel == B2AZ_STEP_QUEUE) {
+    // persistent CTAs (one per SM), each owning groups of <= kQGames slots whose state lives in shared memory
+    const u32 sms = (u32)e->num_sms;
+    u32 groups;
+    if (V.G <= sms * (u32)kQGames) groups = std::max(1u, std::min(sms, (V.G + 31u) / 32u));
+    else groups = (((V.G + (u32)kQGames - 1u) / (u32)kQGames + sms - 1u) / sms) * sms;
+    const u32 per_group = (V.G + groups - 1u) / groups;
+    const u32 grid = std::min(groups, sms);
+    if (V.gumbel_enabled) k_step_q<true><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, per_group, groups);
+    else k_step_q<false><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, per_group, groups);
   } else {
     // small CTAs spread the (one thread per game) population evenly over the SMs
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;
@@ -688,6 +720,7 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
 int b2az_leaf_batch(b2az_engine* e, void* stream, uint32_t* count, const float** canon_dev, const uint32_t** ids_dev) {
   if (!e || !count) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
   if (!e->leaves_pending) { *count = 0; return 0; }
   if (int rc = ensure_canon(e, s)) return rc;
@@ -703,6 +736,7 @@ int b2az_leaf_batch_host(b2az_engine* e, void* stream, uint32_t max, float* cano
                          uint32_t* count) {
   if (!e || !count || !canon_host || !ids_host) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
   *count = 0;
   if (!e->leaves_pending) return 0;
@@ -742,6 +776,7 @@ int b2az_leaf_batch_device(b2az_engine* e, void* stream, const float** canon_dev
                            const uint32_t** count_dev) {
   if (!e) return fail(B2AZ_EINVAL, "null engine");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
   if (!e->leaves_pending) return fail(B2AZ_ESTATE, "call b2az_step first");
   if (int rc = ensure_canon(e, s)) return rc;
@@ -764,6 +799,7 @@ int b2az_submit_eval_host(b2az_engine* e, void* stream, const uint32_t* ids_host
                           const float* pi_host, uint32_t count) {
   if (!e || (count && (!ids_host || !v_host || !pi_host))) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   if (!e->leaves_pending || !e->leaf_count_known) return fail(B2AZ_ESTATE, "no leaf batch is waiting for evaluations");
   if (e->evals_submitted + count > e->leaf_count) return fail(B2AZ_EINVAL, "more evaluations than leaves");
   // contiguous run of rows? (the common case: ids come straight from b2az_leaf_batch_host)
@@ -795,6 +831,7 @@ static int drain_history_impl(b2az_engine* e, void* stream, uint32_t max, u32 ns
                               int dst_is_device, uint32_t* count) {
   if (!e || !count) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   *count = 0;
   if (!e->params.history_enabled || max == 0) return 0;
   unsigned long long wr[2];
@@ -855,6 +892,7 @@ int b2az_drain_history_sym(b2az_engine* e, void* stream, uint32_t max, float* ca
 int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   if (!e || !out) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   memset(out, 0, sizeof(*out));
   Globals G;
   StatsOut so{0, 0};
@@ -904,6 +942,7 @@ int b2az_peek(b2az_engine* e, void* stream, uint32_t game, uint32_t seat, uint8_
   if (!e) return fail(B2AZ_EINVAL, "null engine");
   if (game >= e->view.G || seat >= (u32)kP) return fail(B2AZ_EINVAL, "bad game/seat");
   stream_t s = static_cast<stream_t>(stream);
+  if (e) { if (int rc = bind_device(e)) return rc; }
   PeekOut po;
 #ifndef B2AZ_HOST_EMU
   k_peek<<<1, 1, 0, s>>>(e->view, game, seat, e->peek_buf);

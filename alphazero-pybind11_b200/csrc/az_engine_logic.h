@@ -44,6 +44,7 @@ namespace b2az {
 #define B2AZ_DEVERR_HIST 2u
 #define B2AZ_DEVERR_MOVE 4u
 #define B2AZ_DEVERR_DEPTH 8u
+#define B2AZ_DEVERR_QUEUE 16u
 
 // ------------------------------------------------------------------------------------ atomics
 AZ_HD u32 at_add(u32* p, u32 v) {
@@ -308,6 +309,93 @@ struct PathRegs {
   u32 slots_lo, slots_hi;  // 8 bits per level: child slot | parent's player << 4
   u32 valid;               // the registers describe the pending leaf's path
 };
+// The queue kernel (az_engine_queue.h) keeps the first kPathSm edges in SHARED memory instead, where an indexed
+// access is one LDS / STS and not a chain of selects.
+constexpr int kPathSm = 12;
+struct PathSm {
+  u32 blk[kPathSm];
+  u8 slot[kPathSm];
+  u32 valid;
+};
+AZ_HD void path_begin(PathRegs& pr) {
+  pr.slots_lo = pr.slots_hi = 0;
+  pr.valid = 1;
+}
+AZ_HD void path_begin(PathSm& pr) { pr.valid = 1; }
+// record edge `plen` of the selection path: (block, child slot | parent's player << 4)
+AZ_HD void path_put(const EngineView& E, u32 g, PathRegs& pr, u32 plen, u32 blk, u32 slot_byte) {
+  if (plen >= (u32)kPathRegs) {  // the first kPathRegs levels reach HBM in ctx_store only
+    E.path[(size_t)g * kMaxPath + plen] = blk;
+    E.pslot[(size_t)g * kMaxPath + plen] = (u8)slot_byte;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < kPathRegs; ++i)
+    if (plen == (u32)i) pr.blk[i] = blk;
+  if (plen < 4u) pr.slots_lo |= slot_byte << (8u * plen);
+  else if (plen < 8u) pr.slots_hi |= slot_byte << (8u * (plen - 4u));
+}
+AZ_HD void path_put(const EngineView& E, u32 g, PathSm& pr, u32 plen, u32 blk, u32 slot_byte) {
+  if (plen >= (u32)kPathSm) {
+    E.path[(size_t)g * kMaxPath + plen] = blk;
+    E.pslot[(size_t)g * kMaxPath + plen] = (u8)slot_byte;
+  } else {
+    pr.blk[plen] = blk;
+    pr.slot[plen] = (u8)slot_byte;
+  }
+}
+// edge i of the pending leaf's path; `cached` = the on-chip copy is valid (else everything is in HBM)
+AZ_HD void path_get(const EngineView& E, u32 g, const PathRegs& pr, bool cached, u32 i, u32& b, u32& sb) {
+#if defined(B2AZ_NO_PATHREGS)
+  cached = false;
+#endif
+  if (cached && i < (u32)kPathRegs) {
+    u32 x = pr.blk[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 1; r < kPathRegs; ++r)
+      if (i == (u32)r) x = pr.blk[r];
+    b = x;
+    sb = ((i < 4u ? pr.slots_lo : pr.slots_hi) >> (8u * (i & 3u))) & 0xFFu;
+  } else {
+    b = E.path[(size_t)g * kMaxPath + i];
+    sb = E.pslot[(size_t)g * kMaxPath + i];
+  }
+}
+AZ_HD void path_get(const EngineView& E, u32 g, const PathSm& pr, bool cached, u32 i, u32& b, u32& sb) {
+  if (cached && i < (u32)kPathSm) {
+    b = pr.blk[i];
+    sb = pr.slot[i];
+  } else {
+    b = E.path[(size_t)g * kMaxPath + i];
+    sb = E.pslot[(size_t)g * kMaxPath + i];
+  }
+}
+// the pending leaf's path goes to HBM for a later launch (or for the move code)
+AZ_HD void path_flush(const EngineView& E, u32 g, const PathRegs& pr, u32 path_len) {
+  if (!pr.valid) return;
+  u32* path = E.path + (size_t)g * kMaxPath;
+  u8* pslot = E.pslot + (size_t)g * kMaxPath;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < kPathRegs; ++i)
+    if ((u32)i < path_len) {
+      path[i] = pr.blk[i];
+      pslot[i] = (u8)(((i < 4 ? pr.slots_lo : pr.slots_hi) >> (8 * (i & 3))) & 0xFFu);
+    }
+}
+AZ_HD void path_flush(const EngineView& E, u32 g, const PathSm& pr, u32 path_len) {
+  if (!pr.valid) return;
+  u32* path = E.path + (size_t)g * kMaxPath;
+  u8* pslot = E.pslot + (size_t)g * kMaxPath;
+  for (u32 i = 0; i < (u32)kPathSm && i < path_len; ++i) {
+    path[i] = pr.blk[i];
+    pslot[i] = pr.slot[i];
+  }
+}
 // ------------------------------------------------------------------------------------ Gumbel root search
 // MCTS::set_gumbel_num_sims / reset / init / advance_phase / next_root_child / interior_select /
 // improved_policy / final_action (mcts.cc:28-89, 175-401). All cold: they run once per simulation at the
@@ -508,7 +596,7 @@ AZ_COLD void gumbel_improved_policy(const EngineView E, const TreeHdr& T, float*
 // (mcts.cc:123-128) inlined. n_in_flight is always 0 on this path (the WU-UCT variant is not used by
 // PlayManager). Split in three pieces so that the fused kernel can run the descent ONE
 // LEVEL PER LOOP ITERATION for every game of a warp (run_flat below): begin / level / finish.
-struct Descent {
+struct __attribute__((aligned(16))) Descent {
   C4State s;          // the position replayed along the path
   u32 blk;            // child block of the current node
   u32 cur_n, cur_term, cur_player, cur_k;
@@ -518,6 +606,7 @@ struct Descent {
   bool at_root;
   bool gumbel;        // Gumbel selection is active for this descent (MCTS::gumbel_initialized_)
 };
+static_assert(sizeof(Descent) == 64, "Descent must stay four 16 B vectors (shared-memory record of the queue kernel)");
 // Lazy Gumbel init (mcts.cc:468-472): after the root has been expanded, when a sims target is set.
 AZ_COLD bool gumbel_begin(const EngineView E, u32 tree, const TreeHdr T, Pcg32& rng) {
   GumbelState S = E.gum[tree];
@@ -530,8 +619,8 @@ AZ_COLD bool gumbel_begin(const EngineView E, u32 tree, const TreeHdr T, Pcg32& 
 // GB = false compiles the Gumbel hooks out of the descent (the step kernel picks the instantiation from
 // params.gumbel_enabled): no out-of-line call sites, hence no caller-saved registers, inside the hot loop
 // (spill stores 178 B -> 32 B; throughput unchanged).
-template <bool GB = true>
-AZ_HD void descent_begin(const EngineView& E, u32 g, const TreeHdr& T, const GameSlot& gs, Descent& D, PathRegs& pr,
+template <bool GB = true, class PR = PathRegs>
+AZ_HD void descent_begin(const EngineView& E, u32 g, const TreeHdr& T, const GameSlot& gs, Descent& D, PR& pr,
                          Pcg32& rng) {
   D.gumbel = false;
   if (GB && E.gumbel_enabled) {
@@ -546,14 +635,13 @@ AZ_HD void descent_begin(const EngineView& E, u32 g, const TreeHdr& T, const Gam
   D.at_root = true;
   D.par_blk = kNil; D.par_slot = 0;
   D.plen = 0;
-  pr.slots_lo = pr.slots_hi = 0;
-  pr.valid = 1;
+  path_begin(pr);
 }
 AZ_HD bool descent_more(const Descent& D) { return D.cur_n > 0 && D.cur_term == 0; }
 // One level: load the node's child block, pick best_child, replay the move. Returns false on the
 // (impossible for Connect4) structural error, which ends the descent.
-template <bool GB = true>
-AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
+template <bool GB = true, class PR = PathRegs>
+AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PR& pr) {
   if (D.blk == kNil || D.plen >= (u32)kMaxPath) {  // cannot happen for a non-terminal Connect4 node
     at_or(&E.glob->error, B2AZ_DEVERR_DEPTH);
     return false;
@@ -618,15 +706,7 @@ AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PathRegs& pr) {
   const u32 cterm = (hd.y >> (2u * best)) & 3u;
   const u32 slot_byte = best | (D.cur_player << 4);
   const u32 plen = D.plen;
-  if (plen >= (u32)kPathRegs) {  // the first kPathRegs levels reach HBM in ctx_store only
-    E.path[(size_t)g * kMaxPath + plen] = D.blk;
-    E.pslot[(size_t)g * kMaxPath + plen] = (u8)slot_byte;
-  }
-#pragma unroll
-  for (int i = 0; i < kPathRegs; ++i)
-    if (plen == (u32)i) pr.blk[i] = D.blk;
-  if (plen < 4u) pr.slots_lo |= slot_byte << (8u * plen);
-  else if (plen < 8u) pr.slots_hi |= slot_byte << (8u * (plen - 4u));
+  path_put(E, g, pr, plen, D.blk, slot_byte);
   D.plen = plen + 1u;
   c4_play(D.s, move);
   D.par_blk = D.blk;
@@ -895,8 +975,9 @@ AZ_COLD void root_leaf_priors(const EngineView E, Pcg32& rng, float* p8, u32 lk,
 
 // ------------------------------------------------------------------------------------ process_result
 // MCTS::process_result (mcts.cc:500-555).
+template <class PR>
 AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot& gs, Pcg32& rng, bool noise_enabled,
-                          PathRegs& pr) {
+                          PR& pr) {
   float val0, val1, vald;  // value[0], value[1], value[P] (draw share)
   const u32 lterm = T.leaf_term, lk = T.leaf_k, lplayer = T.leaf_player, lblk = T.leaf_blk;
   const u32 plen = T.path_len;
@@ -963,14 +1044,8 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
   // backprop (mcts.cc:527-545): level i updates the child slot selected at level i. The levels touch
   // different blocks, so their loads are issued together (4 levels at a time) instead of one dependent
   // round trip per level.
-  const u32* path = E.path + (size_t)g * kMaxPath;
-  const u8* pslot = E.pslot + (size_t)g * kMaxPath;
   const float dshare = fdiv(vald, (float)kP);
-#if defined(B2AZ_NO_PATHREGS)
-  const bool cached = false;
-#else
   const bool cached = pr.valid != 0;
-#endif
   pr.valid = 0;
   for (u32 base = 0; base < plen; base += 4u) {
     u32 bi[4], sb[4];
@@ -980,19 +1055,7 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
       const u32 i = base + (u32)t;
       bi[t] = kNil;
       sb[t] = 0;
-      if (i < plen) {
-        if (cached && i < (u32)kPathRegs) {
-          u32 b = pr.blk[0];
-#pragma unroll
-          for (int r = 1; r < kPathRegs; ++r)
-            if (i == (u32)r) b = pr.blk[r];
-          bi[t] = b;
-          sb[t] = ((i < 4u ? pr.slots_lo : pr.slots_hi) >> (8u * (i & 3u))) & 0xFFu;
-        } else {
-          bi[t] = path[i];
-          sb[t] = pslot[i];
-        }
-      }
+      if (i < plen) path_get(E, g, pr, cached, i, bi[t], sb[t]);
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -1304,18 +1367,7 @@ AZ_HD void ctx_load(const EngineView& E, u32 g, Ctx& c) {
   c.pr.slots_lo = c.pr.slots_hi = 0;
 }
 AZ_HD void ctx_store(const EngineView& E, u32 g, Ctx& c) {
-  if (c.pr.valid) {  // the pending leaf's path: a later launch (or the move code) reads it from HBM
-    u32* path = E.path + (size_t)g * kMaxPath;
-    u8* pslot = E.pslot + (size_t)g * kMaxPath;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < kPathRegs; ++i)
-      if ((u32)i < (u32)c.T.path_len) {
-        path[i] = c.pr.blk[i];
-        pslot[i] = (u8)(((i < 4 ? c.pr.slots_lo : c.pr.slots_hi) >> (8 * (i & 3))) & 0xFFu);
-      }
-  }
+  path_flush(E, g, c.pr, (u32)c.T.path_len);  // the pending leaf's path: a later launch (or the move code) reads it
   if (E.rng_mode == 1) E.glob->global_rng = c.rng; else c.gs.rng = c.rng;
   E.trees[(size_t)g * kP + c.gs.player] = c.T;
   E.games[g] = c.gs;
@@ -1465,8 +1517,11 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
       tree_reset(T[seat]);
       if (E.gumbel_enabled) gumbel_set_num_sims(GS[seat], 0u);  // make_mcts: a fresh MCTS has no sims target
     }
-    if (started >= E.games_to_play) {
-      retired = true;  // play_manager.cc:506-509
+    ++cold.games_done;
+    // play_manager.cc:506-509: a slot retires once games_to_play games have been STARTED by anybody. Which slot
+    // that hits depends on completion order; with a per-slot quota every slot plays the same number of games.
+    if (E.slot_quota ? cold.games_done >= E.slot_quota : started >= E.games_to_play) {
+      retired = true;
       gs.active = 0;
       at_sub(&E.glob->active_games, 1u);
     } else {

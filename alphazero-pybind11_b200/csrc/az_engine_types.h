@@ -103,7 +103,8 @@ struct __attribute__((aligned(16))) GameCold {  // touched once per move / per l
   double total_valid_moves;
   unsigned long long sims;    // simulations finished in this slot (summed on demand; no global atomic per sim)
   unsigned long long nmoves;  // moves played in this slot
-  u32 pad_[2];
+  u32 games_done;             // games finished in this slot (slot_quota)
+  u32 pad_;
 };
 static_assert(sizeof(GameCold) == 64, "GameCold layout");
 
@@ -162,6 +163,7 @@ struct EngineView {
   u8 policy_target_pruning, playout_cap, eval_type, rng_mode;
   u32 num_pages, hist_capacity;
   u32 compact_pages;   // a tree is compacted at a move once its arena holds more pages than this
+  u32 slot_quota;      // > 0: every slot retires after this many games (deterministic: b2az_params.per_slot_quota)
   // ---- block pool
   Block* blocks;       // [num_pages * kPageBlocks]
   u32* page_next;      // [num_pages] chain links

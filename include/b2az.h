@@ -31,10 +31,15 @@ extern "C" {
 
 #define B2AZ_GAME_CONNECT4 0
 
+#define B2AZ_STEP_QUEUE 0   /* persistent CTAs, game state in shared memory, work queues (az_engine_queue.h) */
+#define B2AZ_STEP_FLAT 1    /* one thread per game slot, flattened loop (round-1 kernel) */
+
 #define B2AZ_EVAL_NN 0      /* EvalType::NN      (play_manager.h:20) */
 #define B2AZ_EVAL_RANDOM 1  /* EvalType::RANDOM: dumb_eval on the device (game_state.h:160-173) */
 
-#define B2AZ_RNG_PER_GAME 0 /* one pcg32 stream per game slot: pcg32(seed, game_index) */
+#define B2AZ_RNG_PER_GAME 0 /* one generator per game slot: slot g draws from pcg32(seed + g), i.e. it reproduces a
+                               reference PlayManager with concurrent_games = 1 run after
+                               MCTS::seed_thread_rng(seed + g) (mcts.cc:19-21), bit for bit */
 #define B2AZ_RNG_GLOBAL 1   /* ONE pcg32(seed) consumed in ascending game order, exactly like a single
                                reference worker thread after MCTS::seed_thread_rng(seed) (mcts.cc:19-21).
                                Serial by construction; this is the bit-exact parity mode. */
@@ -69,7 +74,11 @@ typedef struct b2az_params {
   float resign_playthrough_percent;
   uint8_t eval_type;             /* B2AZ_EVAL_*; applies to every seat */
   uint8_t rng_mode;              /* B2AZ_RNG_* */
-  uint8_t pad0_, pad1_;
+  uint8_t per_slot_quota;        /* 1: every slot plays exactly games_to_play / concurrent_games games and then retires
+                                    (which slot plays the last games of a run otherwise depends on completion order,
+                                    play_manager.cc:506-513). Slot g then equals a reference PlayManager with
+                                    concurrent_games = 1, games_to_play = quota, seeded seed + g. */
+  uint8_t pad1_;
   uint64_t seed;
   /* engine sizing (no reference counterpart) */
   uint64_t pool_nodes;           /* tree-node pool size in nodes (8 per 192 B block); 0 = sized from visits and free HBM */
@@ -84,7 +93,7 @@ typedef struct b2az_params {
   uint8_t gumbel_full;           /* pi'-matching at interior nodes too */
   uint8_t fast_search_uses_gumbel;
   uint8_t pad3_[2];
-  uint32_t pad2_;
+  uint32_t step_kernel;          /* B2AZ_STEP_*: which fused step kernel runs B2AZ_RNG_PER_GAME (results do not depend on it) */
 } b2az_params;
 
 /* Counters and metrics of PlayManager (play_manager.h:173-366). */
@@ -112,6 +121,7 @@ typedef struct b2az_stats {
 #define B2AZ_DEVERR_HIST 2u      /* history ring overflow (samples dropped) */
 #define B2AZ_DEVERR_MOVE 4u      /* update_root could not find the move (mcts.cc:159-162) */
 #define B2AZ_DEVERR_DEPTH 8u     /* selection path longer than the path buffer */
+#define B2AZ_DEVERR_QUEUE 16u    /* the step kernel's work-queue watchdog fired */
 
 typedef struct b2az_engine b2az_engine;
 

@@ -848,7 +848,7 @@ void* azo_pm_new(const azo_cfg* c) {
   pm->global_rng = std::make_unique<Pcg>(c->seed);
   for (uint32_t g = 0; g < c->concurrent_games; ++g) {  // play_manager.cc:205-255
     c4_clear(pm->games[g].gs);
-    pm->games[g].rng = std::make_unique<Pcg>(c->seed, static_cast<uint64_t>(g));
+    pm->games[g].rng = std::make_unique<Pcg>(c->seed + static_cast<uint64_t>(g));  // slot g == a reference thread after seed_thread_rng(seed + g)
     pm->awaiting_mcts.push_back(g);
   }
   pm->games_started = c->concurrent_games;

@@ -21,8 +21,10 @@
  * (tools/make_golden.py) and are checked against this port on boxes where /root/reference is absent.
  *
  * rng_mode 1 (global) = one pcg32(seed) shared by all games, consumed in the reference's
- * single-worker order; rng_mode 0 (per game) = slot g draws from pcg32(seed, stream g) — the
- * "scalable" parity level of SURVEY.md Appendix A, which the reference cannot run unpatched.
+ * single-worker order; rng_mode 0 (per game) = slot g draws from pcg32(seed + g) on the default
+ * stream, i.e. slot g replays what the UNMODIFIED reference PlayManager does with concurrent_games = 1
+ * after MCTS::seed_thread_rng(seed + g) — the "scalable" parity level, pinned directly to the reference
+ * slot by slot (tests/test_gpu_parity.py::test_fused_kernel_slots_equal_reference_single_game_runs).
  */
 #ifndef AZ_ORACLE_H_
 #define AZ_ORACLE_H_

@@ -456,6 +456,55 @@ def run_random_parity(engine_lib, G, games_to_play, visits, seed, oracle="port",
         ora.close()
 
 
+def run_slots_vs_reference(engine_lib, G, quota, visits, level, seed, chunk=400, extra=None, step_kernel=0):
+    """The fused per-game-RNG kernel pinned DIRECTLY to the unmodified reference: slot g of one engine run
+    (per_slot_quota: every slot plays `quota` games) must equal a reference PlayManager with concurrent_games = 1,
+    games_to_play = quota, RANDOM eval, run on a thread seeded MCTS::seed_thread_rng(seed + g). Compared: the
+    multiset of training samples (canonical, outcome, policy target — bit patterns), scores, total game length /
+    move counts (exact), and the leaf-depth / entropy means (double sums added in another order: 1e-5)."""
+    kw = dict(level_params(level), **(extra or {}))
+    eng = make_engine(engine_lib, G, G * quota, visits, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, seed,
+                      history_capacity=max(1 << 16, G * quota * 42), per_slot_quota=1, step_kernel=step_kernel, **kw)
+    try:
+        for _ in range(10 ** 6):
+            eng.step(chunk)
+            st = eng.stats()
+            if st.active_games == 0:
+                break
+        assert st.device_error == 0 and st.games_completed == G * quota
+        he = eng.drain_history(1 << 22)
+    finally:
+        eng.close()
+    canon, v, pi = [], [], []
+    scores = np.zeros(3, np.float64)
+    length = moves = 0.0
+    depth_sum = ent_sum = 0.0
+    for g in range(G):
+        cfg = refdriver.play_cfg(games_to_play=quota, concurrent_games=1, max_batch_size=1,
+                                 mcts_visits=(visits, visits), history_enabled=1, self_play=1, tree_reuse=1,
+                                 eval_type=b2az.EVAL_RANDOM, **kw)
+        pm = refdriver.RefPlayManager(cfg)
+        pm.play_here(seed + g)
+        c, vv, pp = pm.drain_history(quota * 42 + 1)
+        canon.append(c); v.append(vv); pi.append(pp)
+        scores += pm.scores()
+        m = pm.metrics()
+        length += m["avg_game_length"] * quota
+        # avg_moves_per_turn == 1 for Connect4, so total_move_count == game_length and every move is a full search here
+        depth_sum += m["avg_leaf_depth"] * m["avg_game_length"] * quota
+        ent_sum += m["avg_search_entropy"] * m["avg_game_length"] * quota
+        moves += m["avg_game_length"] * quota
+        pm.close()
+    compare_history(he, (np.concatenate(canon), np.concatenate(v), np.concatenate(pi)), ordered=False)
+    assert np.array_equal(np.array(st.scores[:], np.float64), scores), f"scores differ {st.scores[:]} vs {scores}"
+    assert abs(st.avg_game_length * G * quota - length) < 0.5, "total game length differs"
+    assert st.moves == round(moves)
+    if not kw.get("playout_cap_randomization"):
+        assert abs(st.avg_leaf_depth - depth_sum / moves) <= 1e-5 * max(1.0, depth_sum / moves)
+        assert abs(st.avg_search_entropy - ent_sum / moves) <= 1e-5 * max(1.0, ent_sum / moves)
+    return dict(games=int(st.games_completed), samples=len(he[0]), simulations=int(st.simulations))
+
+
 # ------------------------------------------------------------------------------------ golden traces
 class EnginePM:
     """The engine behind the oracle-shaped interface, so one tracer serves every side."""

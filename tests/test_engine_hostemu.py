@@ -47,6 +47,14 @@ def test_random_eval_vs_reference():
     assert r["games"] == 20
 
 
+@needs_ref
+@pytest.mark.parametrize("level", [0, 1])
+def test_per_game_slots_equal_reference_single_game_runs(level):
+    # B2AZ_RNG_PER_GAME: slot g == the unmodified reference PlayManager(concurrent_games=1) seeded seed + g
+    r = ph.run_slots_vs_reference(EMU, G=6, quota=3, visits=48, level=level, seed=991, chunk=37)
+    assert r["games"] == 18
+
+
 def test_no_tree_reuse_vs_port():
     ph.run_lockstep_parity(EMU, G=3, games_to_play=5, visits=24, level=1, seed=3, oracle="port", tree_reuse=False)
     ph.run_random_parity(EMU, G=4, games_to_play=8, visits=24, seed=3, oracle="port", level=2, tree_reuse=False)

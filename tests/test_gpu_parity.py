@@ -65,6 +65,40 @@ def test_parallel_kernel_400_sims_vs_port():
     assert r["games"] > 100
 
 
+@needs_ref
+@pytest.mark.parametrize("step_kernel", [b2az.STEP_QUEUE, b2az.STEP_FLAT])
+def test_fused_kernel_slots_equal_reference_single_game_runs(step_kernel):
+    """The TIMED kernel (fused launches of 400 generations, per-game RNG, 400 sims/move) against the UNMODIFIED
+    reference: slot g == PlayManager(concurrent_games=1) after MCTS::seed_thread_rng(seed + g); samples, scores,
+    game lengths and search metrics."""
+    r = ph.run_slots_vs_reference(None, G=256, quota=2, visits=400, level=1, seed=20260, chunk=400,
+                                  step_kernel=step_kernel)
+    assert r["games"] == 512 and r["samples"] > 5000
+    r = ph.run_slots_vs_reference(None, G=512, quota=3, visits=100, level=0, seed=7, chunk=400, step_kernel=step_kernel)
+    assert r["games"] == 1536
+
+
+@pytest.mark.parametrize("G", [1, 33, 448, 2000])
+def test_queue_kernel_equals_flat_kernel(G):
+    """k_step_q (work queues, state in shared memory) and k_step (thread per game) run the same per-game state machine:
+    identical samples, scores, simulation and move counts for every group size (partial groups, one game, several
+    groups per CTA), with the NN-free evaluator and fused launches."""
+    out = []
+    for kern in (b2az.STEP_QUEUE, b2az.STEP_FLAT):
+        e = ph.make_engine(None, G, G * 2, 60, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, 99, per_slot_quota=1,
+                           step_kernel=kern, history_capacity=G * 2 * 42, **ph.level_params(1))
+        for _ in range(10 ** 5):
+            e.step(173)
+            st = e.stats()
+            if st.active_games == 0:
+                break
+        assert st.device_error == 0 and st.games_completed == 2 * G
+        out.append((st.simulations, st.moves, list(st.scores), e.drain_history(G * 2 * 42)))
+        e.close()
+    assert out[0][:3] == out[1][:3]
+    ph.compare_history(out[0][3], out[1][3], ordered=False)
+
+
 def test_playout_cap_and_resign_gpu():
     """Playout-cap randomisation + resign_percent / playthrough on the device vs the port (coins from each game's own
     stream on both sides): fused RANDOM-eval launches and the lock-step NN loop."""
