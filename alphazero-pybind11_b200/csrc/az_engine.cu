@@ -25,6 +25,7 @@
 #include "../../include/b2az.h"
 #include "az_engine_logic.h"
 #include "az_engine_queue.h"
+#include "az_engine_waves.h"
 
 #ifndef B2AZ_HOST_EMU
 #include <cuda_runtime.h>
@@ -449,6 +450,26 @@ int b2az_params_default(b2az_params* p) {
   return 0;
 }
 
+#if defined(B2AZ_W_PROF) && !defined(B2AZ_HOST_EMU)
+int b2az_debug_wprof(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_wprof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_wprof, z, sizeof(z));
+  return 0;
+}
+#endif
+#if defined(B2AZ_Q_PROF) && !defined(B2AZ_HOST_EMU)
+// experiment builds only: read (and clear) the queue kernel's time accounting
+int b2az_debug_qprof(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_qprof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_qprof, z, sizeof(z));
+  return 0;
+}
+#endif
+
 int b2az_destroy(b2az_engine* e) {
   if (!e) return 0;
 #ifndef B2AZ_HOST_EMU
@@ -487,7 +508,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
   if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
     return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
-  if (p->step_kernel > B2AZ_STEP_FLAT) return fail(B2AZ_EINVAL, "bad step_kernel");
+  if (p->step_kernel > B2AZ_STEP_WAVES) return fail(B2AZ_EINVAL, "bad step_kernel");
   if (p->per_slot_quota && p->games_to_play % p->concurrent_games != 0)
     return fail(B2AZ_EINVAL, "per_slot_quota: games_to_play must be a multiple of concurrent_games");
   if (p->lanes_per_game > 1)
@@ -505,7 +526,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   e->params = *p;
   e->device = device;
   e->step_kernel = p->step_kernel;
-  if (const char* sk = getenv("B2AZ_STEP_KERNEL")) e->step_kernel = (sk[0] == 'f' || sk[0] == '1') ? B2AZ_STEP_FLAT : B2AZ_STEP_QUEUE;
+  if (const char* sk = getenv("B2AZ_STEP_KERNEL"))
+    e->step_kernel = sk[0] == 'f' ? B2AZ_STEP_FLAT : sk[0] == 'w' ? B2AZ_STEP_WAVES : B2AZ_STEP_QUEUE;
 #ifndef B2AZ_HOST_EMU
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -597,6 +619,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
     CUDA_TRY(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
   CUDA_TRY(cudaFuncSetAttribute(k_step_q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared)));
   CUDA_TRY(cudaFuncSetAttribute(k_step_q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QShared)));
+  CUDA_TRY(cudaFuncSetAttribute(k_step_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WShared)));
+  CUDA_TRY(cudaFuncSetAttribute(k_step_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WShared)));
   InitArgs ia{p->seed, p->rng_mode};
   k_init_pool<<<e->num_sms * 4, 256>>>(V);
   k_init_games<<<e->num_sms * 4, 256>>>(V, ia);
@@ -659,6 +683,16 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
 #ifndef B2AZ_HOST_EMU
   if (V.rng_mode == B2AZ_RNG_GLOBAL) {
     k_step_serial<<<1, 1, 0, s>>>(V, n_steps);  // exactly ONE thread walks the slots
+  } else if (e->step_kernel == B2AZ_STEP_WAVES) {
+    // persistent CTAs (one per SM) owning groups of <= kQGames slots, scheduled in waves (az_engine_waves.h)
+    const u32 sms = (u32)e->num_sms;
+    u32 groups;
+    if (V.G <= sms * (u32)kQGames) groups = std::max(1u, std::min(sms, (V.G + 31u) / 32u));
+    else groups = (((V.G + (u32)kQGames - 1u) / (u32)kQGames + sms - 1u) / sms) * sms;
+    const u32 per_group = (V.G + groups - 1u) / groups;
+    const u32 grid = std::min(groups, sms);
+    if (V.gumbel_enabled) k_step_w<true><<<grid, B2AZ_W_WARPS * 32, sizeof(WShared), s>>>(V, n_steps, per_group, groups);
+    else k_step_w<false><<<grid, B2AZ_W_WARPS * 32, sizeof(WShared), s>>>(V, n_steps, per_group, groups);
   } else if (e->step_kernel == B2AZ_STEP_QUEUE) {
     // persistent CTAs (one per SM), each owning groups of <= kQGames slots whose state lives in shared memory
     const u32 sms = (u32)e->num_sms;

@@ -25,11 +25,30 @@
 
 namespace b2az {
 
+#define B2AZ_Q_WARPS_DEFAULT_MAX 32
 #ifndef B2AZ_Q_WARPS
 #define B2AZ_Q_WARPS 16   // warps per CTA; the pop policy below limits how many of them hold a batch at a time
 #endif
+#ifndef B2AZ_Q_NAP_MAX
+#define B2AZ_Q_NAP_MAX 2048  // longest sleep (ns) of a warp that finds no batch
+#endif
 #ifndef B2AZ_Q_MIN
 #define B2AZ_Q_MIN 32     // batch-size floor of a full group (kQGames games); smaller groups scale it down (QShared::qmin)
+#endif
+
+#if defined(B2AZ_Q_PROF)
+// experiment build: where the warps' time goes (clock64 sums over all warps of all CTAs; accumulated in shared
+// memory per warp and added to the global totals once per launch, so the accounting does not perturb the run)
+//   [0..2] cycles in LEVEL / LEAF / MOVE work   [3] cycles in failed pops + sleeping   [4] cycles in successful pop + push
+//   [5..7] batches per queue   [8..10] games per queue   [11] failed pops
+//   [12] pop: decision loop   [13] pop: slot reads + fence   [14] push: fence
+__device__ unsigned long long g_qprof[16];
+__shared__ unsigned long long s_qprof[B2AZ_Q_WARPS_DEFAULT_MAX][16];
+#define QPROF_ADD(i, v) do { if (lane == 0u) s_qprof[threadIdx.x >> 5][i] += (unsigned long long)(v); } while (0)
+#define QPROF_CLK() clock64()
+#else
+#define QPROF_ADD(i, v) do { } while (0)
+#define QPROF_CLK() 0ll
 #endif
 
 constexpr int kQGames = 448;  // game slots per CTA (shared memory: 272 B each)
@@ -57,13 +76,25 @@ struct QShared {
   u32 inflight;     // games popped and not yet pushed back
   u32 done;         // games that finished this launch
   u32 ng;           // games of the current group
-  u32 qmin;         // a warp only takes a batch of at least this many games while other warps are still working
+  u32 pad_;
   u16 ring[3][kQCap];
 };
 
+// CTA-scope fence between a game's state and the publication of its id. __threadfence_block() is fence.sc.cta
+// (MEMBAR.SC.CTA); release / acquire order is all the hand-off needs.
+__device__ __forceinline__ void q_fence() {
+#if defined(B2AZ_Q_FENCE_SC)
+  __threadfence_block();
+#else
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
+
 // Hand every lane's game (id >= 0) to queue `ns` (Q_DONE: the game is finished for this launch).
 __device__ __forceinline__ void q_push(QShared& S, int id, u32 ns, u32 lane, u32 n_taken) {
-  __threadfence_block();  // the game's state (shared and global) is written before its id is published
+  const long long p0 = QPROF_CLK();
+  q_fence();  // the game's state (shared and global) is written before its id is published
+  QPROF_ADD(14, QPROF_CLK() - p0);
 #pragma unroll
   for (u32 t = 0; t < 3u; ++t) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, id >= 0 && ns == t);
@@ -74,10 +105,13 @@ __device__ __forceinline__ void q_push(QShared& S, int id, u32 ns, u32 lane, u32
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (id >= 0 && ns == t) {
       volatile u16* r = &S.ring[t][(base + (u32)__popc(m & ((1u << lane) - 1u))) & (u32)(kQCap - 1)];
+#if !defined(B2AZ_Q_NO_PUSH_SPIN)
       for (u32 spin = 0; *r != (u16)kQEmpty && spin < (1u << 26); ++spin) {}  // the slot's previous item has been taken
+#endif
       *r = (u16)id;
     }
   }
+  QPROF_ADD(15, QPROF_CLK() - p0);
   const unsigned md = __ballot_sync(0xFFFFFFFFu, id >= 0 && ns == Q_DONE);
   if (lane == 0u) {
     if (md) atomicAdd(&S.done, (u32)__popc(md));
@@ -90,6 +124,7 @@ __device__ __forceinline__ int q_pop(QShared& S, u32 lane, int& id, u32& n) {
   int q = -1;
   u32 base = 0;
   n = 0;
+  const long long p0 = QPROF_CLK();
   if (lane == 0u) {
     volatile u32* head = S.head;
     volatile u32* tail = S.tail;
@@ -97,7 +132,11 @@ __device__ __forceinline__ int q_pop(QShared& S, u32 lane, int& id, u32& n) {
       u32 h[3], a[3];
 #pragma unroll
       for (int t = 0; t < 3; ++t) { h[t] = head[t]; a[t] = tail[t] - h[t]; }
-      const u32 qmin = S.qmin;
+      // full batches while the group is busy; as games finish their steps of this launch the floor comes down with
+      // the number of games still running, so the tail of a launch keeps many warps going with smaller batches
+      const u32 rem = S.ng - *(volatile u32*)&S.done;
+      u32 qmin = rem * (u32)B2AZ_Q_MIN / 384u;
+      qmin = qmin < 1u ? 1u : (qmin > 32u ? 32u : qmin);
       int pick = -1;
       if (a[Q_MOVE] >= qmin) pick = Q_MOVE;
       else if (a[Q_LEAF] >= qmin && a[Q_LEAF] >= a[Q_LEVEL]) pick = Q_LEAF;
@@ -127,6 +166,8 @@ __device__ __forceinline__ int q_pop(QShared& S, u32 lane, int& id, u32& n) {
   q = __shfl_sync(0xFFFFFFFFu, q, 0);
   base = __shfl_sync(0xFFFFFFFFu, base, 0);
   n = __shfl_sync(0xFFFFFFFFu, n, 0);
+  const long long p1 = QPROF_CLK();
+  if (q >= 0) QPROF_ADD(12, p1 - p0);
   id = -1;
   if (q >= 0 && lane < n) {
     volatile u16* r = &S.ring[q][(base + lane) & (u32)(kQCap - 1)];
@@ -136,7 +177,8 @@ __device__ __forceinline__ int q_pop(QShared& S, u32 lane, int& id, u32& n) {
     *r = (u16)kQEmpty;
     id = (int)v;
   }
-  __threadfence_block();  // ids are read before the games' state
+  q_fence();  // ids are read before the games' state
+  if (q >= 0) QPROF_ADD(13, QPROF_CLK() - p1);
   return q;
 }
 
@@ -236,15 +278,16 @@ __global__ void __launch_bounds__(B2AZ_Q_WARPS * 32, 1) k_step_q(EngineView E, u
   extern __shared__ __align__(16) unsigned char q_smem[];
   QShared& S = *reinterpret_cast<QShared*>(q_smem);
   const u32 tid = threadIdx.x, lane = tid & 31u;
+#if defined(B2AZ_Q_PROF)
+  if (lane < 16u) s_qprof[tid >> 5][lane] = 0;
+  __syncwarp();
+#endif
   for (u32 grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const u32 g0 = grp * games_per_group;
     const u32 ng = (g0 >= E.G) ? 0u : (E.G - g0 < games_per_group ? E.G - g0 : games_per_group);
     if (tid < 3u) { S.head[tid] = 0; S.tail[tid] = 0; }
     if (tid == 0u) {
       S.inflight = 0; S.done = 0; S.ng = ng;
-      // full batches for a full group; a small group (few concurrent games) trades batch size for warps in flight
-      const u32 m = ng * (u32)B2AZ_Q_MIN / 384u;
-      S.qmin = m < 1u ? 1u : (m > 32u ? 32u : m);
     }
     for (u32 i = tid; i < 3u * (u32)kQCap; i += blockDim.x) (&S.ring[0][0])[i] = (u16)kQEmpty;
     __syncthreads();
@@ -262,22 +305,28 @@ __global__ void __launch_bounds__(B2AZ_Q_WARPS * 32, 1) k_step_q(EngineView E, u
       q_push(S, id, ns, lane, 0u);
     }
     __syncthreads();
-    u32 idle = 0;
+    u32 idle = 0, nap = 64;
     for (;;) {
       int id;
       u32 n;
+      const long long t0 = QPROF_CLK();
       const int qsel = q_pop(S, lane, id, n);
       if (qsel == -2) break;
       if (qsel < 0) {
-        // watchdog: a scheduling bug must end the launch with an error, not hang the GPU (~4 s of idling)
-        if (++idle > (1u << 24)) {
+        // watchdog: a scheduling bug must end the launch with an error, not hang the GPU (seconds of idling)
+        if (++idle > (1u << 22)) {
           at_or(&E.glob->error, B2AZ_DEVERR_QUEUE);
           break;
         }
-        __nanosleep(128);
+        __nanosleep(nap);  // back off: idle warps must not fight the working ones for the shared-memory pipe
+        if (nap < (u32)B2AZ_Q_NAP_MAX) nap *= 2u;
+        QPROF_ADD(3, QPROF_CLK() - t0);
+        QPROF_ADD(11, 1);
         continue;
       }
       idle = 0;
+      nap = 64;
+      const long long t1 = QPROF_CLK();
       u32 ns = Q_DONE;
       if (id >= 0) {
         QGame& q = S.game[id];
@@ -287,12 +336,21 @@ __global__ void __launch_bounds__(B2AZ_Q_WARPS * 32, 1) k_step_q(EngineView E, u
         else ns = q_move<GB>(E, g, q);
       }
       __syncwarp();
+      const long long t2 = QPROF_CLK();
       q_push(S, id, ns, lane, n);
+      QPROF_ADD(qsel, t2 - t1);
+      QPROF_ADD(4, (t1 - t0) + (QPROF_CLK() - t2));
+      QPROF_ADD(5 + qsel, 1);
+      QPROF_ADD(8 + qsel, n);
     }
     __syncthreads();
     for (u32 i = tid; i < ng; i += blockDim.x) q_store_game(E, g0 + i, S.game[i]);
     __syncthreads();
   }
+#if defined(B2AZ_Q_PROF)
+  __syncwarp();
+  if (lane < 16u) atomicAdd(&g_qprof[lane], s_qprof[tid >> 5][lane]);
+#endif
 }
 
 }  // namespace b2az
