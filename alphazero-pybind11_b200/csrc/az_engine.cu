@@ -166,17 +166,21 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
     memset(&gc, 0, sizeof(gc));
     E.cold[g] = gc;
     TreeHdr T;
+    memset(&T, 0, sizeof(T));
     tree_reset(T);
+    T.region = g / E.region_games;
     E.trees[(size_t)g * kP + 0] = T;
     E.trees[(size_t)g * kP + 1] = T;
+  }
+  for (u32 r = GLOBAL_TID; r < E.n_regions; r += GLOBAL_NT) {
+    E.ring_tickets[2u * r] = 0;                    // pop tickets
+    E.ring_tickets[2u * r + 1u] = E.region_pages;  // push tickets: the ring starts full
   }
   if (GLOBAL_TID == 0) {
     Globals* G = E.glob;
     memset(G, 0, sizeof(Globals));
     G->games_started = E.G;
     G->active_games = E.G;
-    G->ring_push = E.num_pages;
-    G->ring_pop = 0;
     pcg32_seed(G->global_rng, a.seed);
   }
 }
@@ -364,6 +368,7 @@ struct b2az_engine {
   std::vector<float> stage_v, stage_pi;
   bool started = false;
   u32 step_kernel = 0;              // B2AZ_STEP_*
+  u32 group_games = 0, groups = 0;  // slots per persistent CTA (== pool region), number of such groups
 };
 
 namespace {
@@ -477,7 +482,7 @@ int b2az_destroy(b2az_engine* e) {
   cudaDeviceSynchronize();
 #endif
   EngineView& V = e->view;
-  dev_free(V.blocks); dev_free(V.page_next); dev_free(V.ring);
+  dev_free(V.blocks); dev_free(V.page_next); dev_free(V.ring); dev_free(V.ring_tickets);
   dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot); dev_free(V.gum);
   dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game);
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
@@ -568,6 +573,19 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   const u64 min_pages = (u64)G * kP + 16ull;  // every tree can at least hold one page
   if (pages < min_pages) pages = min_pages;
   if (pages > (0xFFFFFFF0ull >> kPageLog2)) pages = 0xFFFFFFF0ull >> kPageLog2;  // block index must fit 32 bits
+  // regions: one per group of slots that a persistent CTA owns (see EngineView::ring_tickets)
+  {
+    const u32 sms = (u32)e->num_sms;
+    u32 groups;
+    if (G <= sms * (u32)kQGames) groups = std::max(1u, std::min(sms, (G + 31u) / 32u));
+    else groups = (((G + (u32)kQGames - 1u) / (u32)kQGames + sms - 1u) / sms) * sms;
+    e->group_games = (G + groups - 1u) / groups;
+    e->groups = (G + e->group_games - 1u) / e->group_games;
+    V.region_games = e->group_games;
+    V.n_regions = e->groups;
+    V.region_pages = (u32)std::max<u64>(pages / V.n_regions, (u64)V.region_games * kP + 2ull);
+    pages = (u64)V.region_pages * V.n_regions;
+  }
   V.num_pages = (u32)pages;
   // compact a tree at a move once it holds more than half of its share of the pool
   V.compact_pages = p->compact_pages ? std::min<u32>(p->compact_pages, 60000u)
@@ -579,6 +597,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   auto A = [&](int r) { if (r && !rc) rc = r; };
   A(dev_alloc_raw(&V.blocks, nblocks));  // every block is fully written before it is read: no memset
   A(dev_alloc(&V.page_next, pages)); A(dev_alloc(&V.ring, pages));
+  A(dev_alloc(&V.ring_tickets, (size_t)V.n_regions * 2));
   A(dev_alloc(&V.trees, (size_t)G * kP)); A(dev_alloc(&V.games, (size_t)G)); A(dev_alloc(&V.cold, (size_t)G));
   if (p->gumbel_enabled) A(dev_alloc(&V.gum, (size_t)G * kP));  // zero = reset state, no sims target
   A(dev_alloc(&V.path, (size_t)G * kMaxPath)); A(dev_alloc(&V.pslot, (size_t)G * kMaxPath));
@@ -639,15 +658,19 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
     V.games[g] = gs;
     memset(&V.cold[g], 0, sizeof(GameCold));
     TreeHdr T;
+    memset(&T, 0, sizeof(T));
     tree_reset(T);
+    T.region = g / V.region_games;
     V.trees[(size_t)g * kP + 0] = T;
     V.trees[(size_t)g * kP + 1] = T;
+  }
+  for (u32 r = 0; r < V.n_regions; ++r) {
+    V.ring_tickets[2u * r] = 0;
+    V.ring_tickets[2u * r + 1u] = V.region_pages;
   }
   memset(V.glob, 0, sizeof(Globals));
   V.glob->games_started = G;
   V.glob->active_games = G;
-  V.glob->ring_push = V.num_pages;
-  V.glob->ring_pop = 0;
   pcg32_seed(V.glob->global_rng, p->seed);
 #endif
   e->row_of_game.assign(G, 0);
@@ -685,24 +708,14 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
     k_step_serial<<<1, 1, 0, s>>>(V, n_steps);  // exactly ONE thread walks the slots
   } else if (e->step_kernel == B2AZ_STEP_WAVES) {
     // persistent CTAs (one per SM) owning groups of <= kQGames slots, scheduled in waves (az_engine_waves.h)
-    const u32 sms = (u32)e->num_sms;
-    u32 groups;
-    if (V.G <= sms * (u32)kQGames) groups = std::max(1u, std::min(sms, (V.G + 31u) / 32u));
-    else groups = (((V.G + (u32)kQGames - 1u) / (u32)kQGames + sms - 1u) / sms) * sms;
-    const u32 per_group = (V.G + groups - 1u) / groups;
-    const u32 grid = std::min(groups, sms);
-    if (V.gumbel_enabled) k_step_w<true><<<grid, B2AZ_W_WARPS * 32, sizeof(WShared), s>>>(V, n_steps, per_group, groups);
-    else k_step_w<false><<<grid, B2AZ_W_WARPS * 32, sizeof(WShared), s>>>(V, n_steps, per_group, groups);
+    const u32 grid = std::min(e->groups, (u32)e->num_sms);
+    if (V.gumbel_enabled) k_step_w<true><<<grid, B2AZ_W_WARPS * 32, sizeof(WShared), s>>>(V, n_steps, e->group_games, e->groups);
+    else k_step_w<false><<<grid, B2AZ_W_WARPS * 32, sizeof(WShared), s>>>(V, n_steps, e->group_games, e->groups);
   } else if (e->step_kernel == B2AZ_STEP_QUEUE) {
     // persistent CTAs (one per SM), each owning groups of <= kQGames slots whose state lives in shared memory
-    const u32 sms = (u32)e->num_sms;
-    u32 groups;
-    if (V.G <= sms * (u32)kQGames) groups = std::max(1u, std::min(sms, (V.G + 31u) / 32u));
-    else groups = (((V.G + (u32)kQGames - 1u) / (u32)kQGames + sms - 1u) / sms) * sms;
-    const u32 per_group = (V.G + groups - 1u) / groups;
-    const u32 grid = std::min(groups, sms);
-    if (V.gumbel_enabled) k_step_q<true><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, per_group, groups);
-    else k_step_q<false><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, per_group, groups);
+    const u32 grid = std::min(e->groups, (u32)e->num_sms);
+    if (V.gumbel_enabled) k_step_q<true><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, e->group_games, e->groups);
+    else k_step_q<false><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, e->group_games, e->groups);
   } else {
     // small CTAs spread the (one thread per game) population evenly over the SMs
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;

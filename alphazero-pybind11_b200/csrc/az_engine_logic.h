@@ -222,8 +222,9 @@ AZ_HD void blk_copy(Block* D, const Block* S) {
 // is needed: a gpu-scope __threadfence compiles to MEMBAR + CCTL.IVALL, which throws away the whole
 // SM's L1 on every page pop (profiles/r3: L1 hit rate 43 %).
 AZ_COLD void pool_push_page(const EngineView E, u32 page) {
-  const unsigned long long t = at_add64(&E.glob->ring_push, 1ULL);
-  u32* slot = &E.ring[t % (unsigned long long)E.num_pages];
+  const u32 region = page / E.region_pages;  // a page always goes back to the region it came from
+  const unsigned long long t = at_add64(&E.ring_tickets[2u * region + 1u], 1ULL);
+  u32* slot = &E.ring[(size_t)region * E.region_pages + (size_t)(t % (unsigned long long)E.region_pages)];
 #if defined(__CUDA_ARCH__)
   for (u32 spin = 0; spin < (1u << 22); ++spin)
     if (at_cas(slot, kNil, page) == kNil) return;
@@ -232,11 +233,11 @@ AZ_COLD void pool_push_page(const EngineView E, u32 page) {
   *slot = page;
 #endif
 }
-AZ_COLD u32 pool_pop_page(const EngineView E) {
+AZ_COLD u32 pool_pop_page(const EngineView E, u32 region) {
   Globals* G = E.glob;
   if (ld_volatile(&G->error) & B2AZ_DEVERR_POOL) return kNil;  // already fatal: do not spin again
-  const unsigned long long t = at_add64(&G->ring_pop, 1ULL);
-  u32* slot = &E.ring[t % (unsigned long long)E.num_pages];
+  const unsigned long long t = at_add64(&E.ring_tickets[2u * region], 1ULL);
+  u32* slot = &E.ring[(size_t)region * E.region_pages + (size_t)(t % (unsigned long long)E.region_pages)];
   u32 page = kNil;
 #if defined(__CUDA_ARCH__)
   for (u32 spin = 0; spin < (1u << 16); ++spin) {
@@ -246,7 +247,7 @@ AZ_COLD u32 pool_pop_page(const EngineView E) {
 #else
   page = at_exch(slot, kNil);
 #endif
-  return page;  // kNil: ring empty = pool exhausted (fatal, reported by the caller)
+  return page;  // kNil: ring empty = the region is exhausted (fatal, reported by the caller)
 }
 // Give every page of a tree's chain back (the chain links are this thread's own writes).
 AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
@@ -260,7 +261,7 @@ AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
 // Bump-allocate one block in the tree's arena.
 AZ_HD u32 tree_alloc_block(const EngineView& E, TreeHdr& T) {
   if (T.cur_page == kNil || T.bump >= kPageBlocks) {
-    const u32 p = pool_pop_page(E);
+    const u32 p = pool_pop_page(E, T.region);
     if (p == kNil) {
       at_or(&E.glob->error, B2AZ_DEVERR_POOL);
       return kNil;
@@ -296,8 +297,7 @@ AZ_HD void tree_reset(TreeHdr& T) {  // a freshly constructed MCTS (mcts.h:52-73
   T.path_len = 0;
   T.depth = 0;
   T.total_leaf_depth = 0;
-  arena_clear(T);
-  T.pad_ = 0;
+  arena_clear(T);  // T.region stays: it belongs to the slot, not to the search
 }
 
 // ------------------------------------------------------------------------------------ path cache
@@ -1238,6 +1238,7 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
   if (T.fc == kNil) return;
   TreeHdr A;
   arena_clear(A);
+  A.region = T.region;
   const u32 root_new = tree_alloc_block(E, A);
   if (root_new == kNil) return;
   blk_copy(E.blocks + root_new, E.blocks + T.fc);

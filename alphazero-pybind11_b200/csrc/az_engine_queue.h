@@ -51,7 +51,6 @@ __shared__ unsigned long long s_qprof[B2AZ_Q_WARPS_DEFAULT_MAX][16];
 #define QPROF_CLK() 0ll
 #endif
 
-constexpr int kQGames = 448;  // game slots per CTA (shared memory: 272 B each)
 constexpr int kQCap = 512;    // ring capacity: a power of two > kQGames
 constexpr u32 kQEmpty = 0xFFFFu;
 enum : u32 { Q_LEVEL = 0, Q_LEAF = 1, Q_MOVE = 2, Q_DONE = 3 };

@@ -34,6 +34,7 @@ constexpr int kMaxHist = 42;           // recorded moves per game
 constexpr int kA = 7;                  // Connect4 action count
 constexpr int kP = 2;                  // players
 constexpr int kKMax = 7;               // children per block (= Connect4 actions)
+constexpr int kQGames = 448;           // game slots per persistent CTA (shared memory: 272 B each) == per pool region
 
 // Every field is a 32-bit word (floats are stored as their bit patterns) so that scalar accesses and
 // the 16 B vector accesses are the same type for the compiler's alias analysis.
@@ -68,7 +69,7 @@ struct __attribute__((aligned(16))) TreeHdr {
   // arena
   u32 first_page, cur_page;
   u32 bump;             // next free block offset inside cur_page
-  u32 pad_;
+  u32 region;           // the pool region this tree allocates from (fixed at creation: slot / region_games)
 };
 static_assert(sizeof(TreeHdr) == 64, "TreeHdr must stay one 64 B record");
 
@@ -144,8 +145,7 @@ struct Globals {
   u32 games_completed, games_started, active_games, error;
   u32 leaf_count;
   u32 pad_;
-  // free-page ring tickets (chains of pages; see pool_pop_page / pool_push_chain)
-  unsigned long long ring_pop, ring_push;
+  unsigned long long pad2_[2];
   Pcg32 global_rng;  // B2AZ_RNG_GLOBAL
 };
 
@@ -167,7 +167,14 @@ struct EngineView {
   // ---- block pool
   Block* blocks;       // [num_pages * kPageBlocks]
   u32* page_next;      // [num_pages] chain links
-  u32* ring;           // [num_pages] free-chain heads (kNil = empty slot)
+  u32* ring;           // [num_pages] free pages: region r owns ring[r * region_pages .. +region_pages) (kNil = empty slot)
+  // The pool is cut into REGIONS of region_pages consecutive pages; the slots [r * region_games, (r+1) * region_games)
+  // allocate from and free into region r only. A region is what one CTA of the persistent step kernels owns, so an
+  // SM's tree traffic stays inside one contiguous ~250 MB stretch of HBM (about 120 2 MB pages: its TLB holds them).
+  // Measured (tools/micro/tlb_probe.cu, profiles/r2i_tlb_probe.jsonl): dependent random 160 B block reads run at
+  // 7.2 G/s when every thread roams the whole pool and at 24 G/s when an SM's threads stay inside such a stretch.
+  unsigned long long* ring_tickets;  // [n_regions][2]  pop / push ticket counters of each region's ring
+  u32 region_games, region_pages, n_regions, pad3_;
   // ---- per tree / per game
   TreeHdr* trees;      // [G * kP]
   GumbelState* gum;    // [G * kP], NULL unless gumbel_enabled
