@@ -1244,7 +1244,10 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
   blk_copy(E.blocks + root_new, E.blocks + T.fc);
   u32 scan_page = A.first_page, scan_off = 0;
   bool failed = false;
-  for (;;) {
+  // One scanned block per iteration, its seven child links handled by straight-line predicated code: in a batch of
+  // 32 games (one per lane) every lane walks its own tree, and the first version's `for j ... continue` loop ran with
+  // 1.8 of 32 lanes active (profiles/r2k: 3.1 ms of a 15.5 ms step went into this function).
+  for (u32 guard = 0; guard < (1u << 24); ++guard) {
     if (scan_page == A.cur_page && scan_off >= A.bump) break;
     if (scan_off >= kPageBlocks) {
       scan_page = E.page_next[scan_page];
@@ -1252,16 +1255,27 @@ AZ_COLD void tree_compact(const EngineView& E, TreeHdr& T) {
       continue;
     }
     Block* B = E.blocks + ((scan_page << kPageLog2) + scan_off);
-#pragma unroll 1
-    for (int j = 0; j < kKMax; ++j) {
-      const u32 src = B->fc[j];
-      if (src == kNil) continue;
-      const u32 dst = tree_alloc_block(E, A);
-      if (dst == kNil) { failed = true; break; }
-      blk_copy(E.blocks + dst, E.blocks + src);
-      B->fc[j] = dst;
+    const V4 f0 = ld_v4(&B->fc[0]), f1 = ld_v4(&B->fc[4]);
+    u32 fc0 = f0.x, fc1 = f0.y, fc2 = f0.z, fc3 = f0.w, fc4 = f1.x, fc5 = f1.y, fc6 = f1.z;
+    bool any = false;
+#define AZ_COMPACT_CHILD(fcj)                                   \
+    if (fcj != kNil && !failed) {                               \
+      const u32 dst = tree_alloc_block(E, A);                   \
+      if (dst == kNil) failed = true;                           \
+      else {                                                    \
+        blk_copy(E.blocks + dst, E.blocks + fcj);               \
+        fcj = dst;                                              \
+        any = true;                                             \
+      }                                                         \
     }
+    AZ_COMPACT_CHILD(fc0) AZ_COMPACT_CHILD(fc1) AZ_COMPACT_CHILD(fc2) AZ_COMPACT_CHILD(fc3)
+    AZ_COMPACT_CHILD(fc4) AZ_COMPACT_CHILD(fc5) AZ_COMPACT_CHILD(fc6)
+#undef AZ_COMPACT_CHILD
     if (failed) break;
+    if (any) {
+      st_v4(&B->fc[0], mk_v4(fc0, fc1, fc2, fc3));
+      st_v4(&B->fc[4], mk_v4(fc4, fc5, fc6, f1.w));
+    }
     ++scan_off;
   }
   if (failed) {  // pool exhausted mid-copy (already flagged): keep the old, intact tree

@@ -27,6 +27,9 @@ namespace b2az {
 #ifndef B2AZ_W_WARPS
 #define B2AZ_W_WARPS 16
 #endif
+#ifndef B2AZ_W_MOVE_WAIT
+#define B2AZ_W_MOVE_WAIT 16  // rounds a game whose search is finished may wait for more movers to share its chunk
+#endif
 #ifndef B2AZ_W_K
 #define B2AZ_W_K 3        // level sub-phases per round while heavy chunks are being worked on
 #endif
@@ -126,14 +129,22 @@ __global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u
     __syncthreads();
     u32 done_snap = S.done;  // read between two barriers: warps that are already working on a round add to it
     __syncthreads();
-    u32 cur = 0, fcur = 0, mcur = 0;
+    u32 cur = 0, fcur = 0, mcur = 0, move_wait = 0;
     for (u32 round = 0; round < (1u << 26); ++round) {  // bounded: a scheduling bug must not hang the GPU
-      const u32 nL = S.n_lev[cur], nF = S.n_leaf[fcur], nM = S.n_mov[mcur];  // not written to during this round
+      const u32 nL = S.n_lev[cur], nF = S.n_leaf[fcur];  // not written to during this round
+      const u32 nM_all = S.n_mov[mcur];
       if (done_snap >= ng) break;
-      if (nL + nF + nM == 0u) {  // cannot happen: every running game is in exactly one list
+      if (nL + nF + nM_all == 0u) {  // cannot happen: every running game is in exactly one list
         if (tid == 0u) at_or(&E.glob->error, B2AZ_DEVERR_QUEUE);
         break;
       }
+      // A MOVE chunk is long (acting rule, sample, two re-roots, maybe a compaction) and everybody waits for it at
+      // the barrier, so movers are collected until a chunk is full — or they have waited B2AZ_W_MOVE_WAIT rounds, or
+      // nothing else is left to do. The waiting games simply sit in the list; no lane idles for them.
+      const bool do_moves = nM_all >= 32u || (nM_all > 0u && (move_wait >= (u32)B2AZ_W_MOVE_WAIT || nL + nF == 0u));
+      const u32 nM = do_moves ? nM_all : 0u;
+      const u32 mout = do_moves ? (mcur ^ 1u) : mcur;  // where this round's new movers go
+      move_wait = (nM_all > 0u && !do_moves) ? move_wait + 1u : 0u;
       const u32 cL = (nL + 31u) >> 5, cF = (nF + 31u) >> 5, cM = (nM + 31u) >> 5;
       const u32 H = cF + cM;
       const u32 Wh = (cL == 0u) ? (H < W ? H : W) : (H < W - 1u ? H : W - 1u);
@@ -146,10 +157,10 @@ __global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u
         for (u32 c = warp; c < H; c += Wh) {
           const long long c0 = WPROF_CLK();
           if (c < cM) {
-            w_chunk<GB>(E, S, Q_MOVE, S.mov[mcur], nM, c, X, fcur ^ 1u, mcur ^ 1u, g0, lane);
+            w_chunk<GB>(E, S, Q_MOVE, S.mov[mcur], nM, c, X, fcur ^ 1u, mout, g0, lane);
             WPROF_ADD(2, WPROF_CLK() - c0); WPROF_ADD(7, 1); WPROF_ADD(10, (nM - c * 32u) < 32u ? nM - c * 32u : 32u);
           } else {
-            w_chunk<GB>(E, S, Q_LEAF, S.leaf[fcur], nF, c - cM, X, fcur ^ 1u, mcur ^ 1u, g0, lane);
+            w_chunk<GB>(E, S, Q_LEAF, S.leaf[fcur], nF, c - cM, X, fcur ^ 1u, mout, g0, lane);
             WPROF_ADD(1, WPROF_CLK() - c0); WPROF_ADD(6, 1);
             WPROF_ADD(9, (nF - (c - cM) * 32u) < 32u ? nF - (c - cM) * 32u : 32u);
           }
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u
             const long long c0 = WPROF_CLK();
             // a game that goes on descending after the LAST sub-phase joins next round's list X, like the games the
             // heavy side starts on a new descent
-            w_chunk<GB>(E, S, Q_LEVEL, S.lev[rd], n, c, (k + 1u == K) ? X : wr, fcur ^ 1u, mcur ^ 1u, g0, lane);
+            w_chunk<GB>(E, S, Q_LEVEL, S.lev[rd], n, c, (k + 1u == K) ? X : wr, fcur ^ 1u, mout, g0, lane);
             WPROF_ADD(0, WPROF_CLK() - c0); WPROF_ADD(5, 1); WPROF_ADD(8, (n - c * 32u) < 32u ? n - c * 32u : 32u);
           }
           if (k + 1u < K) w_bar_level(Wl * 32u);
@@ -175,9 +186,13 @@ __global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u
       __syncthreads();
       // the lists consumed in this round are empty again; the scratch LEVEL lists too
       if (tid < (u32)kWLevBufs && tid != X) S.n_lev[tid] = 0;
-      if (tid == 0u) { S.n_leaf[fcur] = 0; S.n_mov[mcur] = 0; }
+      if (tid == 0u) {
+        S.n_leaf[fcur] = 0;
+        if (do_moves) S.n_mov[mcur] = 0;
+      }
       done_snap = S.done;
-      cur = X; fcur ^= 1u; mcur ^= 1u;
+      cur = X; fcur ^= 1u;
+      if (do_moves) mcur ^= 1u;
       __syncthreads();
       WPROF_ADD(3, WPROF_CLK() - t1);
       if (warp == 0u) WPROF_ADD(4, 1);
