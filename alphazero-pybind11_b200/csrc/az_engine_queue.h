@@ -257,6 +257,52 @@ AZ_D u32 q_leaf(const EngineView& E, u32 g, QGame& q) {
   q.left = left;
   return ns;
 }
+// The two halves of q_leaf as separate pieces (the waves kernel runs them in different rounds): FINISH = the end of a
+// descent (expansion, leaf batch), BOUNDARY = process_result .. descent_begin. Q_PR = "needs BOUNDARY next".
+constexpr u32 Q_PR = Q_LEAF;
+template <bool GB>
+AZ_D u32 q_finish(const EngineView& E, u32 g, QGame& q) {
+  GameSlot gs = q.gs;
+  TreeHdr T = q.T;
+  const Descent D = q.D;
+  descent_finish(E, g, T, gs, gs.rng, D);
+  q.in_descent = 0;
+  bool hit = false;
+  if (E.eval_type == 0) {
+    hit = leaf_emit(E, g, gs, D.s, q.hits < 64u);
+    if (hit) ++q.hits;
+  }
+  u32 left = q.left;
+  if (!hit) --left;
+  q.left = left;
+  q.gs = gs;
+  q.T = T;
+  return (left > 0 && gs.active) ? Q_PR : Q_DONE;
+}
+template <bool GB>
+AZ_D u32 q_boundary(const EngineView& E, u32 g, QGame& q) {
+  GameSlot gs = q.gs;
+  TreeHdr T = q.T;
+  bool move = false;
+  if (gs.initialized) {
+    const u32 cp = gs.player;
+    const bool noise = (E.epsilon > 0.0f) && !gs.capped;
+    process_result(E, g, T, gs, gs.rng, noise, q.path);
+    ++q.sims;
+    const u32 goal = gs.capped ? E.cap_visits[cp] : E.visits[cp];
+    move = T.depth >= goal;
+  } else {
+    gs.initialized = 1;
+    gs.capped = (E.playout_cap && rng_uniform01(gs.rng) < E.playout_cap_percent) ? 1 : 0;
+    if (GB && E.gumbel_enabled) gumbel_arm(E, g, gs.player, gs.capped != 0);
+  }
+  u32 ns = Q_MOVE;
+  if (!move) ns = q_begin<GB>(E, g, q, T, gs);
+  q.gs = gs;
+  q.T = T;
+  if (ns == Q_LEAF) ns = q_finish<GB>(E, g, q);  // a root that was never visited is its own leaf
+  return ns;
+}
 // MOVE: the search budget is reached. play_move() works on the slot's state in HBM.
 template <bool GB>
 AZ_D u32 q_move(const EngineView& E, u32 g, QGame& q) {

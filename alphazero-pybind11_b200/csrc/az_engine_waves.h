@@ -1,21 +1,21 @@
 // az_engine_waves.h — k_step_w: the fused self-play step as a persistent kernel scheduled in WAVES.
 //
-// Same pieces and the same per-game state machine as the queue kernel (az_engine_queue.h: q_level / q_leaf / q_move on
-// a game's shared-memory record), but no dynamic queue: a CTA (one per SM, <= kQGames games) keeps three plain LISTS of
-// game ids — games whose descent goes on (LEVEL), games at a step boundary (LEAF), games whose search budget is reached
-// (MOVE) — and works in rounds separated by CTA barriers:
-//
-//   round:  the LEAF and MOVE lists are cut into chunks of 32 ids and handed to the first warps ("heavy" warps: a leaf
-//           chunk is ~3x a level chunk); the remaining warps take the LEVEL list and run K level sub-phases over it
-//           (a named barrier among the level warps between sub-phases), so both sides finish at about the same time.
-//           Every piece appends each of its games to the list of the piece it needs next (ballot ranks + ONE shared
-//           atomicAdd per warp and target list).
-//   barrier, swap lists, next round.
-//
-// Every warp-level instruction of a chunk works for 32 games that need the same code; nobody polls, nothing is
-// handed over through flags: between two barriers a list is either read or appended to, never both.
-// Measured on the way here (profiles/r2_queue_vs_waves.md): the queue kernel spent 12 k cycles per batch in pop /
-// push hand-shakes and idled half of its warps, for 3.6 k (level) / 10.8 k (leaf) cycles of work per batch.
+// Same pieces and the same per-game state machine as run_flat() (az_engine_logic.h) — hence the same results, game by
+// game — but the lanes of a warp are not married to 32 fixed games. A CTA (one per SM) owns <= kQGames game slots whose
+// working state lives in SHARED memory (QGame, az_engine_queue.h) and keeps three plain LISTS of game ids:
+//     LEVEL     games whose descent goes on: one PUCT level (one 160 B block burst + 7 scores); a game whose descent
+//               ends there is expanded in the same piece (descent_finish)
+//     BOUNDARY  games whose leaf is answered: process_result (priors, backprop) and the start of the next descent
+//     MOVE      games whose search budget is reached (play_move: acting rule, sample, two re-roots, game end)
+// A round cuts the three lists into chunks of 32 ids, one chunk per warp; every piece appends each of its games to the
+// list of the piece it needs next (ballot ranks + ONE shared atomicAdd per warp and target list); one CTA barrier; next
+// round. Both common pieces are one dependent HBM round trip plus a few hundred instructions long, so the warps of a
+// round finish together, and every warp-level instruction works for ~29 games that need the same code (the
+// thread-per-game kernel: 9.6 of 32 lanes, profiles/r49_k_step_ncu_summary.json). Nobody polls and nothing is handed
+// over through flags: between two barriers a list is either read or appended to, never both (three buffers per list:
+// input of this round, output of this round, and the one thread 0 clears for the next round).
+// The road here — a dynamic shared-memory queue (12 k cycles of pop / push hand-shakes per batch), rounds with a long
+// leaf piece next to K level sub-phases (38 % of the warp time at barriers) — is recorded in profiles/r2_step_kernel_log.md.
 #pragma once
 
 #include "az_engine_queue.h"
@@ -30,14 +30,10 @@ namespace b2az {
 #ifndef B2AZ_W_MOVE_WAIT
 #define B2AZ_W_MOVE_WAIT 16  // rounds a game whose search is finished may wait for more movers to share its chunk
 #endif
-#ifndef B2AZ_W_K
-#define B2AZ_W_K 3        // level sub-phases per round while heavy chunks are being worked on
-#endif
-constexpr int kWLevBufs = B2AZ_W_K + 1;
 
 #if defined(B2AZ_W_PROF)
 // experiment build: clock64 sums (lane 0 of every warp, shared accumulators, one global add per launch)
-//   [0] level chunks  [1] leaf chunks  [2] move chunks  [3] waiting at barriers  [4] rounds (warp 0)
+//   [0] level chunks  [1] boundary chunks  [2] move chunks  [3] waiting at the barrier  [4] rounds (warp 0)
 //   [5..7] chunks per kind  [8..10] games per kind
 __device__ unsigned long long g_wprof[16];
 __shared__ unsigned long long s_wprof[B2AZ_W_WARPS][16];
@@ -50,16 +46,11 @@ __shared__ unsigned long long s_wprof[B2AZ_W_WARPS][16];
 
 struct WShared {
   QGame game[kQGames];
-  u16 lev[kWLevBufs][kQGames];  // LEVEL lists: this round's input, K - 1 scratch lists, next round's input
-  u16 leaf[2][kQGames];
-  u16 mov[2][kQGames];
-  u32 n_lev[kWLevBufs];
-  u32 n_leaf[2];
-  u32 n_mov[2];
-  u32 done;
+  u16 list[3][3][kQGames];  // [kind: Q_LEVEL, Q_PR, Q_MOVE][buffer][entry]
+  u32 count[3][3];
 };
 
-// every lane with pred appends `id` to list (count in shared memory): ballot ranks, one atomicAdd per warp
+// every lane with pred appends `id` to a list (count in shared memory): ballot ranks, one atomicAdd per warp
 __device__ __forceinline__ void w_append(u16* list, u32* count, bool pred, u32 id, u32 lane) {
   const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
   if (m == 0u) return;
@@ -70,31 +61,31 @@ __device__ __forceinline__ void w_append(u16* list, u32* count, bool pred, u32 i
   if (pred) list[base + (u32)__popc(m & ((1u << lane) - 1u))] = (u16)id;
 }
 
-// One chunk of 32 ids of `list`: run piece `kind` for every game and hand each game to its next list.
+// One chunk of 32 ids of list `kind` (buffer `in`): run the piece for every game, hand each game to its next list
+// (buffer `out`).
 template <bool GB>
-__device__ __forceinline__ void w_chunk(const EngineView& E, WShared& S, u32 kind, const u16* list, u32 count, u32 chunk,
-                                        u32 lev_out, u32 leaf_out, u32 mov_out, u32 g0, u32 lane) {
+__device__ __forceinline__ void w_chunk(const EngineView& E, WShared& S, u32 kind, u32 in, u32 out, u32 count, u32 chunk,
+                                        u32 g0, u32 lane) {
   const u32 i = chunk * 32u + lane;
   const bool have = i < count;
-  const u32 id = have ? (u32)list[i] : 0u;
+  const u32 id = have ? (u32)S.list[kind][in][i] : 0u;
   u32 ns = 0xFFu;
   if (have) {
     QGame& q = S.game[id];
     const u32 g = g0 + id;
-    if (kind == Q_LEVEL) ns = q_level<GB>(E, g, q);
-    else if (kind == Q_LEAF) ns = q_leaf<GB>(E, g, q);
-    else ns = q_move<GB>(E, g, q);
+    if (kind == Q_LEVEL) {
+      ns = q_level<GB>(E, g, q);
+      if (ns == Q_LEAF) ns = q_finish<GB>(E, g, q);  // the descent ended: expand right here
+    } else if (kind == Q_PR) {
+      ns = q_boundary<GB>(E, g, q);
+    } else {
+      ns = q_move<GB>(E, g, q);
+      if (ns == Q_LEAF) ns = q_finish<GB>(E, g, q);
+    }
   }
   __syncwarp();
-  w_append(S.lev[lev_out], &S.n_lev[lev_out], ns == Q_LEVEL, id, lane);
-  w_append(S.leaf[leaf_out], &S.n_leaf[leaf_out], ns == Q_LEAF, id, lane);
-  w_append(S.mov[mov_out], &S.n_mov[mov_out], ns == Q_MOVE, id, lane);
-  const unsigned md = __ballot_sync(0xFFFFFFFFu, ns == Q_DONE);
-  if (md && lane == 0u) atomicAdd(&S.done, (u32)__popc(md));
-}
-
-__device__ __forceinline__ void w_bar_level(u32 threads) {  // named barrier 1: the level warps of this round
-  asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+#pragma unroll
+  for (u32 t = 0; t < 3u; ++t) w_append(S.list[t][out], &S.count[t][out], ns == t, id, lane);
 }
 
 template <bool GB>
@@ -110,11 +101,9 @@ __global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u
   for (u32 grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const u32 g0 = grp * games_per_group;
     const u32 ng = (g0 >= E.G) ? 0u : (E.G - g0 < games_per_group ? E.G - g0 : games_per_group);
-    if (tid < (u32)kWLevBufs) S.n_lev[tid] = 0;
-    if (tid < 2u) { S.n_leaf[tid] = 0; S.n_mov[tid] = 0; }
-    if (tid == 0u) S.done = 0;
+    if (tid < 9u) (&S.count[0][0])[tid] = 0;
     __syncthreads();
-    // load the group's state; every active game starts at a step boundary (LEAF list 0)
+    // load the group's state; every active game starts at a step boundary (BOUNDARY list, buffer 0)
     for (u32 i0 = 0; i0 < ng; i0 += blockDim.x) {
       const u32 i = i0 + tid;
       bool active = false;
@@ -122,77 +111,47 @@ __global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u
         q_load_game(E, g0 + i, S.game[i], n_steps);
         active = S.game[i].gs.active != 0;
       }
-      w_append(S.leaf[0], &S.n_leaf[0], active, i, lane);
-      const unsigned md = __ballot_sync(0xFFFFFFFFu, i < ng && !active);
-      if (md && lane == 0u) atomicAdd(&S.done, (u32)__popc(md));
+      w_append(S.list[Q_PR][0], &S.count[Q_PR][0], active, i, lane);
     }
     __syncthreads();
-    u32 done_snap = S.done;  // read between two barriers: warps that are already working on a round add to it
-    __syncthreads();
-    u32 cur = 0, fcur = 0, mcur = 0, move_wait = 0;
+    u32 move_wait = 0;
     for (u32 round = 0; round < (1u << 26); ++round) {  // bounded: a scheduling bug must not hang the GPU
-      const u32 nL = S.n_lev[cur], nF = S.n_leaf[fcur];  // not written to during this round
-      const u32 nM_all = S.n_mov[mcur];
-      if (done_snap >= ng) break;
-      if (nL + nF + nM_all == 0u) {  // cannot happen: every running game is in exactly one list
-        if (tid == 0u) at_or(&E.glob->error, B2AZ_DEVERR_QUEUE);
-        break;
-      }
-      // A MOVE chunk is long (acting rule, sample, two re-roots, maybe a compaction) and everybody waits for it at
-      // the barrier, so movers are collected until a chunk is full — or they have waited B2AZ_W_MOVE_WAIT rounds, or
-      // nothing else is left to do. The waiting games simply sit in the list; no lane idles for them.
-      const bool do_moves = nM_all >= 32u || (nM_all > 0u && (move_wait >= (u32)B2AZ_W_MOVE_WAIT || nL + nF == 0u));
-      const u32 nM = do_moves ? nM_all : 0u;
-      const u32 mout = do_moves ? (mcur ^ 1u) : mcur;  // where this round's new movers go
-      move_wait = (nM_all > 0u && !do_moves) ? move_wait + 1u : 0u;
-      const u32 cL = (nL + 31u) >> 5, cF = (nF + 31u) >> 5, cM = (nM + 31u) >> 5;
-      const u32 H = cF + cM;
-      const u32 Wh = (cL == 0u) ? (H < W ? H : W) : (H < W - 1u ? H : W - 1u);
-      const u32 Wl = (cL == 0u) ? 0u : (cL < W - Wh ? cL : W - Wh);
-      const u32 K = (H == 0u) ? 1u : (u32)B2AZ_W_K;
-      const u32 X = (cur + K) % (u32)kWLevBufs;  // next round's LEVEL list (its count is 0: reset at the end of a round)
+      const u32 in = round % 3u, out = (round + 1u) % 3u, clr = (round + 2u) % 3u;
+      // the input lists are not written to during this round
+      const u32 nL = S.count[Q_LEVEL][in], nP = S.count[Q_PR][in], nM = S.count[Q_MOVE][in];
+      if (nL + nP + nM == 0u) break;  // every game has finished its steps of this launch
+      // buffer `clr` was the input of the previous round; it becomes the output of the next one
+      if (tid < 3u) S.count[tid][clr] = 0;
+      // A MOVE chunk is long (acting rule, sample, two re-roots, maybe a compaction) and everybody waits for it at the
+      // barrier, so movers are collected until a chunk is full — or they have waited B2AZ_W_MOVE_WAIT rounds, or nothing
+      // else is left to do. The waiting games are passed on from list to list; no lane idles for them.
+      const bool do_moves = nM >= 32u || (nM > 0u && (move_wait >= (u32)B2AZ_W_MOVE_WAIT || nL + nP == 0u));
+      move_wait = (nM > 0u && !do_moves) ? move_wait + 1u : 0u;
+      const u32 cM = do_moves ? (nM + 31u) >> 5 : 0u, cP = (nP + 31u) >> 5, cL = (nL + 31u) >> 5;
+      const u32 total = cM + cP + cL;
       const long long t0 = WPROF_CLK();
-      if (warp < Wh) {
-        // heavy side: MOVE chunks first (the longest), then LEAF chunks
-        for (u32 c = warp; c < H; c += Wh) {
-          const long long c0 = WPROF_CLK();
-          if (c < cM) {
-            w_chunk<GB>(E, S, Q_MOVE, S.mov[mcur], nM, c, X, fcur ^ 1u, mout, g0, lane);
-            WPROF_ADD(2, WPROF_CLK() - c0); WPROF_ADD(7, 1); WPROF_ADD(10, (nM - c * 32u) < 32u ? nM - c * 32u : 32u);
-          } else {
-            w_chunk<GB>(E, S, Q_LEAF, S.leaf[fcur], nF, c - cM, X, fcur ^ 1u, mout, g0, lane);
-            WPROF_ADD(1, WPROF_CLK() - c0); WPROF_ADD(6, 1);
-            WPROF_ADD(9, (nF - (c - cM) * 32u) < 32u ? nF - (c - cM) * 32u : 32u);
-          }
+      if (nM > 0u && !do_moves && warp == W - 1u) {  // pass the waiting movers on (the last warp gets the fewest chunks)
+        for (u32 i0 = 0; i0 < nM; i0 += 32u) {
+          const u32 i = i0 + lane;
+          w_append(S.list[Q_MOVE][out], &S.count[Q_MOVE][out], i < nM, i < nM ? (u32)S.list[Q_MOVE][in][i] : 0u, lane);
         }
-      } else if (warp < Wh + Wl) {
-        const u32 idx = warp - Wh;
-        for (u32 k = 0; k < K; ++k) {
-          const u32 rd = (cur + k) % (u32)kWLevBufs, wr = (cur + k + 1u) % (u32)kWLevBufs;  // wr == X in the last one
-          const u32 n = S.n_lev[rd];
-          if (n == 0u) break;  // uniform over the level warps: they all read the count after the same barrier
-          const u32 chunks = (n + 31u) >> 5;
-          for (u32 c = idx; c < chunks; c += Wl) {
-            const long long c0 = WPROF_CLK();
-            // a game that goes on descending after the LAST sub-phase joins next round's list X, like the games the
-            // heavy side starts on a new descent
-            w_chunk<GB>(E, S, Q_LEVEL, S.lev[rd], n, c, (k + 1u == K) ? X : wr, fcur ^ 1u, mout, g0, lane);
-            WPROF_ADD(0, WPROF_CLK() - c0); WPROF_ADD(5, 1); WPROF_ADD(8, (n - c * 32u) < 32u ? n - c * 32u : 32u);
-          }
-          if (k + 1u < K) w_bar_level(Wl * 32u);
+      }
+      for (u32 c = warp; c < total; c += W) {  // the longest pieces first
+        const long long c0 = WPROF_CLK();
+        if (c < cM) {
+          w_chunk<GB>(E, S, Q_MOVE, in, out, nM, c, g0, lane);
+          WPROF_ADD(2, WPROF_CLK() - c0); WPROF_ADD(7, 1); WPROF_ADD(10, (nM - c * 32u) < 32u ? nM - c * 32u : 32u);
+        } else if (c < cM + cP) {
+          const u32 cc = c - cM;
+          w_chunk<GB>(E, S, Q_PR, in, out, nP, cc, g0, lane);
+          WPROF_ADD(1, WPROF_CLK() - c0); WPROF_ADD(6, 1); WPROF_ADD(9, (nP - cc * 32u) < 32u ? nP - cc * 32u : 32u);
+        } else {
+          const u32 cc = c - cM - cP;
+          w_chunk<GB>(E, S, Q_LEVEL, in, out, nL, cc, g0, lane);
+          WPROF_ADD(0, WPROF_CLK() - c0); WPROF_ADD(5, 1); WPROF_ADD(8, (nL - cc * 32u) < 32u ? nL - cc * 32u : 32u);
         }
       }
       const long long t1 = WPROF_CLK();
-      __syncthreads();
-      // the lists consumed in this round are empty again; the scratch LEVEL lists too
-      if (tid < (u32)kWLevBufs && tid != X) S.n_lev[tid] = 0;
-      if (tid == 0u) {
-        S.n_leaf[fcur] = 0;
-        if (do_moves) S.n_mov[mcur] = 0;
-      }
-      done_snap = S.done;
-      cur = X; fcur ^= 1u;
-      if (do_moves) mcur ^= 1u;
       __syncthreads();
       WPROF_ADD(3, WPROF_CLK() - t1);
       if (warp == 0u) WPROF_ADD(4, 1);
