@@ -197,6 +197,17 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
   run_flat<GB>(E, g, c, n_steps);
   ctx_store(E, g, c);
 }
+// The same, with the 32 games of a warp in lock step (run_sync): no lane leaves early, the warp votes.
+template <bool GB>
+__global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) {
+  const u32 g = GLOBAL_TID;
+  const bool in_range = g < E.G;
+  const u32 gg = in_range ? g : 0u;
+  Ctx c;
+  ctx_load(E, gg, c);
+  run_sync<GB>(E, gg, c, n_steps, in_range);
+  if (in_range && c.gs.active) ctx_store(E, gg, c);
+}
 // update_inferences' cache half (play_manager.cc:619-642: insert_many of every evaluated leaf), as its own
 // launch BEFORE the step kernel: during k_step the table is then read-only (plus frequency bumps), so lookups
 // need neither fences nor locks.
@@ -513,7 +524,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
   if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
     return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
-  if (p->step_kernel > B2AZ_STEP_WAVES) return fail(B2AZ_EINVAL, "bad step_kernel");
+  if (p->step_kernel > B2AZ_STEP_SYNC) return fail(B2AZ_EINVAL, "bad step_kernel");
   if (p->per_slot_quota && p->games_to_play % p->concurrent_games != 0)
     return fail(B2AZ_EINVAL, "per_slot_quota: games_to_play must be a multiple of concurrent_games");
   if (p->lanes_per_game > 1)
@@ -532,7 +543,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   e->device = device;
   e->step_kernel = p->step_kernel;
   if (const char* sk = getenv("B2AZ_STEP_KERNEL"))
-    e->step_kernel = sk[0] == 'f' ? B2AZ_STEP_FLAT : sk[0] == 'w' ? B2AZ_STEP_WAVES : B2AZ_STEP_QUEUE;
+    e->step_kernel = sk[0] == 'f' ? B2AZ_STEP_FLAT : sk[0] == 'w' ? B2AZ_STEP_WAVES : sk[0] == 's' ? B2AZ_STEP_SYNC : B2AZ_STEP_QUEUE;
 #ifndef B2AZ_HOST_EMU
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -716,6 +727,11 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
     const u32 grid = std::min(e->groups, (u32)e->num_sms);
     if (V.gumbel_enabled) k_step_q<true><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, e->group_games, e->groups);
     else k_step_q<false><<<grid, B2AZ_Q_WARPS * 32, sizeof(QShared), s>>>(V, n_steps, e->group_games, e->groups);
+  } else if (e->step_kernel == B2AZ_STEP_SYNC) {
+    const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;
+    const u32 blocks = (V.G + threads - 1) / threads;
+    if (V.gumbel_enabled) k_step_sync<true><<<blocks, threads, 0, s>>>(V, n_steps);
+    else k_step_sync<false><<<blocks, threads, 0, s>>>(V, n_steps);
   } else {
     // small CTAs spread the (one thread per game) population evenly over the SMs
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;

@@ -1681,4 +1681,67 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
   }
 }
 
+// run_flat() with the warp kept in LOCK STEP: all 32 games of a warp cross the step boundary together, then descend
+// (a lane whose descent has ended waits for the deepest one), then expand together. Per game the order of operations is
+// run_flat()'s, so the results are the same; per warp every piece of code runs ONCE per simulation with (nearly) all
+// lanes active — run_flat() executes the ~1,600-instruction boundary code and the ~500-instruction expansion code in
+// almost every iteration for the few lanes that happen to be there (9.6 of 32 lanes active per issued instruction,
+// profiles/r49_k_step_ncu_summary.json; B2AZ_GATE = 32 measured 1.97 G vs 1.51 G simulations/s, profiles/r2o).
+#if defined(__CUDA_ARCH__)
+#define AZ_WARP_ANY(p) (__any_sync(0xFFFFFFFFu, (p)) != 0)
+#else
+#define AZ_WARP_ANY(p) (p)
+#endif
+template <bool GB = true>
+AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, u32 n_steps, bool alive) {
+  Descent D;
+  u32 left = n_steps, hits = 0;
+  alive = alive && c.gs.active;
+  for (;;) {
+    // ---- step boundary: finish the previous simulation, maybe play a move, start a descent
+    bool go = alive && left > 0;
+    if (go) {
+      bool retired = false;
+      if (c.gs.initialized) {
+        const u32 cp = c.gs.player;
+        const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
+        process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
+        ++c.sims;
+        const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
+        if (c.T.depth >= goal) {
+          ctx_store(E, g, c);
+          retired = play_move(E, g);
+          ctx_load(E, g, c);
+        }
+      } else {
+        c.gs.initialized = 1;
+        c.gs.capped = (E.playout_cap && rng_uniform01(c.rng) < E.playout_cap_percent) ? 1 : 0;
+        if (GB && E.gumbel_enabled) gumbel_arm(E, g, c.gs.player, c.gs.capped != 0);
+      }
+      if (retired) {
+        alive = false;
+        go = false;
+      } else {
+        descent_begin<GB>(E, g, c.T, c.gs, D, c.pr, c.rng);
+      }
+    }
+    if (!AZ_WARP_ANY(go)) break;
+    // ---- descent: one tree level per iteration for every game that is still on its way down
+    bool desc = go && descent_more(D);
+    while (AZ_WARP_ANY(desc)) {
+      if (desc) desc = descent_level<GB>(E, g, D, c.pr) && descent_more(D);
+    }
+    // ---- leaf: expansion, and the leaf batch / position cache with the NN evaluator
+    if (go) {
+      descent_finish(E, g, c.T, c.gs, c.rng, D);
+      bool hit = false;
+      if (E.eval_type == 0) {
+        hit = leaf_emit(E, g, c.gs, D.s, hits < 64u);
+        if (hit) ++hits;
+      }
+      if (!hit) --left;
+    }
+  }
+}
+
 }  // namespace b2az

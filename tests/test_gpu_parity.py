@@ -66,7 +66,7 @@ def test_parallel_kernel_400_sims_vs_port():
 
 
 @needs_ref
-@pytest.mark.parametrize("step_kernel", [b2az.STEP_QUEUE, b2az.STEP_FLAT, b2az.STEP_WAVES])
+@pytest.mark.parametrize("step_kernel", [b2az.STEP_QUEUE, b2az.STEP_FLAT, b2az.STEP_WAVES, b2az.STEP_SYNC])
 def test_fused_kernel_slots_equal_reference_single_game_runs(step_kernel):
     """The TIMED kernel (fused launches of 400 generations, per-game RNG, 400 sims/move) against the UNMODIFIED
     reference: slot g == PlayManager(concurrent_games=1) after MCTS::seed_thread_rng(seed + g); samples, scores,
@@ -84,7 +84,7 @@ def test_queue_kernel_equals_flat_kernel(G):
     identical samples, scores, simulation and move counts for every group size (partial groups, one game, several
     groups per CTA), with the NN-free evaluator and fused launches."""
     out = []
-    for kern in (b2az.STEP_QUEUE, b2az.STEP_FLAT, b2az.STEP_WAVES):
+    for kern in (b2az.STEP_QUEUE, b2az.STEP_FLAT, b2az.STEP_WAVES, b2az.STEP_SYNC):
         e = ph.make_engine(None, G, G * 2, 60, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, 99, per_slot_quota=1,
                            step_kernel=kern, history_capacity=G * 2 * 42, **ph.level_params(1))
         for _ in range(10 ** 5):
@@ -95,9 +95,9 @@ def test_queue_kernel_equals_flat_kernel(G):
         assert st.device_error == 0 and st.games_completed == 2 * G
         out.append((st.simulations, st.moves, list(st.scores), e.drain_history(G * 2 * 42)))
         e.close()
-    assert out[0][:3] == out[1][:3] == out[2][:3]
-    ph.compare_history(out[0][3], out[1][3], ordered=False)
-    ph.compare_history(out[2][3], out[1][3], ordered=False)
+    assert out[0][:3] == out[1][:3] == out[2][:3] == out[3][:3]
+    for i in (0, 2, 3):
+        ph.compare_history(out[i][3], out[1][3], ordered=False)
 
 
 def test_playout_cap_and_resign_gpu():
