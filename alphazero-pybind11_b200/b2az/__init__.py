@@ -19,7 +19,7 @@ DEFAULT_LIB = os.path.join(os.path.dirname(_HERE), "libb2az.so")
 
 EVAL_NN, EVAL_RANDOM = 0, 1
 RNG_PER_GAME, RNG_GLOBAL = 0, 1
-STEP_QUEUE, STEP_FLAT, STEP_WAVES, STEP_SYNC = 0, 1, 2, 3
+STEP_DEFAULT, STEP_FLAT, STEP_WAVES, STEP_SYNC, STEP_QUEUE = 0, 1, 2, 3, 4
 CANON_SHAPE = (4, 6, 7)
 NUM_MOVES = 7
 NUM_PLAYERS = 2

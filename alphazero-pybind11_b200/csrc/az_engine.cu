@@ -197,16 +197,26 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
   run_flat<GB>(E, g, c, n_steps);
   ctx_store(E, g, c);
 }
-// The same, with the 32 games of a warp in lock step (run_sync): no lane leaves early, the warp votes.
+// The same, with the 32 games of a warp in lock step (run_sync): no lane leaves early, the warp votes. The selection
+// path lives in shared memory (one column per thread): an indexed access is one LDS / STS instead of a chain of selects.
 template <bool GB>
 __global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) {
+  __shared__ u32 s_blk[kPathSm][kPathColStride];
+  __shared__ u8 s_slot[kPathSm][kPathColStride];
   const u32 g = GLOBAL_TID;
   const bool in_range = g < E.G;
   const u32 gg = in_range ? g : 0u;
   Ctx c;
   ctx_load(E, gg, c);
-  run_sync<GB>(E, gg, c, n_steps, in_range);
-  if (in_range && c.gs.active) ctx_store(E, gg, c);
+  PathCol pr;
+  pr.blk = &s_blk[0][threadIdx.x];
+  pr.slot = &s_slot[0][threadIdx.x];
+  pr.valid = 0;  // the pending leaf's path (if any) is in HBM
+  run_sync<GB>(E, gg, c, pr, n_steps, in_range);
+  if (in_range && c.gs.active) {
+    path_flush(E, gg, pr, (u32)c.T.path_len);
+    ctx_store(E, gg, c);
+  }
 }
 // update_inferences' cache half (play_manager.cc:619-642: insert_many of every evaluated leaf), as its own
 // launch BEFORE the step kernel: during k_step the table is then read-only (plus frequency bumps), so lookups
@@ -524,7 +534,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->rng_mode != B2AZ_RNG_PER_GAME && p->rng_mode != B2AZ_RNG_GLOBAL) return fail(B2AZ_EINVAL, "bad rng_mode");
   if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
     return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
-  if (p->step_kernel > B2AZ_STEP_SYNC) return fail(B2AZ_EINVAL, "bad step_kernel");
+  if (p->step_kernel > B2AZ_STEP_QUEUE) return fail(B2AZ_EINVAL, "bad step_kernel");
   if (p->per_slot_quota && p->games_to_play % p->concurrent_games != 0)
     return fail(B2AZ_EINVAL, "per_slot_quota: games_to_play must be a multiple of concurrent_games");
   if (p->lanes_per_game > 1)
@@ -541,7 +551,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   b2az_engine* e = new b2az_engine();
   e->params = *p;
   e->device = device;
-  e->step_kernel = p->step_kernel;
+  e->step_kernel = p->step_kernel == B2AZ_STEP_DEFAULT ? B2AZ_STEP_SYNC : p->step_kernel;
   if (const char* sk = getenv("B2AZ_STEP_KERNEL"))
     e->step_kernel = sk[0] == 'f' ? B2AZ_STEP_FLAT : sk[0] == 'w' ? B2AZ_STEP_WAVES : sk[0] == 's' ? B2AZ_STEP_SYNC : B2AZ_STEP_QUEUE;
 #ifndef B2AZ_HOST_EMU

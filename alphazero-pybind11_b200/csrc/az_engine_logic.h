@@ -118,6 +118,10 @@ AZ_HD int popc32(u32 x) {
 #endif
 }
 
+// a / b for a finite positive b: a zero numerator (a terminal node's 0 value, a 0 prior) gives that zero back — exact
+// IEEE, and it keeps those cases off div.rn's slow path (4 % of the step kernel's instructions, profiles/r2r)
+AZ_HD float fdiv_pos(float a, float b) { return a == 0.0f ? a : fdiv(a, b); }
+
 // ------------------------------------------------------------------------------------ 16 B vectors
 struct V4 {
   u32 x, y, z, w;
@@ -394,6 +398,42 @@ AZ_HD void path_flush(const EngineView& E, u32 g, const PathSm& pr, u32 path_len
   for (u32 i = 0; i < (u32)kPathSm && i < path_len; ++i) {
     path[i] = pr.blk[i];
     pslot[i] = pr.slot[i];
+  }
+}
+// The thread-per-game kernels keep the first kPathSm edges in shared memory too, one COLUMN per thread (entry i of
+// thread t at [i * kPathColStride + t]: the 32 lanes of a warp hit 32 different banks).
+constexpr int kPathColStride = 64;
+struct PathCol {
+  u32* blk;   // &s_blk[0][thread]
+  u8* slot;   // &s_slot[0][thread]
+  u32 valid;
+};
+AZ_HD void path_begin(PathCol& pr) { pr.valid = 1; }
+AZ_HD void path_put(const EngineView& E, u32 g, PathCol& pr, u32 plen, u32 blk, u32 slot_byte) {
+  if (plen >= (u32)kPathSm) {
+    E.path[(size_t)g * kMaxPath + plen] = blk;
+    E.pslot[(size_t)g * kMaxPath + plen] = (u8)slot_byte;
+  } else {
+    pr.blk[plen * (u32)kPathColStride] = blk;
+    pr.slot[plen * (u32)kPathColStride] = (u8)slot_byte;
+  }
+}
+AZ_HD void path_get(const EngineView& E, u32 g, const PathCol& pr, bool cached, u32 i, u32& b, u32& sb) {
+  if (cached && i < (u32)kPathSm) {
+    b = pr.blk[i * (u32)kPathColStride];
+    sb = pr.slot[i * (u32)kPathColStride];
+  } else {
+    b = E.path[(size_t)g * kMaxPath + i];
+    sb = E.pslot[(size_t)g * kMaxPath + i];
+  }
+}
+AZ_HD void path_flush(const EngineView& E, u32 g, const PathCol& pr, u32 path_len) {
+  if (!pr.valid) return;
+  u32* path = E.path + (size_t)g * kMaxPath;
+  u8* pslot = E.pslot + (size_t)g * kMaxPath;
+  for (u32 i = 0; i < (u32)kPathSm && i < path_len; ++i) {
+    path[i] = pr.blk[i * (u32)kPathColStride];
+    pslot[i] = pr.slot[i * (u32)kPathColStride];
   }
 }
 // ------------------------------------------------------------------------------------ Gumbel root search
@@ -694,7 +734,7 @@ AZ_HD bool descent_level(const EngineView& E, u32 g, Descent& D, PR& pr) {
     if (j > 0 && (u32)j >= D.cur_k) continue;  // pad slots: 0 / 1 would take the division's slow path
     const u32 nj = r[j].x;
     const float base = (nj == 0) ? fpu_value : u2f(r[j].y);
-    const float u = fadd(base, fdiv(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
+    const float u = fadd(base, fdiv_pos(fmul(fmul(E.cpuct, u2f(r[j].z)), sqrt_n), (float)(nj + 1u)));
     if ((!GB || forced == kNil) ? (j == 0 || u > best_u) : ((u32)j == forced)) {
       best_u = u;
       best = (u32)j;
@@ -1071,8 +1111,8 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
       const u32 n0 = rc[t].x;
       const float qc = n0 ? u2f(rc[t].y) : 0.0f;
       const float dc = n0 ? u2f(rc[t].w) : 0.0f;
-      const float qn = fdiv(fadd(fmul(qc, (float)n0), v), (float)(n0 + 1u));
-      const float dn = fdiv(fadd(fmul(dc, (float)n0), vald), (float)(n0 + 1u));
+      const float qn = fdiv_pos(fadd(fmul(qc, (float)n0), v), (float)(n0 + 1u));
+      const float dn = fdiv_pos(fadd(fmul(dc, (float)n0), vald), (float)(n0 + 1u));
       st_v4(B->rec[sl], mk_v4(n0 + 1u, f2u(qn), rc[t].z, f2u(dn)));
       // first visit of the node (only the leaf can be new): node.v from its own seat (mcts.cc:538-542)
       if (n0 == 0 && lblk != kNil) (E.blocks + lblk)->v = f2u(fadd(lplayer == 0 ? val0 : val1, dshare));
@@ -1692,8 +1732,8 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
 #else
 #define AZ_WARP_ANY(p) (p)
 #endif
-template <bool GB = true>
-AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, u32 n_steps, bool alive) {
+template <bool GB = true, class PR = PathRegs>
+AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, bool alive) {
   Descent D;
   u32 left = n_steps, hits = 0;
   alive = alive && c.gs.active;
@@ -1705,11 +1745,11 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, u32 n_steps, bool alive)
       if (c.gs.initialized) {
         const u32 cp = c.gs.player;
         const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
-        process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
+        process_result(E, g, c.T, c.gs, c.rng, noise, pr);
         ++c.sims;
         const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
         if (c.T.depth >= goal) {
-          ctx_store(E, g, c);
+          ctx_store(E, g, c);  // the path is empty here: process_result has just consumed it
           retired = play_move(E, g);
           ctx_load(E, g, c);
         }
@@ -1722,14 +1762,14 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, u32 n_steps, bool alive)
         alive = false;
         go = false;
       } else {
-        descent_begin<GB>(E, g, c.T, c.gs, D, c.pr, c.rng);
+        descent_begin<GB>(E, g, c.T, c.gs, D, pr, c.rng);
       }
     }
     if (!AZ_WARP_ANY(go)) break;
     // ---- descent: one tree level per iteration for every game that is still on its way down
     bool desc = go && descent_more(D);
     while (AZ_WARP_ANY(desc)) {
-      if (desc) desc = descent_level<GB>(E, g, D, c.pr) && descent_more(D);
+      if (desc) desc = descent_level<GB>(E, g, D, pr) && descent_more(D);
     }
     // ---- leaf: expansion, and the leaf batch / position cache with the NN evaluator
     if (go) {

@@ -31,7 +31,8 @@ extern "C" {
 
 #define B2AZ_GAME_CONNECT4 0
 
-#define B2AZ_STEP_QUEUE 0   /* persistent CTAs, game state in shared memory, work queues (az_engine_queue.h) */
+#define B2AZ_STEP_DEFAULT 0 /* = B2AZ_STEP_SYNC */
+#define B2AZ_STEP_QUEUE 4   /* persistent CTAs, game state in shared memory, work queues (az_engine_queue.h) */
 #define B2AZ_STEP_FLAT 1    /* one thread per game slot, flattened loop (round-1 kernel) */
 #define B2AZ_STEP_SYNC 3    /* one thread per game slot, the 32 games of a warp in lock step (run_sync) */
 #define B2AZ_STEP_WAVES 2   /* persistent CTAs, game state in shared memory, barrier-separated waves (az_engine_waves.h) */
