@@ -201,13 +201,14 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
 // path lives in shared memory (one column per thread): an indexed access is one LDS / STS instead of a chain of selects.
 template <bool GB>
 __global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) {
-  __shared__ u32 s_blk[kPathSm][kPathColStride];
-  __shared__ u8 s_slot[kPathSm][kPathColStride];
   const u32 g = GLOBAL_TID;
   const bool in_range = g < E.G;
   const u32 gg = in_range ? g : 0u;
   Ctx c;
   ctx_load(E, gg, c);
+#if defined(B2AZ_SYNC_PATH_SMEM)
+  __shared__ u32 s_blk[kPathSm][kPathColStride];
+  __shared__ u8 s_slot[kPathSm][kPathColStride];
   PathCol pr;
   pr.blk = &s_blk[0][threadIdx.x];
   pr.slot = &s_slot[0][threadIdx.x];
@@ -217,6 +218,10 @@ __global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) 
     path_flush(E, gg, pr, (u32)c.T.path_len);
     ctx_store(E, gg, c);
   }
+#else
+  run_sync<GB>(E, gg, c, c.pr, n_steps, in_range);
+  if (in_range && c.gs.active) ctx_store(E, gg, c);
+#endif
 }
 // update_inferences' cache half (play_manager.cc:619-642: insert_many of every evaluated leaf), as its own
 // launch BEFORE the step kernel: during k_step the table is then read-only (plus frequency bumps), so lookups

@@ -118,9 +118,16 @@ AZ_HD int popc32(u32 x) {
 #endif
 }
 
-// a / b for a finite positive b: a zero numerator (a terminal node's 0 value, a 0 prior) gives that zero back — exact
-// IEEE, and it keeps those cases off div.rn's slow path (4 % of the step kernel's instructions, profiles/r2r)
-AZ_HD float fdiv_pos(float a, float b) { return a == 0.0f ? a : fdiv(a, b); }
+// a / b for a finite positive b. Experiment (profiles/r2t_sync_ab.jsonl): giving a zero numerator (a terminal node's 0
+// value) back without dividing keeps it off div.rn's slow path (4 % of the step kernel's instructions) but the extra
+// compare + select on every division cost more than that: 2.41 G vs 2.50 G simulations/s. Kept as a knob.
+AZ_HD float fdiv_pos(float a, float b) {
+#if defined(B2AZ_FDIV_POS)
+  return a == 0.0f ? a : fdiv(a, b);
+#else
+  return fdiv(a, b);
+#endif
+}
 
 // ------------------------------------------------------------------------------------ 16 B vectors
 struct V4 {
