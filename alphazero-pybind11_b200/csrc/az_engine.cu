@@ -16,6 +16,7 @@
 // (tests/cpp/, build/libb2az_hostemu.so); the product library never defines the macro and every
 // entry point fails with B2AZ_ECUDA when no CUDA device is usable.
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -384,6 +385,7 @@ struct b2az_engine {
   // host-side bookkeeping of the current leaf batch
   bool leaves_pending = false;      // a step produced leaves that have not all been answered
   u32 leaf_count = 0;               // valid once leaf_count_known
+  u32 device_error_seen = 0;        // Globals::error as read together with leaf_count
   bool leaf_count_known = false;
   bool canon_ready = false;
   u32 leaves_taken = 0;             // legacy build_batch cursor
@@ -412,10 +414,12 @@ int bind_device(b2az_engine* e) {
 
 int sync_leaf_count(b2az_engine* e, stream_t s) {
   if (e->leaf_count_known) return 0;
-  u32 c = 0;
-  if (int rc = copy_d2h(&c, &e->view.glob->leaf_count, sizeof(u32), s)) return rc;
+  u32 c[2] = {0, 0};  // Globals::error and ::leaf_count are neighbours: one copy, one synchronisation per generation
+  static_assert(offsetof(Globals, leaf_count) == offsetof(Globals, error) + sizeof(u32), "Globals layout");
+  if (int rc = copy_d2h(c, &e->view.glob->error, sizeof(c), s)) return rc;
   if (int rc = stream_sync(s)) return rc;
-  e->leaf_count = c;
+  e->device_error_seen = c[0];
+  e->leaf_count = c[1];
   e->leaf_count_known = true;
   return 0;
 }
@@ -439,8 +443,12 @@ int ensure_canon(b2az_engine* e, stream_t s) {
 
 int check_device_error(b2az_engine* e, stream_t s) {
   u32 err = 0;
-  if (int rc = copy_d2h(&err, &e->view.glob->error, sizeof(u32), s)) return rc;
-  if (int rc = stream_sync(s)) return rc;
+  if (e->leaf_count_known) {
+    err = e->device_error_seen;  // read together with the leaf count of this generation
+  } else {
+    if (int rc = copy_d2h(&err, &e->view.glob->error, sizeof(u32), s)) return rc;
+    if (int rc = stream_sync(s)) return rc;
+  }
   if (err & B2AZ_DEVERR_POOL) return fail(B2AZ_ENOMEM, "device tree-node pool exhausted: raise b2az_params.pool_nodes");
   if (err & B2AZ_DEVERR_MOVE) return fail(B2AZ_EMOVE, "device: update_root could not find the move / illegal move");
   if (err & B2AZ_DEVERR_DEPTH) return fail(B2AZ_ESTATE, "device: selection path exceeded the path buffer");

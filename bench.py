@@ -256,27 +256,56 @@ def nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, wor
         def __init__(self, ptr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3}
 
-    v_d = torch.empty((G, 3), dtype=torch.float32, device="cuda")
-    pi_d = torch.empty((G, 7), dtype=torch.float32, device="cuda")
-    x = None
+    # The net runs on the leaf_count rows of the generation only (cache hits were answered inside the step kernel and
+    # produce no row): one 8-byte read of the row count per generation picks a power-of-two bucket, and every bucket
+    # is a captured CUDA graph over static buffers — the reference's own scheme (neural_net.py:513-561).
+    x_all = None
+    buckets = {}
+
+    def bucket_for(n):
+        b = 64
+        while b < n:
+            b *= 2
+        b = min(b, G)
+        if b not in buckets:
+            xin = torch.zeros((b, 4, 6, 7), dtype=torch.float32, device="cuda").contiguous(memory_format=torch.channels_last)
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                for _ in range(2):  # warm-up outside capture (cudnn autotune, lazy init)
+                    net(xin)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    v, pi = net(xin)
+                    v_s, pi_s = v.float().contiguous(), pi.float().contiguous()
+            buckets[b] = (gr, xin, v_s, pi_s)
+        return buckets[b]
+
+    rows_seen = []
 
     def generation():
-        nonlocal x
+        nonlocal x_all
         eng.step(1, stream)
-        cptr, iptr, nptr = eng.leaf_batch_device(stream)
-        if x is None:
-            x = torch.as_tensor(_View(cptr, (G, 4, 6, 7)), device="cuda")
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            v, pi = net(x)
-        v_d.copy_(v)
-        pi_d.copy_(pi)
-        eng.submit_eval_all(v_d.data_ptr(), pi_d.data_ptr())
+        n, cptr, iptr = eng.leaf_batch(stream)  # synchronises to read the row count (8 bytes)
+        rows_seen.append(n)
+        if n == 0:
+            return
+        if x_all is None:
+            x_all = torch.as_tensor(_View(cptr, (G, 4, 6, 7)), device="cuda")
+        gr, xin, v_s, pi_s = bucket_for(n)
+        xin[:n].copy_(x_all[:n])
+        gr.replay()
+        eng.submit_eval(v_s.data_ptr(), pi_s.data_ptr(), n)
 
-    warm, timed = 60, 200
+    warm, timed = 80, 400
     for _ in range(warm):
         generation()
+    for b in (64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):  # no capture inside the timed region
+        if b <= G:
+            bucket_for(b)
     barrier()
     s0 = eng.stats(stream)
+    rows_seen.clear()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(timed):
@@ -286,13 +315,17 @@ def nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, wor
     ms = max_over_ranks(a.elapsed_time(b))
     s1 = eng.stats(stream)
     sims = s1.simulations - s0.simulations
+    moves = s1.moves - s0.moves
     hits, misses = s1.cache_hits - s0.cache_hits, s1.cache_misses - s0.cache_misses
-    out = {"value": world * sims / (ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-           "generations": timed, "ms_per_generation": ms / timed, "net_rows_per_generation": G,
+    out = {"value": world * sims / (ms * 1e-3), "unit": "sims/s", "moves_per_second": world * moves / (ms * 1e-3),
+           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+           "generations": timed, "ms_per_generation": ms / timed,
+           "mean_batch_rows": sum(rows_seen) / max(1, len(rows_seen)), "max_batch_rows": max(rows_seen or [0]),
            "cache_hit_rate": hits / max(1, hits + misses), "device_error": int(s1.device_error),
-           "note": "one generation = b2az_step(1) + k_canonicalize + torch net (bf16 autocast, all concurrent_games rows) + "
-                   "b2az_submit_eval_all; leaf batch and evaluations never leave the device, no host sync per generation; "
-                   "cache hits are answered inside the step kernel"}
+           "net": "connect4 default arch (dense, depth 4, 12 channels, 5x5), random init, bf16 autocast, CUDA-graph buckets",
+           "note": "one generation = b2az_step(1) [cache hits are answered inside the step kernel] + k_canonicalize of the "
+                   "missed leaves + 8-byte row-count read + torch net on exactly those rows (power-of-two bucket) + "
+                   "b2az_submit_eval; leaf batch and evaluations never leave the device"}
     eng.close()
     return out
 
