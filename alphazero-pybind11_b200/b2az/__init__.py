@@ -47,8 +47,8 @@ class Params(C.Structure):
         ("per_slot_quota", C.c_uint8), ("pad1_", C.c_uint8), ("seed", C.c_uint64), ("pool_nodes", C.c_uint64),
         ("history_capacity", C.c_uint32), ("lanes_per_game", C.c_uint32), ("compact_pages", C.c_uint32),
         ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float), ("gumbel_c_scale", C.c_float),
-        ("gumbel_full", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad3_", C.c_uint8 * 2),
-        ("step_kernel", C.c_uint32),
+        ("gumbel_full", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("model_groups", C.c_uint8 * 2),
+        ("step_kernel", C.c_uint32), ("seat_cap_visits", C.c_uint32 * 2),
     ]
 
 
@@ -120,6 +120,9 @@ def load(path=None):
     L.b2az_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
+    L.b2az_leaf_seats_host.argtypes = [vp, vp, vp, u32]
+    L.b2az_cache_insert_host.argtypes = [vp, vp, vp, vp, vp, u32]
+    L.b2az_cache_find_host.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
     L.b2az_tafl_replay_device.argtypes = [u32, u32, u32, u32] + [vp] * 10
     L.b2az_forest_create.argtypes = [C.POINTER(ForestParams), C.c_int, C.POINTER(vp)]
@@ -279,6 +282,27 @@ class Engine:
         s = Stats()
         self._check(self.L.b2az_get_stats(self.h, stream, C.byref(s)))
         return s
+
+    # -- the searching seat of every row of the current leaf batch (several model groups)
+    def leaf_seats_host(self, count, stream=None):
+        seats = np.zeros(count, np.uint8)
+        self._check(self.L.b2az_leaf_seats_host(self.h, stream, _ptr(seats), count))
+        return seats
+
+    # -- the position cache key by key, in order (S3FIFOCache::insert / ::find)
+    def cache_insert(self, keys, v, pi, stream=None):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        v = np.ascontiguousarray(v, np.float32).reshape(len(keys), NUM_PLAYERS + 1)
+        pi = np.ascontiguousarray(pi, np.float32).reshape(len(keys), NUM_MOVES)
+        self._check(self.L.b2az_cache_insert_host(self.h, stream, _ptr(keys), _ptr(v), _ptr(pi), len(keys)))
+
+    def cache_find(self, keys, stream=None):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        found = np.zeros(len(keys), np.uint8)
+        v = np.zeros((len(keys), NUM_PLAYERS + 1), np.float32)
+        pi = np.zeros((len(keys), NUM_MOVES), np.float32)
+        self._check(self.L.b2az_cache_find_host(self.h, stream, _ptr(keys), len(keys), _ptr(found), _ptr(v), _ptr(pi)))
+        return found.astype(bool), v, pi
 
     def peek(self, game, seat, stream=None):
         state = np.zeros(89, np.uint8)

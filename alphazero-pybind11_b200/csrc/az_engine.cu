@@ -232,6 +232,21 @@ __global__ void k_cache_insert(EngineView E) {
   for (u32 r = GLOBAL_TID; r < count; r += GLOBAL_NT)
     cache_insert(E, E.leaf_key[r], E.ev_v + (size_t)r * (kP + 1), E.ev_pi + (size_t)r * kA);
 }
+// b2az_cache_insert_host / b2az_cache_find_host: the position cache driven key by key IN ORDER (one thread), for tools and
+// for the tests that hold it against the reference's S3FIFOCache
+__global__ void k_cache_insert_keys(EngineView E, const u64* keys, const float* v, const float* pi, u32 n) {
+  for (u32 i = 0; i < n; ++i) cache_insert(E, keys[i], v + (size_t)i * (kP + 1), pi + (size_t)i * kA);
+}
+__global__ void k_cache_find_keys(EngineView E, const u64* keys, u32 n, u8* found, float* v, float* pi) {
+  for (u32 i = 0; i < n; ++i) {
+    const u32 idx = cache_find(E, keys[i]);
+    found[i] = idx != kNil;
+    if (idx != kNil) {
+      for (int j = 0; j < kP + 1; ++j) v[(size_t)i * (kP + 1) + j] = E.cache_vals[idx].v[j];
+      for (int j = 0; j < kA; ++j) pi[(size_t)i * kA + j] = E.cache_vals[idx].pi[j];
+    }
+  }
+}
 __global__ void k_step_serial(EngineView E, u32 n_steps) {
   for (u32 s = 0; s < n_steps; ++s)
     for (u32 g = 0; g < E.G; ++g) {
@@ -518,7 +533,7 @@ int b2az_destroy(b2az_engine* e) {
   EngineView& V = e->view;
   dev_free(V.blocks); dev_free(V.page_next); dev_free(V.ring); dev_free(V.ring_tickets);
   dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot); dev_free(V.gum);
-  dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game);
+  dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game); dev_free(V.leaf_seat);
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
   dev_free(V.cache_keys); dev_free(V.cache_meta); dev_free(V.cache_lock); dev_free(V.cache_vals);
   dev_free(V.cache_ghost); dev_free(V.leaf_key); dev_free(V.hit_val);
@@ -548,6 +563,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->max_cache_size != 0 && p->rng_mode == B2AZ_RNG_GLOBAL)
     return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
   if (p->step_kernel > B2AZ_STEP_QUEUE) return fail(B2AZ_EINVAL, "bad step_kernel");
+  if (p->model_groups[0] > 1 || p->model_groups[1] > 1) return fail(B2AZ_EINVAL, "model_groups: a group index must be 0 or 1");
   if (p->per_slot_quota && p->games_to_play % p->concurrent_games != 0)
     return fail(B2AZ_EINVAL, "per_slot_quota: games_to_play must be a multiple of concurrent_games");
   if (p->lanes_per_game > 1)
@@ -578,7 +594,8 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.G = G;
   V.games_to_play = p->games_to_play;
   V.visits[0] = p->mcts_visits[0]; V.visits[1] = p->mcts_visits[1];
-  V.cap_visits[0] = V.cap_visits[1] = p->playout_cap_depth;
+  V.cap_visits[0] = p->seat_cap_visits[0] ? p->seat_cap_visits[0] : p->playout_cap_depth;
+  V.cap_visits[1] = p->seat_cap_visits[1] ? p->seat_cap_visits[1] : p->playout_cap_depth;
   V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.epsilon = p->epsilon; V.root_temp = p->mcts_root_temp;
   V.start_temp = p->start_temp; V.final_temp = p->final_temp; V.half_life = p->temp_decay_half_life;
   V.playout_cap_percent = p->playout_cap_percent;
@@ -588,6 +605,9 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.resign_percent = p->resign_percent; V.resign_playthrough_percent = p->resign_playthrough_percent;
   V.gumbel_enabled = p->gumbel_enabled; V.gumbel_full = p->gumbel_full; V.fast_search_uses_gumbel = p->fast_search_uses_gumbel;
   V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
+  V.seat_group[0] = p->model_groups[0]; V.seat_group[1] = p->model_groups[1];
+  V.hit_cap = 64u;
+  if (const char* hc = getenv("B2AZ_HIT_CAP")) V.hit_cap = (u32)std::max(0, atoi(hc));  // experiment knob
   V.slot_quota = p->per_slot_quota ? p->games_to_play / p->concurrent_games : 0u;
 
   // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
@@ -636,7 +656,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   if (p->gumbel_enabled) A(dev_alloc(&V.gum, (size_t)G * kP));  // zero = reset state, no sims target
   A(dev_alloc(&V.path, (size_t)G * kMaxPath)); A(dev_alloc(&V.pslot, (size_t)G * kMaxPath));
   A(dev_alloc(&V.leaf_p0, (size_t)G)); A(dev_alloc(&V.leaf_p1, (size_t)G));
-  A(dev_alloc(&V.leaf_player, (size_t)G)); A(dev_alloc(&V.leaf_game, (size_t)G));
+  A(dev_alloc(&V.leaf_player, (size_t)G)); A(dev_alloc(&V.leaf_game, (size_t)G)); A(dev_alloc(&V.leaf_seat, (size_t)G));
   A(dev_alloc(&V.hist_partial, p->history_enabled ? (size_t)G * kMaxHist : 1));
   A(dev_alloc(&V.hist_out, p->history_enabled ? (size_t)V.hist_capacity : 1));
   A(dev_alloc(&V.glob, 1));
@@ -845,6 +865,87 @@ int b2az_leaf_batch_host(b2az_engine* e, void* stream, uint32_t max, float* cano
   e->leaves_taken += n;
   *count = n;
   return 0;
+}
+
+int b2az_cache_insert_host(b2az_engine* e, void* stream, const uint64_t* keys_host, const float* v_host, const float* pi_host,
+                           uint32_t n) {
+  if (!e || (n && (!keys_host || !v_host || !pi_host))) return fail(B2AZ_EINVAL, "null argument");
+  if (!e->view.cache_buckets) return fail(B2AZ_ESTATE, "the engine was created without a position cache (max_cache_size = 0)");
+  for (u32 i = 0; i < n; ++i)
+    if (keys_host[i] == 0) return fail(B2AZ_EINVAL, "key 0 is the empty-slot marker");
+  stream_t s = static_cast<stream_t>(stream);
+  if (int rc = bind_device(e)) return rc;
+  if (n == 0) return 0;
+#ifndef B2AZ_HOST_EMU
+  u64* dk = nullptr; float *dv = nullptr, *dp = nullptr;
+  int rc = dev_alloc_raw(&dk, n);
+  if (!rc) rc = dev_alloc_raw(&dv, (size_t)n * (kP + 1));
+  if (!rc) rc = dev_alloc_raw(&dp, (size_t)n * kA);
+  if (!rc) rc = copy_h2d(dk, keys_host, (size_t)n * 8, s);
+  if (!rc) rc = copy_h2d(dv, v_host, (size_t)n * (kP + 1) * 4, s);
+  if (!rc) rc = copy_h2d(dp, pi_host, (size_t)n * kA * 4, s);
+  if (!rc) {
+    k_cache_insert_keys<<<1, 1, 0, s>>>(e->view, dk, dv, dp, n);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_cache_insert_keys launch failed");
+  }
+  if (!rc) rc = stream_sync(s);
+  dev_free(dk); dev_free(dv); dev_free(dp);
+  return rc;
+#else
+  (void)s;
+  for (u32 i = 0; i < n; ++i) cache_insert(e->view, keys_host[i], v_host + (size_t)i * (kP + 1), pi_host + (size_t)i * kA);
+  return 0;
+#endif
+}
+
+int b2az_cache_find_host(b2az_engine* e, void* stream, const uint64_t* keys_host, uint32_t n, uint8_t* found_host, float* v_host,
+                         float* pi_host) {
+  if (!e || (n && (!keys_host || !found_host || !v_host || !pi_host))) return fail(B2AZ_EINVAL, "null argument");
+  if (!e->view.cache_buckets) return fail(B2AZ_ESTATE, "the engine was created without a position cache (max_cache_size = 0)");
+  stream_t s = static_cast<stream_t>(stream);
+  if (int rc = bind_device(e)) return rc;
+  if (n == 0) return 0;
+#ifndef B2AZ_HOST_EMU
+  u64* dk = nullptr; float *dv = nullptr, *dp = nullptr; u8* df = nullptr;
+  int rc = dev_alloc_raw(&dk, n);
+  if (!rc) rc = dev_alloc(&dv, (size_t)n * (kP + 1));
+  if (!rc) rc = dev_alloc(&dp, (size_t)n * kA);
+  if (!rc) rc = dev_alloc(&df, (size_t)n);
+  if (!rc) rc = copy_h2d(dk, keys_host, (size_t)n * 8, s);
+  if (!rc) {
+    k_cache_find_keys<<<1, 1, 0, s>>>(e->view, dk, n, df, dv, dp);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_cache_find_keys launch failed");
+  }
+  if (!rc) rc = copy_d2h(found_host, df, n, s);
+  if (!rc) rc = copy_d2h(v_host, dv, (size_t)n * (kP + 1) * 4, s);
+  if (!rc) rc = copy_d2h(pi_host, dp, (size_t)n * kA * 4, s);
+  if (!rc) rc = stream_sync(s);
+  dev_free(dk); dev_free(dv); dev_free(dp); dev_free(df);
+  return rc;
+#else
+  (void)s;
+  for (u32 i = 0; i < n; ++i) {
+    const u32 idx = cache_find(e->view, keys_host[i]);
+    found_host[i] = idx != kNil;
+    if (idx != kNil) {
+      memcpy(v_host + (size_t)i * (kP + 1), e->view.cache_vals[idx].v, sizeof(float) * (kP + 1));
+      memcpy(pi_host + (size_t)i * kA, e->view.cache_vals[idx].pi, sizeof(float) * kA);
+    }
+  }
+  return 0;
+#endif
+}
+
+int b2az_leaf_seats_host(b2az_engine* e, void* stream, uint8_t* seats_host, uint32_t count) {
+  if (!e || (count && !seats_host)) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (int rc = bind_device(e)) return rc;
+  if (!e->leaves_pending) return fail(B2AZ_ESTATE, "no leaf batch");
+  if (int rc = sync_leaf_count(e, s)) return rc;
+  if (count > e->leaf_count) return fail(B2AZ_EINVAL, "more rows than leaves");
+  if (count == 0) return 0;
+  if (int rc = copy_d2h(seats_host, e->view.leaf_seat, count, s)) return rc;
+  return stream_sync(s);
 }
 
 int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, uint32_t count) {

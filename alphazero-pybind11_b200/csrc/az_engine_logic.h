@@ -927,7 +927,9 @@ AZ_HD void cache_insert(const EngineView& E, u64 key, const float* v, const floa
 AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s, bool allow_hit) {
   u64 key = 0;
   if (E.cache_buckets) {
-    key = c4_cache_key(s);
+    // one table for every model group (the reference keeps one cache per group, play_manager.cc:195-203): the group of
+    // the searching seat is part of the key (bits 56-59 are free in the position encoding)
+    key = c4_cache_key(s) | ((u64)E.seat_group[gs.player] << 56);
     const u32 hit = cache_find(E, key);
     if (hit != kNil && allow_hit) {
       E.hit_val[g] = hit;
@@ -951,6 +953,7 @@ AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s,
   E.leaf_p1[row] = s.p[1];
   E.leaf_player[row] = s.player;
   E.leaf_game[row] = g;
+  E.leaf_seat[row] = gs.player;
   if (E.cache_buckets) {
     E.leaf_key[row] = key;
     E.hit_val[g] = kNil;
@@ -1719,7 +1722,7 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
     if (E.eval_type == 0) {
       // a cache hit is an answered leaf: go on with the next simulation in the same launch (the reference
       // re-queues the game for MCTS at once, play_manager.cc:589-594); bounded so a launch stays short
-      if (leaf_emit(E, g, c.gs, D.s, hits < 64u)) {
+      if (leaf_emit(E, g, c.gs, D.s, hits < E.hit_cap)) {
         ++hits;
         continue;
       }
@@ -1783,7 +1786,7 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, boo
       descent_finish(E, g, c.T, c.gs, c.rng, D);
       bool hit = false;
       if (E.eval_type == 0) {
-        hit = leaf_emit(E, g, c.gs, D.s, hits < 64u);
+        hit = leaf_emit(E, g, c.gs, D.s, hits < E.hit_cap);
         if (hit) ++hits;
       }
       if (!hit) --left;

@@ -231,7 +231,7 @@ AZ_D u32 q_leaf(const EngineView& E, u32 g, QGame& q) {
     if (E.eval_type == 0) {
       // a cache hit is an answered leaf: the game goes on with its next simulation in the same launch
       // (play_manager.cc:589-594); bounded so a launch stays short
-      hit = leaf_emit(E, g, gs, D.s, q.hits < 64u);
+      hit = leaf_emit(E, g, gs, D.s, q.hits < E.hit_cap);
       if (hit) ++q.hits;
     }
     if (!hit) --left;
@@ -269,7 +269,7 @@ AZ_D u32 q_finish(const EngineView& E, u32 g, QGame& q) {
   q.in_descent = 0;
   bool hit = false;
   if (E.eval_type == 0) {
-    hit = leaf_emit(E, g, gs, D.s, q.hits < 64u);
+    hit = leaf_emit(E, g, gs, D.s, q.hits < E.hit_cap);
     if (hit) ++q.hits;
   }
   u32 left = q.left;

@@ -163,6 +163,7 @@ struct EngineView {
   u8 policy_target_pruning, playout_cap, eval_type, rng_mode;
   u32 num_pages, hist_capacity;
   u32 compact_pages;   // a tree is compacted at a move once its arena holds more pages than this
+  u32 hit_cap;         // position-cache hits a game may chain inside ONE launch before it has to emit a leaf row
   u32 slot_quota;      // > 0: every slot retires after this many games (deterministic: b2az_params.per_slot_quota)
   // ---- block pool
   Block* blocks;       // [num_pages * kPageBlocks]
@@ -189,6 +190,9 @@ struct EngineView {
   u64* leaf_p1;
   u8* leaf_player;
   u32* leaf_game;
+  u8* leaf_seat;       // [rows] the SEARCHING seat (the slot's side to move): its model group evaluates the leaf
+  u8 seat_group[kP];   // model group of each seat (PlayParams::model_groups, play_manager.cc:24-31)
+  u8 pad4_[2];
   // ---- position cache (NULL / 0 when max_cache_size == 0)
   u64* cache_keys;        // [buckets][kCacheWays]  0 = empty  (one 32 B sector per bucket)
   u32* cache_meta;        // [buckets]  per way one byte: freq (bits 0-1) | main-queue flag (bit 2)

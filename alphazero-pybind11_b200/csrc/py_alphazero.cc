@@ -38,6 +38,9 @@
 #include "../../include/b2az.h"
 #include "az_connect4.h"
 #include "az_tafl.h"
+#include "py_s3fifo.h"
+#include <random>
+#include <algorithm>
 
 namespace py = pybind11;
 using b2az::C4State;
@@ -227,6 +230,99 @@ struct PlayParams {  // play_manager.h:60-154, same defaults
   uint64_t pool_nodes = 0;
 };
 
+// PlayManager's constructor normalisation (play_manager.cc:24-176): model groups, seat permutations and the per-seat
+// 2-D overrides, with the reference's dimension errors. What the engines carry today: ONE model group, ONE seat
+// permutation, per-seat visit budgets (seat_visits / seat_cap_visits: self_play's asymmetric search budget,
+// game_runner.py:2027-2034); the other per-seat tables must be uniform (every seat the same value), which then
+// replaces the global. Anything else is rejected with "not implemented", never ignored.
+struct SeatTables {
+  std::vector<uint8_t> model_groups;
+  uint32_t num_model_groups = 1;
+  std::vector<std::vector<uint8_t>> seat_perms;
+  std::vector<std::vector<uint32_t>> visits, cap_visits;
+  std::vector<std::vector<float>> epsilon, root_temp;
+  std::vector<std::vector<uint8_t>> root_fpu_zero, gumbel_enabled, gumbel_full, gumbel_use_improved;
+  std::vector<std::vector<uint32_t>> gumbel_m, resign_consecutive;
+  std::vector<std::vector<float>> gumbel_c_visit, gumbel_c_scale, resign_threshold;
+};
+template <typename T>
+bool uniform2d(const std::vector<std::vector<T>>& t) {
+  for (auto& row : t)
+    for (auto& x : row)
+      if (!(x == t[0][0])) return false;
+  return true;
+}
+inline SeatTables normalize_seats(const PlayParams& P, size_t np) {
+  SeatTables N;
+  if (P.mcts_visits.size() != np) throw std::runtime_error{"You must specify MCTS visits for each player"};
+  if (P.model_groups.empty()) for (size_t i = 0; i < np; ++i) N.model_groups.push_back((uint8_t)i);
+  else N.model_groups = P.model_groups;
+  if (N.model_groups.size() < np) throw std::runtime_error{"model_groups must name a group for each player"};
+  N.num_model_groups = *std::max_element(N.model_groups.begin(), N.model_groups.end()) + 1u;
+  std::vector<uint32_t> group_visits(N.num_model_groups, 0);
+  for (size_t i = 0; i < np; ++i) group_visits[N.model_groups[i]] = P.mcts_visits[i];
+  if (P.seat_perms.empty()) N.seat_perms.push_back(N.model_groups);
+  else N.seat_perms = P.seat_perms;
+  const size_t num_perms = N.seat_perms.size();
+  auto validate = [&](const auto& vec, const char* name) {
+    if (vec.size() != num_perms) throw std::runtime_error{std::string(name) + " outer dimension must match number of seat permutations"};
+    for (size_t p = 0; p < num_perms; ++p)
+      if (vec[p].size() != np) throw std::runtime_error{std::string(name) + " inner dimension must match number of players"};
+  };
+  for (auto& perm : N.seat_perms) {
+    if (perm.size() != np) throw std::runtime_error{"seat_perms inner dimension must match number of players"};
+    for (auto g : perm)
+      if (g >= N.num_model_groups) throw std::runtime_error{"seat_perms names a model group that does not exist"};
+  }
+  auto fill = [&](auto& dst, const auto& src, const char* name, auto def) {
+    if (src.empty()) dst.assign(num_perms, std::decay_t<decltype(dst[0])>(np, def));
+    else { validate(src, name); dst = src; }
+  };
+  if (P.seat_visits.empty()) {
+    N.visits.resize(num_perms);
+    for (size_t p = 0; p < num_perms; ++p)
+      for (size_t s = 0; s < np; ++s) N.visits[p].push_back(group_visits[N.seat_perms[p][s]]);
+  } else {
+    validate(P.seat_visits, "seat_visits");
+    N.visits = P.seat_visits;
+  }
+  fill(N.cap_visits, P.seat_cap_visits, "seat_cap_visits", (uint32_t)P.playout_cap_depth);
+  fill(N.epsilon, P.seat_epsilon, "seat_epsilon", P.epsilon);
+  fill(N.root_temp, P.seat_mcts_root_temp, "seat_mcts_root_temp", P.mcts_root_temp);
+  fill(N.root_fpu_zero, P.seat_root_fpu_zero, "seat_root_fpu_zero", (uint8_t)(P.root_fpu_zero ? 1 : 0));
+  fill(N.gumbel_enabled, P.seat_gumbel_enabled, "seat_gumbel_enabled", (uint8_t)(P.gumbel_enabled ? 1 : 0));
+  fill(N.gumbel_m, P.seat_gumbel_m, "seat_gumbel_m", (uint32_t)P.gumbel_m);
+  fill(N.gumbel_c_visit, P.seat_gumbel_c_visit, "seat_gumbel_c_visit", P.gumbel_c_visit);
+  fill(N.gumbel_c_scale, P.seat_gumbel_c_scale, "seat_gumbel_c_scale", P.gumbel_c_scale);
+  fill(N.gumbel_full, P.seat_gumbel_full, "seat_gumbel_full", (uint8_t)(P.gumbel_full ? 1 : 0));
+  fill(N.gumbel_use_improved, P.seat_gumbel_use_improved_policy, "seat_gumbel_use_improved_policy", (uint8_t)0);
+  fill(N.resign_threshold, P.seat_resign_threshold, "seat_resign_threshold", -2.0f);
+  fill(N.resign_consecutive, P.seat_resign_consecutive, "seat_resign_consecutive", (uint32_t)1);
+  return N;
+}
+// What the engines do not carry yet (see SeatTables): rejected loudly. On success the uniform per-seat tables have been
+// folded into `P`'s globals.
+inline void fold_supported_seats(PlayParams& P, const SeatTables& N, const char* engine, uint32_t max_groups) {
+  auto reject = [&](bool bad, const char* what) {
+    if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + engine + " yet");
+  };
+  reject(N.num_model_groups > max_groups, "this many model groups (model_groups / seat_perms with different networks)");
+  reject(N.seat_perms.size() != 1, "more than one seat permutation");
+  reject(!uniform2d(N.epsilon) || !uniform2d(N.root_temp) || !uniform2d(N.root_fpu_zero), "different seat_epsilon / seat_mcts_root_temp / seat_root_fpu_zero per seat");
+  reject(!uniform2d(N.gumbel_enabled) || !uniform2d(N.gumbel_m) || !uniform2d(N.gumbel_c_visit) || !uniform2d(N.gumbel_c_scale) ||
+             !uniform2d(N.gumbel_full), "different Gumbel settings per seat");
+  reject(N.gumbel_use_improved[0][0] != 0 || !uniform2d(N.gumbel_use_improved), "seat_gumbel_use_improved_policy");
+  reject(!uniform2d(N.resign_threshold) || N.resign_threshold[0][0] > -1.5f, "seat_resign_threshold");
+  P.epsilon = N.epsilon[0][0];
+  P.mcts_root_temp = N.root_temp[0][0];
+  P.root_fpu_zero = N.root_fpu_zero[0][0] != 0;
+  P.gumbel_enabled = N.gumbel_enabled[0][0] != 0;
+  P.gumbel_m = N.gumbel_m[0][0];
+  P.gumbel_c_visit = N.gumbel_c_visit[0][0];
+  P.gumbel_c_scale = N.gumbel_c_scale[0][0];
+  P.gumbel_full = N.gumbel_full[0][0] != 0;
+}
+
 // ------------------------------------------------------------------------------------ PlayManager
 class PlayManager;
 struct GameData {  // play_manager.h:33-58, the part Python sees (py_wrapper.cc:265-288)
@@ -242,19 +338,15 @@ class PlayManager {
     auto* t = dynamic_cast<const TaflGS<GAME>*>(gs);
     if (!t) return false;
     if (t->s.turn != 0 || t->hist_len != 0) throw std::runtime_error("the B200 engine starts every game from the initial position");
-    const auto& P = params_;
-    if (P.mcts_visits.size() != (size_t)kP) throw std::runtime_error("You must specify MCTS visits for each player");
+    tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
+    PlayParams eff = params_;
+    fold_supported_seats(eff, tables_, "B200 tafl engine", 1);
+    const PlayParams& P = eff;
     auto reject = [](bool bad, const char* what) {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 tafl engine yet");
     };
-    reject(!P.seat_gumbel_enabled.empty() || !P.seat_gumbel_m.empty() || !P.seat_gumbel_c_visit.empty() ||
-               !P.seat_gumbel_c_scale.empty() || !P.seat_gumbel_full.empty() || !P.seat_gumbel_use_improved_policy.empty() ||
-               !P.seat_resign_threshold.empty() || !P.seat_visits.empty() || !P.seat_cap_visits.empty() ||
-               !P.seat_epsilon.empty() || !P.seat_mcts_root_temp.empty() || !P.seat_root_fpu_zero.empty(),
-           "per-seat overrides");
-    reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
     reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
-    reject(P.mcts_visits[0] != P.mcts_visits[1], "different mcts_visits per seat");
+    reject(tables_.visits[0][0] != tables_.visits[0][1], "different visit budgets per seat");
     reject(P.playout_cap_randomization, "playout_cap_randomization");
     reject(P.resign_percent > 0.0f, "resign_percent");
     reject(P.max_cache_size != 0, "max_cache_size (position cache)");
@@ -272,7 +364,7 @@ class PlayManager {
     sp.forest.max_turns = t->s.max_turns;
     // slab per tree: each half holds the kept subtree + one move's new nodes (1 + 8k words per expanded node)
     sp.forest.words_per_tree = P.pool_nodes ? (uint32_t)P.pool_nodes
-                                            : 2u * (1u + 4u * P.mcts_visits[0] * (1u + 8u * (GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u)));
+                                            : 2u * (1u + 4u * tables_.visits[0][0] * (1u + 8u * (GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u)));
     sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
     sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
     sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
@@ -280,7 +372,7 @@ class PlayManager {
     sp.forest.shaped_dirichlet = P.shaped_dirichlet;
     sp.n_games = P.concurrent_games;
     sp.games_per_slot = P.games_to_play / P.concurrent_games;
-    sp.visits = P.mcts_visits[0];
+    sp.visits = tables_.visits[0][0];
     sp.start_temp = P.start_temp; sp.final_temp = P.final_temp; sp.temp_decay_half_life = P.temp_decay_half_life;
     sp.history_enabled = P.history_enabled; sp.policy_target_pruning = P.policy_target_pruning; sp.tree_reuse = P.tree_reuse;
     // history_ is unbounded in the reference; here the sample ring holds what a run can produce between drains: every
@@ -302,6 +394,9 @@ class PlayManager {
     v_.assign((size_t)G_ * (kP + 1), 0.0f);
     pi_.assign((size_t)G_ * A_, 0.0f);
     row_of_game_.assign(G_, 0xFFFFFFFFu);
+    seats_.assign(G_, 0);
+    group_rows_.assign(tables_.num_model_groups, {});
+    group_next_.assign(tables_.num_model_groups, 0);
     refresh_stats_locked();
   }
   PlayManager(const GameState* gs, PlayParams p) : params_(std::move(p)) {
@@ -313,20 +408,13 @@ class PlayManager {
     if (!c4) throw std::runtime_error("the B200 engine implements Connect4GS and the tafl games only");
     if (c4->s.p[0] || c4->s.p[1] || c4->s.player || c4->s.turn)
       throw std::runtime_error("the B200 engine starts every game from the initial Connect4 position");
-    const auto& P = params_;
-    // play_manager.cc:19-22
-    if (P.mcts_visits.size() != (size_t)kP) throw std::runtime_error("You must specify MCTS visits for each player");
+    tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
+    PlayParams eff = params_;
+    fold_supported_seats(eff, tables_, "B200 engine", 2);
+    const PlayParams& P = eff;
     auto reject = [](bool bad, const char* what) {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
     };
-    reject(!P.seat_gumbel_enabled.empty() || !P.seat_gumbel_m.empty() || !P.seat_gumbel_c_visit.empty() ||
-               !P.seat_gumbel_c_scale.empty() || !P.seat_gumbel_full.empty() || !P.seat_gumbel_use_improved_policy.empty(),
-           "per-seat Gumbel overrides");
-    reject(!P.seat_resign_threshold.empty(), "seat_resign_threshold");
-    reject(!P.model_groups.empty() || !P.seat_perms.empty(), "model_groups / seat_perms");
-    reject(!P.seat_visits.empty() || !P.seat_cap_visits.empty() || !P.seat_epsilon.empty() ||
-               !P.seat_mcts_root_temp.empty() || !P.seat_root_fpu_zero.empty(),
-           "per-seat overrides");
     reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
     EvalType et = EvalType::NN;
     if (!P.eval_type.empty()) {
@@ -341,8 +429,12 @@ class PlayManager {
     bp.concurrent_games = P.concurrent_games;
     bp.max_batch_size = P.max_batch_size;
     bp.max_cache_size = P.max_cache_size;  // one model group: the whole budget (play_manager.cc:195-203)
-    bp.mcts_visits[0] = P.mcts_visits[0];
-    bp.mcts_visits[1] = P.mcts_visits[1];
+    bp.mcts_visits[0] = tables_.visits[0][0];  // seat_visits / seat_cap_visits: the per-seat budgets (play_manager.cc:70-90)
+    bp.mcts_visits[1] = tables_.visits[0][1];
+    bp.seat_cap_visits[0] = tables_.cap_visits[0][0];
+    bp.seat_cap_visits[1] = tables_.cap_visits[0][1];
+    bp.model_groups[0] = tables_.seat_perms[0][0];  // the network that searches for seat s (play_manager.cc:577)
+    bp.model_groups[1] = tables_.seat_perms[0][1];
     bp.cpuct = P.cpuct;
     bp.start_temp = P.start_temp;
     bp.final_temp = P.final_temp;
@@ -425,7 +517,7 @@ class PlayManager {
 
   // build_batch (py_wrapper.cc:449-504)
   std::vector<uint32_t> build_batch(uint32_t group, float* batch, ssize_t ndim, const ssize_t* shape, uint32_t /*shard*/) {
-    if (group != 0) throw std::runtime_error("model group out of range");
+    if (group >= tables_.num_model_groups) throw std::runtime_error("model group out of range");
     std::vector<uint32_t> out;
     const uint32_t mbs = params_.max_batch_size;
     out.reserve(mbs);
@@ -439,7 +531,8 @@ class PlayManager {
     while (out.size() < max_bs()) {
       if (eager_.load() && !out.empty()) break;
       if (remaining_games() == 0) break;
-      const uint32_t avail = leaf_count_ - next_row_;
+      const std::vector<uint32_t>& rows = group_rows_[group];  // this group's rows of the published batch, FIFO
+      const uint32_t avail = (uint32_t)rows.size() - group_next_[group];
       if (avail == 0) {
         if (++empty >= 20u) break;  // MAX_EMPTY x SUB_TIMEOUT = ~10 ms
         cv_.wait_for(lk, std::chrono::microseconds(500));
@@ -453,9 +546,12 @@ class PlayManager {
       const uint32_t cap = (uint32_t)std::min<ssize_t>(shape[0], (ssize_t)max_bs());
       if (out.size() >= cap) break;
       const uint32_t n = std::min<uint32_t>(avail, cap - (uint32_t)out.size());
-      std::memcpy(batch + out.size() * canon_sz_, canon_.data() + (size_t)next_row_ * canon_sz_, (size_t)n * canon_sz_ * sizeof(float));
-      out.insert(out.end(), ids_.begin() + next_row_, ids_.begin() + next_row_ + n);
-      next_row_ += n;
+      for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t r = rows[group_next_[group] + i];
+        std::memcpy(batch + (out.size() + i) * canon_sz_, canon_.data() + (size_t)r * canon_sz_, (size_t)canon_sz_ * sizeof(float));
+      }
+      for (uint32_t i = 0; i < n; ++i) out.push_back(ids_[rows[group_next_[group] + i]]);
+      group_next_[group] += n;
     }
     return out;
   }
@@ -463,7 +559,7 @@ class PlayManager {
   // PlayManager::update_inferences (play_manager.cc:619-642)
   void update_inferences(uint32_t group, const std::vector<uint32_t>& idx, const float* v, ssize_t vrows, ssize_t vcols,
                          const float* pi, ssize_t prows, ssize_t pcols) {
-    if (group != 0) throw std::runtime_error("model group out of range");
+    if (group >= tables_.num_model_groups) throw std::runtime_error("model group out of range");
     if (vcols != kP + 1 || pcols != (ssize_t)A_ || vrows < (ssize_t)idx.size() || prows < (ssize_t)idx.size())
       throw std::runtime_error("Eigen is angry!!!");  // shapes.h:4-6: the reference asserts on bad shapes
     std::unique_lock<std::mutex> lk(mu_);
@@ -485,12 +581,13 @@ class PlayManager {
     return py::int_(v[0]);
   }
   std::vector<uint32_t> pop_games_upto(uint32_t group, size_t n) {
-    if (group != 0) throw std::runtime_error("model group out of range");
+    if (group >= tables_.num_model_groups) throw std::runtime_error("model group out of range");
     std::unique_lock<std::mutex> lk(mu_);
-    if (leaf_count_ == next_row_) cv_.wait_for(lk, std::chrono::milliseconds(10));  // MAX_WAIT (play_manager.h:26)
-    const uint32_t take = (uint32_t)std::min<size_t>(n, leaf_count_ - next_row_);
-    std::vector<uint32_t> out(ids_.begin() + next_row_, ids_.begin() + next_row_ + take);
-    next_row_ += take;
+    if (group_rows_[group].size() == group_next_[group]) cv_.wait_for(lk, std::chrono::milliseconds(10));  // MAX_WAIT (play_manager.h:26)
+    const uint32_t take = (uint32_t)std::min<size_t>(n, group_rows_[group].size() - group_next_[group]);
+    std::vector<uint32_t> out;
+    for (uint32_t i = 0; i < take; ++i) out.push_back(ids_[group_rows_[group][group_next_[group] + i]]);
+    group_next_[group] += take;
     return out;
   }
   void push_inference(uint32_t i) {  // the caller has written game_data(i).v() / .pi() in place
@@ -534,13 +631,17 @@ class PlayManager {
   uint32_t hist_count() const { return hist_count_.load(); }
   size_t awaiting_inference_count() {
     std::lock_guard<std::mutex> lk(mu_);
-    return leaf_count_ - next_row_;
+    size_t n = 0;
+    for (size_t g = 0; g < group_rows_.size(); ++g) n += group_rows_[g].size() - group_next_[g];
+    return n;
   }
   size_t awaiting_mcts_count() {
     std::lock_guard<std::mutex> lk(mu_);
     return leaf_count_ ? answered_ : 0;
   }
   void set_eager(bool e) { eager_.store(e); }
+  uint32_t num_model_groups() const { return tables_.num_model_groups; }
+  size_t num_seat_perms() const { return tables_.seat_perms.size(); }
   uint32_t concurrent() const { return G_; }
 
   // GameData accessors
@@ -576,6 +677,23 @@ class PlayManager {
     games_completed_.store(stats_.games_completed);
     hist_count_.store(stats_.hist_count);
   }
+  // hand the generation's n rows to the batcher threads: row r goes to the queue of the model group that searches for
+  // its seat (play_manager.cc:577, 598)
+  void publish_locked(uint32_t n) {
+    for (auto& g : group_rows_) g.clear();
+    std::fill(group_next_.begin(), group_next_.end(), 0u);
+    for (uint32_t r = 0; r < n; ++r) {
+      row_of_game_[ids_[r]] = r;
+      group_rows_[tables_.num_model_groups > 1 ? tables_.seat_perms[0][seats_[r]] : 0].push_back(r);
+    }
+    answered_ = 0;
+    leaf_count_ = n;
+  }
+  void retract_locked() {
+    leaf_count_ = 0;
+    for (auto& g : group_rows_) g.clear();
+    std::fill(group_next_.begin(), group_next_.end(), 0u);
+  }
   void drive_tafl() {
     for (;;) {
       if (stopped_.load()) return;
@@ -599,15 +717,11 @@ class PlayManager {
       refresh_stats_locked();
       if (stats_.device_error) throw std::runtime_error("play: device error (tree slab / training-sample ring exhausted)");
       if (n == 0) return;  // every slot retired
-      for (uint32_t r = 0; r < n; ++r) row_of_game_[ids_[r]] = r;
-      answered_ = 0;
-      next_row_ = 0;
-      leaf_count_ = n;
+      publish_locked(n);
       cv_.notify_all();
       cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
       if (stopped_.load()) return;
-      leaf_count_ = 0;
-      next_row_ = 0;
+      retract_locked();
       {
         std::lock_guard<std::mutex> lk2(api_);
         if (b2az_tafl_selfplay_submit_eval_host(tsp_, nullptr, ids_.data(), v_.data(), pi_.data(), n) != 0) throw_last("update_inferences");
@@ -638,19 +752,16 @@ class PlayManager {
         std::lock_guard<std::mutex> lk(api_);
         if (b2az_step(eng_, 1, nullptr) != 0) throw_last("play");
         if (b2az_leaf_batch_host(eng_, nullptr, G_, canon_.data(), ids_.data(), &n) != 0) throw_last("play");
+        if (tables_.num_model_groups > 1 && n > 0 && b2az_leaf_seats_host(eng_, nullptr, seats_.data(), n) != 0) throw_last("play");
       }
       std::unique_lock<std::mutex> lk(mu_);
       refresh_stats_locked();
       if (n == 0) return;  // every slot retired
-      for (uint32_t r = 0; r < n; ++r) row_of_game_[ids_[r]] = r;
-      answered_ = 0;
-      next_row_ = 0;
-      leaf_count_ = n;
+      publish_locked(n);
       cv_.notify_all();
       cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
       if (stopped_.load()) return;
-      leaf_count_ = 0;
-      next_row_ = 0;
+      retract_locked();
       {
         std::lock_guard<std::mutex> lk2(api_);
         if (b2az_submit_eval_host(eng_, nullptr, ids_.data(), v_.data(), pi_.data(), n) != 0) throw_last("update_inferences");
@@ -659,6 +770,7 @@ class PlayManager {
   }
 
   PlayParams params_;
+  SeatTables tables_;
   b2az_engine* eng_ = nullptr;
   b2az_tafl_selfplay* tsp_ = nullptr;  // set instead of eng_ for a tafl GameState
   uint32_t canon_sz_ = kCanon, A_ = kA;
@@ -675,7 +787,10 @@ class PlayManager {
   std::atomic<uint32_t> games_completed_{0}, hist_count_{0};
   std::vector<float> canon_, v_, pi_;
   std::vector<uint32_t> ids_, row_of_game_;
-  uint32_t leaf_count_ = 0, next_row_ = 0, answered_ = 0;
+  std::vector<uint8_t> seats_;                    // searching seat of every row (several model groups only)
+  std::vector<std::vector<uint32_t>> group_rows_; // rows of the published batch per model group, FIFO
+  std::vector<uint32_t> group_next_;              // per group: rows already handed out
+  uint32_t leaf_count_ = 0, answered_ = 0;
   b2az_stats stats_{};
 };
 
@@ -857,11 +972,27 @@ PYBIND11_MODULE(alphazero, m) {
              py::gil_scoped_release rel;
              return pm.build_history_batch(c, n, vv, pp);
            })
-      .def("num_model_groups", [](PlayManager&) { return 1; })
-      .def("num_seat_perms", [](PlayManager&) { return 1; })
-      .def("perm_scores", [](PlayManager& pm, size_t) { auto s = pm.stats(); return vec3(s.scores); })
-      .def("perm_games_completed", [](PlayManager& pm, size_t) { return pm.games_completed(); })
+      .def("num_model_groups", &PlayManager::num_model_groups)
+      .def("num_seat_perms", &PlayManager::num_seat_perms)
+      .def("perm_scores", [](PlayManager& pm, size_t i) {
+        if (i >= pm.num_seat_perms()) throw std::out_of_range("perm index");
+        auto s = pm.stats();
+        return vec3(s.scores);
+      })
+      .def("perm_games_completed", [](PlayManager& pm, size_t i) {
+        if (i >= pm.num_seat_perms()) throw std::out_of_range("perm index");
+        return pm.games_completed();
+      })
+      // per-variant tracking (play_manager.h:317-366) only exists for games with variants (Star Gambit Unified)
       .def("num_tracked_variants", [](PlayManager&) { return 0; })
+#define NO_VARIANT(name) .def(name, [](PlayManager&, int) -> float { throw std::out_of_range("this game has no variants"); })
+      NO_VARIANT("variant_games_completed") NO_VARIANT("variant_avg_game_length") NO_VARIANT("variant_avg_leaf_depth")
+      NO_VARIANT("variant_avg_search_entropy") NO_VARIANT("variant_fast_avg_leaf_depth")
+      NO_VARIANT("variant_fast_avg_search_entropy") NO_VARIANT("variant_avg_moves_per_turn") NO_VARIANT("variant_avg_valid_moves")
+#undef NO_VARIANT
+      .def("variant_scores", [](PlayManager&, int) -> py::object { throw std::out_of_range("this game has no variants"); })
+      .def("variant_perm_scores", [](PlayManager&, int, int) -> py::object { throw std::out_of_range("this game has no variants"); })
+      .def("variant_perm_games_completed", [](PlayManager&, int, int) -> uint32_t { throw std::out_of_range("this game has no variants"); })
       .def("set_eager", &PlayManager::set_eager)
       .def("build_batch",
            [](PlayManager& pm, uint32_t group, py::array_t<float, py::array::c_style>& batch, uint32_t shard) {
@@ -873,6 +1004,96 @@ PYBIND11_MODULE(alphazero, m) {
              return pm.build_batch(group, data, nd, shape, shard);
            },
            py::arg("group"), py::arg("batch"), py::arg("shard") = 0);
+
+  // S3FIFOCache / ShardedS3FIFOCache (py_wrapper.cc:222-259): the host containers Python tools hold (cache_utils.py)
+  using b2az_host::S3FIFOCache;
+  using b2az_host::ShardedS3FIFOCache;
+  py::class_<S3FIFOCache>(m, "S3FIFOCache")
+      .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t>(), py::arg("max_size"), py::arg("ghost_size"), py::arg("num_policy"),
+           py::arg("num_value"))
+      .def("find",
+           [](S3FIFOCache& c, uint64_t hash, uint32_t num_policy, uint32_t num_value) -> py::object {
+             if (num_policy != c.num_policy() || num_value != c.num_value()) throw std::runtime_error("S3FIFOCache.find: wrong num_policy / num_value");
+             py::array_t<float> policy(num_policy), value(num_value);
+             if (!c.find(hash, policy.mutable_data(), value.mutable_data())) return py::none();
+             return py::make_tuple(policy, value);
+           },
+           py::arg("hash"), py::arg("num_policy"), py::arg("num_value"))
+      .def("insert",
+           [](S3FIFOCache& c, uint64_t hash, py::array_t<float, py::array::c_style | py::array::forcecast> policy,
+              py::array_t<float, py::array::c_style | py::array::forcecast> value) {
+             if ((uint32_t)policy.size() != c.num_policy() || (uint32_t)value.size() != c.num_value())
+               throw std::runtime_error("S3FIFOCache.insert: wrong policy / value length");
+             c.insert(hash, policy.data(), value.data());
+           },
+           py::arg("hash"), py::arg("policy"), py::arg("value"))
+      .def("hits", &S3FIFOCache::hits).def("misses", &S3FIFOCache::misses).def("evictions", &S3FIFOCache::evictions)
+      .def("reinserts", &S3FIFOCache::reinserts).def("size", &S3FIFOCache::size).def("max_size", &S3FIFOCache::max_size);
+  py::class_<ShardedS3FIFOCache, std::shared_ptr<ShardedS3FIFOCache>>(m, "ShardedS3FIFOCache")
+      .def(py::init<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>(), py::arg("max_size"), py::arg("shards"), py::arg("ghost_size"),
+           py::arg("num_policy"), py::arg("num_value"))
+      .def("hits", &ShardedS3FIFOCache::hits).def("misses", &ShardedS3FIFOCache::misses)
+      .def("evictions", &ShardedS3FIFOCache::evictions).def("reinserts", &ShardedS3FIFOCache::reinserts)
+      .def("size", &ShardedS3FIFOCache::size).def("max_size", &ShardedS3FIFOCache::max_size);
+
+  // playout_eval / playout_eval_batch (py_wrapper.cc:726-770, game_state.cc:10-95): uniform prior over the legal moves of
+  // the given state, value = the outcome of ONE uniformly random playout (relative values where the game uses them).
+  // A host-side tool over the Python-visible GameState objects; the engines' evaluators run on the device.
+  auto playout_one = [](const GameState& gs, std::default_random_engine& re) {
+    py::array_t<uint8_t> valids = gs.valid_moves();
+    const uint32_t A = gs.num_moves();
+    py::array_t<float> policy(A);
+    uint8_t wrap = 0;  // Vector<uint8_t>::sum() wraps mod 256 in the reference (game_state.cc:16)
+    for (uint32_t i = 0; i < A; ++i) wrap = (uint8_t)(wrap + valids.at(i));
+    const float sum = (float)wrap;
+    for (uint32_t i = 0; i < A; ++i) policy.mutable_at(i) = sum > 0.0f ? (float)valids.at(i) / sum : 0.0f;
+    auto sim = gs.copy();
+    for (;;) {
+      if (!sim->scores().is_none()) break;
+      py::array_t<uint8_t> v = sim->valid_moves();
+      std::vector<uint32_t> idx;
+      for (uint32_t i = 0; i < A; ++i)
+        if (v.at(i) != 0) idx.push_back(i);
+      if (idx.empty()) break;
+      std::uniform_int_distribution<uint32_t> dist{0, (uint32_t)idx.size() - 1};
+      sim->play_move(idx[dist(re)]);
+    }
+    py::object sc = sim->scores();
+    const int P = gs.num_players();
+    py::array_t<float> value(P + 1);
+    if (!sc.is_none()) {
+      auto a = sc.cast<py::array_t<float>>();
+      for (int i = 0; i <= P; ++i) value.mutable_at(i) = a.at(i);
+      if (gs.relative_values()) {  // absolute_to_relative (game_state.h:24-34): rotate so that index 0 is the mover
+        std::vector<float> rel(P + 1);
+        const int cp = gs.current_player();
+        for (int i = 0; i < P; ++i) rel[i] = a.at((i + cp) % P);
+        rel[P] = a.at(P);
+        for (int i = 0; i <= P; ++i) value.mutable_at(i) = rel[i];
+      }
+    } else {
+      for (int i = 0; i <= P; ++i) value.mutable_at(i) = (float)(1.0 / (P + 1));
+    }
+    return std::make_pair(value, policy);
+  };
+  m.def("playout_eval", [playout_one](const GameState& gs) {
+    static thread_local std::default_random_engine re{std::random_device{}()};
+    auto r = playout_one(gs, re);
+    return py::make_tuple(r.first, r.second);
+  });
+  m.def("playout_eval_batch", [playout_one](py::list states) {
+    static thread_local std::default_random_engine re{std::random_device{}()};
+    const ssize_t n = (ssize_t)py::len(states);
+    if (n == 0) throw std::runtime_error("playout_eval_batch: empty list");
+    std::vector<std::pair<py::array_t<float>, py::array_t<float>>> rs;
+    for (auto& item : states) rs.push_back(playout_one(*item.cast<const GameState*>(), re));
+    py::array_t<float> v({n, (ssize_t)rs[0].first.size()}), pi({n, (ssize_t)rs[0].second.size()});
+    for (ssize_t i = 0; i < n; ++i) {
+      for (ssize_t j = 0; j < rs[0].first.size(); ++j) v.mutable_at(i, j) = rs[i].first.at(j);
+      for (ssize_t j = 0; j < rs[0].second.size(); ++j) pi.mutable_at(i, j) = rs[i].second.at(j);
+    }
+    return py::make_tuple(v, pi);
+  });
 
   // Tracy hooks (py_wrapper.cc:772-787): profiling is off in this build
   m.def("_tracy_zone_begin", [](const std::string&, const std::string&, uint32_t) {});

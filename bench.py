@@ -244,89 +244,107 @@ def nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, wor
             return torch.softmax(self.v_head(x).float(), 1), torch.softmax(self.pi_head(x).float(), 1)
 
     torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True  # the 6x7 boards with 4..52 channels are far from cuDNN's default heuristics
     net = C4Net().cuda().eval().to(memory_format=torch.channels_last)
-    p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=G, mcts_visits=(SIMS, SIMS), cpuct=1.25,
-                            fpu_reduction=0.25, epsilon=0.25, mcts_root_temp=1.25, start_temp=1.0, final_temp=0.2,
-                            temp_decay_half_life=10.0, root_fpu_zero=1, shaped_dirichlet=1, policy_target_pruning=1,
-                            eval_type=b2az.EVAL_NN, rng_mode=b2az.RNG_PER_GAME, seed=3000 + rank, tree_reuse=1,
-                            history_enabled=1, self_play=1, max_cache_size=200000, history_capacity=8 * G)
-    eng = b2az.Engine(p, device=local)
+    # Two half-populations, each on its own stream: while the net evaluates the leaves of one half, the step kernel of the
+    # other half runs (the reference overlaps the same way: its MCTS threads keep going while the GPU thread evaluates).
+    H = 2
+    Gh = G // H
+    streams = [torch.cuda.Stream() for _ in range(H)]
+    engs = []
+    for h in range(H):
+        p = b2az.default_params(games_to_play=2 ** 31 - 1, concurrent_games=Gh, mcts_visits=(SIMS, SIMS), cpuct=1.25,
+                                fpu_reduction=0.25, epsilon=0.25, mcts_root_temp=1.25, start_temp=1.0, final_temp=0.2,
+                                temp_decay_half_life=10.0, root_fpu_zero=1, shaped_dirichlet=1, policy_target_pruning=1,
+                                eval_type=b2az.EVAL_NN, rng_mode=b2az.RNG_PER_GAME, seed=3000 + 7 * rank + h, tree_reuse=1,
+                                history_enabled=1, self_play=1, max_cache_size=200000 // H, history_capacity=8 * Gh)
+        engs.append(b2az.Engine(p, device=local))
 
     class _View:  # zero-copy: torch wraps the engine's device batch through __cuda_array_interface__
         def __init__(self, ptr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3}
 
-    # The net runs on the leaf_count rows of the generation only (cache hits were answered inside the step kernel and
-    # produce no row): one 8-byte read of the row count per generation picks a power-of-two bucket, and every bucket
-    # is a captured CUDA graph over static buffers — the reference's own scheme (neural_net.py:513-561).
-    x_all = None
-    buckets = {}
+    # The net runs on the rows of the generation only, in a power-of-two bucket; every bucket is a captured CUDA graph
+    # over static buffers — the reference's own scheme (neural_net.py:513-561). Cache hits never become rows: a game
+    # whose leaf is in the cache goes on with its next simulation inside the step kernel.
+    buckets = [dict() for _ in range(H)]
+    x_all = [None] * H
+    rows_seen = []
 
-    def bucket_for(n):
+    def bucket_for(h, n):
         b = 64
         while b < n:
             b *= 2
-        b = min(b, G)
-        if b not in buckets:
-            xin = torch.zeros((b, 4, 6, 7), dtype=torch.float32, device="cuda").contiguous(memory_format=torch.channels_last)
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-                for _ in range(2):  # warm-up outside capture (cudnn autotune, lazy init)
-                    net(xin)
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
+        b = min(b, Gh)
+        if b not in buckets[h]:
+            with torch.cuda.stream(streams[h]):
+                xin = torch.zeros((b, 4, 6, 7), dtype=torch.float32, device="cuda").contiguous(memory_format=torch.channels_last)
                 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-                    v, pi = net(xin)
-                    v_s, pi_s = v.float().contiguous(), pi.float().contiguous()
-            buckets[b] = (gr, xin, v_s, pi_s)
-        return buckets[b]
+                    for _ in range(3):  # warm-up outside capture (cudnn autotune, lazy init)
+                        net(xin)
+                streams[h].synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=streams[h]):
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                        v, pi = net(xin)
+                        v_s, pi_s = v.float().contiguous(), pi.float().contiguous()
+            buckets[h][b] = (gr, xin, v_s, pi_s)
+        return buckets[h][b]
 
-    rows_seen = []
-
-    def generation():
-        nonlocal x_all
-        eng.step(1, stream)
-        n, cptr, iptr = eng.leaf_batch(stream)  # synchronises to read the row count (8 bytes)
+    def evaluate(h):  # leaves of half h -> net -> evaluations, everything on stream h
+        st = streams[h].cuda_stream
+        n, cptr, iptr = engs[h].leaf_batch(st)  # synchronises stream h to read the row count (8 bytes)
         rows_seen.append(n)
         if n == 0:
             return
-        if x_all is None:
-            x_all = torch.as_tensor(_View(cptr, (G, 4, 6, 7)), device="cuda")
-        gr, xin, v_s, pi_s = bucket_for(n)
-        xin[:n].copy_(x_all[:n])
-        gr.replay()
-        eng.submit_eval(v_s.data_ptr(), pi_s.data_ptr(), n)
+        with torch.cuda.stream(streams[h]):
+            if x_all[h] is None:
+                x_all[h] = torch.as_tensor(_View(cptr, (Gh, 4, 6, 7)), device="cuda")
+            gr, xin, v_s, pi_s = bucket_for(h, n)
+            xin[:n].copy_(x_all[h][:n])
+            gr.replay()
+        engs[h].submit_eval(v_s.data_ptr(), pi_s.data_ptr(), n)
 
+    def generation():  # one generation of BOTH halves, software-pipelined
+        for h in range(H):
+            evaluate(h)                              # waits for half h's step, then queues its net
+            engs[h].step(1, streams[h].cuda_stream)  # queued behind the net on stream h; overlaps the other half's net
+
+    for h in range(H):
+        for b in (64, 256, 1024, 4096, 16384, Gh):  # no capture inside the timed region
+            bucket_for(h, min(b, Gh))
+        engs[h].step(1, streams[h].cuda_stream)
     warm, timed = 80, 400
     for _ in range(warm):
         generation()
-    for b in (64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):  # no capture inside the timed region
-        if b <= G:
-            bucket_for(b)
+    torch.cuda.synchronize()
     barrier()
-    s0 = eng.stats(stream)
+    s0 = [e.stats(streams[h].cuda_stream) for h, e in enumerate(engs)]
     rows_seen.clear()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    t0 = time.perf_counter()
     for _ in range(timed):
         generation()
-    b.record()
     torch.cuda.synchronize()
-    ms = max_over_ranks(a.elapsed_time(b))
-    s1 = eng.stats(stream)
-    sims = s1.simulations - s0.simulations
-    moves = s1.moves - s0.moves
-    hits, misses = s1.cache_hits - s0.cache_hits, s1.cache_misses - s0.cache_misses
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    s1 = [e.stats(streams[h].cuda_stream) for h, e in enumerate(engs)]
+    sims = sum(b_.simulations - a_.simulations for a_, b_ in zip(s0, s1))
+    moves = sum(b_.moves - a_.moves for a_, b_ in zip(s0, s1))
+    hits = sum(b_.cache_hits - a_.cache_hits for a_, b_ in zip(s0, s1))
+    misses = sum(b_.cache_misses - a_.cache_misses for a_, b_ in zip(s0, s1))
     out = {"value": world * sims / (ms * 1e-3), "unit": "sims/s", "moves_per_second": world * moves / (ms * 1e-3),
-           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * H,
            "generations": timed, "ms_per_generation": ms / timed,
            "mean_batch_rows": sum(rows_seen) / max(1, len(rows_seen)), "max_batch_rows": max(rows_seen or [0]),
-           "cache_hit_rate": hits / max(1, hits + misses), "device_error": int(s1.device_error),
+           "net_rows_per_second": sum(rows_seen) / (ms * 1e-3),
+           "cache_hit_rate": hits / max(1, hits + misses), "cache_entries": 200000,
+           "device_error": int(max(x_.device_error for x_ in s1)),
            "net": "connect4 default arch (dense, depth 4, 12 channels, 5x5), random init, bf16 autocast, CUDA-graph buckets",
-           "note": "one generation = b2az_step(1) [cache hits are answered inside the step kernel] + k_canonicalize of the "
-                   "missed leaves + 8-byte row-count read + torch net on exactly those rows (power-of-two bucket) + "
-                   "b2az_submit_eval; leaf batch and evaluations never leave the device"}
-    eng.close()
+           "note": "two half-populations of concurrent_games/2 on two streams; per half and generation: b2az_step(1) [cache "
+                   "hits are answered inside the step kernel and the game goes on to its next simulation] + k_canonicalize "
+                   "of the missed leaves + 8-byte row-count read + torch net on exactly those rows + b2az_submit_eval; "
+                   "leaf batch and evaluations never leave the device; wall-clock timed (two streams)"}
+    for e in engs:
+        e.close()
     return out
 
 

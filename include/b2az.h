@@ -95,8 +95,10 @@ typedef struct b2az_params {
   float gumbel_c_scale;          /* 1 */
   uint8_t gumbel_full;           /* pi'-matching at interior nodes too */
   uint8_t fast_search_uses_gumbel;
-  uint8_t pad3_[2];
+  uint8_t model_groups[2];       /* model group (0 or 1) of each seat (PlayParams::model_groups, play_manager.cc:24-31): the
+                                    position cache keeps the groups apart, b2az_leaf_seats_host tells which seat searches */
   uint32_t step_kernel;          /* B2AZ_STEP_*: which fused step kernel runs B2AZ_RNG_PER_GAME (results do not depend on it) */
+  uint32_t seat_cap_visits[2];   /* per-seat fast-search budget (seat_cap_visits, play_manager.cc:82-90); 0 = playout_cap_depth */
 } b2az_params;
 
 /* Counters and metrics of PlayManager (play_manager.h:173-366). */
@@ -155,6 +157,21 @@ int b2az_leaf_batch(b2az_engine* e, void* stream, uint32_t* count, const float**
  * buffers (canonical rows + slot ids), FIFO. */
 int b2az_leaf_batch_host(b2az_engine* e, void* stream, uint32_t max, float* canon_host, uint32_t* ids_host,
                          uint32_t* count);
+
+/* The device position cache (the engine's replacement for S3FIFOCache / ShardedS3FIFOCache, s3fifo_cache.h:41-110) key by
+ * key, in order: insert = S3FIFOCache::insert (an existing key is never overwritten), find = S3FIFOCache::find (counts a
+ * hit or a miss, bumps the entry's frequency; found[i] = 1 and v / pi rows filled on a hit). Keys are opaque non-zero
+ * 64-bit position keys; v is float32[n][3], pi float32[n][7]. For tools that share evaluations with an engine and for
+ * the tests that hold the table against the reference container. */
+int b2az_cache_insert_host(b2az_engine* e, void* stream, const uint64_t* keys_host, const float* v_host,
+                           const float* pi_host, uint32_t n);
+int b2az_cache_find_host(b2az_engine* e, void* stream, const uint64_t* keys_host, uint32_t n, uint8_t* found_host,
+                         float* v_host, float* pi_host);
+
+/* The SEARCHING seat of the first `count` rows of the current leaf batch (the slot's side to move; the leaf's own side to
+ * move is in its canonical planes). A PlayManager with several model groups routes row r to the network of group
+ * model_groups[seat[r]] (play_manager.cc:577, 598: awaiting_inference_[game.seat_perm[cp]]). */
+int b2az_leaf_seats_host(b2az_engine* e, void* stream, uint8_t* seats_host, uint32_t count);
 
 /* update_inferences (play_manager.cc:619-642), zero-copy flavour: v_dev float32[count][3],
  * pi_dev float32[count][7] in leaf-batch row order, count == the leaf count. The buffers are

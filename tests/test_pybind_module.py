@@ -153,7 +153,25 @@ def test_error_conventions():
     p.seat_perms = []
     with pytest.raises(TypeError):
         az.PlayManager(None, p)
+    # the reference's dimension errors (play_manager.cc:57-68)
+    p.seat_visits = [[8, 8], [8, 8]]
+    with pytest.raises(RuntimeError, match="seat_visits outer dimension must match number of seat permutations"):
+        az.PlayManager(az.Connect4GS(), p)
+    p.seat_visits = [[8, 8, 8]]
+    with pytest.raises(RuntimeError, match="seat_visits inner dimension must match number of players"):
+        az.PlayManager(az.Connect4GS(), p)
+    p.seat_visits = []
+    p.seat_epsilon = [[0.25]]
+    with pytest.raises(RuntimeError, match="seat_epsilon inner dimension must match number of players"):
+        az.PlayManager(az.Connect4GS(), p)
+    p.seat_epsilon = [[0.25, 0.0]]
+    with pytest.raises(RuntimeError, match="not implemented"):
+        az.PlayManager(az.Connect4GS(), p)
+    p.seat_epsilon = []
     pm = az.PlayManager(az.Connect4GS(), p)
+    assert pm.num_model_groups() == 2 and pm.num_seat_perms() == 1  # no model_groups: one group per player (play_manager.cc:25-28)
+    p.model_groups = [0, 0]
+    assert az.PlayManager(az.Connect4GS(), p).num_model_groups() == 1
     with pytest.raises(RuntimeError, match="Improper batch size"):  # py_wrapper.cc:474
         t = threading.Thread(target=pm.play)
         t.start()
@@ -169,6 +187,7 @@ def _params(az, G, games, visits, level, seed, max_batch, deterministic=True, ev
     p = az.PlayParams()
     p.games_to_play, p.concurrent_games, p.max_batch_size = games, G, max_batch
     p.mcts_visits = [visits, visits]
+    p.model_groups = [0, 0]  # what game_runner.set_model_groups builds for self-play: one network plays both seats
     p.history_enabled = p.self_play = p.tree_reuse = True
     for k, v in ph.level_params(level).items():
         setattr(p, k, bool(v) if k in ("root_fpu_zero", "shaped_dirichlet", "policy_target_pruning") else v)
@@ -295,3 +314,65 @@ def test_random_eval_play_returns_when_done(kind):
     pm2.stop()
     t.join(timeout=20)
     assert not t.is_alive() and pm2.stopped() and pm2.remaining_games() == 0
+
+
+@pytest.mark.parametrize("kind", kinds())
+def test_two_model_groups_route_leaves_by_searching_seat(kind):
+    """No model_groups = one group per player (play_manager.cc:25-28): build_batch(g) serves the leaves of the searches
+    seat g runs (awaiting_inference_[seat_perm[cp]], play_manager.cc:577-598). With the same evaluator behind both
+    groups the games must equal the one-group run; with the position cache on, the groups must not share entries."""
+    az = module(kind)
+
+    def run(groups, cache, two_nets=False):
+        p = _params(az, G=6, games=6, visits=24, level=1, seed=11, max_batch=6, deterministic=False)
+        p.model_groups = groups
+        p.max_cache_size = cache
+        pm = az.PlayManager(az.Connect4GS(), p)
+        ths = [threading.Thread(target=pm.play) for _ in range(2)]
+        [t.start() for t in ths]
+        batch = np.zeros((6, 4, 6, 7), np.float32)
+        served = [0] * pm.num_model_groups()
+        while pm.remaining_games() > 0:
+            for g in range(pm.num_model_groups()):
+                ids = pm.build_batch(g, batch)
+                if not ids:
+                    continue
+                served[g] += len(ids)
+                v, pi = ph.fake_net(batch[:len(ids)])
+                if g == 1 and two_nets:  # a different "network" for group 1: its evaluations must never answer group 0
+                    v, pi = v[:, ::-1].copy(), pi[:, ::-1].copy()
+                pm.update_inferences(g, ids, v, pi)
+        [t.join() for t in ths]
+        n = pm.hist_count()
+        c, v, pi = np.zeros((n, 4, 6, 7), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 7), np.float32)
+        assert pm.build_history_batch(c, v, pi) == n
+        return pm, served, ph._sorted_rows(c, v, pi)
+
+    one, served1, rows1 = run([0, 0], 0)
+    two, served2, rows2 = run([], 0)
+    assert one.num_model_groups() == 1 and two.num_model_groups() == 2
+    assert min(served2) > 0 and sum(served2) == sum(served1), "both seats search, every leaf is served exactly once"
+    assert np.array_equal(rows1, rows2) and np.array_equal(one.scores(), two.scores())
+    with pytest.raises(RuntimeError, match="model group out of range"):
+        one.build_batch(1, np.zeros((6, 4, 6, 7), np.float32))
+    # a different "network" behind group 1, cache off vs cache on: the reference's cache property (test_cache.py:227-253:
+    # a search with the cache is the search without it) only holds if the two groups never share an entry
+    _, _, rows_off = run([], 0, two_nets=True)
+    _, _, rows_on = run([], 100000, two_nets=True)
+    assert np.array_equal(rows_off, rows_on) and not np.array_equal(rows_off, rows2)
+
+
+def test_playout_eval_contract():
+    """playout_eval / playout_eval_batch (py_wrapper.cc:726-770, game_state.cc:10-95): uniform prior over the legal moves,
+    value = one-hot outcome of a random playout (or 1/(P+1) each if the game cannot go on)."""
+    az = module("emu")
+    g = az.Connect4GS()
+    for m in (3, 3, 3, 3, 3, 3):  # fill column 3
+        g.play_move(m)
+    v, pi = az.playout_eval(g)
+    assert pi.shape == (7,) and pi[3] == 0 and np.allclose(pi[[0, 1, 2, 4, 5, 6]], 1 / 6)
+    assert v.shape == (3,) and sorted(v.tolist()) == [0, 0, 1]
+    vs, pis = az.playout_eval_batch([g, az.Connect4GS(), az.BrandubhGS(20)][:2])
+    assert vs.shape == (2, 3) and pis.shape == (2, 7) and np.allclose(pis[1], 1 / 7) and np.allclose(vs.sum(1), 1)
+    outcomes = np.stack([az.playout_eval(az.Connect4GS())[0] for _ in range(200)])
+    assert outcomes[:, 0].sum() > 60 and outcomes[:, 1].sum() > 40  # both sides win random playouts

@@ -22,6 +22,7 @@ def _params(az, G, per_slot, visits, seed, random_eval, **kw):
     p = az.PlayParams()
     p.games_to_play, p.concurrent_games, p.max_batch_size = G * per_slot, G, G
     p.mcts_visits = [visits, visits]
+    p.model_groups = [0, 0]  # game_runner.set_model_groups for self-play
     p.history_enabled = p.self_play = p.tree_reuse = True
     p.cpuct, p.fpu_reduction = 1.25, 0.25
     for k, v in kw.items():
@@ -116,7 +117,7 @@ def test_tafl_playmanager_validation_and_no_cpu_fallback():
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
         p = _params(az, 2, 1, 8, 1, True)
-        p.mcts_visits = [8, 16]
+        p.seat_visits = [[8, 16]]  # (mcts_visits is per MODEL GROUP in the reference: [8, 16] with one group means 16 for both)
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
         az.PlayManager(gs, _params(az, 2, 1, 8, 1, True, playout_cap_randomization=True))
