@@ -7,8 +7,8 @@ hist_saver / monitor threads and writes the training samples as .ptz files. The 
 straight through the C ABI and requires the samples on disk to be the engine's samples (fp16 storage), and the returned
 SelfPlayResult to carry the engine's statistics.
 
-Runs where /root/reference exists (this container); the module under test is the host-emulation build on a CPU-only
-box (tests/cpp/emu), the CUDA build on a GPU box."""
+The module under test is the host-emulation build on a CPU-only box (tests/cpp/emu), the CUDA build on a GPU box (where
+the reference's Python comes from baseline/_ref/src, staged unmodified by __graft_entry__.build())."""
 import glob
 import importlib
 import os
@@ -22,8 +22,11 @@ import b2az
 import parity_harness as ph
 from conftest import ROOT, has_cuda
 
-REF_SRC = "/root/reference/src"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="needs the reference checkout (/root/reference)")
+# the reference checkout where it exists (this container), else the UNMODIFIED copy that __graft_entry__.build() staged under
+# baseline/_ref/src (git-ignored, shipped to the GPU box)
+REF_SRC = "/root/reference/src" if os.path.isdir("/root/reference/src") else os.path.join(ROOT, "baseline", "_ref", "src")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF_SRC, "game_runner.py")),
+                                reason="needs the reference's Python (/root/reference or baseline/_ref/src)")
 
 
 @pytest.fixture(scope="module")
