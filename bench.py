@@ -523,16 +523,27 @@ def main():
     bps = roofline_bytes_per_sim(depth, kids)
     launch_ms = sum(kernel_ms) / len(kernel_ms)
     achieved = (bps * G * gens) / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    # measured DRAM traffic of the step kernel: ncu cannot run inside a timed bench, so the per-simulation figure comes from
+    # the committed ncu capture — tied to the kernel and to the hash of the kernel source it was taken on, and flagged
+    # stale (not silently reused) when either no longer matches what just ran
+    traffic, traffic_src, traffic_stale = None, None, None
+    kernel_ran = {"f": "k_step", "w": "k_step_w", "q": "k_step_q"}.get(os.environ.get("B2AZ_STEP_KERNEL", "s")[:1], "k_step_sync")
     try:
+        import hashlib
+
         prof = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
         traffic = prof["dram_bytes_per_simulation"] * G * gens  # per launch, like `achieved`
+        sha = hashlib.sha256(open(os.path.join(ROOT, "alphazero-pybind11_b200", "csrc", "az_engine_logic.h"), "rb").read()).hexdigest()
+        traffic_stale = prof.get("kernel") != kernel_ran or prof.get("logic_header_sha256") != sha
+        traffic_src = prof.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_step", "bytes_per_sim": bps, "avg_leaf_depth": depth,
+                "traffic": traffic, "traffic_source": traffic_src, "traffic_stale": traffic_stale,
+                "kernel": kernel_ran, "bytes_per_sim": bps, "avg_leaf_depth": depth,
                 "avg_children": kids, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": bps * G * gens,
-                "note": "latency bound, not bandwidth bound: one dependent block load per tree level per simulation "
+                "note": "latency bound, not bandwidth bound: one dependent 160 B block load per tree level per simulation, "
+                        "1.6 us unloaded (profiles/r2o_tlb_probe2.jsonl); the 32 games of a warp run in lock step "
                         "(DESIGN.md 3); tensor cores unused by design",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
     cpu = None

@@ -29,10 +29,17 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF_SRC, "game_r
                                 reason="needs the reference's Python (/root/reference or baseline/_ref/src)")
 
 
-@pytest.fixture(scope="module")
-def gr():
+KIND = {"emu": None}
+
+
+@pytest.fixture(scope="module", params=[
+    pytest.param("emu", id="host-emulation"),
+    pytest.param("cuda", id="cuda", marks=[pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")])])
+def gr(request):
     """import the reference's game_runner with `alphazero` = this repo's module and a zstandard stand-in"""
-    mod_dir = os.path.join(ROOT, "alphazero-pybind11_b200") if has_cuda() else os.path.join(ROOT, "tests", "cpp", "emu")
+    cuda = request.param == "cuda"
+    KIND["cuda"] = cuda
+    mod_dir = os.path.join(ROOT, "alphazero-pybind11_b200") if cuda else os.path.join(ROOT, "tests", "cpp", "emu")
     saved_path, saved_mods = list(sys.path), dict(sys.modules)
     for name in ("alphazero", "game_runner", "config", "neural_net", "tracy_utils", "frozen_eval", "zstandard"):
         sys.modules.pop(name, None)
@@ -80,7 +87,7 @@ def test_self_play_connect4_unmodified_game_runner(gr):
     assert abs(sum(res.win_rates) - 1.0) < 1e-6 and res.game_length > 6 and res.avg_depth > 0 and res.fast_avg_depth > 0
     assert res.hit_rate == 0 and res.variant_game_counts == {}
     # the same run straight through the C ABI (what self_play() asked the module for: game_runner.py:790-816, 2022-2041)
-    lib = None if has_cuda() else ph.HOSTEMU_LIB
+    lib = None if KIND["cuda"] else ph.HOSTEMU_LIB
     eng = ph.make_engine(lib, G, n, depth, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, 0, cpuct=cfg.cpuct, start_temp=cfg.self_play_temp,
                          final_temp=cfg.final_temp, temp_decay_half_life=float(cfg.temp_decay_half_life),
                          fpu_reduction=cfg.fpu_reduction, epsilon=0.25, playout_cap_randomization=1, playout_cap_depth=fast_depth,
@@ -135,7 +142,7 @@ def test_game_runner_nn_pipeline_two_threads_connect4(gr):
 
 
 def test_self_play_brandubh_unmodified_game_runner(gr):
-    if not has_cuda():
+    if not KIND["cuda"]:
         pytest.skip("the tafl self-play engine has no host-emulation build (device only)")
     import config as ref_config
 
