@@ -64,6 +64,9 @@ class Stats(C.Structure):
         ("cache_reinserts", C.c_uint64), ("cache_size", C.c_uint64), ("cache_max_size", C.c_uint64),
         ("pool_pages_total", C.c_uint64), ("pool_pages_free", C.c_uint64), ("device_error", C.c_uint32),
         ("pad_", C.c_uint32), ("compactions", C.c_uint64),
+        ("sum_game_length", C.c_uint64), ("total_move_count", C.c_uint64), ("full_move_count", C.c_uint64),
+        ("fast_move_count", C.c_uint64), ("sum_leaf_depth", C.c_double), ("sum_search_entropy", C.c_double),
+        ("fast_sum_leaf_depth", C.c_double), ("fast_sum_search_entropy", C.c_double), ("sum_valid_moves", C.c_double),
     ]
 
 
@@ -121,6 +124,9 @@ def load(path=None):
     L.b2az_peek.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), vp]
     L.b2az_c4_batch.argtypes = [C.c_int, u32] + [vp] * 11
     L.b2az_leaf_seats_host.argtypes = [vp, vp, vp, u32]
+    L.b2az_set_games_to_play.argtypes = [vp, u32]
+    L.b2az_history_mark.argtypes = [vp, vp]
+    L.b2az_drain_history_marked.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
     L.b2az_cache_insert_host.argtypes = [vp, vp, vp, vp, vp, u32]
     L.b2az_cache_find_host.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
@@ -282,6 +288,19 @@ class Engine:
         s = Stats()
         self._check(self.L.b2az_get_stats(self.h, stream, C.byref(s)))
         return s
+
+    # -- overlapped drain: mark on the step stream, drain on a second stream while the next step runs
+    def history_mark(self, stream=None):
+        self._check(self.L.b2az_history_mark(self.h, stream))
+
+    def drain_history_marked_into(self, canon_ptr, v_ptr, pi_ptr, max_rows, stream2=None, dst_is_device=0):
+        n = C.c_uint32()
+        self._check(self.L.b2az_drain_history_marked(self.h, stream2, max_rows, canon_ptr, v_ptr, pi_ptr, dst_is_device, C.byref(n)))
+        return n.value
+
+    def set_games_to_play(self, n):
+        self._check(self.L.b2az_set_games_to_play(self.h, int(n)))
+        self.params.games_to_play = int(n)
 
     # -- the searching seat of every row of the current leaf batch (several model groups)
     def leaf_seats_host(self, count, stream=None):

@@ -412,6 +412,11 @@ struct b2az_engine {
   bool started = false;
   u32 step_kernel = 0;              // B2AZ_STEP_*
   u32 group_games = 0, groups = 0;  // slots per persistent CTA (== pool region), number of such groups
+  // overlapped history drain (b2az_history_mark / b2az_drain_history_marked)
+  unsigned long long* hist_mark_host = nullptr;  // pinned: {hist_written, hist_read} as of the mark
+  unsigned long long* hist_read_host = nullptr;  // pinned: the new read counter on its way to the device
+  void* hist_event = nullptr;                    // cudaEvent_t recorded by the mark
+  bool hist_marked = false;
 };
 
 namespace {
@@ -540,6 +545,13 @@ int b2az_destroy(b2az_engine* e) {
   dev_free(e->canon_buf); dev_free(e->ev_v_buf); dev_free(e->ev_pi_buf);
   dev_free(e->peek_buf); dev_free(e->stats_buf); dev_free(e->freepages_buf);
   dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
+#ifndef B2AZ_HOST_EMU
+  if (e->hist_mark_host) cudaFreeHost(e->hist_mark_host);
+  if (e->hist_read_host) cudaFreeHost(e->hist_read_host);
+  if (e->hist_event) cudaEventDestroy((cudaEvent_t)e->hist_event);
+#else
+  free(e->hist_mark_host); free(e->hist_read_host);
+#endif
   delete e;
   return 0;
 }
@@ -1076,6 +1088,95 @@ int b2az_drain_history_sym(b2az_engine* e, void* stream, uint32_t max, float* ca
   return drain_history_impl(e, stream, max, 2u, canon, v, pi, dst_is_device, count);
 }
 
+// ---- overlapped drain: the samples of step k leave the device while step k + 1 runs --------------------------------
+// b2az_history_mark(e, s): on the stream the steps run on, AFTER step k has been enqueued: snapshots the sample counters
+// (an async 16-byte copy into pinned memory + an event). Returns at once. b2az_drain_history_marked(e, s2, ...): on a
+// SECOND stream: waits for the mark, expands the samples up to the mark and copies them out on s2 — step k + 1, already
+// running on the first stream, only appends BEYOND the mark (a sample is complete before the counter a later mark reads
+// can include it: marks are stream-ordered between two step launches), so nothing it writes is touched.
+int b2az_history_mark(b2az_engine* e, void* stream) {
+  if (!e) return fail(B2AZ_EINVAL, "null engine");
+  if (int rc = bind_device(e)) return rc;
+  stream_t s = static_cast<stream_t>(stream);
+#ifndef B2AZ_HOST_EMU
+  if (!e->hist_mark_host) {
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&e->hist_mark_host), 16));
+    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&e->hist_read_host), 8));
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->hist_event = ev;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->hist_mark_host, &e->view.glob->hist_written, 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord((cudaEvent_t)e->hist_event, s));
+#else
+  if (!e->hist_mark_host) {
+    e->hist_mark_host = static_cast<unsigned long long*>(calloc(2, 8));
+    e->hist_read_host = static_cast<unsigned long long*>(calloc(1, 8));
+  }
+  (void)s;
+  memcpy(e->hist_mark_host, &e->view.glob->hist_written, 16);
+#endif
+  e->hist_marked = true;
+  return 0;
+}
+
+int b2az_drain_history_marked(b2az_engine* e, void* stream2, uint32_t max, float* canon, float* v, float* pi, int dst_is_device,
+                              uint32_t* count) {
+  if (!e || !count) return fail(B2AZ_EINVAL, "null argument");
+  *count = 0;
+  if (!e->hist_marked) return fail(B2AZ_ESTATE, "call b2az_history_mark first");
+  if (int rc = bind_device(e)) return rc;
+  stream_t s = static_cast<stream_t>(stream2);
+  if (!e->params.history_enabled || max == 0) return 0;
+#ifndef B2AZ_HOST_EMU
+  CUDA_TRY(cudaEventSynchronize((cudaEvent_t)e->hist_event));  // the host needs the counters
+  CUDA_TRY(cudaStreamWaitEvent(s, (cudaEvent_t)e->hist_event, 0));
+#endif
+  const unsigned long long written = e->hist_mark_host[0];
+  // the read counter is advanced by this call only (b2az_drain_history and this one must not be mixed within a run)
+  const unsigned long long read = std::max(e->hist_mark_host[1], *e->hist_read_host);
+  const u32 n = (u32)std::min<unsigned long long>(written - read, max);
+  if (n == 0) return 0;
+  float *dc = canon, *dv = v, *dp = pi;
+#ifndef B2AZ_HOST_EMU
+  if (!dst_is_device) {
+    if (e->hist_stage_cap < n) {
+      // (the staging buffers may still be in use by an earlier drain on another stream: finish it first)
+      CUDA_TRY(cudaDeviceSynchronize());
+      dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
+      e->hist_canon = e->hist_v = e->hist_pi = nullptr;
+      const u32 cap = (u32)std::max<size_t>(n, 4096);
+      if (int rc = dev_alloc(&e->hist_canon, (size_t)cap * C4_CANON)) return rc;
+      if (int rc = dev_alloc(&e->hist_v, (size_t)cap * 3)) return rc;
+      if (int rc = dev_alloc(&e->hist_pi, (size_t)cap * kA)) return rc;
+      e->hist_stage_cap = cap;
+    }
+    dc = e->hist_canon; dv = e->hist_v; dp = e->hist_pi;
+  }
+  k_hist_expand<<<e->num_sms * 4, 256, 0, s>>>(e->view, read, n, 1u, dc, dv, dp);
+  CUDA_TRY(cudaGetLastError());
+  if (!dst_is_device) {
+    if (int rc = copy_d2h(canon, dc, (size_t)n * C4_CANON * 4, s)) return rc;
+    if (int rc = copy_d2h(v, dv, (size_t)n * 3 * 4, s)) return rc;
+    if (int rc = copy_d2h(pi, dp, (size_t)n * kA * 4, s)) return rc;
+  }
+#else
+  (void)dst_is_device;
+  for (size_t row = 0; row < n; ++row) {
+    const HistEntry& h = e->view.hist_out[(read + row) % (unsigned long long)e->view.hist_capacity];
+    for (u32 el = 0; el < (u32)C4_CANON; ++el) dc[row * C4_CANON + el] = c4_canon_elem(h.p0, h.p1, h.player, el);
+    for (u32 el = 0; el < 3u; ++el) dv[row * 3 + el] = (h.result == el + 1u) ? 1.0f : 0.0f;
+    for (u32 el = 0; el < (u32)kA; ++el) dp[row * kA + el] = h.pi[el];
+  }
+#endif
+  *e->hist_read_host = read + n;
+  // the device copy of the read counter only feeds the ring-overflow check of later game ends: stream-ordered, no wait
+  if (int rc = copy_h2d(&e->view.glob->hist_read, e->hist_read_host, 8, s)) return rc;
+  if (int rc = stream_sync(s)) return rc;  // the caller's host buffers are filled when this returns
+  *count = n;
+  return 0;
+}
+
 int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   if (!e || !out) return fail(B2AZ_EINVAL, "null argument");
   stream_t s = static_cast<stream_t>(stream);
@@ -1121,6 +1222,18 @@ int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out) {
   out->cache_hits = G.cache_hits; out->cache_misses = G.cache_misses; out->cache_evictions = G.cache_evictions;
   out->cache_reinserts = G.cache_reinserts; out->cache_size = G.cache_size;
   out->cache_max_size = (unsigned long long)e->view.cache_buckets * kCacheWays;
+  out->sum_game_length = G.game_length;
+  out->total_move_count = G.total_move_count; out->full_move_count = G.full_move_count; out->fast_move_count = G.fast_move_count;
+  out->sum_leaf_depth = G.total_avg_leaf_depth; out->sum_search_entropy = G.total_search_entropy;
+  out->fast_sum_leaf_depth = G.fast_total_avg_leaf_depth; out->fast_sum_search_entropy = G.fast_total_search_entropy;
+  out->sum_valid_moves = G.total_valid_moves;
+  return 0;
+}
+
+int b2az_set_games_to_play(b2az_engine* e, uint32_t games_to_play) {
+  if (!e) return fail(B2AZ_EINVAL, "null engine");
+  e->view.games_to_play = games_to_play;  // EngineView travels by value with every launch
+  e->params.games_to_play = games_to_play;
   return 0;
 }
 

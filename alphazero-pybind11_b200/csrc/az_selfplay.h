@@ -512,6 +512,9 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
   }
   if (length) out->avg_moves_per_turn = (float)moves / (float)length;
   if (moves) out->avg_valid_moves = (float)(valid / (double)moves);
+  out->sum_game_length = length;
+  out->total_move_count = moves; out->full_move_count = full;
+  out->sum_leaf_depth = leaf_depth; out->sum_search_entropy = entropy; out->sum_valid_moves = valid;
   return 0;
 }
 // The reference-API flavour of one simulation (build_batch / update_inferences with HOST buffers, py_wrapper.cc:449-504,

@@ -437,15 +437,28 @@ def main():
         h_v = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
         h_pi = torch.empty((cap, 7), dtype=torch.float32).pin_memory()
 
+        # Software pipeline, as the reference's own threads do it (hist_saver next to play(), game_runner.py:729-745):
+        # step k + 1 is enqueued, then the samples of step k are drained on a second stream while it runs, then the
+        # statistics are read (which waits for step k + 1). Every sample reaches pinned host memory inside the timed region.
+        drain_stream = torch.cuda.Stream()
+        ds = drain_stream.cuda_stream
+        marked = [False]
+
         def e2e_step():
             eng.step(gens, stream)
-            n = eng.drain_history_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, stream)
+            n = 0
+            if marked[0]:
+                n = eng.drain_history_marked_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, ds)
+            eng.history_mark(stream)
+            marked[0] = True
             st = eng.stats(stream)
             return n, st
 
         for _ in range(args.preroll):
             eng.step(SIMS, stream)
-            eng.drain_history_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, stream)
+            eng.history_mark(stream)
+            eng.drain_history_marked_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, ds)
+        marked[0] = False
         for _ in range(W):
             e2e_step()
         barrier()
@@ -458,6 +471,24 @@ def main():
         for _ in range(K):
             n, st = e2e_step()
             samples += n
+        samples += eng.drain_history_marked_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, ds)  # the last step's
+        nccl = None
+        if dist is not None:
+            # the multi-GPU control plane, once per K steps, INSIDE the timed region: updated weights from
+            # rank 0, the additive statistics of all ranks, the newest training samples gathered on rank 0
+            from b2az import dist as bd
+
+            if "ctl_net" not in globals():
+                globals()["ctl_net"] = torch.nn.Sequential(torch.nn.Conv2d(4, 12, 5, padding=2), torch.nn.Conv2d(16, 12, 5, padding=2),
+                                                           torch.nn.Conv2d(28, 12, 5, padding=2), torch.nn.Conv2d(40, 12, 5, padding=2),
+                                                           torch.nn.Linear(168, 3), torch.nn.Linear(168, 7)).cuda()
+            b_w = bd.broadcast_weights(globals()["ctl_net"])
+            red = bd.allreduce_stats(st)
+            m = min(int(n), 8192)  # the newest samples of this rank, device resident
+            got = bd.gather_history(h_canon[:m].cuda(non_blocking=True), h_v[:m].cuda(non_blocking=True), h_pi[:m].cuda(non_blocking=True))
+            nccl = {"broadcast_bytes": int(b_w), "allreduce_bytes": int(red["nccl_bytes"]),
+                    "gather_bytes": int(bd.gather_history.last_nccl_bytes), "gathered_samples": int(got[0].shape[0]) if got else None,
+                    "global_simulations": red["simulations"]}
         b.record()
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -467,9 +498,11 @@ def main():
         e_sims = st.simulations - st0.simulations
         e2e = {"value": world * e_sims / (e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": int(samples / K * (168 + 3 + 7) * 4 + C.sizeof(b2az.Stats) + 16),
-               "samples_per_step": samples / K, "ms_per_step": e_ms / K,
-               "note": "step kernel + drain of finished training samples to pinned host buffers + stats read, every "
-                       "step; the RANDOM-eval workload has no per-step host inputs"}
+               "samples_per_step": samples / K, "ms_per_step": e_ms / K, "nccl_per_k_steps": nccl,
+               "note": "step kernel + drain of finished training samples to pinned host buffers (overlapped with the next "
+                       "step on a second stream: b2az_history_mark / b2az_drain_history_marked) + stats read, every step; "
+                       "with N > 1 one weight broadcast + one stats all-reduce + one sample gather per K steps inside the "
+                       "timed region; the RANDOM-eval workload has no per-step host inputs"}
         eng.close()
 
         # legacy per-leaf host round trip (EVAL_NN + host buffers), a few generations

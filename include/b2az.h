@@ -120,6 +120,13 @@ typedef struct b2az_stats {
   uint32_t device_error;         /* sticky device-side error bits (B2AZ_DEVERR_*) */
   uint32_t pad_;
   uint64_t compactions;          /* tree arenas compacted (Cheney copies) so far */
+  /* the raw accumulators behind the means above (play_manager.h:288-315), all over COMPLETED games: what a multi-GPU run
+   * all-reduces (a mean of means would weigh the ranks wrongly) */
+  uint64_t sum_game_length;      /* game_length_ */
+  uint64_t total_move_count, full_move_count, fast_move_count;
+  double sum_leaf_depth, sum_search_entropy;            /* over full searches */
+  double fast_sum_leaf_depth, fast_sum_search_entropy;  /* over capped (fast) searches */
+  double sum_valid_moves;                               /* over all moves */
 } b2az_stats;
 
 #define B2AZ_DEVERR_POOL 1u      /* node pool exhausted */
@@ -137,6 +144,10 @@ int b2az_params_default(b2az_params* p);
  * `device`, initialises concurrent_games slots (fresh game, one tree per seat). */
 int b2az_create(const b2az_params* p, int device, b2az_engine** out);
 int b2az_destroy(b2az_engine* e);
+/* Change the games_to_play budget of a running engine (multi-GPU runs keep ONE global budget, play_manager.cc:506-513:
+ * every rank lowers its own target once the all-reduced number of started games reaches the global one). Slots retire
+ * when their next game would exceed the budget, exactly as with the value given at creation. */
+int b2az_set_games_to_play(b2az_engine* e, uint32_t games_to_play);
 
 /* One pass of PlayManager::play()'s loop body (play_manager.cc:272-599) over EVERY active slot:
  * process_result for the evaluation submitted since the last step, play a move when the search
@@ -203,6 +214,15 @@ int b2az_drain_history(b2az_engine* e, void* stream, uint32_t max, float* canon,
  * buffers must hold 2 * max rows. *count = samples popped. */
 int b2az_drain_history_sym(b2az_engine* e, void* stream, uint32_t max, float* canon, float* v, float* pi,
                            int dst_is_device, uint32_t* count);
+
+/* The same drain OVERLAPPED with the next step (build_history_batch runs on its own thread next to play() in the
+ * reference, game_runner.py:729-745). b2az_history_mark: on the stream the steps run on, after step k has been enqueued —
+ * an asynchronous snapshot of the sample counters, returns at once. b2az_drain_history_marked: on a SECOND stream — waits
+ * for the mark only, expands and copies the samples up to it while step k + 1 (already enqueued on the first stream)
+ * runs, and returns when the caller's buffers are filled. Do not mix with b2az_drain_history within one run. */
+int b2az_history_mark(b2az_engine* e, void* stream);
+int b2az_drain_history_marked(b2az_engine* e, void* stream2, uint32_t max, float* canon, float* v, float* pi,
+                              int dst_is_device, uint32_t* count);
 
 int b2az_get_stats(b2az_engine* e, void* stream, b2az_stats* out);
 

@@ -150,3 +150,64 @@ def test_two_rank_tafl_replay_shards_match_single_process(tmp_path):
     crc = [zlib.crc32(one["canonical"][j, : g["lens"][i] + 1].tobytes()) for j, i in enumerate(idx)]
     assert res["idx"] == idx.tolist() and res["ends"] == ends and res["crc"] == crc
     assert res["tot"] == [float((g["lens"][idx] + 1).sum()), float(ends.count(1)), float(ends.count(2)), float(ends.count(3))]
+
+
+BUDGET_WORKER = r"""
+import os, sys, json
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["B2AZ_PKG"]); sys.path.insert(0, os.environ["B2AZ_TESTS"])
+import b2az, parity_harness as ph
+from b2az import dist as bd
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lib = b2az.load(ph.HOSTEMU_LIB)
+# weight broadcast: rank 0's "network" reaches every rank, dtypes and shapes kept
+net = torch.nn.Sequential(torch.nn.Conv2d(4, 3, 3), torch.nn.BatchNorm2d(3), torch.nn.Linear(5, 2))
+torch.manual_seed(rank)
+for p_ in net.parameters():
+    p_.data.normal_()
+nbytes = bd.broadcast_weights(net)
+digest = float(sum(p_.double().sum() for p_ in net.state_dict().values() if p_.dtype.is_floating_point))
+# one GLOBAL games_to_play budget over both ranks (play_manager.cc:506-513)
+base = b2az.default_params(lib, games_to_play=10 ** 6, concurrent_games=12, mcts_visits=(16, 16), eval_type=b2az.EVAL_RANDOM,
+                           rng_mode=b2az.RNG_PER_GAME, seed=500, history_enabled=0, self_play=1, **ph.level_params(0))
+p = bd.shard_params(base, rank, world)
+e = b2az.Engine(p, lib=lib)
+budget = bd.GlobalBudget(e, 40)
+for it in range(100000):
+    e.step(16 if rank == 0 else 48)   # the ranks progress at different speeds
+    g = budget.sync()
+    if g["active_games"] == 0:
+        break
+st = e.stats()
+red = bd.allreduce_stats(st)
+with open(os.environ["B2AZ_OUT"] + f".{rank}", "w") as f:
+    json.dump({"nbytes": nbytes, "digest": digest, "red": red, "local_seed": int(p.seed), "local_games": int(st.games_completed)}, f)
+dist.destroy_process_group()
+"""
+
+
+def test_global_budget_weight_broadcast_and_raw_stat_reduction(tmp_path):
+    import json
+
+    env = dict(os.environ, B2AZ_PKG=os.path.join(ph.ROOT, "alphazero-pybind11_b200"), B2AZ_TESTS=os.path.join(ph.ROOT, "tests"),
+               MASTER_ADDR="127.0.0.1", B2AZ_OUT=str(tmp_path / "out.json"))
+    script = tmp_path / "budget_worker.py"
+    script.write_text(BUDGET_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29751", str(script)], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r0, r1 = (json.load(open(str(tmp_path / "out.json") + f".{k}")) for k in (0, 1))
+    assert r0["digest"] == r1["digest"] and r0["nbytes"] > 0, "every rank holds rank 0's weights after the broadcast"
+    assert (r0["local_seed"], r1["local_seed"]) == (500, 506), "rank r owns slots [6r, 6r + 6): seed + lo"
+    red = r0["red"]
+    # 12 slots, a budget of 40 games: all slots retire; the overshoot is bounded by the games started between two syncs
+    assert red["active_games"] == 0 and 40 <= red["games_completed"] <= 40 + 12
+    assert red["games_completed"] == r0["local_games"] + r1["local_games"] and r1["local_games"] > r0["local_games"] > 0
+    assert sum(red["scores"]) == red["games_completed"]
+    assert red["avg_game_length"] > 7 and 0 < red["avg_leaf_depth"] < 10 and red["avg_valid_moves"] > 1
+    with pytest.raises(ValueError, match="world size"):
+        bd.shard_params(b2az.default_params(b2az.load(ph.HOSTEMU_LIB), concurrent_games=4), 0, 8)

@@ -69,3 +69,45 @@ def test_cache_rejected_in_parity_mode():
     lib = b2az.load(ph.HOSTEMU_LIB)
     with pytest.raises(b2az.B2azError, match="parity"):
         b2az.Engine(b2az.default_params(lib, max_cache_size=100, rng_mode=b2az.RNG_GLOBAL), lib=lib)
+
+
+@pytest.mark.parametrize("lib_path", LIBS)
+def test_overlapped_history_drain_equals_the_plain_drain(lib_path):
+    """b2az_history_mark + b2az_drain_history_marked (samples of step k leave on a second stream while step k + 1 runs)
+    deliver exactly the samples, in exactly the order, of b2az_drain_history after every step."""
+    G = 64 if lib_path else 2048
+    kw = dict(history_capacity=G * 42 * 2, per_slot_quota=1, **ph.level_params(1))
+    a = ph.make_engine(lib_path, G, 3 * G, 40, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, 77, **kw)
+    b = ph.make_engine(lib_path, G, 3 * G, 40, b2az.EVAL_RANDOM, b2az.RNG_PER_GAME, 77, **kw)
+    s1 = s2 = None
+    if lib_path is None:
+        import torch
+
+        t1, t2 = torch.cuda.Stream(), torch.cuda.Stream()
+        s1, s2 = t1.cuda_stream, t2.cuda_stream
+    cap = G * 42
+    bufs = [np.zeros((cap, 4, 6, 7), np.float32), np.zeros((cap, 3), np.float32), np.zeros((cap, 7), np.float32)]
+    got_a, got_b = [], []
+    marked = False
+    for it in range(10 ** 5):
+        a.step(57)
+        h = a.drain_history(cap)
+        if len(h[0]):
+            got_a.append(h)
+        b.step(57, s1)          # step k + 1 is enqueued ...
+        if marked:              # ... while the samples of step k are drained on the second stream
+            n = b.drain_history_marked_into(*[x.ctypes.data for x in bufs], cap, s2)
+            if n:
+                got_b.append(tuple(x[:n].copy() for x in bufs))
+        b.history_mark(s1)
+        marked = True
+        if a.stats().active_games == 0 and b.stats(s1).active_games == 0:
+            break
+    n = b.drain_history_marked_into(*[x.ctypes.data for x in bufs], cap, s2)
+    if n:
+        got_b.append(tuple(x[:n].copy() for x in bufs))
+    assert a.stats().games_completed == b.stats(s1).games_completed == 3 * G and b.stats(s1).device_error == 0
+    cat = lambda parts: tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+    ph.compare_history(cat(got_a), cat(got_b), ordered=lib_path is not None)  # (atomics order the ring on the device)
+    a.close()
+    b.close()
