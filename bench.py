@@ -459,8 +459,30 @@ def main():
             eng.history_mark(stream)
             eng.drain_history_marked_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, ds)
         marked[0] = False
+        ctl_net = None
+
+        def control_plane(st, n):
+            """the multi-GPU control plane of a self-play run, once per K steps INSIDE the timed region:
+            updated weights from rank 0, the additive statistics of all ranks, the newest samples gathered on rank 0"""
+            nonlocal ctl_net
+            from b2az import dist as bd
+
+            if ctl_net is None:  # a stand-in with the parameter count of the connect4 default net (config.py:44-47)
+                ctl_net = torch.nn.Sequential(torch.nn.Conv2d(4, 12, 5, padding=2), torch.nn.Conv2d(16, 12, 5, padding=2),
+                                              torch.nn.Conv2d(28, 12, 5, padding=2), torch.nn.Conv2d(40, 12, 5, padding=2),
+                                              torch.nn.Linear(168, 3), torch.nn.Linear(168, 7)).cuda()
+            b_w = bd.broadcast_weights(ctl_net)
+            red = bd.allreduce_stats(st)
+            m = max(1, min(int(n), 8192))  # the newest samples of this rank, device resident
+            got = bd.gather_history(h_canon[:m].cuda(non_blocking=True), h_v[:m].cuda(non_blocking=True), h_pi[:m].cuda(non_blocking=True))
+            return {"broadcast_bytes": int(b_w), "allreduce_bytes": int(red["nccl_bytes"]),
+                    "gather_bytes": int(bd.gather_history.last_nccl_bytes), "gathered_samples": int(got[0].shape[0]) if got else None,
+                    "global_simulations": red["simulations"]}
+
         for _ in range(W):
-            e2e_step()
+            n_w, st_w = e2e_step()
+        if dist is not None:
+            control_plane(st_w, n_w)  # warm-up: NCCL sets its channels up on first use
         barrier()
         st0 = eng.stats(stream)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -472,23 +494,7 @@ def main():
             n, st = e2e_step()
             samples += n
         samples += eng.drain_history_marked_into(h_canon.data_ptr(), h_v.data_ptr(), h_pi.data_ptr(), cap, ds)  # the last step's
-        nccl = None
-        if dist is not None:
-            # the multi-GPU control plane, once per K steps, INSIDE the timed region: updated weights from
-            # rank 0, the additive statistics of all ranks, the newest training samples gathered on rank 0
-            from b2az import dist as bd
-
-            if "ctl_net" not in globals():
-                globals()["ctl_net"] = torch.nn.Sequential(torch.nn.Conv2d(4, 12, 5, padding=2), torch.nn.Conv2d(16, 12, 5, padding=2),
-                                                           torch.nn.Conv2d(28, 12, 5, padding=2), torch.nn.Conv2d(40, 12, 5, padding=2),
-                                                           torch.nn.Linear(168, 3), torch.nn.Linear(168, 7)).cuda()
-            b_w = bd.broadcast_weights(globals()["ctl_net"])
-            red = bd.allreduce_stats(st)
-            m = min(int(n), 8192)  # the newest samples of this rank, device resident
-            got = bd.gather_history(h_canon[:m].cuda(non_blocking=True), h_v[:m].cuda(non_blocking=True), h_pi[:m].cuda(non_blocking=True))
-            nccl = {"broadcast_bytes": int(b_w), "allreduce_bytes": int(red["nccl_bytes"]),
-                    "gather_bytes": int(bd.gather_history.last_nccl_bytes), "gathered_samples": int(got[0].shape[0]) if got else None,
-                    "global_simulations": red["simulations"]}
+        nccl = control_plane(st, n) if dist is not None else None
         b.record()
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
