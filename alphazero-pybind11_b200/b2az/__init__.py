@@ -83,16 +83,21 @@ class TaflSelfplayParams(C.Structure):  # b2az_tafl_selfplay_params (include/b2a
     _fields_ = [("forest", ForestParams), ("n_games", C.c_uint32), ("games_per_slot", C.c_uint32), ("visits", C.c_uint32),
                 ("start_temp", C.c_float), ("final_temp", C.c_float), ("temp_decay_half_life", C.c_float),
                 ("history_enabled", C.c_uint8), ("policy_target_pruning", C.c_uint8), ("tree_reuse", C.c_uint8),
-                ("pad_", C.c_uint8), ("hist_capacity", C.c_uint32)]
+                ("pad_", C.c_uint8), ("hist_capacity", C.c_uint32), ("seat_visits", C.c_uint32 * 2),
+                ("seat_cap_visits", C.c_uint32 * 2), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
+                ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
+                ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2)]
 
 
 SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_completed", "u4"), ("pending", "u4"),
                        ("move_count", "u4"), ("full_move_count", "u4"), ("total_move_count", "u4"),
                        ("total_full_move_count", "u4"), ("game_length", "u4"), ("picked", "u4"), ("error", "u4"),
-                       ("pad_", "u4"), ("g_leaf_depth", "f8"), ("g_entropy", "f8"), ("g_valid_moves", "f8"),
+                       ("capped", "u4"), ("g_leaf_depth", "f8"), ("g_entropy", "f8"), ("g_valid_moves", "f8"),
                        ("leaf_depth", "f8"), ("entropy", "f8"), ("valid_moves", "f8"), ("simulations", "u8"),
-                       ("scores", "f4", 3), ("pad2_", "u4")])  # b2az_tafl_selfplay_slot
-assert SLOT_DTYPE.itemsize == 120
+                       ("scores", "f4", 3), ("playthrough", "u4"), ("fast_move_count", "u4"), ("total_fast_move_count", "u4"),
+                       ("g_fast_leaf_depth", "f8"), ("g_fast_entropy", "f8"), ("fast_leaf_depth", "f8"), ("fast_entropy", "f8"),
+                       ("resign_scores", "f4", 3), ("pad3_", "u4"), ("coin_state", "u8"), ("coin_inc", "u8")])  # b2az_tafl_selfplay_slot
+assert SLOT_DTYPE.itemsize == 192
 
 _libs = {}
 
@@ -541,7 +546,9 @@ class TaflSelfplay:
     def __init__(self, game, n_games, max_turns, visits, games_per_slot=1, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False,
                  seed=0, words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, shaped_dirichlet=False, gumbel_m=0,
                  gumbel_c_visit=50.0, gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0,
-                 history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None):
+                 history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None,
+                 seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
+                 playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0):
         self.L = lib or load()
         self.game, self.n = game, n_games
         S, P = TAFL_DIMS[game]
@@ -553,7 +560,14 @@ class TaflSelfplay:
         p = TaflSelfplayParams(forest=fp, n_games=n_games, games_per_slot=games_per_slot, visits=visits, start_temp=start_temp,
                                final_temp=final_temp, temp_decay_half_life=temp_decay_half_life,
                                history_enabled=int(history_enabled), policy_target_pruning=int(policy_target_pruning),
-                               tree_reuse=int(tree_reuse), hist_capacity=hist_capacity)
+                               tree_reuse=int(tree_reuse), hist_capacity=hist_capacity, playout_cap_depth=playout_cap_depth,
+                               playout_cap_percent=playout_cap_percent, resign_percent=resign_percent,
+                               resign_playthrough_percent=resign_playthrough_percent,
+                               playout_cap_randomization=int(playout_cap_randomization),
+                               fast_search_uses_gumbel=int(fast_search_uses_gumbel))
+        for seat in range(2):
+            p.seat_visits[seat] = (seat_visits or (0, 0))[seat]
+            p.seat_cap_visits[seat] = (seat_cap_visits or (0, 0))[seat]
         self.hist_capacity = hist_capacity or n_games * max_turns
         self.h = C.c_void_p()
         self._check(self.L.b2az_tafl_selfplay_create(C.byref(p), device, C.byref(self.h)))

@@ -1365,6 +1365,7 @@ int b2az_forest_update_root(b2az_forest*, void*, const uint32_t*) FOREST_NO_CUDA
 int b2az_forest_counts(b2az_forest*, void*, uint32_t*, float*, uint32_t*) FOREST_NO_CUDA()
 #else
 int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1374,6 +1375,7 @@ int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev)
   return 0;
 }
 int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f || !canon_host) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1384,6 +1386,7 @@ int b2az_forest_leaf_canon_host(b2az_forest* f, void* stream, float* canon_host)
 }
 int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev, const float* pi_dev,
                                int root_noise_enabled) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f || !v_dev || !pi_dev) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1393,6 +1396,7 @@ int b2az_forest_process_result(b2az_forest* f, void* stream, const float* v_dev,
 }
 int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v_host, const float* pi_host,
                                     int root_noise_enabled) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f || !v_host || !pi_host) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1407,6 +1411,7 @@ int b2az_forest_process_result_host(b2az_forest* f, void* stream, const float* v
   return stream_sync(s);
 }
 int b2az_forest_find_leaf_batched(b2az_forest* f, void* stream, const float** canon_dev) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (!f->view.max_in_flight) return fail(B2AZ_ESTATE, "b2az_forest: created with max_in_flight == 0");
@@ -1418,6 +1423,7 @@ int b2az_forest_find_leaf_batched(b2az_forest* f, void* stream, const float** ca
 }
 int b2az_forest_process_result_batched(b2az_forest* f, void* stream, uint32_t leaf_index, const float* v, const float* pi,
                                        int root_noise_enabled, int host_pointers) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f || !v || !pi) return fail(B2AZ_EINVAL, "null argument");
   if (leaf_index >= f->view.max_in_flight) return fail(B2AZ_EINVAL, "b2az_forest: leaf_index out of range");
@@ -1438,6 +1444,7 @@ int b2az_forest_process_result_batched(b2az_forest* f, void* stream, uint32_t le
   return host_pointers ? stream_sync(s) : 0;
 }
 int b2az_forest_simulate_batched(b2az_forest* f, void* stream, uint32_t n_rounds, uint32_t width) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (width == 0 || width > f->view.max_in_flight) return fail(B2AZ_EINVAL, "b2az_forest: width must be in [1, max_in_flight]");
@@ -1447,6 +1454,7 @@ int b2az_forest_simulate_batched(b2az_forest* f, void* stream, uint32_t n_rounds
   return 0;
 }
 int b2az_forest_reset_batch(b2az_forest* f, void* stream) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   k_forest_reset_batch<<<148, 128, 0, static_cast<cudaStream_t>(stream)>>>(f->view);
@@ -1455,6 +1463,7 @@ int b2az_forest_reset_batch(b2az_forest* f, void* stream) {
 }
 int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pruned, int pick_move, float* probs_host,
                       uint32_t* moves_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (pick_move && !moves_host) return fail(B2AZ_EINVAL, "b2az_forest_probs: pick_move needs moves_host");
@@ -1475,6 +1484,7 @@ int b2az_forest_probs(b2az_forest* f, void* stream, float temp, int pruned, int 
   return rc;
 }
 int b2az_forest_root_noise(b2az_forest* f, void* stream, int add_noise) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1483,6 +1493,7 @@ int b2az_forest_root_noise(b2az_forest* f, void* stream, int add_noise) {
   return 0;
 }
 int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims, int root_noise_enabled) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (n_sims == 0) return 0;
@@ -1492,6 +1503,7 @@ int b2az_forest_simulate(b2az_forest* f, void* stream, uint32_t n_sims, int root
   return 0;
 }
 int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (!f->view.gumbel_enabled) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
@@ -1500,6 +1512,7 @@ int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n) {
   return 0;
 }
 int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_host, float* policy_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   if (!f->view.gumbel_enabled) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
@@ -1521,6 +1534,7 @@ int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_hos
   return rc;
 }
 int b2az_forest_advance(b2az_forest* f, void* stream) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1529,6 +1543,7 @@ int b2az_forest_advance(b2az_forest* f, void* stream) {
   return 0;
 }
 int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f || !moves_host) return fail(B2AZ_EINVAL, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1538,6 +1553,7 @@ int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_
   return stream_sync(s);
 }
 int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

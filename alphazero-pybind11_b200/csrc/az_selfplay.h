@@ -24,18 +24,27 @@ struct SpSlot {                       // b2az_tafl_selfplay_slot in include/b2az
   u32 total_move_count, total_full_move_count, game_length;  // PlayManager::total_move_count_ / full_move_count_ / game_length_
   u32 picked;                         // scratch: the move pick_move returned
   u32 error;                          // 1 = output ring full (samples dropped)
-  u32 pad_;
+  u32 capped;                         // GameData::capped: the current search is a fast (playout-cap) search
   double g_leaf_depth, g_entropy, g_valid_moves;  // GameData::total_avg_leaf_depth / total_search_entropy / total_valid_moves
   double leaf_depth, entropy, valid_moves;        // PlayManager::total_avg_leaf_depth_ / total_search_entropy_ / total_valid_moves_
   unsigned long long simulations;
   float scores[3];
-  u32 pad2_;
+  u32 playthrough;                    // GameData::playthrough (set once per game slot, never cleared: play_manager.cc:328-329)
+  // fast (capped) searches: GameData::fast_* / PlayManager::fast_* (play_manager.cc:436-446, 489-505)
+  u32 fast_move_count, total_fast_move_count;
+  double g_fast_leaf_depth, g_fast_entropy, fast_leaf_depth, fast_entropy;
+  float resign_scores[3];             // resign_scores_
+  u32 pad3_;
+  Pcg32 coin;                         // playout-cap and resign-playthrough coins (see sp_coin)
 };
-static_assert(sizeof(SpSlot) == 120, "b2az_tafl_selfplay_slot layout");
+static_assert(sizeof(SpSlot) == 192, "b2az_tafl_selfplay_slot layout");
 
 struct SpView {
   SpSlot* slots;
-  u32 n_games, games_per_slot, visits;
+  u32 n_games, games_per_slot, visits;  // visits: the largest search budget of any seat (launch sizing)
+  u32 seat_visits[2], seat_cap_visits[2];  // seat_visits_ / seat_cap_visits_ (play_manager.cc:70-90)
+  u32 playout_cap, fast_search_uses_gumbel;
+  float playout_cap_percent, resign_percent, resign_playthrough_percent;
   float start_temp, final_temp, half_life;
   u32 history_enabled, policy_target_pruning, tree_reuse;
   float* st_canon;    // [n_games][max_turns][CANON]
@@ -74,17 +83,30 @@ __device__ __forceinline__ void sp_emit_canon(const TaflState& s, float* out, u3
     for (u32 c = lane; c < (u32)CELLS; c += 32u) out[pl * CELLS + c] = v;
   }
 }
-// MCTS::set_gumbel_num_sims(visits) on the tree of the seat to move, then under tree reuse the root temperature and
+// The reference flips its playout-cap and resign-playthrough coins with a thread_local std::default_random_engine seeded
+// from std::random_device (play_manager.cc:261-262): unseedable, so there is nothing to replay. Here every slot has its
+// OWN coin stream, separate from the stream that drives the search: at the deterministic corners (playout_cap_percent
+// 0 or 1, resign_playthrough_percent 0 or 1) a slot is then still the reference bit for bit, in between only the
+// coin values differ (tests/test_tafl_selfplay.py).
+__device__ __forceinline__ bool sp_coin(SpSlot& G, float p) { return rng_uniform01(G.coin) < p; }
+// the search budget of the seat to move (play_manager.cc:284-285)
+__device__ __forceinline__ u32 sp_goal(const SpView& S, const SpSlot& G, u32 cp) {
+  return G.capped ? S.seat_cap_visits[cp] : S.seat_visits[cp];
+}
+// MCTS::set_gumbel_num_sims on the tree of the seat to move — the full budget, or for a capped search the cap when
+// fast_search_uses_gumbel and 0 (= PUCT for this search) otherwise — then under tree reuse the root temperature and
 // fresh noise on a root that has been visited (play_manager.cc:523-553; also the first call of a run, 556-568)
-__device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, u32 tn, u32 lane, bool reused_root) {
+__device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, const SpSlot& G, u32 tn, u32 lane, bool reused_root) {
   if (lane == 0) {
-    if (F.gum) { F.gum[tn].num_sims_target = S.visits; fg_reset(F.gum[tn]); }
+    const u32 cp = tn & 1u;
+    const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[cp] : 0u) : S.seat_visits[cp];
+    if (F.gum) { F.gum[tn].num_sims_target = target; fg_reset(F.gum[tn]); }
     if (reused_root) {
       ForestTree& R = F.trees[tn];
       if (R.n > 0 && R.blk != 0) {
         u32* pool = F.pool + (size_t)tn * F.words_per_tree;
         fr_apply_root_policy_temp(F, pool, R.blk, R.k);
-        if (F.epsilon > 0.0f) {
+        if (F.epsilon > 0.0f && !G.capped) {
           Pcg32 rng = FOREST_RNG(F, tn);
           fr_add_root_noise(F, tn, rng, pool, R.blk, R.k);
           FOREST_RNG(F, tn) = rng;
@@ -101,9 +123,12 @@ __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
     SpSlot& G = S.slots[g];
     G.active = 1;
     G.games_started = 1;
-    // game.initialized = true; set_gumbel_num_sims on the first seat's tree (play_manager.cc:556-568)
-    const u32 t0 = 2u * g + F.trees[2u * g].state.player;
-    if (F.gum) { F.gum[t0].num_sims_target = S.visits; fg_reset(F.gum[t0]); }
+    pcg32_seed_stream(G.coin, seed + g, 0x5EEDC01ull);
+    // game.initialized = true; the first playout-cap coin; set_gumbel_num_sims on the first seat's tree (play_manager.cc:556-568)
+    G.capped = (S.playout_cap && sp_coin(G, S.playout_cap_percent)) ? 1u : 0u;
+    const u32 cp0 = F.trees[2u * g].state.player, t0 = 2u * g + cp0;
+    const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[cp0] : 0u) : S.seat_visits[cp0];
+    if (F.gum) { F.gum[t0].num_sims_target = target; fg_reset(F.gum[t0]); }
   }
 }
 
@@ -114,13 +139,15 @@ __global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_sp_search(ForestView 
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
-    const u32 t = 2u * g + F.trees[2u * g].state.player;
-    const bool noise = F.epsilon > 0.0f;  // seat_epsilon > 0 && !capped
-    for (u32 i = 0; i < n_sims; ++i) {
+    const u32 cp = F.trees[2u * g].state.player, t = 2u * g + cp;
+    const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;  // seat_epsilon > 0 && !capped
+    const u32 goal = sp_goal(S, S.slots[g], cp), have = F.trees[t].depth;
+    const u32 todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;  // this slot's own budget
+    for (u32 i = 0; i < todo; ++i) {
       forest_find_leaf<GAME, false>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr);
       forest_process_result<GAME, true, false>(F, t, nullptr, nullptr, lane, noise, F.trees[t].leaf);
     }
-    if (lane == 0) S.slots[g].simulations += n_sims;
+    if (lane == 0) S.slots[g].simulations += todo;
   }
 }
 // the evaluator-in-the-middle form of the same step (EvalType::NN): leaves' canonical planes out, (v, pi) rows in;
@@ -144,7 +171,7 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
     // forest_process_result reads row t of its inputs: hand it pointers moved so that row t is row g
     forest_process_result<GAME, false, false>(F, t, ev_v + (size_t)g * 3 - (size_t)t * 3,
                                               ev_pi + (size_t)g * Tafl<GAME>::A - (size_t)t * Tafl<GAME>::A, lane,
-                                              F.epsilon > 0.0f, F.trees[t].leaf);
+                                              F.epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf);
     if (lane == 0) S.slots[g].simulations += 1;
   }
 }
@@ -163,8 +190,9 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
     if (!G.active) continue;
     const u32 cp = F.trees[2u * g].state.player, t = 2u * g + cp;
     ForestTree& R = F.trees[t];
-    if (R.depth < S.visits) continue;  // mcts.depth() >= goal_depth
+    if (R.depth < sp_goal(S, G, cp)) continue;  // mcts.depth() >= goal_depth
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    const bool capped = G.capped != 0;
     // temperature schedule (play_manager.cc:285-302)
     float temp = S.start_temp;
     if (S.half_life != 0.0f) {
@@ -173,10 +201,36 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       temp = fmul(temp, az_expf(fmul(-lambda, (float)R.state.turn)));
       temp = fadd(temp, S.final_temp);
     }
-    // acting rule (play_manager.cc:372-416)
+    // resign_percent (play_manager.cc:305-333): MCTS::root_value (mcts.h:78-100) against 1 - resign_percent
+    u32 resign_term = 0;  // 1 + index of the score that would be awarded
+    if (S.resign_percent > 0.0f && !G.playthrough) {
+      if (lane == 0) {
+        float q = 0.0f, d = 0.0f;
+        bool found = false;
+        const u32 b = R.blk, k = b ? R.k : 0u;
+        for (u32 j = 0; j < k; ++j) {
+          const float qj = u2f(pool[fb_q(b, k) + j]);
+          if (pool[fb_n(b, k) + j] > 0 && qj > q) { q = qj; d = u2f(pool[fb_d(b, k) + j]); found = true; }
+        }
+        if (!found && R.n > 0) { q = R.v; d = R.d; }
+        const float w = fsub(q, fdiv(d, 2.0f));
+        const float l = (float)dsub(dsub(1.0, (double)w), (double)d);
+        const double resign_val = dsub(1.0, (double)S.resign_percent);
+        u32 tm = 0;
+        if ((double)w > resign_val) tm = cp + 1u;
+        else if ((double)l > resign_val) tm = ((cp + 1u) % 2u) + 1u;
+        else if ((double)d > resign_val) tm = 3u;
+        if (tm != 0) {
+          if (sp_coin(G, S.resign_playthrough_percent)) G.playthrough = 1;
+          else resign_term = tm;
+        }
+      }
+      resign_term = __shfl_sync(0xFFFFFFFFu, resign_term, 0);
+    }
+    // acting rule (play_manager.cc:367-406): Gumbel's final action only after a full search
     float* act = S.scratch_pi + (size_t)g * T::A;
     u32 chosen = 0xFFFFFFFFu;
-    if (F.gumbel_enabled) {
+    if (F.gumbel_enabled && !capped) {
       if (lane == 0) chosen = fg_final_action(F, t, R, F.gum[t], pool);
       chosen = __shfl_sync(0xFFFFFFFFu, chosen, 0);
       if (chosen == 0xFFFFFFFFu) {  // the search never initialised: pick_move(probs(0)) (mcts.cc:379-381)
@@ -187,8 +241,8 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       forest_probs<GAME>(F, t, temp, act, &G.picked, 1u, 0u, lane);
       chosen = G.picked;
     }
-    // training sample (play_manager.cc:417-435)
-    if (S.history_enabled) {
+    // training sample (play_manager.cc:407-424): full searches only
+    if (S.history_enabled && !capped) {
       const size_t row = (size_t)g * F.max_turns + G.pending;
       sp_emit_canon<GAME>(R.state, S.st_canon + row * T::CANON, lane);
       float* pi = S.st_pi + row * T::A;
@@ -203,10 +257,9 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       if (lane == 0) S.st_player[row] = (u8)cp;
     }
     if (lane == 0) {
-      if (S.history_enabled) G.pending += 1;
+      if (S.history_enabled && !capped) G.pending += 1;
       // metrics (play_manager.cc:436-446; MCTS::avg_leaf_depth mcts.h:112, normalized_root_entropy mcts.cc:737-750)
       const float ald = R.depth == 0 ? 0.0f : fdiv((float)R.total_leaf_depth, (float)R.depth);
-      G.g_leaf_depth += (double)ald;
       float ent = 0.0f;
       const u32 b = R.blk, k = b ? R.k : 0u;
       if (k > 1 && R.n > 1) {
@@ -221,8 +274,15 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
         }
         ent = fdiv(e, log_k);
       }
-      G.g_entropy += (double)ent;
-      G.full_move_count += 1;
+      if (!capped) {
+        G.g_leaf_depth += (double)ald;
+        G.g_entropy += (double)ent;
+        G.full_move_count += 1;
+      } else {
+        G.g_fast_leaf_depth += (double)ald;
+        G.g_fast_entropy += (double)ent;
+        G.fast_move_count += 1;
+      }
       G.g_valid_moves += (double)k;
       G.move_count += 1;
     }
@@ -234,7 +294,9 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
     forest_update_root<GAME>(F, 2u * g + 1u, chosen, sm[wib], lane);
     __syncwarp();
     const TaflState ns = F.trees[2u * g].state;
-    const u32 term = T::terminal(ns);
+    u32 term = T::terminal(ns);
+    if (term == 0 && resign_term != 0) term = resign_term;  // play_manager.cc:440-444
+    else resign_term = 0;
     if (term != 0) {
       const float s0 = term == 1 ? 1.0f : 0.0f, s1 = term == 2 ? 1.0f : 0.0f, sd = term == 3 ? 1.0f : 0.0f;
       if (S.history_enabled) {
@@ -258,11 +320,17 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       if (lane == 0) {
         G.pending = 0;
         G.scores[0] = fadd(G.scores[0], s0); G.scores[1] = fadd(G.scores[1], s1); G.scores[2] = fadd(G.scores[2], sd);
+        if (resign_term != 0) {
+          G.resign_scores[0] = fadd(G.resign_scores[0], s0); G.resign_scores[1] = fadd(G.resign_scores[1], s1);
+          G.resign_scores[2] = fadd(G.resign_scores[2], sd);
+        }
         G.games_completed += 1;
         G.game_length += ns.turn;
         G.leaf_depth += G.g_leaf_depth; G.entropy += G.g_entropy; G.valid_moves += G.g_valid_moves;
         G.total_move_count += G.move_count; G.total_full_move_count += G.full_move_count;
+        G.fast_leaf_depth += G.g_fast_leaf_depth; G.fast_entropy += G.g_fast_entropy; G.total_fast_move_count += G.fast_move_count;
         G.g_leaf_depth = 0; G.g_entropy = 0; G.g_valid_moves = 0; G.move_count = 0; G.full_move_count = 0;
+        G.g_fast_leaf_depth = 0; G.g_fast_entropy = 0; G.fast_move_count = 0;
         if (G.games_started >= S.games_per_slot) {
           G.active = 0;  // `continue`: the slot is not pushed back
           retire = true;
@@ -280,6 +348,9 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       __syncwarp();
       if (retire) continue;
     }
+    // a move has been played: the next search's playout cap (play_manager.cc:523-524; `&&` short-circuits the coin)
+    if (lane == 0) G.capped = (S.playout_cap && sp_coin(G, S.playout_cap_percent)) ? 1u : 0u;
+    __syncwarp();
     const u32 tn = 2u * g + F.trees[2u * g].state.player;
     if (!S.tree_reuse) {
       // set_gumbel_num_sims happens BEFORE the trees are replaced by fresh MCTS objects (play_manager.cc:531-545), so
@@ -287,14 +358,20 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       if (lane == 0) { sp_reset_search(F, 2u * g); sp_reset_search(F, 2u * g + 1u); }
       __syncwarp();
     } else {
-      sp_arm(F, S, tn, lane, true);
+      sp_arm(F, S, G, tn, lane, true);
     }
   }
 }
-__global__ void k_sp_count_active(SpView S, u32* out) {
-  u32 c = 0;
-  for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) c += S.slots[g].active ? 1u : 0u;
+// out[0] = active slots, out[1] = OR of every tree's sticky error bits (a search on a full slab is a search on a wrong
+// tree: the calls that synchronise report it instead of returning 0)
+__global__ void k_sp_count_active(ForestView F, SpView S, u32* out) {
+  u32 c = 0, err = 0;
+  for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) {
+    c += S.slots[g].active ? 1u : 0u;
+    err |= F.trees[2u * g].error | F.trees[2u * g + 1u].error | (S.slots[g].error ? 0x100u : 0u);
+  }
   if (c) atomicAdd(out, c);
+  if (err) atomicOr(out + 1, err);
 }
 #endif  // !B2AZ_HOST_EMU
 
@@ -329,10 +406,20 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   using namespace b2az;
   if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
   if (p->n_games == 0 || p->n_games > 0x7FFFFFFFu / 2u) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: bad n_games");
-  if (p->games_per_slot == 0 || p->visits == 0) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: games_per_slot and visits must be positive");
+  if (p->games_per_slot == 0 || (p->visits == 0 && (p->seat_visits[0] == 0 || p->seat_visits[1] == 0)))
+    return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: games_per_slot and visits must be positive");
   if (p->forest.max_in_flight != 0) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: PlayManager runs one leaf per game (max_in_flight must be 0)");
   b2az_forest_params fp = p->forest;
   fp.n_trees = 2u * p->n_games;
+  if (fp.words_per_tree == 0) {
+    // sized from the search: each half of a tree's slab holds the kept subtree plus one search's new nodes; an expanded
+    // node is 1 + 8 k words. Budget 8 x visits nodes at a typical branching (Brandubh 64, 11x11 boards 200) per half —
+    // a search that outgrows it is reported as B2AZ_ENOMEM by the calls that synchronise, never silently truncated.
+    const uint64_t k_typ = p->forest.game == B2AZ_TAFL_BRANDUBH ? 64u : 200u;
+    const uint64_t vmax = std::max<uint64_t>(p->visits, std::max(p->seat_visits[0], p->seat_visits[1]));
+    const uint64_t want = 2ull * (1ull + 8ull * vmax * (1ull + 8ull * k_typ));
+    fp.words_per_tree = (uint32_t)std::min<uint64_t>(want, 1ull << 26);
+  }
   b2az_forest* f = nullptr;
   if (int rc = b2az_forest_create(&fp, device, &f)) return rc;
 #ifdef B2AZ_HOST_EMU
@@ -343,7 +430,16 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   f->view.rng_pair = 1;
   SpView& S = sp->view;
   memset(&S, 0, sizeof(S));
-  S.n_games = p->n_games; S.games_per_slot = p->games_per_slot; S.visits = p->visits;
+  S.n_games = p->n_games; S.games_per_slot = p->games_per_slot;
+  for (int seat = 0; seat < 2; ++seat) {
+    S.seat_visits[seat] = p->seat_visits[seat] ? p->seat_visits[seat] : p->visits;
+    S.seat_cap_visits[seat] = p->seat_cap_visits[seat] ? p->seat_cap_visits[seat] : (p->playout_cap_depth ? p->playout_cap_depth : 25u);
+  }
+  S.visits = std::max(std::max(S.seat_visits[0], S.seat_visits[1]), std::max(S.seat_cap_visits[0], S.seat_cap_visits[1]));
+  S.playout_cap = p->playout_cap_randomization ? 1u : 0u;
+  S.fast_search_uses_gumbel = p->fast_search_uses_gumbel ? 1u : 0u;
+  S.playout_cap_percent = p->playout_cap_percent;
+  S.resign_percent = p->resign_percent; S.resign_playthrough_percent = p->resign_playthrough_percent;
   S.start_temp = p->start_temp; S.final_temp = p->final_temp; S.half_life = p->temp_decay_half_life;
   S.history_enabled = p->history_enabled ? 1u : 0u;
   S.policy_target_pruning = p->policy_target_pruning ? 1u : 0u;
@@ -363,7 +459,7 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
     if (int rc = dev_alloc_raw(&S.out_slot, (size_t)S.out_cap)) return bail(rc);
   }
   if (int rc = dev_alloc(&S.out_count, 1)) return bail(rc);
-  if (int rc = dev_alloc(&sp->active_dev, 1)) return bail(rc);
+  if (int rc = dev_alloc(&sp->active_dev, 2)) return bail(rc);
   k_sp_init<<<148, 128>>>(f->view, S, p->forest.seed);
   if (cudaGetLastError() != cudaSuccess) return bail(fail(B2AZ_ECUDA, "k_sp_init launch failed"));
   if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B2AZ_ECUDA, "k_sp_init failed"));
@@ -386,11 +482,19 @@ int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay*, void*, const uint32
 static int sp_active(b2az_tafl_selfplay* sp, cudaStream_t s, uint32_t* active_out) {
   using namespace b2az;
   if (!active_out) return 0;
-  CUDA_TRY(cudaMemsetAsync(sp->active_dev, 0, 4, s));
-  k_sp_count_active<<<148, 128, 0, s>>>(sp->view, sp->active_dev);
+  uint32_t host[2] = {0, 0};
+  CUDA_TRY(cudaMemsetAsync(sp->active_dev, 0, 8, s));
+  k_sp_count_active<<<148, 128, 0, s>>>(sp->forest->view, sp->view, sp->active_dev);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(active_out, sp->active_dev, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(host, sp->active_dev, 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  *active_out = host[0];
+  if (host[1] & (1u | 4u | 16u))
+    return fail(B2AZ_ENOMEM, "tafl self-play: a tree's node slab is full (the search went on on a truncated tree): raise "
+                             "b2az_forest_params.words_per_tree");
+  if (host[1] & 0x100u) return fail(B2AZ_ENOMEM, "tafl self-play: the training-sample ring is full: drain more often or raise hist_capacity");
+  if (host[1] & 2u) return fail(B2AZ_ESTATE, "tafl self-play: selection path longer than the path buffer");
+  if (host[1] & 8u) return fail(B2AZ_EMOVE, "tafl self-play: update_root could not find the move");
   return 0;
 }
 int b2az_tafl_selfplay_play(b2az_tafl_selfplay* sp, void* stream, uint32_t n_moves, uint32_t* active_out) {
@@ -434,6 +538,7 @@ int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay* sp, void* stream, cons
     }
     CUDA_TRY(cudaMemcpyAsync(sp->ev_v, v, G * 3 * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(sp->ev_pi, pi, G * f->actions * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));  // b2az.h: calls taking host buffers synchronise before returning (pinned buffers!)
     v = sp->ev_v; pi = sp->ev_pi;
   }
   FOREST_DISPATCH(f, (k_sp_process_result<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, v, pi)));
@@ -491,9 +596,11 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
     if (e & 2u) out->device_error |= B2AZ_DEVERR_DEPTH;
     if (e & 8u) out->device_error |= B2AZ_DEVERR_MOVE;
   }
-  double leaf_depth = 0, entropy = 0, valid = 0;
-  uint64_t moves = 0, full = 0, length = 0;
+  double leaf_depth = 0, entropy = 0, valid = 0, fast_depth = 0, fast_entropy = 0;
+  uint64_t moves = 0, full = 0, length = 0, fast = 0;
   for (const SpSlot& g : sp->h_slots) {
+    for (int i = 0; i < 3; ++i) out->resign_scores[i] += g.resign_scores[i];
+    fast_depth += g.fast_leaf_depth; fast_entropy += g.fast_entropy; fast += g.total_fast_move_count;
     out->simulations += g.simulations;
     out->games_completed += g.games_completed;
     out->games_started += g.games_started;
@@ -510,6 +617,11 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
     out->avg_leaf_depth = (float)(leaf_depth / (double)full);
     out->avg_search_entropy = (float)(entropy / (double)full);
   }
+  if (fast) {
+    out->fast_avg_leaf_depth = (float)(fast_depth / (double)fast);
+    out->fast_avg_search_entropy = (float)(fast_entropy / (double)fast);
+  }
+  out->fast_move_count = fast; out->fast_sum_leaf_depth = fast_depth; out->fast_sum_search_entropy = fast_entropy;
   if (length) out->avg_moves_per_turn = (float)moves / (float)length;
   if (moves) out->avg_valid_moves = (float)(valid / (double)moves);
   out->sum_game_length = length;

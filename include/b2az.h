@@ -380,17 +380,30 @@ typedef struct b2az_tafl_selfplay_params {
   float start_temp, final_temp, temp_decay_half_life;  /* play_manager.cc:285-302 */
   uint8_t history_enabled, policy_target_pruning, tree_reuse, pad_;
   uint32_t hist_capacity;        /* rows of the training-sample ring between drains; 0 = n_games * max_turns */
+  uint32_t seat_visits[2];       /* per-seat search budget (seat_visits, play_manager.cc:70-80); 0 = visits */
+  uint32_t seat_cap_visits[2];   /* per-seat fast-search budget (seat_cap_visits, :82-90); 0 = playout_cap_depth */
+  uint32_t playout_cap_depth;    /* PlayParams::playout_cap_depth (25) */
+  float playout_cap_percent;     /* PlayParams::playout_cap_percent */
+  float resign_percent, resign_playthrough_percent;  /* play_manager.cc:305-333 */
+  uint8_t playout_cap_randomization; /* fast searches: no sample, no root noise, PUCT acting (play_manager.cc:523-553) */
+  uint8_t fast_search_uses_gumbel;
+  uint8_t pad2_[2];
 } b2az_tafl_selfplay_params;
 typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
   uint32_t active, games_started, games_completed, pending;
   uint32_t move_count, full_move_count;                          /* current game */
   uint32_t total_move_count, total_full_move_count, game_length; /* finished games */
-  uint32_t picked, error, pad_;                                  /* error: 1 = sample ring full (samples dropped) */
+  uint32_t picked, error, capped;                                /* error: 1 = sample ring full (samples dropped) */
   double g_leaf_depth, g_entropy, g_valid_moves;                 /* current game */
   double leaf_depth, entropy, valid_moves;                       /* total_avg_leaf_depth_, total_search_entropy_, total_valid_moves_ */
   unsigned long long simulations;
   float scores[3];                                               /* scores_: seat 0 wins, seat 1 wins, draws */
-  uint32_t pad2_;
+  uint32_t playthrough;
+  uint32_t fast_move_count, total_fast_move_count;               /* capped (fast) searches */
+  double g_fast_leaf_depth, g_fast_entropy, fast_leaf_depth, fast_entropy;
+  float resign_scores[3];                                        /* resign_scores_ */
+  uint32_t pad3_;
+  uint64_t coin_state, coin_inc;                                 /* the slot's coin stream (playout cap, resign playthrough) */
 } b2az_tafl_selfplay_slot;
 typedef struct b2az_tafl_selfplay b2az_tafl_selfplay;
 int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2az_tafl_selfplay** out);

@@ -335,6 +335,11 @@ struct AzRefTaflSpCfg {
   uint32_t gumbel_m;
   float gumbel_c_visit, gumbel_c_scale;
   uint8_t root_fpu_zero, shaped_dirichlet, policy_target_pruning, gumbel_enabled, tree_reuse, history_enabled, pad_[2];
+  // per-seat budgets, playout-cap randomisation and resignation (0 / false = the reference's defaults)
+  uint32_t seat_visits[2], seat_cap_visits[2];
+  uint32_t playout_cap_depth;
+  float playout_cap_percent, resign_percent, resign_playthrough_percent;
+  uint8_t playout_cap_randomization, fast_search_uses_gumbel, pad2_[2];
 };
 int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRefTaflSpCfg* c, uint32_t hist_cap,
                         float* canon_out, float* v_out, float* pi_out, uint32_t* n_hist, float* scores3,
@@ -366,8 +371,14 @@ int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRef
     p.history_enabled = c->history_enabled != 0;
     p.self_play = true;
     p.model_groups = {0, 0};
-    p.playout_cap_randomization = false;
-    p.resign_percent = 0.0f;
+    p.playout_cap_randomization = c->playout_cap_randomization != 0;
+    if (c->playout_cap_depth) p.playout_cap_depth = c->playout_cap_depth;
+    p.playout_cap_percent = c->playout_cap_percent;
+    p.fast_search_uses_gumbel = c->fast_search_uses_gumbel != 0;
+    p.resign_percent = c->resign_percent;
+    p.resign_playthrough_percent = c->resign_playthrough_percent;
+    if (c->seat_visits[0] && c->seat_visits[1]) p.seat_visits = {{c->seat_visits[0], c->seat_visits[1]}};
+    if (c->seat_cap_visits[0] && c->seat_cap_visits[1]) p.seat_cap_visits = {{c->seat_cap_visits[0], c->seat_cap_visits[1]}};
     p.eval_type = {EvalType::RANDOM, EvalType::RANDOM};
     PlayManager pm{std::move(gs), p};
     MCTS::seed_thread_rng(seed);
@@ -391,6 +402,12 @@ int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRef
     metrics4[1] = pm.avg_leaf_depth();
     metrics4[2] = pm.avg_valid_moves();
     metrics4[3] = pm.avg_search_entropy();
+    // (the array is 10 floats long on the Python side) fast-search metrics and resign scores
+    metrics4[4] = pm.fast_avg_leaf_depth();
+    metrics4[5] = pm.fast_avg_search_entropy();
+    auto rs = pm.resign_scores();
+    for (int i = 0; i < 3; ++i) metrics4[6 + i] = rs(i);
+    metrics4[9] = pm.avg_moves_per_turn();
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -39,12 +39,17 @@ class SelfplayCfg(C.Structure):  # AzRefTaflSpCfg (oracle/ref_tafl_driver.cc)
                 ("temp_decay_half_life", C.c_float), ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float),
                 ("gumbel_c_scale", C.c_float), ("root_fpu_zero", C.c_uint8), ("shaped_dirichlet", C.c_uint8),
                 ("policy_target_pruning", C.c_uint8), ("gumbel_enabled", C.c_uint8), ("tree_reuse", C.c_uint8),
-                ("history_enabled", C.c_uint8), ("pad_", C.c_uint8 * 2)]
+                ("history_enabled", C.c_uint8), ("pad_", C.c_uint8 * 2), ("seat_visits", C.c_uint32 * 2),
+                ("seat_cap_visits", C.c_uint32 * 2), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
+                ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
+                ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2)]
 
 
 def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, epsilon=0.0,
              root_policy_temp=1.0, shaped_dirichlet=False, policy_target_pruning=False, gumbel_m=0, gumbel_c_visit=50.0,
-             gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0, tree_reuse=True):
+             gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0, tree_reuse=True,
+             seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
+             playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0):
     """The unmodified PlayManager, one slot, games_to_play games one after the other (EvalType::RANDOM) after
     MCTS::seed_thread_rng(seed). Returns dict(canonical, v, pi in history_ order, scores, games_completed,
     avg_game_length, avg_leaf_depth, avg_valid_moves, avg_search_entropy)."""
@@ -55,11 +60,18 @@ def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduc
                       temp_decay_half_life=temp_decay_half_life, gumbel_m=gumbel_m or 16, gumbel_c_visit=gumbel_c_visit,
                       gumbel_c_scale=gumbel_c_scale, root_fpu_zero=int(root_fpu_zero), shaped_dirichlet=int(shaped_dirichlet),
                       policy_target_pruning=int(policy_target_pruning), gumbel_enabled=int(gumbel_m > 0),
-                      tree_reuse=int(tree_reuse), history_enabled=1)
+                      tree_reuse=int(tree_reuse), history_enabled=1, playout_cap_depth=playout_cap_depth,
+                      playout_cap_percent=playout_cap_percent, resign_percent=resign_percent,
+                      resign_playthrough_percent=resign_playthrough_percent,
+                      playout_cap_randomization=int(playout_cap_randomization),
+                      fast_search_uses_gumbel=int(fast_search_uses_gumbel))
+    for seat in range(2):
+        cfg.seat_visits[seat] = (seat_visits or (0, 0))[seat]
+        cfg.seat_cap_visits[seat] = (seat_cap_visits or (0, 0))[seat]
     canon = np.zeros((cap, P, S, S), np.float32)
     v, pi = np.zeros((cap, 3), np.float32), np.zeros((cap, A), np.float32)
     n, done = C.c_uint32(0), C.c_uint32(0)
-    scores, metrics = np.zeros(3, np.float32), np.zeros(4, np.float32)
+    scores, metrics = np.zeros(3, np.float32), np.zeros(10, np.float32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib().azref_tafl_selfplay(game, max_turns, seed, C.byref(cfg), cap, p(canon), p(v), p(pi),
                                    C.cast(C.byref(n), C.c_void_p), p(scores), C.cast(C.byref(done), C.c_void_p), p(metrics))
@@ -68,7 +80,8 @@ def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduc
     k = n.value
     return dict(canonical=canon[:k], v=v[:k], pi=pi[:k], scores=scores, games_completed=done.value,
                 avg_game_length=metrics[0], avg_leaf_depth=metrics[1], avg_valid_moves=metrics[2],
-                avg_search_entropy=metrics[3])
+                avg_search_entropy=metrics[3], fast_avg_leaf_depth=metrics[4], fast_avg_search_entropy=metrics[5],
+                resign_scores=metrics[6:9].copy(), avg_moves_per_turn=metrics[9])
 
 
 def dims(game):

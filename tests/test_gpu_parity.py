@@ -278,3 +278,50 @@ def test_full_size_properties():
     assert st.games_completed == 0 and len(canon) == 0
     st2, _ = run(1201)
     assert (st2.simulations, st2.moves, st2.pool_pages_free) == (st.simulations, st.moves, st.pool_pages_free)
+
+
+def test_engine_driven_from_a_fresh_thread_on_another_device():
+    """The CUDA current device is per host thread (a new Python thread starts on device 0): every C-ABI entry point binds
+    the engine's device itself. Create the engine on the LAST device and drive it — steps, leaf batches, evaluations,
+    history, statistics, peeks — from a thread that never called cudaSetDevice."""
+    import threading
+
+    import torch
+
+    dev = torch.cuda.device_count() - 1
+    eng = ph.make_engine(None, 96, 96, 24, b2az.EVAL_NN, b2az.RNG_PER_GAME, 5, device=dev, history_capacity=96 * 42,
+                         max_cache_size=50000, **ph.level_params(1))
+    out = {}
+
+    def drive():
+        try:
+            while True:
+                eng.step(1)
+                ids, canon = eng.leaf_batch_host()
+                if len(ids) == 0:
+                    break
+                v, pi = ph.fake_net(canon)
+                eng.submit_eval_host(ids, v, pi)
+            out["peek"] = eng.peek(0, 0)
+            out["stats"] = eng.stats()
+            out["hist"] = eng.drain_history(96 * 42)
+        except Exception as ex:  # noqa: BLE001
+            out["error"] = repr(ex)
+
+    t = threading.Thread(target=drive)
+    t.start()
+    t.join(timeout=300)
+    assert not t.is_alive() and "error" not in out, out.get("error")
+    assert out["stats"].games_completed == 96 and out["stats"].device_error == 0 and len(out["hist"][0]) > 500
+    eng.close()
+    ref = ph.make_engine(None, 96, 96, 24, b2az.EVAL_NN, b2az.RNG_PER_GAME, 5, device=0, history_capacity=96 * 42,
+                         max_cache_size=50000, **ph.level_params(1))
+    while True:
+        ref.step(1)
+        ids, canon = ref.leaf_batch_host()
+        if len(ids) == 0:
+            break
+        v, pi = ph.fake_net(canon)
+        ref.submit_eval_host(ids, v, pi)
+    ph.compare_history(out["hist"], ref.drain_history(96 * 42), ordered=False)
+    ref.close()

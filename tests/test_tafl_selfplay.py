@@ -88,6 +88,74 @@ def test_selfplay_equals_the_reference_playmanager(name):
         assert s["simulations"] == visits * s["total_move_count"]
 
 
+# Per-seat budgets, playout-cap randomisation and resignation against the unmodified reference. The reference flips its
+# playout-cap / playthrough coins with an unseedable engine (play_manager.cc:261-262), so the bit-exact cases sit at
+# the deterministic corners: every search capped (percent 1) or none (0), every resignation honoured (playthrough 0) or
+# none (1). In between only the coin VALUES differ (this engine has its own coin stream per slot, apart from the search's).
+FEATURE_CASES = {
+    "brandubh_seat_visits": (0, 5, 2, 40, dict(seat_visits=(48, 24), epsilon=0.25, root_policy_temp=1.25, policy_target_pruning=True)),
+    "brandubh_all_capped_puct": (0, 4, 2, 40, dict(playout_cap_randomization=True, playout_cap_percent=1.0, playout_cap_depth=12,
+                                                   epsilon=0.25, start_temp=1.0, final_temp=0.3, temp_decay_half_life=8.0)),
+    "brandubh_all_capped_gumbel_fast": (0, 4, 2, 40, dict(playout_cap_randomization=True, playout_cap_percent=1.0,
+                                                          seat_cap_visits=(16, 20), gumbel_m=8, fast_search_uses_gumbel=True)),
+    "brandubh_all_capped_gumbel_puct_fast": (0, 4, 1, 40, dict(playout_cap_randomization=True, playout_cap_percent=1.0,
+                                                               playout_cap_depth=14, gumbel_m=8, epsilon=0.25)),
+    "brandubh_never_capped": (0, 4, 1, 40, dict(playout_cap_randomization=True, playout_cap_percent=0.0, playout_cap_depth=12,
+                                                gumbel_m=16)),
+    "brandubh_resign_always": (0, 6, 2, 60, dict(resign_percent=0.62, resign_playthrough_percent=0.0, epsilon=0.25)),
+    "brandubh_resign_playthrough_always": (0, 4, 1, 40, dict(resign_percent=0.62, resign_playthrough_percent=1.0)),
+    "tawlbwrdd_seat_visits_resign": (2, 3, 1, 24, dict(seat_visits=(40, 28), resign_percent=0.62, resign_playthrough_percent=0.0)),
+}
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("name", sorted(FEATURE_CASES))
+def test_selfplay_features_equal_the_reference_at_the_deterministic_corners(name):
+    game, slots, per_slot, max_turns, kw = FEATURE_CASES[name]
+    visits = 40
+    seed = 4000 + 13 * sorted(FEATURE_CASES).index(name)
+    canon, v, pi, slot, st = run_device(game, slots, per_slot, max_turns, visits, kw, seed)
+    resigned = 0.0
+    for g in range(slots):
+        ref = tafl_ref.selfplay(game, seed + g, max_turns, per_slot, visits, **kw)
+        rows = slot == g
+        assert rows.sum() == len(ref["v"]), f"{name} slot {g}: {rows.sum()} samples vs {len(ref['v'])}"
+        assert np.array_equal(canon[rows].view(np.uint32), ref["canonical"].view(np.uint32)), f"{name} slot {g}: canonical"
+        assert np.array_equal(v[rows].view(np.uint32), ref["v"].view(np.uint32)), f"{name} slot {g}: outcomes"
+        assert np.array_equal(pi[rows].view(np.uint32), ref["pi"].view(np.uint32)), f"{name} slot {g}: policy targets"
+        s = st[g]
+        assert s["games_completed"] == ref["games_completed"] == per_slot and s["active"] == 0
+        assert np.array_equal(s["scores"], ref["scores"]) and np.array_equal(s["resign_scores"], ref["resign_scores"])
+        assert f32(f32(s["game_length"]) / f32(s["games_completed"])) == ref["avg_game_length"]
+        if s["total_full_move_count"]:
+            assert f32(s["leaf_depth"] / float(s["total_full_move_count"])) == ref["avg_leaf_depth"]
+            assert f32(s["entropy"] / float(s["total_full_move_count"])) == ref["avg_search_entropy"]
+        if s["total_fast_move_count"]:
+            assert f32(s["fast_leaf_depth"] / float(s["total_fast_move_count"])) == ref["fast_avg_leaf_depth"]
+            assert f32(s["fast_entropy"] / float(s["total_fast_move_count"])) == ref["fast_avg_search_entropy"]
+        assert f32(s["valid_moves"] / float(s["total_move_count"])) == ref["avg_valid_moves"]
+        resigned += float(s["resign_scores"].sum())
+    if "all_capped" in name:
+        assert len(v) == 0 and (st["total_fast_move_count"] == st["total_move_count"]).all(), "capped searches record nothing"
+    if name == "brandubh_resign_always":
+        assert resigned > 0, "pick a resign_percent that triggers"
+    if "playthrough_always" in name:
+        assert resigned == 0 and (st["playthrough"] == 1).any()
+
+
+@pytest.mark.gpu
+def test_selfplay_playout_cap_mix_statistics():
+    """Between the corners the coins are this engine's own: 75 % of the searches are fast ones (no sample, cap budget),
+    and the simulation count is exactly what the full / fast move counts say."""
+    game, slots, max_turns, visits, cap = 0, 256, 40, 40, 10
+    kw = dict(playout_cap_randomization=True, playout_cap_percent=0.75, playout_cap_depth=cap, epsilon=0.25, gumbel_m=0)
+    canon, v, pi, slot, st = run_device(game, slots, 1, max_turns, visits, kw, 99)
+    full, fast, total = int(st["total_full_move_count"].sum()), int(st["total_fast_move_count"].sum()), int(st["total_move_count"].sum())
+    assert full + fast == total and 0.70 < fast / total < 0.80
+    assert len(v) == full and int(st["simulations"].sum()) == full * visits + fast * cap
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_selfplay_equals_the_golden_fixture(name):
