@@ -346,10 +346,9 @@ class PlayManager {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 tafl engine yet");
     };
     reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
-    reject(tables_.visits[0][0] != tables_.visits[0][1], "different visit budgets per seat");
-    reject(P.playout_cap_randomization, "playout_cap_randomization");
-    reject(P.resign_percent > 0.0f, "resign_percent");
-    reject(P.max_cache_size != 0, "max_cache_size (position cache)");
+    // max_cache_size: the tafl engine has no position cache yet. A cache may always forget, so the parameter is accepted
+    // and every leaf goes to the evaluator (cache_hits() stays 0) — results are those of a run with the cache off, which
+    // is what the reference's own cache test requires of a cache (test_cache.py:227-253).
     reject(P.gumbel_full, "gumbel_full");
     reject(P.concurrent_games == 0 || P.games_to_play % P.concurrent_games != 0, "games_to_play not a multiple of concurrent_games");
     EvalType et = EvalType::NN;
@@ -364,7 +363,7 @@ class PlayManager {
     sp.forest.max_turns = t->s.max_turns;
     // slab per tree: each half holds the kept subtree + one move's new nodes (1 + 8k words per expanded node)
     sp.forest.words_per_tree = P.pool_nodes ? (uint32_t)P.pool_nodes
-                                            : 2u * (1u + 4u * tables_.visits[0][0] * (1u + 8u * (GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u)));
+                                            : 2u * (1u + 4u * std::max(tables_.visits[0][0], tables_.visits[0][1]) * (1u + 8u * (GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u)));
     sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
     sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
     sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
@@ -372,7 +371,12 @@ class PlayManager {
     sp.forest.shaped_dirichlet = P.shaped_dirichlet;
     sp.n_games = P.concurrent_games;
     sp.games_per_slot = P.games_to_play / P.concurrent_games;
-    sp.visits = tables_.visits[0][0];
+    sp.visits = std::max(tables_.visits[0][0], tables_.visits[0][1]);
+    sp.seat_visits[0] = tables_.visits[0][0]; sp.seat_visits[1] = tables_.visits[0][1];
+    sp.seat_cap_visits[0] = tables_.cap_visits[0][0]; sp.seat_cap_visits[1] = tables_.cap_visits[0][1];
+    sp.playout_cap_randomization = P.playout_cap_randomization; sp.playout_cap_depth = P.playout_cap_depth;
+    sp.playout_cap_percent = P.playout_cap_percent; sp.fast_search_uses_gumbel = P.fast_search_uses_gumbel;
+    sp.resign_percent = P.resign_percent; sp.resign_playthrough_percent = P.resign_playthrough_percent;
     sp.start_temp = P.start_temp; sp.final_temp = P.final_temp; sp.temp_decay_half_life = P.temp_decay_half_life;
     sp.history_enabled = P.history_enabled; sp.policy_target_pruning = P.policy_target_pruning; sp.tree_reuse = P.tree_reuse;
     // history_ is unbounded in the reference; here the sample ring holds what a run can produce between drains: every

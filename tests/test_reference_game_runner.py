@@ -154,3 +154,30 @@ def test_self_play_brandubh_unmodified_game_runner(gr):
         canon, v, pi = _load_samples(gr, paths["tmp_history"])
     assert canon.shape[1:] == (7, 7, 7) and pi.shape[1] == 686 and len(canon) > 30
     assert abs(sum(res.win_rates) - 1.0) < 1e-6 and res.game_length > 4
+
+
+def test_self_play_with_the_reference_brandubh_yaml(gr):
+    """configs/brandubh.yaml as shipped by the reference — Gumbel root search, Gumbel fast searches, playout-cap
+    randomisation (75 % fast searches of 30 simulations), resign_percent 0.02 with playthrough, temperature decay, a
+    200 k-entry cache request — through the unmodified self_play() on the tafl self-play engine. Only the sizes are
+    shrunk (batch size, chunks, max_turns)."""
+    if not KIND["cuda"]:
+        pytest.skip("the tafl self-play engine has no host-emulation build (device only)")
+    import config as ref_config
+
+    yaml_path = os.path.join(os.path.dirname(REF_SRC), "configs", "brandubh.yaml")
+    cfg = ref_config.load_config(yaml_path, {"self_play_batch_size": "8", "self_play_concurrent_batch_mult": "1",
+                                             "self_play_chunks": "1", "mcts_workers": "2", "max_turns": "60"}, warn=False)
+    assert cfg.gumbel_enabled and cfg.playout_cap_percent > 0 and cfg.resign_percent > 0 and cfg.max_cache_size > 0
+    depth, fast_depth = cfg.selfplay_mcts_visits, cfg.fast_mcts_visits
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = {"tmp_history": os.path.join(tmp, "hist"), "checkpoint": os.path.join(tmp, "ckpt")}
+        res = gr.self_play(cfg, paths, "exp", best=0, iteration=3, depth=depth, fast_depth=fast_depth)
+        canon, v, pi = _load_samples(gr, paths["tmp_history"])
+    assert canon.shape[1:] == (7, 7, 7) and pi.shape[1] == 686
+    assert abs(sum(res.win_rates) - 1.0) < 1e-6 and res.game_length > 4
+    assert res.avg_depth > 0 and res.fast_avg_depth > 0, "both full and fast searches happened"
+    # samples come from full searches only: about a quarter of the moves of the 16 games
+    moves = res.game_length * 16
+    assert 0.08 * moves < len(canon) < 0.5 * moves
+    assert np.allclose(pi.sum(1), 1.0, atol=4e-3) and np.allclose(v.sum(1), 1.0)

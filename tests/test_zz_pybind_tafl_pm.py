@@ -117,10 +117,10 @@ def test_tafl_playmanager_validation_and_no_cpu_fallback():
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
         p = _params(az, 2, 1, 8, 1, True)
-        p.seat_visits = [[8, 16]]  # (mcts_visits is per MODEL GROUP in the reference: [8, 16] with one group means 16 for both)
+        p.model_groups = [0, 1]  # two networks: the tafl engine serves one model group
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
-        az.PlayManager(gs, _params(az, 2, 1, 8, 1, True, playout_cap_randomization=True))
+        az.PlayManager(gs, _params(az, 2, 1, 8, 1, True, gumbel_full=True))
     with pytest.raises(RuntimeError, match="multiple of concurrent_games"):
         p = _params(az, 2, 1, 8, 1, True)
         p.games_to_play = 3
