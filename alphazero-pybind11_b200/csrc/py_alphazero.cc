@@ -38,6 +38,7 @@
 #include "../../include/b2az.h"
 #include "az_connect4.h"
 #include "az_tafl.h"
+#include "az_stargambit.h"
 #include "py_s3fifo.h"
 #include <random>
 #include <algorithm>
@@ -169,6 +170,7 @@ class Connect4GS : public GameState {  // connect4_gs.h:24-92
 };
 
 #include "py_tafl_gs.h"  // BrandubhGS / OpenTaflGS / TawlbwrddGS
+#include "py_stargambit_gs.h"  // StarGambit{Skirmish,Showdown,Clash,Battle}GS, StarGambitUnifiedGS (+ pinned subclasses)
 
 // ------------------------------------------------------------------------------------ PlayParams
 enum class EvalType : uint8_t { NN = 0, RANDOM = 1, PLAYOUT = 2 };
@@ -869,6 +871,7 @@ PYBIND11_MODULE(alphazero, m) {
   bind_tafl_gs<BrandubhGS>(m, "BrandubhGS");    // py_wrapper.cc:527-536
   bind_tafl_gs<OpenTaflGS>(m, "OpenTaflGS");    // py_wrapper.cc:538-547
   bind_tafl_gs<TawlbwrddGS>(m, "TawlbwrddGS");  // py_wrapper.cc:549-558
+  bind_star_gambit(m);                         // py_wrapper.cc:589-695
 
   py::enum_<EvalType>(m, "EvalType").value("NN", EvalType::NN).value("RANDOM", EvalType::RANDOM).value("PLAYOUT", EvalType::PLAYOUT);
 

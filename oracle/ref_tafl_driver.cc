@@ -31,6 +31,7 @@
 #include "play_manager.h"
 #include "opentafl_gs.cc"
 #include "tawlbwrdd_gs.cc"
+#include "star_gambit_gs.h"  // Star Gambit: star_gambit_gs.o is linked in (its header has no non-inline definitions)
 
 using namespace alphazero;
 
@@ -42,6 +43,14 @@ std::unique_ptr<GameState> make_game(int game, uint16_t max_turns) {
     case 0: return std::make_unique<brandubh_gs::BrandubhGS>(max_turns);
     case 1: return std::make_unique<opentafl_gs::OpenTaflGS>(max_turns);
     case 2: return std::make_unique<tawlbwrdd_gs::TawlbwrddGS>(max_turns);
+    // Star Gambit: 10 + variant = the variant's own class, 20 + variant = StarGambitUnifiedGS pinned to it,
+    // 24 = StarGambitUnifiedGS with the random variant mix (an unseedable mt19937: not a parity target)
+    case 10: return std::make_unique<star_gambit_gs::StarGambitSkirmishGS>();
+    case 11: return std::make_unique<star_gambit_gs::StarGambitShowdownGS>();
+    case 12: return std::make_unique<star_gambit_gs::StarGambitClashGS>();
+    case 13: return std::make_unique<star_gambit_gs::StarGambitBattleGS>();
+    case 20: case 21: case 22: case 23: return std::make_unique<star_gambit_gs::StarGambitUnifiedGS>(game - 20);
+    case 24: return std::make_unique<star_gambit_gs::StarGambitUnifiedGS>(-1);
   }
   return nullptr;
 }
@@ -49,7 +58,8 @@ std::string state_bytes(int game, const GameState& gs) {
   switch (game) {
     case 0: return static_cast<const brandubh_gs::BrandubhGS&>(gs).to_bytes();
     case 1: return static_cast<const opentafl_gs::OpenTaflGS&>(gs).to_bytes();
-    default: return static_cast<const tawlbwrdd_gs::TawlbwrddGS&>(gs).to_bytes();
+    case 2: return static_cast<const tawlbwrdd_gs::TawlbwrddGS&>(gs).to_bytes();
+    default: return gs.to_bytes();  // virtual for the Star Gambit classes (game_state.h)
   }
 }
 uint64_t next_u64(uint64_t& s) {  // splitmix64
@@ -199,6 +209,99 @@ int azref_tafl_position(int game, const int8_t* board, int8_t player, uint16_t t
   }
 }
 
+// ---- Star Gambit (games 10-13 the variants' own classes, 20-23 StarGambitUnifiedGS pinned to a variant)
+// azref_sg_replay: the state after k = 0..len moves of a transcript. Per position: the inner state's to_bytes()
+// (star_gambit_gs.cc:2246-2288; for the Unified classes the 25-byte prefix is skipped; the key history after hist_len is
+// replaced by its 64-bit FNV-1a) padded to `bytes_stride`, its
+// length, player, turn, terminal (0, 1 + winner, 3 draw), scores [3], n_valid, valid [A] (may be NULL),
+// canonical [C*D*D] (may be NULL).
+int azref_sg_replay(int game, const uint32_t* moves, uint32_t len, uint32_t bytes_stride, uint8_t* bytes_out,
+                    uint32_t* bytes_len, uint8_t* players, uint32_t* turns, uint8_t* terminal, float* scores,
+                    uint32_t* n_valid, uint8_t* valid, float* canonical) {
+  try {
+    auto gs = make_game(game, 0);
+    if (!gs || game < 10) { g_err = "unknown game"; return -1; }
+    const size_t A = gs->num_moves();
+    auto c0 = gs->canonicalized();
+    const size_t C = (size_t)c0.size();
+    for (uint32_t k = 0; k <= len; ++k) {
+      if (k > 0) gs->play_move(moves[k - 1]);
+      std::string b = gs->to_bytes();
+      if (game >= 20) b = b.substr(25);
+      {  // the key history can be thousands of entries long: keep [units .. hist_len] and replace the keys by their FNV-1a
+        uint32_t nu = 0;
+        std::memcpy(&nu, b.data(), 4);
+        const size_t fixed = 4 + 9 * (size_t)nu + 8 + 1 + 4 + 3 + 4;
+        uint64_t h = 0xcbf29ce484222325ULL;
+        for (size_t i = fixed; i < b.size(); ++i) h = (h ^ (uint8_t)b[i]) * 0x100000001b3ULL;
+        b.resize(fixed);
+        b.append(reinterpret_cast<const char*>(&h), 8);
+      }
+      if (b.size() > bytes_stride) { g_err = "bytes_stride too small"; return -1; }
+      std::memset(bytes_out + (size_t)k * bytes_stride, 0, bytes_stride);
+      std::memcpy(bytes_out + (size_t)k * bytes_stride, b.data(), b.size());
+      bytes_len[k] = (uint32_t)b.size();
+      players[k] = gs->current_player();
+      turns[k] = gs->current_turn();
+      auto sc = gs->scores();
+      terminal[k] = 0;
+      for (int j = 0; j < 3; ++j) scores[k * 3 + j] = 0.0f;
+      if (sc.has_value()) {
+        terminal[k] = 4;
+        for (int j = 0; j < 3; ++j) {
+          scores[k * 3 + j] = (*sc)(j);
+          if ((*sc)(j) == 1.0f && terminal[k] == 4) terminal[k] = (uint8_t)(j + 1);
+        }
+      }
+      auto vm = gs->valid_moves();
+      uint32_t nv = 0;
+      for (size_t m = 0; m < A; ++m) nv += vm(m) ? 1u : 0u;
+      n_valid[k] = nv;
+      if (valid) std::memcpy(valid + (size_t)k * A, vm.data(), A);
+      if (canonical) {
+        auto c = gs->canonicalized();
+        std::memcpy(canonical + (size_t)k * C, c.data(), C * sizeof(float));
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// get_units() / get_fire_info(move) of the position after the transcript (py_wrapper.cc:589-670): units_out
+// [n][8] ints (player, type, slot, hp, anchor_q, anchor_r, facing, moves_left), fire_out [5] ints.
+int azref_sg_units(int game, const uint32_t* moves, uint32_t len, uint32_t fire_move, int32_t* units_out, uint32_t cap,
+                   int32_t* fire_out) {
+  try {
+    auto gs = make_game(game, 0);
+    if (!gs || game < 10) { g_err = "unknown game"; return -1; }
+    for (uint32_t k = 0; k < len; ++k) gs->play_move(moves[k]);
+    std::vector<star_gambit_gs::UnitInfo> us;
+    star_gambit_gs::FireInfo fi{};
+    using namespace star_gambit_gs;
+    switch (game) {
+      case 10: us = static_cast<StarGambitSkirmishGS&>(*gs).get_units(); fi = static_cast<StarGambitSkirmishGS&>(*gs).get_fire_info(fire_move); break;
+      case 11: us = static_cast<StarGambitShowdownGS&>(*gs).get_units(); fi = static_cast<StarGambitShowdownGS&>(*gs).get_fire_info(fire_move); break;
+      case 12: us = static_cast<StarGambitClashGS&>(*gs).get_units(); fi = static_cast<StarGambitClashGS&>(*gs).get_fire_info(fire_move); break;
+      case 13: us = static_cast<StarGambitBattleGS&>(*gs).get_units(); fi = static_cast<StarGambitBattleGS&>(*gs).get_fire_info(fire_move); break;
+      default: us = static_cast<StarGambitUnifiedGS&>(*gs).get_units(); fi = static_cast<StarGambitUnifiedGS&>(*gs).get_fire_info(fire_move); break;
+    }
+    uint32_t n = 0;
+    for (const auto& u : us) {
+      if (n >= cap) break;
+      int32_t* o = units_out + (size_t)n * 8;
+      o[0] = u.player; o[1] = u.type; o[2] = u.slot; o[3] = u.hp; o[4] = u.anchor_q; o[5] = u.anchor_r; o[6] = u.facing; o[7] = u.moves_left;
+      ++n;
+    }
+    fire_out[0] = fi.has_target; fire_out[1] = fi.target_player; fire_out[2] = fi.target_type; fire_out[3] = fi.target_slot; fire_out[4] = fi.damage;
+    return (int)us.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // One single-tree search run through the reference's MCTS class (mcts.h:50-150), exactly the way Python drives it
 // (py_wrapper.cc:192-220; play.py): seed the thread's generator, then for every move `sims` x (find_leaf ->
 // evaluate -> process_result(root_noise_enabled = false)), record counts() / root_q_values(), play the most
@@ -221,7 +324,8 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
     MCTS::seed_thread_rng(seed);
     // epsilon > 0: process_result(root_noise_enabled = true), and after every move the reused root gets the root
     // temperature again and fresh noise, as PlayManager does (play_manager.cc:546-553)
-    MCTS mcts{cpuct, 2, A, epsilon, root_policy_temp, fpu_reduction, false, root_fpu_zero != 0, shaped_dirichlet != 0, gumbel_m > 0,
+    // relative_values: Star Gambit evaluators answer in the mover's frame (mcts.cc:522-524)
+    MCTS mcts{cpuct, 2, A, epsilon, root_policy_temp, fpu_reduction, gs->relative_values(), root_fpu_zero != 0, shaped_dirichlet != 0, gumbel_m > 0,
               gumbel_m > 0 ? gumbel_m : 16u, gumbel_c_visit, gumbel_c_scale, false};
     uint32_t played = 0;
     for (uint32_t m = 0; m < n_moves; ++m) {

@@ -178,5 +178,65 @@ def symmetries(game, canon, v, pi):
     co, vo, po = np.zeros((8, P, S, S), np.float32), np.zeros((8, 3), np.float32), np.zeros((8, A), np.float32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     n = lib().azref_tafl_symmetries(game, p(canon), p(v), p(pi), p(co), p(vo), p(po))
-    assert n == 8
-    return co, vo, po
+    assert n in (2, 8)  # tafl: eightSym; Star Gambit: identity + NW-axis mirror
+    return co[:n], vo[:n], po[:n]
+
+
+# ---- Star Gambit (oracle/ref_tafl_driver.cc: games 10-13 the variants' own classes, 20-23 StarGambitUnifiedGS pinned)
+SG_SKIRMISH, SG_SHOWDOWN, SG_CLASH, SG_BATTLE = 10, 11, 12, 13
+SG_UNIFIED = 20  # + variant
+SG_BYTES_STRIDE = 256
+
+
+def sg_lib():
+    L = lib()
+    if not hasattr(L, "_sg_ready"):
+        vp, u32 = C.c_void_p, C.c_uint32
+        L.azref_sg_replay.argtypes = [C.c_int, vp, u32, u32] + [vp] * 9
+        L.azref_sg_units.argtypes = [C.c_int, vp, u32, u32, vp, u32, vp]
+        L._sg_ready = True
+    return L
+
+
+def sg_dims(game):
+    """(board dim of the action / observation grid, actions, planes)"""
+    unified = game >= 20
+    variant = game % 10
+    D = 13 if unified or variant == 3 else 11
+    return D, D * D * 10 + 19, 36 if unified else 32
+
+
+def sg_random_game(game, seed, max_len=4096):
+    sg_lib()
+    buf = np.zeros(max_len, np.uint32)
+    n = lib().azref_tafl_random_game(game, 0, seed, max_len, buf.ctypes.data_as(C.c_void_p))
+    return buf[:n].copy()
+
+
+def sg_replay(game, moves, want_valid=True, want_canonical=True):
+    """The reference's observable state after k = 0..len moves of a Star Gambit transcript."""
+    D, A, P = sg_dims(game)
+    moves = np.ascontiguousarray(moves, np.uint32)
+    n = len(moves) + 1
+    out = dict(bytes=np.zeros((n, SG_BYTES_STRIDE), np.uint8), bytes_len=np.zeros(n, np.uint32),
+               players=np.zeros(n, np.uint8), turns=np.zeros(n, np.uint32), terminal=np.zeros(n, np.uint8),
+               scores=np.zeros((n, 3), np.float32), n_valid=np.zeros(n, np.uint32),
+               valid=np.zeros((n, A), np.uint8) if want_valid else None,
+               canonical=np.zeros((n, P, D, D), np.float32) if want_canonical else None)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = sg_lib().azref_sg_replay(game, p(moves), len(moves), SG_BYTES_STRIDE, p(out["bytes"]), p(out["bytes_len"]),
+                                  p(out["players"]), p(out["turns"]), p(out["terminal"]), p(out["scores"]),
+                                  p(out["n_valid"]), p(out["valid"]), p(out["canonical"]))
+    if rc != 0:
+        raise RuntimeError(lib().azref_tafl_last_error().decode())
+    return out
+
+
+def sg_units(game, moves, fire_move=0):
+    moves = np.ascontiguousarray(moves, np.uint32)
+    units = np.zeros((32, 8), np.int32)
+    fire = np.zeros(5, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = sg_lib().azref_sg_units(game, p(moves), len(moves), int(fire_move), p(units), 32, p(fire))
+    assert n >= 0, lib().azref_tafl_last_error().decode()
+    return units[:n].copy(), fire
