@@ -136,6 +136,8 @@ def load(path=None):
     L.b2az_cache_find_host.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
     L.b2az_tafl_replay_device.argtypes = [u32, u32, u32, u32] + [vp] * 10
+    L.b2az_sg_replay.argtypes = [C.c_int, u32, u32, u32] + [vp] * 8
+    L.b2az_sg_replay_device.argtypes = [u32, u32, u32, vp, vp, vp, u32] + [vp] * 7
     L.b2az_forest_create.argtypes = [C.POINTER(ForestParams), C.c_int, C.POINTER(vp)]
     L.b2az_forest_destroy.argtypes = [vp]
     L.b2az_forest_find_leaf.argtypes = [vp, vp, C.POINTER(vp)]
@@ -385,6 +387,39 @@ def tafl_replay(game, moves, lens, max_turns, want_valid=True, want_canonical=Tr
     rc = L.b2az_tafl_replay(device, game, n, max_len, max_turns, _ptr(moves), _ptr(lens), _ptr(out["boards"]),
                             _ptr(out["players"]), _ptr(out["turns"]), _ptr(out["reps"]), _ptr(out["terminal"]),
                             _ptr(out["n_valid"]), _ptr(out["valid"]), _ptr(out["canonical"]), _ptr(out["status"]))
+    if rc != 0:
+        raise B2azError(rc, L.b2az_last_error().decode())
+    return out
+
+
+SG_STATE_BYTES = 200
+
+
+def sg_dims(game):
+    """Star Gambit game id (10 + variant: the variant's own class; 20 + variant: the Unified 13x13 view) ->
+    (grid side D, actions, canonical planes)."""
+    if not (10 <= game <= 13 or 20 <= game <= 23):
+        raise B2azError(-1, f"unknown Star Gambit game {game}")
+    D = 13 if game >= 20 or game == 13 else 11
+    return D, D * D * 10 + 19, 36 if game >= 20 else 32
+
+
+def sg_replay(game, moves, lens, want_valid=True, want_canonical=True, device=0, lib=None):
+    """Star Gambit game kernels on a batch of transcripts: the position after every move of every game.
+    moves uint16[n][max_len], lens[n]. Returns arrays shaped [n][max_len + 1][...]; `states` rows are the device's
+    SGState records (units 9 B each in the reference's field order, then n_units, reserves, player, acted, over,
+    winner, variant, pad, turn)."""
+    L = lib or load()
+    D, A, P = sg_dims(game)
+    moves = np.ascontiguousarray(moves, np.uint16)
+    n, max_len = moves.shape
+    lens = np.ascontiguousarray(lens, np.uint32)
+    R = (n, max_len + 1)
+    out = dict(states=np.zeros(R + (SG_STATE_BYTES,), np.uint8), terminal=np.zeros(R, np.uint8),
+               n_valid=np.zeros(R, np.uint32), valid=np.zeros(R + (A,), np.uint8) if want_valid else None,
+               canonical=np.zeros(R + (P, D, D), np.float32) if want_canonical else None, status=np.zeros(n, np.int32))
+    rc = L.b2az_sg_replay(device, game, n, max_len, _ptr(moves), _ptr(lens), _ptr(out["states"]), _ptr(out["terminal"]),
+                          _ptr(out["n_valid"]), _ptr(out["valid"]), _ptr(out["canonical"]), _ptr(out["status"]))
     if rc != 0:
         raise B2azError(rc, L.b2az_last_error().decode())
     return out

@@ -1323,5 +1323,6 @@ int b2az_c4_batch(int device, uint32_t n, const int8_t* boards_host, const uint8
 }  // extern "C"
 
 #include "az_tafl_kernels.h"
+#include "az_stargambit_kernels.h"
 #include "az_forest.h"
 #include "az_selfplay.h"

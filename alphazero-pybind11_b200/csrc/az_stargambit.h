@@ -279,21 +279,22 @@ AZ_HD bool sg_deploy_anchor(int type, int player, int facing, int side, int& aq,
   }
   return true;
 }
+AZ_HD bool sg_deploy_ok(const SGState& s, const SGBoards& b, int side, int type, int f) {
+  const int p = s.player & 1;
+  if (s.reserves[p][type] == 0) return false;
+  int aq, ar;
+  if (!sg_deploy_anchor(type, p, f, side, aq, ar)) return false;
+  int hq[3], hr[3];
+  const int n = sg_hexes(type, p, aq, ar, f, side, hq, hr);
+  bool ok = true;
+  for (int j = 0; j < n; ++j) ok = ok && sg_inb(hq[j], hr[j], side) && !sg_occ_test(b.all, hq[j], hr[j]);
+  return ok;
+}
 AZ_HD u32 sg_deploy_mask(const SGState& s, const SGBoards& b, int side) {
   u32 mask = 0;
-  const int p = s.player & 1;
-  for (int type = 0; type < 3; ++type) {
-    if (s.reserves[p][type] == 0) continue;
-    for (int f = 0; f < 6; ++f) {
-      int aq, ar;
-      if (!sg_deploy_anchor(type, p, f, side, aq, ar)) continue;
-      int hq[3], hr[3];
-      const int n = sg_hexes(type, p, aq, ar, f, side, hq, hr);
-      bool ok = true;
-      for (int j = 0; j < n; ++j) ok = ok && sg_inb(hq[j], hr[j], side) && !sg_occ_test(b.all, hq[j], hr[j]);
-      if (ok) mask |= 1u << (type * 6 + f);
-    }
-  }
+  for (int type = 0; type < 3; ++type)
+    for (int f = 0; f < 6; ++f)
+      if (sg_deploy_ok(s, b, side, type, f)) mask |= 1u << (type * 6 + f);
   return mask;
 }
 AZ_HD bool sg_turn_one(const SGState& s) { return s.turn == 1 || s.turn == 2; }
@@ -397,8 +398,13 @@ AZ_HD bool sg_check_repetition(SGState& s, H& hist) {  // star_gambit_gs.cc:1246
   if (hist.push_count(sg_position_key(s)) >= 3) { s.over = 1; s.winner = 2; return true; }
   return false;
 }
-template <class H>
-AZ_HD void sg_end_turn(SGState& s, H& hist, const SGSpace& sp) {  // execute_end_turn (1263-1290)
+// `any_valid(s)`: does the side to move have a legal action (valid_moves().sum() != 0)? The scalar default walks the
+// units; the device passes a lane-parallel test.
+struct SGAnyValidScalar {
+  AZ_HD bool operator()(const SGState& s, const SGSpace& sp) const { return sg_valid_moves(s, sp, SGNoEmit()) != 0; }
+};
+template <class H, class AnyValid>
+AZ_HD void sg_end_turn(SGState& s, H& hist, const SGSpace& sp, AnyValid&& any_valid) {  // execute_end_turn (1263-1290)
   s.player = (u8)(1 - s.player);
   ++s.turn;
   s.acted = 0;
@@ -408,7 +414,7 @@ AZ_HD void sg_end_turn(SGState& s, H& hist, const SGSpace& sp) {  // execute_end
     SGUnit& u = s.units[i];
     if (u.player == s.player && u.hp > 0) { u.moves_left = (u8)sg_max_moves(u.type); u.fired = 0; }
   }
-  if (sg_valid_moves(s, sp, SGNoEmit()) == 0) { s.over = 1; s.winner = (int8_t)(1 - s.player); }
+  if (!any_valid(s, sp)) { s.over = 1; s.winner = (int8_t)(1 - s.player); }
 }
 AZ_HD int sg_unit_at(const SGState& s, int q, int r, int side) {  // find_unit_at_hex (413-433)
   for (int i = 0; i < (int)s.n_units; ++i) {
@@ -441,8 +447,8 @@ AZ_HD bool sg_fire_target(const SGState& s, int ui, int ci, int side, int& targe
 }
 
 // play_move (star_gambit_gs.cc:1093-1238). Returns false only for ids outside the space.
-template <class H>
-AZ_HD bool sg_play(SGState& s, H& hist, const SGSpace& sp, u32 move) {
+template <class H, class AnyValid>
+AZ_HD bool sg_play(SGState& s, H& hist, const SGSpace& sp, u32 move, AnyValid&& any_valid) {
   if (move >= (u32)sp.num_moves()) return false;
   if (move < (u32)sp.deploy_offset()) {
     const int slot = (int)(move % 10u), pos = (int)(move / 10u);
@@ -496,12 +502,14 @@ AZ_HD bool sg_play(SGState& s, H& hist, const SGSpace& sp, u32 move) {
       u.q = (int8_t)aq; u.r = (int8_t)ar; u.moves_left = 0; u.fired = (u8)((1u << sg_num_cannons(type)) - 1u);
     }
     --s.reserves[s.player & 1][type];
-    sg_end_turn(s, hist, sp);
+    sg_end_turn(s, hist, sp, any_valid);
   } else {
-    sg_end_turn(s, hist, sp);
+    sg_end_turn(s, hist, sp, any_valid);
   }
   return true;
 }
+template <class H>
+AZ_HD bool sg_play(SGState& s, H& hist, const SGSpace& sp, u32 move) { return sg_play(s, hist, sp, move, SGAnyValidScalar()); }
 AZ_HD u32 sg_terminal(const SGState& s) {  // 0 running, 1 + winner, 3 draw (scores(), 1347-1363)
   if (!s.over) return 0;
   return s.winner == 2 ? 3u : s.winner == 0 ? 1u : s.winner == 1 ? 2u : 4u;  // 4: over without a winner (all zeros)

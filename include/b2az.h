@@ -287,6 +287,35 @@ int b2az_tafl_positions(int device, uint32_t game, uint32_t n, uint32_t max_turn
 int b2az_tafl_symmetries(int device, uint32_t game, uint32_t n, const float* canon_host, const float* v_host,
                          const float* pi_host, float* canon_out, float* v_out, float* pi_out);
 
+/* ---- Star Gambit (star_gambit_gs.h / .cc). Game ids: B2AZ_SG_GAME(variant) = the variant's own class
+ * (StarGambit{Skirmish,Showdown,Clash,Battle}GS: 11x11 or 13x13 grid, 32 planes, 1229 or 1709 actions),
+ * B2AZ_SG_UNIFIED(variant) = StarGambitUnifiedGS pinned to the variant (13x13 canvas, 36 planes, 1709 actions). */
+#define B2AZ_SG_SKIRMISH 0
+#define B2AZ_SG_SHOWDOWN 1
+#define B2AZ_SG_CLASH 2
+#define B2AZ_SG_BATTLE 3
+#define B2AZ_SG_GAME(variant) (10u + (variant))
+#define B2AZ_SG_UNIFIED(variant) (20u + (variant))
+#define B2AZ_SG_STATE_BYTES 200  /* 20 units x 9 B (star_gambit_gs.h:359-371 order), n_units, reserves[2][4], player,
+                                    has_taken_action, game_over, winner, variant, 2 pad, turn u32 */
+
+/* Star Gambit game kernels on a batch of transcripts: StarGambitGS::play_move / valid_moves / scores / canonicalized
+ * and the position-key history (star_gambit_gs.cc:784-923, 1093-1290, 1313-1382, 1384-1669; Unified 2522-2616)
+ * replayed on the device from the start position, one warp per game. moves uint16[n][max_len], lens[n]. Outputs
+ * (host, any may be NULL) hold the position after k = 0..lens[i] moves at row i*(max_len+1)+k: states
+ * uint8[..][B2AZ_SG_STATE_BYTES], terminal (0 = scores() is nullopt, 1 + winner, 3 = draw), n_valid, valid
+ * uint8[..][A], canonical float[..][P][D][D]; status[n] = 0, B2AZ_EMOVE for an id outside the action space. */
+int b2az_sg_replay(int device, uint32_t game, uint32_t n, uint32_t max_len, const uint16_t* moves, const uint32_t* lens,
+                   uint8_t* states, uint8_t* terminal, uint32_t* n_valid, uint8_t* valid, float* canonical,
+                   int32_t* status);
+/* The same with every buffer already in device memory (what a device-resident loop and the throughput measurement
+ * use): hist_dev is scratch of n*hist_cap*8 bytes for the key histories (hist_cap >= max_len + 2 never overflows);
+ * output pointers may be NULL; the launch is enqueued on `stream`. */
+int b2az_sg_replay_device(uint32_t game, uint32_t n, uint32_t max_len, const uint16_t* moves_dev,
+                          const uint32_t* lens_dev, void* hist_dev, uint32_t hist_cap, uint8_t* states_dev,
+                          uint8_t* terminal_dev, uint32_t* n_valid_dev, uint8_t* valid_dev, float* canonical_dev,
+                          int32_t* status_dev, void* stream);
+
 /* ---- Batched single-tree MCTS over the tafl games ("forest"): the reference's `MCTS` class (mcts.h:50-150, bound at
  * py_wrapper.cc:192-220) for n_trees trees at once, one warp per tree on the device. Tree i starts at the game's
  * start position and draws from pcg32(seed + i) — a reference MCTS driven after MCTS::seed_thread_rng(seed + i).
