@@ -86,7 +86,8 @@ class TaflSelfplayParams(C.Structure):  # b2az_tafl_selfplay_params (include/b2a
                 ("pad_", C.c_uint8), ("hist_capacity", C.c_uint32), ("seat_visits", C.c_uint32 * 2),
                 ("seat_cap_visits", C.c_uint32 * 2), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
                 ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
-                ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2)]
+                ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2),
+                ("n_variant_half_life", C.c_uint32), ("variant_half_life", C.c_float * 4)]
 
 
 SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_completed", "u4"), ("pending", "u4"),
@@ -367,6 +368,18 @@ TAFL_BRANDUBH, TAFL_OPENTAFL, TAFL_TAWLBWRDD = 0, 1, 2
 TAFL_DIMS = {0: (7, 7), 1: (11, 8), 2: (11, 7)}  # game -> (board side S, canonical planes)
 
 
+def game_dims(game):
+    """(grid side, canonical planes, actions) of a game of the wide-tree search: B2AZ_TAFL_* or a Star Gambit id
+    (10 + variant: the variant's own class, 20 + variant: the Unified 13x13 view)."""
+    if game in TAFL_DIMS:
+        S, P = TAFL_DIMS[game]
+        return S, P, 2 * S ** 3
+    if 10 <= game <= 13 or 20 <= game <= 23:
+        D = 13 if game >= 20 or game == 13 else 11
+        return D, 36 if game >= 20 else 32, D * D * 10 + 19
+    raise B2azError(-1, f"unknown game {game}")
+
+
 def tafl_replay(game, moves, lens, max_turns, want_valid=True, want_canonical=True, device=0, lib=None):
     """Tafl game kernels on a batch of transcripts: the position after every move of every game.
     moves uint16[n][max_len], lens[n]. Returns arrays shaped [n][max_len + 1][...] (rows beyond a game's length
@@ -455,12 +468,14 @@ class Forest:
 
     def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
                  words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0,
-                 gumbel_full=False, shaped_dirichlet=False, serial_shuffle=False, max_in_flight=0, device=0, lib=None):
+                 gumbel_full=False, shaped_dirichlet=False, serial_shuffle=False, max_in_flight=0, device=0, lib=None,
+                 relative_values=None):
         self.L = lib or load()
         self.game, self.n = game, n_trees
-        S, P = TAFL_DIMS[game]
-        self.S, self.P, self.A = S, P, 2 * S ** 3
-        p = ForestParams(game=game, n_trees=n_trees, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
+        self.S, self.P, self.A = game_dims(game)
+        if relative_values is None:  # GameState::relative_values(): true for the Star Gambit classes
+            relative_values = game >= 10
+        p = ForestParams(game=game, relative_values=int(relative_values), n_trees=n_trees, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
                          fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
                          root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
                          gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, gumbel_full=int(gumbel_full),
@@ -583,12 +598,12 @@ class TaflSelfplay:
                  gumbel_c_visit=50.0, gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0,
                  history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None,
                  seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
-                 playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0):
+                 playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
+                 temp_decay_half_life_by_variant=None):
         self.L = lib or load()
         self.game, self.n = game, n_games
-        S, P = TAFL_DIMS[game]
-        self.S, self.P, self.A = S, P, 2 * S ** 3
-        fp = ForestParams(game=game, n_trees=2 * n_games, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
+        self.S, self.P, self.A = game_dims(game)
+        fp = ForestParams(game=game, relative_values=int(game >= 10), n_trees=2 * n_games, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
                           fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
                           root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
                           gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, shaped_dirichlet=int(shaped_dirichlet))
@@ -600,6 +615,9 @@ class TaflSelfplay:
                                resign_playthrough_percent=resign_playthrough_percent,
                                playout_cap_randomization=int(playout_cap_randomization),
                                fast_search_uses_gumbel=int(fast_search_uses_gumbel))
+        for i, hl in enumerate((temp_decay_half_life_by_variant or [])[:4]):
+            p.variant_half_life[i] = hl
+            p.n_variant_half_life = i + 1
         for seat in range(2):
             p.seat_visits[seat] = (seat_visits or (0, 0))[seat]
             p.seat_cap_visits[seat] = (seat_cap_visits or (0, 0))[seat]

@@ -31,6 +31,11 @@
 
 #include "az_rng.h"
 #include "az_tafl.h"
+#include "az_stargambit_kernels.h"
+
+// Template id of the Star Gambit instantiation of the forest: ONE instantiation serves the eight game ids
+// (B2AZ_SG_GAME / B2AZ_SG_UNIFIED, ForestView::game carries the id: variant and frame are run-time values)
+#define B2AZ_FOREST_SG 10
 
 namespace b2az {
 
@@ -91,6 +96,12 @@ struct ForestView {
   float* leaf_canon;   // [max(1, max_in_flight)][n_trees][CANON]
   ForestLeaf* inflight; // [n_trees][max_in_flight] (WU-UCT), null when max_in_flight == 0
   u32 max_in_flight;
+  u32 relative_values;  // MCTS::relative_values_: evaluations arrive in the leaf mover's frame (mcts.cc:522-524)
+  u32 actions, canon;   // num_moves and canonical floats of the game (compile-time constants for the tafl games)
+  SGState* sg_state;    // Star Gambit: [n_trees] root positions (ForestTree::state is the tafl record)
+  u64* sg_hist;         // [n_trees][sg_hist_cap] position keys of the root since the last deploy
+  u64* sg_pkeys;        // [n_trees][kFPath + 2] keys appended along the current path
+  u32 sg_hist_cap;
   u32 rng_pair;         // self-play: trees 2g and 2g+1 (the two seats' MCTS objects of game g, play_manager.h game.mcts[])
                         // draw from ONE generator (the reference's thread-local one), kept in tree 2g
 };
@@ -114,6 +125,11 @@ struct ForestSmem {   // per warp
   u32 lines[2 * Tafl<GAME>::S + 2];
   u16 moves[kFMaxK];
   u32 draws[kFMaxK / 2 + 2];   // the shuffle's uniform draws, generated lane-parallel (pcg32 jump-ahead)
+};
+
+template <>
+struct ForestSmem<B2AZ_FOREST_SG> : SGWarpSmem {  // map / moves / cell_unit of the Star Gambit warp functions
+  u32 draws[kSGMaxK / 2 + 2];
 };
 
 // pcg32 is an LCG underneath: state_d = A_d * state_0 + C_d * inc with A_d = M^d, C_d = 1 + M + ... + M^(d-1)
@@ -278,6 +294,168 @@ __device__ __forceinline__ u32 forest_legal_moves(const TaflState& s, ForestSmem
   forest_shuffle(rng, sm.moves, sm.draws, k, lane, serial_shuffle);  // every lane ends with the same generator state
   return k;
 }
+
+// ---- The game under the search. FGame<GAME>::Pos is the working position of one descent (every lane holds a copy);
+// the tafl games keep three bitboards, Star Gambit a unit list (az_stargambit_kernels.h).
+template <int GAME>
+struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
+  typedef Tafl<GAME> T;
+  struct Pos {
+    TaflState s;
+    const TaflKey* hist;
+    TaflKey* pkeys;
+    u32 base_len, pk_len;
+  };
+  static __device__ __forceinline__ u32 actions(const ForestView&) { return (u32)T::A; }
+  static __device__ __forceinline__ u32 canon(const ForestView&) { return (u32)T::CANON; }
+  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32, Pos& P) {
+    P.s = F.trees[t].state;
+    P.hist = F.hist + (size_t)t * (F.max_turns + 2u);
+    P.pkeys = F.pkeys + (size_t)t * (kFPath + 2);
+    P.base_len = F.trees[t].hist_len;
+    P.pk_len = 0;
+  }
+  static __device__ __forceinline__ bool play(Pos& P, u32 mv, u32 lane) {
+    return forest_play<GAME>(P.s, mv, P.hist, P.base_len, P.pkeys, P.pk_len, lane);
+  }
+  static __device__ __forceinline__ u32 player(const Pos& P) { return P.s.player; }
+  static __device__ __forceinline__ u32 legal(const Pos& P, ForestSmem<GAME>& sm, Pcg32& rng, u32 lane, u32* err, bool serial) {
+    return forest_legal_moves<GAME>(P.s, sm, rng, lane, err, serial);
+  }
+  static __device__ __forceinline__ u32 terminal(const Pos& P, u32 k) {
+    const u32 pre = T::terminal_pre(P.s);
+    return pre ? pre : T::terminal_post(P.s, k != 0);
+  }
+  static __device__ __forceinline__ void emit_canon(const Pos& P, ForestSmem<GAME>&, float* out, u32 lane) {
+    const TaflState& s = P.s;
+    constexpr int CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
+#pragma unroll
+    for (int j = 0; j < CHUNKS; ++j) {
+      const u32 c = 32u * j + lane;
+      if (c < (u32)CELLS) {
+        out[c] = (float)((b128_word(s.king, j) >> lane) & 1u);
+        out[CELLS + c] = (float)((b128_word(s.def, j) >> lane) & 1u);
+        out[2 * CELLS + c] = (float)((b128_word(s.atk, j) >> lane) & 1u);
+      }
+    }
+#pragma unroll
+    for (int pl = 3; pl < T::PLANES; ++pl) {
+      const float v = T::canon_elem(s, (u32)(pl * CELLS));
+#pragma unroll
+      for (int j = 0; j < CHUNKS; ++j) {
+        const u32 c = 32u * j + lane;
+        if (c < (u32)CELLS) out[pl * CELLS + c] = v;
+      }
+    }
+  }
+  // gs.play_move(move) on the tree's root position with its persistent repetition history (update_root's caller)
+  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, u32 lane) {
+    ForestTree& R = F.trees[t];
+    TaflKey* hist = F.hist + (size_t)t * (F.max_turns + 2u);
+    TaflState s = R.state;
+    u32 hist_len = R.hist_len, err = 0;
+    if (s.turn == 0) {
+      if (lane == 0) hist[0] = T::key(s);
+      hist_len = 1;
+      __syncwarp();
+    }
+    bool cap;
+    if (!T::play(s, move, &cap)) return 8u;
+    if (cap) hist_len = 0;
+    const TaflKey key = T::key(s);
+    u32 same = 0;
+    for (u32 i = lane; i < hist_len; i += 32u) same += T::key_eq(hist[i], key) ? 1u : 0u;
+    same = warp_sum(same) + 1u;
+    if (hist_len + 1u > F.max_turns + 2u) {
+      err |= 2u;
+    } else {
+      if (lane == 0) hist[hist_len] = key;
+      ++hist_len;
+    }
+    s.rep = (u8)(same > 255u ? 255u : same);
+    if (lane == 0 && !err) { R.state = s; R.hist_len = hist_len; }
+    return err;
+  }
+  static __device__ __forceinline__ void init(const ForestView& F, u32 t) {
+    T::init(F.trees[t].state, F.max_turns);
+    F.trees[t].hist_len = 0;
+  }
+  static __device__ __forceinline__ void info(const ForestView& F, u32 t, u32* turn, u32* rep, u32* player) {
+    *turn = F.trees[t].state.turn; *rep = F.trees[t].state.rep; *player = F.trees[t].state.player;
+  }
+  // the root position as the scheduler sees it (GameData::gs): current_player / current_turn / scores / variant
+  static __device__ __forceinline__ u32 root_player(const ForestView& F, u32 t) { return F.trees[t].state.player; }
+  static __device__ __forceinline__ u32 root_turn(const ForestView& F, u32 t) { return F.trees[t].state.turn; }
+  static __device__ __forceinline__ u32 root_terminal(const ForestView& F, u32 t) { return T::terminal(F.trees[t].state); }
+  static __device__ __forceinline__ int root_variant(const ForestView&, u32) { return -1; }
+};
+template <>
+struct FGame<B2AZ_FOREST_SG> {  // Star Gambit: the variants' own classes and the Unified view
+  struct Pos {
+    SGState s;
+    SGHistWarp hist;
+    SGSpace sp;
+    bool unified;
+  };
+  static __device__ __forceinline__ u32 actions(const ForestView& F) { return F.actions; }
+  static __device__ __forceinline__ u32 canon(const ForestView& F) { return F.canon; }
+  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32 lane, Pos& P) {
+    P.s = F.sg_state[t];
+    P.unified = sg_game_unified(F.game);
+    P.sp = sg_space(P.s.variant, P.unified);
+    P.hist.base = F.sg_hist + (size_t)t * F.sg_hist_cap;
+    P.hist.base_len = F.trees[t].hist_len;
+    P.hist.keys = F.sg_pkeys + (size_t)t * (kFPath + 2);
+    P.hist.len = 0; P.hist.cap = kFPath + 2; P.hist.lane = lane; P.hist.overflow = false;
+  }
+  static __device__ __forceinline__ bool play(Pos& P, u32 mv, u32 lane) {
+    return sg_play(P.s, P.hist, P.sp, mv, SGAnyValidWarp{lane}) && !P.hist.overflow;
+  }
+  static __device__ __forceinline__ u32 player(const Pos& P) { return P.s.player; }
+  static __device__ __forceinline__ u32 legal(const Pos& P, ForestSmem<B2AZ_FOREST_SG>& sm, Pcg32& rng, u32 lane, u32* err, bool serial) {
+    u32 k = sg_warp_legal(P.s, P.sp, sm, lane);
+    if (k > (u32)kSGMaxK) { *err |= 4u; k = 0; }
+    forest_shuffle(rng, sm.moves, sm.draws, k, lane, serial);
+    return k;
+  }
+  static __device__ __forceinline__ u32 terminal(const Pos& P, u32) { const u32 t = sg_terminal(P.s); return t > 3u ? 3u : t; }
+  static __device__ __forceinline__ void emit_canon(const Pos& P, ForestSmem<B2AZ_FOREST_SG>& sm, float* out, u32 lane) {
+    sg_warp_canon(P.s, P.hist, P.sp, P.unified, sm, lane, out);
+  }
+  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, u32 lane) {
+    ForestTree& R = F.trees[t];
+    SGState s = F.sg_state[t];
+    const bool unified = sg_game_unified(F.game);
+    const SGSpace sp = sg_space(s.variant, unified);
+    SGHistWarp h;
+    h.base = nullptr; h.base_len = 0; h.keys = F.sg_hist + (size_t)t * F.sg_hist_cap; h.len = R.hist_len; h.cap = F.sg_hist_cap;
+    h.lane = lane; h.overflow = false;
+    if (!sg_play(s, h, sp, move, SGAnyValidWarp{lane})) return 8u;
+    if (h.overflow) return 2u;
+    if (lane == 0) { F.sg_state[t] = s; R.hist_len = h.len; }
+    return 0;
+  }
+  static __device__ __forceinline__ void init(const ForestView& F, u32 t) {  // (one thread per tree)
+    SGState s;
+    sg_init(s, sg_game_variant(F.game));
+    F.sg_state[t] = s;
+    F.sg_hist[(size_t)t * F.sg_hist_cap] = sg_position_key(s);
+    F.trees[t].hist_len = 1;
+  }
+  static __device__ __forceinline__ void info(const ForestView& F, u32 t, u32* turn, u32* rep, u32* player) {
+    *turn = F.sg_state[t].turn; *rep = 0; *player = F.sg_state[t].player;
+  }
+  static __device__ __forceinline__ u32 root_player(const ForestView& F, u32 t) { return F.sg_state[t].player; }
+  static __device__ __forceinline__ u32 root_turn(const ForestView& F, u32 t) { return F.sg_state[t].turn; }
+  static __device__ __forceinline__ u32 root_terminal(const ForestView& F, u32 t) {
+    const SGState& s = F.sg_state[t];
+    if (!s.over) return 0u;
+    return s.winner == 0 ? 1u : s.winner == 1 ? 2u : 3u;
+  }
+  static __device__ __forceinline__ int root_variant(const ForestView& F, u32 t) {  // get_variant_id(): Unified only
+    return sg_game_unified(F.game) ? (int)F.sg_state[t].variant : -1;
+  }
+};
 
 // ---- Gumbel root search over a wide root (mcts.cc:28-66, 175-283, 336-401). Root-only and a few hundred scalar
 // steps per move, so it runs on lane 0; the formulas and their float order are those of the Connect4 engine's
@@ -516,13 +694,11 @@ __device__ __noinline__ void fr_add_root_noise(const ForestView& F, u32 t, Pcg32
 template <int GAME, bool BATCHED>
 __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon,
                                  ForestLeaf& Lf, float* canon_out) {
-  typedef Tafl<GAME> T;
+  typedef FGame<GAME> G;
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
-  const TaflKey* hist = F.hist + (size_t)t * (F.max_turns + 2u);
-  TaflKey* pkeys = F.pkeys + (size_t)t * (kFPath + 2);
-  TaflState s = R.state;
-  u32 base_len = R.hist_len, pk_len = 0;
+  typename G::Pos pos;
+  G::open(F, t, lane, pos);
   u32 err = 0;
   // current_ = &root_
   u32 cur_n = R.n, cur_term = R.term, cur_blk = R.blk, cur_k = R.k, cur_player = R.player;
@@ -593,7 +769,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       }
     }
     ++plen;
-    if (!forest_play<GAME>(s, mvw & 0xFFFFu, hist, base_len, pkeys, pk_len, lane)) { err |= 8u; break; }
+    if (!G::play(pos, mvw & 0xFFFFu, lane)) { err |= 8u; break; }
     par_blk = b; par_slot = best_j; par_k = k;
     cur_n = pool[fb_n(b, k) + best_j];
     cur_v = u2f(pool[fb_v(b, k) + best_j]);
@@ -614,11 +790,10 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   if (cur_n == 0 && !err && !(BATCHED && cur_expanded)) {
     // current_->player, scores, add_children(valid_moves) incl. the shuffle (mcts.cc:490-496)
     leaf_new = 1;
-    leaf_player = s.player;
+    leaf_player = G::player(pos);
     Pcg32 rng = FOREST_RNG(F, t);
-    const u32 k = forest_legal_moves<GAME>(s, sm, rng, lane, &err, F.serial_shuffle != 0);
-    const u32 pre = T::terminal_pre(s);
-    leaf_term = pre ? pre : T::terminal_post(s, k != 0);
+    const u32 k = G::legal(pos, sm, rng, lane, &err, F.serial_shuffle != 0);
+    leaf_term = G::terminal(pos, k);
     // children of a terminal node are never visited: their draws are consumed above, their storage is skipped
     leaf_k = leaf_term ? 0u : k;
     leaf_blk = 0;
@@ -647,28 +822,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       }
     }
   }
-  if (emit_canon) {
-    float* out = canon_out;
-    constexpr int CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
-#pragma unroll
-    for (int j = 0; j < CHUNKS; ++j) {
-      const u32 c = 32u * j + lane;
-      if (c < (u32)CELLS) {
-        out[c] = (float)((b128_word(s.king, j) >> lane) & 1u);
-        out[CELLS + c] = (float)((b128_word(s.def, j) >> lane) & 1u);
-        out[2 * CELLS + c] = (float)((b128_word(s.atk, j) >> lane) & 1u);
-      }
-    }
-#pragma unroll
-    for (int pl = 3; pl < T::PLANES; ++pl) {
-      const float v = T::canon_elem(s, (u32)(pl * CELLS));
-#pragma unroll
-      for (int j = 0; j < CHUNKS; ++j) {
-        const u32 c = 32u * j + lane;
-        if (c < (u32)CELLS) out[pl * CELLS + c] = v;
-      }
-    }
-  }
+  if (emit_canon) G::emit_canon(pos, sm, canon_out, lane);
   if (lane == 0) {
     R.total_leaf_depth += plen;
     Lf.path_len = plen;
@@ -683,7 +837,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
 template <int GAME, bool RANDOM, bool BATCHED>
 __device__ void forest_process_result(const ForestView& F, u32 t, const float* ev_v, const float* ev_pi, u32 lane,
                                       bool root_noise_enabled, ForestLeaf& Lf) {
-  typedef Tafl<GAME> T;
+  const u32 A = FGame<GAME>::actions(F);
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
   float val0, val1, vald;
@@ -695,6 +849,8 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
       val0 = val1 = vald = (float)(1.0 / 3.0);
     } else {
       val0 = ev_v[(size_t)t * 3 + 0]; val1 = ev_v[(size_t)t * 3 + 1]; vald = ev_v[(size_t)t * 3 + 2];
+      // relative_to_absolute(value, current_->player, 2) (mcts.cc:522-524, game_state.h:37-48): seat 1's answer swaps
+      if (F.relative_values && lplayer == 1u) { const float sw = val0; val0 = val1; val1 = sw; }
     }
     if (lk > 0 && lblk != 0) {
       // set_policy_normalized (mcts.cc:109-121); the same code for the root and interior nodes here
@@ -709,7 +865,7 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
         const u32 j = c0 + lane;
         float p = 0.0f;
         if (j < lk) {
-          p = RANDOM ? rp : ev_pi[(size_t)t * T::A + (pool[fb_mv(lblk, lk) + j] & 0xFFFFu)];
+          p = RANDOM ? rp : ev_pi[(size_t)t * A + (pool[fb_mv(lblk, lk) + j] & 0xFFFFu)];
           pool[fb_pol(lblk, lk) + j] = f2u(p);
         }
         const u32 cnt = lk - c0 < 32u ? lk - c0 : 32u;
@@ -781,19 +937,21 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
 // MCTS::update_root(gs, move) (mcts.cc:151-173) followed by gs.play_move(move) on the tree's root position
 template <int GAME>
 __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestSmem<GAME>& sm, u32 lane) {
-  typedef Tafl<GAME> T;
+  typedef FGame<GAME> G;
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
-  TaflKey* hist = F.hist + (size_t)t * (F.max_turns + 2u);
   u32 err = 0;
-  TaflState s = R.state;
   u32 blk = R.blk, k = R.k;
   const u32 root_term = R.term;
   if (blk == 0) {
     // root_.children.empty(): add_children(gs.valid_moves()) — the shuffle draws happen; the block is only stored
     // when it can be descended into later (a terminal root keeps no children here, see find_leaf)
     Pcg32 rng = FOREST_RNG(F, t);
-    k = forest_legal_moves<GAME>(s, sm, rng, lane, &err, F.serial_shuffle != 0);
+    {
+      typename G::Pos pos;
+      G::open(F, t, lane, pos);
+      k = G::legal(pos, sm, rng, lane, &err, F.serial_shuffle != 0);
+    }
     if (lane == 0) FOREST_RNG(F, t) = rng;
     // the chosen child is a fresh node whatever its slot: only membership matters
     bool found = false;
@@ -872,34 +1030,9 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     __syncwarp();
   }
   // gs.play_move(move) with the persistent repetition history
-  u32 hist_len = R.hist_len;
-  if (!err) {
-    if (s.turn == 0) {
-      if (lane == 0) hist[0] = T::key(s);
-      hist_len = 1;
-      __syncwarp();
-    }
-    bool cap;
-    if (!T::play(s, move, &cap)) {
-      err |= 8u;
-    } else {
-      if (cap) hist_len = 0;
-      const TaflKey key = T::key(s);
-      u32 same = 0;
-      for (u32 i = lane; i < hist_len; i += 32u) same += T::key_eq(hist[i], key) ? 1u : 0u;
-      same = warp_sum(same) + 1u;
-      if (hist_len + 1u > F.max_turns + 2u) {
-        err |= 2u;
-      } else {
-        if (lane == 0) hist[hist_len] = key;
-        ++hist_len;
-      }
-      s.rep = (u8)(same > 255u ? 255u : same);
-    }
-  }
+  if (!err) err |= G::root_play(F, t, move, lane);
   if (lane == 0) {
     if (F.gumbel_enabled) fg_reset(F.gum[t]);  // update_root ends with reset_gumbel_state() (mcts.cc:172)
-    if (!err) { R.state = s; R.hist_len = hist_len; }
     R.depth = 0;
     R.total_leaf_depth = 0;
     R.leaf.path_len = 0;
@@ -915,7 +1048,7 @@ __global__ void __launch_bounds__(128) k_forest_find_leaf(ForestView F) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
-    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, F.leaf_canon + (size_t)t * Tafl<GAME>::CANON);
+    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, F.leaf_canon + (size_t)t * FGame<GAME>::canon(F));
 }
 template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, const float* ev_v, const float* ev_pi,
@@ -969,7 +1102,7 @@ __global__ void __launch_bounds__(128) k_forest_find_leaf_batched(ForestView F) 
       continue;
     }
     forest_find_leaf<GAME, true>(F, t, sm[wib], lane, true, F.inflight[(size_t)t * F.max_in_flight + li],
-                                 F.leaf_canon + ((size_t)li * F.n_trees + t) * Tafl<GAME>::CANON);
+                                 F.leaf_canon + ((size_t)li * F.n_trees + t) * FGame<GAME>::canon(F));
     if (lane == 0) R.in_flight = li + 1u;
     __syncwarp();
   }
@@ -1038,12 +1171,12 @@ __global__ void __launch_bounds__(128) k_forest_advance(ForestView F) {
 // the cumulative pick run on lane 0 over the A entries (once per move: not a hot path).
 template <int GAME>
 __device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out, u32* picked_out, u32 pick, u32 pruned, u32 lane) {
-  typedef Tafl<GAME> T;
+  const u32 A = FGame<GAME>::actions(F);
   {
     ForestTree& R = F.trees[t];
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
     const u32 b = R.blk, k = b ? R.k : 0u;
-    for (u32 m = lane; m < (u32)T::A; m += 32u) out[m] = 0.0f;
+    for (u32 m = lane; m < A; m += 32u) out[m] = 0.0f;
     __syncwarp();
     u32 total = 0;
     for (u32 j = lane; j < k; j += 32u) total += pool[fb_n(b, k) + j];
@@ -1076,13 +1209,13 @@ __device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out,
       }
       __syncwarp();
       float ptotal = 0.0f;  // pruned.sum() over the dense vector in move order (zero entries do not change a sum)
-      for (u32 c0 = 0; c0 < (u32)T::A; c0 += 32u) {
-        const float val = c0 + lane < (u32)T::A ? out[c0 + lane] : 0.0f;
+      for (u32 c0 = 0; c0 < A; c0 += 32u) {
+        const float val = c0 + lane < A ? out[c0 + lane] : 0.0f;
         ptotal = seq_sum_masked(ptotal, val, val != 0.0f);
       }
       use_pruned = ptotal != 0.0f;
       if (!use_pruned) {
-        for (u32 m = lane; m < (u32)T::A; m += 32u) out[m] = 0.0f;
+        for (u32 m = lane; m < A; m += 32u) out[m] = 0.0f;
         __syncwarp();
       }
     }
@@ -1096,7 +1229,6 @@ __device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out,
     // sum and pow(0, e > 0) == 0, so only the non-zero entries (at most k of the A) carry the arithmetic: every chunk of
     // 32 moves is loaded one per lane and its non-zero values are folded in ascending move order with ballots + shuffles
     // (every lane accumulates the same sequence); the element-wise steps run one move per lane.
-    constexpr u32 A = (u32)T::A;
     auto dense_sum = [&]() {
       float acc = 0.0f;
       for (u32 c0 = 0; c0 < A; c0 += 32u) {
@@ -1189,32 +1321,33 @@ template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick, u32 pruned) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
-    forest_probs<GAME>(F, t, temp, probs + (size_t)t * Tafl<GAME>::A, picked + t, pick, pruned, lane);
+    forest_probs<GAME>(F, t, temp, probs + (size_t)t * FGame<GAME>::actions(F), picked + t, pick, pruned, lane);
 }
 // MCTS::counts / root_q_values (mcts.cc:557-573) + a few scalars per tree
 template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_counts(ForestView F, u32* counts, float* q, u32* info) {
-  typedef Tafl<GAME> T;
+  const u32 A = FGame<GAME>::actions(F);
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
     const ForestTree& R = F.trees[t];
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
-    for (u32 m = lane; m < (u32)T::A; m += 32u) {
-      if (counts) counts[(size_t)t * T::A + m] = 0u;
-      if (q) q[(size_t)t * T::A + m] = 0.0f;
+    for (u32 m = lane; m < A; m += 32u) {
+      if (counts) counts[(size_t)t * A + m] = 0u;
+      if (q) q[(size_t)t * A + m] = 0.0f;
     }
     __syncwarp();
     const u32 b = R.blk, k = R.k;
     if (b)
       for (u32 j = lane; j < k; j += 32u) {
         const u32 mv = pool[fb_mv(b, k) + j] & 0xFFFFu;
-        if (counts) counts[(size_t)t * T::A + mv] = pool[fb_n(b, k) + j];
-        if (q) q[(size_t)t * T::A + mv] = u2f(pool[fb_q(b, k) + j]);
+        if (counts) counts[(size_t)t * A + mv] = pool[fb_n(b, k) + j];
+        if (q) q[(size_t)t * A + mv] = u2f(pool[fb_q(b, k) + j]);
       }
     if (info && lane == 0) {
       u32* o = info + (size_t)t * 12;
-      o[0] = R.depth; o[1] = R.n; o[2] = R.k; o[3] = R.term; o[4] = R.player; o[5] = R.state.turn; o[6] = R.state.rep;
-      o[7] = R.error; o[8] = R.bump; o[9] = f2u(R.v); o[10] = R.total_leaf_depth; o[11] = R.state.player;
+      o[0] = R.depth; o[1] = R.n; o[2] = R.k; o[3] = R.term; o[4] = R.player;
+      FGame<GAME>::info(F, t, &o[5], &o[6], &o[11]);
+      o[7] = R.error; o[8] = R.bump; o[9] = f2u(R.v); o[10] = R.total_leaf_depth;
     }
   }
 }
@@ -1228,15 +1361,15 @@ __global__ void k_forest_gumbel_arm(ForestView F, u32 n) {
 // gumbel_final_action + gumbel_improved_policy per tree
 template <int GAME>
 __global__ void __launch_bounds__(128) k_forest_gumbel_result(ForestView F, u32* action, float* policy) {
-  typedef Tafl<GAME> T;
+  const u32 A = FGame<GAME>::actions(F);
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
     const ForestTree& R = F.trees[t];
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
     if (policy) {
-      for (u32 m = lane; m < (u32)T::A; m += 32u) policy[(size_t)t * T::A + m] = 0.0f;
+      for (u32 m = lane; m < A; m += 32u) policy[(size_t)t * A + m] = 0.0f;
       __syncwarp();
-      if (lane == 0) fg_improved_policy(F, t, R, pool, policy + (size_t)t * T::A);
+      if (lane == 0) fg_improved_policy(F, t, R, pool, policy + (size_t)t * A);
     }
     if (action && lane == 0) action[t] = fg_final_action(F, t, R, F.gum[t], pool);
     __syncwarp();
@@ -1244,11 +1377,10 @@ __global__ void __launch_bounds__(128) k_forest_gumbel_result(ForestView F, u32*
 }
 template <int GAME>
 __global__ void k_forest_init(ForestView F, unsigned long long seed) {
-  typedef Tafl<GAME> T;
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
     ForestTree& R = F.trees[t];
     memset(&R, 0, sizeof(ForestTree));
-    T::init(R.state, F.max_turns);
+    FGame<GAME>::init(F, t);
     R.bump = 1;
     pcg32_seed(R.rng, seed + t);  // tree t == a reference MCTS driven after MCTS::seed_thread_rng(seed + t)
   }
@@ -1270,7 +1402,8 @@ struct b2az_forest {
   switch ((F)->view.game) {                                                               \
     case B2AZ_TAFL_BRANDUBH: { constexpr int G_ = B2AZ_TAFL_BRANDUBH; CALL; } break;      \
     case B2AZ_TAFL_OPENTAFL: { constexpr int G_ = B2AZ_TAFL_OPENTAFL; CALL; } break;      \
-    default: { constexpr int G_ = B2AZ_TAFL_TAWLBWRDD; CALL; } break;                     \
+    case B2AZ_TAFL_TAWLBWRDD: { constexpr int G_ = B2AZ_TAFL_TAWLBWRDD; CALL; } break;    \
+    default: { constexpr int G_ = B2AZ_FOREST_SG; CALL; } break;                          \
   }
 static inline unsigned forest_ctas(const b2az_forest* f) { return std::max(1u, std::min((f->view.n_trees + 3u) / 4u, 148u * 8u)); }
 #endif
@@ -1280,14 +1413,14 @@ extern "C" {
 int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out) {
   using namespace b2az;
   if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
-  if (p->game > B2AZ_TAFL_TAWLBWRDD) return fail(B2AZ_EINVAL, "b2az_forest: unknown tafl game");
+  const bool is_sg = (p->game >= 10 && p->game <= 13) || (p->game >= 20 && p->game <= 23);
+  if (p->game > B2AZ_TAFL_TAWLBWRDD && !is_sg) return fail(B2AZ_EINVAL, "b2az_forest: unknown game");
   if (p->n_trees == 0 || p->max_turns == 0 || p->max_turns > 65535u) return fail(B2AZ_EINVAL, "b2az_forest: bad n_trees / max_turns");
   if (!(p->root_policy_temp > 0.0f)) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp must be positive (1 = off)");
   if (p->epsilon < 0.0f || p->epsilon > 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: epsilon must be in [0, 1]");
   if (p->gumbel_enabled && (p->gumbel_m == 0 || p->gumbel_m > (uint32_t)kFMaxM))
     return fail(B2AZ_EINVAL, "b2az_forest: gumbel_m must be in [1, 64]");
   if (p->gumbel_full) return fail(B2AZ_EINVAL, "b2az_forest: gumbel_full (pi'-matching at interior nodes) is not implemented yet");
-  if (p->relative_values) return fail(B2AZ_EINVAL, "b2az_forest: relative_values is not implemented (tafl values are absolute)");
 #ifdef B2AZ_HOST_EMU
   (void)device;
   return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
@@ -1302,15 +1435,29 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   memset(&V, 0, sizeof(V));
   V.n_trees = p->n_trees; V.max_turns = p->max_turns; V.game = p->game;
   V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.root_fpu_zero = p->root_fpu_zero ? 1u : 0u;
-  const uint32_t S = p->game == B2AZ_TAFL_BRANDUBH ? 7u : 11u, planes = p->game == B2AZ_TAFL_OPENTAFL ? 8u : 7u;
-  f->actions = 2u * S * S * S;
-  f->canon = planes * S * S;
+  if (is_sg) {
+    const SGSpace sp = sg_space((int)(p->game % 10u), p->game >= 20u);
+    f->actions = (uint32_t)sp.num_moves();
+    f->canon = (uint32_t)(sp.planes(p->game >= 20u) * sp.udim * sp.udim);
+  } else {
+    const uint32_t S = p->game == B2AZ_TAFL_BRANDUBH ? 7u : 11u, planes = p->game == B2AZ_TAFL_OPENTAFL ? 8u : 7u;
+    f->actions = 2u * S * S * S;
+    f->canon = planes * S * S;
+  }
+  V.actions = f->actions; V.canon = f->canon; V.relative_values = p->relative_values ? 1u : 0u;
   V.words_per_tree = p->words_per_tree ? p->words_per_tree : (1u << 20);
   auto bail = [&](int rc) { b2az_forest_destroy(f); return rc; };
   if (int rc = dev_alloc(&V.trees, (size_t)V.n_trees)) return bail(rc);
   if (int rc = dev_alloc_raw(&V.pool, (size_t)V.n_trees * V.words_per_tree)) return bail(rc);
-  if (int rc = dev_alloc(&V.hist, (size_t)V.n_trees * (V.max_turns + 2u))) return bail(rc);
-  if (int rc = dev_alloc(&V.pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
+  if (is_sg) {  // position keys since the last deploy (a turn is several actions: the bound is generous, overflow is reported)
+    V.sg_hist_cap = 2048u;
+    if (int rc = dev_alloc(&V.sg_state, (size_t)V.n_trees)) return bail(rc);
+    if (int rc = dev_alloc(&V.sg_hist, (size_t)V.n_trees * V.sg_hist_cap)) return bail(rc);
+    if (int rc = dev_alloc(&V.sg_pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
+  } else {
+    if (int rc = dev_alloc(&V.hist, (size_t)V.n_trees * (V.max_turns + 2u))) return bail(rc);
+    if (int rc = dev_alloc(&V.pkeys, (size_t)V.n_trees * (kFPath + 2))) return bail(rc);
+  }
   V.max_in_flight = p->max_in_flight;
   if (V.max_in_flight > 64u) return bail(fail(B2AZ_EINVAL, "b2az_forest: max_in_flight must be <= 64"));
   if (int rc = dev_alloc(&V.leaf_canon, (size_t)V.n_trees * f->canon * std::max(1u, V.max_in_flight))) return bail(rc);
@@ -1341,6 +1488,7 @@ int b2az_forest_destroy(b2az_forest* f) {
   dev_free(f->view.trees); dev_free(f->view.pool); dev_free(f->view.hist); dev_free(f->view.pkeys);
   dev_free(f->view.leaf_canon); dev_free(f->moves_dev); dev_free(f->ev_v); dev_free(f->ev_pi);
   dev_free(f->view.gum); dev_free(f->view.gum_g); dev_free(f->view.noise); dev_free(f->view.inflight);
+  dev_free(f->view.sg_state); dev_free(f->view.sg_hist); dev_free(f->view.sg_pkeys);
   delete f;
   return 0;
 }

@@ -47,7 +47,10 @@ struct SpView {
   float playout_cap_percent, resign_percent, resign_playthrough_percent;
   float start_temp, final_temp, half_life;
   u32 history_enabled, policy_target_pruning, tree_reuse;
-  float* st_canon;    // [n_games][max_turns][CANON]
+  u32 stage_rows;     // staging rows per slot: the game's max_turns (tafl) / a bound on the actions of a Star Gambit game
+  u32 n_variant_half_life;
+  float variant_half_life[4];  // temp_decay_half_life_by_variant
+  float* st_canon;    // [n_games][stage_rows][CANON]
   float* st_pi;       // [n_games][max_turns][A]
   u8* st_player;      // [n_games][max_turns]
   float* scratch_pi;  // [n_games][A]: the acting distribution
@@ -64,24 +67,6 @@ __device__ __forceinline__ void sp_reset_search(const ForestView& F, u32 t) {
   R.n = 0; R.v = 0.0f; R.d = 0.0f; R.blk = 0; R.k = 0; R.player = 0; R.term = 0;
   R.depth = 0; R.total_leaf_depth = 0; R.bump = 1; R.half = 0; R.nif = 0; R.expanded = 0; R.in_flight = 0;
   if (F.gum) { F.gum[t].num_sims_target = 0; fg_reset(F.gum[t]); }
-}
-template <int GAME>
-__device__ __forceinline__ void sp_emit_canon(const TaflState& s, float* out, u32 lane) {  // GameState::canonicalized()
-  typedef Tafl<GAME> T;
-  constexpr int CELLS = T::CELLS, CHUNKS = (CELLS + 31) / 32;
-#pragma unroll
-  for (int j = 0; j < CHUNKS; ++j) {
-    const u32 c = 32u * j + lane;
-    if (c < (u32)CELLS) {
-      out[c] = (float)((b128_word(s.king, j) >> lane) & 1u);
-      out[CELLS + c] = (float)((b128_word(s.def, j) >> lane) & 1u);
-      out[2 * CELLS + c] = (float)((b128_word(s.atk, j) >> lane) & 1u);
-    }
-  }
-  for (int pl = 3; pl < T::PLANES; ++pl) {
-    const float v = T::canon_elem(s, (u32)(pl * CELLS));
-    for (u32 c = lane; c < (u32)CELLS; c += 32u) out[pl * CELLS + c] = v;
-  }
 }
 // The reference flips its playout-cap and resign-playthrough coins with a thread_local std::default_random_engine seeded
 // from std::random_device (play_manager.cc:261-262): unseedable, so there is nothing to replay. Here every slot has its
@@ -126,7 +111,7 @@ __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
     pcg32_seed_stream(G.coin, seed + g, 0x5EEDC01ull);
     // game.initialized = true; the first playout-cap coin; set_gumbel_num_sims on the first seat's tree (play_manager.cc:556-568)
     G.capped = (S.playout_cap && sp_coin(G, S.playout_cap_percent)) ? 1u : 0u;
-    const u32 cp0 = F.trees[2u * g].state.player, t0 = 2u * g + cp0;
+    const u32 cp0 = 0u, t0 = 2u * g + cp0;  // player 0 opens every game of this engine (attackers / Star Gambit's P0)
     const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[cp0] : 0u) : S.seat_visits[cp0];
     if (F.gum) { F.gum[t0].num_sims_target = target; fg_reset(F.gum[t0]); }
   }
@@ -139,7 +124,7 @@ __global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_sp_search(ForestView 
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
-    const u32 cp = F.trees[2u * g].state.player, t = 2u * g + cp;
+    const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
     const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;  // seat_epsilon > 0 && !capped
     const u32 goal = sp_goal(S, S.slots[g], cp), have = F.trees[t].depth;
     const u32 todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;  // this slot's own budget
@@ -158,8 +143,8 @@ __global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, fl
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
-    const u32 t = 2u * g + F.trees[2u * g].state.player;
-    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, canon + (size_t)g * Tafl<GAME>::CANON);
+    const u32 t = 2u * g + FGame<GAME>::root_player(F, 2u * g);
+    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, canon + (size_t)g * FGame<GAME>::canon(F));
   }
 }
 template <int GAME>
@@ -167,10 +152,10 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
   const u32 lane = threadIdx.x & 31u;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
-    const u32 t = 2u * g + F.trees[2u * g].state.player;
+    const u32 t = 2u * g + FGame<GAME>::root_player(F, 2u * g);
     // forest_process_result reads row t of its inputs: hand it pointers moved so that row t is row g
     forest_process_result<GAME, false, false>(F, t, ev_v + (size_t)g * 3 - (size_t)t * 3,
-                                              ev_pi + (size_t)g * Tafl<GAME>::A - (size_t)t * Tafl<GAME>::A, lane,
+                                              ev_pi + (size_t)g * FGame<GAME>::actions(F) - (size_t)t * FGame<GAME>::actions(F), lane,
                                               F.epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf);
     if (lane == 0) S.slots[g].simulations += 1;
   }
@@ -182,23 +167,29 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
 #endif
 template <int GAME>
 __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F, SpView S) {
-  typedef Tafl<GAME> T;
+  typedef FGame<GAME> GM;
+  const u32 A = GM::actions(F), CANON = GM::canon(F);
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     SpSlot& G = S.slots[g];
     if (!G.active) continue;
-    const u32 cp = F.trees[2u * g].state.player, t = 2u * g + cp;
+    const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
     ForestTree& R = F.trees[t];
     if (R.depth < sp_goal(S, G, cp)) continue;  // mcts.depth() >= goal_depth
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
     const bool capped = G.capped != 0;
     // temperature schedule (play_manager.cc:285-302)
     float temp = S.start_temp;
-    if (S.half_life != 0.0f) {
-      const float lambda = fdiv(0.693f, S.half_life);
+    float half_life = S.half_life;
+    {  // temp_decay_half_life_by_variant (play_manager.cc:289-296)
+      const int vid = GM::root_variant(F, 2u * g);
+      if (S.n_variant_half_life && vid >= 0 && vid < (int)S.n_variant_half_life) half_life = S.variant_half_life[vid];
+    }
+    if (half_life != 0.0f) {
+      const float lambda = fdiv(0.693f, half_life);
       temp = fsub(temp, S.final_temp);
-      temp = fmul(temp, az_expf(fmul(-lambda, (float)R.state.turn)));
+      temp = fmul(temp, az_expf(fmul(-lambda, (float)GM::root_turn(F, 2u * g))));
       temp = fadd(temp, S.final_temp);
     }
     // resign_percent (play_manager.cc:305-333): MCTS::root_value (mcts.h:78-100) against 1 - resign_percent
@@ -228,7 +219,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       resign_term = __shfl_sync(0xFFFFFFFFu, resign_term, 0);
     }
     // acting rule (play_manager.cc:367-406): Gumbel's final action only after a full search
-    float* act = S.scratch_pi + (size_t)g * T::A;
+    float* act = S.scratch_pi + (size_t)g * A;
     u32 chosen = 0xFFFFFFFFu;
     if (F.gumbel_enabled && !capped) {
       if (lane == 0) chosen = fg_final_action(F, t, R, F.gum[t], pool);
@@ -243,11 +234,19 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
     }
     // training sample (play_manager.cc:407-424): full searches only
     if (S.history_enabled && !capped) {
-      const size_t row = (size_t)g * F.max_turns + G.pending;
-      sp_emit_canon<GAME>(R.state, S.st_canon + row * T::CANON, lane);
-      float* pi = S.st_pi + row * T::A;
+      // (a game longer than the staging area — only Star Gambit's action count is unbounded a priori — overwrites its
+      // last row and reports it)
+      const u32 prow = G.pending < S.stage_rows ? G.pending : S.stage_rows - 1u;
+      if (G.pending >= S.stage_rows && lane == 0) G.error |= 2u;
+      const size_t row = (size_t)g * S.stage_rows + prow;
+      {
+        typename GM::Pos pos;  // GameState::canonicalized() of the root position
+        GM::open(F, t, lane, pos);
+        GM::emit_canon(pos, sm[wib], S.st_canon + row * CANON, lane);
+      }
+      float* pi = S.st_pi + row * A;
       if (F.gumbel_enabled) {
-        for (u32 m = lane; m < (u32)T::A; m += 32u) pi[m] = 0.0f;
+        for (u32 m = lane; m < A; m += 32u) pi[m] = 0.0f;
         __syncwarp();
         if (lane == 0) fg_improved_policy(F, t, R, pool, pi);
         __syncwarp();
@@ -257,7 +256,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       if (lane == 0) S.st_player[row] = (u8)cp;
     }
     if (lane == 0) {
-      if (S.history_enabled && !capped) G.pending += 1;
+      if (S.history_enabled && !capped && G.pending < S.stage_rows) G.pending += 1;
       // metrics (play_manager.cc:436-446; MCTS::avg_leaf_depth mcts.h:112, normalized_root_entropy mcts.cc:737-750)
       const float ald = R.depth == 0 ? 0.0f : fdiv((float)R.total_leaf_depth, (float)R.depth);
       float ent = 0.0f;
@@ -293,8 +292,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
     __syncwarp();
     forest_update_root<GAME>(F, 2u * g + 1u, chosen, sm[wib], lane);
     __syncwarp();
-    const TaflState ns = F.trees[2u * g].state;
-    u32 term = T::terminal(ns);
+    u32 term = GM::root_terminal(F, 2u * g);
     if (term == 0 && resign_term != 0) term = resign_term;  // play_manager.cc:440-444
     else resign_term = 0;
     if (term != 0) {
@@ -307,11 +305,14 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
         for (u32 i = 0; i < cnt; ++i) {  // partial_history.back() first
           const u32 dst = base + i;
           if (dst >= S.out_cap) { if (lane == 0) G.error |= 1u; break; }
-          const size_t src = (size_t)g * F.max_turns + (cnt - 1u - i);
-          for (u32 e = lane; e < (u32)T::CANON; e += 32u) S.out_canon[(size_t)dst * T::CANON + e] = S.st_canon[src * T::CANON + e];
-          for (u32 e = lane; e < (u32)T::A; e += 32u) S.out_pi[(size_t)dst * T::A + e] = S.st_pi[src * T::A + e];
+          const size_t src = (size_t)g * S.stage_rows + (cnt - 1u - i);
+          for (u32 e = lane; e < CANON; e += 32u) S.out_canon[(size_t)dst * CANON + e] = S.st_canon[src * CANON + e];
+          for (u32 e = lane; e < A; e += 32u) S.out_pi[(size_t)dst * A + e] = S.st_pi[src * A + e];
           if (lane == 0) {
-            S.out_v[(size_t)dst * 3 + 0] = s0; S.out_v[(size_t)dst * 3 + 1] = s1; S.out_v[(size_t)dst * 3 + 2] = sd;
+            // relative_values games store the outcome in the frame of the sample's mover (absolute_to_relative,
+            // play_manager.cc:451-455)
+            const bool sw = F.relative_values && S.st_player[src] == 1;
+            S.out_v[(size_t)dst * 3 + 0] = sw ? s1 : s0; S.out_v[(size_t)dst * 3 + 1] = sw ? s0 : s1; S.out_v[(size_t)dst * 3 + 2] = sd;
             S.out_slot[dst] = g;
           }
         }
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
           G.resign_scores[2] = fadd(G.resign_scores[2], sd);
         }
         G.games_completed += 1;
-        G.game_length += ns.turn;
+        G.game_length += GM::root_turn(F, 2u * g);
         G.leaf_depth += G.g_leaf_depth; G.entropy += G.g_entropy; G.valid_moves += G.g_valid_moves;
         G.total_move_count += G.move_count; G.total_full_move_count += G.full_move_count;
         G.fast_leaf_depth += G.g_fast_leaf_depth; G.fast_entropy += G.g_fast_entropy; G.total_fast_move_count += G.fast_move_count;
@@ -337,9 +338,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
         } else {
           G.games_started += 1;
           for (u32 j = 0; j < 2u; ++j) {  // game.gs = base_gs_->copy(); fresh MCTS per seat
-            ForestTree& N = F.trees[2u * g + j];
-            T::init(N.state, F.max_turns);
-            N.hist_len = 0;
+            GM::init(F, 2u * g + j);  // (Unified: the pinned variant again; the random mix is an unseedable mt19937 in the reference)
             sp_reset_search(F, 2u * g + j);
           }
         }
@@ -351,7 +350,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
     // a move has been played: the next search's playout cap (play_manager.cc:523-524; `&&` short-circuits the coin)
     if (lane == 0) G.capped = (S.playout_cap && sp_coin(G, S.playout_cap_percent)) ? 1u : 0u;
     __syncwarp();
-    const u32 tn = 2u * g + F.trees[2u * g].state.player;
+    const u32 tn = 2u * g + GM::root_player(F, 2u * g);
     if (!S.tree_reuse) {
       // set_gumbel_num_sims happens BEFORE the trees are replaced by fresh MCTS objects (play_manager.cc:531-545), so
       // without tree reuse the new objects have no simulation target (the reference's behaviour, reproduced)
@@ -444,7 +443,10 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   S.history_enabled = p->history_enabled ? 1u : 0u;
   S.policy_target_pruning = p->policy_target_pruning ? 1u : 0u;
   S.tree_reuse = p->tree_reuse ? 1u : 0u;
+  S.n_variant_half_life = std::min(p->n_variant_half_life, 4u);
+  for (int i = 0; i < 4; ++i) S.variant_half_life[i] = p->variant_half_life[i];
   S.out_cap = S.history_enabled ? (p->hist_capacity ? p->hist_capacity : p->n_games * fp.max_turns) : 1u;
+  S.stage_rows = fp.max_turns;
   const size_t G = p->n_games, MT = fp.max_turns, A = f->actions, C = f->canon;
   auto bail = [&](int rc) { b2az_tafl_selfplay_destroy(sp); return rc; };
   if (int rc = dev_alloc(&S.slots, G)) return bail(rc);

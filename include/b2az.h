@@ -402,7 +402,9 @@ int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, floa
  * improved policy / probs_pruned(1) / probs(1), play_manager.cc:417-435), scores and metrics, bit for bit.
  * forest.n_trees is ignored (2 * n_games trees are made); forest.max_in_flight must be 0. */
 typedef struct b2az_tafl_selfplay_params {
-  b2az_forest_params forest;     /* game, max_turns, search parameters (cpuct, epsilon, Gumbel ...), seed, slab size */
+  b2az_forest_params forest;     /* game (B2AZ_TAFL_*, B2AZ_SG_GAME / B2AZ_SG_UNIFIED), max_turns (Star Gambit: the bound
+                                    on the training samples of one game, e.g. 768), search parameters (cpuct, epsilon,
+                                    Gumbel, relative_values ...), seed, slab size */
   uint32_t n_games;              /* PlayParams::concurrent_games */
   uint32_t games_per_slot;       /* games every slot plays before it retires (games_to_play = n_games * games_per_slot) */
   uint32_t visits;               /* PlayParams::mcts_visits (both seats) */
@@ -417,6 +419,8 @@ typedef struct b2az_tafl_selfplay_params {
   uint8_t playout_cap_randomization; /* fast searches: no sample, no root noise, PUCT acting (play_manager.cc:523-553) */
   uint8_t fast_search_uses_gumbel;
   uint8_t pad2_[2];
+  uint32_t n_variant_half_life;  /* PlayParams::temp_decay_half_life_by_variant (play_manager.cc:289-296): entries used */
+  float variant_half_life[4];    /* indexed by GameState::get_variant_id() (StarGambitUnifiedGS: the variant) */
 } b2az_tafl_selfplay_params;
 typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
   uint32_t active, games_started, games_completed, pending;

@@ -17,6 +17,9 @@ import tafl_ref
 
 NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
 MAX_TURNS = {0: 150, 1: 400, 2: 400}
+for _g in (10, 11, 12, 13, 20, 21, 22, 23):  # Star Gambit (tests/test_stargambit_search.py): max_turns is unused by the search
+    NAMES[_g] = f"stargambit{_g}"
+    MAX_TURNS[_g] = 768
 needs_tafl_ref = pytest.mark.skipif(not tafl_ref.available(), reason="oracle/_ref/libazref_tafl.so not built")
 GOLDEN = os.path.join(ph.ROOT, "tests", "golden", "forest_random_eval.npz")
 # (game, trees, moves, sims per move, seed, cpuct, fpu_reduction, root_fpu_zero)
