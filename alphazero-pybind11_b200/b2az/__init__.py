@@ -157,6 +157,10 @@ def load(path=None):
     L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
     L.b2az_forest_update_root.argtypes = [vp, vp, vp]
     L.b2az_forest_counts.argtypes = [vp, vp, vp, vp, vp]
+    L.b2az_forest_principal_variation.argtypes = [vp, vp, u32, vp, vp]
+    L.b2az_forest_leaf_path.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.b2az_forest_root_ops.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.b2az_forest_set_root.argtypes = [vp, u32, vp, u32, vp, u32]
     L.b2az_tafl_symmetries.argtypes = [C.c_int, u32, u32] + [vp] * 6
     L.b2az_tafl_positions.argtypes = [C.c_int, u32, u32, u32] + [vp] * 12
     L.b2az_tafl_selfplay_create.argtypes = [C.POINTER(TaflSelfplayParams), C.c_int, C.POINTER(vp)]
@@ -464,7 +468,7 @@ class Forest:
     """n_trees device-resident single-tree searches over a tafl game: the reference's `MCTS` class, batched
     (find_leaf / process_result / update_root / counts)."""
     INFO = ("depth", "root_n", "root_k", "root_term", "root_player", "turn", "rep", "error", "words_used", "root_v_bits",
-            "total_leaf_depth", "player")
+            "total_leaf_depth", "player", "root_value_w_bits", "root_value_l_bits", "root_value_d_bits", "in_flight")
 
     def __init__(self, game, n_trees, max_turns, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, seed=0,
                  words_per_tree=0, epsilon=0.0, root_policy_temp=1.0, gumbel_m=0, gumbel_c_visit=50.0, gumbel_c_scale=1.0,
@@ -567,7 +571,7 @@ class Forest:
     def counts(self, stream=None, want_q=True):
         counts = np.zeros((self.n, self.A), np.uint32)
         q = np.zeros((self.n, self.A), np.float32) if want_q else None
-        info = np.zeros((self.n, 12), np.uint32)
+        info = np.zeros((self.n, 16), np.uint32)
         self._check(self.L.b2az_forest_counts(self.h, stream, _ptr(counts), _ptr(q), _ptr(info)))
         return counts, q, {k: info[:, i] for i, k in enumerate(self.INFO)}
 

@@ -1344,10 +1344,21 @@ __global__ void __launch_bounds__(128) k_forest_counts(ForestView F, u32* counts
         if (q) q[(size_t)t * A + mv] = u2f(pool[fb_q(b, k) + j]);
       }
     if (info && lane == 0) {
-      u32* o = info + (size_t)t * 12;
+      u32* o = info + (size_t)t * 16;
       o[0] = R.depth; o[1] = R.n; o[2] = R.k; o[3] = R.term; o[4] = R.player;
       FGame<GAME>::info(F, t, &o[5], &o[6], &o[11]);
       o[7] = R.error; o[8] = R.bump; o[9] = f2u(R.v); o[10] = R.total_leaf_depth;
+      {  // MCTS::root_value (mcts.h:78-100): win / loss / draw from the best-Q visited child, else the root's own value
+        float qv = 0.0f, dv = 0.0f;
+        bool found = false;
+        for (u32 j = 0; b && j < k; ++j) {
+          const float qj = u2f(pool[fb_q(b, k) + j]);
+          if (pool[fb_n(b, k) + j] > 0 && qj > qv) { qv = qj; dv = u2f(pool[fb_d(b, k) + j]); found = true; }
+        }
+        if (!found && R.n > 0) { qv = R.v; dv = R.d; }
+        const float w = fsub(qv, fdiv(dv, 2.0f));
+        o[12] = f2u(w); o[13] = f2u((float)dsub(dsub(1.0, (double)w), (double)dv)); o[14] = f2u(dv); o[15] = R.in_flight;
+      }
     }
   }
 }
@@ -1373,6 +1384,62 @@ __global__ void __launch_bounds__(128) k_forest_gumbel_result(ForestView F, u32*
     }
     if (action && lane == 0) action[t] = fg_final_action(F, t, R, F.gum[t], pool);
     __syncwarp();
+  }
+}
+// MCTS::principal_variation(depth) (mcts.cc:676-715): the most-visited line from the root (first maximum in child
+// order; the root step is the Gumbel final action when Gumbel is active). out [n_trees][depth], len [n_trees].
+__global__ void k_forest_pv(ForestView F, u32 depth, u32* out, u32* len) {
+  for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
+    const ForestTree& R = F.trees[t];
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    u32 b = R.blk, k = b ? R.k : 0u, n = 0;
+    for (u32 i = 0; i < depth && b != 0 && k != 0; ++i) {
+      u32 best = 0xFFFFFFFFu;
+      if (i == 0 && F.gumbel_enabled) {
+        const u32 mv = fg_final_action(F, t, R, F.gum[t], pool);
+        for (u32 j = 0; j < k && best == 0xFFFFFFFFu; ++j)
+          if ((pool[fb_mv(b, k) + j] & 0xFFFFu) == mv) best = j;
+      }
+      if (best == 0xFFFFFFFFu) {
+        u32 best_n = 0;
+        for (u32 j = 0; j < k; ++j) {
+          const u32 nj = pool[fb_n(b, k) + j];
+          if (nj > best_n) { best_n = nj; best = j; }
+        }
+      }
+      if (best == 0xFFFFFFFFu || pool[fb_n(b, k) + best] == 0) break;
+      out[(size_t)t * depth + n++] = pool[fb_mv(b, k) + best] & 0xFFFFu;
+      const u32 nb = pool[fb_fc(b, k) + best];
+      b = nb; k = nb ? pool[nb] : 0u;
+    }
+    len[t] = n;
+  }
+}
+// the moves along the path of a pending leaf (MCTS::path_ / one InFlightLeaf): what the caller replays on its own copy
+// of the root position to obtain the leaf GameState find_leaf returns. slot < 0: the plain find_leaf's leaf.
+__global__ void k_forest_leaf_path(ForestView F, int slot, u32* out, u32* len) {
+  for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
+    const ForestLeaf& L = slot < 0 ? F.trees[t].leaf : F.inflight[(size_t)t * F.max_in_flight + (u32)slot];
+    const u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    for (u32 i = 0; i < L.path_len; ++i) {
+      const u32 b = L.path_blk[i], k = pool[b];
+      out[(size_t)t * kFPath + i] = pool[fb_mv(b, k) + L.path_slot[i]] & 0xFFFFu;
+    }
+    len[t] = L.path_len;
+  }
+}
+// MCTS::apply_root_policy_temp (mcts.cc:448-460) and / or MCTS::add_root_noise (mcts.cc:403-446), separately callable
+__global__ void k_forest_root_ops(ForestView F, u32 apply_temp, u32 add_noise) {
+  for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
+    ForestTree& R = F.trees[t];
+    if (R.blk == 0 || R.k == 0) continue;
+    u32* pool = F.pool + (size_t)t * F.words_per_tree;
+    if (apply_temp) fr_apply_root_policy_temp(F, pool, R.blk, R.k);
+    if (add_noise && F.noise) {
+      Pcg32 rng = FOREST_RNG(F, t);
+      fr_add_root_noise(F, t, rng, pool, R.blk, R.k);
+      FOREST_RNG(F, t) = rng;
+    }
   }
 }
 template <int GAME>
@@ -1511,6 +1578,10 @@ int b2az_forest_set_gumbel_num_sims(b2az_forest*, void*, uint32_t) FOREST_NO_CUD
 int b2az_forest_gumbel_result(b2az_forest*, void*, uint32_t*, float*) FOREST_NO_CUDA()
 int b2az_forest_update_root(b2az_forest*, void*, const uint32_t*) FOREST_NO_CUDA()
 int b2az_forest_counts(b2az_forest*, void*, uint32_t*, float*, uint32_t*) FOREST_NO_CUDA()
+int b2az_forest_principal_variation(b2az_forest*, void*, uint32_t, uint32_t*, uint32_t*) FOREST_NO_CUDA()
+int b2az_forest_leaf_path(b2az_forest*, void*, int, uint32_t*, uint32_t*) FOREST_NO_CUDA()
+int b2az_forest_root_ops(b2az_forest*, void*, int, int) FOREST_NO_CUDA()
+int b2az_forest_set_root(b2az_forest*, uint32_t, const void*, uint32_t, const void*, uint32_t) FOREST_NO_CUDA()
 #else
 int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev) {
   if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
@@ -1700,6 +1771,79 @@ int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_
   CUDA_TRY(cudaGetLastError());
   return stream_sync(s);
 }
+int b2az_forest_principal_variation(b2az_forest* f, void* stream, uint32_t depth, uint32_t* moves_host, uint32_t* len_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));
+  using namespace b2az;
+  if (!f || !moves_host || !len_host || depth == 0) return fail(B2AZ_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees;
+  u32 *dm = nullptr, *dl = nullptr;
+  int rc = dev_alloc(&dm, n * depth);
+  if (!rc) rc = dev_alloc(&dl, n);
+  if (!rc) {
+    k_forest_pv<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f->view, depth, dm, dl);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_pv launch failed");
+  }
+  if (!rc) rc = copy_d2h(moves_host, dm, n * depth * 4, s);
+  if (!rc) rc = copy_d2h(len_host, dl, n * 4, s);
+  if (!rc) rc = stream_sync(s);
+  dev_free(dm); dev_free(dl);
+  return rc;
+}
+int b2az_forest_leaf_path(b2az_forest* f, void* stream, int slot, uint32_t* moves_host, uint32_t* len_host) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));
+  using namespace b2az;
+  if (!f || !moves_host || !len_host) return fail(B2AZ_EINVAL, "null argument");
+  if (slot >= (int)f->view.max_in_flight) return fail(B2AZ_EINVAL, "b2az_forest_leaf_path: slot out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = f->view.n_trees;
+  u32 *dm = nullptr, *dl = nullptr;
+  int rc = dev_alloc(&dm, n * kFPath);
+  if (!rc) rc = dev_alloc(&dl, n);
+  if (!rc) {
+    k_forest_leaf_path<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(f->view, slot, dm, dl);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_leaf_path launch failed");
+  }
+  if (!rc) rc = copy_d2h(moves_host, dm, n * kFPath * 4, s);
+  if (!rc) rc = copy_d2h(len_host, dl, n * 4, s);
+  if (!rc) rc = stream_sync(s);
+  dev_free(dm); dev_free(dl);
+  return rc;
+}
+int b2az_forest_root_ops(b2az_forest* f, void* stream, int apply_temp, int add_noise) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));
+  using namespace b2az;
+  if (!f) return fail(B2AZ_EINVAL, "null forest");
+  if (add_noise && !f->view.noise) return fail(B2AZ_ESTATE, "b2az_forest: created with epsilon == 0 (no noise buffers)");
+  k_forest_root_ops<<<(f->view.n_trees + 127u) / 128u, 128, 0, static_cast<cudaStream_t>(stream)>>>(f->view, apply_temp ? 1u : 0u, add_noise ? 1u : 0u);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int b2az_forest_set_root(b2az_forest* f, uint32_t tree, const void* state, uint32_t state_bytes, const void* hist,
+                         uint32_t hist_count) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));
+  using namespace b2az;
+  if (!f || !state) return fail(B2AZ_EINVAL, "null argument");
+  if (tree >= f->view.n_trees) return fail(B2AZ_EINVAL, "b2az_forest_set_root: tree out of range");
+  const bool sg = f->view.sg_state != nullptr;
+  const size_t want = sg ? sizeof(SGState) : sizeof(TaflState), key = sg ? sizeof(u64) : sizeof(TaflKey);
+  const size_t cap = sg ? f->view.sg_hist_cap : (size_t)f->view.max_turns + 2u;
+  if (state_bytes != want) return fail(B2AZ_EINVAL, "b2az_forest_set_root: state record of the wrong size");
+  if (hist_count > cap || (hist_count && !hist)) return fail(B2AZ_EINVAL, "b2az_forest_set_root: history too long");
+  ForestTree h;
+  CUDA_TRY(cudaMemcpy(&h, f->view.trees + tree, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.n != 0 || h.blk != 0 || h.expanded != 0) return fail(B2AZ_ESTATE, "b2az_forest_set_root: the tree has been searched already");
+  if (sg) {
+    CUDA_TRY(cudaMemcpy(f->view.sg_state + tree, state, want, cudaMemcpyHostToDevice));
+    if (hist_count) CUDA_TRY(cudaMemcpy(f->view.sg_hist + (size_t)tree * cap, hist, hist_count * key, cudaMemcpyHostToDevice));
+  } else {
+    memcpy(&h.state, state, want);
+    if (hist_count) CUDA_TRY(cudaMemcpy(f->view.hist + (size_t)tree * cap, hist, hist_count * key, cudaMemcpyHostToDevice));
+  }
+  h.hist_len = hist_count;
+  CUDA_TRY(cudaMemcpy(f->view.trees + tree, &h, sizeof(h), cudaMemcpyHostToDevice));
+  return 0;
+}
 int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host) {
   if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
@@ -1711,14 +1855,14 @@ int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, floa
   int rc = 0;
   if (counts_host) rc = rc ? rc : dev_alloc(&dc, n * A);
   if (q_host) rc = rc ? rc : dev_alloc(&dq, n * A);
-  if (info_host) rc = rc ? rc : dev_alloc(&di, n * 12);
+  if (info_host) rc = rc ? rc : dev_alloc(&di, n * 16);
   if (!rc) {
     FOREST_DISPATCH(f, (k_forest_counts<G_><<<forest_ctas(f), 128, 0, s>>>(f->view, dc, dq, di)));
     if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_forest_counts launch failed");
   }
   if (!rc && counts_host) rc = copy_d2h(counts_host, dc, n * A * 4, s);
   if (!rc && q_host) rc = copy_d2h(q_host, dq, n * A * 4, s);
-  if (!rc && info_host) rc = copy_d2h(info_host, di, n * 12 * 4, s);
+  if (!rc && info_host) rc = copy_d2h(info_host, di, n * 16 * 4, s);
   if (!rc) rc = stream_sync(s);
   dev_free(dc); dev_free(dq); dev_free(di);
   return rc;

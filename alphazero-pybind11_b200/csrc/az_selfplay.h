@@ -610,7 +610,7 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
     for (int i = 0; i < 3; ++i) out->scores[i] += g.scores[i];
     leaf_depth += g.leaf_depth; entropy += g.entropy; valid += g.valid_moves;
     moves += g.total_move_count; full += g.total_full_move_count; length += g.game_length;
-    if (g.error & 1u) out->device_error |= B2AZ_DEVERR_HIST;
+    if (g.error & 3u) out->device_error |= B2AZ_DEVERR_HIST;  // 1: sample ring full, 2: a game outgrew its staging rows
   }
   out->moves = moves;
   out->hist_count = sp->view.history_enabled ? std::min(count, sp->view.out_cap) - std::min(sp->hist_head, count) : 0u;

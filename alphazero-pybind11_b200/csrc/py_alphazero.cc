@@ -171,6 +171,7 @@ class Connect4GS : public GameState {  // connect4_gs.h:24-92
 
 #include "py_tafl_gs.h"  // BrandubhGS / OpenTaflGS / TawlbwrddGS
 #include "py_stargambit_gs.h"  // StarGambit{Skirmish,Showdown,Clash,Battle}GS, StarGambitUnifiedGS (+ pinned subclasses)
+#include "py_mcts.h"           // MCTS: one tree of the device search behind the reference's single-tree API
 
 // ------------------------------------------------------------------------------------ PlayParams
 enum class EvalType : uint8_t { NN = 0, RANDOM = 1, PLAYOUT = 2 };
@@ -334,21 +335,20 @@ struct GameData {  // play_manager.h:33-58, the part Python sees (py_wrapper.cc:
 
 class PlayManager {
  public:
-  // PlayManager(BrandubhGS | OpenTaflGS | TawlbwrddGS, params): the tafl self-play engine (b2az_tafl_selfplay_*)
-  template <int GAME>
-  bool try_tafl(const GameState* gs) {
-    auto* t = dynamic_cast<const TaflGS<GAME>*>(gs);
-    if (!t) return false;
-    if (t->s.turn != 0 || t->hist_len != 0) throw std::runtime_error("the B200 engine starts every game from the initial position");
+  // PlayManager(BrandubhGS | OpenTaflGS | TawlbwrddGS | StarGambit*GS, params): the wide-tree self-play engine
+  // (b2az_tafl_selfplay_*). `rows` = staging rows per game slot (the game's max_turns for the tafl games, a bound on the
+  // samples of one Star Gambit game), `k_typ` = a typical branching factor for sizing the node slabs.
+  void setup_wide(uint32_t game, uint32_t rows, int planes, int side, int actions, uint32_t k_typ, bool relative_values,
+                  const char* who) {
     tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
     PlayParams eff = params_;
-    fold_supported_seats(eff, tables_, "B200 tafl engine", 1);
+    fold_supported_seats(eff, tables_, who, 1);
     const PlayParams& P = eff;
-    auto reject = [](bool bad, const char* what) {
-      if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 tafl engine yet");
+    auto reject = [who](bool bad, const char* what) {
+      if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + who + " yet");
     };
-    reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
-    // max_cache_size: the tafl engine has no position cache yet. A cache may always forget, so the parameter is accepted
+    reject(!P.temp_decay_half_life_by_variant.empty() && game < 20, "temp_decay_half_life_by_variant");
+    // max_cache_size: this engine has no position cache yet. A cache may always forget, so the parameter is accepted
     // and every leaf goes to the evaluator (cache_hits() stays 0) — results are those of a run with the cache off, which
     // is what the reference's own cache test requires of a cache (test_cache.py:227-253).
     reject(P.gumbel_full, "gumbel_full");
@@ -361,11 +361,12 @@ class PlayManager {
     }
     random_eval_ = (et == EvalType::RANDOM);
     b2az_tafl_selfplay_params sp{};
-    sp.forest.game = GAME;
-    sp.forest.max_turns = t->s.max_turns;
+    sp.forest.game = game;
+    sp.forest.max_turns = rows;
+    sp.forest.relative_values = relative_values;
     // slab per tree: each half holds the kept subtree + one move's new nodes (1 + 8k words per expanded node)
     sp.forest.words_per_tree = P.pool_nodes ? (uint32_t)P.pool_nodes
-                                            : 2u * (1u + 4u * std::max(tables_.visits[0][0], tables_.visits[0][1]) * (1u + 8u * (GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u)));
+                                            : 2u * (1u + 4u * std::max(tables_.visits[0][0], tables_.visits[0][1]) * (1u + 8u * k_typ));
     sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
     sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
     sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
@@ -381,16 +382,41 @@ class PlayManager {
     sp.resign_percent = P.resign_percent; sp.resign_playthrough_percent = P.resign_playthrough_percent;
     sp.start_temp = P.start_temp; sp.final_temp = P.final_temp; sp.temp_decay_half_life = P.temp_decay_half_life;
     sp.history_enabled = P.history_enabled; sp.policy_target_pruning = P.policy_target_pruning; sp.tree_reuse = P.tree_reuse;
+    sp.n_variant_half_life = (uint32_t)std::min<size_t>(4, P.temp_decay_half_life_by_variant.size());
+    for (uint32_t i = 0; i < sp.n_variant_half_life; ++i) sp.variant_half_life[i] = P.temp_decay_half_life_by_variant[i];
     // history_ is unbounded in the reference; here the sample ring holds what a run can produce between drains: every
     // sample of the run when that fits an 8 GB budget (play() first, build_history_batch afterwards works), else the
     // budget — a full ring drops samples and play() then fails loudly (B2AZ_DEVERR_HIST)
-    const uint64_t row_bytes = 4ull * (TaflGS<GAME>::P * TaflGS<GAME>::S * TaflGS<GAME>::S + TaflGS<GAME>::A + 4);
-    const uint64_t want = (uint64_t)P.games_to_play * t->s.max_turns, floor_rows = (uint64_t)P.concurrent_games * t->s.max_turns;
+    const uint64_t row_bytes = 4ull * ((uint64_t)planes * side * side + actions + 4);
+    const uint64_t want = (uint64_t)P.games_to_play * rows, floor_rows = (uint64_t)P.concurrent_games * rows;
     sp.hist_capacity = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(floor_rows, std::min<uint64_t>(want, (8ull << 30) / row_bytes)));
     if (b2az_tafl_selfplay_create(&sp, P.device, &tsp_) != 0) throw_last("PlayManager");
-    canon_sz_ = TaflGS<GAME>::P * TaflGS<GAME>::S * TaflGS<GAME>::S;
-    A_ = TaflGS<GAME>::A;
-    cdims_[0] = TaflGS<GAME>::P; cdims_[1] = cdims_[2] = TaflGS<GAME>::S;
+    canon_sz_ = (uint32_t)(planes * side * side);
+    A_ = (uint32_t)actions;
+    cdims_[0] = planes; cdims_[1] = cdims_[2] = side;
+  }
+  template <int GAME>
+  bool try_tafl(const GameState* gs) {
+    auto* t = dynamic_cast<const TaflGS<GAME>*>(gs);
+    if (!t) return false;
+    if (t->s.turn != 0 || t->hist_len != 0) throw std::runtime_error("the B200 engine starts every game from the initial position");
+    setup_wide(GAME, t->s.max_turns, TaflGS<GAME>::P, TaflGS<GAME>::S, TaflGS<GAME>::A, GAME == B2AZ_TAFL_BRANDUBH ? 64u : 200u,
+               false, "B200 tafl engine");
+    return true;
+  }
+  // PlayManager(StarGambit{Skirmish,Showdown,Clash,Battle}GS | StarGambitUnifiedGS pinned to a variant, params)
+  bool try_star_gambit(const GameState* gs) {
+    auto* t = dynamic_cast<const StarGambitBase*>(gs);
+    if (!t) return false;
+    if (t->s.turn != 1 || t->s.n_units != 2) throw std::runtime_error("the B200 engine starts every game from the initial position");
+    if (t->unified && (t->pinned < 0 || t->pinned > 3))
+      throw std::runtime_error("StarGambitUnifiedGS with the random variant mix is not implemented by the B200 Star Gambit engine yet: "
+                               "run one PlayManager per pinned variant");
+    const auto sp = t->space();
+    // a Star Gambit game has no fixed bound on its actions (200 turns of several actions each): 512 staged samples per
+    // game slot; a longer game reports B2AZ_DEVERR_HIST instead of dropping samples silently
+    setup_wide((t->unified ? 20u : 10u) + t->s.variant, 512u, sp.planes(t->unified), sp.udim, sp.num_moves(), 64u, true,
+               "B200 Star Gambit engine");
     return true;
   }
   void size_buffers() {
@@ -406,12 +432,13 @@ class PlayManager {
     refresh_stats_locked();
   }
   PlayManager(const GameState* gs, PlayParams p) : params_(std::move(p)) {
-    if (try_tafl<B2AZ_TAFL_BRANDUBH>(gs) || try_tafl<B2AZ_TAFL_OPENTAFL>(gs) || try_tafl<B2AZ_TAFL_TAWLBWRDD>(gs)) {
+    if (try_tafl<B2AZ_TAFL_BRANDUBH>(gs) || try_tafl<B2AZ_TAFL_OPENTAFL>(gs) || try_tafl<B2AZ_TAFL_TAWLBWRDD>(gs) ||
+        try_star_gambit(gs)) {
       size_buffers();
       return;
     }
     auto* c4 = dynamic_cast<const Connect4GS*>(gs);
-    if (!c4) throw std::runtime_error("the B200 engine implements Connect4GS and the tafl games only");
+    if (!c4) throw std::runtime_error("the B200 engine implements Connect4GS, the tafl games and Star Gambit only");
     if (c4->s.p[0] || c4->s.p[1] || c4->s.player || c4->s.turn)
       throw std::runtime_error("the B200 engine starts every game from the initial Connect4 position");
     tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
@@ -872,6 +899,7 @@ PYBIND11_MODULE(alphazero, m) {
   bind_tafl_gs<OpenTaflGS>(m, "OpenTaflGS");    // py_wrapper.cc:538-547
   bind_tafl_gs<TawlbwrddGS>(m, "TawlbwrddGS");  // py_wrapper.cc:549-558
   bind_star_gambit(m);                         // py_wrapper.cc:589-695
+  bind_mcts(m);                                // py_wrapper.cc:191-220
 
   py::enum_<EvalType>(m, "EvalType").value("NN", EvalType::NN).value("RANDOM", EvalType::RANDOM).value("PLAYOUT", EvalType::PLAYOUT);
 

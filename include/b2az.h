@@ -389,10 +389,24 @@ int b2az_forest_advance(b2az_forest* f, void* stream);
 /* MCTS::update_root(gs, move) (mcts.cc:151-173) followed by gs.play_move(move) on the tree's root position;
  * moves_host[n_trees], 0xFFFFFFFF = leave that tree alone. */
 int b2az_forest_update_root(b2az_forest* f, void* stream, const uint32_t* moves_host);
-/* MCTS::counts / root_q_values (mcts.cc:557-573): uint32[n_trees][A], float32[n_trees][A]; info uint32[n_trees][12] =
+/* MCTS::counts / root_q_values (mcts.cc:557-573): uint32[n_trees][A], float32[n_trees][A]; info uint32[n_trees][16] =
  * depth, root n, root children, root terminal code, root player, turn, repetition count, error bits, slab words
- * used, root v (bits), total_leaf_depth, side to move. Any pointer may be NULL. */
+ * used, root v (bits), total_leaf_depth, side to move, MCTS::root_value() win / loss / draw (float bits, mcts.h:78-100),
+ * in_flight_count. Any pointer may be NULL. */
 int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host);
+/* MCTS::principal_variation(depth) (mcts.cc:676-715): moves_host uint32[n_trees][depth], len_host[n_trees]. */
+int b2az_forest_principal_variation(b2az_forest* f, void* stream, uint32_t depth, uint32_t* moves_host, uint32_t* len_host);
+/* The moves from the root to a pending leaf (MCTS::path_, or in-flight leaf `slot` of a WU-UCT forest; slot < 0 = the
+ * plain find_leaf's leaf): moves_host uint32[n_trees][96], len_host[n_trees]. A caller that holds the root GameState
+ * replays them to obtain the leaf position find_leaf returns (py_wrapper.cc:199). */
+int b2az_forest_leaf_path(b2az_forest* f, void* stream, int slot, uint32_t* moves_host, uint32_t* len_host);
+/* MCTS::apply_root_policy_temp (mcts.cc:448-460) and / or MCTS::add_root_noise (mcts.cc:403-446) on every expanded root. */
+int b2az_forest_root_ops(b2az_forest* f, void* stream, int apply_temp, int add_noise);
+/* Start tree `tree` from another position than the game's initial one (the GameState a caller hands to
+ * MCTS::find_leaf): `state` is the engine's position record (TaflState 72 B / B2AZ_SG_STATE_BYTES) as the host GameState
+ * classes of the alphazero module hold it, `hist` its repetition keys. Only before the tree's first search. */
+int b2az_forest_set_root(b2az_forest* f, uint32_t tree, const void* state, uint32_t state_bytes, const void* hist,
+                         uint32_t hist_count);
 
 /* ---- PlayManager::play (play_manager.cc:258-600) over the tafl games on the device: n_games game slots, each with the
  * two seats' search trees (GameData::mcts[0..1]) and ONE pcg32 stream, playing games_per_slot games one after the

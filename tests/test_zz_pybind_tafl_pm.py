@@ -132,3 +132,36 @@ def test_tafl_playmanager_validation_and_no_cpu_fallback():
     if not has_cuda():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             az.PlayManager(gs, _params(az, 2, 1, 8, 1, True))
+
+
+# ---- Star Gambit behind the same PlayManager surface (py_alphazero.cc try_star_gambit)
+@pytest.mark.parametrize("ref_game,make,G,visits,kw", [
+    pytest.param(11, lambda az: az.StarGambitShowdownGS(), 3, 32, dict(epsilon=0.25, mcts_root_temp=1.25, policy_target_pruning=True),
+                 marks=gpu, id="showdown-puct"),
+    pytest.param(22, lambda az: az.StarGambitUnifiedClashGS(), 3, 32, dict(gumbel_enabled=True, gumbel_m=16), marks=gpu,
+                 id="unified-clash-gumbel"),
+])
+@needs_tafl_ref
+def test_star_gambit_play_equals_the_reference(ref_game, make, G, visits, kw):
+    az = module("cuda")
+    seed = 6100 + ref_game
+    pm = az.PlayManager(make(az), _params(az, G, 1, visits, seed, True, **kw))
+    pm.play()
+    assert pm.games_completed() == G and pm.remaining_games() == 0
+    D, A, P = tafl_ref.sg_dims(ref_game)
+    cap = G * 512
+    canon, v, pi = np.zeros((cap, P, D, D), np.float32), np.zeros((cap, 3), np.float32), np.zeros((cap, A), np.float32)
+    n = pm.build_history_batch(canon, v, pi)
+    rkw = {REF_KW.get(k, k): x for k, x in kw.items() if k != "gumbel_enabled"}
+    refs = [tafl_ref.selfplay(ref_game, seed + g, 1024, 1, visits, **rkw) for g in range(G)]
+    want = _rows(np.concatenate([r["canonical"] for r in refs]), np.concatenate([r["v"] for r in refs]),
+                 np.concatenate([r["pi"] for r in refs]))
+    assert _rows(canon[:n], v[:n], pi[:n]) == want
+    assert np.array_equal(pm.scores(), np.sum([r["scores"] for r in refs], axis=0))
+
+
+def test_star_gambit_random_mix_is_rejected_loudly():
+    az = module("emu")
+    p = _params(az, 2, 1, 8, 1, True)
+    with pytest.raises(RuntimeError, match="random variant mix"):
+        az.PlayManager(az.StarGambitUnifiedGS(), p)
