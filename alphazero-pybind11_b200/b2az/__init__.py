@@ -124,6 +124,7 @@ def load(path=None):
     L.b2az_submit_eval_host.argtypes = [vp, vp, vp, vp, vp, u32]
     L.b2az_leaf_batch_device.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.b2az_submit_eval_all.argtypes = [vp, vp, vp]
+    L.b2az_leaf_valid_device.argtypes = [vp, vp, C.POINTER(vp)]
     L.b2az_drain_history.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
     L.b2az_drain_history_sym.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, C.POINTER(u32)]
     L.b2az_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]

@@ -266,6 +266,18 @@ __global__ void k_canonicalize(EngineView E, const u32* __restrict__ count_ptr, 
     out[i] = c4_canon_elem(E.leaf_p0[row], E.leaf_p1[row], E.leaf_player[row], e);
   }
 }
+// GameState::valid_moves() of every leaf of the batch: uint8[B][7] next to the canonical batch (the mask half of the
+// zero-copy feed; the reference's net masks its policy head with it)
+__global__ void k_leaf_valid(EngineView E, const u32* __restrict__ count_ptr, u8* __restrict__ out) {
+  const u32 count = *count_ptr;
+  for (u32 row = GLOBAL_TID; row < count; row += GLOBAL_NT) {
+    C4State s;
+    s.p[0] = E.leaf_p0[row]; s.p[1] = E.leaf_p1[row]; s.turn = 0; s.player = 0;
+    const u32 m = c4_valid_mask(s);
+#pragma unroll
+    for (int w = 0; w < 7; ++w) out[(size_t)row * 7 + w] = (u8)((m >> w) & 1u);
+  }
+}
 // nsym = 1: one row per sample. nsym = 2: every sample followed by its mirror image (Connect4GS::symmetries,
 // connect4_gs.cc:151-170: canonical(f, h, w) <- canonical(f, h, 6 - w), pi(w) <- pi(6 - w), v unchanged), the
 // order game_runner.exploit_symmetries writes them in (game_runner.py:1083-1115).
@@ -388,6 +400,7 @@ struct b2az_engine {
   EngineView view;
   // owned device buffers
   float* canon_buf = nullptr;   // [G][168]
+  u8* valid_buf = nullptr;      // [G][7] legal-move mask of the leaf batch (b2az_leaf_valid_device), allocated on first use
   float* ev_v_buf = nullptr;    // [G][3]   (legacy host path staging target)
   float* ev_pi_buf = nullptr;   // [G][7]
   PeekOut* peek_buf = nullptr;
@@ -542,7 +555,7 @@ int b2az_destroy(b2az_engine* e) {
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
   dev_free(V.cache_keys); dev_free(V.cache_meta); dev_free(V.cache_lock); dev_free(V.cache_vals);
   dev_free(V.cache_ghost); dev_free(V.leaf_key); dev_free(V.hit_val);
-  dev_free(e->canon_buf); dev_free(e->ev_v_buf); dev_free(e->ev_pi_buf);
+  dev_free(e->canon_buf); dev_free(e->valid_buf); dev_free(e->ev_v_buf); dev_free(e->ev_pi_buf);
   dev_free(e->peek_buf); dev_free(e->stats_buf); dev_free(e->freepages_buf);
   dev_free(e->hist_canon); dev_free(e->hist_v); dev_free(e->hist_pi);
 #ifndef B2AZ_HOST_EMU
@@ -983,6 +996,25 @@ int b2az_leaf_batch_device(b2az_engine* e, void* stream, const float** canon_dev
   if (ids_dev) *ids_dev = e->view.leaf_game;
   if (count_dev) *count_dev = &e->view.glob->leaf_count;
   return 0;
+}
+
+int b2az_leaf_valid_device(b2az_engine* e, void* stream, const uint8_t** valid_dev) {
+  if (!e || !valid_dev) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (int rc = bind_device(e)) return rc;
+  if (e->view.eval_type != B2AZ_EVAL_NN) return fail(B2AZ_ESTATE, "leaf batches only exist with B2AZ_EVAL_NN");
+  if (!e->leaves_pending) return fail(B2AZ_ESTATE, "call b2az_step first");
+#ifdef B2AZ_HOST_EMU
+  (void)s;
+  return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+#else
+  if (!e->valid_buf)
+    if (int rc = dev_alloc(&e->valid_buf, (size_t)e->view.G * 7)) return rc;
+  k_leaf_valid<<<e->num_sms * 4, 256, 0, s>>>(e->view, &e->view.glob->leaf_count, e->valid_buf);
+  CUDA_TRY(cudaGetLastError());
+  *valid_dev = e->valid_buf;
+  return 0;
+#endif
 }
 
 int b2az_submit_eval_all(b2az_engine* e, const float* v_dev, const float* pi_dev) {

@@ -326,6 +326,82 @@ inline void fold_supported_seats(PlayParams& P, const SeatTables& N, const char*
   P.gumbel_full = N.gumbel_full[0][0] != 0;
 }
 
+// ------------------------------------------------------------------------------------ DLPack (dlpack.h v0.8 ABI, restated)
+// The zero-copy evaluator feed (SURVEY.md 8b "additive exports"; north_star: "fed zero-copy ... via DLPack"): the leaf
+// batch stays in the engine's device buffers and is handed to torch as DLPack capsules; the evaluations come back the
+// same way (any object with __dlpack__, e.g. a torch CUDA tensor, or a raw capsule).
+namespace dl {
+struct DLDevice { int32_t device_type; int32_t device_id; };  // kDLCUDA = 2
+struct DLDataType { uint8_t code; uint8_t bits; uint16_t lanes; };  // kDLUInt = 1, kDLFloat = 2
+struct DLTensor {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;
+  uint64_t byte_offset;
+};
+struct DLManagedTensor {
+  DLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(DLManagedTensor*);
+};
+struct Owned {  // the engine owns the memory: the capsule only carries the shape
+  DLManagedTensor m;
+  int64_t shape[4];
+};
+inline py::capsule make(void* data, int device, uint8_t code, uint8_t bits, std::initializer_list<int64_t> shape) {
+  auto* o = new Owned();
+  int nd = 0;
+  for (int64_t d : shape) o->shape[nd++] = d;
+  o->m.dl_tensor = DLTensor{data, DLDevice{2, device}, nd, DLDataType{code, bits, 1}, o->shape, nullptr, 0};
+  o->m.manager_ctx = o;
+  o->m.deleter = [](DLManagedTensor* m) { delete static_cast<Owned*>(m->manager_ctx); };
+  return py::capsule(&o->m, "dltensor", [](PyObject* cap) {
+    if (PyCapsule_IsValid(cap, "dltensor")) {  // never consumed: free the descriptor ("used_dltensor" belongs to the consumer)
+      auto* m = static_cast<DLManagedTensor*>(PyCapsule_GetPointer(cap, "dltensor"));
+      if (m && m->deleter) m->deleter(m);
+    }
+  });
+}
+// a consumed view of an incoming tensor: keeps the producer's object alive until released
+struct In {
+  py::object keep;  // the capsule (renamed "used_dltensor": this side calls the deleter)
+  DLManagedTensor* m = nullptr;
+  ~In() { release(); }
+  void release() {
+    if (m && m->deleter) m->deleter(m);
+    m = nullptr;
+    keep = py::object();
+  }
+};
+inline void take(py::object obj, In& in, int device, int64_t rows, int64_t cols, const char* what) {
+  py::object cap = obj;
+  if (!PyCapsule_CheckExact(obj.ptr())) {
+    if (!py::hasattr(obj, "__dlpack__")) throw std::runtime_error(std::string(what) + ": expected a DLPack capsule or an object with __dlpack__");
+    cap = obj.attr("__dlpack__")();
+  }
+  if (!PyCapsule_IsValid(cap.ptr(), "dltensor")) throw std::runtime_error(std::string(what) + ": not an unconsumed dltensor capsule");
+  auto* m = static_cast<DLManagedTensor*>(PyCapsule_GetPointer(cap.ptr(), "dltensor"));
+  PyCapsule_SetName(cap.ptr(), "used_dltensor");
+  PyCapsule_SetDestructor(cap.ptr(), nullptr);
+  in.release();
+  in.keep = cap;
+  in.m = m;
+  const DLTensor& t = m->dl_tensor;
+  bool ok = t.device.device_type == 2 && t.device.device_id == device && t.dtype.code == 2 && t.dtype.bits == 32 && t.dtype.lanes == 1 &&
+            t.ndim == 2 && t.shape[0] >= rows && t.shape[1] == cols;
+  if (ok && t.strides) ok = t.strides[1] == 1 && (t.strides[0] == cols || t.shape[0] <= 1);
+  if (!ok) {
+    in.release();
+    throw std::runtime_error(std::string(what) + ": expected a contiguous float32 CUDA tensor [rows >= " + std::to_string(rows) + ", " +
+                             std::to_string(cols) + "] on device " + std::to_string(device));
+  }
+}
+inline const float* ptr(const In& in) { return reinterpret_cast<const float*>(static_cast<const char*>(in.m->dl_tensor.data) + in.m->dl_tensor.byte_offset); }
+}  // namespace dl
+
 // ------------------------------------------------------------------------------------ PlayManager
 class PlayManager;
 struct GameData {  // play_manager.h:33-58, the part Python sees (py_wrapper.cc:265-288)
@@ -656,6 +732,75 @@ class PlayManager {
     return cur;
   }
 
+  // ---- the zero-copy evaluator feed (additive: SURVEY.md 8b). A synchronous driver of its own — the caller alternates
+  // leaf_batch_dlpack / update_inferences_dlpack until remaining_games() == 0; play() must not be running.
+  // leaf_batch_dlpack(group) -> (canonical capsule float32[B,C,H,W] cuda, valid-move capsule uint8[B,A] cuda | None, B).
+  // Connect4: the B leaves of this generation, compacted (cache hits never become rows). Wide-tree games: B =
+  // concurrent_games, row g = slot g (retired slots keep stale rows; their answers are ignored), no mask.
+  py::tuple leaf_batch_dlpack(uint32_t group) {
+    if (group != 0 || tables_.num_model_groups != 1) throw std::runtime_error("leaf_batch_dlpack: one model group only");
+    if (random_eval_) throw std::runtime_error("leaf_batch_dlpack: needs EvalType.NN");
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (driver_active_) throw std::runtime_error("leaf_batch_dlpack: play() is driving this PlayManager");
+    }
+    std::lock_guard<std::mutex> lk(api_);
+    dl_v_.release(); dl_pi_.release();  // the previous answers have been consumed by the step that ran since
+    if (tsp_) {
+      const float* canon = nullptr;
+      if (b2az_tafl_selfplay_find_leaf(tsp_, nullptr, &canon) != 0) throw_last("leaf_batch_dlpack");
+      dl_rows_ = G_;
+      return py::make_tuple(dl::make(const_cast<float*>(canon), params_.device, 2, 32, {(int64_t)G_, cdims_[0], cdims_[1], cdims_[2]}),
+                            py::none(), G_);
+    }
+    uint32_t n = 0;
+    const float* canon = nullptr;
+    const uint32_t* ids = nullptr;
+    for (int tries = 0; tries < 1 << 20; ++tries) {  // a generation whose leaves all hit the cache has no rows: step on
+      if (!dl_stepped_ && b2az_step(eng_, 1, nullptr) != 0) throw_last("leaf_batch_dlpack");
+      dl_stepped_ = false;
+      if (b2az_leaf_batch(eng_, nullptr, &n, &canon, &ids) != 0) throw_last("leaf_batch_dlpack");
+      if (n > 0) break;
+      b2az_stats st;
+      if (b2az_get_stats(eng_, nullptr, &st) != 0) throw_last("leaf_batch_dlpack");
+      if (st.active_games == 0) break;
+    }
+    dl_rows_ = n;
+    refresh_stats_unlocked_api();
+    if (n == 0) return py::make_tuple(py::none(), py::none(), 0u);
+    const uint8_t* valid = nullptr;
+    if (b2az_leaf_valid_device(eng_, nullptr, &valid) != 0) throw_last("leaf_batch_dlpack");
+    return py::make_tuple(dl::make(const_cast<float*>(canon), params_.device, 2, 32, {(int64_t)n, cdims_[0], cdims_[1], cdims_[2]}),
+                          dl::make(const_cast<uint8_t*>(valid), params_.device, 1, 8, {(int64_t)n, (int64_t)A_}), n);
+  }
+  // update_inferences_dlpack(group, v float32[B,P+1], pi float32[B,A]): CUDA tensors (anything with __dlpack__) in the row
+  // order of the batch; the engine reads them in place on its next step, which is enqueued here.
+  void update_inferences_dlpack(uint32_t group, py::object v, py::object pi) {
+    if (group != 0) throw std::runtime_error("update_inferences_dlpack: one model group only");
+    std::lock_guard<std::mutex> lk(api_);
+    if (dl_rows_ == 0) throw std::runtime_error("update_inferences_dlpack: no leaf batch is waiting (call leaf_batch_dlpack)");
+    dl::take(v, dl_v_, params_.device, dl_rows_, kP + 1, "update_inferences_dlpack(v)");
+    dl::take(pi, dl_pi_, params_.device, dl_rows_, A_, "update_inferences_dlpack(pi)");
+    if (tsp_) {
+      uint32_t active = 0;
+      if (b2az_tafl_selfplay_process_result(tsp_, nullptr, dl::ptr(dl_v_), dl::ptr(dl_pi_), 0, &active) != 0) throw_last("update_inferences_dlpack");
+    } else {
+      if (b2az_submit_eval(eng_, dl::ptr(dl_v_), dl::ptr(dl_pi_), dl_rows_) != 0) throw_last("update_inferences_dlpack");
+      if (b2az_step(eng_, 1, nullptr) != 0) throw_last("update_inferences_dlpack");  // consumes the answers (stream ordered)
+      dl_stepped_ = true;
+    }
+    dl_rows_ = 0;
+    refresh_stats_unlocked_api();
+  }
+  void refresh_stats_unlocked_api() {  // (api_ is held by the caller; mu_ is never taken under api_: lock order mu_ -> api_)
+    b2az_stats st;
+    const int rc = tsp_ ? b2az_tafl_selfplay_get_stats(tsp_, nullptr, &st) : b2az_get_stats(eng_, nullptr, &st);
+    if (rc != 0) throw_last("stats");
+    dl_stats_ = st;
+    games_completed_.store((uint32_t)st.games_completed);
+    hist_count_.store((uint32_t)st.hist_count);
+    if (st.active_games == 0) finished_.store(true);
+  }
   b2az_stats stats() {
     refresh_stats();
     std::lock_guard<std::mutex> lk(mu_);
@@ -825,6 +970,10 @@ class PlayManager {
   std::vector<uint32_t> group_next_;              // per group: rows already handed out
   uint32_t leaf_count_ = 0, answered_ = 0;
   b2az_stats stats_{};
+  dl::In dl_v_, dl_pi_;      // the evaluations of the DLPack feed, kept alive until the engine has read them
+  uint32_t dl_rows_ = 0;
+  bool dl_stepped_ = false;  // update_inferences_dlpack has already run the next generation's step
+  b2az_stats dl_stats_{};
 };
 
 py::array_t<float> vec3(const float* p) {
@@ -1029,6 +1178,8 @@ PYBIND11_MODULE(alphazero, m) {
       .def("variant_perm_scores", [](PlayManager&, int, int) -> py::object { throw std::out_of_range("this game has no variants"); })
       .def("variant_perm_games_completed", [](PlayManager&, int, int) -> uint32_t { throw std::out_of_range("this game has no variants"); })
       .def("set_eager", &PlayManager::set_eager)
+      .def("leaf_batch_dlpack", &PlayManager::leaf_batch_dlpack, py::arg("group") = 0)
+      .def("update_inferences_dlpack", &PlayManager::update_inferences_dlpack, py::arg("group"), py::arg("v"), py::arg("pi"))
       .def("build_batch",
            [](PlayManager& pm, uint32_t group, py::array_t<float, py::array::c_style>& batch, uint32_t shard) {
              float* data = batch.mutable_data();

@@ -196,6 +196,9 @@ int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, ui
  * simply runs on all concurrent_games rows. */
 int b2az_leaf_batch_device(b2az_engine* e, void* stream, const float** canon_dev, const uint32_t** ids_dev,
                            const uint32_t** count_dev);
+/* The legal-move masks of the same leaf batch, uint8[B][7] in device memory (row i belongs to row i of the canonical
+ * batch): the valid-move half of the zero-copy feed (SURVEY.md 8b "additive exports"). Enqueued on `stream`. */
+int b2az_leaf_valid_device(b2az_engine* e, void* stream, const uint8_t** valid_dev);
 int b2az_submit_eval_all(b2az_engine* e, const float* v_dev, const float* pi_dev);
 /* update_inferences, legacy flavour: row i answers slot ids_host[i]; may be called several times
  * with disjoint subsets. */
