@@ -308,7 +308,7 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
   };
   static __device__ __forceinline__ u32 actions(const ForestView&) { return (u32)T::A; }
   static __device__ __forceinline__ u32 canon(const ForestView&) { return (u32)T::CANON; }
-  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32, Pos& P) {
+  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32, ForestSmem<GAME>&, Pos& P) {
     P.s = F.trees[t].state;
     P.hist = F.hist + (size_t)t * (F.max_turns + 2u);
     P.pkeys = F.pkeys + (size_t)t * (kFPath + 2);
@@ -348,8 +348,14 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
       }
     }
   }
+  // a training sample's position while its game is still running: the canonical planes themselves (a few hundred floats)
+  static __device__ __forceinline__ u32 stage_floats(const ForestView&) { return (u32)T::CANON; }
+  static __device__ __forceinline__ void stage(const Pos& P, ForestSmem<GAME>& sm, float* row, u32 lane) { emit_canon(P, sm, row, lane); }
+  static __device__ __forceinline__ void unstage(const ForestView&, const float* row, ForestSmem<GAME>&, float* out, u32 lane) {
+    for (u32 e = lane; e < (u32)T::CANON; e += 32u) out[e] = row[e];
+  }
   // gs.play_move(move) on the tree's root position with its persistent repetition history (update_root's caller)
-  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, u32 lane) {
+  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, ForestSmem<GAME>&, u32 lane) {
     ForestTree& R = F.trees[t];
     TaflKey* hist = F.hist + (size_t)t * (F.max_turns + 2u);
     TaflState s = R.state;
@@ -392,47 +398,72 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
 template <>
 struct FGame<B2AZ_FOREST_SG> {  // Star Gambit: the variants' own classes and the Unified view
   struct Pos {
-    SGState s;
+    SGState* sp_;  // the warp's working position (shared memory, SGWarpSmem::st)
     SGHistWarp hist;
     SGSpace sp;
     bool unified;
   };
   static __device__ __forceinline__ u32 actions(const ForestView& F) { return F.actions; }
   static __device__ __forceinline__ u32 canon(const ForestView& F) { return F.canon; }
-  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32 lane, Pos& P) {
-    P.s = F.sg_state[t];
+  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32 lane, ForestSmem<B2AZ_FOREST_SG>& sm, Pos& P) {
+    P.sp_ = &sm.st;
+    sg_warp_load(sm.st, F.sg_state + t, lane);
     P.unified = sg_game_unified(F.game);
-    P.sp = sg_space(P.s.variant, P.unified);
+    P.sp = sg_space(sm.st.variant, P.unified);
     P.hist.base = F.sg_hist + (size_t)t * F.sg_hist_cap;
     P.hist.base_len = F.trees[t].hist_len;
     P.hist.keys = F.sg_pkeys + (size_t)t * (kFPath + 2);
     P.hist.len = 0; P.hist.cap = kFPath + 2; P.hist.lane = lane; P.hist.overflow = false;
   }
   static __device__ __forceinline__ bool play(Pos& P, u32 mv, u32 lane) {
-    return sg_play(P.s, P.hist, P.sp, mv, SGAnyValidWarp{lane}) && !P.hist.overflow;
+    const bool ok = sg_play(*P.sp_, P.hist, P.sp, mv, SGAnyValidWarp{lane}) && !P.hist.overflow;
+    __syncwarp();
+    return ok;
   }
-  static __device__ __forceinline__ u32 player(const Pos& P) { return P.s.player; }
+  static __device__ __forceinline__ u32 player(const Pos& P) { return P.sp_->player; }
   static __device__ __forceinline__ u32 legal(const Pos& P, ForestSmem<B2AZ_FOREST_SG>& sm, Pcg32& rng, u32 lane, u32* err, bool serial) {
-    u32 k = sg_warp_legal(P.s, P.sp, sm, lane);
+    u32 k = sg_warp_legal(*P.sp_, P.sp, sm, lane);
     if (k > (u32)kSGMaxK) { *err |= 4u; k = 0; }
     forest_shuffle(rng, sm.moves, sm.draws, k, lane, serial);
     return k;
   }
-  static __device__ __forceinline__ u32 terminal(const Pos& P, u32) { const u32 t = sg_terminal(P.s); return t > 3u ? 3u : t; }
+  static __device__ __forceinline__ u32 terminal(const Pos& P, u32) { const u32 t = sg_terminal(*P.sp_); return t > 3u ? 3u : t; }
   static __device__ __forceinline__ void emit_canon(const Pos& P, ForestSmem<B2AZ_FOREST_SG>& sm, float* out, u32 lane) {
-    sg_warp_canon(P.s, P.hist, P.sp, P.unified, sm, lane, out);
+    sg_warp_canon(*P.sp_, P.hist.count(sg_position_key(*P.sp_)), P.sp, P.unified, sm, lane, out);
   }
-  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, u32 lane) {
+  // A training sample's position while its game is still running (PlayManager's partial_history): the 200-byte
+  // position record + its repetition count instead of the 24 KB of canonical planes, which are written once, into the
+  // output ring, when the game ends.
+  static __device__ __forceinline__ u32 stage_floats(const ForestView&) { return (u32)(sizeof(SGState) / 4u + 1u); }
+  static __device__ __forceinline__ void stage(const Pos& P, ForestSmem<B2AZ_FOREST_SG>&, float* row, u32 lane) {
+    const int rc = P.hist.count(sg_position_key(*P.sp_));
+    u32* w = reinterpret_cast<u32*>(row);
+    const u32* src = reinterpret_cast<const u32*>(P.sp_);
+    for (u32 i = lane; i < (u32)(sizeof(SGState) / 4u); i += 32u) w[i] = src[i];
+    if (lane == 0) w[sizeof(SGState) / 4u] = (u32)rc;
+  }
+  static __device__ __forceinline__ void unstage(const ForestView& F, const float* row, ForestSmem<B2AZ_FOREST_SG>& sm, float* out, u32 lane) {
+    const u32* w = reinterpret_cast<const u32*>(row);
+    SGState& s = sm.st;
+    sg_warp_load(s, reinterpret_cast<const SGState*>(row), lane);
+    const bool unified = sg_game_unified(F.game);
+    sg_warp_canon(s, (int)w[sizeof(SGState) / 4u], sg_space(s.variant, unified), unified, sm, lane, out);
+  }
+  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, ForestSmem<B2AZ_FOREST_SG>& sm, u32 lane) {
     ForestTree& R = F.trees[t];
-    SGState s = F.sg_state[t];
+    SGState& s = sm.st;
+    sg_warp_load(s, F.sg_state + t, lane);
     const bool unified = sg_game_unified(F.game);
     const SGSpace sp = sg_space(s.variant, unified);
     SGHistWarp h;
     h.base = nullptr; h.base_len = 0; h.keys = F.sg_hist + (size_t)t * F.sg_hist_cap; h.len = R.hist_len; h.cap = F.sg_hist_cap;
     h.lane = lane; h.overflow = false;
-    if (!sg_play(s, h, sp, move, SGAnyValidWarp{lane})) return 8u;
+    const bool ok = sg_play(s, h, sp, move, SGAnyValidWarp{lane});
+    __syncwarp();
+    if (!ok) return 8u;
     if (h.overflow) return 2u;
-    if (lane == 0) { F.sg_state[t] = s; R.hist_len = h.len; }
+    sg_warp_store(F.sg_state + t, s, lane);
+    if (lane == 0) R.hist_len = h.len;
     return 0;
   }
   static __device__ __forceinline__ void init(const ForestView& F, u32 t) {  // (one thread per tree)
@@ -698,7 +729,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
   typename G::Pos pos;
-  G::open(F, t, lane, pos);
+  G::open(F, t, lane, sm, pos);
   u32 err = 0;
   // current_ = &root_
   u32 cur_n = R.n, cur_term = R.term, cur_blk = R.blk, cur_k = R.k, cur_player = R.player;
@@ -949,7 +980,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     Pcg32 rng = FOREST_RNG(F, t);
     {
       typename G::Pos pos;
-      G::open(F, t, lane, pos);
+      G::open(F, t, lane, sm, pos);
       k = G::legal(pos, sm, rng, lane, &err, F.serial_shuffle != 0);
     }
     if (lane == 0) FOREST_RNG(F, t) = rng;
@@ -1030,7 +1061,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
     __syncwarp();
   }
   // gs.play_move(move) with the persistent repetition history
-  if (!err) err |= G::root_play(F, t, move, lane);
+  if (!err) err |= G::root_play(F, t, move, sm, lane);
   if (lane == 0) {
     if (F.gumbel_enabled) fg_reset(F.gum[t]);  // update_root ends with reset_gumbel_state() (mcts.cc:172)
     R.depth = 0;
@@ -1080,7 +1111,7 @@ __global__ void __launch_bounds__(128) k_forest_root_noise(ForestView F, u32 add
 #define B2AZ_FOREST_MINB 8  /* 64 registers, 32 warps per SM: 100 -> 140 M sims/s (Brandubh, Gumbel) */
 #endif
 template <int GAME>
-__global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_forest_simulate(ForestView F, u32 n_sims, u32 root_noise_enabled) {
+__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_MINB) k_forest_simulate(ForestView F, u32 n_sims, u32 root_noise_enabled) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)

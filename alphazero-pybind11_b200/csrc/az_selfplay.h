@@ -48,9 +48,10 @@ struct SpView {
   float start_temp, final_temp, half_life;
   u32 history_enabled, policy_target_pruning, tree_reuse;
   u32 stage_rows;     // staging rows per slot: the game's max_turns (tafl) / a bound on the actions of a Star Gambit game
+  u32 st_stride;      // floats per staged position (FGame::stage_floats: the planes for tafl, the position record for Star Gambit)
   u32 n_variant_half_life;
   float variant_half_life[4];  // temp_decay_half_life_by_variant
-  float* st_canon;    // [n_games][stage_rows][CANON]
+  float* st_canon;    // [n_games][stage_rows][st_stride]
   float* st_pi;       // [n_games][max_turns][A]
   u8* st_player;      // [n_games][max_turns]
   float* scratch_pi;  // [n_games][A]: the acting distribution
@@ -119,7 +120,7 @@ __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
 
 // the hot kernel: `n_sims` x (MCTS::find_leaf, dumb_eval, MCTS::process_result) on the tree of the seat to move
 template <int GAME>
-__global__ void __launch_bounds__(128, B2AZ_FOREST_MINB) k_sp_search(ForestView F, SpView S, u32 n_sims) {
+__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_MINB) k_sp_search(ForestView F, SpView S, u32 n_sims) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
 #define B2AZ_SP_MOVE_MINB 8  /* 64 registers, 32 warps per SM: the lane-0 stretches of the move step are latency bound (measured: 1 / 4 / 6 / 8 -> Brandubh 112.6 / 112.7 / 115.7 / 118.2 M sims/s, OpenTafl 46.8 / 46.9 / 46.5 / 49.1) */
 #endif
 template <int GAME>
-__global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F, SpView S) {
+__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F, SpView S) {
   typedef FGame<GAME> GM;
   const u32 A = GM::actions(F), CANON = GM::canon(F);
   __shared__ ForestSmem<GAME> sm[4];
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
       const size_t row = (size_t)g * S.stage_rows + prow;
       {
         typename GM::Pos pos;  // GameState::canonicalized() of the root position
-        GM::open(F, t, lane, pos);
-        GM::emit_canon(pos, sm[wib], S.st_canon + row * CANON, lane);
+        GM::open(F, t, lane, sm[wib], pos);
+        GM::stage(pos, sm[wib], S.st_canon + row * S.st_stride, lane);
       }
       float* pi = S.st_pi + row * A;
       if (F.gumbel_enabled) {
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(128, B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F
           const u32 dst = base + i;
           if (dst >= S.out_cap) { if (lane == 0) G.error |= 1u; break; }
           const size_t src = (size_t)g * S.stage_rows + (cnt - 1u - i);
-          for (u32 e = lane; e < CANON; e += 32u) S.out_canon[(size_t)dst * CANON + e] = S.st_canon[src * CANON + e];
+          GM::unstage(F, S.st_canon + src * S.st_stride, sm[wib], S.out_canon + (size_t)dst * CANON, lane);
           for (u32 e = lane; e < A; e += 32u) S.out_pi[(size_t)dst * A + e] = S.st_pi[src * A + e];
           if (lane == 0) {
             // relative_values games store the outcome in the frame of the sample's mover (absolute_to_relative,
@@ -447,12 +448,13 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   for (int i = 0; i < 4; ++i) S.variant_half_life[i] = p->variant_half_life[i];
   S.out_cap = S.history_enabled ? (p->hist_capacity ? p->hist_capacity : p->n_games * fp.max_turns) : 1u;
   S.stage_rows = fp.max_turns;
+  S.st_stride = f->view.sg_state ? (uint32_t)(sizeof(SGState) / 4u + 1u) : f->canon;
   const size_t G = p->n_games, MT = fp.max_turns, A = f->actions, C = f->canon;
   auto bail = [&](int rc) { b2az_tafl_selfplay_destroy(sp); return rc; };
   if (int rc = dev_alloc(&S.slots, G)) return bail(rc);
   if (int rc = dev_alloc_raw(&S.scratch_pi, G * A)) return bail(rc);
   if (S.history_enabled) {
-    if (int rc = dev_alloc_raw(&S.st_canon, G * MT * C)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.st_canon, G * MT * S.st_stride)) return bail(rc);
     if (int rc = dev_alloc_raw(&S.st_pi, G * MT * A)) return bail(rc);
     if (int rc = dev_alloc_raw(&S.st_player, G * MT)) return bail(rc);
     if (int rc = dev_alloc_raw(&S.out_canon, (size_t)S.out_cap * C)) return bail(rc);

@@ -47,10 +47,27 @@ struct SGHistWarp {  // `base` (read-only, e.g. a search root's history) followe
 };
 
 struct SGWarpSmem {
+  // The working position: ONE copy per warp. Every lane runs the scalar rule code on it redundantly — reads are
+  // broadcasts, and the lanes of a converged warp store identical values (the control flow depends on the position
+  // only; lane-dependent sections end in warp-synchronising primitives). A private copy per lane would be 32 x 200 B of
+  // local memory per warp, which falls out of L1 at a few warps per SM (measured: 9.5 M simulations/s regardless of the
+  // number of game slots).
+  SGState st;
   u32 map[kSGMapWords];
   u16 moves[kSGMaxK];
   u8 cell_unit[13 * 13 + 3];
 };
+// cooperative copies between the warp's working position and a position record in global memory
+__device__ __forceinline__ void sg_warp_load(SGState& dst, const SGState* src, u32 lane) {
+  __syncwarp();
+  for (u32 i = lane; i < (u32)(sizeof(SGState) / 4u); i += 32u) reinterpret_cast<u32*>(&dst)[i] = reinterpret_cast<const u32*>(src)[i];
+  __syncwarp();
+}
+__device__ __forceinline__ void sg_warp_store(SGState* dst, const SGState& src, u32 lane) {
+  __syncwarp();
+  for (u32 i = lane; i < (u32)(sizeof(SGState) / 4u); i += 32u) reinterpret_cast<u32*>(dst)[i] = reinterpret_cast<const u32*>(&src)[i];
+  __syncwarp();
+}
 
 // occupancy sets by warp reduction: lane i contributes unit i
 __device__ __forceinline__ void sg_warp_boards(const SGState& s, int side, u32 lane, SGBoards& b) {
@@ -137,7 +154,8 @@ __device__ __forceinline__ u32 sg_warp_legal(const SGState& s, const SGSpace& sp
 }
 
 // canonicalized() written by the warp: out[plane][udim][udim]
-__device__ __forceinline__ void sg_warp_canon(const SGState& s, const SGHistWarp& hist, const SGSpace& sp, bool unified,
+// (`rc` = how often the position's key occurs in its key history: position_history_ scanned by the caller)
+__device__ __forceinline__ void sg_warp_canon(const SGState& s, int rc, const SGSpace& sp, bool unified,
                                               SGWarpSmem& sm, u32 lane, float* out) {
   const int cells = sp.dim * sp.dim, ucells = sp.udim * sp.udim;
   for (int i = (int)lane; i < cells; i += 32) sm.cell_unit[i] = 0;
@@ -156,7 +174,6 @@ __device__ __forceinline__ void sg_warp_canon(const SGState& s, const SGHistWarp
   float g[10];
   {
     g[0] = s.acted ? 1.0f : 0.0f;
-    const int rc = hist.count(sg_position_key(s));
     g[1] = rc == 0 ? 0.0f : rc == 1 ? 0.5f : 1.0f;
     const int my = s.player & 1, opp = 1 - my;
 #pragma unroll
@@ -238,8 +255,10 @@ __global__ void __launch_bounds__(128) k_sg_replay(SGReplayArgs a) {
   const SGSpace sp = sg_space(variant, unified);
   const u32 A = (u32)sp.num_moves(), C = (u32)(sp.planes(unified) * sp.udim * sp.udim);
   for (u32 gi = GLOBAL_TID >> 5; gi < a.n; gi += GLOBAL_NT >> 5) {
-    SGState s;
+    SGState& s = sm.st;
+    __syncwarp();
     sg_init(s, variant);
+    __syncwarp();
     SGHistWarp hist;
     hist.base = nullptr; hist.base_len = 0; hist.keys = a.hist + (size_t)gi * a.hist_cap; hist.len = 0; hist.cap = a.hist_cap;
     hist.lane = lane; hist.overflow = false;
@@ -247,7 +266,9 @@ __global__ void __launch_bounds__(128) k_sg_replay(SGReplayArgs a) {
     const u32 len = a.lens[gi];
     for (u32 k = 0; k <= len; ++k) {
       if (k > 0) {
-        if (!sg_play(s, hist, sp, (u32)a.moves[(size_t)gi * a.max_len + (k - 1u)], SGAnyValidWarp{lane})) {
+        const bool ok = sg_play(s, hist, sp, (u32)a.moves[(size_t)gi * a.max_len + (k - 1u)], SGAnyValidWarp{lane});
+        __syncwarp();
+        if (!ok) {
           if (lane == 0 && a.status) a.status[gi] = B2AZ_EMOVE;
           break;
         }
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(128) k_sg_replay(SGReplayArgs a) {
           for (u32 m = lane; m < A; m += 32u) a.valid[row * A + m] = (u8)((sm.map[m >> 5] >> (m & 31u)) & 1u);
         __syncwarp();
       }
-      if (a.canonical) sg_warp_canon(s, hist, sp, unified, sm, lane, a.canonical + row * C);
+      if (a.canonical) sg_warp_canon(s, hist.count(sg_position_key(s)), sp, unified, sm, lane, a.canonical + row * C);
     }
     if (hist.overflow && lane == 0 && a.status) a.status[gi] = B2AZ_ENOMEM;
   }

@@ -348,6 +348,151 @@ def nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, wor
     return out
 
 
+def c4_net(torch):
+    """Random-init dense conv net of the connect4 default shape (depth 4, 12 channels, 5x5 kernels: src/config.py:44-47),
+    shared by every NN leg (torch.manual_seed(0))."""
+    nn = torch.nn
+
+    class C4Net(nn.Module):
+        def __init__(self, depth=4, ch=12, k=5):
+            super().__init__()
+            self.convs = nn.ModuleList()
+            c_in = 4
+            for _ in range(depth):
+                self.convs.append(nn.Conv2d(c_in, ch, k, padding=k // 2))
+                c_in += ch
+            self.v_head = nn.Sequential(nn.Conv2d(c_in, 4, 1), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 42, 3))
+            self.pi_head = nn.Sequential(nn.Conv2d(c_in, 4, 1), nn.ReLU(), nn.Flatten(), nn.Linear(4 * 42, 7))
+
+        def forward(self, x):
+            for conv in self.convs:
+                x = torch.cat([x, torch.relu(conv(x))], 1)
+            return torch.softmax(self.v_head(x).float(), 1), torch.softmax(self.pi_head(x).float(), 1)
+
+    torch.manual_seed(0)
+    return C4Net().cuda().eval()
+
+
+def reference_nn_leg(args, torch, seconds=8.0, warm=3.0):
+    """SURVEY.md 8d "Throughput B", REFERENCE side: the UNMODIFIED reference PlayManager
+    (oracle/_ref/libazref.so) with its MCTS worker threads on the box's host cores, its S3-FIFO cache (200,000 entries),
+    the self-play flags of connect4.yaml, and the same random-init torch net on this B200 answering its leaf batches
+    (bf16 autocast) — batches taken with build_batch and answered with update_inferences the way game_runner.py's
+    batcher and result worker do (src/game_runner.py:648-727), one Python thread."""
+    import numpy as np
+    import refdriver
+
+    if not refdriver.available():
+        return {"unavailable": "oracle/_ref/libazref.so not built"}
+    L = refdriver.lib()
+    threads = host_threads()
+    workers = max(1, threads - 2)  # one core for this batcher thread, as in the reference's thread budget
+    G, B = 4096, 4096
+    cfg = refdriver.play_cfg(games_to_play=2 ** 31 - 1, concurrent_games=G, max_batch_size=B, max_cache_size=200000,
+                             queue_shards=min(workers, 255), cache_shards=min(threads, 255), mcts_visits=(SIMS, SIMS), cpuct=1.25,
+                             fpu_reduction=0.25, epsilon=0.25, mcts_root_temp=1.25, start_temp=1.0, final_temp=0.2,
+                             temp_decay_half_life=10.0, root_fpu_zero=1, shaped_dirichlet=1, policy_target_pruning=1,
+                             self_play=1, tree_reuse=1, eval_type=0, history_enabled=1)
+    pm = refdriver.RefPlayManager(cfg)
+    net = c4_net(torch)
+    pm.start_workers(workers, 4242, True)
+    xin = torch.empty((B, 4, 6, 7), dtype=torch.float32).pin_memory()
+    rows, batches = 0, 0
+    t_start = time.perf_counter()
+    c0 = t0 = None
+    hist_drained = 0
+    while True:
+        now = time.perf_counter()
+        if c0 is None and now - t_start >= warm:
+            c0, t0 = L.azref_pm_progress_sims(pm.h, SIMS), now
+            rows = batches = 0
+        if c0 is not None and now - t0 >= seconds:
+            break
+        ids, canon = pm.build_batch(max_rows=B)
+        n = len(ids)
+        if n == 0:
+            continue
+        xin[:n].copy_(torch.from_numpy(canon))
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            v, pi = net(xin[:n].cuda(non_blocking=True))
+        pm.update_inferences(ids, v.float().cpu().numpy(), pi.float().cpu().numpy())
+        rows += n
+        batches += 1
+        if batches % 64 == 0:  # the history saver: keep history_ from growing without bound
+            hist_drained += len(pm.drain_history(65536)[1])
+    c1, t1 = L.azref_pm_progress_sims(pm.h, SIMS), time.perf_counter()
+    cs = np.zeros(6, np.uint64)
+    L.azref_pm_cache_stats(pm.h, refdriver.P(cs))
+    L.azref_pm_stop(pm.h)
+    pm.join()
+    pm.close()
+    dt = t1 - t0
+    return {"value": (c1 - c0) / dt, "unit": "sims/s", "cores": workers, "kind": "reference", "host_threads": threads,
+            "concurrent_games": G, "max_batch_size": B, "mean_batch_rows": rows / max(1, batches),
+            "net_rows_per_second": rows / dt, "cache_hit_rate": float(cs[0]) / max(1.0, float(cs[0] + cs[1])),
+            "cache_entries": 200000, "seconds": dt,
+            "note": "the unmodified reference PlayManager + its cache on the host cores, the same torch net on this B200 "
+                    "(bf16 autocast), build_batch / update_inferences from one Python thread"}
+
+
+def pybind_dlpack_leg(args, torch, local):
+    """SURVEY.md 8d "Throughput B", this repo's side THROUGH THE DROP-IN MODULE: alphazero.PlayManager (csrc/py_alphazero.cc)
+    with the zero-copy DLPack feed — leaf_batch_dlpack hands torch the canonical batch and the legal-move masks in the
+    engine's device buffers, update_inferences_dlpack takes the CUDA tensors back; no host copy per leaf."""
+    import importlib.util
+    import sysconfig
+
+    path = os.path.join(ROOT, "alphazero-pybind11_b200", "alphazero" + sysconfig.get_config_var("EXT_SUFFIX"))
+    spec = importlib.util.spec_from_file_location("alphazero", path)
+    az = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(az)
+    G = args.games
+    p = az.PlayParams()
+    p.games_to_play, p.concurrent_games, p.max_batch_size = 2 ** 31 - 1 - (2 ** 31 - 1) % G, G, G
+    p.mcts_visits = [SIMS, SIMS]
+    p.model_groups = [0, 0]
+    p.history_enabled = p.self_play = p.tree_reuse = True
+    p.cpuct, p.fpu_reduction, p.epsilon, p.mcts_root_temp = 1.25, 0.25, 0.25, 1.25
+    p.start_temp, p.final_temp, p.temp_decay_half_life = 1.0, 0.2, 10.0
+    p.root_fpu_zero = p.shaped_dirichlet = p.policy_target_pruning = True
+    p.max_cache_size = 200000
+    p.seed, p.device = 777, local
+    pm = az.PlayManager(az.Connect4GS(), p)
+    net = c4_net(torch).to(memory_format=torch.channels_last)
+    torch.backends.cudnn.benchmark = True
+
+    def generation():
+        canon, valid, n = pm.leaf_batch_dlpack(0)
+        if n == 0:
+            return 0
+        x = torch.from_dlpack(canon)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            v, pi = net(x)
+        pi = pi * torch.from_dlpack(valid)  # the reference masks the policy head with valid_moves (neural_net.py)
+        pm.update_inferences_dlpack(0, v.float().contiguous(), pi.float().contiguous())
+        return n
+
+    for _ in range(40):
+        generation()
+    torch.cuda.synchronize()
+    s0 = pm.simulations()
+    h0, m0 = pm.cache_hits(), pm.cache_misses()
+    rows, gens = 0, 200
+    t0 = time.perf_counter()
+    for _ in range(gens):
+        rows += generation()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sims = pm.simulations() - s0
+    hits, misses = pm.cache_hits() - h0, pm.cache_misses() - m0
+    pm.stop()
+    return {"value": sims / dt, "unit": "sims/s", "generations": gens, "ms_per_generation": dt / gens * 1e3,
+            "mean_batch_rows": rows / gens, "net_rows_per_second": rows / dt, "h2d_bytes_per_step": 0,
+            "d2h_bytes_per_step": 4, "cache_hit_rate": hits / max(1, hits + misses), "cache_entries": 200000,
+            "note": "alphazero.PlayManager (the drop-in pybind module) + leaf_batch_dlpack / update_inferences_dlpack + "
+                    "torch net (eager, bf16 autocast, channels_last); one 4-byte row-count read per generation"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -548,6 +693,20 @@ def main():
     if not args.no_e2e:
         e2e_nn_dev = nn_device_leg(args, torch, b2az, local, stream, barrier, max_over_ranks, world, rank)
 
+    # ---------------------------------------------------------------- NN through the drop-in module (DLPack) and the
+    # reference's own PlayManager with the same net on the same GPU (Throughput B, both arms)
+    e2e_nn_pybind = e2e_nn_reference = None
+    if not args.no_e2e and world == 1:
+        for name, fn in (("pybind", lambda: pybind_dlpack_leg(args, torch, local)), ("reference", lambda: reference_nn_leg(args, torch))):
+            try:
+                r = fn()
+            except Exception as ex:  # a secondary leg never breaks the headline line
+                r = {"failed": repr(ex)[:300]}
+            if name == "pybind":
+                e2e_nn_pybind = r
+            else:
+                e2e_nn_reference = r
+
     # ---------------------------------------------------------------- roofline + cpu baseline (rank 0)
     if rank != 0:
         if dist is not None:
@@ -604,7 +763,14 @@ def main():
                                                      "--gumbel-m", "16"]),
                          ("brandubh_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "0", "--games", "8192", "--moves", "16",
                                                 "--cpu-seconds", "5"]),
-                         ("opentafl_game_kernels", ["tools/tafl_bench.py", "--game", "1", "--games", "8192", "--reps", "3"])):
+                         ("opentafl_game_kernels", ["tools/tafl_bench.py", "--game", "1", "--games", "8192", "--reps", "3"]),
+                         # BASELINE.json configs[4]: Star Gambit Unified with the Gumbel root search (configs/star_gambit_unified.yaml);
+                         # one leg per end of the variant mix (11x11 Skirmish, 13x13 Battle), 120 simulations per move
+                         ("star_gambit_unified_battle_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "23", "--games", "1024",
+                                                                  "--moves", "16", "--cpu-seconds", "5"]),
+                         ("star_gambit_unified_skirmish_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "20", "--games", "1024",
+                                                                    "--moves", "16", "--cpu-seconds", "5"]),
+                         ("star_gambit_game_kernels", ["tools/sg_bench.py", "--game", "23", "--games", "4096", "--moves", "64"])):
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], stdout=subprocess.PIPE,
                                    stderr=subprocess.PIPE, text=True, timeout=300)
@@ -616,7 +782,7 @@ def main():
             "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "moves_per_second": moves_per_s, "clocks": clocks, "e2e": e2e, "e2e_nn_host": e2e_nn,
-            "e2e_nn_device": e2e_nn_dev,
+            "e2e_nn_device": e2e_nn_dev, "e2e_nn_pybind_dlpack": e2e_nn_pybind, "e2e_nn_reference": e2e_nn_reference,
             "gpu_launches": K * world, "roofline": roofline, "cpu_baseline": cpu,
             "pool_pages": {"total": pool[0], "free": pool[1]}, "other_configs": extra}
     print(json.dumps(line), flush=True)

@@ -21,6 +21,9 @@ import tafl_ref  # noqa: E402
 
 NAMES = {0: "brandubh", 1: "opentafl", 2: "tawlbwrdd"}
 MAX_TURNS = {0: 150, 1: 400, 2: 400}  # configs/*.yaml max_turns
+for _v, _n in enumerate(("skirmish", "showdown", "clash", "battle")):  # Star Gambit: --game 10 + variant / 20 + variant (Unified)
+    NAMES[10 + _v], NAMES[20 + _v] = f"star gambit {_n}", f"star gambit unified ({_n})"
+    MAX_TURNS[10 + _v] = MAX_TURNS[20 + _v] = 640  # staged training samples per game slot (a game is <= 200 turns of several actions)
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -50,13 +53,14 @@ if __name__ == "__main__":
     mt = a.max_turns or MAX_TURNS[a.game]
     kw = (dict(epsilon=0.25, root_policy_temp=1.25, shaped_dirichlet=True, policy_target_pruning=True, start_temp=1.0,
                final_temp=0.2, temp_decay_half_life=10.0) if a.puct else dict(gumbel_m=16, root_policy_temp=1.25))
-    words = 2 * (1 + 3 * a.sims * (1 + 8 * (48 if a.game == 0 else 140)))
+    words = 2 * (1 + 3 * a.sims * (1 + 8 * (48 if a.game == 0 or a.game >= 10 else 140)))
+    ring = a.games * (a.drain + 2) * (1 if a.game >= 10 else 4)  # (a Star Gambit sample is 31 KB)
     sp = b2az.TaflSelfplay(a.game, a.games, mt, a.sims, games_per_slot=1 << 20, seed=seed, words_per_tree=words, device=local,
-                           hist_capacity=a.games * (a.drain + 2) * 4,
+                           hist_capacity=ring,
                            lib=b2az.load(os.environ.get("B2AZ_LIB_PATH")), **kw)  # experiment builds via env
     stream = torch.cuda.current_stream().cuda_stream
     # the consumer's buffers: pinned host memory, allocated once (what a history saver would hold)
-    cap = a.games * (a.drain + 2) * 4
+    cap = ring
     pinned = (torch.empty((cap, sp.P, sp.S, sp.S), dtype=torch.float32).pin_memory(), torch.empty((cap, 3), dtype=torch.float32).pin_memory(),
               torch.empty((cap, sp.A), dtype=torch.float32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory())
     host_out = (pinned[0].numpy(), pinned[1].numpy(), pinned[2].numpy(), pinned[3].numpy().view("uint32"))
@@ -143,7 +147,7 @@ if __name__ == "__main__":
     # depth D and children k measured by the engine in this run; peak = MEASURED_PEAKS.json hbm_gbs (else 6650)
     D = float(st1["leaf_depth"].sum() / full)
     k = float(st1["valid_moves"].sum() / max(1, int(st1["total_move_count"].sum())))
-    bps = D * (12 * k + 8) + D * 28 + (16 * k + 16) + 3 * 16 + 8
+    bps = D * (12 * k + 8) + D * 28 + (16 * k + 16) + (200 if a.game >= 10 else 3 * 16 + 8)  # state: SGState / three bitboards
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
