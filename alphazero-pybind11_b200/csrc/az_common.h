@@ -9,10 +9,13 @@
 #define AZ_D __device__ __forceinline__
 // cold paths (move making, root noise, compaction): kept out of line so the per-simulation loop stays small
 #define AZ_COLD __host__ __device__ __noinline__
+// large rule functions that are called from several places of a kernel: one out-of-line copy (instruction-cache footprint)
+#define AZ_HD_CALL __host__ __device__ __noinline__
 #else
 #define AZ_HD inline
 #define AZ_D inline
 #define AZ_COLD inline
+#define AZ_HD_CALL inline
 #endif
 
 namespace b2az {

@@ -722,10 +722,18 @@ __device__ __noinline__ void fr_add_root_noise(const ForestView& F, u32 t, Pcg32
 // BATCHED = MCTS::find_leaf_batched (mcts.cc:752-789, WU-UCT): the descent may pass nodes that a previous in-flight
 // call expanded but that have no visit yet, every node on the path (and the leaf) gets ++n_in_flight AFTER the
 // selection made at it, and the leaf goes to the tree's in-flight list instead of current_/path_.
-template <int GAME, bool BATCHED>
+// LOCK: the CTA's warps walk their trees in lock step — one CTA-wide vote per tree level, so that all of them run the
+// same stretch of code at the same time (the kernels are 110-200 KB of SASS against a 32 KB instruction cache per SM:
+// warps scattered over the code starve on instruction fetch, profiles/r3j_k_sp_search_sg_ncu_summary.json). A warp
+// without a simulation to do (`live` false) only takes part in the votes.
+template <int GAME, bool BATCHED, bool LOCK = false>
 __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon,
-                                 ForestLeaf& Lf, float* canon_out) {
+                                 ForestLeaf& Lf, float* canon_out, bool live = true) {
   typedef FGame<GAME> G;
+  if (LOCK && !live) {
+    while (__syncthreads_or(0)) {}
+    return;
+  }
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
   typename G::Pos pos;
@@ -746,8 +754,12 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     __syncwarp();
     gumbel_on = G.initialized != 0;
   }
-  while ((BATCHED ? ((cur_n > 0 || cur_nif > 0) && cur_blk != 0) : (cur_n > 0)) && cur_term == 0) {
-    if (plen >= (u32)kFPath || cur_blk == 0) { err |= 2u; break; }
+  bool descending = true;
+  for (;;) {
+    bool go = descending && (BATCHED ? ((cur_n > 0 || cur_nif > 0) && cur_blk != 0) : (cur_n > 0)) && cur_term == 0;
+    if (go && (plen >= (u32)kFPath || cur_blk == 0)) { err |= 2u; go = false; }
+    if (LOCK) { if (!__syncthreads_or(go ? 1 : 0)) break; } else if (!go) break;
+    if (!go) { descending = false; continue; }
     const u32 b = cur_blk, k = cur_k;
     u32 best_j = 0xFFFFFFFFu;
     if (gumbel_on && at_root) {  // the root child comes from the sequential-halving schedule (mcts.cc:476-478)
@@ -800,7 +812,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       }
     }
     ++plen;
-    if (!G::play(pos, mvw & 0xFFFFu, lane)) { err |= 8u; break; }
+    if (!G::play(pos, mvw & 0xFFFFu, lane)) { err |= 8u; descending = false; continue; }
     par_blk = b; par_slot = best_j; par_k = k;
     cur_n = pool[fb_n(b, k) + best_j];
     cur_v = u2f(pool[fb_v(b, k) + best_j]);

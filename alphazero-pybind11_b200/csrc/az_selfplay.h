@@ -136,6 +136,35 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_
     if (lane == 0) S.slots[g].simulations += todo;
   }
 }
+// The same search with the 16 warps of a 512-thread CTA in lock step (forest_find_leaf LOCK): every tree level is one
+// CTA-wide round, the expansions run together, the backups run together. Slots that need fewer simulations (capped
+// searches, retired slots) sit the rounds out.
+template <int GAME>
+__global__ void __launch_bounds__(512, GAME == B2AZ_FOREST_SG ? 1 : 2) k_sp_search_lock(ForestView F, SpView S, u32 n_sims) {
+  __shared__ ForestSmem<GAME> sm[16];
+  const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  for (u32 g0 = blockIdx.x * 16u; g0 < S.n_games; g0 += gridDim.x * 16u) {
+    const u32 g = g0 + wib;
+    const bool has = g < S.n_games && S.slots[g].active != 0;
+    u32 t = 0, todo = 0;
+    bool noise = false;
+    if (has) {
+      const u32 cp = FGame<GAME>::root_player(F, 2u * g);
+      t = 2u * g + cp;
+      noise = F.epsilon > 0.0f && !S.slots[g].capped;
+      const u32 goal = sp_goal(S, S.slots[g], cp), have = F.trees[t].depth;
+      todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;
+    }
+    for (u32 i = 0;; ++i) {
+      const bool live = has && i < todo;
+      if (!__syncthreads_or(live ? 1 : 0)) break;
+      forest_find_leaf<GAME, false, true>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr, live);
+      __syncthreads();
+      if (live) forest_process_result<GAME, true, false>(F, t, nullptr, nullptr, lane, noise, F.trees[t].leaf);
+    }
+    if (has && lane == 0) S.slots[g].simulations += todo;
+  }
+}
 // the evaluator-in-the-middle form of the same step (EvalType::NN): leaves' canonical planes out, (v, pi) rows in;
 // row g of both belongs to slot g
 template <int GAME>
@@ -377,6 +406,12 @@ __global__ void k_sp_count_active(ForestView F, SpView S, u32* out) {
 
 }  // namespace b2az
 
+// which search kernel: B2AZ_SP_LOCKSTEP=0 / 1 overrides; default = lock step for Star Gambit (measured)
+static inline bool sp_lockstep(uint32_t game) {
+  static const int env = [] { const char* e = getenv("B2AZ_SP_LOCKSTEP"); return e ? atoi(e) : -1; }();
+  return env >= 0 ? env != 0 : game >= 10u;
+}
+
 struct b2az_tafl_selfplay {
   b2az_forest* forest = nullptr;
   b2az::SpView view;
@@ -508,7 +543,12 @@ int b2az_tafl_selfplay_play(b2az_tafl_selfplay* sp, void* stream, uint32_t n_mov
   cudaStream_t s = (cudaStream_t)stream;
   b2az_forest* f = sp->forest;
   for (uint32_t m = 0; m < n_moves; ++m) {
-    FOREST_DISPATCH(f, (k_sp_search<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, sp->view.visits)));
+    if (sp_lockstep(f->view.game)) {
+      const unsigned ctas = std::max(1u, std::min((sp->view.n_games + 15u) / 16u, 148u * 2u));
+      FOREST_DISPATCH(f, (k_sp_search_lock<G_><<<ctas, 512, 0, s>>>(f->view, sp->view, sp->view.visits)));
+    } else {
+      FOREST_DISPATCH(f, (k_sp_search<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, sp->view.visits)));
+    }
     FOREST_DISPATCH(f, (k_sp_move<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view)));
   }
   CUDA_TRY(cudaGetLastError());

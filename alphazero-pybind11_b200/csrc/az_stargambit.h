@@ -140,7 +140,7 @@ AZ_HD int sg_unit_hexes(const SGUnit& u, int side, int* hq, int* hr) {
 struct SGBoards {  // occupancy of the alive units: all, and per player
   SGOcc all, pl[2];
 };
-AZ_HD void sg_boards(const SGState& s, int side, SGBoards& b) {
+AZ_HD_CALL void sg_boards(const SGState& s, int side, SGBoards& b) {
   sg_occ_clear(b.all); sg_occ_clear(b.pl[0]); sg_occ_clear(b.pl[1]);
   for (int i = 0; i < (int)s.n_units; ++i) {
     const SGUnit& u = s.units[i];
@@ -156,7 +156,7 @@ AZ_HD void sg_boards(const SGState& s, int side, SGBoards& b) {
 
 // compute_{fighter,cruiser,dreadnought}_move (star_gambit_gs.cc:448-600): `dir` is the unit type's own move index.
 // Returns false when a hex of the new placement leaves the board.
-AZ_HD bool sg_compute_move(const SGUnit& u, int dir, int side, int& nq, int& nr, int& nf) {
+AZ_HD_CALL bool sg_compute_move(const SGUnit& u, int dir, int side, int& nq, int& nr, int& nf) {
   const int f = u.facing, q = u.q, r = u.r;
   if (u.type == SG_FIGHTER) {  // 0 forward, 1 forward-left, 2 forward-right; faces where it moves
     if (dir < 0 || dir > 2) return false;
@@ -222,7 +222,7 @@ AZ_HD void sg_cannon(int type, int idx, int& doff, int& src) {
 }
 
 // the ten action slots of unit `ui` that valid_moves() would mark (bit = SpatialAction slot)
-AZ_HD u32 sg_unit_slots(const SGState& s, const SGBoards& b, int ui, int side) {
+AZ_HD_CALL u32 sg_unit_slots(const SGState& s, const SGBoards& b, int ui, int side) {
   const SGUnit& u = s.units[ui];
   if (u.player != s.player || u.hp == 0 || u.type == SG_PORTAL) return 0;
   int hq[3], hr[3];
@@ -279,7 +279,7 @@ AZ_HD bool sg_deploy_anchor(int type, int player, int facing, int side, int& aq,
   }
   return true;
 }
-AZ_HD bool sg_deploy_ok(const SGState& s, const SGBoards& b, int side, int type, int f) {
+AZ_HD_CALL bool sg_deploy_ok(const SGState& s, const SGBoards& b, int side, int type, int f) {
   const int p = s.player & 1;
   if (s.reserves[p][type] == 0) return false;
   int aq, ar;
@@ -333,7 +333,7 @@ struct SGNoEmit {
 };
 
 // compute_position_hash (star_gambit_gs.cc:1365-1382)
-AZ_HD u64 sg_position_key(const SGState& s) {
+AZ_HD_CALL u64 sg_position_key(const SGState& s) {
   u64 h = (u64)s.player * 0x9e3779b97f4a7c15ULL;
   for (int i = 0; i < (int)s.n_units; ++i) {
     const SGUnit& u = s.units[i];
@@ -363,7 +363,7 @@ struct SGHistFlat {
   }
 };
 
-AZ_HD void sg_init(SGState& s, int variant) {  // StarGambitGS() (star_gambit_gs.cc:251-290); the caller pushes the first key
+AZ_HD_CALL void sg_init(SGState& s, int variant) {  // StarGambitGS() (star_gambit_gs.cc:251-290); the caller pushes the first key
   for (int i = 0; i < (int)sizeof(SGState); ++i) ((u8*)&s)[i] = 0;
   s.variant = (u8)variant;
   const int side = sg_side(variant);
@@ -379,7 +379,7 @@ AZ_HD void sg_init(SGState& s, int variant) {  // StarGambitGS() (star_gambit_gs
   s.player = 0; s.turn = 1; s.acted = 0; s.over = 0; s.winner = -1;
 }
 
-AZ_HD void sg_check_game_end(SGState& s) {  // star_gambit_gs.cc:1313-1345
+AZ_HD_CALL void sg_check_game_end(SGState& s) {  // star_gambit_gs.cc:1313-1345
   for (int i = 0; i < (int)s.n_units; ++i)
     if (s.units[i].type == SG_PORTAL && s.units[i].hp == 0) {
       s.over = 1; s.winner = (int8_t)(1 - s.units[i].player);
@@ -404,7 +404,7 @@ struct SGAnyValidScalar {
   AZ_HD bool operator()(const SGState& s, const SGSpace& sp) const { return sg_valid_moves(s, sp, SGNoEmit()) != 0; }
 };
 template <class H, class AnyValid>
-AZ_HD void sg_end_turn(SGState& s, H& hist, const SGSpace& sp, AnyValid&& any_valid) {  // execute_end_turn (1263-1290)
+AZ_HD_CALL void sg_end_turn(SGState& s, H& hist, const SGSpace& sp, AnyValid&& any_valid) {  // execute_end_turn (1263-1290)
   s.player = (u8)(1 - s.player);
   ++s.turn;
   s.acted = 0;
@@ -416,7 +416,7 @@ AZ_HD void sg_end_turn(SGState& s, H& hist, const SGSpace& sp, AnyValid&& any_va
   }
   if (!any_valid(s, sp)) { s.over = 1; s.winner = (int8_t)(1 - s.player); }
 }
-AZ_HD int sg_unit_at(const SGState& s, int q, int r, int side) {  // find_unit_at_hex (413-433)
+AZ_HD_CALL int sg_unit_at(const SGState& s, int q, int r, int side) {  // find_unit_at_hex (413-433)
   for (int i = 0; i < (int)s.n_units; ++i) {
     if (s.units[i].hp == 0) continue;
     int hq[3], hr[3];
@@ -427,7 +427,7 @@ AZ_HD int sg_unit_at(const SGState& s, int q, int r, int side) {  // find_unit_a
   return -1;
 }
 // execute_fire's target search (978-1045): the first unit of ANY side (but the shooter) in range 1 then 2
-AZ_HD bool sg_fire_target(const SGState& s, int ui, int ci, int side, int& target, int& damage) {
+AZ_HD_CALL bool sg_fire_target(const SGState& s, int ui, int ci, int side, int& target, int& damage) {
   const SGUnit& u = s.units[ui];
   if (ci >= sg_num_cannons(u.type)) return false;
   int doff, src, hq[3], hr[3];
@@ -448,7 +448,7 @@ AZ_HD bool sg_fire_target(const SGState& s, int ui, int ci, int side, int& targe
 
 // play_move (star_gambit_gs.cc:1093-1238). Returns false only for ids outside the space.
 template <class H, class AnyValid>
-AZ_HD bool sg_play(SGState& s, H& hist, const SGSpace& sp, u32 move, AnyValid&& any_valid) {
+AZ_HD_CALL bool sg_play(SGState& s, H& hist, const SGSpace& sp, u32 move, AnyValid&& any_valid) {
   if (move >= (u32)sp.num_moves()) return false;
   if (move < (u32)sp.deploy_offset()) {
     const int slot = (int)(move % 10u), pos = (int)(move / 10u);

@@ -70,7 +70,7 @@ __device__ __forceinline__ void sg_warp_store(SGState* dst, const SGState& src, 
 }
 
 // occupancy sets by warp reduction: lane i contributes unit i
-__device__ __forceinline__ void sg_warp_boards(const SGState& s, int side, u32 lane, SGBoards& b) {
+__device__ __noinline__ void sg_warp_boards(const SGState& s, int side, u32 lane, SGBoards& b) {
   SGOcc mine;
   sg_occ_clear(mine);
   u32 pl = 0;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void sg_warp_boards(const SGState& s, int side, u32 l
 }
 struct SGAnyValidWarp {  // valid_moves().sum() != 0, one unit / one deploy per lane
   u32 lane;
-  __device__ __forceinline__ bool operator()(const SGState& s, const SGSpace& sp) const {
+  __device__ __noinline__ bool operator()(const SGState& s, const SGSpace& sp) const {
     if (s.over) return false;
     SGBoards b;
     sg_warp_boards(s, sp.side, lane, b);
@@ -103,7 +103,7 @@ struct SGAnyValidWarp {  // valid_moves().sum() != 0, one unit / one deploy per 
   }
 };
 // valid_moves() into sm.map (one bit per action id) and sm.moves (ascending ids); returns their number
-__device__ __forceinline__ u32 sg_warp_legal(const SGState& s, const SGSpace& sp, SGWarpSmem& sm, u32 lane) {
+__device__ __noinline__ u32 sg_warp_legal(const SGState& s, const SGSpace& sp, SGWarpSmem& sm, u32 lane) {
   for (u32 w = lane; w < (u32)kSGMapWords; w += 32u) sm.map[w] = 0;
   __syncwarp();
   if (!s.over) {
@@ -155,7 +155,7 @@ __device__ __forceinline__ u32 sg_warp_legal(const SGState& s, const SGSpace& sp
 
 // canonicalized() written by the warp: out[plane][udim][udim]
 // (`rc` = how often the position's key occurs in its key history: position_history_ scanned by the caller)
-__device__ __forceinline__ void sg_warp_canon(const SGState& s, int rc, const SGSpace& sp, bool unified,
+__device__ __noinline__ void sg_warp_canon(const SGState& s, int rc, const SGSpace& sp, bool unified,
                                               SGWarpSmem& sm, u32 lane, float* out) {
   const int cells = sp.dim * sp.dim, ucells = sp.udim * sp.udim;
   for (int i = (int)lane; i < cells; i += 32) sm.cell_unit[i] = 0;
