@@ -102,6 +102,7 @@ struct ForestView {
   u64* sg_hist;         // [n_trees][sg_hist_cap] position keys of the root since the last deploy
   u64* sg_pkeys;        // [n_trees][kFPath + 2] keys appended along the current path
   u32 sg_hist_cap;
+  float sg_probs[4];    // game 24 (StarGambitUnifiedGS with the variant mix): the variants' weights
   u32 rng_pair;         // self-play: trees 2g and 2g+1 (the two seats' MCTS objects of game g, play_manager.h game.mcts[])
                         // draw from ONE generator (the reference's thread-local one), kept in tree 2g
 };
@@ -382,7 +383,7 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
     if (lane == 0 && !err) { R.state = s; R.hist_len = hist_len; }
     return err;
   }
-  static __device__ __forceinline__ void init(const ForestView& F, u32 t) {
+  static __device__ __forceinline__ void init(const ForestView& F, u32 t, int = -1) {
     T::init(F.trees[t].state, F.max_turns);
     F.trees[t].hist_len = 0;
   }
@@ -394,6 +395,7 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
   static __device__ __forceinline__ u32 root_turn(const ForestView& F, u32 t) { return F.trees[t].state.turn; }
   static __device__ __forceinline__ u32 root_terminal(const ForestView& F, u32 t) { return T::terminal(F.trees[t].state); }
   static __device__ __forceinline__ int root_variant(const ForestView&, u32) { return -1; }
+  static __device__ __forceinline__ int pick_variant(const ForestView&, Pcg32&) { return -1; }
 };
 template <>
 struct FGame<B2AZ_FOREST_SG> {  // Star Gambit: the variants' own classes and the Unified view
@@ -466,9 +468,11 @@ struct FGame<B2AZ_FOREST_SG> {  // Star Gambit: the variants' own classes and th
     if (lane == 0) R.hist_len = h.len;
     return 0;
   }
-  static __device__ __forceinline__ void init(const ForestView& F, u32 t) {  // (one thread per tree)
+  // (one thread per tree) `variant` < 0: the game id's own; game 24 (the variant mix) without a pick yet: by tree pair
+  static __device__ __forceinline__ void init(const ForestView& F, u32 t, int variant = -1) {
     SGState s;
-    sg_init(s, sg_game_variant(F.game));
+    if (variant < 0) variant = F.game == 24u ? (int)((t >> 1) & 3u) : sg_game_variant(F.game);
+    sg_init(s, variant);
     F.sg_state[t] = s;
     F.sg_hist[(size_t)t * F.sg_hist_cap] = sg_position_key(s);
     F.trees[t].hist_len = 1;
@@ -485,6 +489,19 @@ struct FGame<B2AZ_FOREST_SG> {  // Star Gambit: the variants' own classes and th
   }
   static __device__ __forceinline__ int root_variant(const ForestView& F, u32 t) {  // get_variant_id(): Unified only
     return sg_game_unified(F.game) ? (int)F.sg_state[t].variant : -1;
+  }
+  // StarGambitUnifiedGS::randomize_start (star_gambit_gs.cc:2421-2425): a variant drawn from the weights. The reference
+  // draws from an unseedable mt19937 (2357-2362); here the slot's coin stream decides. -1: the game id fixes the variant.
+  static __device__ __forceinline__ int pick_variant(const ForestView& F, Pcg32& coin) {
+    if (F.game != 24u) return -1;
+    const float total = fadd(fadd(F.sg_probs[0], F.sg_probs[1]), fadd(F.sg_probs[2], F.sg_probs[3]));
+    const float u = fmul(rng_uniform01(coin), total);
+    float acc = 0.0f;
+    for (int v = 0; v < 3; ++v) {
+      acc = fadd(acc, F.sg_probs[v]);
+      if (u < acc) return v;
+    }
+    return 3;
   }
 };
 
@@ -879,7 +896,8 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
 // BATCHED = MCTS::process_result_batched (mcts.cc:791-845): the same with --n_in_flight along the path.
 template <int GAME, bool RANDOM, bool BATCHED>
 __device__ void forest_process_result(const ForestView& F, u32 t, const float* ev_v, const float* ev_pi, u32 lane,
-                                      bool root_noise_enabled, ForestLeaf& Lf) {
+                                      bool root_noise_enabled, ForestLeaf& Lf, u32 row = 0xFFFFFFFFu) {
+  const size_t er = row == 0xFFFFFFFFu ? (size_t)t : (size_t)row;  // the evaluator's row of this tree (self-play: the game slot)
   const u32 A = FGame<GAME>::actions(F);
   ForestTree& R = F.trees[t];
   u32* pool = F.pool + (size_t)t * F.words_per_tree;
@@ -891,7 +909,7 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
     if (RANDOM) {
       val0 = val1 = vald = (float)(1.0 / 3.0);
     } else {
-      val0 = ev_v[(size_t)t * 3 + 0]; val1 = ev_v[(size_t)t * 3 + 1]; vald = ev_v[(size_t)t * 3 + 2];
+      val0 = ev_v[er * 3 + 0]; val1 = ev_v[er * 3 + 1]; vald = ev_v[er * 3 + 2];
       // relative_to_absolute(value, current_->player, 2) (mcts.cc:522-524, game_state.h:37-48): seat 1's answer swaps
       if (F.relative_values && lplayer == 1u) { const float sw = val0; val0 = val1; val1 = sw; }
     }
@@ -908,7 +926,7 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
         const u32 j = c0 + lane;
         float p = 0.0f;
         if (j < lk) {
-          p = RANDOM ? rp : ev_pi[(size_t)t * A + (pool[fb_mv(lblk, lk) + j] & 0xFFFFu)];
+          p = RANDOM ? rp : ev_pi[er * A + (pool[fb_mv(lblk, lk) + j] & 0xFFFFu)];
           pool[fb_pol(lblk, lk) + j] = f2u(p);
         }
         const u32 cnt = lk - c0 < 32u ? lk - c0 : 32u;
@@ -1523,7 +1541,7 @@ extern "C" {
 int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** out) {
   using namespace b2az;
   if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
-  const bool is_sg = (p->game >= 10 && p->game <= 13) || (p->game >= 20 && p->game <= 23);
+  const bool is_sg = (p->game >= 10 && p->game <= 13) || (p->game >= 20 && p->game <= 24);  // 24: Unified, variant mix
   if (p->game > B2AZ_TAFL_TAWLBWRDD && !is_sg) return fail(B2AZ_EINVAL, "b2az_forest: unknown game");
   if (p->n_trees == 0 || p->max_turns == 0 || p->max_turns > 65535u) return fail(B2AZ_EINVAL, "b2az_forest: bad n_trees / max_turns");
   if (!(p->root_policy_temp > 0.0f)) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp must be positive (1 = off)");
@@ -1546,7 +1564,8 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   V.n_trees = p->n_trees; V.max_turns = p->max_turns; V.game = p->game;
   V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.root_fpu_zero = p->root_fpu_zero ? 1u : 0u;
   if (is_sg) {
-    const SGSpace sp = sg_space((int)(p->game % 10u), p->game >= 20u);
+    const SGSpace sp = sg_space(p->game == 24u ? B2AZ_SG_BATTLE : (int)(p->game % 10u), p->game >= 20u);
+    for (int i = 0; i < 4; ++i) V.sg_probs[i] = 0.25f;
     f->actions = (uint32_t)sp.num_moves();
     f->canon = (uint32_t)(sp.planes(p->game >= 20u) * sp.udim * sp.udim);
   } else {

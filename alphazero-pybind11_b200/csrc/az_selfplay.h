@@ -103,6 +103,7 @@ __device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, con
   __syncwarp();
 }
 
+template <int GAME>
 __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
   for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) {
     pcg32_seed(F.trees[2u * g].rng, seed + g);  // slot g == a reference run after MCTS::seed_thread_rng(seed + g)
@@ -110,6 +111,10 @@ __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
     G.active = 1;
     G.games_started = 1;
     pcg32_seed_stream(G.coin, seed + g, 0x5EEDC01ull);
+    {  // base_gs_->copy() + randomize_start() for the first game of the slot (Unified variant mix only)
+      const int v = FGame<GAME>::pick_variant(F, G.coin);
+      if (v >= 0) { FGame<GAME>::init(F, 2u * g, v); FGame<GAME>::init(F, 2u * g + 1u, v); }
+    }
     // game.initialized = true; the first playout-cap coin; set_gumbel_num_sims on the first seat's tree (play_manager.cc:556-568)
     G.capped = (S.playout_cap && sp_coin(G, S.playout_cap_percent)) ? 1u : 0u;
     const u32 cp0 = 0u, t0 = 2u * g + cp0;  // player 0 opens every game of this engine (attackers / Star Gambit's P0)
@@ -183,10 +188,8 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
     const u32 t = 2u * g + FGame<GAME>::root_player(F, 2u * g);
-    // forest_process_result reads row t of its inputs: hand it pointers moved so that row t is row g
-    forest_process_result<GAME, false, false>(F, t, ev_v + (size_t)g * 3 - (size_t)t * 3,
-                                              ev_pi + (size_t)g * FGame<GAME>::actions(F) - (size_t)t * FGame<GAME>::actions(F), lane,
-                                              F.epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf);
+    forest_process_result<GAME, false, false>(F, t, ev_v, ev_pi, lane, F.epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf,
+                                              /*row=*/g);  // row g of the evaluator's output belongs to slot g
     if (lane == 0) S.slots[g].simulations += 1;
   }
 }
@@ -264,11 +267,9 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
     }
     // training sample (play_manager.cc:407-424): full searches only
     if (S.history_enabled && !capped) {
-      // (a game longer than the staging area — only Star Gambit's action count is unbounded a priori — overwrites its
-      // last row and reports it)
-      const u32 prow = G.pending < S.stage_rows ? G.pending : S.stage_rows - 1u;
-      if (G.pending >= S.stage_rows && lane == 0) G.error |= 2u;
-      const size_t row = (size_t)g * S.stage_rows + prow;
+      // (the staging area of a slot is a ring: a game with more full searches than `stage_rows` — only Star Gambit's
+      // action count has no small bound — keeps its most recent stage_rows samples)
+      const size_t row = (size_t)g * S.stage_rows + G.pending % S.stage_rows;
       {
         typename GM::Pos pos;  // GameState::canonicalized() of the root position
         GM::open(F, t, lane, sm[wib], pos);
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
       if (lane == 0) S.st_player[row] = (u8)cp;
     }
     if (lane == 0) {
-      if (S.history_enabled && !capped && G.pending < S.stage_rows) G.pending += 1;
+      if (S.history_enabled && !capped) G.pending += 1;
       // metrics (play_manager.cc:436-446; MCTS::avg_leaf_depth mcts.h:112, normalized_root_entropy mcts.cc:737-750)
       const float ald = R.depth == 0 ? 0.0f : fdiv((float)R.total_leaf_depth, (float)R.depth);
       float ent = 0.0f;
@@ -328,14 +329,14 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
     if (term != 0) {
       const float s0 = term == 1 ? 1.0f : 0.0f, s1 = term == 2 ? 1.0f : 0.0f, sd = term == 3 ? 1.0f : 0.0f;
       if (S.history_enabled) {
-        const u32 cnt = G.pending;
+        const u32 cnt = G.pending < S.stage_rows ? G.pending : S.stage_rows;
         u32 base = 0;
         if (lane == 0) base = atomicAdd(S.out_count, cnt);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         for (u32 i = 0; i < cnt; ++i) {  // partial_history.back() first
           const u32 dst = base + i;
           if (dst >= S.out_cap) { if (lane == 0) G.error |= 1u; break; }
-          const size_t src = (size_t)g * S.stage_rows + (cnt - 1u - i);
+          const size_t src = (size_t)g * S.stage_rows + (G.pending - 1u - i) % S.stage_rows;
           GM::unstage(F, S.st_canon + src * S.st_stride, sm[wib], S.out_canon + (size_t)dst * CANON, lane);
           for (u32 e = lane; e < A; e += 32u) S.out_pi[(size_t)dst * A + e] = S.st_pi[src * A + e];
           if (lane == 0) {
@@ -367,8 +368,9 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
           retire = true;
         } else {
           G.games_started += 1;
+          const int nv = GM::pick_variant(F, G.coin);  // game.gs->randomize_start()
           for (u32 j = 0; j < 2u; ++j) {  // game.gs = base_gs_->copy(); fresh MCTS per seat
-            GM::init(F, 2u * g + j);  // (Unified: the pinned variant again; the random mix is an unseedable mt19937 in the reference)
+            GM::init(F, 2u * g + j, nv);
             sp_reset_search(F, 2u * g + j);
           }
         }
@@ -499,7 +501,12 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   }
   if (int rc = dev_alloc(&S.out_count, 1)) return bail(rc);
   if (int rc = dev_alloc(&sp->active_dev, 2)) return bail(rc);
-  k_sp_init<<<148, 128>>>(f->view, S, p->forest.seed);
+  if (fp.game == 24u) {
+    float tot = 0.0f;
+    for (int i = 0; i < 4; ++i) tot += p->variant_probs[i] > 0.0f ? p->variant_probs[i] : 0.0f;
+    for (int i = 0; i < 4; ++i) f->view.sg_probs[i] = tot > 0.0f ? (p->variant_probs[i] > 0.0f ? p->variant_probs[i] : 0.0f) : 0.25f;
+  }
+  FOREST_DISPATCH(f, (k_sp_init<G_><<<148, 128>>>(f->view, S, p->forest.seed)));
   if (cudaGetLastError() != cudaSuccess) return bail(fail(B2AZ_ECUDA, "k_sp_init launch failed"));
   if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(B2AZ_ECUDA, "k_sp_init failed"));
   *out = sp;
@@ -652,7 +659,7 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
     for (int i = 0; i < 3; ++i) out->scores[i] += g.scores[i];
     leaf_depth += g.leaf_depth; entropy += g.entropy; valid += g.valid_moves;
     moves += g.total_move_count; full += g.total_full_move_count; length += g.game_length;
-    if (g.error & 3u) out->device_error |= B2AZ_DEVERR_HIST;  // 1: sample ring full, 2: a game outgrew its staging rows
+    if (g.error & 1u) out->device_error |= B2AZ_DEVERR_HIST;
   }
   out->moves = moves;
   out->hist_count = sp->view.history_enabled ? std::min(count, sp->view.out_cap) - std::min(sp->hist_head, count) : 0u;

@@ -460,6 +460,7 @@ class PlayManager {
     sp.history_enabled = P.history_enabled; sp.policy_target_pruning = P.policy_target_pruning; sp.tree_reuse = P.tree_reuse;
     sp.n_variant_half_life = (uint32_t)std::min<size_t>(4, P.temp_decay_half_life_by_variant.size());
     for (uint32_t i = 0; i < sp.n_variant_half_life; ++i) sp.variant_half_life[i] = P.temp_decay_half_life_by_variant[i];
+    for (int i = 0; i < 4; ++i) sp.variant_probs[i] = sg_probs_[i];
     // history_ is unbounded in the reference; here the sample ring holds what a run can produce between drains: every
     // sample of the run when that fits an 8 GB budget (play() first, build_history_batch afterwards works), else the
     // budget — a full ring drops samples and play() then fails loudly (B2AZ_DEVERR_HIST)
@@ -485,13 +486,12 @@ class PlayManager {
     auto* t = dynamic_cast<const StarGambitBase*>(gs);
     if (!t) return false;
     if (t->s.turn != 1 || t->s.n_units != 2) throw std::runtime_error("the B200 engine starts every game from the initial position");
-    if (t->unified && (t->pinned < 0 || t->pinned > 3))
-      throw std::runtime_error("StarGambitUnifiedGS with the random variant mix is not implemented by the B200 Star Gambit engine yet: "
-                               "run one PlayManager per pinned variant");
+    const bool mix = t->unified && (t->pinned < 0 || t->pinned > 3);  // every new game draws its variant (randomize_start)
+    if (mix) for (int i = 0; i < 4; ++i) sg_probs_[i] = t->probs[i];
     const auto sp = t->space();
-    // a Star Gambit game has no fixed bound on its actions (200 turns of several actions each): 512 staged samples per
-    // game slot; a longer game reports B2AZ_DEVERR_HIST instead of dropping samples silently
-    setup_wide((t->unified ? 20u : 10u) + t->s.variant, 512u, sp.planes(t->unified), sp.udim, sp.num_moves(), 64u, true,
+    // a Star Gambit game has no small bound on its actions (200 turns of several actions each): 512 staged samples per
+    // game slot; a longer game keeps its most recent 512
+    setup_wide(mix ? 24u : (t->unified ? 20u : 10u) + t->s.variant, 512u, sp.planes(t->unified), sp.udim, sp.num_moves(), 64u, true,
                "B200 Star Gambit engine");
     return true;
   }
@@ -970,6 +970,7 @@ class PlayManager {
   std::vector<uint32_t> group_next_;              // per group: rows already handed out
   uint32_t leaf_count_ = 0, answered_ = 0;
   b2az_stats stats_{};
+  float sg_probs_[4] = {0.25f, 0.25f, 0.25f, 0.25f};  // StarGambitUnifiedGS variant weights (variant mix)
   dl::In dl_v_, dl_pi_;      // the evaluations of the DLPack feed, kept alive until the engine has read them
   uint32_t dl_rows_ = 0;
   bool dl_stepped_ = false;  // update_inferences_dlpack has already run the next generation's step

@@ -109,7 +109,8 @@ class TaflGS : public GameState {
     return a;
   }
   // board int8[3][S][S] + turn u16 + max_turns u16 + player + repetition count + the repetition table
-  // (brandubh_gs.cc:18-40; the table is written as one entry per stored key with count 1)
+  // (brandubh_gs.cc:18-40: one entry per DISTINCT position with its count; the reference's from_bytes assigns
+  // counts[key] = entry_count, so equal keys are merged here — first occurrence order)
   std::string to_bytes() const override {
     std::string out(3 * CELLS, '\0');
     for (uint32_t e = 0; e < (uint32_t)(3 * CELLS); ++e) out[e] = (char)T::board_byte(s, e);
@@ -118,16 +119,26 @@ class TaflGS : public GameState {
     out.append(reinterpret_cast<const char*>(&mt), 2);
     out.push_back((char)s.player);
     out.push_back((char)s.rep);
-    const uint32_t n = hist_len;
+    std::vector<uint32_t> first;   // indices of the distinct keys
+    std::vector<uint8_t> counts;
+    for (uint32_t i = 0; i < hist_len; ++i) {
+      size_t j = 0;
+      for (; j < first.size(); ++j)
+        if (T::key_eq(hist[first[j]], hist[i])) break;
+      if (j == first.size()) { first.push_back(i); counts.push_back(1); }
+      else if (counts[j] < 255) ++counts[j];
+    }
+    const uint32_t n = (uint32_t)first.size();
     out.append(reinterpret_cast<const char*>(&n), 4);
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t d = 0; d < n; ++d) {
+      const uint32_t i = first[d];
       b2az::TaflState k = s;
       k.king = hist[i].king; k.def = hist[i].def; k.atk = hist[i].atkp;
       const uint8_t kp = (uint8_t)((T::NARROW ? k.atk.lo >> 63 : k.atk.hi >> 63) & 1ULL);
       if (T::NARROW) k.atk.lo &= ~(1ULL << 63); else k.atk.hi &= ~(1ULL << 63);
       for (uint32_t e = 0; e < (uint32_t)(3 * CELLS); ++e) out.push_back((char)T::board_byte(k, e));
       out.push_back((char)kp);
-      out.push_back((char)1);
+      out.push_back((char)counts[d]);
     }
     return out;
   }

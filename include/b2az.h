@@ -299,6 +299,7 @@ int b2az_tafl_symmetries(int device, uint32_t game, uint32_t n, const float* can
 #define B2AZ_SG_BATTLE 3
 #define B2AZ_SG_GAME(variant) (10u + (variant))
 #define B2AZ_SG_UNIFIED(variant) (20u + (variant))
+#define B2AZ_SG_UNIFIED_MIX 24u  /* StarGambitUnifiedGS(-1, probs): every new game draws its variant (self-play engine) */
 #define B2AZ_SG_STATE_BYTES 200  /* 20 units x 9 B (star_gambit_gs.h:359-371 order), n_units, reserves[2][4], player,
                                     has_taken_action, game_over, winner, variant, 2 pad, turn u32 */
 
@@ -419,8 +420,8 @@ int b2az_forest_set_root(b2az_forest* f, uint32_t tree, const void* state, uint3
  * improved policy / probs_pruned(1) / probs(1), play_manager.cc:417-435), scores and metrics, bit for bit.
  * forest.n_trees is ignored (2 * n_games trees are made); forest.max_in_flight must be 0. */
 typedef struct b2az_tafl_selfplay_params {
-  b2az_forest_params forest;     /* game (B2AZ_TAFL_*, B2AZ_SG_GAME / B2AZ_SG_UNIFIED), max_turns (Star Gambit: the bound
-                                    on the training samples of one game, e.g. 768), search parameters (cpuct, epsilon,
+  b2az_forest_params forest;     /* game (B2AZ_TAFL_*, B2AZ_SG_GAME / B2AZ_SG_UNIFIED), max_turns (Star Gambit: how many
+                                    training samples of one game are staged, e.g. 768; a longer game keeps its last ones), search parameters (cpuct, epsilon,
                                     Gumbel, relative_values ...), seed, slab size */
   uint32_t n_games;              /* PlayParams::concurrent_games */
   uint32_t games_per_slot;       /* games every slot plays before it retires (games_to_play = n_games * games_per_slot) */
@@ -438,6 +439,7 @@ typedef struct b2az_tafl_selfplay_params {
   uint8_t pad2_[2];
   uint32_t n_variant_half_life;  /* PlayParams::temp_decay_half_life_by_variant (play_manager.cc:289-296): entries used */
   float variant_half_life[4];    /* indexed by GameState::get_variant_id() (StarGambitUnifiedGS: the variant) */
+  float variant_probs[4];        /* game B2AZ_SG_UNIFIED_MIX: StarGambitUnifiedGS's variant weights (all 0 = 0.25 each) */
 } b2az_tafl_selfplay_params;
 typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
   uint32_t active, games_started, games_completed, pending;

@@ -103,3 +103,23 @@ def test_selfplay_equals_the_reference_playmanager(name):
         assert f32(s["leaf_depth"] / float(s["total_full_move_count"])) == ref["avg_leaf_depth"]
         assert f32(s["valid_moves"] / float(s["total_move_count"])) == ref["avg_valid_moves"]
     assert len(np.unique(v, axis=0)) >= 2  # both frames of the outcome occur
+
+
+@pytest.mark.gpu
+def test_selfplay_variant_mix_with_one_weighted_variant_equals_the_pinned_run():
+    """game 24 (StarGambitUnifiedGS with the variant mix) draws the variant of every new game from the slot's coin stream —
+    apart from the search's generator, so a mix that can only draw Clash is the pinned-Clash run, sample for sample."""
+    def run(game, **kw):
+        sp = b2az.TaflSelfplay(game, 4, STAGE_ROWS, 24, games_per_slot=2, seed=31, hist_capacity=8 * STAGE_ROWS, gumbel_m=8, **kw)
+        active = 4
+        while active:
+            active = sp.play(16)
+        out = sp.drain_history()
+        st, err = sp.slots()
+        sp.close()
+        assert (err == 0).all() and (st["error"] == 0).all()
+        return out
+    a = run(22)
+    b = run(24, variant_probs=[0.0, 0.0, 1.0, 0.0])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

@@ -160,8 +160,21 @@ def test_star_gambit_play_equals_the_reference(ref_game, make, G, visits, kw):
     assert np.array_equal(pm.scores(), np.sum([r["scores"] for r in refs], axis=0))
 
 
-def test_star_gambit_random_mix_is_rejected_loudly():
-    az = module("emu")
-    p = _params(az, 2, 1, 8, 1, True)
-    with pytest.raises(RuntimeError, match="random variant mix"):
-        az.PlayManager(az.StarGambitUnifiedGS(), p)
+@pytest.mark.parametrize("kind", [pytest.param("cuda", marks=gpu)])
+def test_star_gambit_unified_variant_mix_through_the_module(kind):
+    """PlayManager(StarGambitUnifiedGS(-1, probs)): every new game draws its variant (randomize_start,
+    star_gambit_gs.cc:2421-2425; play_manager.cc:515-516). The reference's draw is unseedable, so the check is on the
+    distribution: only variants with weight occur, and all of them do."""
+    az = module(kind)
+    p = _params(az, 24, 2, 12, 9, True, gumbel_enabled=True, gumbel_m=8)
+    pm = az.PlayManager(az.StarGambitUnifiedGS(-1, [0.5, 0.0, 0.25, 0.25]), p)
+    pm.play()
+    assert pm.games_completed() == 48
+    cap = 48 * 512
+    canon, v, pi = np.zeros((cap, 36, 13, 13), np.float32), np.zeros((cap, 3), np.float32), np.zeros((cap, 1709), np.float32)
+    n = pm.build_history_batch(canon, v, pi)
+    assert n > 48
+    variants = canon[:n, 32:36].reshape(n, 4, -1).max(axis=2)  # one-hot plane per sample
+    assert (variants.sum(axis=1) == 1).all()
+    seen = set(np.argmax(variants, axis=1).tolist())
+    assert seen == {0, 2, 3}, seen
