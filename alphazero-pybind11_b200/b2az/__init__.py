@@ -87,7 +87,8 @@ class TaflSelfplayParams(C.Structure):  # b2az_tafl_selfplay_params (include/b2a
                 ("seat_cap_visits", C.c_uint32 * 2), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
                 ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
                 ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2),
-                ("n_variant_half_life", C.c_uint32), ("variant_half_life", C.c_float * 4), ("variant_probs", C.c_float * 4)]
+                ("n_variant_half_life", C.c_uint32), ("variant_half_life", C.c_float * 4), ("variant_probs", C.c_float * 4),
+                ("cache_entries", C.c_uint32)]
 
 
 SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_completed", "u4"), ("pending", "u4"),
@@ -604,7 +605,7 @@ class TaflSelfplay:
                  history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None,
                  seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
                  playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
-                 temp_decay_half_life_by_variant=None, variant_probs=None):
+                 temp_decay_half_life_by_variant=None, variant_probs=None, cache_entries=0):
         self.L = lib or load()
         self.game, self.n = game, n_games
         self.S, self.P, self.A = game_dims(game)
@@ -620,6 +621,7 @@ class TaflSelfplay:
                                resign_playthrough_percent=resign_playthrough_percent,
                                playout_cap_randomization=int(playout_cap_randomization),
                                fast_search_uses_gumbel=int(fast_search_uses_gumbel))
+        p.cache_entries = cache_entries
         for i, w in enumerate((variant_probs or [])[:4]):
             p.variant_probs[i] = w
         for i, hl in enumerate((temp_decay_half_life_by_variant or [])[:4]):

@@ -349,6 +349,19 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
       }
     }
   }
+  // hash_game_state's equality class (brandubh_gs.cc:105-109: board + side to move + repetition count; OpenTafl adds the
+  // turn, opentafl_gs.cc:102-107) as a 64-bit key of the position cache; the VALUE is free, 0 is reserved
+  static __device__ __forceinline__ u64 state_key(const Pos& P, const ForestView&) {
+    const TaflState& s = P.s;
+    u64 h = 0x9E3779B97F4A7C15ULL + (u64)GAME;
+    const u64 w[7] = {s.king.lo, s.king.hi, s.def.lo, s.def.hi, s.atk.lo, s.atk.hi,
+                      (u64)s.player | ((u64)s.rep << 8) | (GAME == B2AZ_TAFL_OPENTAFL ? (u64)s.turn << 16 : 0ULL)};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { h = (h ^ w[i]) * 0xBF58476D1CE4E5B9ULL; h ^= h >> 29; }
+    h = (h ^ (h >> 32)) * 0x94D049BB133111EBULL;
+    h ^= h >> 31;
+    return h ? h : 1ULL;
+  }
   // a training sample's position while its game is still running: the canonical planes themselves (a few hundred floats)
   static __device__ __forceinline__ u32 stage_floats(const ForestView&) { return (u32)T::CANON; }
   static __device__ __forceinline__ void stage(const Pos& P, ForestSmem<GAME>& sm, float* row, u32 lane) { emit_canon(P, sm, row, lane); }
@@ -432,6 +445,25 @@ struct FGame<B2AZ_FOREST_SG> {  // Star Gambit: the variants' own classes and th
   static __device__ __forceinline__ u32 terminal(const Pos& P, u32) { const u32 t = sg_terminal(*P.sp_); return t > 3u ? 3u : t; }
   static __device__ __forceinline__ void emit_canon(const Pos& P, ForestSmem<B2AZ_FOREST_SG>& sm, float* out, u32 lane) {
     sg_warp_canon(*P.sp_, P.hist.count(sg_position_key(*P.sp_)), P.sp, P.unified, sm, lane, out);
+  }
+  // hash_game_state's equality class (star_gambit_gs.cc:321-338: side to move, has_taken_action, every unit's nine
+  // fields, the reserves; the Unified view adds the variant, 2399-2402) as a 64-bit key; 0 is reserved
+  static __device__ __forceinline__ u64 state_key(const Pos& P, const ForestView&) {
+    const SGState& s = *P.sp_;
+    u64 h = 0x9E3779B97F4A7C15ULL ^ ((u64)s.player | ((u64)s.acted << 8) | ((u64)(P.unified ? s.variant + 1u : 0u) << 16));
+    const u8* b = reinterpret_cast<const u8*>(s.units);
+    const int nb = (int)s.n_units * (int)sizeof(SGUnit);
+    for (int i = 0; i < nb; i += 8) {
+      u64 w = 0;
+      for (int j = 0; j < 8 && i + j < nb; ++j) w |= (u64)b[i + j] << (8 * j);
+      h = (h ^ w) * 0xBF58476D1CE4E5B9ULL; h ^= h >> 29;
+    }
+    u64 r = 0;
+    for (int i = 0; i < 8; ++i) r |= (u64)(&s.reserves[0][0])[i] << (8 * i);
+    h = (h ^ r) * 0xBF58476D1CE4E5B9ULL; h ^= h >> 29;
+    h = (h ^ (h >> 32)) * 0x94D049BB133111EBULL;
+    h ^= h >> 31;
+    return h ? h : 1ULL;
   }
   // A training sample's position while its game is still running (PlayManager's partial_history): the 200-byte
   // position record + its repetition count instead of the 24 KB of canonical planes, which are written once, into the
@@ -745,7 +777,7 @@ __device__ __noinline__ void fr_add_root_noise(const ForestView& F, u32 t, Pcg32
 // without a simulation to do (`live` false) only takes part in the votes.
 template <int GAME, bool BATCHED, bool LOCK = false>
 __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& sm, u32 lane, bool emit_canon,
-                                 ForestLeaf& Lf, float* canon_out, bool live = true) {
+                                 ForestLeaf& Lf, float* canon_out, bool live = true, u64* key_out = nullptr) {
   typedef FGame<GAME> G;
   if (LOCK && !live) {
     while (__syncthreads_or(0)) {}
@@ -883,6 +915,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
     }
   }
   if (emit_canon) G::emit_canon(pos, sm, canon_out, lane);
+  if (key_out) *key_out = G::state_key(pos, F);  // the leaf position's cache key (hash_game_state)
   if (lane == 0) {
     R.total_leaf_depth += plen;
     Lf.path_len = plen;

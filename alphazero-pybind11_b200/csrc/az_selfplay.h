@@ -39,7 +39,26 @@ struct SpSlot {                       // b2az_tafl_selfplay_slot in include/b2az
 };
 static_assert(sizeof(SpSlot) == 192, "b2az_tafl_selfplay_slot layout");
 
+// Device position cache of the wide-tree engine (S3FIFOCache / ShardedS3FIFOCache, s3fifo_cache.h:15-318, for the tafl
+// games and Star Gambit): 4-way set-associative table keyed by the 64-bit state key (the reference's cache is keyed by
+// the 64-bit absl hash alone as well), dense value rows pi[A] + v[3] per entry (what the reference stores), a 2-bit
+// frequency per way: a hit bumps it, an insert into a full set replaces the way with the lowest frequency and ages the
+// others. An existing key is never overwritten (s3fifo_cache.h:84). Lookups (k_sp_find_leaf) and inserts
+// (k_sp_process_result) run in different launches, so a reader never meets a half-written row.
+struct SpCache {
+  u64* keys;     // [sets * 4], 0 = empty
+  u8* freq;      // [sets * 4]
+  u32* stamp;    // [sets * 4] epoch of the launch that wrote the way
+  u32 epoch;     // this insert launch's epoch (> 0)
+  float* v;      // [sets * 4][3]
+  float* pi;     // [sets * 4][A]
+  u32 sets;      // power of two; 0 = no cache
+  unsigned long long* ctr;  // hits, misses, inserts, evictions
+};
 struct SpView {
+  SpCache cache;
+  u32* wait;          // [n_games] (cache only): the slot's leaf missed the cache and waits for the evaluator
+  u64* leaf_key;      // [n_games] (cache only): the waiting leaf's key
   SpSlot* slots;
   u32 n_games, games_per_slot, visits;  // visits: the largest search budget of any seat (launch sizing)
   u32 seat_visits[2], seat_cap_visits[2];  // seat_visits_ / seat_cap_visits_ (play_manager.cc:70-90)
@@ -170,16 +189,92 @@ __global__ void __launch_bounds__(512, GAME == B2AZ_FOREST_SG ? 1 : 2) k_sp_sear
     if (has && lane == 0) S.slots[g].simulations += todo;
   }
 }
+__device__ __forceinline__ int sp_cache_lookup(const SpCache& c, u64 key, u32 lane) {  // entry index or -1
+  const u32 set = (u32)(key >> 17) & (c.sets - 1u);
+  const u64 k = lane < 4u ? c.keys[(size_t)set * 4u + lane] : 0ULL;
+  const u32 m = __ballot_sync(0xFFFFFFFFu, lane < 4u && k == key);
+  if (!m) return -1;
+  const u32 e = set * 4u + (u32)(__ffs((int)m) - 1);
+  if (lane == 0) { const u8 f = c.freq[e]; if (f < 3) c.freq[e] = (u8)(f + 1); }
+  return (int)e;
+}
+// One way is written by at most one slot per launch: the writer first wins the way's `stamp` word for this launch's epoch,
+// and a way stamped with the current epoch is never chosen as a victim — otherwise a second slot could evict the
+// freshly claimed way while its 10 KB row is still being written and leave a row mixed from two evaluations.
+__device__ __forceinline__ void sp_cache_insert(const SpCache& c, u64 key, const float* v, const float* pi, u32 A, u32 lane) {
+  const u32 set = (u32)(key >> 17) & (c.sets - 1u);
+  const size_t i0 = (size_t)set * 4u;
+  const u64 k = lane < 4u ? c.keys[i0 + lane] : ~0ULL;
+  const u32 f = lane < 4u ? c.freq[i0 + lane] : 255u;
+  const u32 st = lane < 4u ? c.stamp[i0 + lane] : c.epoch;
+  if (__ballot_sync(0xFFFFFFFFu, lane < 4u && k == key)) return;  // the first value wins
+  const bool cand = lane < 4u && st != c.epoch;
+  // an empty way first, else the lowest frequency (lowest way on ties), among the ways not written in this launch
+  u32 best = cand ? (((k == 0ULL ? 0u : 1u + f) << 2) | lane) : 0xFFFFFFFFu;
+#pragma unroll
+  for (int o = 2; o > 0; o >>= 1) {
+    const u32 ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+    best = ob < best ? ob : best;
+  }
+  best = __shfl_sync(0xFFFFFFFFu, best, 0);
+  if (best == 0xFFFFFFFFu) return;  // every way of the set was written in this launch: a cache may forget
+  const u32 way = best & 3u;
+  const u64 old = __shfl_sync(0xFFFFFFFFu, k, (int)way);
+  const u32 old_st = __shfl_sync(0xFFFFFFFFu, st, (int)way);
+  const u32 e = set * 4u + way;
+  u32 ok = 0;
+  if (lane == 0) ok = atomicCAS(&c.stamp[e], old_st, c.epoch) == old_st ? 1u : 0u;
+  ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+  if (!ok) return;  // another slot took the way in this launch
+  if (lane < 4u && old != 0ULL && lane != way && f > 0u && f != 255u) c.freq[i0 + lane] = (u8)(f - 1u);  // ageing
+  if (lane == 0) {
+    c.keys[e] = key;
+    c.freq[e] = 0;
+    atomicAdd(&c.ctr[2], 1ULL);
+    if (old != 0ULL) atomicAdd(&c.ctr[3], 1ULL);
+  }
+  if (lane < 3u) c.v[(size_t)e * 3u + lane] = v[lane];
+  for (u32 i = lane; i < A; i += 32u) c.pi[(size_t)e * A + i] = pi[i];
+}
+
 // the evaluator-in-the-middle form of the same step (EvalType::NN): leaves' canonical planes out, (v, pi) rows in;
-// row g of both belongs to slot g
+// row g of both belongs to slot g. With the position cache a slot keeps simulating while its leaves hit
+// (play_manager.cc:589-594) and stops at its first miss (wait[g] = 1) or when its search is complete.
 template <int GAME>
 __global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, float* canon) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
-    if (!S.slots[g].active) continue;
-    const u32 t = 2u * g + FGame<GAME>::root_player(F, 2u * g);
-    forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, canon + (size_t)g * FGame<GAME>::canon(F));
+    if (!S.slots[g].active) {
+      if (S.wait && lane == 0) S.wait[g] = 0;
+      continue;
+    }
+    const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
+    float* row = canon + (size_t)g * FGame<GAME>::canon(F);
+    if (!S.cache.sets) {
+      forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, row);
+      continue;
+    }
+    const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;
+    const u32 goal = sp_goal(S, S.slots[g], cp);
+    u32 pending = 0;
+    for (u32 guard = 0; guard <= goal; ++guard) {
+      if (F.trees[t].depth >= goal) break;  // the search is complete: k_sp_move plays the move
+      u64 key = 0;
+      forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, row, true, &key);
+      const int e = sp_cache_lookup(S.cache, key, lane);
+      if (e < 0) {
+        pending = 1;
+        if (lane == 0) { S.leaf_key[g] = key; atomicAdd(&S.cache.ctr[1], 1ULL); }
+        break;
+      }
+      if (lane == 0) atomicAdd(&S.cache.ctr[0], 1ULL);
+      forest_process_result<GAME, false, false>(F, t, S.cache.v, S.cache.pi, lane, noise, F.trees[t].leaf, (u32)e);
+      if (lane == 0) S.slots[g].simulations += 1;
+      __syncwarp();
+    }
+    if (lane == 0) S.wait[g] = pending;
+    __syncwarp();
   }
 }
 template <int GAME>
@@ -187,9 +282,15 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
   const u32 lane = threadIdx.x & 31u;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
+    if (S.wait && !S.wait[g]) continue;  // (cache) nothing of this slot waits for the evaluator
     const u32 t = 2u * g + FGame<GAME>::root_player(F, 2u * g);
     forest_process_result<GAME, false, false>(F, t, ev_v, ev_pi, lane, F.epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf,
                                               /*row=*/g);  // row g of the evaluator's output belongs to slot g
+    if (S.cache.sets) {  // update_inferences' insert_many (play_manager.cc:619-642)
+      const u32 A = FGame<GAME>::actions(F);
+      sp_cache_insert(S.cache, S.leaf_key[g], ev_v + (size_t)g * 3, ev_pi + (size_t)g * A, A, lane);
+      if (lane == 0) S.wait[g] = 0;
+    }
     if (lane == 0) S.slots[g].simulations += 1;
   }
 }
@@ -422,7 +523,7 @@ struct b2az_tafl_selfplay {
   uint32_t hist_head = 0;  // rows of the sample ring already handed out (the ring restarts once it has been emptied)
   std::vector<float> h_canon, h_v, h_pi;  // host staging of the reference-API flavour (leaf_batch_host / submit_eval_host)
   std::vector<b2az::SpSlot> h_slots;
-  std::vector<uint32_t> h_tree_err;
+  std::vector<uint32_t> h_tree_err, h_wait;
 };
 
 extern "C" {
@@ -433,6 +534,8 @@ int b2az_tafl_selfplay_destroy(b2az_tafl_selfplay* sp) {
   dev_free(sp->view.slots); dev_free(sp->view.st_canon); dev_free(sp->view.st_pi); dev_free(sp->view.st_player);
   dev_free(sp->view.scratch_pi); dev_free(sp->view.out_canon); dev_free(sp->view.out_v); dev_free(sp->view.out_pi);
   dev_free(sp->view.out_slot); dev_free(sp->view.out_count); dev_free(sp->active_dev);
+  dev_free(sp->view.cache.keys); dev_free(sp->view.cache.freq); dev_free(sp->view.cache.stamp); dev_free(sp->view.cache.v); dev_free(sp->view.cache.pi);
+  dev_free(sp->view.cache.ctr); dev_free(sp->view.wait); dev_free(sp->view.leaf_key);
   dev_free(sp->ev_v); dev_free(sp->ev_pi); dev_free(sp->leaf_canon);
   b2az_forest_destroy(sp->forest);
   delete sp;
@@ -498,6 +601,20 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
     if (int rc = dev_alloc_raw(&S.out_v, (size_t)S.out_cap * 3)) return bail(rc);
     if (int rc = dev_alloc_raw(&S.out_pi, (size_t)S.out_cap * A)) return bail(rc);
     if (int rc = dev_alloc_raw(&S.out_slot, (size_t)S.out_cap)) return bail(rc);
+  }
+  if (p->cache_entries) {  // max_cache_size (one model group): sets of four, rounded up to a power of two
+    uint32_t sets = 1;
+    while (sets < 0x40000000u && (uint64_t)sets * 4u < p->cache_entries) sets <<= 1;
+    S.cache.sets = sets;
+    const size_t E = (size_t)sets * 4u;
+    if (int rc = dev_alloc(&S.cache.keys, E)) return bail(rc);
+    if (int rc = dev_alloc(&S.cache.freq, E)) return bail(rc);
+    if (int rc = dev_alloc(&S.cache.stamp, E)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.cache.v, E * 3)) return bail(rc);
+    if (int rc = dev_alloc_raw(&S.cache.pi, E * A)) return bail(rc);
+    if (int rc = dev_alloc(&S.cache.ctr, 4)) return bail(rc);
+    if (int rc = dev_alloc(&S.wait, G)) return bail(rc);
+    if (int rc = dev_alloc(&S.leaf_key, G)) return bail(rc);
   }
   if (int rc = dev_alloc(&S.out_count, 1)) return bail(rc);
   if (int rc = dev_alloc(&sp->active_dev, 2)) return bail(rc);
@@ -592,6 +709,7 @@ int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay* sp, void* stream, cons
     CUDA_TRY(cudaStreamSynchronize(s));  // b2az.h: calls taking host buffers synchronise before returning (pinned buffers!)
     v = sp->ev_v; pi = sp->ev_pi;
   }
+  ++sp->view.cache.epoch;  // one epoch per insert launch (sp_cache_insert)
   FOREST_DISPATCH(f, (k_sp_process_result<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view, v, pi)));
   FOREST_DISPATCH(f, (k_sp_move<G_><<<SP_CTAS(sp), 128, 0, s>>>(f->view, sp->view)));
   CUDA_TRY(cudaGetLastError());
@@ -640,8 +758,12 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
   sp->h_tree_err.resize(sp->forest->view.n_trees);
   CUDA_TRY(cudaMemcpy2DAsync(sp->h_tree_err.data(), 4, &sp->forest->view.trees[0].error, sizeof(ForestTree), 4,
                              (size_t)sp->forest->view.n_trees, cudaMemcpyDeviceToHost, s));
+  unsigned long long ctr[4] = {0, 0, 0, 0};
+  if (sp->view.cache.sets) CUDA_TRY(cudaMemcpyAsync(ctr, sp->view.cache.ctr, sizeof(ctr), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   memset(out, 0, sizeof(*out));
+  out->cache_hits = ctr[0]; out->cache_misses = ctr[1]; out->cache_evictions = ctr[3];
+  out->cache_size = ctr[2] - ctr[3]; out->cache_max_size = (uint64_t)sp->view.cache.sets * 4u;
   for (uint32_t e : sp->h_tree_err) {  // the trees' sticky bits (az_forest.h ForestTree::error)
     if (e & (1u | 4u | 16u)) out->device_error |= B2AZ_DEVERR_POOL;
     if (e & 2u) out->device_error |= B2AZ_DEVERR_DEPTH;
@@ -696,10 +818,15 @@ int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay* sp, void* stream, uin
   sp->h_slots.resize(G);
   CUDA_TRY(cudaMemcpyAsync(sp->h_canon.data(), dev, (size_t)G * C * 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(sp->h_slots.data(), sp->view.slots, (size_t)G * sizeof(SpSlot), cudaMemcpyDeviceToHost, s));
+  if (sp->view.wait) {
+    sp->h_wait.resize(G);
+    CUDA_TRY(cudaMemcpyAsync(sp->h_wait.data(), sp->view.wait, (size_t)G * 4, cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   uint32_t n = 0;
   for (uint32_t g = 0; g < G; ++g) {
     if (!sp->h_slots[g].active) continue;
+    if (sp->view.wait && !sp->h_wait[g]) continue;  // (cache) its leaves hit: nothing for the evaluator
     if (n >= max_rows) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_leaf_batch_host: more active slots than max_rows");
     memcpy(canon_host + (size_t)n * C, sp->h_canon.data() + (size_t)g * C, C * 4);
     ids_host[n++] = g;

@@ -424,9 +424,6 @@ class PlayManager {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + who + " yet");
     };
     reject(!P.temp_decay_half_life_by_variant.empty() && game < 20, "temp_decay_half_life_by_variant");
-    // max_cache_size: this engine has no position cache yet. A cache may always forget, so the parameter is accepted
-    // and every leaf goes to the evaluator (cache_hits() stays 0) — results are those of a run with the cache off, which
-    // is what the reference's own cache test requires of a cache (test_cache.py:227-253).
     reject(P.gumbel_full, "gumbel_full");
     reject(P.concurrent_games == 0 || P.games_to_play % P.concurrent_games != 0, "games_to_play not a multiple of concurrent_games");
     EvalType et = EvalType::NN;
@@ -461,6 +458,7 @@ class PlayManager {
     sp.n_variant_half_life = (uint32_t)std::min<size_t>(4, P.temp_decay_half_life_by_variant.size());
     for (uint32_t i = 0; i < sp.n_variant_half_life; ++i) sp.variant_half_life[i] = P.temp_decay_half_life_by_variant[i];
     for (int i = 0; i < 4; ++i) sp.variant_probs[i] = sg_probs_[i];
+    sp.cache_entries = P.max_cache_size;  // one model group: the whole budget (play_manager.cc:195-203)
     // history_ is unbounded in the reference; here the sample ring holds what a run can produce between drains: every
     // sample of the run when that fits an 8 GB budget (play() first, build_history_batch afterwards works), else the
     // budget — a full ring drops samples and play() then fails loudly (B2AZ_DEVERR_HIST)
@@ -894,12 +892,14 @@ class PlayManager {
       std::unique_lock<std::mutex> lk(mu_);
       refresh_stats_locked();
       if (stats_.device_error) throw std::runtime_error("play: device error (tree slab / training-sample ring exhausted)");
-      if (n == 0) return;  // every slot retired
-      publish_locked(n);
-      cv_.notify_all();
-      cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
-      if (stopped_.load()) return;
-      retract_locked();
+      if (n == 0 && stats_.active_games == 0) return;  // every slot retired
+      if (n > 0) {
+        publish_locked(n);
+        cv_.notify_all();
+        cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
+        if (stopped_.load()) return;
+        retract_locked();
+      }  // (n == 0 with slots still cycling: every leaf of this round hit the position cache — only the moves are due)
       {
         std::lock_guard<std::mutex> lk2(api_);
         if (b2az_tafl_selfplay_submit_eval_host(tsp_, nullptr, ids_.data(), v_.data(), pi_.data(), n) != 0) throw_last("update_inferences");

@@ -440,6 +440,8 @@ typedef struct b2az_tafl_selfplay_params {
   uint32_t n_variant_half_life;  /* PlayParams::temp_decay_half_life_by_variant (play_manager.cc:289-296): entries used */
   float variant_half_life[4];    /* indexed by GameState::get_variant_id() (StarGambitUnifiedGS: the variant) */
   float variant_probs[4];        /* game B2AZ_SG_UNIFIED_MIX: StarGambitUnifiedGS's variant weights (all 0 = 0.25 each) */
+  uint32_t cache_entries;        /* PlayParams::max_cache_size: entries of the device position cache (EvalType::NN form:
+                                    a slot keeps simulating while its leaves hit, play_manager.cc:589-594); 0 = no cache */
 } b2az_tafl_selfplay_params;
 typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
   uint32_t active, games_started, games_completed, pending;

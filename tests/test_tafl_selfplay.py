@@ -237,3 +237,64 @@ def test_selfplay_fails_loudly_without_a_gpu_and_on_bad_arguments():
         with pytest.raises(b2az.B2azError) as ei:
             b2az.TaflSelfplay(0, 2, 30, 8)
         assert "no CPU fallback" in str(ei.value)
+
+
+def _nn_run(game, slots, max_turns, visits, seed, cache_entries, kw):
+    """EvalType::NN form driven with a deterministic pure-function evaluator (a function of the canonical planes only)."""
+    import ctypes as C
+    import zlib
+
+    cudart = C.CDLL("libcudart.so.12")
+    sp = b2az.TaflSelfplay(game, slots, max_turns, visits, games_per_slot=1, seed=seed, cache_entries=cache_entries,
+                           hist_capacity=slots * max_turns, **kw)
+    S, P, A = sp.S, sp.P, sp.A
+    canon = np.zeros((slots, P, S, S), np.float32)
+    active, steps = slots, 0
+    while active:
+        ptr = sp.find_leaf()
+        assert cudart.cudaMemcpy(canon.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), canon.nbytes, 2) == 0
+        vs, pis = np.zeros((slots, 3), np.float32), np.zeros((slots, A), np.float32)
+        for g in range(slots):
+            rng = np.random.default_rng(zlib.crc32(canon[g].tobytes()))
+            v = rng.random(3).astype(np.float32) + np.float32(0.05)
+            vs[g] = v / v.sum()
+            pi = rng.random(A).astype(np.float32) ** 4 + np.float32(1e-3)
+            pis[g] = pi / pi.sum()
+        active = sp.process_result(vs, pis, want_active=True)
+        steps += 1
+        assert steps < 400000
+    out = sp.drain_history()
+    st = sp.stats()
+    slots_, err = sp.slots()
+    sp.close()
+    assert (err == 0).all() and (slots_["error"] == 0).all()
+    return out, st, steps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("game,slots,max_turns,visits,kw", [
+    (0, 5, 40, 32, dict(epsilon=0.25, root_policy_temp=1.25, policy_target_pruning=True)),
+    (1, 3, 16, 24, dict(gumbel_m=8)),
+    (10, 3, 600, 16, dict(gumbel_m=8)),
+])
+def test_position_cache_on_equals_cache_off(game, slots, max_turns, visits, kw):
+    """The device position cache of the wide-tree engine (az_selfplay.h SpCache; S3FIFOCache's role for the tafl games and
+    Star Gambit): with a pure-function evaluator a run with the cache equals the run without it, sample for sample — the
+    reference's own criterion for a cache (test_cache.py:227-253) — while the evaluator is asked less often."""
+    def same(x, y):  # slot by slot: the order in which slots finish (and append their samples) is not part of the result
+        for g in range(slots):
+            rx, ry = x[3] == g, y[3] == g
+            assert rx.sum() == ry.sum() and rx.sum() > 0
+            for a, b in zip(x[:3], y[:3]):
+                assert np.array_equal(a[rx].view(np.uint32), b[ry].view(np.uint32)), g
+
+    off, st0, steps0 = _nn_run(game, slots, max_turns, visits, 321, 0, kw)
+    on, st1, steps1 = _nn_run(game, slots, max_turns, visits, 321, 1 << 14, kw)
+    same(off, on)
+    assert st0.cache_hits == 0 and st0.cache_max_size == 0
+    assert st1.cache_hits > 0 and st1.cache_misses > 0 and st1.cache_max_size == 1 << 14
+    assert st1.simulations == st0.simulations and st1.cache_hits + st1.cache_misses == st1.simulations
+    assert steps1 <= steps0
+    tiny, st2, _ = _nn_run(game, slots, max_turns, visits, 321, 16, kw)  # 16 entries: evictions all the time, same games
+    same(off, tiny)
+    assert st2.cache_evictions > 0
