@@ -159,6 +159,7 @@ def load(path=None):
     L.b2az_forest_gumbel_result.argtypes = [vp, vp, vp, vp]
     L.b2az_forest_update_root.argtypes = [vp, vp, vp]
     L.b2az_forest_counts.argtypes = [vp, vp, vp, vp, vp]
+    L.b2az_tafl_selfplay_variant_stats.argtypes = [vp, vp, vp]
     L.b2az_forest_principal_variation.argtypes = [vp, vp, u32, vp, vp]
     L.b2az_forest_leaf_path.argtypes = [vp, vp, C.c_int, vp, vp]
     L.b2az_forest_root_ops.argtypes = [vp, vp, C.c_int, C.c_int]
@@ -383,6 +384,8 @@ def game_dims(game):
     if 10 <= game <= 13 or 20 <= game <= 24:  # 24: the Unified view with the variant mix (self-play engine)
         D = 13 if game >= 20 or game == 13 else 11
         return D, 36 if game >= 20 else 32, D * D * 10 + 19
+    if game == 30:  # Connect4 under the wide-tree search API
+        return 7, 4, 7
     raise B2azError(-1, f"unknown game {game}")
 
 
@@ -681,6 +684,16 @@ class TaflSelfplay:
         st = Stats()
         self._check(self.L.b2az_tafl_selfplay_get_stats(self.h, stream, C.byref(st)))
         return st
+
+    VARIANT_DTYPE = np.dtype([("scores", "f4", 3), ("games_completed", "u4"), ("game_length", "u4"), ("total_move_count", "u4"),
+                              ("full_move_count", "u4"), ("fast_move_count", "u4"), ("leaf_depth", "f8"), ("entropy", "f8"),
+                              ("valid_moves", "f8"), ("fast_leaf_depth", "f8"), ("fast_entropy", "f8")])  # b2az_variant_stats
+
+    def variant_stats(self, stream=None):
+        """PlayManager's per-variant tables (StarGambitUnifiedGS): a record array of 4, sums over completed games."""
+        out = np.zeros(4, self.VARIANT_DTYPE)
+        self._check(self.L.b2az_tafl_selfplay_variant_stats(self.h, stream, _ptr(out)))
+        return out
 
     def slots(self, stream=None):
         out = np.zeros(self.n, SLOT_DTYPE)

@@ -31,11 +31,15 @@
 
 #include "az_rng.h"
 #include "az_tafl.h"
+#include "az_connect4.h"
 #include "az_stargambit_kernels.h"
 
 // Template id of the Star Gambit instantiation of the forest: ONE instantiation serves the eight game ids
 // (B2AZ_SG_GAME / B2AZ_SG_UNIFIED, ForestView::game carries the id: variant and frame are run-time values)
 #define B2AZ_FOREST_SG 10
+// Connect4 under the same search (game id 30): what the `MCTS` class of the Python module needs for Connect4GS — the
+// batched PlayManager engine (az_engine_logic.h) remains the fast path for Connect4 self-play
+#define B2AZ_FOREST_C4 30
 
 namespace b2az {
 
@@ -128,6 +132,11 @@ struct ForestSmem {   // per warp
   u32 draws[kFMaxK / 2 + 2];   // the shuffle's uniform draws, generated lane-parallel (pcg32 jump-ahead)
 };
 
+template <>
+struct ForestSmem<B2AZ_FOREST_C4> {
+  u16 moves[8];
+  u32 draws[8];
+};
 template <>
 struct ForestSmem<B2AZ_FOREST_SG> : SGWarpSmem {  // map / moves / cell_unit of the Star Gambit warp functions
   u32 draws[kSGMaxK / 2 + 2];
@@ -407,6 +416,58 @@ struct FGame {  // Brandubh / OpenTafl / Tawlbwrdd
   static __device__ __forceinline__ u32 root_player(const ForestView& F, u32 t) { return F.trees[t].state.player; }
   static __device__ __forceinline__ u32 root_turn(const ForestView& F, u32 t) { return F.trees[t].state.turn; }
   static __device__ __forceinline__ u32 root_terminal(const ForestView& F, u32 t) { return T::terminal(F.trees[t].state); }
+  static __device__ __forceinline__ int root_variant(const ForestView&, u32) { return -1; }
+  static __device__ __forceinline__ int pick_variant(const ForestView&, Pcg32&) { return -1; }
+};
+template <>
+struct FGame<B2AZ_FOREST_C4> {  // Connect4 (connect4_gs.cc): two 64-bit stone sets; the root lives in ForestTree::state's
+  struct Pos { C4State s; };     // first words (king.lo / king.hi = the players' stones)
+  static __device__ __forceinline__ C4State load(const TaflState& t) {
+    C4State s; s.p[0] = t.king.lo; s.p[1] = t.king.hi; s.turn = t.turn; s.player = t.player; return s;
+  }
+  static __device__ __forceinline__ void store(TaflState& t, const C4State& s) {
+    t.king.lo = s.p[0]; t.king.hi = s.p[1]; t.turn = s.turn; t.player = (u8)s.player;
+  }
+  static __device__ __forceinline__ u32 actions(const ForestView&) { return 7u; }
+  static __device__ __forceinline__ u32 canon(const ForestView&) { return (u32)C4_CANON; }
+  static __device__ __forceinline__ void open(const ForestView& F, u32 t, u32, ForestSmem<B2AZ_FOREST_C4>&, Pos& P) { P.s = load(F.trees[t].state); }
+  static __device__ __forceinline__ bool play(Pos& P, u32 mv, u32) { return mv < 7u && c4_play(P.s, mv); }
+  static __device__ __forceinline__ u32 player(const Pos& P) { return P.s.player; }
+  static __device__ __forceinline__ u32 legal(const Pos& P, ForestSmem<B2AZ_FOREST_C4>& sm, Pcg32& rng, u32 lane, u32*, bool serial) {
+    const u32 m = c4_valid_mask(P.s), k = (u32)__popc(m);
+    if (lane < 7u && ((m >> lane) & 1u)) sm.moves[__popc(m & ((1u << lane) - 1u))] = (u16)lane;
+    __syncwarp();
+    forest_shuffle(rng, sm.moves, sm.draws, k, lane, serial);
+    return k;
+  }
+  static __device__ __forceinline__ u32 terminal(const Pos& P, u32) { return c4_terminal(P.s); }
+  static __device__ __forceinline__ void emit_canon(const Pos& P, ForestSmem<B2AZ_FOREST_C4>&, float* out, u32 lane) {
+    for (u32 e = lane; e < (u32)C4_CANON; e += 32u) out[e] = c4_canon_elem(P.s.p[0], P.s.p[1], P.s.player, e);
+  }
+  static __device__ __forceinline__ u64 state_key(const Pos& P, const ForestView&) { const u64 h = c4_hash(P.s); return h ? h : 1ULL; }
+  static __device__ __forceinline__ u32 stage_floats(const ForestView&) { return (u32)C4_CANON; }
+  static __device__ __forceinline__ void stage(const Pos& P, ForestSmem<B2AZ_FOREST_C4>& sm, float* row, u32 lane) { emit_canon(P, sm, row, lane); }
+  static __device__ __forceinline__ void unstage(const ForestView&, const float* row, ForestSmem<B2AZ_FOREST_C4>&, float* out, u32 lane) {
+    for (u32 e = lane; e < (u32)C4_CANON; e += 32u) out[e] = row[e];
+  }
+  static __device__ __forceinline__ u32 root_play(const ForestView& F, u32 t, u32 move, ForestSmem<B2AZ_FOREST_C4>&, u32 lane) {
+    C4State s = load(F.trees[t].state);
+    if (move >= 7u || !c4_play(s, move)) return 8u;
+    if (lane == 0) store(F.trees[t].state, s);
+    return 0;
+  }
+  static __device__ __forceinline__ void init(const ForestView& F, u32 t, int = -1) {
+    C4State s;
+    c4_init(s);
+    store(F.trees[t].state, s);
+    F.trees[t].hist_len = 0;
+  }
+  static __device__ __forceinline__ void info(const ForestView& F, u32 t, u32* turn, u32* rep, u32* player) {
+    *turn = F.trees[t].state.turn; *rep = 0; *player = F.trees[t].state.player;
+  }
+  static __device__ __forceinline__ u32 root_player(const ForestView& F, u32 t) { return F.trees[t].state.player; }
+  static __device__ __forceinline__ u32 root_turn(const ForestView& F, u32 t) { return F.trees[t].state.turn; }
+  static __device__ __forceinline__ u32 root_terminal(const ForestView& F, u32 t) { return c4_terminal(load(F.trees[t].state)); }
   static __device__ __forceinline__ int root_variant(const ForestView&, u32) { return -1; }
   static __device__ __forceinline__ int pick_variant(const ForestView&, Pcg32&) { return -1; }
 };
@@ -1564,6 +1625,7 @@ struct b2az_forest {
     case B2AZ_TAFL_BRANDUBH: { constexpr int G_ = B2AZ_TAFL_BRANDUBH; CALL; } break;      \
     case B2AZ_TAFL_OPENTAFL: { constexpr int G_ = B2AZ_TAFL_OPENTAFL; CALL; } break;      \
     case B2AZ_TAFL_TAWLBWRDD: { constexpr int G_ = B2AZ_TAFL_TAWLBWRDD; CALL; } break;    \
+    case B2AZ_FOREST_C4: { constexpr int G_ = B2AZ_FOREST_C4; CALL; } break;              \
     default: { constexpr int G_ = B2AZ_FOREST_SG; CALL; } break;                          \
   }
 static inline unsigned forest_ctas(const b2az_forest* f) { return std::max(1u, std::min((f->view.n_trees + 3u) / 4u, 148u * 8u)); }
@@ -1575,7 +1637,8 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   using namespace b2az;
   if (!p || !out) return fail(B2AZ_EINVAL, "null argument");
   const bool is_sg = (p->game >= 10 && p->game <= 13) || (p->game >= 20 && p->game <= 24);  // 24: Unified, variant mix
-  if (p->game > B2AZ_TAFL_TAWLBWRDD && !is_sg) return fail(B2AZ_EINVAL, "b2az_forest: unknown game");
+  const bool is_c4 = p->game == B2AZ_FOREST_C4;
+  if (p->game > B2AZ_TAFL_TAWLBWRDD && !is_sg && !is_c4) return fail(B2AZ_EINVAL, "b2az_forest: unknown game");
   if (p->n_trees == 0 || p->max_turns == 0 || p->max_turns > 65535u) return fail(B2AZ_EINVAL, "b2az_forest: bad n_trees / max_turns");
   if (!(p->root_policy_temp > 0.0f)) return fail(B2AZ_EINVAL, "b2az_forest: root_policy_temp must be positive (1 = off)");
   if (p->epsilon < 0.0f || p->epsilon > 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: epsilon must be in [0, 1]");
@@ -1601,6 +1664,9 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
     for (int i = 0; i < 4; ++i) V.sg_probs[i] = 0.25f;
     f->actions = (uint32_t)sp.num_moves();
     f->canon = (uint32_t)(sp.planes(p->game >= 20u) * sp.udim * sp.udim);
+  } else if (is_c4) {
+    f->actions = 7u;
+    f->canon = (uint32_t)C4_CANON;
   } else {
     const uint32_t S = p->game == B2AZ_TAFL_BRANDUBH ? 7u : 11u, planes = p->game == B2AZ_TAFL_OPENTAFL ? 8u : 7u;
     f->actions = 2u * S * S * S;

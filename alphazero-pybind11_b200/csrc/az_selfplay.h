@@ -55,7 +55,16 @@ struct SpCache {
   u32 sets;      // power of two; 0 = no cache
   unsigned long long* ctr;  // hits, misses, inserts, evictions
 };
+// PlayManager's per-variant tables (variant_scores_ / variant_metrics_, play_manager.cc:468-484), one set per slot
+struct SpVariantAcc {                 // b2az_variant_stats in include/b2az.h (same layout)
+  float scores[3];
+  u32 games_completed;
+  u32 game_length, total_move_count, full_move_count, fast_move_count;
+  double leaf_depth, entropy, valid_moves, fast_leaf_depth, fast_entropy;
+};
+static_assert(sizeof(SpVariantAcc) == 72, "b2az_variant_stats layout");
 struct SpView {
+  SpVariantAcc* variants;  // [n_games][4], null unless the game has variants (StarGambitUnifiedGS)
   SpCache cache;
   u32* wait;          // [n_games] (cache only): the slot's leaf missed the cache and waits for the evaluator
   u64* leaf_key;      // [n_games] (cache only): the waiting leaf's key
@@ -459,6 +468,16 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
         }
         G.games_completed += 1;
         G.game_length += GM::root_turn(F, 2u * g);
+        const int vid = GM::root_variant(F, 2u * g);
+        if (S.variants && vid >= 0 && vid < 4) {  // play_manager.cc:468-484
+          SpVariantAcc& V = S.variants[(size_t)g * 4u + (u32)vid];
+          V.scores[0] = fadd(V.scores[0], s0); V.scores[1] = fadd(V.scores[1], s1); V.scores[2] = fadd(V.scores[2], sd);
+          V.games_completed += 1;
+          V.game_length += GM::root_turn(F, 2u * g);
+          V.leaf_depth += G.g_leaf_depth; V.entropy += G.g_entropy; V.valid_moves += G.g_valid_moves;
+          V.fast_leaf_depth += G.g_fast_leaf_depth; V.fast_entropy += G.g_fast_entropy;
+          V.total_move_count += G.move_count; V.full_move_count += G.full_move_count; V.fast_move_count += G.fast_move_count;
+        }
         G.leaf_depth += G.g_leaf_depth; G.entropy += G.g_entropy; G.valid_moves += G.g_valid_moves;
         G.total_move_count += G.move_count; G.total_full_move_count += G.full_move_count;
         G.fast_leaf_depth += G.g_fast_leaf_depth; G.fast_entropy += G.g_fast_entropy; G.total_fast_move_count += G.fast_move_count;
@@ -535,7 +554,7 @@ int b2az_tafl_selfplay_destroy(b2az_tafl_selfplay* sp) {
   dev_free(sp->view.scratch_pi); dev_free(sp->view.out_canon); dev_free(sp->view.out_v); dev_free(sp->view.out_pi);
   dev_free(sp->view.out_slot); dev_free(sp->view.out_count); dev_free(sp->active_dev);
   dev_free(sp->view.cache.keys); dev_free(sp->view.cache.freq); dev_free(sp->view.cache.stamp); dev_free(sp->view.cache.v); dev_free(sp->view.cache.pi);
-  dev_free(sp->view.cache.ctr); dev_free(sp->view.wait); dev_free(sp->view.leaf_key);
+  dev_free(sp->view.cache.ctr); dev_free(sp->view.wait); dev_free(sp->view.leaf_key); dev_free(sp->view.variants);
   dev_free(sp->ev_v); dev_free(sp->ev_pi); dev_free(sp->leaf_canon);
   b2az_forest_destroy(sp->forest);
   delete sp;
@@ -616,6 +635,8 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
     if (int rc = dev_alloc(&S.wait, G)) return bail(rc);
     if (int rc = dev_alloc(&S.leaf_key, G)) return bail(rc);
   }
+  if (fp.game >= 20u)
+    if (int rc = dev_alloc(&S.variants, G * 4)) return bail(rc);
   if (int rc = dev_alloc(&S.out_count, 1)) return bail(rc);
   if (int rc = dev_alloc(&sp->active_dev, 2)) return bail(rc);
   if (fp.game == 24u) {
@@ -640,6 +661,7 @@ int b2az_tafl_selfplay_slots(b2az_tafl_selfplay*, void*, b2az_tafl_selfplay_slot
 int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay*, void*, b2az_stats*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay*, void*, uint32_t, float*, uint32_t*, uint32_t*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay*, void*, const uint32_t*, const float*, const float*, uint32_t) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_variant_stats(b2az_tafl_selfplay*, void*, b2az_variant_stats*) FOREST_NO_CUDA()
 #else
 #define SP_CTAS(sp) std::max(1u, std::min(((sp)->view.n_games + 3u) / 4u, 148u * 8u))
 static int sp_active(b2az_tafl_selfplay* sp, cudaStream_t s, uint32_t* active_out) {
@@ -800,6 +822,30 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stat
   out->sum_game_length = length;
   out->total_move_count = moves; out->full_move_count = full;
   out->sum_leaf_depth = leaf_depth; out->sum_search_entropy = entropy; out->sum_valid_moves = valid;
+  return 0;
+}
+// PlayManager's per-variant tables summed over the slots: out[4] (num_tracked_variants() == 4 for StarGambitUnifiedGS)
+int b2az_tafl_selfplay_variant_stats(b2az_tafl_selfplay* sp, void* stream, b2az_variant_stats* out4) {
+  using namespace b2az;
+  if (!sp || !out4) return fail(B2AZ_EINVAL, "null argument");
+  static_assert(sizeof(b2az_variant_stats) == sizeof(SpVariantAcc), "variant stats layout");
+  memset(out4, 0, 4 * sizeof(b2az_variant_stats));
+  if (!sp->view.variants) return fail(B2AZ_ESTATE, "this game has no variants");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)sp->view.n_games * 4u;
+  std::vector<SpVariantAcc> h(n);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), sp->view.variants, n * sizeof(SpVariantAcc), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i) {
+    const SpVariantAcc& a = h[i];
+    b2az_variant_stats& o = out4[i & 3u];
+    for (int j = 0; j < 3; ++j) o.scores[j] += a.scores[j];
+    o.games_completed += a.games_completed; o.game_length += a.game_length; o.total_move_count += a.total_move_count;
+    o.full_move_count += a.full_move_count; o.fast_move_count += a.fast_move_count;
+    o.leaf_depth += a.leaf_depth; o.entropy += a.entropy; o.valid_moves += a.valid_moves;
+    o.fast_leaf_depth += a.fast_leaf_depth; o.fast_entropy += a.fast_entropy;
+  }
   return 0;
 }
 // The reference-API flavour of one simulation (build_batch / update_inferences with HOST buffers, py_wrapper.cc:449-504,

@@ -485,6 +485,7 @@ class PlayManager {
     if (!t) return false;
     if (t->s.turn != 1 || t->s.n_units != 2) throw std::runtime_error("the B200 engine starts every game from the initial position");
     const bool mix = t->unified && (t->pinned < 0 || t->pinned > 3);  // every new game draws its variant (randomize_start)
+    has_variants_ = t->unified;
     if (mix) for (int i = 0; i < 4; ++i) sg_probs_[i] = t->probs[i];
     const auto sp = t->space();
     // a Star Gambit game has no small bound on its actions (200 turns of several actions each): 512 staged samples per
@@ -790,6 +791,15 @@ class PlayManager {
     dl_rows_ = 0;
     refresh_stats_unlocked_api();
   }
+  int num_tracked_variants() const { return has_variants_ ? 4 : 0; }
+  b2az_variant_stats variant(int v) {
+    if (!has_variants_) throw std::out_of_range("this game has no variants");
+    if (v < 0 || v >= 4) throw std::out_of_range("variant out of range");
+    b2az_variant_stats out[4];
+    std::lock_guard<std::mutex> lk(api_);
+    if (b2az_tafl_selfplay_variant_stats(tsp_, nullptr, out) != 0) throw_last("variant stats");
+    return out[v];
+  }
   void refresh_stats_unlocked_api() {  // (api_ is held by the caller; mu_ is never taken under api_: lock order mu_ -> api_)
     b2az_stats st;
     const int rc = tsp_ ? b2az_tafl_selfplay_get_stats(tsp_, nullptr, &st) : b2az_get_stats(eng_, nullptr, &st);
@@ -971,6 +981,7 @@ class PlayManager {
   uint32_t leaf_count_ = 0, answered_ = 0;
   b2az_stats stats_{};
   float sg_probs_[4] = {0.25f, 0.25f, 0.25f, 0.25f};  // StarGambitUnifiedGS variant weights (variant mix)
+  bool has_variants_ = false;                          // num_variants() > 0: per-variant score tables
   dl::In dl_v_, dl_pi_;      // the evaluations of the DLPack feed, kept alive until the engine has read them
   uint32_t dl_rows_ = 0;
   bool dl_stepped_ = false;  // update_inferences_dlpack has already run the next generation's step
@@ -1168,16 +1179,27 @@ PYBIND11_MODULE(alphazero, m) {
         if (i >= pm.num_seat_perms()) throw std::out_of_range("perm index");
         return pm.games_completed();
       })
-      // per-variant tracking (play_manager.h:317-366) only exists for games with variants (Star Gambit Unified)
-      .def("num_tracked_variants", [](PlayManager&) { return 0; })
-#define NO_VARIANT(name) .def(name, [](PlayManager&, int) -> float { throw std::out_of_range("this game has no variants"); })
-      NO_VARIANT("variant_games_completed") NO_VARIANT("variant_avg_game_length") NO_VARIANT("variant_avg_leaf_depth")
-      NO_VARIANT("variant_avg_search_entropy") NO_VARIANT("variant_fast_avg_leaf_depth")
-      NO_VARIANT("variant_fast_avg_search_entropy") NO_VARIANT("variant_avg_moves_per_turn") NO_VARIANT("variant_avg_valid_moves")
-#undef NO_VARIANT
-      .def("variant_scores", [](PlayManager&, int) -> py::object { throw std::out_of_range("this game has no variants"); })
-      .def("variant_perm_scores", [](PlayManager&, int, int) -> py::object { throw std::out_of_range("this game has no variants"); })
-      .def("variant_perm_games_completed", [](PlayManager&, int, int) -> uint32_t { throw std::out_of_range("this game has no variants"); })
+      // per-variant tracking (play_manager.h:218-275): games with variants (StarGambitUnifiedGS) only
+      .def("num_tracked_variants", &PlayManager::num_tracked_variants)
+#define VAR_F(name, expr) .def(name, [](PlayManager& pm, int v) -> float { const b2az_variant_stats m = pm.variant(v); return expr; })
+      VAR_F("variant_avg_game_length", m.games_completed ? (float)m.game_length / (float)m.games_completed : 0.0f)
+      VAR_F("variant_avg_leaf_depth", m.full_move_count ? (float)(m.leaf_depth / (double)m.full_move_count) : 0.0f)
+      VAR_F("variant_avg_search_entropy", m.full_move_count ? (float)(m.entropy / (double)m.full_move_count) : 0.0f)
+      VAR_F("variant_fast_avg_leaf_depth", m.fast_move_count ? (float)(m.fast_leaf_depth / (double)m.fast_move_count) : 0.0f)
+      VAR_F("variant_fast_avg_search_entropy", m.fast_move_count ? (float)(m.fast_entropy / (double)m.fast_move_count) : 0.0f)
+      VAR_F("variant_avg_moves_per_turn", m.game_length ? (float)m.total_move_count / (float)m.game_length : 0.0f)
+      VAR_F("variant_avg_valid_moves", m.total_move_count ? (float)(m.valid_moves / (double)m.total_move_count) : 0.0f)
+#undef VAR_F
+      .def("variant_games_completed", [](PlayManager& pm, int v) { return pm.variant(v).games_completed; })
+      .def("variant_scores", [](PlayManager& pm, int v) { return vec3(pm.variant(v).scores); })
+      .def("variant_perm_scores", [](PlayManager& pm, int v, int p) {  // one seat permutation on this engine
+        if (p != 0) throw std::out_of_range("seat permutation out of range");
+        return vec3(pm.variant(v).scores);
+      })
+      .def("variant_perm_games_completed", [](PlayManager& pm, int v, int p) {
+        if (p != 0) throw std::out_of_range("seat permutation out of range");
+        return pm.variant(v).games_completed;
+      })
       .def("set_eager", &PlayManager::set_eager)
       .def("leaf_batch_dlpack", &PlayManager::leaf_batch_dlpack, py::arg("group") = 0)
       .def("update_inferences_dlpack", &PlayManager::update_inferences_dlpack, py::arg("group"), py::arg("v"), py::arg("pi"))

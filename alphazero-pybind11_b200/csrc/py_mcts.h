@@ -3,8 +3,7 @@
 // tree themselves (play.py, mcts_analysis.py, frozen_eval.py). Selection, expansion (with the child shuffle), priors,
 // backup, re-rooting, Gumbel bookkeeping and the policy read-outs run on the device; the object keeps a host copy of the
 // root position so that find_leaf can return the leaf GameState (the root copy replayed along the device's path).
-// Games: the tafl games and Star Gambit (the games of the wide-tree search); Connect4's search lives in the batched
-// PlayManager engine only.
+// Games: Connect4, the tafl games and Star Gambit.
 #pragma once
 
 class MCTS {
@@ -216,12 +215,22 @@ class MCTS {
     if (gs.num_moves() != num_moves_) throw std::runtime_error("MCTS: num_moves does not match the GameState");
     if (f_) return;
     if (!(try_tafl<B2AZ_TAFL_BRANDUBH>(gs) || try_tafl<B2AZ_TAFL_OPENTAFL>(gs) || try_tafl<B2AZ_TAFL_TAWLBWRDD>(gs))) {
-      auto* sg = dynamic_cast<const StarGambitBase*>(&gs);
-      if (!sg) throw std::runtime_error("MCTS: the B200 single-tree search implements the tafl games and Star Gambit");
-      fp_.game = (sg->unified ? 20u : 10u) + sg->s.variant;
-      fp_.max_turns = 512;
-      create();
-      check(b2az_forest_set_root(f_, 0, &sg->s, (uint32_t)sizeof(sg->s), sg->hist.data(), (uint32_t)sg->hist.size()), "set_root");
+      if (auto* c4 = dynamic_cast<const Connect4GS*>(&gs)) {  // the root record: stones in the first words (FGame<B2AZ_FOREST_C4>)
+        fp_.game = 30u;
+        fp_.max_turns = 64;
+        create();
+        b2az::TaflState ts;
+        std::memset(&ts, 0, sizeof(ts));
+        ts.king.lo = c4->s.p[0]; ts.king.hi = c4->s.p[1]; ts.turn = c4->s.turn; ts.player = (uint8_t)c4->s.player;
+        check(b2az_forest_set_root(f_, 0, &ts, (uint32_t)sizeof(ts), nullptr, 0), "set_root");
+      } else {
+        auto* sg = dynamic_cast<const StarGambitBase*>(&gs);
+        if (!sg) throw std::runtime_error("MCTS: the B200 single-tree search implements Connect4, the tafl games and Star Gambit");
+        fp_.game = (sg->unified ? 20u : 10u) + sg->s.variant;
+        fp_.max_turns = 512;
+        create();
+        check(b2az_forest_set_root(f_, 0, &sg->s, (uint32_t)sizeof(sg->s), sg->hist.data(), (uint32_t)sg->hist.size()), "set_root");
+      }
     }
     root_ = gs.copy();
     if (have_pending_gumbel_ && fp_.gumbel_enabled) {

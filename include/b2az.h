@@ -299,6 +299,7 @@ int b2az_tafl_symmetries(int device, uint32_t game, uint32_t n, const float* can
 #define B2AZ_SG_BATTLE 3
 #define B2AZ_SG_GAME(variant) (10u + (variant))
 #define B2AZ_SG_UNIFIED(variant) (20u + (variant))
+#define B2AZ_FOREST_CONNECT4 30u /* Connect4 under the wide-tree search API (b2az_forest_*): the `MCTS` class over Connect4GS */
 #define B2AZ_SG_UNIFIED_MIX 24u  /* StarGambitUnifiedGS(-1, probs): every new game draws its variant (self-play engine) */
 #define B2AZ_SG_STATE_BYTES 200  /* 20 units x 9 B (star_gambit_gs.h:359-371 order), n_units, reserves[2][4], player,
                                     has_taken_action, game_over, winner, variant, 2 pad, turn u32 */
@@ -476,6 +477,15 @@ int b2az_tafl_selfplay_process_result(b2az_tafl_selfplay* sp, void* stream, cons
  * game's moves last first, like history_), with the slot they came from; the rest stay for the next call. */
 int b2az_tafl_selfplay_drain_history(b2az_tafl_selfplay* sp, void* stream, uint32_t max_rows, float* canon_host, float* v_host,
                                      float* pi_host, uint32_t* slot_host, uint32_t* n_out);
+/* PlayManager's per-variant tables (variant_scores_, variant_metrics_: play_manager.cc:468-484, play_manager.h:218-275) for
+ * games with variants (StarGambitUnifiedGS: B2AZ_SG_UNIFIED(v), B2AZ_SG_UNIFIED_MIX): out4[v], sums over completed games. */
+typedef struct b2az_variant_stats {
+  float scores[3];
+  uint32_t games_completed;
+  uint32_t game_length, total_move_count, full_move_count, fast_move_count;
+  double leaf_depth, entropy, valid_moves, fast_leaf_depth, fast_entropy;
+} b2az_variant_stats;
+int b2az_tafl_selfplay_variant_stats(b2az_tafl_selfplay* sp, void* stream, b2az_variant_stats* out4);
 /* b2az_get_stats for this engine: PlayManager's counters and getters (play_manager.h:173-180, 288-316) over all slots. */
 int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay* sp, void* stream, b2az_stats* out);
 /* The reference-API flavour of one simulation with HOST buffers (build_batch / update_inferences, py_wrapper.cc:449-504,

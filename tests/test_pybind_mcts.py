@@ -3,6 +3,7 @@ the reference's single-tree API, py_wrapper.cc:191-220) driven the way the refer
 (find_leaf -> evaluate -> process_result, counts / probs / root_value, update_root + play_move), against the UNMODIFIED
 reference MCTS class over the unmodified games (oracle/_ref/libazref_tafl.so, azref_tafl_search) — same seed, same
 pseudo-network: visit counts and Q values bit-exact after every move's search."""
+import ctypes as C
 import zlib
 
 import numpy as np
@@ -101,3 +102,54 @@ def test_mcts_without_a_device_fails_loudly():
     with pytest.raises(RuntimeError, match="two-player"):
         az.MCTS(1.25, 3, 10)
     assert az.MCTS.pick_move(np.array([0.0, 1.0, 0.0], np.float32)) == 1
+
+
+@pytest.mark.parametrize("kind", [pytest.param("cuda", marks=gpu)])
+def test_connect4_tree_equals_the_reference_mcts(kind):
+    """MCTS over Connect4GS (game 30 of the wide-tree search) against the unmodified reference MCTS class driven through
+    oracle/ref_driver.cc — same seed, same pseudo-network, a position that is not the start position."""
+    import refdriver
+
+    if not refdriver.available():
+        pytest.skip("oracle/_ref/libazref.so not built")
+    az = module(kind)
+    L = refdriver.lib()
+    net = net_for(7)
+    seed, sims = 2024, 60
+    gs = az.Connect4GS()
+    rgs = L.azref_c4_new()
+    for mv in (3, 3, 4):
+        gs.play_move(mv)
+        assert L.azref_c4_play(rgs, mv) == 0
+    cfg = refdriver.MctsCfg(cpuct=1.25, num_players=2, num_moves=7, epsilon=0.0, root_policy_temp=1.0, fpu_reduction=0.25,
+                            gumbel_m=16, gumbel_c_visit=50.0, gumbel_c_scale=1.0)
+    rt = L.azref_mcts_new(C.byref(cfg))
+    L.azref_seed_thread_rng(seed)
+    mcts = az.MCTS(1.25, 2, 7, 0.0, 1.0, 0.25)
+    mcts.seed(seed)
+    canon = np.zeros((4, 6, 7), np.float32)
+    for move_no in range(6):
+        for _ in range(sims):
+            leaf = mcts.find_leaf(gs)
+            v, pi = net(np.asarray(leaf.canonicalized()))
+            mcts.process_result(gs, v, pi, False)
+            rleaf = L.azref_mcts_find_leaf(rt, rgs)
+            L.azref_c4_canonical(rleaf, refdriver.P(canon))
+            rv, rpi = net(canon)
+            L.azref_mcts_process_result(rt, rgs, refdriver.P(rv), 3, refdriver.P(rpi), 7, 0)
+        rc, rq = np.zeros(7, np.uint32), np.zeros(7, np.float32)
+        L.azref_mcts_counts(rt, refdriver.P(rc))
+        L.azref_mcts_root_q(rt, refdriver.P(rq))
+        assert np.array_equal(np.asarray(mcts.counts()), rc), move_no
+        assert np.array_equal(np.asarray(mcts.root_q_values()).view(np.uint32), rq.view(np.uint32)), move_no
+        rwld = np.zeros(3, np.float32)
+        L.azref_mcts_root_value(rt, refdriver.P(rwld))
+        assert np.array_equal(np.asarray(mcts.root_value()).view(np.uint32), rwld.view(np.uint32))
+        mv = int(np.argmax(rc))
+        mcts.update_root(gs, mv)
+        gs.play_move(mv)
+        assert L.azref_mcts_update_root(rt, rgs, mv) == 0 and L.azref_c4_play(rgs, mv) == 0
+        if gs.scores() is not None:
+            break
+    L.azref_mcts_free(rt)
+    L.azref_c4_free(rgs)

@@ -178,3 +178,11 @@ def test_star_gambit_unified_variant_mix_through_the_module(kind):
     assert (variants.sum(axis=1) == 1).all()
     seen = set(np.argmax(variants, axis=1).tolist())
     assert seen == {0, 2, 3}, seen
+    # the per-variant tables (play_manager.h:218-275) add up to the global ones
+    assert pm.num_tracked_variants() == 4 and pm.variant_games_completed(1) == 0
+    assert sum(pm.variant_games_completed(v) for v in range(4)) == 48
+    assert np.array_equal(np.sum([np.asarray(pm.variant_scores(v)) for v in range(4)], axis=0), np.asarray(pm.scores()))
+    lengths = sum(pm.variant_avg_game_length(v) * pm.variant_games_completed(v) for v in range(4))
+    assert abs(lengths - pm.avg_game_length() * 48) < 1e-2 * lengths
+    assert all(pm.variant_avg_valid_moves(v) > 1 for v in (0, 2, 3)) and pm.variant_avg_leaf_depth(0) > 0
+    assert np.array_equal(np.asarray(pm.variant_perm_scores(2, 0)), np.asarray(pm.variant_scores(2)))
