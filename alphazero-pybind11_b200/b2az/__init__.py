@@ -608,11 +608,11 @@ class TaflSelfplay:
                  history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None,
                  seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
                  playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
-                 temp_decay_half_life_by_variant=None, variant_probs=None, cache_entries=0):
+                 temp_decay_half_life_by_variant=None, variant_probs=None, cache_entries=0, gumbel_full=False):
         self.L = lib or load()
         self.game, self.n = game, n_games
         self.S, self.P, self.A = game_dims(game)
-        fp = ForestParams(game=game, relative_values=int(game >= 10), n_trees=2 * n_games, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
+        fp = ForestParams(game=game, relative_values=int(10 <= game <= 24), gumbel_full=int(gumbel_full), n_trees=2 * n_games, max_turns=max_turns, words_per_tree=words_per_tree, cpuct=cpuct,
                           fpu_reduction=fpu_reduction, epsilon=epsilon, root_policy_temp=root_policy_temp,
                           root_fpu_zero=int(root_fpu_zero), seed=seed, gumbel_enabled=int(gumbel_m > 0), gumbel_m=gumbel_m,
                           gumbel_c_visit=gumbel_c_visit, gumbel_c_scale=gumbel_c_scale, shaped_dirichlet=int(shaped_dirichlet))

@@ -25,8 +25,7 @@
 //
 // Scope of this version: PUCT selection, or Gumbel root search (sequential halving over the top-m root children,
 // improved-policy targets, final action; mcts.cc:175-283, 336-401) with PUCT below the root; root policy
-// temperature and (shaped) Dirichlet noise (mcts.cc:403-460); relative_values == false, gumbel_full == false.
-// b2az_forest_create rejects anything else.
+// temperature and (shaped) Dirichlet noise (mcts.cc:403-460), gumbel_full (pi'-matching at interior nodes), relative_values.
 #pragma once
 
 #include "az_rng.h"
@@ -86,6 +85,7 @@ struct ForestView {
   float cpuct, fpu_reduction;
   u32 root_fpu_zero;
   u32 gumbel_enabled, gumbel_m;
+  u32 gumbel_full;      // pi'-matching at interior nodes as well (mcts.cc:285-334)
   float gumbel_c_visit, gumbel_c_scale;
   float epsilon, root_policy_temp;
   u32 shaped_dirichlet;
@@ -774,6 +774,52 @@ __device__ __noinline__ void fg_improved_policy(const ForestView& F, u32 t, cons
   for (u32 i = 0; i < k; ++i) out[pool[fb_mv(b, k) + i] & 0xFFFFu] = fdiv(z[i], z_sum);
 }
 
+// MCTS::gumbel_interior_select (mcts.cc:285-334; gumbel_full): argmax_a [ pi'(a) - N(a) / (1 + sum N) ] with
+// pi' = softmax(log prior + sigma * completedQ) at an INTERIOR node whose children live in block b; `node_v` is the
+// node's stored value. Sequential float order of the reference; lane 0; the tree's Gumbel scratch row holds z.
+__device__ __noinline__ u32 fg_interior_select(const ForestView& F, u32 t, const u32* pool, u32 b, u32 k, float node_v) {
+  float* z = F.gum_g + (size_t)t * (2 * kFMaxK) + kFMaxK;
+  u32 max_visit = 0, sum_n = 0;
+  float sum_visits = 0.0f, sum_priors_visited = 0.0f, weighted_num = 0.0f;
+  for (u32 i = 0; i < k; ++i) {
+    const u32 n = pool[fb_n(b, k) + i];
+    if (n > max_visit) max_visit = n;
+    sum_n += n;
+    sum_visits = fadd(sum_visits, (float)n);
+    if (n > 0) {
+      const float p = u2f(pool[fb_pol(b, k) + i]);
+      sum_priors_visited = fadd(sum_priors_visited, p);
+      weighted_num = fadd(weighted_num, fmul(p, u2f(pool[fb_q(b, k) + i])));
+    }
+  }
+  float v_mix = node_v;
+  if (sum_priors_visited > 0.0f) {
+    const float weighted_q = fdiv(weighted_num, sum_priors_visited);
+    v_mix = fdiv(fadd(node_v, fmul(sum_visits, weighted_q)), fadd(sum_visits, 1.0f));
+  }
+  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  float z_max = -INFINITY;
+  for (u32 i = 0; i < k; ++i) {
+    const float completed_q = pool[fb_n(b, k) + i] > 0 ? u2f(pool[fb_q(b, k) + i]) : v_mix;
+    z[i] = fadd(az_logf(fadd(u2f(pool[fb_pol(b, k) + i]), FG_LOG_FLOOR)), fmul(sigma_scale, completed_q));
+    if (z[i] > z_max) z_max = z[i];
+  }
+  float z_sum = 0.0f;
+  for (u32 i = 0; i < k; ++i) {
+    z[i] = az_expf(fsub(z[i], z_max));
+    z_sum = fadd(z_sum, z[i]);
+  }
+  const float inv = z_sum > 0.0f ? fdiv(1.0f, z_sum) : 0.0f;
+  const float denom = fadd(1.0f, (float)sum_n);
+  u32 best = 0;
+  float best_score = -INFINITY;
+  for (u32 i = 0; i < k; ++i) {
+    const float score = fsub(fmul(z[i], inv), fdiv((float)pool[fb_n(b, k) + i], denom));
+    if (score > best_score) { best_score = score; best = i; }
+  }
+  return best;
+}
+
 // ---- root policy temperature and Dirichlet noise over a wide root (mcts.cc:403-460); lane 0, policy array in HBM.
 // Same formulas / float order as the Connect4 engine's add_root_noise (az_engine_logic.h); the noise values live
 // in the tree's Gumbel scratch row (never needed at the same time: Gumbel replaces the noise, mcts.cc:514-518).
@@ -876,6 +922,10 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       u32 forced = 0;
       if (lane == 0) forced = fg_next_root_child(F, t, R, F.gum[t], pool);
       best_j = __shfl_sync(0xFFFFFFFFu, forced, 0);
+    } else if (gumbel_on && F.gumbel_full) {  // pi'-matching below the root as well (mcts.cc:479-481)
+      u32 sel = 0;
+      if (lane == 0) sel = fg_interior_select(F, t, pool, b, k, cur_v);
+      best_j = __shfl_sync(0xFFFFFFFFu, sel, 0);
     } else {
     // Node::best_child (mcts.cc:130-149)
     float seen = 0.0f;
@@ -1644,7 +1694,6 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (p->epsilon < 0.0f || p->epsilon > 1.0f) return fail(B2AZ_EINVAL, "b2az_forest: epsilon must be in [0, 1]");
   if (p->gumbel_enabled && (p->gumbel_m == 0 || p->gumbel_m > (uint32_t)kFMaxM))
     return fail(B2AZ_EINVAL, "b2az_forest: gumbel_m must be in [1, 64]");
-  if (p->gumbel_full) return fail(B2AZ_EINVAL, "b2az_forest: gumbel_full (pi'-matching at interior nodes) is not implemented yet");
 #ifdef B2AZ_HOST_EMU
   (void)device;
   return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
@@ -1698,6 +1747,7 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
     if (int rc = dev_alloc(&V.noise, (size_t)V.n_trees * kFMaxK)) return bail(rc);
   V.gumbel_enabled = p->gumbel_enabled ? 1u : 0u;
   V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
+  V.gumbel_full = (p->gumbel_enabled && p->gumbel_full) ? 1u : 0u;
   if (V.gumbel_enabled) {
     if (int rc = dev_alloc(&V.gum, (size_t)V.n_trees)) return bail(rc);
     if (int rc = dev_alloc(&V.gum_g, (size_t)V.n_trees * 2 * kFMaxK)) return bail(rc);

@@ -424,7 +424,6 @@ class PlayManager {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + who + " yet");
     };
     reject(!P.temp_decay_half_life_by_variant.empty() && game < 20, "temp_decay_half_life_by_variant");
-    reject(P.gumbel_full, "gumbel_full");
     reject(P.concurrent_games == 0 || P.games_to_play % P.concurrent_games != 0, "games_to_play not a multiple of concurrent_games");
     EvalType et = EvalType::NN;
     if (!P.eval_type.empty()) {
@@ -443,6 +442,7 @@ class PlayManager {
     sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
     sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
     sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
+    sp.forest.gumbel_full = P.gumbel_full;
     sp.forest.gumbel_c_visit = P.gumbel_c_visit; sp.forest.gumbel_c_scale = P.gumbel_c_scale;
     sp.forest.shaped_dirichlet = P.shaped_dirichlet;
     sp.n_games = P.concurrent_games;

@@ -14,7 +14,6 @@ class MCTS {
        bool gumbel_full = false)
       : num_players_(num_players), num_moves_(num_moves) {
     if (num_players != 2) throw std::runtime_error("MCTS: the B200 search implements two-player games");
-    if (gumbel_full) throw std::runtime_error("MCTS: gumbel_full is not implemented by the B200 search yet");
     std::memset(&fp_, 0, sizeof(fp_));
     fp_.n_trees = 1;
     fp_.words_per_tree = 1u << 24;  // 64 MB of node slab for the one tree
@@ -22,6 +21,7 @@ class MCTS {
     fp_.root_fpu_zero = root_fpu_zero; fp_.relative_values = relative_values; fp_.gumbel_enabled = gumbel_enabled;
     fp_.gumbel_m = gumbel_m; fp_.gumbel_c_visit = gumbel_c_visit; fp_.gumbel_c_scale = gumbel_c_scale;
     fp_.shaped_dirichlet = shaped_dirichlet;
+    fp_.gumbel_full = gumbel_full;
     fp_.max_in_flight = 64;
     fp_.seed = std::random_device{}();  // the reference's thread-local generator starts from random_device as well
   }

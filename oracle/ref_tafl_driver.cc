@@ -37,6 +37,7 @@ using namespace alphazero;
 
 namespace {
 thread_local std::string g_err;
+bool g_gumbel_full = false;  // azref_tafl_set_gumbel_full: MCTS(gumbel_full) / PlayParams::gumbel_full of the next runs
 
 std::unique_ptr<GameState> make_game(int game, uint16_t max_turns) {
   switch (game) {
@@ -73,6 +74,7 @@ uint64_t next_u64(uint64_t& s) {  // splitmix64
 extern "C" {
 
 const char* azref_tafl_last_error() { return g_err.c_str(); }
+void azref_tafl_set_gumbel_full(int on) { g_gumbel_full = on != 0; }
 
 int azref_tafl_dims(int game, uint32_t* side, uint32_t* actions, uint32_t* planes) {
   auto gs = make_game(game, 10);
@@ -326,7 +328,7 @@ int azref_tafl_search(int game, uint16_t max_turns, uint64_t seed, float cpuct, 
     // temperature again and fresh noise, as PlayManager does (play_manager.cc:546-553)
     // relative_values: Star Gambit evaluators answer in the mover's frame (mcts.cc:522-524)
     MCTS mcts{cpuct, 2, A, epsilon, root_policy_temp, fpu_reduction, gs->relative_values(), root_fpu_zero != 0, shaped_dirichlet != 0, gumbel_m > 0,
-              gumbel_m > 0 ? gumbel_m : 16u, gumbel_c_visit, gumbel_c_scale, false};
+              gumbel_m > 0 ? gumbel_m : 16u, gumbel_c_visit, gumbel_c_scale, g_gumbel_full};
     uint32_t played = 0;
     for (uint32_t m = 0; m < n_moves; ++m) {
       if (gs->scores().has_value()) break;
@@ -471,6 +473,7 @@ int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRef
     p.gumbel_m = c->gumbel_m;
     p.gumbel_c_visit = c->gumbel_c_visit;
     p.gumbel_c_scale = c->gumbel_c_scale;
+    p.gumbel_full = g_gumbel_full;
     p.tree_reuse = c->tree_reuse != 0;
     p.history_enabled = c->history_enabled != 0;
     p.self_play = true;

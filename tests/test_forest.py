@@ -44,7 +44,7 @@ def run_forest(game, trees, n_moves, sims, seed, cpuct, fpu, rfz, evaluator, mov
     # each half of the slab must hold the kept subtree + one move's search (1 + 8k words per expanded node);
     # slab_moves = how many moves' worth of nodes one half can hold (re-rooting compacts into the other half)
     words = 2 * (1 + (slab_moves or n_moves + 1) * sims * (1 + 8 * (64 if game == 0 else 200)))
-    gkw = dict(gumbel_m=gumbel[0], gumbel_c_visit=gumbel[1], gumbel_c_scale=gumbel[2]) if gumbel else {}
+    gkw = dict(gumbel_m=gumbel[0], gumbel_c_visit=gumbel[1], gumbel_c_scale=gumbel[2], gumbel_full=len(gumbel) > 3 and gumbel[3]) if gumbel else {}
     if noise:  # (epsilon, root_policy_temp, shaped_dirichlet)
         gkw.update(epsilon=noise[0], root_policy_temp=noise[1], shaped_dirichlet=noise[2])
     rn = bool(noise and noise[0] > 0)
@@ -253,8 +253,36 @@ def test_forest_probs_and_pick_move_vs_reference(game, temp, sims):
 def test_forest_refuses_without_cuda_or_unsupported_params():
     lib = b2az.load(ph.HOSTEMU_LIB)
     with pytest.raises(b2az.B2azError) as ei:
-        b2az.Forest(0, 4, 150, gumbel_m=16, gumbel_full=True, lib=lib)
-    assert "not implemented" in str(ei.value)
+        b2az.Forest(0, 4, 150, gumbel_m=100, lib=lib)
+    assert "gumbel_m" in str(ei.value)
     with pytest.raises(b2az.B2azError) as ei:
         b2az.Forest(0, 4, 150, lib=lib)
     assert ei.value.code == -2
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("game,trees,n_moves,sims,m,evaluator", [(0, 4, 8, 64, 8, None), (0, 3, 6, 48, 16, pseudo_net), (23, 3, 8, 48, 8, None)])
+def test_forest_gumbel_full_vs_reference(game, trees, n_moves, sims, m, evaluator):
+    """gumbel_full (mcts.cc:285-334, 479-481): pi'-matching at the interior nodes as well — argmax of pi'(a) - N(a) / (1 + sum N)
+    with pi' = softmax(log prior + sigma * completedQ) instead of PUCT below the root."""
+    if evaluator is not None and game >= 10:
+        pytest.skip("pseudo_net is sized for the tafl games")
+    gum = (m, 50.0, 1.0)
+    tafl_ref.lib().azref_tafl_set_gumbel_full(1)
+    try:
+        refs = [tafl_ref.search(game, 61 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, evaluator, *gum) for i in range(trees)]
+    finally:
+        tafl_ref.lib().azref_tafl_set_gumbel_full(0)
+    got = run_forest(game, trees, n_moves, sims, 61, 1.25, 0.25, False, evaluator, moves_ref=[r[2] for r in refs], gumbel=gum + (True,))
+    plain = [tafl_ref.search(game, 61 + i, n_moves, sims, MAX_TURNS[game], 1.25, 0.25, False, evaluator, *gum) for i in range(trees)]
+    differs = False
+    for i, (rc, rq, rm, rd, rp) in enumerate(refs):
+        for mv in range(len(rm)):
+            counts, q, info, action, policy = got[mv]
+            assert np.array_equal(counts[i], rc[mv]), f"{NAMES[game]} tree {i} move {mv}: visit counts differ"
+            assert np.array_equal(q[i].view(np.uint32), rq[mv].view(np.uint32)), f"tree {i} move {mv}: Q values differ"
+            assert action[i] == rm[mv] and np.array_equal(policy[i].view(np.uint32), rp[mv].view(np.uint32))
+            assert info["total_leaf_depth"][i] == rd[mv]
+        differs |= len(plain[i][0]) != len(rc) or not np.array_equal(plain[i][0][: len(rc)], rc[: len(plain[i][0])])
+    assert differs  # (the option really changes the search)

@@ -101,6 +101,7 @@ def test_mcts_without_a_device_fails_loudly():
         mcts.find_leaf(gs)
     with pytest.raises(RuntimeError, match="two-player"):
         az.MCTS(1.25, 3, 10)
+    az.MCTS(1.25, 2, gs.num_moves(), 0.0, 1.0, 0.0, False, False, False, True, 16, 50.0, 1.0, True)  # gumbel_full is accepted
     assert az.MCTS.pick_move(np.array([0.0, 1.0, 0.0], np.float32)) == 1
 
 

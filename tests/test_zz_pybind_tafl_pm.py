@@ -120,7 +120,9 @@ def test_tafl_playmanager_validation_and_no_cpu_fallback():
         p.model_groups = [0, 1]  # two networks: the tafl engine serves one model group
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
-        az.PlayManager(gs, _params(az, 2, 1, 8, 1, True, gumbel_full=True))
+        p = _params(az, 2, 1, 8, 1, True)
+        p.eval_type = [az.EvalType.PLAYOUT, az.EvalType.PLAYOUT]
+        az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="multiple of concurrent_games"):
         p = _params(az, 2, 1, 8, 1, True)
         p.games_to_play = 3
