@@ -140,6 +140,7 @@ def load(path=None):
     L.b2az_tafl_replay.argtypes = [C.c_int, u32, u32, u32, u32] + [vp] * 11
     L.b2az_tafl_replay_device.argtypes = [u32, u32, u32, u32] + [vp] * 10
     L.b2az_sg_replay.argtypes = [C.c_int, u32, u32, u32] + [vp] * 8
+    L.b2az_sg_symmetries.argtypes = [C.c_int, u32, u32] + [vp] * 6 + [C.c_int, C.c_int, vp]
     L.b2az_sg_replay_device.argtypes = [u32, u32, u32, vp, vp, vp, u32] + [vp] * 7
     L.b2az_forest_create.argtypes = [C.POINTER(ForestParams), C.c_int, C.POINTER(vp)]
     L.b2az_forest_destroy.argtypes = [vp]
@@ -445,6 +446,22 @@ def sg_replay(game, moves, lens, want_valid=True, want_canonical=True, device=0,
     if rc != 0:
         raise B2azError(rc, L.b2az_last_error().decode())
     return out
+
+
+def sg_symmetries(game, canon, v, pi, fp16=False, device=0, lib=None):
+    """Every Star Gambit sample followed by its NW-axis mirror image: ([n,2,P,D,D], [n,2,3], [n,2,A]), float32 or float16."""
+    L = lib or load()
+    D, A, P = sg_dims(game if game != 24 else 23)
+    canon = np.ascontiguousarray(canon, np.float32).reshape(-1, P, D, D)
+    n = canon.shape[0]
+    v = np.ascontiguousarray(v, np.float32).reshape(n, 3)
+    pi = np.ascontiguousarray(pi, np.float32).reshape(n, A)
+    dt = np.float16 if fp16 else np.float32
+    co, vo, po = np.zeros((n, 2, P, D, D), dt), np.zeros((n, 2, 3), dt), np.zeros((n, 2, A), dt)
+    rc = L.b2az_sg_symmetries(device, game, n, _ptr(canon), _ptr(v), _ptr(pi), _ptr(co), _ptr(vo), _ptr(po), 0, int(fp16), None)
+    if rc != 0:
+        raise B2azError(rc, L.b2az_last_error().decode())
+    return co, vo, po
 
 
 def tafl_positions(game, boards, players, turns, reps, max_turns, moves=None, device=0, lib=None):

@@ -16,6 +16,9 @@
 #pragma once
 
 #include "az_stargambit.h"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace b2az {
 
@@ -289,9 +292,94 @@ __global__ void __launch_bounds__(128) k_sg_replay(SGReplayArgs a) {
     if (hist.overflow && lane == 0 && a.status) a.status[gi] = B2AZ_ENOMEM;
   }
 }
+// GameState::symmetries for Star Gambit (star_gambit_gs.cc:1671-1805, Unified 2623-2727): every sample followed by its
+// NW-axis mirror image, gathered through the inverse index maps of az_stargambit.h; OUT = float or __half (the fp16 form
+// game_runner.save_compressed stores, game_runner.py:200-210)
+template <class OUT>
+__device__ __forceinline__ OUT sg_out_cast(float x);
+template <>
+__device__ __forceinline__ float sg_out_cast<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ __half sg_out_cast<__half>(float x) { return __float2half_rn(x); }
+template <class OUT>
+__global__ void k_sg_symmetries(u32 n, u32 planes, u32 dim, const float* __restrict__ canon, const float* __restrict__ v,
+                                const float* __restrict__ pi, OUT* __restrict__ canon_out, OUT* __restrict__ v_out,
+                                OUT* __restrict__ pi_out) {
+  const u32 side = (dim - 1u) / 2u;
+  const size_t C = (size_t)planes * dim * dim, A = (size_t)dim * dim * 10u + 19u, per = C + A + 3;
+  const size_t total = (size_t)n * 2u * per;
+  for (size_t i = GLOBAL_TID; i < total; i += GLOBAL_NT) {
+    const size_t row = i / per, e = i % per;  // row = sample * 2 + sym
+    const u32 sample = (u32)(row / 2u), sym = (u32)(row % 2u);
+    if (e < C) {
+      const int src = sym ? sg_mirror_canon_src((int)dim, (int)side, (int)planes, (int)e) : (int)e;
+      canon_out[row * C + e] = sg_out_cast<OUT>(src < 0 ? 0.0f : canon[(size_t)sample * C + (size_t)src]);
+    } else if (e < C + A) {
+      const int mv = (int)(e - C);
+      const int src = sym ? sg_mirror_pi_src((int)dim, (int)side, mv) : mv;
+      pi_out[row * A + (size_t)mv] = sg_out_cast<OUT>(src < 0 ? 0.0f : pi[(size_t)sample * A + (size_t)src]);
+    } else {
+      const u32 j = (u32)(e - C - A);
+      v_out[row * 3 + j] = sg_out_cast<OUT>(v[(size_t)sample * 3 + j]);
+    }
+  }
+}
 #endif  // !B2AZ_HOST_EMU
 
 }  // namespace b2az
+
+extern "C" int b2az_sg_symmetries(int device, uint32_t game, uint32_t n, const float* canon, const float* v, const float* pi,
+                                  void* canon_out, void* v_out, void* pi_out, int device_pointers, int fp16_out, void* stream) {
+  using namespace b2az;
+  if (n == 0) return 0;
+  if (!canon || !v || !pi || !canon_out || !v_out || !pi_out) return fail(B2AZ_EINVAL, "null argument");
+  if (!((game >= 10 && game <= 13) || (game >= 20 && game <= 24))) return fail(B2AZ_EINVAL, "unknown Star Gambit game");
+#ifdef B2AZ_HOST_EMU
+  (void)device; (void)device_pointers; (void)fp16_out; (void)stream;
+  return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B2AZ_ECUDA, "no CUDA device: libb2az has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  const bool unified = game >= 20;
+  const SGSpace sp = sg_space(game == 24u ? B2AZ_SG_BATTLE : (int)(game % 10u), unified);
+  const u32 planes = (u32)sp.planes(unified), dim = (u32)sp.udim;
+  const size_t C = (size_t)planes * dim * dim, A = (size_t)sp.num_moves(), osz = fp16_out ? 2 : 4;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float *dc = canon, *dv = v, *dp = pi;
+  void *oc = canon_out, *ov = v_out, *op = pi_out;
+  float *tc = nullptr, *tv = nullptr, *tp = nullptr;
+  void *toc = nullptr, *tov = nullptr, *top = nullptr;
+  int rc = 0;
+  if (!device_pointers) {
+    auto al = [&](void** p, size_t bytes) { if (!rc && cudaMalloc(p, bytes) != cudaSuccess) rc = fail(B2AZ_ENOMEM, "b2az_sg_symmetries: cudaMalloc failed"); };
+    al((void**)&tc, n * C * 4); al((void**)&tv, (size_t)n * 12); al((void**)&tp, n * A * 4);
+    al(&toc, (size_t)n * 2 * C * osz); al(&tov, (size_t)n * 6 * osz); al(&top, (size_t)n * 2 * A * osz);
+    if (!rc) {
+      cudaMemcpyAsync(tc, canon, n * C * 4, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(tv, v, (size_t)n * 12, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(tp, pi, n * A * 4, cudaMemcpyHostToDevice, s);
+    }
+    dc = tc; dv = tv; dp = tp; oc = toc; ov = tov; op = top;
+  }
+  if (!rc) {
+    if (fp16_out) k_sg_symmetries<__half><<<148 * 8, 256, 0, s>>>(n, planes, dim, dc, dv, dp, (__half*)oc, (__half*)ov, (__half*)op);
+    else k_sg_symmetries<float><<<148 * 8, 256, 0, s>>>(n, planes, dim, dc, dv, dp, (float*)oc, (float*)ov, (float*)op);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2AZ_ECUDA, "k_sg_symmetries launch failed");
+  }
+  if (!device_pointers) {
+    if (!rc) {
+      cudaMemcpyAsync(canon_out, toc, (size_t)n * 2 * C * osz, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(v_out, tov, (size_t)n * 6 * osz, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(pi_out, top, (size_t)n * 2 * A * osz, cudaMemcpyDeviceToHost, s);
+      const cudaError_t err = cudaStreamSynchronize(s);
+      if (err != cudaSuccess) rc = fail(B2AZ_ECUDA, std::string("k_sg_symmetries: ") + cudaGetErrorString(err));
+    }
+    cudaFree(tc); cudaFree(tv); cudaFree(tp); cudaFree(toc); cudaFree(tov); cudaFree(top);
+  }
+  return rc;
+#endif
+}
 
 extern "C" int b2az_sg_replay_device(uint32_t game, uint32_t n, uint32_t max_len, const uint16_t* moves_dev,
                                      const uint32_t* lens_dev, void* hist_dev, uint32_t hist_cap, uint8_t* states_dev,

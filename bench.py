@@ -766,9 +766,9 @@ def main():
                          ("opentafl_game_kernels", ["tools/tafl_bench.py", "--game", "1", "--games", "8192", "--reps", "3"]),
                          # BASELINE.json configs[4]: Star Gambit Unified with the Gumbel root search (configs/star_gambit_unified.yaml);
                          # one leg per end of the variant mix (11x11 Skirmish, 13x13 Battle), 120 simulations per move
-                         ("star_gambit_unified_battle_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "23", "--games", "1024",
+                         ("star_gambit_unified_battle_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "23", "--games", "8192",
                                                                   "--moves", "16", "--cpu-seconds", "5"]),
-                         ("star_gambit_unified_skirmish_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "20", "--games", "1024",
+                         ("star_gambit_unified_skirmish_selfplay", ["tools/tafl_selfplay_bench.py", "--game", "20", "--games", "8192",
                                                                     "--moves", "16", "--cpu-seconds", "5"]),
                          ("star_gambit_game_kernels", ["tools/sg_bench.py", "--game", "23", "--games", "4096", "--moves", "64"])):
             try:

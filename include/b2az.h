@@ -321,6 +321,15 @@ int b2az_sg_replay_device(uint32_t game, uint32_t n, uint32_t max_len, const uin
                           uint8_t* terminal_dev, uint32_t* n_valid_dev, uint8_t* valid_dev, float* canonical_dev,
                           int32_t* status_dev, void* stream);
 
+/* GameState::symmetries for Star Gambit (identity + the NW-axis mirror, star_gambit_gs.cc:1671-1805; Unified 2623-2727) on a
+ * batch of n samples: canon float32[n][P][D][D], v float32[n][3], pi float32[n][A] -> canon_out [n][2][P][D][D], v_out
+ * [n][2][3], pi_out [n][2][A] (every sample followed by its mirror image: the order game_runner.exploit_symmetries writes,
+ * game_runner.py:1050-1144). device_pointers != 0: every buffer is device memory and the launch is enqueued on `stream`
+ * (e.g. straight from the self-play engine's sample ring); fp16_out != 0: the outputs are IEEE half (the form
+ * game_runner.save_compressed stores, game_runner.py:200-210). */
+int b2az_sg_symmetries(int device, uint32_t game, uint32_t n, const float* canon, const float* v, const float* pi,
+                       void* canon_out, void* v_out, void* pi_out, int device_pointers, int fp16_out, void* stream);
+
 /* ---- Batched single-tree MCTS over the tafl games ("forest"): the reference's `MCTS` class (mcts.h:50-150, bound at
  * py_wrapper.cc:192-220) for n_trees trees at once, one warp per tree on the device. Tree i starts at the game's
  * start position and draws from pcg32(seed + i) — a reference MCTS driven after MCTS::seed_thread_rng(seed + i).

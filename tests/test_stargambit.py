@@ -82,3 +82,30 @@ def test_replay_kernel_many_games_equal_their_first_copy():
     c = out["canonical"].reshape(reps, n, *out["canonical"].shape[1:])
     assert np.array_equal(c, np.broadcast_to(c[:1], c.shape))
     assert np.array_equal(out["n_valid"].reshape(reps, n, -1), np.broadcast_to(out["n_valid"].reshape(reps, n, -1)[:1], (reps, n, 97)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("game", [10, 13, 22])
+def test_symmetry_kernel_matches_reference(game):
+    """b2az_sg_symmetries (identity + NW-axis mirror on the device, float32 and the fp16 packing of save_compressed) against
+    GameState::symmetries of the unmodified reference."""
+    if not has_cuda():
+        pytest.skip("no CUDA device")
+    import b2az
+    import tafl_ref
+
+    if not tafl_ref.available():
+        pytest.skip("oracle/_ref/libazref_tafl.so not built")
+    D, A, P = b2az.sg_dims(game)
+    rng = np.random.default_rng(game)
+    n = 5
+    canon = rng.random((n, P, D, D), dtype=np.float32)
+    v = rng.random((n, 3), dtype=np.float32)
+    pi = rng.random((n, A), dtype=np.float32)
+    co, vo, po = b2az.sg_symmetries(game, canon, v, pi)
+    ch, vh, ph_ = b2az.sg_symmetries(game, canon, v, pi, fp16=True)
+    for i in range(n):
+        rc, rv, rp = tafl_ref.symmetries(game, canon[i], v[i], pi[i])
+        assert np.array_equal(co[i].view(np.uint32), rc.view(np.uint32)), i
+        assert np.array_equal(vo[i], rv) and np.array_equal(po[i].view(np.uint32), rp.view(np.uint32)), i
+        assert np.array_equal(ch[i], rc.astype(np.float16)) and np.array_equal(ph_[i], rp.astype(np.float16)), i
