@@ -47,10 +47,11 @@ extern "C" {
                                reference worker thread after MCTS::seed_thread_rng(seed) (mcts.cc:19-21).
                                Serial by construction; this is the bit-exact parity mode. */
 
-/* Mirrors PlayParams (play_manager.h:60-154) for the Connect4 PUCT path, plus engine sizing.
- * Fields keep the reference's names and meaning. Not (yet) carried: per-seat 2-D overrides,
- * Gumbel, resign, model groups / seat permutations, playout eval. b2az_create rejects a
- * non-default value for anything it does not implement instead of ignoring it. */
+/* Mirrors PlayParams (play_manager.h:60-154) for the Connect4 engine, plus engine sizing. Fields keep the
+ * reference's names and meaning: PUCT and Gumbel search (incl. gumbel_full), playout-cap randomisation, resignation,
+ * per-seat visit budgets and two model groups are carried. Not carried: the other per-seat 2-D overrides (the host
+ * side folds them when they are uniform), seat permutations, playout eval. b2az_create rejects a non-default value
+ * for anything it does not implement instead of ignoring it. */
 typedef struct b2az_params {
   uint32_t game;                 /* B2AZ_GAME_* */
   uint32_t games_to_play;
@@ -84,10 +85,10 @@ typedef struct b2az_params {
   uint8_t pad1_;
   uint64_t seed;
   /* engine sizing (no reference counterpart) */
-  uint64_t pool_nodes;           /* tree-node pool size in nodes (8 per 192 B block); 0 = sized from visits and free HBM */
+  uint64_t pool_nodes;           /* tree-node pool size in nodes (7 per 160 B child block); 0 = sized from visits and free HBM */
   uint32_t history_capacity;     /* finished-sample ring, in samples; 0 = default */
   uint32_t lanes_per_game;       /* threads per game slot: 0 or 1 (Connect4 runs one thread per game) */
-  uint32_t compact_pages;        /* a tree's arena (12 KB pages) is compacted at a move once it holds more
+  uint32_t compact_pages;        /* a tree's arena (10 KB pages of 64 blocks) is compacted at a move once it holds more
                                     pages than this; 0 = half of the tree's share of the pool */
   /* Gumbel AlphaZero (play_manager.h:104-116) */
   uint32_t gumbel_m;             /* 16 */
