@@ -49,7 +49,14 @@ class Params(C.Structure):
         ("gumbel_m", C.c_uint32), ("gumbel_c_visit", C.c_float), ("gumbel_c_scale", C.c_float),
         ("gumbel_full", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("model_groups", C.c_uint8 * 2),
         ("step_kernel", C.c_uint32), ("seat_cap_visits", C.c_uint32 * 2),
+        ("n_seat_perms", C.c_uint32), ("seat_perms", (C.c_uint8 * 2) * 8), ("perm_seat_visits", (C.c_uint32 * 2) * 8),
+        ("perm_seat_cap_visits", (C.c_uint32 * 2) * 8), ("group_random", C.c_uint8 * 2), ("pad5_", C.c_uint8 * 2),
     ]
+
+
+class PermStats(C.Structure):  # b2az_perm_stats (include/b2az.h)
+    _fields_ = [("scores", C.c_float * 3), ("games_completed", C.c_uint32), ("variant_scores", (C.c_float * 3) * 4),
+                ("variant_games_completed", C.c_uint32 * 4)]
 
 
 class Stats(C.Structure):
@@ -88,7 +95,9 @@ class TaflSelfplayParams(C.Structure):  # b2az_tafl_selfplay_params (include/b2a
                 ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
                 ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2),
                 ("n_variant_half_life", C.c_uint32), ("variant_half_life", C.c_float * 4), ("variant_probs", C.c_float * 4),
-                ("cache_entries", C.c_uint32)]
+                ("cache_entries", C.c_uint32),
+                ("n_seat_perms", C.c_uint32), ("seat_perms", (C.c_uint8 * 2) * 8), ("perm_seat_visits", (C.c_uint32 * 2) * 8),
+                ("perm_seat_cap_visits", (C.c_uint32 * 2) * 8), ("group_random", C.c_uint8 * 2), ("pad4_", C.c_uint8 * 2)]
 
 
 SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_completed", "u4"), ("pending", "u4"),
@@ -177,6 +186,10 @@ def load(path=None):
     L.b2az_tafl_selfplay_get_stats.argtypes = [vp, vp, C.POINTER(Stats)]
     L.b2az_tafl_selfplay_leaf_batch_host.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32)]
     L.b2az_tafl_selfplay_submit_eval_host.argtypes = [vp, vp, vp, vp, vp, u32]
+    L.b2az_tafl_selfplay_leaf_groups_host.argtypes = [vp, vp, u32]
+    L.b2az_tafl_selfplay_perm_stats.argtypes = [vp, vp, vp, C.POINTER(u32)]
+    L.b2az_leaf_groups_host.argtypes = [vp, vp, vp, u32]
+    L.b2az_perm_scores.argtypes = [vp, vp, vp, C.POINTER(u32)]
     _libs[path] = L
     return L
 
@@ -197,6 +210,23 @@ def default_params(lib=None, **kw):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def fill_perms(p, seat_perms=None, perm_seat_visits=None, perm_seat_cap_visits=None, group_random=None):
+    """PlayParams::seat_perms and the per-permutation budgets into a Params / TaflSelfplayParams structure."""
+    for i, perm in enumerate(seat_perms or []):
+        p.seat_perms[i][0], p.seat_perms[i][1] = perm
+        p.n_seat_perms = i + 1
+    for i, row in enumerate(perm_seat_visits or []):
+        p.perm_seat_visits[i][0], p.perm_seat_visits[i][1] = row
+    for i, row in enumerate(perm_seat_cap_visits or []):
+        p.perm_seat_cap_visits[i][0], p.perm_seat_cap_visits[i][1] = row
+    for i, r in enumerate(group_random or []):
+        p.group_random[i] = int(r)
+
+
+def perm_stats_array(n=8):
+    return (PermStats * n)()
 
 
 class Engine:
@@ -325,6 +355,19 @@ class Engine:
         return seats
 
     # -- the position cache key by key, in order (S3FIFOCache::insert / ::find)
+
+    def leaf_groups_host(self, count, stream=None):
+        """Model group of the first `count` rows of the leaf batch (seat_perms[slot's permutation][searching seat])."""
+        groups = np.empty(count, np.uint8)
+        self._check(self.L.b2az_leaf_groups_host(self.h, stream, _ptr(groups), count))
+        return groups
+
+    def perm_scores(self, stream=None):
+        """[(scores[3], games_completed)] per seat permutation (perm_scores / perm_games_completed)."""
+        out, n = perm_stats_array(), C.c_uint32(0)
+        self._check(self.L.b2az_perm_scores(self.h, stream, out, C.byref(n)))
+        return [(np.array(out[i].scores[:], np.float32), int(out[i].games_completed)) for i in range(n.value)]
+
     def cache_insert(self, keys, v, pi, stream=None):
         keys = np.ascontiguousarray(keys, np.uint64)
         v = np.ascontiguousarray(v, np.float32).reshape(len(keys), NUM_PLAYERS + 1)
@@ -625,7 +668,8 @@ class TaflSelfplay:
                  history_enabled=True, policy_target_pruning=False, tree_reuse=True, hist_capacity=0, device=0, lib=None,
                  seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
                  playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
-                 temp_decay_half_life_by_variant=None, variant_probs=None, cache_entries=0, gumbel_full=False):
+                 temp_decay_half_life_by_variant=None, variant_probs=None, cache_entries=0, gumbel_full=False,
+                 seat_perms=None, perm_seat_visits=None, perm_seat_cap_visits=None, group_random=None):
         self.L = lib or load()
         self.game, self.n = game, n_games
         self.S, self.P, self.A = game_dims(game)
@@ -650,6 +694,7 @@ class TaflSelfplay:
         for seat in range(2):
             p.seat_visits[seat] = (seat_visits or (0, 0))[seat]
             p.seat_cap_visits[seat] = (seat_cap_visits or (0, 0))[seat]
+        fill_perms(p, seat_perms, perm_seat_visits, perm_seat_cap_visits, group_random)
         self.hist_capacity = hist_capacity or n_games * max_turns
         self.h = C.c_void_p()
         self._check(self.L.b2az_tafl_selfplay_create(C.byref(p), device, C.byref(self.h)))
@@ -696,6 +741,35 @@ class TaflSelfplay:
         self._check(self.L.b2az_tafl_selfplay_drain_history(self.h, stream, len(slot), _ptr(canon), _ptr(v), _ptr(pi), _ptr(slot),
                                                             C.byref(n)))
         return canon[:n.value], v[:n.value], pi[:n.value], slot[:n.value]
+
+    def leaf_batch_host(self, stream=None):
+        """build_batch with host buffers: (slot ids uint32[n], canonical float32[n,P,S,S]) of the slots whose leaf waits."""
+        canon = np.empty((self.n, self.P, self.S, self.S), np.float32)
+        ids = np.empty(self.n, np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.L.b2az_tafl_selfplay_leaf_batch_host(self.h, stream, self.n, _ptr(canon), _ptr(ids), C.byref(n)))
+        return ids[:n.value], canon[:n.value]
+
+    def submit_eval_host(self, ids, v, pi, stream=None):
+        """update_inferences with host buffers (row i for slot ids[i]); plays the move of every complete search."""
+        ids = np.ascontiguousarray(ids, np.uint32)
+        v, pi = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(pi, np.float32)
+        assert v.shape == (len(ids), 3) and pi.shape == (len(ids), self.A)
+        self._check(self.L.b2az_tafl_selfplay_submit_eval_host(self.h, stream, _ptr(ids), _ptr(v), _ptr(pi), len(ids)))
+
+    def leaf_groups_host(self, n):
+        """Model group of every row of the last leaf_batch_host."""
+        groups = np.empty(n, np.uint8)
+        self._check(self.L.b2az_tafl_selfplay_leaf_groups_host(self.h, _ptr(groups), n))
+        return groups
+
+    def perm_stats(self, stream=None):
+        """Per seat permutation: dict(scores[3], games_completed, variant_scores[4][3], variant_games_completed[4])."""
+        out, n = perm_stats_array(), C.c_uint32(0)
+        self._check(self.L.b2az_tafl_selfplay_perm_stats(self.h, stream, out, C.byref(n)))
+        return [dict(scores=np.array(out[i].scores[:], np.float32), games_completed=int(out[i].games_completed),
+                     variant_scores=np.array([list(r) for r in out[i].variant_scores], np.float32),
+                     variant_games_completed=list(out[i].variant_games_completed)) for i in range(n.value)]
 
     def stats(self, stream=None):
         st = Stats()

@@ -589,6 +589,13 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
     return fail(B2AZ_EINVAL, "the position cache changes the evaluation order: not available in B2AZ_RNG_GLOBAL (parity) mode");
   if (p->step_kernel > B2AZ_STEP_QUEUE) return fail(B2AZ_EINVAL, "bad step_kernel");
   if (p->model_groups[0] > 1 || p->model_groups[1] > 1) return fail(B2AZ_EINVAL, "model_groups: a group index must be 0 or 1");
+  if (p->n_seat_perms > (uint32_t)kMaxPerms) return fail(B2AZ_EINVAL, "seat_perms: at most 8 seat permutations");
+  if (p->n_seat_perms > 1 && p->concurrent_games % p->n_seat_perms != 0)
+    return fail(B2AZ_EINVAL, "seat_perms: concurrent_games must be a multiple of the number of seat permutations (slot g plays permutation g % n)");
+  for (uint32_t pm = 0; pm < p->n_seat_perms && pm < (uint32_t)kMaxPerms; ++pm)
+    if (p->seat_perms[pm][0] > 1 || p->seat_perms[pm][1] > 1) return fail(B2AZ_EINVAL, "seat_perms: a group index must be 0 or 1");
+  if (p->n_seat_perms > 1 && p->rng_mode == B2AZ_RNG_GLOBAL)
+    return fail(B2AZ_EINVAL, "seat_perms: not available in B2AZ_RNG_GLOBAL (parity) mode (the hand-out order is per slot here)");
   if (p->per_slot_quota && p->games_to_play % p->concurrent_games != 0)
     return fail(B2AZ_EINVAL, "per_slot_quota: games_to_play must be a multiple of concurrent_games");
   if (p->lanes_per_game > 1)
@@ -618,9 +625,15 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   memset(&V, 0, sizeof(V));
   V.G = G;
   V.games_to_play = p->games_to_play;
-  V.visits[0] = p->mcts_visits[0]; V.visits[1] = p->mcts_visits[1];
-  V.cap_visits[0] = p->seat_cap_visits[0] ? p->seat_cap_visits[0] : p->playout_cap_depth;
-  V.cap_visits[1] = p->seat_cap_visits[1] ? p->seat_cap_visits[1] : p->playout_cap_depth;
+  V.n_perms = std::max(1u, p->n_seat_perms);
+  for (u32 pm = 0; pm < V.n_perms; ++pm)
+    for (int seat = 0; seat < 2; ++seat) {
+      V.visits[pm][seat] = p->perm_seat_visits[pm][seat] ? p->perm_seat_visits[pm][seat] : p->mcts_visits[seat];
+      const u32 cv = p->perm_seat_cap_visits[pm][seat] ? p->perm_seat_cap_visits[pm][seat] : p->seat_cap_visits[seat];
+      V.cap_visits[pm][seat] = cv ? cv : p->playout_cap_depth;
+      V.seat_group[pm][seat] = p->n_seat_perms ? p->seat_perms[pm][seat] : p->model_groups[seat];
+    }
+  V.random_groups = p->eval_type == B2AZ_EVAL_NN ? ((p->group_random[0] ? 1u : 0u) | (p->group_random[1] ? 2u : 0u)) : 0u;
   V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.epsilon = p->epsilon; V.root_temp = p->mcts_root_temp;
   V.start_temp = p->start_temp; V.final_temp = p->final_temp; V.half_life = p->temp_decay_half_life;
   V.playout_cap_percent = p->playout_cap_percent;
@@ -630,13 +643,13 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   V.resign_percent = p->resign_percent; V.resign_playthrough_percent = p->resign_playthrough_percent;
   V.gumbel_enabled = p->gumbel_enabled; V.gumbel_full = p->gumbel_full; V.fast_search_uses_gumbel = p->fast_search_uses_gumbel;
   V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
-  V.seat_group[0] = p->model_groups[0]; V.seat_group[1] = p->model_groups[1];
   V.hit_cap = 64u;
   if (const char* hc = getenv("B2AZ_HIT_CAP")) V.hit_cap = (u32)std::max(0, atoi(hc));  // experiment knob
   V.slot_quota = p->per_slot_quota ? p->games_to_play / p->concurrent_games : 0u;
 
   // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
-  const u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
+  u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
+  for (u32 pm = 0; pm < V.n_perms; ++pm) max_visits = std::max<u64>(max_visits, std::max(V.visits[pm][0], V.visits[pm][1]));
   // a search adds <= one block per simulation; budget = 4 searches' worth + slack per tree
   const u64 tree_blocks = 4ull * max_visits + 2ull * kPageBlocks;
   u64 pool_blocks = p->pool_nodes ? (p->pool_nodes + kKMax - 1) / kKMax : tree_blocks * (u64)G * kP;
@@ -970,7 +983,22 @@ int b2az_leaf_seats_host(b2az_engine* e, void* stream, uint8_t* seats_host, uint
   if (count > e->leaf_count) return fail(B2AZ_EINVAL, "more rows than leaves");
   if (count == 0) return 0;
   if (int rc = copy_d2h(seats_host, e->view.leaf_seat, count, s)) return rc;
-  return stream_sync(s);
+  if (int rc = stream_sync(s)) return rc;
+  for (uint32_t i = 0; i < count; ++i) seats_host[i] &= 15u;  // (bits 4-7 carry the model group)
+  return 0;
+}
+int b2az_leaf_groups_host(b2az_engine* e, void* stream, uint8_t* groups_host, uint32_t count) {
+  if (!e || (count && !groups_host)) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (int rc = bind_device(e)) return rc;
+  if (!e->leaves_pending) return fail(B2AZ_ESTATE, "no leaf batch");
+  if (int rc = sync_leaf_count(e, s)) return rc;
+  if (count > e->leaf_count) return fail(B2AZ_EINVAL, "more rows than leaves");
+  if (count == 0) return 0;
+  if (int rc = copy_d2h(groups_host, e->view.leaf_seat, count, s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  for (uint32_t i = 0; i < count; ++i) groups_host[i] >>= 4;
+  return 0;
 }
 
 int b2az_submit_eval(b2az_engine* e, const float* v_dev, const float* pi_dev, uint32_t count) {
@@ -1206,6 +1234,24 @@ int b2az_drain_history_marked(b2az_engine* e, void* stream2, uint32_t max, float
   if (int rc = copy_h2d(&e->view.glob->hist_read, e->hist_read_host, 8, s)) return rc;
   if (int rc = stream_sync(s)) return rc;  // the caller's host buffers are filled when this returns
   *count = n;
+  return 0;
+}
+
+int b2az_perm_scores(b2az_engine* e, void* stream, b2az_perm_stats* out8, uint32_t* n_perms_out) {
+  if (!e || !out8) return fail(B2AZ_EINVAL, "null argument");
+  stream_t s = static_cast<stream_t>(stream);
+  if (int rc = bind_device(e)) return rc;
+  Globals G;
+  if (int rc = copy_d2h(&G, e->view.glob, sizeof(G), s)) return rc;
+  if (int rc = stream_sync(s)) return rc;
+  const u32 P = e->view.n_perms;
+  memset(out8, 0, P * sizeof(b2az_perm_stats));
+  for (u32 pm = 0; pm < P; ++pm)
+    for (int i = 0; i < 3; ++i) {  // perm_scores_ holds integer win counts (play_manager.cc:466-467)
+      out8[pm].scores[i] = (float)G.perm_wins[pm][i];
+      out8[pm].games_completed += (uint32_t)G.perm_wins[pm][i];
+    }
+  if (n_perms_out) *n_perms_out = P;
   return 0;
 }
 

@@ -101,6 +101,8 @@ AZ_HD void mem_fence() {
   __threadfence();
 #endif
 }
+// the seat permutation slot g plays (EngineView::n_perms)
+AZ_HD u32 slot_perm(const EngineView& E, u32 g) { return E.n_perms > 1u ? g % E.n_perms : 0u; }
 template <typename T>
 AZ_HD T ld_volatile(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 template <typename T>
@@ -921,15 +923,21 @@ AZ_HD void cache_insert(const EngineView& E, u64 key, const float* v, const floa
 #endif
 }
 
+// eval_types_[group] == RANDOM next to an NN group (play_manager.cc:577-587): the searches of that group run dumb_eval
+// inline and never enter the leaf batch
+AZ_HD bool slot_random(const EngineView& E, u32 g, const GameSlot& gs) {
+  return E.random_groups != 0u && ((E.random_groups >> E.seat_group[slot_perm(E, g)][gs.player]) & 1u) != 0u;
+}
 // What happens to a fresh leaf with the NN evaluator (play_manager.cc:586-598): look the position up in the
 // cache — every leaf, terminal ones included, like the reference — and on a miss put it into the leaf batch.
 // Returns true on a cache hit (the caller goes on with the next simulation right away).
 AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s, bool allow_hit) {
+  if (slot_random(E, g, gs)) return allow_hit;  // answered on the spot like a cache hit; a launch's chain stays bounded (hit_cap)
   u64 key = 0;
   if (E.cache_buckets) {
     // one table for every model group (the reference keeps one cache per group, play_manager.cc:195-203): the group of
     // the searching seat is part of the key (bits 56-59 are free in the position encoding)
-    key = c4_cache_key(s) | ((u64)E.seat_group[gs.player] << 56);
+    key = c4_cache_key(s) | ((u64)E.seat_group[slot_perm(E, g)][gs.player] << 56);
     const u32 hit = cache_find(E, key);
     if (hit != kNil && allow_hit) {
       E.hit_val[g] = hit;
@@ -953,7 +961,7 @@ AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s,
   E.leaf_p1[row] = s.p[1];
   E.leaf_player[row] = s.player;
   E.leaf_game[row] = g;
-  E.leaf_seat[row] = gs.player;
+  E.leaf_seat[row] = (u8)(gs.player | (E.seat_group[slot_perm(E, g)][gs.player] << 4));
   if (E.cache_buckets) {
     E.leaf_key[row] = key;
     E.hit_val[g] = kNil;
@@ -1039,7 +1047,7 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
     u32 ps[kKMax];  // the leaf's child priors (f32 bits), child order
 #pragma unroll
     for (int j = 0; j < kKMax; ++j) ps[j] = 0u;
-    if (E.eval_type == 1) {  // dumb_eval (game_state.h:160-173): uniform over the legal moves, value 1/3
+    if (E.eval_type == 1 || slot_random(E, g, gs)) {  // dumb_eval (game_state.h:160-173): uniform over the legal moves, value 1/3
       const float third = (float)(1.0 / 3.0);
       val0 = val1 = vald = third;
       // every legal move is a child here, so Vector<uint8_t>::sum() == lk
@@ -1406,7 +1414,7 @@ AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_befor
 // set_gumbel_num_sims for the tree that searches next (play_manager.cc:531-539, 562-570): the full budget, or for a
 // capped search the cap when fast_search_uses_gumbel, else 0 = "PUCT for this search".
 AZ_COLD void gumbel_arm(const EngineView E, u32 g, u32 seat, bool capped) {
-  const u32 target = capped ? (E.fast_search_uses_gumbel ? E.cap_visits[seat] : 0u) : E.visits[seat];
+  const u32 target = capped ? (E.fast_search_uses_gumbel ? E.cap_visits[slot_perm(E, g)][seat] : 0u) : E.visits[slot_perm(E, g)][seat];
   GumbelState S = E.gum[(size_t)g * kP + seat];
   gumbel_set_num_sims(S, target);
   E.gum[(size_t)g * kP + seat] = S;
@@ -1561,6 +1569,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     gs.hist_n = 0;
     Globals* G = E.glob;
     at_add64(&G->wins[term - 1u], 1ULL);
+    at_add64(&G->perm_wins[slot_perm(E, g)][term - 1u], 1ULL);
     if (resign_term != 0) at_add64(&G->resign_wins[resign_term - 1u], 1ULL);
     at_add(&G->games_completed, 1u);
     at_add64(&G->game_length, (unsigned long long)gs.turn);
@@ -1598,7 +1607,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     gs.capped = (E.playout_cap && rng_uniform01(rng) < E.playout_cap_percent) ? 1 : 0;
     if (E.gumbel_enabled) {  // set_gumbel_num_sims for the seat that searches next (play_manager.cc:531-539)
       const u32 ncp = gs.player;
-      gumbel_set_num_sims(GS[ncp], gs.capped ? (E.fast_search_uses_gumbel ? E.cap_visits[ncp] : 0u) : E.visits[ncp]);
+      gumbel_set_num_sims(GS[ncp], gs.capped ? (E.fast_search_uses_gumbel ? E.cap_visits[slot_perm(E, g)][ncp] : 0u) : E.visits[slot_perm(E, g)][ncp]);
     }
     if (!E.tree_reuse) {
       for (int seat = 0; seat < kP; ++seat) {
@@ -1658,7 +1667,7 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
     const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
     process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
     ++c.sims;
-    const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
+    const u32 goal = c.gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
     if (c.T.depth >= goal) {
       ctx_store(E, g, c);
       retired = play_move(E, g);
@@ -1701,7 +1710,7 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
         const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
         process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
         ++c.sims;
-        const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
+        const u32 goal = c.gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
         if (c.T.depth >= goal) {
           ctx_store(E, g, c);
           retired = play_move(E, g);
@@ -1757,7 +1766,7 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, boo
         const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
         process_result(E, g, c.T, c.gs, c.rng, noise, pr);
         ++c.sims;
-        const u32 goal = c.gs.capped ? E.cap_visits[cp] : E.visits[cp];
+        const u32 goal = c.gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
         if (c.T.depth >= goal) {
           ctx_store(E, g, c);  // the path is empty here: process_result has just consumed it
           retired = play_move(E, g);

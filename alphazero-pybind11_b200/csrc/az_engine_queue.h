@@ -243,7 +243,7 @@ AZ_D u32 q_leaf(const EngineView& E, u32 g, QGame& q) {
       const bool noise = (E.epsilon > 0.0f) && !gs.capped;
       process_result(E, g, T, gs, gs.rng, noise, q.path);
       ++q.sims;
-      const u32 goal = gs.capped ? E.cap_visits[cp] : E.visits[cp];
+      const u32 goal = gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
       move = T.depth >= goal;
     } else {
       gs.initialized = 1;
@@ -289,7 +289,7 @@ AZ_D u32 q_boundary(const EngineView& E, u32 g, QGame& q) {
     const bool noise = (E.epsilon > 0.0f) && !gs.capped;
     process_result(E, g, T, gs, gs.rng, noise, q.path);
     ++q.sims;
-    const u32 goal = gs.capped ? E.cap_visits[cp] : E.visits[cp];
+    const u32 goal = gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
     move = T.depth >= goal;
   } else {
     gs.initialized = 1;

@@ -16,6 +16,7 @@
 
 namespace b2az {
 
+constexpr int kSpMaxPerms = 8;
 struct SpSlot {                       // b2az_tafl_selfplay_slot in include/b2az.h (same layout)
   u32 active;                         // the slot is still cycling (play_manager.cc:506-508)
   u32 games_started, games_completed;
@@ -70,7 +71,14 @@ struct SpView {
   u64* leaf_key;      // [n_games] (cache only): the waiting leaf's key
   SpSlot* slots;
   u32 n_games, games_per_slot, visits;  // visits: the largest search budget of any seat (launch sizing)
-  u32 seat_visits[2], seat_cap_visits[2];  // seat_visits_ / seat_cap_visits_ (play_manager.cc:70-90)
+  // seat permutations (play_manager.cc:46-90, 213-221): slot g plays permutation g % n_perms (the reference hands the
+  // permutations out round robin, i % num_perms at construction and games_started_ % num_perms afterwards: with
+  // n_games a multiple of n_perms and the slots finishing in order that is g % n_perms for every game of slot g)
+  u32 n_perms;
+  u32 seat_visits[kSpMaxPerms][2], seat_cap_visits[kSpMaxPerms][2];  // seat_visits_ / seat_cap_visits_ (play_manager.cc:70-90)
+  u8 perm_group[kSpMaxPerms][2];  // seat_perms_[perm][seat]: the model group that searches for the seat (play_manager.cc:577)
+  u32 random_groups;  // bit i: model group i is EvalType::RANDOM — its searches run dumb_eval inline (play_manager.cc:578-587)
+  u8* leaf_group;     // [n_games] model group of the slot's waiting leaf (several groups only)
   u32 playout_cap, fast_search_uses_gumbel;
   float playout_cap_percent, resign_percent, resign_playthrough_percent;
   float start_temp, final_temp, half_life;
@@ -104,16 +112,18 @@ __device__ __forceinline__ void sp_reset_search(const ForestView& F, u32 t) {
 // coin values differ (tests/test_tafl_selfplay.py).
 __device__ __forceinline__ bool sp_coin(SpSlot& G, float p) { return rng_uniform01(G.coin) < p; }
 // the search budget of the seat to move (play_manager.cc:284-285)
-__device__ __forceinline__ u32 sp_goal(const SpView& S, const SpSlot& G, u32 cp) {
-  return G.capped ? S.seat_cap_visits[cp] : S.seat_visits[cp];
+__device__ __forceinline__ u32 sp_perm(const SpView& S, u32 g) { return S.n_perms > 1u ? g % S.n_perms : 0u; }
+__device__ __forceinline__ u32 sp_goal(const SpView& S, const SpSlot& G, u32 g, u32 cp) {
+  const u32 p = sp_perm(S, g);
+  return G.capped ? S.seat_cap_visits[p][cp] : S.seat_visits[p][cp];
 }
 // MCTS::set_gumbel_num_sims on the tree of the seat to move — the full budget, or for a capped search the cap when
 // fast_search_uses_gumbel and 0 (= PUCT for this search) otherwise — then under tree reuse the root temperature and
 // fresh noise on a root that has been visited (play_manager.cc:523-553; also the first call of a run, 556-568)
 __device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, const SpSlot& G, u32 tn, u32 lane, bool reused_root) {
   if (lane == 0) {
-    const u32 cp = tn & 1u;
-    const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[cp] : 0u) : S.seat_visits[cp];
+    const u32 cp = tn & 1u, pm = sp_perm(S, tn >> 1);
+    const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[pm][cp] : 0u) : S.seat_visits[pm][cp];
     if (F.gum) { F.gum[tn].num_sims_target = target; fg_reset(F.gum[tn]); }
     if (reused_root) {
       ForestTree& R = F.trees[tn];
@@ -146,7 +156,8 @@ __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
     // game.initialized = true; the first playout-cap coin; set_gumbel_num_sims on the first seat's tree (play_manager.cc:556-568)
     G.capped = (S.playout_cap && sp_coin(G, S.playout_cap_percent)) ? 1u : 0u;
     const u32 cp0 = 0u, t0 = 2u * g + cp0;  // player 0 opens every game of this engine (attackers / Star Gambit's P0)
-    const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[cp0] : 0u) : S.seat_visits[cp0];
+    const u32 pm0 = sp_perm(S, g);
+    const u32 target = G.capped ? (S.fast_search_uses_gumbel ? S.seat_cap_visits[pm0][cp0] : 0u) : S.seat_visits[pm0][cp0];
     if (F.gum) { F.gum[t0].num_sims_target = target; fg_reset(F.gum[t0]); }
   }
 }
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_
     if (!S.slots[g].active) continue;
     const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
     const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;  // seat_epsilon > 0 && !capped
-    const u32 goal = sp_goal(S, S.slots[g], cp), have = F.trees[t].depth;
+    const u32 goal = sp_goal(S, S.slots[g], g, cp), have = F.trees[t].depth;
     const u32 todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;  // this slot's own budget
     for (u32 i = 0; i < todo; ++i) {
       forest_find_leaf<GAME, false>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr);
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(512, GAME == B2AZ_FOREST_SG ? 1 : 2) k_sp_sear
       const u32 cp = FGame<GAME>::root_player(F, 2u * g);
       t = 2u * g + cp;
       noise = F.epsilon > 0.0f && !S.slots[g].capped;
-      const u32 goal = sp_goal(S, S.slots[g], cp), have = F.trees[t].depth;
+      const u32 goal = sp_goal(S, S.slots[g], g, cp), have = F.trees[t].depth;
       todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;
     }
     for (u32 i = 0;; ++i) {
@@ -260,17 +271,36 @@ __global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, fl
     }
     const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
     float* row = canon + (size_t)g * FGame<GAME>::canon(F);
-    if (!S.cache.sets) {
+    // the model group that searches for this seat under the slot's seat permutation (play_manager.cc:577)
+    const u32 group = S.perm_group[sp_perm(S, g)][cp];
+    if (S.leaf_group && lane == 0) S.leaf_group[g] = (u8)group;
+    const bool random_group = ((S.random_groups >> group) & 1u) != 0;
+    if (!S.cache.sets && !random_group) {
       forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, row);
+      if (S.wait && lane == 0) S.wait[g] = 1;
+      continue;
+    }
+    if (random_group) {  // eval_types_[group] == RANDOM: dumb_eval inline, nothing for the evaluator (play_manager.cc:578-587)
+      const u32 goal = sp_goal(S, S.slots[g], g, cp), have = F.trees[t].depth;
+      const u32 todo = have < goal ? goal - have : 0u;
+      const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;
+      for (u32 i = 0; i < todo; ++i) {
+        forest_find_leaf<GAME, false>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr);
+        forest_process_result<GAME, true, false>(F, t, nullptr, nullptr, lane, noise, F.trees[t].leaf);
+      }
+      if (lane == 0) { S.slots[g].simulations += todo; S.wait[g] = 0; }
+      __syncwarp();
       continue;
     }
     const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;
-    const u32 goal = sp_goal(S, S.slots[g], cp);
+    const u32 goal = sp_goal(S, S.slots[g], g, cp);
     u32 pending = 0;
     for (u32 guard = 0; guard <= goal; ++guard) {
       if (F.trees[t].depth >= goal) break;  // the search is complete: k_sp_move plays the move
       u64 key = 0;
       forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, row, true, &key);
+      if (group) key ^= 0x9E3779B97F4A7C15ull;  // one table for both model groups (the reference keeps a cache per group)
+      if (key == 0ULL) key = 1ULL;
       const int e = sp_cache_lookup(S.cache, key, lane);
       if (e < 0) {
         pending = 1;
@@ -319,7 +349,7 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
     if (!G.active) continue;
     const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
     ForestTree& R = F.trees[t];
-    if (R.depth < sp_goal(S, G, cp)) continue;  // mcts.depth() >= goal_depth
+    if (R.depth < sp_goal(S, G, g, cp)) continue;  // mcts.depth() >= goal_depth
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
     const bool capped = G.capped != 0;
     // temperature schedule (play_manager.cc:285-302)
@@ -543,6 +573,7 @@ struct b2az_tafl_selfplay {
   std::vector<float> h_canon, h_v, h_pi;  // host staging of the reference-API flavour (leaf_batch_host / submit_eval_host)
   std::vector<b2az::SpSlot> h_slots;
   std::vector<uint32_t> h_tree_err, h_wait;
+  std::vector<uint8_t> h_group_all, h_group;  // model group per slot / per row of the last leaf_batch_host
 };
 
 extern "C" {
@@ -554,7 +585,7 @@ int b2az_tafl_selfplay_destroy(b2az_tafl_selfplay* sp) {
   dev_free(sp->view.scratch_pi); dev_free(sp->view.out_canon); dev_free(sp->view.out_v); dev_free(sp->view.out_pi);
   dev_free(sp->view.out_slot); dev_free(sp->view.out_count); dev_free(sp->active_dev);
   dev_free(sp->view.cache.keys); dev_free(sp->view.cache.freq); dev_free(sp->view.cache.stamp); dev_free(sp->view.cache.v); dev_free(sp->view.cache.pi);
-  dev_free(sp->view.cache.ctr); dev_free(sp->view.wait); dev_free(sp->view.leaf_key); dev_free(sp->view.variants);
+  dev_free(sp->view.cache.ctr); dev_free(sp->view.wait); dev_free(sp->view.leaf_key); dev_free(sp->view.leaf_group); dev_free(sp->view.variants);
   dev_free(sp->ev_v); dev_free(sp->ev_pi); dev_free(sp->leaf_canon);
   b2az_forest_destroy(sp->forest);
   delete sp;
@@ -568,6 +599,11 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   if (p->games_per_slot == 0 || (p->visits == 0 && (p->seat_visits[0] == 0 || p->seat_visits[1] == 0)))
     return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: games_per_slot and visits must be positive");
   if (p->forest.max_in_flight != 0) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: PlayManager runs one leaf per game (max_in_flight must be 0)");
+  if (p->n_seat_perms > (uint32_t)b2az::kSpMaxPerms) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: at most 8 seat permutations");
+  if (p->n_seat_perms > 1 && p->n_games % p->n_seat_perms != 0)
+    return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: n_games must be a multiple of the number of seat permutations (slot g plays permutation g % n)");
+  for (uint32_t pm = 0; pm < p->n_seat_perms; ++pm)
+    if (p->seat_perms[pm][0] > 1 || p->seat_perms[pm][1] > 1) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: a model group index must be 0 or 1");
   b2az_forest_params fp = p->forest;
   fp.n_trees = 2u * p->n_games;
   if (fp.words_per_tree == 0) {
@@ -575,7 +611,8 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
     // node is 1 + 8 k words. Budget 8 x visits nodes at a typical branching (Brandubh 64, 11x11 boards 200) per half —
     // a search that outgrows it is reported as B2AZ_ENOMEM by the calls that synchronise, never silently truncated.
     const uint64_t k_typ = p->forest.game == B2AZ_TAFL_BRANDUBH ? 64u : 200u;
-    const uint64_t vmax = std::max<uint64_t>(p->visits, std::max(p->seat_visits[0], p->seat_visits[1]));
+    uint64_t vmax = std::max<uint64_t>(p->visits, std::max(p->seat_visits[0], p->seat_visits[1]));
+    for (uint32_t pm = 0; pm < p->n_seat_perms; ++pm) vmax = std::max<uint64_t>(vmax, std::max(p->perm_seat_visits[pm][0], p->perm_seat_visits[pm][1]));
     const uint64_t want = 2ull * (1ull + 8ull * vmax * (1ull + 8ull * k_typ));
     fp.words_per_tree = (uint32_t)std::min<uint64_t>(want, 1ull << 26);
   }
@@ -590,11 +627,20 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   SpView& S = sp->view;
   memset(&S, 0, sizeof(S));
   S.n_games = p->n_games; S.games_per_slot = p->games_per_slot;
-  for (int seat = 0; seat < 2; ++seat) {
-    S.seat_visits[seat] = p->seat_visits[seat] ? p->seat_visits[seat] : p->visits;
-    S.seat_cap_visits[seat] = p->seat_cap_visits[seat] ? p->seat_cap_visits[seat] : (p->playout_cap_depth ? p->playout_cap_depth : 25u);
-  }
-  S.visits = std::max(std::max(S.seat_visits[0], S.seat_visits[1]), std::max(S.seat_cap_visits[0], S.seat_cap_visits[1]));
+  S.n_perms = std::max(1u, p->n_seat_perms);
+  S.visits = 0;
+  bool several_groups = false;
+  for (uint32_t pm = 0; pm < S.n_perms; ++pm)
+    for (int seat = 0; seat < 2; ++seat) {
+      const uint32_t sv = p->perm_seat_visits[pm][seat] ? p->perm_seat_visits[pm][seat] : p->seat_visits[seat];
+      const uint32_t cv = p->perm_seat_cap_visits[pm][seat] ? p->perm_seat_cap_visits[pm][seat] : p->seat_cap_visits[seat];
+      S.seat_visits[pm][seat] = sv ? sv : p->visits;
+      S.seat_cap_visits[pm][seat] = cv ? cv : (p->playout_cap_depth ? p->playout_cap_depth : 25u);
+      S.visits = std::max(S.visits, std::max(S.seat_visits[pm][seat], S.seat_cap_visits[pm][seat]));
+      S.perm_group[pm][seat] = p->n_seat_perms ? p->seat_perms[pm][seat] : 0;
+      several_groups |= S.perm_group[pm][seat] != 0;
+    }
+  S.random_groups = (p->group_random[0] ? 1u : 0u) | (p->group_random[1] ? 2u : 0u);
   S.playout_cap = p->playout_cap_randomization ? 1u : 0u;
   S.fast_search_uses_gumbel = p->fast_search_uses_gumbel ? 1u : 0u;
   S.playout_cap_percent = p->playout_cap_percent;
@@ -632,9 +678,14 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
     if (int rc = dev_alloc_raw(&S.cache.v, E * 3)) return bail(rc);
     if (int rc = dev_alloc_raw(&S.cache.pi, E * A)) return bail(rc);
     if (int rc = dev_alloc(&S.cache.ctr, 4)) return bail(rc);
-    if (int rc = dev_alloc(&S.wait, G)) return bail(rc);
     if (int rc = dev_alloc(&S.leaf_key, G)) return bail(rc);
   }
+  // wait[g]: the slot's leaf waits for the evaluator (cache: its leaves may all have hit; an EvalType::RANDOM group next
+  // to an NN one: its searches never wait)
+  if (S.cache.sets || S.random_groups)
+    if (int rc = dev_alloc(&S.wait, G)) return bail(rc);
+  if (several_groups)
+    if (int rc = dev_alloc(&S.leaf_group, G)) return bail(rc);
   if (fp.game >= 20u)
     if (int rc = dev_alloc(&S.variants, G * 4)) return bail(rc);
   if (int rc = dev_alloc(&S.out_count, 1)) return bail(rc);
@@ -662,6 +713,8 @@ int b2az_tafl_selfplay_get_stats(b2az_tafl_selfplay*, void*, b2az_stats*) FOREST
 int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay*, void*, uint32_t, float*, uint32_t*, uint32_t*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay*, void*, const uint32_t*, const float*, const float*, uint32_t) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_variant_stats(b2az_tafl_selfplay*, void*, b2az_variant_stats*) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_leaf_groups_host(b2az_tafl_selfplay*, uint8_t*, uint32_t) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_perm_stats(b2az_tafl_selfplay*, void*, b2az_perm_stats*, uint32_t*) FOREST_NO_CUDA()
 #else
 #define SP_CTAS(sp) std::max(1u, std::min(((sp)->view.n_games + 3u) / 4u, 148u * 8u))
 static int sp_active(b2az_tafl_selfplay* sp, cudaStream_t s, uint32_t* active_out) {
@@ -868,6 +921,11 @@ int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay* sp, void* stream, uin
     sp->h_wait.resize(G);
     CUDA_TRY(cudaMemcpyAsync(sp->h_wait.data(), sp->view.wait, (size_t)G * 4, cudaMemcpyDeviceToHost, s));
   }
+  sp->h_group.clear();
+  if (sp->view.leaf_group) {
+    sp->h_group_all.resize(G);
+    CUDA_TRY(cudaMemcpyAsync(sp->h_group_all.data(), sp->view.leaf_group, (size_t)G, cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   uint32_t n = 0;
   for (uint32_t g = 0; g < G; ++g) {
@@ -875,6 +933,7 @@ int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay* sp, void* stream, uin
     if (sp->view.wait && !sp->h_wait[g]) continue;  // (cache) its leaves hit: nothing for the evaluator
     if (n >= max_rows) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_leaf_batch_host: more active slots than max_rows");
     memcpy(canon_host + (size_t)n * C, sp->h_canon.data() + (size_t)g * C, C * 4);
+    sp->h_group.push_back(sp->view.leaf_group ? sp->h_group_all[g] : (uint8_t)0);
     ids_host[n++] = g;
   }
   *n_out = n;
@@ -896,6 +955,43 @@ int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay* sp, void* stream, co
     memcpy(&sp->h_pi[(size_t)ids[i] * A], pi + (size_t)i * A, A * 4);
   }
   return b2az_tafl_selfplay_process_result(sp, stream, sp->h_v.data(), sp->h_pi.data(), 1, nullptr);
+}
+int b2az_tafl_selfplay_leaf_groups_host(b2az_tafl_selfplay* sp, uint8_t* groups_host, uint32_t n) {
+  using namespace b2az;
+  if (!sp || (n && !groups_host)) return fail(B2AZ_EINVAL, "null argument");
+  if (n > sp->h_group.size()) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_leaf_groups_host: more rows than the last leaf batch had");
+  if (n) memcpy(groups_host, sp->h_group.data(), n);
+  return 0;
+}
+// perm_scores_ / variant_perm_scores_ (play_manager.cc:205-255, 466-474): slot g plays permutation g % n_perms
+int b2az_tafl_selfplay_perm_stats(b2az_tafl_selfplay* sp, void* stream, b2az_perm_stats* out8, uint32_t* n_perms_out) {
+  using namespace b2az;
+  if (!sp || !out8) return fail(B2AZ_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(sp->forest->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t G = sp->view.n_games, P = sp->view.n_perms;
+  memset(out8, 0, P * sizeof(b2az_perm_stats));
+  sp->h_slots.resize(G);
+  CUDA_TRY(cudaMemcpyAsync(sp->h_slots.data(), sp->view.slots, (size_t)G * sizeof(SpSlot), cudaMemcpyDeviceToHost, s));
+  std::vector<SpVariantAcc> hv;
+  if (sp->view.variants) {
+    hv.resize((size_t)G * 4u);
+    CUDA_TRY(cudaMemcpyAsync(hv.data(), sp->view.variants, hv.size() * sizeof(SpVariantAcc), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (uint32_t g = 0; g < G; ++g) {
+    b2az_perm_stats& o = out8[g % P];
+    for (int i = 0; i < 3; ++i) o.scores[i] += sp->h_slots[g].scores[i];
+    o.games_completed += sp->h_slots[g].games_completed;
+    if (!hv.empty())
+      for (uint32_t v = 0; v < 4u; ++v) {
+        const SpVariantAcc& a = hv[(size_t)g * 4u + v];
+        for (int i = 0; i < 3; ++i) o.variant_scores[v][i] += a.scores[i];
+        o.variant_games_completed[v] += a.games_completed;
+      }
+  }
+  if (n_perms_out) *n_perms_out = P;
+  return 0;
 }
 int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host) {
   using namespace b2az;

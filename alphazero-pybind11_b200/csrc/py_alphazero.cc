@@ -310,7 +310,7 @@ inline void fold_supported_seats(PlayParams& P, const SeatTables& N, const char*
     if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + engine + " yet");
   };
   reject(N.num_model_groups > max_groups, "this many model groups (model_groups / seat_perms with different networks)");
-  reject(N.seat_perms.size() != 1, "more than one seat permutation");
+  reject(N.seat_perms.size() > 8, "more than eight seat permutations");
   reject(!uniform2d(N.epsilon) || !uniform2d(N.root_temp) || !uniform2d(N.root_fpu_zero), "different seat_epsilon / seat_mcts_root_temp / seat_root_fpu_zero per seat");
   reject(!uniform2d(N.gumbel_enabled) || !uniform2d(N.gumbel_m) || !uniform2d(N.gumbel_c_visit) || !uniform2d(N.gumbel_c_scale) ||
              !uniform2d(N.gumbel_full), "different Gumbel settings per seat");
@@ -324,6 +324,43 @@ inline void fold_supported_seats(PlayParams& P, const SeatTables& N, const char*
   P.gumbel_c_visit = N.gumbel_c_visit[0][0];
   P.gumbel_c_scale = N.gumbel_c_scale[0][0];
   P.gumbel_full = N.gumbel_full[0][0] != 0;
+}
+
+// eval_types_[group] (play_manager.cc:577-587): all RANDOM -> the fused on-device evaluator; all NN -> the leaf batch; a
+// RANDOM group next to an NN one (game_runner.play_past against iteration 0: RandPlayer) -> group_random of the engine.
+struct EvalPlan {
+  bool all_random = false;
+  uint8_t group_random[2] = {0, 0};
+};
+inline EvalPlan plan_eval(const PlayParams& P, const SeatTables& N, const char* who) {
+  EvalPlan e;
+  if (P.eval_type.empty()) return e;
+  uint32_t n_random = 0, n_used = 0;
+  for (uint32_t g = 0; g < N.num_model_groups; ++g) {
+    bool used = false;
+    for (auto& perm : N.seat_perms)
+      for (auto x : perm) used |= x == g;
+    if (!used) continue;
+    ++n_used;
+    const EvalType et = g < P.eval_type.size() ? P.eval_type[g] : EvalType::NN;
+    if (et == EvalType::PLAYOUT) throw std::runtime_error(std::string("EvalType.PLAYOUT is not implemented by the ") + who + " yet");
+    if (et == EvalType::RANDOM) { ++n_random; if (g < 2) e.group_random[g] = 1; }
+  }
+  if (n_random == n_used) { e.all_random = true; e.group_random[0] = e.group_random[1] = 0; }
+  return e;
+}
+// PlayParams::seat_perms and the per-permutation budgets into a b2az_params / b2az_tafl_selfplay_params
+template <class CP>
+inline void fill_perms(CP& cp, const SeatTables& N, const EvalPlan& ev) {
+  cp.n_seat_perms = (uint32_t)N.seat_perms.size();
+  for (size_t i = 0; i < N.seat_perms.size(); ++i)
+    for (int s = 0; s < 2; ++s) {
+      cp.seat_perms[i][s] = N.seat_perms[i][s];
+      cp.perm_seat_visits[i][s] = N.visits[i][s];
+      cp.perm_seat_cap_visits[i][s] = N.cap_visits[i][s];
+    }
+  cp.group_random[0] = ev.group_random[0];
+  cp.group_random[1] = ev.group_random[1];
 }
 
 // ------------------------------------------------------------------------------------ DLPack (dlpack.h v0.8 ABI, restated)
@@ -418,27 +455,23 @@ class PlayManager {
                   const char* who) {
     tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
     PlayParams eff = params_;
-    fold_supported_seats(eff, tables_, who, 1);
+    fold_supported_seats(eff, tables_, who, 2);
     const PlayParams& P = eff;
     auto reject = [who](bool bad, const char* what) {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + who + " yet");
     };
     reject(!P.temp_decay_half_life_by_variant.empty() && game < 20, "temp_decay_half_life_by_variant");
     reject(P.concurrent_games == 0 || P.games_to_play % P.concurrent_games != 0, "games_to_play not a multiple of concurrent_games");
-    EvalType et = EvalType::NN;
-    if (!P.eval_type.empty()) {
-      et = P.eval_type[0];
-      for (auto e : P.eval_type) reject(e != et, "mixed eval_type");
-      reject(et == EvalType::PLAYOUT, "EvalType.PLAYOUT");
-    }
-    random_eval_ = (et == EvalType::RANDOM);
+    const EvalPlan ev = plan_eval(P, tables_, who);
+    random_eval_ = ev.all_random;
     b2az_tafl_selfplay_params sp{};
+    fill_perms(sp, tables_, ev);
     sp.forest.game = game;
     sp.forest.max_turns = rows;
     sp.forest.relative_values = relative_values;
     // slab per tree: each half holds the kept subtree + one move's new nodes (1 + 8k words per expanded node)
     sp.forest.words_per_tree = P.pool_nodes ? (uint32_t)P.pool_nodes
-                                            : 2u * (1u + 4u * std::max(tables_.visits[0][0], tables_.visits[0][1]) * (1u + 8u * k_typ));
+                                            : 2u * (1u + 4u * max_seat_visits() * (1u + 8u * k_typ));
     sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
     sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
     sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
@@ -447,7 +480,7 @@ class PlayManager {
     sp.forest.shaped_dirichlet = P.shaped_dirichlet;
     sp.n_games = P.concurrent_games;
     sp.games_per_slot = P.games_to_play / P.concurrent_games;
-    sp.visits = std::max(tables_.visits[0][0], tables_.visits[0][1]);
+    sp.visits = max_seat_visits();
     sp.seat_visits[0] = tables_.visits[0][0]; sp.seat_visits[1] = tables_.visits[0][1];
     sp.seat_cap_visits[0] = tables_.cap_visits[0][0]; sp.seat_cap_visits[1] = tables_.cap_visits[0][1];
     sp.playout_cap_randomization = P.playout_cap_randomization; sp.playout_cap_depth = P.playout_cap_depth;
@@ -494,6 +527,11 @@ class PlayManager {
                "B200 Star Gambit engine");
     return true;
   }
+  uint32_t max_seat_visits() const {
+    uint32_t m = 1;
+    for (auto& row : tables_.visits) for (auto x : row) m = std::max(m, x);
+    return m;
+  }
   void size_buffers() {
     G_ = params_.concurrent_games;
     canon_.resize((size_t)G_ * canon_sz_);
@@ -524,15 +562,11 @@ class PlayManager {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
     };
     reject(!P.temp_decay_half_life_by_variant.empty(), "temp_decay_half_life_by_variant");
-    EvalType et = EvalType::NN;
-    if (!P.eval_type.empty()) {
-      et = P.eval_type[0];
-      for (auto e : P.eval_type) reject(e != et, "mixed eval_type");
-      reject(et == EvalType::PLAYOUT, "EvalType.PLAYOUT");
-    }
-    random_eval_ = (et == EvalType::RANDOM);
+    const EvalPlan ev = plan_eval(P, tables_, "B200 engine");
+    random_eval_ = ev.all_random;
     b2az_params bp;
     b2az_params_default(&bp);
+    fill_perms(bp, tables_, ev);
     bp.games_to_play = P.games_to_play;
     bp.concurrent_games = P.concurrent_games;
     bp.max_batch_size = P.max_batch_size;
@@ -791,6 +825,13 @@ class PlayManager {
     dl_rows_ = 0;
     refresh_stats_unlocked_api();
   }
+  b2az_perm_stats perm(size_t i) {
+    if (i >= tables_.seat_perms.size()) throw std::out_of_range("seat permutation out of range");
+    b2az_perm_stats out[8];
+    std::lock_guard<std::mutex> lk(api_);
+    if ((tsp_ ? b2az_tafl_selfplay_perm_stats(tsp_, nullptr, out, nullptr) : b2az_perm_scores(eng_, nullptr, out, nullptr)) != 0) throw_last("perm stats");
+    return out[i];
+  }
   int num_tracked_variants() const { return has_variants_ ? 4 : 0; }
   b2az_variant_stats variant(int v) {
     if (!has_variants_) throw std::out_of_range("this game has no variants");
@@ -870,7 +911,7 @@ class PlayManager {
     std::fill(group_next_.begin(), group_next_.end(), 0u);
     for (uint32_t r = 0; r < n; ++r) {
       row_of_game_[ids_[r]] = r;
-      group_rows_[tables_.num_model_groups > 1 ? tables_.seat_perms[0][seats_[r]] : 0].push_back(r);
+      group_rows_[tables_.num_model_groups > 1 ? std::min<uint32_t>(seats_[r], tables_.num_model_groups - 1u) : 0].push_back(r);
     }
     answered_ = 0;
     leaf_count_ = n;
@@ -940,11 +981,14 @@ class PlayManager {
         std::lock_guard<std::mutex> lk(api_);
         if (b2az_step(eng_, 1, nullptr) != 0) throw_last("play");
         if (b2az_leaf_batch_host(eng_, nullptr, G_, canon_.data(), ids_.data(), &n) != 0) throw_last("play");
-        if (tables_.num_model_groups > 1 && n > 0 && b2az_leaf_seats_host(eng_, nullptr, seats_.data(), n) != 0) throw_last("play");
+        if (tables_.num_model_groups > 1 && n > 0 && b2az_leaf_groups_host(eng_, nullptr, seats_.data(), n) != 0) throw_last("play");
       }
       std::unique_lock<std::mutex> lk(mu_);
       refresh_stats_locked();
-      if (n == 0) return;  // every slot retired
+      if (n == 0) {
+        if (stats_.active_games == 0) return;  // every slot retired
+        continue;  // only searches of an EvalType::RANDOM group are under way: nothing for the evaluators this generation
+      }
       publish_locked(n);
       cv_.notify_all();
       cv_.wait(lk, [&] { return answered_ == leaf_count_ || stopped_.load(); });
@@ -975,7 +1019,7 @@ class PlayManager {
   std::atomic<uint32_t> games_completed_{0}, hist_count_{0};
   std::vector<float> canon_, v_, pi_;
   std::vector<uint32_t> ids_, row_of_game_;
-  std::vector<uint8_t> seats_;                    // searching seat of every row (several model groups only)
+  std::vector<uint8_t> seats_;                    // model group of every row (several model groups only)
   std::vector<std::vector<uint32_t>> group_rows_; // rows of the published batch per model group, FIFO
   std::vector<uint32_t> group_next_;              // per group: rows already handed out
   uint32_t leaf_count_ = 0, answered_ = 0;
@@ -1170,15 +1214,8 @@ PYBIND11_MODULE(alphazero, m) {
            })
       .def("num_model_groups", &PlayManager::num_model_groups)
       .def("num_seat_perms", &PlayManager::num_seat_perms)
-      .def("perm_scores", [](PlayManager& pm, size_t i) {
-        if (i >= pm.num_seat_perms()) throw std::out_of_range("perm index");
-        auto s = pm.stats();
-        return vec3(s.scores);
-      })
-      .def("perm_games_completed", [](PlayManager& pm, size_t i) {
-        if (i >= pm.num_seat_perms()) throw std::out_of_range("perm index");
-        return pm.games_completed();
-      })
+      .def("perm_scores", [](PlayManager& pm, size_t i) { return vec3(pm.perm(i).scores); })
+      .def("perm_games_completed", [](PlayManager& pm, size_t i) { return pm.perm(i).games_completed; })
       // per-variant tracking (play_manager.h:218-275): games with variants (StarGambitUnifiedGS) only
       .def("num_tracked_variants", &PlayManager::num_tracked_variants)
 #define VAR_F(name, expr) .def(name, [](PlayManager& pm, int v) -> float { const b2az_variant_stats m = pm.variant(v); return expr; })
@@ -1192,13 +1229,13 @@ PYBIND11_MODULE(alphazero, m) {
 #undef VAR_F
       .def("variant_games_completed", [](PlayManager& pm, int v) { return pm.variant(v).games_completed; })
       .def("variant_scores", [](PlayManager& pm, int v) { return vec3(pm.variant(v).scores); })
-      .def("variant_perm_scores", [](PlayManager& pm, int v, int p) {  // one seat permutation on this engine
-        if (p != 0) throw std::out_of_range("seat permutation out of range");
-        return vec3(pm.variant(v).scores);
+      .def("variant_perm_scores", [](PlayManager& pm, int v, int p) {
+        if (v < 0 || v >= pm.num_tracked_variants()) throw std::out_of_range("variant out of range");
+        return vec3(pm.perm((size_t)p).variant_scores[v]);
       })
       .def("variant_perm_games_completed", [](PlayManager& pm, int v, int p) {
-        if (p != 0) throw std::out_of_range("seat permutation out of range");
-        return pm.variant(v).games_completed;
+        if (v < 0 || v >= pm.num_tracked_variants()) throw std::out_of_range("variant out of range");
+        return pm.perm((size_t)p).variant_games_completed[v];
       })
       .def("set_eager", &PlayManager::set_eager)
       .def("leaf_batch_dlpack", &PlayManager::leaf_batch_dlpack, py::arg("group") = 0)

@@ -49,8 +49,8 @@ extern "C" {
 
 /* Mirrors PlayParams (play_manager.h:60-154) for the Connect4 engine, plus engine sizing. Fields keep the
  * reference's names and meaning: PUCT and Gumbel search (incl. gumbel_full), playout-cap randomisation, resignation,
- * per-seat visit budgets and two model groups are carried. Not carried: the other per-seat 2-D overrides (the host
- * side folds them when they are uniform), seat permutations, playout eval. b2az_create rejects a non-default value
+ * per-seat visit budgets, two model groups and seat permutations are carried. Not carried: the other per-seat 2-D
+ * overrides (the host side folds them when they are uniform), playout eval. b2az_create rejects a non-default value
  * for anything it does not implement instead of ignoring it. */
 typedef struct b2az_params {
   uint32_t game;                 /* B2AZ_GAME_* */
@@ -100,7 +100,28 @@ typedef struct b2az_params {
                                     position cache keeps the groups apart, b2az_leaf_seats_host tells which seat searches */
   uint32_t step_kernel;          /* B2AZ_STEP_*: which fused step kernel runs B2AZ_RNG_PER_GAME (results do not depend on it) */
   uint32_t seat_cap_visits[2];   /* per-seat fast-search budget (seat_cap_visits, play_manager.cc:82-90); 0 = playout_cap_depth */
+  /* Seat permutations (PlayParams::seat_perms, play_manager.cc:46-90, 213-221; what game_runner.play_past and
+   * tournament.py build): seat_perms[p][seat] = the model group (0 or 1) that searches for `seat` in the games of
+   * permutation p. Slot g plays permutation g % n_seat_perms in every one of its games (the reference's round-robin
+   * hand-out when the slots finish in order), so concurrent_games must be a multiple of n_seat_perms.
+   * 0 = one seating given by model_groups. */
+  uint32_t n_seat_perms;         /* <= 8 */
+  uint8_t seat_perms[8][2];
+  uint32_t perm_seat_visits[8][2];      /* seat_visits_[p][seat] (play_manager.cc:70-80); 0 = mcts_visits[seat] */
+  uint32_t perm_seat_cap_visits[8][2];  /* seat_cap_visits_[p][seat] (:82-90); 0 = seat_cap_visits[seat] */
+  uint8_t group_random[2];       /* eval_type NN only: model group i is EvalType::RANDOM (eval_types_[group],
+                                    play_manager.cc:578-587): its searches run dumb_eval on the device and never
+                                    show up in the leaf batch */
+  uint8_t pad5_[2];
 } b2az_params;
+
+/* PlayManager's per-permutation tables (perm_scores_, variant_perm_scores_: play_manager.cc:205-255, 466-474). */
+typedef struct b2az_perm_stats {
+  float scores[3];
+  uint32_t games_completed;
+  float variant_scores[4][3];    /* games with variants (StarGambitUnifiedGS) */
+  uint32_t variant_games_completed[4];
+} b2az_perm_stats;
 
 /* Counters and metrics of PlayManager (play_manager.h:173-366). */
 typedef struct b2az_stats {
@@ -184,6 +205,10 @@ int b2az_cache_find_host(b2az_engine* e, void* stream, const uint64_t* keys_host
  * move is in its canonical planes). A PlayManager with several model groups routes row r to the network of group
  * model_groups[seat[r]] (play_manager.cc:577, 598: awaiting_inference_[game.seat_perm[cp]]). */
 int b2az_leaf_seats_host(b2az_engine* e, void* stream, uint8_t* seats_host, uint32_t count);
+/* The MODEL GROUP of the same rows: seat_perms[slot's permutation][searching seat] (play_manager.cc:577). */
+int b2az_leaf_groups_host(b2az_engine* e, void* stream, uint8_t* groups_host, uint32_t count);
+/* perm_scores(p) / perm_games_completed(p) for p < n_seat_perms (one entry without permutations): out8[p]. */
+int b2az_perm_scores(b2az_engine* e, void* stream, b2az_perm_stats* out8, uint32_t* n_perms_out);
 
 /* update_inferences (play_manager.cc:619-642), zero-copy flavour: v_dev float32[count][3],
  * pi_dev float32[count][7] in leaf-batch row order, count == the leaf count. The buffers are
@@ -453,6 +478,19 @@ typedef struct b2az_tafl_selfplay_params {
   float variant_probs[4];        /* game B2AZ_SG_UNIFIED_MIX: StarGambitUnifiedGS's variant weights (all 0 = 0.25 each) */
   uint32_t cache_entries;        /* PlayParams::max_cache_size: entries of the device position cache (EvalType::NN form:
                                     a slot keeps simulating while its leaves hit, play_manager.cc:589-594); 0 = no cache */
+  /* Seat permutations and model groups (PlayParams::seat_perms / model_groups, play_manager.cc:24-90, 213-221; what
+   * game_runner.play_past and tournament.py build): seat_perms[p][seat] = the model group (0 or 1) that searches for
+   * `seat` in the games of permutation p. Slot g plays permutation g % n_seat_perms in every one of its games (the
+   * reference's round-robin hand-out when the slots finish in order), so n_games must be a multiple of n_seat_perms.
+   * 0 = one seating, one model group. One position-cache table serves both groups (the group is part of the key). */
+  uint32_t n_seat_perms;         /* <= 8 */
+  uint8_t seat_perms[8][2];
+  uint32_t perm_seat_visits[8][2];      /* seat_visits_[p][seat] (play_manager.cc:70-80); 0 = seat_visits[seat] */
+  uint32_t perm_seat_cap_visits[8][2];  /* seat_cap_visits_[p][seat] (:82-90); 0 = seat_cap_visits[seat] */
+  uint8_t group_random[2];       /* model group i is EvalType::RANDOM next to an NN group (eval_types_[group],
+                                    play_manager.cc:578-587): its searches run dumb_eval on the device and never
+                                    show up in the leaf batch */
+  uint8_t pad4_[2];
 } b2az_tafl_selfplay_params;
 typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
   uint32_t active, games_started, games_completed, pending;
@@ -506,6 +544,13 @@ int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay* sp, void* stream, uin
                                        uint32_t* ids_host, uint32_t* n_out);
 int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay* sp, void* stream, const uint32_t* ids, const float* v, const float* pi,
                                         uint32_t n);
+/* The model group of every row of the last b2az_tafl_selfplay_leaf_batch_host (row i = slot ids[i]): the group that
+ * searches for the slot's side to move under the slot's seat permutation (awaiting_inference_[game.seat_perm[cp]],
+ * play_manager.cc:577, 598). All 0 with one model group. */
+int b2az_tafl_selfplay_leaf_groups_host(b2az_tafl_selfplay* sp, uint8_t* groups_host, uint32_t n);
+/* PlayManager's per-permutation tables (perm_scores_, variant_perm_scores_: play_manager.cc:205-255, 466-474): out[p] for
+ * p < n_seat_perms (one entry when there are no permutations). */
+int b2az_tafl_selfplay_perm_stats(b2az_tafl_selfplay* sp, void* stream, b2az_perm_stats* out8, uint32_t* n_perms_out);
 /* slots_host[n_games]; tree_errors_host[2 * n_games] = the trees' sticky error bits (see b2az_forest_counts). */
 int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host);
 

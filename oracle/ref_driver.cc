@@ -221,6 +221,13 @@ struct AzRefPlayCfg {
   uint8_t pad_;
   float resign_percent;
   float resign_playthrough_percent;
+  // model groups / seat permutations (play_manager.h:117-120): used when has_groups != 0
+  uint8_t has_groups;
+  uint8_t model_groups[2];
+  uint8_t n_seat_perms;
+  uint8_t seat_perms[8][2];
+  uint8_t group_eval[2];  // EvalType per model group when has_groups (eval_types_[group], play_manager.cc:578)
+  uint8_t pad2_[2];
 };
 
 struct RefPM {
@@ -265,6 +272,12 @@ static PlayParams to_params(const AzRefPlayCfg& c) {
   p.resign_percent = c.resign_percent;
   p.resign_playthrough_percent = c.resign_playthrough_percent;
   if (c.eval_type != 0) p.eval_type = {static_cast<EvalType>(c.eval_type), static_cast<EvalType>(c.eval_type)};
+  if (c.has_groups) {
+    p.model_groups = {c.model_groups[0], c.model_groups[1]};
+    p.seat_perms.clear();
+    for (uint8_t i = 0; i < c.n_seat_perms; ++i) p.seat_perms.push_back({c.seat_perms[i][0], c.seat_perms[i][1]});
+    p.eval_type = {static_cast<EvalType>(c.group_eval[0]), static_cast<EvalType>(c.group_eval[1])};
+  }
   return p;
 }
 
@@ -277,6 +290,14 @@ void* azref_pm_new_connect4(const AzRefPlayCfg* c) {
     out = r;
   });
   return rc == 0 ? out : nullptr;
+}
+// perm_scores(p) -> s3, returns perm_games_completed(p) (play_manager.h:211-217)
+uint32_t azref_pm_perm_scores(void* h, uint32_t perm, float* s3) {
+  auto* r = static_cast<RefPM*>(h);
+  if (perm >= r->pm->num_seat_perms()) return 0xFFFFFFFFu;
+  const auto& sc = r->pm->perm_scores(perm);
+  for (int i = 0; i < 3; ++i) s3[i] = sc(i);
+  return r->pm->perm_games_completed(perm);
 }
 void azref_pm_free(void* h) {
   auto* r = static_cast<RefPM*>(h);

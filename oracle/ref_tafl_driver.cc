@@ -446,6 +446,10 @@ struct AzRefTaflSpCfg {
   uint32_t playout_cap_depth;
   float playout_cap_percent, resign_percent, resign_playthrough_percent;
   uint8_t playout_cap_randomization, fast_search_uses_gumbel, pad2_[2];
+  // two model groups under ONE seat permutation (model_groups = {0, 1}, seat_perms = {seat_perm}, mcts_visits = group_visits:
+  // seat_visits_[0][s] = mcts_visits_[seat_perm[s]], play_manager.cc:70-80) when has_perm != 0
+  uint8_t has_perm, seat_perm[2], pad3_;
+  uint32_t group_visits[2];
 };
 int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRefTaflSpCfg* c, uint32_t hist_cap,
                         float* canon_out, float* v_out, float* pi_out, uint32_t* n_hist, float* scores3,
@@ -487,6 +491,11 @@ int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRef
     if (c->seat_visits[0] && c->seat_visits[1]) p.seat_visits = {{c->seat_visits[0], c->seat_visits[1]}};
     if (c->seat_cap_visits[0] && c->seat_cap_visits[1]) p.seat_cap_visits = {{c->seat_cap_visits[0], c->seat_cap_visits[1]}};
     p.eval_type = {EvalType::RANDOM, EvalType::RANDOM};
+    if (c->has_perm) {
+      p.model_groups = {0, 1};
+      p.mcts_visits = {c->group_visits[0], c->group_visits[1]};
+      p.seat_perms = {{c->seat_perm[0], c->seat_perm[1]}};
+    }
     PlayManager pm{std::move(gs), p};
     MCTS::seed_thread_rng(seed);
     pm.play();
@@ -502,9 +511,9 @@ int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRef
       ++n;
     }
     *n_hist = n;
-    auto sc = pm.scores();
+    auto sc = c->has_perm ? pm.perm_scores(0) : pm.scores();
     for (int i = 0; i < 3; ++i) scores3[i] = sc(i);
-    *games_completed = pm.games_completed();
+    *games_completed = c->has_perm ? pm.perm_games_completed(0) : pm.games_completed();
     metrics4[0] = pm.avg_game_length();
     metrics4[1] = pm.avg_leaf_depth();
     metrics4[2] = pm.avg_valid_moves();

@@ -25,6 +25,8 @@ class PlayCfg(C.Structure):
         ("gumbel_c_visit", C.c_float), ("gumbel_c_scale", C.c_float), ("gumbel_full", C.c_uint8),
         ("fast_search_uses_gumbel", C.c_uint8), ("eval_type", C.c_uint8), ("pad_", C.c_uint8),
         ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
+        ("has_groups", C.c_uint8), ("model_groups", C.c_uint8 * 2), ("n_seat_perms", C.c_uint8),
+        ("seat_perms", (C.c_uint8 * 2) * 8), ("group_eval", C.c_uint8 * 2), ("pad2_", C.c_uint8 * 2),
     ]
 
 
@@ -105,6 +107,8 @@ def lib():
             getattr(L, name).restype = u32
         for name in ("azref_pm_scores", "azref_pm_resign_scores", "azref_pm_metrics", "azref_pm_cache_stats"):
             getattr(L, name).argtypes = [vp, vp]
+        L.azref_pm_perm_scores.argtypes = [vp, u32, vp]
+        L.azref_pm_perm_scores.restype = u32
         L.azref_pm_progress_sims.argtypes = [vp, u32]
         L.azref_pm_progress_sims.restype = C.c_double
         L.azref_pm_game_state_bytes.argtypes = [vp, u32, vp]
@@ -199,6 +203,13 @@ class RefPlayManager:
         pi = np.empty((max_rows, 7), np.float32)
         n = self.L.azref_pm_drain_history(self.h, max_rows, P(canon), P(v), P(pi))
         return canon[:n], v[:n], pi[:n]
+
+    def perm_scores(self, perm):
+        """(perm_scores(perm) float32[3], perm_games_completed(perm))"""
+        s = np.zeros(3, np.float32)
+        n = self.L.azref_pm_perm_scores(self.h, perm, P(s))
+        assert n != 0xFFFFFFFF, "perm out of range"
+        return s, n
 
     def scores(self):
         s = np.zeros(3, np.float32)

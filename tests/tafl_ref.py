@@ -42,14 +42,16 @@ class SelfplayCfg(C.Structure):  # AzRefTaflSpCfg (oracle/ref_tafl_driver.cc)
                 ("history_enabled", C.c_uint8), ("pad_", C.c_uint8 * 2), ("seat_visits", C.c_uint32 * 2),
                 ("seat_cap_visits", C.c_uint32 * 2), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
                 ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
-                ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2)]
+                ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2),
+                ("has_perm", C.c_uint8), ("seat_perm", C.c_uint8 * 2), ("pad3_", C.c_uint8), ("group_visits", C.c_uint32 * 2)]
 
 
 def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, epsilon=0.0,
              root_policy_temp=1.0, shaped_dirichlet=False, policy_target_pruning=False, gumbel_m=0, gumbel_c_visit=50.0,
              gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0, tree_reuse=True,
              seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
-             playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0):
+             playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
+             seat_perm=None, group_visits=None):
     """The unmodified PlayManager, one slot, games_to_play games one after the other (EvalType::RANDOM) after
     MCTS::seed_thread_rng(seed). Returns dict(canonical, v, pi in history_ order, scores, games_completed,
     avg_game_length, avg_leaf_depth, avg_valid_moves, avg_search_entropy)."""
@@ -68,6 +70,10 @@ def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduc
     for seat in range(2):
         cfg.seat_visits[seat] = (seat_visits or (0, 0))[seat]
         cfg.seat_cap_visits[seat] = (seat_cap_visits or (0, 0))[seat]
+    if seat_perm is not None:  # model_groups = [0, 1], seat_perms = [seat_perm], mcts_visits = group_visits (per group)
+        cfg.has_perm = 1
+        cfg.seat_perm[0], cfg.seat_perm[1] = seat_perm
+        cfg.group_visits[0], cfg.group_visits[1] = group_visits
     canon = np.zeros((cap, P, S, S), np.float32)
     v, pi = np.zeros((cap, 3), np.float32), np.zeros((cap, A), np.float32)
     n, done = C.c_uint32(0), C.c_uint32(0)

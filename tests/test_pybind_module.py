@@ -147,9 +147,14 @@ def test_error_conventions():
     with pytest.raises(RuntimeError, match="You must specify MCTS visits for each player"):  # play_manager.cc:21
         az.PlayManager(az.Connect4GS(), p)
     p.mcts_visits = [8, 8]
-    p.seat_perms = [[0, 1], [1, 0]]
-    with pytest.raises(RuntimeError, match="not implemented"):
+    p.seat_perms = [[0, 1], [1, 0], [0, 1]]  # slot g plays permutation g % 3: needs a multiple of 3 slots
+    with pytest.raises(RuntimeError, match="multiple of the number of seat permutations"):
         az.PlayManager(az.Connect4GS(), p)
+    p.seat_perms = [[0, 2], [2, 0]]
+    with pytest.raises(RuntimeError, match="seat_perms names a model group that does not exist"):  # play_manager.cc:52
+        az.PlayManager(az.Connect4GS(), p)
+    p.seat_perms = [[0, 1], [1, 0]]
+    assert az.PlayManager(az.Connect4GS(), p).num_seat_perms() == 2
     p.seat_perms = []
     with pytest.raises(TypeError):
         az.PlayManager(None, p)
@@ -360,6 +365,47 @@ def test_two_model_groups_route_leaves_by_searching_seat(kind):
     _, _, rows_off = run([], 0, two_nets=True)
     _, _, rows_on = run([], 100000, two_nets=True)
     assert np.array_equal(rows_off, rows_on) and not np.array_equal(rows_off, rows2)
+
+
+@pytest.mark.parametrize("kind", kinds())
+@pytest.mark.parametrize("past_is_random", [False, True])
+def test_play_past_shape_seat_perms_and_mixed_evaluators(kind, past_is_random):
+    """What game_runner.play_past builds (game_runner.py:2203-2242): two players = two model groups, seat_perms
+    [[0, 1], [1, 0]], n = bs * cb * n_perms games, and against iteration 0 a RandPlayer (EvalType.RANDOM) for group 1.
+    Then its read-out (2268-2290): perm_scores / perm_games_completed per permutation."""
+    az = module(kind)
+    p = _params(az, G=4, games=8, visits=16, level=1, seed=5, max_batch=4, deterministic=False)
+    p.model_groups = [0, 1]
+    p.seat_perms = [[0, 1], [1, 0]]
+    p.eval_type = [az.EvalType.NN, az.EvalType.RANDOM if past_is_random else az.EvalType.NN]
+    pm = az.PlayManager(az.Connect4GS(), p)
+    assert pm.num_model_groups() == 2 and pm.num_seat_perms() == 2
+    ths = [threading.Thread(target=pm.play) for _ in range(2)]
+    [t.start() for t in ths]
+    batch = np.zeros((4, 4, 6, 7), np.float32)
+    served = [0, 0]
+    while pm.remaining_games() > 0:
+        for g in range(2):
+            ids = pm.build_batch(g, batch)
+            if not ids:
+                continue
+            served[g] += len(ids)
+            v, pi = ph.fake_net(batch[:len(ids)])
+            if g == 1:
+                v, pi = v[:, ::-1].copy(), pi[:, ::-1].copy()
+            pm.update_inferences(g, ids, v, pi)
+    [t.join() for t in ths]
+    assert pm.games_completed() == 8
+    assert served[0] > 0 and (served[1] == 0) == past_is_random, served
+    total = np.zeros(3, np.float32)
+    for perm in range(2):
+        assert pm.perm_games_completed(perm) == 4  # n / n_perms games under every seating
+        sc = np.asarray(pm.perm_scores(perm))
+        assert sc.sum() == 4
+        total += sc
+    assert np.array_equal(total, np.asarray(pm.scores()))
+    with pytest.raises(IndexError):
+        pm.perm_scores(2)
 
 
 def test_playout_eval_contract():

@@ -117,7 +117,7 @@ def test_tafl_playmanager_validation_and_no_cpu_fallback():
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
         p = _params(az, 2, 1, 8, 1, True)
-        p.model_groups = [0, 1]  # two networks: the tafl engine serves one model group
+        p.model_groups = [0, 2]  # three networks: the engines carry two model groups
         az.PlayManager(gs, p)
     with pytest.raises(RuntimeError, match="not implemented"):
         p = _params(az, 2, 1, 8, 1, True)
