@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
 }
 // The same, with the 32 games of a warp in lock step (run_sync): no lane leaves early, the warp votes. The selection
 // path lives in shared memory (one column per thread): an indexed access is one LDS / STS instead of a chain of selects.
-template <bool GB>
+template <bool GB, bool PX = false>
 __global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) {
   const u32 g = GLOBAL_TID;
   const bool in_range = g < E.G;
@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) 
   pr.blk = &s_blk[0][threadIdx.x];
   pr.slot = &s_slot[0][threadIdx.x];
   pr.valid = 0;  // the pending leaf's path (if any) is in HBM
-  run_sync<GB>(E, gg, c, pr, n_steps, in_range);
+  run_sync<GB, PathCol, PX>(E, gg, c, pr, n_steps, in_range);
   if (in_range && c.gs.active) {
     path_flush(E, gg, pr, (u32)c.T.path_len);
     ctx_store(E, gg, c);
   }
 #else
-  run_sync<GB>(E, gg, c, c.pr, n_steps, in_range);
+  run_sync<GB, PathRegs, PX>(E, gg, c, c.pr, n_steps, in_range);
   if (in_range && c.gs.active) ctx_store(E, gg, c);
 #endif
 }
@@ -811,8 +811,14 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
   } else if (e->step_kernel == B2AZ_STEP_SYNC) {
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;
     const u32 blocks = (V.G + threads - 1) / threads;
-    if (V.gumbel_enabled) k_step_sync<true><<<blocks, threads, 0, s>>>(V, n_steps);
-    else k_step_sync<false><<<blocks, threads, 0, s>>>(V, n_steps);
+    const bool px = V.n_perms > 1u || V.random_groups != 0u;  // seat permutations / a RANDOM group next to an NN one
+    if (px) {
+      if (V.gumbel_enabled) k_step_sync<true, true><<<blocks, threads, 0, s>>>(V, n_steps);
+      else k_step_sync<false, true><<<blocks, threads, 0, s>>>(V, n_steps);
+    } else {
+      if (V.gumbel_enabled) k_step_sync<true, false><<<blocks, threads, 0, s>>>(V, n_steps);
+      else k_step_sync<false, false><<<blocks, threads, 0, s>>>(V, n_steps);
+    }
   } else {
     // small CTAs spread the (one thread per game) population evenly over the SMs
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;

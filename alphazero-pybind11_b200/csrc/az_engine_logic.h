@@ -928,16 +928,23 @@ AZ_HD void cache_insert(const EngineView& E, u64 key, const float* v, const floa
 AZ_HD bool slot_random(const EngineView& E, u32 g, const GameSlot& gs) {
   return E.random_groups != 0u && ((E.random_groups >> E.seat_group[slot_perm(E, g)][gs.player]) & 1u) != 0u;
 }
+// PX = false: the instantiation for runs with one seat permutation and no RANDOM group next to an NN one (self-play, the
+// bench): the per-slot lookups compile away (measured: the runtime form costs the hot kernel 8 %, profiles/r4a_bench.json)
+template <bool PX>
+AZ_HD u32 slot_perm_t(const EngineView& E, u32 g) { return PX ? slot_perm(E, g) : 0u; }
+template <bool PX>
+AZ_HD bool slot_random_t(const EngineView& E, u32 g, const GameSlot& gs) { return PX ? slot_random(E, g, gs) : false; }
 // What happens to a fresh leaf with the NN evaluator (play_manager.cc:586-598): look the position up in the
 // cache — every leaf, terminal ones included, like the reference — and on a miss put it into the leaf batch.
 // Returns true on a cache hit (the caller goes on with the next simulation right away).
+template <bool PX = true>
 AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s, bool allow_hit) {
-  if (slot_random(E, g, gs)) return allow_hit;  // answered on the spot like a cache hit; a launch's chain stays bounded (hit_cap)
+  if (slot_random_t<PX>(E, g, gs)) return allow_hit;  // answered on the spot like a cache hit; a launch's chain stays bounded (hit_cap)
   u64 key = 0;
   if (E.cache_buckets) {
     // one table for every model group (the reference keeps one cache per group, play_manager.cc:195-203): the group of
     // the searching seat is part of the key (bits 56-59 are free in the position encoding)
-    key = c4_cache_key(s) | ((u64)E.seat_group[slot_perm(E, g)][gs.player] << 56);
+    key = c4_cache_key(s) | ((u64)E.seat_group[slot_perm_t<PX>(E, g)][gs.player] << 56);
     const u32 hit = cache_find(E, key);
     if (hit != kNil && allow_hit) {
       E.hit_val[g] = hit;
@@ -961,7 +968,7 @@ AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s,
   E.leaf_p1[row] = s.p[1];
   E.leaf_player[row] = s.player;
   E.leaf_game[row] = g;
-  E.leaf_seat[row] = (u8)(gs.player | (E.seat_group[slot_perm(E, g)][gs.player] << 4));
+  E.leaf_seat[row] = (u8)(gs.player | (E.seat_group[slot_perm_t<PX>(E, g)][gs.player] << 4));
   if (E.cache_buckets) {
     E.leaf_key[row] = key;
     E.hit_val[g] = kNil;
@@ -1033,7 +1040,7 @@ AZ_COLD void root_leaf_priors(const EngineView E, Pcg32& rng, float* p8, u32 lk,
 
 // ------------------------------------------------------------------------------------ process_result
 // MCTS::process_result (mcts.cc:500-555).
-template <class PR>
+template <class PR, bool PX = true>
 AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot& gs, Pcg32& rng, bool noise_enabled,
                           PR& pr) {
   float val0, val1, vald;  // value[0], value[1], value[P] (draw share)
@@ -1047,7 +1054,7 @@ AZ_HD void process_result(const EngineView& E, u32 g, TreeHdr& T, const GameSlot
     u32 ps[kKMax];  // the leaf's child priors (f32 bits), child order
 #pragma unroll
     for (int j = 0; j < kKMax; ++j) ps[j] = 0u;
-    if (E.eval_type == 1 || slot_random(E, g, gs)) {  // dumb_eval (game_state.h:160-173): uniform over the legal moves, value 1/3
+    if (E.eval_type == 1 || slot_random_t<PX>(E, g, gs)) {  // dumb_eval (game_state.h:160-173): uniform over the legal moves, value 1/3
       const float third = (float)(1.0 / 3.0);
       val0 = val1 = vald = third;
       // every legal move is a child here, so Vector<uint8_t>::sum() == lk
@@ -1751,7 +1758,7 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
 #else
 #define AZ_WARP_ANY(p) (p)
 #endif
-template <bool GB = true, class PR = PathRegs>
+template <bool GB = true, class PR = PathRegs, bool PX = true>
 AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, bool alive) {
   Descent D;
   u32 left = n_steps, hits = 0;
@@ -1764,9 +1771,9 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, boo
       if (c.gs.initialized) {
         const u32 cp = c.gs.player;
         const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
-        process_result(E, g, c.T, c.gs, c.rng, noise, pr);
+        process_result<PR, PX>(E, g, c.T, c.gs, c.rng, noise, pr);
         ++c.sims;
-        const u32 goal = c.gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
+        const u32 goal = c.gs.capped ? E.cap_visits[slot_perm_t<PX>(E, g)][cp] : E.visits[slot_perm_t<PX>(E, g)][cp];
         if (c.T.depth >= goal) {
           ctx_store(E, g, c);  // the path is empty here: process_result has just consumed it
           retired = play_move(E, g);
@@ -1795,7 +1802,7 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, boo
       descent_finish(E, g, c.T, c.gs, c.rng, D);
       bool hit = false;
       if (E.eval_type == 0) {
-        hit = leaf_emit(E, g, c.gs, D.s, hits < E.hit_cap);
+        hit = leaf_emit<PX>(E, g, c.gs, D.s, hits < E.hit_cap);
         if (hit) ++hits;
       }
       if (!hit) --left;

@@ -18,8 +18,10 @@
 //   build_history_batch  b2az_drain_history into the caller's arrays.
 // max_cache_size > 0 turns on the device position cache (the engine's replacement for ShardedS3FIFOCache).
 // Gumbel root search, playout-cap randomisation and resign_percent are carried by the engine.
-// Not carried (rejected with RuntimeError instead of being ignored): model groups / seat permutations /
-// per-seat overrides (incl. per-seat resign thresholds), PLAYOUT eval, external caches.
+// Two model groups, seat permutations (slot g plays permutation g % n), per-seat visit budgets and a RANDOM group next
+// to an NN one are carried. Not carried (rejected with RuntimeError instead of being ignored): per-seat overrides that
+// differ between seats (epsilon, root temperature, Gumbel settings, resign thresholds), PLAYOUT eval. External caches
+// size the device cache but are not shared between PlayManagers (see the constructor).
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -1148,9 +1150,19 @@ PYBIND11_MODULE(alphazero, m) {
   py::class_<PlayManager>(m, "PlayManager")
       .def(py::init([](const GameState* gs, PlayParams params) { return std::make_unique<PlayManager>(gs, std::move(params)); }),
            py::arg().none(false), py::arg())
+      // PlayManager(gs, params, caches) (play_manager.cc:644-649; tournament.py:224, visit_sweep_elo.py:324): the reference
+      // shares the given host caches between successive PlayManagers. The engine's position cache lives in HBM inside the
+      // engine, so the given objects only SIZE it (the sum of their max_size(), as if params.max_cache_size had been set);
+      // its hits / misses are reported by this PlayManager's cache_hits() / cache_misses(), the host objects stay empty and
+      // nothing carries over to the next PlayManager. A cache may forget, so the games are the same — only colder.
       .def(py::init([](const GameState* gs, PlayParams params, std::vector<py::object> caches) {
-             for (auto& c : caches)
-               if (!c.is_none()) throw std::runtime_error("external caches are not implemented by the B200 engine yet");
+             uint64_t total = 0;
+             for (auto& c : caches) {
+               if (c.is_none()) continue;
+               if (!py::hasattr(c, "max_size")) throw py::type_error("caches: expected S3FIFOCache / ShardedS3FIFOCache objects or None");
+               total += c.attr("max_size")().cast<uint64_t>();
+             }
+             params.max_cache_size = (uint32_t)std::min<uint64_t>(total, 0x7FFFFFFFull);
              return std::make_unique<PlayManager>(gs, std::move(params));
            }),
            py::arg().none(false), py::arg(), py::arg("caches"))

@@ -408,6 +408,43 @@ def test_play_past_shape_seat_perms_and_mixed_evaluators(kind, past_is_random):
         pm.perm_scores(2)
 
 
+@pytest.mark.parametrize("kind", kinds())
+def test_external_caches_size_the_device_cache(kind):
+    """PlayManager(gs, params, caches=[...]) (play_manager.cc:644-649, tournament.py:224): accepted; the objects size the
+    engine's device cache (they are not shared between PlayManagers, see py_alphazero.cc). Same games as max_cache_size."""
+    az = module(kind)
+
+    def run(make):
+        p = _params(az, G=4, games=4, visits=24, level=1, seed=3, max_batch=4, deterministic=False)
+        pm = make(p)
+        ths = [threading.Thread(target=pm.play) for _ in range(2)]
+        [t.start() for t in ths]
+        batch = np.zeros((4, 4, 6, 7), np.float32)
+        while pm.remaining_games() > 0:
+            ids = pm.build_batch(0, batch)
+            if ids:
+                v, pi = ph.fake_net(batch[:len(ids)])
+                pm.update_inferences(0, ids, v, pi)
+        [t.join() for t in ths]
+        n = pm.hist_count()
+        c, v, pi = np.zeros((n, 4, 6, 7), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 7), np.float32)
+        assert pm.build_history_batch(c, v, pi) == n
+        return pm, ph._sorted_rows(c, v, pi)
+
+    def with_param(p):
+        p.max_cache_size = 4096
+        return az.PlayManager(az.Connect4GS(), p)
+
+    ext = az.ShardedS3FIFOCache(4096, 2, 3686, 7, 3)
+    a, rows_a = run(with_param)
+    b, rows_b = run(lambda p: az.PlayManager(az.Connect4GS(), p, caches=[ext, None]))
+    assert np.array_equal(rows_a, rows_b)
+    assert b.cache_hits() == a.cache_hits() > 0 and b.cache_misses() == a.cache_misses()
+    assert ext.size() == 0  # the host object is not filled
+    with pytest.raises(TypeError):
+        az.PlayManager(az.Connect4GS(), _params(az, 2, 2, 8, 0, 1, 2), caches=[object()])
+
+
 def test_playout_eval_contract():
     """playout_eval / playout_eval_batch (py_wrapper.cc:726-770, game_state.cc:10-95): uniform prior over the legal moves,
     value = one-hot outcome of a random playout (or 1/(P+1) each if the game cannot go on)."""
