@@ -97,7 +97,12 @@ class TaflSelfplayParams(C.Structure):  # b2az_tafl_selfplay_params (include/b2a
                 ("n_variant_half_life", C.c_uint32), ("variant_half_life", C.c_float * 4), ("variant_probs", C.c_float * 4),
                 ("cache_entries", C.c_uint32),
                 ("n_seat_perms", C.c_uint32), ("seat_perms", (C.c_uint8 * 2) * 8), ("perm_seat_visits", (C.c_uint32 * 2) * 8),
-                ("perm_seat_cap_visits", (C.c_uint32 * 2) * 8), ("group_random", C.c_uint8 * 2), ("pad4_", C.c_uint8 * 2)]
+                ("perm_seat_cap_visits", (C.c_uint32 * 2) * 8), ("group_random", C.c_uint8 * 2), ("has_seat_search", C.c_uint8),
+                ("pad4_", C.c_uint8), ("seat_epsilon", (C.c_float * 2) * 8), ("seat_root_temp", (C.c_float * 2) * 8),
+                ("seat_root_fpu_zero", (C.c_uint8 * 2) * 8), ("seat_gumbel_enabled", (C.c_uint8 * 2) * 8),
+                ("seat_gumbel_full", (C.c_uint8 * 2) * 8), ("seat_gumbel_m", (C.c_uint32 * 2) * 8),
+                ("seat_gumbel_c_visit", (C.c_float * 2) * 8), ("seat_gumbel_c_scale", (C.c_float * 2) * 8),
+                ("seat_resign_threshold", (C.c_float * 2) * 8), ("seat_resign_consecutive", (C.c_uint32 * 2) * 8)]
 
 
 SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_completed", "u4"), ("pending", "u4"),
@@ -107,7 +112,7 @@ SLOT_DTYPE = np.dtype([("active", "u4"), ("games_started", "u4"), ("games_comple
                        ("leaf_depth", "f8"), ("entropy", "f8"), ("valid_moves", "f8"), ("simulations", "u8"),
                        ("scores", "f4", 3), ("playthrough", "u4"), ("fast_move_count", "u4"), ("total_fast_move_count", "u4"),
                        ("g_fast_leaf_depth", "f8"), ("g_fast_entropy", "f8"), ("fast_leaf_depth", "f8"), ("fast_entropy", "f8"),
-                       ("resign_scores", "f4", 3), ("pad3_", "u4"), ("coin_state", "u8"), ("coin_inc", "u8")])  # b2az_tafl_selfplay_slot
+                       ("resign_scores", "f4", 3), ("resign_streak", "u2", 2), ("coin_state", "u8"), ("coin_inc", "u8")])  # b2az_tafl_selfplay_slot
 assert SLOT_DTYPE.itemsize == 192
 
 _libs = {}
@@ -669,7 +674,7 @@ class TaflSelfplay:
                  seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
                  playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
                  temp_decay_half_life_by_variant=None, variant_probs=None, cache_entries=0, gumbel_full=False,
-                 seat_perms=None, perm_seat_visits=None, perm_seat_cap_visits=None, group_random=None):
+                 seat_perms=None, perm_seat_visits=None, perm_seat_cap_visits=None, group_random=None, seat_search=None):
         self.L = lib or load()
         self.game, self.n = game, n_games
         self.S, self.P, self.A = game_dims(game)
@@ -695,6 +700,18 @@ class TaflSelfplay:
             p.seat_visits[seat] = (seat_visits or (0, 0))[seat]
             p.seat_cap_visits[seat] = (seat_cap_visits or (0, 0))[seat]
         fill_perms(p, seat_perms, perm_seat_visits, perm_seat_cap_visits, group_random)
+        if seat_search:  # {field: [[seat 0, seat 1] per permutation]} for every seat_* field of the structure
+            p.has_seat_search = 1
+            defaults = dict(seat_epsilon=epsilon, seat_root_temp=root_policy_temp, seat_root_fpu_zero=int(root_fpu_zero),
+                            seat_gumbel_enabled=int(gumbel_m > 0), seat_gumbel_full=int(gumbel_full), seat_gumbel_m=gumbel_m or 16,
+                            seat_gumbel_c_visit=gumbel_c_visit, seat_gumbel_c_scale=gumbel_c_scale, seat_resign_threshold=-2.0,
+                            seat_resign_consecutive=1)
+            for name, dflt in defaults.items():
+                rows = seat_search.get(name)
+                for pm in range(max(1, len(seat_perms or []))):
+                    for seat in range(2):
+                        getattr(p, name)[pm][seat] = rows[pm][seat] if rows is not None else dflt
+            assert not set(seat_search) - set(defaults), set(seat_search) - set(defaults)
         self.hist_capacity = hist_capacity or n_games * max_turns
         self.h = C.c_void_p()
         self._check(self.L.b2az_tafl_selfplay_create(C.byref(p), device, C.byref(self.h)))

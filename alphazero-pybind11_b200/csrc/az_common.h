@@ -11,11 +11,14 @@
 #define AZ_COLD __host__ __device__ __noinline__
 // large rule functions that are called from several places of a kernel: one out-of-line copy (instruction-cache footprint)
 #define AZ_HD_CALL __host__ __device__ __noinline__
+// a kernel's view parameter stays in the constant bank even though out-of-line helpers take it by reference
+#define AZ_GRID_CONSTANT __grid_constant__
 #else
 #define AZ_HD inline
 #define AZ_D inline
 #define AZ_COLD inline
 #define AZ_HD_CALL inline
+#define AZ_GRID_CONSTANT
 #endif
 
 namespace b2az {

@@ -189,7 +189,7 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
 // One thread per game slot. <= 144 registers so that seven 64-thread CTAs (14 warps) fit an SM: at the
 // BASELINE size (65,536 games over 148 SMs = 443 threads per SM) every game is resident at once.
 template <bool GB>
-__global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
+__global__ void __launch_bounds__(64, 7) k_step(const AZ_GRID_CONSTANT EngineView E, u32 n_steps) {
   const u32 g = GLOBAL_TID;
   if (g >= E.G) return;
   Ctx c;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
 // The same, with the 32 games of a warp in lock step (run_sync): no lane leaves early, the warp votes. The selection
 // path lives in shared memory (one column per thread): an indexed access is one LDS / STS instead of a chain of selects.
 template <bool GB, bool PX = false>
-__global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) {
+__global__ void __launch_bounds__(64, 7) k_step_sync(const AZ_GRID_CONSTANT EngineView E, u32 n_steps) {
   const u32 g = GLOBAL_TID;
   const bool in_range = g < E.G;
   const u32 gg = in_range ? g : 0u;
@@ -247,7 +247,7 @@ __global__ void k_cache_find_keys(EngineView E, const u64* keys, u32 n, u8* foun
     }
   }
 }
-__global__ void k_step_serial(EngineView E, u32 n_steps) {
+__global__ void k_step_serial(const AZ_GRID_CONSTANT EngineView E, u32 n_steps) {
   for (u32 s = 0; s < n_steps; ++s)
     for (u32 g = 0; g < E.G; ++g) {
       Ctx c;
@@ -397,6 +397,7 @@ struct b2az_engine {
   b2az_params params;
   int device = 0;
   int num_sms = 148;
+  uint32_t n_perms = 1;         // seat permutations (b2az_params.n_seat_perms; the tables live at view.perms)
   EngineView view;
   // owned device buffers
   float* canon_buf = nullptr;   // [G][168]
@@ -552,6 +553,7 @@ int b2az_destroy(b2az_engine* e) {
   dev_free(V.blocks); dev_free(V.page_next); dev_free(V.ring); dev_free(V.ring_tickets);
   dev_free(V.trees); dev_free(V.games); dev_free(V.cold); dev_free(V.path); dev_free(V.pslot); dev_free(V.gum);
   dev_free(V.leaf_p0); dev_free(V.leaf_p1); dev_free(V.leaf_player); dev_free(V.leaf_game); dev_free(V.leaf_seat);
+  dev_free(const_cast<PermTables*>(V.perms));
   dev_free(V.hist_partial); dev_free(V.hist_out); dev_free(V.glob);
   dev_free(V.cache_keys); dev_free(V.cache_meta); dev_free(V.cache_lock); dev_free(V.cache_vals);
   dev_free(V.cache_ghost); dev_free(V.leaf_key); dev_free(V.hit_val);
@@ -625,15 +627,25 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   memset(&V, 0, sizeof(V));
   V.G = G;
   V.games_to_play = p->games_to_play;
-  V.n_perms = std::max(1u, p->n_seat_perms);
-  for (u32 pm = 0; pm < V.n_perms; ++pm)
+  // seat_visits_ / seat_cap_visits_ / seat_perms_ of every permutation (play_manager.cc:46-90); permutation 0 also fills
+  // the view's own fields, which is all a one-seating run reads
+  PermTables pt;
+  memset(&pt, 0, sizeof(pt));
+  pt.n_perms = std::max(1u, p->n_seat_perms);
+  for (u32 pm = 0; pm < pt.n_perms; ++pm)
     for (int seat = 0; seat < 2; ++seat) {
-      V.visits[pm][seat] = p->perm_seat_visits[pm][seat] ? p->perm_seat_visits[pm][seat] : p->mcts_visits[seat];
+      pt.visits[pm][seat] = p->perm_seat_visits[pm][seat] ? p->perm_seat_visits[pm][seat] : p->mcts_visits[seat];
       const u32 cv = p->perm_seat_cap_visits[pm][seat] ? p->perm_seat_cap_visits[pm][seat] : p->seat_cap_visits[seat];
-      V.cap_visits[pm][seat] = cv ? cv : p->playout_cap_depth;
-      V.seat_group[pm][seat] = p->n_seat_perms ? p->seat_perms[pm][seat] : p->model_groups[seat];
+      pt.cap_visits[pm][seat] = cv ? cv : p->playout_cap_depth;
+      pt.seat_group[pm][seat] = p->n_seat_perms ? p->seat_perms[pm][seat] : p->model_groups[seat];
     }
-  V.random_groups = p->eval_type == B2AZ_EVAL_NN ? ((p->group_random[0] ? 1u : 0u) | (p->group_random[1] ? 2u : 0u)) : 0u;
+  pt.random_groups = p->eval_type == B2AZ_EVAL_NN ? ((p->group_random[0] ? 1u : 0u) | (p->group_random[1] ? 2u : 0u)) : 0u;
+  for (int seat = 0; seat < 2; ++seat) {
+    V.visits[seat] = pt.visits[0][seat];
+    V.cap_visits[seat] = pt.cap_visits[0][seat];
+    V.seat_group[seat] = pt.seat_group[0][seat];
+  }
+  e->n_perms = pt.n_perms;
   V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.epsilon = p->epsilon; V.root_temp = p->mcts_root_temp;
   V.start_temp = p->start_temp; V.final_temp = p->final_temp; V.half_life = p->temp_decay_half_life;
   V.playout_cap_percent = p->playout_cap_percent;
@@ -649,7 +661,7 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
 
   // ---- pool sizing: 192 B blocks (8 child nodes each), pages of 64 blocks
   u64 max_visits = (u64)std::max(p->mcts_visits[0], p->mcts_visits[1]);
-  for (u32 pm = 0; pm < V.n_perms; ++pm) max_visits = std::max<u64>(max_visits, std::max(V.visits[pm][0], V.visits[pm][1]));
+  for (u32 pm = 0; pm < pt.n_perms; ++pm) max_visits = std::max<u64>(max_visits, std::max(pt.visits[pm][0], pt.visits[pm][1]));
   // a search adds <= one block per simulation; budget = 4 searches' worth + slack per tree
   const u64 tree_blocks = 4ull * max_visits + 2ull * kPageBlocks;
   u64 pool_blocks = p->pool_nodes ? (p->pool_nodes + kKMax - 1) / kKMax : tree_blocks * (u64)G * kP;
@@ -695,6 +707,13 @@ int b2az_create(const b2az_params* p, int device, b2az_engine** out) {
   A(dev_alloc(&V.path, (size_t)G * kMaxPath)); A(dev_alloc(&V.pslot, (size_t)G * kMaxPath));
   A(dev_alloc(&V.leaf_p0, (size_t)G)); A(dev_alloc(&V.leaf_p1, (size_t)G));
   A(dev_alloc(&V.leaf_player, (size_t)G)); A(dev_alloc(&V.leaf_game, (size_t)G)); A(dev_alloc(&V.leaf_seat, (size_t)G));
+  if (pt.n_perms > 1u || pt.random_groups != 0u) {
+    PermTables* dpt = nullptr;
+    A(dev_alloc(&dpt, 1));
+    V.perms = dpt;
+    A(copy_h2d(dpt, &pt, sizeof(pt), nullptr));
+    A(stream_sync(nullptr));
+  }
   A(dev_alloc(&V.hist_partial, p->history_enabled ? (size_t)G * kMaxHist : 1));
   A(dev_alloc(&V.hist_out, p->history_enabled ? (size_t)V.hist_capacity : 1));
   A(dev_alloc(&V.glob, 1));
@@ -811,7 +830,7 @@ int b2az_step(b2az_engine* e, uint32_t n_steps, void* stream) {
   } else if (e->step_kernel == B2AZ_STEP_SYNC) {
     const u32 threads = V.G <= (u32)e->num_sms * 32u * 32u ? 32u : 64u;
     const u32 blocks = (V.G + threads - 1) / threads;
-    const bool px = V.n_perms > 1u || V.random_groups != 0u;  // seat permutations / a RANDOM group next to an NN one
+    const bool px = V.perms != nullptr;  // seat permutations / a RANDOM group next to an NN one
     if (px) {
       if (V.gumbel_enabled) k_step_sync<true, true><<<blocks, threads, 0, s>>>(V, n_steps);
       else k_step_sync<false, true><<<blocks, threads, 0, s>>>(V, n_steps);
@@ -1250,7 +1269,7 @@ int b2az_perm_scores(b2az_engine* e, void* stream, b2az_perm_stats* out8, uint32
   Globals G;
   if (int rc = copy_d2h(&G, e->view.glob, sizeof(G), s)) return rc;
   if (int rc = stream_sync(s)) return rc;
-  const u32 P = e->view.n_perms;
+  const u32 P = e->n_perms;
   memset(out8, 0, P * sizeof(b2az_perm_stats));
   for (u32 pm = 0; pm < P; ++pm)
     for (int i = 0; i < 3; ++i) {  // perm_scores_ holds integer win counts (play_manager.cc:466-467)

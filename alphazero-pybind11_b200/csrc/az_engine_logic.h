@@ -102,7 +102,22 @@ AZ_HD void mem_fence() {
 #endif
 }
 // the seat permutation slot g plays (EngineView::n_perms)
-AZ_HD u32 slot_perm(const EngineView& E, u32 g) { return E.n_perms > 1u ? g % E.n_perms : 0u; }
+AZ_HD u32 slot_perm(const EngineView& E, u32 g) { return E.perms ? g % E.perms->n_perms : 0u; }
+// the search budget of `seat` in slot g (seat_visits_ / seat_cap_visits_[perm][seat], play_manager.cc:284-285)
+template <bool PX = true>
+AZ_HD u32 seat_budget(const EngineView& E, u32 g, u32 seat, bool capped) {
+  if (PX && E.perms) {
+    const u32 pm = g % E.perms->n_perms;
+    return capped ? E.perms->cap_visits[pm][seat] : E.perms->visits[pm][seat];
+  }
+  return capped ? E.cap_visits[seat] : E.visits[seat];
+}
+// the model group that searches for `seat` in slot g (seat_perms_[perm][seat], play_manager.cc:577)
+template <bool PX = true>
+AZ_HD u32 seat_group_of(const EngineView& E, u32 g, u32 seat) {
+  if (PX && E.perms) return E.perms->seat_group[g % E.perms->n_perms][seat];
+  return E.seat_group[seat];
+}
 template <typename T>
 AZ_HD T ld_volatile(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 template <typename T>
@@ -234,7 +249,7 @@ AZ_HD void blk_copy(Block* D, const Block* S) {
 // generation where every game re-rooted). A slot carries everything (the page id), so no memory fence
 // is needed: a gpu-scope __threadfence compiles to MEMBAR + CCTL.IVALL, which throws away the whole
 // SM's L1 on every page pop (profiles/r3: L1 hit rate 43 %).
-AZ_COLD void pool_push_page(const EngineView E, u32 page) {
+AZ_COLD void pool_push_page(const EngineView& E, u32 page) {
   const u32 region = page / E.region_pages;  // a page always goes back to the region it came from
   const unsigned long long t = at_add64(&E.ring_tickets[2u * region + 1u], 1ULL);
   u32* slot = &E.ring[(size_t)region * E.region_pages + (size_t)(t % (unsigned long long)E.region_pages)];
@@ -246,7 +261,7 @@ AZ_COLD void pool_push_page(const EngineView E, u32 page) {
   *slot = page;
 #endif
 }
-AZ_COLD u32 pool_pop_page(const EngineView E, u32 region) {
+AZ_COLD u32 pool_pop_page(const EngineView& E, u32 region) {
   Globals* G = E.glob;
   if (ld_volatile(&G->error) & B2AZ_DEVERR_POOL) return kNil;  // already fatal: do not spin again
   const unsigned long long t = at_add64(&E.ring_tickets[2u * region], 1ULL);
@@ -263,7 +278,7 @@ AZ_COLD u32 pool_pop_page(const EngineView E, u32 region) {
   return page;  // kNil: ring empty = the region is exhausted (fatal, reported by the caller)
 }
 // Give every page of a tree's chain back (the chain links are this thread's own writes).
-AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
+AZ_COLD void pool_push_chain(const EngineView& E, u32 head) {
   u32 p = head;
   for (u32 guard = 0; p != kNil && guard < 0x10000u; ++guard) {
     const u32 nx = E.page_next[p];
@@ -509,7 +524,7 @@ AZ_HD u32 rank_top(const float* score, const u32* idx, u32 k, u32 take) {
   return out;
 }
 // init_gumbel_state (mcts.cc:190-227)
-AZ_COLD void gumbel_init(const EngineView E, GumbelState& S, const TreeHdr& T, Pcg32& rng) {
+AZ_COLD void gumbel_init(const EngineView& E, GumbelState& S, const TreeHdr& T, Pcg32& rng) {
   const u32 num_legal = T.k;
   if (num_legal == 0 || T.fc == kNil) return;
   const u32 remaining = T.depth < S.num_sims_target ? S.num_sims_target - T.depth : 0u;
@@ -567,7 +582,7 @@ AZ_HD void gumbel_advance_phase(const EngineView& E, GumbelState& S, const TreeH
   S.sims_in_phase = 0;
 }
 // gumbel_next_root_child (mcts.cc:266-283)
-AZ_COLD u32 gumbel_next_root_child(const EngineView E, GumbelState& S, const TreeHdr& T) {
+AZ_COLD u32 gumbel_next_root_child(const EngineView& E, GumbelState& S, const TreeHdr& T) {
   if ((u32)S.phase_idx < (u32)S.n_phases) {
     if (S.sims_in_phase >= S.phase_numc[S.phase_idx] * S.phase_vper[S.phase_idx]) gumbel_advance_phase(E, S, T);
   }
@@ -612,7 +627,7 @@ AZ_HD float gumbel_pi_prime(const EngineView& E, const Block* B, u32 k, float ra
   return z_sum;
 }
 // gumbel_interior_select (mcts.cc:285-334)
-AZ_COLD u32 gumbel_interior_select(const EngineView E, u32 blk, u32 k, float node_v) {
+AZ_COLD u32 gumbel_interior_select(const EngineView& E, u32 blk, u32 k, float node_v) {
   const Block* B = E.blocks + blk;
   float z[kKMax];
   u32 ns[kKMax], sum_visits = 0;
@@ -628,7 +643,7 @@ AZ_COLD u32 gumbel_interior_select(const EngineView E, u32 blk, u32 k, float nod
   return best;
 }
 // gumbel_improved_policy (mcts.cc:336-373): pi' over all moves (zeros for illegal ones)
-AZ_COLD void gumbel_improved_policy(const EngineView E, const TreeHdr& T, float* out) {
+AZ_COLD void gumbel_improved_policy(const EngineView& E, const TreeHdr& T, float* out) {
   for (int m = 0; m < kA; ++m) out[m] = 0.0f;
   const u32 k = T.k;
   if (k == 0 || T.fc == kNil) return;
@@ -657,7 +672,7 @@ struct __attribute__((aligned(16))) Descent {
 };
 static_assert(sizeof(Descent) == 64, "Descent must stay four 16 B vectors (shared-memory record of the queue kernel)");
 // Lazy Gumbel init (mcts.cc:468-472): after the root has been expanded, when a sims target is set.
-AZ_COLD bool gumbel_begin(const EngineView E, u32 tree, const TreeHdr T, Pcg32& rng) {
+AZ_COLD bool gumbel_begin(const EngineView& E, u32 tree, const TreeHdr T, Pcg32& rng) {
   GumbelState S = E.gum[tree];
   if (!S.initialized && S.num_sims_target > 0 && T.n > 0 && T.k > 0) {
     gumbel_init(E, S, T, rng);
@@ -926,12 +941,10 @@ AZ_HD void cache_insert(const EngineView& E, u64 key, const float* v, const floa
 // eval_types_[group] == RANDOM next to an NN group (play_manager.cc:577-587): the searches of that group run dumb_eval
 // inline and never enter the leaf batch
 AZ_HD bool slot_random(const EngineView& E, u32 g, const GameSlot& gs) {
-  return E.random_groups != 0u && ((E.random_groups >> E.seat_group[slot_perm(E, g)][gs.player]) & 1u) != 0u;
+  return E.perms && E.perms->random_groups != 0u && ((E.perms->random_groups >> seat_group_of(E, g, gs.player)) & 1u) != 0u;
 }
 // PX = false: the instantiation for runs with one seat permutation and no RANDOM group next to an NN one (self-play, the
-// bench): the per-slot lookups compile away (measured: the runtime form costs the hot kernel 8 %, profiles/r4a_bench.json)
-template <bool PX>
-AZ_HD u32 slot_perm_t(const EngineView& E, u32 g) { return PX ? slot_perm(E, g) : 0u; }
+// bench): the per-slot lookups compile away 
 template <bool PX>
 AZ_HD bool slot_random_t(const EngineView& E, u32 g, const GameSlot& gs) { return PX ? slot_random(E, g, gs) : false; }
 // What happens to a fresh leaf with the NN evaluator (play_manager.cc:586-598): look the position up in the
@@ -944,7 +957,7 @@ AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s,
   if (E.cache_buckets) {
     // one table for every model group (the reference keeps one cache per group, play_manager.cc:195-203): the group of
     // the searching seat is part of the key (bits 56-59 are free in the position encoding)
-    key = c4_cache_key(s) | ((u64)E.seat_group[slot_perm_t<PX>(E, g)][gs.player] << 56);
+    key = c4_cache_key(s) | ((u64)seat_group_of<PX>(E, g, gs.player) << 56);
     const u32 hit = cache_find(E, key);
     if (hit != kNil && allow_hit) {
       E.hit_val[g] = hit;
@@ -968,7 +981,7 @@ AZ_HD bool leaf_emit(const EngineView& E, u32 g, GameSlot& gs, const C4State& s,
   E.leaf_p1[row] = s.p[1];
   E.leaf_player[row] = s.player;
   E.leaf_game[row] = g;
-  E.leaf_seat[row] = (u8)(gs.player | (E.seat_group[slot_perm_t<PX>(E, g)][gs.player] << 4));
+  E.leaf_seat[row] = (u8)(gs.player | (seat_group_of<PX>(E, g, gs.player) << 4));
   if (E.cache_buckets) {
     E.leaf_key[row] = key;
     E.hit_val[g] = kNil;
@@ -1026,7 +1039,7 @@ AZ_COLD void add_root_noise(const EngineView& E, Pcg32& rng, float* pol, u32 k) 
 
 // set_policy_normalized at the root (mcts.cc:109-121 with the temperature branch) + add_root_noise
 // (mcts.cc:511-519): the priors of a root that has just been evaluated.
-AZ_COLD void root_leaf_priors(const EngineView E, Pcg32& rng, float* p8, u32 lk, bool noise_enabled) {
+AZ_COLD void root_leaf_priors(const EngineView& E, Pcg32& rng, float* p8, u32 lk, bool noise_enabled) {
   const bool apply_temp = (E.root_temp != 1.0f);
   const float inv_temp = fdiv(1.0f, E.root_temp);
   float sum = 0.0f;
@@ -1420,8 +1433,8 @@ AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_befor
 
 // set_gumbel_num_sims for the tree that searches next (play_manager.cc:531-539, 562-570): the full budget, or for a
 // capped search the cap when fast_search_uses_gumbel, else 0 = "PUCT for this search".
-AZ_COLD void gumbel_arm(const EngineView E, u32 g, u32 seat, bool capped) {
-  const u32 target = capped ? (E.fast_search_uses_gumbel ? E.cap_visits[slot_perm(E, g)][seat] : 0u) : E.visits[slot_perm(E, g)][seat];
+AZ_COLD void gumbel_arm(const EngineView& E, u32 g, u32 seat, bool capped) {
+  const u32 target = capped ? (E.fast_search_uses_gumbel ? seat_budget(E, g, seat, true) : 0u) : seat_budget(E, g, seat, false);
   GumbelState S = E.gum[(size_t)g * kP + seat];
   gumbel_set_num_sims(S, target);
   E.gum[(size_t)g * kP + seat] = S;
@@ -1457,7 +1470,7 @@ AZ_HD void ctx_store(const EngineView& E, u32 g, Ctx& c) {
 // The move part of PlayManager::play()'s loop body (play_manager.cc:286-555). Works on the slot's state
 // in HBM (the caller stores its register copy before and reloads it after), so nothing of the hot
 // loop's state has its address taken. Returns true when the slot retired.
-AZ_COLD bool play_move(const EngineView E, u32 g) {
+AZ_COLD bool play_move(const EngineView& E, u32 g) {
   GameSlot gs = E.games[g];
   Pcg32 rng = (E.rng_mode == 1) ? E.glob->global_rng : gs.rng;
   const u32 cp = gs.player;
@@ -1614,7 +1627,7 @@ AZ_COLD bool play_move(const EngineView E, u32 g) {
     gs.capped = (E.playout_cap && rng_uniform01(rng) < E.playout_cap_percent) ? 1 : 0;
     if (E.gumbel_enabled) {  // set_gumbel_num_sims for the seat that searches next (play_manager.cc:531-539)
       const u32 ncp = gs.player;
-      gumbel_set_num_sims(GS[ncp], gs.capped ? (E.fast_search_uses_gumbel ? E.cap_visits[slot_perm(E, g)][ncp] : 0u) : E.visits[slot_perm(E, g)][ncp]);
+      gumbel_set_num_sims(GS[ncp], gs.capped ? (E.fast_search_uses_gumbel ? seat_budget(E, g, ncp, true) : 0u) : seat_budget(E, g, ncp, false));
     }
     if (!E.tree_reuse) {
       for (int seat = 0; seat < kP; ++seat) {
@@ -1674,7 +1687,7 @@ AZ_HD void game_step(const EngineView& E, u32 g, Ctx& c) {
     const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
     process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
     ++c.sims;
-    const u32 goal = c.gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
+    const u32 goal = seat_budget(E, g, cp, c.gs.capped != 0);
     if (c.T.depth >= goal) {
       ctx_store(E, g, c);
       retired = play_move(E, g);
@@ -1717,7 +1730,7 @@ AZ_HD void run_flat(const EngineView& E, u32 g, Ctx& c, u32 n_steps) {
         const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
         process_result(E, g, c.T, c.gs, c.rng, noise, c.pr);
         ++c.sims;
-        const u32 goal = c.gs.capped ? E.cap_visits[slot_perm(E, g)][cp] : E.visits[slot_perm(E, g)][cp];
+        const u32 goal = seat_budget(E, g, cp, c.gs.capped != 0);
         if (c.T.depth >= goal) {
           ctx_store(E, g, c);
           retired = play_move(E, g);
@@ -1773,7 +1786,7 @@ AZ_HD void run_sync(const EngineView& E, u32 g, Ctx& c, PR& pr, u32 n_steps, boo
         const bool noise = (E.epsilon > 0.0f) && !c.gs.capped;
         process_result<PR, PX>(E, g, c.T, c.gs, c.rng, noise, pr);
         ++c.sims;
-        const u32 goal = c.gs.capped ? E.cap_visits[slot_perm_t<PX>(E, g)][cp] : E.visits[slot_perm_t<PX>(E, g)][cp];
+        const u32 goal = seat_budget<PX>(E, g, cp, c.gs.capped != 0);
         if (c.T.depth >= goal) {
           ctx_store(E, g, c);  // the path is empty here: process_result has just consumed it
           retired = play_move(E, g);

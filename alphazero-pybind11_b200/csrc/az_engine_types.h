@@ -151,13 +151,19 @@ struct Globals {
   unsigned long long perm_wins[kMaxPerms][3];  // perm_scores_ (play_manager.cc:205-211, 466-467)
 };
 
+// slot g plays permutation g % n_perms in every one of its games (the reference's round-robin hand-out when the slots
+// finish in order; G is a multiple of n_perms)
+struct PermTables {
+  u32 n_perms;
+  u32 random_groups;   // NN mode (eval_type 0): bit i = model group i is EvalType::RANDOM, its searches run dumb_eval inline
+  u32 visits[kMaxPerms][2], cap_visits[kMaxPerms][2];  // seat_visits_ / seat_cap_visits_[perm][seat]
+  u8 seat_group[kMaxPerms][2];                         // seat_perms_[perm][seat]
+};
+
 struct EngineView {
   // ---- parameters (PlayParams subset, play_manager.h:60-154)
   u32 G, games_to_play;
-  // seat permutations (play_manager.cc:46-90, 213-221): slot g plays permutation g % n_perms in every one of its games
-  // (the reference's round-robin hand-out when the slots finish in order; G is a multiple of n_perms)
-  u32 n_perms;
-  u32 visits[kMaxPerms][2], cap_visits[kMaxPerms][2];  // seat_visits_ / seat_cap_visits_[perm][seat]
+  u32 visits[2], cap_visits[2];  // one seating (the usual case); several: EngineView::perms
   float cpuct, fpu_reduction, epsilon, root_temp;
   float start_temp, final_temp, half_life, playout_cap_percent;
   float resign_percent, resign_playthrough_percent;
@@ -196,8 +202,12 @@ struct EngineView {
   u8* leaf_player;
   u32* leaf_game;
   u8* leaf_seat;       // [rows] bits 0-3: the SEARCHING seat (the slot's side to move); bits 4-7: its model group, which evaluates the leaf
-  u8 seat_group[kMaxPerms][kP];  // seat_perms_[perm][seat]: the model group that searches for the seat (play_manager.cc:577)
-  u32 random_groups;   // NN mode (eval_type 0): bit i = model group i is EvalType::RANDOM, its searches run dumb_eval inline
+  u8 seat_group[kP];   // model group of each seat (PlayParams::model_groups, play_manager.cc:24-31) with one seating
+  u8 pad4_[2];
+  // Seat permutations and a RANDOM group next to an NN one (play_manager.cc:46-90, 213-221, 577-587): a table in device
+  // memory, NULL for the usual one-seating run — kept out of this structure, which every kernel takes by value and hands
+  // on to its out-of-line helpers (a larger view costs the step kernel 9 %: 656 B more stack per thread, profiles/r4b)
+  const PermTables* perms;
   // ---- position cache (NULL / 0 when max_cache_size == 0)
   u64* cache_keys;        // [buckets][kCacheWays]  0 = empty  (one 32 B sector per bucket)
   u32* cache_meta;        // [buckets]  per way one byte: freq (bits 0-1) | main-queue flag (bit 2)

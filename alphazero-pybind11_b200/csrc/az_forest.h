@@ -80,7 +80,20 @@ struct ForestGumbel {            // MCTS::gumbel_* members (mcts.h:163-176), one
   u16 survivors[kFMaxM];         // child indices in rank order
 };
 
+// The search settings PlayManager::make_mcts hands every seat's MCTS object (play_manager.cc:602-617: seat_epsilon_,
+// seat_mcts_root_temp_, seat_root_fpu_zero_, seat_gumbel_*_ [perm][seat]). Set 0 = the forest's own parameters; the
+// self-play engine fills one set per (seat permutation, seat): tree t = 2 * slot + seat, slot plays permutation slot % n.
+struct SeatSearch {
+  float epsilon, root_policy_temp, gumbel_c_visit, gumbel_c_scale;
+  u32 gumbel_m;
+  u8 root_fpu_zero, gumbel_enabled, gumbel_full, pad_;
+};
+constexpr int kFSeatSets = 16;
 struct ForestView {
+  u32 n_seat_sets;  // 0: every tree uses seat[0]; n: tree t uses seat[((t >> 1) % n) * 2 + (t & 1)]
+  // [kFSeatSets] in device memory, not in the view: the forest kernels copy the view to their stack (their helpers take it
+  // by reference) and every 100 B of it cost the searches about 1 % (profiles/r4e_forest_view_ab.jsonl)
+  const SeatSearch* seat;
   u32 n_trees, words_per_tree, max_turns, game;
   float cpuct, fpu_reduction;
   u32 root_fpu_zero;
@@ -111,6 +124,20 @@ struct ForestView {
                         // draw from ONE generator (the reference's thread-local one), kept in tree 2g
 };
 // the generator tree t draws from
+// the search settings of tree t (SeatSearch)
+#ifdef B2AZ_EXP_SEAT0  /* experiment build: what the per-tree lookup costs */
+#define FSEAT(F, t) ((F).seat[0])
+#else
+#define FSEAT(F, t) ((F).seat[(F).n_seat_sets ? ((((t) >> 1) % (F).n_seat_sets) * 2u + ((t) & 1u)) : 0u])
+#endif
+// The forest kernels take their views by value and their out-of-line helpers by reference, i.e. every thread keeps a copy
+// on its stack. __grid_constant__ parameters (no copy, helpers read the constant bank through a generic pointer) measured
+// 5 % slower on k_forest_simulate and equal on the self-play kernels (profiles/r4e_forest_view_ab.jsonl): not used here.
+#ifdef B2AZ_EXP_GC_FOREST  /* experiment build */
+#define AZ_GC_F AZ_GRID_CONSTANT
+#else
+#define AZ_GC_F
+#endif
 #define FOREST_RNG(F, t) ((F).trees[(F).rng_pair ? ((t) & ~1u) : (t)].rng)
 
 #ifndef B2AZ_HOST_EMU
@@ -647,8 +674,8 @@ __device__ __noinline__ void fg_rank_top(const float* score, const u16* ids, u32
     out[r] = ids ? ids[best] : (u16)best;
   }
 }
-__device__ __forceinline__ float fg_sigma_scale(const ForestView& F, u32 max_visit) {
-  return fmul(fadd(F.gumbel_c_visit, (float)max_visit), F.gumbel_c_scale);
+__device__ __forceinline__ float fg_sigma_scale(const ForestView& F, u32 t, u32 max_visit) {
+  return fmul(fadd(FSEAT(F, t).gumbel_c_visit, (float)max_visit), FSEAT(F, t).gumbel_c_scale);
 }
 // init_gumbel_state (mcts.cc:190-227); lane 0 only
 __device__ __noinline__ void fg_init(const ForestView& F, u32 t, ForestTree& R, ForestGumbel& G, const u32* pool) {
@@ -656,7 +683,7 @@ __device__ __noinline__ void fg_init(const ForestView& F, u32 t, ForestTree& R, 
   if (num_legal == 0 || b == 0) return;
   const u32 remaining = R.depth < G.num_sims_target ? G.num_sims_target - R.depth : 0u;
   if (remaining == 0) return;
-  u32 m = F.gumbel_m < num_legal ? F.gumbel_m : num_legal;
+  u32 m = FSEAT(F, t).gumbel_m < num_legal ? FSEAT(F, t).gumbel_m : num_legal;
   if (remaining < m) m = remaining;
   if (m < 1u) m = 1u;
   G.effective_m = m;
@@ -685,7 +712,7 @@ __device__ __noinline__ void fg_advance_phase(const ForestView& F, u32 t, const 
     const u32 n = pool[fb_n(b, k) + G.survivors[r]];
     if (n > max_visit) max_visit = n;
   }
-  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  const float sigma_scale = fg_sigma_scale(F, t, max_visit);
   float score[kFMaxM];
   u16 ids[kFMaxM];
   for (u32 r = 0; r < G.n_surv; ++r) {
@@ -723,7 +750,7 @@ __device__ __noinline__ u32 fg_final_action(const ForestView& F, u32 t, const Fo
     const u32 n = pool[fb_n(b, k) + i];
     if (n > max_visit) max_visit = n;
   }
-  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  const float sigma_scale = fg_sigma_scale(F, t, max_visit);
   u32 best = G.survivors[0];
   float best_score = -INFINITY;
   for (u32 r = 0; r < G.n_surv; ++r) {
@@ -758,7 +785,7 @@ __device__ __noinline__ void fg_improved_policy(const ForestView& F, u32 t, cons
     const float weighted_q = fdiv(weighted_num, sum_priors_visited);
     v_mix = fdiv(fadd(R.v, fmul(sum_visits, weighted_q)), fadd(sum_visits, 1.0f));
   }
-  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  const float sigma_scale = fg_sigma_scale(F, t, max_visit);
   float z_max = -INFINITY;
   for (u32 i = 0; i < k; ++i) {
     const float completed_q = pool[fb_n(b, k) + i] > 0 ? u2f(pool[fb_q(b, k) + i]) : v_mix;
@@ -797,7 +824,7 @@ __device__ __noinline__ u32 fg_interior_select(const ForestView& F, u32 t, const
     const float weighted_q = fdiv(weighted_num, sum_priors_visited);
     v_mix = fdiv(fadd(node_v, fmul(sum_visits, weighted_q)), fadd(sum_visits, 1.0f));
   }
-  const float sigma_scale = fg_sigma_scale(F, max_visit);
+  const float sigma_scale = fg_sigma_scale(F, t, max_visit);
   float z_max = -INFINITY;
   for (u32 i = 0; i < k; ++i) {
     const float completed_q = pool[fb_n(b, k) + i] > 0 ? u2f(pool[fb_q(b, k) + i]) : v_mix;
@@ -823,9 +850,10 @@ __device__ __noinline__ u32 fg_interior_select(const ForestView& F, u32 t, const
 // ---- root policy temperature and Dirichlet noise over a wide root (mcts.cc:403-460); lane 0, policy array in HBM.
 // Same formulas / float order as the Connect4 engine's add_root_noise (az_engine_logic.h); the noise values live
 // in the tree's Gumbel scratch row (never needed at the same time: Gumbel replaces the noise, mcts.cc:514-518).
-__device__ __noinline__ void fr_apply_root_policy_temp(const ForestView& F, u32* pool, u32 b, u32 k) {  // mcts.cc:448-460
-  if (F.root_policy_temp == 1.0f || b == 0) return;
-  const float e = fdiv(1.0f, F.root_policy_temp);
+__device__ __noinline__ void fr_apply_root_policy_temp(const ForestView& F, u32 t, u32* pool, u32 b, u32 k) {  // mcts.cc:448-460
+  const float root_temp = FSEAT(F, t).root_policy_temp;
+  if (root_temp == 1.0f || b == 0) return;
+  const float e = fdiv(1.0f, root_temp);
   float sum = 0.0f;
   for (u32 j = 0; j < k; ++j) {
     const float p = az_powf(u2f(pool[fb_pol(b, k) + j]), e);
@@ -869,9 +897,10 @@ __device__ __noinline__ void fr_add_root_noise(const ForestView& F, u32 t, Pcg32
     }
   }
   const float fsum = (float)sum;
-  const float keep = fsub(1.0f, F.epsilon);
+  const float eps = FSEAT(F, t).epsilon;
+  const float keep = fsub(1.0f, eps);
   for (u32 j = 0; j < k; ++j)
-    pool[fb_pol(b, k) + j] = f2u(fadd(fmul(u2f(pool[fb_pol(b, k) + j]), keep), fdiv(fmul(F.epsilon, noise[j]), fsum)));
+    pool[fb_pol(b, k) + j] = f2u(fadd(fmul(u2f(pool[fb_pol(b, k) + j]), keep), fdiv(fmul(eps, noise[j]), fsum)));
 }
 
 // MCTS::find_leaf (mcts.cc:462-498) for tree t
@@ -904,7 +933,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   bool at_root = true;
   // lazy Gumbel init (mcts.cc:468-472): once the root is expanded and a sims target is set
   bool gumbel_on = false;
-  if (F.gumbel_enabled) {
+  if (FSEAT(F, t).gumbel_enabled) {
     ForestGumbel& G = F.gum[t];
     if (lane == 0 && !G.initialized && G.num_sims_target > 0 && R.n > 0 && R.k > 0 && R.blk != 0) fg_init(F, t, R, G, pool);
     __syncwarp();
@@ -922,7 +951,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       u32 forced = 0;
       if (lane == 0) forced = fg_next_root_child(F, t, R, F.gum[t], pool);
       best_j = __shfl_sync(0xFFFFFFFFu, forced, 0);
-    } else if (gumbel_on && F.gumbel_full) {  // pi'-matching below the root as well (mcts.cc:479-481)
+    } else if (gumbel_on && FSEAT(F, t).gumbel_full) {  // pi'-matching below the root as well (mcts.cc:479-481)
       u32 sel = 0;
       if (lane == 0) sel = fg_interior_select(F, t, pool, b, k, cur_v);
       best_j = __shfl_sync(0xFFFFFFFFu, sel, 0);
@@ -935,7 +964,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       const float pj = j < k ? u2f(pool[fb_pol(b, k) + j]) : 0.0f;
       seen = seq_sum_masked(seen, pj, j < k && nj > 0);  // usually a handful of visited children
     }
-    const float fpu = (at_root && F.root_fpu_zero) ? 0.0f : F.fpu_reduction;
+    const float fpu = (at_root && FSEAT(F, t).root_fpu_zero) ? 0.0f : F.fpu_reduction;
     const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
     const float sqrt_n = fsqrt((float)(cur_n + (BATCHED ? cur_nif : 0u)));  // sqrt(n + n_in_flight) (mcts.cc:138)
     float best_u = 0.0f;
@@ -1082,11 +1111,11 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
       }
       __syncwarp();
       const bool is_root = plen == 0;
-      if (is_root && F.root_policy_temp != 1.0f) {
+      if (is_root && FSEAT(F, t).root_policy_temp != 1.0f) {
         // set_policy_normalized(pi, apply_temp = true, 1 / T): every prior is raised to 1/T BEFORE the in-order sum
         // (mcts.cc:111-120); az_powf is out of line and scalar: lane 0 redoes the root's priors serially
         if (lane == 0) {
-          const float e = fdiv(1.0f, F.root_policy_temp);
+          const float e = fdiv(1.0f, FSEAT(F, t).root_policy_temp);
           float tsum = 0.0f;
           for (u32 j = 0; j < lk; ++j) {
             const float p = az_powf(u2f(pool[fb_pol(lblk, lk) + j]), e);
@@ -1100,7 +1129,7 @@ __device__ void forest_process_result(const ForestView& F, u32 t, const float* e
       }
       __syncwarp();
       // Gumbel replaces Dirichlet noise (mcts.cc:514-518)
-      if (is_root && root_noise_enabled && F.epsilon > 0.0f && !F.gumbel_enabled && lane == 0) {
+      if (is_root && root_noise_enabled && FSEAT(F, t).epsilon > 0.0f && !FSEAT(F, t).gumbel_enabled && lane == 0) {
         Pcg32 rng = FOREST_RNG(F, t);
         fr_add_root_noise(F, t, rng, pool, lblk, lk);
         FOREST_RNG(F, t) = rng;
@@ -1237,7 +1266,7 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
   // gs.play_move(move) with the persistent repetition history
   if (!err) err |= G::root_play(F, t, move, sm, lane);
   if (lane == 0) {
-    if (F.gumbel_enabled) fg_reset(F.gum[t]);  // update_root ends with reset_gumbel_state() (mcts.cc:172)
+    if (F.gum) fg_reset(F.gum[t]);  // update_root ends with reset_gumbel_state() (mcts.cc:172)
     R.depth = 0;
     R.total_leaf_depth = 0;
     R.leaf.path_len = 0;
@@ -1249,14 +1278,14 @@ __device__ void forest_update_root(const ForestView& F, u32 t, u32 move, ForestS
 
 // ---- kernels: one warp per tree, 4 warps per CTA
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_find_leaf(ForestView F) {
+__global__ void __launch_bounds__(128) k_forest_find_leaf(const AZ_GC_F ForestView F) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
     forest_find_leaf<GAME, false>(F, t, sm[wib], lane, true, F.trees[t].leaf, F.leaf_canon + (size_t)t * FGame<GAME>::canon(F));
 }
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, const float* ev_v, const float* ev_pi,
+__global__ void __launch_bounds__(128) k_forest_process_result(const AZ_GC_F ForestView F, const float* ev_v, const float* ev_pi,
                                                                u32 root_noise_enabled) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
@@ -1265,14 +1294,14 @@ __global__ void __launch_bounds__(128) k_forest_process_result(ForestView F, con
 // PlayManager's step after a move under tree reuse (play_manager.cc:546-553): the reused root gets the root
 // temperature again and fresh noise — MCTS::apply_root_policy_temp() then add_root_noise() for trees with root_n > 0
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_root_noise(ForestView F, u32 add_noise) {
+__global__ void __launch_bounds__(128) k_forest_root_noise(const AZ_GC_F ForestView F, u32 add_noise) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
     ForestTree& R = F.trees[t];
     if (lane == 0 && R.n > 0 && R.blk != 0) {
       u32* pool = F.pool + (size_t)t * F.words_per_tree;
-      fr_apply_root_policy_temp(F, pool, R.blk, R.k);
-      if (add_noise && F.epsilon > 0.0f) {
+      fr_apply_root_policy_temp(F, t, pool, R.blk, R.k);
+      if (add_noise && FSEAT(F, t).epsilon > 0.0f) {
         Pcg32 rng = FOREST_RNG(F, t);
         fr_add_root_noise(F, t, rng, pool, R.blk, R.k);
         FOREST_RNG(F, t) = rng;
@@ -1285,7 +1314,7 @@ __global__ void __launch_bounds__(128) k_forest_root_noise(ForestView F, u32 add
 #define B2AZ_FOREST_MINB 8  /* 64 registers, 32 warps per SM: 100 -> 140 M sims/s (Brandubh, Gumbel) */
 #endif
 template <int GAME>
-__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_MINB) k_forest_simulate(ForestView F, u32 n_sims, u32 root_noise_enabled) {
+__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_MINB) k_forest_simulate(const AZ_GC_F ForestView F, u32 n_sims, u32 root_noise_enabled) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
@@ -1296,7 +1325,7 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_
 }
 // ---- WU-UCT: MCTS::find_leaf_batched / process_result_batched / reset_batch (mcts.cc:752-851)
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_find_leaf_batched(ForestView F) {
+__global__ void __launch_bounds__(128) k_forest_find_leaf_batched(const AZ_GC_F ForestView F) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1313,7 +1342,7 @@ __global__ void __launch_bounds__(128) k_forest_find_leaf_batched(ForestView F) 
   }
 }
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_process_result_batched(ForestView F, u32 leaf_index, const float* ev_v,
+__global__ void __launch_bounds__(128) k_forest_process_result_batched(const AZ_GC_F ForestView F, u32 leaf_index, const float* ev_v,
                                                                        const float* ev_pi, u32 root_noise_enabled) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1324,7 +1353,7 @@ __global__ void __launch_bounds__(128) k_forest_process_result_batched(ForestVie
 }
 // n_rounds x (width x find_leaf_batched, then width x process_result_batched with dumb_eval, then reset_batch) fused
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_simulate_batched(ForestView F, u32 n_rounds, u32 width) {
+__global__ void __launch_bounds__(128) k_forest_simulate_batched(const AZ_GC_F ForestView F, u32 n_rounds, u32 width) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1336,11 +1365,11 @@ __global__ void __launch_bounds__(128) k_forest_simulate_batched(ForestView F, u
     if (lane == 0) F.trees[t].in_flight = 0;
   }
 }
-__global__ void k_forest_reset_batch(ForestView F) {
+__global__ void k_forest_reset_batch(const AZ_GC_F ForestView F) {
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) F.trees[t].in_flight = 0;
 }
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_update_root(ForestView F, const u32* moves) {
+__global__ void __launch_bounds__(128) k_forest_update_root(const AZ_GC_F ForestView F, const u32* moves) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
@@ -1349,7 +1378,7 @@ __global__ void __launch_bounds__(128) k_forest_update_root(ForestView F, const 
 // Greedy self-play step entirely on the device: every tree that is not over plays its most visited root move
 // (lowest move id on ties — argmax of MCTS::counts()) through update_root + play_move. Used by the throughput tool.
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_advance(ForestView F) {
+__global__ void __launch_bounds__(128) k_forest_advance(const AZ_GC_F ForestView F) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1523,14 +1552,14 @@ __device__ void forest_probs(const ForestView& F, u32 t, float temp, float* out,
   }
 }
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_probs(ForestView F, float temp, float* probs, u32* picked, u32 pick, u32 pruned) {
+__global__ void __launch_bounds__(128) k_forest_probs(const AZ_GC_F ForestView F, float temp, float* probs, u32* picked, u32 pick, u32 pruned) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5)
     forest_probs<GAME>(F, t, temp, probs + (size_t)t * FGame<GAME>::actions(F), picked + t, pick, pruned, lane);
 }
 // MCTS::counts / root_q_values (mcts.cc:557-573) + a few scalars per tree
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_counts(ForestView F, u32* counts, float* q, u32* info) {
+__global__ void __launch_bounds__(128) k_forest_counts(const AZ_GC_F ForestView F, u32* counts, float* q, u32* info) {
   const u32 A = FGame<GAME>::actions(F);
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1568,7 +1597,7 @@ __global__ void __launch_bounds__(128) k_forest_counts(ForestView F, u32* counts
   }
 }
 // MCTS::set_gumbel_num_sims(n) (mcts.cc:175-178) for every tree
-__global__ void k_forest_gumbel_arm(ForestView F, u32 n) {
+__global__ void k_forest_gumbel_arm(const AZ_GC_F ForestView F, u32 n) {
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
     F.gum[t].num_sims_target = n;
     fg_reset(F.gum[t]);
@@ -1576,7 +1605,7 @@ __global__ void k_forest_gumbel_arm(ForestView F, u32 n) {
 }
 // gumbel_final_action + gumbel_improved_policy per tree
 template <int GAME>
-__global__ void __launch_bounds__(128) k_forest_gumbel_result(ForestView F, u32* action, float* policy) {
+__global__ void __launch_bounds__(128) k_forest_gumbel_result(const AZ_GC_F ForestView F, u32* action, float* policy) {
   const u32 A = FGame<GAME>::actions(F);
   const u32 lane = threadIdx.x & 31u;
   for (u32 t = GLOBAL_TID >> 5; t < F.n_trees; t += GLOBAL_NT >> 5) {
@@ -1593,14 +1622,14 @@ __global__ void __launch_bounds__(128) k_forest_gumbel_result(ForestView F, u32*
 }
 // MCTS::principal_variation(depth) (mcts.cc:676-715): the most-visited line from the root (first maximum in child
 // order; the root step is the Gumbel final action when Gumbel is active). out [n_trees][depth], len [n_trees].
-__global__ void k_forest_pv(ForestView F, u32 depth, u32* out, u32* len) {
+__global__ void k_forest_pv(const AZ_GC_F ForestView F, u32 depth, u32* out, u32* len) {
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
     const ForestTree& R = F.trees[t];
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
     u32 b = R.blk, k = b ? R.k : 0u, n = 0;
     for (u32 i = 0; i < depth && b != 0 && k != 0; ++i) {
       u32 best = 0xFFFFFFFFu;
-      if (i == 0 && F.gumbel_enabled) {
+      if (i == 0 && FSEAT(F, t).gumbel_enabled) {
         const u32 mv = fg_final_action(F, t, R, F.gum[t], pool);
         for (u32 j = 0; j < k && best == 0xFFFFFFFFu; ++j)
           if ((pool[fb_mv(b, k) + j] & 0xFFFFu) == mv) best = j;
@@ -1622,7 +1651,7 @@ __global__ void k_forest_pv(ForestView F, u32 depth, u32* out, u32* len) {
 }
 // the moves along the path of a pending leaf (MCTS::path_ / one InFlightLeaf): what the caller replays on its own copy
 // of the root position to obtain the leaf GameState find_leaf returns. slot < 0: the plain find_leaf's leaf.
-__global__ void k_forest_leaf_path(ForestView F, int slot, u32* out, u32* len) {
+__global__ void k_forest_leaf_path(const AZ_GC_F ForestView F, int slot, u32* out, u32* len) {
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
     const ForestLeaf& L = slot < 0 ? F.trees[t].leaf : F.inflight[(size_t)t * F.max_in_flight + (u32)slot];
     const u32* pool = F.pool + (size_t)t * F.words_per_tree;
@@ -1634,12 +1663,12 @@ __global__ void k_forest_leaf_path(ForestView F, int slot, u32* out, u32* len) {
   }
 }
 // MCTS::apply_root_policy_temp (mcts.cc:448-460) and / or MCTS::add_root_noise (mcts.cc:403-446), separately callable
-__global__ void k_forest_root_ops(ForestView F, u32 apply_temp, u32 add_noise) {
+__global__ void k_forest_root_ops(const AZ_GC_F ForestView F, u32 apply_temp, u32 add_noise) {
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
     ForestTree& R = F.trees[t];
     if (R.blk == 0 || R.k == 0) continue;
     u32* pool = F.pool + (size_t)t * F.words_per_tree;
-    if (apply_temp) fr_apply_root_policy_temp(F, pool, R.blk, R.k);
+    if (apply_temp) fr_apply_root_policy_temp(F, t, pool, R.blk, R.k);
     if (add_noise && F.noise) {
       Pcg32 rng = FOREST_RNG(F, t);
       fr_add_root_noise(F, t, rng, pool, R.blk, R.k);
@@ -1648,7 +1677,7 @@ __global__ void k_forest_root_ops(ForestView F, u32 apply_temp, u32 add_noise) {
   }
 }
 template <int GAME>
-__global__ void k_forest_init(ForestView F, unsigned long long seed) {
+__global__ void k_forest_init(const AZ_GC_F ForestView F, unsigned long long seed) {
   for (u32 t = GLOBAL_TID; t < F.n_trees; t += GLOBAL_NT) {
     ForestTree& R = F.trees[t];
     memset(&R, 0, sizeof(ForestTree));
@@ -1752,6 +1781,15 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
     if (int rc = dev_alloc(&V.gum, (size_t)V.n_trees)) return bail(rc);
     if (int rc = dev_alloc(&V.gum_g, (size_t)V.n_trees * 2 * kFMaxK)) return bail(rc);
   }
+  V.n_seat_sets = 0;
+  {
+    SeatSearch* sets = nullptr;
+    if (int rc = dev_alloc(&sets, (size_t)kFSeatSets)) return bail(rc);
+    V.seat = sets;
+    const SeatSearch s0{V.epsilon, V.root_policy_temp, V.gumbel_c_visit, V.gumbel_c_scale, V.gumbel_m, (u8)(V.root_fpu_zero ? 1 : 0),
+                        (u8)(V.gumbel_enabled ? 1 : 0), (u8)(V.gumbel_full ? 1 : 0), 0};
+    CUDA_TRY(cudaMemcpy(sets, &s0, sizeof(s0), cudaMemcpyHostToDevice));
+  }
   FOREST_DISPATCH(f, (k_forest_init<G_><<<148, 128>>>(V, p->seed)));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
@@ -1766,6 +1804,7 @@ int b2az_forest_destroy(b2az_forest* f) {
   dev_free(f->view.trees); dev_free(f->view.pool); dev_free(f->view.hist); dev_free(f->view.pkeys);
   dev_free(f->view.leaf_canon); dev_free(f->moves_dev); dev_free(f->ev_v); dev_free(f->ev_pi);
   dev_free(f->view.gum); dev_free(f->view.gum_g); dev_free(f->view.noise); dev_free(f->view.inflight);
+  dev_free(const_cast<SeatSearch*>(f->view.seat));
   dev_free(f->view.sg_state); dev_free(f->view.sg_hist); dev_free(f->view.sg_pkeys);
   delete f;
   return 0;
@@ -1793,6 +1832,7 @@ int b2az_forest_principal_variation(b2az_forest*, void*, uint32_t, uint32_t*, ui
 int b2az_forest_leaf_path(b2az_forest*, void*, int, uint32_t*, uint32_t*) FOREST_NO_CUDA()
 int b2az_forest_root_ops(b2az_forest*, void*, int, int) FOREST_NO_CUDA()
 int b2az_forest_set_root(b2az_forest*, uint32_t, const void*, uint32_t, const void*, uint32_t) FOREST_NO_CUDA()
+int b2az_forest_get_root(b2az_forest*, uint32_t, void*, uint32_t, void*, uint32_t, uint32_t*) FOREST_NO_CUDA()
 #else
 int b2az_forest_find_leaf(b2az_forest* f, void* stream, const float** canon_dev) {
   if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
@@ -2053,6 +2093,32 @@ int b2az_forest_set_root(b2az_forest* f, uint32_t tree, const void* state, uint3
   }
   h.hist_len = hist_count;
   CUDA_TRY(cudaMemcpy(f->view.trees + tree, &h, sizeof(h), cudaMemcpyHostToDevice));
+  return 0;
+}
+// the inverse of b2az_forest_set_root: the root position of `tree` as the host GameState classes hold it (GameData::gs)
+int b2az_forest_get_root(b2az_forest* f, uint32_t tree, void* state, uint32_t state_bytes, void* hist, uint32_t hist_cap,
+                         uint32_t* hist_count) {
+  if (f) CUDA_TRY(cudaSetDevice(f->device));
+  using namespace b2az;
+  if (!f || !state || !hist_count) return fail(B2AZ_EINVAL, "null argument");
+  if (tree >= f->view.n_trees) return fail(B2AZ_EINVAL, "b2az_forest_get_root: tree out of range");
+  const bool sg = f->view.sg_state != nullptr;
+  const size_t want = sg ? sizeof(SGState) : sizeof(TaflState), key = sg ? sizeof(u64) : sizeof(TaflKey);
+  const size_t cap = sg ? f->view.sg_hist_cap : (size_t)f->view.max_turns + 2u;
+  if (state_bytes != want) return fail(B2AZ_EINVAL, "b2az_forest_get_root: state record of the wrong size");
+  CUDA_TRY(cudaDeviceSynchronize());
+  ForestTree h;
+  CUDA_TRY(cudaMemcpy(&h, f->view.trees + tree, sizeof(h), cudaMemcpyDeviceToHost));
+  if (sg) CUDA_TRY(cudaMemcpy(state, f->view.sg_state + tree, want, cudaMemcpyDeviceToHost));
+  else memcpy(state, &h.state, want);
+  const uint32_t n = h.hist_len;
+  *hist_count = n;
+  if (n > cap) return fail(B2AZ_ESTATE, "b2az_forest_get_root: corrupt history length");
+  if (n) {
+    if (!hist || hist_cap < n) return fail(B2AZ_EINVAL, "b2az_forest_get_root: history buffer too small");
+    CUDA_TRY(cudaMemcpy(hist, sg ? (const void*)(f->view.sg_hist + (size_t)tree * cap) : (const void*)(f->view.hist + (size_t)tree * cap),
+                        n * key, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 int b2az_forest_counts(b2az_forest* f, void* stream, uint32_t* counts_host, float* q_host, uint32_t* info_host) {

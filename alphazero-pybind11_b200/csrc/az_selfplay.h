@@ -35,7 +35,7 @@ struct SpSlot {                       // b2az_tafl_selfplay_slot in include/b2az
   u32 fast_move_count, total_fast_move_count;
   double g_fast_leaf_depth, g_fast_entropy, fast_leaf_depth, fast_entropy;
   float resign_scores[3];             // resign_scores_
-  u32 pad3_;
+  u16 resign_streak[2];               // GameData::resign_streak (never cleared between the games of a slot, like the reference)
   Pcg32 coin;                         // playout-cap and resign-playthrough coins (see sp_coin)
 };
 static_assert(sizeof(SpSlot) == 192, "b2az_tafl_selfplay_slot layout");
@@ -77,9 +77,12 @@ struct SpView {
   u32 n_perms;
   u32 seat_visits[kSpMaxPerms][2], seat_cap_visits[kSpMaxPerms][2];  // seat_visits_ / seat_cap_visits_ (play_manager.cc:70-90)
   u8 perm_group[kSpMaxPerms][2];  // seat_perms_[perm][seat]: the model group that searches for the seat (play_manager.cc:577)
+  float seat_resign_threshold[kSpMaxPerms][2];   // seat_resign_threshold_ (-2 = off), play_manager.cc:335-366
+  u32 seat_resign_consecutive[kSpMaxPerms][2];   // seat_resign_consecutive_
   u32 random_groups;  // bit i: model group i is EvalType::RANDOM — its searches run dumb_eval inline (play_manager.cc:578-587)
   u8* leaf_group;     // [n_games] model group of the slot's waiting leaf (several groups only)
   u32 playout_cap, fast_search_uses_gumbel;
+  u32 gumbel_targets;  // PlayParams::gumbel_enabled: the policy target is gumbel_improved_policy() (play_manager.cc:412-419)
   float playout_cap_percent, resign_percent, resign_playthrough_percent;
   float start_temp, final_temp, half_life;
   u32 history_enabled, policy_target_pruning, tree_reuse;
@@ -129,8 +132,8 @@ __device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, con
       ForestTree& R = F.trees[tn];
       if (R.n > 0 && R.blk != 0) {
         u32* pool = F.pool + (size_t)tn * F.words_per_tree;
-        fr_apply_root_policy_temp(F, pool, R.blk, R.k);
-        if (F.epsilon > 0.0f && !G.capped) {
+        fr_apply_root_policy_temp(F, tn, pool, R.blk, R.k);
+        if (FSEAT(F, tn).epsilon > 0.0f && !G.capped) {
           Pcg32 rng = FOREST_RNG(F, tn);
           fr_add_root_noise(F, tn, rng, pool, R.blk, R.k);
           FOREST_RNG(F, tn) = rng;
@@ -142,7 +145,7 @@ __device__ __forceinline__ void sp_arm(const ForestView& F, const SpView& S, con
 }
 
 template <int GAME>
-__global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
+__global__ void k_sp_init(const AZ_GC_F ForestView F, const AZ_GC_F SpView S, unsigned long long seed) {
   for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) {
     pcg32_seed(F.trees[2u * g].rng, seed + g);  // slot g == a reference run after MCTS::seed_thread_rng(seed + g)
     SpSlot& G = S.slots[g];
@@ -164,13 +167,13 @@ __global__ void k_sp_init(ForestView F, SpView S, unsigned long long seed) {
 
 // the hot kernel: `n_sims` x (MCTS::find_leaf, dumb_eval, MCTS::process_result) on the tree of the seat to move
 template <int GAME>
-__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_MINB) k_sp_search(ForestView F, SpView S, u32 n_sims) {
+__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_MINB) k_sp_search(const AZ_GC_F ForestView F, const AZ_GC_F SpView S, u32 n_sims) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
     const u32 cp = FGame<GAME>::root_player(F, 2u * g), t = 2u * g + cp;
-    const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;  // seat_epsilon > 0 && !capped
+    const bool noise = FSEAT(F, t).epsilon > 0.0f && !S.slots[g].capped;  // seat_epsilon > 0 && !capped
     const u32 goal = sp_goal(S, S.slots[g], g, cp), have = F.trees[t].depth;
     const u32 todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;  // this slot's own budget
     for (u32 i = 0; i < todo; ++i) {
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_FOREST_
 // CTA-wide round, the expansions run together, the backups run together. Slots that need fewer simulations (capped
 // searches, retired slots) sit the rounds out.
 template <int GAME>
-__global__ void __launch_bounds__(512, GAME == B2AZ_FOREST_SG ? 1 : 2) k_sp_search_lock(ForestView F, SpView S, u32 n_sims) {
+__global__ void __launch_bounds__(512, GAME == B2AZ_FOREST_SG ? 1 : 2) k_sp_search_lock(const AZ_GC_F ForestView F, const AZ_GC_F SpView S, u32 n_sims) {
   __shared__ ForestSmem<GAME> sm[16];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g0 = blockIdx.x * 16u; g0 < S.n_games; g0 += gridDim.x * 16u) {
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(512, GAME == B2AZ_FOREST_SG ? 1 : 2) k_sp_sear
     if (has) {
       const u32 cp = FGame<GAME>::root_player(F, 2u * g);
       t = 2u * g + cp;
-      noise = F.epsilon > 0.0f && !S.slots[g].capped;
+      noise = FSEAT(F, t).epsilon > 0.0f && !S.slots[g].capped;
       const u32 goal = sp_goal(S, S.slots[g], g, cp), have = F.trees[t].depth;
       todo = have < goal ? (goal - have < n_sims ? goal - have : n_sims) : 0u;
     }
@@ -261,7 +264,7 @@ __device__ __forceinline__ void sp_cache_insert(const SpCache& c, u64 key, const
 // row g of both belongs to slot g. With the position cache a slot keeps simulating while its leaves hit
 // (play_manager.cc:589-594) and stops at its first miss (wait[g] = 1) or when its search is complete.
 template <int GAME>
-__global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, float* canon) {
+__global__ void __launch_bounds__(128) k_sp_find_leaf(const AZ_GC_F ForestView F, const AZ_GC_F SpView S, float* canon) {
   __shared__ ForestSmem<GAME> sm[4];
   const u32 lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, fl
     if (random_group) {  // eval_types_[group] == RANDOM: dumb_eval inline, nothing for the evaluator (play_manager.cc:578-587)
       const u32 goal = sp_goal(S, S.slots[g], g, cp), have = F.trees[t].depth;
       const u32 todo = have < goal ? goal - have : 0u;
-      const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;
+      const bool noise = FSEAT(F, t).epsilon > 0.0f && !S.slots[g].capped;
       for (u32 i = 0; i < todo; ++i) {
         forest_find_leaf<GAME, false>(F, t, sm[wib], lane, false, F.trees[t].leaf, nullptr);
         forest_process_result<GAME, true, false>(F, t, nullptr, nullptr, lane, noise, F.trees[t].leaf);
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, fl
       __syncwarp();
       continue;
     }
-    const bool noise = F.epsilon > 0.0f && !S.slots[g].capped;
+    const bool noise = FSEAT(F, t).epsilon > 0.0f && !S.slots[g].capped;
     const u32 goal = sp_goal(S, S.slots[g], g, cp);
     u32 pending = 0;
     for (u32 guard = 0; guard <= goal; ++guard) {
@@ -317,13 +320,13 @@ __global__ void __launch_bounds__(128) k_sp_find_leaf(ForestView F, SpView S, fl
   }
 }
 template <int GAME>
-__global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView S, const float* ev_v, const float* ev_pi) {
+__global__ void __launch_bounds__(128) k_sp_process_result(const AZ_GC_F ForestView F, const AZ_GC_F SpView S, const float* ev_v, const float* ev_pi) {
   const u32 lane = threadIdx.x & 31u;
   for (u32 g = GLOBAL_TID >> 5; g < S.n_games; g += GLOBAL_NT >> 5) {
     if (!S.slots[g].active) continue;
     if (S.wait && !S.wait[g]) continue;  // (cache) nothing of this slot waits for the evaluator
     const u32 t = 2u * g + FGame<GAME>::root_player(F, 2u * g);
-    forest_process_result<GAME, false, false>(F, t, ev_v, ev_pi, lane, F.epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf,
+    forest_process_result<GAME, false, false>(F, t, ev_v, ev_pi, lane, FSEAT(F, t).epsilon > 0.0f && !S.slots[g].capped, F.trees[t].leaf,
                                               /*row=*/g);  // row g of the evaluator's output belongs to slot g
     if (S.cache.sets) {  // update_inferences' insert_many (play_manager.cc:619-642)
       const u32 A = FGame<GAME>::actions(F);
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(128) k_sp_process_result(ForestView F, SpView 
 #define B2AZ_SP_MOVE_MINB 8  /* 64 registers, 32 warps per SM: the lane-0 stretches of the move step are latency bound (measured: 1 / 4 / 6 / 8 -> Brandubh 112.6 / 112.7 / 115.7 / 118.2 M sims/s, OpenTafl 46.8 / 46.9 / 46.5 / 49.1) */
 #endif
 template <int GAME>
-__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE_MINB) k_sp_move(ForestView F, SpView S) {
+__global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE_MINB) k_sp_move(const AZ_GC_F ForestView F, const AZ_GC_F SpView S) {
   typedef FGame<GAME> GM;
   const u32 A = GM::actions(F), CANON = GM::canon(F);
   __shared__ ForestSmem<GAME> sm[4];
@@ -391,10 +394,36 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
       }
       resign_term = __shfl_sync(0xFFFFFFFFu, resign_term, 0);
     }
+    // per-seat opt-in resign (play_manager.cc:335-366): the seat's expected score W - L at or below its threshold for
+    // `consecutive` own moves in a row
+    {
+      const u32 pm = sp_perm(S, g);
+      const float seat_thresh = S.seat_resign_threshold[pm][cp];
+      if (resign_term == 0 && !G.playthrough && seat_thresh > -2.0f) {
+        if (lane == 0) {
+          float q = 0.0f, d = 0.0f;
+          bool found = false;
+          const u32 b = R.blk, k = b ? R.k : 0u;
+          for (u32 j = 0; j < k; ++j) {
+            const float qj = u2f(pool[fb_q(b, k) + j]);
+            if (pool[fb_n(b, k) + j] > 0 && qj > q) { q = qj; d = u2f(pool[fb_d(b, k) + j]); found = true; }
+          }
+          if (!found && R.n > 0) { q = R.v; d = R.d; }
+          const float w = fsub(q, fdiv(d, 2.0f));
+          const float l = (float)dsub(dsub(1.0, (double)w), (double)d);
+          const float v_self = fsub(w, l);
+          if (v_self <= seat_thresh) G.resign_streak[cp] = (u16)(G.resign_streak[cp] < 0xFFFFu ? G.resign_streak[cp] + 1u : 0xFFFFu);
+          else G.resign_streak[cp] = 0;
+          const u32 need = S.seat_resign_consecutive[pm][cp] > 1u ? S.seat_resign_consecutive[pm][cp] : 1u;
+          if (G.resign_streak[cp] >= need) resign_term = ((cp + 1u) % 2u) + 1u;  // the opponent wins
+        }
+        resign_term = __shfl_sync(0xFFFFFFFFu, resign_term, 0);
+      }
+    }
     // acting rule (play_manager.cc:367-406): Gumbel's final action only after a full search
     float* act = S.scratch_pi + (size_t)g * A;
     u32 chosen = 0xFFFFFFFFu;
-    if (F.gumbel_enabled && !capped) {
+    if (FSEAT(F, t).gumbel_enabled && !capped) {
       if (lane == 0) chosen = fg_final_action(F, t, R, F.gum[t], pool);
       chosen = __shfl_sync(0xFFFFFFFFu, chosen, 0);
       if (chosen == 0xFFFFFFFFu) {  // the search never initialised: pick_move(probs(0)) (mcts.cc:379-381)
@@ -416,13 +445,13 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
         GM::stage(pos, sm[wib], S.st_canon + row * S.st_stride, lane);
       }
       float* pi = S.st_pi + row * A;
-      if (F.gumbel_enabled) {
+      if (S.gumbel_targets) {  // params_.gumbel_enabled — the GLOBAL flag, whatever the seat's own search is (play_manager.cc:412-419)
         for (u32 m = lane; m < A; m += 32u) pi[m] = 0.0f;
         __syncwarp();
         if (lane == 0) fg_improved_policy(F, t, R, pool, pi);
         __syncwarp();
       } else {
-        forest_probs<GAME>(F, t, 1.0f, pi, nullptr, 0u, (S.policy_target_pruning && F.epsilon > 0.0f) ? 1u : 0u, lane);
+        forest_probs<GAME>(F, t, 1.0f, pi, nullptr, 0u, (S.policy_target_pruning && FSEAT(F, t).epsilon > 0.0f) ? 1u : 0u, lane);
       }
       if (lane == 0) S.st_player[row] = (u8)cp;
     }
@@ -545,7 +574,7 @@ __global__ void __launch_bounds__(128, GAME == B2AZ_FOREST_SG ? 4 : B2AZ_SP_MOVE
 }
 // out[0] = active slots, out[1] = OR of every tree's sticky error bits (a search on a full slab is a search on a wrong
 // tree: the calls that synchronise report it instead of returning 0)
-__global__ void k_sp_count_active(ForestView F, SpView S, u32* out) {
+__global__ void k_sp_count_active(const AZ_GC_F ForestView F, const AZ_GC_F SpView S, u32* out) {
   u32 c = 0, err = 0;
   for (u32 g = GLOBAL_TID; g < S.n_games; g += GLOBAL_NT) {
     c += S.slots[g].active ? 1u : 0u;
@@ -606,6 +635,17 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
     if (p->seat_perms[pm][0] > 1 || p->seat_perms[pm][1] > 1) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: a model group index must be 0 or 1");
   b2az_forest_params fp = p->forest;
   fp.n_trees = 2u * p->n_games;
+  if (p->has_seat_search) {  // the forest allocates its Dirichlet / Gumbel scratch from the globals: the union of the seats
+    for (uint32_t pm = 0; pm < std::max(1u, p->n_seat_perms) && pm < (uint32_t)b2az::kSpMaxPerms; ++pm)
+      for (int seat = 0; seat < 2; ++seat) {
+        fp.epsilon = std::max(fp.epsilon, p->seat_epsilon[pm][seat]);
+        if (p->seat_gumbel_enabled[pm][seat]) {
+          if (!fp.gumbel_enabled) { fp.gumbel_m = p->seat_gumbel_m[pm][seat]; fp.gumbel_c_visit = p->seat_gumbel_c_visit[pm][seat]; fp.gumbel_c_scale = p->seat_gumbel_c_scale[pm][seat]; }
+          fp.gumbel_enabled = 1;
+          if (p->seat_gumbel_m[pm][seat] == 0) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay: seat_gumbel_m must be > 0");
+        }
+      }
+  }
   if (fp.words_per_tree == 0) {
     // sized from the search: each half of a tree's slab holds the kept subtree plus one search's new nodes; an expanded
     // node is 1 + 8 k words. Budget 8 x visits nodes at a typical branching (Brandubh 64, 11x11 boards 200) per half —
@@ -641,6 +681,13 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
       several_groups |= S.perm_group[pm][seat] != 0;
     }
   S.random_groups = (p->group_random[0] ? 1u : 0u) | (p->group_random[1] ? 2u : 0u);
+  for (uint32_t pm = 0; pm < (uint32_t)kSpMaxPerms; ++pm)
+    for (int seat = 0; seat < 2; ++seat) {
+      const bool on = p->has_seat_search && pm < S.n_perms;
+      S.seat_resign_threshold[pm][seat] = on ? p->seat_resign_threshold[pm][seat] : -2.0f;
+      S.seat_resign_consecutive[pm][seat] = on ? p->seat_resign_consecutive[pm][seat] : 1u;
+    }
+  S.gumbel_targets = p->forest.gumbel_enabled ? 1u : 0u;
   S.playout_cap = p->playout_cap_randomization ? 1u : 0u;
   S.fast_search_uses_gumbel = p->fast_search_uses_gumbel ? 1u : 0u;
   S.playout_cap_percent = p->playout_cap_percent;
@@ -656,6 +703,20 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   S.st_stride = f->view.sg_state ? (uint32_t)(sizeof(SGState) / 4u + 1u) : f->canon;
   const size_t G = p->n_games, MT = fp.max_turns, A = f->actions, C = f->canon;
   auto bail = [&](int rc) { b2az_tafl_selfplay_destroy(sp); return rc; };
+  if (p->has_seat_search) {  // make_mcts(perm, seat): every seat's own search settings (play_manager.cc:602-617)
+    ForestView& FV = f->view;
+    FV.n_seat_sets = S.n_perms;
+    SeatSearch sets[kFSeatSets];
+    memset(sets, 0, sizeof(sets));
+    for (uint32_t pm = 0; pm < S.n_perms; ++pm)
+      for (int seat = 0; seat < 2; ++seat)
+        sets[pm * 2 + seat] = SeatSearch{p->seat_epsilon[pm][seat], p->seat_root_temp[pm][seat], p->seat_gumbel_c_visit[pm][seat],
+                                         p->seat_gumbel_c_scale[pm][seat], p->seat_gumbel_m[pm][seat],
+                                         (u8)(p->seat_root_fpu_zero[pm][seat] ? 1 : 0), (u8)(p->seat_gumbel_enabled[pm][seat] ? 1 : 0),
+                                         (u8)(p->seat_gumbel_enabled[pm][seat] && p->seat_gumbel_full[pm][seat] ? 1 : 0), 0};
+    if (cudaMemcpy(const_cast<SeatSearch*>(FV.seat), sets, sizeof(sets), cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(B2AZ_ECUDA, "b2az_tafl_selfplay: seat table upload failed"));
+  }
   if (int rc = dev_alloc(&S.slots, G)) return bail(rc);
   if (int rc = dev_alloc_raw(&S.scratch_pi, G * A)) return bail(rc);
   if (S.history_enabled) {
@@ -714,6 +775,7 @@ int b2az_tafl_selfplay_leaf_batch_host(b2az_tafl_selfplay*, void*, uint32_t, flo
 int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay*, void*, const uint32_t*, const float*, const float*, uint32_t) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_variant_stats(b2az_tafl_selfplay*, void*, b2az_variant_stats*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_leaf_groups_host(b2az_tafl_selfplay*, uint8_t*, uint32_t) FOREST_NO_CUDA()
+int b2az_tafl_selfplay_root_state(b2az_tafl_selfplay*, uint32_t, void*, uint32_t, void*, uint32_t, uint32_t*) FOREST_NO_CUDA()
 int b2az_tafl_selfplay_perm_stats(b2az_tafl_selfplay*, void*, b2az_perm_stats*, uint32_t*) FOREST_NO_CUDA()
 #else
 #define SP_CTAS(sp) std::max(1u, std::min(((sp)->view.n_games + 3u) / 4u, 148u * 8u))
@@ -955,6 +1017,13 @@ int b2az_tafl_selfplay_submit_eval_host(b2az_tafl_selfplay* sp, void* stream, co
     memcpy(&sp->h_pi[(size_t)ids[i] * A], pi + (size_t)i * A, A * 4);
   }
   return b2az_tafl_selfplay_process_result(sp, stream, sp->h_v.data(), sp->h_pi.data(), 1, nullptr);
+}
+int b2az_tafl_selfplay_root_state(b2az_tafl_selfplay* sp, uint32_t slot, void* state, uint32_t state_bytes, void* hist,
+                                  uint32_t hist_cap, uint32_t* hist_count) {
+  using namespace b2az;
+  if (!sp) return fail(B2AZ_EINVAL, "null argument");
+  if (slot >= sp->view.n_games) return fail(B2AZ_EINVAL, "b2az_tafl_selfplay_root_state: slot out of range");
+  return b2az_forest_get_root(sp->forest, 2u * slot, state, state_bytes, hist, hist_cap, hist_count);
 }
 int b2az_tafl_selfplay_leaf_groups_host(b2az_tafl_selfplay* sp, uint8_t* groups_host, uint32_t n) {
   using namespace b2az;

@@ -307,17 +307,19 @@ inline SeatTables normalize_seats(const PlayParams& P, size_t np) {
 }
 // What the engines do not carry yet (see SeatTables): rejected loudly. On success the uniform per-seat tables have been
 // folded into `P`'s globals.
-inline void fold_supported_seats(PlayParams& P, const SeatTables& N, const char* engine, uint32_t max_groups) {
+inline void fold_supported_seats(PlayParams& P, const SeatTables& N, const char* engine, uint32_t max_groups, bool per_seat_search) {
   auto reject = [&](bool bad, const char* what) {
     if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + engine + " yet");
   };
   reject(N.num_model_groups > max_groups, "this many model groups (model_groups / seat_perms with different networks)");
   reject(N.seat_perms.size() > 8, "more than eight seat permutations");
-  reject(!uniform2d(N.epsilon) || !uniform2d(N.root_temp) || !uniform2d(N.root_fpu_zero), "different seat_epsilon / seat_mcts_root_temp / seat_root_fpu_zero per seat");
-  reject(!uniform2d(N.gumbel_enabled) || !uniform2d(N.gumbel_m) || !uniform2d(N.gumbel_c_visit) || !uniform2d(N.gumbel_c_scale) ||
-             !uniform2d(N.gumbel_full), "different Gumbel settings per seat");
+  if (!per_seat_search) {  // (the wide-tree engine carries a search-settings record per (permutation, seat))
+    reject(!uniform2d(N.epsilon) || !uniform2d(N.root_temp) || !uniform2d(N.root_fpu_zero), "different seat_epsilon / seat_mcts_root_temp / seat_root_fpu_zero per seat");
+    reject(!uniform2d(N.gumbel_enabled) || !uniform2d(N.gumbel_m) || !uniform2d(N.gumbel_c_visit) || !uniform2d(N.gumbel_c_scale) ||
+               !uniform2d(N.gumbel_full), "different Gumbel settings per seat");
+    reject(!uniform2d(N.resign_threshold) || N.resign_threshold[0][0] > -1.5f, "seat_resign_threshold");
+  }
   reject(N.gumbel_use_improved[0][0] != 0 || !uniform2d(N.gumbel_use_improved), "seat_gumbel_use_improved_policy");
-  reject(!uniform2d(N.resign_threshold) || N.resign_threshold[0][0] > -1.5f, "seat_resign_threshold");
   P.epsilon = N.epsilon[0][0];
   P.mcts_root_temp = N.root_temp[0][0];
   P.root_fpu_zero = N.root_fpu_zero[0][0] != 0;
@@ -457,7 +459,7 @@ class PlayManager {
                   const char* who) {
     tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
     PlayParams eff = params_;
-    fold_supported_seats(eff, tables_, who, 2);
+    fold_supported_seats(eff, tables_, who, 2, true);
     const PlayParams& P = eff;
     auto reject = [who](bool bad, const char* what) {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the " + who + " yet");
@@ -468,6 +470,20 @@ class PlayManager {
     random_eval_ = ev.all_random;
     b2az_tafl_selfplay_params sp{};
     fill_perms(sp, tables_, ev);
+    sp.has_seat_search = 1;  // make_mcts(perm, seat) (play_manager.cc:602-617) + the per-seat resign rule (:335-366)
+    for (size_t i = 0; i < tables_.seat_perms.size(); ++i)
+      for (int s = 0; s < 2; ++s) {
+        sp.seat_epsilon[i][s] = tables_.epsilon[i][s];
+        sp.seat_root_temp[i][s] = tables_.root_temp[i][s];
+        sp.seat_root_fpu_zero[i][s] = tables_.root_fpu_zero[i][s];
+        sp.seat_gumbel_enabled[i][s] = tables_.gumbel_enabled[i][s];
+        sp.seat_gumbel_full[i][s] = tables_.gumbel_full[i][s];
+        sp.seat_gumbel_m[i][s] = tables_.gumbel_m[i][s];
+        sp.seat_gumbel_c_visit[i][s] = tables_.gumbel_c_visit[i][s];
+        sp.seat_gumbel_c_scale[i][s] = tables_.gumbel_c_scale[i][s];
+        sp.seat_resign_threshold[i][s] = tables_.resign_threshold[i][s];
+        sp.seat_resign_consecutive[i][s] = tables_.resign_consecutive[i][s];
+      }
     sp.forest.game = game;
     sp.forest.max_turns = rows;
     sp.forest.relative_values = relative_values;
@@ -476,7 +492,8 @@ class PlayManager {
                                             : 2u * (1u + 4u * max_seat_visits() * (1u + 8u * k_typ));
     sp.forest.cpuct = P.cpuct; sp.forest.fpu_reduction = P.fpu_reduction; sp.forest.epsilon = P.epsilon;
     sp.forest.root_policy_temp = P.mcts_root_temp; sp.forest.root_fpu_zero = P.root_fpu_zero;
-    sp.forest.gumbel_enabled = P.gumbel_enabled; sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
+    sp.forest.gumbel_enabled = params_.gumbel_enabled;  // the GLOBAL flag: it alone picks the policy target (play_manager.cc:412-419)
+    sp.forest.gumbel_m = P.gumbel_m; sp.forest.seed = P.seed;
     sp.forest.gumbel_full = P.gumbel_full;
     sp.forest.gumbel_c_visit = P.gumbel_c_visit; sp.forest.gumbel_c_scale = P.gumbel_c_scale;
     sp.forest.shaped_dirichlet = P.shaped_dirichlet;
@@ -546,7 +563,7 @@ class PlayManager {
     group_next_.assign(tables_.num_model_groups, 0);
     refresh_stats_locked();
   }
-  PlayManager(const GameState* gs, PlayParams p) : params_(std::move(p)) {
+  PlayManager(const GameState* gs, PlayParams p) : params_(std::move(p)), base_gs_(gs->copy()) {
     if (try_tafl<B2AZ_TAFL_BRANDUBH>(gs) || try_tafl<B2AZ_TAFL_OPENTAFL>(gs) || try_tafl<B2AZ_TAFL_TAWLBWRDD>(gs) ||
         try_star_gambit(gs)) {
       size_buffers();
@@ -558,7 +575,7 @@ class PlayManager {
       throw std::runtime_error("the B200 engine starts every game from the initial Connect4 position");
     tables_ = normalize_seats(params_, kP);  // play_manager.cc:19-176, with its errors
     PlayParams eff = params_;
-    fold_supported_seats(eff, tables_, "B200 engine", 2);
+    fold_supported_seats(eff, tables_, "B200 engine", 2, false);
     const PlayParams& P = eff;
     auto reject = [](bool bad, const char* what) {
       if (bad) throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
@@ -874,12 +891,33 @@ class PlayManager {
   uint32_t concurrent() const { return G_; }
 
   // GameData accessors
-  Connect4GS game_state(uint32_t i) {
-    if (tsp_) throw std::runtime_error("game_data(i).gs() is not implemented by the B200 tafl engine yet");
-    uint8_t st[89];
+  // GameData::gs (play_manager.h:37): the slot's current position as a host GameState of the game's own class
+  std::unique_ptr<GameState> game_state(uint32_t i) {
     std::lock_guard<std::mutex> lk(api_);
+    if (tsp_) {
+      std::unique_ptr<GameState> g = base_gs_->copy();
+      uint32_t n = 0;
+      if (auto* sg = dynamic_cast<StarGambitBase*>(g.get())) {
+        sg->hist.assign(4096, 0);
+        if (b2az_tafl_selfplay_root_state(tsp_, i, &sg->s, (uint32_t)sizeof(sg->s), sg->hist.data(), (uint32_t)sg->hist.size(), &n) != 0) throw_last("game_data");
+        sg->hist.resize(n);
+        return g;
+      }
+      auto fill = [&](auto* t) {
+        if (!t) return false;
+        t->hist.assign((size_t)t->s.max_turns + 66, b2az::TaflKey{});
+        if (b2az_tafl_selfplay_root_state(tsp_, i, &t->s, (uint32_t)sizeof(t->s), t->hist.data(), (uint32_t)t->hist.size(), &n) != 0) throw_last("game_data");
+        t->hist_len = n;
+        return true;
+      };
+      if (fill(dynamic_cast<TaflGS<B2AZ_TAFL_BRANDUBH>*>(g.get())) || fill(dynamic_cast<TaflGS<B2AZ_TAFL_OPENTAFL>*>(g.get())) ||
+          fill(dynamic_cast<TaflGS<B2AZ_TAFL_TAWLBWRDD>*>(g.get())))
+        return g;
+      throw std::runtime_error("game_data(i).gs(): unknown game class");
+    }
+    uint8_t st[89];
     if (b2az_peek(eng_, nullptr, i, 0, st, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != 0) throw_last("game_data");
-    return Connect4GS::from_bytes(std::string(reinterpret_cast<char*>(st), 89));
+    return std::make_unique<Connect4GS>(Connect4GS::from_bytes(std::string(reinterpret_cast<char*>(st), 89)));
   }
   // the slot's pending leaf row (canonical planes + the v / pi the evaluator writes), or -1
   ssize_t row(uint32_t i) {
@@ -1004,6 +1042,7 @@ class PlayManager {
   }
 
   PlayParams params_;
+  std::unique_ptr<GameState> base_gs_;  // base_gs_ of the reference: the class (and variant mix) every game starts from
   SeatTables tables_;
   b2az_engine* eng_ = nullptr;
   b2az_tafl_selfplay* tsp_ = nullptr;  // set instead of eng_ for a tafl GameState
@@ -1128,7 +1167,7 @@ PYBIND11_MODULE(alphazero, m) {
 
   py::class_<GameData>(m, "GameData")
       .def("gs", [](const GameData& gd) { return gd.pm->game_state(gd.index); })
-      .def("valid_moves", [](const GameData& gd) { return gd.pm->game_state(gd.index).valid_moves(); })
+      .def("valid_moves", [](const GameData& gd) { return gd.pm->game_state(gd.index)->valid_moves(); })
       .def("v", [](const GameData& gd) {
         const ssize_t r = gd.pm->row(gd.index);
         if (r < 0) throw std::runtime_error("GameData.v(): the game has no pending leaf");

@@ -447,6 +447,10 @@ int b2az_forest_root_ops(b2az_forest* f, void* stream, int apply_temp, int add_n
  * classes of the alphazero module hold it, `hist` its repetition keys. Only before the tree's first search. */
 int b2az_forest_set_root(b2az_forest* f, uint32_t tree, const void* state, uint32_t state_bytes, const void* hist,
                          uint32_t hist_count);
+/* The inverse: the root position of `tree` (GameData::gs() of a PlayManager slot, py_wrapper.cc:265-288): the position
+ * record into state[state_bytes], up to hist_cap repetition keys into hist, their number into *hist_count. Synchronises. */
+int b2az_forest_get_root(b2az_forest* f, uint32_t tree, void* state, uint32_t state_bytes, void* hist, uint32_t hist_cap,
+                         uint32_t* hist_count);
 
 /* ---- PlayManager::play (play_manager.cc:258-600) over the tafl games on the device: n_games game slots, each with the
  * two seats' search trees (GameData::mcts[0..1]) and ONE pcg32 stream, playing games_per_slot games one after the
@@ -490,7 +494,17 @@ typedef struct b2az_tafl_selfplay_params {
   uint8_t group_random[2];       /* model group i is EvalType::RANDOM next to an NN group (eval_types_[group],
                                     play_manager.cc:578-587): its searches run dumb_eval on the device and never
                                     show up in the leaf batch */
-  uint8_t pad4_[2];
+  uint8_t has_seat_search;       /* 1: the per-(permutation, seat) search settings below replace forest.epsilon /
+                                    root_policy_temp / root_fpu_zero / gumbel_* — what make_mcts hands every seat's MCTS
+                                    (seat_epsilon_ ... seat_gumbel_full_, play_manager.cc:92-164, 602-617) — and the
+                                    per-seat resign rule is on (seat_resign_threshold_ / _consecutive_, :335-366) */
+  uint8_t pad4_;
+  float seat_epsilon[8][2], seat_root_temp[8][2];
+  uint8_t seat_root_fpu_zero[8][2], seat_gumbel_enabled[8][2], seat_gumbel_full[8][2];
+  uint32_t seat_gumbel_m[8][2];
+  float seat_gumbel_c_visit[8][2], seat_gumbel_c_scale[8][2];
+  float seat_resign_threshold[8][2];     /* -2 = off */
+  uint32_t seat_resign_consecutive[8][2];
 } b2az_tafl_selfplay_params;
 typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's counters (play_manager.cc:462-505) */
   uint32_t active, games_started, games_completed, pending;
@@ -505,7 +519,7 @@ typedef struct b2az_tafl_selfplay_slot {  /* per-slot share of PlayManager's cou
   uint32_t fast_move_count, total_fast_move_count;               /* capped (fast) searches */
   double g_fast_leaf_depth, g_fast_entropy, fast_leaf_depth, fast_entropy;
   float resign_scores[3];                                        /* resign_scores_ */
-  uint32_t pad3_;
+  uint16_t resign_streak[2];                                     /* GameData::resign_streak (per-seat resign rule) */
   uint64_t coin_state, coin_inc;                                 /* the slot's coin stream (playout cap, resign playthrough) */
 } b2az_tafl_selfplay_slot;
 typedef struct b2az_tafl_selfplay b2az_tafl_selfplay;
@@ -553,6 +567,10 @@ int b2az_tafl_selfplay_leaf_groups_host(b2az_tafl_selfplay* sp, uint8_t* groups_
 int b2az_tafl_selfplay_perm_stats(b2az_tafl_selfplay* sp, void* stream, b2az_perm_stats* out8, uint32_t* n_perms_out);
 /* slots_host[n_games]; tree_errors_host[2 * n_games] = the trees' sticky error bits (see b2az_forest_counts). */
 int b2az_tafl_selfplay_slots(b2az_tafl_selfplay* sp, void* stream, b2az_tafl_selfplay_slot* slots_host, uint32_t* tree_errors_host);
+/* GameData::gs() of slot `slot` (play_manager.h:33-58): b2az_forest_get_root of the slot's first tree (both seats' trees
+ * hold the same position). */
+int b2az_tafl_selfplay_root_state(b2az_tafl_selfplay* sp, uint32_t slot, void* state, uint32_t state_bytes, void* hist,
+                                  uint32_t hist_cap, uint32_t* hist_count);
 
 #ifdef __cplusplus
 }

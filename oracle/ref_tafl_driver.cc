@@ -448,8 +448,15 @@ struct AzRefTaflSpCfg {
   uint8_t playout_cap_randomization, fast_search_uses_gumbel, pad2_[2];
   // two model groups under ONE seat permutation (model_groups = {0, 1}, seat_perms = {seat_perm}, mcts_visits = group_visits:
   // seat_visits_[0][s] = mcts_visits_[seat_perm[s]], play_manager.cc:70-80) when has_perm != 0
-  uint8_t has_perm, seat_perm[2], pad3_;
+  uint8_t has_perm, seat_perm[2], has_seat;
   uint32_t group_visits[2];
+  // per-seat search settings and the per-seat resign rule (PlayParams::seat_* with one permutation) when has_seat != 0
+  float seat_epsilon[2], seat_root_temp[2];
+  uint8_t seat_root_fpu_zero[2], seat_gumbel_enabled[2];
+  uint32_t seat_gumbel_m[2];
+  float seat_gumbel_c_visit[2], seat_gumbel_c_scale[2];
+  float seat_resign_threshold[2];
+  uint32_t seat_resign_consecutive[2];
 };
 int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRefTaflSpCfg* c, uint32_t hist_cap,
                         float* canon_out, float* v_out, float* pi_out, uint32_t* n_hist, float* scores3,
@@ -495,6 +502,17 @@ int azref_tafl_selfplay(int game, uint16_t max_turns, uint64_t seed, const AzRef
       p.model_groups = {0, 1};
       p.mcts_visits = {c->group_visits[0], c->group_visits[1]};
       p.seat_perms = {{c->seat_perm[0], c->seat_perm[1]}};
+    }
+    if (c->has_seat) {
+      p.seat_epsilon = {{c->seat_epsilon[0], c->seat_epsilon[1]}};
+      p.seat_mcts_root_temp = {{c->seat_root_temp[0], c->seat_root_temp[1]}};
+      p.seat_root_fpu_zero = {{c->seat_root_fpu_zero[0], c->seat_root_fpu_zero[1]}};
+      p.seat_gumbel_enabled = {{c->seat_gumbel_enabled[0], c->seat_gumbel_enabled[1]}};
+      p.seat_gumbel_m = {{c->seat_gumbel_m[0], c->seat_gumbel_m[1]}};
+      p.seat_gumbel_c_visit = {{c->seat_gumbel_c_visit[0], c->seat_gumbel_c_visit[1]}};
+      p.seat_gumbel_c_scale = {{c->seat_gumbel_c_scale[0], c->seat_gumbel_c_scale[1]}};
+      p.seat_resign_threshold = {{c->seat_resign_threshold[0], c->seat_resign_threshold[1]}};
+      p.seat_resign_consecutive = {{c->seat_resign_consecutive[0], c->seat_resign_consecutive[1]}};
     }
     PlayManager pm{std::move(gs), p};
     MCTS::seed_thread_rng(seed);

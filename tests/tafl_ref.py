@@ -43,7 +43,11 @@ class SelfplayCfg(C.Structure):  # AzRefTaflSpCfg (oracle/ref_tafl_driver.cc)
                 ("seat_cap_visits", C.c_uint32 * 2), ("playout_cap_depth", C.c_uint32), ("playout_cap_percent", C.c_float),
                 ("resign_percent", C.c_float), ("resign_playthrough_percent", C.c_float),
                 ("playout_cap_randomization", C.c_uint8), ("fast_search_uses_gumbel", C.c_uint8), ("pad2_", C.c_uint8 * 2),
-                ("has_perm", C.c_uint8), ("seat_perm", C.c_uint8 * 2), ("pad3_", C.c_uint8), ("group_visits", C.c_uint32 * 2)]
+                ("has_perm", C.c_uint8), ("seat_perm", C.c_uint8 * 2), ("has_seat", C.c_uint8), ("group_visits", C.c_uint32 * 2),
+                ("seat_epsilon", C.c_float * 2), ("seat_root_temp", C.c_float * 2), ("seat_root_fpu_zero", C.c_uint8 * 2),
+                ("seat_gumbel_enabled", C.c_uint8 * 2), ("seat_gumbel_m", C.c_uint32 * 2), ("seat_gumbel_c_visit", C.c_float * 2),
+                ("seat_gumbel_c_scale", C.c_float * 2), ("seat_resign_threshold", C.c_float * 2),
+                ("seat_resign_consecutive", C.c_uint32 * 2)]
 
 
 def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduction=0.25, root_fpu_zero=False, epsilon=0.0,
@@ -51,7 +55,7 @@ def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduc
              gumbel_c_scale=1.0, start_temp=1.0, final_temp=1.0, temp_decay_half_life=0.0, tree_reuse=True,
              seat_visits=None, seat_cap_visits=None, playout_cap_randomization=False, playout_cap_depth=25,
              playout_cap_percent=0.75, fast_search_uses_gumbel=False, resign_percent=0.0, resign_playthrough_percent=0.0,
-             seat_perm=None, group_visits=None):
+             seat_perm=None, group_visits=None, seat_cfg=None):
     """The unmodified PlayManager, one slot, games_to_play games one after the other (EvalType::RANDOM) after
     MCTS::seed_thread_rng(seed). Returns dict(canonical, v, pi in history_ order, scores, games_completed,
     avg_game_length, avg_leaf_depth, avg_valid_moves, avg_search_entropy)."""
@@ -74,6 +78,15 @@ def selfplay(game, seed, max_turns, games_to_play, visits, cpuct=1.25, fpu_reduc
         cfg.has_perm = 1
         cfg.seat_perm[0], cfg.seat_perm[1] = seat_perm
         cfg.group_visits[0], cfg.group_visits[1] = group_visits
+    if seat_cfg is not None:  # per-seat settings {field: (seat 0, seat 1)}; missing fields take the globals
+        cfg.has_seat = 1
+        dflt = dict(seat_epsilon=epsilon, seat_root_temp=root_policy_temp, seat_root_fpu_zero=int(root_fpu_zero),
+                    seat_gumbel_enabled=int(gumbel_m > 0), seat_gumbel_m=gumbel_m or 16, seat_gumbel_c_visit=gumbel_c_visit,
+                    seat_gumbel_c_scale=gumbel_c_scale, seat_resign_threshold=-2.0, seat_resign_consecutive=1)
+        assert not set(seat_cfg) - set(dflt)
+        for name, d in dflt.items():
+            for i in range(2):
+                getattr(cfg, name)[i] = seat_cfg[name][i] if name in seat_cfg else d
     canon = np.zeros((cap, P, S, S), np.float32)
     v, pi = np.zeros((cap, 3), np.float32), np.zeros((cap, A), np.float32)
     n, done = C.c_uint32(0), C.c_uint32(0)

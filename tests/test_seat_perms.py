@@ -269,3 +269,50 @@ def test_wide_engine_mixed_evaluators_route_by_group(group_random, cache):
         assert np.array_equal(perm[p]["scores"], fused[5][p]["scores"]) and perm[p]["games_completed"] == fused[5][p]["games_completed"]
     for g in (0, 1):
         assert (rows_by_group[g] > 0) == (not group_random[g])
+
+
+# per-seat search settings (PlayParams::seat_epsilon / seat_mcts_root_temp / seat_root_fpu_zero / seat_gumbel_*: every seat's
+# MCTS object is built with its own, play_manager.cc:92-164, 602-617) and the per-seat resign rule (:335-366)
+SEAT_CASES = {
+    "gumbel_seat_vs_puct_seat": (0, 4, 2, 40, 40, dict(policy_target_pruning=True), dict(
+        seat_gumbel_enabled=(1, 0), seat_gumbel_m=(8, 16), seat_epsilon=(0.0, 0.25), seat_root_temp=(1.0, 1.25),
+        seat_root_fpu_zero=(0, 1))),
+    "two_gumbel_seats_different_scales": (0, 4, 1, 40, 48, dict(), dict(
+        seat_gumbel_enabled=(1, 1), seat_gumbel_m=(16, 4), seat_gumbel_c_visit=(50.0, 20.0), seat_gumbel_c_scale=(1.0, 0.5),
+        seat_epsilon=(0.25, 0.0))),
+    "seat_resign_rule": (0, 6, 2, 60, 32, dict(epsilon=0.25), dict(
+        seat_resign_threshold=(0.0, -2.0), seat_resign_consecutive=(8, 1))),  # W - L = 2 q_best - 1 <= 0: no winning line found, eight own moves in a row
+    "tawlbwrdd_seat_resign_both": (2, 3, 1, 24, 32, dict(), dict(
+        seat_resign_threshold=(0.0, 0.0), seat_resign_consecutive=(5, 8), seat_epsilon=(0.25, 0.0))),
+}
+
+
+@pytest.mark.gpu
+@needs_tafl_ref
+@pytest.mark.parametrize("name", sorted(SEAT_CASES))
+def test_wide_engine_per_seat_settings_vs_reference(name):
+    game, slots, per_slot, max_turns, visits, kw, seat = SEAT_CASES[name]
+    seed = 31337 + 7 * sorted(SEAT_CASES).index(name)
+    words = 2 * (1 + (max_turns + 2) * visits * (1 + 8 * (64 if game == 0 else 200)))
+    sp = b2az.TaflSelfplay(game, slots, max_turns, visits, games_per_slot=per_slot, seed=seed, words_per_tree=words,
+                           hist_capacity=slots * per_slot * max_turns, seat_search={k: [v] for k, v in seat.items()}, **kw)
+    active, rounds = slots, 0
+    while active:
+        active = sp.play(8)
+        rounds += 1
+        assert rounds < 10000
+    canon, v, pi, slot, st, _ = _finish(sp)
+    resigned = 0
+    for g in range(slots):
+        ref = tafl_ref.selfplay(game, seed + g, max_turns, per_slot, visits, seat_cfg=seat, **kw)
+        rows = slot == g
+        assert rows.sum() == len(ref["v"]), f"{name} slot {g}: {rows.sum()} samples vs {len(ref['v'])}"
+        assert np.array_equal(canon[rows].view(np.uint32), ref["canonical"].view(np.uint32)), f"{name} slot {g}: canonical"
+        assert np.array_equal(v[rows].view(np.uint32), ref["v"].view(np.uint32)), f"{name} slot {g}: outcomes"
+        assert np.array_equal(pi[rows].view(np.uint32), ref["pi"].view(np.uint32)), f"{name} slot {g}: policy targets"
+        assert np.array_equal(st[g]["scores"], ref["scores"])
+        assert np.array_equal(st[g]["resign_scores"], ref["resign_scores"])
+        assert np.float32(np.float32(st[g]["game_length"]) / np.float32(st[g]["games_completed"])) == ref["avg_game_length"]
+        resigned += ref["resign_scores"].sum()
+    if "resign" in name:
+        assert resigned > 0, "the case never exercised the per-seat resign rule"

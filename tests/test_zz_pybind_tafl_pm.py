@@ -89,10 +89,18 @@ def test_nn_hand_off_equals_the_random_eval_run(kind):
     t.start()
     S, A, P = tafl_ref.dims(game)
     batch = np.zeros((G, P, S, S), np.float32)
+    first = True
     while pm.remaining_games() > 0:
         ids = pm.build_batch(0, batch)
         if not ids:
             continue
+        if first:  # game_data(i).gs() (py_wrapper.cc:265-288): the first leaf of a fresh search is the root position itself
+            first = False
+            for r, i in enumerate(ids):
+                gs = pm.game_data(i).gs()
+                assert type(gs).__name__ == "BrandubhGS" and gs.current_turn() == 0 and gs.current_player() == 0
+                assert np.array_equal(np.asarray(gs.canonicalized()), batch[r])
+                assert np.array_equal(np.asarray(pm.game_data(i).valid_moves()), np.asarray(gs.valid_moves()))
         v, pi = np.zeros((len(ids), 3), np.float32), np.zeros((len(ids), A), np.float32)
         for r in range(len(ids)):
             board = (batch[r, :3] > 0).astype(np.int8)
