@@ -189,7 +189,7 @@ __global__ void k_init_games(EngineView E, InitArgs a) {
 // One thread per game slot. <= 144 registers so that seven 64-thread CTAs (14 warps) fit an SM: at the
 // BASELINE size (65,536 games over 148 SMs = 443 threads per SM) every game is resident at once.
 template <bool GB>
-__global__ void __launch_bounds__(64, 7) k_step(const AZ_GRID_CONSTANT EngineView E, u32 n_steps) {
+__global__ void __launch_bounds__(64, 7) k_step(EngineView E, u32 n_steps) {
   const u32 g = GLOBAL_TID;
   if (g >= E.G) return;
   Ctx c;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(64, 7) k_step(const AZ_GRID_CONSTANT EngineVie
 // The same, with the 32 games of a warp in lock step (run_sync): no lane leaves early, the warp votes. The selection
 // path lives in shared memory (one column per thread): an indexed access is one LDS / STS instead of a chain of selects.
 template <bool GB, bool PX = false>
-__global__ void __launch_bounds__(64, 7) k_step_sync(const AZ_GRID_CONSTANT EngineView E, u32 n_steps) {
+__global__ void __launch_bounds__(64, 7) k_step_sync(EngineView E, u32 n_steps) {
   const u32 g = GLOBAL_TID;
   const bool in_range = g < E.G;
   const u32 gg = in_range ? g : 0u;
@@ -247,7 +247,7 @@ __global__ void k_cache_find_keys(EngineView E, const u64* keys, u32 n, u8* foun
     }
   }
 }
-__global__ void k_step_serial(const AZ_GRID_CONSTANT EngineView E, u32 n_steps) {
+__global__ void k_step_serial(EngineView E, u32 n_steps) {
   for (u32 s = 0; s < n_steps; ++s)
     for (u32 g = 0; g < E.G; ++g) {
       Ctx c;

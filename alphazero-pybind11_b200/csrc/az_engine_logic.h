@@ -249,7 +249,7 @@ AZ_HD void blk_copy(Block* D, const Block* S) {
 // generation where every game re-rooted). A slot carries everything (the page id), so no memory fence
 // is needed: a gpu-scope __threadfence compiles to MEMBAR + CCTL.IVALL, which throws away the whole
 // SM's L1 on every page pop (profiles/r3: L1 hit rate 43 %).
-AZ_COLD void pool_push_page(const EngineView& E, u32 page) {
+AZ_COLD void pool_push_page(const EngineView E, u32 page) {
   const u32 region = page / E.region_pages;  // a page always goes back to the region it came from
   const unsigned long long t = at_add64(&E.ring_tickets[2u * region + 1u], 1ULL);
   u32* slot = &E.ring[(size_t)region * E.region_pages + (size_t)(t % (unsigned long long)E.region_pages)];
@@ -261,7 +261,7 @@ AZ_COLD void pool_push_page(const EngineView& E, u32 page) {
   *slot = page;
 #endif
 }
-AZ_COLD u32 pool_pop_page(const EngineView& E, u32 region) {
+AZ_COLD u32 pool_pop_page(const EngineView E, u32 region) {
   Globals* G = E.glob;
   if (ld_volatile(&G->error) & B2AZ_DEVERR_POOL) return kNil;  // already fatal: do not spin again
   const unsigned long long t = at_add64(&E.ring_tickets[2u * region], 1ULL);
@@ -278,7 +278,7 @@ AZ_COLD u32 pool_pop_page(const EngineView& E, u32 region) {
   return page;  // kNil: ring empty = the region is exhausted (fatal, reported by the caller)
 }
 // Give every page of a tree's chain back (the chain links are this thread's own writes).
-AZ_COLD void pool_push_chain(const EngineView& E, u32 head) {
+AZ_COLD void pool_push_chain(const EngineView E, u32 head) {
   u32 p = head;
   for (u32 guard = 0; p != kNil && guard < 0x10000u; ++guard) {
     const u32 nx = E.page_next[p];
@@ -524,7 +524,7 @@ AZ_HD u32 rank_top(const float* score, const u32* idx, u32 k, u32 take) {
   return out;
 }
 // init_gumbel_state (mcts.cc:190-227)
-AZ_COLD void gumbel_init(const EngineView& E, GumbelState& S, const TreeHdr& T, Pcg32& rng) {
+AZ_COLD void gumbel_init(const EngineView E, GumbelState& S, const TreeHdr& T, Pcg32& rng) {
   const u32 num_legal = T.k;
   if (num_legal == 0 || T.fc == kNil) return;
   const u32 remaining = T.depth < S.num_sims_target ? S.num_sims_target - T.depth : 0u;
@@ -582,7 +582,7 @@ AZ_HD void gumbel_advance_phase(const EngineView& E, GumbelState& S, const TreeH
   S.sims_in_phase = 0;
 }
 // gumbel_next_root_child (mcts.cc:266-283)
-AZ_COLD u32 gumbel_next_root_child(const EngineView& E, GumbelState& S, const TreeHdr& T) {
+AZ_COLD u32 gumbel_next_root_child(const EngineView E, GumbelState& S, const TreeHdr& T) {
   if ((u32)S.phase_idx < (u32)S.n_phases) {
     if (S.sims_in_phase >= S.phase_numc[S.phase_idx] * S.phase_vper[S.phase_idx]) gumbel_advance_phase(E, S, T);
   }
@@ -627,7 +627,7 @@ AZ_HD float gumbel_pi_prime(const EngineView& E, const Block* B, u32 k, float ra
   return z_sum;
 }
 // gumbel_interior_select (mcts.cc:285-334)
-AZ_COLD u32 gumbel_interior_select(const EngineView& E, u32 blk, u32 k, float node_v) {
+AZ_COLD u32 gumbel_interior_select(const EngineView E, u32 blk, u32 k, float node_v) {
   const Block* B = E.blocks + blk;
   float z[kKMax];
   u32 ns[kKMax], sum_visits = 0;
@@ -643,7 +643,7 @@ AZ_COLD u32 gumbel_interior_select(const EngineView& E, u32 blk, u32 k, float no
   return best;
 }
 // gumbel_improved_policy (mcts.cc:336-373): pi' over all moves (zeros for illegal ones)
-AZ_COLD void gumbel_improved_policy(const EngineView& E, const TreeHdr& T, float* out) {
+AZ_COLD void gumbel_improved_policy(const EngineView E, const TreeHdr& T, float* out) {
   for (int m = 0; m < kA; ++m) out[m] = 0.0f;
   const u32 k = T.k;
   if (k == 0 || T.fc == kNil) return;
@@ -672,7 +672,7 @@ struct __attribute__((aligned(16))) Descent {
 };
 static_assert(sizeof(Descent) == 64, "Descent must stay four 16 B vectors (shared-memory record of the queue kernel)");
 // Lazy Gumbel init (mcts.cc:468-472): after the root has been expanded, when a sims target is set.
-AZ_COLD bool gumbel_begin(const EngineView& E, u32 tree, const TreeHdr T, Pcg32& rng) {
+AZ_COLD bool gumbel_begin(const EngineView E, u32 tree, const TreeHdr T, Pcg32& rng) {
   GumbelState S = E.gum[tree];
   if (!S.initialized && S.num_sims_target > 0 && T.n > 0 && T.k > 0) {
     gumbel_init(E, S, T, rng);
@@ -1039,7 +1039,7 @@ AZ_COLD void add_root_noise(const EngineView& E, Pcg32& rng, float* pol, u32 k) 
 
 // set_policy_normalized at the root (mcts.cc:109-121 with the temperature branch) + add_root_noise
 // (mcts.cc:511-519): the priors of a root that has just been evaluated.
-AZ_COLD void root_leaf_priors(const EngineView& E, Pcg32& rng, float* p8, u32 lk, bool noise_enabled) {
+AZ_COLD void root_leaf_priors(const EngineView E, Pcg32& rng, float* p8, u32 lk, bool noise_enabled) {
   const bool apply_temp = (E.root_temp != 1.0f);
   const float inv_temp = fdiv(1.0f, E.root_temp);
   float sum = 0.0f;
@@ -1433,7 +1433,7 @@ AZ_COLD void update_root(const EngineView& E, TreeHdr& T, u32 move, u32 vm_befor
 
 // set_gumbel_num_sims for the tree that searches next (play_manager.cc:531-539, 562-570): the full budget, or for a
 // capped search the cap when fast_search_uses_gumbel, else 0 = "PUCT for this search".
-AZ_COLD void gumbel_arm(const EngineView& E, u32 g, u32 seat, bool capped) {
+AZ_COLD void gumbel_arm(const EngineView E, u32 g, u32 seat, bool capped) {
   const u32 target = capped ? (E.fast_search_uses_gumbel ? seat_budget(E, g, seat, true) : 0u) : seat_budget(E, g, seat, false);
   GumbelState S = E.gum[(size_t)g * kP + seat];
   gumbel_set_num_sims(S, target);
@@ -1470,7 +1470,7 @@ AZ_HD void ctx_store(const EngineView& E, u32 g, Ctx& c) {
 // The move part of PlayManager::play()'s loop body (play_manager.cc:286-555). Works on the slot's state
 // in HBM (the caller stores its register copy before and reloads it after), so nothing of the hot
 // loop's state has its address taken. Returns true when the slot retired.
-AZ_COLD bool play_move(const EngineView& E, u32 g) {
+AZ_COLD bool play_move(const EngineView E, u32 g) {
   GameSlot gs = E.games[g];
   Pcg32 rng = (E.rng_mode == 1) ? E.glob->global_rng : gs.rng;
   const u32 cp = gs.player;

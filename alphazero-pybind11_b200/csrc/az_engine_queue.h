@@ -319,7 +319,7 @@ AZ_D u32 q_move(const EngineView& E, u32 g, QGame& q) {
 }
 
 template <bool GB>
-__global__ void __launch_bounds__(B2AZ_Q_WARPS * 32, 1) k_step_q(const AZ_GRID_CONSTANT EngineView E, u32 n_steps, u32 games_per_group, u32 n_groups) {
+__global__ void __launch_bounds__(B2AZ_Q_WARPS * 32, 1) k_step_q(EngineView E, u32 n_steps, u32 games_per_group, u32 n_groups) {
   extern __shared__ __align__(16) unsigned char q_smem[];
   QShared& S = *reinterpret_cast<QShared*>(q_smem);
   const u32 tid = threadIdx.x, lane = tid & 31u;

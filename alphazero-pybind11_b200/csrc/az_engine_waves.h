@@ -89,7 +89,7 @@ __device__ __forceinline__ void w_chunk(const EngineView& E, WShared& S, u32 kin
 }
 
 template <bool GB>
-__global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(const AZ_GRID_CONSTANT EngineView E, u32 n_steps, u32 games_per_group, u32 n_groups) {
+__global__ void __launch_bounds__(B2AZ_W_WARPS * 32, 1) k_step_w(EngineView E, u32 n_steps, u32 games_per_group, u32 n_groups) {
   extern __shared__ __align__(16) unsigned char w_smem[];
   WShared& S = *reinterpret_cast<WShared*>(w_smem);
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
