@@ -91,16 +91,15 @@ struct SeatSearch {
 constexpr int kFSeatSets = 16;
 struct ForestView {
   u32 n_seat_sets;  // 0: every tree uses seat[0]; n: tree t uses seat[((t >> 1) % n) * 2 + (t & 1)]
-  // [kFSeatSets] in device memory, not in the view: the forest kernels copy the view to their stack (their helpers take it
-  // by reference) and every 100 B of it cost the searches about 1 % (profiles/r4e_forest_view_ab.jsonl)
-  const SeatSearch* seat;
+  // The search settings (epsilon, root temperature, root FPU, Gumbel) live in a table in device memory, seat[0] = the
+  // forest's own. Measured alternatives: the table inside the view (+392 B, which every thread copies to its stack: the
+  // helpers take the view by reference) and a 24 B in-view default next to the table were both slower (2.5 - 7 %,
+  // profiles/r4e_forest_view_ab.jsonl, r4i_seat_table_ab.txt); the eight fields this table replaced are gone from the view
+  // (no effect either way, r4j_slim_view_ab.txt). Against the build before per-seat settings existed the searches lost
+  // about 4 % (three table reads per simulation on the critical path).
+  const SeatSearch* seat;  // [kFSeatSets]
   u32 n_trees, words_per_tree, max_turns, game;
   float cpuct, fpu_reduction;
-  u32 root_fpu_zero;
-  u32 gumbel_enabled, gumbel_m;
-  u32 gumbel_full;      // pi'-matching at interior nodes as well (mcts.cc:285-334)
-  float gumbel_c_visit, gumbel_c_scale;
-  float epsilon, root_policy_temp;
   u32 shaped_dirichlet;
   u32 serial_shuffle;  // diagnostics: always take the sequential std::shuffle path
   ForestGumbel* gum;   // [n_trees], null unless gumbel_enabled
@@ -124,12 +123,9 @@ struct ForestView {
                         // draw from ONE generator (the reference's thread-local one), kept in tree 2g
 };
 // the generator tree t draws from
-// the search settings of tree t (SeatSearch)
-#ifdef B2AZ_EXP_SEAT0  /* experiment build: what the per-tree lookup costs */
-#define FSEAT(F, t) ((F).seat[0])
-#else
-#define FSEAT(F, t) ((F).seat[(F).n_seat_sets ? ((((t) >> 1) % (F).n_seat_sets) * 2u + ((t) & 1u)) : 0u])
-#endif
+// the search settings of tree t (SeatSearch): the forest's own, or the (permutation, seat) record of a self-play engine
+AZ_HD SeatSearch fseat(const ForestView& F, u32 t) { return F.seat[F.n_seat_sets ? (((t >> 1) % F.n_seat_sets) * 2u + (t & 1u)) : 0u]; }
+#define FSEAT(F, t) fseat((F), (t))
 // The forest kernels take their views by value and their out-of-line helpers by reference, i.e. every thread keeps a copy
 // on its stack. __grid_constant__ parameters (no copy, helpers read the constant bank through a generic pointer) measured
 // 5 % slower on k_forest_simulate and equal on the self-play kernels (profiles/r4e_forest_view_ab.jsonl): not used here.
@@ -1736,7 +1732,7 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   ForestView& V = f->view;
   memset(&V, 0, sizeof(V));
   V.n_trees = p->n_trees; V.max_turns = p->max_turns; V.game = p->game;
-  V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction; V.root_fpu_zero = p->root_fpu_zero ? 1u : 0u;
+  V.cpuct = p->cpuct; V.fpu_reduction = p->fpu_reduction;
   if (is_sg) {
     const SGSpace sp = sg_space(p->game == 24u ? B2AZ_SG_BATTLE : (int)(p->game % 10u), p->game >= 20u);
     for (int i = 0; i < 4; ++i) V.sg_probs[i] = 0.25f;
@@ -1770,14 +1766,11 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
   if (V.max_in_flight)
     if (int rc = dev_alloc(&V.inflight, (size_t)V.n_trees * V.max_in_flight)) return bail(rc);
   if (int rc = dev_alloc(&f->moves_dev, (size_t)V.n_trees)) return bail(rc);
-  V.epsilon = p->epsilon; V.root_policy_temp = p->root_policy_temp; V.shaped_dirichlet = p->shaped_dirichlet ? 1u : 0u;
+  V.shaped_dirichlet = p->shaped_dirichlet ? 1u : 0u;
   V.serial_shuffle = p->debug_serial_shuffle ? 1u : 0u;
-  if (V.epsilon > 0.0f)
+  if (p->epsilon > 0.0f)
     if (int rc = dev_alloc(&V.noise, (size_t)V.n_trees * kFMaxK)) return bail(rc);
-  V.gumbel_enabled = p->gumbel_enabled ? 1u : 0u;
-  V.gumbel_m = p->gumbel_m; V.gumbel_c_visit = p->gumbel_c_visit; V.gumbel_c_scale = p->gumbel_c_scale;
-  V.gumbel_full = (p->gumbel_enabled && p->gumbel_full) ? 1u : 0u;
-  if (V.gumbel_enabled) {
+  if (p->gumbel_enabled) {
     if (int rc = dev_alloc(&V.gum, (size_t)V.n_trees)) return bail(rc);
     if (int rc = dev_alloc(&V.gum_g, (size_t)V.n_trees * 2 * kFMaxK)) return bail(rc);
   }
@@ -1786,8 +1779,8 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
     SeatSearch* sets = nullptr;
     if (int rc = dev_alloc(&sets, (size_t)kFSeatSets)) return bail(rc);
     V.seat = sets;
-    const SeatSearch s0{V.epsilon, V.root_policy_temp, V.gumbel_c_visit, V.gumbel_c_scale, V.gumbel_m, (u8)(V.root_fpu_zero ? 1 : 0),
-                        (u8)(V.gumbel_enabled ? 1 : 0), (u8)(V.gumbel_full ? 1 : 0), 0};
+    const SeatSearch s0{p->epsilon, p->root_policy_temp, p->gumbel_c_visit, p->gumbel_c_scale, p->gumbel_m, (u8)(p->root_fpu_zero ? 1 : 0),
+                        (u8)(p->gumbel_enabled ? 1 : 0), (u8)(p->gumbel_enabled && p->gumbel_full ? 1 : 0), 0};
     CUDA_TRY(cudaMemcpy(sets, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   }
   FOREST_DISPATCH(f, (k_forest_init<G_><<<148, 128>>>(V, p->seed)));
@@ -1976,7 +1969,7 @@ int b2az_forest_set_gumbel_num_sims(b2az_forest* f, void* stream, uint32_t n) {
   if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
-  if (!f->view.gumbel_enabled) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
+  if (!f->view.gum) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
   k_forest_gumbel_arm<<<148, 128, 0, static_cast<cudaStream_t>(stream)>>>(f->view, n);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1985,7 +1978,7 @@ int b2az_forest_gumbel_result(b2az_forest* f, void* stream, uint32_t* action_hos
   if (f) CUDA_TRY(cudaSetDevice(f->device));  // the CUDA current device is per host thread
   using namespace b2az;
   if (!f) return fail(B2AZ_EINVAL, "null forest");
-  if (!f->view.gumbel_enabled) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
+  if (!f->view.gum) return fail(B2AZ_ESTATE, "b2az_forest: created without gumbel_enabled");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = f->view.n_trees, A = f->actions;
   u32* da = nullptr;

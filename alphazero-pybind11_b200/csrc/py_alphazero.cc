@@ -470,7 +470,14 @@ class PlayManager {
     random_eval_ = ev.all_random;
     b2az_tafl_selfplay_params sp{};
     fill_perms(sp, tables_, ev);
-    sp.has_seat_search = 1;  // make_mcts(perm, seat) (play_manager.cc:602-617) + the per-seat resign rule (:335-366)
+    // make_mcts(perm, seat) (play_manager.cc:602-617) + the per-seat resign rule (:335-366): only when a seat differs from
+    // the others (uniform tables have been folded into the globals, which the search reads from the constant bank)
+    bool any_resign = false;
+    for (auto& row : tables_.resign_threshold) for (float x : row) any_resign |= x > -2.0f;
+    // (a uniform seat_gumbel_enabled that differs from the global flag also needs the table: the global picks the policy target)
+    sp.has_seat_search = (any_resign || P.gumbel_enabled != params_.gumbel_enabled || !uniform2d(tables_.epsilon) || !uniform2d(tables_.root_temp) || !uniform2d(tables_.root_fpu_zero) ||
+                          !uniform2d(tables_.gumbel_enabled) || !uniform2d(tables_.gumbel_m) || !uniform2d(tables_.gumbel_c_visit) ||
+                          !uniform2d(tables_.gumbel_c_scale) || !uniform2d(tables_.gumbel_full)) ? 1 : 0;
     for (size_t i = 0; i < tables_.seat_perms.size(); ++i)
       for (int s = 0; s < 2; ++s) {
         sp.seat_epsilon[i][s] = tables_.epsilon[i][s];

@@ -196,3 +196,42 @@ def test_star_gambit_unified_variant_mix_through_the_module(kind):
     assert abs(lengths - pm.avg_game_length() * 48) < 1e-2 * lengths
     assert all(pm.variant_avg_valid_moves(v) > 1 for v in (0, 2, 3)) and pm.variant_avg_leaf_depth(0) > 0
     assert np.array_equal(np.asarray(pm.variant_perm_scores(2, 0)), np.asarray(pm.variant_scores(2)))
+
+
+@pytest.mark.parametrize("kind", [pytest.param("cuda", marks=gpu)])
+@needs_tafl_ref
+def test_per_seat_overrides_through_the_module(kind):
+    """PlayParams::seat_* (play_manager.h:121-153; what tournament.py sets per player) through alphazero.PlayManager on
+    Brandubh: a Gumbel seat against a PUCT seat with noise, the per-seat resign rule; slot g == the unmodified reference
+    PlayManager with the same overrides, seeded seed + g. Uniform overrides fold into the globals (no table)."""
+    az = module(kind)
+    game, G, max_turns, visits, seed = 0, 4, 40, 32, 4300
+    p = _params(az, G, 2, visits, seed, True, policy_target_pruning=True)
+    p.seat_gumbel_enabled = [[1, 0]]
+    p.seat_gumbel_m = [[8, 16]]
+    p.seat_epsilon = [[0.0, 0.25]]
+    p.seat_mcts_root_temp = [[1.0, 1.25]]
+    p.seat_root_fpu_zero = [[0, 1]]
+    p.seat_resign_threshold = [[0.0, -2.0]]
+    p.seat_resign_consecutive = [[8, 1]]
+    pm = az.PlayManager(az.BrandubhGS(max_turns), p)
+    pm.play()
+    canon, v, pi = _history(az, pm, game, G * 2 * max_turns)
+    seat = dict(seat_gumbel_enabled=(1, 0), seat_gumbel_m=(8, 16), seat_epsilon=(0.0, 0.25), seat_root_temp=(1.0, 1.25),
+                seat_root_fpu_zero=(0, 1), seat_resign_threshold=(0.0, -2.0), seat_resign_consecutive=(8, 1))
+    refs = [tafl_ref.selfplay(game, seed + g, max_turns, 2, visits, policy_target_pruning=True, seat_cfg=seat) for g in range(G)]
+    want = _rows(np.concatenate([r["canonical"] for r in refs]), np.concatenate([r["v"] for r in refs]),
+                 np.concatenate([r["pi"] for r in refs]))
+    assert _rows(canon, v, pi) == want
+    assert np.array_equal(pm.scores(), np.sum([r["scores"] for r in refs], axis=0))
+    assert np.array_equal(pm.resign_scores(), np.sum([r["resign_scores"] for r in refs], axis=0))
+    # uniform per-seat tables equal the globals
+    q = _params(az, G, 1, visits, seed, True, epsilon=0.25, mcts_root_temp=1.25)
+    pm0 = az.PlayManager(az.BrandubhGS(max_turns), q)
+    pm0.play()
+    q = _params(az, G, 1, visits, seed, True)
+    q.seat_epsilon = [[0.25, 0.25]]
+    q.seat_mcts_root_temp = [[1.25, 1.25]]
+    pm1 = az.PlayManager(az.BrandubhGS(max_turns), q)
+    pm1.play()
+    assert _rows(*_history(az, pm0, game, G * max_turns)) == _rows(*_history(az, pm1, game, G * max_turns))
