@@ -126,6 +126,11 @@ struct ForestView {
 // the search settings of tree t (SeatSearch): the forest's own, or the (permutation, seat) record of a self-play engine
 AZ_HD SeatSearch fseat(const ForestView& F, u32 t) { return F.seat[F.n_seat_sets ? (((t >> 1) % F.n_seat_sets) * 2u + (t & 1u)) : 0u]; }
 #define FSEAT(F, t) fseat((F), (t))
+// the three flag bytes of the record (root_fpu_zero | gumbel_enabled << 8 | gumbel_full << 16) in one load: what a descent reads
+AZ_HD u32 fseat_flags(const ForestView& F, u32 t) {
+  const SeatSearch* p = F.seat + (F.n_seat_sets ? (((t >> 1) % F.n_seat_sets) * 2u + (t & 1u)) : 0u);
+  return (u32)p->root_fpu_zero | ((u32)p->gumbel_enabled << 8) | ((u32)p->gumbel_full << 16);
+}
 // The forest kernels take their views by value and their out-of-line helpers by reference, i.e. every thread keeps a copy
 // on its stack. __grid_constant__ parameters (no copy, helpers read the constant bank through a generic pointer) measured
 // 5 % slower on k_forest_simulate and equal on the self-play kernels (profiles/r4e_forest_view_ab.jsonl): not used here.
@@ -929,7 +934,8 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
   bool at_root = true;
   // lazy Gumbel init (mcts.cc:468-472): once the root is expanded and a sims target is set
   bool gumbel_on = false;
-  if (FSEAT(F, t).gumbel_enabled) {
+  const u32 sflags = fseat_flags(F, t);  // once per descent
+  if (sflags & 0xFF00u) {
     ForestGumbel& G = F.gum[t];
     if (lane == 0 && !G.initialized && G.num_sims_target > 0 && R.n > 0 && R.k > 0 && R.blk != 0) fg_init(F, t, R, G, pool);
     __syncwarp();
@@ -947,7 +953,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       u32 forced = 0;
       if (lane == 0) forced = fg_next_root_child(F, t, R, F.gum[t], pool);
       best_j = __shfl_sync(0xFFFFFFFFu, forced, 0);
-    } else if (gumbel_on && FSEAT(F, t).gumbel_full) {  // pi'-matching below the root as well (mcts.cc:479-481)
+    } else if (gumbel_on && (sflags & 0xFF0000u)) {  // pi'-matching below the root as well (mcts.cc:479-481)
       u32 sel = 0;
       if (lane == 0) sel = fg_interior_select(F, t, pool, b, k, cur_v);
       best_j = __shfl_sync(0xFFFFFFFFu, sel, 0);
@@ -960,7 +966,7 @@ __device__ void forest_find_leaf(const ForestView& F, u32 t, ForestSmem<GAME>& s
       const float pj = j < k ? u2f(pool[fb_pol(b, k) + j]) : 0.0f;
       seen = seq_sum_masked(seen, pj, j < k && nj > 0);  // usually a handful of visited children
     }
-    const float fpu = (at_root && FSEAT(F, t).root_fpu_zero) ? 0.0f : F.fpu_reduction;
+    const float fpu = (at_root && (sflags & 0xFFu)) ? 0.0f : F.fpu_reduction;
     const float fpu_value = fsub(cur_v, fmul(fpu, fsqrt(seen)));
     const float sqrt_n = fsqrt((float)(cur_n + (BATCHED ? cur_nif : 0u)));  // sqrt(n + n_in_flight) (mcts.cc:138)
     float best_u = 0.0f;
