@@ -28,12 +28,14 @@ def test_header_symbols_exported():
 def test_struct_layouts_match_header():
     # sizes computed by the C compiler for the header's structs must equal the ctypes mirrors
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "b2az.h"\nint main(){printf("%zu %zu\\n", sizeof(b2az_params), sizeof(b2az_stats));return 0;}\n'
+    src = '#include <stdio.h>\n#include "b2az.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2az_params), sizeof(b2az_stats), sizeof(b2az_tafl_selfplay_params), sizeof(b2az_perm_stats), sizeof(b2az_forest_params), sizeof(b2az_tafl_selfplay_slot));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ph.ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         out = subprocess.check_output([os.path.join(d, "t")], text=True).split()
     assert int(out[0]) == C.sizeof(b2az.Params) and int(out[1]) == C.sizeof(b2az.Stats)
+    assert int(out[2]) == C.sizeof(b2az.TaflSelfplayParams) and int(out[3]) == C.sizeof(b2az.PermStats)
+    assert int(out[4]) == C.sizeof(b2az.ForestParams) and int(out[5]) == b2az.SLOT_DTYPE.itemsize
 
 
 @pytest.mark.skipif(has_cuda(), reason="only meaningful on a box without a GPU")
