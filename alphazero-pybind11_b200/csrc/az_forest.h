@@ -90,14 +90,13 @@ struct SeatSearch {
 };
 constexpr int kFSeatSets = 16;
 struct ForestView {
-  u32 n_seat_sets;  // 0: every tree uses seat[0]; n: tree t uses seat[((t >> 1) % n) * 2 + (t & 1)]
-  // The search settings (epsilon, root temperature, root FPU, Gumbel) live in a table in device memory, seat[0] = the
-  // forest's own. Measured alternatives: the table inside the view (+392 B, which every thread copies to its stack: the
-  // helpers take the view by reference) and a 24 B in-view default next to the table were both slower (2.5 - 7 %,
-  // profiles/r4e_forest_view_ab.jsonl, r4i_seat_table_ab.txt); the eight fields this table replaced are gone from the view
-  // (no effect either way, r4j_slim_view_ab.txt). Against the build before per-seat settings existed the searches lost
-  // about 4 % (three table reads per simulation on the critical path).
-  const SeatSearch* seat;  // [kFSeatSets]
+  // The search settings (epsilon, root temperature, root FPU, Gumbel) live in device memory, one record per tree. Measured
+  // alternatives, all slower: the (permutation, seat) table inside the view (+392 B, which every thread copies to its
+  // stack: the helpers take the view by reference), a 24 B in-view default next to a table, and a 16-entry table indexed
+  // with ((t >> 1) % n) * 2 + (t & 1) at every use (profiles/r4e_forest_view_ab.jsonl, r4i_seat_table_ab.txt,
+  // r4q_per_tree_settings_ab.txt). Against the build before per-seat settings existed the searches keep a loss of 2 %.
+  const SeatSearch* seat;  // [n_trees]: one record per tree, like the members of the reference's MCTS objects (no index arithmetic
+                           // in the search: the kernels are instruction-fetch bound, profiles/r4p_k_sp_search_ncu_summary.json)
   u32 n_trees, words_per_tree, max_turns, game;
   float cpuct, fpu_reduction;
   u32 shaped_dirichlet;
@@ -124,11 +123,11 @@ struct ForestView {
 };
 // the generator tree t draws from
 // the search settings of tree t (SeatSearch): the forest's own, or the (permutation, seat) record of a self-play engine
-AZ_HD SeatSearch fseat(const ForestView& F, u32 t) { return F.seat[F.n_seat_sets ? (((t >> 1) % F.n_seat_sets) * 2u + (t & 1u)) : 0u]; }
+AZ_HD SeatSearch fseat(const ForestView& F, u32 t) { return F.seat[t]; }
 #define FSEAT(F, t) fseat((F), (t))
 // the three flag bytes of the record (root_fpu_zero | gumbel_enabled << 8 | gumbel_full << 16) in one load: what a descent reads
 AZ_HD u32 fseat_flags(const ForestView& F, u32 t) {
-  const SeatSearch* p = F.seat + (F.n_seat_sets ? (((t >> 1) % F.n_seat_sets) * 2u + (t & 1u)) : 0u);
+  const SeatSearch* p = F.seat + t;
   return (u32)p->root_fpu_zero | ((u32)p->gumbel_enabled << 8) | ((u32)p->gumbel_full << 16);
 }
 // The forest kernels take their views by value and their out-of-line helpers by reference, i.e. every thread keeps a copy
@@ -1780,14 +1779,14 @@ int b2az_forest_create(const b2az_forest_params* p, int device, b2az_forest** ou
     if (int rc = dev_alloc(&V.gum, (size_t)V.n_trees)) return bail(rc);
     if (int rc = dev_alloc(&V.gum_g, (size_t)V.n_trees * 2 * kFMaxK)) return bail(rc);
   }
-  V.n_seat_sets = 0;
   {
     SeatSearch* sets = nullptr;
-    if (int rc = dev_alloc(&sets, (size_t)kFSeatSets)) return bail(rc);
+    if (int rc = dev_alloc(&sets, (size_t)V.n_trees)) return bail(rc);
     V.seat = sets;
     const SeatSearch s0{p->epsilon, p->root_policy_temp, p->gumbel_c_visit, p->gumbel_c_scale, p->gumbel_m, (u8)(p->root_fpu_zero ? 1 : 0),
                         (u8)(p->gumbel_enabled ? 1 : 0), (u8)(p->gumbel_enabled && p->gumbel_full ? 1 : 0), 0};
-    CUDA_TRY(cudaMemcpy(sets, &s0, sizeof(s0), cudaMemcpyHostToDevice));
+    std::vector<SeatSearch> h((size_t)V.n_trees, s0);  // every tree: the forest's own settings
+    CUDA_TRY(cudaMemcpy(sets, h.data(), h.size() * sizeof(SeatSearch), cudaMemcpyHostToDevice));
   }
   FOREST_DISPATCH(f, (k_forest_init<G_><<<148, 128>>>(V, p->seed)));
   CUDA_TRY(cudaGetLastError());

@@ -705,7 +705,6 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
   auto bail = [&](int rc) { b2az_tafl_selfplay_destroy(sp); return rc; };
   if (p->has_seat_search) {  // make_mcts(perm, seat): every seat's own search settings (play_manager.cc:602-617)
     ForestView& FV = f->view;
-    FV.n_seat_sets = S.n_perms;
     SeatSearch sets[kFSeatSets];
     memset(sets, 0, sizeof(sets));
     for (uint32_t pm = 0; pm < S.n_perms; ++pm)
@@ -714,7 +713,10 @@ int b2az_tafl_selfplay_create(const b2az_tafl_selfplay_params* p, int device, b2
                                          p->seat_gumbel_c_scale[pm][seat], p->seat_gumbel_m[pm][seat],
                                          (u8)(p->seat_root_fpu_zero[pm][seat] ? 1 : 0), (u8)(p->seat_gumbel_enabled[pm][seat] ? 1 : 0),
                                          (u8)(p->seat_gumbel_enabled[pm][seat] && p->seat_gumbel_full[pm][seat] ? 1 : 0), 0};
-    if (cudaMemcpy(const_cast<SeatSearch*>(FV.seat), sets, sizeof(sets), cudaMemcpyHostToDevice) != cudaSuccess)
+    // tree t = 2 * slot + seat; slot plays permutation slot % n_perms
+    std::vector<SeatSearch> h((size_t)FV.n_trees);
+    for (uint32_t t = 0; t < FV.n_trees; ++t) h[t] = sets[((t >> 1) % S.n_perms) * 2u + (t & 1u)];
+    if (cudaMemcpy(const_cast<SeatSearch*>(FV.seat), h.data(), h.size() * sizeof(SeatSearch), cudaMemcpyHostToDevice) != cudaSuccess)
       return bail(fail(B2AZ_ECUDA, "b2az_tafl_selfplay: seat table upload failed"));
   }
   if (int rc = dev_alloc(&S.slots, G)) return bail(rc);
